@@ -1,0 +1,112 @@
+"""CPU tests of the control plane + host reference collectives (BASELINE config #1:
+'NCCL-API allreduce correctness world_size=2 on CPU/gloo (plumbing, no GPU)')."""
+import multiprocessing as mp
+
+import pytest
+import torch
+
+from helpers import run_host_ranks
+from uccl_b200 import Communicator
+
+
+@pytest.fixture(scope="module")
+def world4():
+    return Communicator.local_world(4, host=True, heap_bytes=64 << 20, stage_bytes=1 << 20, timeout_ms=20000)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.int32, torch.int64, torch.float64])
+@pytest.mark.parametrize("op", ["sum", "max", "min", "avg"])
+def test_host_allreduce(world4, dtype, op):
+    n = 4
+    count = 70001  # spans several stage chunks for 8-byte types
+    gen = torch.Generator().manual_seed(0)
+    ins = [(torch.randint(-8, 8, (count,), generator=gen)).to(dtype) for _ in range(n)]
+    ref = torch.stack([x.double() for x in ins])
+    if op == "sum":
+        exp = ref.sum(0)
+    elif op == "avg":
+        exp = ref.sum(0) / n
+        if not dtype.is_floating_point:
+            exp = torch.div(ref.sum(0), n, rounding_mode="trunc")
+    elif op == "max":
+        exp = ref.max(0).values
+    else:
+        exp = ref.min(0).values
+
+    def fn(c):
+        x = ins[c.rank].clone()
+        c.all_reduce(x, op)
+        return x
+
+    outs = run_host_ranks(world4, fn)
+    for o in outs:
+        assert torch.allclose(o.double(), exp.to(dtype).double(), rtol=1e-2, atol=1e-2)
+        assert torch.equal(o, outs[0])
+
+
+def test_host_other_collectives(world4):
+    n = 4
+
+    def fn(c):
+        r = c.rank
+        g = torch.empty(n * 33, dtype=torch.float32)
+        c.all_gather(g, torch.full((33,), float(r)))
+        rs = torch.empty(50, dtype=torch.float32)
+        c.reduce_scatter(rs, torch.arange(n * 50, dtype=torch.float32) * (r + 1), "sum")
+        b = torch.full((17,), float(r))
+        c.broadcast(b, root=2)
+        red = torch.full((9,), float(r + 1))
+        c.reduce(red, root=1, op="prod")
+        a2a = torch.empty(n * 3, dtype=torch.int32)
+        c.all_to_all(a2a, (torch.arange(n * 3, dtype=torch.int32) + 100 * r))
+        c.barrier()
+        return g, rs, b, red, a2a
+
+    outs = run_host_ranks(world4, fn)
+    for r, (g, rs, b, red, a2a) in enumerate(outs):
+        assert torch.equal(g.view(n, 33)[:, 0], torch.arange(n, dtype=torch.float32))
+        exp_rs = torch.arange(n * 50, dtype=torch.float32).view(n, 50)[r] * sum(range(1, n + 1))
+        assert torch.equal(rs, exp_rs)
+        assert torch.equal(b, torch.full((17,), 2.0))
+        if r == 1:
+            assert torch.equal(red, torch.full((9,), 24.0))
+        exp_a2a = torch.cat([torch.arange(3, dtype=torch.int32) + 3 * r + 100 * s for s in range(n)])
+        assert torch.equal(a2a, exp_a2a)
+
+
+def test_symmetric_heap_alloc(world4):
+    c = world4[0]
+    free0 = c.native.heap_free_bytes
+    a = c.empty(1000, dtype=torch.float32)
+    b = c.empty(3, 5, dtype=torch.bfloat16)
+    assert c.is_symmetric(a) and c.is_symmetric(b)
+    assert not c.is_symmetric(torch.empty(4))
+    assert a.data_ptr() % 256 == 0 and b.data_ptr() % 256 == 0
+    a.fill_(3.0)
+    assert a.sum().item() == 3000.0
+    del a, b
+    import gc
+
+    gc.collect()
+    assert c.native.heap_free_bytes == free0
+
+
+def _mp_worker(rank, n, uid, q):
+    torch.set_num_threads(1)
+    c = Communicator.init(uid, rank, n, host=True, heap_bytes=32 << 20, stage_bytes=1 << 20, timeout_ms=20000)
+    x = torch.arange(5000, dtype=torch.float32) + rank
+    c.all_reduce(x, "sum")
+    exp = sum(torch.arange(5000, dtype=torch.float32) + r for r in range(n))
+    q.put((rank, bool(torch.equal(x, exp))))
+
+
+def test_multiprocess_bootstrap_world2():
+    """Two real processes: TCP rendezvous + shm symmetric heaps + allreduce (world_size=2)."""
+    ctx = mp.get_context("spawn")
+    uid = Communicator.create_unique_id()
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_mp_worker, args=(r, 2, uid, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in ps]
+    assert got == [(0, True), (1, True)]

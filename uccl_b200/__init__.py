@@ -1,0 +1,42 @@
+"""uccl_b200 -- a Blackwell-native (sm_100a, NVLink 5 / NVSwitch) GPU communication library
+with the capabilities of uccl-project/uccl:
+
+* ``uccl_b200.collective``  NCCL-style collectives (hand-written P2P / NVLS kernels over a
+  symmetric heap) + torch ProcessGroup glue + DDP hooks
+* ``uccl_b200.ep``          DeepEP-compatible expert-parallel dispatch / combine
+* ``uccl_b200.p2p``         NIXL-style initiator/target transfer engine (KV-cache moves)
+
+Reference entry points mirrored: ``uccl/__init__.py:12-54`` (version + library path helpers).
+"""
+from __future__ import annotations
+
+import os
+
+__version__ = "0.1.0"
+
+from . import _native  # noqa: E402
+
+
+def lib_dir() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
+
+
+def nccl_shim_path() -> str:
+    """Absolute path of the NCCL-API drop-in (``libuccl_b200_nccl.so``).
+
+    The reference exposes ``uccl.nccl_plugin_path()`` for ``NCCL_NET_PLUGIN``; on one NVSwitch
+    node no byte ever reaches a net plugin, so the drop-in here is the NCCL *API* itself."""
+    return os.path.join(lib_dir(), "libuccl_b200_nccl.so")
+
+
+def nccl_plugin_path() -> str:  # reference-compatible alias
+    return nccl_shim_path()
+
+
+def build(force: bool = False):
+    from . import _build
+
+    return _build.build(force=force)
+
+
+from .parallel.comm import Communicator  # noqa: E402,F401

@@ -1,0 +1,161 @@
+// pybind11 bindings (nanobind, which the reference uses for uccl.p2p / uccl.ep, is not
+// available offline).  Device pointers and CUDA streams cross the boundary as integers
+// (tensor.data_ptr(), torch.cuda.current_stream().cuda_stream) so this module does not
+// need any torch headers and builds in seconds.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "../coll/comm.h"
+#include "../common/log.h"
+#include "../common/param.h"
+
+namespace py = pybind11;
+using namespace ub;
+
+void bind_ep(py::module_& m);
+void bind_p2p(py::module_& m);
+void bind_util(py::module_& m);
+
+static inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline void* P(uintptr_t p) { return reinterpret_cast<void*>(p); }
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "uccl_b200 native core: symmetric-heap fabric, sm_100a collectives, EP, P2P engine";
+  m.attr("MAX_RANKS") = kMaxRanks;
+  m.attr("LL_MAX_BYTES") = (uint64_t)kLLMaxData;
+
+  m.def("create_unique_id", [] {
+    UniqueId id = Bootstrap::create_id();
+    return py::bytes(id.data, sizeof(id.data));
+  });
+  m.def("set_log_level", [](int lv) { set_log_level(lv); });
+  m.def("dtype_size", [](int dt) { return dtype_size(dt); });
+  m.def("algo_name", [](int a) { return std::string(algo_name(a)); });
+  m.def("param", [](const std::string& name, int64_t dflt) { return param_load(name.c_str(), dflt); });
+
+  py::class_<TuneEntry>(m, "TuneEntry")
+      .def(py::init([](uint64_t max_bytes, int algo, int ctas) { return TuneEntry{max_bytes, algo, ctas}; }))
+      .def_readwrite("max_bytes", &TuneEntry::max_bytes)
+      .def_readwrite("algo", &TuneEntry::algo)
+      .def_readwrite("ctas", &TuneEntry::ctas);
+
+  py::class_<Comm, std::shared_ptr<Comm>>(m, "Comm")
+      .def_static(
+          "create",
+          [](py::bytes uid, int rank, int nranks, int device, size_t heap_bytes, size_t stage_bytes, bool host_fake,
+             int timeout_ms, int max_ctas) {
+            std::string s = uid;
+            UB_CHECK(s.size() == sizeof(UniqueId), "unique id must be %zu bytes", sizeof(UniqueId));
+            UniqueId id;
+            memcpy(id.data, s.data(), sizeof(id.data));
+            CommConfig cfg;
+            cfg.heap_bytes = heap_bytes;
+            cfg.stage_bytes = stage_bytes;
+            cfg.host_fake = host_fake;
+            cfg.timeout_ms = timeout_ms;
+            cfg.max_ctas = max_ctas;
+            py::gil_scoped_release rel;
+            return Comm::create(id, rank, nranks, device, cfg);
+          },
+          py::arg("uid"), py::arg("rank"), py::arg("nranks"), py::arg("device"), py::arg("heap_bytes"),
+          py::arg("stage_bytes") = (size_t)(64ull << 20), py::arg("host_fake") = false, py::arg("timeout_ms") = -1,
+          py::arg("max_ctas") = -1)
+      .def_static(
+          "create_local",
+          [](std::vector<int> devices, size_t heap_bytes, size_t stage_bytes, bool host_fake, int timeout_ms,
+             int max_ctas) {
+            CommConfig cfg;
+            cfg.heap_bytes = heap_bytes;
+            cfg.stage_bytes = stage_bytes;
+            cfg.host_fake = host_fake;
+            cfg.timeout_ms = timeout_ms;
+            cfg.max_ctas = max_ctas;
+            return Comm::create_local(devices, cfg);
+          },
+          py::arg("devices"), py::arg("heap_bytes"), py::arg("stage_bytes") = (size_t)(64ull << 20),
+          py::arg("host_fake") = false, py::arg("timeout_ms") = -1, py::arg("max_ctas") = -1)
+      .def_property_readonly("rank", &Comm::rank)
+      .def_property_readonly("nranks", &Comm::nranks)
+      .def_property_readonly("device", &Comm::device)
+      .def_property_readonly("has_multicast", &Comm::has_multicast)
+      .def_property_readonly("is_host", &Comm::is_host)
+      .def_property_readonly("launches", &Comm::launches)
+      .def_property_readonly("error_word", &Comm::error_word)
+      .def_property_readonly("heap_base", [](const Comm& c) { return (uintptr_t)c.fabric().local(); })
+      .def_property_readonly("heap_bytes", [](const Comm& c) { return c.fabric().heap_bytes(); })
+      .def_property_readonly("heap_free_bytes", &Comm::heap_free_bytes)
+      .def_property_readonly("stage_bytes", [](const Comm& c) { return (uint64_t)c.layout().stage_bytes; })
+      .def("describe", &Comm::describe)
+      .def("alloc", [](Comm& c, size_t bytes, size_t align) { return (uintptr_t)c.alloc(bytes, align); },
+           py::arg("bytes"), py::arg("align") = 256)
+      .def("free", [](Comm& c, uintptr_t p) { c.free(P(p)); })
+      .def("in_heap", [](const Comm& c, uintptr_t p, size_t n) { return c.in_heap(P(p), n); })
+      .def("heap_offset", [](const Comm& c, uintptr_t p) { return c.heap_offset(P(p)); })
+      .def("peer_ptr", [](const Comm& c, uintptr_t p, int peer) { return (uintptr_t)c.peer_ptr(P(p), peer); })
+      .def("mc_ptr", [](const Comm& c, uintptr_t p) { return (uintptr_t)c.mc_ptr(P(p)); })
+      .def(
+          "allreduce",
+          [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, uintptr_t stream, int algo,
+             float scale, int out_dtype, int max_ctas) {
+            ArOpts o;
+            o.algo = algo;
+            o.scale = scale;
+            o.out_dtype = out_dtype;
+            o.max_ctas = max_ctas;
+            py::gil_scoped_release rel;
+            c.allreduce(P(in), P(out), count, dtype, op, S(stream), o);
+          },
+          py::arg("inp"), py::arg("out"), py::arg("count"), py::arg("dtype"), py::arg("op"), py::arg("stream"),
+          py::arg("algo") = 0, py::arg("scale") = 1.0f, py::arg("out_dtype") = -1, py::arg("max_ctas") = -1)
+      .def("allgather",
+           [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.allgather(P(in), P(out), count, dtype, S(stream));
+           })
+      .def("reduce_scatter",
+           [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.reduce_scatter(P(in), P(out), count, dtype, op, S(stream));
+           })
+      .def("broadcast",
+           [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int root, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.broadcast(P(in), P(out), count, dtype, root, S(stream));
+           })
+      .def("reduce",
+           [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int root, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.reduce(P(in), P(out), count, dtype, op, root, S(stream));
+           })
+      .def("alltoall",
+           [](Comm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.alltoall(P(in), P(out), count, dtype, S(stream));
+           })
+      .def("alltoallv",
+           [](Comm& c, uintptr_t in, std::vector<size_t> scounts, std::vector<size_t> sdispls, uintptr_t out,
+              std::vector<size_t> rcounts, std::vector<size_t> rdispls, int dtype, uintptr_t stream) {
+             const size_t n = (size_t)c.nranks();
+             UB_CHECK(scounts.size() == n && sdispls.size() == n && rcounts.size() == n && rdispls.size() == n,
+                      "alltoallv: count/displacement lists must have nranks entries");
+             py::gil_scoped_release rel;
+             c.alltoallv(P(in), scounts.data(), sdispls.data(), P(out), rcounts.data(), rdispls.data(), dtype,
+                         S(stream));
+           })
+      .def("barrier",
+           [](Comm& c, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.barrier(S(stream));
+           })
+      .def("select_allreduce",
+           [](const Comm& c, size_t bytes, bool symmetric, int dtype, int op) {
+             int ctas = 0;
+             int algo = c.select_allreduce(bytes, symmetric, dtype, op, &ctas);
+             return py::make_tuple(algo, ctas);
+           })
+      .def("set_tuning", &Comm::set_tuning);
+
+  bind_util(m);
+  bind_ep(m);
+  bind_p2p(m);
+}

@@ -1,0 +1,609 @@
+#include "comm.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../common/log.h"
+#include "../common/param.h"
+#include "../fabric/cu_api.h"
+#include "../kernels/launch.h"
+
+namespace ub {
+
+UB_PARAM(TimeoutMs, "TIMEOUT_MS", 20000)
+UB_PARAM(MaxCtas, "MAX_CTAS", 64)
+UB_PARAM(ArLLMaxBytes, "AR_LL_MAX_BYTES", 128 << 10)
+UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
+UB_PARAM(NvlsCtas, "NVLS_CTAS", 32)
+
+const char* algo_name(int algo) {
+  switch (algo) {
+    case ALGO_AUTO: return "auto";
+    case ALGO_ONESHOT_LL: return "oneshot_ll";
+    case ALGO_ONESHOT_MC: return "oneshot_mc";
+    case ALGO_TWOSHOT_P2P: return "twoshot_p2p";
+    case ALGO_TWOSHOT_NVLS: return "twoshot_nvls";
+    case ALGO_STAGED_P2P: return "staged_p2p";
+    case ALGO_STAGED_NVLS: return "staged_nvls";
+    default: return "?";
+  }
+}
+
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  bool active = false;
+  explicit DeviceGuard(int dev) {
+    if (dev < 0) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      active = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (active) cudaSetDevice(prev);
+  }
+};
+bool aligned16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+bool is_float_dtype(int dt) { return dt == kF16 || dt == kF32 || dt == kF64 || dt == kBF16 || dt == kF8E4M3 || dt == kF8E5M2; }
+}  // namespace
+
+std::shared_ptr<Comm> Comm::create(const UniqueId& id, int rank, int nranks, int device, const CommConfig& cfg) {
+  Bootstrap bs(id, rank, nranks);
+  HeapLayout l = HeapLayout::make(cfg.stage_bytes);
+  UB_CHECK(cfg.heap_bytes > l.user_off, "heap_bytes (%zu) must exceed the control+staging region (%lu)",
+           cfg.heap_bytes, (unsigned long)l.user_off);
+  auto f = Fabric::create(bs, device, cfg.heap_bytes, l.ctrl_bytes(), cfg.host_fake);
+  std::shared_ptr<Comm> c(new Comm());
+  c->init(f, cfg);
+  bs.barrier();
+  return c;
+}
+
+std::vector<std::shared_ptr<Comm>> Comm::create_local(const std::vector<int>& devices, const CommConfig& cfg) {
+  HeapLayout l = HeapLayout::make(cfg.stage_bytes);
+  UB_CHECK(cfg.heap_bytes > l.user_off, "heap_bytes (%zu) must exceed the control+staging region (%lu)",
+           cfg.heap_bytes, (unsigned long)l.user_off);
+  auto fs = Fabric::create_local(devices, cfg.heap_bytes, l.ctrl_bytes(), cfg.host_fake);
+  std::vector<std::shared_ptr<Comm>> out;
+  for (auto& f : fs) {
+    std::shared_ptr<Comm> c(new Comm());
+    c->init(f, cfg);
+    out.push_back(c);
+  }
+  return out;
+}
+
+void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
+  fabric_ = f;
+  cfg_ = cfg;
+  layout_ = HeapLayout::make(cfg.stage_bytes);
+  max_ctas_ = cfg.max_ctas > 0 ? cfg.max_ctas : (int)ubParamMaxCtas();
+  max_ctas_ = std::min(max_ctas_, kMaxSyncBlocks);
+  memset(&dev_, 0, sizeof(dev_));
+  dev_.rank = f->rank();
+  dev_.nranks = f->nranks();
+  for (int r = 0; r < f->nranks(); ++r) dev_.heap[r] = f->heap(r);
+  dev_.mc = f->mc();
+  dev_.sig_off = layout_.sig_off;
+  dev_.epoch_off = layout_.epoch_off;
+  int64_t tmo = cfg.timeout_ms >= 0 ? cfg.timeout_ms : ubParamTimeoutMs();
+  dev_.timeout_ns = (uint64_t)tmo * 1000000ull;
+  if (!f->is_host()) {
+    DeviceGuard g(f->device());
+    void* h = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) == cudaSuccess) {
+      memset(h, 0, 64);
+      err_host_ = (uint32_t*)h;
+      void* d = nullptr;
+      if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) dev_.err = (uint32_t*)d;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
+  free_[layout_.user_off] = f->heap_bytes() - layout_.user_off;
+  UB_INFO(SUB_INIT, "%s", describe().c_str());
+}
+
+Comm::~Comm() {
+  if (err_host_) cudaFreeHost(err_host_);
+}
+
+std::string Comm::describe() const {
+  char b[320];
+  snprintf(b, sizeof(b), "Comm(rank=%d/%d, dev=%d, heap=%zuMiB user_off=%luMiB stage=%luMiB, nvls=%d, max_ctas=%d)",
+           rank(), nranks(), device(), fabric_->heap_bytes() >> 20, (unsigned long)(layout_.user_off >> 20),
+           (unsigned long)(layout_.stage_bytes >> 20), has_multicast() ? 1 : 0, max_ctas_);
+  return std::string(b);
+}
+
+// ------------------------------------------------------------- heap allocator
+void* Comm::alloc(size_t bytes, size_t align) {
+  std::lock_guard<std::mutex> g(mu_);
+  if (align < 256) align = 256;
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes == 0) bytes = 256;
+  for (auto it = free_.begin(); it != free_.end(); ++it) {
+    uint64_t off = it->first, sz = it->second;
+    uint64_t aoff = (off + align - 1) / align * align;
+    if (aoff + bytes > off + sz) continue;
+    free_.erase(it);
+    if (aoff > off) free_[off] = aoff - off;
+    if (aoff + bytes < off + sz) free_[aoff + bytes] = off + sz - (aoff + bytes);
+    used_[aoff] = bytes;
+    return fabric_->local() + aoff;
+  }
+  UB_THROW("symmetric heap exhausted: need %zu bytes (heap %zu MiB); raise heap_bytes", bytes,
+           fabric_->heap_bytes() >> 20);
+}
+
+void Comm::free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> g(mu_);
+  uint64_t off = fabric_->offset_of(p);
+  auto it = used_.find(off);
+  UB_CHECK(it != used_.end(), "free(): pointer %p was not allocated from this heap", p);
+  uint64_t sz = it->second;
+  used_.erase(it);
+  auto ins = free_.emplace(off, sz).first;
+  // coalesce with next / previous
+  auto nx = std::next(ins);
+  if (nx != free_.end() && ins->first + ins->second == nx->first) {
+    ins->second += nx->second;
+    free_.erase(nx);
+  }
+  if (ins != free_.begin()) {
+    auto pv = std::prev(ins);
+    if (pv->first + pv->second == ins->first) {
+      pv->second += ins->second;
+      free_.erase(ins);
+    }
+  }
+}
+
+size_t Comm::heap_free_bytes() const {
+  std::lock_guard<std::mutex> g(mu_);
+  size_t t = 0;
+  for (auto& kv : free_) t += kv.second;
+  return t;
+}
+
+// ------------------------------------------------------------------ helpers
+CollArgs Comm::base_args() const {
+  CollArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in_off = kNoOff;
+  a.out_off = kNoOff;
+  a.ep.scale = 1.0f;
+  a.ep.idiv = 1;
+  a.misc_off = layout_.misc_off;
+  a.ll_off = layout_.ll_off;
+  a.stage_in_off = layout_.stage_in_off;
+  a.stage_out_off = layout_.stage_out_off;
+  a.stage_bytes = layout_.stage_bytes;
+  return a;
+}
+
+int Comm::ctas_for(uint64_t bytes, int cap, int per_cta_bytes) const {
+  uint64_t c = (bytes + per_cta_bytes - 1) / per_cta_bytes;
+  if (c < 1) c = 1;
+  if (c > (uint64_t)cap) c = cap;
+  return (int)c;
+}
+
+void Comm::check_buf(const void* p, const char* what) const {
+  UB_CHECK(p != nullptr, "%s is null", what);
+}
+
+void Comm::set_tuning(bool symmetric, const std::vector<TuneEntry>& table) {
+  auto t = table;
+  std::sort(t.begin(), t.end(), [](const TuneEntry& a, const TuneEntry& b) { return a.max_bytes < b.max_bytes; });
+  (symmetric ? tune_sym_ : tune_unsym_) = t;
+}
+
+int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int* ctas) const {
+  const int n = nranks();
+  const bool mc = has_multicast();
+  const bool nvls_ok = mc && nvls_reduce_supported(dtype, op);
+  int algo = (int)ubParamArForceAlgo();
+  int c = -1;
+  if (algo == ALGO_AUTO) {
+    const auto& tab = symmetric ? tune_sym_ : tune_unsym_;
+    for (const auto& e : tab) {
+      if (bytes <= e.max_bytes) {
+        algo = e.algo;
+        c = e.ctas;
+        break;
+      }
+    }
+  }
+  if (algo == ALGO_AUTO) {
+    uint64_t ll_max = std::min<uint64_t>((uint64_t)ubParamArLLMaxBytes(), kLLMaxData);
+    if (bytes <= ll_max || n == 1) algo = mc ? ALGO_ONESHOT_MC : ALGO_ONESHOT_LL;
+    else if (symmetric) algo = nvls_ok ? ALGO_TWOSHOT_NVLS : ALGO_TWOSHOT_P2P;
+    else algo = nvls_ok ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
+    if (n == 1 && bytes > kLLMaxData) algo = ALGO_STAGED_P2P;
+  }
+  // degrade gracefully when a tuned/forced choice is impossible here
+  if ((algo == ALGO_ONESHOT_MC) && !mc) algo = ALGO_ONESHOT_LL;
+  if ((algo == ALGO_TWOSHOT_NVLS) && !nvls_ok) algo = ALGO_TWOSHOT_P2P;
+  if ((algo == ALGO_STAGED_NVLS) && !nvls_ok) algo = ALGO_STAGED_P2P;
+  if ((algo == ALGO_TWOSHOT_P2P || algo == ALGO_TWOSHOT_NVLS) && !symmetric)
+    algo = (algo == ALGO_TWOSHOT_NVLS) ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
+  if ((algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) && bytes > kLLMaxData)
+    algo = symmetric ? (nvls_ok ? ALGO_TWOSHOT_NVLS : ALGO_TWOSHOT_P2P) : (nvls_ok ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P);
+  if (c <= 0) {
+    switch (algo) {
+      case ALGO_ONESHOT_LL:
+      case ALGO_ONESHOT_MC: c = ctas_for(bytes, std::min(max_ctas_, 32), 8192); break;  // 512 thr x 16 B
+      case ALGO_TWOSHOT_NVLS:
+      case ALGO_STAGED_NVLS: c = ctas_for(bytes, std::min<int>(max_ctas_, (int)ubParamNvlsCtas()), 128 << 10); break;
+      default: c = ctas_for(bytes, max_ctas_, 128 << 10); break;
+    }
+  }
+  c = std::max(1, std::min(c, std::min(max_ctas_, kMaxSyncBlocks)));
+  if (ctas) *ctas = c;
+  return algo;
+}
+
+static cudaError_t launch_ar_any(int algo, int dtype, int op, int out_dtype, const DevComm& d, const CollArgs& a,
+                                 int grid, int block, cudaStream_t st) {
+  switch (dtype) {
+    case kF32: case kBF16: case kF16: return launch_allreduce_f(algo, dtype, op, out_dtype, d, a, grid, block, st);
+    case kI8: case kU8: case kI32: case kU32: case kI64: case kU64:
+      if (out_dtype != dtype) return cudaErrorInvalidValue;
+      return launch_allreduce_i(algo, dtype, op, d, a, grid, block, st);
+    default:
+      if (out_dtype != dtype) return cudaErrorInvalidValue;
+      return launch_allreduce_x(algo, dtype, op, d, a, grid, block, st);
+  }
+}
+
+// ------------------------------------------------------------------ allreduce
+void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t stream,
+                     const ArOpts& opts) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "allreduce: bad dtype %d", dtype);
+  UB_CHECK(op >= 0 && op < kNumOps, "allreduce: bad op %d", op);
+  if (count == 0) return;
+  check_buf(in, "sendbuff");
+  check_buf(out, "recvbuff");
+  const int n = nranks();
+  const int out_dtype = opts.out_dtype < 0 ? dtype : opts.out_dtype;
+  const size_t esize = dtype_size(dtype), osize = dtype_size(out_dtype);
+  const size_t bytes = count * esize, out_bytes = count * osize;
+  float scale = opts.scale;
+  int idiv = 1;
+  if (op == kAvg) {
+    if (is_float_dtype(dtype)) scale *= 1.0f / (float)n;
+    else idiv = n;
+  }
+  if (is_host()) {
+    UB_CHECK(out_dtype == dtype, "host backend: fused cast unsupported");
+    host_allreduce(in, out, count, dtype, op, is_float_dtype(dtype) ? scale : 1.0f);
+    return;
+  }
+  DeviceGuard g(device());
+  if (n == 1 && out_dtype == dtype && scale == 1.0f && idiv == 1) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(aligned16(in) && aligned16(out), "allreduce: buffers must be 16-byte aligned (in=%p out=%p)", in, out);
+  const bool sym = in_heap(in, bytes) && in_heap(out, out_bytes);
+  int ctas = 0;
+  int algo = opts.algo != ALGO_AUTO ? opts.algo : ALGO_AUTO;
+  if (algo == ALGO_AUTO) {
+    algo = select_allreduce(bytes, sym, dtype, op, &ctas);
+  } else {
+    int dummy_algo = select_allreduce(bytes, sym, dtype, op, &ctas);
+    (void)dummy_algo;
+    // validate a forced choice
+    if (algo == ALGO_ONESHOT_MC || algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
+      UB_CHECK(has_multicast(), "allreduce: algo %s needs NVLS multicast", algo_name(algo));
+    if (algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
+      UB_CHECK(nvls_reduce_supported(dtype, op), "allreduce: NVLS cannot reduce dtype %d op %d", dtype, op);
+    if (algo == ALGO_TWOSHOT_P2P || algo == ALGO_TWOSHOT_NVLS)
+      UB_CHECK(sym, "allreduce: algo %s needs buffers from the symmetric heap", algo_name(algo));
+    if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC)
+      UB_CHECK(bytes <= kLLMaxData, "allreduce: one-shot limited to %lu bytes", (unsigned long)kLLMaxData);
+    if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) ctas = ctas_for(bytes, std::min(max_ctas_, 32), 8192);
+    else if (algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
+      ctas = ctas_for(bytes, std::min<int>(max_ctas_, (int)ubParamNvlsCtas()), 128 << 10);
+    else ctas = ctas_for(bytes, max_ctas_, 128 << 10);
+  }
+  if (opts.max_ctas > 0) ctas = std::min(ctas, opts.max_ctas);
+  if (out_dtype != dtype) {
+    UB_CHECK(algo != ALGO_ONESHOT_LL && algo != ALGO_ONESHOT_MC || true, "unreachable");
+    if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC)
+      algo = sym ? ALGO_TWOSHOT_P2P : ALGO_STAGED_P2P;  // cast is fused only in the two-shot/staged kernels
+    UB_CHECK(bytes % 16 == 0 && out_bytes % 16 == 0,
+             "allreduce with fused cast needs 16-byte multiples on both sides (count=%zu)", count);
+  }
+
+  CollArgs a = base_args();
+  a.ep.scale = scale;
+  a.ep.idiv = idiv;
+  const bool oneshot = (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC);
+  const size_t main_bytes = oneshot ? bytes : (bytes / 16 * 16);
+  const int block = 512;
+  if (main_bytes) {
+    a.in = in;
+    a.out = out;
+    a.bytes = main_bytes;
+    a.count = main_bytes / esize;
+    if (sym) {
+      a.in_off = heap_offset(in);
+      a.out_off = heap_offset(out);
+    }
+    cudaError_t e = launch_ar_any(algo, dtype, op, out_dtype, dev_, a, ctas, block, stream);
+    UB_CHECK(e == cudaSuccess, "allreduce launch failed (algo=%s dtype=%d op=%d ctas=%d): %s", algo_name(algo),
+             dtype, op, ctas, cudaGetErrorString(e));
+    ++launches_;
+  }
+  if (main_bytes < bytes) {  // < 16-byte tail through the packet path
+    CollArgs t = base_args();
+    t.ep = a.ep;
+    t.in = (const char*)in + main_bytes;
+    t.out = (char*)out + main_bytes;
+    t.bytes = bytes - main_bytes;
+    t.count = t.bytes / esize;
+    cudaError_t e = launch_ar_any(has_multicast() ? ALGO_ONESHOT_MC : ALGO_ONESHOT_LL, dtype, op, dtype, dev_, t, 1,
+                                  block, stream);
+    UB_CHECK(e == cudaSuccess, "allreduce tail launch failed: %s", cudaGetErrorString(e));
+    ++launches_;
+  }
+  UB_TRACE(SUB_COLL, "allreduce bytes=%zu algo=%s ctas=%d sym=%d", bytes, algo_name(algo), ctas, sym ? 1 : 0);
+}
+
+// ------------------------------------------------------------------ allgather
+void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "allgather: bad dtype %d", dtype);
+  if (count_per_rank == 0) return;
+  check_buf(in, "sendbuff");
+  check_buf(out, "recvbuff");
+  const int n = nranks();
+  const size_t bytes = count_per_rank * dtype_size(dtype);
+  if (is_host()) {
+    host_allgather(in, out, bytes);
+    return;
+  }
+  DeviceGuard g(device());
+  if (n == 1) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(aligned16(in) && aligned16(out), "allgather: buffers must be 16-byte aligned");
+  CollArgs a = base_args();
+  a.in = in;
+  a.out = out;
+  a.bytes = bytes;
+  a.count = count_per_rank;
+  const bool out_sym = in_heap(out, bytes * n);
+  const bool in_sym = in_heap(in, bytes);
+  int mode;
+  if (out_sym && bytes % 16 == 0) {
+    a.out_off = heap_offset(out);
+    mode = has_multicast() ? 1 : 0;
+  } else {
+    mode = 2;
+    if (in_sym) a.in_off = heap_offset(in);
+  }
+  int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
+  cudaError_t e = launch_allgather(mode, dev_, a, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "allgather launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+// ------------------------------------------------------------- reduce_scatter
+void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "reduce_scatter: bad dtype %d", dtype);
+  UB_CHECK(op >= 0 && op < kNumOps, "reduce_scatter: bad op %d", op);
+  if (recv_count == 0) return;
+  check_buf(in, "sendbuff");
+  check_buf(out, "recvbuff");
+  const int n = nranks();
+  const size_t bytes = recv_count * dtype_size(dtype);
+  if (is_host()) {
+    host_reduce_scatter(in, out, recv_count, dtype, op);
+    return;
+  }
+  DeviceGuard g(device());
+  CollArgs a = base_args();
+  if (op == kAvg) {
+    if (is_float_dtype(dtype)) a.ep.scale = 1.0f / (float)n;
+    else a.ep.idiv = n;
+  }
+  if (n == 1 && op != kAvg) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(aligned16(in) && aligned16(out), "reduce_scatter: buffers must be 16-byte aligned");
+  a.in = in;
+  a.out = out;
+  a.bytes = bytes;
+  a.count = recv_count;
+  const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
+  if (in_sym) a.in_off = heap_offset(in);
+  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op);
+  int ctas = ctas_for(bytes, nvls ? std::min<int>(max_ctas_, (int)ubParamNvlsCtas()) : max_ctas_, 64 << 10);
+  cudaError_t e;
+  if (dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2)
+    e = launch_red_f(0, dtype, op, nvls, dev_, a, ctas, 512, stream);
+  else
+    e = launch_red_i(0, dtype, op, dev_, a, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "reduce_scatter launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+// ------------------------------------------------------------------ broadcast
+void Comm::broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "broadcast: bad dtype %d", dtype);
+  UB_CHECK(root >= 0 && root < nranks(), "broadcast: bad root %d", root);
+  if (count == 0) return;
+  check_buf(out, "recvbuff");
+  const size_t bytes = count * dtype_size(dtype);
+  if (rank() == root) check_buf(in, "sendbuff");
+  if (is_host()) {
+    host_broadcast(in, out, bytes, root);
+    return;
+  }
+  DeviceGuard g(device());
+  if (nranks() == 1) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(aligned16(out) && (rank() != root || aligned16(in)), "broadcast: buffers must be 16-byte aligned");
+  CollArgs a = base_args();
+  a.in = rank() == root ? in : out;
+  a.out = out;
+  a.bytes = bytes;
+  a.count = count;
+  a.root = root;
+  int mode = 0;
+  if (in_heap(out, bytes)) {
+    a.out_off = heap_offset(out);
+    mode = has_multicast() ? 1 : 2;
+  }
+  int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
+  cudaError_t e = launch_broadcast(mode, dev_, a, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "broadcast launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+// --------------------------------------------------------------------- reduce
+void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "reduce: bad dtype %d", dtype);
+  UB_CHECK(op >= 0 && op < kNumOps, "reduce: bad op %d", op);
+  UB_CHECK(root >= 0 && root < nranks(), "reduce: bad root %d", root);
+  if (count == 0) return;
+  check_buf(in, "sendbuff");
+  if (rank() == root) check_buf(out, "recvbuff");
+  const int n = nranks();
+  const size_t bytes = count * dtype_size(dtype);
+  if (is_host()) {
+    host_reduce(in, out, count, dtype, op, root);
+    return;
+  }
+  DeviceGuard g(device());
+  CollArgs a = base_args();
+  if (op == kAvg) {
+    if (is_float_dtype(dtype)) a.ep.scale = 1.0f / (float)n;
+    else a.ep.idiv = n;
+  }
+  if (n == 1 && op != kAvg) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(aligned16(in) && (rank() != root || aligned16(out)), "reduce: buffers must be 16-byte aligned");
+  a.in = in;
+  a.out = rank() == root ? out : const_cast<void*>(in);
+  a.bytes = bytes;
+  a.count = count;
+  a.root = root;
+  if (in_heap(in, bytes)) a.in_off = heap_offset(in);
+  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op);
+  int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
+  cudaError_t e;
+  if (is_float_dtype(dtype)) e = launch_red_f(1, dtype, op, nvls, dev_, a, ctas, 512, stream);
+  else e = launch_red_i(1, dtype, op, dev_, a, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "reduce launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+// ------------------------------------------------------------------- alltoall
+void Comm::alltoall(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "alltoall: bad dtype %d", dtype);
+  if (count_per_peer == 0) return;
+  check_buf(in, "sendbuff");
+  check_buf(out, "recvbuff");
+  const int n = nranks();
+  const size_t bytes = count_per_peer * dtype_size(dtype);
+  if (is_host()) {
+    host_alltoall(in, out, bytes);
+    return;
+  }
+  DeviceGuard g(device());
+  if (n == 1) {
+    if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  UB_CHECK(in != out, "alltoall: in-place operation is not supported");
+  UB_CHECK(aligned16(in) && aligned16(out), "alltoall: buffers must be 16-byte aligned");
+  CollArgs a = base_args();
+  a.in = in;
+  a.out = out;
+  a.bytes = bytes;
+  a.count = count_per_peer;
+  int mode = 0;
+  if (in_heap(out, bytes * n)) {
+    a.out_off = heap_offset(out);
+    mode = 1;
+  } else if (in_heap(in, bytes * n)) {
+    a.in_off = heap_offset(in);
+  }
+  int ctas = ctas_for(bytes, max_ctas_, 32 << 10);
+  cudaError_t e = launch_alltoall(mode, dev_, a, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "alltoall launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+void Comm::alltoallv(const void* in, const size_t* send_counts, const size_t* send_displs, void* out,
+                     const size_t* recv_counts, const size_t* recv_displs, int dtype, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "alltoallv: bad dtype %d", dtype);
+  UB_CHECK(!is_host(), "alltoallv: host backend does not implement it");
+  const int n = nranks();
+  const size_t es = dtype_size(dtype);
+  DeviceGuard g(device());
+  size_t in_total = 0;
+  for (int p = 0; p < n; ++p) in_total = std::max(in_total, (send_displs[p] + send_counts[p]) * es);
+  if (n == 1) {
+    size_t b = std::min(send_counts[0], recv_counts[0]) * es;
+    if (b) UB_CUDA(cudaMemcpyAsync((char*)out + recv_displs[0] * es, (const char*)in + send_displs[0] * es, b,
+                                   cudaMemcpyDeviceToDevice, stream));
+    return;
+  }
+  CollArgs a = base_args();
+  a.out = out;
+  a.in = in;
+  if (in_heap(in, in_total)) {
+    a.in_off = heap_offset(in);
+  } else {
+    // stage the send buffer once into the heap staging area (must fit)
+    UB_CHECK(in_total <= layout_.stage_bytes,
+             "alltoallv: non-symmetric send buffer (%zu B) exceeds the staging area (%lu B); allocate it from the "
+             "symmetric heap or raise stage_bytes",
+             in_total, (unsigned long)layout_.stage_bytes);
+    if (in_total)
+      UB_CUDA(cudaMemcpyAsync(fabric_->local() + layout_.stage_in_off, in, in_total, cudaMemcpyDeviceToDevice,
+                              stream));
+    a.in_off = layout_.stage_in_off;
+  }
+  A2AvArgs v;
+  memset(&v, 0, sizeof(v));
+  size_t maxb = 0;
+  for (int p = 0; p < n; ++p) {
+    v.send_off[p] = send_displs[p] * es;
+    v.send_bytes[p] = send_counts[p] * es;
+    v.recv_off[p] = recv_displs[p] * es;
+    v.recv_bytes[p] = recv_counts[p] * es;
+    maxb = std::max(maxb, (size_t)v.recv_bytes[p]);
+  }
+  v.table_off = layout_.a2av_tab_off;
+  int ctas = ctas_for(maxb, max_ctas_, 32 << 10);
+  cudaError_t e = launch_alltoallv(dev_, a, v, ctas, 512, stream);
+  UB_CHECK(e == cudaSuccess, "alltoallv launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+void Comm::barrier(cudaStream_t stream) {
+  if (is_host()) {
+    host_barrier();
+    return;
+  }
+  if (nranks() == 1) return;
+  DeviceGuard g(device());
+  cudaError_t e = launch_barrier(dev_, kDomUser0, stream);
+  UB_CHECK(e == cudaSuccess, "barrier launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+}  // namespace ub

@@ -1,0 +1,261 @@
+// Host ("fake GPU") backend of the communicator: the same symmetric-heap protocol
+// (epoch barriers in shared memory + peers reading each other's staging area), run
+// by CPU threads/processes over POSIX shm or malloc heaps.  It exists so that the
+// control plane (bootstrap, heap layout, allocator, barrier protocol, argument
+// checking, NCCL shim, Python bindings) is exercised by CI on GPU-less machines;
+// the pattern follows ukernel's MockBackend idea
+// (experimental/ukernel/src/ccl/test/common/backend_test_utils.h:211).
+#include <sched.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "../common/log.h"
+#include "comm.h"
+
+namespace ub {
+
+namespace {
+
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+inline float f16_to_f32(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+  uint32_t u;
+  if (exp == 0) {
+    if (man == 0) u = sign;
+    else {
+      int e = -1;
+      do {
+        ++e;
+        man <<= 1;
+      } while (!(man & 0x400u));
+      u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+    }
+  } else if (exp == 31) {
+    u = sign | 0x7f800000u | (man << 13);
+  } else {
+    u = sign | ((exp + 112) << 23) | (man << 13);
+  }
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint16_t f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  uint32_t sign = (x >> 16) & 0x8000u;
+  int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+  uint32_t man = x & 0x7fffffu;
+  if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));
+  if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+  if (exp <= 0) {
+    if (exp < -10) return (uint16_t)sign;
+    man |= 0x800000u;
+    uint32_t shift = (uint32_t)(14 - exp);
+    uint32_t half = man >> shift;
+    uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+    if (rem > halfway || (rem == halfway && (half & 1))) ++half;
+    return (uint16_t)(sign | half);
+  }
+  uint32_t half = ((uint32_t)exp << 10) | (man >> 13);
+  uint32_t rem = man & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) ++half;
+  return (uint16_t)(sign | half);
+}
+
+template <typename A>
+inline A apply(int op, A a, A b) {
+  switch (op) {
+    case kSum: case kAvg: return a + b;
+    case kProd: return a * b;
+    case kMax: return a > b ? a : b;
+    default: return a < b ? a : b;
+  }
+}
+
+// dst[i] = op over r of srcs[r][i]  (count elements of dtype), then scale / int-average
+void reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale) {
+  auto loop = [&](auto load, auto store, auto acc_zero, bool is_float) {
+    using A = decltype(acc_zero);
+    for (size_t i = 0; i < count; ++i) {
+      A acc = load(srcs[0], i);
+      for (int r = 1; r < n; ++r) acc = apply<A>(op, acc, load(srcs[r], i));
+      if (is_float) {
+        if (scale != 1.0f) acc = (A)(acc * (A)scale);
+      } else if (op == kAvg) {
+        acc = (A)(acc / (A)n);
+      }
+      store(dst, i, acc);
+    }
+  };
+#define UB_PLAIN(T, FL)                                                                         \
+  loop([](const void* p, size_t i) { return ((const T*)p)[i]; },                                \
+       [](void* p, size_t i, T v) { ((T*)p)[i] = v; }, (T)0, FL)
+  switch (dtype) {
+    case kI8: UB_PLAIN(int8_t, false); break;
+    case kU8: UB_PLAIN(uint8_t, false); break;
+    case kI32: UB_PLAIN(int32_t, false); break;
+    case kU32: UB_PLAIN(uint32_t, false); break;
+    case kI64: UB_PLAIN(int64_t, false); break;
+    case kU64: UB_PLAIN(uint64_t, false); break;
+    case kF32: UB_PLAIN(float, true); break;
+    case kF64: UB_PLAIN(double, true); break;
+    case kBF16:
+      loop([](const void* p, size_t i) { return bf16_to_f32(((const uint16_t*)p)[i]); },
+           [](void* p, size_t i, float v) { ((uint16_t*)p)[i] = f32_to_bf16(v); }, 0.0f, true);
+      break;
+    case kF16:
+      loop([](const void* p, size_t i) { return f16_to_f32(((const uint16_t*)p)[i]); },
+           [](void* p, size_t i, float v) { ((uint16_t*)p)[i] = f32_to_f16(v); }, 0.0f, true);
+      break;
+    default: UB_THROW("host backend: dtype %d unsupported", dtype);
+  }
+#undef UB_PLAIN
+}
+
+}  // namespace
+
+void Comm::host_barrier() {
+  const int n = nranks(), me = rank();
+  ++host_epoch_;
+  const uint32_t e = host_epoch_;
+  const uint64_t off = layout_.sig_off + ((uint64_t)kDomColl * kMaxSyncBlocks + 0) * kMaxRanks * sizeof(uint32_t);
+  for (int p = 0; p < n; ++p) {
+    if (p == me) continue;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(fabric_->heap(p) + off) + me;
+    __atomic_store_n(slot, e, __ATOMIC_RELEASE);
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  for (int p = 0; p < n; ++p) {
+    if (p == me) continue;
+    uint32_t* slot = reinterpret_cast<uint32_t*>(fabric_->local() + off) + p;
+    uint32_t spins = 0;
+    while ((int32_t)(__atomic_load_n(slot, __ATOMIC_ACQUIRE) - e) < 0) {
+      if ((++spins & 0xff) == 0) {
+        sched_yield();
+        if (dev_.timeout_ns) {
+          auto dt = std::chrono::steady_clock::now() - t0;
+          if ((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(dt).count() > dev_.timeout_ns)
+            UB_THROW("host barrier timeout: rank %d waiting for rank %d (epoch %u)", me, p, e);
+        }
+      }
+    }
+  }
+}
+
+// All host collectives: copy my input into my stage (chunked), barrier, read peers' stages.
+void Comm::host_allreduce(const void* in, void* out, size_t count, int dtype, int op, float scale) {
+  const int n = nranks(), me = rank();
+  const size_t es = dtype_size(dtype);
+  const size_t chunk_elems = layout_.stage_bytes / es;
+  for (size_t base = 0; base < count; base += chunk_elems) {
+    const size_t c = std::min(chunk_elems, count - base);
+    memcpy(fabric_->local() + layout_.stage_in_off, (const char*)in + base * es, c * es);
+    host_barrier();
+    // two-shot: reduce my shard into my stage_out, then gather all shards
+    uint64_t lo, hi;
+    split_range(c, n, me, lo, hi);
+    const void* srcs[kMaxRanks];
+    for (int r = 0; r < n; ++r) srcs[r] = fabric_->heap(r) + layout_.stage_in_off + lo * es;
+    reduce_n(fabric_->local() + layout_.stage_out_off + lo * es, srcs, n, hi - lo, dtype, op, scale);
+    host_barrier();
+    for (int r = 0; r < n; ++r) {
+      uint64_t l2, h2;
+      split_range(c, n, r, l2, h2);
+      memcpy((char*)out + (base + l2) * es, fabric_->heap(r) + layout_.stage_out_off + l2 * es, (h2 - l2) * es);
+    }
+    host_barrier();
+  }
+}
+
+void Comm::host_allgather(const void* in, void* out, size_t bytes) {
+  const int n = nranks();
+  const size_t chunk = layout_.stage_bytes;
+  for (size_t base = 0; base < bytes; base += chunk) {
+    const size_t c = std::min(chunk, bytes - base);
+    memcpy(fabric_->local() + layout_.stage_in_off, (const char*)in + base, c);
+    host_barrier();
+    for (int r = 0; r < n; ++r)
+      memcpy((char*)out + (size_t)r * bytes + base, fabric_->heap(r) + layout_.stage_in_off, c);
+    host_barrier();
+  }
+}
+
+void Comm::host_reduce_scatter(const void* in, void* out, size_t count, int dtype, int op) {
+  const int n = nranks(), me = rank();
+  const size_t es = dtype_size(dtype);
+  const size_t chunk_elems = layout_.stage_bytes / n / es;
+  const float scale = (op == kAvg) ? 1.0f / (float)n : 1.0f;
+  for (size_t base = 0; base < count; base += chunk_elems) {
+    const size_t c = std::min(chunk_elems, count - base);
+    for (int d = 0; d < n; ++d)
+      memcpy(fabric_->local() + layout_.stage_in_off + (size_t)d * chunk_elems * es,
+             (const char*)in + ((size_t)d * count + base) * es, c * es);
+    host_barrier();
+    const void* srcs[kMaxRanks];
+    for (int r = 0; r < n; ++r) srcs[r] = fabric_->heap(r) + layout_.stage_in_off + (size_t)me * chunk_elems * es;
+    reduce_n((char*)out + base * es, srcs, n, c, dtype, op, scale);
+    host_barrier();
+  }
+}
+
+void Comm::host_broadcast(const void* in, void* out, size_t bytes, int root) {
+  const size_t chunk = layout_.stage_bytes;
+  for (size_t base = 0; base < bytes; base += chunk) {
+    const size_t c = std::min(chunk, bytes - base);
+    if (rank() == root) memcpy(fabric_->local() + layout_.stage_in_off, (const char*)in + base, c);
+    host_barrier();
+    if (rank() != root) memcpy((char*)out + base, fabric_->heap(root) + layout_.stage_in_off, c);
+    else if (in != out) memcpy((char*)out + base, (const char*)in + base, c);
+    host_barrier();
+  }
+}
+
+void Comm::host_reduce(const void* in, void* out, size_t count, int dtype, int op, int root) {
+  const int n = nranks();
+  const size_t es = dtype_size(dtype);
+  const size_t chunk_elems = layout_.stage_bytes / es;
+  const float scale = (op == kAvg) ? 1.0f / (float)n : 1.0f;
+  for (size_t base = 0; base < count; base += chunk_elems) {
+    const size_t c = std::min(chunk_elems, count - base);
+    memcpy(fabric_->local() + layout_.stage_in_off, (const char*)in + base * es, c * es);
+    host_barrier();
+    if (rank() == root) {
+      const void* srcs[kMaxRanks];
+      for (int r = 0; r < n; ++r) srcs[r] = fabric_->heap(r) + layout_.stage_in_off;
+      reduce_n((char*)out + base * es, srcs, n, c, dtype, op, scale);
+    }
+    host_barrier();
+  }
+}
+
+void Comm::host_alltoall(const void* in, void* out, size_t bytes) {
+  const int n = nranks(), me = rank();
+  const size_t chunk = layout_.stage_bytes / n;
+  for (size_t base = 0; base < bytes; base += chunk) {
+    const size_t c = std::min(chunk, bytes - base);
+    for (int d = 0; d < n; ++d)
+      memcpy(fabric_->local() + layout_.stage_in_off + (size_t)d * chunk, (const char*)in + (size_t)d * bytes + base, c);
+    host_barrier();
+    for (int r = 0; r < n; ++r)
+      memcpy((char*)out + (size_t)r * bytes + base, fabric_->heap(r) + layout_.stage_in_off + (size_t)me * chunk, c);
+    host_barrier();
+  }
+}
+
+}  // namespace ub

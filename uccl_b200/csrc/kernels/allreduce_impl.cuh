@@ -1,0 +1,309 @@
+// AllReduce kernels for one NVSwitch node (2/4/8 ranks), all sm_100a, all operating
+// directly on NVLink-mapped peer memory from the symmetric heap.
+//
+//   ar_oneshot<MC>     small messages: every rank pushes LL16 packets {data,flag,data,flag}
+//                      into every peer's scratch (P2P stores, or ONE multimem.st through the
+//                      switch), then reduces the N slots locally.  No barrier at all.
+//                      (reference counterparts: allreducePacket / allreduceNvlsPacket,
+//                       experimental/lite/collective/allreduce_packet.cu:14-168,
+//                       allreduce_nvls_packet.cu:13-61)
+//   ar_twoshot<NVLS>   zero-copy on symmetric buffers: reduce my 1/N shard straight from the
+//                      peers' inputs (8 P2P loads, or one multimem.ld_reduce) and broadcast it
+//                      into the peers' outputs (P2P stores, or one multimem.st).
+//                      (reference: allreduceRsAgZeroCopy / allreduceNvls,
+//                       allreduce_rsag_zero_copy.cu:40-109, allreduce_nvls_zero_copy.cu:16-74)
+//   ar_staged<NVLS>    arbitrary (non-symmetric) user buffers: copy-in -> reduce -> gather
+//                      through heap staging, chunked, with block-sliced dependencies so only
+//                      same-index blocks of different ranks ever synchronise (no grid barrier).
+//                      (reference: allreduceRsAg / allreduceNvlsBlockPipeline)
+// Fused epilogue everywhere: post-scale (avg / user scale) and output dtype cast happen in
+// registers before the result is stored -- the reference has no such fusion.
+#pragma once
+#include "coll_common.cuh"
+
+namespace ub {
+
+// ------------------------------------------------------------------ one-shot LL
+template <typename T, int OP, bool MC>
+__global__ void __launch_bounds__(512) ar_oneshot(const __grid_constant__ DevComm c,
+                                                  const __grid_constant__ CollArgs a) {
+  uint32_t* misc = reinterpret_cast<uint32_t*>(c.heap[c.rank] + a.misc_off);
+  __shared__ uint32_t s_flag;
+  if (threadIdx.x == 0) s_flag = ld_volatile(misc + kLLEpoch) + 1;
+  __syncthreads();
+  const uint32_t flag = s_flag;
+  const uint64_t parity_off = a.ll_off + (uint64_t)(flag & 1u) * (kMaxRanks * kLLSlotBytes);
+  const uint64_t nunits = (a.bytes + 15) / 16;
+  const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
+  const int n = c.nranks, rank = c.rank;
+
+  // phase 1: publish my data as packets into every peer's slot[rank]
+  for (uint64_t u = gtid; u < nunits; u += gstride) {
+    uint4 d = load16_partial(a.in, u * 16, a.bytes);
+    uint4 p0 = make_uint4(d.x, flag, d.y, flag);
+    uint4 p1 = make_uint4(d.z, flag, d.w, flag);
+    const uint64_t off = parity_off + (uint64_t)rank * kLLSlotBytes + u * 32;
+    if constexpr (MC) {
+      multimem_st_v4(c.mc + off, p0);
+      multimem_st_v4(c.mc + off + 16, p1);
+    } else {
+      for (int k = 1; k < n; ++k) {
+        int p = rank + k;
+        if (p >= n) p -= n;
+        st_v4(c.heap[p] + off, p0);
+        st_v4(c.heap[p] + off + 16, p1);
+      }
+    }
+  }
+  // phase 2: wait for the peers' packets in my own scratch, reduce in rank order
+  // (identical order on every rank => bitwise identical results everywhere)
+  char* my_ll = c.heap[rank] + parity_off;
+  for (uint64_t u = gtid; u < nunits; u += gstride) {
+    Vec16<T, OP> acc;
+    for (int s = 0; s < n; ++s) {
+      uint4 d;
+      if (s == rank) {
+        d = load16_partial(a.in, u * 16, a.bytes);
+      } else {
+        const char* slot = my_ll + (uint64_t)s * kLLSlotBytes + u * 32;
+        uint4 p0, p1;
+        SpinGuard g(c.timeout_ns);
+        while (true) {
+          p0 = ld_volatile_v4(slot);
+          p1 = ld_volatile_v4(slot + 16);
+          if (p0.y == flag && p0.w == flag && p1.y == flag && p1.w == flag) break;
+          if (g.expired()) comm_abort(c, 10, s, (int)flag);
+        }
+        d = make_uint4(p0.x, p0.z, p1.x, p1.z);
+      }
+      if (s == 0) acc.init(d);
+      else acc.accum(d);
+    }
+    acc.epilogue(a.ep);
+    store16_partial(a.out, u * 16, a.bytes, acc.pack_same());
+  }
+  // last block to finish bumps the epoch (graph-replay safe: no host-side counter)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    uint32_t old = atomicAdd(misc + kLLDone, 1u);
+    if (old == gridDim.x - 1) {
+      misc[kLLDone] = 0;
+      misc[kLLEpoch] = flag;
+      __threadfence();
+    }
+  }
+}
+
+// ------------------------------------------------------------ two-shot zero-copy
+// in/out are symmetric (same offset on every rank). bytes % 16 == 0.
+template <typename T, int OP, typename TO, bool NVLS>
+__global__ void __launch_bounds__(512, 1) ar_twoshot(const __grid_constant__ DevComm c,
+                                                     const __grid_constant__ CollArgs a) {
+  constexpr int N = Vec16<T, OP>::N;
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  sync_barrier(c, s);  // every rank's input is complete (and nobody still reads my output)
+
+  const uint64_t nvec = a.bytes / 16;
+  uint64_t blo, bhi, lo, hi;
+  split_range(nvec, gridDim.x, blockIdx.x, blo, bhi);
+  split_range(bhi - blo, n, rank, lo, hi);
+  lo += blo;
+  hi += blo;
+
+  if constexpr (NVLS) {
+    const char* in_mc = c.mc + a.in_off;
+    TO* out_mc = reinterpret_cast<TO*>(c.mc + a.out_off);
+    constexpr int U = 4;
+    for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
+      uint4 r[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        uint64_t vv = v + (uint64_t)j * blockDim.x;
+        if (vv < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + vv * 16);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        uint64_t vv = v + (uint64_t)j * blockDim.x;
+        if (vv < hi) {
+          Vec16<T, OP> acc;
+          acc.init(r[j]);
+          acc.epilogue(a.ep);
+          store_out<T, OP, TO, true>(out_mc, vv * N, acc);
+        }
+      }
+    }
+  } else {
+    constexpr int U = 2;
+    for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
+      uint4 r[U][kMaxRanks];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        uint64_t vv = v + (uint64_t)j * blockDim.x;
+        if (vv < hi) {
+#pragma unroll
+          for (int q = 0; q < kMaxRanks; ++q)
+            if (q < n) r[j][q] = ld_v4(c.heap[q] + a.in_off + vv * 16);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        uint64_t vv = v + (uint64_t)j * blockDim.x;
+        if (vv < hi) {
+          // accumulate in global rank order so the rounding is independent of who reduces
+          Vec16<T, OP> acc;
+          acc.init(r[j][0]);
+#pragma unroll
+          for (int q = 1; q < kMaxRanks; ++q)
+            if (q < n) acc.accum(r[j][q]);
+          acc.epilogue(a.ep);
+#pragma unroll
+          for (int k = 0; k < kMaxRanks; ++k) {
+            if (k < n) {
+              int p = rank + k;
+              if (p >= n) p -= n;
+              store_out<T, OP, TO, false>(reinterpret_cast<TO*>(c.heap[p] + a.out_off), vv * N, acc);
+            }
+          }
+        }
+      }
+    }
+  }
+  sync_barrier(c, s);  // every rank's output is complete
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------- staged
+// Arbitrary local in/out (16-byte aligned, bytes % 16 == 0). Works chunk by chunk
+// through stage_in / stage_out in the heap. Block b of every rank owns slice b of
+// each chunk in all three phases, so a block only depends on same-index peer blocks.
+template <typename T, int OP, typename TO, bool NVLS>
+__global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevComm c,
+                                                    const __grid_constant__ CollArgs a) {
+  constexpr int N = Vec16<T, OP>::N;
+  constexpr uint64_t kOutVecBytes = (uint64_t)N * sizeof(TO);  // output bytes per input vector
+  // slice boundaries must keep the 16-byte bulk copies of phase 3 aligned
+  constexpr uint64_t G = kOutVecBytes >= 16 ? 1 : 16 / kOutVecBytes;
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+
+  const uint64_t nvec_total = a.bytes / 16;
+  // vectors per chunk limited by both stages
+  uint64_t cap_in = a.stage_bytes / 16, cap_out = a.stage_bytes / kOutVecBytes;
+  const uint64_t chunk_vec = (cap_in < cap_out ? cap_in : cap_out) / G * G;
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+  char* my_stage_in = c.heap[rank] + a.stage_in_off;
+  char* my_stage_out = c.heap[rank] + a.stage_out_off;
+
+  for (uint64_t base = 0; base < nvec_total; base += chunk_vec) {
+    const uint64_t cvec = (nvec_total - base) < chunk_vec ? (nvec_total - base) : chunk_vec;
+    uint64_t blo, bhi;
+    split_range(cvec, gridDim.x, blockIdx.x, blo, bhi, G);
+    // 1. copy-in my slice
+    for (uint64_t v = blo + threadIdx.x; v < bhi; v += blockDim.x)
+      st_v4(my_stage_in + v * 16, ld_v4(in + (base + v) * 16));
+    sync_barrier(c, s);
+    // 2. reduce my shard of the slice
+    uint64_t lo, hi;
+    split_range(bhi - blo, n, rank, lo, hi, G);
+    lo += blo;
+    hi += blo;
+    if constexpr (NVLS) {
+      const char* in_mc = c.mc + a.stage_in_off;
+      TO* out_mc = reinterpret_cast<TO*>(c.mc + a.stage_out_off);
+      for (uint64_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+        Vec16<T, OP> acc;
+        acc.init(MmLdRed<T, OP>::ld(in_mc + v * 16));
+        acc.epilogue(a.ep);
+        store_out<T, OP, TO, true>(out_mc, v * N, acc);
+      }
+    } else {
+      for (uint64_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+        uint4 r[kMaxRanks];
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+          if (q < n) r[q] = ld_v4(c.heap[q] + a.stage_in_off + v * 16);
+        Vec16<T, OP> acc;
+        acc.init(r[0]);
+#pragma unroll
+        for (int q = 1; q < kMaxRanks; ++q)
+          if (q < n) acc.accum(r[q]);
+        acc.epilogue(a.ep);
+        store_out<T, OP, TO, false>(reinterpret_cast<TO*>(my_stage_out), v * N, acc);
+        store_out<T, OP, TO, false>(reinterpret_cast<TO*>(out) + base * N, v * N, acc);
+      }
+    }
+    sync_barrier(c, s);
+    // 3. gather the slice into the user output
+    if constexpr (NVLS) {
+      const uint64_t ob_lo = blo * kOutVecBytes, ob_hi = bhi * kOutVecBytes;
+      for (uint64_t o = ob_lo + (uint64_t)threadIdx.x * 16; o < ob_hi; o += (uint64_t)blockDim.x * 16)
+        st_v4(out + base * kOutVecBytes + o, ld_v4(my_stage_out + o));
+    } else {
+      for (int k = 1; k < n; ++k) {
+        int p = rank + k;
+        if (p >= n) p -= n;
+        uint64_t plo, phi;
+        split_range(bhi - blo, n, p, plo, phi, G);
+        const uint64_t ob_lo = (plo + blo) * kOutVecBytes, ob_hi = (phi + blo) * kOutVecBytes;
+        const char* src = c.heap[p] + a.stage_out_off;
+        for (uint64_t o = ob_lo + (uint64_t)threadIdx.x * 16; o < ob_hi; o += (uint64_t)blockDim.x * 16)
+          st_v4(out + base * kOutVecBytes + o, ld_v4(src + o));
+      }
+    }
+  }
+  sync_barrier(c, s);  // peers are done pulling from my stage_out before anyone reuses it
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------ launchers
+enum ArAlgo : int {
+  AR_AUTO = 0,
+  AR_ONESHOT_LL = 1,
+  AR_ONESHOT_MC = 2,
+  AR_TWOSHOT_P2P = 3,
+  AR_TWOSHOT_NVLS = 4,
+  AR_STAGED_P2P = 5,
+  AR_STAGED_NVLS = 6,
+  AR_NUM_ALGOS = 7
+};
+
+template <typename T, int OP, typename TO>
+cudaError_t launch_ar_typed(int algo, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st) {
+  constexpr bool same = std::is_same<T, TO>::value;
+  switch (algo) {
+    case AR_ONESHOT_LL:
+      if constexpr (same) { ar_oneshot<T, OP, false><<<grid, block, 0, st>>>(c, a); break; }
+      return cudaErrorInvalidValue;
+    case AR_ONESHOT_MC:
+      if constexpr (same) { ar_oneshot<T, OP, true><<<grid, block, 0, st>>>(c, a); break; }
+      return cudaErrorInvalidValue;
+    case AR_TWOSHOT_P2P: ar_twoshot<T, OP, TO, false><<<grid, block, 0, st>>>(c, a); break;
+    case AR_STAGED_P2P: ar_staged<T, OP, TO, false><<<grid, block, 0, st>>>(c, a); break;
+    case AR_TWOSHOT_NVLS:
+      if constexpr (MmLdRed<T, OP>::ok) { ar_twoshot<T, OP, TO, true><<<grid, block, 0, st>>>(c, a); break; }
+      return cudaErrorInvalidValue;
+    case AR_STAGED_NVLS:
+      if constexpr (MmLdRed<T, OP>::ok) { ar_staged<T, OP, TO, true><<<grid, block, 0, st>>>(c, a); break; }
+      return cudaErrorInvalidValue;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_ar_ops(int algo, int op, const DevComm& c, const CollArgs& a, int grid, int block,
+                          cudaStream_t st) {
+  switch (op) {
+    case kSum: case kAvg: return launch_ar_typed<T, kSum, T>(algo, c, a, grid, block, st);
+    case kProd: return launch_ar_typed<T, kProd, T>(algo, c, a, grid, block, st);
+    case kMax: return launch_ar_typed<T, kMax, T>(algo, c, a, grid, block, st);
+    case kMin: return launch_ar_typed<T, kMin, T>(algo, c, a, grid, block, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace ub

@@ -1,0 +1,327 @@
+// AllGather / ReduceScatter / Broadcast / Reduce / AllToAll(v) kernels over the
+// symmetric heap.  The reference only ships native AllGather + AllReduce (+ one
+// broadcast); ReduceScatter, Reduce and AllToAll fall back to NCCL or are stubs
+// (experimental/lite/nccl/nccl.cu:1747,1952-1966,2069-2102).  Here they are all native.
+//
+// Rule used everywhere: block b of every rank owns slice b of the data in every phase,
+// so cross-rank dependencies only exist between same-index blocks and the per-block
+// cross-rank barrier (prims.cuh) is sufficient -- no grid-wide sync is ever needed.
+//
+// "Source resolution": a collective that reads peers' inputs needs them in the heap.
+// If the user input is symmetric (in_off != kNoOff) peers read it in place (zero copy);
+// otherwise each block first copies its slice into stage_in and peers read that.
+#pragma once
+#include "coll_common.cuh"
+
+namespace ub {
+
+__device__ __forceinline__ void copy_bytes16(char* dst, const char* src, uint64_t lo, uint64_t hi,
+                                             uint64_t total_bytes_src, uint64_t total_bytes_dst) {
+  // copies 16-byte units [lo, hi) (unit index), partial-tail aware on both sides;
+  // degrades to a byte loop when either side is not 16-byte aligned (odd segment sizes).
+  if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    for (uint64_t u = lo + threadIdx.x; u < hi; u += blockDim.x) {
+      uint4 v = load16_partial(src, u * 16, total_bytes_src);
+      store16_partial(dst, u * 16, total_bytes_dst, v);
+    }
+  } else {
+    uint64_t total = total_bytes_src < total_bytes_dst ? total_bytes_src : total_bytes_dst;
+    uint64_t b0 = lo * 16, b1 = hi * 16 < total ? hi * 16 : total;
+    for (uint64_t i = b0 + threadIdx.x; i < b1; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+// ------------------------------------------------------------------ AllGather
+// a.bytes = bytes contributed by each rank. out holds n * bytes.
+// MODE 0: push P2P (out symmetric)   MODE 1: push multicast (out symmetric, NVLS)
+// MODE 2: pull (in symmetric or staged copy-in; out arbitrary)
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevComm c,
+                                                    const __grid_constant__ CollArgs a) {
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  const uint64_t units = (a.bytes + 15) / 16;
+  const char* in = reinterpret_cast<const char*>(a.in);
+  if constexpr (MODE == 0 || MODE == 1) {
+    sync_barrier_relaxed(c, s);  // peers have entered: their `out` may be overwritten now
+    uint64_t blo, bhi;
+    split_range(units, gridDim.x, blockIdx.x, blo, bhi);
+    const uint64_t dst_off = a.out_off + (uint64_t)rank * a.bytes;
+    for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
+      uint4 v = load16_partial(in, u * 16, a.bytes);
+      if constexpr (MODE == 1) {
+        if (u * 16 + 16 <= a.bytes) multimem_st_v4(c.mc + dst_off + u * 16, v);
+        else
+          for (int p = 0; p < n; ++p) store16_partial(c.heap[p] + dst_off, u * 16, a.bytes, v);
+      } else {
+        for (int k = 0; k < n; ++k) {
+          int p = rank + k;
+          if (p >= n) p -= n;
+          store16_partial(c.heap[p] + dst_off, u * 16, a.bytes, v);
+        }
+      }
+    }
+    sync_barrier(c, s);
+  } else {
+    const bool staged = (a.in_off == kNoOff);
+    char* out = reinterpret_cast<char*>(a.out);
+    const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
+    for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+      const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+      const uint64_t cu = (cb + 15) / 16;
+      uint64_t blo, bhi;
+      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      if (staged) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
+      sync_barrier(c, s);
+      const uint64_t src_off = staged ? a.stage_in_off : (a.in_off + base);
+      for (int k = 0; k < n; ++k) {
+        int p = rank + k;
+        if (p >= n) p -= n;
+        if (p == rank && staged) {
+          copy_bytes16(out + (uint64_t)p * a.bytes + base, in + base, blo, bhi, cb, cb);
+        } else {
+          copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
+        }
+      }
+      if (staged) sync_barrier_relaxed(c, s);  // peers finished reading my stage before I refill it
+      if (a.bytes == 0) break;
+    }
+    if (!staged) sync_barrier_relaxed(c, s);  // nobody still reads my input when I return
+  }
+  sync_end(s);
+}
+
+// ------------------------------------------------------------- ReduceScatter
+// a.count = elements each rank receives; input holds n * count elements of T.
+// NVLS requires a symmetric input. Output is a plain local buffer.
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevComm c,
+                                                    const __grid_constant__ CollArgs a) {
+  constexpr int N = Vec16<T, OP>::N;
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  const bool staged = (a.in_off == kNoOff);
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+  // per-destination chunk so that n chunks fit the stage
+  const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
+  for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+    const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+    const uint64_t cu = (cb + 15) / 16;
+    uint64_t blo, bhi;
+    split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+    if (staged) {
+      for (int d = 0; d < n; ++d)
+        copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes, in + (uint64_t)d * a.bytes + base,
+                     blo, bhi, cb, cb);
+    }
+    sync_barrier(c, s);
+    const uint64_t src_off =
+        staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes) : (a.in_off + (uint64_t)rank * a.bytes + base);
+    for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
+      Vec16<T, OP> acc;
+      if constexpr (NVLS) {
+        acc.init(MmLdRed<T, OP>::ld(c.mc + src_off + u * 16));
+      } else {
+        uint4 r[kMaxRanks];
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+          if (q < n) r[q] = ld_v4(c.heap[q] + src_off + u * 16);
+        acc.init(r[0]);
+#pragma unroll
+        for (int q = 1; q < kMaxRanks; ++q)
+          if (q < n) acc.accum(r[q]);
+      }
+      acc.epilogue(a.ep);
+      store16_partial(out + base, u * 16, cb, acc.pack_same());
+    }
+    sync_barrier_relaxed(c, s);  // peers finished reading my input / stage
+    if (a.bytes == 0) break;
+  }
+  (void)N;
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------ Broadcast
+// Only `out` is meaningful on every rank (non-roots may pass any `in`), so the variant is
+// chosen from `out` alone: symmetric out -> root pushes (MODE 1 multicast, MODE 2 P2P);
+// otherwise MODE 0: root copies into its stage and everyone pulls.
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ DevComm c,
+                                                       const __grid_constant__ CollArgs a) {
+  const int n = c.nranks, rank = c.rank, root = a.root;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+  if constexpr (MODE == 1 || MODE == 2) {
+    sync_barrier_relaxed(c, s);
+    if (rank == root) {
+      const uint64_t units = (a.bytes + 15) / 16;
+      uint64_t blo, bhi;
+      split_range(units, gridDim.x, blockIdx.x, blo, bhi);
+      for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
+        uint4 v = load16_partial(in, u * 16, a.bytes);
+        if (MODE == 1 && u * 16 + 16 <= a.bytes) {
+          multimem_st_v4(c.mc + a.out_off + u * 16, v);
+        } else {
+          for (int p = 0; p < n; ++p) store16_partial(c.heap[p] + a.out_off, u * 16, a.bytes, v);
+        }
+      }
+    }
+    sync_barrier(c, s);
+  } else {
+    const uint64_t chunk_bytes = a.stage_bytes / 16 * 16;
+    for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
+      const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+      const uint64_t cu = (cb + 15) / 16;
+      uint64_t blo, bhi;
+      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      if (rank == root) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
+      sync_barrier(c, s);
+      if (rank != root) {
+        copy_bytes16(out + base, c.heap[root] + a.stage_in_off, blo, bhi, cb, cb);
+      } else if (out != in) {
+        copy_bytes16(out + base, in + base, blo, bhi, cb, cb);
+      }
+      sync_barrier_relaxed(c, s);
+    }
+  }
+  sync_end(s);
+}
+
+// --------------------------------------------------------------------- Reduce
+template <typename T, int OP, bool NVLS>
+__global__ void __launch_bounds__(512, 1) reduce_kernel(const __grid_constant__ DevComm c,
+                                                        const __grid_constant__ CollArgs a) {
+  const int n = c.nranks, rank = c.rank, root = a.root;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  const bool staged = (a.in_off == kNoOff);
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+  const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
+  for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+    const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+    const uint64_t cu = (cb + 15) / 16;
+    uint64_t blo, bhi;
+    split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+    if (staged) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
+    sync_barrier(c, s);
+    if (rank == root) {
+      const uint64_t src_off = staged ? a.stage_in_off : (a.in_off + base);
+      for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
+        Vec16<T, OP> acc;
+        if constexpr (NVLS) {
+          acc.init(MmLdRed<T, OP>::ld(c.mc + src_off + u * 16));
+        } else {
+          uint4 r[kMaxRanks];
+#pragma unroll
+          for (int q = 0; q < kMaxRanks; ++q)
+            if (q < n) r[q] = ld_v4(c.heap[q] + src_off + u * 16);
+          acc.init(r[0]);
+#pragma unroll
+          for (int q = 1; q < kMaxRanks; ++q)
+            if (q < n) acc.accum(r[q]);
+        }
+        acc.epilogue(a.ep);
+        store16_partial(out + base, u * 16, cb, acc.pack_same());
+      }
+    }
+    sync_barrier_relaxed(c, s);
+    if (a.bytes == 0) break;
+  }
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------- AllToAll
+// a.bytes = bytes exchanged with each peer. in/out hold n * bytes.
+// MODE 0: pull (in symmetric or staged)   MODE 1: push (out symmetric)
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ DevComm c,
+                                                     const __grid_constant__ CollArgs a) {
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+  if constexpr (MODE == 1) {
+    sync_barrier_relaxed(c, s);
+    const uint64_t units = (a.bytes + 15) / 16;
+    uint64_t blo, bhi;
+    split_range(units, gridDim.x, blockIdx.x, blo, bhi);
+    for (int k = 0; k < n; ++k) {
+      int p = rank + k;
+      if (p >= n) p -= n;
+      copy_bytes16(c.heap[p] + a.out_off + (uint64_t)rank * a.bytes, in + (uint64_t)p * a.bytes, blo, bhi, a.bytes,
+                   a.bytes);
+    }
+    sync_barrier(c, s);
+  } else {
+    const bool staged = (a.in_off == kNoOff);
+    const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
+    for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+      const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+      const uint64_t cu = (cb + 15) / 16;
+      uint64_t blo, bhi;
+      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      if (staged) {
+        for (int d = 0; d < n; ++d)
+          copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes,
+                       in + (uint64_t)d * a.bytes + base, blo, bhi, cb, cb);
+      }
+      sync_barrier(c, s);
+      for (int k = 0; k < n; ++k) {
+        int p = rank + k;
+        if (p >= n) p -= n;
+        const uint64_t src_off = staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes)
+                                        : (a.in_off + (uint64_t)rank * a.bytes + base);
+        copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
+      }
+      sync_barrier_relaxed(c, s);
+      if (a.bytes == 0) break;
+    }
+  }
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------ AllToAllv
+// Variable counts: every rank publishes its (send offset, send bytes) row for each
+// destination into the heap (misc area), then each rank pulls its column.
+static __global__ void __launch_bounds__(512, 1) a2av_kernel(const __grid_constant__ DevComm c,
+                                                      const __grid_constant__ CollArgs a,
+                                                      const __grid_constant__ A2AvArgs v) {
+  // input must be symmetric (host stages it otherwise): peers read in_off + send_off[me].
+  const int n = c.nranks, rank = c.rank;
+  BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
+  // per-block private copy of the table so that same-index blocks suffice for ordering
+  uint64_t* my_tab = reinterpret_cast<uint64_t*>(c.heap[rank] + v.table_off) + (uint64_t)blockIdx.x * kMaxRanks * 2;
+  if (threadIdx.x < n) {
+    my_tab[threadIdx.x * 2 + 0] = v.send_off[threadIdx.x];
+    my_tab[threadIdx.x * 2 + 1] = v.send_bytes[threadIdx.x];
+  }
+  sync_barrier(c, s);
+  char* out = reinterpret_cast<char*>(a.out);
+  for (int k = 0; k < n; ++k) {
+    int p = rank + k;
+    if (p >= n) p -= n;
+    const uint64_t* ptab =
+        reinterpret_cast<const uint64_t*>(c.heap[p] + v.table_off) + (uint64_t)blockIdx.x * kMaxRanks * 2;
+    const uint64_t soff = ptab[rank * 2 + 0];
+    uint64_t sbytes = ptab[rank * 2 + 1];
+    if (sbytes > v.recv_bytes[p]) sbytes = v.recv_bytes[p];
+    const uint64_t units = (sbytes + 15) / 16;
+    uint64_t blo, bhi;
+    split_range(units, gridDim.x, blockIdx.x, blo, bhi);
+    const char* src = c.heap[p] + a.in_off + soff;
+    char* dst = out + v.recv_off[p];
+    // offsets may be only element-aligned: fall back to byte copies when not 16-byte aligned
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+      copy_bytes16(dst, src, blo, bhi, sbytes, sbytes);
+    } else {
+      uint64_t lo = blo * 16, hi = bhi * 16 < sbytes ? bhi * 16 : sbytes;
+      for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) dst[i] = src[i];
+    }
+  }
+  sync_barrier_relaxed(c, s);
+  sync_end(s);
+}
+
+}  // namespace ub

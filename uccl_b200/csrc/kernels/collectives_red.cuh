@@ -1,0 +1,32 @@
+// Typed launch helpers for ReduceScatter / Reduce.
+#pragma once
+#include "collectives_impl.cuh"
+namespace ub {
+template <typename T, int OP>
+cudaError_t launch_red_typed(int which, bool nvls, const DevComm& c, const CollArgs& a, int grid, int block,
+                             cudaStream_t st) {
+  if (nvls) {
+    if constexpr (MmLdRed<T, OP>::ok) {
+      if (which == 0) rs_kernel<T, OP, true><<<grid, block, 0, st>>>(c, a);
+      else reduce_kernel<T, OP, true><<<grid, block, 0, st>>>(c, a);
+      return cudaGetLastError();
+    } else {
+      return cudaErrorInvalidValue;
+    }
+  }
+  if (which == 0) rs_kernel<T, OP, false><<<grid, block, 0, st>>>(c, a);
+  else reduce_kernel<T, OP, false><<<grid, block, 0, st>>>(c, a);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_red_ops(int which, int op, bool nvls, const DevComm& c, const CollArgs& a, int grid, int block,
+                           cudaStream_t st) {
+  switch (op) {
+    case kSum: case kAvg: return launch_red_typed<T, kSum>(which, nvls, c, a, grid, block, st);
+    case kProd: return launch_red_typed<T, kProd>(which, nvls, c, a, grid, block, st);
+    case kMax: return launch_red_typed<T, kMax>(which, nvls, c, a, grid, block, st);
+    case kMin: return launch_red_typed<T, kMin>(which, nvls, c, a, grid, block, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+}  // namespace ub

@@ -1,0 +1,138 @@
+// Host-safe shared types: constants, device communicator descriptor, dtype/op tables,
+// heap control-region layout and collective launch arguments.  Included by both the
+// CUDA kernels and the plain C++ runtime.
+#pragma once
+#include <stdint.h>
+#ifdef __CUDACC__
+#define UB_HD __host__ __device__
+#else
+#define UB_HD
+#endif
+
+namespace ub {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxSyncBlocks = 512;   // max grid of any kernel that uses a cross-rank barrier
+constexpr int kNumSyncDomains = 8;    // independent barrier domains (collectives, ep, p2p, ...)
+
+// Passed by value to every kernel (fits in param space; __grid_constant__).
+struct DevComm {
+  int rank;
+  int nranks;
+  char* heap[kMaxRanks];  // heap[r] = VA (in *this* process/device) of rank r's symmetric heap
+  char* mc;               // multicast VA of the heap (nullptr when NVLS is unavailable)
+  uint64_t sig_off;       // offset of sync-domain signal slots inside each heap
+  uint64_t epoch_off;     // offset of local per-block epoch counters
+  uint64_t timeout_ns;    // spin timeout (0 = infinite)
+  uint32_t* err;          // host-mapped error word (set before trap)
+};
+
+enum DType : int {
+  kI8 = 0,
+  kU8 = 1,
+  kI32 = 2,
+  kU32 = 3,
+  kI64 = 4,
+  kU64 = 5,
+  kF16 = 6,
+  kF32 = 7,
+  kF64 = 8,
+  kBF16 = 9,
+  kF8E4M3 = 10,
+  kF8E5M2 = 11,
+  kNumDTypes = 12
+};
+enum RedOp : int { kSum = 0, kProd = 1, kMax = 2, kMin = 3, kAvg = 4, kNumOps = 5 };
+
+UB_HD inline int dtype_size(int dt) {
+  switch (dt) {
+    case kI8: case kU8: case kF8E4M3: case kF8E5M2: return 1;
+    case kF16: case kBF16: return 2;
+    case kI32: case kU32: case kF32: return 4;
+    default: return 8;
+  }
+}
+
+// Post-reduction epilogue parameters (fused scale / integer average).
+struct Epilogue {
+  float scale;  // multiplies floating accumulators (1.0f = none); avg => 1/nranks
+  int idiv;     // divides integer accumulators (1 = none); avg => nranks
+};
+
+inline bool nvls_reduce_supported(int dtype, int op) {
+  if (dtype == kF32) return op == kSum || op == kAvg;
+  if (dtype == kBF16 || dtype == kF16) return op == kSum || op == kAvg || op == kMax || op == kMin;
+  return false;
+}
+
+// Sync-domain assignment (independent barrier epochs so different subsystems may
+// run concurrently on different streams).
+enum SyncDomain : int { kDomColl = 0, kDomEp = 1, kDomEpLL = 2, kDomP2P = 3, kDomUser0 = 4 };
+
+constexpr uint64_t kSigBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * kMaxRanks * sizeof(uint32_t);
+constexpr uint64_t kEpochBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * sizeof(uint32_t);
+constexpr uint64_t kMiscBytes = 4096;
+constexpr uint64_t kA2AvTabBytes = (uint64_t)kMaxSyncBlocks * kMaxRanks * 2 * sizeof(uint64_t);
+constexpr uint64_t kLLMaxData = 256u << 10;           // max payload of the one-shot LL path
+constexpr uint64_t kLLSlotBytes = 2 * kLLMaxData;     // 8 data bytes per 16-byte packet
+constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src ranks
+
+// misc words
+enum MiscWord : int { kLLEpoch = 0, kLLDone = 1, kMiscWords = 64 };
+
+struct HeapLayout {
+  uint64_t sig_off, epoch_off, misc_off, a2av_tab_off, ll_off, stage_in_off, stage_out_off, user_off;
+  uint64_t stage_bytes;
+  static HeapLayout make(uint64_t stage_bytes) {
+    HeapLayout l;
+    l.sig_off = 0;
+    l.epoch_off = l.sig_off + kSigBytes;
+    l.misc_off = l.epoch_off + kEpochBytes;
+    l.a2av_tab_off = l.misc_off + kMiscBytes;
+    l.ll_off = (l.a2av_tab_off + kA2AvTabBytes + 4095) / 4096 * 4096;
+    l.stage_bytes = (stage_bytes + 4095) / 4096 * 4096;
+    l.stage_in_off = l.ll_off + kLLBytes;
+    l.stage_out_off = l.stage_in_off + l.stage_bytes;
+    l.user_off = l.stage_out_off + l.stage_bytes;
+    l.user_off = (l.user_off + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    return l;
+  }
+  uint64_t ctrl_bytes() const { return stage_in_off; }  // region that must start zeroed
+};
+
+constexpr uint64_t kNoOff = ~0ull;
+
+struct CollArgs {
+  const void* in;
+  void* out;
+  uint64_t in_off;   // offset of `in` inside the symmetric heap, kNoOff if it is a plain local buffer
+  uint64_t out_off;  // same for `out`
+  uint64_t count;    // elements (of the input dtype) per rank-visible buffer; see each kernel
+  uint64_t bytes;    // count * sizeof(T)
+  Epilogue ep;
+  int root;
+  uint64_t misc_off, ll_off, stage_in_off, stage_out_off, stage_bytes;
+};
+
+// Split [0, total) into `parts` nearly equal contiguous ranges whose boundaries are
+// multiples of `gran` (except the final end).
+UB_HD inline void split_range(uint64_t total, int parts, int idx, uint64_t& lo, uint64_t& hi,
+                                            uint64_t gran = 1) {
+  uint64_t units = (total + gran - 1) / gran;
+  uint64_t per = (units + parts - 1) / parts * gran;
+  lo = per * (uint64_t)idx;
+  if (lo > total) lo = total;
+  hi = lo + per;
+  if (hi > total) hi = total;
+}
+
+// AllToAllv launch arguments.
+struct A2AvArgs {
+  uint64_t send_off[kMaxRanks];   // byte offsets inside `in`
+  uint64_t send_bytes[kMaxRanks];
+  uint64_t recv_off[kMaxRanks];   // byte offsets inside `out`
+  uint64_t recv_bytes[kMaxRanks];
+  uint64_t table_off;             // heap offset of a [kMaxRanks][2] u64 table (symmetric)
+};
+
+}  // namespace ub

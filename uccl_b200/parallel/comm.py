@@ -1,0 +1,308 @@
+"""Torch-facing communicator over the native symmetric-heap fabric.
+
+One :class:`Communicator` per rank.  Three ways to get one:
+
+* :meth:`Communicator.from_torch_dist` -- one process per GPU (the production layout);
+  ``torch.distributed`` (any backend, e.g. gloo or nccl) is used once to ship the
+  128-byte unique id, everything after that is our own fabric.
+* :meth:`Communicator.init` -- explicit ``(uid, rank, world)`` like ``ncclCommInitRank``.
+* :meth:`Communicator.local_world` -- all ranks inside this process (``ncclCommInitAll``
+  style; with ``devices=[0]*n`` it gives *virtual ranks* on one GPU, which is what the
+  single-GPU test-suite uses to exercise the cross-rank kernels).
+
+API parity notes (reference): the NCCL-style collective entry points mirror
+``experimental/lite/nccl/nccl.cu:1838-2102`` (AllReduce/ReduceScatter/AllGather/Broadcast/
+Reduce/AllToAll); `empty()` is the ``ncclMemAlloc`` analogue (`nccl.cu:2384-2430`) -- buffers
+from it are zero-copy for every collective (peer-mapped and multicast-bound).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+
+from .. import _native
+
+_DTYPE = {
+    torch.int8: 0,
+    torch.uint8: 1,
+    torch.int32: 2,
+    torch.int64: 4,
+    torch.float16: 6,
+    torch.float32: 7,
+    torch.float64: 8,
+    torch.bfloat16: 9,
+}
+for _name, _code in (("uint32", 3), ("uint64", 5), ("float8_e4m3fn", 10), ("float8_e5m2", 11)):
+    if hasattr(torch, _name):
+        _DTYPE[getattr(torch, _name)] = _code
+_DTYPE[torch.bool] = 1
+
+_OPS = {"sum": 0, "prod": 1, "product": 1, "max": 2, "min": 3, "avg": 4, "mean": 4}
+
+ALGOS = {
+    "auto": 0,
+    "oneshot_ll": 1,
+    "oneshot_mc": 2,
+    "twoshot_p2p": 3,
+    "twoshot_nvls": 4,
+    "staged_p2p": 5,
+    "staged_nvls": 6,
+}
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPE[dt]
+    except KeyError as e:  # pragma: no cover
+        raise TypeError(f"uccl_b200: unsupported dtype {dt}") from e
+
+
+def op_code(op) -> int:
+    if isinstance(op, int):
+        return op
+    name = str(op).lower().split(".")[-1]
+    try:
+        return _OPS[name]
+    except KeyError as e:
+        raise ValueError(f"uccl_b200: unsupported reduce op {op!r}") from e
+
+
+class _HeapBlock:
+    """Owns one symmetric-heap allocation; exposes it to torch without copying."""
+
+    def __init__(self, comm: "Communicator", nbytes: int):
+        self._comm = comm
+        self.nbytes = int(nbytes)
+        self.ptr = comm._c.alloc(max(self.nbytes, 1), 256)
+        self.__cuda_array_interface__ = {
+            "shape": (max(self.nbytes, 1),),
+            "typestr": "|u1",
+            "data": (self.ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+    def __del__(self):
+        try:
+            self._comm._c.free(self.ptr)
+        except Exception:
+            pass
+
+
+class Communicator:
+    def __init__(self, c, group=None):
+        self._c = c
+        self.group = group
+        self.rank: int = c.rank
+        self.world_size: int = c.nranks
+        self.device_index: int = c.device
+        self.is_host: bool = c.is_host
+        self.device = torch.device("cpu") if self.is_host else torch.device("cuda", c.device)
+
+    # ------------------------------------------------------------------ construction
+    @staticmethod
+    def create_unique_id() -> bytes:
+        return _native.C().create_unique_id()
+
+    @classmethod
+    def init(cls, uid: bytes, rank: int, world_size: int, device: Optional[int] = None,
+             heap_bytes: int = 1 << 30, stage_bytes: int = 64 << 20, host: Optional[bool] = None,
+             timeout_ms: int = -1, max_ctas: int = -1) -> "Communicator":
+        C = _native.C()
+        if host is None:
+            host = not torch.cuda.is_available()
+        if device is None:
+            device = -1 if host else torch.cuda.current_device()
+        if not host:
+            torch.cuda.set_device(device)
+            torch.cuda.init()
+        c = C.Comm.create(uid, rank, world_size, device, heap_bytes, stage_bytes, host, timeout_ms, max_ctas)
+        return cls(c)
+
+    @classmethod
+    def from_torch_dist(cls, group=None, device: Optional[int] = None, **kw) -> "Communicator":
+        import torch.distributed as dist
+
+        rank = dist.get_rank(group)
+        world = dist.get_world_size(group)
+        box = [cls.create_unique_id() if rank == 0 else None]
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=group)
+        comm = cls.init(box[0], rank, world, device=device, **kw)
+        comm.group = group
+        return comm
+
+    @classmethod
+    def local_world(cls, world_size: Optional[int] = None, devices: Optional[Sequence[int]] = None,
+                    heap_bytes: int = 1 << 30, stage_bytes: int = 64 << 20, host: Optional[bool] = None,
+                    timeout_ms: int = -1, max_ctas: int = -1) -> List["Communicator"]:
+        C = _native.C()
+        if host is None:
+            host = not torch.cuda.is_available()
+        if devices is None:
+            n = world_size or (1 if host else torch.cuda.device_count())
+            devices = [-1] * n if host else [i % torch.cuda.device_count() for i in range(n)]
+        if not host:
+            torch.cuda.init()
+        cs = C.Comm.create_local(list(devices), heap_bytes, stage_bytes, host, timeout_ms, max_ctas)
+        return [cls(c) for c in cs]
+
+    # ------------------------------------------------------------------------- memory
+    def empty(self, *shape, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """A tensor living in the symmetric heap (same offset on every rank when all ranks
+        allocate in the same order).  Zero-copy for every collective / EP / P2P op."""
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        blk = _HeapBlock(self, nbytes)
+        if self.is_host:
+            buf = (ctypes.c_ubyte * max(nbytes, 1)).from_address(blk.ptr)
+            flat = torch.frombuffer(buf, dtype=torch.uint8)
+            flat._uccl_block = blk  # keep alive
+        else:
+            flat = torch.as_tensor(blk, device=self.device)
+        t = flat[:nbytes].view(dtype).reshape(shape)
+        t._uccl_block = blk
+        return t
+
+    def zeros(self, *shape, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        t = self.empty(*shape, dtype=dtype)
+        t.zero_()
+        return t
+
+    def is_symmetric(self, t: torch.Tensor) -> bool:
+        return bool(self._c.in_heap(t.data_ptr(), t.numel() * t.element_size()))
+
+    def peer_ptr(self, t: torch.Tensor, peer: int) -> int:
+        return self._c.peer_ptr(t.data_ptr(), peer)
+
+    @property
+    def has_multicast(self) -> bool:
+        return bool(self._c.has_multicast)
+
+    @property
+    def native(self):
+        return self._c
+
+    def describe(self) -> str:
+        return self._c.describe()
+
+    # ------------------------------------------------------------------------ helpers
+    def _stream(self, stream=None) -> int:
+        if self.is_host:
+            return 0
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        return stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+
+    @staticmethod
+    def _check(t: torch.Tensor, name: str):
+        if not t.is_contiguous():
+            raise ValueError(f"uccl_b200: {name} must be contiguous")
+
+    # -------------------------------------------------------------------- collectives
+    def all_reduce(self, tensor: torch.Tensor, op="sum", out: Optional[torch.Tensor] = None, *,
+                   scale: float = 1.0, algo="auto", max_ctas: int = -1, stream=None) -> torch.Tensor:
+        """out = scale * reduce_over_ranks(tensor); in place when ``out`` is None.  If ``out``
+        has a different float dtype the cast is fused into the kernel epilogue."""
+        self._check(tensor, "tensor")
+        if out is None:
+            out = tensor
+        self._check(out, "out")
+        if out.numel() != tensor.numel():
+            raise ValueError("uccl_b200: all_reduce out/in element count mismatch")
+        out_dt = -1 if out.dtype == tensor.dtype else dtype_code(out.dtype)
+        a = ALGOS[algo] if isinstance(algo, str) else int(algo)
+        self._c.allreduce(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype), op_code(op),
+                          self._stream(stream), a, float(scale), out_dt, max_ctas)
+        return out
+
+    def all_gather(self, out: torch.Tensor, tensor: torch.Tensor, stream=None) -> torch.Tensor:
+        self._check(tensor, "tensor")
+        self._check(out, "out")
+        if out.numel() != tensor.numel() * self.world_size:
+            raise ValueError("uccl_b200: all_gather out must hold world_size * tensor.numel() elements")
+        self._c.allgather(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype),
+                          self._stream(stream))
+        return out
+
+    def reduce_scatter(self, out: torch.Tensor, tensor: torch.Tensor, op="sum", stream=None) -> torch.Tensor:
+        self._check(tensor, "tensor")
+        self._check(out, "out")
+        if tensor.numel() != out.numel() * self.world_size:
+            raise ValueError("uccl_b200: reduce_scatter input must hold world_size * out.numel() elements")
+        self._c.reduce_scatter(tensor.data_ptr(), out.data_ptr(), out.numel(), dtype_code(tensor.dtype), op_code(op),
+                               self._stream(stream))
+        return out
+
+    def broadcast(self, tensor: torch.Tensor, root: int = 0, out: Optional[torch.Tensor] = None,
+                  stream=None) -> torch.Tensor:
+        self._check(tensor, "tensor")
+        if out is None:
+            out = tensor
+        self._c.broadcast(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype), root,
+                          self._stream(stream))
+        return out
+
+    def reduce(self, tensor: torch.Tensor, root: int = 0, op="sum", out: Optional[torch.Tensor] = None,
+               stream=None) -> torch.Tensor:
+        self._check(tensor, "tensor")
+        if out is None:
+            out = tensor
+        self._c.reduce(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype), op_code(op), root,
+                       self._stream(stream))
+        return out
+
+    def all_to_all(self, out: torch.Tensor, tensor: torch.Tensor, stream=None) -> torch.Tensor:
+        self._check(tensor, "tensor")
+        self._check(out, "out")
+        if tensor.numel() % self.world_size or out.numel() != tensor.numel():
+            raise ValueError("uccl_b200: all_to_all needs equal splits (numel divisible by world size)")
+        self._c.alltoall(tensor.data_ptr(), out.data_ptr(), tensor.numel() // self.world_size,
+                         dtype_code(tensor.dtype), self._stream(stream))
+        return out
+
+    def all_to_all_v(self, out: torch.Tensor, tensor: torch.Tensor, send_counts: Iterable[int],
+                     recv_counts: Iterable[int], send_displs: Optional[Iterable[int]] = None,
+                     recv_displs: Optional[Iterable[int]] = None, stream=None) -> torch.Tensor:
+        sc, rc = [int(x) for x in send_counts], [int(x) for x in recv_counts]
+
+        def _excl(v):
+            o, acc = [], 0
+            for x in v:
+                o.append(acc)
+                acc += x
+            return o
+
+        sd = [int(x) for x in send_displs] if send_displs is not None else _excl(sc)
+        rd = [int(x) for x in recv_displs] if recv_displs is not None else _excl(rc)
+        self._c.alltoallv(tensor.data_ptr(), sc, sd, out.data_ptr(), rc, rd, dtype_code(tensor.dtype),
+                          self._stream(stream))
+        return out
+
+    def barrier(self, stream=None) -> None:
+        self._c.barrier(self._stream(stream))
+
+    # ----------------------------------------------------------------------- tuning
+    def select_allreduce(self, nbytes: int, symmetric: bool, dtype: torch.dtype = torch.float32, op="sum"):
+        algo, ctas = self._c.select_allreduce(int(nbytes), bool(symmetric), dtype_code(dtype), op_code(op))
+        return _native.C().algo_name(algo), ctas
+
+    def set_tuning(self, symmetric: bool, table):
+        """table: iterable of (max_bytes, algo_name_or_id, ctas)"""
+        C = _native.C()
+        ents = []
+        for mb, algo, ctas in table:
+            a = ALGOS[algo] if isinstance(algo, str) else int(algo)
+            ents.append(C.TuneEntry(int(mb), a, int(ctas)))
+        self._c.set_tuning(bool(symmetric), ents)
+
+
+def launch_count(comms: Iterable[Communicator]) -> int:
+    return sum(int(c._c.launches) for c in comms)
