@@ -1,0 +1,74 @@
+// Host runtime of the expert-parallel buffer (B200-native counterpart of the reference's
+// `class Buffer`, ep/src/uccl_ep.cc:315-1600).  No IPC-handle exchange, proxies or ring
+// buffers: the buffer is one block of the communicator's symmetric heap carved into
+//   [ctrl | dispatch arena 0 .. S-1 | combine arena]
+// and every kernel addresses peers through the fabric's mapped VAs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <memory>
+#include <vector>
+
+#include "../coll/comm.h"
+#include "ep_types.h"
+
+namespace ub {
+
+struct EpDispatchOut {
+  uintptr_t recv_x, recv_scales, recv_topk_idx, recv_topk_w, recv_src_idx;
+  int slot;
+  int capacity;
+};
+
+class EpBuffer {
+ public:
+  EpBuffer(std::shared_ptr<Comm> comm, size_t num_nvl_bytes, int num_slots);
+  ~EpBuffer();
+
+  int rank() const { return comm_->rank(); }
+  int nranks() const { return comm_->nranks(); }
+  size_t arena_bytes() const { return arena_bytes_; }
+  int num_slots() const { return num_slots_; }
+  int capacity_for(int hidden, int mode, int topk) const;
+  int combine_capacity_for(int hidden, int topk) const;
+  uint64_t launches() const { return launches_; }
+
+  // topk_idx != 0: full layout (counts + membership + positions); topk_idx == 0: positions only
+  void layout(uintptr_t topk_idx, int T, int K, int E, uintptr_t tokens_per_rank, uintptr_t tokens_per_expert,
+              uintptr_t is_token_in_rank, uintptr_t token_pos, cudaStream_t st);
+
+  EpDispatchOut dispatch(uintptr_t x, uintptr_t x_scales, uintptr_t topk_idx, uintptr_t topk_w, uintptr_t token_pos,
+                         uintptr_t send_slot, uintptr_t tokens_per_rank, uintptr_t tokens_per_expert, int T, int H,
+                         int K, int E, int mode, bool cached, int reuse_slot, uintptr_t rank_prefix,
+                         int expert_alignment, int num_worst_tokens, bool round_scale, int num_sms, cudaStream_t st);
+  // CPU wait for the counts of the latest non-cached dispatch. Returns recv_total (>= 0),
+  // throws on overflow (-2) / timeout.
+  int wait_counts(int E_local, std::vector<int>* per_expert, double timeout_s);
+  uintptr_t dev_counts_ptr() const { return (uintptr_t)dev_counts_; }
+
+  // zero-copy combine input: a [num_tokens, hidden] bf16 view of the combine arena
+  uintptr_t combine_input_ptr(int num_tokens, int hidden, int topk);
+  void combine(uintptr_t x, int num_recv, uintptr_t topk_w, uintptr_t send_slot, uintptr_t bias0, uintptr_t bias1,
+               uintptr_t out, uintptr_t out_topk_w, int T, int H, int K, int num_sms, cudaStream_t st);
+
+ private:
+  EpArena carve(int slot, int H, int mode, int K) const;
+  std::shared_ptr<Comm> comm_;
+  char* base_ = nullptr;      // local VA of the EP block
+  uint64_t base_off_ = 0;     // its heap offset
+  size_t bytes_ = 0;
+  size_t ctrl_bytes_ = 0;
+  size_t arena_bytes_ = 0;
+  int num_slots_ = 2;
+  int next_slot_ = 0;
+  int32_t* host_counts_ = nullptr;  // pinned + mapped
+  int32_t* host_counts_dev_ = nullptr;
+  int32_t* dev_counts_ = nullptr;
+  uint64_t launches_ = 0;
+};
+
+cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st);
+cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st);
+
+}  // namespace ub

@@ -1,0 +1,428 @@
+// Expert-parallel dispatch / combine kernels for one NVSwitch node (sm_100a).
+//
+// What the reference does (ep/src/layout.cu:9-150, ep/src/intranode.cu:12-1152): a layout
+// kernel, a notify kernel that all-to-alls the counts, then sender CTAs copy tokens into the
+// *receiver's ring buffer* and receiver CTAs copy them again into recv_x (two passes over the
+// payload, FP8 cast done beforehand by separate torch kernels, ep/bench/utils.py:666-675).
+//
+// B200-native design here -- direct placement, one pass, fused cast:
+//   * counts are exchanged inside the dispatch kernel (peer stores + block barrier), every rank
+//     then knows the full R x R matrix and therefore the exact slot of each of its tokens in each
+//     destination arena: no ring, no receiver CTAs, no second copy;
+//   * each warp loads a token once, (optionally) computes the per-128-channel amax, scales and
+//     casts to e4m3 in registers, and stores the row + scales + remapped top-k metadata straight
+//     into every destination rank's arena over NVLink;
+//   * combine is a pull: the source rank reads the (<= R) expert-output rows it needs from the
+//     peers' symmetric arenas, reduces in fp32 in a fixed order and writes bf16 once.
+#include "../kernels/prims.cuh"
+#include "ep_types.h"
+
+namespace ub {
+
+// ----------------------------------------------------------------------------- layout
+// Single CTA, 1024 threads: histogram per expert, per-rank membership and the exclusive
+// per-rank running position of every token (needed for direct placement).
+// If a.topk_idx == nullptr the membership is read from a.is_token_in_rank instead.
+__global__ void __launch_bounds__(1024, 1) ep_layout_kernel(const EpLayoutArgs a) {
+  extern __shared__ int s_dyn[];
+  int* s_expert = s_dyn;                  // [E]
+  __shared__ int s_warp_tot[32][kMaxRanks];
+  __shared__ int s_warp_off[32][kMaxRanks];
+  __shared__ int s_running[kMaxRanks];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int R = a.R, E_local = a.E / a.R;
+  for (int e = tid; e < a.E; e += blockDim.x) s_expert[e] = 0;
+  if (tid < kMaxRanks) s_running[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < a.T; base += blockDim.x) {
+    const int t = base + tid;
+    unsigned mask = 0;
+    if (t < a.T) {
+      if (a.topk_idx) {
+        for (int k = 0; k < a.K; ++k) {
+          long long e = a.topk_idx[(size_t)t * a.K + k];
+          if (e >= 0 && e < a.E) {
+            atomicAdd(&s_expert[(int)e], 1);
+            mask |= 1u << ((int)e / E_local);
+          }
+        }
+      } else {
+        for (int r = 0; r < R; ++r) mask |= (a.is_token_in_rank[(size_t)t * R + r] ? 1u : 0u) << r;
+      }
+    }
+    int pos_in_warp[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) {
+      unsigned b = __ballot_sync(0xffffffffu, (mask >> r) & 1u);
+      pos_in_warp[r] = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) s_warp_tot[warp][r] = __popc(b);
+    }
+    __syncthreads();
+    if (tid < 32 * kMaxRanks) {
+      const int w = tid / kMaxRanks, r = tid % kMaxRanks;
+      int off = 0;
+      for (int i = 0; i < w; ++i) off += s_warp_tot[i][r];
+      s_warp_off[w][r] = off;
+    }
+    __syncthreads();
+    if (t < a.T) {
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) {
+        if (r < R) {
+          const bool in = (mask >> r) & 1u;
+          if (a.topk_idx) a.is_token_in_rank[(size_t)t * R + r] = in ? 1 : 0;
+          a.token_pos[(size_t)t * R + r] = in ? (s_running[r] + s_warp_off[warp][r] + pos_in_warp[r]) : -1;
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < kMaxRanks) s_running[tid] += s_warp_off[31][tid] + s_warp_tot[31][tid];
+    __syncthreads();
+  }
+  if (tid < R && a.tokens_per_rank) a.tokens_per_rank[tid] = s_running[tid];
+  if (a.tokens_per_expert && a.topk_idx)
+    for (int e = tid; e < a.E; e += blockDim.x) a.tokens_per_expert[e] = s_expert[e];
+}
+
+// --------------------------------------------------------------------------- dispatch
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 p = __bfloat1622float2(h[i]);
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float d) {
+  __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_constant__ DevComm c,
+                                                             const __grid_constant__ EpDispatchArgs a) {
+  const int R = c.nranks, me = c.rank;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E_local = a.E / R;
+  __shared__ int s_M[kMaxRanks][kMaxRanks];
+  __shared__ int s_base[kMaxRanks];
+  __shared__ int s_abort;
+  __shared__ int s_recv_total;
+  __shared__ float s_scales[16][64];
+
+  BlockSync s = sync_begin(c, kDomEp, blockIdx.x);
+  if (tid == 0) {
+    s_abort = 0;
+    s_recv_total = 0;
+  }
+  if (!a.cached) {
+    // ---- phase 0: all-gather the R x R count matrix (each block keeps a private copy so that
+    //      only same-index blocks of different ranks need to synchronise)
+    if (tid < R * R) {
+      const int dst = tid / R, j = tid % R;
+      int* p = reinterpret_cast<int*>(c.heap[dst] + a.cnt_tab_off) + ((size_t)blockIdx.x * kMaxRanks + me) * kMaxRanks + j;
+      *p = a.tokens_per_rank[j];
+    }
+    if (blockIdx.x == 0) {
+      for (int i = tid; i < R * E_local; i += blockDim.x) {
+        const int dst = i / E_local, e = i % E_local;
+        int* p = reinterpret_cast<int*>(c.heap[dst] + a.exp_tab_off) + (size_t)me * kEpMaxLocalExperts + e;
+        *p = a.tokens_per_expert[dst * E_local + e];
+      }
+    }
+    sync_barrier(c, s);
+    const int* my_tab = reinterpret_cast<const int*>(c.heap[me] + a.cnt_tab_off) + (size_t)blockIdx.x * kMaxRanks * kMaxRanks;
+    if (tid < R * R) s_M[tid / R][tid % R] = my_tab[(tid / R) * kMaxRanks + (tid % R)];
+    __syncthreads();
+    if (tid < R) {
+      int base = 0, tot = 0;
+      for (int q = 0; q < R; ++q) {
+        if (q < me) base += s_M[q][tid];
+        tot += s_M[q][tid];
+      }
+      s_base[tid] = base;
+      if (tot > a.arena.capacity) s_abort = 1;  // identical decision on every rank (same matrix)
+      if (tid == me) s_recv_total = tot;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+      if (a.rank_prefix && tid < R * R) a.rank_prefix[tid] = s_M[tid / R][tid % R];
+      const int* exp_tab = reinterpret_cast<const int*>(c.heap[me] + a.exp_tab_off);
+      for (int e = tid; e < E_local; e += blockDim.x) {
+        int tot = 0;
+        for (int q = 0; q < R; ++q) tot += exp_tab[(size_t)q * kEpMaxLocalExperts + e];
+        const int al = a.expert_alignment > 1 ? a.expert_alignment : 1;
+        tot = (tot + al - 1) / al * al;
+        a.dev_counts[1 + e] = tot;
+        if (a.host_counts) a.host_counts[1 + e] = tot;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        const int v = s_abort ? -2 : s_recv_total;
+        a.dev_counts[0] = v;
+        if (a.host_counts) {
+          __threadfence_system();
+          a.host_counts[0] = v;
+          __threadfence_system();
+        }
+      }
+    }
+  } else {
+    sync_barrier_relaxed(c, s);  // peers have entered this dispatch: their arena may be overwritten
+    if (tid < R) s_base[tid] = 0;
+    __syncthreads();
+  }
+
+  if (!s_abort) {
+    const size_t in_row_bytes = (MODE == EP_X_FP8_SCALED) ? (size_t)a.H : (size_t)a.H * 2;
+    const size_t out_row_bytes = (MODE == EP_X_BF16) ? (size_t)a.H * 2 : (size_t)a.H;
+    const int n_scales = a.H / 128;
+    const int warps_total = gridDim.x * (blockDim.x >> 5);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + warp; t < a.T; t += warps_total) {
+      int my = -1;
+      if (lane < R) {
+        if (a.cached) {
+          my = a.send_slot[(size_t)t * R + lane];
+        } else {
+          const int p = a.token_pos[(size_t)t * R + lane];
+          my = p >= 0 ? s_base[lane] + p : -1;
+          a.send_slot[(size_t)t * R + lane] = my;
+        }
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
+      if (mask == 0) continue;
+      char* dst_x[kMaxRanks];
+      int slots[kMaxRanks];
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) {
+        slots[r] = __shfl_sync(0xffffffffu, my, r);
+        dst_x[r] = ((mask >> r) & 1u) ? c.heap[r] + a.arena.x_off + (size_t)slots[r] * out_row_bytes : nullptr;
+      }
+      const char* src = reinterpret_cast<const char*>(a.x) + (size_t)t * in_row_bytes;
+
+      if constexpr (MODE == EP_X_FUSED_FP8) {
+        const int units = a.H / 16;  // 16 output bytes (16 channels) per lane-iteration
+        for (int u0 = 0; u0 < units; u0 += 32) {
+          const int u = u0 + lane;
+          const bool valid = u < units;
+          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+          if (valid) {
+            v0 = ld_nc_v4(src + (size_t)u * 32);
+            v1 = ld_nc_v4(src + (size_t)u * 32 + 16);
+          }
+          float f[16];
+          bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
+          bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
+          // 128 channels = 8 consecutive lanes
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+          amax = fmaxf(amax, 1e-4f);
+          float scale, scale_inv;
+          if (a.round_scale) {
+            // power-of-two inverse scale (UE8M0 compatible): 2^ceil(log2(amax / 448))
+            const float raw = amax * (1.0f / 448.0f);
+            int ex = ((__float_as_int(raw) >> 23) & 0xff) - 127;
+            if ((__float_as_int(raw) & 0x7fffff) != 0) ex += 1;
+            scale_inv = __int_as_float((ex + 127) << 23);
+            scale = __int_as_float((127 - ex) << 23);
+          } else {
+            scale = 448.0f / amax;
+            scale_inv = amax * (1.0f / 448.0f);
+          }
+          uint4 o;
+          o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+          o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+          o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
+          o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
+          if (valid) {
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r)
+              if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)u * 16, o);
+            if ((lane & 7) == 0) s_scales[warp][u >> 3] = scale_inv;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+          if ((mask >> r) & 1u) {
+            float* ds = reinterpret_cast<float*>(c.heap[r] + a.arena.scales_off) + (size_t)slots[r] * n_scales;
+            for (int j = lane; j < n_scales; j += 32) ds[j] = s_scales[warp][j];
+          }
+        }
+        __syncwarp();
+      } else {
+        const int chunks = (int)(out_row_bytes / 16);
+        for (int i0 = 0; i0 < chunks; i0 += 128) {
+          uint4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 32 + lane;
+            if (i < chunks) v[j] = ld_nc_v4(src + (size_t)i * 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * 32 + lane;
+            if (i < chunks) {
+#pragma unroll
+              for (int r = 0; r < kMaxRanks; ++r)
+                if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)i * 16, v[j]);
+            }
+          }
+        }
+        if constexpr (MODE == EP_X_FP8_SCALED) {
+          const float* ssrc = a.x_scales + (size_t)t * n_scales;
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r) {
+            if ((mask >> r) & 1u) {
+              float* ds = reinterpret_cast<float*>(c.heap[r] + a.arena.scales_off) + (size_t)slots[r] * n_scales;
+              for (int j = lane; j < n_scales; j += 32) ds[j] = ssrc[j];
+            }
+          }
+        }
+      }
+      // ---- metadata: remapped top-k ids / weights + source token index
+      long long idx = -1;
+      float w = 0.f;
+      if (a.topk_idx && lane < a.K) {
+        idx = a.topk_idx[(size_t)t * a.K + lane];
+        if (a.topk_weights) w = a.topk_weights[(size_t)t * a.K + lane];
+      }
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r) {
+        if ((mask >> r) & 1u) {
+          const int slot = slots[r];
+          if (a.topk_idx && lane < a.K) {
+            const bool mine = idx >= (long long)r * E_local && idx < (long long)(r + 1) * E_local;
+            long long* di = reinterpret_cast<long long*>(c.heap[r] + a.arena.topk_idx_off) + (size_t)slot * a.K + lane;
+            *di = mine ? idx - (long long)r * E_local : -1;
+            if (a.topk_weights) {
+              float* dw = reinterpret_cast<float*>(c.heap[r] + a.arena.topk_w_off) + (size_t)slot * a.K + lane;
+              *dw = mine ? w : 0.f;
+            }
+          }
+          if (lane == 0) reinterpret_cast<int*>(c.heap[r] + a.arena.src_idx_off)[slot] = t;
+        }
+      }
+    }
+    // CUDA-graph friendly mode: pad the tail of recv_topk_idx with -1 (local writes)
+    if (!a.cached && a.num_worst_tokens > 0 && a.topk_idx) {
+      long long* ti = reinterpret_cast<long long*>(c.heap[me] + a.arena.topk_idx_off);
+      const size_t lo = (size_t)s_recv_total * a.K, hi = (size_t)a.num_worst_tokens * a.K;
+      for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + tid; i < hi; i += (size_t)gridDim.x * blockDim.x) ti[i] = -1;
+    }
+  }
+  sync_barrier(c, s);  // all my stores are visible at every destination; all inbound rows have landed
+  sync_end(s);
+}
+
+// ---------------------------------------------------------------------------- combine
+__global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constant__ DevComm c,
+                                                            const __grid_constant__ EpCombineArgs a) {
+  const int R = c.nranks;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  BlockSync s = sync_begin(c, kDomEp, blockIdx.x);
+  sync_barrier(c, s);  // every rank's expert outputs are in its combine arena
+  const size_t row_bytes = (size_t)a.H * 2;
+  const int chunks = (int)(row_bytes / 16);
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int t = blockIdx.x * (blockDim.x >> 5) + warp; t < a.T; t += warps_total) {
+    const int my = lane < R ? a.send_slot[(size_t)t * R + lane] : -1;
+    const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
+    const char* src[kMaxRanks];
+    int slots[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; ++r) {
+      slots[r] = __shfl_sync(0xffffffffu, my, r);
+      src[r] = ((mask >> r) & 1u) ? c.heap[r] + a.x_off + (size_t)slots[r] * row_bytes : nullptr;
+    }
+    char* out = reinterpret_cast<char*>(a.out) + (size_t)t * row_bytes;
+    const char* b0 = a.bias0 ? reinterpret_cast<const char*>(a.bias0) + (size_t)t * row_bytes : nullptr;
+    const char* b1 = a.bias1 ? reinterpret_cast<const char*>(a.bias1) + (size_t)t * row_bytes : nullptr;
+    for (int i0 = 0; i0 < chunks; i0 += 64) {
+      uint4 v[2][kMaxRanks];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j * 32 + lane;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (i < chunks && ((mask >> r) & 1u)) v[j][r] = ld_nc_v4(src[r] + (size_t)i * 16);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j * 32 + lane;
+        if (i < chunks) {
+          float acc[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+          if (b0) {
+            float f[8];
+            bf16x8_to_float(ld_nc_v4(b0 + (size_t)i * 16), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+          }
+          if (b1) {
+            float f[8];
+            bf16x8_to_float(ld_nc_v4(b1 + (size_t)i * 16), f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+          }
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r) {
+            if ((mask >> r) & 1u) {
+              float f[8];
+              bf16x8_to_float(v[j][r], f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            }
+          }
+          uint4 o;
+          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+          st_v4(out + (size_t)i * 16, o);
+        }
+      }
+    }
+    if (a.out_topk_w && a.topk_w_off != kNoOff && lane < a.K) {
+      float w = 0.f;
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if ((mask >> r) & 1u)
+          w += reinterpret_cast<const float*>(c.heap[r] + a.topk_w_off)[(size_t)slots[r] * a.K + lane];
+      a.out_topk_w[(size_t)t * a.K + lane] = w;
+    }
+  }
+  sync_barrier_relaxed(c, s);  // nobody still reads my arena when I return
+  sync_end(s);
+}
+
+// --------------------------------------------------------------------------- launchers
+cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st) {
+  size_t smem = (size_t)a.E * sizeof(int);
+  ep_layout_kernel<<<1, 1024, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st) {
+  switch (a.mode) {
+    case EP_X_BF16: ep_dispatch_kernel<EP_X_BF16><<<grid, 512, 0, st>>>(c, a); break;
+    case EP_X_FP8_SCALED: ep_dispatch_kernel<EP_X_FP8_SCALED><<<grid, 512, 0, st>>>(c, a); break;
+    case EP_X_FUSED_FP8: ep_dispatch_kernel<EP_X_FUSED_FP8><<<grid, 512, 0, st>>>(c, a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
+  ep_combine_kernel<<<grid, 512, 0, st>>>(c, a);
+  return cudaGetLastError();
+}
+
+}  // namespace ub

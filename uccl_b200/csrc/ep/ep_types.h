@@ -1,0 +1,101 @@
+// Host-safe argument structs of the expert-parallel (EP) kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../kernels/types.h"
+
+namespace ub {
+
+constexpr int kEpMaxTopk = 32;          // DeepEP HT limit (ep/src/intranode.cu:213)
+constexpr int kEpMaxLocalExperts = 1024;  // ep/include/ep_configs.cuh:6
+constexpr int kEpMaxBlocks = 256;
+
+enum EpXMode : int {
+  EP_X_BF16 = 0,       // bf16 in  -> bf16 out (plain permutation)
+  EP_X_FP8_SCALED = 1, // (fp8, float scales[H/128]) in -> same out (DeepEP pre-quantised input)
+  EP_X_FUSED_FP8 = 2   // bf16 in -> per-128 amax / scale / e4m3 cast fused into the send -> (fp8, scales) out
+};
+
+// One receive arena (a "slot" of the dispatch ring) inside the symmetric heap.
+struct EpArena {
+  uint64_t x_off;        // [cap][H * elem]
+  uint64_t scales_off;   // [cap][H/128] float (fp8 modes)
+  uint64_t topk_idx_off; // [cap][K] int64
+  uint64_t topk_w_off;   // [cap][K] float
+  uint64_t src_idx_off;  // [cap] int32
+  int capacity;          // tokens
+};
+
+struct EpLayoutArgs {
+  const int64_t* topk_idx;  // [T, K]
+  int T, K, E, R;
+  int32_t* tokens_per_rank;    // [R]
+  int32_t* tokens_per_expert;  // [E]
+  uint8_t* is_token_in_rank;   // [T, R] (torch.bool)
+  int32_t* token_pos;          // [T, R] exclusive position among my tokens going to rank r, -1 if none
+};
+
+struct EpDispatchArgs {
+  const void* x;
+  const float* x_scales;
+  const int64_t* topk_idx;    // may be null
+  const float* topk_weights;  // may be null
+  const int32_t* token_pos;   // [T, R] (non-cached) -- rank-local positions
+  int32_t* send_slot;         // [T, R] absolute slot inside each destination arena (written when !cached, read when cached)
+  const int32_t* tokens_per_rank;    // [R] device
+  const int32_t* tokens_per_expert;  // [E] device (may be null when cached)
+  int T, H, K, E;
+  int mode;    // EpXMode
+  int cached;  // 1: reuse send_slot, skip the count exchange
+  EpArena arena;
+  uint64_t cnt_tab_off;  // symmetric: [kEpMaxBlocks][R src][R dst] int32
+  uint64_t exp_tab_off;  // symmetric: [R src][kEpMaxLocalExperts] int32
+  int32_t* rank_prefix;  // local [R][R]: M[src][dst] token counts (handle)
+  int32_t* dev_counts;   // local [1 + kEpMaxLocalExperts]: recv total, per-local-expert recv counts
+  volatile int32_t* host_counts;  // host-mapped mirror of dev_counts (CPU spins on [0]); may be null
+  int expert_alignment;
+  int num_worst_tokens;
+  int round_scale;  // power-of-two scales (UE8M0-compatible), like DeepEP's round_scale
+};
+
+struct EpCombineArgs {
+  uint64_t x_off;            // symmetric: expert outputs [num_recv, H] bf16 (in the combine arena)
+  uint64_t topk_w_off;       // symmetric: [num_recv, K] float, or kNoOff
+  const int32_t* send_slot;  // [T, R] from dispatch
+  const void* bias0;         // optional [T, H] bf16
+  const void* bias1;
+  void* out;                 // [T, H] bf16
+  float* out_topk_w;         // [T, K] or null
+  int T, H, K;
+};
+
+// ---- low-latency (decode) mode -------------------------------------------------------
+struct EpLLArgs {
+  // dispatch
+  const void* x;               // [T, H] bf16
+  const int64_t* topk_idx;     // [T, K]
+  int T, H, K, E;              // E = total experts
+  int max_tokens_per_rank;     // M
+  int use_fp8, round_scale, use_ue8m0;
+  uint64_t recv_x_off;         // symmetric [E_local][R*M][H (fp8|bf16)]
+  uint64_t recv_scales_off;    // symmetric [E_local][R*M][H/128] float
+  uint64_t recv_src_off;       // symmetric [E_local][R*M] int32 (source token index)
+  uint64_t recv_cnt_off;       // symmetric [E_local][R] int32 : -(n)-1 encoded counts per (expert, src rank)
+  uint64_t send_cnt_off;       // local scratch [E] int32 atomic slot counters
+  // packed outputs (local)
+  void* packed_x;              // [E_local][R*M][H]
+  float* packed_scales;        // [E_local][R*M][H/128]
+  int32_t* packed_src_info;    // [E_local][R*M]
+  int64_t* layout_range;       // [E_local][R]  (count << 32 | begin)
+  int32_t* packed_recv_count;  // [E_local]
+  // combine
+  const void* comb_x;          // [E_local][R*M][H] bf16 expert outputs (symmetric offset in comb_x_off)
+  uint64_t comb_x_off;
+  const float* topk_weights;   // [T, K]
+  void* combined;              // [T, H] bf16
+  uint64_t comb_recv_off;      // symmetric [T_max][K][H] bf16 staging at the source rank
+  uint64_t comb_flag_off;      // symmetric [E] int32 flags
+  int phase;                   // 1 = send, 2 = recv, 3 = both
+};
+
+}  // namespace ub

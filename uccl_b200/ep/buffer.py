@@ -1,0 +1,335 @@
+"""DeepEP-compatible expert-parallel ``Buffer`` on top of the native sm_100a kernels.
+
+API surface follows the reference's ``ep/bench/buffer.py`` (ctor :58-69, get_dispatch_layout
+:736, dispatch :837, combine :1190, low_latency_* :263-566, configs :680-733) so code written
+against ``deep_ep.Buffer`` / ``uccl.ep`` switches over unchanged.  Differences that matter:
+
+* results (``recv_x`` ...) are zero-copy *views* of a ring of receive arenas inside the
+  symmetric heap -- valid until ``num_slots`` further dispatches (default 2);
+* ``dispatch(..., use_fp8=True)`` fuses the per-128-channel amax/scale/e4m3 cast into the
+  send (the reference casts with separate torch kernels beforehand, ep/bench/utils.py:666-675);
+* ``get_combine_buffer`` hands out the symmetric arena the expert MLP should write into so
+  that ``combine`` is a single zero-copy pull-reduce (any other tensor is copied in first).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import torch
+
+from .. import _native
+from ..parallel.comm import Communicator
+from .utils import EventHandle, EventOverlap
+
+
+class Config:
+    """Performance knobs (reference: ``Config(num_sms, nvl_send, nvl_recv, rdma_send, rdma_recv)``,
+    ep/src/uccl_ep.cc:1641-1646).  Only ``num_sms`` matters here: there are no chunked ring
+    buffers to size, the other fields are accepted and ignored."""
+
+    def __init__(self, num_sms: int = 24, num_max_nvl_chunked_send_tokens: int = 6,
+                 num_max_nvl_chunked_recv_tokens: int = 256, num_max_rdma_chunked_send_tokens: int = 6,
+                 num_max_rdma_chunked_recv_tokens: int = 256):
+        self.num_sms = num_sms
+        self.num_max_nvl_chunked_send_tokens = num_max_nvl_chunked_send_tokens
+        self.num_max_nvl_chunked_recv_tokens = num_max_nvl_chunked_recv_tokens
+        self.num_max_rdma_chunked_send_tokens = num_max_rdma_chunked_send_tokens
+        self.num_max_rdma_chunked_recv_tokens = num_max_rdma_chunked_recv_tokens
+
+    def get_nvl_buffer_size_hint(self, hidden_bytes: int, num_ranks: int, num_max_tokens_per_rank: int = 4096,
+                                 num_topk: int = 8, num_slots: int = 2) -> int:
+        """Bytes for worst-case routing (every token of every rank lands here)."""
+        cap = num_ranks * num_max_tokens_per_rank
+        per_tok = hidden_bytes + (hidden_bytes // 128) * 4 + num_topk * 12 + 4
+        return int((num_slots + 1) * (cap * per_tok + 8 * 256) + (1 << 20))
+
+
+class Buffer:
+    num_sms: int = 24
+
+    def __init__(self, group=None, num_nvl_bytes: int = 0, num_rdma_bytes: int = 0, low_latency_mode: bool = False,
+                 num_qps_per_rank: int = 24, allow_nvlink_for_low_latency_mode: bool = True,
+                 allow_mnnvl: bool = False, explicitly_destroy: bool = False, is_intranode: Optional[bool] = None,
+                 comm: Optional[Communicator] = None, num_slots: int = 2):
+        """Either pass a ``torch.distributed`` group (one process per GPU; a private
+        Communicator sized for ``num_nvl_bytes + num_rdma_bytes`` is created) or an existing
+        ``comm`` (e.g. one rank of ``Communicator.local_world``)."""
+        self.group = group
+        self.low_latency_mode = low_latency_mode
+        self.explicitly_destroy = explicitly_destroy
+        self.num_nvl_bytes = int(num_nvl_bytes)
+        self.num_rdma_bytes = int(num_rdma_bytes)
+        total = self.num_nvl_bytes + self.num_rdma_bytes
+        if comm is None:
+            assert group is not None, "Buffer needs a process group or a Communicator"
+            heap = total + (256 << 20)
+            comm = Communicator.from_torch_dist(group, heap_bytes=heap, stage_bytes=16 << 20)
+        self.comm = comm
+        self.rank = comm.rank
+        self.group_size = comm.world_size
+        self.device = comm.device
+        C = _native.C()
+        self._C = C
+        self.runtime = C.EpBuffer(comm.native, max(self.num_nvl_bytes, 1 << 20), num_slots)
+        self._ll = None
+        if self.num_rdma_bytes > 0 or low_latency_mode:
+            from .low_latency import LowLatencyRuntime
+
+            self._ll = LowLatencyRuntime(self, self.num_rdma_bytes)
+        with torch.cuda.device(self.device):
+            self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._layout_cache = None
+        self._destroyed = False
+
+    # ------------------------------------------------------------------ misc parity API
+    def destroy(self):
+        self._destroyed = True
+        self.runtime = None
+        self._ll = None
+
+    @staticmethod
+    def is_sm90_compiled() -> bool:
+        return True  # sm_100a build: every sm_90+ feature (fp8, TMA, clusters) is available
+
+    @staticmethod
+    def set_num_sms(new_num_sms: int) -> None:
+        assert new_num_sms % 2 == 0, "The SM count must be even"
+        Buffer.num_sms = new_num_sms
+
+    @staticmethod
+    def capture() -> EventOverlap:
+        return EventOverlap(EventHandle())
+
+    def get_comm_stream(self) -> torch.cuda.Stream:
+        return self.comm_stream
+
+    @staticmethod
+    def get_dispatch_config(num_ranks: int) -> Config:
+        return Config(Buffer.num_sms)
+
+    @staticmethod
+    def get_combine_config(num_ranks: int) -> Config:
+        return Config(Buffer.num_sms)
+
+    @staticmethod
+    def get_low_latency_rdma_size_hint(num_max_dispatch_tokens_per_rank: int, hidden: int, num_ranks: int,
+                                       num_experts: int) -> int:
+        from .low_latency import ll_size_hint
+
+        return ll_size_hint(num_max_dispatch_tokens_per_rank, hidden, num_ranks, num_experts)
+
+    # ------------------------------------------------------------------ stream choreography
+    def _enter(self, previous_event, allocate_on_comm_stream):
+        compute = torch.cuda.current_stream(self.device)
+        if previous_event is not None and previous_event.event is not None:
+            self.comm_stream.wait_event(previous_event.event.event)
+        else:
+            self.comm_stream.wait_stream(compute)
+        return compute
+
+    def _exit(self, compute, async_finish, tensors) -> EventOverlap:
+        if async_finish:
+            ev = EventHandle(self.comm_stream)
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.comm_stream)
+                    t.record_stream(compute)
+            return EventOverlap(ev, tuple(tensors))
+        compute.wait_stream(self.comm_stream)
+        return EventOverlap()
+
+    # ------------------------------------------------------------------------- layout
+    def get_dispatch_layout(self, topk_idx: torch.Tensor, num_experts: int,
+                            previous_event: Optional[EventOverlap] = None, async_finish: bool = False,
+                            allocate_on_comm_stream: bool = False):
+        assert topk_idx.dtype == torch.int64 and topk_idx.dim() == 2 and topk_idx.is_contiguous()
+        T, K = topk_idx.shape
+        R = self.group_size
+        dev = self.device
+        compute = self._enter(previous_event, allocate_on_comm_stream)
+        with torch.cuda.stream(self.comm_stream):
+            num_tokens_per_rank = torch.empty(R, dtype=torch.int32, device=dev)
+            num_tokens_per_expert = torch.empty(num_experts, dtype=torch.int32, device=dev)
+            is_token_in_rank = torch.empty((T, R), dtype=torch.bool, device=dev)
+            token_pos = torch.empty((T, R), dtype=torch.int32, device=dev)
+            self.runtime.layout(topk_idx.data_ptr(), T, K, num_experts, num_tokens_per_rank.data_ptr(),
+                                num_tokens_per_expert.data_ptr(), is_token_in_rank.data_ptr(), token_pos.data_ptr(),
+                                self.comm_stream.cuda_stream)
+        # positions ride along with is_token_in_rank so dispatch() does not need to rescan
+        self._layout_cache = (is_token_in_rank.data_ptr(), T, token_pos)
+        ev = self._exit(compute, async_finish, (topk_idx, num_tokens_per_rank, num_tokens_per_expert,
+                                                is_token_in_rank, token_pos))
+        return num_tokens_per_rank, None, num_tokens_per_expert, is_token_in_rank, ev
+
+    # ----------------------------------------------------------------------- dispatch
+    def dispatch(self, x: Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]], handle: Optional[Tuple] = None,
+                 num_tokens_per_rank: Optional[torch.Tensor] = None,
+                 num_tokens_per_rdma_rank: Optional[torch.Tensor] = None,
+                 is_token_in_rank: Optional[torch.Tensor] = None,
+                 num_tokens_per_expert: Optional[torch.Tensor] = None, topk_idx: Optional[torch.Tensor] = None,
+                 topk_weights: Optional[torch.Tensor] = None, expert_alignment: int = 1, num_worst_tokens: int = 0,
+                 config: Optional[Config] = None, previous_event: Optional[EventOverlap] = None,
+                 async_finish: bool = False, allocate_on_comm_stream: bool = False, use_fp8: bool = False,
+                 round_scale: bool = False):
+        C = self._C
+        config = config or self.get_dispatch_config(self.group_size)
+        R = self.group_size
+        dev = self.device
+        if isinstance(x, tuple):
+            x_data, x_scales = x
+            assert x_data.dtype == torch.float8_e4m3fn and x_scales.dtype == torch.float32
+            assert x_scales.is_contiguous() and x_scales.shape == (x_data.size(0), x_data.size(1) // 128)
+            mode = C.EP_X_FP8_SCALED
+            assert not use_fp8
+        else:
+            x_data, x_scales = x, None
+            assert x_data.dtype == torch.bfloat16
+            mode = C.EP_X_FUSED_FP8 if use_fp8 else C.EP_X_BF16
+        assert x_data.dim() == 2 and x_data.is_contiguous()
+        T, H = x_data.shape
+        out_fp8 = mode != C.EP_X_BF16
+        compute = self._enter(previous_event, allocate_on_comm_stream)
+
+        if handle is not None:
+            # cached mode: only the payload moves (reference: buffer.py:1013-1023)
+            (rank_prefix, send_slot, recv_src_idx, h_is_in_rank, num_recv, slot, h_K) = handle
+            assert send_slot.shape == (T, R)
+            with torch.cuda.stream(self.comm_stream):
+                o = self.runtime.dispatch(x_data.data_ptr(), x_scales.data_ptr() if x_scales is not None else 0, 0, 0,
+                                          0, send_slot.data_ptr(), 0, 0, T, H, h_K, 0, mode, True, -1, 0, 1, 0,
+                                          round_scale, config.num_sms, self.comm_stream.cuda_stream)
+            recv_x = self._view_x(o, num_recv, H, out_fp8)
+            ev = self._exit(compute, async_finish, (x_data, x_scales, send_slot))
+            return recv_x, None, None, None, None, ev
+
+        assert num_tokens_per_rank is not None and is_token_in_rank is not None and num_tokens_per_expert is not None
+        K = 0
+        if topk_idx is not None:
+            assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous() and topk_idx.size(0) == T
+            K = topk_idx.size(1)
+            if topk_weights is not None:
+                assert topk_weights.dtype == torch.float32 and topk_weights.is_contiguous()
+        E = num_tokens_per_expert.numel()
+        E_local = E // R
+        with torch.cuda.stream(self.comm_stream):
+            cache = self._layout_cache
+            if cache is not None and cache[0] == is_token_in_rank.data_ptr() and cache[1] == T:
+                token_pos = cache[2]
+            else:
+                token_pos = torch.empty((T, R), dtype=torch.int32, device=dev)
+                self.runtime.layout(0, T, 0, 0, 0, 0, is_token_in_rank.data_ptr(), token_pos.data_ptr(),
+                                    self.comm_stream.cuda_stream)
+            send_slot = torch.empty((T, R), dtype=torch.int32, device=dev)
+            rank_prefix = torch.empty((R, R), dtype=torch.int32, device=dev)
+            o = self.runtime.dispatch(
+                x_data.data_ptr(), x_scales.data_ptr() if x_scales is not None else 0,
+                topk_idx.data_ptr() if topk_idx is not None else 0,
+                topk_weights.data_ptr() if topk_weights is not None else 0, token_pos.data_ptr(),
+                send_slot.data_ptr(), num_tokens_per_rank.data_ptr(), num_tokens_per_expert.data_ptr(), T, H, K, E,
+                mode, False, -1, rank_prefix.data_ptr(), expert_alignment, num_worst_tokens, round_scale,
+                config.num_sms, self.comm_stream.cuda_stream)
+        if num_worst_tokens > 0:
+            num_recv = num_worst_tokens
+            per_expert: List[int] = []
+        else:
+            num_recv, per_expert = self.runtime.wait_counts(E_local, 0.0)
+        recv_x = self._view_x(o, num_recv, H, out_fp8)
+        recv_topk_idx = recv_topk_weights = None
+        if topk_idx is not None:
+            recv_topk_idx = self._view(o.recv_topk_idx, (num_recv, K), torch.int64)
+            if topk_weights is not None:
+                recv_topk_weights = self._view(o.recv_topk_w, (num_recv, K), torch.float32)
+        recv_src_idx = self._view(o.recv_src_idx, (num_recv,), torch.int32)
+        handle = (rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, o.slot, K)
+        ev = self._exit(compute, async_finish, (x_data, x_scales, topk_idx, topk_weights, send_slot, rank_prefix,
+                                                token_pos, num_tokens_per_rank, num_tokens_per_expert))
+        return recv_x, recv_topk_idx, recv_topk_weights, per_expert, handle, ev
+
+    def _view(self, ptr: int, shape, dtype) -> torch.Tensor:
+        numel = 1
+        for s in shape:
+            numel *= int(s)
+        nbytes = max(numel * torch.empty((), dtype=dtype).element_size(), 1)
+        holder = _RawView(ptr, nbytes, self)
+        flat = torch.as_tensor(holder, device=self.device)
+        nb = numel * torch.empty((), dtype=dtype).element_size()
+        return flat[:nb].view(dtype).reshape(shape)
+
+    def _view_x(self, o, num_recv, H, out_fp8):
+        if out_fp8:
+            x = self._view(o.recv_x, (num_recv, H), torch.float8_e4m3fn)
+            s = self._view(o.recv_scales, (num_recv, H // 128), torch.float32)
+            return (x, s)
+        return self._view(o.recv_x, (num_recv, H), torch.bfloat16)
+
+    # ------------------------------------------------------------------------ combine
+    def get_combine_buffer(self, num_tokens: int, hidden: int, num_topk: int = 0) -> torch.Tensor:
+        """[num_tokens, hidden] bf16 view of the symmetric combine arena: write the expert
+        outputs here and pass it to :meth:`combine` for a zero-copy pull-reduce."""
+        ptr = self.runtime.combine_input_ptr(num_tokens, hidden, num_topk)
+        return self._view(ptr, (num_tokens, hidden), torch.bfloat16)
+
+    def combine(self, x: torch.Tensor, handle: Tuple, topk_weights: Optional[torch.Tensor] = None,
+                bias: Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor], None] = None,
+                config: Optional[Config] = None, previous_event: Optional[EventOverlap] = None,
+                async_finish: bool = False, allocate_on_comm_stream: bool = False):
+        config = config or self.get_combine_config(self.group_size)
+        (rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, slot, K) = handle
+        assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
+        assert x.size(0) >= num_recv or x.size(0) == num_recv
+        H = x.size(1)
+        T = send_slot.size(0)
+        b0 = b1 = None
+        if bias is not None:
+            if isinstance(bias, tuple):
+                b0, b1 = bias
+            else:
+                b0 = bias
+        compute = self._enter(previous_event, allocate_on_comm_stream)
+        with torch.cuda.stream(self.comm_stream):
+            out = torch.empty((T, H), dtype=torch.bfloat16, device=self.device)
+            out_w = None
+            if topk_weights is not None:
+                assert topk_weights.dtype == torch.float32 and topk_weights.is_contiguous()
+                Kw = topk_weights.size(1)
+                out_w = torch.empty((T, Kw), dtype=torch.float32, device=self.device)
+            else:
+                Kw = 0
+            self.runtime.combine(x.data_ptr(), x.size(0), topk_weights.data_ptr() if topk_weights is not None else 0,
+                                 send_slot.data_ptr(), b0.data_ptr() if b0 is not None else 0,
+                                 b1.data_ptr() if b1 is not None else 0, out.data_ptr(),
+                                 out_w.data_ptr() if out_w is not None else 0, T, H, Kw, config.num_sms,
+                                 self.comm_stream.cuda_stream)
+        ev = self._exit(compute, async_finish, (x, topk_weights, b0, b1, out, out_w, send_slot))
+        return out, out_w, ev
+
+    # ------------------------------------------------------------------ low latency
+    def _need_ll(self):
+        assert self._ll is not None, "construct Buffer with low_latency_mode=True / num_rdma_bytes > 0"
+        return self._ll
+
+    def clean_low_latency_buffer(self, num_max_dispatch_tokens_per_rank: int, hidden: int, num_experts: int):
+        self._need_ll().clean(num_max_dispatch_tokens_per_rank, hidden, num_experts)
+
+    def low_latency_dispatch(self, x, topk_idx, num_max_dispatch_tokens_per_rank: int, num_experts: int, **kw):
+        return self._need_ll().dispatch(x, topk_idx, num_max_dispatch_tokens_per_rank, num_experts, **kw)
+
+    def low_latency_combine(self, x, topk_idx, topk_weights, handle, **kw):
+        return self._need_ll().combine(x, topk_idx, topk_weights, handle, **kw)
+
+    def get_next_low_latency_combine_buffer(self, handle):
+        return self._need_ll().next_combine_buffer(handle)
+
+
+class _RawView:
+    """Exposes raw heap memory to torch through ``__cuda_array_interface__`` (no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int, keepalive):
+        self._keep = keepalive
+        self.__cuda_array_interface__ = {
+            "shape": (int(nbytes),),
+            "typestr": "|u1",
+            "data": (int(ptr), False),
+            "version": 3,
+            "strides": None,
+        }
