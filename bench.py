@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): EP dispatch+combine at EP=N on N B200s of one node, the
+reference's DeepEP-intranode config (4096 tokens/rank, hidden 7168, top-8 of 256 experts,
+bf16 -> fp8 dispatch, bf16 combine), plus an AllReduce bus-bandwidth sweep next to NCCL.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W   (torchrun for N > 1)
+prints ONE JSON line on rank 0.  `value` = whole-job tokens/s through dispatch+combine
+(weak scaling: 4096 tokens per GPU), device-timed with CUDA events, max over ranks.
+
+A "step" = one dispatch (payload + fused fp8 cast + metadata, cached layout handle -- the same
+thing the reference times, ep/bench/test_intranode.py:457-539) followed by one combine.
+The e2e number runs the whole public API per step: pinned-host -> device copy of the inputs,
+get_dispatch_layout, non-cached dispatch (incl. the count exchange and its CPU sync), combine,
+and a device -> host read of the result checksum.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+BASELINE_DISPATCH_US = 571.0  # ep/README.md:154-160 (8xB200, EP=8, FP8 dispatch)
+BASELINE_COMBINE_US = 727.0   # ep/README.md:160     (8xB200, EP=8, BF16 combine)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--metric", default="ep", choices=["ep", "allreduce"])
+    p.add_argument("--tokens", type=int, default=4096)
+    p.add_argument("--hidden", type=int, default=7168)
+    p.add_argument("--topk", type=int, default=8)
+    p.add_argument("--experts", type=int, default=256)
+    p.add_argument("--num-sms", type=int, default=int(os.environ.get("UCCL_B200_EP_SMS", "64")))
+    p.add_argument("--no-allreduce-sweep", action="store_true")
+    p.add_argument("--out", default=None, help="also write the JSON line to this file")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons of this rank's GPU during the timed region (NVML)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._ok = True
+        except Exception:
+            self._ok = False
+
+    def _run(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(1.0)
+        if not self._ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------- reference
+def run_reference(args):
+    """The unmodified reference from baseline/_ref through its own public API.  For the EP
+    metric that is `uccl.ep.Buffer`, a native module the offline install cannot build (needs
+    nanobind + libibverbs headers + its docker toolchain) -- see DESIGN.md."""
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    rank = int(os.environ.get("RANK", "0"))
+    if args.metric == "ep":
+        why = None
+        if not os.path.isdir(os.path.join(ref, "uccl")):
+            why = "baseline/_ref/uccl not installed"
+        else:
+            sys.path.insert(0, ref)
+            try:
+                import uccl  # noqa: F401
+                from uccl import ep  # noqa: F401
+            except Exception as e:  # ImportError: native ep module absent
+                why = ("reference installs offline only as a pure-python stub: uccl.ep native module missing "
+                       f"(needs nanobind/libibverbs to build): {type(e).__name__}: {e}")
+        if why is None:
+            why = "uccl.ep imported but no offline-buildable DeepEP runtime is wired"
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
+        return 0
+    # allreduce: the reference's collective product is stock NCCL + its net plugin
+    # (README.md:109-119); on one NVSwitch node no byte reaches the plugin, so this arm is NCCL
+    # launched the way the reference documents (NCCL_NET_PLUGIN from uccl.nccl_plugin_path()).
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ref)
+    try:
+        import uccl
+
+        plugin = uccl.nccl_plugin_path()
+        if os.path.exists(plugin):
+            os.environ["NCCL_NET_PLUGIN"] = plugin
+    except Exception:
+        pass
+    n = args.gpus
+    if n == 1:
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "allreduce bus bandwidth is undefined at 1 GPU"}))
+        return 0
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = 1 << 30
+    x = torch.ones(size // 2, dtype=torch.bfloat16, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        dist.all_reduce(x)
+    torch.cuda.synchronize()
+    dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        dist.all_reduce(x)
+    e.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e) / args.steps], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    busbw = size / (ms.item() * 1e-3) * 2 * (n - 1) / n / 1e9
+    if rank == 0:
+        print(json.dumps({"impl": "reference", "metric": "allreduce_busbw_1GiB_bf16", "value": busbw, "unit": "GB/s",
+                          "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(),
+                          "higher_is_better": True, "dtype": "bf16", "data": "synthetic"}))
+    dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------- ours
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from uccl_b200 import Communicator
+    from uccl_b200.ep import Buffer
+
+    n = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU"
+    dist = None
+    if n > 1:
+        assert world == n, f"launch with torchrun --nproc-per-node {n} (WORLD_SIZE={world})"
+        import torch.distributed as dist  # type: ignore
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    T, H, K, E = args.tokens, args.hidden, args.topk, args.experts
+    assert E % n == 0
+    # worst case: every token of every rank lands on one rank
+    cap_tokens = n * T
+    arena = cap_tokens * (H * 2 + K * 4) + (1 << 20)
+    nvl_bytes = 3 * arena + (2 << 20)
+    heap = nvl_bytes + (1 << 30) + (2 << 30 if n > 1 else 0)
+    if n > 1:
+        comm = Communicator.from_torch_dist(None, heap_bytes=heap, stage_bytes=256 << 20)
+    else:
+        comm = Communicator.local_world(1, devices=[dev.index], heap_bytes=heap, stage_bytes=64 << 20)[0]
+    buf = Buffer(comm=comm, num_nvl_bytes=nvl_bytes)
+    cfg = Buffer.get_dispatch_config(n)
+    cfg.num_sms = args.num_sms
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # synthetic inputs (random-init MoE tokens; routing = top-k of |N(0,1)|+1 scores like the reference test)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    x_host = torch.randn(T, H, generator=g).to(torch.bfloat16).pin_memory()
+    scores = torch.randn(T, E, generator=g).abs() + 1
+    idx_host = scores.topk(K, dim=-1, largest=True, sorted=False).indices.to(torch.int64).contiguous().pin_memory()
+    w_host = torch.rand(T, K, generator=g).float().pin_memory()
+    x = x_host.to(dev, non_blocking=True)
+    topk_idx = idx_host.to(dev, non_blocking=True)
+    topk_w = w_host.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    # one full (non-cached) round to obtain the handle used by the kernel-timed loop
+    tpr, _, tpe, in_rank, _ = buf.get_dispatch_layout(topk_idx, E)
+    recv_x, recv_idx, recv_w, per_expert, handle, _ = buf.dispatch(
+        x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe, topk_idx=topk_idx,
+        topk_weights=topk_w, use_fp8=True, config=cfg)
+    num_recv = handle[4]
+    comb_in = buf.get_combine_buffer(num_recv, H, K)
+    comb_in.normal_()  # stand-in for the expert MLP output (bf16), lives in the symmetric arena
+    barrier()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_cached():
+        buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
+        out, _, _ = buf.combine(comb_in, handle, config=cfg)
+        return out
+
+    def launches():
+        return int(buf.runtime.launches) + int(comm.native.launches)
+
+    for _ in range(max(args.warmup, 3)):
+        step_cached()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed per step, L2 flushed between steps
+    sampler = ClockSampler(dev.index)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    l0 = launches()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        step_cached()
+        ends[i].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    gpu_launches = launches() - l0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    ms_per_step = max_over_ranks(sum(step_ms) / len(step_ms))
+    tokens_per_s = n * T / (ms_per_step * 1e-3)
+
+    # ---- split dispatch / combine (device-timed, same hygiene) for the roofline lines
+    def timed(fn, iters):
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            ts.append((s, e))
+        barrier()
+        v = [a.elapsed_time(b) for a, b in ts]
+        return max_over_ranks(sum(v) / len(v))
+
+    it = max(5, min(args.steps, 20))
+    disp_ms = timed(lambda: buf.dispatch(x, handle=handle, use_fp8=True, config=cfg), it)
+    comb_ms = timed(lambda: buf.combine(comb_in, handle, config=cfg), it)
+    disp_bytes = num_recv * (H + H // 128 * 4)   # fp8 payload + scales received per rank
+    comb_bytes = num_recv * H * 2                # bf16 rows pulled per rank
+    remote_frac = (n - 1) / n
+    nvlink_gbs = 770.0  # measured peer-copy bandwidth per direction (B200_PROFILING.md)
+
+    # ---- end-to-end through the public API, inputs from pinned host memory every step
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        idd = idx_host.to(dev, non_blocking=True)
+        wd = w_host.to(dev, non_blocking=True)
+        a, _, b, c, _ = buf.get_dispatch_layout(idd, E)
+        rx, ri, rw, pe, h, _ = buf.dispatch(xd, num_tokens_per_rank=a, is_token_in_rank=c, num_tokens_per_expert=b,
+                                            topk_idx=idd, topk_weights=wd, use_fp8=True, config=cfg)
+        cin = buf.get_combine_buffer(h[4], H, K)
+        out, _, _ = buf.combine(cin, h, config=cfg)
+        return out[:, :8].float().sum(dim=1).cpu()  # D2H read of a per-token checksum
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(e2e_steps):
+        res = step_e2e()
+    e.record()
+    barrier()
+    e2e_ms = max_over_ranks(s.elapsed_time(e) / e2e_steps)
+    h2d = x_host.numel() * 2 + idx_host.numel() * 8 + w_host.numel() * 4
+    d2h = res.numel() * 4
+
+    out = {
+        "metric": "ep_dispatch_combine_tokens_per_s",
+        "value": tokens_per_s,
+        "unit": "tokens/s",
+        "n_gpus": n,
+        "steps": args.steps,
+        "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": (tokens_per_s / (8 * 4096 / ((BASELINE_DISPATCH_US + BASELINE_COMBINE_US) * 1e-6))) if n == 8 else None,
+        "dtype": "bf16",
+        "data": "synthetic",
+        "impl": "ours",
+        "config": {
+            "model": "DeepEP intranode dispatch+combine (DeepSeek-V3 MoE shape)",
+            "global_batch": n * T, "seq_len": T, "tokens_per_rank": T, "hidden": H, "num_topk": K,
+            "num_experts": E, "parallelism": f"ep{n}", "dispatch": "bf16 -> fused e4m3 + per-128 scales",
+            "combine": "bf16", "num_sms": cfg.num_sms, "handle": "cached (as the reference times it)",
+            "l2": "256 MiB flush write between timed steps (untimed); per-step working set > 126 MB L2",
+        },
+        "dispatch_us": disp_ms * 1e3,
+        "combine_us": comb_ms * 1e3,
+        "dispatch_recv_GBps": disp_bytes / (disp_ms * 1e-3) / 1e9,
+        "combine_recv_GBps": comb_bytes / (comb_ms * 1e-3) / 1e9,
+        "roofline": {
+            "nvlink_GBps_measured": nvlink_gbs,
+            "dispatch_floor_us": disp_bytes * remote_frac / (nvlink_gbs * 1e9) * 1e6 if n > 1 else None,
+            "combine_floor_us": comb_bytes * remote_frac / (nvlink_gbs * 1e9) * 1e6 if n > 1 else None,
+            "dispatch_frac_of_floor": (disp_bytes * remote_frac / (nvlink_gbs * 1e9)) / (disp_ms * 1e-3) if n > 1 else None,
+            "combine_frac_of_floor": (comb_bytes * remote_frac / (nvlink_gbs * 1e9)) / (comb_ms * 1e-3) if n > 1 else None,
+        },
+        "baseline_us": {"dispatch": BASELINE_DISPATCH_US, "combine": BASELINE_COMBINE_US, "n_gpus": 8},
+        "num_recv_tokens": num_recv,
+        "clocks": clocks,
+        "e2e": {"value": n * T / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": gpu_launches,
+        "wall_s_timed_region": wall,
+        "nvls": bool(comm.has_multicast),
+    }
+
+    if n > 1 and not args.no_allreduce_sweep:
+        out["allreduce"] = allreduce_sweep(comm, dist, dev, n, max_over_ranks, barrier)
+
+    if rank == 0:
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def allreduce_sweep(comm, dist, dev, n, max_over_ranks, barrier):
+    """Bus bandwidth (nccl-tests formula) of our allreduce on symmetric buffers vs NCCL, bf16 sum."""
+    import torch
+
+    rows = []
+    sizes = [1 << 10, 8 << 10, 64 << 10, 512 << 10, 4 << 20, 32 << 20, 256 << 20, 1 << 30]
+    big = comm.empty(max(sizes) // 2, dtype=torch.bfloat16)
+    big.fill_(1.0)
+    plain = torch.ones(max(sizes) // 2, dtype=torch.bfloat16, device=dev)
+    for sz in sizes:
+        cnt = sz // 2
+        iters = 20 if sz <= (4 << 20) else 5
+
+        def timeit(fn):
+            for _ in range(3):
+                fn()
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record()
+            barrier()
+            return max_over_ranks(s.elapsed_time(e) / iters)
+
+        ours = timeit(lambda: comm.all_reduce(big[:cnt], "sum"))
+        ours_plain = timeit(lambda: comm.all_reduce(plain[:cnt], "sum"))
+        nccl = timeit(lambda: dist.all_reduce(plain[:cnt]))
+        f = 2 * (n - 1) / n
+        rows.append({"bytes": sz, "algo": comm.select_allreduce(sz, True, torch.bfloat16)[0],
+                     "ours_us": ours * 1e3, "ours_busbw_GBps": sz / (ours * 1e-3) * f / 1e9,
+                     "ours_unregistered_us": ours_plain * 1e3,
+                     "ours_unregistered_busbw_GBps": sz / (ours_plain * 1e-3) * f / 1e9,
+                     "nccl_us": nccl * 1e3, "nccl_busbw_GBps": sz / (nccl * 1e-3) * f / 1e9})
+    return rows
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -8,6 +8,7 @@
 #include "../coll/comm.h"
 #include "../common/log.h"
 #include "../common/param.h"
+#include "../kernels/launch.h"
 
 namespace py = pybind11;
 using namespace ub;
@@ -27,6 +28,10 @@ PYBIND11_MODULE(_C, m) {
   m.def("create_unique_id", [] {
     UniqueId id = Bootstrap::create_id();
     return py::bytes(id.data, sizeof(id.data));
+  });
+  m.def("preload_kernels", [] {
+    cudaError_t e = preload_all_kernels();
+    UB_CHECK(e == cudaSuccess, "preload failed: %s", cudaGetErrorString(e));
   });
   m.def("set_log_level", [](int lv) { set_log_level(lv); });
   m.def("dtype_size", [](int dt) { return dtype_size(dt); });

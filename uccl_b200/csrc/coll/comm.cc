@@ -101,6 +101,10 @@ void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
       (void)cudaGetLastError();
     }
   }
+  if (!f->is_host()) {
+    DeviceGuard g(f->device());
+    preload_all_kernels();
+  }
   free_[layout_.user_off] = f->heap_bytes() - layout_.user_off;
   UB_INFO(SUB_INIT, "%s", describe().c_str());
 }

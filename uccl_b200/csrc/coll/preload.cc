@@ -1,0 +1,80 @@
+// Force-load every kernel of this library (see launch.h for why).
+#include <cstring>
+#include <mutex>
+
+#include "../common/log.h"
+#include "../ep/ep_buffer.h"
+#include "../kernels/launch.h"
+
+namespace ub {
+
+bool g_preload = false;
+cudaError_t preload_p2p_kernels();  // p2p/p2p_kernels.cu
+
+cudaError_t preload_all_kernels() {
+  static std::mutex mu;
+  static uint64_t done_mask = 0;  // per device (lazy loading is per context)
+  std::lock_guard<std::mutex> g(mu);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return cudaSuccess;
+  }
+  if (done_mask & (1ull << (dev & 63))) return cudaSuccess;
+  DevComm c;
+  memset(&c, 0, sizeof(c));
+  CollArgs a;
+  memset(&a, 0, sizeof(a));
+  A2AvArgs v;
+  memset(&v, 0, sizeof(v));
+  g_preload = true;
+  int loaded = 0;
+  auto ok = [&](cudaError_t e) {
+    if (e == cudaSuccess) ++loaded;
+    else (void)cudaGetLastError();  // unsupported combination: nothing to load
+  };
+  for (int algo = 1; algo <= 6; ++algo)
+    for (int op = 0; op < 4; ++op) {
+      for (int dt : {(int)kF32, (int)kBF16, (int)kF16}) ok(launch_allreduce_f(algo, dt, op, dt, c, a, 1, 512, 0));
+      for (int dt : {(int)kI8, (int)kU8, (int)kI32, (int)kU32, (int)kI64, (int)kU64})
+        ok(launch_allreduce_i(algo, dt, op, c, a, 1, 512, 0));
+      for (int dt : {(int)kF64, (int)kF8E4M3, (int)kF8E5M2}) ok(launch_allreduce_x(algo, dt, op, c, a, 1, 512, 0));
+    }
+  for (int algo = 3; algo <= 6; ++algo) {
+    ok(launch_allreduce_f(algo, kF32, kSum, kBF16, c, a, 1, 512, 0));
+    ok(launch_allreduce_f(algo, kF32, kSum, kF16, c, a, 1, 512, 0));
+    ok(launch_allreduce_f(algo, kBF16, kSum, kF32, c, a, 1, 512, 0));
+    ok(launch_allreduce_f(algo, kF16, kSum, kF32, c, a, 1, 512, 0));
+  }
+  for (int m = 0; m < 3; ++m) ok(launch_allgather(m, c, a, 1, 512, 0));
+  for (int m = 0; m < 3; ++m) ok(launch_broadcast(m, c, a, 1, 512, 0));
+  for (int m = 0; m < 2; ++m) ok(launch_alltoall(m, c, a, 1, 512, 0));
+  ok(launch_alltoallv(c, a, v, 1, 512, 0));
+  ok(launch_barrier(c, 0, 0));
+  for (int which = 0; which < 2; ++which)
+    for (int op = 0; op < 4; ++op) {
+      for (int dt : {(int)kF32, (int)kBF16, (int)kF16, (int)kF64, (int)kF8E4M3, (int)kF8E5M2})
+        for (int nv = 0; nv < 2; ++nv) ok(launch_red_f(which, dt, op, nv != 0, c, a, 1, 512, 0));
+      for (int dt : {(int)kI8, (int)kU8, (int)kI32, (int)kU32, (int)kI64, (int)kU64})
+        ok(launch_red_i(which, dt, op, c, a, 1, 512, 0));
+    }
+  EpLayoutArgs la;
+  memset(&la, 0, sizeof(la));
+  ok(launch_ep_layout(la, 0));
+  EpDispatchArgs da;
+  memset(&da, 0, sizeof(da));
+  for (int m = 0; m < 3; ++m) {
+    da.mode = m;
+    ok(launch_ep_dispatch(c, da, 1, 0));
+  }
+  EpCombineArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  ok(launch_ep_combine(c, ca, 1, 0));
+  ok(preload_p2p_kernels());
+  g_preload = false;
+  done_mask |= 1ull << (dev & 63);
+  UB_INFO(SUB_INIT, "preloaded %d kernel functions", loaded);
+  return cudaSuccess;
+}
+
+}  // namespace ub

@@ -14,6 +14,7 @@
 //     into every destination rank's arena over NVLink;
 //   * combine is a pull: the source rank reads the (<= R) expert-output rows it needs from the
 //     peers' symmetric arenas, reduces in fp32 in a fixed order and writes bf16 once.
+#include "../kernels/launch.h"
 #include "../kernels/prims.cuh"
 #include "ep_types.h"
 
@@ -406,22 +407,22 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
 // --------------------------------------------------------------------------- launchers
 cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st) {
   size_t smem = (size_t)a.E * sizeof(int);
-  ep_layout_kernel<<<1, 1024, smem, st>>>(a);
+  UB_LAUNCH((ep_layout_kernel), 1, 1024, smem, st, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st) {
   switch (a.mode) {
-    case EP_X_BF16: ep_dispatch_kernel<EP_X_BF16><<<grid, 512, 0, st>>>(c, a); break;
-    case EP_X_FP8_SCALED: ep_dispatch_kernel<EP_X_FP8_SCALED><<<grid, 512, 0, st>>>(c, a); break;
-    case EP_X_FUSED_FP8: ep_dispatch_kernel<EP_X_FUSED_FP8><<<grid, 512, 0, st>>>(c, a); break;
+    case EP_X_BF16: UB_LAUNCH((ep_dispatch_kernel<EP_X_BF16>), grid, 512, 0, st, c, a); break;
+    case EP_X_FP8_SCALED: UB_LAUNCH((ep_dispatch_kernel<EP_X_FP8_SCALED>), grid, 512, 0, st, c, a); break;
+    case EP_X_FUSED_FP8: UB_LAUNCH((ep_dispatch_kernel<EP_X_FUSED_FP8>), grid, 512, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
 cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
-  ep_combine_kernel<<<grid, 512, 0, st>>>(c, a);
+  UB_LAUNCH((ep_combine_kernel), grid, 512, 0, st, c, a);
   return cudaGetLastError();
 }
 

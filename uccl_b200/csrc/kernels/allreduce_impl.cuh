@@ -19,6 +19,7 @@
 // Fused epilogue everywhere: post-scale (avg / user scale) and output dtype cast happen in
 // registers before the result is stored -- the reference has no such fusion.
 #pragma once
+#include "launch.h"
 #include "coll_common.cuh"
 
 namespace ub {
@@ -276,18 +277,18 @@ cudaError_t launch_ar_typed(int algo, const DevComm& c, const CollArgs& a, int g
   constexpr bool same = std::is_same<T, TO>::value;
   switch (algo) {
     case AR_ONESHOT_LL:
-      if constexpr (same) { ar_oneshot<T, OP, false><<<grid, block, 0, st>>>(c, a); break; }
+      if constexpr (same) { UB_LAUNCH((ar_oneshot<T, OP, false>), grid, block, 0, st, c, a); break; }
       return cudaErrorInvalidValue;
     case AR_ONESHOT_MC:
-      if constexpr (same) { ar_oneshot<T, OP, true><<<grid, block, 0, st>>>(c, a); break; }
+      if constexpr (same) { UB_LAUNCH((ar_oneshot<T, OP, true>), grid, block, 0, st, c, a); break; }
       return cudaErrorInvalidValue;
-    case AR_TWOSHOT_P2P: ar_twoshot<T, OP, TO, false><<<grid, block, 0, st>>>(c, a); break;
-    case AR_STAGED_P2P: ar_staged<T, OP, TO, false><<<grid, block, 0, st>>>(c, a); break;
+    case AR_TWOSHOT_P2P: UB_LAUNCH((ar_twoshot<T, OP, TO, false>), grid, block, 0, st, c, a); break;
+    case AR_STAGED_P2P: UB_LAUNCH((ar_staged<T, OP, TO, false>), grid, block, 0, st, c, a); break;
     case AR_TWOSHOT_NVLS:
-      if constexpr (MmLdRed<T, OP>::ok) { ar_twoshot<T, OP, TO, true><<<grid, block, 0, st>>>(c, a); break; }
+      if constexpr (MmLdRed<T, OP>::ok) { UB_LAUNCH((ar_twoshot<T, OP, TO, true>), grid, block, 0, st, c, a); break; }
       return cudaErrorInvalidValue;
     case AR_STAGED_NVLS:
-      if constexpr (MmLdRed<T, OP>::ok) { ar_staged<T, OP, TO, true><<<grid, block, 0, st>>>(c, a); break; }
+      if constexpr (MmLdRed<T, OP>::ok) { UB_LAUNCH((ar_staged<T, OP, TO, true>), grid, block, 0, st, c, a); break; }
       return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }

@@ -1,35 +1,36 @@
 // Data-movement collectives (no arithmetic): AllGather, Broadcast, AllToAll(v).
 #include "collectives_impl.cuh"
+#include "launch.h"
 namespace ub {
 cudaError_t launch_allgather(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st) {
   switch (mode) {
-    case 0: ag_kernel<0><<<grid, block, 0, st>>>(c, a); break;
-    case 1: ag_kernel<1><<<grid, block, 0, st>>>(c, a); break;
-    case 2: ag_kernel<2><<<grid, block, 0, st>>>(c, a); break;
+    case 0: UB_LAUNCH((ag_kernel<0>), grid, block, 0, st, c, a); break;
+    case 1: UB_LAUNCH((ag_kernel<1>), grid, block, 0, st, c, a); break;
+    case 2: UB_LAUNCH((ag_kernel<2>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 cudaError_t launch_broadcast(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st) {
   switch (mode) {
-    case 0: bcast_kernel<0><<<grid, block, 0, st>>>(c, a); break;
-    case 1: bcast_kernel<1><<<grid, block, 0, st>>>(c, a); break;
-    case 2: bcast_kernel<2><<<grid, block, 0, st>>>(c, a); break;
+    case 0: UB_LAUNCH((bcast_kernel<0>), grid, block, 0, st, c, a); break;
+    case 1: UB_LAUNCH((bcast_kernel<1>), grid, block, 0, st, c, a); break;
+    case 2: UB_LAUNCH((bcast_kernel<2>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 cudaError_t launch_alltoall(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st) {
   switch (mode) {
-    case 0: a2a_kernel<0><<<grid, block, 0, st>>>(c, a); break;
-    case 1: a2a_kernel<1><<<grid, block, 0, st>>>(c, a); break;
+    case 0: UB_LAUNCH((a2a_kernel<0>), grid, block, 0, st, c, a); break;
+    case 1: UB_LAUNCH((a2a_kernel<1>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 cudaError_t launch_alltoallv(const DevComm& c, const CollArgs& a, const A2AvArgs& v, int grid, int block,
                              cudaStream_t st) {
-  a2av_kernel<<<grid, block, 0, st>>>(c, a, v);
+  UB_LAUNCH((a2av_kernel), grid, block, 0, st, c, a, v);
   return cudaGetLastError();
 }
 }  // namespace ub
@@ -41,7 +42,7 @@ __global__ void barrier_kernel(const __grid_constant__ DevComm c, int domain) {
   sync_end(s);
 }
 cudaError_t launch_barrier(const DevComm& c, int domain, cudaStream_t st) {
-  barrier_kernel<<<1, 32, 0, st>>>(c, domain);
+  UB_LAUNCH((barrier_kernel), 1, 32, 0, st, c, domain);
   return cudaGetLastError();
 }
 }  // namespace ub

@@ -1,5 +1,6 @@
 // Typed launch helpers for ReduceScatter / Reduce.
 #pragma once
+#include "launch.h"
 #include "collectives_impl.cuh"
 namespace ub {
 template <typename T, int OP>
@@ -7,15 +8,15 @@ cudaError_t launch_red_typed(int which, bool nvls, const DevComm& c, const CollA
                              cudaStream_t st) {
   if (nvls) {
     if constexpr (MmLdRed<T, OP>::ok) {
-      if (which == 0) rs_kernel<T, OP, true><<<grid, block, 0, st>>>(c, a);
-      else reduce_kernel<T, OP, true><<<grid, block, 0, st>>>(c, a);
+      if (which == 0) UB_LAUNCH((rs_kernel<T, OP, true>), grid, block, 0, st, c, a);
+      else UB_LAUNCH((reduce_kernel<T, OP, true>), grid, block, 0, st, c, a);
       return cudaGetLastError();
     } else {
       return cudaErrorInvalidValue;
     }
   }
-  if (which == 0) rs_kernel<T, OP, false><<<grid, block, 0, st>>>(c, a);
-  else reduce_kernel<T, OP, false><<<grid, block, 0, st>>>(c, a);
+  if (which == 0) UB_LAUNCH((rs_kernel<T, OP, false>), grid, block, 0, st, c, a);
+  else UB_LAUNCH((reduce_kernel<T, OP, false>), grid, block, 0, st, c, a);
   return cudaGetLastError();
 }
 template <typename T>

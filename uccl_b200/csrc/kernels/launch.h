@@ -5,6 +5,25 @@
 #include "types.h"
 
 namespace ub {
+// CUDA lazy module loading may need a context synchronisation when a kernel is launched for
+// the first time; if another kernel of this process is spinning on a peer that has not been
+// launched yet (single-process multi-rank worlds) that is a deadlock.  preload_all_kernels()
+// walks every launcher in "preload mode" (cudaFuncGetAttributes instead of a launch) so all
+// functions are resident before the first collective.
+extern bool g_preload;
+cudaError_t preload_all_kernels();
+#define UB_LAUNCH(kern, grid, block, smem, st, ...)                         \
+  do {                                                                     \
+    auto _ub_k = kern;                                                     \
+    if (::ub::g_preload) {                                                 \
+      cudaFuncAttributes _ub_fa;                                           \
+      cudaError_t _ub_e = cudaFuncGetAttributes(&_ub_fa, _ub_k);           \
+      if (_ub_e != cudaSuccess) return _ub_e;                              \
+    } else {                                                               \
+      _ub_k<<<grid, block, smem, st>>>(__VA_ARGS__);                       \
+    }                                                                      \
+  } while (0)
+
 // allreduce: algo ids = ArAlgo in allreduce_impl.cuh (same numbering as ArAlgoId in comm.h)
 cudaError_t launch_allreduce_f(int algo, int dtype, int op, int out_dtype, const DevComm& c, const CollArgs& a,
                                int grid, int block, cudaStream_t st);
