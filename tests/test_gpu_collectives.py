@@ -202,7 +202,10 @@ def test_broadcast_reduce_alltoall(n):
         outs = run_ranks(comms, prepare, lambda c, st: c.all_to_all(st[1], st[0]))
         for r, (_, o) in enumerate(outs):
             exp_a = torch.cat([a_ins[s][r * per:(r + 1) * per] for s in range(n)])
-            assert torch.equal(o.cpu(), exp_a)
+            got = o.cpu()
+            bad = (got != exp_a).nonzero().flatten()
+            assert bad.numel() == 0, (f"all_to_all sym_out={sym_out} sym_in={sym_in} rank={r}: {bad.numel()} mismatches, "
+                                      f"first at {int(bad[0])}: got {float(got[bad[0]])} want {float(exp_a[bad[0]])}")
 
 
 @pytest.mark.parametrize("n", [2, 4])

@@ -1,0 +1,161 @@
+"""GPU tests of the P2P transfer engine: same-process endpoints (direct pointers) and two real
+processes on one GPU (CUDA-IPC mapped peer memory) -- fill-pattern oracles in the style of the
+reference's p2p/tests/test_engine_{send,read,write}.py and test_engine_onesided_ipc.py."""
+import multiprocessing as mp
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def _pair():
+    from uccl_b200.p2p import Endpoint
+
+    ng = torch.cuda.device_count()
+    a = Endpoint(0)
+    b = Endpoint(1 if ng > 1 else 0)
+    ok, conn = a.connect(remote_metadata=b.get_metadata())
+    assert ok
+    ok2, ip, gpu, conn_b = b.accept(5000)
+    assert ok2 and gpu == 0
+    return a, b, conn, conn_b
+
+
+def test_metadata_roundtrip():
+    from uccl_b200.p2p import Endpoint
+
+    e = Endpoint(0)
+    ip, port, gpu = Endpoint.parse_metadata(e.get_metadata())
+    assert ip == "127.0.0.1" and port > 0 and gpu == 0
+
+
+@pytest.mark.parametrize("nbytes", [1, 100, 4096, 1 << 20, (8 << 20) + 13])
+def test_send_recv_same_process(nbytes):
+    a, b, conn, conn_b = _pair()
+    src = torch.randint(0, 255, (nbytes,), dtype=torch.uint8, device=f"cuda:{a.local_gpu_idx}")
+    dst = torch.zeros(nbytes, dtype=torch.uint8, device=f"cuda:{b.local_gpu_idx}")
+    torch.cuda.synchronize()
+    ok, rt = b.recv_async(conn_b, 0, dst.data_ptr(), nbytes)
+    assert ok
+    assert a.send(conn, 0, src.data_ptr(), nbytes)
+    assert b.wait(rt, 10000)
+    assert torch.equal(dst.cpu(), src.cpu())
+
+
+def test_onesided_vector_write_read():
+    a, b, conn, conn_b = _pair()
+    dev_a, dev_b = f"cuda:{a.local_gpu_idx}", f"cuda:{b.local_gpu_idx}"
+    # "KV blocks": distinct value per iov, odd sizes to exercise the tail path
+    sizes = [128 << 10, (256 << 10) + 7, 4096, 33, 1 << 20]
+    srcs = [torch.full((s,), i + 1, dtype=torch.uint8, device=dev_a) for i, s in enumerate(sizes)]
+    dsts = [torch.zeros(s, dtype=torch.uint8, device=dev_b) for s in sizes]
+    descs_b = b.register_memory(dsts)
+    blob = b.get_serialized_descs(descs_b)
+    remote = a.deserialize_descs(blob)
+    local = a.register_memory(srcs)
+    torch.cuda.synchronize()
+    ok, tid = a.transfer(conn, "write", local, remote)
+    assert ok and a.wait(tid, 10000)
+    for i, d in enumerate(dsts):
+        assert bool((d == i + 1).all())
+    # read them back into fresh buffers
+    back = [torch.zeros(s, dtype=torch.uint8, device=dev_a) for s in sizes]
+    lb = a.register_memory(back)
+    ok, tid = a.transfer(conn, "read", lb, remote)
+    assert ok
+    done = False
+    for _ in range(2000000):
+        ok, done = a.poll_async(tid)
+        assert ok
+        if done:
+            break
+    assert done
+    for i, d in enumerate(back):
+        assert bool((d == i + 1).all())
+    st = a.stats()
+    assert st["kernel_launches"] >= 2 and st["memcpy_fallbacks"] == 0
+
+
+def test_notifications():
+    a, b, conn, conn_b = _pair()
+    assert a.send_notif(conn, b"kv-ready:42")
+    import time
+
+    got = []
+    for _ in range(200):
+        got = b.get_notifs()
+        if got:
+            break
+        time.sleep(0.01)
+    assert got and got[0][1] == b"kv-ready:42"
+
+
+def _server(q_md, q_res, nbytes):
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    torch.cuda.set_device(0)
+    e = Endpoint(0)
+    q_md.put(e.get_metadata())
+    ok, ip, gpu, conn = e.accept(60000)
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda:0")
+    win = torch.full((nbytes,), 7, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    # two-sided receive, then advertise a window for the client's one-sided read
+    okr = e.recv(conn, 0, buf.data_ptr(), nbytes)
+    desc = e.register_memory([win])
+    e.send_notif(conn, e.get_serialized_descs(desc))
+    # wait for the client's "done" notification
+    import time
+
+    t0 = time.time()
+    fin = False
+    while time.time() - t0 < 60 and not fin:
+        for _, m in e.get_notifs():
+            if m == b"done":
+                fin = True
+        time.sleep(0.005)
+    q_res.put((bool(ok), bool(okr), int(buf.sum().item()), fin))
+
+
+def _client(q_md, q_res, nbytes):
+    import time
+
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    torch.cuda.set_device(0)
+    e = Endpoint(0)
+    md = q_md.get(timeout=60)
+    ok, conn = e.connect(remote_metadata=md)
+    src = torch.ones(nbytes, dtype=torch.uint8, device="cuda:0")
+    torch.cuda.synchronize()
+    oks = e.send(conn, 0, src.data_ptr(), nbytes)
+    blob = None
+    t0 = time.time()
+    while blob is None and time.time() - t0 < 60:
+        for _, m in e.get_notifs():
+            blob = m
+        time.sleep(0.005)
+    remote = e.deserialize_descs(blob)
+    dst = torch.zeros(nbytes, dtype=torch.uint8, device="cuda:0")
+    okr = e.read(conn, 0, dst.data_ptr(), nbytes, remote[0])
+    val = int(dst.sum().item())
+    e.send_notif(conn, b"done")
+    q_res.put((bool(ok), bool(oks), bool(okr), val))
+
+
+def test_two_processes_cuda_ipc():
+    nbytes = (2 << 20) + 48
+    ctx = mp.get_context("spawn")
+    q_md, q_s, q_c = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_server, args=(q_md, q_s, nbytes)), ctx.Process(target=_client, args=(q_md, q_c, nbytes))]
+    [p.start() for p in ps]
+    rs = q_s.get(timeout=180)
+    rc = q_c.get(timeout=180)
+    [p.join(30) for p in ps]
+    assert rs == (True, True, nbytes, True)
+    assert rc == (True, True, True, 7 * nbytes)

@@ -1,0 +1,314 @@
+"""``uccl.collective``-compatible module: point-to-point send/recv (+async, batched) and
+allgather between the ranks of a ``torch.distributed`` job, plus the native NCCL-style
+collectives of this package.
+
+Reference surface: ``p2p/collective.py:43-854`` (CollectiveContext + module functions
+init_collective / send / recv / isend / irecv / test / wait / wait_all / batch_isend_irecv /
+allgather / iallgather / register_tensor / deregister_tensor / finalize_collective).
+
+Design here: the reference builds a full mesh of RDMA connections and routes *intra-node*
+traffic to ``torch.distributed`` NCCL (p2p/collective.py:483-485).  On an NVSwitch node every
+peer is NVLink-reachable, so send/recv ride our P2P engine (CUDA-IPC mapped peer HBM + in-kernel
+TMA copies); ``allgather`` uses the native symmetric-heap kernel when a Communicator exists and
+the P2P ring otherwise.  Pipeline-parallel users can still pass ``use_nccl_p2p=True`` to keep
+send/recv on NCCL p2p as the north-star allows.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Union
+
+import torch
+import torch.distributed as dist
+
+from .p2p import Endpoint
+from .parallel.comm import Communicator
+
+
+class P2POp:
+    """Mirror of ``torch.distributed.P2POp`` for :func:`batch_isend_irecv`."""
+
+    def __init__(self, op, tensor: torch.Tensor, peer: int):
+        name = getattr(op, "__name__", str(op))
+        assert name in ("isend", "irecv"), "op must be isend or irecv"
+        self.op = name
+        self.tensor = tensor
+        self.peer = peer
+
+    def __repr__(self):
+        return f"P2POp({self.op}, peer={self.peer}, numel={self.tensor.numel()})"
+
+
+class CollectiveContext:
+    def __init__(self, num_cpus: int = 4, local_gpu_idx: Optional[int] = None, group=None,
+                 use_nccl_p2p: bool = False, with_native_collectives: bool = True, heap_bytes: int = 1 << 30):
+        assert dist.is_initialized(), "torch.distributed must be initialised first"
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world_size = dist.get_world_size(group)
+        self.local_gpu_idx = local_gpu_idx if local_gpu_idx is not None else torch.cuda.current_device()
+        self.use_nccl_p2p = use_nccl_p2p
+        self.num_cpus = num_cpus
+        self.ep: Optional[Endpoint] = None
+        self.send_connections: Dict[int, int] = {}
+        self.recv_connections: Dict[int, int] = {}
+        self.comm: Optional[Communicator] = None
+        self._with_native = with_native_collectives
+        self._heap_bytes = heap_bytes
+        self._registered: Dict[int, int] = {}
+        self.initialized = False
+
+    # ------------------------------------------------------------------------- init
+    def init(self):
+        if self.initialized:
+            return
+        torch.cuda.set_device(self.local_gpu_idx)
+        self.ep = Endpoint(self.local_gpu_idx, self.num_cpus)
+        md = self.ep.get_metadata()
+        all_md: List[Optional[bytes]] = [None] * self.world_size
+        dist.all_gather_object(all_md, md, group=self.group)
+        # unidirectional connections like the reference: i -> j for every ordered pair.
+        # Lower rank connects first to every higher rank, then accepts from lower ranks.
+        for peer in range(self.world_size):
+            if peer == self.rank:
+                continue
+            ok, conn = self.ep.connect(remote_metadata=all_md[peer])
+            assert ok, f"connect to rank {peer} failed"
+            self.send_connections[peer] = conn
+        # identify inbound connections by a hello notification carrying the sender's rank
+        for peer, conn in self.send_connections.items():
+            self.ep.send_notif(conn, b"rank:%d" % self.rank)
+        pending = self.world_size - 1
+        accepted = []
+        while len(accepted) < pending:
+            ok, ip, gpu, conn = self.ep.accept(60000)
+            assert ok, "accept timed out"
+            accepted.append(conn)
+        import time
+
+        t0 = time.time()
+        while len(self.recv_connections) < pending:
+            for conn, msg in self.ep.get_notifs():
+                if msg.startswith(b"rank:"):
+                    self.recv_connections[int(msg[5:])] = conn
+            assert time.time() - t0 < 60, "peer identification timed out"
+            time.sleep(0.001)
+        if self._with_native:
+            self.comm = Communicator.from_torch_dist(self.group, device=self.local_gpu_idx,
+                                                     heap_bytes=self._heap_bytes)
+        dist.barrier(group=self.group)
+        self.initialized = True
+
+    # ----------------------------------------------------------------- registration
+    def register_tensor(self, tensor: torch.Tensor) -> int:
+        ptr = tensor.data_ptr()
+        if ptr in self._registered:
+            return self._registered[ptr]
+        ok, mr = self.ep.reg(ptr, tensor.numel() * tensor.element_size())
+        assert ok
+        self._registered[ptr] = mr
+        return mr
+
+    def check_tensor_registered(self, tensor: torch.Tensor) -> Optional[int]:
+        return self._registered.get(tensor.data_ptr())
+
+    def deregister_tensor(self, tensor: torch.Tensor) -> bool:
+        mr = self._registered.pop(tensor.data_ptr(), None)
+        return bool(mr is not None and self.ep.dereg(mr))
+
+    # -------------------------------------------------------------------- send/recv
+    @staticmethod
+    def _buf(t: torch.Tensor):
+        assert t.is_contiguous(), "tensor must be contiguous"
+        return t.data_ptr(), t.numel() * t.element_size()
+
+    def isend(self, tensor: torch.Tensor, dst: int) -> Union[int, "dist.Work"]:
+        if self.use_nccl_p2p:
+            return dist.isend(tensor, dst, group=self.group)
+        torch.cuda.current_stream().synchronize()  # payload must be materialised before the side-stream copy
+        ptr, n = self._buf(tensor)
+        ok, tid = self.ep.send_async(self.send_connections[dst], 0, ptr, n)
+        assert ok
+        return tid
+
+    def irecv(self, tensor: torch.Tensor, src: int) -> Union[int, "dist.Work"]:
+        if self.use_nccl_p2p:
+            return dist.irecv(tensor, src, group=self.group)
+        ptr, n = self._buf(tensor)
+        ok, tid = self.ep.recv_async(self.recv_connections[src], 0, ptr, n)
+        assert ok
+        return tid
+
+    def send(self, tensor: torch.Tensor, dst: int):
+        self.wait(self.isend(tensor, dst))
+
+    def recv(self, tensor: torch.Tensor, src: int):
+        self.wait(self.irecv(tensor, src))
+
+    def test(self, handle) -> bool:
+        if not isinstance(handle, int):
+            return handle.is_completed()
+        ok, done = self.ep.poll_async(handle)
+        if not ok:
+            raise RuntimeError("uccl_b200.collective: transfer failed")
+        return bool(done)
+
+    def wait(self, handle):
+        if not isinstance(handle, int):
+            handle.wait()
+            return
+        if not self.ep.wait(handle, -1):
+            raise RuntimeError("uccl_b200.collective: transfer failed")
+
+    def wait_all(self, handles):
+        for h in handles:
+            self.wait(h)
+
+    def P2POp(self, op, tensor: torch.Tensor, peer: int) -> P2POp:
+        return P2POp(op, tensor, peer)
+
+    def batch_isend_irecv(self, ops: List[P2POp]):
+        # post every receive first so that senders find their advertisements immediately
+        handles = []
+        for o in ops:
+            if o.op == "irecv":
+                handles.append(self.irecv(o.tensor, o.peer))
+        for o in ops:
+            if o.op == "isend":
+                handles.append(self.isend(o.tensor, o.peer))
+        return handles
+
+    # -------------------------------------------------------------------- allgather
+    def iallgather(self, send_tensor: torch.Tensor, recv_tensor: torch.Tensor):
+        assert recv_tensor.numel() == send_tensor.numel() * self.world_size
+        if self.comm is not None:
+            self.comm.all_gather(recv_tensor, send_tensor)
+            ev = torch.cuda.Event()
+            ev.record()
+            return [ev]
+        chunks = recv_tensor.view(self.world_size, -1)
+        chunks[self.rank].copy_(send_tensor.view(-1))
+        ops = []
+        for peer in range(self.world_size):
+            if peer == self.rank:
+                continue
+            ops.append(P2POp(self.irecv, chunks[peer], peer))
+            ops.append(P2POp(self.isend, send_tensor, peer))
+        return self.batch_isend_irecv(ops)
+
+    def allgather(self, send_tensor: torch.Tensor, recv_tensor: torch.Tensor):
+        for h in self.iallgather(send_tensor, recv_tensor):
+            if isinstance(h, torch.cuda.Event):
+                h.synchronize()
+            else:
+                self.wait(h)
+
+    def finalize(self):
+        if self.ep is not None:
+            for conn in list(self.send_connections.values()):
+                self.ep.remove_remote_endpoint(conn)
+        self.ep = None
+        self.comm = None
+        self.initialized = False
+
+
+_ctx: Optional[CollectiveContext] = None
+
+
+def init_collective(num_cpus: int = 4, local_gpu_idx: Optional[int] = None, **kw) -> CollectiveContext:
+    global _ctx
+    _ctx = CollectiveContext(num_cpus, local_gpu_idx, **kw)
+    _ctx.init()
+    return _ctx
+
+
+def get_collective() -> CollectiveContext:
+    if _ctx is None:
+        raise RuntimeError("call init_collective() first")
+    return _ctx
+
+
+def register_tensor(tensor):
+    return get_collective().register_tensor(tensor)
+
+
+def deregister_tensor(tensor):
+    return get_collective().deregister_tensor(tensor)
+
+
+def send(tensor, dst):
+    return get_collective().send(tensor, dst)
+
+
+def recv(tensor, src):
+    return get_collective().recv(tensor, src)
+
+
+def isend(tensor, dst):
+    return get_collective().isend(tensor, dst)
+
+
+def irecv(tensor, src):
+    return get_collective().irecv(tensor, src)
+
+
+def test(handle):
+    return get_collective().test(handle)
+
+
+def wait(handle):
+    return get_collective().wait(handle)
+
+
+def wait_all(handles):
+    return get_collective().wait_all(handles)
+
+
+def batch_isend_irecv(ops):
+    return get_collective().batch_isend_irecv(ops)
+
+
+def allgather(send_tensor, recv_tensor):
+    return get_collective().allgather(send_tensor, recv_tensor)
+
+
+def iallgather(send_tensor, recv_tensor):
+    return get_collective().iallgather(send_tensor, recv_tensor)
+
+
+def finalize_collective():
+    global _ctx
+    if _ctx is not None:
+        _ctx.finalize()
+    _ctx = None
+
+
+# ---- native NCCL-style collectives on the module's communicator -----------------------------
+def _comm() -> Communicator:
+    c = get_collective().comm
+    if c is None:
+        raise RuntimeError("native collectives disabled (with_native_collectives=False)")
+    return c
+
+
+def all_reduce(tensor, op="sum", **kw):
+    return _comm().all_reduce(tensor, op, **kw)
+
+
+def all_gather(out, tensor):
+    return _comm().all_gather(out, tensor)
+
+
+def reduce_scatter(out, tensor, op="sum"):
+    return _comm().reduce_scatter(out, tensor, op)
+
+
+def broadcast(tensor, root=0):
+    return _comm().broadcast(tensor, root)
+
+
+def all_to_all(out, tensor):
+    return _comm().all_to_all(out, tensor)
+
+
+def barrier():
+    return _comm().barrier()

@@ -84,6 +84,7 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("device", &Comm::device)
       .def_property_readonly("has_multicast", &Comm::has_multicast)
       .def_property_readonly("is_host", &Comm::is_host)
+      .def_property_readonly("single_process", [](const Comm& c) { return c.fabric().single_process(); })
       .def_property_readonly("launches", &Comm::launches)
       .def_property_readonly("error_word", &Comm::error_word)
       .def_property_readonly("heap_base", [](const Comm& c) { return (uintptr_t)c.fabric().local(); })

@@ -185,6 +185,7 @@ EpDispatchOut EpBuffer::dispatch(uintptr_t x, uintptr_t x_scales, uintptr_t topk
   cudaError_t e = launch_ep_dispatch(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep dispatch launch failed: %s", cudaGetErrorString(e));
   ++launches_;
+  last_stream_ = st;
   EpDispatchOut o;
   char* heap = comm_->fabric().local();
   o.recv_x = (uintptr_t)(heap + a.arena.x_off);
@@ -208,6 +209,12 @@ int EpBuffer::wait_counts(int E_local, std::vector<int>* per_expert, double time
       if (dt.count() > timeout_s)
         UB_THROW("EP dispatch: CPU timed out after %.1f s waiting for the receive counts (rank %d)", timeout_s, rank());
       if (comm_->error_word()) UB_THROW("EP dispatch: device reported error 0x%x", comm_->error_word());
+      if ((spins & 0xfffff) == 0) {
+        // a dead context (trap in any kernel of this process) never writes the counts: fail fast
+        cudaError_t q = cudaStreamQuery(last_stream_);
+        if (q != cudaSuccess && q != cudaErrorNotReady)
+          UB_THROW("EP dispatch: CUDA error while waiting for the receive counts: %s", cudaGetErrorString(q));
+      }
       sched_yield();
     }
   }

@@ -65,6 +65,7 @@ class EpBuffer {
   int32_t* host_counts_dev_ = nullptr;
   int32_t* dev_counts_ = nullptr;
   uint64_t launches_ = 0;
+  cudaStream_t last_stream_ = nullptr;
 };
 
 cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st);

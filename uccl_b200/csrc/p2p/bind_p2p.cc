@@ -1,0 +1,151 @@
+// Python bindings of the P2P engine (role of the reference's nanobind module p2p/engine_api.cc).
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "../common/log.h"
+#include "endpoint.h"
+
+namespace py = pybind11;
+using namespace ub;
+
+namespace {
+XferDesc desc_from_bytes(const std::string& s) {
+  UB_CHECK(s.size() == sizeof(XferDesc), "descriptor must be %zu bytes (got %zu)", sizeof(XferDesc), s.size());
+  XferDesc d;
+  memcpy(&d, s.data(), sizeof(d));
+  return d;
+}
+py::bytes desc_to_bytes(const XferDesc& d) { return py::bytes((const char*)&d, sizeof(d)); }
+template <typename T>
+std::vector<T> to_ptrs(const std::vector<uintptr_t>& v) {
+  std::vector<T> o;
+  for (auto p : v) o.push_back((T)p);
+  return o;
+}
+}  // namespace
+
+void bind_p2p(py::module_& m) {
+  m.attr("XFER_DESC_BYTES") = (int)sizeof(XferDesc);
+  py::class_<Endpoint, std::shared_ptr<Endpoint>>(m, "P2PEndpoint")
+      .def(py::init<int, int>(), py::arg("local_gpu_idx"), py::arg("num_streams") = 4)
+      .def_property_readonly("gpu_idx", &Endpoint::gpu_idx)
+      .def_property_readonly("port", &Endpoint::port)
+      .def("get_metadata", [](const Endpoint& e) { return py::bytes(e.get_metadata()); })
+      .def_static("parse_metadata",
+                  [](const std::string& md) {
+                    std::string ip;
+                    uint16_t port = 0;
+                    int gpu = 0;
+                    UB_CHECK(Endpoint::parse_metadata(md, &ip, &port, &gpu), "bad metadata blob");
+                    return py::make_tuple(ip, (int)port, gpu);
+                  })
+      .def("connect",
+           [](Endpoint& e, const std::string& ip, int gpu, int port) {
+             uint64_t id = 0;
+             bool ok;
+             {
+               py::gil_scoped_release rel;
+               ok = e.connect(ip, gpu, (uint16_t)port, &id);
+             }
+             return py::make_tuple(ok, id);
+           })
+      .def("accept",
+           [](Endpoint& e, int timeout_ms) {
+             std::string ip;
+             int gpu = -1;
+             uint64_t id = 0;
+             bool ok;
+             {
+               py::gil_scoped_release rel;
+               ok = e.accept(&ip, &gpu, &id, timeout_ms);
+             }
+             return py::make_tuple(ok, ip, gpu, id);
+           },
+           py::arg("timeout_ms") = -1)
+      .def("add_remote_endpoint",
+           [](Endpoint& e, const std::string& md) {
+             uint64_t id = 0;
+             bool ok;
+             {
+               py::gil_scoped_release rel;
+               ok = e.add_remote_endpoint(md, &id);
+             }
+             return py::make_tuple(ok, id);
+           })
+      .def("remove_remote_endpoint", &Endpoint::remove_remote_endpoint)
+      .def("start_passive_accept", &Endpoint::start_passive_accept)
+      .def("reg",
+           [](Endpoint& e, uintptr_t p, size_t n) {
+             uint64_t id = 0;
+             bool ok = e.reg((const void*)p, n, &id);
+             return py::make_tuple(ok, id);
+           })
+      .def("dereg", &Endpoint::dereg)
+      .def("describe",
+           [](Endpoint& e, uintptr_t p, size_t n) {
+             XferDesc d;
+             UB_CHECK(e.describe((const void*)p, n, &d), "cannot describe pointer %p", (void*)p);
+             return desc_to_bytes(d);
+           })
+      .def("send_async",
+           [](Endpoint& e, uint64_t conn, std::vector<uintptr_t> ptrs, std::vector<size_t> sizes) {
+             uint64_t tid = 0;
+             bool ok = e.send_async(conn, to_ptrs<const void*>(ptrs), sizes, &tid);
+             return py::make_tuple(ok, tid);
+           })
+      .def("recv_async",
+           [](Endpoint& e, uint64_t conn, std::vector<uintptr_t> ptrs, std::vector<size_t> sizes) {
+             uint64_t tid = 0;
+             bool ok = e.recv_async(conn, to_ptrs<void*>(ptrs), sizes, &tid);
+             return py::make_tuple(ok, tid);
+           })
+      .def("write_async",
+           [](Endpoint& e, uint64_t conn, std::vector<uintptr_t> src, std::vector<size_t> sizes,
+              std::vector<std::string> remote) {
+             std::vector<XferDesc> r;
+             for (auto& s : remote) r.push_back(desc_from_bytes(s));
+             uint64_t tid = 0;
+             bool ok = e.write_async(conn, to_ptrs<const void*>(src), sizes, r, &tid);
+             return py::make_tuple(ok, tid);
+           })
+      .def("read_async",
+           [](Endpoint& e, uint64_t conn, std::vector<uintptr_t> dst, std::vector<size_t> sizes,
+              std::vector<std::string> remote) {
+             std::vector<XferDesc> r;
+             for (auto& s : remote) r.push_back(desc_from_bytes(s));
+             uint64_t tid = 0;
+             bool ok = e.read_async(conn, to_ptrs<void*>(dst), sizes, r, &tid);
+             return py::make_tuple(ok, tid);
+           })
+      .def("poll_async",
+           [](Endpoint& e, uint64_t tid) {
+             bool done = false;
+             bool ok = e.poll_async(tid, &done);
+             return py::make_tuple(ok, done);
+           })
+      .def("wait",
+           [](Endpoint& e, uint64_t tid, int timeout_ms) {
+             py::gil_scoped_release rel;
+             return e.wait(tid, timeout_ms);
+           },
+           py::arg("tid"), py::arg("timeout_ms") = -1)
+      .def("send_notif", &Endpoint::send_notif)
+      .def("get_notifs",
+           [](Endpoint& e) {
+             py::list out;
+             for (auto& kv : e.get_notifs()) out.append(py::make_tuple(kv.first, py::bytes(kv.second)));
+             return out;
+           })
+      .def("stats", [](const Endpoint& e) {
+        P2PStats s = e.stats();
+        py::dict d;
+        d["bytes_sent"] = s.bytes_sent;
+        d["bytes_received"] = s.bytes_received;
+        d["bytes_read"] = s.bytes_read;
+        d["bytes_written"] = s.bytes_written;
+        d["transfers"] = s.transfers;
+        d["kernel_launches"] = s.kernel_launches;
+        d["memcpy_fallbacks"] = s.memcpy_fallbacks;
+        return d;
+      });
+}

@@ -1,0 +1,782 @@
+#include "endpoint.h"
+
+#include <arpa/inet.h>
+#include <errno.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <poll.h>
+#include <sys/eventfd.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include "../common/log.h"
+#include "../common/param.h"
+#include "../fabric/cu_api.h"
+
+namespace ub {
+
+UB_PARAM(P2PCtas, "P2P_CTAS", 32)
+UB_PARAM(P2PChunkKB, "P2P_CHUNK_KB", 32)
+UB_PARAM(P2PUseKernel, "P2P_USE_KERNEL", 1)
+
+cudaError_t launch_p2p_copy(const P2PCopyBatch& b, int grid, cudaStream_t st);
+
+namespace {
+enum MsgType : uint32_t { MSG_HELLO = 1, MSG_ADV = 2, MSG_DONE = 3, MSG_NOTIF = 4, MSG_BYE = 5 };
+struct MsgHdr {
+  uint32_t type;
+  uint32_t len;
+  uint64_t seq;
+};
+struct Hello {
+  int32_t gpu;
+  int32_t pid;
+};
+bool write_full(int fd, const void* p, size_t n) {
+  const char* c = (const char*)p;
+  while (n) {
+    ssize_t w = ::send(fd, c, n, MSG_NOSIGNAL);
+    if (w < 0) {
+      if (errno == EINTR || errno == EAGAIN) continue;
+      return false;
+    }
+    c += w;
+    n -= (size_t)w;
+  }
+  return true;
+}
+bool read_full(int fd, void* p, size_t n) {
+  char* c = (char*)p;
+  while (n) {
+    ssize_t r = ::recv(fd, c, n, 0);
+    if (r < 0) {
+      if (errno == EINTR || errno == EAGAIN) continue;
+      return false;
+    }
+    if (r == 0) return false;
+    c += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+}  // namespace
+
+struct Endpoint::Conn {
+  uint64_t id = 0;
+  int fd = -1;
+  int remote_gpu = -1;
+  int remote_pid = -1;
+  std::string ip;
+  std::mutex send_mu;
+  std::map<uint64_t, std::vector<XferDesc>> advs;  // seq -> advertised windows (from the peer's recv)
+  std::map<uint64_t, bool> dones;                  // seq -> DONE received
+  uint64_t next_send_seq = 0, next_recv_seq = 0;
+  bool alive = true;
+};
+
+struct Endpoint::Transfer {
+  enum State { SEND_WAIT_ADV, COPYING, RECV_WAIT_DONE, DONE, FAILED };
+  uint64_t id = 0;
+  State state = DONE;
+  std::shared_ptr<Conn> conn;
+  uint64_t seq = 0;
+  bool notify_done = false;  // send DONE{seq} to the peer when the copy finishes
+  std::vector<const char*> src;
+  std::vector<size_t> sizes;
+  cudaEvent_t ev = nullptr;
+};
+
+Endpoint::Endpoint(int local_gpu_idx, int num_streams) : gpu_(local_gpu_idx) {
+  UB_CUDA(cudaSetDevice(gpu_));
+  UB_CUDA(cudaFree(0));
+  for (int i = 0; i < std::max(1, num_streams); ++i) {
+    cudaStream_t s;
+    UB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    streams_.push_back(s);
+  }
+  ip_ = param_load_str("P2P_IP", "127.0.0.1");
+  listen_fd_ = ::socket(AF_INET, SOCK_STREAM, 0);
+  UB_CHECK(listen_fd_ >= 0, "socket failed: %s", strerror(errno));
+  int one = 1;
+  setsockopt(listen_fd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+  sockaddr_in addr;
+  memset(&addr, 0, sizeof(addr));
+  addr.sin_family = AF_INET;
+  addr.sin_addr.s_addr = htonl(INADDR_ANY);
+  addr.sin_port = 0;
+  UB_CHECK(::bind(listen_fd_, (sockaddr*)&addr, sizeof(addr)) == 0, "bind failed: %s", strerror(errno));
+  UB_CHECK(::listen(listen_fd_, 128) == 0, "listen failed: %s", strerror(errno));
+  socklen_t al = sizeof(addr);
+  getsockname(listen_fd_, (sockaddr*)&addr, &al);
+  port_ = ntohs(addr.sin_port);
+  wake_fd_ = eventfd(0, EFD_NONBLOCK);
+  engine_ = std::thread([this] { engine_loop(); });
+  UB_INFO(SUB_P2P, "p2p endpoint gpu %d listening on %s:%u", gpu_, ip_.c_str(), (unsigned)port_);
+}
+
+Endpoint::~Endpoint() {
+  stop_ = true;
+  wake();
+  if (engine_.joinable()) engine_.join();
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto& kv : conns_)
+      if (kv.second->fd >= 0) ::close(kv.second->fd);
+    conns_.clear();
+  }
+  if (listen_fd_ >= 0) ::close(listen_fd_);
+  if (wake_fd_ >= 0) ::close(wake_fd_);
+  cudaSetDevice(gpu_);
+  for (auto& kv : ipc_open_) cudaIpcCloseMemHandle(kv.second);
+  for (auto s : streams_) cudaStreamDestroy(s);
+  for (auto e : event_pool_) cudaEventDestroy(e);
+}
+
+void Endpoint::wake() {
+  uint64_t one = 1;
+  if (wake_fd_ >= 0) (void)!::write(wake_fd_, &one, sizeof(one));
+}
+
+std::string Endpoint::get_metadata() const {
+  // 4-byte IPv4 + 2-byte port (network order) + 4-byte gpu index (like the reference's 10-byte blob)
+  std::string md(10, '\0');
+  in_addr a;
+  inet_pton(AF_INET, ip_.c_str(), &a);
+  memcpy(&md[0], &a, 4);
+  uint16_t p = htons(port_);
+  memcpy(&md[4], &p, 2);
+  int32_t g = gpu_;
+  memcpy(&md[6], &g, 4);
+  return md;
+}
+
+bool Endpoint::parse_metadata(const std::string& md, std::string* ip, uint16_t* port, int* gpu_idx) {
+  if (md.size() != 10) return false;
+  char buf[INET_ADDRSTRLEN];
+  in_addr a;
+  memcpy(&a, &md[0], 4);
+  if (!inet_ntop(AF_INET, &a, buf, sizeof(buf))) return false;
+  uint16_t p;
+  memcpy(&p, &md[4], 2);
+  int32_t g;
+  memcpy(&g, &md[6], 4);
+  if (ip) *ip = buf;
+  if (port) *port = ntohs(p);
+  if (gpu_idx) *gpu_idx = g;
+  return true;
+}
+
+std::shared_ptr<Endpoint::Conn> Endpoint::find_conn(uint64_t id) {
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = conns_.find(id);
+  return it == conns_.end() ? nullptr : it->second;
+}
+
+bool Endpoint::connect(const std::string& ip, int remote_gpu_idx, uint16_t remote_port, uint64_t* conn_id) {
+  int fd = -1;
+  sockaddr_in addr;
+  memset(&addr, 0, sizeof(addr));
+  addr.sin_family = AF_INET;
+  addr.sin_port = htons(remote_port);
+  if (inet_pton(AF_INET, ip.c_str(), &addr.sin_addr) != 1) return false;
+  // retry loop like the reference's connect (p2p/engine.cc:1322-1357)
+  for (int attempt = 0; attempt < 200; ++attempt) {
+    fd = ::socket(AF_INET, SOCK_STREAM, 0);
+    if (fd < 0) return false;
+    if (::connect(fd, (sockaddr*)&addr, sizeof(addr)) == 0) break;
+    ::close(fd);
+    fd = -1;
+    std::this_thread::sleep_for(std::chrono::milliseconds(25));
+  }
+  if (fd < 0) {
+    UB_WARN("p2p connect to %s:%u failed", ip.c_str(), (unsigned)remote_port);
+    return false;
+  }
+  int one = 1;
+  setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+  MsgHdr h{MSG_HELLO, sizeof(Hello), 0};
+  Hello me{gpu_, (int32_t)getpid()};
+  Hello peer;
+  MsgHdr rh;
+  if (!write_full(fd, &h, sizeof(h)) || !write_full(fd, &me, sizeof(me)) || !read_full(fd, &rh, sizeof(rh)) ||
+      rh.type != MSG_HELLO || !read_full(fd, &peer, sizeof(peer))) {
+    ::close(fd);
+    return false;
+  }
+  auto c = std::make_shared<Conn>();
+  c->fd = fd;
+  c->remote_gpu = peer.gpu;
+  c->remote_pid = peer.pid;
+  c->ip = ip;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    c->id = next_conn_++;
+    conns_[c->id] = c;
+  }
+  if (conn_id) *conn_id = c->id;
+  (void)remote_gpu_idx;
+  wake();
+  return true;
+}
+
+bool Endpoint::add_remote_endpoint(const std::string& metadata, uint64_t* conn_id) {
+  std::string ip;
+  uint16_t port;
+  int gpu;
+  if (!parse_metadata(metadata, &ip, &port, &gpu)) return false;
+  return connect(ip, gpu, port, conn_id);
+}
+
+bool Endpoint::accept(std::string* ip, int* remote_gpu_idx, uint64_t* conn_id, int timeout_ms) {
+  std::unique_lock<std::mutex> lk(mu_);
+  auto pred = [this] { return !accepted_.empty() || stop_.load(); };
+  if (timeout_ms < 0) accept_cv_.wait(lk, pred);
+  else if (!accept_cv_.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return false;
+  if (accepted_.empty()) return false;
+  uint64_t id = accepted_.front();
+  accepted_.pop_front();
+  auto c = conns_[id];
+  if (ip) *ip = c->ip;
+  if (remote_gpu_idx) *remote_gpu_idx = c->remote_gpu;
+  if (conn_id) *conn_id = id;
+  return true;
+}
+
+bool Endpoint::remove_remote_endpoint(uint64_t conn_id) {
+  std::shared_ptr<Conn> c;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = conns_.find(conn_id);
+    if (it == conns_.end()) return false;
+    c = it->second;
+    conns_.erase(it);
+    for (auto& kv : transfers_)
+      if (kv.second->conn == c && kv.second->state != Transfer::DONE) kv.second->state = Transfer::FAILED;
+  }
+  send_msg(*c, MSG_BYE, 0, nullptr, 0);
+  c->alive = false;
+  ::shutdown(c->fd, SHUT_RDWR);
+  ::close(c->fd);
+  c->fd = -1;
+  wake();
+  return true;
+}
+
+bool Endpoint::send_msg(Conn& c, uint32_t type, uint64_t seq, const void* payload, uint32_t len) {
+  std::lock_guard<std::mutex> g(c.send_mu);
+  if (c.fd < 0) return false;
+  MsgHdr h{type, len, seq};
+  if (!write_full(c.fd, &h, sizeof(h))) return false;
+  if (len && !write_full(c.fd, payload, len)) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------ registration
+bool Endpoint::reg(const void* ptr, size_t size, uint64_t* mr_id) {
+  if (!ptr || !size) return false;
+  XferDesc d;
+  if (!describe(ptr, size, &d)) return false;  // also caches the IPC export of the allocation
+  std::lock_guard<std::mutex> g(mu_);
+  uint64_t id = next_mr_++;
+  mrs_[id] = MR{ptr, size};
+  if (mr_id) *mr_id = id;
+  return true;
+}
+
+bool Endpoint::dereg(uint64_t mr_id) {
+  std::lock_guard<std::mutex> g(mu_);
+  return mrs_.erase(mr_id) > 0;
+}
+
+bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
+  memset(out, 0, sizeof(*out));
+  out->addr = (uint64_t)ptr;
+  out->size = size;
+  out->pid = (int32_t)getpid();
+  out->dev = gpu_;
+  cudaPointerAttributes attr;
+  memset(&attr, 0, sizeof(attr));
+  cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  if (attr.type == cudaMemoryTypeHost) {
+    out->kind = 1;
+    out->base = (uint64_t)ptr;
+    return true;
+  }
+  if (attr.type != cudaMemoryTypeDevice) {
+    UB_WARN("p2p: pointer %p is neither device nor pinned host memory", ptr);
+    return false;
+  }
+  out->dev = attr.device;
+  CUdeviceptr base = 0;
+  size_t asz = 0;
+  CUresult (*getRange)(CUdeviceptr*, size_t*, CUdeviceptr) = nullptr;
+  {
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", (void**)&getRange, cudaEnableDefault, &st) != cudaSuccess)
+      getRange = nullptr;
+  }
+  if (!getRange || getRange(&base, &asz, (CUdeviceptr)ptr) != CUDA_SUCCESS) {
+    (void)cudaGetLastError();
+    base = (CUdeviceptr)ptr;
+  }
+  out->base = (uint64_t)base;
+  std::lock_guard<std::mutex> g(mu_);
+  auto it = ipc_export_.find((uint64_t)base);
+  if (it == ipc_export_.end()) {
+    cudaIpcMemHandle_t h;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != attr.device) cudaSetDevice(attr.device);
+    cudaError_t ie = cudaIpcGetMemHandle(&h, (void*)base);
+    if (prev != attr.device) cudaSetDevice(prev);
+    std::string hs;
+    if (ie == cudaSuccess) hs.assign((const char*)&h, sizeof(h));
+    else (void)cudaGetLastError();  // e.g. VMM memory: only usable by same-process peers
+    it = ipc_export_.emplace((uint64_t)base, hs).first;
+  }
+  if (it->second.empty()) {
+    out->kind = 2;
+  } else {
+    out->kind = 0;
+    memcpy(out->ipc_handle, it->second.data(), 64);
+  }
+  return true;
+}
+
+bool Endpoint::advertise(uint64_t conn, const void* ptr, size_t size, XferDesc* out) {
+  (void)conn;
+  return describe(ptr, size, out);
+}
+
+void* Endpoint::map_remote(const XferDesc& d) {
+  if (d.pid == (int32_t)getpid()) return (void*)d.addr;  // same-process short-circuit (reference: direct_addr)
+  if (d.kind != 0) {
+    UB_WARN("p2p: descriptor kind %u from another process cannot be mapped", d.kind);
+    return nullptr;
+  }
+  std::string key((const char*)d.ipc_handle, 64);
+  void* base = nullptr;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = ipc_open_.find(key);
+    if (it != ipc_open_.end()) base = it->second;
+  }
+  if (!base) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, d.ipc_handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      UB_WARN("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    std::lock_guard<std::mutex> g(mu_);
+    ipc_open_[key] = base;
+  }
+  return (char*)base + (d.addr - d.base);
+}
+
+// ------------------------------------------------------------------ data path
+bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
+                           const std::vector<size_t>& sizes, cudaEvent_t ev) {
+  cudaStream_t st;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    st = streams_[next_stream_++ % streams_.size()];
+  }
+  const size_t n = src.size();
+  bool any_host = false;
+  for (size_t i = 0; i < n; ++i) {
+    cudaPointerAttributes a;
+    memset(&a, 0, sizeof(a));
+    if (cudaPointerGetAttributes(&a, src[i]) != cudaSuccess || a.type == cudaMemoryTypeHost ||
+        a.type == cudaMemoryTypeUnregistered)
+      any_host = true;
+    if (cudaPointerGetAttributes(&a, dst[i]) != cudaSuccess || a.type == cudaMemoryTypeHost ||
+        a.type == cudaMemoryTypeUnregistered)
+      any_host = true;
+    (void)cudaGetLastError();
+  }
+  if (any_host || !ubParamP2PUseKernel()) {
+    for (size_t i = 0; i < n; ++i)
+      if (cudaMemcpyAsync(dst[i], src[i], sizes[i], cudaMemcpyDefault, st) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> g(mu_);
+    stats_.memcpy_fallbacks += n;
+  } else {
+    const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(48, ubParamP2PChunkKB())) * 1024;
+    for (size_t i0 = 0; i0 < n; i0 += kP2PMaxEntries) {
+      P2PCopyBatch b;
+      memset(&b, 0, sizeof(b));
+      b.chunk_bytes = chunk;
+      const size_t m = std::min<size_t>(kP2PMaxEntries, n - i0);
+      uint32_t total = 0;
+      for (size_t j = 0; j < m; ++j) {
+        auto& e = b.e[j];
+        e.src = src[i0 + j];
+        e.dst = dst[i0 + j];
+        e.bytes = sizes[i0 + j];
+        const bool al = ((((uintptr_t)e.src) | ((uintptr_t)e.dst)) & 15) == 0;
+        e.bulk_bytes = al ? (e.bytes / 16 * 16) : 0;
+        b.chunk_prefix[j] = total;
+        total += (uint32_t)((e.bulk_bytes + chunk - 1) / chunk);
+      }
+      b.chunk_prefix[m] = total;
+      b.n = (int)m;
+      int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ubParamP2PCtas(), std::max<uint32_t>(total, 1)));
+      cudaError_t e = launch_p2p_copy(b, grid, st);
+      if (e != cudaSuccess) {
+        UB_WARN("p2p copy kernel launch failed: %s", cudaGetErrorString(e));
+        return false;
+      }
+      std::lock_guard<std::mutex> g(mu_);
+      stats_.kernel_launches++;
+    }
+  }
+  return cudaEventRecord(ev, st) == cudaSuccess;
+}
+
+static cudaEvent_t new_event() {
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+
+bool Endpoint::send_async(uint64_t conn, const std::vector<const void*>& ptrs, const std::vector<size_t>& sizes,
+                          uint64_t* tid) {
+  auto c = find_conn(conn);
+  if (!c || ptrs.size() != sizes.size() || ptrs.empty()) return false;
+  for (size_t s : sizes)
+    if (s > 0xffffffffull * 16) return false;
+  auto t = std::make_shared<Transfer>();
+  t->conn = c;
+  t->state = Transfer::SEND_WAIT_ADV;
+  t->notify_done = true;
+  for (auto p : ptrs) t->src.push_back((const char*)p);
+  t->sizes = sizes;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    t->seq = c->next_send_seq++;
+    t->id = next_tid_++;
+    transfers_[t->id] = t;
+    stats_.transfers++;
+    for (size_t s : sizes) stats_.bytes_sent += s;
+  }
+  if (tid) *tid = t->id;
+  wake();
+  return true;
+}
+
+bool Endpoint::recv_async(uint64_t conn, const std::vector<void*>& ptrs, const std::vector<size_t>& sizes,
+                          uint64_t* tid) {
+  auto c = find_conn(conn);
+  if (!c || ptrs.size() != sizes.size() || ptrs.empty()) return false;
+  std::vector<XferDesc> descs(ptrs.size());
+  for (size_t i = 0; i < ptrs.size(); ++i)
+    if (!describe(ptrs[i], sizes[i], &descs[i])) return false;
+  auto t = std::make_shared<Transfer>();
+  t->conn = c;
+  t->state = Transfer::RECV_WAIT_DONE;
+  t->sizes = sizes;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    t->seq = c->next_recv_seq++;
+    t->id = next_tid_++;
+    transfers_[t->id] = t;
+    stats_.transfers++;
+    for (size_t s : sizes) stats_.bytes_received += s;
+  }
+  if (!send_msg(*c, MSG_ADV, t->seq, descs.data(), (uint32_t)(descs.size() * sizeof(XferDesc)))) return false;
+  if (tid) *tid = t->id;
+  wake();
+  return true;
+}
+
+bool Endpoint::write_async(uint64_t conn, const std::vector<const void*>& src, const std::vector<size_t>& sizes,
+                           const std::vector<XferDesc>& remote, uint64_t* tid) {
+  auto c = find_conn(conn);
+  if (!c || src.size() != sizes.size() || src.size() != remote.size() || src.empty()) return false;
+  cudaSetDevice(gpu_);
+  std::vector<const char*> s;
+  std::vector<char*> d;
+  for (size_t i = 0; i < src.size(); ++i) {
+    if (sizes[i] > remote[i].size) return false;
+    void* r = map_remote(remote[i]);
+    if (!r) return false;
+    s.push_back((const char*)src[i]);
+    d.push_back((char*)r);
+  }
+  auto t = std::make_shared<Transfer>();
+  t->conn = c;
+  t->state = Transfer::COPYING;
+  t->ev = new_event();
+  if (!launch_copy(s, d, sizes, t->ev)) return false;
+  std::lock_guard<std::mutex> g(mu_);
+  t->id = next_tid_++;
+  transfers_[t->id] = t;
+  stats_.transfers++;
+  for (size_t b : sizes) stats_.bytes_written += b;
+  if (tid) *tid = t->id;
+  return true;
+}
+
+bool Endpoint::read_async(uint64_t conn, const std::vector<void*>& dst, const std::vector<size_t>& sizes,
+                          const std::vector<XferDesc>& remote, uint64_t* tid) {
+  auto c = find_conn(conn);
+  if (!c || dst.size() != sizes.size() || dst.size() != remote.size() || dst.empty()) return false;
+  cudaSetDevice(gpu_);
+  std::vector<const char*> s;
+  std::vector<char*> d;
+  for (size_t i = 0; i < dst.size(); ++i) {
+    if (sizes[i] > remote[i].size) return false;
+    void* r = map_remote(remote[i]);
+    if (!r) return false;
+    s.push_back((const char*)r);
+    d.push_back((char*)dst[i]);
+  }
+  auto t = std::make_shared<Transfer>();
+  t->conn = c;
+  t->state = Transfer::COPYING;
+  t->ev = new_event();
+  if (!launch_copy(s, d, sizes, t->ev)) return false;
+  std::lock_guard<std::mutex> g(mu_);
+  t->id = next_tid_++;
+  transfers_[t->id] = t;
+  stats_.transfers++;
+  for (size_t b : sizes) stats_.bytes_read += b;
+  if (tid) *tid = t->id;
+  return true;
+}
+
+bool Endpoint::poll_async(uint64_t tid, bool* done) {
+  std::shared_ptr<Transfer> t;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = transfers_.find(tid);
+    if (it == transfers_.end()) return false;
+    t = it->second;
+  }
+  if (t->state == Transfer::COPYING && !t->notify_done) {
+    // one-sided ops are driven by the caller: no engine-thread latency on the hot path
+    cudaError_t q = cudaEventQuery(t->ev);
+    if (q == cudaSuccess) t->state = Transfer::DONE;
+    else if (q != cudaErrorNotReady) t->state = Transfer::FAILED;
+    (void)cudaGetLastError();
+  }
+  const bool fin = t->state == Transfer::DONE || t->state == Transfer::FAILED;
+  if (done) *done = fin;
+  if (fin) {
+    std::lock_guard<std::mutex> g(mu_);
+    transfers_.erase(tid);
+    if (t->ev) cudaEventDestroy(t->ev);
+    t->ev = nullptr;
+    return t->state == Transfer::DONE;
+  }
+  return true;
+}
+
+bool Endpoint::wait(uint64_t tid, int timeout_ms) {
+  auto t0 = std::chrono::steady_clock::now();
+  bool done = false;
+  uint32_t spins = 0;
+  while (true) {
+    if (!poll_async(tid, &done)) return false;
+    if (done) return true;
+    if ((++spins & 0x3f) == 0) {
+      if (timeout_ms >= 0 &&
+          std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(timeout_ms))
+        return false;
+      std::this_thread::yield();
+    }
+  }
+}
+
+bool Endpoint::send_notif(uint64_t conn, const std::string& msg) {
+  auto c = find_conn(conn);
+  if (!c) return false;
+  return send_msg(*c, MSG_NOTIF, 0, msg.data(), (uint32_t)msg.size());
+}
+
+std::vector<std::pair<uint64_t, std::string>> Endpoint::get_notifs() {
+  std::lock_guard<std::mutex> g(mu_);
+  std::vector<std::pair<uint64_t, std::string>> out(notifs_.begin(), notifs_.end());
+  notifs_.clear();
+  return out;
+}
+
+P2PStats Endpoint::stats() const {
+  std::lock_guard<std::mutex> g(mu_);
+  return stats_;
+}
+
+// ------------------------------------------------------------------ engine thread
+void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<char>& payload) {
+  std::lock_guard<std::mutex> g(mu_);
+  switch (type) {
+    case MSG_ADV: {
+      std::vector<XferDesc> d(payload.size() / sizeof(XferDesc));
+      memcpy(d.data(), payload.data(), d.size() * sizeof(XferDesc));
+      c.advs[seq] = std::move(d);
+      break;
+    }
+    case MSG_DONE: c.dones[seq] = true; break;
+    case MSG_NOTIF: notifs_.emplace_back(c.id, std::string(payload.begin(), payload.end())); break;
+    case MSG_BYE: c.alive = false; break;
+    default: break;
+  }
+}
+
+void Endpoint::progress_locked() {
+  // called with mu_ held
+  for (auto& kv : transfers_) {
+    auto t = kv.second;
+    Conn& c = *t->conn;
+    switch (t->state) {
+      case Transfer::SEND_WAIT_ADV: {
+        auto it = c.advs.find(t->seq);
+        if (it == c.advs.end()) {
+          if (!c.alive) t->state = Transfer::FAILED;
+          break;
+        }
+        std::vector<XferDesc> descs = std::move(it->second);
+        c.advs.erase(it);
+        if (descs.size() != t->src.size()) {
+          UB_WARN("p2p send: receiver posted %zu buffers, sender has %zu", descs.size(), t->src.size());
+          t->state = Transfer::FAILED;
+          break;
+        }
+        std::vector<char*> dst;
+        bool ok = true;
+        mu_.unlock();  // map_remote / launch_copy take mu_ themselves
+        for (size_t i = 0; i < descs.size() && ok; ++i) {
+          if (descs[i].size < t->sizes[i]) ok = false;
+          void* r = ok ? map_remote(descs[i]) : nullptr;
+          if (!r) ok = false;
+          dst.push_back((char*)r);
+        }
+        cudaEvent_t ev = ok ? new_event() : nullptr;
+        if (ok) ok = launch_copy(t->src, dst, t->sizes, ev);
+        mu_.lock();
+        t->ev = ev;
+        t->state = ok ? Transfer::COPYING : Transfer::FAILED;
+        return;  // tables may have changed while unlocked: restart the scan next tick
+      }
+      case Transfer::COPYING: {
+        if (!t->notify_done) break;  // caller-driven
+        cudaError_t q = cudaEventQuery(t->ev);
+        if (q == cudaSuccess) {
+          mu_.unlock();
+          bool ok = send_msg(c, MSG_DONE, t->seq, nullptr, 0);
+          mu_.lock();
+          t->state = ok ? Transfer::DONE : Transfer::FAILED;
+          return;
+        } else if (q != cudaErrorNotReady) {
+          (void)cudaGetLastError();
+          t->state = Transfer::FAILED;
+        }
+        break;
+      }
+      case Transfer::RECV_WAIT_DONE: {
+        auto it = c.dones.find(t->seq);
+        if (it != c.dones.end()) {
+          c.dones.erase(it);
+          t->state = Transfer::DONE;
+        } else if (!c.alive) {
+          t->state = Transfer::FAILED;
+        }
+        break;
+      }
+      default: break;
+    }
+  }
+}
+
+void Endpoint::engine_loop() {
+  cudaSetDevice(gpu_);
+  while (!stop_) {
+    std::vector<pollfd> fds;
+    std::vector<std::shared_ptr<Conn>> cs;
+    bool active = false;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      for (auto& kv : conns_)
+        if (kv.second->fd >= 0 && kv.second->alive) {
+          fds.push_back({kv.second->fd, POLLIN, 0});
+          cs.push_back(kv.second);
+        }
+      for (auto& kv : transfers_)
+        if (kv.second->state == Transfer::SEND_WAIT_ADV || kv.second->state == Transfer::RECV_WAIT_DONE ||
+            (kv.second->state == Transfer::COPYING && kv.second->notify_done))
+          active = true;
+    }
+    const size_t nconn = fds.size();
+    fds.push_back({listen_fd_, POLLIN, 0});
+    fds.push_back({wake_fd_, POLLIN, 0});
+    int rc = ::poll(fds.data(), fds.size(), active ? 0 : 20);
+    if (rc > 0) {
+      for (size_t i = 0; i < nconn; ++i) {
+        if (!(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) continue;
+        MsgHdr h;
+        if (!read_full(cs[i]->fd, &h, sizeof(h))) {
+          cs[i]->alive = false;
+          continue;
+        }
+        std::vector<char> payload(h.len);
+        if (h.len && !read_full(cs[i]->fd, payload.data(), h.len)) {
+          cs[i]->alive = false;
+          continue;
+        }
+        handle_message(*cs[i], h.type, h.seq, payload);
+      }
+      if (fds[nconn].revents & POLLIN) {
+        sockaddr_in pa;
+        socklen_t pl = sizeof(pa);
+        int fd = ::accept(listen_fd_, (sockaddr*)&pa, &pl);
+        if (fd >= 0) {
+          int one = 1;
+          setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+          MsgHdr h;
+          Hello peer;
+          if (read_full(fd, &h, sizeof(h)) && h.type == MSG_HELLO && read_full(fd, &peer, sizeof(peer))) {
+            MsgHdr rh{MSG_HELLO, sizeof(Hello), 0};
+            Hello me{gpu_, (int32_t)getpid()};
+            write_full(fd, &rh, sizeof(rh));
+            write_full(fd, &me, sizeof(me));
+            auto c = std::make_shared<Conn>();
+            c->fd = fd;
+            c->remote_gpu = peer.gpu;
+            c->remote_pid = peer.pid;
+            char buf[INET_ADDRSTRLEN];
+            inet_ntop(AF_INET, &pa.sin_addr, buf, sizeof(buf));
+            c->ip = buf;
+            std::lock_guard<std::mutex> g(mu_);
+            c->id = next_conn_++;
+            conns_[c->id] = c;
+            accepted_.push_back(c->id);
+            accept_cv_.notify_all();
+          } else {
+            ::close(fd);
+          }
+        }
+      }
+      if (fds[nconn + 1].revents & POLLIN) {
+        uint64_t v;
+        (void)!::read(wake_fd_, &v, sizeof(v));
+      }
+    }
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      progress_locked();
+    }
+  }
+  accept_cv_.notify_all();
+}
+
+}  // namespace ub

@@ -1,0 +1,119 @@
+// NIXL-style initiator/target transfer engine for one NVSwitch node.
+//
+// API parity target: the reference's `class Endpoint` (p2p/engine.h:246-552) -- connection,
+// memory-registration and transfer id tables; blocking + async send/recv (+vector), one-sided
+// read/write (+vector) against advertised descriptors, async handles polled to completion,
+// metadata exchange, notifications.  What differs by design: there is exactly one transport
+// (peer HBM mapped through CUDA IPC, moved by the in-kernel TMA copy engine of
+// p2p_kernels.cu on side streams), so the RDMA/TCP/NCCL backends, shm jring mailboxes and
+// per-op cudaIpcOpen/Close of the reference disappear; control messages ride one TCP
+// connection per (unidirectional) conn.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "p2p_types.h"
+
+namespace ub {
+
+struct P2PStats {
+  uint64_t bytes_sent = 0, bytes_received = 0, bytes_read = 0, bytes_written = 0;
+  uint64_t transfers = 0, kernel_launches = 0, memcpy_fallbacks = 0;
+};
+
+class Endpoint {
+ public:
+  explicit Endpoint(int local_gpu_idx, int num_streams = 4);
+  ~Endpoint();
+  Endpoint(const Endpoint&) = delete;
+
+  // ---- identity / metadata (ip, port, gpu index)
+  std::string get_metadata() const;
+  static bool parse_metadata(const std::string& md, std::string* ip, uint16_t* port, int* gpu_idx);
+  int gpu_idx() const { return gpu_; }
+  uint16_t port() const { return port_; }
+
+  // ---- connections (a conn is initiator -> target; both sides may use it in both directions)
+  bool connect(const std::string& ip, int remote_gpu_idx, uint16_t remote_port, uint64_t* conn_id);
+  bool accept(std::string* ip, int* remote_gpu_idx, uint64_t* conn_id, int timeout_ms = -1);
+  bool add_remote_endpoint(const std::string& metadata, uint64_t* conn_id);
+  bool remove_remote_endpoint(uint64_t conn_id);
+  bool start_passive_accept() { return true; }  // the accept thread always runs
+  bool conn_is_local(uint64_t) const { return true; }
+
+  // ---- memory registration
+  bool reg(const void* ptr, size_t size, uint64_t* mr_id);
+  bool dereg(uint64_t mr_id);
+  bool describe(const void* ptr, size_t size, XferDesc* out);  // window descriptor for any registered/unregistered ptr
+
+  // ---- two-sided
+  bool send_async(uint64_t conn, const std::vector<const void*>& ptrs, const std::vector<size_t>& sizes, uint64_t* tid);
+  bool recv_async(uint64_t conn, const std::vector<void*>& ptrs, const std::vector<size_t>& sizes, uint64_t* tid);
+  // ---- one-sided against advertised descriptors
+  bool write_async(uint64_t conn, const std::vector<const void*>& src, const std::vector<size_t>& sizes,
+                   const std::vector<XferDesc>& remote, uint64_t* tid);
+  bool read_async(uint64_t conn, const std::vector<void*>& dst, const std::vector<size_t>& sizes,
+                  const std::vector<XferDesc>& remote, uint64_t* tid);
+  bool advertise(uint64_t conn, const void* ptr, size_t size, XferDesc* out);
+
+  // poll once: *done = finished (the handle is released when done, like the reference's poll_async)
+  bool poll_async(uint64_t tid, bool* done);
+  bool wait(uint64_t tid, int timeout_ms = -1);
+
+  // ---- notifications (uccl_engine_send_notif / get_notifs)
+  bool send_notif(uint64_t conn, const std::string& msg);
+  std::vector<std::pair<uint64_t, std::string>> get_notifs();
+
+  P2PStats stats() const;
+
+ private:
+  struct Conn;
+  struct Transfer;
+  void engine_loop();
+  void handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<char>& payload);
+  bool send_msg(Conn& c, uint32_t type, uint64_t seq, const void* payload, uint32_t len);
+  void progress_locked();
+  bool launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
+                   const std::vector<size_t>& sizes, cudaEvent_t ev);
+  void* map_remote(const XferDesc& d);
+  std::shared_ptr<Conn> find_conn(uint64_t id);
+  void wake();
+
+  int gpu_;
+  uint16_t port_ = 0;
+  std::string ip_;
+  int listen_fd_ = -1;
+  int wake_fd_ = -1;
+  std::atomic<bool> stop_{false};
+  std::thread engine_;
+  mutable std::mutex mu_;  // guards every table below
+  std::condition_variable accept_cv_;
+  std::map<uint64_t, std::shared_ptr<Conn>> conns_;
+  std::deque<uint64_t> accepted_;
+  std::map<uint64_t, std::shared_ptr<Transfer>> transfers_;
+  std::deque<std::pair<uint64_t, std::string>> notifs_;
+  uint64_t next_conn_ = 1, next_tid_ = 1, next_mr_ = 1;
+  struct MR {
+    const void* ptr;
+    size_t size;
+  };
+  std::map<uint64_t, MR> mrs_;
+  std::unordered_map<std::string, void*> ipc_open_;  // handle bytes -> mapped base
+  std::unordered_map<uint64_t, std::string> ipc_export_;  // allocation base -> handle bytes
+  std::vector<cudaStream_t> streams_;
+  size_t next_stream_ = 0;
+  std::vector<cudaEvent_t> event_pool_;
+  P2PStats stats_;
+};
+
+}  // namespace ub

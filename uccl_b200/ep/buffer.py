@@ -118,6 +118,19 @@ class Buffer:
 
         return ll_size_hint(num_max_dispatch_tokens_per_rank, hidden, num_ranks, num_experts)
 
+    def _sms(self, config: "Config") -> int:
+        """SMs (CTAs) for one kernel.  All ranks of a single-process world that share a GPU must
+        be co-resident (their kernels wait for each other), so the budget is split between them."""
+        n = int(config.num_sms)
+        if self.comm.native.single_process and self.group_size > 1:
+            share = torch.cuda.get_device_properties(self.device).multi_processor_count
+            import collections
+
+            per_dev = collections.Counter()
+            per_dev[self.device.index] = self.group_size  # conservative: assume every rank is on this GPU
+            n = max(1, min(n, share // self.group_size))
+        return n
+
     # ------------------------------------------------------------------ stream choreography
     def _enter(self, previous_event, allocate_on_comm_stream):
         compute = torch.cuda.current_stream(self.device)
@@ -197,7 +210,7 @@ class Buffer:
             with torch.cuda.stream(self.comm_stream):
                 o = self.runtime.dispatch(x_data.data_ptr(), x_scales.data_ptr() if x_scales is not None else 0, 0, 0,
                                           0, send_slot.data_ptr(), 0, 0, T, H, h_K, 0, mode, True, -1, 0, 1, 0,
-                                          round_scale, config.num_sms, self.comm_stream.cuda_stream)
+                                          round_scale, self._sms(config), self.comm_stream.cuda_stream)
             recv_x = self._view_x(o, num_recv, H, out_fp8)
             ev = self._exit(compute, async_finish, (x_data, x_scales, send_slot))
             return recv_x, None, None, None, None, ev
@@ -227,7 +240,7 @@ class Buffer:
                 topk_weights.data_ptr() if topk_weights is not None else 0, token_pos.data_ptr(),
                 send_slot.data_ptr(), num_tokens_per_rank.data_ptr(), num_tokens_per_expert.data_ptr(), T, H, K, E,
                 mode, False, -1, rank_prefix.data_ptr(), expert_alignment, num_worst_tokens, round_scale,
-                config.num_sms, self.comm_stream.cuda_stream)
+                self._sms(config), self.comm_stream.cuda_stream)
         if num_worst_tokens > 0:
             num_recv = num_worst_tokens
             per_expert: List[int] = []
@@ -298,7 +311,7 @@ class Buffer:
             self.runtime.combine(x.data_ptr(), x.size(0), topk_weights.data_ptr() if topk_weights is not None else 0,
                                  send_slot.data_ptr(), b0.data_ptr() if b0 is not None else 0,
                                  b1.data_ptr() if b1 is not None else 0, out.data_ptr(),
-                                 out_w.data_ptr() if out_w is not None else 0, T, H, Kw, config.num_sms,
+                                 out_w.data_ptr() if out_w is not None else 0, T, H, Kw, self._sms(config),
                                  self.comm_stream.cuda_stream)
         ev = self._exit(compute, async_finish, (x, topk_weights, b0, b1, out, out_w, send_slot))
         return out, out_w, ev

@@ -1,0 +1,283 @@
+"""NIXL-style P2P transfer engine (KV-cache / weight moves between GPUs of one node).
+
+Python surface mirrors the reference's ``uccl.p2p.Endpoint`` (p2p/engine_api.cc:141-1517;
+list in SURVEY 2.6) so callers switch over unchanged; the engine underneath is the native
+``P2PEndpoint`` (csrc/p2p): peer HBM mapped once per allocation through CUDA IPC, bytes moved
+by an in-kernel TMA (cp.async.bulk) copy pipeline on side streams, vectorised per launch.
+"""
+from __future__ import annotations
+
+import os
+import socket
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+from .. import _native
+
+XFER_DESC_BYTES = 128
+
+
+class XferDesc:
+    """A registered memory window (reference: XferDesc, p2p/engine_api.cc:15-22)."""
+
+    __slots__ = ("raw", "mr_id")
+
+    def __init__(self, raw: bytes, mr_id: int = 0):
+        assert len(raw) == XFER_DESC_BYTES
+        self.raw = bytes(raw)
+        self.mr_id = mr_id
+
+    @property
+    def addr(self) -> int:
+        return struct.unpack_from("<Q", self.raw, 72)[0]
+
+    @property
+    def size(self) -> int:
+        return struct.unpack_from("<Q", self.raw, 80)[0]
+
+    def __repr__(self):
+        return f"XferDesc(addr=0x{self.addr:x}, size={self.size})"
+
+
+def get_oob_ip() -> str:
+    return os.environ.get("UCCL_B200_P2P_IP", "127.0.0.1")
+
+
+def _registry_path(gpu_idx: int) -> str:
+    return f"/dev/shm/uccl_b200_p2p_{os.getuid()}_gpu{gpu_idx}"
+
+
+class Endpoint:
+    def __init__(self, local_gpu_idx: Optional[int] = None, num_cpus: int = 4):
+        import torch
+
+        C = _native.C()
+        if local_gpu_idx is None:
+            local_gpu_idx = torch.cuda.current_device()
+        torch.cuda.init()
+        self._e = C.P2PEndpoint(int(local_gpu_idx), max(1, int(num_cpus)))
+        self.local_gpu_idx = int(local_gpu_idx)
+        self._mrs = {}
+        self._ipc_pending = {}
+        # local rendezvous file for connect_local (reference: shm inbox keyed by GPU BDF)
+        try:
+            with open(_registry_path(self.local_gpu_idx), "wb") as f:
+                f.write(self.get_metadata())
+        except OSError:
+            pass
+
+    # ------------------------------------------------------------------ metadata
+    def get_metadata(self) -> bytes:
+        return bytes(self._e.get_metadata())
+
+    @staticmethod
+    def parse_metadata(metadata: bytes) -> Tuple[str, int, int]:
+        return _native.C().P2PEndpoint.parse_metadata(bytes(metadata))
+
+    # --------------------------------------------------------------- connections
+    def connect(self, ip_addr=None, remote_gpu_idx: int = 0, remote_port: int = 0, remote_metadata=None):
+        if remote_metadata is None and isinstance(ip_addr, (bytes, bytearray)):
+            remote_metadata = ip_addr
+        if remote_metadata is not None:
+            return self._e.add_remote_endpoint(bytes(remote_metadata))
+        return self._e.connect(str(ip_addr), int(remote_gpu_idx), int(remote_port))
+
+    def accept(self, timeout_ms: int = -1):
+        return self._e.accept(timeout_ms)
+
+    def start_passive_accept(self) -> bool:
+        return self._e.start_passive_accept()
+
+    def add_remote_endpoint(self, metadata: bytes):
+        return self._e.add_remote_endpoint(bytes(metadata))
+
+    def remove_remote_endpoint(self, conn_id: int) -> bool:
+        return self._e.remove_remote_endpoint(conn_id)
+
+    def connect_local(self, remote_gpu_idx: int):
+        with open(_registry_path(int(remote_gpu_idx)), "rb") as f:
+            md = f.read()
+        return self._e.add_remote_endpoint(md)
+
+    def accept_local(self, timeout_ms: int = -1):
+        ok, ip, gpu, conn = self._e.accept(timeout_ms)
+        return ok, gpu, conn
+
+    # -------------------------------------------------------------- registration
+    def reg(self, ptr: int, size: int):
+        ok, mr = self._e.reg(int(ptr), int(size))
+        if ok:
+            self._mrs[mr] = (int(ptr), int(size))
+        return ok, mr
+
+    def regv(self, ptrs: Sequence[int], sizes: Sequence[int]):
+        ids = []
+        for p, s in zip(ptrs, sizes):
+            ok, mr = self.reg(p, s)
+            if not ok:
+                return False, ids
+            ids.append(mr)
+        return True, ids
+
+    def dereg(self, mr_id: int) -> bool:
+        self._mrs.pop(mr_id, None)
+        return self._e.dereg(mr_id)
+
+    def register_memory(self, tensors) -> List[XferDesc]:
+        descs = []
+        for t in tensors:
+            ptr, size = t.data_ptr(), t.numel() * t.element_size()
+            ok, mr = self.reg(ptr, size)
+            if not ok:
+                raise RuntimeError("uccl_b200.p2p: register_memory failed")
+            descs.append(XferDesc(bytes(self._e.describe(ptr, size)), mr))
+        return descs
+
+    def deregister_memory(self, descs: Sequence[XferDesc]) -> None:
+        for d in descs:
+            if d.mr_id:
+                self.dereg(d.mr_id)
+
+    @staticmethod
+    def get_serialized_descs(descs: Sequence[XferDesc]) -> bytes:
+        return struct.pack("<I", len(descs)) + b"".join(d.raw for d in descs)
+
+    @staticmethod
+    def deserialize_descs(blob: bytes) -> List[XferDesc]:
+        (n,) = struct.unpack_from("<I", blob, 0)
+        return [XferDesc(blob[4 + i * XFER_DESC_BYTES: 4 + (i + 1) * XFER_DESC_BYTES]) for i in range(n)]
+
+    # ------------------------------------------------------------------ two-sided
+    def send_async(self, conn_id, mr_id, ptr, size):
+        return self._e.send_async(conn_id, [int(ptr)], [int(size)])
+
+    def recv_async(self, conn_id, mr_id, ptr, size):
+        return self._e.recv_async(conn_id, [int(ptr)], [int(size)])
+
+    def sendv_async(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
+        return self._e.send_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes])
+
+    def recvv_async(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
+        return self._e.recv_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes])
+
+    def _block(self, res) -> bool:
+        ok, tid = res
+        return bool(ok) and bool(self._e.wait(tid, -1))
+
+    def send(self, conn_id, mr_id, ptr, size) -> bool:
+        return self._block(self.send_async(conn_id, mr_id, ptr, size))
+
+    def recv(self, conn_id, mr_id, ptr, size) -> bool:
+        return self._block(self.recv_async(conn_id, mr_id, ptr, size))
+
+    def sendv(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None) -> bool:
+        return self._block(self.sendv_async(conn_id, mr_ids, ptrs, sizes))
+
+    def recvv(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None) -> bool:
+        return self._block(self.recvv_async(conn_id, mr_ids, ptrs, sizes))
+
+    # ------------------------------------------------------------------ one-sided
+    def advertise(self, conn_id, mr_id, ptr, size):
+        return True, bytes(self._e.describe(int(ptr), int(size)))
+
+    def advertisev(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
+        return True, [bytes(self._e.describe(int(p), int(s))) for p, s in zip(ptrs, sizes)]
+
+    @staticmethod
+    def _raw(d):
+        return d.raw if isinstance(d, XferDesc) else bytes(d)
+
+    def write_async(self, conn_id, mr_id, ptr, size, fifo_blob):
+        return self._e.write_async(conn_id, [int(ptr)], [int(size)], [self._raw(fifo_blob)])
+
+    def read_async(self, conn_id, mr_id, ptr, size, fifo_blob):
+        return self._e.read_async(conn_id, [int(ptr)], [int(size)], [self._raw(fifo_blob)])
+
+    def writev_async(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None):
+        return self._e.write_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes],
+                                   [self._raw(b) for b in fifo_blobs])
+
+    def readv_async(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None):
+        return self._e.read_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes],
+                                  [self._raw(b) for b in fifo_blobs])
+
+    def write(self, conn_id, mr_id, ptr, size, fifo_blob) -> bool:
+        return self._block(self.write_async(conn_id, mr_id, ptr, size, fifo_blob))
+
+    def read(self, conn_id, mr_id, ptr, size, fifo_blob) -> bool:
+        return self._block(self.read_async(conn_id, mr_id, ptr, size, fifo_blob))
+
+    def writev(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None) -> bool:
+        return self._block(self.writev_async(conn_id, mr_ids, ptrs, sizes, fifo_blobs))
+
+    def readv(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None) -> bool:
+        return self._block(self.readv_async(conn_id, mr_ids, ptrs, sizes, fifo_blobs))
+
+    # ------------------------------------------ IPC-named variants (same engine here)
+    def send_ipc(self, conn_id, ptr, size) -> bool:
+        return self.send(conn_id, 0, ptr, size)
+
+    def recv_ipc(self, conn_id, ptr, size) -> bool:
+        return self.recv(conn_id, 0, ptr, size)
+
+    def send_ipc_async(self, conn_id, ptr, size):
+        return self.send_async(conn_id, 0, ptr, size)
+
+    def recv_ipc_async(self, conn_id, ptr, size):
+        return self.recv_async(conn_id, 0, ptr, size)
+
+    def advertise_ipc(self, conn_id, ptr, size):
+        return self.advertise(conn_id, 0, ptr, size)
+
+    def advertisev_ipc(self, conn_id, ptrs, sizes, num_iovs=None):
+        return self.advertisev(conn_id, None, ptrs, sizes)
+
+    def write_ipc(self, conn_id, ptr, size, info_blob) -> bool:
+        return self.write(conn_id, 0, ptr, size, info_blob)
+
+    def read_ipc(self, conn_id, ptr, size, info_blob) -> bool:
+        return self.read(conn_id, 0, ptr, size, info_blob)
+
+    def write_ipc_async(self, conn_id, ptr, size, info_blob):
+        return self.write_async(conn_id, 0, ptr, size, info_blob)
+
+    def read_ipc_async(self, conn_id, ptr, size, info_blob):
+        return self.read_async(conn_id, 0, ptr, size, info_blob)
+
+    def writev_ipc(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None) -> bool:
+        return self.writev(conn_id, None, ptrs, sizes, info_blobs)
+
+    def readv_ipc(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None) -> bool:
+        return self.readv(conn_id, None, ptrs, sizes, info_blobs)
+
+    def writev_ipc_async(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None):
+        return self.writev_async(conn_id, None, ptrs, sizes, info_blobs)
+
+    def readv_ipc_async(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None):
+        return self.readv_async(conn_id, None, ptrs, sizes, info_blobs)
+
+    # ---------------------------------------------------------------- descriptor API
+    def transfer(self, conn_id: int, op: str, local_descs: Sequence[XferDesc], remote_descs: Sequence[XferDesc]):
+        """NIXL-style: move every (local, remote) window pair with ONE kernel launch."""
+        assert op in ("read", "write") and len(local_descs) == len(remote_descs)
+        ptrs = [d.addr for d in local_descs]
+        sizes = [min(l.size, r.size) for l, r in zip(local_descs, remote_descs)]
+        blobs = [r.raw for r in remote_descs]
+        fn = self._e.write_async if op == "write" else self._e.read_async
+        return fn(conn_id, ptrs, sizes, blobs)
+
+    def poll_async(self, transfer_id: int):
+        return self._e.poll_async(transfer_id)
+
+    def wait(self, transfer_id: int, timeout_ms: int = -1) -> bool:
+        return self._e.wait(transfer_id, timeout_ms)
+
+    # -------------------------------------------------------------- notifications
+    def send_notif(self, conn_id: int, msg: bytes) -> bool:
+        return self._e.send_notif(conn_id, bytes(msg))
+
+    def get_notifs(self):
+        return self._e.get_notifs()
+
+    def stats(self) -> dict:
+        return dict(self._e.stats())
