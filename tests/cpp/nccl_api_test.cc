@@ -1,0 +1,109 @@
+// NCCL-API plumbing test (BASELINE config #1): two processes, world_size = 2, host backend.
+// Exercises ncclGetUniqueId / ncclCommInitRank (TCP rendezvous + shm heaps), AllReduce,
+// AllGather, ReduceScatter, Broadcast, Reduce, CommCount/UserRank, CommSplit, error paths.
+#include <nccl.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CHECK(x)                                                                              \
+  do {                                                                                        \
+    ncclResult_t _r = (x);                                                                    \
+    if (_r != ncclSuccess) {                                                                  \
+      fprintf(stderr, "rank %d: %s failed: %s (%s)\n", g_rank, #x, ncclGetErrorString(_r), ncclGetLastError(nullptr)); \
+      exit(2);                                                                                \
+    }                                                                                         \
+  } while (0)
+#define EXPECT(c)                                                         \
+  do {                                                                    \
+    if (!(c)) {                                                           \
+      fprintf(stderr, "rank %d: expectation failed: %s (line %d)\n", g_rank, #c, __LINE__); \
+      exit(3);                                                            \
+    }                                                                     \
+  } while (0)
+
+static int g_rank = -1;
+
+static int run(int rank, int n, ncclUniqueId id) {
+  g_rank = rank;
+  ncclComm_t comm;
+  CHECK(ncclCommInitRank(&comm, n, id, rank));
+  int cnt = 0, ur = -1, ver = 0;
+  CHECK(ncclCommCount(comm, &cnt));
+  CHECK(ncclCommUserRank(comm, &ur));
+  CHECK(ncclGetVersion(&ver));
+  EXPECT(cnt == n && ur == rank && ver >= 20000);
+
+  const size_t N = 100003;
+  std::vector<float> x(N), y(N, 0.f);
+  for (size_t i = 0; i < N; ++i) x[i] = (float)(i % 97) + rank;
+  CHECK(ncclAllReduce(x.data(), y.data(), N, ncclFloat, ncclSum, comm, nullptr));
+  for (size_t i = 0; i < N; ++i) EXPECT(y[i] == 2.f * (i % 97) + 1.f);
+  // in place, avg
+  CHECK(ncclAllReduce(x.data(), x.data(), N, ncclFloat, ncclAvg, comm, nullptr));
+  for (size_t i = 0; i < N; ++i) EXPECT(std::fabs(x[i] - ((i % 97) + 0.5f)) < 1e-5f);
+
+  std::vector<int> g(n * 10), mine(10, rank + 1);
+  CHECK(ncclAllGather(mine.data(), g.data(), 10, ncclInt32, comm, nullptr));
+  for (int r = 0; r < n; ++r)
+    for (int i = 0; i < 10; ++i) EXPECT(g[r * 10 + i] == r + 1);
+
+  std::vector<double> rs_in(n * 7), rs_out(7);
+  for (size_t i = 0; i < rs_in.size(); ++i) rs_in[i] = (double)i * (rank + 1);
+  CHECK(ncclReduceScatter(rs_in.data(), rs_out.data(), 7, ncclDouble, ncclSum, comm, nullptr));
+  for (int i = 0; i < 7; ++i) EXPECT(rs_out[i] == (double)(rank * 7 + i) * 3.0);
+
+  std::vector<long long> b(33, rank == 1 ? 42 : -1);
+  CHECK(ncclBroadcast(b.data(), b.data(), 33, ncclInt64, 1, comm, nullptr));
+  for (auto v : b) EXPECT(v == 42);
+
+  std::vector<float> red(5, (float)(rank + 2)), red_out(5, 0.f);
+  CHECK(ncclReduce(red.data(), red_out.data(), 5, ncclFloat, ncclProd, 0, comm, nullptr));
+  if (rank == 0)
+    for (auto v : red_out) EXPECT(v == 6.f);
+
+  // error paths
+  EXPECT(ncclAllReduce(x.data(), y.data(), 4, (ncclDataType_t)99, ncclSum, comm, nullptr) == ncclInvalidArgument);
+  EXPECT(ncclBroadcast(b.data(), b.data(), 1, ncclInt64, 7, comm, nullptr) == ncclInvalidArgument);
+
+  // split into singleton communicators
+  ncclComm_t sub;
+  CHECK(ncclCommSplit(comm, rank, 0, &sub, nullptr));
+  int sc = 0;
+  CHECK(ncclCommCount(sub, &sc));
+  EXPECT(sc == 1);
+  float one = 3.f, out = 0.f;
+  CHECK(ncclAllReduce(&one, &out, 1, ncclFloat, ncclSum, sub, nullptr));
+  EXPECT(out == 3.f);
+  CHECK(ncclCommDestroy(sub));
+  CHECK(ncclCommDestroy(comm));
+  return 0;
+}
+
+int main() {
+  setenv("UCCL_B200_HOST_FAKE", "1", 1);
+  setenv("UCCL_B200_TIMEOUT_MS", "30000", 0);
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) {
+    fprintf(stderr, "ncclGetUniqueId failed\n");
+    return 1;
+  }
+  pid_t pid = fork();
+  if (pid == 0) {
+    _exit(run(1, 2, id));
+  }
+  int rc = run(0, 2, id);
+  int st = 0;
+  waitpid(pid, &st, 0);
+  if (rc != 0 || !WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+    fprintf(stderr, "FAILED (rank0 rc=%d, rank1 status=%d)\n", rc, st);
+    return 1;
+  }
+  printf("nccl_api_test: OK\n");
+  return 0;
+}

@@ -1,0 +1,43 @@
+"""Builds and runs the C++ NCCL-API test against libuccl_b200_nccl.so on the host backend."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build_test(tmp_path):
+    from uccl_b200 import _build
+
+    _build.build()
+    shim = _build.nccl_shim_path()
+    assert shim.exists()
+    exe = tmp_path / "nccl_api_test"
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests/cpp/nccl_api_test.cc"), "-I/usr/include",
+           "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl", "-Wl,-rpath," + str(shim.parent),
+           "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    return exe
+
+
+@pytest.mark.timeout(300)
+def test_nccl_api_world2_cpu(tmp_path):
+    exe = _build_test(tmp_path)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=240)
+    sys.stdout.write(r.stdout)
+    sys.stderr.write(r.stderr)
+    assert r.returncode == 0, r.stderr
+    assert "nccl_api_test: OK" in r.stdout
+
+
+def test_exported_symbols():
+    from uccl_b200 import _build
+
+    _build.build()
+    out = subprocess.run(["nm", "-D", str(_build.nccl_shim_path())], capture_output=True, text=True).stdout
+    for sym in ("ncclAllReduce", "ncclAllGather", "ncclReduceScatter", "ncclBroadcast", "ncclReduce", "ncclSend",
+                "ncclRecv", "ncclAllToAll", "ncclGroupStart", "ncclGroupEnd", "ncclCommInitRank", "ncclCommInitAll",
+                "ncclCommSplit", "ncclGetUniqueId", "ncclMemAlloc", "ncclMemFree", "ncclCommRegister"):
+        assert f" T {sym}\n" in out, sym

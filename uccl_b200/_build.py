@@ -67,6 +67,7 @@ def _includes():
         "-I" + pybind11.get_include(),
         "-I" + sysconfig.get_paths()["include"],
         "-I/usr/local/cuda/include",
+        "-I/usr/include",
     ]
 
 
@@ -114,12 +115,24 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
         with ThreadPoolExecutor(max_workers=jobs) as ex:
             list(ex.map(lambda so: _compile_one(so[0], so[1], verbose), todo))
     out = module_path()
-    if todo or not out.exists():
-        cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", str(out)] + [str(o) for o in objs] + ["-lrt", "-lpthread", "-ldl"]
+    shim_objs = [o for o in objs if o.name == "coll_nccl_shim.o"]
+    bind_objs = [o for o in objs if o.name.startswith("bind_") or "_bind_" in o.name]
+    core_objs = [o for o in objs if o not in shim_objs and o not in bind_objs]
+
+    def link(target: Path, these):
+        target.parent.mkdir(parents=True, exist_ok=True)
+        cmd = [NVCC] + ARCH_FLAGS + ["-shared", "-o", str(target)] + [str(o) for o in these] + ["-lrt", "-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("link failed")
+            raise RuntimeError(f"link failed: {target}")
+
+    if todo or not out.exists():
+        link(out, core_objs + bind_objs)
+    shim = nccl_shim_path()
+    if shim_objs and (todo or not shim.exists()):
+        # NCCL-API drop-in: same kernels/runtime, nccl.h symbols, no python
+        link(shim, core_objs + shim_objs)
     return out
 
 

@@ -598,6 +598,47 @@ void Comm::alltoallv(const void* in, const size_t* send_counts, const size_t* se
   ++launches_;
 }
 
+void Comm::group_p2p(const std::vector<P2pOp>& ops, cudaStream_t stream) {
+  if (ops.empty()) return;
+  UB_CHECK(!is_host(), "send/recv: host backend does not implement point-to-point");
+  const int n = nranks();
+  std::vector<std::vector<const P2pOp*>> sends(n), recvs(n);
+  for (const auto& o : ops) {
+    UB_CHECK(o.peer >= 0 && o.peer < n, "send/recv: bad peer %d", o.peer);
+    UB_CHECK(o.buf != nullptr || o.bytes == 0, "send/recv: null buffer");
+    UB_CHECK((((uintptr_t)o.buf) & 15) == 0, "send/recv: buffers must be 16-byte aligned");
+    (o.is_send ? sends : recvs)[o.peer].push_back(&o);
+  }
+  size_t rounds = 0;
+  for (int p = 0; p < n; ++p) rounds = std::max(rounds, std::max(sends[p].size(), recvs[p].size()));
+  DeviceGuard g(device());
+  for (size_t r = 0; r < rounds; ++r) {
+    SendRecvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sr_flag_off = layout_.sr_flag_off;
+    a.sr_stage_off = layout_.sr_stage_off;
+    for (int p = 0; p < n; ++p) {
+      const P2pOp* s = r < sends[p].size() ? sends[p][r] : nullptr;
+      const P2pOp* v = r < recvs[p].size() ? recvs[p][r] : nullptr;
+      if ((!s || s->bytes == 0) && (!v || v->bytes == 0)) continue;
+      if (s) {
+        a.sbuf[p] = (const char*)s->buf;
+        a.sbytes[p] = s->bytes;
+      }
+      if (v) {
+        a.rbuf[p] = (char*)v->buf;
+        a.rbytes[p] = v->bytes;
+      }
+      if (p == rank()) UB_CHECK(s && v, "send/recv to self must be posted as a matching pair in one group");
+      a.peers[a.npeers++] = p;
+    }
+    if (a.npeers == 0) continue;
+    cudaError_t e = launch_sendrecv(dev_, a, stream);
+    UB_CHECK(e == cudaSuccess, "send/recv launch failed: %s", cudaGetErrorString(e));
+    ++launches_;
+  }
+}
+
 void Comm::barrier(cudaStream_t stream) {
   if (is_host()) {
     host_barrier();

@@ -88,6 +88,14 @@ class Comm {
   void alltoallv(const void* in, const size_t* send_counts, const size_t* send_displs, void* out,
                  const size_t* recv_counts, const size_t* recv_displs, int dtype, cudaStream_t stream);
   void barrier(cudaStream_t stream);
+  // grouped point-to-point (ncclGroupStart .. ncclSend/ncclRecv .. ncclGroupEnd)
+  struct P2pOp {
+    bool is_send;
+    void* buf;
+    size_t bytes;
+    int peer;
+  };
+  void group_p2p(const std::vector<P2pOp>& ops, cudaStream_t stream);
 
   // which algorithm AUTO would pick (for tests / tuner)
   int select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int* ctas) const;

@@ -1,0 +1,472 @@
+// NCCL-API drop-in: exports the nccl.h symbol set on top of the native communicator, so code
+// written against NCCL (nccl-tests style harnesses, frameworks that dlopen/LD_PRELOAD libnccl)
+// runs on the hand-written sm_100a kernels.
+//
+// Reference counterpart: experimental/lite/nccl/nccl.cu:1351-2430 (which falls back to a
+// dlopen'd NCCL for ReduceScatter/Reduce and leaves AllToAll(v)/PreMulSum/CommAbort as stubs).
+// Differences here: every collective incl. ReduceScatter / Reduce / Send / Recv is native; the
+// buffers may be ordinary cudaMalloc memory (staged kernels) or come from ncclMemAlloc
+// (symmetric heap -> zero-copy kernels); ncclCommInitAll supports ndev > 1 (single-process world).
+//
+// UCCL_B200_HOST_FAKE=1 selects the host backend (pointers are host memory, streams ignored):
+// this is the GPU-less CI configuration "NCCL-API allreduce correctness world_size=2 on CPU".
+#include <nccl.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../common/log.h"
+#include "../common/param.h"
+#include "comm.h"
+#include "../fabric/cu_api.h"
+#include <algorithm>
+
+using namespace ub;
+
+UB_PARAM(ShimHeapMB, "NCCL_HEAP_MB", 2048)
+UB_PARAM(ShimStageMB, "NCCL_STAGE_MB", 128)
+UB_PARAM(ShimHostFake, "HOST_FAKE", 0)
+
+struct ncclComm {
+  std::shared_ptr<Comm> comm;
+  std::string last_error;
+  ncclResult_t async_error = ncclSuccess;
+  bool finalized = false;
+};
+
+namespace {
+
+std::mutex g_mu;
+std::set<ncclComm*> g_comms;
+thread_local int g_group_depth = 0;
+struct PendingP2p {
+  ncclComm* comm;
+  Comm::P2pOp op;
+  cudaStream_t stream;
+};
+thread_local std::vector<PendingP2p> g_pending;
+thread_local std::string g_last_error;
+
+CommConfig shim_config() {
+  CommConfig cfg;
+  cfg.heap_bytes = (size_t)ubParamShimHeapMB() << 20;
+  cfg.stage_bytes = (size_t)ubParamShimStageMB() << 20;
+  cfg.host_fake = ubParamShimHostFake() != 0;
+  if (cfg.host_fake) {
+    cfg.heap_bytes = std::min<size_t>(cfg.heap_bytes, 256ull << 20);
+    cfg.stage_bytes = std::min<size_t>(cfg.stage_bytes, 8ull << 20);
+  }
+  return cfg;
+}
+
+template <typename F>
+ncclResult_t guarded(ncclComm* c, F&& f) {
+  try {
+    f();
+    return ncclSuccess;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    if (c) c->last_error = e.what();
+    const char* w = e.what();
+    if (strstr(w, "bad ") || strstr(w, "null") || strstr(w, "must be") || strstr(w, "needs")) return ncclInvalidArgument;
+    if (strstr(w, "cuda") || strstr(w, "CUDA") || strstr(w, "launch failed")) return ncclUnhandledCudaError;
+    return ncclInternalError;
+  }
+}
+
+bool valid(ncclComm_t c) { return c != nullptr && c->comm != nullptr; }
+
+ncclResult_t flush_group() {
+  // launch queued send/recv per (comm, stream)
+  std::vector<PendingP2p> pend;
+  pend.swap(g_pending);
+  ncclResult_t res = ncclSuccess;
+  std::map<std::pair<ncclComm*, cudaStream_t>, std::vector<Comm::P2pOp>> by;
+  for (auto& p : pend) by[{p.comm, p.stream}].push_back(p.op);
+  for (auto& kv : by) {
+    ncclComm* c = kv.first.first;
+    ncclResult_t r = guarded(c, [&] { c->comm->group_p2p(kv.second, kv.first.second); });
+    if (r != ncclSuccess) res = r;
+  }
+  return res;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define UB_EXPORT __attribute__((visibility("default")))
+
+UB_EXPORT ncclResult_t ncclGetVersion(int* version) {
+  if (!version) return ncclInvalidArgument;
+  *version = NCCL_VERSION_CODE;
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclGetUniqueId(ncclUniqueId* uniqueId) {
+  if (!uniqueId) return ncclInvalidArgument;
+  static_assert(sizeof(ncclUniqueId) >= sizeof(UniqueId), "unique id does not fit");
+  return guarded(nullptr, [&] {
+    UniqueId id = Bootstrap::create_id();
+    memset(uniqueId, 0, sizeof(*uniqueId));
+    memcpy(uniqueId->internal, id.data, sizeof(id.data));
+  });
+}
+
+UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank,
+                                              ncclConfig_t* /*config*/) {
+  if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return ncclInvalidArgument;
+  if (nranks > kMaxRanks) {
+    g_last_error = "uccl_b200: communicators are limited to one NVSwitch node (<= 8 ranks)";
+    return ncclInvalidUsage;
+  }
+  *comm = nullptr;
+  return guarded(nullptr, [&] {
+    UniqueId id;
+    memcpy(id.data, commId.internal, sizeof(id.data));
+    CommConfig cfg = shim_config();
+    int dev = -1;
+    if (!cfg.host_fake) UB_CHECK(cudaGetDevice(&dev) == cudaSuccess, "cudaGetDevice failed");
+    auto c = new ncclComm();
+    try {
+      c->comm = Comm::create(id, rank, nranks, dev, cfg);
+    } catch (...) {
+      delete c;
+      throw;
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    g_comms.insert(c);
+    *comm = c;
+  });
+}
+
+UB_EXPORT ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank) {
+  return ncclCommInitRankConfig(comm, nranks, commId, rank, nullptr);
+}
+
+UB_EXPORT ncclResult_t ncclCommInitRankScalable(ncclComm_t* newcomm, int nranks, int myrank, int nId,
+                                                ncclUniqueId* commIds, ncclConfig_t* config) {
+  if (nId < 1 || !commIds) return ncclInvalidArgument;
+  return ncclCommInitRankConfig(newcomm, nranks, commIds[0], myrank, config);
+}
+
+UB_EXPORT ncclResult_t ncclCommInitAll(ncclComm_t* comms, int ndev, const int* devlist) {
+  if (!comms || ndev < 1 || ndev > kMaxRanks) return ncclInvalidArgument;
+  return guarded(nullptr, [&] {
+    CommConfig cfg = shim_config();
+    std::vector<int> devs(ndev);
+    for (int i = 0; i < ndev; ++i) devs[i] = cfg.host_fake ? -1 : (devlist ? devlist[i] : i);
+    auto cs = Comm::create_local(devs, cfg);
+    std::lock_guard<std::mutex> g(g_mu);
+    for (int i = 0; i < ndev; ++i) {
+      auto c = new ncclComm();
+      c->comm = cs[i];
+      g_comms.insert(c);
+      comms[i] = c;
+    }
+  });
+}
+
+UB_EXPORT ncclResult_t ncclCommFinalize(ncclComm_t comm) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  comm->finalized = true;
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclCommDestroy(ncclComm_t comm) {
+  if (!comm) return ncclSuccess;
+  {
+    std::lock_guard<std::mutex> g(g_mu);
+    g_comms.erase(comm);
+  }
+  if (comm->comm && !comm->comm->is_host()) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(comm->comm->device());
+    cudaDeviceSynchronize();
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  delete comm;
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclCommAbort(ncclComm_t comm) { return ncclCommDestroy(comm); }
+
+UB_EXPORT ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, ncclConfig_t* config) {
+  if (!valid(comm) || !newcomm) return ncclInvalidArgument;
+  *newcomm = nullptr;
+  Comm& c = *comm->comm;
+  const int n = c.nranks(), me = c.rank();
+  struct Rec {
+    int color, key, rank, pad;
+    char uid[128];
+  };
+  std::vector<Rec> all(n);
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.color = color;
+  mine.key = key;
+  mine.rank = me;
+  ncclResult_t r = guarded(comm, [&] {
+    UniqueId id = Bootstrap::create_id();  // every rank offers one; the group leader's is used
+    memcpy(mine.uid, id.data, sizeof(id.data));
+    if (c.is_host()) {
+      c.allgather(&mine, all.data(), sizeof(Rec), kU8, nullptr);
+    } else {
+      Rec *d_in = nullptr, *d_out = nullptr;
+      UB_CUDA(cudaMalloc((void**)&d_in, sizeof(Rec)));
+      UB_CUDA(cudaMalloc((void**)&d_out, sizeof(Rec) * n));
+      UB_CUDA(cudaMemcpy(d_in, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+      c.allgather(d_in, d_out, sizeof(Rec), kU8, nullptr);
+      UB_CUDA(cudaMemcpy(all.data(), d_out, sizeof(Rec) * n, cudaMemcpyDeviceToHost));
+      cudaFree(d_in);
+      cudaFree(d_out);
+    }
+  });
+  if (r != ncclSuccess) return r;
+  if (color == NCCL_SPLIT_NOCOLOR) return ncclSuccess;
+  std::vector<Rec> grp;
+  for (auto& x : all)
+    if (x.color == color) grp.push_back(x);
+  std::sort(grp.begin(), grp.end(), [](const Rec& a, const Rec& b) { return a.key != b.key ? a.key < b.key : a.rank < b.rank; });
+  int newrank = -1;
+  for (size_t i = 0; i < grp.size(); ++i)
+    if (grp[i].rank == me) newrank = (int)i;
+  ncclUniqueId uid;
+  memset(&uid, 0, sizeof(uid));
+  memcpy(uid.internal, grp[0].uid, 128);
+  return ncclCommInitRankConfig(newcomm, (int)grp.size(), uid, newrank, config);
+}
+
+UB_EXPORT ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t*, ncclConfig_t*, int) {
+  g_last_error = "uccl_b200: ncclCommShrink is not supported";
+  return ncclInvalidUsage;
+}
+
+UB_EXPORT const char* ncclGetErrorString(ncclResult_t result) {
+  switch (result) {
+    case ncclSuccess: return "no error";
+    case ncclUnhandledCudaError: return "unhandled cuda error (run with UCCL_B200_DEBUG=INFO for details)";
+    case ncclSystemError: return "unhandled system error";
+    case ncclInternalError: return "internal error";
+    case ncclInvalidArgument: return "invalid argument";
+    case ncclInvalidUsage: return "invalid usage";
+    case ncclRemoteError: return "remote process exited or there was a network error";
+    case ncclInProgress: return "operation in progress";
+    default: return "unknown result code";
+  }
+}
+
+UB_EXPORT const char* ncclGetLastError(ncclComm_t comm) {
+  if (comm && !comm->last_error.empty()) return comm->last_error.c_str();
+  return g_last_error.c_str();
+}
+
+UB_EXPORT ncclResult_t ncclCommGetAsyncError(ncclComm_t comm, ncclResult_t* asyncError) {
+  if (!valid(comm) || !asyncError) return ncclInvalidArgument;
+  *asyncError = comm->comm->error_word() ? ncclInternalError : ncclSuccess;
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclCommCount(const ncclComm_t comm, int* count) {
+  if (!valid(comm) || !count) return ncclInvalidArgument;
+  *count = comm->comm->nranks();
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclCommCuDevice(const ncclComm_t comm, int* device) {
+  if (!valid(comm) || !device) return ncclInvalidArgument;
+  *device = comm->comm->device();
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclCommUserRank(const ncclComm_t comm, int* rank) {
+  if (!valid(comm) || !rank) return ncclInvalidArgument;
+  *rank = comm->comm->rank();
+  return ncclSuccess;
+}
+
+// Registration is implicit: heap memory is already peer-mapped and multicast-bound.
+UB_EXPORT ncclResult_t ncclCommRegister(const ncclComm_t comm, void* buff, size_t, void** handle) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  if (handle) *handle = buff;
+  return ncclSuccess;
+}
+UB_EXPORT ncclResult_t ncclCommDeregister(const ncclComm_t comm, void*) { return valid(comm) ? ncclSuccess : ncclInvalidArgument; }
+UB_EXPORT ncclResult_t ncclCommWindowRegister(ncclComm_t comm, void* buff, size_t, ncclWindow_t* win, int) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  if (win) *win = (ncclWindow_t)buff;
+  return ncclSuccess;
+}
+UB_EXPORT ncclResult_t ncclCommWindowDeregister(ncclComm_t comm, ncclWindow_t) { return valid(comm) ? ncclSuccess : ncclInvalidArgument; }
+
+// ncclMemAlloc hands out symmetric-heap memory of the (single) communicator of this process on
+// the current device, falling back to cudaMalloc when there is none yet.
+UB_EXPORT ncclResult_t ncclMemAlloc(void** ptr, size_t size) {
+  if (!ptr) return ncclInvalidArgument;
+  return guarded(nullptr, [&] {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    ncclComm* owner = nullptr;
+    {
+      std::lock_guard<std::mutex> g(g_mu);
+      for (auto* c : g_comms)
+        if (c->comm && !c->comm->is_host() && c->comm->device() == dev) {
+          owner = c;
+          break;
+        }
+    }
+    if (owner) {
+      *ptr = owner->comm->alloc(size);
+    } else {
+      UB_CUDA(cudaMalloc(ptr, size));
+    }
+  });
+}
+
+UB_EXPORT ncclResult_t ncclMemFree(void* ptr) {
+  if (!ptr) return ncclSuccess;
+  return guarded(nullptr, [&] {
+    std::lock_guard<std::mutex> g(g_mu);
+    for (auto* c : g_comms)
+      if (c->comm && c->comm->in_heap(ptr, 1)) {
+        c->comm->free(ptr);
+        return;
+      }
+    UB_CUDA(cudaFree(ptr));
+  });
+}
+
+UB_EXPORT ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t*, void*, ncclDataType_t, ncclScalarResidence_t, ncclComm_t) {
+  g_last_error = "uccl_b200: use the fused `scale` epilogue of the native API instead of PreMulSum";
+  return ncclInvalidUsage;
+}
+UB_EXPORT ncclResult_t ncclRedOpDestroy(ncclRedOp_t, ncclComm_t) { return ncclSuccess; }
+
+UB_EXPORT ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
+                                     ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->allreduce(sendbuff, recvbuff, count, (int)datatype, (int)op, stream); });
+}
+
+UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
+                                  ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->reduce(sendbuff, recvbuff, count, (int)datatype, (int)op, root, stream); });
+}
+
+UB_EXPORT ncclResult_t ncclBroadcast(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
+                                     int root, ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream); });
+}
+
+UB_EXPORT ncclResult_t ncclBcast(void* buff, size_t count, ncclDataType_t datatype, int root, ncclComm_t comm,
+                                 cudaStream_t stream) {
+  return ncclBroadcast(buff, buff, count, datatype, root, comm, stream);
+}
+
+UB_EXPORT ncclResult_t ncclReduceScatter(const void* sendbuff, void* recvbuff, size_t recvcount,
+                                         ncclDataType_t datatype, ncclRedOp_t op, ncclComm_t comm,
+                                         cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, (int)op, stream); });
+}
+
+UB_EXPORT ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype,
+                                     ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream); });
+}
+
+// Not part of nccl.h 2.27 but exported by newer NCCL / the reference's shim (as stubs there).
+UB_EXPORT ncclResult_t ncclAllToAll(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
+                                    ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->alltoall(sendbuff, recvbuff, count, (int)datatype, stream); });
+}
+
+UB_EXPORT ncclResult_t ncclAllToAllv(const void* sendbuff, const size_t sendcounts[], const size_t sdispls[],
+                                     void* recvbuff, const size_t recvcounts[], const size_t rdispls[],
+                                     ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  return guarded(comm, [&] {
+    comm->comm->alltoallv(sendbuff, sendcounts, sdispls, recvbuff, recvcounts, rdispls, (int)datatype, stream);
+  });
+}
+
+UB_EXPORT ncclResult_t ncclGroupStart() {
+  ++g_group_depth;
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclGroupEnd() {
+  if (g_group_depth <= 0) return ncclInvalidUsage;
+  if (--g_group_depth > 0) return ncclSuccess;
+  return flush_group();
+}
+
+UB_EXPORT ncclResult_t ncclGroupSimulateEnd(ncclSimInfo_t* simInfo) {
+  if (simInfo) simInfo->estimatedTime = 0.f;
+  return ncclSuccess;
+}
+
+static ncclResult_t post_p2p(bool is_send, void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm,
+                             cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  if ((int)dt < 0 || (int)dt >= kNumDTypes || peer < 0 || peer >= comm->comm->nranks()) return ncclInvalidArgument;
+  PendingP2p p;
+  p.comm = comm;
+  p.op.is_send = is_send;
+  p.op.buf = buf;
+  p.op.bytes = count * (size_t)dtype_size((int)dt);
+  p.op.peer = peer;
+  p.stream = stream;
+  g_pending.push_back(p);
+  if (g_group_depth == 0) return flush_group();
+  return ncclSuccess;
+}
+
+UB_EXPORT ncclResult_t ncclSend(const void* sendbuff, size_t count, ncclDataType_t datatype, int peer, ncclComm_t comm,
+                                cudaStream_t stream) {
+  return post_p2p(true, const_cast<void*>(sendbuff), count, datatype, peer, comm, stream);
+}
+
+UB_EXPORT ncclResult_t ncclRecv(void* recvbuff, size_t count, ncclDataType_t datatype, int peer, ncclComm_t comm,
+                                cudaStream_t stream) {
+  return post_p2p(false, recvbuff, count, datatype, peer, comm, stream);
+}
+
+// pnccl* aliases (profiling entry points of nccl.h)
+#define UB_ALIAS(ret, name, params, args) \
+  UB_EXPORT ret p##name params { return name args; }
+UB_ALIAS(ncclResult_t, ncclGetVersion, (int* v), (v))
+UB_ALIAS(ncclResult_t, ncclGetUniqueId, (ncclUniqueId * u), (u))
+UB_ALIAS(ncclResult_t, ncclCommInitRank, (ncclComm_t * c, int n, ncclUniqueId id, int r), (c, n, id, r))
+UB_ALIAS(ncclResult_t, ncclCommInitAll, (ncclComm_t * c, int n, const int* d), (c, n, d))
+UB_ALIAS(ncclResult_t, ncclCommDestroy, (ncclComm_t c), (c))
+UB_ALIAS(ncclResult_t, ncclCommCount, (const ncclComm_t c, int* n), (c, n))
+UB_ALIAS(ncclResult_t, ncclCommUserRank, (const ncclComm_t c, int* r), (c, r))
+UB_ALIAS(ncclResult_t, ncclGroupStart, (), ())
+UB_ALIAS(ncclResult_t, ncclGroupEnd, (), ())
+UB_ALIAS(ncclResult_t, ncclAllReduce,
+         (const void* s, void* r, size_t n, ncclDataType_t d, ncclRedOp_t o, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, o, c, st))
+UB_ALIAS(ncclResult_t, ncclAllGather, (const void* s, void* r, size_t n, ncclDataType_t d, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, c, st))
+UB_ALIAS(ncclResult_t, ncclReduceScatter,
+         (const void* s, void* r, size_t n, ncclDataType_t d, ncclRedOp_t o, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, o, c, st))
+UB_ALIAS(ncclResult_t, ncclBroadcast,
+         (const void* s, void* r, size_t n, ncclDataType_t d, int root, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, root, c, st))
+UB_ALIAS(ncclResult_t, ncclSend, (const void* s, size_t n, ncclDataType_t d, int p, ncclComm_t c, cudaStream_t st),
+         (s, n, d, p, c, st))
+UB_ALIAS(ncclResult_t, ncclRecv, (void* r, size_t n, ncclDataType_t d, int p, ncclComm_t c, cudaStream_t st),
+         (r, n, d, p, c, st))
+
+}  // extern "C"

@@ -51,6 +51,11 @@ cudaError_t preload_all_kernels() {
   for (int m = 0; m < 2; ++m) ok(launch_alltoall(m, c, a, 1, 512, 0));
   ok(launch_alltoallv(c, a, v, 1, 512, 0));
   ok(launch_barrier(c, 0, 0));
+  {
+    SendRecvArgs sr;
+    memset(&sr, 0, sizeof(sr));
+    ok(launch_sendrecv(c, sr, 0));
+  }
   for (int which = 0; which < 2; ++which)
     for (int op = 0; op < 4; ++op) {
       for (int dt : {(int)kF32, (int)kBF16, (int)kF16, (int)kF64, (int)kF8E4M3, (int)kF8E5M2})

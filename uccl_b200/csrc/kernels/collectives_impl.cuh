@@ -325,3 +325,95 @@ static __global__ void __launch_bounds__(512, 1) a2av_kernel(const __grid_consta
 }
 
 }  // namespace ub
+
+namespace ub {
+// ------------------------------------------------------------------ Send / Recv
+// ncclSend/ncclRecv for arbitrary (non-symmetric) user buffers: the sender stages chunks in its
+// own heap and publishes a sequence number in the receiver's heap; the receiver pulls the chunk
+// over NVLink and acks.  Grid = npeers * kSrBlocks CTAs; in each CTA warps 0-7 run the send
+// flow and warps 8-15 the receive flow of one (peer, sub-block) so both directions always make
+// progress (no deadlock for symmetric exchanges).  Sequence counters are persistent and
+// monotonic per (peer, sub-block): no reset, graph-replay safe.
+// (reference: lite's host-staged ncclSend/Recv, experimental/lite/nccl/nccl.cu:1145-1350,2033-2067)
+__device__ __forceinline__ void half_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_constant__ DevComm c,
+                                                                const __grid_constant__ SendRecvArgs a) {
+  const int me = c.rank;
+  const int pi = blockIdx.x / kSrBlocks, j = blockIdx.x % kSrBlocks;
+  const int peer = a.peers[pi];
+  const bool is_send = threadIdx.x < 256;
+  const int t = threadIdx.x & 255;
+  // flag words (u32) inside every heap: ready[src][j], ack[dst][j], sseq[dst][j], rseq[src][j]
+  auto flags = [&](int rank) { return reinterpret_cast<uint32_t*>(c.heap[rank] + a.sr_flag_off); };
+  const int W = kMaxRanks * kSrBlocks;
+  uint32_t* my_flags = flags(me);
+  if (peer == me) {
+    // self send/recv: plain local copy by the whole CTA slice
+    const uint64_t bytes = a.sbytes[me] < a.rbytes[me] ? a.sbytes[me] : a.rbytes[me];
+    uint64_t lo, hi;
+    split_range((bytes + 15) / 16, kSrBlocks, j, lo, hi);
+    copy_bytes16(a.rbuf[me], a.sbuf[me], lo, hi, bytes, bytes);
+    return;
+  }
+  if (is_send) {
+    const uint64_t bytes = a.sbytes[peer];
+    if (bytes == 0) return;
+    uint64_t lo, hi;
+    split_range((bytes + 15) / 16, kSrBlocks, j, lo, hi);
+    uint32_t seq = my_flags[2 * W + peer * kSrBlocks + j];
+    uint32_t* my_ack = my_flags + 1 * W + peer * kSrBlocks + j;
+    uint32_t* peer_ready = flags(peer) + 0 * W + me * kSrBlocks + j;
+    char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    const uint64_t cu = kSrChunkBytes / 16;
+    for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
+      const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;
+      ++seq;
+      if (t == 0) {
+        SpinGuard g(c.timeout_ns);
+        while ((int32_t)(ld_acquire_sys(my_ack) - (seq - kSrSlots)) < 0 && seq > (uint32_t)kSrSlots) {
+          if (g.expired()) comm_abort(c, 20, peer, (int)seq);
+        }
+      }
+      half_sync(1);
+      char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
+      for (uint64_t u = u0 + t; u < u1; u += 256) {
+        uint4 v = load16_partial(a.sbuf[peer], u * 16, bytes);
+        st_v4(slot + (u - u0) * 16, v);
+      }
+      half_sync(1);
+      if (t == 0) st_release_sys(peer_ready, seq);
+    }
+    if (t == 0) my_flags[2 * W + peer * kSrBlocks + j] = seq;
+  } else {
+    const uint64_t bytes = a.rbytes[peer];
+    if (bytes == 0) return;
+    uint64_t lo, hi;
+    split_range((bytes + 15) / 16, kSrBlocks, j, lo, hi);
+    uint32_t seq = my_flags[3 * W + peer * kSrBlocks + j];
+    uint32_t* my_ready = my_flags + 0 * W + peer * kSrBlocks + j;
+    uint32_t* peer_ack = flags(peer) + 1 * W + me * kSrBlocks + j;
+    const char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    const uint64_t cu = kSrChunkBytes / 16;
+    for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
+      const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;
+      ++seq;
+      if (t == 0) {
+        SpinGuard g(c.timeout_ns);
+        while ((int32_t)(ld_acquire_sys(my_ready) - seq) < 0) {
+          if (g.expired()) comm_abort(c, 21, peer, (int)seq);
+        }
+      }
+      half_sync(2);
+      const char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
+      for (uint64_t u = u0 + t; u < u1; u += 256) {
+        uint4 v = ld_v4(slot + (u - u0) * 16);
+        store16_partial(a.rbuf[peer], u * 16, bytes, v);
+      }
+      half_sync(2);
+      if (t == 0) st_release_sys(peer_ack, seq);
+    }
+    if (t == 0) my_flags[3 * W + peer * kSrBlocks + j] = seq;
+  }
+}
+}  // namespace ub

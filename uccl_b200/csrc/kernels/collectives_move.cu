@@ -36,6 +36,10 @@ cudaError_t launch_alltoallv(const DevComm& c, const CollArgs& a, const A2AvArgs
 }  // namespace ub
 
 namespace ub {
+cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st) {
+  UB_LAUNCH((sendrecv_kernel), (a.npeers > 0 ? a.npeers : 1) * kSrBlocks, 512, 0, st, c, a);
+  return cudaGetLastError();
+}
 __global__ void barrier_kernel(const __grid_constant__ DevComm c, int domain) {
   BlockSync s = sync_begin(c, domain, blockIdx.x);
   sync_barrier(c, s);

@@ -41,5 +41,6 @@ cudaError_t launch_red_f(int which, int dtype, int op, bool nvls, const DevComm&
                          int block, cudaStream_t st);
 cudaError_t launch_red_i(int which, int dtype, int op, const DevComm& c, const CollArgs& a, int grid, int block,
                          cudaStream_t st);
+cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st);
 cudaError_t launch_barrier(const DevComm& c, int domain, cudaStream_t st);
 }  // namespace ub

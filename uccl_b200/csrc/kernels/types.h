@@ -73,6 +73,11 @@ constexpr uint64_t kSigBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * kMax
 constexpr uint64_t kEpochBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * sizeof(uint32_t);
 constexpr uint64_t kMiscBytes = 4096;
 constexpr uint64_t kA2AvTabBytes = (uint64_t)kMaxSyncBlocks * kMaxRanks * 2 * sizeof(uint64_t);
+constexpr int kSrBlocks = 4;                         // CTAs per send/recv peer pair
+constexpr int kSrSlots = 2;                          // staging slots per (peer, block)
+constexpr uint64_t kSrChunkBytes = 512u << 10;       // bytes per staging slot
+constexpr uint64_t kSrStageBytes = (uint64_t)kMaxRanks * kSrBlocks * kSrSlots * kSrChunkBytes;
+constexpr uint64_t kSrFlagBytes = 4096;              // ready/ack/sseq/rseq words
 constexpr uint64_t kLLMaxData = 256u << 10;           // max payload of the one-shot LL path
 constexpr uint64_t kLLSlotBytes = 2 * kLLMaxData;     // 8 data bytes per 16-byte packet
 constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src ranks
@@ -81,7 +86,7 @@ constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src
 enum MiscWord : int { kLLEpoch = 0, kLLDone = 1, kMiscWords = 64 };
 
 struct HeapLayout {
-  uint64_t sig_off, epoch_off, misc_off, a2av_tab_off, ll_off, stage_in_off, stage_out_off, user_off;
+  uint64_t sig_off, epoch_off, misc_off, a2av_tab_off, sr_flag_off, ll_off, sr_stage_off, stage_in_off, stage_out_off, user_off;
   uint64_t stage_bytes;
   static HeapLayout make(uint64_t stage_bytes) {
     HeapLayout l;
@@ -89,15 +94,17 @@ struct HeapLayout {
     l.epoch_off = l.sig_off + kSigBytes;
     l.misc_off = l.epoch_off + kEpochBytes;
     l.a2av_tab_off = l.misc_off + kMiscBytes;
-    l.ll_off = (l.a2av_tab_off + kA2AvTabBytes + 4095) / 4096 * 4096;
+    l.sr_flag_off = l.a2av_tab_off + kA2AvTabBytes;
+    l.ll_off = (l.sr_flag_off + kSrFlagBytes + 4095) / 4096 * 4096;
     l.stage_bytes = (stage_bytes + 4095) / 4096 * 4096;
-    l.stage_in_off = l.ll_off + kLLBytes;
+    l.sr_stage_off = l.ll_off + kLLBytes;
+    l.stage_in_off = l.sr_stage_off + kSrStageBytes;
     l.stage_out_off = l.stage_in_off + l.stage_bytes;
     l.user_off = l.stage_out_off + l.stage_bytes;
     l.user_off = (l.user_off + (2u << 20) - 1) / (2u << 20) * (2u << 20);
     return l;
   }
-  uint64_t ctrl_bytes() const { return stage_in_off; }  // region that must start zeroed
+  uint64_t ctrl_bytes() const { return sr_stage_off; }  // region that must start zeroed
 };
 
 constexpr uint64_t kNoOff = ~0ull;
@@ -125,6 +132,17 @@ UB_HD inline void split_range(uint64_t total, int parts, int idx, uint64_t& lo, 
   hi = lo + per;
   if (hi > total) hi = total;
 }
+
+// Grouped send/recv launch arguments: at most one send and one recv per peer per launch.
+struct SendRecvArgs {
+  const char* sbuf[kMaxRanks];
+  char* rbuf[kMaxRanks];
+  uint64_t sbytes[kMaxRanks];  // 0 = no send to that peer
+  uint64_t rbytes[kMaxRanks];  // 0 = no recv from that peer
+  int peers[kMaxRanks];        // active peer list
+  int npeers;
+  uint64_t sr_flag_off, sr_stage_off;
+};
 
 // AllToAllv launch arguments.
 struct A2AvArgs {
