@@ -11,7 +11,7 @@ from uccl_b200 import Communicator
 
 @pytest.fixture(scope="module")
 def world4():
-    return Communicator.local_world(4, host=True, heap_bytes=64 << 20, stage_bytes=1 << 20, timeout_ms=20000)
+    return Communicator.local_world(4, host=True, heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=20000)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.int32, torch.int64, torch.float64])
@@ -93,7 +93,7 @@ def test_symmetric_heap_alloc(world4):
 
 def _mp_worker(rank, n, uid, q):
     torch.set_num_threads(1)
-    c = Communicator.init(uid, rank, n, host=True, heap_bytes=32 << 20, stage_bytes=1 << 20, timeout_ms=20000)
+    c = Communicator.init(uid, rank, n, host=True, heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=20000)
     x = torch.arange(5000, dtype=torch.float32) + rank
     c.all_reduce(x, "sum")
     exp = sum(torch.arange(5000, dtype=torch.float32) + r for r in range(n))

@@ -87,6 +87,7 @@ void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
   dev_.mc = f->mc();
   dev_.sig_off = layout_.sig_off;
   dev_.epoch_off = layout_.epoch_off;
+  dev_.xchg_off = layout_.xchg_off;
   int64_t tmo = cfg.timeout_ms >= 0 ? cfg.timeout_ms : ubParamTimeoutMs();
   dev_.timeout_ns = (uint64_t)tmo * 1000000ull;
   if (!f->is_host()) {

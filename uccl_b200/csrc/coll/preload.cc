@@ -75,6 +75,16 @@ cudaError_t preload_all_kernels() {
   EpCombineArgs ca;
   memset(&ca, 0, sizeof(ca));
   ok(launch_ep_combine(c, ca, 1, 0));
+  {
+    EpLLDispatchArgs ld;
+    memset(&ld, 0, sizeof(ld));
+    ld.H = 128;
+    ld.E = 8;
+    ok(launch_ep_ll_dispatch(c, ld, 1, 0));
+    EpLLCombineArgs lc;
+    memset(&lc, 0, sizeof(lc));
+    ok(launch_ep_ll_combine(c, lc, 1, 0));
+  }
   ok(preload_p2p_kernels());
   g_preload = false;
   done_mask |= 1ull << (dev & 63);

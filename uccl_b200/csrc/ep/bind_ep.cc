@@ -53,6 +53,21 @@ void bind_ep(py::module_& m) {
              return py::make_tuple(total, pe);
            },
            py::arg("E_local"), py::arg("timeout_s") = 0.0)
+      .def("ll_init", &EpBuffer::ll_init)
+      .def_static("ll_size_hint", &EpBuffer::ll_size_hint)
+      .def("ll_dispatch",
+           [](EpBuffer& b, uintptr_t x, uintptr_t ti, int T, int H, int K, int E, int M, bool use_fp8, bool round_scale,
+              uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, uintptr_t st) {
+             auto o = b.ll_dispatch(x, ti, T, H, K, E, M, use_fp8, round_scale, recv_count, layout_range, send_pos,
+                                    num_sms, (cudaStream_t)st);
+             return py::make_tuple(o.recv_x, o.recv_scales, o.recv_src_info, o.combine_x, o.buffer_idx);
+           })
+      .def("ll_combine_buffer", &EpBuffer::ll_combine_buffer)
+      .def("ll_combine",
+           [](EpBuffer& b, uintptr_t x, int idx, uintptr_t tw, uintptr_t sp, uintptr_t out, int T, int H, int K, int E,
+              int M, int num_sms, uintptr_t st) {
+             b.ll_combine(x, idx, tw, sp, out, T, H, K, E, M, num_sms, (cudaStream_t)st);
+           })
       .def("combine_input_ptr", &EpBuffer::combine_input_ptr)
       .def("combine", [](EpBuffer& b, uintptr_t x, int num_recv, uintptr_t tw, uintptr_t ss, uintptr_t b0,
                          uintptr_t b1, uintptr_t out, uintptr_t otw, int T, int H, int K, int num_sms, uintptr_t st) {

@@ -62,6 +62,11 @@ EpBuffer::EpBuffer(std::shared_ptr<Comm> comm, size_t num_nvl_bytes, int num_slo
 }
 
 EpBuffer::~EpBuffer() {
+  if (ll_send_cnt_) cudaFree(ll_send_cnt_);
+  try {
+    if (ll_base_) comm_->free(ll_base_);
+  } catch (...) {
+  }
   if (host_counts_) cudaFreeHost(host_counts_);
   if (dev_counts_) cudaFree(dev_counts_);
   try {
@@ -275,6 +280,131 @@ void EpBuffer::combine(uintptr_t x, int num_recv, uintptr_t topk_w, uintptr_t se
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
   cudaError_t e = launch_ep_combine(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep combine launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+}
+
+// ------------------------------------------------------------------ low latency
+namespace {
+size_t ll_cnt_tab_bytes(int E) { return align_up((size_t)kEpLLMaxBlocks * kMaxRanks * E * 4, 4096); }
+size_t ll_half_bytes(int M, int H, int R, int E) {
+  const size_t rows = (size_t)(E / R) * R * M;
+  size_t b = 0;
+  b += align_up(rows * (size_t)H * 2, 256);        // recv_x (bf16 worst case)
+  b += align_up(rows * (size_t)(H / 128) * 4, 256);  // scales
+  b += align_up(rows * 4, 256);                      // src info
+  b += align_up(rows * (size_t)H * 2, 256);        // combine input (bf16 expert outputs)
+  return b;
+}
+}  // namespace
+
+size_t EpBuffer::ll_size_hint(int M, int H, int R, int E) {
+  return ll_cnt_tab_bytes(E) + 2 * ll_half_bytes(M, H, R, E) + 4096;
+}
+
+void EpBuffer::ll_init(size_t ll_bytes) {
+  if (ll_base_) return;
+  DevGuard g(comm_->device());
+  ll_bytes_ = align_up(ll_bytes, 4096);
+  ll_base_ = (char*)comm_->alloc(ll_bytes_, 4096);
+  UB_CUDA(cudaMemset(ll_base_, 0, std::min<size_t>(ll_bytes_, 8u << 20)));
+  UB_CUDA(cudaMalloc((void**)&ll_send_cnt_, sizeof(int32_t) * 2 * kMaxRanks * kEpMaxLocalExperts));
+  UB_CUDA(cudaMemset(ll_send_cnt_, 0, sizeof(int32_t) * 2 * kMaxRanks * kEpMaxLocalExperts));
+  UB_CUDA(cudaDeviceSynchronize());
+}
+
+EpBuffer::LLLayout EpBuffer::ll_layout(int buffer_idx, int H, int E, int M) const {
+  const int R = nranks();
+  UB_CHECK(ll_base_ != nullptr, "low-latency buffer not initialised (construct Buffer with num_rdma_bytes > 0)");
+  UB_CHECK(ll_size_hint(M, H, R, E) <= ll_bytes_, "low-latency buffer too small: need %zu bytes, have %zu",
+           ll_size_hint(M, H, R, E), ll_bytes_);
+  const size_t rows = (size_t)(E / R) * R * M;
+  LLLayout l;
+  uint64_t off = comm_->heap_offset(ll_base_);
+  l.cnt_tab_off = off;
+  off += ll_cnt_tab_bytes(E) + (uint64_t)buffer_idx * ll_half_bytes(M, H, R, E);
+  l.recv_x_off = off;
+  off += align_up(rows * (size_t)H * 2, 256);
+  l.recv_scales_off = off;
+  off += align_up(rows * (size_t)(H / 128) * 4, 256);
+  l.recv_src_off = off;
+  off += align_up(rows * 4, 256);
+  l.comb_x_off = off;
+  return l;
+}
+
+EpBuffer::LLOut EpBuffer::ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, int H, int K, int E, int M, bool use_fp8,
+                                      bool round_scale, uintptr_t recv_count, uintptr_t layout_range,
+                                      uintptr_t send_pos, int num_sms, cudaStream_t st) {
+  const int R = nranks();
+  UB_CHECK(E > 0 && E % R == 0 && E <= kMaxRanks * kEpMaxLocalExperts, "ll_dispatch: bad num_experts %d", E);
+  UB_CHECK(H % 128 == 0 && H <= 8192, "ll_dispatch: hidden must be a multiple of 128 and <= 8192 (got %d)", H);
+  UB_CHECK(K > 0 && K <= 32, "ll_dispatch: bad num_topk %d", K);
+  UB_CHECK(T <= M, "ll_dispatch: %d tokens exceed num_max_dispatch_tokens_per_rank %d", T, M);
+  UB_CHECK((x & 15) == 0, "ll_dispatch: x must be 16-byte aligned");
+  DevGuard g(comm_->device());
+  const int idx = ll_next_;
+  ll_next_ ^= 1;
+  LLLayout l = ll_layout(idx, H, E, M);
+  EpLLDispatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = (const void*)x;
+  a.topk_idx = (const int64_t*)topk_idx;
+  a.T = T;
+  a.H = H;
+  a.K = K;
+  a.E = E;
+  a.M = M;
+  a.use_fp8 = use_fp8 ? 1 : 0;
+  a.round_scale = round_scale ? 1 : 0;
+  a.recv_x_off = l.recv_x_off;
+  a.recv_scales_off = l.recv_scales_off;
+  a.recv_src_off = l.recv_src_off;
+  a.cnt_tab_off = l.cnt_tab_off;
+  a.send_cnt = ll_send_cnt_;
+  a.parity = ll_parity_;
+  ll_parity_ ^= 1;
+  a.send_pos = (int64_t*)send_pos;
+  a.recv_count = (int32_t*)recv_count;
+  a.layout_range = (int64_t*)layout_range;
+  int grid = std::max(1, std::min(num_sms, kEpLLMaxBlocks));
+  cudaError_t e = launch_ep_ll_dispatch(comm_->dev(), a, grid, st);
+  UB_CHECK(e == cudaSuccess, "ep ll_dispatch launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+  char* heap = comm_->fabric().local();
+  LLOut o;
+  o.recv_x = (uintptr_t)(heap + l.recv_x_off);
+  o.recv_scales = (uintptr_t)(heap + l.recv_scales_off);
+  o.recv_src_info = (uintptr_t)(heap + l.recv_src_off);
+  o.combine_x = (uintptr_t)(heap + l.comb_x_off);
+  o.buffer_idx = idx;
+  return o;
+}
+
+uintptr_t EpBuffer::ll_combine_buffer(int buffer_idx, int H, int E, int M) const {
+  LLLayout l = ll_layout(buffer_idx, H, E, M);
+  return (uintptr_t)(comm_->fabric().local() + l.comb_x_off);
+}
+
+void EpBuffer::ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T,
+                          int H, int K, int E, int M, int num_sms, cudaStream_t st) {
+  const int R = nranks();
+  DevGuard g(comm_->device());
+  LLLayout l = ll_layout(buffer_idx, H, E, M);
+  char* arena = comm_->fabric().local() + l.comb_x_off;
+  const size_t bytes = (size_t)(E / R) * R * M * H * 2;
+  if (x != (uintptr_t)arena) UB_CUDA(cudaMemcpyAsync(arena, (void*)x, bytes, cudaMemcpyDeviceToDevice, st));
+  EpLLCombineArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_off = l.comb_x_off;
+  a.send_pos = (const int64_t*)send_pos;
+  a.topk_weights = (const float*)topk_w;
+  a.out = (void*)out;
+  a.T = T;
+  a.H = H;
+  a.K = K;
+  int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
+  cudaError_t e = launch_ep_ll_combine(comm_->dev(), a, grid, st);
+  UB_CHECK(e == cudaSuccess, "ep ll_combine launch failed: %s", cudaGetErrorString(e));
   ++launches_;
 }
 

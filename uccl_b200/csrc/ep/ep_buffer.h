@@ -46,6 +46,19 @@ class EpBuffer {
   int wait_counts(int E_local, std::vector<int>* per_expert, double timeout_s);
   uintptr_t dev_counts_ptr() const { return (uintptr_t)dev_counts_; }
 
+  // ---- low-latency mode (double-buffered region of `ll_bytes`, allocated on first use)
+  void ll_init(size_t ll_bytes);
+  struct LLOut {
+    uintptr_t recv_x, recv_scales, recv_src_info, combine_x;
+    int buffer_idx;
+  };
+  static size_t ll_size_hint(int M, int H, int R, int E);
+  LLOut ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, int H, int K, int E, int M, bool use_fp8, bool round_scale,
+                    uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, cudaStream_t st);
+  uintptr_t ll_combine_buffer(int buffer_idx, int H, int E, int M) const;
+  void ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T, int H, int K,
+                  int E, int M, int num_sms, cudaStream_t st);
+
   // zero-copy combine input: a [num_tokens, hidden] bf16 view of the combine arena
   uintptr_t combine_input_ptr(int num_tokens, int hidden, int topk);
   void combine(uintptr_t x, int num_recv, uintptr_t topk_w, uintptr_t send_slot, uintptr_t bias0, uintptr_t bias1,
@@ -66,10 +79,23 @@ class EpBuffer {
   int32_t* dev_counts_ = nullptr;
   uint64_t launches_ = 0;
   cudaStream_t last_stream_ = nullptr;
+  // low latency
+  struct LLLayout {
+    uint64_t cnt_tab_off, recv_x_off, recv_scales_off, recv_src_off, comb_x_off;
+  };
+  LLLayout ll_layout(int buffer_idx, int H, int E, int M) const;
+  char* ll_base_ = nullptr;
+  size_t ll_bytes_ = 0;
+  int ll_next_ = 0;
+  int32_t* ll_send_cnt_ = nullptr;
+  int ll_parity_ = 0;
 };
 
 cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st);
 cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ep_ll_combine(const DevComm& c, const EpLLCombineArgs& a, int grid, cudaStream_t st);
+constexpr int kEpLLMaxBlocks = 64;
 
 }  // namespace ub

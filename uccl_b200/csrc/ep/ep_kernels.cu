@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
             scale = __int_as_float((127 - ex) << 23);
           } else {
             scale = 448.0f / amax;
-            scale_inv = amax * (1.0f / 448.0f);
+            scale_inv = __fdiv_rn(amax, 448.0f);  // bit-identical to torch's amax / 448
           }
           uint4 o;
           o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);

@@ -1,0 +1,287 @@
+// Low-latency (decode) expert-parallel kernels, sm_100a.
+//
+// Reference behaviour (ep/src/internode_ll.cu:50-731, 735-1304): dispatch casts each token to
+// fp8, atomically claims a slot per (expert, source-rank) region at the destination, stores the
+// message there, then a RECV phase waits for per-(expert, rank) count flags and *re-packs* the
+// regions into the contiguous per-expert layout; combine pushes expert outputs back into a
+// [token][topk] staging area at the source and a RECV phase does the weighted reduction.
+//
+// B200-native design: ONE pass each way.
+//   dispatch: every rank all-gathers its per-expert histogram first (E ints to each peer + one
+//     block barrier), so each sender knows the exact packed offset of its tokens inside every
+//     remote expert's contiguous block.  A warp stages the (fp8-cast) token + scales in shared
+//     memory once and one elected lane issues cp.async.bulk (TMA) stores straight into the final
+//     packed position on each destination GPU -- no staging regions, no re-pack kernel phase.
+//   combine: the token's home rank pulls its K expert-output rows from the peers' symmetric
+//     buffers and does the top-k weighted sum in fp32 -- no [token][topk] staging, no recv phase.
+#include "../kernels/launch.h"
+#include "../kernels/prims.cuh"
+#include "ep_types.h"
+
+namespace ub {
+
+constexpr int kLLWarps = 8;  // 256 threads: one staged token per warp (<= 14.6 KB each at H = 7168 bf16)
+
+__device__ __forceinline__ void ll_bf16x8_to_float(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 p = __bfloat1622float2(h[i]);
+    f[2 * i] = p.x;
+    f[2 * i + 1] = p.y;
+  }
+}
+__device__ __forceinline__ uint32_t ll_pack4_e4m3(float a, float b, float c, float d) {
+  __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+__global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const __grid_constant__ DevComm c,
+                                                                          const __grid_constant__ EpLLDispatchArgs a) {
+  extern __shared__ __align__(128) unsigned char ll_smem[];
+  const int R = c.nranks, me = c.rank;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = a.E, E_local = E / R;
+  const int n_scales = a.H / 128;
+  const size_t row_bytes = a.use_fp8 ? (size_t)a.H : (size_t)a.H * 2;
+  const size_t scale_bytes = a.use_fp8 ? (size_t)n_scales * 4 : 0;
+  const size_t stage_stride = (row_bytes + scale_bytes + 127) / 128 * 128;
+  int* s_cnt = reinterpret_cast<int*>(ll_smem);         // [E] my histogram, then reused
+  int* s_begin = s_cnt + E;                             // [E] packed offset of my tokens at each expert
+  unsigned char* s_stage = ll_smem + (((size_t)2 * E * 4 + 127) / 128 * 128) + (size_t)warp * stage_stride;
+
+  BlockSync s = sync_begin(c, kDomEpLL, blockIdx.x);
+  // ---- phase A: histogram + all-gather of the [R][E] count matrix
+  for (int e = tid; e < E; e += blockDim.x) s_cnt[e] = 0;
+  if (blockIdx.x == 0)
+    for (int e = tid; e < E; e += blockDim.x) a.send_cnt[(1 - a.parity) * E + e] = 0;  // for the next call
+  __syncthreads();
+  for (int i = tid; i < a.T * a.K; i += blockDim.x) {
+    const long long e = a.topk_idx[i];
+    if (e >= 0 && e < E) atomicAdd(&s_cnt[(int)e], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < R * E; i += blockDim.x) {
+    const int dst = i / E, e = i % E;
+    int* p = reinterpret_cast<int*>(c.heap[dst] + a.cnt_tab_off) + ((size_t)blockIdx.x * kMaxRanks + me) * E + e;
+    *p = s_cnt[e];
+  }
+  sync_barrier(c, s);
+  const int* tab = reinterpret_cast<const int*>(c.heap[me] + a.cnt_tab_off) + (size_t)blockIdx.x * kMaxRanks * E;
+  for (int e = tid; e < E; e += blockDim.x) {
+    int b = 0;
+    for (int q = 0; q < me; ++q) b += tab[(size_t)q * E + e];
+    s_begin[e] = b;
+  }
+  if (blockIdx.x == 0) {
+    for (int el = tid; el < E_local; el += blockDim.x) {
+      int run = 0;
+      for (int q = 0; q < R; ++q) {
+        const int cnt = tab[(size_t)q * E + me * E_local + el];
+        a.layout_range[(size_t)el * R + q] = ((int64_t)run << 32) | (int64_t)cnt;
+        run += cnt;
+      }
+      a.recv_count[el] = run;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: one warp per token
+  const int warps_total = gridDim.x * kLLWarps;
+  for (int t = blockIdx.x * kLLWarps + warp; t < a.T; t += warps_total) {
+    const char* src = reinterpret_cast<const char*>(a.x) + (size_t)t * a.H * 2;
+    // stage the row (cast or copy) + scales in shared memory
+    if (a.use_fp8) {
+      const int units = a.H / 16;
+      float* sc = reinterpret_cast<float*>(s_stage + row_bytes);
+      for (int u0 = 0; u0 < units; u0 += 32) {
+        const int u = u0 + lane;
+        const bool valid = u < units;
+        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
+        if (valid) {
+          v0 = ld_nc_v4(src + (size_t)u * 32);
+          v1 = ld_nc_v4(src + (size_t)u * 32 + 16);
+        }
+        float f[16];
+        ll_bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
+        ll_bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+        amax = fmaxf(amax, 1e-4f);
+        float scale, scale_inv;
+        if (a.round_scale) {
+          const float raw = amax * (1.0f / 448.0f);
+          int ex = ((__float_as_int(raw) >> 23) & 0xff) - 127;
+          if ((__float_as_int(raw) & 0x7fffff) != 0) ex += 1;
+          scale_inv = __int_as_float((ex + 127) << 23);
+          scale = __int_as_float((127 - ex) << 23);
+        } else {
+          scale = 448.0f / amax;
+          scale_inv = __fdiv_rn(amax, 448.0f);  // bit-identical to torch's amax / 448
+        }
+        if (valid) {
+          uint4 o;
+          o.x = ll_pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+          o.y = ll_pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+          o.z = ll_pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
+          o.w = ll_pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
+          *reinterpret_cast<uint4*>(s_stage + (size_t)u * 16) = o;
+          if ((lane & 7) == 0) sc[u >> 3] = scale_inv;
+        }
+      }
+    } else {
+      const int chunks = (int)(row_bytes / 16);
+      for (int i = lane; i < chunks; i += 32) *reinterpret_cast<uint4*>(s_stage + (size_t)i * 16) = ld_nc_v4(src + (size_t)i * 16);
+    }
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
+    __syncwarp();
+    // claim slots + issue the stores, one top-k entry per lane for the bookkeeping
+    long long e = -1;
+    if (lane < a.K) e = a.topk_idx[(size_t)t * a.K + lane];
+    int slot = -1;
+    if (e >= 0 && e < E) slot = s_begin[(int)e] + atomicAdd(&a.send_cnt[a.parity * E + (int)e], 1);
+    if (lane < a.K) {
+      int64_t pos = -1;
+      if (slot >= 0) {
+        const int r = (int)e / E_local, el = (int)e % E_local;
+        pos = ((int64_t)r << 32) | (int64_t)((size_t)el * R * a.M + slot);
+      }
+      a.send_pos[(size_t)t * a.K + lane] = pos;
+    }
+    const bool bulk_ok = (row_bytes % 16 == 0) && (scale_bytes % 16 == 0);
+    for (int k = 0; k < a.K; ++k) {
+      const long long ek = __shfl_sync(0xffffffffu, e, k);
+      const int sk = __shfl_sync(0xffffffffu, slot, k);
+      if (ek < 0 || sk < 0) continue;
+      const int r = (int)ek / E_local, el = (int)ek % E_local;
+      const size_t row = (size_t)el * R * a.M + sk;
+      char* dx = c.heap[r] + a.recv_x_off + row * row_bytes;
+      char* ds = c.heap[r] + a.recv_scales_off + row * scale_bytes;
+      if (bulk_ok) {
+        if (lane == 0) {
+          tma_store_1d(dx, s_stage, (uint32_t)row_bytes);
+          if (scale_bytes) tma_store_1d(ds, s_stage + row_bytes, (uint32_t)scale_bytes);
+        }
+      } else {
+        for (size_t i = lane * 4; i < row_bytes + scale_bytes; i += 128) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(s_stage + i);
+          if (i < row_bytes) *reinterpret_cast<uint32_t*>(dx + i) = w;
+          else *reinterpret_cast<uint32_t*>(ds + (i - row_bytes)) = w;
+        }
+      }
+      if (lane == 0) reinterpret_cast<int*>(c.heap[r] + a.recv_src_off)[row] = t;
+    }
+    if (lane == 0) {
+      tma_store_commit();
+      tma_store_wait_read<0>();  // the staging row may be overwritten by the next token
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma_store_wait<0>();  // all bulk stores of this thread are globally visible before the barrier
+  sync_barrier(c, s);
+  sync_end(s);
+}
+
+__global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_constant__ DevComm c,
+                                                               const __grid_constant__ EpLLCombineArgs a) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  BlockSync s = sync_begin(c, kDomEpLL, blockIdx.x);
+  sync_barrier(c, s);
+  const size_t row_bytes = (size_t)a.H * 2;
+  const int chunks = (int)(row_bytes / 16);
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  for (int t = blockIdx.x * (blockDim.x >> 5) + warp; t < a.T; t += warps_total) {
+    long long pos = -1;
+    float w = 0.f;
+    if (lane < a.K) {
+      pos = a.send_pos[(size_t)t * a.K + lane];
+      w = a.topk_weights[(size_t)t * a.K + lane];
+    }
+    char* out = reinterpret_cast<char*>(a.out) + (size_t)t * row_bytes;
+    for (int i0 = 0; i0 < chunks; i0 += 32) {
+      const int i = i0 + lane;
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+      // issue all K loads first (independent), then accumulate in top-k order
+      uint4 v[9];
+      bool on[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        on[k] = false;
+        if (k < a.K) {
+          const long long pk = __shfl_sync(0xffffffffu, pos, k);
+          if (pk >= 0 && i < chunks) {
+            const int r = (int)(pk >> 32);
+            const size_t row = (size_t)(pk & 0xffffffffll);
+            v[k] = ld_nc_v4(c.heap[r] + a.x_off + row * row_bytes + (size_t)i * 16);
+            on[k] = true;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float wk = __shfl_sync(0xffffffffu, w, k < a.K ? k : 0);
+        if (on[k]) {
+          float f[8];
+          ll_bf16x8_to_float(v[k], f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += wk * f[q];
+        }
+      }
+      // top-k beyond 9 (DeepEP LL limit is 9): generic tail loop
+      for (int k = 9; k < a.K; ++k) {
+        const long long pk = __shfl_sync(0xffffffffu, pos, k);
+        const float wk = __shfl_sync(0xffffffffu, w, k);
+        if (pk >= 0 && i < chunks) {
+          const int r = (int)(pk >> 32);
+          const size_t row = (size_t)(pk & 0xffffffffll);
+          float f[8];
+          ll_bf16x8_to_float(ld_nc_v4(c.heap[r] + a.x_off + row * row_bytes + (size_t)i * 16), f);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[q] += wk * f[q];
+        }
+      }
+      if (i < chunks) {
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+        st_v4(out + (size_t)i * 16, o);
+      }
+    }
+  }
+  sync_barrier_relaxed(c, s);
+  sync_end(s);
+}
+
+// ------------------------------------------------------------------ launchers
+cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, int grid, cudaStream_t st) {
+  const size_t row_bytes = a.use_fp8 ? (size_t)a.H : (size_t)a.H * 2;
+  const size_t scale_bytes = a.use_fp8 ? (size_t)(a.H / 128) * 4 : 0;
+  const size_t stage_stride = (row_bytes + scale_bytes + 127) / 128 * 128;
+  const size_t smem = (((size_t)2 * a.E * 4 + 127) / 128 * 128) + (size_t)kLLWarps * stage_stride;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(ep_ll_dispatch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  UB_LAUNCH((ep_ll_dispatch_kernel), grid, kLLWarps * 32, smem, st, c, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ep_ll_combine(const DevComm& c, const EpLLCombineArgs& a, int grid, cudaStream_t st) {
+  UB_LAUNCH((ep_ll_combine_kernel), grid, 512, 0, st, c, a);
+  return cudaGetLastError();
+}
+
+}  // namespace ub

@@ -70,32 +70,28 @@ struct EpCombineArgs {
 };
 
 // ---- low-latency (decode) mode -------------------------------------------------------
-struct EpLLArgs {
-  // dispatch
-  const void* x;               // [T, H] bf16
-  const int64_t* topk_idx;     // [T, K]
-  int T, H, K, E;              // E = total experts
-  int max_tokens_per_rank;     // M
-  int use_fp8, round_scale, use_ue8m0;
-  uint64_t recv_x_off;         // symmetric [E_local][R*M][H (fp8|bf16)]
-  uint64_t recv_scales_off;    // symmetric [E_local][R*M][H/128] float
-  uint64_t recv_src_off;       // symmetric [E_local][R*M] int32 (source token index)
-  uint64_t recv_cnt_off;       // symmetric [E_local][R] int32 : -(n)-1 encoded counts per (expert, src rank)
-  uint64_t send_cnt_off;       // local scratch [E] int32 atomic slot counters
-  // packed outputs (local)
-  void* packed_x;              // [E_local][R*M][H]
-  float* packed_scales;        // [E_local][R*M][H/128]
-  int32_t* packed_src_info;    // [E_local][R*M]
-  int64_t* layout_range;       // [E_local][R]  (count << 32 | begin)
-  int32_t* packed_recv_count;  // [E_local]
-  // combine
-  const void* comb_x;          // [E_local][R*M][H] bf16 expert outputs (symmetric offset in comb_x_off)
-  uint64_t comb_x_off;
-  const float* topk_weights;   // [T, K]
-  void* combined;              // [T, H] bf16
-  uint64_t comb_recv_off;      // symmetric [T_max][K][H] bf16 staging at the source rank
-  uint64_t comb_flag_off;      // symmetric [E] int32 flags
-  int phase;                   // 1 = send, 2 = recv, 3 = both
+struct EpLLDispatchArgs {
+  const void* x;             // [T, H] bf16
+  const int64_t* topk_idx;   // [T, K]
+  int T, H, K, E, M;         // E total experts, M = max dispatch tokens per rank
+  int use_fp8, round_scale;
+  uint64_t recv_x_off;       // symmetric [E_local][R*M][row_bytes]
+  uint64_t recv_scales_off;  // symmetric [E_local][R*M][H/128] float
+  uint64_t recv_src_off;     // symmetric [E_local][R*M] int32 (source token index)
+  uint64_t cnt_tab_off;      // symmetric [blocks][R][E] int32
+  int32_t* send_cnt;         // local [2][E] slot counters (parity double-buffered)
+  int parity;
+  int64_t* send_pos;         // local [T, K]: (dst rank << 32) | row index at the destination, -1 if unused
+  int32_t* recv_count;       // local [E_local]
+  int64_t* layout_range;     // local [E_local, R]: (begin << 32) | count
+};
+
+struct EpLLCombineArgs {
+  uint64_t x_off;             // symmetric [E_local][R*M][H] bf16 expert outputs
+  const int64_t* send_pos;    // [T, K] from dispatch
+  const float* topk_weights;  // [T, K]
+  void* out;                  // [T, H] bf16
+  int T, H, K;
 };
 
 }  // namespace ub

@@ -98,14 +98,64 @@ __global__ void __launch_bounds__(512) ar_oneshot(const __grid_constant__ DevCom
 }
 
 // ------------------------------------------------------------ two-shot zero-copy
-// in/out are symmetric (same offset on every rank). bytes % 16 == 0.
+// in/out live in the symmetric heap; bytes % 16 == 0.  The ranks exchange their actual heap
+// offsets in the entry barrier, so buffers need not sit at identical offsets on every rank
+// (the NVLS variant needs identical offsets for the multicast address and silently takes the
+// P2P data path of the same kernel when they differ).
+template <typename T, int OP, typename TO>
+__device__ __forceinline__ void twoshot_p2p_body(const DevComm& c, const CollArgs& a, const uint64_t* s_off,
+                                                 uint64_t lo, uint64_t hi) {
+  constexpr int N = Vec16<T, OP>::N;
+  constexpr int U = 2;
+  const int n = c.nranks, rank = c.rank;
+  const char* src[kMaxRanks];
+  TO* dst[kMaxRanks];
+#pragma unroll
+  for (int q = 0; q < kMaxRanks; ++q) {
+    src[q] = q < n ? c.heap[q] + s_off[q] : nullptr;
+    int p = rank + q;
+    if (p >= n) p -= n;
+    dst[q] = q < n ? reinterpret_cast<TO*>(c.heap[p] + s_off[kMaxRanks + p]) : nullptr;
+  }
+  for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
+    uint4 r[U][kMaxRanks];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      uint64_t vv = v + (uint64_t)j * blockDim.x;
+      if (vv < hi) {
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+          if (q < n) r[j][q] = ld_v4(src[q] + vv * 16);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      uint64_t vv = v + (uint64_t)j * blockDim.x;
+      if (vv < hi) {
+        // accumulate in global rank order so the rounding is independent of who reduces
+        Vec16<T, OP> acc;
+        acc.init(r[j][0]);
+#pragma unroll
+        for (int q = 1; q < kMaxRanks; ++q)
+          if (q < n) acc.accum(r[j][q]);
+        acc.epilogue(a.ep);
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; ++k)
+          if (k < n) store_out<T, OP, TO, false>(dst[k], vv * N, acc);
+      }
+    }
+  }
+}
+
 template <typename T, int OP, typename TO, bool NVLS>
 __global__ void __launch_bounds__(512, 1) ar_twoshot(const __grid_constant__ DevComm c,
                                                      const __grid_constant__ CollArgs a) {
   constexpr int N = Vec16<T, OP>::N;
   const int n = c.nranks, rank = c.rank;
+  __shared__ uint64_t s_off[2 * kMaxRanks];
   BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
-  sync_barrier(c, s);  // every rank's input is complete (and nobody still reads my output)
+  // every rank's input is complete (and nobody still reads my output); learn the peers' offsets
+  sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
 
   const uint64_t nvec = a.bytes / 16;
   uint64_t blo, bhi, lo, hi;
@@ -114,63 +164,34 @@ __global__ void __launch_bounds__(512, 1) ar_twoshot(const __grid_constant__ Dev
   lo += blo;
   hi += blo;
 
-  if constexpr (NVLS) {
-    const char* in_mc = c.mc + a.in_off;
-    TO* out_mc = reinterpret_cast<TO*>(c.mc + a.out_off);
-    constexpr int U = 4;
-    for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
-      uint4 r[U];
+  bool use_mc = false;
+  if constexpr (NVLS) use_mc = all_equal(s_off, n) && all_equal(s_off + kMaxRanks, n);
+  if (use_mc) {
+    if constexpr (NVLS) {
+      const char* in_mc = c.mc + a.in_off;
+      TO* out_mc = reinterpret_cast<TO*>(c.mc + a.out_off);
+      constexpr int U = 4;
+      for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
+        uint4 r[U];
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        uint64_t vv = v + (uint64_t)j * blockDim.x;
-        if (vv < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + vv * 16);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        uint64_t vv = v + (uint64_t)j * blockDim.x;
-        if (vv < hi) {
-          Vec16<T, OP> acc;
-          acc.init(r[j]);
-          acc.epilogue(a.ep);
-          store_out<T, OP, TO, true>(out_mc, vv * N, acc);
+        for (int j = 0; j < U; ++j) {
+          uint64_t vv = v + (uint64_t)j * blockDim.x;
+          if (vv < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + vv * 16);
         }
-      }
-    }
-  } else {
-    constexpr int U = 2;
-    for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
-      uint4 r[U][kMaxRanks];
 #pragma unroll
-      for (int j = 0; j < U; ++j) {
-        uint64_t vv = v + (uint64_t)j * blockDim.x;
-        if (vv < hi) {
-#pragma unroll
-          for (int q = 0; q < kMaxRanks; ++q)
-            if (q < n) r[j][q] = ld_v4(c.heap[q] + a.in_off + vv * 16);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        uint64_t vv = v + (uint64_t)j * blockDim.x;
-        if (vv < hi) {
-          // accumulate in global rank order so the rounding is independent of who reduces
-          Vec16<T, OP> acc;
-          acc.init(r[j][0]);
-#pragma unroll
-          for (int q = 1; q < kMaxRanks; ++q)
-            if (q < n) acc.accum(r[j][q]);
-          acc.epilogue(a.ep);
-#pragma unroll
-          for (int k = 0; k < kMaxRanks; ++k) {
-            if (k < n) {
-              int p = rank + k;
-              if (p >= n) p -= n;
-              store_out<T, OP, TO, false>(reinterpret_cast<TO*>(c.heap[p] + a.out_off), vv * N, acc);
-            }
+        for (int j = 0; j < U; ++j) {
+          uint64_t vv = v + (uint64_t)j * blockDim.x;
+          if (vv < hi) {
+            Vec16<T, OP> acc;
+            acc.init(r[j]);
+            acc.epilogue(a.ep);
+            store_out<T, OP, TO, true>(out_mc, vv * N, acc);
           }
         }
       }
     }
+  } else {
+    twoshot_p2p_body<T, OP, TO>(c, a, s_off, lo, hi);
   }
   sync_barrier(c, s);  // every rank's output is complete
   sync_end(s);

@@ -39,54 +39,56 @@ template <int MODE>
 __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevComm c,
                                                     const __grid_constant__ CollArgs a) {
   const int n = c.nranks, rank = c.rank;
+  __shared__ uint64_t s_off[2 * kMaxRanks];
   BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
   const uint64_t units = (a.bytes + 15) / 16;
   const char* in = reinterpret_cast<const char*>(a.in);
+  // entry barrier: peers have entered (their `out` may be overwritten / their `in` is complete)
+  // and everybody learns everybody's heap offsets
+  sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
   if constexpr (MODE == 0 || MODE == 1) {
-    sync_barrier_relaxed(c, s);  // peers have entered: their `out` may be overwritten now
     uint64_t blo, bhi;
     split_range(units, gridDim.x, blockIdx.x, blo, bhi);
-    const uint64_t dst_off = a.out_off + (uint64_t)rank * a.bytes;
+    const bool use_mc = (MODE == 1) && all_equal(s_off + kMaxRanks, n);
     for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
       uint4 v = load16_partial(in, u * 16, a.bytes);
-      if constexpr (MODE == 1) {
-        if (u * 16 + 16 <= a.bytes) multimem_st_v4(c.mc + dst_off + u * 16, v);
-        else
-          for (int p = 0; p < n; ++p) store16_partial(c.heap[p] + dst_off, u * 16, a.bytes, v);
+      if (use_mc && u * 16 + 16 <= a.bytes) {
+        multimem_st_v4(c.mc + a.out_off + (uint64_t)rank * a.bytes + u * 16, v);
       } else {
         for (int k = 0; k < n; ++k) {
           int p = rank + k;
           if (p >= n) p -= n;
-          store16_partial(c.heap[p] + dst_off, u * 16, a.bytes, v);
+          store16_partial(c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes, u * 16, a.bytes, v);
         }
       }
     }
     sync_barrier(c, s);
   } else {
-    const bool staged = (a.in_off == kNoOff);
+    bool staged = false;
+    for (int q = 0; q < n; ++q) staged = staged || (s_off[q] == kNoOff);  // consensus: any plain input => stage
     char* out = reinterpret_cast<char*>(a.out);
     const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
-    for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+    for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
       split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
-      if (staged) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
-      sync_barrier(c, s);
-      const uint64_t src_off = staged ? a.stage_in_off : (a.in_off + base);
+      if (staged) {
+        copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
+        sync_barrier(c, s);
+      }
       for (int k = 0; k < n; ++k) {
         int p = rank + k;
         if (p >= n) p -= n;
-        if (p == rank && staged) {
+        if (p == rank) {
           copy_bytes16(out + (uint64_t)p * a.bytes + base, in + base, blo, bhi, cb, cb);
         } else {
+          const uint64_t src_off = staged ? a.stage_in_off : (s_off[p] + base);
           copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
         }
       }
-      if (staged) sync_barrier_relaxed(c, s);  // peers finished reading my stage before I refill it
-      if (a.bytes == 0) break;
+      sync_barrier_relaxed(c, s);  // peers finished reading my stage / input
     }
-    if (!staged) sync_barrier_relaxed(c, s);  // nobody still reads my input when I return
   }
   sync_end(s);
 }
@@ -97,15 +99,18 @@ __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevC
 template <typename T, int OP, bool NVLS>
 __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevComm c,
                                                     const __grid_constant__ CollArgs a) {
-  constexpr int N = Vec16<T, OP>::N;
   const int n = c.nranks, rank = c.rank;
+  __shared__ uint64_t s_off[2 * kMaxRanks];
   BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
-  const bool staged = (a.in_off == kNoOff);
+  sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
+  bool staged = false;
+  for (int q = 0; q < n; ++q) staged = staged || (s_off[q] == kNoOff);
+  const bool same = all_equal(s_off, n);
   const char* in = reinterpret_cast<const char*>(a.in);
   char* out = reinterpret_cast<char*>(a.out);
   // per-destination chunk so that n chunks fit the stage
   const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
-  for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+  for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
     const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
@@ -114,19 +119,24 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
       for (int d = 0; d < n; ++d)
         copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes, in + (uint64_t)d * a.bytes + base,
                      blo, bhi, cb, cb);
+      sync_barrier(c, s);
     }
-    sync_barrier(c, s);
-    const uint64_t src_off =
-        staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes) : (a.in_off + (uint64_t)rank * a.bytes + base);
+    const uint64_t rel = staged ? (uint64_t)rank * chunk_bytes : ((uint64_t)rank * a.bytes + base);
     for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
       Vec16<T, OP> acc;
+      bool done = false;
       if constexpr (NVLS) {
-        acc.init(MmLdRed<T, OP>::ld(c.mc + src_off + u * 16));
-      } else {
+        if (staged || same) {
+          const uint64_t o = staged ? a.stage_in_off : a.in_off;
+          acc.init(MmLdRed<T, OP>::ld(c.mc + o + rel + u * 16));
+          done = true;
+        }
+      }
+      if (!done) {
         uint4 r[kMaxRanks];
 #pragma unroll
         for (int q = 0; q < kMaxRanks; ++q)
-          if (q < n) r[q] = ld_v4(c.heap[q] + src_off + u * 16);
+          if (q < n) r[q] = ld_v4(c.heap[q] + (staged ? a.stage_in_off : s_off[q]) + rel + u * 16);
         acc.init(r[0]);
 #pragma unroll
         for (int q = 1; q < kMaxRanks; ++q)
@@ -136,9 +146,7 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
       store16_partial(out + base, u * 16, cb, acc.pack_same());
     }
     sync_barrier_relaxed(c, s);  // peers finished reading my input / stage
-    if (a.bytes == 0) break;
   }
-  (void)N;
   sync_end(s);
 }
 
@@ -154,17 +162,19 @@ __global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ D
   const char* in = reinterpret_cast<const char*>(a.in);
   char* out = reinterpret_cast<char*>(a.out);
   if constexpr (MODE == 1 || MODE == 2) {
-    sync_barrier_relaxed(c, s);
+    __shared__ uint64_t s_off[2 * kMaxRanks];
+    sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
     if (rank == root) {
+      const bool use_mc = (MODE == 1) && all_equal(s_off + kMaxRanks, n);
       const uint64_t units = (a.bytes + 15) / 16;
       uint64_t blo, bhi;
       split_range(units, gridDim.x, blockIdx.x, blo, bhi);
       for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
         uint4 v = load16_partial(in, u * 16, a.bytes);
-        if (MODE == 1 && u * 16 + 16 <= a.bytes) {
+        if (use_mc && u * 16 + 16 <= a.bytes) {
           multimem_st_v4(c.mc + a.out_off + u * 16, v);
         } else {
-          for (int p = 0; p < n; ++p) store16_partial(c.heap[p] + a.out_off, u * 16, a.bytes, v);
+          for (int p = 0; p < n; ++p) store16_partial(c.heap[p] + s_off[kMaxRanks + p], u * 16, a.bytes, v);
         }
       }
     }
@@ -194,29 +204,39 @@ template <typename T, int OP, bool NVLS>
 __global__ void __launch_bounds__(512, 1) reduce_kernel(const __grid_constant__ DevComm c,
                                                         const __grid_constant__ CollArgs a) {
   const int n = c.nranks, rank = c.rank, root = a.root;
+  __shared__ uint64_t s_off[2 * kMaxRanks];
   BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
-  const bool staged = (a.in_off == kNoOff);
+  sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
+  bool staged = false;
+  for (int q = 0; q < n; ++q) staged = staged || (s_off[q] == kNoOff);
+  const bool same = all_equal(s_off, n);
   const char* in = reinterpret_cast<const char*>(a.in);
   char* out = reinterpret_cast<char*>(a.out);
   const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
-  for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+  for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
     const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
     split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
-    if (staged) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
-    sync_barrier(c, s);
+    if (staged) {
+      copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
+      sync_barrier(c, s);
+    }
     if (rank == root) {
-      const uint64_t src_off = staged ? a.stage_in_off : (a.in_off + base);
       for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
         Vec16<T, OP> acc;
+        bool done = false;
         if constexpr (NVLS) {
-          acc.init(MmLdRed<T, OP>::ld(c.mc + src_off + u * 16));
-        } else {
+          if (staged || same) {
+            acc.init(MmLdRed<T, OP>::ld(c.mc + (staged ? a.stage_in_off : a.in_off + base) + u * 16));
+            done = true;
+          }
+        }
+        if (!done) {
           uint4 r[kMaxRanks];
 #pragma unroll
           for (int q = 0; q < kMaxRanks; ++q)
-            if (q < n) r[q] = ld_v4(c.heap[q] + src_off + u * 16);
+            if (q < n) r[q] = ld_v4(c.heap[q] + (staged ? a.stage_in_off : s_off[q] + base) + u * 16);
           acc.init(r[0]);
 #pragma unroll
           for (int q = 1; q < kMaxRanks; ++q)
@@ -227,7 +247,6 @@ __global__ void __launch_bounds__(512, 1) reduce_kernel(const __grid_constant__ 
       }
     }
     sync_barrier_relaxed(c, s);
-    if (a.bytes == 0) break;
   }
   sync_end(s);
 }
@@ -239,25 +258,27 @@ template <int MODE>
 __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ DevComm c,
                                                      const __grid_constant__ CollArgs a) {
   const int n = c.nranks, rank = c.rank;
+  __shared__ uint64_t s_off[2 * kMaxRanks];
   BlockSync s = sync_begin(c, kDomColl, blockIdx.x);
   const char* in = reinterpret_cast<const char*>(a.in);
   char* out = reinterpret_cast<char*>(a.out);
+  sync_exchange(c, s, kDomColl, a.in_off, a.out_off, s_off);
   if constexpr (MODE == 1) {
-    sync_barrier_relaxed(c, s);
     const uint64_t units = (a.bytes + 15) / 16;
     uint64_t blo, bhi;
     split_range(units, gridDim.x, blockIdx.x, blo, bhi);
     for (int k = 0; k < n; ++k) {
       int p = rank + k;
       if (p >= n) p -= n;
-      copy_bytes16(c.heap[p] + a.out_off + (uint64_t)rank * a.bytes, in + (uint64_t)p * a.bytes, blo, bhi, a.bytes,
-                   a.bytes);
+      copy_bytes16(c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes, in + (uint64_t)p * a.bytes, blo, bhi,
+                   a.bytes, a.bytes);
     }
     sync_barrier(c, s);
   } else {
-    const bool staged = (a.in_off == kNoOff);
+    bool staged = false;
+    for (int q = 0; q < n; ++q) staged = staged || (s_off[q] == kNoOff);
     const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
-    for (uint64_t base = 0; base < a.bytes || base == 0; base += chunk_bytes) {
+    for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
@@ -266,17 +287,16 @@ __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ Dev
         for (int d = 0; d < n; ++d)
           copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes,
                        in + (uint64_t)d * a.bytes + base, blo, bhi, cb, cb);
+        sync_barrier(c, s);
       }
-      sync_barrier(c, s);
       for (int k = 0; k < n; ++k) {
         int p = rank + k;
         if (p >= n) p -= n;
         const uint64_t src_off = staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes)
-                                        : (a.in_off + (uint64_t)rank * a.bytes + base);
+                                        : (s_off[p] + (uint64_t)rank * a.bytes + base);
         copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
       }
       sync_barrier_relaxed(c, s);
-      if (a.bytes == 0) break;
     }
   }
   sync_end(s);
@@ -294,7 +314,7 @@ static __global__ void __launch_bounds__(512, 1) a2av_kernel(const __grid_consta
   // per-block private copy of the table so that same-index blocks suffice for ordering
   uint64_t* my_tab = reinterpret_cast<uint64_t*>(c.heap[rank] + v.table_off) + (uint64_t)blockIdx.x * kMaxRanks * 2;
   if (threadIdx.x < n) {
-    my_tab[threadIdx.x * 2 + 0] = v.send_off[threadIdx.x];
+    my_tab[threadIdx.x * 2 + 0] = a.in_off + v.send_off[threadIdx.x];  // absolute heap offset of the segment
     my_tab[threadIdx.x * 2 + 1] = v.send_bytes[threadIdx.x];
   }
   sync_barrier(c, s);
@@ -310,7 +330,7 @@ static __global__ void __launch_bounds__(512, 1) a2av_kernel(const __grid_consta
     const uint64_t units = (sbytes + 15) / 16;
     uint64_t blo, bhi;
     split_range(units, gridDim.x, blockIdx.x, blo, bhi);
-    const char* src = c.heap[p] + a.in_off + soff;
+    const char* src = c.heap[p] + soff;
     char* dst = out + v.recv_off[p];
     // offsets may be only element-aligned: fall back to byte copies when not 16-byte aligned
     if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {

@@ -268,6 +268,39 @@ __device__ __forceinline__ void sync_barrier(const DevComm& c, BlockSync& s) {
   s.e += 1;
   __syncthreads();
 }
+// Barrier that also all-gathers two 64-bit words per rank (e.g. the heap offsets of this
+// rank's input / output buffers) between same-index blocks.  `sh` is shared memory for
+// 2 * kMaxRanks words: sh[r] = word0 of rank r, sh[kMaxRanks + r] = word1 of rank r.
+// Lets zero-copy kernels work even when ranks allocated their symmetric buffers at different
+// offsets (e.g. Python GC freed blocks in a different order on different ranks).
+__device__ __forceinline__ void sync_exchange(const DevComm& c, BlockSync& s, int domain, uint64_t w0, uint64_t w1,
+                                              uint64_t* sh) {
+  const int t = threadIdx.x;
+  const uint64_t idx = ((uint64_t)domain * kMaxSyncBlocks + blockIdx.x) * kMaxRanks;
+  if (t < c.nranks && t != c.rank) {
+    uint64_t* p = reinterpret_cast<uint64_t*>(c.heap[t] + c.xchg_off + (idx + c.rank) * 16);
+    p[0] = w0;
+    p[1] = w1;  // ordered before the signal by the release store of the same thread below
+  }
+  sync_barrier(c, s);
+  if (t < c.nranks) {
+    if (t == c.rank) {
+      sh[t] = w0;
+      sh[kMaxRanks + t] = w1;
+    } else {
+      const volatile uint64_t* p = reinterpret_cast<const volatile uint64_t*>(c.heap[c.rank] + c.xchg_off + (idx + t) * 16);
+      sh[t] = p[0];
+      sh[kMaxRanks + t] = p[1];
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ bool all_equal(const uint64_t* sh, int n) {
+  bool same = true;
+  for (int r = 1; r < n; ++r) same = same && (sh[r] == sh[0]);
+  return same;
+}
+
 // Relaxed variant: only a rendezvous, no data ordering (cheaper: no release fence).
 __device__ __forceinline__ void sync_barrier_relaxed(const DevComm& c, BlockSync& s) {
   __syncthreads();

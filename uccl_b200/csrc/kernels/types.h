@@ -23,6 +23,7 @@ struct DevComm {
   char* mc;               // multicast VA of the heap (nullptr when NVLS is unavailable)
   uint64_t sig_off;       // offset of sync-domain signal slots inside each heap
   uint64_t epoch_off;     // offset of local per-block epoch counters
+  uint64_t xchg_off;      // offset of the per-(domain, block, src) 16-byte exchange slots
   uint64_t timeout_ns;    // spin timeout (0 = infinite)
   uint32_t* err;          // host-mapped error word (set before trap)
 };
@@ -72,6 +73,7 @@ enum SyncDomain : int { kDomColl = 0, kDomEp = 1, kDomEpLL = 2, kDomP2P = 3, kDo
 constexpr uint64_t kSigBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * kMaxRanks * sizeof(uint32_t);
 constexpr uint64_t kEpochBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * sizeof(uint32_t);
 constexpr uint64_t kMiscBytes = 4096;
+constexpr uint64_t kXchgBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * kMaxRanks * 16;
 constexpr uint64_t kA2AvTabBytes = (uint64_t)kMaxSyncBlocks * kMaxRanks * 2 * sizeof(uint64_t);
 constexpr int kSrBlocks = 4;                         // CTAs per send/recv peer pair
 constexpr int kSrSlots = 2;                          // staging slots per (peer, block)
@@ -86,13 +88,14 @@ constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src
 enum MiscWord : int { kLLEpoch = 0, kLLDone = 1, kMiscWords = 64 };
 
 struct HeapLayout {
-  uint64_t sig_off, epoch_off, misc_off, a2av_tab_off, sr_flag_off, ll_off, sr_stage_off, stage_in_off, stage_out_off, user_off;
+  uint64_t sig_off, epoch_off, xchg_off, misc_off, a2av_tab_off, sr_flag_off, ll_off, sr_stage_off, stage_in_off, stage_out_off, user_off;
   uint64_t stage_bytes;
   static HeapLayout make(uint64_t stage_bytes) {
     HeapLayout l;
     l.sig_off = 0;
     l.epoch_off = l.sig_off + kSigBytes;
-    l.misc_off = l.epoch_off + kEpochBytes;
+    l.xchg_off = l.epoch_off + kEpochBytes;
+    l.misc_off = l.xchg_off + kXchgBytes;
     l.a2av_tab_off = l.misc_off + kMiscBytes;
     l.sr_flag_off = l.a2av_tab_off + kA2AvTabBytes;
     l.ll_off = (l.sr_flag_off + kSrFlagBytes + 4095) / 4096 * 4096;
