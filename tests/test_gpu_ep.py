@@ -201,13 +201,18 @@ def test_low_latency_dispatch_combine(n, use_fp8):
     E_local = E // n
     bufs = get_buffers(n)
     xs, idxs, ws = make_inputs(n, T, H, K, E, seed=100 + n)
+    # allocate the LL regions up front (device-synchronising calls must not race with kernels of
+    # other virtual ranks that are already spinning on this GPU)
+    from uccl_b200.ep.low_latency import LowLatencyRuntime, ll_size_hint
+
+    for b in bufs:
+        if b._ll is None:
+            with torch.cuda.device(b.device):
+                b._ll = LowLatencyRuntime(b, ll_size_hint(M, H, n, 16))
+    torch.cuda.synchronize()
 
     def fn(b):
         r, dev = b.rank, b.device
-        if b._ll is None:
-            from uccl_b200.ep.low_latency import LowLatencyRuntime
-
-            b._ll = LowLatencyRuntime(b, 0)
         x, idx, w = xs[r].to(dev), idxs[r].to(dev), ws[r].to(dev)
         recv_x, recv_count, handle, _, _ = b.low_latency_dispatch(x, idx, M, E, use_fp8=use_fp8)
         torch.cuda.current_stream().synchronize()

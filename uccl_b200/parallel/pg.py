@@ -1,0 +1,204 @@
+"""``torch.distributed`` integration: a process-group backend named ``"uccl_b200"`` whose
+collectives run on the native kernels, so ``dist.all_reduce`` / DDP / FSDP-style code uses this
+library by changing one string::
+
+    import uccl_b200.parallel.pg            # registers the backend
+    dist.init_process_group("uccl_b200", rank=r, world_size=n, store=store)
+
+Role in the reference: the NCCL drop-in path that ``examples/ddp_train.py`` exercises through
+``NCCL_NET_PLUGIN`` (examples/ddp_run.sh:19-25) and the ukernel torch extension's ProcessGroup
+(experimental/ukernel/py/ukernel_ccl/__init__.py:171-290).  The unique id travels through the
+c10d store; on a GPU-less box the communicator falls back to the host backend so the same code
+path is covered by CPU CI (world_size >= 2 over shm).
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .comm import Communicator
+
+BACKEND_NAME = "uccl_b200"
+
+_OP_NAMES = {
+    dist.ReduceOp.SUM: "sum",
+    dist.ReduceOp.PRODUCT: "prod",
+    dist.ReduceOp.MAX: "max",
+    dist.ReduceOp.MIN: "min",
+    dist.ReduceOp.AVG: "avg",
+}
+
+
+def _op_name(op) -> str:
+    try:
+        return _OP_NAMES[op]
+    except (KeyError, TypeError):
+        for k, v in _OP_NAMES.items():
+            if op == k:
+                return v
+        raise ValueError(f"uccl_b200: unsupported reduce op {op}")
+
+
+class _Work(dist._Work if hasattr(dist, "_Work") else dist.Work):
+    """Stream-ordered completion: the kernels were enqueued on the caller's current stream, so
+    `wait()` has nothing to block on (same contract as NCCL's work.wait() on the current stream)."""
+
+    def __init__(self, result):
+        super().__init__()
+        self._result = result
+        self._fut = torch.futures.Future()
+        self._fut.set_result(result)
+
+    def wait(self, timeout=None):
+        return True
+
+    def is_completed(self):
+        return True
+
+    def is_success(self):
+        return True
+
+    def get_future(self):
+        return self._fut
+
+    def result(self):
+        return self._result
+
+
+class ProcessGroupUCCL(dist.ProcessGroup):
+    def __init__(self, store, rank: int, world_size: int, timeout=None, heap_bytes: Optional[int] = None):
+        super().__init__(rank, world_size)
+        self._rank, self._world = rank, world_size
+        key = "uccl_b200/uid/%d" % int(os.environ.get("UCCL_B200_PG_SEQ", "0"))
+        if rank == 0:
+            store.set(key, Communicator.create_unique_id())
+        uid = bytes(store.get(key))
+        host = not torch.cuda.is_available()
+        heap = heap_bytes or int(os.environ.get("UCCL_B200_PG_HEAP_MB", "128" if host else "2048")) << 20
+        stage = (8 << 20) if host else (128 << 20)
+        self.comm = Communicator.init(uid, rank, world_size, heap_bytes=heap, stage_bytes=stage, host=host)
+
+    # ---- required plumbing
+    def getBackendName(self):
+        return BACKEND_NAME
+
+    def size(self):
+        return self._world
+
+    def rank(self):
+        return self._rank
+
+    def _prep(self, t: torch.Tensor) -> torch.Tensor:
+        if not t.is_contiguous():
+            raise ValueError("uccl_b200: tensors must be contiguous")
+        return t
+
+    # ---- collectives (signatures of c10d::ProcessGroup)
+    def allreduce(self, tensors: List[torch.Tensor], opts=None):
+        op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        for t in tensors:
+            self.comm.all_reduce(self._prep(t), op)
+        return _Work(tensors)
+
+    def allreduce_coalesced(self, tensors, opts=None):
+        return self.allreduce(tensors, opts)
+
+    def broadcast(self, tensors: List[torch.Tensor], opts=None):
+        root = opts.rootRank if opts is not None else 0
+        for t in tensors:
+            self.comm.broadcast(self._prep(t), root=root)
+        return _Work(tensors)
+
+    def allgather(self, output_tensors: List[List[torch.Tensor]], input_tensors: List[torch.Tensor], opts=None):
+        for outs, inp in zip(output_tensors, input_tensors):
+            flat = torch.empty((self._world,) + tuple(inp.shape), dtype=inp.dtype, device=inp.device)
+            self.comm.all_gather(flat, self._prep(inp))
+            for i, o in enumerate(outs):
+                o.copy_(flat[i])
+        return _Work(output_tensors)
+
+    def _allgather_base(self, output: torch.Tensor, input: torch.Tensor, opts=None):
+        self.comm.all_gather(self._prep(output), self._prep(input))
+        return _Work(output)
+
+    def allgather_into_tensor_coalesced(self, outputs, inputs, opts=None):
+        for o, i in zip(outputs, inputs):
+            self.comm.all_gather(self._prep(o), self._prep(i))
+        return _Work(outputs)
+
+    def reduce_scatter(self, output_tensors: List[torch.Tensor], input_tensors: List[List[torch.Tensor]], opts=None):
+        op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        for out, ins in zip(output_tensors, input_tensors):
+            flat = torch.stack([self._prep(t) for t in ins]).contiguous()
+            self.comm.reduce_scatter(self._prep(out), flat, op)
+        return _Work(output_tensors)
+
+    def _reduce_scatter_base(self, output: torch.Tensor, input: torch.Tensor, opts=None):
+        op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        self.comm.reduce_scatter(self._prep(output), self._prep(input), op)
+        return _Work(output)
+
+    def reduce_scatter_tensor_coalesced(self, outputs, inputs, opts=None):
+        op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        for o, i in zip(outputs, inputs):
+            self.comm.reduce_scatter(self._prep(o), self._prep(i), op)
+        return _Work(outputs)
+
+    def reduce(self, tensors: List[torch.Tensor], opts=None):
+        op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        root = opts.rootRank if opts is not None else 0
+        for t in tensors:
+            self.comm.reduce(self._prep(t), root=root, op=op)
+        return _Work(tensors)
+
+    def alltoall_base(self, output: torch.Tensor, input: torch.Tensor, output_split_sizes, input_split_sizes,
+                      opts=None):
+        if not output_split_sizes and not input_split_sizes:
+            self.comm.all_to_all(self._prep(output), self._prep(input))
+        else:
+            row = input[0].numel() if input.dim() > 1 else 1
+            sc = [int(s) * row for s in (input_split_sizes or [input.size(0) // self._world] * self._world)]
+            rc = [int(s) * row for s in (output_split_sizes or [output.size(0) // self._world] * self._world)]
+            self.comm.all_to_all_v(self._prep(output), self._prep(input), sc, rc)
+        return _Work(output)
+
+    def alltoall(self, output_tensors, input_tensors, opts=None):
+        inp = torch.stack([self._prep(t) for t in input_tensors]).contiguous()
+        out = torch.empty_like(inp)
+        self.comm.all_to_all(out, inp)
+        for i, o in enumerate(output_tensors):
+            o.copy_(out[i])
+        return _Work(output_tensors)
+
+    def barrier(self, opts=None):
+        self.comm.barrier()
+        if not self.comm.is_host:
+            torch.cuda.current_stream().synchronize()
+        return _Work(None)
+
+    def send(self, tensors, dst_rank, tag=0):
+        raise NotImplementedError("uccl_b200 process group: use the NCCL group (or uccl_b200.collective) for "
+                                  "pipeline send/recv -- the north-star keeps PP p2p on NCCL")
+
+    def recv(self, tensors, src_rank, tag=0):
+        raise NotImplementedError("uccl_b200 process group: use the NCCL group (or uccl_b200.collective) for "
+                                  "pipeline send/recv")
+
+
+def _create(store, rank, world_size, timeout=None):
+    return ProcessGroupUCCL(store, rank, world_size, timeout)
+
+
+def register() -> None:
+    if BACKEND_NAME.upper() in getattr(dist.Backend, "backend_list", []) or hasattr(dist.Backend, BACKEND_NAME.upper()):
+        return
+    try:
+        dist.Backend.register_backend(BACKEND_NAME, _create, devices=["cpu", "cuda"])
+    except TypeError:
+        dist.Backend.register_backend(BACKEND_NAME, _create)
+
+
+register()
