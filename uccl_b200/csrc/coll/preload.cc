@@ -76,6 +76,11 @@ cudaError_t preload_all_kernels() {
   memset(&ca, 0, sizeof(ca));
   ok(launch_ep_combine(c, ca, 1, 0));
   {
+    DevComm c4 = c;
+    c4.nranks = 4;
+    ok(launch_ep_combine(c4, ca, 1, 0));
+  }
+  {
     EpLLDispatchArgs ld;
     memset(&ld, 0, sizeof(ld));
     ld.H = 128;

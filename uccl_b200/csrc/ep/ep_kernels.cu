@@ -206,47 +206,58 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
 
       if constexpr (MODE == EP_X_FUSED_FP8) {
         const int units = a.H / 16;  // 16 output bytes (16 channels) per lane-iteration
-        for (int u0 = 0; u0 < units; u0 += 32) {
-          const int u = u0 + lane;
-          const bool valid = u < units;
-          uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-          if (valid) {
-            v0 = ld_nc_v4(src + (size_t)u * 32);
-            v1 = ld_nc_v4(src + (size_t)u * 32 + 16);
-          }
-          float f[16];
-          bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
-          bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
-          float amax = 0.f;
+        constexpr int PF = 4;        // iterations whose loads are in flight together (8 x 16 B per lane)
+        for (int ub = 0; ub < units; ub += 32 * PF) {
+          uint4 v0[PF], v1[PF];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
-          // 128 channels = 8 consecutive lanes
-          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-          amax = fmaxf(amax, 1e-4f);
-          float scale, scale_inv;
-          if (a.round_scale) {
-            // power-of-two inverse scale (UE8M0 compatible): 2^ceil(log2(amax / 448))
-            const float raw = amax * (1.0f / 448.0f);
-            int ex = ((__float_as_int(raw) >> 23) & 0xff) - 127;
-            if ((__float_as_int(raw) & 0x7fffff) != 0) ex += 1;
-            scale_inv = __int_as_float((ex + 127) << 23);
-            scale = __int_as_float((127 - ex) << 23);
-          } else {
-            scale = 448.0f / amax;
-            scale_inv = __fdiv_rn(amax, 448.0f);  // bit-identical to torch's amax / 448
+          for (int j = 0; j < PF; ++j) {
+            const int u = ub + j * 32 + lane;
+            v0[j] = make_uint4(0, 0, 0, 0);
+            v1[j] = v0[j];
+            if (u < units) {
+              v0[j] = ld_nc_v4(src + (size_t)u * 32);
+              v1[j] = ld_nc_v4(src + (size_t)u * 32 + 16);
+            }
           }
-          uint4 o;
-          o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
-          o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
-          o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
-          o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
-          if (valid) {
 #pragma unroll
-            for (int r = 0; r < kMaxRanks; ++r)
-              if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)u * 16, o);
-            if ((lane & 7) == 0) s_scales[warp][u >> 3] = scale_inv;
+          for (int j = 0; j < PF; ++j) {
+            const int u = ub + j * 32 + lane;
+            if (ub + j * 32 >= units) break;  // warp-uniform
+            const bool valid = u < units;
+            float f[16];
+            bf16x8_to_float(v0[j], *reinterpret_cast<float(*)[8]>(&f[0]));
+            bf16x8_to_float(v1[j], *reinterpret_cast<float(*)[8]>(&f[8]));
+            float amax = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
+            // 128 channels = 8 consecutive lanes
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+            amax = fmaxf(amax, 1e-4f);
+            float scale, scale_inv;
+            if (a.round_scale) {
+              // power-of-two inverse scale (UE8M0 compatible): 2^ceil(log2(amax / 448))
+              const float raw = amax * (1.0f / 448.0f);
+              int ex = ((__float_as_int(raw) >> 23) & 0xff) - 127;
+              if ((__float_as_int(raw) & 0x7fffff) != 0) ex += 1;
+              scale_inv = __int_as_float((ex + 127) << 23);
+              scale = __int_as_float((127 - ex) << 23);
+            } else {
+              scale = 448.0f / amax;
+              scale_inv = __fdiv_rn(amax, 448.0f);  // bit-identical to torch's amax / 448
+            }
+            uint4 o;
+            o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+            o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+            o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
+            o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
+            if (valid) {
+#pragma unroll
+              for (int r = 0; r < kMaxRanks; ++r)
+                if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)u * 16, o);
+              if ((lane & 7) == 0) s_scales[warp][u >> 3] = scale_inv;
+            }
           }
         }
         __syncwarp();
@@ -324,6 +335,8 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------- combine
+// FEW = true: every token has at most two source rows (EP degree <= 2): deeper chunk pipeline.
+template <bool FEW>
 __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constant__ DevComm c,
                                                             const __grid_constant__ EpCombineArgs a) {
   const int R = c.nranks;
@@ -346,48 +359,101 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
     char* out = reinterpret_cast<char*>(a.out) + (size_t)t * row_bytes;
     const char* b0 = a.bias0 ? reinterpret_cast<const char*>(a.bias0) + (size_t)t * row_bytes : nullptr;
     const char* b1 = a.bias1 ? reinterpret_cast<const char*>(a.bias1) + (size_t)t * row_bytes : nullptr;
-    for (int i0 = 0; i0 < chunks; i0 += 64) {
-      uint4 v[2][kMaxRanks];
+    auto add_bias = [&](float (&acc)[8], int i) {
+      if (b0) {
+        float f[8];
+        bf16x8_to_float(ld_nc_v4(b0 + (size_t)i * 16), f);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = i0 + j * 32 + lane;
-#pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r)
-          if (i < chunks && ((mask >> r) & 1u)) v[j][r] = ld_nc_v4(src[r] + (size_t)i * 16);
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
       }
+      if (b1) {
+        float f[8];
+        bf16x8_to_float(ld_nc_v4(b1 + (size_t)i * 16), f);
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int i = i0 + j * 32 + lane;
-        if (i < chunks) {
-          float acc[8];
+        for (int q = 0; q < 8; ++q) acc[q] += f[q];
+      }
+    };
+    auto store_acc = [&](const float (&acc)[8], int i) {
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-          if (b0) {
-            float f[8];
-            bf16x8_to_float(ld_nc_v4(b0 + (size_t)i * 16), f);
+      for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+      st_v4(out + (size_t)i * 16, o);
+    };
+    if constexpr (FEW) {
+      // few sources (small EP degree / sparse routing): trade width for depth -- 8 chunks of up
+      // to 2 rows in flight per lane instead of 2 chunks of up to 8 rows
+      const int r0 = mask ? __ffs(mask) - 1 : -1;
+      const unsigned m1 = mask & (mask - 1);
+      const int r1 = m1 ? __ffs(m1) - 1 : -1;
+      const int sl0 = __shfl_sync(0xffffffffu, my, r0 < 0 ? 0 : r0);
+      const int sl1 = __shfl_sync(0xffffffffu, my, r1 < 0 ? 0 : r1);
+      const char* p0 = r0 >= 0 ? c.heap[r0] + a.x_off + (size_t)sl0 * row_bytes : nullptr;
+      const char* p1 = r1 >= 0 ? c.heap[r1] + a.x_off + (size_t)sl1 * row_bytes : nullptr;
+      constexpr int D = 8;
+      for (int i0 = 0; i0 < chunks; i0 += 32 * D) {
+        uint4 v0[D], v1[D];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += f[q];
+        for (int j = 0; j < D; ++j) {
+          const int i = i0 + j * 32 + lane;
+          if (i < chunks) {
+            if (p0) v0[j] = ld_nc_v4(p0 + (size_t)i * 16);
+            if (p1) v1[j] = ld_nc_v4(p1 + (size_t)i * 16);
           }
-          if (b1) {
-            float f[8];
-            bf16x8_to_float(ld_nc_v4(b1 + (size_t)i * 16), f);
+        }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] += f[q];
-          }
+        for (int j = 0; j < D; ++j) {
+          const int i = i0 + j * 32 + lane;
+          if (i < chunks) {
+            float acc[8];
 #pragma unroll
-          for (int r = 0; r < kMaxRanks; ++r) {
-            if ((mask >> r) & 1u) {
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            add_bias(acc, i);
+            if (p0) {
               float f[8];
-              bf16x8_to_float(v[j][r], f);
+              bf16x8_to_float(v0[j], f);
 #pragma unroll
               for (int q = 0; q < 8; ++q) acc[q] += f[q];
             }
-          }
-          uint4 o;
-          __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+            if (p1) {
+              float f[8];
+              bf16x8_to_float(v1[j], f);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-          st_v4(out + (size_t)i * 16, o);
+              for (int q = 0; q < 8; ++q) acc[q] += f[q];
+            }
+            store_acc(acc, i);
+          }
+        }
+      }
+    } else {
+      for (int i0 = 0; i0 < chunks; i0 += 64) {
+        uint4 v[2][kMaxRanks];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = i0 + j * 32 + lane;
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r)
+            if (i < chunks && ((mask >> r) & 1u)) v[j][r] = ld_nc_v4(src[r] + (size_t)i * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = i0 + j * 32 + lane;
+          if (i < chunks) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            add_bias(acc, i);
+#pragma unroll
+            for (int r = 0; r < kMaxRanks; ++r) {
+              if ((mask >> r) & 1u) {
+                float f[8];
+                bf16x8_to_float(v[j][r], f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] += f[q];
+              }
+            }
+            store_acc(acc, i);
+          }
         }
       }
     }
@@ -422,7 +488,8 @@ cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int gr
 }
 
 cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
-  UB_LAUNCH((ep_combine_kernel), grid, 512, 0, st, c, a);
+  if (c.nranks <= 2) UB_LAUNCH((ep_combine_kernel<true>), grid, 512, 0, st, c, a);
+  else UB_LAUNCH((ep_combine_kernel<false>), grid, 512, 0, st, c, a);
   return cudaGetLastError();
 }
 
