@@ -77,7 +77,7 @@ def _defines():
         d.append("-DUB_HAVE_EP")
     if list(CSRC.glob("p2p/*.cc")):
         d.append("-DUB_HAVE_P2P")
-    if list(CSRC.glob("common/*.cc")):
+    if list(CSRC.glob("common/bind_util.cc")):
         d.append("-DUB_HAVE_UTIL")
     return d
 
