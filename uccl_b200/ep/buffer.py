@@ -316,6 +316,13 @@ class Buffer:
         ev = self._exit(compute, async_finish, (x, topk_weights, b0, b1, out, out_w, send_slot))
         return out, out_w, ev
 
+    # ------------------------------------------------------------------ internode (not provided)
+    def internode_dispatch(self, *a, **kw):
+        raise NotImplementedError("uccl_b200 targets one NVSwitch node: use dispatch() (every rank is NVLink-reachable)")
+
+    def internode_combine(self, *a, **kw):
+        raise NotImplementedError("uccl_b200 targets one NVSwitch node: use combine()")
+
     # ------------------------------------------------------------------ low latency
     def _need_ll(self):
         assert self._ll is not None, "construct Buffer with low_latency_mode=True / num_rdma_bytes > 0"
