@@ -12,9 +12,10 @@ namespace ub {
 
 UB_PARAM(TimeoutMs, "TIMEOUT_MS", 20000)
 UB_PARAM(MaxCtas, "MAX_CTAS", 64)
-UB_PARAM(ArLLMaxBytes, "AR_LL_MAX_BYTES", 128 << 10)
+UB_PARAM(ArLLMaxBytes, "AR_LL_MAX_BYTES", 0)  // 0: per-world-size default
+UB_PARAM(ArP2PMinBytes, "AR_P2P_MIN_BYTES", -1)  // symmetric buffers >= this use twoshot_p2p even with NVLS (-1: default)
 UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
-UB_PARAM(NvlsCtas, "NVLS_CTAS", 32)
+UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 
 const char* algo_name(int algo) {
   switch (algo) {
@@ -189,6 +190,13 @@ CollArgs Comm::base_args() const {
   return a;
 }
 
+int Comm::nvls_ctas() const {
+  // bytes in flight needed per rank ~ (algbw / nranks) x multimem latency  =>  CTAs ~ 1 / nranks
+  int64_t v = ubParamNvlsCtas();
+  if (v <= 0) v = 256 / std::max(1, nranks());
+  return (int)std::max<int64_t>(8, std::min<int64_t>(v, max_ctas_));
+}
+
 int Comm::ctas_for(uint64_t bytes, int cap, int per_cta_bytes) const {
   uint64_t c = (bytes + per_cta_bytes - 1) / per_cta_bytes;
   if (c < 1) c = 1;
@@ -223,10 +231,18 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
     }
   }
   if (algo == ALGO_AUTO) {
-    uint64_t ll_max = std::min<uint64_t>((uint64_t)ubParamArLLMaxBytes(), kLLMaxData);
+    // defaults measured on B200 (benchmarks/allreduce_perf.py, profiles/): the packet path wins
+    // until its N-fold traffic outweighs the two barriers of the two-shot kernels
+    uint64_t ll_max = (uint64_t)ubParamArLLMaxBytes();
+    if (ll_max == 0) ll_max = n <= 2 ? (1u << 20) : (n <= 4 ? (512u << 10) : (256u << 10));
+    ll_max = std::min<uint64_t>(ll_max, kLLMaxData);
+    // with 2 ranks the switch cannot reduce traffic (both paths move `size` per direction) and the
+    // plain P2P kernel sustains more bytes in flight per SM than multimem.ld_reduce
+    int64_t p2p_min = ubParamArP2PMinBytes();
+    if (p2p_min < 0) p2p_min = n <= 2 ? (8 << 20) : INT64_MAX;
     if (bytes <= ll_max || n == 1) algo = mc ? ALGO_ONESHOT_MC : ALGO_ONESHOT_LL;
-    else if (symmetric) algo = nvls_ok ? ALGO_TWOSHOT_NVLS : ALGO_TWOSHOT_P2P;
-    else algo = nvls_ok ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
+    else if (symmetric) algo = (nvls_ok && (int64_t)bytes < p2p_min) ? ALGO_TWOSHOT_NVLS : ALGO_TWOSHOT_P2P;
+    else algo = (nvls_ok && n > 2) ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
     if (n == 1 && bytes > kLLMaxData) algo = ALGO_STAGED_P2P;
   }
   // degrade gracefully when a tuned/forced choice is impossible here
@@ -240,9 +256,10 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
   if (c <= 0) {
     switch (algo) {
       case ALGO_ONESHOT_LL:
-      case ALGO_ONESHOT_MC: c = ctas_for(bytes, std::min(max_ctas_, 32), 8192); break;  // 512 thr x 16 B
-      case ALGO_TWOSHOT_NVLS:
-      case ALGO_STAGED_NVLS: c = ctas_for(bytes, std::min<int>(max_ctas_, (int)ubParamNvlsCtas()), 128 << 10); break;
+      case ALGO_ONESHOT_MC: c = ctas_for(bytes, std::min(max_ctas_, 64), 8192); break;  // 512 thr x 16 B
+      case ALGO_TWOSHOT_NVLS: c = ctas_for(bytes, nvls_ctas(), 64 << 10); break;
+      case ALGO_STAGED_NVLS:
+      case ALGO_STAGED_P2P: c = ctas_for(bytes, max_ctas_, 64 << 10); break;
       default: c = ctas_for(bytes, max_ctas_, 128 << 10); break;
     }
   }
@@ -310,9 +327,9 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       UB_CHECK(sym, "allreduce: algo %s needs buffers from the symmetric heap", algo_name(algo));
     if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC)
       UB_CHECK(bytes <= kLLMaxData, "allreduce: one-shot limited to %lu bytes", (unsigned long)kLLMaxData);
-    if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) ctas = ctas_for(bytes, std::min(max_ctas_, 32), 8192);
-    else if (algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
-      ctas = ctas_for(bytes, std::min<int>(max_ctas_, (int)ubParamNvlsCtas()), 128 << 10);
+    if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) ctas = ctas_for(bytes, std::min(max_ctas_, 64), 8192);
+    else if (algo == ALGO_TWOSHOT_NVLS) ctas = ctas_for(bytes, nvls_ctas(), 64 << 10);
+    else if (algo == ALGO_STAGED_NVLS || algo == ALGO_STAGED_P2P) ctas = ctas_for(bytes, max_ctas_, 64 << 10);
     else ctas = ctas_for(bytes, max_ctas_, 128 << 10);
   }
   if (opts.max_ctas > 0) ctas = std::min(ctas, opts.max_ctas);
@@ -429,7 +446,7 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
   if (in_sym) a.in_off = heap_offset(in);
   const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op);
-  int ctas = ctas_for(bytes, nvls ? std::min<int>(max_ctas_, (int)ubParamNvlsCtas()) : max_ctas_, 64 << 10);
+  int ctas = ctas_for(bytes, nvls ? nvls_ctas() : max_ctas_, 64 << 10);
   cudaError_t e;
   if (dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2)
     e = launch_red_f(0, dtype, op, nvls, dev_, a, ctas, 512, stream);

@@ -108,6 +108,7 @@ class Comm {
   void init(std::shared_ptr<Fabric> f, const CommConfig& cfg);
   CollArgs base_args() const;
   int ctas_for(uint64_t bytes, int cap, int per_cta_bytes) const;
+  int nvls_ctas() const;
   void check_buf(const void* p, const char* what) const;
   // host fake implementations (host_coll.cc)
   void host_barrier();

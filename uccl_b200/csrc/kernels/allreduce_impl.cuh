@@ -39,21 +39,34 @@ __global__ void __launch_bounds__(512) ar_oneshot(const __grid_constant__ DevCom
   const uint64_t gstride = (uint64_t)gridDim.x * blockDim.x;
   const int n = c.nranks, rank = c.rank;
 
-  // phase 1: publish my data as packets into every peer's slot[rank]
-  for (uint64_t u = gtid; u < nunits; u += gstride) {
-    uint4 d = load16_partial(a.in, u * 16, a.bytes);
-    uint4 p0 = make_uint4(d.x, flag, d.y, flag);
-    uint4 p1 = make_uint4(d.z, flag, d.w, flag);
-    const uint64_t off = parity_off + (uint64_t)rank * kLLSlotBytes + u * 32;
-    if constexpr (MC) {
-      multimem_st_v4(c.mc + off, p0);
-      multimem_st_v4(c.mc + off + 16, p1);
-    } else {
-      for (int k = 1; k < n; ++k) {
-        int p = rank + k;
-        if (p >= n) p -= n;
-        st_v4(c.heap[p] + off, p0);
-        st_v4(c.heap[p] + off + 16, p1);
+  // phase 1: publish my data as packets into every peer's slot[rank] (4 loads in flight per thread)
+  {
+    constexpr int B = 4;
+    for (uint64_t u0 = gtid; u0 < nunits; u0 += gstride * B) {
+      uint4 d[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * gstride;
+        if (u < nunits) d[j] = load16_partial(a.in, u * 16, a.bytes);
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * gstride;
+        if (u >= nunits) continue;
+        uint4 p0 = make_uint4(d[j].x, flag, d[j].y, flag);
+        uint4 p1 = make_uint4(d[j].z, flag, d[j].w, flag);
+        const uint64_t off = parity_off + (uint64_t)rank * kLLSlotBytes + u * 32;
+        if constexpr (MC) {
+          multimem_st_v4(c.mc + off, p0);
+          multimem_st_v4(c.mc + off + 16, p1);
+        } else {
+          for (int k = 1; k < n; ++k) {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            st_v4(c.heap[p] + off, p0);
+            st_v4(c.heap[p] + off + 16, p1);
+          }
+        }
       }
     }
   }
@@ -225,8 +238,7 @@ __global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevC
     uint64_t blo, bhi;
     split_range(cvec, gridDim.x, blockIdx.x, blo, bhi, G);
     // 1. copy-in my slice
-    for (uint64_t v = blo + threadIdx.x; v < bhi; v += blockDim.x)
-      st_v4(my_stage_in + v * 16, ld_v4(in + (base + v) * 16));
+    copy_units16(my_stage_in, in + base * 16, blo, bhi);
     sync_barrier(c, s);
     // 2. reduce my shard of the slice
     uint64_t lo, hi;
@@ -236,44 +248,66 @@ __global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevC
     if constexpr (NVLS) {
       const char* in_mc = c.mc + a.stage_in_off;
       TO* out_mc = reinterpret_cast<TO*>(c.mc + a.stage_out_off);
-      for (uint64_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-        Vec16<T, OP> acc;
-        acc.init(MmLdRed<T, OP>::ld(in_mc + v * 16));
-        acc.epilogue(a.ep);
-        store_out<T, OP, TO, true>(out_mc, v * N, acc);
+      constexpr int U = 4;
+      for (uint64_t v0 = lo + threadIdx.x; v0 < hi; v0 += (uint64_t)U * blockDim.x) {
+        uint4 r[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + v * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) {
+            Vec16<T, OP> acc;
+            acc.init(r[j]);
+            acc.epilogue(a.ep);
+            store_out<T, OP, TO, true>(out_mc, v * N, acc);
+          }
+        }
       }
     } else {
-      for (uint64_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
-        uint4 r[kMaxRanks];
+      constexpr int U = 2;
+      for (uint64_t v0 = lo + threadIdx.x; v0 < hi; v0 += (uint64_t)U * blockDim.x) {
+        uint4 r[U][kMaxRanks];
 #pragma unroll
-        for (int q = 0; q < kMaxRanks; ++q)
-          if (q < n) r[q] = ld_v4(c.heap[q] + a.stage_in_off + v * 16);
-        Vec16<T, OP> acc;
-        acc.init(r[0]);
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) {
 #pragma unroll
-        for (int q = 1; q < kMaxRanks; ++q)
-          if (q < n) acc.accum(r[q]);
-        acc.epilogue(a.ep);
-        store_out<T, OP, TO, false>(reinterpret_cast<TO*>(my_stage_out), v * N, acc);
-        store_out<T, OP, TO, false>(reinterpret_cast<TO*>(out) + base * N, v * N, acc);
+            for (int q = 0; q < kMaxRanks; ++q)
+              if (q < n) r[j][q] = ld_v4(c.heap[q] + a.stage_in_off + v * 16);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) {
+            Vec16<T, OP> acc;
+            acc.init(r[j][0]);
+#pragma unroll
+            for (int q = 1; q < kMaxRanks; ++q)
+              if (q < n) acc.accum(r[j][q]);
+            acc.epilogue(a.ep);
+            store_out<T, OP, TO, false>(reinterpret_cast<TO*>(my_stage_out), v * N, acc);
+            store_out<T, OP, TO, false>(reinterpret_cast<TO*>(out) + base * N, v * N, acc);
+          }
+        }
       }
     }
     sync_barrier(c, s);
     // 3. gather the slice into the user output
     if constexpr (NVLS) {
-      const uint64_t ob_lo = blo * kOutVecBytes, ob_hi = bhi * kOutVecBytes;
-      for (uint64_t o = ob_lo + (uint64_t)threadIdx.x * 16; o < ob_hi; o += (uint64_t)blockDim.x * 16)
-        st_v4(out + base * kOutVecBytes + o, ld_v4(my_stage_out + o));
+      copy_units16(out + base * kOutVecBytes, my_stage_out, blo * kOutVecBytes / 16, bhi * kOutVecBytes / 16);
     } else {
       for (int k = 1; k < n; ++k) {
         int p = rank + k;
         if (p >= n) p -= n;
         uint64_t plo, phi;
         split_range(bhi - blo, n, p, plo, phi, G);
-        const uint64_t ob_lo = (plo + blo) * kOutVecBytes, ob_hi = (phi + blo) * kOutVecBytes;
-        const char* src = c.heap[p] + a.stage_out_off;
-        for (uint64_t o = ob_lo + (uint64_t)threadIdx.x * 16; o < ob_hi; o += (uint64_t)blockDim.x * 16)
-          st_v4(out + base * kOutVecBytes + o, ld_v4(src + o));
+        copy_units16(out + base * kOutVecBytes, c.heap[p] + a.stage_out_off, (plo + blo) * kOutVecBytes / 16,
+                     (phi + blo) * kOutVecBytes / 16);
       }
     }
   }

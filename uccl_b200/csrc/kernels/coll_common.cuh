@@ -26,4 +26,18 @@ __device__ __forceinline__ void store16_partial(void* base, uint64_t off, uint64
     if (off + i < bytes) ((unsigned char*)p)[i] = s[i];
 }
 
+// Aligned 16-byte-unit copy of units [lo, hi) with 8 loads in flight per thread.
+__device__ __forceinline__ void copy_units16(char* dst, const char* src, uint64_t lo, uint64_t hi) {
+  constexpr int B = 8;
+  uint64_t u = lo + threadIdx.x;
+  for (; u + (uint64_t)(B - 1) * blockDim.x < hi; u += (uint64_t)B * blockDim.x) {
+    uint4 v[B];
+#pragma unroll
+    for (int j = 0; j < B; ++j) v[j] = ld_v4(src + (u + (uint64_t)j * blockDim.x) * 16);
+#pragma unroll
+    for (int j = 0; j < B; ++j) st_v4(dst + (u + (uint64_t)j * blockDim.x) * 16, v[j]);
+  }
+  for (; u < hi; u += blockDim.x) st_v4(dst + u * 16, ld_v4(src + u * 16));
+}
+
 }  // namespace ub

@@ -19,8 +19,22 @@ __device__ __forceinline__ void copy_bytes16(char* dst, const char* src, uint64_
                                              uint64_t total_bytes_src, uint64_t total_bytes_dst) {
   // copies 16-byte units [lo, hi) (unit index), partial-tail aware on both sides;
   // degrades to a byte loop when either side is not 16-byte aligned (odd segment sizes).
+  // Loads are issued in batches of 8 before the dependent stores: with one load per store the
+  // loop is bound by the (NVLink) load latency instead of the bandwidth.
   if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
-    for (uint64_t u = lo + threadIdx.x; u < hi; u += blockDim.x) {
+    constexpr int B = 8;
+    const uint64_t full_src = total_bytes_src / 16, full_dst = total_bytes_dst / 16;
+    const uint64_t full = full_src < full_dst ? full_src : full_dst;  // units that need no tail handling
+    const uint64_t fhi = hi < full ? hi : full;
+    uint64_t u = lo + threadIdx.x;
+    for (; u + (uint64_t)(B - 1) * blockDim.x < fhi; u += (uint64_t)B * blockDim.x) {
+      uint4 v[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) v[j] = ld_v4(src + (u + (uint64_t)j * blockDim.x) * 16);
+#pragma unroll
+      for (int j = 0; j < B; ++j) st_v4(dst + (u + (uint64_t)j * blockDim.x) * 16, v[j]);
+    }
+    for (; u < hi; u += blockDim.x) {
       uint4 v = load16_partial(src, u * 16, total_bytes_src);
       store16_partial(dst, u * 16, total_bytes_dst, v);
     }
@@ -50,15 +64,26 @@ __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevC
     uint64_t blo, bhi;
     split_range(units, gridDim.x, blockIdx.x, blo, bhi);
     const bool use_mc = (MODE == 1) && all_equal(s_off + kMaxRanks, n);
-    for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
-      uint4 v = load16_partial(in, u * 16, a.bytes);
-      if (use_mc && u * 16 + 16 <= a.bytes) {
-        multimem_st_v4(c.mc + a.out_off + (uint64_t)rank * a.bytes + u * 16, v);
-      } else {
-        for (int k = 0; k < n; ++k) {
-          int p = rank + k;
-          if (p >= n) p -= n;
-          store16_partial(c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes, u * 16, a.bytes, v);
+    constexpr int B = 4;
+    for (uint64_t u0 = blo + threadIdx.x; u0 < bhi; u0 += (uint64_t)B * blockDim.x) {
+      uint4 v[B];
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+        if (u < bhi) v[j] = load16_partial(in, u * 16, a.bytes);
+      }
+#pragma unroll
+      for (int j = 0; j < B; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+        if (u >= bhi) continue;
+        if (use_mc && u * 16 + 16 <= a.bytes) {
+          multimem_st_v4(c.mc + a.out_off + (uint64_t)rank * a.bytes + u * 16, v[j]);
+        } else {
+          for (int k = 0; k < n; ++k) {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            store16_partial(c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes, u * 16, a.bytes, v[j]);
+          }
         }
       }
     }
@@ -122,28 +147,38 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
       sync_barrier(c, s);
     }
     const uint64_t rel = staged ? (uint64_t)rank * chunk_bytes : ((uint64_t)rank * a.bytes + base);
-    for (uint64_t u = blo + threadIdx.x; u < bhi; u += blockDim.x) {
-      Vec16<T, OP> acc;
-      bool done = false;
-      if constexpr (NVLS) {
-        if (staged || same) {
-          const uint64_t o = staged ? a.stage_in_off : a.in_off;
-          acc.init(MmLdRed<T, OP>::ld(c.mc + o + rel + u * 16));
-          done = true;
+    constexpr int U = 2;
+    const bool use_mc = NVLS && (staged || same);
+    for (uint64_t u0 = blo + threadIdx.x; u0 < bhi; u0 += (uint64_t)U * blockDim.x) {
+      uint4 r[U][kMaxRanks];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+        if (u >= bhi) continue;
+        if constexpr (NVLS) {
+          if (use_mc) {
+            r[j][0] = MmLdRed<T, OP>::ld(c.mc + (staged ? a.stage_in_off : a.in_off) + rel + u * 16);
+            continue;
+          }
         }
-      }
-      if (!done) {
-        uint4 r[kMaxRanks];
 #pragma unroll
         for (int q = 0; q < kMaxRanks; ++q)
-          if (q < n) r[q] = ld_v4(c.heap[q] + (staged ? a.stage_in_off : s_off[q]) + rel + u * 16);
-        acc.init(r[0]);
-#pragma unroll
-        for (int q = 1; q < kMaxRanks; ++q)
-          if (q < n) acc.accum(r[q]);
+          if (q < n) r[j][q] = ld_v4(c.heap[q] + (staged ? a.stage_in_off : s_off[q]) + rel + u * 16);
       }
-      acc.epilogue(a.ep);
-      store16_partial(out + base, u * 16, cb, acc.pack_same());
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+        if (u >= bhi) continue;
+        Vec16<T, OP> acc;
+        acc.init(r[j][0]);
+        if (!use_mc) {
+#pragma unroll
+          for (int q = 1; q < kMaxRanks; ++q)
+            if (q < n) acc.accum(r[j][q]);
+        }
+        acc.epilogue(a.ep);
+        store16_partial(out + base, u * 16, cb, acc.pack_same());
+      }
     }
     sync_barrier_relaxed(c, s);  // peers finished reading my input / stage
   }

@@ -80,7 +80,7 @@ constexpr int kSrSlots = 2;                          // staging slots per (peer,
 constexpr uint64_t kSrChunkBytes = 512u << 10;       // bytes per staging slot
 constexpr uint64_t kSrStageBytes = (uint64_t)kMaxRanks * kSrBlocks * kSrSlots * kSrChunkBytes;
 constexpr uint64_t kSrFlagBytes = 4096;              // ready/ack/sseq/rseq words
-constexpr uint64_t kLLMaxData = 256u << 10;           // max payload of the one-shot LL path
+constexpr uint64_t kLLMaxData = 1u << 20;           // max payload of the one-shot LL path
 constexpr uint64_t kLLSlotBytes = 2 * kLLMaxData;     // 8 data bytes per 16-byte packet
 constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src ranks
 

@@ -357,7 +357,25 @@ bool Endpoint::advertise(uint64_t conn, const void* ptr, size_t size, XferDesc* 
 }
 
 void* Endpoint::map_remote(const XferDesc& d) {
-  if (d.pid == (int32_t)getpid()) return (void*)d.addr;  // same-process short-circuit (reference: direct_addr)
+  if (d.pid == (int32_t)getpid()) {
+    // same-process short-circuit (reference: direct_addr); a pointer of another device needs
+    // peer access from ours (cudaMalloc memory is not peer-mapped by default)
+    if (d.kind != 1 && d.dev != gpu_) {
+      std::lock_guard<std::mutex> g(mu_);
+      if (!(peer_enabled_mask_ & (1u << (d.dev & 31)))) {
+        int prev = -1;
+        cudaGetDevice(&prev);
+        cudaSetDevice(gpu_);
+        cudaError_t e = cudaDeviceEnablePeerAccess(d.dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+          UB_WARN("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", gpu_, d.dev, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        if (prev >= 0 && prev != gpu_) cudaSetDevice(prev);
+        peer_enabled_mask_ |= 1u << (d.dev & 31);
+      }
+    }
+    return (void*)d.addr;
+  }
   if (d.kind != 0) {
     UB_WARN("p2p: descriptor kind %u from another process cannot be mapped", d.kind);
     return nullptr;

@@ -114,6 +114,7 @@ class Endpoint {
   size_t next_stream_ = 0;
   std::vector<cudaEvent_t> event_pool_;
   P2PStats stats_;
+  uint32_t peer_enabled_mask_ = 0;
 };
 
 }  // namespace ub
