@@ -41,7 +41,8 @@ def parse_args():
     p.add_argument("--hidden", type=int, default=7168)
     p.add_argument("--topk", type=int, default=8)
     p.add_argument("--experts", type=int, default=256)
-    p.add_argument("--num-sms", type=int, default=int(os.environ.get("UCCL_B200_EP_SMS", "64")))
+    p.add_argument("--num-sms", type=int, default=int(os.environ.get("UCCL_B200_EP_SMS", "0")),
+                   help="CTAs per EP kernel (0: 148 at 1 GPU, 96 otherwise)")
     p.add_argument("--no-allreduce-sweep", action="store_true")
     p.add_argument("--out", default=None, help="also write the JSON line to this file")
     return p.parse_args()
@@ -218,7 +219,7 @@ def main():
         comm = Communicator.local_world(1, devices=[dev.index], heap_bytes=heap, stage_bytes=64 << 20)[0]
     buf = Buffer(comm=comm, num_nvl_bytes=nvl_bytes)
     cfg = Buffer.get_dispatch_config(n)
-    cfg.num_sms = args.num_sms
+    cfg.num_sms = args.num_sms if args.num_sms > 0 else (148 if n == 1 else 96)
 
     def barrier():
         torch.cuda.synchronize()

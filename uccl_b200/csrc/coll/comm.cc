@@ -404,7 +404,7 @@ void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype
   int mode;
   if (out_sym && bytes % 16 == 0) {
     a.out_off = heap_offset(out);
-    mode = has_multicast() ? 1 : 0;
+    mode = (has_multicast() && n > 2) ? 1 : 0;  // with 2 ranks multicast saves nothing and issues slower
   } else {
     mode = 2;
     if (in_sym) a.in_off = heap_offset(in);
@@ -445,7 +445,7 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   a.count = recv_count;
   const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
   if (in_sym) a.in_off = heap_offset(in);
-  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op);
+  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
   int ctas = ctas_for(bytes, nvls ? nvls_ctas() : max_ctas_, 64 << 10);
   cudaError_t e;
   if (dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2)
@@ -483,7 +483,7 @@ void Comm::broadcast(const void* in, void* out, size_t count, int dtype, int roo
   int mode = 0;
   if (in_heap(out, bytes)) {
     a.out_off = heap_offset(out);
-    mode = has_multicast() ? 1 : 2;
+    mode = (has_multicast() && nranks() > 2) ? 1 : 2;
   }
   int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
   cudaError_t e = launch_broadcast(mode, dev_, a, ctas, 512, stream);
@@ -522,7 +522,7 @@ void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, in
   a.count = count;
   a.root = root;
   if (in_heap(in, bytes)) a.in_off = heap_offset(in);
-  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op);
+  const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
   int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
   cudaError_t e;
   if (is_float_dtype(dtype)) e = launch_red_f(1, dtype, op, nvls, dev_, a, ctas, 512, stream);

@@ -194,66 +194,63 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
   sync_barrier(c, s);
   const size_t row_bytes = (size_t)a.H * 2;
   const int chunks = (int)(row_bytes / 16);
-  const int warps_total = gridDim.x * (blockDim.x >> 5);
-  for (int t = blockIdx.x * (blockDim.x >> 5) + warp; t < a.T; t += warps_total) {
+  // One CTA per token, its warps split the row: the K source rows of a token live in K different
+  // expert blocks (different 2 MiB pages, possibly on K different GPUs); keeping a CTA on ONE
+  // token keeps the SM's TLB working set at K pages and gives 16 warps x K loads in flight per token.
+  const int nwarps = blockDim.x >> 5;
+  for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
     long long pos = -1;
     float w = 0.f;
     if (lane < a.K) {
       pos = a.send_pos[(size_t)t * a.K + lane];
       w = a.topk_weights[(size_t)t * a.K + lane];
     }
+    // per-top-k row pointers / weights in registers (K <= 9 fast path, generic tail below)
+    const char* rowp[9];
+    float wk[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const long long pk = __shfl_sync(0xffffffffu, pos, k);
+      wk[k] = __shfl_sync(0xffffffffu, w, k);
+      rowp[k] = nullptr;
+      if (k < a.K && pk >= 0)
+        rowp[k] = c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes;
+    }
     char* out = reinterpret_cast<char*>(a.out) + (size_t)t * row_bytes;
-    for (int i0 = 0; i0 < chunks; i0 += 32) {
+    for (int i0 = warp * 32; i0 < chunks; i0 += nwarps * 32) {  // warp-uniform trip count
       const int i = i0 + lane;
+      const bool valid = i < chunks;
+      uint4 v[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (rowp[k] && valid) v[k] = ld_nc_v4(rowp[k] + (size_t)i * 16);
       float acc[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-      // issue all K loads first (independent), then accumulate in top-k order
-      uint4 v[9];
-      bool on[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        on[k] = false;
-        if (k < a.K) {
-          const long long pk = __shfl_sync(0xffffffffu, pos, k);
-          if (pk >= 0 && i < chunks) {
-            const int r = (int)(pk >> 32);
-            const size_t row = (size_t)(pk & 0xffffffffll);
-            v[k] = ld_nc_v4(c.heap[r] + a.x_off + row * row_bytes + (size_t)i * 16);
-            on[k] = true;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float wk = __shfl_sync(0xffffffffu, w, k < a.K ? k : 0);
-        if (on[k]) {
+        if (rowp[k] && valid) {
           float f[8];
           ll_bf16x8_to_float(v[k], f);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += wk * f[q];
+          for (int q = 0; q < 8; ++q) acc[q] += wk[k] * f[q];
         }
       }
-      // top-k beyond 9 (DeepEP LL limit is 9): generic tail loop
-      for (int k = 9; k < a.K; ++k) {
+      for (int k = 9; k < a.K; ++k) {  // DeepEP's LL limit is 9; keep larger top-k correct
         const long long pk = __shfl_sync(0xffffffffu, pos, k);
-        const float wk = __shfl_sync(0xffffffffu, w, k);
-        if (pk >= 0 && i < chunks) {
-          const int r = (int)(pk >> 32);
-          const size_t row = (size_t)(pk & 0xffffffffll);
+        const float wkk = __shfl_sync(0xffffffffu, w, k);
+        if (pk >= 0 && valid) {
           float f[8];
-          ll_bf16x8_to_float(ld_nc_v4(c.heap[r] + a.x_off + row * row_bytes + (size_t)i * 16), f);
+          ll_bf16x8_to_float(ld_nc_v4(c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes + (size_t)i * 16), f);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += wk * f[q];
+          for (int q = 0; q < 8; ++q) acc[q] += wkk * f[q];
         }
       }
-      if (i < chunks) {
-        uint4 o;
-        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+      uint4 o;
+      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-        st_v4(out + (size_t)i * 16, o);
-      }
+      for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+      if (valid) st_v4(out + (size_t)i * 16, o);
     }
   }
   sync_barrier_relaxed(c, s);

@@ -44,10 +44,11 @@ class LowLatencyRuntime:
         # signalling is epoch based: nothing to zero (reference needs clean_low_latency_buffer, buffer.py:1797)
         self._ensure(M, H, E)
 
-    def _sms(self):
+    def _sms(self, combine: bool = False):
         from .buffer import Config
 
-        return self.buf._sms(Config(min(self.buf.num_sms * 2, 64)))
+        # dispatch: one warp per token (8 warps / CTA); combine: one CTA per token
+        return self.buf._sms(Config(128 if combine else min(self.buf.num_sms * 2, 64)))
 
     def dispatch(self, x: torch.Tensor, topk_idx: torch.Tensor, num_max_dispatch_tokens_per_rank: int,
                  num_experts: int, cumulative_local_expert_recv_stats: Optional[torch.Tensor] = None,
@@ -108,7 +109,7 @@ class LowLatencyRuntime:
             if out is None:
                 out = torch.empty((T, H), dtype=torch.bfloat16, device=b.device)
             self.rt.ll_combine(x.data_ptr(), idx, topk_weights.data_ptr(), send_pos.data_ptr(), out.data_ptr(), T, H,
-                               K, E, M, self._sms(), b.comm_stream.cuda_stream)
+                               K, E, M, self._sms(combine=True), b.comm_stream.cuda_stream)
         ev = b._exit(compute, async_finish, (x, topk_weights, send_pos, out))
         hook = (lambda: None) if return_recv_hook else None
         return out, ev, hook
