@@ -68,17 +68,20 @@ cudaError_t preload_all_kernels() {
   ok(launch_ep_layout(la, 0));
   EpDispatchArgs da;
   memset(&da, 0, sizeof(da));
-  for (int m = 0; m < 3; ++m) {
-    da.mode = m;
-    ok(launch_ep_dispatch(c, da, 1, 0));
-  }
   EpCombineArgs ca;
   memset(&ca, 0, sizeof(ca));
-  ok(launch_ep_combine(c, ca, 1, 0));
-  {
-    DevComm c4 = c;
-    c4.nranks = 4;
-    ok(launch_ep_combine(c4, ca, 1, 0));
+  int dummy_bias = 0;
+  for (int nr : {1, 2, 4, 8}) {
+    DevComm cn = c;
+    cn.nranks = nr;
+    for (int m = 0; m < 3; ++m) {
+      da.mode = m;
+      ok(launch_ep_dispatch(cn, da, 1, 0));
+    }
+    ca.bias0 = nullptr;
+    ok(launch_ep_combine(cn, ca, 1, 0));
+    ca.bias0 = &dummy_bias;
+    ok(launch_ep_combine(cn, ca, 1, 0));
   }
   {
     EpLLDispatchArgs ld;

@@ -102,10 +102,12 @@ __device__ __forceinline__ uint32_t pack4_e4m3(float a, float b, float c, float 
   return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
-template <int MODE>
+// NR = number of ranks (1, 2, 4, 8): per-destination loops are unrolled to NR, so small EP degrees
+// do not pay for predicated-off stores / address arithmetic of absent ranks.
+template <int MODE, int NR>
 __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_constant__ DevComm c,
                                                              const __grid_constant__ EpDispatchArgs a) {
-  const int R = c.nranks, me = c.rank;
+  const int R = c.nranks, me = c.rank;  // R <= NR
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int E_local = a.E / R;
   __shared__ int s_M[kMaxRanks][kMaxRanks];
@@ -195,10 +197,10 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
       }
       const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
       if (mask == 0) continue;
-      char* dst_x[kMaxRanks];
-      int slots[kMaxRanks];
+      char* dst_x[NR];
+      int slots[NR];
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r) {
+      for (int r = 0; r < NR; ++r) {
         slots[r] = __shfl_sync(0xffffffffu, my, r);
         dst_x[r] = ((mask >> r) & 1u) ? c.heap[r] + a.arena.x_off + (size_t)slots[r] * out_row_bytes : nullptr;
       }
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
             o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
             if (valid) {
 #pragma unroll
-              for (int r = 0; r < kMaxRanks; ++r)
+              for (int r = 0; r < NR; ++r)
                 if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)u * 16, o);
               if ((lane & 7) == 0) s_scales[warp][u >> 3] = scale_inv;
             }
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
         }
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kMaxRanks; ++r) {
+        for (int r = 0; r < NR; ++r) {
           if ((mask >> r) & 1u) {
             float* ds = reinterpret_cast<float*>(c.heap[r] + a.arena.scales_off) + (size_t)slots[r] * n_scales;
             for (int j = lane; j < n_scales; j += 32) ds[j] = s_scales[warp][j];
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
             const int i = i0 + j * 32 + lane;
             if (i < chunks) {
 #pragma unroll
-              for (int r = 0; r < kMaxRanks; ++r)
+              for (int r = 0; r < NR; ++r)
                 if ((mask >> r) & 1u) st_v4(dst_x[r] + (size_t)i * 16, v[j]);
             }
           }
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
         if constexpr (MODE == EP_X_FP8_SCALED) {
           const float* ssrc = a.x_scales + (size_t)t * n_scales;
 #pragma unroll
-          for (int r = 0; r < kMaxRanks; ++r) {
+          for (int r = 0; r < NR; ++r) {
             if ((mask >> r) & 1u) {
               float* ds = reinterpret_cast<float*>(c.heap[r] + a.arena.scales_off) + (size_t)slots[r] * n_scales;
               for (int j = lane; j < n_scales; j += 32) ds[j] = ssrc[j];
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
         if (a.topk_weights) w = a.topk_weights[(size_t)t * a.K + lane];
       }
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r) {
+      for (int r = 0; r < NR; ++r) {
         if ((mask >> r) & 1u) {
           const int slot = slots[r];
           if (a.topk_idx && lane < a.K) {
@@ -335,8 +337,9 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------- combine
-// FEW = true: every token has at most two source rows (EP degree <= 2): deeper chunk pipeline.
-template <bool FEW>
+// NR = rank-count bucket (1, 2, 4, 8): source loops are unrolled to NR.  NR <= 2 takes a deeper
+// chunk pipeline (few rows per token).  BIAS = false drops the bias code from the hot loop.
+template <int NR, bool BIAS>
 __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constant__ DevComm c,
                                                             const __grid_constant__ EpCombineArgs a) {
   const int R = c.nranks;
@@ -349,10 +352,10 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
   for (int t = blockIdx.x * (blockDim.x >> 5) + warp; t < a.T; t += warps_total) {
     const int my = lane < R ? a.send_slot[(size_t)t * R + lane] : -1;
     const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
-    const char* src[kMaxRanks];
-    int slots[kMaxRanks];
+    const char* src[NR];
+    int slots[NR];
 #pragma unroll
-    for (int r = 0; r < kMaxRanks; ++r) {
+    for (int r = 0; r < NR; ++r) {
       slots[r] = __shfl_sync(0xffffffffu, my, r);
       src[r] = ((mask >> r) & 1u) ? c.heap[r] + a.x_off + (size_t)slots[r] * row_bytes : nullptr;
     }
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
     const char* b0 = a.bias0 ? reinterpret_cast<const char*>(a.bias0) + (size_t)t * row_bytes : nullptr;
     const char* b1 = a.bias1 ? reinterpret_cast<const char*>(a.bias1) + (size_t)t * row_bytes : nullptr;
     auto add_bias = [&](float (&acc)[8], int i) {
+      if constexpr (!BIAS) return;
       if (b0) {
         float f[8];
         bf16x8_to_float(ld_nc_v4(b0 + (size_t)i * 16), f);
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
       for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
       st_v4(out + (size_t)i * 16, o);
     };
-    if constexpr (FEW) {
+    if constexpr (NR <= 2) {
       // few sources (small EP degree / sparse routing): trade width for depth -- 8 chunks of up
       // to 2 rows in flight per lane instead of 2 chunks of up to 8 rows
       const int r0 = mask ? __ffs(mask) - 1 : -1;
@@ -398,7 +402,9 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
           const int i = i0 + j * 32 + lane;
           if (i < chunks) {
             if (p0) v0[j] = ld_nc_v4(p0 + (size_t)i * 16);
-            if (p1) v1[j] = ld_nc_v4(p1 + (size_t)i * 16);
+            if constexpr (NR == 2) {
+              if (p1) v1[j] = ld_nc_v4(p1 + (size_t)i * 16);
+            }
           }
         }
 #pragma unroll
@@ -415,11 +421,13 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
 #pragma unroll
               for (int q = 0; q < 8; ++q) acc[q] += f[q];
             }
-            if (p1) {
-              float f[8];
-              bf16x8_to_float(v1[j], f);
+            if constexpr (NR == 2) {
+              if (p1) {
+                float f[8];
+                bf16x8_to_float(v1[j], f);
 #pragma unroll
-              for (int q = 0; q < 8; ++q) acc[q] += f[q];
+                for (int q = 0; q < 8; ++q) acc[q] += f[q];
+              }
             }
             store_acc(acc, i);
           }
@@ -427,12 +435,12 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
       }
     } else {
       for (int i0 = 0; i0 < chunks; i0 += 64) {
-        uint4 v[2][kMaxRanks];
+        uint4 v[2][NR];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int i = i0 + j * 32 + lane;
 #pragma unroll
-          for (int r = 0; r < kMaxRanks; ++r)
+          for (int r = 0; r < NR; ++r)
             if (i < chunks && ((mask >> r) & 1u)) v[j][r] = ld_nc_v4(src[r] + (size_t)i * 16);
         }
 #pragma unroll
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
             for (int q = 0; q < 8; ++q) acc[q] = 0.f;
             add_bias(acc, i);
 #pragma unroll
-            for (int r = 0; r < kMaxRanks; ++r) {
+            for (int r = 0; r < NR; ++r) {
               if ((mask >> r) & 1u) {
                 float f[8];
                 bf16x8_to_float(v[j][r], f);
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(512, 1) ep_combine_kernel(const __grid_constan
     if (a.out_topk_w && a.topk_w_off != kNoOff && lane < a.K) {
       float w = 0.f;
 #pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)
+      for (int r = 0; r < NR; ++r)
         if ((mask >> r) & 1u)
           w += reinterpret_cast<const float*>(c.heap[r] + a.topk_w_off)[(size_t)slots[r] * a.K + lane];
       a.out_topk_w[(size_t)t * a.K + lane] = w;
@@ -477,20 +485,40 @@ cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st) {
+template <int NR>
+static cudaError_t launch_ep_dispatch_nr(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st) {
   switch (a.mode) {
-    case EP_X_BF16: UB_LAUNCH((ep_dispatch_kernel<EP_X_BF16>), grid, 512, 0, st, c, a); break;
-    case EP_X_FP8_SCALED: UB_LAUNCH((ep_dispatch_kernel<EP_X_FP8_SCALED>), grid, 512, 0, st, c, a); break;
-    case EP_X_FUSED_FP8: UB_LAUNCH((ep_dispatch_kernel<EP_X_FUSED_FP8>), grid, 512, 0, st, c, a); break;
+    case EP_X_BF16: UB_LAUNCH((ep_dispatch_kernel<EP_X_BF16, NR>), grid, 512, 0, st, c, a); break;
+    case EP_X_FP8_SCALED: UB_LAUNCH((ep_dispatch_kernel<EP_X_FP8_SCALED, NR>), grid, 512, 0, st, c, a); break;
+    case EP_X_FUSED_FP8: UB_LAUNCH((ep_dispatch_kernel<EP_X_FUSED_FP8, NR>), grid, 512, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
 
-cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
-  if (c.nranks <= 2) UB_LAUNCH((ep_combine_kernel<true>), grid, 512, 0, st, c, a);
-  else UB_LAUNCH((ep_combine_kernel<false>), grid, 512, 0, st, c, a);
+cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st) {
+  switch (c.nranks) {
+    case 1: return launch_ep_dispatch_nr<1>(c, a, grid, st);
+    case 2: return launch_ep_dispatch_nr<2>(c, a, grid, st);
+    case 3: case 4: return launch_ep_dispatch_nr<4>(c, a, grid, st);
+    default: return launch_ep_dispatch_nr<8>(c, a, grid, st);
+  }
+}
+
+template <int NR>
+static cudaError_t launch_ep_combine_nr(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
+  if (a.bias0 || a.bias1) UB_LAUNCH((ep_combine_kernel<NR, true>), grid, 512, 0, st, c, a);
+  else UB_LAUNCH((ep_combine_kernel<NR, false>), grid, 512, 0, st, c, a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st) {
+  switch (c.nranks) {
+    case 1: return launch_ep_combine_nr<1>(c, a, grid, st);
+    case 2: return launch_ep_combine_nr<2>(c, a, grid, st);
+    case 3: case 4: return launch_ep_combine_nr<4>(c, a, grid, st);
+    default: return launch_ep_combine_nr<8>(c, a, grid, st);
+  }
 }
 
 }  // namespace ub
