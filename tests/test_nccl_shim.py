@@ -41,3 +41,26 @@ def test_exported_symbols():
                 "ncclRecv", "ncclAllToAll", "ncclGroupStart", "ncclGroupEnd", "ncclCommInitRank", "ncclCommInitAll",
                 "ncclCommSplit", "ncclGetUniqueId", "ncclMemAlloc", "ncclMemFree", "ncclCommRegister"):
         assert f" T {sym}\n" in out, sym
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n", [2, 4])
+def test_nccl_api_gpu(tmp_path, n):
+    """NCCL C API on the GPU: InitAll, staged + zero-copy allreduce, allgather, reduce-scatter,
+    broadcast, native grouped send/recv."""
+    from uccl_b200 import _build
+
+    _build.build()
+    shim = _build.nccl_shim_path()
+    exe = tmp_path / "nccl_gpu_test"
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests/cpp/nccl_gpu_test.cc"), "-I/usr/include",
+           "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl", "-Wl,-rpath," + str(shim.parent),
+           "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32")
+    r = subprocess.run([str(exe), str(n)], capture_output=True, text=True, timeout=240, env=env)
+    sys.stdout.write(r.stdout)
+    sys.stderr.write(r.stderr)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "nccl_gpu_test: OK" in r.stdout
