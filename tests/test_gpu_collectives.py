@@ -260,3 +260,41 @@ def test_nvls_paths_if_available():
                              lambda c, x: c.all_reduce(x, "sum", algo="staged_nvls"))
             for o in outs:
                 assert torch.allclose(o.cpu().double(), exp, **_tol(dtype))
+
+
+def test_cuda_graph_replay():
+    """Device-side epochs make every kernel CUDA-graph replayable (no host-side launch counters):
+    capture one allreduce per rank, replay three times with new inputs."""
+    n = 2
+    comms = get_world(n)
+    count = 1 << 16
+    xs = [c.empty(count, dtype=torch.float32) for c in comms]
+    small = [c.empty(256, dtype=torch.float32) for c in comms]
+    for x, s in zip(xs, small):
+        x.zero_()
+        s.zero_()
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=c.device) for c in comms]
+    graphs = []
+    for c, st, x, s in zip(comms, streams, xs, small):
+        with torch.cuda.device(c.device):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                c.all_reduce(x, "sum", algo="twoshot_p2p")
+                c.all_reduce(s, "sum", algo="oneshot_ll")
+            graphs.append(g)
+    for rep in range(3):
+        for r, (x, s) in enumerate(zip(xs, small)):
+            x.fill_(float(rep + r + 1))
+            s.fill_(float(10 * rep + r))
+        torch.cuda.synchronize()
+        for c, st, g in zip(comms, streams, graphs):
+            with torch.cuda.device(c.device), torch.cuda.stream(st):
+                g.replay()
+        for st in streams:
+            st.synchronize()
+        exp = sum(float(rep + r + 1) for r in range(n))
+        exp_s = sum(float(10 * rep + r) for r in range(n))
+        for x, s in zip(xs, small):
+            assert bool((x == exp).all()), (rep, x[:4])
+            assert bool((s == exp_s).all()), (rep, s[:4])
