@@ -11,7 +11,7 @@
 namespace ub {
 
 UB_PARAM(TimeoutMs, "TIMEOUT_MS", 20000)
-UB_PARAM(MaxCtas, "MAX_CTAS", 64)
+UB_PARAM(MaxCtas, "MAX_CTAS", 128)
 UB_PARAM(ArLLMaxBytes, "AR_LL_MAX_BYTES", 0)  // 0: per-world-size default
 UB_PARAM(ArP2PMinBytes, "AR_P2P_MIN_BYTES", -1)  // symmetric buffers >= this use twoshot_p2p even with NVLS (-1: default)
 UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
@@ -234,7 +234,7 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
     // defaults measured on B200 (benchmarks/allreduce_perf.py, profiles/): the packet path wins
     // until its N-fold traffic outweighs the two barriers of the two-shot kernels
     uint64_t ll_max = (uint64_t)ubParamArLLMaxBytes();
-    if (ll_max == 0) ll_max = n <= 2 ? (1u << 20) : (n <= 4 ? (512u << 10) : (256u << 10));
+    if (ll_max == 0) ll_max = n <= 2 ? (512u << 10) : (n <= 4 ? (256u << 10) : (128u << 10));
     ll_max = std::min<uint64_t>(ll_max, kLLMaxData);
     // with 2 ranks the switch cannot reduce traffic (both paths move `size` per direction) and the
     // plain P2P kernel sustains more bytes in flight per SM than multimem.ld_reduce

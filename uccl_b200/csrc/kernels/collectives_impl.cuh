@@ -45,6 +45,42 @@ __device__ __forceinline__ void copy_bytes16(char* dst, const char* src, uint64_
   }
 }
 
+// Pull one 16-byte-unit range [lo, hi) from each of `n` sources into `n` destinations, issuing the
+// loads of ALL sources before the dependent stores (n x 2 loads in flight per thread): a loop over
+// peers with an inner copy loop would expose one NVLink round trip per peer.
+template <typename SrcFn, typename DstFn>
+__device__ __forceinline__ void gather_units16(int n, uint64_t lo, uint64_t hi, uint64_t src_bytes, uint64_t dst_bytes,
+                                               SrcFn src_of, DstFn dst_of) {
+  bool aligned = true;
+  for (int k = 0; k < n; ++k) aligned = aligned && ((((uintptr_t)src_of(k) | (uintptr_t)dst_of(k)) & 15) == 0);
+  if (!aligned) {
+    for (int k = 0; k < n; ++k) copy_bytes16(dst_of(k), src_of(k), lo, hi, src_bytes, dst_bytes);
+    return;
+  }
+  constexpr int B = 2;
+  for (uint64_t u0 = lo + threadIdx.x; u0 < hi; u0 += (uint64_t)B * blockDim.x) {
+    uint4 v[B][kMaxRanks];
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+      if (u < hi) {
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; ++k)
+          if (k < n) v[j][k] = load16_partial(src_of(k), u * 16, src_bytes);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+      const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+      if (u < hi) {
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; ++k)
+          if (k < n) store16_partial(dst_of(k), u * 16, dst_bytes, v[j][k]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ AllGather
 // a.bytes = bytes contributed by each rank. out holds n * bytes.
 // MODE 0: push P2P (out symmetric)   MODE 1: push multicast (out symmetric, NVLS)
@@ -102,16 +138,19 @@ __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevC
         copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
         sync_barrier(c, s);
       }
-      for (int k = 0; k < n; ++k) {
-        int p = rank + k;
-        if (p >= n) p -= n;
-        if (p == rank) {
-          copy_bytes16(out + (uint64_t)p * a.bytes + base, in + base, blo, bhi, cb, cb);
-        } else {
-          const uint64_t src_off = staged ? a.stage_in_off : (s_off[p] + base);
-          copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
-        }
-      }
+      gather_units16(
+          n, blo, bhi, cb, cb,
+          [&](int k) -> const char* {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            if (p == rank) return in + base;
+            return c.heap[p] + (staged ? a.stage_in_off : (s_off[p] + base));
+          },
+          [&](int k) -> char* {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            return out + (uint64_t)p * a.bytes + base;
+          });
       sync_barrier_relaxed(c, s);  // peers finished reading my stage / input
     }
   }
@@ -302,12 +341,18 @@ __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ Dev
     const uint64_t units = (a.bytes + 15) / 16;
     uint64_t blo, bhi;
     split_range(units, gridDim.x, blockIdx.x, blo, bhi);
-    for (int k = 0; k < n; ++k) {
-      int p = rank + k;
-      if (p >= n) p -= n;
-      copy_bytes16(c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes, in + (uint64_t)p * a.bytes, blo, bhi,
-                   a.bytes, a.bytes);
-    }
+    gather_units16(
+        n, blo, bhi, a.bytes, a.bytes,
+        [&](int k) -> const char* {
+          int p = rank + k;
+          if (p >= n) p -= n;
+          return in + (uint64_t)p * a.bytes;
+        },
+        [&](int k) -> char* {
+          int p = rank + k;
+          if (p >= n) p -= n;
+          return c.heap[p] + s_off[kMaxRanks + p] + (uint64_t)rank * a.bytes;
+        });
     sync_barrier(c, s);
   } else {
     bool staged = false;
@@ -324,13 +369,19 @@ __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ Dev
                        in + (uint64_t)d * a.bytes + base, blo, bhi, cb, cb);
         sync_barrier(c, s);
       }
-      for (int k = 0; k < n; ++k) {
-        int p = rank + k;
-        if (p >= n) p -= n;
-        const uint64_t src_off = staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes)
-                                        : (s_off[p] + (uint64_t)rank * a.bytes + base);
-        copy_bytes16(out + (uint64_t)p * a.bytes + base, c.heap[p] + src_off, blo, bhi, cb, cb);
-      }
+      gather_units16(
+          n, blo, bhi, cb, cb,
+          [&](int k) -> const char* {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            return c.heap[p] + (staged ? (a.stage_in_off + (uint64_t)rank * chunk_bytes)
+                                       : (s_off[p] + (uint64_t)rank * a.bytes + base));
+          },
+          [&](int k) -> char* {
+            int p = rank + k;
+            if (p >= n) p -= n;
+            return out + (uint64_t)p * a.bytes + base;
+          });
       sync_barrier_relaxed(c, s);
     }
   }
