@@ -298,3 +298,22 @@ def test_cuda_graph_replay():
         for x, s in zip(xs, small):
             assert bool((x == exp).all()), (rep, x[:4])
             assert bool((s == exp_s).all()), (rep, s[:4])
+
+
+def test_device_trace():
+    n = 2
+    comms = get_world(n)
+    for c in comms:
+        c.enable_trace(4096)
+    xs = [c.empty(1 << 16, dtype=torch.float32) for c in comms]
+    for x in xs:
+        x.fill_(1.0)
+    run_ranks(comms, lambda c: xs[c.rank], lambda c, x: c.all_reduce(x, "sum", algo="twoshot_p2p"))
+    for c in comms:
+        ev = c.dump_trace()
+        kinds = [e["event"] for e in ev]
+        assert kinds.count("barrier_enter") == kinds.count("barrier_exit") >= 2
+        assert "kernel_begin" in kinds
+        assert all(ev[i]["t_ns"] <= ev[i + 1]["t_ns"] for i in range(len(ev) - 1))
+        c.disable_trace()
+    assert bool((xs[0] == 2.0).all())

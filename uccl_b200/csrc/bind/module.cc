@@ -159,7 +159,16 @@ PYBIND11_MODULE(_C, m) {
              int algo = c.select_allreduce(bytes, symmetric, dtype, op, &ctas);
              return py::make_tuple(algo, ctas);
            })
-      .def("set_tuning", &Comm::set_tuning);
+      .def("set_tuning", &Comm::set_tuning)
+      .def("enable_trace", &Comm::enable_trace)
+      .def("disable_trace", &Comm::disable_trace)
+      .def("dump_trace",
+           [](Comm& c, bool reset) {
+             py::list out;
+             for (auto& e : c.dump_trace(reset)) out.append(py::make_tuple(e.t_ns, e.code, e.block, e.aux));
+             return out;
+           },
+           py::arg("reset") = true);
 
   bind_util(m);
   bind_ep(m);

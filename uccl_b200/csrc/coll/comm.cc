@@ -113,6 +113,48 @@ void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
 
 Comm::~Comm() {
   if (err_host_) cudaFreeHost(err_host_);
+  if (trace_dev_) cudaFree(trace_dev_);
+}
+
+void Comm::enable_trace(size_t max_events) {
+  UB_CHECK(!is_host(), "tracing needs a CUDA communicator");
+  DeviceGuard g(device());
+  disable_trace();
+  UB_CUDA(cudaMalloc((void**)&trace_dev_, (2 + 2 * max_events) * sizeof(unsigned long long)));
+  UB_CUDA(cudaMemset(trace_dev_, 0, (2 + 2 * max_events) * sizeof(unsigned long long)));
+  trace_cap_ = max_events;
+  dev_.trace = trace_dev_;
+  dev_.trace_cap = (uint32_t)max_events;
+}
+
+void Comm::disable_trace() {
+  if (trace_dev_) {
+    DeviceGuard g(device());
+    cudaDeviceSynchronize();
+    cudaFree(trace_dev_);
+  }
+  trace_dev_ = nullptr;
+  trace_cap_ = 0;
+  dev_.trace = nullptr;
+  dev_.trace_cap = 0;
+}
+
+std::vector<Comm::TraceEvent> Comm::dump_trace(bool reset) {
+  std::vector<TraceEvent> out;
+  if (!trace_dev_) return out;
+  DeviceGuard g(device());
+  UB_CUDA(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h(2 + 2 * trace_cap_);
+  UB_CUDA(cudaMemcpy(h.data(), trace_dev_, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  const size_t n = std::min<size_t>((size_t)h[0], trace_cap_);
+  out.reserve(n);
+  for (size_t i = 0; i < n; ++i) {
+    const unsigned long long tag = h[3 + 2 * i];
+    out.push_back(TraceEvent{h[2 + 2 * i], (uint32_t)(tag >> 48), (uint32_t)((tag >> 32) & 0xffff), (uint32_t)(tag & 0xffffffffu)});
+  }
+  std::sort(out.begin(), out.end(), [](const TraceEvent& a, const TraceEvent& b) { return a.t_ns < b.t_ns; });
+  if (reset) UB_CUDA(cudaMemset(trace_dev_, 0, 2 * sizeof(unsigned long long)));
+  return out;
 }
 
 std::string Comm::describe() const {

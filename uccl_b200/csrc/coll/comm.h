@@ -101,6 +101,14 @@ class Comm {
   int select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int* ctas) const;
   void set_tuning(bool symmetric, const std::vector<TuneEntry>& table);
   uint32_t error_word() const { return err_host_ ? *err_host_ : 0; }
+  // in-kernel tracing (device timeline of every block's barriers / phases)
+  struct TraceEvent {
+    uint64_t t_ns;
+    uint32_t code, block, aux;
+  };
+  void enable_trace(size_t max_events);
+  void disable_trace();
+  std::vector<TraceEvent> dump_trace(bool reset = true);
   uint64_t launches() const { return launches_; }
 
  private:
@@ -127,6 +135,8 @@ class Comm {
   uint32_t* err_host_ = nullptr;
   uint64_t launches_ = 0;
   uint32_t host_epoch_ = 0;
+  unsigned long long* trace_dev_ = nullptr;
+  size_t trace_cap_ = 0;
   std::vector<TuneEntry> tune_sym_, tune_unsym_;
   // heap allocator
   mutable std::mutex mu_;

@@ -231,6 +231,20 @@ static __device__ __noinline__ void comm_abort(const DevComm& c, int code, int a
   __trap();
 }
 
+// --------------------------------------------------------------- in-kernel tracing
+// NPKit-style device timeline (reference: experimental/lite/core/npkit.hpp:30-60 stamps
+// clock64() events at compile time).  Here it is a runtime switch: when the communicator has a
+// trace buffer, thread 0 of every block appends {globaltimer, code|block|aux} -- every cross-rank
+// barrier is stamped, so wait time vs copy time per block falls out of any kernel for free.
+__device__ __forceinline__ void trace_event(const DevComm& c, uint32_t code, uint32_t aux) {
+  if (c.trace == nullptr || threadIdx.x != 0) return;
+  const unsigned long long idx = atomicAdd(c.trace, 1ull);
+  if (idx < c.trace_cap) {
+    c.trace[2 + 2 * idx] = globaltimer_ns();
+    c.trace[3 + 2 * idx] = ((unsigned long long)code << 48) | ((unsigned long long)(blockIdx.x & 0xffff) << 32) | aux;
+  }
+}
+
 // ------------------------------------------------------- cross-rank block barrier
 // Slot layout inside every heap: sig[domain][block][src_rank] (u32, single writer each).
 // Epochs are monotonic so no reset is ever needed; the local epoch of (domain, block)
@@ -249,6 +263,7 @@ __device__ __forceinline__ BlockSync sync_begin(const DevComm& c, int domain, in
   s.my_sig = reinterpret_cast<uint32_t*>(c.heap[c.rank] + s.sig_block_off);
   s.epoch_ptr = reinterpret_cast<uint32_t*>(c.heap[c.rank] + c.epoch_off) + idx;
   s.e = ld_volatile(s.epoch_ptr) + 1;
+  trace_event(c, TR_KERNEL_BEGIN, (uint32_t)domain);
   return s;
 }
 
@@ -256,6 +271,7 @@ __device__ __forceinline__ BlockSync sync_begin(const DevComm& c, int domain, in
 // rank) before the barrier and all later reads after it.
 __device__ __forceinline__ void sync_barrier(const DevComm& c, BlockSync& s) {
   __syncthreads();
+  trace_event(c, TR_BARRIER_ENTER, s.e);
   const int t = threadIdx.x;
   if (t < c.nranks && t != c.rank) {
     uint32_t* peer_slot = reinterpret_cast<uint32_t*>(c.heap[t] + s.sig_block_off) + c.rank;
@@ -267,6 +283,7 @@ __device__ __forceinline__ void sync_barrier(const DevComm& c, BlockSync& s) {
   }
   s.e += 1;
   __syncthreads();
+  trace_event(c, TR_BARRIER_EXIT, s.e - 1);
 }
 // Barrier that also all-gathers two 64-bit words per rank (e.g. the heap offsets of this
 // rank's input / output buffers) between same-index blocks.  `sh` is shared memory for
@@ -304,6 +321,7 @@ __device__ __forceinline__ bool all_equal(const uint64_t* sh, int n) {
 // Relaxed variant: only a rendezvous, no data ordering (cheaper: no release fence).
 __device__ __forceinline__ void sync_barrier_relaxed(const DevComm& c, BlockSync& s) {
   __syncthreads();
+  trace_event(c, TR_BARRIER_ENTER, s.e);
   const int t = threadIdx.x;
   if (t < c.nranks && t != c.rank) {
     uint32_t* peer_slot = reinterpret_cast<uint32_t*>(c.heap[t] + s.sig_block_off) + c.rank;
@@ -315,6 +333,7 @@ __device__ __forceinline__ void sync_barrier_relaxed(const DevComm& c, BlockSync
   }
   s.e += 1;
   __syncthreads();
+  trace_event(c, TR_BARRIER_EXIT, s.e - 1);
 }
 __device__ __forceinline__ void sync_end(BlockSync& s) {
   if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(s.epoch_ptr) = s.e - 1;

@@ -26,6 +26,17 @@ struct DevComm {
   uint64_t xchg_off;      // offset of the per-(domain, block, src) 16-byte exchange slots
   uint64_t timeout_ns;    // spin timeout (0 = infinite)
   uint32_t* err;          // host-mapped error word (set before trap)
+  unsigned long long* trace;  // optional device trace buffer: [0] = write index, then {t_ns, tag} pairs
+  uint32_t trace_cap;     // capacity in events (0 = tracing off)
+};
+
+// trace event codes (tag = code << 48 | block << 32 | aux)
+enum TraceCode : uint32_t {
+  TR_KERNEL_BEGIN = 1,
+  TR_KERNEL_END = 2,
+  TR_BARRIER_ENTER = 3,
+  TR_BARRIER_EXIT = 4,
+  TR_PHASE = 5,
 };
 
 enum DType : int {

@@ -289,6 +289,40 @@ class Communicator:
     def barrier(self, stream=None) -> None:
         self._c.barrier(self._stream(stream))
 
+    # ---------------------------------------------------------------------- tracing
+    _TRACE_CODES = {1: "kernel_begin", 2: "kernel_end", 3: "barrier_enter", 4: "barrier_exit", 5: "phase"}
+
+    def enable_trace(self, max_events: int = 1 << 16) -> None:
+        """Record a device-side timeline ({globaltimer ns, event, block, aux}) of every kernel of
+        this communicator (NPKit analogue; barrier wait time per block falls out directly)."""
+        self._c.enable_trace(int(max_events))
+
+    def disable_trace(self) -> None:
+        self._c.disable_trace()
+
+    def dump_trace(self, reset: bool = True):
+        return [dict(t_ns=t, event=self._TRACE_CODES.get(c, str(c)), block=b, aux=a)
+                for t, c, b, a in self._c.dump_trace(reset)]
+
+    def trace_to_chrome(self, path: str, reset: bool = True) -> int:
+        """Write the trace as a chrome://tracing JSON (barrier waits as duration events per block)."""
+        import json
+
+        ev, open_b = [], {}
+        for e in self.dump_trace(reset):
+            key = e["block"]
+            if e["event"] == "barrier_enter":
+                open_b[key] = e
+            elif e["event"] == "barrier_exit" and key in open_b:
+                s = open_b.pop(key)
+                ev.append({"name": f"barrier e{e['aux']}", "ph": "X", "pid": self.rank, "tid": key,
+                           "ts": s["t_ns"] / 1e3, "dur": (e["t_ns"] - s["t_ns"]) / 1e3})
+            else:
+                ev.append({"name": e["event"], "ph": "i", "pid": self.rank, "tid": key, "ts": e["t_ns"] / 1e3, "s": "t"})
+        with open(path, "w") as f:
+            json.dump({"traceEvents": ev}, f)
+        return len(ev)
+
     # ----------------------------------------------------------------------- tuning
     def select_allreduce(self, nbytes: int, symmetric: bool, dtype: torch.dtype = torch.float32, op="sum"):
         algo, ctas = self._c.select_allreduce(int(nbytes), bool(symmetric), dtype_code(dtype), op_code(op))
