@@ -13,17 +13,17 @@
 
 #define CK(x)                                                                            \
   do {                                                                                   \
-    cudaError_t e = (x);                                                                 \
-    if (e != cudaSuccess) {                                                              \
-      fprintf(stderr, "CUDA %s @%d\n", cudaGetErrorString(e), __LINE__);                 \
+    cudaError_t ck_err_ = (x);                                                                 \
+    if (ck_err_ != cudaSuccess) {                                                              \
+      fprintf(stderr, "CUDA %s @%d\n", cudaGetErrorString(ck_err_), __LINE__);                 \
       exit(2);                                                                           \
     }                                                                                    \
   } while (0)
 #define NK(x)                                                                            \
   do {                                                                                   \
-    ncclResult_t r = (x);                                                                \
-    if (r != ncclSuccess) {                                                              \
-      fprintf(stderr, "NCCL %s (%s) @%d\n", ncclGetErrorString(r), ncclGetLastError(nullptr), __LINE__); \
+    ncclResult_t nk_res_ = (x);                                                                \
+    if (nk_res_ != ncclSuccess) {                                                              \
+      fprintf(stderr, "NCCL %s (%s) @%d\n", ncclGetErrorString(nk_res_), ncclGetLastError(nullptr), __LINE__); \
       exit(3);                                                                           \
     }                                                                                    \
   } while (0)

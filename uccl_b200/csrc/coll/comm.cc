@@ -399,8 +399,19 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       a.out_off = heap_offset(out);
     }
     cudaError_t e = launch_ar_any(algo, dtype, op, out_dtype, dev_, a, ctas, block, stream);
-    UB_CHECK(e == cudaSuccess, "allreduce launch failed (algo=%s dtype=%d op=%d ctas=%d): %s", algo_name(algo),
-             dtype, op, ctas, cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      CUcontext cctx = nullptr, sctx = nullptr;
+      CUdevice cdev = -1;
+      if (cu().CtxGetCurrent) cu().CtxGetCurrent(&cctx);
+      if (cu().CtxGetDevice) cu().CtxGetDevice(&cdev);
+      if (cu().StreamGetCtx) cu().StreamGetCtx((CUstream)stream, &sctx);
+      UB_THROW("allreduce launch failed (rank %d algo=%s dtype=%d op=%d ctas=%d, comm device %d, current device %d, "
+               "driver ctx %p on device %d, stream %p in ctx %p): %s",
+               rank(), algo_name(algo), dtype, op, ctas, device(), cur, (void*)cctx, (int)cdev, (void*)stream,
+               (void*)sctx, cudaGetErrorString(e));
+    }
     ++launches_;
   }
   if (main_bytes < bytes) {  // < 16-byte tail through the packet path

@@ -15,6 +15,8 @@ struct CuApi {
   CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
   CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
   CUresult (*CtxGetCurrent)(CUcontext*) = nullptr;
+  CUresult (*CtxGetDevice)(CUdevice*) = nullptr;
+  CUresult (*StreamGetCtx)(CUstream, CUcontext*) = nullptr;
   CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*,
                                           CUmemAllocationGranularity_flags) = nullptr;
   CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*,
@@ -70,6 +72,8 @@ inline const CuApi& cu() {
     UB_GET(MemImportFromShareableHandle, "cuMemImportFromShareableHandle");
     a->ok = ok;
     // multicast is optional (absent on drivers < 12.1 / non-NVSwitch systems)
+    get("cuCtxGetDevice", (void**)&a->CtxGetDevice);
+    get("cuStreamGetCtx", (void**)&a->StreamGetCtx);
     get("cuMulticastCreate", (void**)&a->MulticastCreate);
     get("cuMulticastAddDevice", (void**)&a->MulticastAddDevice);
     get("cuMulticastBindMem", (void**)&a->MulticastBindMem);
