@@ -170,6 +170,56 @@ def test_reduce_scatter(n, sym, dtype, op):
             assert torch.allclose(o.cpu().double(), exp[r].double(), **_tol(dtype))
 
 
+@pytest.mark.parametrize("n", [2, 4, 8])
+@pytest.mark.parametrize("ll", [True, False])
+def test_ll_exchange_vs_barrier_paths(n, ll):
+    """all_gather / all_to_all / reduce_scatter through the barrier-free LL-packet kernels (ll=True) and
+    through the barrier-based kernels (ll=False) on the same inputs; repeated calls flip the packet parity."""
+    comms = get_world(n)
+    for c in comms:
+        c.set_xchg_ll_max((1 << 20) if ll else -1)
+    try:
+        for it, count in enumerate([4, 1024, 20480, 4, 65536]):
+            for dtype, op in ((torch.float32, "sum"), (torch.bfloat16, "max"), (torch.int32, "sum")):
+                if (count * dtype.itemsize) % 16:
+                    continue
+                ins = _inputs(n, n * count, dtype, seed=100 * it + count)
+                # all_gather of every rank's first `count` elements (out-of-place, then in-place)
+                exp_ag = torch.cat([x[:count] for x in ins])
+
+                def prep_ag(c):
+                    return ins[c.rank][:count].to(c.device), torch.zeros(n * count, dtype=dtype, device=c.device)
+
+                outs = run_ranks(comms, prep_ag, lambda c, st: c.all_gather(st[1], st[0]))
+                for _, o in outs:
+                    assert torch.equal(o.cpu(), exp_ag)
+
+                def prep_ag_inplace(c):
+                    out = torch.zeros(n * count, dtype=dtype, device=c.device)
+                    out[c.rank * count:(c.rank + 1) * count].copy_(ins[c.rank][:count])
+                    return out
+
+                outs = run_ranks(comms, prep_ag_inplace,
+                                 lambda c, o: c.all_gather(o, o[c.rank * count:(c.rank + 1) * count]))
+                for o in outs:
+                    assert torch.equal(o.cpu(), exp_ag)
+                # all_to_all
+                outs = run_ranks(comms, lambda c: (ins[c.rank].to(c.device), torch.zeros(n * count, dtype=dtype, device=c.device)),
+                                 lambda c, st: c.all_to_all(st[1], st[0]))
+                for r, (_, o) in enumerate(outs):
+                    exp = torch.cat([ins[s][r * count:(r + 1) * count] for s in range(n)])
+                    assert torch.equal(o.cpu(), exp)
+                # reduce_scatter
+                exp_rs = _ref(ins, op).view(n, count)
+                outs = run_ranks(comms, lambda c: (ins[c.rank].to(c.device), torch.zeros(count, dtype=dtype, device=c.device)),
+                                 lambda c, st: c.reduce_scatter(st[1], st[0], op))
+                for r, (_, o) in enumerate(outs):
+                    assert torch.allclose(o.cpu().double(), exp_rs[r], **_tol(dtype))
+    finally:
+        for c in comms:
+            c.set_xchg_ll_max(0)
+
+
 @pytest.mark.parametrize("n", [2, 8])
 def test_broadcast_reduce_alltoall(n):
     comms = get_world(n)

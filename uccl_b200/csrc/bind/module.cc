@@ -160,6 +160,8 @@ PYBIND11_MODULE(_C, m) {
              return py::make_tuple(algo, ctas);
            })
       .def("set_tuning", &Comm::set_tuning)
+      .def("set_xchg_ll_max", &Comm::set_xchg_ll_max)
+      .def("xchg_ll_max", &Comm::xchg_ll_max)
       .def("enable_trace", &Comm::enable_trace)
       .def("disable_trace", &Comm::disable_trace)
       .def("dump_trace",

@@ -15,6 +15,9 @@ UB_PARAM(MaxCtas, "MAX_CTAS", 128)
 UB_PARAM(ArLLMaxBytes, "AR_LL_MAX_BYTES", 0)  // 0: per-world-size default
 UB_PARAM(ArP2PMinBytes, "AR_P2P_MIN_BYTES", -1)  // symmetric buffers >= this use twoshot_p2p even with NVLS (-1: default)
 UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
+// LL-packet AllGather / AllToAll / ReduceScatter for per-rank pieces up to this many bytes
+// (0: per-world-size default, -1: never)
+UB_PARAM(XchgLLMaxBytes, "XCHG_LL_MAX_BYTES", 0)
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 
 const char* algo_name(int algo) {
@@ -81,6 +84,7 @@ void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
   layout_ = HeapLayout::make(cfg.stage_bytes);
   max_ctas_ = cfg.max_ctas > 0 ? cfg.max_ctas : (int)ubParamMaxCtas();
   max_ctas_ = std::min(max_ctas_, kMaxSyncBlocks);
+  xchg_ll_max_ = ubParamXchgLLMaxBytes();
   memset(&dev_, 0, sizeof(dev_));
   dev_.rank = f->rank();
   dev_.nranks = f->nranks();
@@ -323,6 +327,14 @@ static cudaError_t launch_ar_any(int algo, int dtype, int op, int out_dtype, con
   }
 }
 
+// per-rank piece size up to which the barrier-free LL exchange kernels are used
+static uint64_t xchg_ll_limit(int64_t v, int n, bool symmetric_push) {
+  if (v < 0) return 0;
+  uint64_t m = v > 0 ? (uint64_t)v : (n <= 2 ? (256u << 10) : (128u << 10));
+  if (v == 0 && symmetric_push) m = 32u << 10;  // the push kernels only pay one barrier
+  return std::min<uint64_t>(m, kLLMaxData);
+}
+
 // ------------------------------------------------------------------ allreduce
 void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t stream,
                      const ArOpts& opts) {
@@ -455,14 +467,19 @@ void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype
   const bool out_sym = in_heap(out, bytes * n);
   const bool in_sym = in_heap(in, bytes);
   int mode;
-  if (out_sym && bytes % 16 == 0) {
+  int ctas;
+  if (bytes % 16 == 0 && bytes <= xchg_ll_limit(xchg_ll_max_, n, out_sym)) {
+    mode = (has_multicast() && n > 2) ? 4 : 3;
+    ctas = ctas_for(bytes * (uint64_t)(n - 1), std::min(max_ctas_, 64), 16 << 10);
+  } else if (out_sym && bytes % 16 == 0) {
     a.out_off = heap_offset(out);
     mode = (has_multicast() && n > 2) ? 1 : 0;  // with 2 ranks multicast saves nothing and issues slower
+    ctas = ctas_for(bytes, max_ctas_, 64 << 10);
   } else {
     mode = 2;
     if (in_sym) a.in_off = heap_offset(in);
+    ctas = ctas_for(bytes * (uint64_t)n, max_ctas_, 64 << 10);  // every CTA moves a slice of all n pieces
   }
-  int ctas = ctas_for(bytes, max_ctas_, 64 << 10);
   cudaError_t e = launch_allgather(mode, dev_, a, ctas, 512, stream);
   UB_CHECK(e == cudaSuccess, "allgather launch failed: %s", cudaGetErrorString(e));
   ++launches_;
@@ -499,12 +516,19 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
   if (in_sym) a.in_off = heap_offset(in);
   const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
-  int ctas = ctas_for(bytes, nvls ? nvls_ctas() : max_ctas_, 64 << 10);
+  const bool fdt =
+      dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2;
   cudaError_t e;
-  if (dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2)
-    e = launch_red_f(0, dtype, op, nvls, dev_, a, ctas, 512, stream);
-  else
-    e = launch_red_i(0, dtype, op, dev_, a, ctas, 512, stream);
+  if (n > 1 && bytes % 16 == 0 && bytes <= xchg_ll_limit(xchg_ll_max_, n, false)) {
+    const int ctas = ctas_for(bytes * (uint64_t)(n - 1), std::min(max_ctas_, 64), 16 << 10);
+    e = fdt ? launch_rs_ll_f(dtype, op, dev_, a, ctas, 512, stream) : launch_rs_ll_i(dtype, op, dev_, a, ctas, 512, stream);
+    UB_CHECK(e == cudaSuccess, "reduce_scatter (LL) launch failed: %s", cudaGetErrorString(e));
+    ++launches_;
+    return;
+  }
+  int ctas = ctas_for(in_sym ? bytes : bytes * (uint64_t)n, nvls && in_sym ? nvls_ctas() : max_ctas_, 64 << 10);
+  if (fdt) e = launch_red_f(0, dtype, op, nvls, dev_, a, ctas, 512, stream);
+  else e = launch_red_i(0, dtype, op, dev_, a, ctas, 512, stream);
   UB_CHECK(e == cudaSuccess, "reduce_scatter launch failed: %s", cudaGetErrorString(e));
   ++launches_;
 }
@@ -609,13 +633,17 @@ void Comm::alltoall(const void* in, void* out, size_t count_per_peer, int dtype,
   a.bytes = bytes;
   a.count = count_per_peer;
   int mode = 0;
-  if (in_heap(out, bytes * n)) {
+  int ctas = ctas_for(bytes * (uint64_t)n, max_ctas_, 64 << 10);
+  const bool out_sym = in_heap(out, bytes * n);
+  if (bytes % 16 == 0 && bytes <= xchg_ll_limit(xchg_ll_max_, n, out_sym)) {
+    mode = 2;
+    ctas = ctas_for(bytes * (uint64_t)(n - 1), std::min(max_ctas_, 64), 16 << 10);
+  } else if (out_sym) {
     a.out_off = heap_offset(out);
     mode = 1;
   } else if (in_heap(in, bytes * n)) {
     a.in_off = heap_offset(in);
   }
-  int ctas = ctas_for(bytes, max_ctas_, 32 << 10);
   cudaError_t e = launch_alltoall(mode, dev_, a, ctas, 512, stream);
   UB_CHECK(e == cudaSuccess, "alltoall launch failed: %s", cudaGetErrorString(e));
   ++launches_;

@@ -100,6 +100,9 @@ class Comm {
   // which algorithm AUTO would pick (for tests / tuner)
   int select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int* ctas) const;
   void set_tuning(bool symmetric, const std::vector<TuneEntry>& table);
+  // LL-packet AllGather/AllToAll/ReduceScatter threshold (per-rank piece bytes): 0 default, <0 off
+  void set_xchg_ll_max(int64_t bytes) { xchg_ll_max_ = bytes; }
+  int64_t xchg_ll_max() const { return xchg_ll_max_; }
   uint32_t error_word() const { return err_host_ ? *err_host_ : 0; }
   // in-kernel tracing (device timeline of every block's barriers / phases)
   struct TraceEvent {
@@ -132,6 +135,7 @@ class Comm {
   DevComm dev_;
   CommConfig cfg_;
   int max_ctas_ = 64;
+  int64_t xchg_ll_max_ = 0;
   uint32_t* err_host_ = nullptr;
   uint64_t launches_ = 0;
   uint32_t host_epoch_ = 0;

@@ -46,9 +46,9 @@ cudaError_t preload_all_kernels() {
     ok(launch_allreduce_f(algo, kBF16, kSum, kF32, c, a, 1, 512, 0));
     ok(launch_allreduce_f(algo, kF16, kSum, kF32, c, a, 1, 512, 0));
   }
-  for (int m = 0; m < 3; ++m) ok(launch_allgather(m, c, a, 1, 512, 0));
+  for (int m = 0; m < 5; ++m) ok(launch_allgather(m, c, a, 1, 512, 0));
   for (int m = 0; m < 3; ++m) ok(launch_broadcast(m, c, a, 1, 512, 0));
-  for (int m = 0; m < 2; ++m) ok(launch_alltoall(m, c, a, 1, 512, 0));
+  for (int m = 0; m < 3; ++m) ok(launch_alltoall(m, c, a, 1, 512, 0));
   ok(launch_alltoallv(c, a, v, 1, 512, 0));
   ok(launch_barrier(c, 0, 0));
   {
@@ -63,6 +63,12 @@ cudaError_t preload_all_kernels() {
       for (int dt : {(int)kI8, (int)kU8, (int)kI32, (int)kU32, (int)kI64, (int)kU64})
         ok(launch_red_i(which, dt, op, c, a, 1, 512, 0));
     }
+  for (int op = 0; op < 4; ++op) {
+    for (int dt : {(int)kF32, (int)kBF16, (int)kF16, (int)kF64, (int)kF8E4M3, (int)kF8E5M2})
+      ok(launch_rs_ll_f(dt, op, c, a, 1, 512, 0));
+    for (int dt : {(int)kI8, (int)kU8, (int)kI32, (int)kU32, (int)kI64, (int)kU64})
+      ok(launch_rs_ll_i(dt, op, c, a, 1, 512, 0));
+  }
   EpLayoutArgs la;
   memset(&la, 0, sizeof(la));
   ok(launch_ep_layout(la, 0));

@@ -1,5 +1,6 @@
 // Data-movement collectives (no arithmetic): AllGather, Broadcast, AllToAll(v).
 #include "collectives_impl.cuh"
+#include "ll_exchange.cuh"
 #include "launch.h"
 namespace ub {
 cudaError_t launch_allgather(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st) {
@@ -7,6 +8,8 @@ cudaError_t launch_allgather(int mode, const DevComm& c, const CollArgs& a, int 
     case 0: UB_LAUNCH((ag_kernel<0>), grid, block, 0, st, c, a); break;
     case 1: UB_LAUNCH((ag_kernel<1>), grid, block, 0, st, c, a); break;
     case 2: UB_LAUNCH((ag_kernel<2>), grid, block, 0, st, c, a); break;
+    case 3: UB_LAUNCH((xchg_ll_kernel<0, false>), grid, block, 0, st, c, a); break;
+    case 4: UB_LAUNCH((xchg_ll_kernel<0, true>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
@@ -24,6 +27,7 @@ cudaError_t launch_alltoall(int mode, const DevComm& c, const CollArgs& a, int g
   switch (mode) {
     case 0: UB_LAUNCH((a2a_kernel<0>), grid, block, 0, st, c, a); break;
     case 1: UB_LAUNCH((a2a_kernel<1>), grid, block, 0, st, c, a); break;
+    case 2: UB_LAUNCH((xchg_ll_kernel<1, false>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -31,8 +31,10 @@ cudaError_t launch_allreduce_i(int algo, int dtype, int op, const DevComm& c, co
                                int block, cudaStream_t st);
 cudaError_t launch_allreduce_x(int algo, int dtype, int op, const DevComm& c, const CollArgs& a, int grid,
                                int block, cudaStream_t st);
+// allgather modes: 0 push P2P, 1 push multicast, 2 pull/staged, 3 LL packets, 4 LL packets via multicast
 cudaError_t launch_allgather(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st);
 cudaError_t launch_broadcast(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st);
+// alltoall modes: 0 pull/staged, 1 push, 2 LL packets
 cudaError_t launch_alltoall(int mode, const DevComm& c, const CollArgs& a, int grid, int block, cudaStream_t st);
 cudaError_t launch_alltoallv(const DevComm& c, const CollArgs& a, const A2AvArgs& v, int grid, int block,
                              cudaStream_t st);
@@ -41,6 +43,11 @@ cudaError_t launch_red_f(int which, int dtype, int op, bool nvls, const DevComm&
                          int block, cudaStream_t st);
 cudaError_t launch_red_i(int which, int dtype, int op, const DevComm& c, const CollArgs& a, int grid, int block,
                          cudaStream_t st);
+// barrier-free LL ReduceScatter (ll_exchange.cuh); bytes per rank % 16 == 0
+cudaError_t launch_rs_ll_f(int dtype, int op, const DevComm& c, const CollArgs& a, int grid, int block,
+                           cudaStream_t st);
+cudaError_t launch_rs_ll_i(int dtype, int op, const DevComm& c, const CollArgs& a, int grid, int block,
+                           cudaStream_t st);
 cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st);
 cudaError_t launch_barrier(const DevComm& c, int domain, cudaStream_t st);
 }  // namespace ub

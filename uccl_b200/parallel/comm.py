@@ -338,5 +338,11 @@ class Communicator:
         self._c.set_tuning(bool(symmetric), ents)
 
 
+    def set_xchg_ll_max(self, nbytes: int):
+        """Per-rank piece size up to which all_gather / all_to_all / reduce_scatter use the barrier-free
+        LL-packet kernels (0: built-in default per world size, negative: never)."""
+        self._c.set_xchg_ll_max(int(nbytes))
+
+
 def launch_count(comms: Iterable[Communicator]) -> int:
     return sum(int(c._c.launches) for c in comms)
