@@ -1,0 +1,283 @@
+"""ukernel: planner (structure + simulated execution), persistent-worker FIFOs and the ukernel
+communicator.  Mirrors the reference's test layering (planner / lowering / ring-allreduce simulator /
+executor with mock backends: experimental/ukernel/src/ccl/test/unit/test_components.cc:240-635, then
+multi-process collectives) -- the CPU half runs the same FIFO protocol with host threads."""
+import threading
+
+import pytest
+import torch
+
+from uccl_b200 import Communicator
+from uccl_b200 import ukernel as uk
+from helpers import get_world
+
+
+# ------------------------------------------------------------------ planner (CPU)
+@pytest.mark.parametrize("algo", ["ring", "fullmesh"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 8])
+def test_plan_allreduce_structure(algo, n):
+    for nbytes in (16, 48, 4000, (1 << 16) + 32):
+        for lanes in (1, 3):
+            assert uk.validate("allreduce", nbytes, n, lanes, 4096, 4, algo) == ""
+    text, ops = uk.plan("allreduce", 1 << 16, n, 0, nlanes=2, tile_bytes=4096, elem_size=4, algo=algo)
+    assert ("ring" if algo == "ring" else "fullmesh") in text
+    if n > 1:
+        sends = [o for o in ops if o["kind"] == "send"]
+        recvs = [o for o in ops if o["kind"] == "recv"]
+        assert len(sends) == len(recvs) > 0
+        if algo == "ring":  # a ring only ever talks to its two neighbours
+            assert {o["peer"] for o in sends} == {1 % n} and {o["peer"] for o in recvs} == {(n - 1) % n}
+        else:
+            assert {o["peer"] for o in sends} == set(range(1, n))
+    for i, o in enumerate(ops):  # dependencies point backwards and stay on the op's lane
+        for d in o["deps"]:
+            assert d < i and ops[d]["lane"] == o["lane"]
+
+
+def test_plan_other_collectives_structure():
+    for n in (2, 4, 8):
+        assert uk.validate("alltoall", 5000, n, 2, 1024) == ""
+        assert uk.validate("allgather", 5008, n, 3, 1024) == ""
+        assert uk.validate("barrier", 0, n) == ""
+    assert uk._uk().select_algo(uk.COLLS["allreduce"], 8, 1 << 20) == uk.ALGOS["fullmesh"]
+    # ring needs (n-1) scratch slots per lane, the full mesh n
+    assert uk._uk().scratch_bytes(uk.ALGOS["ring"], 8, 2, 4096) == 2 * 7 * 4096
+    assert uk._uk().scratch_bytes(uk.ALGOS["fullmesh"], 8, 2, 4096) == 2 * 8 * 4096
+
+
+@pytest.mark.parametrize("algo", ["ring", "fullmesh"])
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("dtype,op", [(torch.float32, "sum"), (torch.int32, "max"), (torch.bfloat16, "sum")])
+def test_simulated_allreduce(algo, n, dtype, op):
+    """All ranks' plans executed over host memory by the greedy reference scheduler."""
+    for count in (8, 1000, 70000):
+        g = torch.Generator().manual_seed(count)
+        if dtype.is_floating_point:
+            ins = [torch.randn(count, generator=g).to(dtype) for _ in range(n)]
+        else:
+            ins = [torch.randint(-99, 99, (count,), generator=g).to(dtype) for _ in range(n)]
+        outs = [torch.zeros(count, dtype=dtype) for _ in range(n)]
+        assert uk.simulate("allreduce", ins, outs, op, nlanes=3, tile_bytes=4096, algo=algo) == ""
+        ref = torch.stack([x.double() for x in ins])
+        ref = ref.sum(0) if op == "sum" else ref.max(0).values
+        tol = dict(rtol=3e-2, atol=0.3) if dtype == torch.bfloat16 else dict(rtol=1e-5, atol=1e-4)
+        for o in outs:
+            assert torch.allclose(o.double(), ref, **tol)
+        for o in outs[1:]:  # every rank ends with the very same bits
+            assert torch.equal(o, outs[0])
+        # in place
+        bufs = [x.clone() for x in ins]
+        assert uk.simulate("allreduce", bufs, bufs, op, nlanes=2, tile_bytes=2048, algo=algo) == ""
+        for b in bufs:
+            assert torch.equal(b, outs[0]) or torch.allclose(b.double(), ref, **tol)
+
+
+def test_simulated_alltoall_allgather():
+    n, per = 4, 3000
+    ins = [torch.arange(n * per, dtype=torch.float32) + 1e5 * r for r in range(n)]
+    outs = [torch.zeros(n * per) for _ in range(n)]
+    assert uk.simulate("alltoall", ins, outs, nlanes=2, tile_bytes=4096) == ""
+    for r in range(n):
+        assert torch.equal(outs[r], torch.cat([ins[s][r * per:(r + 1) * per] for s in range(n)]))
+    gin = [torch.full((per,), float(r)) for r in range(n)]
+    gout = [torch.zeros(n * per) for _ in range(n)]
+    assert uk.simulate("allgather", gin, gout, nlanes=3, tile_bytes=1024) == ""
+    for o in gout:
+        assert torch.equal(o, torch.cat(gin))
+
+
+# ------------------------------------------------------------------ worker + communicator, host threads
+def test_host_worker_tasks():
+    w = uk.Worker(device=-1, nlanes=2)
+    a = torch.arange(1000, dtype=torch.float32)
+    b = torch.ones(1000)
+    c = torch.zeros(1000)
+    flag = torch.zeros(1, dtype=torch.int64)
+    w.copy(0, c.data_ptr(), a.data_ptr(), 4000)
+    w.reduce(0, c.data_ptr(), c.data_ptr(), b.data_ptr(), 4000, torch.float32, "sum")
+    w.signal(0, flag.data_ptr(), 5)
+    t = w.wait_value(1, flag.data_ptr(), 5)  # lane 1 is released by lane 0's signal
+    w.wait(1, t)
+    w.wait_all()
+    assert torch.equal(c, a + 1) and flag.item() == 5
+    # more tasks than ring entries: the producer blocks on the consumer, nothing is lost
+    acc = torch.zeros(4, dtype=torch.int64)
+    one = torch.ones(4, dtype=torch.int64)
+    n_tasks = uk._uk().RING_ENTRIES * 2 + 7
+    for _ in range(n_tasks):
+        w.reduce(0, acc.data_ptr(), acc.data_ptr(), one.data_ptr(), 32, torch.int64, "sum")
+    w.wait_all()
+    assert acc.tolist() == [n_tasks] * 4
+    assert w.stats()["reduces"] == n_tasks + 1 and w.error == 0
+    w.stop()
+
+
+def _run_threads(comms, fn):
+    res, errs = [None] * len(comms), []
+
+    def body(c):
+        try:
+            res[c.rank] = fn(c)
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=body, args=(c,)) for c in comms]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    return res
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_host_ukcomm_collectives(n):
+    comms = Communicator.local_world(n, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20)
+
+    def fn(c):
+        pg = uk.ProcessGroup(c, nlanes=2, tile_bytes=4096, staging_bytes=64 << 10)
+        x = torch.full((50000,), float(c.rank + 1))  # > staging: several segments
+        pg.all_reduce(x, "sum")
+        y = torch.arange(n * 1000, dtype=torch.float32) + 10000 * c.rank
+        z = torch.zeros(n * 1000)
+        pg.all_to_all_single(z, y)
+        g = torch.zeros(n * 777)
+        pg.all_gather_into_tensor(g, torch.full((777,), float(c.rank)))
+        pg.barrier()
+        xr = torch.full((5000,), float(c.rank + 1))
+        w = pg._uk.all_reduce(xr, "max", algo="ring")
+        w.wait()
+        assert w.is_completed()
+        xa = torch.full((64,), float(c.rank))
+        pg.all_reduce(xa, "avg")
+        st = pg._uk.stats()
+        pg.shutdown()
+        return x, z, g, xr, xa, st
+
+    for r, (x, z, g, xr, xa, st) in enumerate(_run_threads(comms, fn)):
+        assert torch.all(x == n * (n + 1) / 2)
+        exp = torch.cat([torch.arange(r * 1000, (r + 1) * 1000, dtype=torch.float32) + 10000 * s for s in range(n)])
+        assert torch.equal(z, exp)
+        assert torch.equal(g, torch.cat([torch.full((777,), float(s)) for s in range(n)]))
+        assert torch.all(xr == float(n))
+        assert torch.allclose(xa, torch.full((64,), (n - 1) / 2))
+        assert st["ops"] == 6 and st["segments"] > st["ops"]
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_gpu_worker_tasks():
+    dev = torch.device("cuda", 0)
+    a = torch.randn(1 << 20, device=dev)
+    b = torch.randn(1 << 20, device=dev)
+    c = torch.zeros(1 << 20, device=dev)
+    h = torch.randn(4099, device=dev).to(torch.bfloat16)
+    h2 = torch.randn(4099, device=dev).to(torch.bfloat16)
+    hout = torch.zeros(4099, device=dev, dtype=torch.bfloat16)
+    odd = torch.zeros(1001, device=dev, dtype=torch.uint8)
+    odd_src = torch.arange(1001, device=dev).to(torch.uint8)
+    flag = torch.zeros(2, device=dev, dtype=torch.int64)
+    torch.cuda.synchronize()
+    w = uk.Worker(device=0, nlanes=2, idle_us=2000)
+    w.copy(0, c.data_ptr(), a.data_ptr(), a.numel() * 4)
+    w.reduce(0, c.data_ptr(), c.data_ptr(), b.data_ptr(), a.numel() * 4, torch.float32, "sum")
+    w.signal(0, flag.data_ptr(), 3)
+    w.wait_value(1, flag.data_ptr(), 3)  # lane 1 runs after lane 0's copy+reduce
+    w.reduce(1, hout.data_ptr(), h.data_ptr(), h2.data_ptr(), 4099 * 2, torch.bfloat16, "max")
+    w.copy(1, odd.data_ptr() + 1, odd_src.data_ptr() + 1, 999)  # unaligned byte copy
+    w.wait_all()
+    # a device-wide synchronisation must not hang on the idle worker: it quits after idle_us ...
+    torch.cuda.synchronize()
+    first = w.kernel_launches
+    assert first >= 1
+    # ... and is relaunched transparently by the next task
+    c2 = torch.zeros_like(c)
+    torch.cuda.synchronize()
+    t = w.copy(1, c2.data_ptr(), c.data_ptr(), c.numel() * 4)
+    w.wait(1, t)
+    assert w.kernel_launches > first
+    w.stop()
+    assert w.error == 0
+    torch.cuda.synchronize()
+    assert torch.equal(c2, c)
+    assert torch.equal(c, a + b)
+    assert torch.equal(hout, torch.maximum(h, h2))
+    assert torch.equal(odd[1:1000], odd_src[1:1000]) and odd[0] == 0 and odd[1000] == 0
+    assert flag[0].item() == 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 4])
+def test_gpu_ukcomm_collectives(n):
+    comms = get_world(n)
+    uks = [uk.UkCommunicator(c, nlanes=2, tile_bytes=64 << 10, staging_bytes=1 << 20) for c in comms]
+    try:
+        count = (1 << 19) + 12  # 2 MiB + tail: two staged segments
+        ins = [torch.randn(count, generator=torch.Generator().manual_seed(r)) for r in range(n)]
+        ref = torch.stack(ins).sum(0)
+        xs, works = [], []
+        for c, u in zip(comms, uks):
+            with torch.cuda.device(c.device):
+                s = torch.cuda.Stream(device=c.device)
+                base = ins[c.rank].to(c.device)
+                warm = base * 1.0  # load the elementwise kernel before any worker spins (lazy module loading)
+                xs.append([s, base, None, None])
+            torch.cuda.synchronize(c.device)
+        for c, u, st in zip(comms, uks, xs):
+            with torch.cuda.device(c.device), torch.cuda.stream(st[0]):
+                x = st[1] * 1.0  # produced on the side stream, right before the collective
+                works.append(u.all_reduce(x, "sum"))
+                y = x * 2.0  # consumer on the same stream: ordered after the worker by cuStreamWaitValue64
+                st[2], st[3] = x, y
+        for (s, _, x, y), w in zip(xs, works):
+            s.synchronize()
+            w.wait()
+            assert torch.allclose(x.cpu(), ref, rtol=1e-5, atol=1e-4)
+            assert torch.allclose(y.cpu(), 2 * ref, rtol=1e-5, atol=2e-4)
+        # zero-copy on symmetric buffers, ring algorithm, bf16
+        bufs = []
+        for c, u in zip(comms, uks):
+            with torch.cuda.device(c.device):
+                b = c.empty(40000, dtype=torch.bfloat16)
+                b.copy_(torch.full((40000,), float(c.rank + 1)))
+                bufs.append(b)
+        for c in comms:
+            torch.cuda.synchronize(c.device)
+        works = []
+        for c, u, b in zip(comms, uks, bufs):
+            with torch.cuda.device(c.device):
+                works.append(u.all_reduce(b, "sum", algo="ring"))
+        for w in works:
+            w.wait()
+        for c, b in zip(comms, bufs):
+            torch.cuda.synchronize(c.device)
+            assert torch.all(b.float().cpu() == n * (n + 1) / 2)
+        assert uks[0].stats()["zero_copy_ops"] == 1
+        # all_to_all + all_gather + barrier
+        per = 3001
+        outs, works = [], []
+        for c in comms:
+            with torch.cuda.device(c.device):
+                y = (torch.arange(n * per, dtype=torch.float32) + 1e5 * c.rank).to(c.device)
+                z = torch.zeros(n * per, device=c.device)
+                g = torch.zeros(n * 500, device=c.device)
+                gi = torch.full((500,), float(c.rank)).to(c.device)
+                outs.append((y, z, g, gi))
+            torch.cuda.synchronize(c.device)
+        for c, u, (y, z, g, gi) in zip(comms, uks, outs):
+            with torch.cuda.device(c.device):
+                works.append(u.all_to_all_single(z, y))
+                works.append(u.all_gather_into_tensor(g, gi))
+                works.append(u.barrier())
+        for w in works:
+            w.wait()
+        for r, (y, z, g, gi) in enumerate(outs):
+            torch.cuda.synchronize(comms[r].device)
+            exp = torch.cat([torch.arange(r * per, (r + 1) * per, dtype=torch.float32) + 1e5 * s for s in range(n)])
+            assert torch.equal(z.cpu(), exp)
+            assert torch.equal(g.cpu(), torch.cat([torch.full((500,), float(s)) for s in range(n)]))
+        del bufs
+    finally:
+        for u in uks:
+            u.stop()

@@ -40,12 +40,14 @@ def nccl_shim_path() -> Path:
 
 def _sources():
     cu = sorted(CSRC.glob("kernels/*.cu")) + sorted(CSRC.glob("ep/*.cu")) + sorted(CSRC.glob("p2p/*.cu"))
+    cu += sorted(CSRC.glob("ukernel/*.cu"))
     cc = (
         sorted(CSRC.glob("fabric/*.cc"))
         + sorted(CSRC.glob("coll/*.cc"))
         + sorted(CSRC.glob("ep/*.cc"))
         + sorted(CSRC.glob("p2p/*.cc"))
         + sorted(CSRC.glob("common/*.cc"))
+        + sorted(CSRC.glob("ukernel/*.cc"))
     )
     bind = sorted(CSRC.glob("bind/*.cc"))
     return cu, cc, bind
@@ -79,6 +81,8 @@ def _defines():
         d.append("-DUB_HAVE_P2P")
     if list(CSRC.glob("common/bind_util.cc")):
         d.append("-DUB_HAVE_UTIL")
+    if list(CSRC.glob("ukernel/bind_uk.cc")):
+        d.append("-DUB_HAVE_UK")
     return d
 
 

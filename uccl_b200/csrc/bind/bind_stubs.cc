@@ -10,3 +10,6 @@ void bind_p2p(py::module_&) {}
 #ifndef UB_HAVE_UTIL
 void bind_util(py::module_&) {}
 #endif
+#ifndef UB_HAVE_UK
+void bind_uk(py::module_&) {}
+#endif

@@ -16,6 +16,7 @@ using namespace ub;
 void bind_ep(py::module_& m);
 void bind_p2p(py::module_& m);
 void bind_util(py::module_& m);
+void bind_uk(py::module_& m);
 
 static inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline void* P(uintptr_t p) { return reinterpret_cast<void*>(p); }
@@ -175,4 +176,5 @@ PYBIND11_MODULE(_C, m) {
   bind_util(m);
   bind_ep(m);
   bind_p2p(m);
+  bind_uk(m);
 }

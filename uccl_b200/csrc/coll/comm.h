@@ -150,4 +150,7 @@ class Comm {
 
 const char* algo_name(int algo);
 
+// CPU reference reduction used by the host backends: dst[i] = op_r srcs[r][i], then * scale (floats)
+void host_reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale);
+
 }  // namespace ub

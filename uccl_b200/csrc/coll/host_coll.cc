@@ -130,6 +130,10 @@ void reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype
 
 }  // namespace
 
+void host_reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale) {
+  reduce_n(dst, srcs, n, count, dtype, op, scale);
+}
+
 void Comm::host_barrier() {
   const int n = nranks(), me = rank();
   ++host_epoch_;

@@ -10,6 +10,9 @@ namespace ub {
 
 bool g_preload = false;
 cudaError_t preload_p2p_kernels();  // p2p/p2p_kernels.cu
+}  // namespace ub
+#include "../ukernel/uk_worker.h"
+namespace ub {
 
 cudaError_t preload_all_kernels() {
   static std::mutex mu;
@@ -100,6 +103,11 @@ cudaError_t preload_all_kernels() {
     ok(launch_ep_ll_combine(c, lc, 1, 0));
   }
   ok(preload_p2p_kernels());
+  {
+    UkWorkerArgs uw;
+    memset(&uw, 0, sizeof(uw));
+    ok(launch_uk_worker(uw, 0));
+  }
   g_preload = false;
   done_mask |= 1ull << (dev & 63);
   UB_INFO(SUB_INIT, "preloaded %d kernel functions", loaded);

@@ -17,6 +17,8 @@ struct CuApi {
   CUresult (*CtxGetCurrent)(CUcontext*) = nullptr;
   CUresult (*CtxGetDevice)(CUdevice*) = nullptr;
   CUresult (*StreamGetCtx)(CUstream, CUcontext*) = nullptr;
+  CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
+  CUresult (*StreamWaitValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
   CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*,
                                           CUmemAllocationGranularity_flags) = nullptr;
   CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*,
@@ -74,6 +76,8 @@ inline const CuApi& cu() {
     // multicast is optional (absent on drivers < 12.1 / non-NVSwitch systems)
     get("cuCtxGetDevice", (void**)&a->CtxGetDevice);
     get("cuStreamGetCtx", (void**)&a->StreamGetCtx);
+    get("cuStreamWriteValue64", (void**)&a->StreamWriteValue64);
+    get("cuStreamWaitValue64", (void**)&a->StreamWaitValue64);
     get("cuMulticastCreate", (void**)&a->MulticastCreate);
     get("cuMulticastAddDevice", (void**)&a->MulticastAddDevice);
     get("cuMulticastBindMem", (void**)&a->MulticastBindMem);

@@ -1,0 +1,219 @@
+"""ukernel: launch-free collectives executed by a persistent worker kernel.
+
+Three layers (all native, see ``csrc/ukernel``):
+
+* :class:`Worker` -- per-lane CPU->device FIFOs drained by one persistent CTA each
+  (copy / reduce / signal / wait tasks); on a CPU-only machine the same FIFOs are drained by
+  host threads.
+* the **planner** (:func:`plan`, :func:`validate`, :func:`simulate`) -- tile DAGs for ring and
+  full-mesh AllReduce, AllToAll, AllGather and Barrier.
+* :class:`UkCommunicator` / :class:`ProcessGroup` -- collectives over a
+  :class:`uccl_b200.Communicator`'s symmetric heap, ordered against torch streams with stream
+  memory operations instead of kernel launches.
+
+Reference parity: ``experimental/ukernel`` (persistent kernel, CCL planner/executor, torch
+ProcessGroup with ``all_reduce / all_to_all_single / barrier``: ``ukernel_ccl/__init__.py:171-290``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from .. import _native
+from ..parallel.comm import Communicator, dtype_code, op_code
+
+COLLS = {"allreduce": 0, "alltoall": 1, "allgather": 2, "barrier": 3}
+ALGOS = {"auto": 0, "ring": 1, "fullmesh": 2}
+
+
+def _uk():
+    return _native.C().uk
+
+
+def plan(coll: str, nbytes: int, nranks: int, rank: int, nlanes: int = 1, tile_bytes: int = 1 << 20,
+         elem_size: int = 1, algo: str = "auto"):
+    """Plan of one rank: ``(text, [op dict, ...])``."""
+    return _uk().plan(COLLS[coll], int(nbytes), nranks, rank, nlanes, int(tile_bytes), elem_size, ALGOS[algo])
+
+
+def validate(coll: str, nbytes: int, nranks: int, nlanes: int = 1, tile_bytes: int = 1 << 20, elem_size: int = 1,
+             algo: str = "auto") -> str:
+    """Cross-rank structural validation of the plans of all ranks; '' when consistent."""
+    return _uk().validate(COLLS[coll], int(nbytes), nranks, nlanes, int(tile_bytes), elem_size, ALGOS[algo])
+
+
+def simulate(coll: str, ins: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], op="sum", nlanes: int = 1,
+             tile_bytes: int = 1 << 20, algo: str = "auto") -> str:
+    """Execute the plans of all ranks over CPU tensors with the reference scheduler (greedy: a rank
+    runs ahead as far as its dependencies allow).  Returns '' on success, else the failure."""
+    n = len(ins)
+    assert len(outs) == n and all(t.device.type == "cpu" and t.is_contiguous() for t in list(ins) + list(outs))
+    dt = ins[0].dtype
+    if coll == "allreduce":
+        nbytes = ins[0].numel() * ins[0].element_size()
+    elif coll == "alltoall":
+        nbytes = ins[0].numel() * ins[0].element_size() // n
+    else:
+        nbytes = ins[0].numel() * ins[0].element_size()
+    return _uk().simulate(COLLS[coll], nbytes, n, nlanes, int(tile_bytes), dtype_code(dt), op_code(op), ALGOS[algo],
+                          [t.data_ptr() for t in ins], [t.data_ptr() for t in outs])
+
+
+class Worker:
+    """Raw task interface to the persistent worker (``device=-1``: host threads)."""
+
+    def __init__(self, device: int = 0, nlanes: int = 2, timeout_ms: int = 20000, idle_us: int = -1,
+                 start: bool = True):
+        self._w = _uk().Worker(int(device), int(nlanes), int(timeout_ms), int(idle_us))
+        self.nlanes = nlanes
+        if start:
+            self._w.start()
+
+    def copy(self, lane: int, dst: int, src: int, nbytes: int) -> int:
+        return self._w.push(lane, _uk().OP_COPY, dst=dst, src=src, bytes=int(nbytes))
+
+    def reduce(self, lane: int, dst: int, a: int, b: int, nbytes: int, dtype: torch.dtype, op="sum") -> int:
+        return self._w.push(lane, _uk().OP_REDUCE, dst=dst, src=a, src2=b, bytes=int(nbytes), dtype=dtype_code(dtype),
+                            redop=op_code(op))
+
+    def signal(self, lane: int, addr: int, value: int = 1) -> int:
+        return self._w.push(lane, _uk().OP_SIGNAL, sig_addr=addr, sig_val=int(value))
+
+    def wait_value(self, lane: int, addr: int, value: int) -> int:
+        return self._w.push(lane, _uk().OP_WAIT, sig_addr=addr, sig_val=int(value))
+
+    def wait(self, lane: int, ticket: int, timeout_s: float = 30.0):
+        self._w.wait(lane, ticket, timeout_s)
+
+    def wait_all(self, timeout_s: float = 30.0):
+        self._w.wait_all(timeout_s)
+
+    def done(self, lane: int, ticket: int) -> bool:
+        return self._w.done(lane, ticket)
+
+    def stats(self) -> dict:
+        return self._w.stats()
+
+    def stop(self):
+        self._w.stop()
+
+    @property
+    def error(self) -> int:
+        return self._w.error
+
+    @property
+    def kernel_launches(self) -> int:
+        """How often the worker kernel was (re)launched: it quits after ``idle_us`` without work so that
+        device-wide synchronisation, cudaFree and lazy module loads never wait on an idle worker."""
+        return self._w.kernel_launches
+
+
+class UkWork:
+    """Handle of one enqueued collective (host-side wait; on CUDA the issuing stream is already
+    ordered after the collective, so ``wait()`` is only needed before touching results on the host
+    from another stream)."""
+
+    def __init__(self, uk, ticket: int, result=None):
+        self._uk, self._ticket, self._result = uk, ticket, result
+
+    def is_completed(self) -> bool:
+        return self._uk.test(self._ticket)
+
+    def wait(self, timeout_s: float = 60.0):
+        self._uk.wait(self._ticket, timeout_s)
+        return True
+
+    def result(self):
+        return self._result
+
+
+class UkCommunicator:
+    """Collectives executed by the persistent worker over ``comm``'s symmetric heap.  Construction
+    is collective (every rank, same arguments).  Tensors allocated with ``comm.empty`` are used in
+    place; anything else is staged through the heap in ``staging_bytes`` segments."""
+
+    def __init__(self, comm: Communicator, nlanes: int = 4, tile_bytes: int = 1 << 20,
+                 staging_bytes: int = 32 << 20):
+        self.comm = comm
+        self.rank, self.world_size = comm.rank, comm.world_size
+        self._u = _uk().Comm(comm._c, int(nlanes), int(tile_bytes), int(staging_bytes))
+
+    def _stream(self, stream) -> int:
+        if self.comm.is_host:
+            return 0
+        return (stream or torch.cuda.current_stream(self.comm.device)).cuda_stream
+
+    def _check(self, t: torch.Tensor):
+        if not t.is_contiguous():
+            raise ValueError("uccl_b200.ukernel: tensors must be contiguous")
+        if t.device != self.comm.device:
+            raise ValueError(f"uccl_b200.ukernel: tensor on {t.device}, communicator on {self.comm.device}")
+
+    def all_reduce(self, tensor: torch.Tensor, op="sum", out: Optional[torch.Tensor] = None, algo: str = "auto",
+                   stream=None) -> UkWork:
+        out = tensor if out is None else out
+        self._check(tensor), self._check(out)
+        code = op_code(op)
+        avg = code == 4
+        t = self._u.all_reduce(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype),
+                               0 if avg else code, ALGOS[algo], self._stream(stream))
+        if avg:
+            if self.comm.is_host:
+                self._u.wait(t, 60.0)
+            out.div_(self.world_size)  # CUDA: the current stream is already ordered after the collective
+        return UkWork(self._u, t, out)
+
+    def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor, stream=None) -> UkWork:
+        self._check(inp), self._check(out)
+        if inp.numel() % self.world_size or out.numel() != inp.numel():
+            raise ValueError("uccl_b200.ukernel: all_to_all_single needs equal splits")
+        t = self._u.all_to_all(inp.data_ptr(), out.data_ptr(), inp.numel() // self.world_size, dtype_code(inp.dtype),
+                               self._stream(stream))
+        return UkWork(self._u, t, out)
+
+    def all_gather_into_tensor(self, out: torch.Tensor, inp: torch.Tensor, stream=None) -> UkWork:
+        self._check(inp), self._check(out)
+        if out.numel() != inp.numel() * self.world_size:
+            raise ValueError("uccl_b200.ukernel: all_gather output must hold world_size * input elements")
+        t = self._u.all_gather(inp.data_ptr(), out.data_ptr(), inp.numel(), dtype_code(inp.dtype), self._stream(stream))
+        return UkWork(self._u, t, out)
+
+    def barrier(self, stream=None) -> UkWork:
+        return UkWork(self._u, self._u.barrier(self._stream(stream)))
+
+    def stats(self) -> dict:
+        return self._u.stats()
+
+    def stop(self):
+        self._u.stop()
+
+
+class ProcessGroup:
+    """The reference's ``ukernel_ccl.ProcessGroup`` surface: ``all_reduce``, ``all_to_all_single``,
+    ``barrier`` (synchronous by default, ``async_op=True`` returns the work handle)."""
+
+    def __init__(self, comm: Communicator, **kw):
+        self._uk = UkCommunicator(comm, **kw)
+        self.rank, self.world_size = comm.rank, comm.world_size
+
+    def _finish(self, w: UkWork, async_op: bool):
+        if async_op:
+            return w
+        w.wait()
+        return None
+
+    def all_reduce(self, tensor, op="sum", async_op: bool = False):
+        return self._finish(self._uk.all_reduce(tensor, op), async_op)
+
+    def all_to_all_single(self, output, input, async_op: bool = False):
+        return self._finish(self._uk.all_to_all_single(output, input), async_op)
+
+    def all_gather_into_tensor(self, output, input, async_op: bool = False):
+        return self._finish(self._uk.all_gather_into_tensor(output, input), async_op)
+
+    def barrier(self, async_op: bool = False):
+        return self._finish(self._uk.barrier(), async_op)
+
+    def shutdown(self):
+        self._uk.stop()
