@@ -162,6 +162,37 @@ def test_dispatch_combine(n, mode):
         assert torch.allclose(o["comb_w"], exp_cw, rtol=1e-5, atol=1e-6)
 
 
+def test_internode_api_runs_on_the_fabric():
+    """The reference's internode_dispatch / internode_combine signatures (incl. the per-RDMA-rank
+    histogram) are accepted and give exactly the intranode results inside one NVLink domain."""
+    n, T, H, K = 2, 129, 512, 2
+    E = n * 2
+    bufs = get_buffers(n)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=77)
+
+    def fn(b):
+        dev = b.device
+        x, idx, w = xs[b.rank].to(dev), idxs[b.rank].to(dev), ws[b.rank].to(dev)
+        tpr, tprr, tpe, in_rank, _ = b.get_dispatch_layout(idx, E)
+        a = b.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe, topk_idx=idx,
+                       topk_weights=w)
+        torch.cuda.current_stream().synchronize()
+        ref = (a[0].clone(), a[1].clone(), a[2].clone(), list(a[3]))
+        c = b.internode_dispatch(x, None, tpr, tprr, in_rank, tpe, idx, w)
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(c[0], ref[0]) and torch.equal(c[1], ref[1]) and torch.equal(c[2], ref[2]) and c[3] == ref[3]
+        cb = b.get_combine_buffer(c[0].size(0), H, K)
+        cb.copy_(c[0])
+        comb, _, _ = b.internode_combine(cb, c[4], topk_weights=c[2])
+        torch.cuda.current_stream().synchronize()
+        assert b.get_num_rdma_ranks() == 1
+        return comb.cpu(), in_rank.cpu()
+
+    for r, (comb, in_rank) in enumerate(run_threads(bufs, fn)):
+        exp = xs[r].float() * in_rank.sum(1).float()[:, None]
+        assert torch.allclose(comb.float(), exp, rtol=2e-2, atol=2e-1)
+
+
 def test_dispatch_realistic_shape_single_rank():
     """EP=1 with the BASELINE shape (hidden 7168, top-8): pure local permutation + fused cast."""
     n = 1

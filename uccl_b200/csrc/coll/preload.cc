@@ -4,6 +4,7 @@
 
 #include "../common/log.h"
 #include "../ep/ep_buffer.h"
+#include "../ep/proxy.h"
 #include "../kernels/launch.h"
 
 namespace ub {
@@ -103,6 +104,14 @@ cudaError_t preload_all_kernels() {
     ok(launch_ep_ll_combine(c, lc, 1, 0));
   }
   ok(preload_p2p_kernels());
+  {
+    D2HQueueDev dq;
+    memset(&dq, 0, sizeof(dq));
+    ok(launch_d2h_bench(dq, 1, 32, 0, 0));
+    ok(launch_d2h_latency(dq, 0, nullptr, 0));
+    ok(launch_d2h_issue(dq, 0, 0, 0, 0, 0, 0, 0, 0));
+    ok(launch_u64_add(nullptr, 0, 0));
+  }
   {
     UkWorkerArgs uw;
     memset(&uw, 0, sizeof(uw));

@@ -3,6 +3,7 @@
 #include <pybind11/stl.h>
 
 #include "ep_buffer.h"
+#include "proxy.h"
 
 namespace py = pybind11;
 using namespace ub;
@@ -72,5 +73,53 @@ void bind_ep(py::module_& m) {
       .def("combine", [](EpBuffer& b, uintptr_t x, int num_recv, uintptr_t tw, uintptr_t ss, uintptr_t b0,
                          uintptr_t b1, uintptr_t out, uintptr_t otw, int T, int H, int K, int num_sms, uintptr_t st) {
         b.combine(x, num_recv, tw, ss, b0, b1, out, otw, T, H, K, num_sms, (cudaStream_t)st);
+      });
+
+  // ---- GPU -> CPU command queue + proxy
+  m.attr("D2H_NOP") = (int)D2H_NOP;
+  m.attr("D2H_WRITE") = (int)D2H_WRITE;
+  m.attr("D2H_ATOMIC") = (int)D2H_ATOMIC;
+  m.attr("D2H_NOTIFY") = (int)D2H_NOTIFY;
+  py::class_<Proxy, std::shared_ptr<Proxy>>(m, "EpProxy")
+      .def(py::init([](std::shared_ptr<Comm> c, uint32_t cap) {
+             py::gil_scoped_release rel;
+             return std::make_shared<Proxy>(c, cap);
+           }),
+           py::arg("comm"), py::arg("capacity") = 4096)
+      .def("start", &Proxy::start)
+      .def("stop", &Proxy::stop, py::call_guard<py::gil_scoped_release>())
+      .def_property_readonly("running", &Proxy::running)
+      .def("drain", &Proxy::drain, py::arg("timeout_s") = 30.0, py::call_guard<py::gil_scoped_release>())
+      .def("consumed", &Proxy::consumed)
+      .def("poll_notifications", &Proxy::poll_notifications)
+      // raw device handle (ring, head, tail, ack, capacity) for kernels of other extensions
+      .def("queue_handle",
+           [](Proxy& p) {
+             D2HQueueDev q = p.queue();
+             return py::make_tuple((uintptr_t)q.ring, (uintptr_t)q.head, (uintptr_t)q.tail, (uintptr_t)q.ack, q.capacity);
+           })
+      .def("issue_from_device",
+           [](Proxy& p, int type, int dst, uint32_t aux, uint64_t so, uint64_t doff, uint32_t bytes, uint32_t value,
+              uintptr_t st) { p.issue_from_device((uint32_t)type, dst, aux, so, doff, bytes, value, (cudaStream_t)st); },
+           py::arg("type"), py::arg("dst_rank") = 0, py::arg("aux") = 0, py::arg("src_off") = 0, py::arg("dst_off") = 0,
+           py::arg("bytes") = 0, py::arg("value") = 0, py::arg("stream") = 0)
+      .def("bench_throughput",
+           [](Proxy& p, int blocks, int threads, int per_thread, uintptr_t st) {
+             py::gil_scoped_release rel;
+             return p.bench_throughput(blocks, threads, per_thread, (cudaStream_t)st);
+           },
+           py::arg("blocks") = 8, py::arg("threads") = 128, py::arg("per_thread") = 64, py::arg("stream") = 0)
+      .def("bench_latency",
+           [](Proxy& p, int iters, uintptr_t st) {
+             py::gil_scoped_release rel;
+             return p.bench_latency(iters, (cudaStream_t)st);
+           },
+           py::arg("iters") = 1000, py::arg("stream") = 0)
+      .def("stats", [](Proxy& p) {
+        auto s = p.stats();
+        py::dict d;
+        d["cmds"] = s.cmds, d["nops"] = s.nops, d["writes"] = s.writes, d["atomics"] = s.atomics;
+        d["notifies"] = s.notifies, d["bytes"] = s.bytes, d["avg_handle_us"] = s.avg_handle_us;
+        return d;
       });
 }

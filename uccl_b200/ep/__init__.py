@@ -2,3 +2,4 @@
 from .buffer import Buffer, Config  # noqa: F401
 from .utils import (EventHandle, EventOverlap, bench, calc_diff, inplace_unique,  # noqa: F401
                     per_token_cast_back, per_token_cast_to_fp8)
+from .proxy import FifoProxy, Proxy  # noqa: F401,E402

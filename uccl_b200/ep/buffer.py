@@ -316,12 +316,38 @@ class Buffer:
         ev = self._exit(compute, async_finish, (x, topk_weights, b0, b1, out, out_w, send_slot))
         return out, out_w, ev
 
-    # ------------------------------------------------------------------ internode (not provided)
-    def internode_dispatch(self, *a, **kw):
-        raise NotImplementedError("uccl_b200 targets one NVSwitch node: use dispatch() (every rank is NVLink-reachable)")
+    # ------------------------------------------------------------------ internode entry points
+    # The reference routes to RDMA+NVLink two-hop kernels when the group spans several nodes
+    # (ep/bench/buffer.py:1333-1552 -> ep/src/internode.cu).  Inside one NVLink domain every rank is
+    # a single load/store hop away, so the same call signatures run the direct-placement kernels;
+    # `num_tokens_per_rdma_rank` (the per-node histogram of the two-hop scheme) is accepted and
+    # ignored.  Callers written against the internode API therefore work unchanged on an NVSwitch
+    # node; a group that is not fully peer-mapped cannot be constructed in the first place.
+    def internode_dispatch(self, x, handle: Optional[Tuple] = None, num_tokens_per_rank: Optional[torch.Tensor] = None,
+                           num_tokens_per_rdma_rank: Optional[torch.Tensor] = None,
+                           is_token_in_rank: Optional[torch.Tensor] = None,
+                           num_tokens_per_expert: Optional[torch.Tensor] = None,
+                           topk_idx: Optional[torch.Tensor] = None, topk_weights: Optional[torch.Tensor] = None,
+                           expert_alignment: int = 1, num_worst_tokens: int = 0, config: Optional[Config] = None,
+                           previous_event: Optional[EventOverlap] = None, async_finish: bool = False,
+                           allocate_on_comm_stream: bool = False, **kw):
+        return self.dispatch(x, handle=handle, num_tokens_per_rank=num_tokens_per_rank,
+                             num_tokens_per_rdma_rank=None, is_token_in_rank=is_token_in_rank,
+                             num_tokens_per_expert=num_tokens_per_expert, topk_idx=topk_idx,
+                             topk_weights=topk_weights, expert_alignment=expert_alignment,
+                             num_worst_tokens=num_worst_tokens, config=config, previous_event=previous_event,
+                             async_finish=async_finish, allocate_on_comm_stream=allocate_on_comm_stream, **kw)
 
-    def internode_combine(self, *a, **kw):
-        raise NotImplementedError("uccl_b200 targets one NVSwitch node: use combine()")
+    def internode_combine(self, x: torch.Tensor, handle: Tuple, topk_weights: Optional[torch.Tensor] = None,
+                          bias=None, config: Optional[Config] = None, previous_event: Optional[EventOverlap] = None,
+                          async_finish: bool = False, allocate_on_comm_stream: bool = False):
+        return self.combine(x, handle, topk_weights=topk_weights, bias=bias, config=config,
+                            previous_event=previous_event, async_finish=async_finish,
+                            allocate_on_comm_stream=allocate_on_comm_stream)
+
+    def get_num_rdma_ranks(self) -> int:
+        """Number of RDMA (inter-node) hops groups: always 1 -- the whole group is one NVLink domain."""
+        return 1
 
     # ------------------------------------------------------------------ low latency
     def _need_ll(self):
