@@ -245,8 +245,11 @@ def test_gpu_ukcomm_collectives(n):
         for c in comms:
             torch.cuda.synchronize(c.device)
         works = []
-        for c, u, b in zip(comms, uks, bufs):
-            with torch.cuda.device(c.device):
+        # one stream per rank: virtual ranks share a device, and a shared stream would serialise
+        # rank 1's "inputs ready" write behind rank 0's wait for the collective (= deadlock)
+        streams = [st[0] for st in xs]
+        for c, u, b, s in zip(comms, uks, bufs, streams):
+            with torch.cuda.device(c.device), torch.cuda.stream(s):
                 works.append(u.all_reduce(b, "sum", algo="ring"))
         for w in works:
             w.wait()
@@ -265,8 +268,8 @@ def test_gpu_ukcomm_collectives(n):
                 gi = torch.full((500,), float(c.rank)).to(c.device)
                 outs.append((y, z, g, gi))
             torch.cuda.synchronize(c.device)
-        for c, u, (y, z, g, gi) in zip(comms, uks, outs):
-            with torch.cuda.device(c.device):
+        for c, u, (y, z, g, gi), s in zip(comms, uks, outs, streams):
+            with torch.cuda.device(c.device), torch.cuda.stream(s):
                 works.append(u.all_to_all_single(z, y))
                 works.append(u.all_gather_into_tensor(g, gi))
                 works.append(u.barrier())

@@ -5,6 +5,7 @@
 #include "../common/log.h"
 #include "../ep/ep_buffer.h"
 #include "../ep/proxy.h"
+#include "../p2p/compress.h"
 #include "../kernels/launch.h"
 
 namespace ub {
@@ -104,6 +105,10 @@ cudaError_t preload_all_kernels() {
     ok(launch_ep_ll_combine(c, lc, 1, 0));
   }
   ok(preload_p2p_kernels());
+  ok(cmp_compress_async(nullptr, 0, kBF16, nullptr, 0));
+  ok(cmp_compress_async(nullptr, 0, kF32, nullptr, 0));
+  ok(cmp_decompress_async(nullptr, nullptr, 0, kBF16, 0));
+  ok(cmp_decompress_async(nullptr, nullptr, 0, kF32, 0));
   {
     D2HQueueDev dq;
     memset(&dq, 0, sizeof(dq));

@@ -3,6 +3,7 @@
 #include <pybind11/stl.h>
 
 #include "../common/log.h"
+#include "compress.h"
 #include "endpoint.h"
 
 namespace py = pybind11;
@@ -148,4 +149,17 @@ void bind_p2p(py::module_& m) {
         d["memcpy_fallbacks"] = s.memcpy_fallbacks;
         return d;
       });
+
+  // ---- compression hook
+  m.attr("CMP_HEADER_BYTES") = (int)sizeof(CmpHeader);
+  m.def("cmp_supported", &cmp_dtype_supported);
+  m.def("cmp_bound", &cmp_bound);
+  m.def("cmp_compress", [](uintptr_t src, size_t count, int dtype, uintptr_t dst, uintptr_t st) {
+    cudaError_t e = cmp_compress_async((const void*)src, count, dtype, (void*)dst, (cudaStream_t)st);
+    UB_CHECK(e == cudaSuccess, "cmp_compress: %s", cudaGetErrorString(e));
+  });
+  m.def("cmp_decompress", [](uintptr_t src, uintptr_t dst, size_t count, int dtype, uintptr_t st) {
+    cudaError_t e = cmp_decompress_async((const void*)src, (void*)dst, count, dtype, (cudaStream_t)st);
+    UB_CHECK(e == cudaSuccess, "cmp_decompress: %s", cudaGetErrorString(e));
+  });
 }

@@ -170,6 +170,49 @@ class Endpoint:
     def recv(self, conn_id, mr_id, ptr, size) -> bool:
         return self._block(self.recv_async(conn_id, mr_id, ptr, size))
 
+    # ---- compression hook (reference: UCCL_P2P_COMPRESS_STRATEGY, p2p/rdma/compression.h) -- a 16-byte
+    # header {compressed?, payload bytes} precedes the payload; both sides must use the *_compressed pair
+    def send_compressed(self, conn_id, tensor, strategy=None) -> bool:
+        import struct
+
+        import torch
+
+        from .compress import Compressor
+
+        comp = Compressor(strategy)
+        raw_bytes = tensor.numel() * tensor.element_size()
+        if comp.wants(tensor):
+            payload, nbytes = comp.compress(tensor)
+            flag = 1
+        else:
+            payload, nbytes, flag = tensor, raw_bytes, 0
+        hdr = torch.frombuffer(bytearray(struct.pack("<QQ", flag, nbytes)), dtype=torch.uint8).to(tensor.device)
+        torch.cuda.current_stream(tensor.device).synchronize()
+        return self.send(conn_id, 0, hdr.data_ptr(), 16) and self.send(conn_id, 0, payload.data_ptr(), nbytes)
+
+    def recv_compressed(self, conn_id, out) -> bool:
+        import struct
+
+        import torch
+
+        from .compress import Compressor
+
+        hdr = torch.zeros(16, dtype=torch.uint8, device=out.device)
+        torch.cuda.current_stream(out.device).synchronize()
+        if not self.recv(conn_id, 0, hdr.data_ptr(), 16):
+            return False
+        flag, nbytes = struct.unpack("<QQ", bytes(hdr.cpu().numpy().tobytes()))
+        if not flag:
+            assert nbytes == out.numel() * out.element_size()
+            return self.recv(conn_id, 0, out.data_ptr(), nbytes)
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
+        torch.cuda.current_stream(out.device).synchronize()
+        if not self.recv(conn_id, 0, buf.data_ptr(), nbytes):
+            return False
+        Compressor("for").decompress(buf, out.numel(), out.dtype, out=out.view(-1))
+        torch.cuda.current_stream(out.device).synchronize()
+        return True
+
     def sendv(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None) -> bool:
         return self._block(self.sendv_async(conn_id, mr_ids, ptrs, sizes))
 
