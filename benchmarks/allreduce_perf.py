@@ -59,6 +59,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    def ll_variants(row, fn, per, tot, f, iters):
+        """the same call with the LL-packet exchange forced off / forced on (threshold tuning data)"""
+        if per * es > (1 << 20) or (per * es) % 16:
+            return
+        for name, v in (("plain_noll", -1), ("plain_ll", 1 << 20)):
+            comm.set_xchg_ll_max(v)
+            ms = timeit(fn, iters)
+            row[name] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
+        comm.set_xchg_ll_max(0)
+
     rows = []
     size = args.min
     cta_list = [int(c) for c in args.ctas.split(",") if c] or [-1]
@@ -98,6 +108,7 @@ def main():
             for name, i_, o_ in (("sym_out", plain_in, big_out), ("sym_in", big_in, plain_out), ("plain", plain_in, plain_out)):
                 ms = timeit(lambda: comm.all_gather(o_[:per * n], i_[:per]), iters)
                 row[name] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
+            ll_variants(row, lambda: comm.all_gather(plain_out[:per * n], plain_in[:per]), per, tot, f, iters)
             ms = timeit(lambda: dist.all_gather_into_tensor(plain_out[:per * n], plain_in[:per]), iters)
             row["nccl"] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
         elif args.coll == "reduce_scatter":
@@ -107,6 +118,7 @@ def main():
             for name, i_ in (("sym_in", big_in), ("plain", plain_in)):
                 ms = timeit(lambda: comm.reduce_scatter(plain_out[:per], i_[:per * n], "sum"), iters)
                 row[name] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
+            ll_variants(row, lambda: comm.reduce_scatter(plain_out[:per], plain_in[:per * n], "sum"), per, tot, f, iters)
             ms = timeit(lambda: dist.reduce_scatter_tensor(plain_out[:per], plain_in[:per * n]), iters)
             row["nccl"] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
         elif args.coll == "alltoall":
@@ -116,6 +128,7 @@ def main():
             for name, i_, o_ in (("sym_out", plain_in, big_out), ("sym_in", big_in, plain_out), ("plain", plain_in, plain_out)):
                 ms = timeit(lambda: comm.all_to_all(o_[:per * n], i_[:per * n]), iters)
                 row[name] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
+            ll_variants(row, lambda: comm.all_to_all(plain_out[:per * n], plain_in[:per * n]), per, tot, f, iters)
             ms = timeit(lambda: dist.all_to_all_single(plain_out[:per * n], plain_in[:per * n]), iters)
             row["nccl"] = {"us": ms * 1e3, "busbw": tot / (ms * 1e-3) * f / 1e9}
         else:

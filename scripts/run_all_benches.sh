@@ -9,8 +9,8 @@ R="scripts/run_node.sh $N"
 $R bench.py --gpus "$N" --steps 20 --warmup 5 | tee "$OUT/bench$N.json"
 $R benchmarks/allreduce_perf.py --out "$OUT/ar$N.json"
 for coll in allgather reduce_scatter alltoall; do
-  $R benchmarks/coll_sweep.py --coll $coll --out "$OUT/${coll}$N.json" || true
+  $R benchmarks/allreduce_perf.py --coll $coll --out "$OUT/${coll}$N.json" || true
 done
-$R benchmarks/ep_sweep.py --out "$OUT/ep$N.json"
+$R benchmarks/ep_sweep.py --ll --out "$OUT/ep$N.json"
 python benchmarks/p2p_bench.py --out "$OUT/p2p.json" || true
 python benchmarks/d2h_fifo_bench.py --out "$OUT/d2h.json" || true
