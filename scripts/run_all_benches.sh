@@ -12,5 +12,6 @@ for coll in allgather reduce_scatter alltoall; do
   $R benchmarks/allreduce_perf.py --coll $coll --out "$OUT/${coll}$N.json" || true
 done
 $R benchmarks/ep_sweep.py --ll --out "$OUT/ep$N.json"
+$R benchmarks/ep_baseline.py --out "$OUT/ep_baseline$N.json" || true
 python benchmarks/p2p_bench.py --out "$OUT/p2p.json" || true
 python benchmarks/d2h_fifo_bench.py --out "$OUT/d2h.json" || true

@@ -367,3 +367,35 @@ def test_device_trace():
         assert all(ev[i]["t_ns"] <= ev[i + 1]["t_ns"] for i in range(len(ev) - 1))
         c.disable_trace()
     assert bool((xs[0] == 2.0).all())
+
+
+def test_torch_mem_pool_in_symmetric_heap():
+    """Tensors created under comm.use_mem_pool() live in the symmetric heap: collectives take the
+    zero-copy algorithms on them, although the ranks allocate at different offsets."""
+    n = 2
+    comms = get_world(n)
+    count = 1 << 20
+    ins = _inputs(n, count, torch.float32, seed=5)
+    exp = _ref(ins, "sum")
+    keep = []
+
+    def prepare(c):
+        with c.use_mem_pool():
+            if c.rank == 1:
+                keep.append(torch.empty(12345, device=c.device))  # skew rank 1's offsets
+            x = torch.empty(count, device=c.device)
+        assert c._c.in_heap(x.data_ptr(), x.numel() * 4)
+        x.copy_(ins[c.rank])
+        algo, _ = c.select_allreduce(count * 4, True, torch.float32)
+        assert algo.startswith("twoshot")
+        return x
+
+    outs = run_ranks(comms, prepare, lambda c, x: c.all_reduce(x, "sum"))
+    for o in outs:
+        assert torch.allclose(o.cpu().double(), exp, rtol=1e-5, atol=1e-5)
+    from uccl_b200 import _native
+
+    st = _native.C().pool_stats()
+    assert st["allocs"] >= 3 and st["fallback_allocs"] == 0
+    y = torch.empty(8, device=comms[0].device)  # outside the context: ordinary allocator again
+    assert not comms[0]._c.in_heap(y.data_ptr(), 32)

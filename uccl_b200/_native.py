@@ -34,3 +34,8 @@ def is_built() -> bool:
     from . import _build
 
     return _build.module_path().exists()
+
+
+def module_path() -> str:
+    """Filesystem path of the loaded extension (exports the C symbols torch's pluggable allocator needs)."""
+    return C().__file__

@@ -173,6 +173,17 @@ PYBIND11_MODULE(_C, m) {
            },
            py::arg("reset") = true);
 
+  m.def("pool_install", &pool_install);
+  m.def("pool_set_thread_comm", &pool_set_thread_comm);
+  m.def("pool_clear_thread_comm", &pool_clear_thread_comm);
+  m.def("pool_stats", [] {
+    uint64_t a, f, l, fb;
+    pool_stats(&a, &f, &l, &fb);
+    py::dict d;
+    d["allocs"] = a, d["frees"] = f, d["live_bytes"] = l, d["fallback_allocs"] = fb;
+    return d;
+  });
+
   bind_util(m);
   bind_ep(m);
   bind_p2p(m);

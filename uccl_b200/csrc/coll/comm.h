@@ -153,4 +153,10 @@ const char* algo_name(int algo);
 // CPU reference reduction used by the host backends: dst[i] = op_r srcs[r][i], then * scale (floats)
 void host_reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale);
 
+// torch.cuda.MemPool backend (mem_pool.cc): which communicator serves `uccl_b200_pool_malloc`
+void pool_install(std::shared_ptr<Comm> c);            // default for c->device()
+void pool_set_thread_comm(std::shared_ptr<Comm> c);    // per-thread override (virtual ranks)
+void pool_clear_thread_comm();
+void pool_stats(uint64_t* allocs, uint64_t* frees, uint64_t* live_bytes, uint64_t* fallback_allocs);
+
 }  // namespace ub

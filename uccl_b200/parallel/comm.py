@@ -338,6 +338,48 @@ class Communicator:
         self._c.set_tuning(bool(symmetric), ents)
 
 
+    # ------------------------------------------------------------------ torch memory pool
+    def mem_pool(self):
+        """A ``torch.cuda.MemPool`` whose blocks live in this communicator's symmetric heap::
+
+            pool = comm.mem_pool()
+            with torch.cuda.use_mem_pool(pool):
+                grads = torch.empty(n, device="cuda")      # peer-mapped + multicast-bound
+            comm.all_reduce(grads)                          # zero-copy two-shot / NVLS path
+
+        (the torch-side analogue of ``ncclMemAlloc``).  When the heap is exhausted the pool falls back
+        to ``cudaMalloc`` for that block, which then simply takes the staged paths."""
+        if self.is_host:
+            raise RuntimeError("uccl_b200: mem_pool needs a CUDA communicator")
+        if getattr(self, "_pool", None) is None:
+            from torch.cuda.memory import CUDAPluggableAllocator
+
+            C = _native.C()
+            C.pool_install(self._c)
+            self._pool_alloc = CUDAPluggableAllocator(_native.module_path(), "uccl_b200_pool_malloc",
+                                                      "uccl_b200_pool_free")
+            self._pool = torch.cuda.MemPool(self._pool_alloc.allocator())
+        return self._pool
+
+    def use_mem_pool(self):
+        """Context manager: route this thread's CUDA allocations into the symmetric heap."""
+        import contextlib
+
+        pool = self.mem_pool()
+        C = _native.C()
+        comm = self
+
+        @contextlib.contextmanager
+        def ctx():
+            C.pool_set_thread_comm(comm._c)  # several communicators may share one device (virtual ranks)
+            try:
+                with torch.cuda.use_mem_pool(pool, device=comm.device):
+                    yield pool
+            finally:
+                C.pool_clear_thread_comm()
+
+        return ctx()
+
     def set_xchg_ll_max(self, nbytes: int):
         """Per-rank piece size up to which all_gather / all_to_all / reduce_scatter use the barrier-free
         LL-packet kernels (0: built-in default per world size, negative: never)."""
