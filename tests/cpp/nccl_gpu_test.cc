@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
       CK(cudaMalloc(&d_in, N * 4));
       CK(cudaMalloc(&d_out, N * 4));
       CK(cudaMemcpy(d_in, h.data(), N * 4, cudaMemcpyHostToDevice));
-      CK(cudaDeviceSynchronize());  // pageable H2D may still be in flight; `st` is non-blocking
+      CK(cudaStreamSynchronize(0));  // pageable H2D may still be in flight (null stream); `st` is non-blocking
       // 1. allreduce on plain buffers (staged + tail)
       NK(ncclAllReduce(d_in, d_out, N, ncclFloat, ncclSum, comms[r], st));
       CK(cudaStreamSynchronize(st));
@@ -72,7 +72,7 @@ int main(int argc, char** argv) {
       float* sym;
       NK(ncclMemAlloc((void**)&sym, 4096 * 4));
       CK(cudaMemcpy(sym, h.data(), 4096 * 4, cudaMemcpyHostToDevice));
-      CK(cudaDeviceSynchronize());  // pageable H2D may still be in flight; `st` is non-blocking
+      CK(cudaStreamSynchronize(0));  // pageable H2D may still be in flight (null stream); `st` is non-blocking
       NK(ncclAllReduce(sym, sym, 4096, ncclFloat, ncclMax, comms[r], st));
       CK(cudaStreamSynchronize(st));
       CK(cudaMemcpy(o.data(), sym, 4096 * 4, cudaMemcpyDeviceToHost));
@@ -103,9 +103,9 @@ int main(int argc, char** argv) {
       std::vector<float> hs(M);
       for (size_t i = 0; i < M; ++i) hs[i] = (float)(r * 1000 + (i % 251));
       CK(cudaMemcpy(s_buf, hs.data(), M * 4, cudaMemcpyHostToDevice));
-      CK(cudaDeviceSynchronize());  // pageable H2D may still be in flight; `st` is non-blocking
+      CK(cudaStreamSynchronize(0));  // pageable H2D may still be in flight (null stream); `st` is non-blocking
       CK(cudaMemset(r_buf, 0, M * 4));
-      CK(cudaDeviceSynchronize());  // cudaMemset is asynchronous and `st` does not order with the null stream
+      CK(cudaStreamSynchronize(0));  // cudaMemset is asynchronous; `st` does not order with the null stream (no device-wide sync: virtual ranks share the GPU)
       NK(ncclGroupStart());
       NK(ncclSend(s_buf, M, ncclFloat, (r + 1) % n, comms[r], st));
       NK(ncclRecv(r_buf, M, ncclFloat, (r + n - 1) % n, comms[r], st));
@@ -130,7 +130,7 @@ int main(int argc, char** argv) {
         for (int p = 0; p < n; ++p)
           for (size_t i = 0; i < C; ++i) ha[p * C + i] = (float)(rep * 7 + r * 100 + p);
         CK(cudaMemcpy(a_in, ha.data(), C * n * 4, cudaMemcpyHostToDevice));
-        CK(cudaDeviceSynchronize());  // pageable H2D may still be in flight; `st` is non-blocking
+        CK(cudaStreamSynchronize(0));  // pageable H2D may still be in flight (null stream); `st` is non-blocking
         NK(ncclGroupStart());
         for (int p = 0; p < n; ++p) {
           NK(ncclSend(a_in + p * C, C, ncclFloat, p, comms[r], st));
