@@ -67,6 +67,18 @@ static int run(int rank, int n, ncclUniqueId id) {
   if (rank == 0)
     for (auto v : red_out) EXPECT(v == 6.f);
 
+  // user-defined PreMulSum: 0.25 * (sum over ranks), fused into the reduction
+  {
+    float scalar = 0.25f;
+    ncclRedOp_t premul;
+    CHECK(ncclRedOpCreatePreMulSum(&premul, &scalar, ncclFloat, ncclScalarHostImmediate, comm));
+    std::vector<float> pin(9, (float)(rank + 1)), pout(9, 0.f);
+    CHECK(ncclAllReduce(pin.data(), pout.data(), 9, ncclFloat, premul, comm, nullptr));
+    for (auto v : pout) EXPECT(v == 0.25f * 3.f);
+    CHECK(ncclRedOpDestroy(premul, comm));
+    EXPECT(ncclAllReduce(pin.data(), pout.data(), 9, ncclFloat, premul, comm, nullptr) == ncclInvalidArgument);
+  }
+
   // error paths
   EXPECT(ncclAllReduce(x.data(), y.data(), 4, (ncclDataType_t)99, ncclSum, comm, nullptr) == ncclInvalidArgument);
   EXPECT(ncclBroadcast(b.data(), b.data(), 1, ncclInt64, 7, comm, nullptr) == ncclInvalidArgument);

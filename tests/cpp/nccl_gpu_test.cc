@@ -77,6 +77,24 @@ int main(int argc, char** argv) {
       CK(cudaStreamSynchronize(st));
       CK(cudaMemcpy(o.data(), sym, 4096 * 4, cudaMemcpyDeviceToHost));
       for (int i = 0; i < 4096; i += 97) EXPECT(o[i] == (float)(i % 7) + (n - 1));
+      // 2b. PreMulSum (device-resident bf16-free path: float scalar on the host), allreduce + reduce_scatter
+      {
+        float scalar = 0.5f;
+        ncclRedOp_t premul;
+        NK(ncclRedOpCreatePreMulSum(&premul, &scalar, ncclFloat, ncclScalarHostImmediate, comms[r]));
+        NK(ncclAllReduce(d_in, d_out, 4096, ncclFloat, premul, comms[r], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(o.data(), d_out, 4096 * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 4096; i += 101) EXPECT(o[i] == 0.5f * (n * (float)(i % 7) + n * (n - 1) / 2.0f));
+        NK(ncclReduceScatter(d_in, d_out, 1024, ncclFloat, premul, comms[r], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpy(o.data(), d_out, 1024 * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 1024; i += 53) {
+          const size_t gi = (size_t)r * 1024 + i;
+          EXPECT(o[i] == 0.5f * (n * (float)(gi % 7) + n * (n - 1) / 2.0f));
+        }
+        NK(ncclRedOpDestroy(premul, comms[r]));
+      }
       // 3. allgather / reduce_scatter
       const size_t P = 5000;
       float *ag_out, *rs_out;

@@ -486,7 +486,8 @@ void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype
 }
 
 // ------------------------------------------------------------- reduce_scatter
-void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream) {
+void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream,
+                          float scale) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "reduce_scatter: bad dtype %d", dtype);
   UB_CHECK(op >= 0 && op < kNumOps, "reduce_scatter: bad op %d", op);
   if (recv_count == 0) return;
@@ -494,17 +495,20 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   check_buf(out, "recvbuff");
   const int n = nranks();
   const size_t bytes = recv_count * dtype_size(dtype);
+  UB_CHECK(scale == 1.0f || is_float_dtype(dtype), "reduce_scatter: scale needs a floating-point dtype");
   if (is_host()) {
+    UB_CHECK(scale == 1.0f, "host backend: fused scale unsupported");
     host_reduce_scatter(in, out, recv_count, dtype, op);
     return;
   }
   DeviceGuard g(device());
   CollArgs a = base_args();
+  a.ep.scale = scale;
   if (op == kAvg) {
-    if (is_float_dtype(dtype)) a.ep.scale = 1.0f / (float)n;
+    if (is_float_dtype(dtype)) a.ep.scale *= 1.0f / (float)n;
     else a.ep.idiv = n;
   }
-  if (n == 1 && op != kAvg) {
+  if (n == 1 && op != kAvg && scale == 1.0f) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -569,7 +573,8 @@ void Comm::broadcast(const void* in, void* out, size_t count, int dtype, int roo
 }
 
 // --------------------------------------------------------------------- reduce
-void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream) {
+void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream,
+                  float scale) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "reduce: bad dtype %d", dtype);
   UB_CHECK(op >= 0 && op < kNumOps, "reduce: bad op %d", op);
   UB_CHECK(root >= 0 && root < nranks(), "reduce: bad root %d", root);
@@ -578,17 +583,20 @@ void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, in
   if (rank() == root) check_buf(out, "recvbuff");
   const int n = nranks();
   const size_t bytes = count * dtype_size(dtype);
+  UB_CHECK(scale == 1.0f || is_float_dtype(dtype), "reduce: scale needs a floating-point dtype");
   if (is_host()) {
+    UB_CHECK(scale == 1.0f, "host backend: fused scale unsupported");
     host_reduce(in, out, count, dtype, op, root);
     return;
   }
   DeviceGuard g(device());
   CollArgs a = base_args();
+  a.ep.scale = scale;
   if (op == kAvg) {
-    if (is_float_dtype(dtype)) a.ep.scale = 1.0f / (float)n;
+    if (is_float_dtype(dtype)) a.ep.scale *= 1.0f / (float)n;
     else a.ep.idiv = n;
   }
-  if (n == 1 && op != kAvg) {
+  if (n == 1 && op != kAvg && scale == 1.0f) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }

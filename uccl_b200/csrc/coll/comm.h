@@ -81,9 +81,12 @@ class Comm {
   void allreduce(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t stream,
                  const ArOpts& opts = ArOpts());
   void allgather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream);
-  void reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream);
+  // `scale`: fused post-scale of the result (float dtypes), multiplied with the 1/N of kAvg
+  void reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream,
+                      float scale = 1.0f);
   void broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream);
-  void reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream);
+  void reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream,
+              float scale = 1.0f);
   void alltoall(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream);
   void alltoallv(const void* in, const size_t* send_counts, const size_t* send_displs, void* out,
                  const size_t* recv_counts, const size_t* recv_displs, int dtype, cudaStream_t stream);

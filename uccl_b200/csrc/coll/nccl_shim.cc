@@ -12,6 +12,7 @@
 // this is the GPU-less CI configuration "NCCL-API allreduce correctness world_size=2 on CPU".
 #include <nccl.h>
 
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -33,6 +34,8 @@ UB_PARAM(ShimHostFake, "HOST_FAKE", 0)
 
 struct ncclComm {
   std::shared_ptr<Comm> comm;
+  std::map<int, float> premul;  // user-created PreMulSum ops: op id -> scalar
+  int next_op = (int)ncclNumOps;
   std::string last_error;
   ncclResult_t async_error = ncclSuccess;
   bool finalized = false;
@@ -341,22 +344,97 @@ UB_EXPORT ncclResult_t ncclMemFree(void* ptr) {
   });
 }
 
-UB_EXPORT ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t*, void*, ncclDataType_t, ncclScalarResidence_t, ncclComm_t) {
-  g_last_error = "uccl_b200: use the fused `scale` epilogue of the native API instead of PreMulSum";
-  return ncclInvalidUsage;
+// PreMulSum(s) = sum_r s * x_r.  With the same scalar on every rank -- the way it is used for
+// averaging (torch's _make_nccl_premul_sum(1/world)) -- this is s * sum_r x_r, i.e. exactly the fused
+// post-scale epilogue of the kernels (one multiply in fp32 before the single rounding).  Per-rank
+// different scalars are not supported.  The scalar is read when the op is created.
+UB_EXPORT ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, ncclDataType_t datatype,
+                                                ncclScalarResidence_t residence, ncclComm_t comm) {
+  if (!valid(comm) || !op || !scalar) return ncclInvalidArgument;
+  return guarded(comm, [&] {
+    unsigned char raw[8] = {0};
+    const size_t es = dtype_size((int)datatype);
+    if (residence == ncclScalarDevice && !comm->comm->is_host()) {
+      UB_CUDA(cudaMemcpy(raw, scalar, es, cudaMemcpyDeviceToHost));
+    } else {
+      memcpy(raw, scalar, es);
+    }
+    float v = 1.0f;
+    switch ((int)datatype) {
+      case kF32: memcpy(&v, raw, 4); break;
+      case kF64: {
+        double d;
+        memcpy(&d, raw, 8);
+        v = (float)d;
+        break;
+      }
+      case kF16: {
+        uint16_t h;
+        memcpy(&h, raw, 2);
+        const uint32_t sign = (h >> 15) & 1, ex = (h >> 10) & 0x1f, man = h & 0x3ff;
+        if (ex == 0) v = (float)man * 5.9604644775390625e-08f;  // 2^-24
+        else if (ex == 31) v = man ? NAN : INFINITY;
+        else {
+          const uint32_t bits = ((ex + 112) << 23) | (man << 13);
+          memcpy(&v, &bits, 4);
+        }
+        if (sign) v = -v;
+        break;
+      }
+      case kBF16: {
+        uint16_t h;
+        memcpy(&h, raw, 2);
+        const uint32_t bits = (uint32_t)h << 16;
+        memcpy(&v, &bits, 4);
+        break;
+      }
+      default: UB_THROW("PreMulSum needs a floating-point datatype (got %d)", (int)datatype);
+    }
+    std::lock_guard<std::mutex> g(g_mu);
+    const int id = comm->next_op++;
+    comm->premul[id] = v;
+    *op = (ncclRedOp_t)id;
+  });
 }
-UB_EXPORT ncclResult_t ncclRedOpDestroy(ncclRedOp_t, ncclComm_t) { return ncclSuccess; }
+UB_EXPORT ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t comm) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  std::lock_guard<std::mutex> g(g_mu);
+  return comm->premul.erase((int)op) ? ncclSuccess : ncclInvalidArgument;
+}
+
+namespace {
+// built-in op -> (op, 1); PreMulSum handle -> (sum, scalar)
+bool resolve_op(ncclComm* c, ncclRedOp_t op, int* out_op, float* scale) {
+  *scale = 1.0f;
+  if ((int)op < (int)ncclNumOps) {
+    *out_op = (int)op;
+    return true;
+  }
+  std::lock_guard<std::mutex> g(g_mu);
+  auto it = c->premul.find((int)op);
+  if (it == c->premul.end()) return false;
+  *out_op = kSum;
+  *scale = it->second;
+  return true;
+}
+}  // namespace
 
 UB_EXPORT ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                      ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->allreduce(sendbuff, recvbuff, count, (int)datatype, (int)op, stream); });
+  int rop;
+  ArOpts o;
+  if (!resolve_op(comm, op, &rop, &o.scale)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->allreduce(sendbuff, recvbuff, count, (int)datatype, rop, stream, o); });
 }
 
 UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                   ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->reduce(sendbuff, recvbuff, count, (int)datatype, (int)op, root, stream); });
+  int rop;
+  float scale;
+  if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
+  return guarded(comm, [&] { comm->comm->reduce(sendbuff, recvbuff, count, (int)datatype, rop, root, stream, scale); });
 }
 
 UB_EXPORT ncclResult_t ncclBroadcast(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
@@ -374,7 +452,11 @@ UB_EXPORT ncclResult_t ncclReduceScatter(const void* sendbuff, void* recvbuff, s
                                          ncclDataType_t datatype, ncclRedOp_t op, ncclComm_t comm,
                                          cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, (int)op, stream); });
+  int rop;
+  float scale;
+  if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
+  return guarded(comm,
+                 [&] { comm->comm->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, rop, stream, scale); });
 }
 
 UB_EXPORT ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype,
