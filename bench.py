@@ -301,10 +301,25 @@ def main():
     # cudaMemcpyPeer pairs and these kernels all top out at on this box (profiles/RESULTS.md)
 
     # ---- end-to-end through the public API, inputs from pinned host memory every step
-    def step_e2e():
-        xd = x_host.to(dev, non_blocking=True)
-        idd = idx_host.to(dev, non_blocking=True)
-        wd = w_host.to(dev, non_blocking=True)
+    # Inputs of step i+1 are copied on a side stream while step i runs (every step still copies its
+    # own inputs inside the timed region; the copies are just not serialised with the kernels).
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            xd = x_host.to(dev, non_blocking=True)
+            idd = idx_host.to(dev, non_blocking=True)
+            wd = w_host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return xd, idd, wd, ev
+
+    def step_e2e(inputs):
+        xd, idd, wd, ev = inputs
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ev)
+        for t in (xd, idd, wd):
+            t.record_stream(cur)
         a, _, b, c, _ = buf.get_dispatch_layout(idd, E)
         rx, ri, rw, pe, h, _ = buf.dispatch(xd, num_tokens_per_rank=a, is_token_in_rank=c, num_tokens_per_expert=b,
                                             topk_idx=idd, topk_weights=wd, use_fp8=True, config=cfg)
@@ -312,14 +327,22 @@ def main():
         out, _, _ = buf.combine(cin, h, config=cfg)
         return out[:, :8].float().sum(dim=1).cpu()  # D2H read of a per-token checksum
 
-    for _ in range(3):
-        step_e2e()
+    def run_e2e(steps):
+        nxt = prefetch()
+        res = None
+        for i in range(steps):
+            cur_in = nxt
+            if i + 1 < steps:
+                nxt = prefetch()
+            res = step_e2e(cur_in)
+        return res
+
+    run_e2e(3)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(e2e_steps):
-        res = step_e2e()
+    res = run_e2e(e2e_steps)
     e.record()
     barrier()
     e2e_ms = max_over_ranks(s.elapsed_time(e) / e2e_steps)
@@ -365,7 +388,8 @@ def main():
         "num_recv_tokens": num_recv,
         "clocks": clocks,
         "e2e": {"value": n * T / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "note": "pinned-host inputs of step i+1 are copied on a side stream during step i"},
         "gpu_launches": gpu_launches,
         "wall_s_timed_region": wall,
         "nvls": bool(comm.has_multicast),
