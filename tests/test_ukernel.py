@@ -178,7 +178,7 @@ def test_gpu_worker_tasks():
     odd = torch.zeros(1001, device=dev, dtype=torch.uint8)
     odd_src = torch.arange(1001, device=dev).to(torch.uint8)
     flag = torch.zeros(2, device=dev, dtype=torch.int64)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     w = uk.Worker(device=0, nlanes=2, idle_us=2000)
     w.copy(0, c.data_ptr(), a.data_ptr(), a.numel() * 4)
     w.reduce(0, c.data_ptr(), c.data_ptr(), b.data_ptr(), a.numel() * 4, torch.float32, "sum")
@@ -188,18 +188,18 @@ def test_gpu_worker_tasks():
     w.copy(1, odd.data_ptr() + 1, odd_src.data_ptr() + 1, 999)  # unaligned byte copy
     w.wait_all()
     # a device-wide synchronisation must not hang on the idle worker: it quits after idle_us ...
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     first = w.kernel_launches
     assert first >= 1
     # ... and is relaunched transparently by the next task
     c2 = torch.zeros_like(c)
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     t = w.copy(1, c2.data_ptr(), c.data_ptr(), c.numel() * 4)
     w.wait(1, t)
     assert w.kernel_launches > first
     w.stop()
     assert w.error == 0
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     assert torch.equal(c2, c)
     assert torch.equal(c, a + b)
     assert torch.equal(hout, torch.maximum(h, h2))

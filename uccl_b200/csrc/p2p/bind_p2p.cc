@@ -1,4 +1,6 @@
 // Python bindings of the P2P engine (role of the reference's nanobind module p2p/engine_api.cc).
+#include <algorithm>
+
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
@@ -55,10 +57,18 @@ void bind_p2p(py::module_& m) {
              std::string ip;
              int gpu = -1;
              uint64_t id = 0;
-             bool ok;
-             {
-               py::gil_scoped_release rel;
-               ok = e.accept(&ip, &gpu, &id, timeout_ms);
+             // sliced so that Ctrl-C interrupts a blocking accept (reference: check_python_signals()
+             // polled inside blocking loops, p2p/engine.cc:388-392)
+             bool ok = false;
+             int waited = 0;
+             while (!ok && (timeout_ms < 0 || waited < timeout_ms)) {
+               const int slice = timeout_ms < 0 ? 100 : std::min(100, timeout_ms - waited);
+               {
+                 py::gil_scoped_release rel;
+                 ok = e.accept(&ip, &gpu, &id, slice);
+               }
+               waited += slice;
+               if (PyErr_CheckSignals() != 0) throw py::error_already_set();
              }
              return py::make_tuple(ok, ip, gpu, id);
            },
@@ -126,8 +136,21 @@ void bind_p2p(py::module_& m) {
            })
       .def("wait",
            [](Endpoint& e, uint64_t tid, int timeout_ms) {
-             py::gil_scoped_release rel;
-             return e.wait(tid, timeout_ms);
+             bool done = false;
+             int waited = 0;
+             while (!done && (timeout_ms < 0 || waited < timeout_ms)) {
+               const int slice = timeout_ms < 0 ? 100 : std::min(100, timeout_ms - waited);
+               bool valid = true;
+               {
+                 py::gil_scoped_release rel;
+                 done = e.wait(tid, slice);
+                 if (!done) valid = e.poll_async(tid, &done);  // false: unknown / failed transfer, not a timeout
+               }
+               if (!valid) return false;
+               waited += slice;
+               if (!done && PyErr_CheckSignals() != 0) throw py::error_already_set();
+             }
+             return done;
            },
            py::arg("tid"), py::arg("timeout_ms") = -1)
       .def("send_notif", &Endpoint::send_notif)
