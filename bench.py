@@ -37,6 +37,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--metric", default="ep", choices=["ep", "allreduce"])
+    p.add_argument("--no-graph", action="store_true", help="launch the timed steps eagerly instead of replaying CUDA graphs")
     p.add_argument("--tokens", type=int, default=4096)
     p.add_argument("--hidden", type=int, default=7168)
     p.add_argument("--topk", type=int, default=8)
@@ -268,6 +269,38 @@ def main():
         step_cached()
     barrier()
 
+    # ---- the step is launch-bound at small N (two short kernels per step, ~0.5 ms of Python per call):
+    # capture dispatch and combine into CUDA graphs so the timed region measures the GPU, not the
+    # interpreter (the kernels keep their cross-rank epochs on the device, so replays are safe).
+    graphs = None
+    per_step_launches = 2
+    if not args.no_graph:
+        try:
+            l_before = launches()
+            g_d, g_c = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_d):
+                buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
+            with torch.cuda.graph(g_c):
+                buf.combine(comb_in, handle, config=cfg)
+            per_step_launches = launches() - l_before
+            graphs = (g_d, g_c)
+        except Exception as exc:  # pragma: no cover - fall back to eager launches
+            if rank == 0:
+                print(f"[bench] CUDA graph capture unavailable ({type(exc).__name__}: {exc}); eager launches",
+                      file=sys.stderr)
+            graphs = None
+            torch.cuda.synchronize()
+    use_graph = torch.tensor([1 if graphs is not None else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(use_graph, op=dist.ReduceOp.MIN)  # every rank must take the same path
+    if int(use_graph.item()) == 0:
+        graphs = None
+    if graphs is not None:
+        for _ in range(3):
+            graphs[0].replay()
+            graphs[1].replay()
+    barrier()
+
     # ---- timed region: exactly K steps, device-timed per step, L2 flushed between steps
     sampler = ClockSampler(dev.index)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -279,14 +312,19 @@ def main():
     for i in range(args.steps):
         flush.zero_()
         starts[i].record()
-        buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
-        mids[i].record()
-        buf.combine(comb_in, handle, config=cfg)
+        if graphs is not None:
+            graphs[0].replay()
+            mids[i].record()
+            graphs[1].replay()
+        else:
+            buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
+            mids[i].record()
+            buf.combine(comb_in, handle, config=cfg)
         ends[i].record()
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    gpu_launches = launches() - l0
+    gpu_launches = (launches() - l0) if graphs is None else per_step_launches * args.steps
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     ms_per_step = max_over_ranks(sum(step_ms) / len(step_ms))
     tokens_per_s = n * T / (ms_per_step * 1e-3)
@@ -368,6 +406,7 @@ def main():
             "global_batch": n * T, "seq_len": T, "tokens_per_rank": T, "hidden": H, "num_topk": K,
             "num_experts": E, "parallelism": f"ep{n}", "dispatch": "bf16 -> fused e4m3 + per-128 scales",
             "combine": "bf16", "num_sms": cfg.num_sms, "handle": "cached (as the reference times it)",
+            "launch": "cuda_graph_replay" if graphs is not None else "eager",
             "l2": "256 MiB flush write between timed steps (untimed); per-step working set > 126 MB L2",
         },
         "dispatch_us": disp_ms * 1e3,
@@ -391,6 +430,7 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "note": "pinned-host inputs of step i+1 are copied on a side stream during step i"},
         "gpu_launches": gpu_launches,
+        "step_us_min_med_max": [min(step_ms) * 1e3, statistics.median(step_ms) * 1e3, max(step_ms) * 1e3],
         "wall_s_timed_region": wall,
         "nvls": bool(comm.has_multicast),
     }

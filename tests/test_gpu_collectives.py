@@ -220,6 +220,35 @@ def test_ll_exchange_vs_barrier_paths(n, ll):
             c.set_xchg_ll_max(0)
 
 
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_reduce_scatter_push_staging(n):
+    """Plain-buffer reduce_scatter with the push staging variant, several double-buffered chunks
+    (1 MiB stage), odd sizes, and the same results as the pull variant bit for bit."""
+    comms = get_world(n, heap_mb=160, stage_mb=1, max_ctas=4)
+    for c in comms:
+        c.set_xchg_ll_max(-1)
+    try:
+        for dtype, op, count in ((torch.float32, "sum", (1 << 18) + 4), (torch.bfloat16, "max", 70001),
+                                 (torch.int32, "sum", 1000)):
+            ins = _inputs(n, n * count, dtype, seed=count)
+            exp = _ref(ins, op).view(n, count)
+            res = {}
+            for push in (False, True):
+                for c in comms:
+                    c.set_rs_push(push)
+                outs = run_ranks(comms, lambda c: (ins[c.rank].to(c.device), torch.zeros(count, dtype=dtype, device=c.device)),
+                                 lambda c, st: c.reduce_scatter(st[1], st[0], op))
+                res[push] = [o.cpu() for _, o in outs]
+                for r in range(n):
+                    assert torch.allclose(res[push][r].double(), exp[r], **_tol(dtype))
+            for r in range(n):
+                assert torch.equal(res[True][r], res[False][r])
+    finally:
+        for c in comms:
+            c.set_rs_push(False)
+            c.set_xchg_ll_max(0)
+
+
 @pytest.mark.parametrize("n", [2, 8])
 def test_broadcast_reduce_alltoall(n):
     comms = get_world(n)

@@ -162,6 +162,8 @@ PYBIND11_MODULE(_C, m) {
            })
       .def("set_tuning", &Comm::set_tuning)
       .def("set_xchg_ll_max", &Comm::set_xchg_ll_max)
+      .def("set_rs_push", &Comm::set_rs_push)
+      .def("rs_push", &Comm::rs_push)
       .def("xchg_ll_max", &Comm::xchg_ll_max)
       .def("enable_trace", &Comm::enable_trace)
       .def("disable_trace", &Comm::disable_trace)

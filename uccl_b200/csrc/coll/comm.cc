@@ -18,6 +18,7 @@ UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
 // LL-packet AllGather / AllToAll / ReduceScatter for per-rank pieces up to this many bytes
 // (0: per-world-size default, -1: never)
 UB_PARAM(XchgLLMaxBytes, "XCHG_LL_MAX_BYTES", 0)
+UB_PARAM(RsPush, "RS_PUSH", 0)  // staged ReduceScatter: 1 = push into the peers' stages, 0 = copy-in + pull
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 
 const char* algo_name(int algo) {
@@ -85,6 +86,7 @@ void Comm::init(std::shared_ptr<Fabric> f, const CommConfig& cfg) {
   max_ctas_ = cfg.max_ctas > 0 ? cfg.max_ctas : (int)ubParamMaxCtas();
   max_ctas_ = std::min(max_ctas_, kMaxSyncBlocks);
   xchg_ll_max_ = ubParamXchgLLMaxBytes();
+  rs_push_ = ubParamRsPush() != 0;
   memset(&dev_, 0, sizeof(dev_));
   dev_.rank = f->rank();
   dev_.nranks = f->nranks();
@@ -519,6 +521,7 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   a.count = recv_count;
   const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
   if (in_sym) a.in_off = heap_offset(in);
+  a.variant = rs_push_ ? 1 : 0;
   const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
   const bool fdt =
       dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2;

@@ -106,6 +106,10 @@ class Comm {
   // LL-packet AllGather/AllToAll/ReduceScatter threshold (per-rank piece bytes): 0 default, <0 off
   void set_xchg_ll_max(int64_t bytes) { xchg_ll_max_ = bytes; }
   int64_t xchg_ll_max() const { return xchg_ll_max_; }
+  // staged (plain-buffer) ReduceScatter: push pieces into the peers' stages instead of copy-in + pull.
+  // Must be set identically on every rank.
+  void set_rs_push(bool on) { rs_push_ = on; }
+  bool rs_push() const { return rs_push_; }
   uint32_t error_word() const { return err_host_ ? *err_host_ : 0; }
   // in-kernel tracing (device timeline of every block's barriers / phases)
   struct TraceEvent {
@@ -139,6 +143,7 @@ class Comm {
   CommConfig cfg_;
   int max_ctas_ = 64;
   int64_t xchg_ll_max_ = 0;
+  bool rs_push_ = false;
   uint32_t* err_host_ = nullptr;
   uint64_t launches_ = 0;
   uint32_t host_epoch_ = 0;

@@ -172,6 +172,64 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
   const bool same = all_equal(s_off, n);
   const char* in = reinterpret_cast<const char*>(a.in);
   char* out = reinterpret_cast<char*>(a.out);
+  if (staged && a.variant == 1) {
+    // Push staging: every rank stores piece d of its (plain) input straight into slot[rank] of
+    // rank d's stage over NVLink, then each rank reduces its n slots from *local* memory.  Compared
+    // with the pull scheme below (copy all n pieces into the own stage, peers read them) this
+    // drops the local copy of the whole input: the only bytes moved besides the NVLink traffic are
+    // the 1/n that end up in the result.  stage_in / stage_out alternate as halves, so the barrier
+    // of chunk k+1 doubles as "everybody is done reading chunk k-1's half".
+    const uint64_t chunk_bytes = a.stage_bytes / n / 16 * 16;
+    int k = 0;
+    for (uint64_t base = 0; base < a.bytes; base += chunk_bytes, ++k) {
+      const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
+      const uint64_t cu = (cb + 15) / 16;
+      uint64_t blo, bhi;
+      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      const uint64_t half = (k & 1) ? a.stage_out_off : a.stage_in_off;
+      gather_units16(
+          n, blo, bhi, cb, cb,
+          [&](int j) -> const char* {
+            int d = rank + j;
+            if (d >= n) d -= n;
+            return in + (uint64_t)d * a.bytes + base;
+          },
+          [&](int j) -> char* {
+            int d = rank + j;
+            if (d >= n) d -= n;
+            return c.heap[d] + half + (uint64_t)rank * chunk_bytes;
+          });
+      sync_barrier(c, s);  // every peer's slice b of this chunk has landed in my stage
+      const char* my = c.heap[rank] + half;
+      constexpr int U = 2;
+      for (uint64_t u0 = blo + threadIdx.x; u0 < bhi; u0 += (uint64_t)U * blockDim.x) {
+        uint4 r[U][kMaxRanks];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+          if (u >= bhi) continue;
+#pragma unroll
+          for (int q = 0; q < kMaxRanks; ++q)
+            if (q < n) r[j][q] = ld_v4(my + (uint64_t)q * chunk_bytes + u * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t u = u0 + (uint64_t)j * blockDim.x;
+          if (u >= bhi) continue;
+          Vec16<T, OP> acc;
+          acc.init(r[j][0]);
+#pragma unroll
+          for (int q = 1; q < kMaxRanks; ++q)
+            if (q < n) acc.accum(r[j][q]);
+          acc.epilogue(a.ep);
+          store16_partial(out + base, u * 16, cb, acc.pack_same());
+        }
+      }
+    }
+    sync_barrier_relaxed(c, s);  // the next collective may overwrite the stage halves
+    sync_end(s);
+    return;
+  }
   // per-destination chunk so that n chunks fit the stage
   const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
   for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {

@@ -132,6 +132,7 @@ struct CollArgs {
   uint64_t bytes;    // count * sizeof(T)
   Epilogue ep;
   int root;
+  int variant;  // kernel-specific algorithm switch (e.g. ReduceScatter staging: 0 = pull, 1 = push)
   uint64_t misc_off, ll_off, stage_in_off, stage_out_off, stage_bytes;
 };
 

@@ -380,6 +380,11 @@ class Communicator:
 
         return ctx()
 
+    def set_rs_push(self, on: bool):
+        """Staged (plain-buffer) reduce_scatter: push pieces into the peers' stages (True) instead of
+        copy-in + pull (False).  Collective setting: use the same value on every rank."""
+        self._c.set_rs_push(bool(on))
+
     def set_xchg_ll_max(self, nbytes: int):
         """Per-rank piece size up to which all_gather / all_to_all / reduce_scatter use the barrier-free
         LL-packet kernels (0: built-in default per world size, negative: never)."""
