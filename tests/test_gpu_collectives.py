@@ -240,7 +240,11 @@ def test_reduce_scatter_push_staging(n):
                                  lambda c, st: c.reduce_scatter(st[1], st[0], op))
                 res[push] = [o.cpu() for _, o in outs]
                 for r in range(n):
-                    assert torch.allclose(res[push][r].double(), exp[r], **_tol(dtype))
+                    got = res[push][r].double()
+                    bad = (~torch.isclose(got, exp[r], **_tol(dtype))).nonzero().flatten()
+                    assert bad.numel() == 0, (f"push={push} rank={r} {dtype} {op} count={count}: {bad.numel()} bad, "
+                                              f"first at {bad[:4].tolist()}, last at {bad[-1].item()}, "
+                                              f"got {got[bad[:3]].tolist()} want {exp[r][bad[:3]].tolist()}")
             for r in range(n):
                 assert torch.equal(res[True][r], res[False][r])
     finally:
