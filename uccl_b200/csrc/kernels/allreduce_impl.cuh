@@ -236,7 +236,11 @@ __global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevC
   for (uint64_t base = 0; base < nvec_total; base += chunk_vec) {
     const uint64_t cvec = (nvec_total - base) < chunk_vec ? (nvec_total - base) : chunk_vec;
     uint64_t blo, bhi;
-    split_range(cvec, gridDim.x, blockIdx.x, blo, bhi, G);
+    // slice boundaries of a full chunk, clamped: every block keeps the same stage range in every
+    // chunk (see chunk_slice in coll_common.cuh)
+    split_range(nvec_total < chunk_vec ? nvec_total : chunk_vec, gridDim.x, blockIdx.x, blo, bhi, G);
+    if (blo > cvec) blo = cvec;
+    if (bhi > cvec) bhi = cvec;
     // 1. copy-in my slice
     copy_units16(my_stage_in, in + base * 16, blo, bhi);
     sync_barrier(c, s);

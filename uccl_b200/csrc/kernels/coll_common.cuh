@@ -40,4 +40,19 @@ __device__ __forceinline__ void copy_units16(char* dst, const char* src, uint64_
   for (; u < hi; u += blockDim.x) st_v4(dst + u * 16, ld_v4(src + u * 16));
 }
 
+// 16-byte units [blo, bhi) of the current chunk (`cb` bytes) that block blockIdx.x owns.
+// The boundaries are those of a FULL chunk (clamped to the current one), so a block touches the
+// same range of the staging area in every chunk of a kernel.  The kernels only synchronise
+// same-index blocks across ranks; if a short tail chunk were re-sliced, a faster peer block of
+// another index could overwrite stage bytes that this block is still reading from the previous
+// chunk (observed as corrupted results with 8 ranks and a message slightly larger than the stage).
+__device__ __forceinline__ void chunk_slice(uint64_t msg_bytes, uint64_t chunk_bytes, uint64_t cb, uint64_t& blo,
+                                            uint64_t& bhi, uint64_t gran = 1) {
+  const uint64_t full = msg_bytes < chunk_bytes ? msg_bytes : chunk_bytes;
+  const uint64_t cu = (cb + 15) / 16;
+  split_range((full + 15) / 16, gridDim.x, blockIdx.x, blo, bhi, gran);
+  if (blo > cu) blo = cu;
+  if (bhi > cu) bhi = cu;
+}
+
 }  // namespace ub

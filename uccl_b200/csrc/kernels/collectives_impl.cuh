@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevC
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
-      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (staged) {
         copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
         sync_barrier(c, s);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
-      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       const uint64_t half = (k & 1) ? a.stage_out_off : a.stage_in_off;
       gather_units16(
           n, blo, bhi, cb, cb,
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
     const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
-    split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+    chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
     if (staged) {
       for (int d = 0; d < n; ++d)
         copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes, in + (uint64_t)d * a.bytes + base,
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ D
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
-      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (rank == root) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
       sync_barrier(c, s);
       if (rank != root) {
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(512, 1) reduce_kernel(const __grid_constant__ 
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
     const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
-    split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+    chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
     if (staged) {
       copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
       sync_barrier(c, s);
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ Dev
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
       const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
-      split_range(cu, gridDim.x, blockIdx.x, blo, bhi);
+      chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (staged) {
         for (int d = 0; d < n; ++d)
           copy_bytes16(c.heap[rank] + a.stage_in_off + (uint64_t)d * chunk_bytes,
