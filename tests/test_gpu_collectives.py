@@ -249,7 +249,7 @@ def test_reduce_scatter_push_staging(n):
                 assert torch.equal(res[True][r], res[False][r])
     finally:
         for c in comms:
-            c.set_rs_push(False)
+            c.set_rs_push(True)
             c.set_xchg_ll_max(0)
 
 

@@ -18,7 +18,7 @@ UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
 // LL-packet AllGather / AllToAll / ReduceScatter for per-rank pieces up to this many bytes
 // (0: per-world-size default, -1: never)
 UB_PARAM(XchgLLMaxBytes, "XCHG_LL_MAX_BYTES", 0)
-UB_PARAM(RsPush, "RS_PUSH", 0)  // staged ReduceScatter: 1 = push into the peers' stages, 0 = copy-in + pull
+UB_PARAM(RsPush, "RS_PUSH", 1)  // staged ReduceScatter: 1 = push into the peers' stages (default), 0 = copy-in + pull
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 
 const char* algo_name(int algo) {

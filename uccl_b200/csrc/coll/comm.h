@@ -143,7 +143,7 @@ class Comm {
   CommConfig cfg_;
   int max_ctas_ = 64;
   int64_t xchg_ll_max_ = 0;
-  bool rs_push_ = false;
+  bool rs_push_ = true;
   uint32_t* err_host_ = nullptr;
   uint64_t launches_ = 0;
   uint32_t host_epoch_ = 0;
