@@ -136,6 +136,8 @@ def test_host_ukcomm_collectives(n):
     comms = Communicator.local_world(n, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20)
 
     def fn(c):
+        if c.rank == 1:
+            c._c.alloc(12345, 256)  # ranks need not allocate symmetrically: region offsets are exchanged
         pg = uk.ProcessGroup(c, nlanes=2, tile_bytes=4096, staging_bytes=64 << 10)
         x = torch.full((50000,), float(c.rank + 1))  # > staging: several segments
         pg.all_reduce(x, "sum")
@@ -211,6 +213,13 @@ def test_gpu_worker_tasks():
 @pytest.mark.parametrize("n", [2, 4])
 def test_gpu_ukcomm_collectives(n):
     comms = get_world(n)
+    bufs = []
+    for c in comms:  # candidates for the zero-copy path: allocated before the heaps are skewed
+        with torch.cuda.device(c.device):
+            b = c.empty(40000, dtype=torch.bfloat16)
+            b.copy_(torch.full((40000,), float(c.rank + 1)))
+            bufs.append(b)
+    skew = comms[1]._c.alloc(54321, 256)  # rank 1's regions land at other offsets than everybody else's
     uks = [uk.UkCommunicator(c, nlanes=2, tile_bytes=64 << 10, staging_bytes=1 << 20) for c in comms]
     try:
         count = (1 << 19) + 12  # 2 MiB + tail: two staged segments
@@ -236,27 +245,23 @@ def test_gpu_ukcomm_collectives(n):
             assert torch.allclose(x.cpu(), ref, rtol=1e-5, atol=1e-4)
             assert torch.allclose(y.cpu(), 2 * ref, rtol=1e-5, atol=2e-4)
         # zero-copy on symmetric buffers, ring algorithm, bf16
-        bufs = []
-        for c, u in zip(comms, uks):
-            with torch.cuda.device(c.device):
-                b = c.empty(40000, dtype=torch.bfloat16)
-                b.copy_(torch.full((40000,), float(c.rank + 1)))
-                bufs.append(b)
         for c in comms:
             torch.cuda.synchronize(c.device)
         works = []
+        # zero-copy is only legal when the buffers sit at the same heap offset on every rank
+        symmetric = len({c._c.heap_offset(b.data_ptr()) for c, b in zip(comms, bufs)}) == 1
         # one stream per rank: virtual ranks share a device, and a shared stream would serialise
         # rank 1's "inputs ready" write behind rank 0's wait for the collective (= deadlock)
         streams = [st[0] for st in xs]
         for c, u, b, s in zip(comms, uks, bufs, streams):
             with torch.cuda.device(c.device), torch.cuda.stream(s):
-                works.append(u.all_reduce(b, "sum", algo="ring"))
+                works.append(u.all_reduce(b, "sum", algo="ring", symmetric=symmetric))
         for w in works:
             w.wait()
         for c, b in zip(comms, bufs):
             torch.cuda.synchronize(c.device)
             assert torch.all(b.float().cpu() == n * (n + 1) / 2)
-        assert uks[0].stats()["zero_copy_ops"] == 1
+        assert uks[0].stats()["zero_copy_ops"] == (1 if symmetric else 0)
         # all_to_all + all_gather + barrier
         per = 3001
         outs, works = [], []
@@ -284,3 +289,4 @@ def test_gpu_ukcomm_collectives(n):
     finally:
         for u in uks:
             u.stop()
+        comms[1]._c.free(skew)

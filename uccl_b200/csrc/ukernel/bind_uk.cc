@@ -150,24 +150,28 @@ void bind_uk(py::module_& m) {
       .def_property_readonly("nranks", &UkComm::nranks)
       .def_property_readonly("nlanes", &UkComm::nlanes)
       .def("all_reduce",
-           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int algo, uintptr_t stream) {
+           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int algo, uintptr_t stream,
+              bool symmetric) {
              py::gil_scoped_release rel;
-             return u.all_reduce((const void*)in, (void*)out, count, dtype, op, (UkAlgo)algo, (cudaStream_t)stream);
+             return u.all_reduce((const void*)in, (void*)out, count, dtype, op, (UkAlgo)algo, (cudaStream_t)stream,
+                                 symmetric);
            },
            py::arg("inp"), py::arg("out"), py::arg("count"), py::arg("dtype"), py::arg("op"), py::arg("algo") = 0,
-           py::arg("stream") = 0)
+           py::arg("stream") = 0, py::arg("symmetric") = false)
       .def("all_to_all",
-           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream, bool symmetric) {
              py::gil_scoped_release rel;
-             return u.all_to_all((const void*)in, (void*)out, count, dtype, (cudaStream_t)stream);
+             return u.all_to_all((const void*)in, (void*)out, count, dtype, (cudaStream_t)stream, symmetric);
            },
-           py::arg("inp"), py::arg("out"), py::arg("count_per_peer"), py::arg("dtype"), py::arg("stream") = 0)
+           py::arg("inp"), py::arg("out"), py::arg("count_per_peer"), py::arg("dtype"), py::arg("stream") = 0,
+           py::arg("symmetric") = false)
       .def("all_gather",
-           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream, bool symmetric) {
              py::gil_scoped_release rel;
-             return u.all_gather((const void*)in, (void*)out, count, dtype, (cudaStream_t)stream);
+             return u.all_gather((const void*)in, (void*)out, count, dtype, (cudaStream_t)stream, symmetric);
            },
-           py::arg("inp"), py::arg("out"), py::arg("count_per_rank"), py::arg("dtype"), py::arg("stream") = 0)
+           py::arg("inp"), py::arg("out"), py::arg("count_per_rank"), py::arg("dtype"), py::arg("stream") = 0,
+           py::arg("symmetric") = false)
       .def("barrier",
            [](UkComm& u, uintptr_t stream) {
              py::gil_scoped_release rel;

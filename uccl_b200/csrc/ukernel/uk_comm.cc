@@ -44,9 +44,18 @@ UkComm::UkComm(std::shared_ptr<Comm> comm, const UkCommConfig& cfg) : comm_(comm
   lane_sync_ = flags_ + (uint64_t)L * n;
   ready_ = lane_sync_ + 1;
   expected_.assign((size_t)L * n, 0);
+  my_offs_[0] = comm_->heap_offset(ctrl_);
+  my_offs_[1] = scratch_ ? comm_->heap_offset(scratch_) : 0;
+  my_offs_[2] = comm_->heap_offset(stage_in_);
+  my_offs_[3] = comm_->heap_offset(stage_out_);
+  region_bytes_[0] = ctrl_bytes, region_bytes_[1] = scratch_bytes;
+  region_bytes_[2] = region_bytes_[3] = cfg_.staging_bytes;
+  all_offs_.assign((size_t)n * kRegions, 0);
   worker_.reset(new UkWorker(comm_->is_host() ? -1 : comm_->device(), L));
   if (comm_->is_host()) {
     memset(ctrl_, 0, ctrl_bytes);
+    comm_->allgather(my_offs_, all_offs_.data(), kRegions, kU64, nullptr);
+    offs_ready_ = true;
     comm_->barrier(nullptr);  // every rank has zeroed its counters before anybody signals
     worker_->start();
     return;
@@ -54,6 +63,14 @@ UkComm::UkComm(std::shared_ptr<Comm> comm, const UkCommConfig& cfg) : comm_(comm
   DevGuard g(comm_->device());
   UB_CUDA(cudaStreamCreateWithFlags(&setup_stream_, cudaStreamNonBlocking));
   UB_CUDA(cudaMemsetAsync(ctrl_, 0, ctrl_bytes, setup_stream_));
+  // all-gather the region offsets on the device; the table is read back lazily (first operation),
+  // because this constructor must not block on peers that are constructed later by the same thread
+  UB_CUDA(cudaMalloc((void**)&offs_dev_, sizeof(uint64_t) * kRegions * (n + 1)));
+  UB_CUDA(cudaHostAlloc((void**)&offs_host_, sizeof(uint64_t) * kRegions * n, cudaHostAllocDefault));
+  UB_CUDA(cudaMemcpyAsync(offs_dev_, my_offs_, sizeof(my_offs_), cudaMemcpyHostToDevice, setup_stream_));
+  comm_->allgather(offs_dev_, offs_dev_ + kRegions, kRegions, kU64, setup_stream_);
+  UB_CUDA(cudaMemcpyAsync(offs_host_, offs_dev_ + kRegions, sizeof(uint64_t) * kRegions * n, cudaMemcpyDeviceToHost,
+                          setup_stream_));
   // the cross-rank barrier runs on the device; the worker kernel is ordered after it, so this
   // constructor never blocks on a peer (ranks of a single-process world are built one by one)
   comm_->barrier(setup_stream_);
@@ -72,7 +89,10 @@ UkComm::~UkComm() {
   }
   if (setup_stream_) {
     DevGuard g(comm_->device());
+    cudaStreamSynchronize(setup_stream_);
     cudaStreamDestroy(setup_stream_);
+    if (offs_dev_) cudaFree(offs_dev_);
+    if (offs_host_) cudaFreeHost(offs_host_);
   }
   worker_.reset();
   if (stage_out_) comm_->free(stage_out_);
@@ -111,8 +131,28 @@ void UkComm::lane_barrier() {
   }
 }
 
+void UkComm::resolve_offsets() {
+  if (offs_ready_) return;
+  DevGuard g(comm_->device());
+  UB_CUDA(cudaStreamSynchronize(setup_stream_));  // every rank has been constructed by the time of the first op
+  memcpy(all_offs_.data(), offs_host_, sizeof(uint64_t) * all_offs_.size());
+  offs_ready_ = true;
+}
+
+// Address, in this rank's address space, of peer `peer`'s instance of the buffer `local_ptr` points into.
+char* UkComm::remote(const char* local_ptr, int peer) const {
+  const char* bases[kRegions] = {ctrl_, scratch_, stage_in_, stage_out_};
+  for (int r = 0; r < kRegions; ++r) {
+    if (bases[r] && local_ptr >= bases[r] && local_ptr < bases[r] + region_bytes_[r])
+      return comm_->fabric().heap(peer) + all_offs_[(size_t)peer * kRegions + r] + (local_ptr - bases[r]);
+  }
+  // a caller-declared symmetric user buffer: same offset everywhere
+  return (char*)comm_->peer_ptr(local_ptr, peer);
+}
+
 void UkComm::begin_op(cudaStream_t stream) {
   UB_CHECK(worker_->running(), "ukernel: communicator was stopped");
+  resolve_offsets();
   UB_CHECK(worker_->error() == 0, "ukernel: worker reported error 0x%x", worker_->error());
   ++ops_;
   ++stats_.ops;
@@ -208,7 +248,7 @@ void UkComm::run_plan(const UkPlan& plan, const Bufs& b, int dtype, int op) {
       case UkPlanOp::Send: {
         if (o.bytes) {
           t.op = UK_COPY;
-          t.dst = (uint64_t)comm_->peer_ptr(local(b, o.dst), o.peer);
+          t.dst = (uint64_t)remote(local(b, o.dst), o.peer);
           t.src = (uint64_t)local(b, o.src);
           t.bytes = o.bytes;
           push(o.lane, t);
@@ -216,7 +256,7 @@ void UkComm::run_plan(const UkPlan& plan, const Bufs& b, int dtype, int op) {
         UkTask s;
         memset(&s, 0, sizeof(s));
         s.op = UK_SIGNAL;
-        s.sig_addr = (uint64_t)comm_->peer_ptr(flags_ + (uint64_t)o.lane * n + comm_->rank(), o.peer);
+        s.sig_addr = (uint64_t)remote((const char*)(flags_ + (uint64_t)o.lane * n + comm_->rank()), o.peer);
         s.sig_val = 1;
         push(o.lane, s);
         break;
@@ -249,7 +289,7 @@ void UkComm::copy_sliced(char* dst, const char* src, uint64_t bytes) {
 }
 
 uint64_t UkComm::all_reduce(const void* in, void* out, size_t count, int dtype, int op, UkAlgo algo,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, bool symmetric) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel all_reduce: bad dtype %d", dtype);
   UB_CHECK(op == kSum || op == kProd || op == kMax || op == kMin, "ukernel all_reduce: op %d unsupported", op);
   const uint64_t es = dtype_size(dtype), bytes = count * es;
@@ -257,7 +297,7 @@ uint64_t UkComm::all_reduce(const void* in, void* out, size_t count, int dtype, 
   UkPlanParams p;
   p.nranks = comm_->nranks(), p.rank = comm_->rank(), p.nlanes = cfg_.nlanes;
   p.tile_bytes = cfg_.tile_bytes, p.elem_size = es, p.algo = algo;
-  const bool zero_copy = bytes > 0 && comm_->in_heap(in, bytes) && comm_->in_heap(out, bytes) &&
+  const bool zero_copy = symmetric && bytes > 0 && comm_->in_heap(in, bytes) && comm_->in_heap(out, bytes) &&
                          (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
   if (zero_copy) {
     ++stats_.zero_copy_ops;
@@ -277,7 +317,8 @@ uint64_t UkComm::all_reduce(const void* in, void* out, size_t count, int dtype, 
   return end_op(stream);
 }
 
-uint64_t UkComm::all_to_all(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream) {
+uint64_t UkComm::all_to_all(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream,
+                            bool symmetric) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel all_to_all: bad dtype %d", dtype);
   UB_CHECK(in != out, "ukernel all_to_all: in-place operation is not supported");
   const int n = comm_->nranks();
@@ -285,7 +326,7 @@ uint64_t UkComm::all_to_all(const void* in, void* out, size_t count_per_peer, in
   begin_op(stream);
   UkPlanParams p;
   p.nranks = n, p.rank = comm_->rank(), p.nlanes = cfg_.nlanes, p.tile_bytes = cfg_.tile_bytes;
-  const bool zero_copy = block > 0 && comm_->in_heap(in, block * n) && comm_->in_heap(out, block * n) &&
+  const bool zero_copy = symmetric && block > 0 && comm_->in_heap(in, block * n) && comm_->in_heap(out, block * n) &&
                          (((uintptr_t)in | (uintptr_t)out | block) & 15) == 0;
   if (zero_copy) {
     ++stats_.zero_copy_ops;
@@ -324,14 +365,15 @@ uint64_t UkComm::all_to_all(const void* in, void* out, size_t count_per_peer, in
   return end_op(stream);
 }
 
-uint64_t UkComm::all_gather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream) {
+uint64_t UkComm::all_gather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream,
+                            bool symmetric) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel all_gather: bad dtype %d", dtype);
   const int n = comm_->nranks();
   const uint64_t block = count_per_rank * dtype_size(dtype);
   begin_op(stream);
   UkPlanParams p;
   p.nranks = n, p.rank = comm_->rank(), p.nlanes = cfg_.nlanes, p.tile_bytes = cfg_.tile_bytes;
-  const bool zero_copy = block > 0 && comm_->in_heap(in, block) && comm_->in_heap(out, block * n) &&
+  const bool zero_copy = symmetric && block > 0 && comm_->in_heap(in, block) && comm_->in_heap(out, block * n) &&
                          (((uintptr_t)in | (uintptr_t)out | block) & 15) == 0;
   if (zero_copy) {
     ++stats_.zero_copy_ops;

@@ -34,9 +34,14 @@ class UkComm {
 
   // Asynchronous collectives; return an operation ticket for wait()/test().  `stream`: the user's
   // stream that produced `in` and will consume `out` (ignored by the host backend).
-  uint64_t all_reduce(const void* in, void* out, size_t count, int dtype, int op, UkAlgo algo, cudaStream_t stream);
-  uint64_t all_to_all(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream);
-  uint64_t all_gather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream);
+  // `symmetric`: in/out are heap tensors at the SAME heap offsets on every rank (allocated in the same
+  // order everywhere) and may be used in place by the peers; otherwise the data is staged.
+  uint64_t all_reduce(const void* in, void* out, size_t count, int dtype, int op, UkAlgo algo, cudaStream_t stream,
+                      bool symmetric = false);
+  uint64_t all_to_all(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream,
+                      bool symmetric = false);
+  uint64_t all_gather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream,
+                      bool symmetric = false);
   uint64_t barrier(cudaStream_t stream);
   bool test(uint64_t ticket);
   void wait(uint64_t ticket, double timeout_s = 60.0);
@@ -59,6 +64,8 @@ class UkComm {
   void push(int lane, const UkTask& t);
   void copy_sliced(char* dst, const char* src, uint64_t bytes);
   char* local(const Bufs& b, const UkRef& r) const;
+  char* remote(const char* local_ptr, int peer) const;  // the peer's mapping of the peer's own copy of this buffer
+  void resolve_offsets();
 
   std::shared_ptr<Comm> comm_;
   UkCommConfig cfg_;
@@ -76,6 +83,15 @@ class UkComm {
   bool stream_ops_ = false;  // cuStreamWrite/WaitValue64 usable
   std::map<uint64_t, std::vector<uint64_t>> tickets_;  // op -> per-lane tickets
   cudaStream_t setup_stream_ = nullptr;
+  // heap offsets of {ctrl, scratch, stage_in, stage_out} on every rank: ranks may have allocated at
+  // different offsets (fragmented heaps), so they are all-gathered once instead of assumed equal
+  enum { kRegions = 4 };
+  uint64_t my_offs_[kRegions] = {0, 0, 0, 0};
+  uint64_t region_bytes_[kRegions] = {0, 0, 0, 0};
+  std::vector<uint64_t> all_offs_;  // [rank][region]
+  uint64_t* offs_dev_ = nullptr;    // device staging of my_offs_ / the gathered table
+  uint64_t* offs_host_ = nullptr;   // pinned
+  bool offs_ready_ = false;
   Stats stats_;
 };
 

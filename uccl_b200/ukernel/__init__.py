@@ -130,8 +130,10 @@ class UkWork:
 
 class UkCommunicator:
     """Collectives executed by the persistent worker over ``comm``'s symmetric heap.  Construction
-    is collective (every rank, same arguments).  Tensors allocated with ``comm.empty`` are used in
-    place; anything else is staged through the heap in ``staging_bytes`` segments."""
+    is collective (every rank, same arguments).  Data is staged through the heap in ``staging_bytes``
+    segments unless the caller declares the tensors symmetric (``symmetric=True``: ``comm.empty`` buffers
+    at the same heap offset on every rank).  The communicator's own regions may sit at different
+    offsets on different ranks (fragmented heaps): their offsets are all-gathered at construction."""
 
     def __init__(self, comm: Communicator, nlanes: int = 4, tile_bytes: int = 1 << 20,
                  staging_bytes: int = 32 << 20):
@@ -151,32 +153,36 @@ class UkCommunicator:
             raise ValueError(f"uccl_b200.ukernel: tensor on {t.device}, communicator on {self.comm.device}")
 
     def all_reduce(self, tensor: torch.Tensor, op="sum", out: Optional[torch.Tensor] = None, algo: str = "auto",
-                   stream=None) -> UkWork:
+                   stream=None, symmetric: bool = False) -> UkWork:
+        """``symmetric=True``: tensor/out come from ``comm.empty`` at the same heap offset on every rank
+        (same allocation order everywhere) and are used in place by the peers; otherwise staged."""
         out = tensor if out is None else out
         self._check(tensor), self._check(out)
         code = op_code(op)
         avg = code == 4
         t = self._u.all_reduce(tensor.data_ptr(), out.data_ptr(), tensor.numel(), dtype_code(tensor.dtype),
-                               0 if avg else code, ALGOS[algo], self._stream(stream))
+                               0 if avg else code, ALGOS[algo], self._stream(stream), bool(symmetric))
         if avg:
             if self.comm.is_host:
                 self._u.wait(t, 60.0)
             out.div_(self.world_size)  # CUDA: the current stream is already ordered after the collective
         return UkWork(self._u, t, out)
 
-    def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor, stream=None) -> UkWork:
+    def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor, stream=None, symmetric: bool = False) -> UkWork:
         self._check(inp), self._check(out)
         if inp.numel() % self.world_size or out.numel() != inp.numel():
             raise ValueError("uccl_b200.ukernel: all_to_all_single needs equal splits")
         t = self._u.all_to_all(inp.data_ptr(), out.data_ptr(), inp.numel() // self.world_size, dtype_code(inp.dtype),
-                               self._stream(stream))
+                               self._stream(stream), bool(symmetric))
         return UkWork(self._u, t, out)
 
-    def all_gather_into_tensor(self, out: torch.Tensor, inp: torch.Tensor, stream=None) -> UkWork:
+    def all_gather_into_tensor(self, out: torch.Tensor, inp: torch.Tensor, stream=None,
+                               symmetric: bool = False) -> UkWork:
         self._check(inp), self._check(out)
         if out.numel() != inp.numel() * self.world_size:
             raise ValueError("uccl_b200.ukernel: all_gather output must hold world_size * input elements")
-        t = self._u.all_gather(inp.data_ptr(), out.data_ptr(), inp.numel(), dtype_code(inp.dtype), self._stream(stream))
+        t = self._u.all_gather(inp.data_ptr(), out.data_ptr(), inp.numel(), dtype_code(inp.dtype), self._stream(stream),
+                               bool(symmetric))
         return UkWork(self._u, t, out)
 
     def barrier(self, stream=None) -> UkWork:
