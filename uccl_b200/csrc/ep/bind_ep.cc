@@ -43,6 +43,7 @@ void bind_ep(py::module_& m) {
              return b.dispatch(x, xs, ti, tw, pos, ss, tpr, tpe, T, H, K, E, mode, cached, reuse_slot, rank_prefix,
                                expert_alignment, num_worst_tokens, round_scale, num_sms, (cudaStream_t)st);
            })
+      .def_property_readonly("base_offset", &EpBuffer::base_offset)
       .def("wait_counts",
            [](EpBuffer& b, int E_local, double timeout_s) {
              std::vector<int> pe;

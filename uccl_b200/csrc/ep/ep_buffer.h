@@ -32,6 +32,7 @@ class EpBuffer {
   int capacity_for(int hidden, int mode, int topk) const;
   int combine_capacity_for(int hidden, int topk) const;
   uint64_t launches() const { return launches_; }
+  uint64_t base_offset() const { return base_off_; }  // heap offset of the EP block (must match on every rank)
 
   // topk_idx != 0: full layout (counts + membership + positions); topk_idx == 0: positions only
   void layout(uintptr_t topk_idx, int T, int K, int E, uintptr_t tokens_per_rank, uintptr_t tokens_per_expert,

@@ -71,6 +71,7 @@ class Buffer:
         C = _native.C()
         self._C = C
         self.runtime = C.EpBuffer(comm.native, max(self.num_nvl_bytes, 1 << 20), num_slots)
+        self._check_symmetric_placement()
         self._ll = None
         if self.num_rdma_bytes > 0 or low_latency_mode:
             from .low_latency import LowLatencyRuntime
@@ -80,6 +81,25 @@ class Buffer:
             self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._layout_cache = None
         self._destroyed = False
+
+    def _check_symmetric_placement(self):
+        """The kernels address a peer's arenas as `peer_heap + my_offset`, so the EP block must sit at the
+        same heap offset on every rank (true when the Buffer is created right after the communicator, or
+        after the same sequence of symmetric allocations everywhere).  Verified when a process group is
+        available; a mismatch would otherwise corrupt memory silently."""
+        grp = self.group if self.group is not None else getattr(self.comm, "group", None)
+        try:
+            import torch.distributed as dist
+
+            if grp is None or not dist.is_initialized() or dist.get_world_size(grp) != self.group_size:
+                return
+            offs = [None] * self.group_size
+            dist.all_gather_object(offs, int(self.runtime.base_offset), group=grp)
+        except Exception:  # pragma: no cover - the check is best effort
+            return
+        if len(set(offs)) != 1:
+            raise RuntimeError(f"uccl_b200.ep.Buffer: the EP block landed at different symmetric-heap offsets {offs}; "
+                               "create the Buffer before other (rank-dependent) heap allocations")
 
     # ------------------------------------------------------------------ misc parity API
     def destroy(self):
