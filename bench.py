@@ -306,6 +306,10 @@ def main():
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # The host-side barrier above releases the ranks up to ~1 ms apart; without re-aligning the GPUs the
+    # first timed dispatch would absorb that skew in its cross-rank entry barrier.  A device-side
+    # barrier kernel (untimed) lines the GPUs up to within microseconds.
+    comm.barrier()
     l0 = launches()
     sampler.start()
     wall0 = time.perf_counter()

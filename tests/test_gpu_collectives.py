@@ -246,7 +246,11 @@ def test_reduce_scatter_push_staging(n):
                                               f"first at {bad[:4].tolist()}, last at {bad[-1].item()}, "
                                               f"got {got[bad[:3]].tolist()} want {exp[r][bad[:3]].tolist()}")
             for r in range(n):
-                assert torch.equal(res[True][r], res[False][r])
+                if comms[0].has_multicast and dtype.is_floating_point:
+                    # the pull variant reduces inside the switch (multimem.ld_reduce): same value up to rounding
+                    assert torch.allclose(res[True][r].double(), res[False][r].double(), **_tol(dtype))
+                else:
+                    assert torch.equal(res[True][r], res[False][r])
     finally:
         for c in comms:
             c.set_rs_push(True)

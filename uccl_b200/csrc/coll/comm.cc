@@ -470,8 +470,13 @@ void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype
   const bool in_sym = in_heap(in, bytes);
   int mode;
   int ctas;
-  if (bytes % 16 == 0 && bytes <= xchg_ll_limit(xchg_ll_max_, n, out_sym)) {
-    mode = (has_multicast() && n > 2) ? 4 : 3;
+  const bool ll_mc = has_multicast() && n > 2;
+  // with multicast one multimem.st publishes a packet to every peer, which keeps the LL path ahead
+  // of the barrier-based kernels up to 512 KiB pieces (measured on 8 GPUs: profiles/allgather8.json)
+  uint64_t ag_ll_max = xchg_ll_limit(xchg_ll_max_, n, out_sym && !ll_mc);
+  if (xchg_ll_max_ == 0 && ll_mc) ag_ll_max = std::min<uint64_t>(512u << 10, kLLMaxData);
+  if (bytes % 16 == 0 && bytes <= ag_ll_max) {
+    mode = ll_mc ? 4 : 3;
     ctas = ctas_for(bytes * (uint64_t)(n - 1), std::min(max_ctas_, 64), 16 << 10);
   } else if (out_sym && bytes % 16 == 0) {
     a.out_off = heap_offset(out);
@@ -521,7 +526,11 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
   a.count = recv_count;
   const bool in_sym = in_heap(in, bytes * n) && (bytes % 16 == 0);
   if (in_sym) a.in_off = heap_offset(in);
-  a.variant = rs_push_ ? 1 : 0;
+  // staged input: pushing pieces into the peers' stages wins except for very large messages on
+  // NVLS systems, where copy-in + multimem.ld_reduce is ahead (8 GPUs, 1 GiB: 1.74 ms vs 1.91 ms;
+  // 64 MiB: 171 us vs 160 us -- profiles/reduce_scatter8*.json)
+  const bool nvls_possible = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
+  a.variant = (rs_push_ && !(nvls_possible && bytes * (uint64_t)n >= (256ull << 20))) ? 1 : 0;
   const bool nvls = has_multicast() && nvls_reduce_supported(dtype, op) && n > 2;
   const bool fdt =
       dtype == kF32 || dtype == kBF16 || dtype == kF16 || dtype == kF64 || dtype == kF8E4M3 || dtype == kF8E5M2;
