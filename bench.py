@@ -132,7 +132,7 @@ def run_reference(args):
         if why is None:
             why = "uccl.ep imported but no offline-buildable DeepEP runtime is wired"
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": why[:300]}))
+            emit({"impl": "reference", "unavailable": why[:300]})
         return 0
     # allreduce: the reference's collective product is stock NCCL + its net plugin
     # (README.md:109-119); on one NVSwitch node no byte reaches the plugin, so this arm is NCCL
@@ -152,7 +152,7 @@ def run_reference(args):
     n = args.gpus
     if n == 1:
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "allreduce bus bandwidth is undefined at 1 GPU"}))
+            emit({"impl": "reference", "unavailable": "allreduce bus bandwidth is undefined at 1 GPU"})
         return 0
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -173,16 +173,37 @@ def run_reference(args):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     busbw = size / (ms.item() * 1e-3) * 2 * (n - 1) / n / 1e9
     if rank == 0:
-        print(json.dumps({"impl": "reference", "metric": "allreduce_busbw_1GiB_bf16", "value": busbw, "unit": "GB/s",
-                          "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(),
-                          "higher_is_better": True, "dtype": "bf16", "data": "synthetic"}))
+        emit({"impl": "reference", "metric": "allreduce_busbw_1GiB_bf16", "value": busbw, "unit": "GB/s",
+              "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(),
+              "higher_is_better": True, "dtype": "bf16", "data": "synthetic"})
     dist.destroy_process_group()
     return 0
 
 
 # ------------------------------------------------------------------------------- ours
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON result line: libraries (e.g. the "NCCL version ..." banner) print to
+    fd 1 too, so fd 1 is pointed at stderr for the rest of the run and the result goes to a saved copy."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT_OUT
+
+
+def emit(obj) -> None:
+    out = _claim_stdout()
+    out.write((obj if isinstance(obj, str) else json.dumps(obj)) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -444,7 +465,7 @@ def main():
 
     if rank == 0:
         line = json.dumps(out)
-        print(line, flush=True)
+        emit(line)
         if args.out:
             with open(args.out, "w") as f:
                 f.write(line + "\n")

@@ -14,7 +14,16 @@ P = os.path.join(ROOT, "profiles")
 
 def load(name):
     path = os.path.join(P, name)
-    return json.load(open(path)) if os.path.exists(path) else None
+    if not os.path.exists(path):
+        return None
+    txt = open(path).read().strip()
+    try:
+        return json.loads(txt)
+    except json.JSONDecodeError:  # bench.py prints one JSON line, possibly after launcher chatter
+        for line in reversed(txt.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return None
 
 
 def us(v):
@@ -92,7 +101,9 @@ def p2p_table(d):
 def bench_line(d):
     c = d.get("clocks", {})
     e = d.get("e2e", {})
-    return (f"| {d['n_gpus']} | {d['value'] / 1e6:.1f} M tok/s | {d['ms_per_step'] * 1e3:.1f} µs | "
+    mm = d.get("step_us_min_med_max")
+    spread = f" (min/med/max {mm[0]:.0f}/{mm[1]:.0f}/{mm[2]:.0f})" if mm else ""
+    return (f"| {d['n_gpus']} | {d['value'] / 1e6:.1f} M tok/s | {d['ms_per_step'] * 1e3:.1f} µs{spread} | "
             f"{d.get('dispatch_us', 0):.1f} / {d.get('combine_us', 0):.1f} µs | {('%.2f' % d['vs_baseline']) if d.get('vs_baseline') else '-'} | "
             f"{e.get('value', 0) / 1e6:.1f} M tok/s | {d.get('gpu_launches')} | {c.get('sm_mhz')} MHz {c.get('reasons')} |")
 
