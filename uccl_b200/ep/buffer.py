@@ -60,6 +60,7 @@ class Buffer:
         self.num_nvl_bytes = int(num_nvl_bytes)
         self.num_rdma_bytes = int(num_rdma_bytes)
         total = self.num_nvl_bytes + self.num_rdma_bytes
+        self._private_comm = comm is None
         if comm is None:
             assert group is not None, "Buffer needs a process group or a Communicator"
             heap = total + (256 << 20)
@@ -87,6 +88,8 @@ class Buffer:
         same heap offset on every rank (true when the Buffer is created right after the communicator, or
         after the same sequence of symmetric allocations everywhere).  Verified when a process group is
         available; a mismatch would otherwise corrupt memory silently."""
+        if self._private_comm:
+            return  # a fresh private communicator: the EP block is its first allocation on every rank
         grp = self.group if self.group is not None else getattr(self.comm, "group", None)
         try:
             import torch.distributed as dist
