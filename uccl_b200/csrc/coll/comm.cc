@@ -372,8 +372,7 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
   if (algo == ALGO_AUTO) {
     algo = select_allreduce(bytes, sym, dtype, op, &ctas);
   } else {
-    int dummy_algo = select_allreduce(bytes, sym, dtype, op, &ctas);
-    (void)dummy_algo;
+    (void)select_allreduce(bytes, sym, dtype, op, &ctas);
     // validate a forced choice
     if (algo == ALGO_ONESHOT_MC || algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
       UB_CHECK(has_multicast(), "allreduce: algo %s needs NVLS multicast", algo_name(algo));
@@ -390,7 +389,6 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
   }
   if (opts.max_ctas > 0) ctas = std::min(ctas, opts.max_ctas);
   if (out_dtype != dtype) {
-    UB_CHECK(algo != ALGO_ONESHOT_LL && algo != ALGO_ONESHOT_MC || true, "unreachable");
     if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC)
       algo = sym ? ALGO_TWOSHOT_P2P : ALGO_STAGED_P2P;  // cast is fused only in the two-shot/staged kernels
     UB_CHECK(bytes % 16 == 0 && out_bytes % 16 == 0,

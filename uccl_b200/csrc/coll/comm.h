@@ -23,7 +23,7 @@ struct CommConfig {
   size_t stage_bytes = 64ull << 20;
   bool host_fake = false;
   int timeout_ms = -1;  // -1: from UCCL_B200_TIMEOUT_MS (default 20000)
-  int max_ctas = -1;    // -1: from UCCL_B200_MAX_CTAS (default 64)
+  int max_ctas = -1;    // -1: from UCCL_B200_MAX_CTAS (default 128)
 };
 
 // algorithm ids (shared with Python)
