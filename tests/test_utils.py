@@ -103,3 +103,67 @@ def test_eqds_pacer_is_fair_and_rate_limited():
     assert max(grants) - min(grants) <= 2 * 65536   # round-robin fairness
     assert total <= 900e9 * 2000e-6 * 1.02          # never above line rate
     assert total >= min(4 * (64 << 20), 900e9 * 2000e-6 * 0.9)
+
+
+# ------------------------------------------------------------------ stage-slice invariant
+def _slices(C, msg, chunk, parts):
+    """[(chunk index, block, lo, hi)] in 16-byte units for every chunk of a `msg`-byte message."""
+    out = []
+    base, k = 0, 0
+    while base < msg:
+        cb = min(chunk, msg - base)
+        for b in range(parts):
+            lo, hi = C.chunk_slice(msg, chunk, cb, parts, b)
+            out.append((k, b, lo, hi))
+        base += chunk
+        k += 1
+    return out
+
+
+def test_chunk_slices_are_stable_across_chunks():
+    """The chunked (staged) kernels only synchronise same-index blocks across ranks, so a block must
+    own the same range of the staging area in every chunk: ranges of different blocks may never
+    overlap across chunks (regression: a short tail chunk used to be re-sliced and a faster peer block of
+    another index overwrote stage bytes still being read), and every chunk must be fully covered."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from uccl_b200 import _native
+
+    C = _native.C()
+
+    @settings(max_examples=200, deadline=None)
+    @given(chunk16=st.integers(1, 1 << 14), nfull=st.integers(0, 6), tail=st.integers(0, (1 << 18) - 1),
+           parts=st.integers(1, 148))
+    def prop(chunk16, nfull, tail, parts):
+        chunk = chunk16 * 16
+        msg = nfull * chunk + (tail % chunk)
+        if msg == 0:
+            msg = 1
+        sl = _slices(C, msg, chunk, parts)
+        nchunks = max(k for k, *_ in sl) + 1
+        own = {}  # block -> union range over chunks
+        for k, b, lo, hi in sl:
+            assert lo <= hi
+            if lo < hi:
+                plo, phi = own.get(b, (lo, hi))
+                own[b] = (min(plo, lo), max(phi, hi))
+        # coverage of every chunk, in order, without gaps
+        for k in range(nchunks):
+            cb = min(chunk, msg - k * chunk)
+            cu = (cb + 15) // 16
+            pos = 0
+            for kk, b, lo, hi in sl:
+                if kk == k and lo < hi:
+                    assert lo == pos
+                    pos = hi
+            assert pos == cu
+        # ranges owned by different blocks (over all chunks) are disjoint
+        spans = sorted(own.values())
+        for (alo, ahi), (blo, bhi) in zip(spans, spans[1:]):
+            assert ahi <= blo
+
+    prop()
+    # the concrete case that exposed the bug: 8 ranks, 1 MiB stage, 140002-byte pieces, 4 CTAs
+    sl = _slices(C, 140002, 131072, 4)
+    assert [s for s in sl if s[0] == 1 and s[2] < s[3]] == [(1, 0, 0, 559)]

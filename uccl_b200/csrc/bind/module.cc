@@ -175,6 +175,17 @@ PYBIND11_MODULE(_C, m) {
            },
            py::arg("reset") = true);
 
+  // slicing helpers of the chunked kernels (host-callable twins, for property tests)
+  m.def("split_range", [](uint64_t total, int parts, int idx, uint64_t gran) {
+    uint64_t lo, hi;
+    split_range(total, parts, idx, lo, hi, gran);
+    return py::make_tuple(lo, hi);
+  }, py::arg("total"), py::arg("parts"), py::arg("idx"), py::arg("gran") = 1);
+  m.def("chunk_slice", [](uint64_t msg_bytes, uint64_t chunk_bytes, uint64_t cb, int parts, int idx, uint64_t gran) {
+    uint64_t lo, hi;
+    chunk_slice_hd(msg_bytes, chunk_bytes, cb, parts, idx, lo, hi, gran);
+    return py::make_tuple(lo, hi);
+  }, py::arg("msg_bytes"), py::arg("chunk_bytes"), py::arg("cb"), py::arg("parts"), py::arg("idx"), py::arg("gran") = 1);
   m.def("pool_install", &pool_install);
   m.def("pool_set_thread_comm", &pool_set_thread_comm);
   m.def("pool_clear_thread_comm", &pool_clear_thread_comm);

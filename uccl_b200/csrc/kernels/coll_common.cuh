@@ -48,11 +48,7 @@ __device__ __forceinline__ void copy_units16(char* dst, const char* src, uint64_
 // chunk (observed as corrupted results with 8 ranks and a message slightly larger than the stage).
 __device__ __forceinline__ void chunk_slice(uint64_t msg_bytes, uint64_t chunk_bytes, uint64_t cb, uint64_t& blo,
                                             uint64_t& bhi, uint64_t gran = 1) {
-  const uint64_t full = msg_bytes < chunk_bytes ? msg_bytes : chunk_bytes;
-  const uint64_t cu = (cb + 15) / 16;
-  split_range((full + 15) / 16, gridDim.x, blockIdx.x, blo, bhi, gran);
-  if (blo > cu) blo = cu;
-  if (bhi > cu) bhi = cu;
+  chunk_slice_hd(msg_bytes, chunk_bytes, cb, (int)gridDim.x, (int)blockIdx.x, blo, bhi, gran);
 }
 
 }  // namespace ub

@@ -148,6 +148,18 @@ UB_HD inline void split_range(uint64_t total, int parts, int idx, uint64_t& lo, 
   if (hi > total) hi = total;
 }
 
+// 16-byte units [lo, hi) of the current chunk (`cb` bytes) owned by part `idx` of `parts`.
+// Boundaries are those of a FULL chunk (clamped to the current one), so a block touches the same
+// range of the staging area in every chunk of a kernel; see chunk_slice() in coll_common.cuh.
+UB_HD inline void chunk_slice_hd(uint64_t msg_bytes, uint64_t chunk_bytes, uint64_t cb, int parts, int idx,
+                                               uint64_t& lo, uint64_t& hi, uint64_t gran = 1) {
+  const uint64_t full = msg_bytes < chunk_bytes ? msg_bytes : chunk_bytes;
+  const uint64_t cu = (cb + 15) / 16;
+  split_range((full + 15) / 16, parts, idx, lo, hi, gran);
+  if (lo > cu) lo = cu;
+  if (hi > cu) hi = cu;
+}
+
 // Grouped send/recv launch arguments: at most one send and one recv per peer per launch.
 struct SendRecvArgs {
   const char* sbuf[kMaxRanks];
