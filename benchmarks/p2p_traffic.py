@@ -49,7 +49,10 @@ def main():
         ok, conn = ep.connect(remote_metadata=mds[dst][0])
         assert ok
         remote = ep.deserialize_descs(mds[dst][1])[rank]
-    n_in = (1 if a.pattern == "permutation" and world > 1 else 0) if a.pattern == "permutation" else (world - 1 if rank == 0 else 0)
+    if a.pattern == "permutation":
+        n_in = 1 if (world > 1 and a.shift % world != 0) else 0
+    else:
+        n_in = world - 1 if rank == 0 else 0
     for _ in range(n_in):
         ep.accept(60000)
     local_desc = ep.register_memory([src])[0]
