@@ -1,5 +1,7 @@
 """CPU unit tests of the host utilities (rings, pool, histogram, seqnos, congestion control) --
 the plain-`main` unit tests of the reference (include/util/util_test.cc, collective/*/timely_test.cc)."""
+import pytest
+
 from uccl_b200 import _native
 
 U = _native.C().util
@@ -167,3 +169,36 @@ def test_chunk_slices_are_stable_across_chunks():
     # the concrete case that exposed the bug: 8 ranks, 1 MiB stage, 140002-byte pieces, 4 CTAs
     sl = _slices(C, 140002, 131072, 4)
     assert [s for s in sl if s[0] == 1 and s[2] < s[3]] == [(1, 0, 0, 559)]
+
+
+def test_compression_strategy_selection(monkeypatch):
+    from uccl_b200.p2p import compress
+
+    monkeypatch.delenv("UCCL_B200_P2P_COMPRESS", raising=False)
+    monkeypatch.delenv("UCCL_P2P_COMPRESS_STRATEGY", raising=False)
+    assert compress.default_strategy() == "none"
+    monkeypatch.setenv("UCCL_P2P_COMPRESS_STRATEGY", "split")  # the reference's names map onto our codec
+    assert compress.default_strategy() == "for"
+    monkeypatch.setenv("UCCL_B200_P2P_COMPRESS", "none")      # our own variable wins
+    assert compress.default_strategy() == "none"
+    monkeypatch.setenv("UCCL_B200_P2P_COMPRESS", "zstd")
+    with pytest.raises(ValueError):
+        compress.default_strategy()
+    c = compress.Compressor("for")
+    import torch
+
+    assert not c.wants(torch.zeros(8))  # CPU tensors / small tensors are never compressed
+    from uccl_b200 import _native
+
+    C = _native.C()
+    assert C.cmp_supported(9) and C.cmp_supported(7) and not C.cmp_supported(2)  # bf16, f32, not int32
+    # worst case = header + metadata + raw planes + 8 exponent bits per element
+    assert C.cmp_bound(4096, 9) >= 64 + 4096 + 4096 and C.cmp_bound(4096 * 3, 7) >= 3 * 4096 * 4
+
+
+def test_mem_pool_needs_cuda_communicator():
+    from uccl_b200 import Communicator
+
+    c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
+    with pytest.raises(RuntimeError):
+        c.mem_pool()
