@@ -202,3 +202,21 @@ def test_mem_pool_needs_cuda_communicator():
     c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
     with pytest.raises(RuntimeError):
         c.mem_pool()
+
+
+def test_ue8m0_scale_packing_roundtrip():
+    import torch
+
+    from uccl_b200.ep import pack_ue8m0, unpack_ue8m0
+
+    g = torch.Generator().manual_seed(3)
+    exps = torch.randint(-40, 40, (3, 17, 56), generator=g)          # [experts, rows, hidden/128] for hidden 7168
+    scales = torch.pow(torch.tensor(2.0), exps.float())
+    packed = pack_ue8m0(scales)
+    assert packed.dtype == torch.int32 and packed.shape == (3, 17, 14)
+    assert packed.stride(-2) == 1 and packed.stride(-1) == 17           # column-major last two dimensions
+    assert torch.equal(unpack_ue8m0(packed), scales)
+    # byte i of word j is the biased exponent of scale 4j+i
+    w = int(packed[1, 5, 2].item()) & 0xFFFFFFFF
+    for i in range(4):
+        assert (w >> (8 * i)) & 0xFF == int(exps[1, 5, 8 + i].item()) + 127

@@ -55,7 +55,9 @@ class LowLatencyRuntime:
                  dispatch_wait_recv_cost_stats: Optional[torch.Tensor] = None, use_fp8: bool = True,
                  round_scale: bool = False, use_ue8m0: bool = False, async_finish: bool = False,
                  return_recv_hook: bool = False):
-        assert not use_ue8m0, "UE8M0-packed scales are not implemented; use round_scale=True for power-of-two scales"
+        if use_ue8m0:
+            assert use_fp8 and round_scale, "use_ue8m0 needs use_fp8=True and round_scale=True (power-of-two scales)"
+            assert x.size(1) % 512 == 0, "use_ue8m0 packs four per-128-channel scales per word: hidden % 512 == 0"
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
         assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous()
         b = self.buf
@@ -78,8 +80,13 @@ class LowLatencyRuntime:
                 cumulative_local_expert_recv_stats.add_(recv_count)
         rows = R * M
         if use_fp8:
-            recv_x = (b._view(rx, (E_local, rows, H), torch.float8_e4m3fn),
-                      b._view(rs, (E_local, rows, H // 128), torch.float32))
+            scales = b._view(rs, (E_local, rows, H // 128), torch.float32)
+            if use_ue8m0:
+                from .utils import pack_ue8m0
+
+                with torch.cuda.stream(b.comm_stream):
+                    scales = pack_ue8m0(scales)  # [E_local, rows, H // 512] int32, column-major last two dims
+            recv_x = (b._view(rx, (E_local, rows, H), torch.float8_e4m3fn), scales)
         else:
             recv_x = b._view(rx, (E_local, rows, H), torch.bfloat16)
         src_info = b._view(rsrc, (E_local, rows), torch.int32)

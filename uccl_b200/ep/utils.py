@@ -101,3 +101,23 @@ def bench(fn, num_warmups: int = 5, num_tests: int = 20, flush_l2: bool = True):
     torch.cuda.synchronize()
     ts = [s.elapsed_time(e) / 1e3 for s, e in zip(starts, ends)]
     return sum(ts) / len(ts), min(ts), max(ts)
+
+
+def pack_ue8m0(scales: torch.Tensor) -> torch.Tensor:
+    """Power-of-two fp32 scales ``[..., rows, C]`` (C % 4 == 0) -> UE8M0: the biased exponent byte of each
+    scale, four per ``int32``, shaped ``[..., rows, C // 4]`` with the last two dimensions stored
+    column-major (TMA-friendly; reference: ``low_latency_dispatch(use_ue8m0=True)``,
+    ep/bench/buffer.py:301-316 -- the scale format SM100 block-scaled GEMMs consume)."""
+    assert scales.dtype == torch.float32 and scales.size(-1) % 4 == 0
+    bits = scales.contiguous().view(torch.int32)
+    exp = ((bits >> 23) & 0xFF).to(torch.uint8)  # sign is 0 and the mantissa is 0 for power-of-two scales
+    packed = exp.view(torch.int32)  # little endian: scale 4j+i sits in byte i of word j
+    storage = packed.transpose(-1, -2).contiguous()
+    return storage.transpose(-1, -2)
+
+
+def unpack_ue8m0(packed: torch.Tensor) -> torch.Tensor:
+    """Inverse of :func:`pack_ue8m0`: ``[..., rows, C // 4]`` int32 -> fp32 scales ``[..., rows, C]``."""
+    assert packed.dtype == torch.int32
+    exp = packed.contiguous().view(torch.uint8).to(torch.int32)
+    return (exp << 23).view(torch.float32)
