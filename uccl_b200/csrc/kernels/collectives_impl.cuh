@@ -131,7 +131,6 @@ __global__ void __launch_bounds__(512, 1) ag_kernel(const __grid_constant__ DevC
     const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
     for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-      const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
       chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (staged) {
@@ -183,7 +182,6 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
     int k = 0;
     for (uint64_t base = 0; base < a.bytes; base += chunk_bytes, ++k) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-      const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
       chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       const uint64_t half = (k & 1) ? a.stage_out_off : a.stage_in_off;
@@ -234,7 +232,6 @@ __global__ void __launch_bounds__(512, 1) rs_kernel(const __grid_constant__ DevC
   const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
   for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-    const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
     chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
     if (staged) {
@@ -315,7 +312,6 @@ __global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ D
     const uint64_t chunk_bytes = a.stage_bytes / 16 * 16;
     for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-      const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
       chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (rank == root) copy_bytes16(c.heap[rank] + a.stage_in_off, in + base, blo, bhi, cb, cb);
@@ -347,7 +343,6 @@ __global__ void __launch_bounds__(512, 1) reduce_kernel(const __grid_constant__ 
   const uint64_t chunk_bytes = staged ? (a.stage_bytes / 16 * 16) : a.bytes;
   for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
     const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-    const uint64_t cu = (cb + 15) / 16;
     uint64_t blo, bhi;
     chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
     if (staged) {
@@ -418,7 +413,6 @@ __global__ void __launch_bounds__(512, 1) a2a_kernel(const __grid_constant__ Dev
     const uint64_t chunk_bytes = staged ? (a.stage_bytes / n / 16 * 16) : a.bytes;
     for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
       const uint64_t cb = (a.bytes - base) < chunk_bytes ? (a.bytes - base) : chunk_bytes;
-      const uint64_t cu = (cb + 15) / 16;
       uint64_t blo, bhi;
       chunk_slice(a.bytes, chunk_bytes, cb, blo, bhi);
       if (staged) {
