@@ -146,11 +146,8 @@ class Buffer:
         be co-resident (their kernels wait for each other), so the budget is split between them."""
         n = int(config.num_sms)
         if self.comm.native.single_process and self.group_size > 1:
+            # conservative: assume every rank of the single-process world sits on this GPU
             share = torch.cuda.get_device_properties(self.device).multi_processor_count
-            import collections
-
-            per_dev = collections.Counter()
-            per_dev[self.device.index] = self.group_size  # conservative: assume every rank is on this GPU
             n = max(1, min(n, share // self.group_size))
         return n
 
