@@ -74,6 +74,28 @@ def test_host_other_collectives(world4):
         assert torch.equal(a2a, exp_a2a)
 
 
+def test_host_alltoallv_multi_round(world4):
+    """Variable-size all-to-all incl. empty pairs and messages larger than the per-destination stage
+    slice (several rounds, ranks finishing in different rounds)."""
+    n = len(world4)
+    # rank s sends cnt[s][d] int64 values to rank d; one pair is far larger than the others
+    cnt = [[(s * 7 + d * 3) % 5 * 1000 for d in range(n)] for s in range(n)]
+    cnt[1][2] = 300000  # 2.4 MB through a 256 KiB slice (1 MiB stage / 4 ranks)
+    cnt[3][0] = 0
+
+    def fn(c):
+        r = c.rank
+        x = torch.cat([torch.full((cnt[r][d],), 1000 * r + d, dtype=torch.int64) for d in range(n)] + [torch.empty(0, dtype=torch.int64)])
+        out = torch.zeros(sum(cnt[s][r] for s in range(n)), dtype=torch.int64)
+        c.all_to_all_v(out, x, cnt[r], [cnt[s][r] for s in range(n)])
+        return out
+
+    outs = run_host_ranks(world4, fn)
+    for r, o in enumerate(outs):
+        exp = torch.cat([torch.full((cnt[s][r],), 1000 * s + r, dtype=torch.int64) for s in range(n)])
+        assert torch.equal(o, exp)
+
+
 def test_symmetric_heap_alloc(world4):
     c = world4[0]
     free0 = c.native.heap_free_bytes

@@ -670,9 +670,17 @@ void Comm::alltoall(const void* in, void* out, size_t count_per_peer, int dtype,
 void Comm::alltoallv(const void* in, const size_t* send_counts, const size_t* send_displs, void* out,
                      const size_t* recv_counts, const size_t* recv_displs, int dtype, cudaStream_t stream) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "alltoallv: bad dtype %d", dtype);
-  UB_CHECK(!is_host(), "alltoallv: host backend does not implement it");
   const int n = nranks();
   const size_t es = dtype_size(dtype);
+  if (is_host()) {
+    std::vector<size_t> sb(n), so(n), rb(n), ro(n);
+    for (int p = 0; p < n; ++p) {
+      sb[p] = send_counts[p] * es, so[p] = send_displs[p] * es;
+      rb[p] = recv_counts[p] * es, ro[p] = recv_displs[p] * es;
+    }
+    host_alltoallv(in, sb.data(), so.data(), out, rb.data(), ro.data());
+    return;
+  }
   DeviceGuard g(device());
   size_t in_total = 0;
   for (int p = 0; p < n; ++p) in_total = std::max(in_total, (send_displs[p] + send_counts[p]) * es);

@@ -136,6 +136,8 @@ class Comm {
   void host_broadcast(const void* in, void* out, size_t bytes, int root);
   void host_reduce(const void* in, void* out, size_t count, int dtype, int op, int root);
   void host_alltoall(const void* in, void* out, size_t bytes);
+  void host_alltoallv(const void* in, const size_t* send_bytes, const size_t* send_off, void* out,
+                      const size_t* recv_bytes, const size_t* recv_off);
 
   std::shared_ptr<Fabric> fabric_;
   HeapLayout layout_;

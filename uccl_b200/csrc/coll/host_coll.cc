@@ -262,4 +262,40 @@ void Comm::host_alltoall(const void* in, void* out, size_t bytes) {
   }
 }
 
+// Variable-size all-to-all: rounds of (stage one slice per destination, barrier, read my slice from
+// every peer's stage, barrier).  The number of rounds is not known locally (a rank only knows its own
+// counts), so every rank publishes a "more data after this round" flag next to its stage and all ranks
+// continue while anybody's flag is set -- they all read the same flags, hence run the same rounds.
+void Comm::host_alltoallv(const void* in, const size_t* send_bytes, const size_t* send_off, void* out,
+                          const size_t* recv_bytes, const size_t* recv_off) {
+  const int n = nranks(), me = rank();
+  const size_t chunk = (layout_.stage_bytes / n) / 16 * 16;
+  UB_CHECK(chunk > 0, "host alltoallv: staging area too small");
+  for (size_t base = 0;; base += chunk) {
+    bool more = false;
+    for (int d = 0; d < n; ++d) {
+      if (send_bytes[d] > base) {
+        const size_t c = std::min(chunk, send_bytes[d] - base);
+        memcpy(fabric_->local() + layout_.stage_in_off + (size_t)d * chunk, (const char*)in + send_off[d] + base, c);
+        more = more || send_bytes[d] > base + chunk;
+      }
+      more = more || recv_bytes[d] > base + chunk;
+    }
+    __atomic_store_n(reinterpret_cast<uint32_t*>(fabric_->local() + layout_.stage_out_off), more ? 1u : 0u,
+                     __ATOMIC_RELEASE);
+    host_barrier();
+    bool any_more = false;
+    for (int r = 0; r < n; ++r) {
+      if (recv_bytes[r] > base) {
+        const size_t c = std::min(chunk, recv_bytes[r] - base);
+        memcpy((char*)out + recv_off[r] + base, fabric_->heap(r) + layout_.stage_in_off + (size_t)me * chunk, c);
+      }
+      any_more = any_more ||
+                 __atomic_load_n(reinterpret_cast<uint32_t*>(fabric_->heap(r) + layout_.stage_out_off), __ATOMIC_ACQUIRE);
+    }
+    host_barrier();
+    if (!any_more) break;
+  }
+}
+
 }  // namespace ub
