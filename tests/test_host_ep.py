@@ -1,0 +1,154 @@
+"""CPU reference backend of the DeepEP Buffer API (`uccl_b200.ep.host_ep.HostBuffer`): the EP contract
+of SURVEY Appendix C checked without a GPU -- receive order, local-expert remapping, cached handles,
+fp8 payloads, expert_alignment, num_worst_tokens, unweighted combine, low-latency dispatch/combine."""
+import threading
+
+import pytest
+import torch
+
+from uccl_b200 import Communicator
+from uccl_b200.ep import Buffer, per_token_cast_back, per_token_cast_to_fp8
+from uccl_b200.ep.host_ep import HostBuffer
+
+
+def _run(comms, fn):
+    res, errs = [None] * len(comms), []
+
+    def body(c):
+        try:
+            res[c.rank] = fn(c)
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=body, args=(c,)) for c in comms]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    return res
+
+
+def _inputs(n, T, H, K, E, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    xs = [(torch.randn(T, H, generator=g) * 2).to(torch.bfloat16) for _ in range(n)]
+    idxs, ws = [], []
+    for _ in range(n):
+        idx = torch.rand(T, E, generator=g).topk(K, dim=1).indices
+        idxs.append(idx.masked_fill(torch.rand(T, K, generator=g) < 0.1, -1).contiguous())
+        ws.append(torch.rand(T, K, generator=g))
+    return xs, idxs, ws
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_host_ep_dispatch_combine(n):
+    T, H, K, E = 37, 256, 3, 8
+    e_per = E // n
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    xs, idxs, ws = _inputs(n, T, H, K, E, seed=n)
+
+    def fn(c):
+        b = Buffer(comm=c, num_nvl_bytes=1 << 20)
+        assert isinstance(b, HostBuffer)
+        r = c.rank
+        tpr, _, tpe, inr, _ = b.get_dispatch_layout(idxs[r], E)
+        rx, ri, rw, pe, h, _ = b.dispatch(xs[r], num_tokens_per_rank=tpr, is_token_in_rank=inr,
+                                          num_tokens_per_expert=tpe, topk_idx=idxs[r], topk_weights=ws[r],
+                                          expert_alignment=4)
+        comb, cw, _ = b.combine(rx, h, topk_weights=rw, bias=torch.ones(T, H, dtype=torch.bfloat16))
+        rx_cached, *_ = b.dispatch(xs[r], handle=h)
+        (q, s), *_ = b.dispatch(xs[r], handle=h, use_fp8=True)
+        pre_q, pre_s = per_token_cast_to_fp8(xs[r])
+        (q2, s2), *_ = b.dispatch((pre_q, pre_s), handle=h)
+        # CUDA-graph friendly variant: fixed-size outputs, no per-expert list
+        wx, wi, ww, wpe, wh, _ = b.dispatch(xs[r], num_tokens_per_rank=tpr, is_token_in_rank=inr,
+                                            num_tokens_per_expert=tpe, topk_idx=idxs[r], topk_weights=ws[r],
+                                            num_worst_tokens=n * T)
+        return dict(rx=rx, ri=ri, rw=rw, pe=pe, h=h, comb=comb, cw=cw, rxc=rx_cached, q=q, s=s, q2=q2, s2=s2, inr=inr,
+                    tpr=tpr, tpe=tpe, wx=wx, wi=wi, wpe=wpe)
+
+    res = _run(comms, fn)
+    for r, o in enumerate(res):
+        rows, eidx, ew, src = [], [], [], []
+        for s_ in range(n):
+            sel = res[s_]["inr"][:, r].nonzero().flatten()
+            rows.append(xs[s_][sel])
+            li = idxs[s_][sel]
+            mine = (li >= r * e_per) & (li < (r + 1) * e_per)
+            eidx.append(torch.where(mine, li - r * e_per, torch.full_like(li, -1)))
+            ew.append(torch.where(mine, ws[s_][sel], torch.zeros_like(ws[s_][sel])))
+            src.append(sel.to(torch.int32))
+        exp_rows = torch.cat(rows)
+        assert torch.equal(o["rx"], exp_rows) and torch.equal(o["rxc"], exp_rows)
+        assert torch.equal(o["ri"], torch.cat(eidx)) and torch.equal(o["rw"], torch.cat(ew))
+        assert torch.equal(o["h"][2], torch.cat(src)) and o["h"][4] == exp_rows.size(0)
+        assert torch.equal(o["tpr"], o["inr"].sum(0).to(torch.int32))
+        assert torch.equal(o["tpe"], torch.bincount(idxs[r][idxs[r] >= 0], minlength=E).to(torch.int32))
+        counts = [int(sum((idxs[s_] == r * e_per + e).sum() for s_ in range(n))) for e in range(e_per)]
+        assert o["pe"] == [(c + 3) // 4 * 4 for c in counts]
+        # fp8 payloads: fused cast == pre-cast input, and both dequantise to the bf16 rows
+        assert torch.equal(o["q"].view(torch.uint8), o["q2"].view(torch.uint8)) and torch.equal(o["s"], o["s2"])
+        assert torch.allclose(per_token_cast_back(o["q"], o["s"]).float(), exp_rows.float(), rtol=0.07, atol=0.15)
+        # unweighted combine (+ bias) returns fan-out * x + 1, weights are summed back
+        fan = o["inr"].sum(1).float()
+        assert torch.allclose(o["comb"].float(), xs[r].float() * fan[:, None] + 1.0, rtol=2e-2, atol=1e-1)
+        assert torch.allclose(o["cw"], torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])))
+        # worst-case mode pads to the requested size with -1 expert ids
+        assert o["wx"].size(0) == n * T and o["wpe"] == []
+        assert torch.equal(o["wx"][:exp_rows.size(0)], exp_rows) and bool((o["wi"][exp_rows.size(0):] == -1).all())
+
+
+def test_host_ep_low_latency():
+    n, T, H, K, E, M = 4, 29, 512, 4, 16, 32
+    e_per = E // n
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    xs, idxs, ws = _inputs(n, T, H, K, E, seed=11)
+
+    def fn(c):
+        b = Buffer(comm=c, num_rdma_bytes=1 << 20, low_latency_mode=True)
+        r = c.rank
+        stats = torch.zeros(e_per, dtype=torch.int32)
+        (qx, qs), cnt, hq, _, hook = b.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=True, round_scale=True,
+                                                           use_ue8m0=True, cumulative_local_expert_recv_stats=stats,
+                                                           return_recv_hook=True)
+        hook()
+        bx, cntb, hb, _, _ = b.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=False)
+        out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb)
+        return dict(qx=qx, qs=qs, cnt=cnt, stats=stats, bx=bx, cntb=cntb, out=out, hb=hb)
+
+    res = _run(comms, fn)
+    for r, o in enumerate(res):
+        counts = [int(sum((idxs[s_] == r * e_per + e).sum() for s_ in range(n))) for e in range(e_per)]
+        assert o["cnt"].tolist() == counts == o["cntb"].tolist() == o["stats"].tolist()
+        assert o["bx"].shape == (e_per, n * M, H) and o["qx"].dtype == torch.float8_e4m3fn
+        assert o["qs"].dtype == torch.int32 and o["qs"].shape == (e_per, n * M, H // 512)
+        src_info, layout_range = o["hb"][0], o["hb"][1]
+        for e in range(e_per):
+            # rows of expert e: source-rank major, token order minor; layout_range packs (count << 32 | begin)
+            exp_rows, exp_src = [], []
+            for s_ in range(n):
+                toks = (idxs[s_] == r * e_per + e).any(1).nonzero().flatten()
+                exp_rows.append(xs[s_][toks])
+                exp_src.append(toks.to(torch.int32))
+                lr = int(layout_range[e, s_])
+                assert lr >> 32 == toks.numel() and (lr & 0xFFFFFFFF) == sum(x.size(0) for x in exp_rows[:-1])
+            assert torch.equal(o["bx"][e, :counts[e]], torch.cat(exp_rows))
+            assert torch.equal(src_info[e, :counts[e]], torch.cat(exp_src))
+        wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(o["out"].float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)
+
+
+def test_deep_ep_package_uses_the_same_buffer():
+    import deep_ep
+
+    c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
+    b = deep_ep.Buffer(comm=c)
+    assert isinstance(b, HostBuffer)
+    x = torch.randn(8, 128).to(torch.bfloat16)
+    idx = torch.tensor([[0, 1]] * 8)
+    tpr, _, tpe, inr, _ = b.get_dispatch_layout(idx, 2)
+    rx, ri, rw, pe, h, _ = b.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=inr, num_tokens_per_expert=tpe,
+                                      topk_idx=idx, topk_weights=torch.ones(8, 2))
+    out, _, _ = b.combine(rx, h)
+    assert torch.equal(out, x) and pe == [8, 8]

@@ -47,6 +47,15 @@ class Config:
 class Buffer:
     num_sms: int = 24
 
+    def __new__(cls, group=None, *args, comm: Optional[Communicator] = None, **kwargs):
+        if comm is not None and comm.is_host:
+            # CPU reference backend with the same API (GPU-less CI): see host_ep.HostBuffer
+            from .host_ep import HostBuffer
+
+            return HostBuffer(comm, **{k: v for k, v in kwargs.items() if k in ("num_nvl_bytes", "num_rdma_bytes",
+                                                                                 "low_latency_mode")})
+        return super().__new__(cls)
+
     def __init__(self, group=None, num_nvl_bytes: int = 0, num_rdma_bytes: int = 0, low_latency_mode: bool = False,
                  num_qps_per_rank: int = 24, allow_nvlink_for_low_latency_mode: bool = True,
                  allow_mnnvl: bool = False, explicitly_destroy: bool = False, is_intranode: Optional[bool] = None,
