@@ -152,3 +152,39 @@ def test_deep_ep_package_uses_the_same_buffer():
                                       topk_idx=idx, topk_weights=torch.ones(8, 2))
     out, _, _ = b.combine(rx, h)
     assert torch.equal(out, x) and pe == [8, 8]
+
+
+def test_moe_layer_on_the_cpu_backend():
+    """models.ExpertParallelMoE through the host Buffer == dense single-process evaluation of the same experts."""
+    import torch.nn.functional as F
+
+    from uccl_b200.models.moe import ExpertParallelMoE
+
+    n, T, H, FFN, E, K = 2, 24, 128, 64, 4, 2
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    torch.manual_seed(5)
+    router_w = (torch.randn(E, H) * H ** -0.5).to(torch.bfloat16)
+    xs = [torch.randn(T, H).to(torch.bfloat16) for _ in range(n)]
+    mods = [None] * n
+
+    def fn(c):
+        torch.manual_seed(100 + c.rank)
+        m = ExpertParallelMoE(H, FFN, E, K, Buffer(comm=c))
+        with torch.no_grad():
+            m.router.weight.copy_(router_w)
+        mods[c.rank] = m
+        return m(xs[c.rank])
+
+    ys = _run(comms, fn)
+    e_per = E // n
+    for r in range(n):
+        x = xs[r]
+        w, idx = torch.topk(F.softmax((x @ router_w.T).float(), dim=-1), K, dim=-1)
+        ref = torch.zeros(T, H)
+        for t in range(T):
+            for k in range(K):
+                e = int(idx[t, k])
+                m = mods[e // e_per]
+                h = F.silu(x[t:t + 1] @ m.w1[e % e_per]) @ m.w2[e % e_per]
+                ref[t] += (h * w[t, k].to(h.dtype)).float()[0]
+        assert torch.allclose(ys[r].float(), ref, rtol=5e-2, atol=5e-2), (ys[r][0, :4], ref[0, :4])
