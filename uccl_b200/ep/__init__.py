@@ -3,3 +3,4 @@ from .buffer import Buffer, Config  # noqa: F401
 from .utils import (EventHandle, EventOverlap, bench, calc_diff, inplace_unique,  # noqa: F401
                     per_token_cast_back, per_token_cast_to_fp8, pack_ue8m0, unpack_ue8m0)
 from .proxy import FifoProxy, Proxy  # noqa: F401,E402
+from .autograd import ep_combine, ep_dispatch  # noqa: F401,E402

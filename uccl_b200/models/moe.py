@@ -27,9 +27,34 @@ class ExpertParallelMoE(nn.Module):
         self.w1 = nn.Parameter(torch.randn(self.local_experts, hidden, ffn, dtype=dtype) * hidden ** -0.5)
         self.w2 = nn.Parameter(torch.randn(self.local_experts, ffn, hidden, dtype=dtype) * ffn ** -0.5)
 
-    @torch.no_grad()
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: [tokens, hidden] bf16 (inference path; the comm ops are not autograd-registered)."""
+        """x: [tokens, hidden] bf16.  With gradients enabled the differentiable dispatch/combine of
+        ``uccl_b200.ep.autograd`` is used (training); otherwise the zero-copy inference path."""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(x)
+        with torch.no_grad():
+            return self._forward_infer(x)
+
+    def _forward_train(self, x: torch.Tensor) -> torch.Tensor:
+        from ..ep.autograd import ep_combine, ep_dispatch
+
+        logits = self.router(x).float()
+        w, idx = torch.topk(F.softmax(logits, dim=-1), self.top_k, dim=-1)
+        idx = idx.to(torch.int64).contiguous()
+        recv_x, recv_idx, recv_w, _, handle = ep_dispatch(self.buffer, x.contiguous(), idx, w.float().contiguous(),
+                                                          self.num_experts)
+        out = torch.zeros(recv_x.size(0), self.hidden, dtype=recv_x.dtype, device=recv_x.device)
+        for e in range(self.local_experts):
+            sel = (recv_idx == e)
+            rows = sel.any(dim=1).nonzero().flatten()
+            if rows.numel() == 0:
+                continue
+            gate = (recv_w * sel).sum(dim=1)[rows].to(recv_x.dtype)
+            h = F.silu(recv_x[rows] @ self.w1[e]) @ self.w2[e]
+            out = out.index_add(0, rows, h * gate[:, None])
+        return ep_combine(self.buffer, out, handle)
+
+    def _forward_infer(self, x: torch.Tensor) -> torch.Tensor:
         buf = self.buffer
         logits = self.router(x).float()
         w, idx = torch.topk(F.softmax(logits, dim=-1), self.top_k, dim=-1)
