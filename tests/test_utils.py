@@ -220,3 +220,33 @@ def test_ue8m0_scale_packing_roundtrip():
     w = int(packed[1, 5, 2].item()) & 0xFFFFFFFF
     for i in range(4):
         assert (w >> (8 * i)) & 0xFF == int(exps[1, 5, 8 + i].item()) + 127
+
+
+def test_tuning_table_from_sweep_and_env(tmp_path, monkeypatch):
+    import json
+    import os
+
+    import torch
+
+    from uccl_b200 import Communicator
+    from uccl_b200.utils import tuner
+
+    sweep = {"rows": [
+        {"bytes": 4096, "oneshot_ll": {"us": 12.0}, "twoshot_p2p": {"us": 19.0}, "staged_p2p": {"us": 30.0}, "nccl": {"us": 25.0}},
+        {"bytes": 1 << 20, "oneshot_ll": {"us": 40.0}, "twoshot_p2p@32": {"us": 22.0}, "twoshot_p2p@64": {"us": 21.0},
+         "staged_p2p": {"us": 33.0}},
+    ]}
+    t = tuner.tuning_from_sweep(sweep)
+    assert t["symmetric"] == [(4096, "oneshot_ll", -1, 12.0), (1 << 20, "twoshot_p2p", 64, 21.0)]
+    assert t["plain"] == [(4096, "oneshot_ll", -1, 12.0), (1 << 20, "staged_p2p", -1, 33.0)]
+    path = tmp_path / "tune.json"
+    tuner.save_tuning(str(path), t, meta={"n_gpus": 2})
+    c = Communicator.local_world(2, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
+    monkeypatch.setenv("UCCL_B200_TUNE_FILE", str(path))
+    assert tuner.load_tuning_from_env(c)
+    assert c.select_allreduce(1 << 20, True, torch.bfloat16) == ("twoshot_p2p", 64)
+    assert c.select_allreduce(2048, False, torch.bfloat16)[0] == "oneshot_ll"
+    # the shipped 8xB200 table parses
+    shipped = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "tuning_8xB200.json")
+    d = json.load(open(shipped))
+    assert {"symmetric", "plain"} <= set(d["tables"])

@@ -100,3 +100,37 @@ def load_tuning(comm, path: str) -> None:
         d = json.load(f)
     for key, rows in d.get("tables", {}).items():
         comm.set_tuning(key == "symmetric", [(int(r[0]), r[1], int(r[2])) for r in rows])
+
+
+def tuning_from_sweep(sweep: dict) -> Dict[str, List[Tuple[int, str, int, float]]]:
+    """Tables from the JSON that ``benchmarks/allreduce_perf.py`` writes (one row per message size with
+    the device-timed latency of every algorithm, optionally ``algo@ctas`` columns): the fastest symmetric
+    algorithm and the fastest plain-buffer algorithm per size.  CTA count -1 keeps the built-in choice."""
+    sym_algos = ("oneshot_ll", "oneshot_mc", "twoshot_p2p", "twoshot_nvls")
+    plain_algos = ("oneshot_ll", "oneshot_mc", "staged_p2p", "staged_nvls")
+    out: Dict[str, List[Tuple[int, str, int, float]]] = {"symmetric": [], "plain": []}
+    for row in sweep["rows"]:
+        for key, cands in (("symmetric", sym_algos), ("plain", plain_algos)):
+            best = None
+            for col, v in row.items():
+                if not isinstance(v, dict) or "us" not in v:
+                    continue
+                algo, _, ctas = col.partition("@")
+                if algo not in cands:
+                    continue
+                if best is None or v["us"] < best[3]:
+                    best = (int(row["bytes"]), algo, int(ctas) if ctas else -1, float(v["us"]))
+            if best is not None:
+                out[key].append(best)
+    return out
+
+
+def load_tuning_from_env(comm) -> bool:
+    """Install the table named by ``UCCL_B200_TUNE_FILE`` (written by :func:`save_tuning`), if any."""
+    import os
+
+    path = os.environ.get("UCCL_B200_TUNE_FILE", "")
+    if not path:
+        return False
+    load_tuning(comm, path)
+    return True
