@@ -101,6 +101,10 @@ class Communicator:
         self.device_index: int = c.device
         self.is_host: bool = c.is_host
         self.device = torch.device("cpu") if self.is_host else torch.device("cuda", c.device)
+        if os.environ.get("UCCL_B200_TUNE_FILE"):  # measured (algorithm, CTAs) per size: utils/tuner.py
+            from ..utils.tuner import load_tuning_from_env
+
+            load_tuning_from_env(self)
 
     # ------------------------------------------------------------------ construction
     @staticmethod
