@@ -290,3 +290,38 @@ def test_gpu_ukcomm_collectives(n):
         for u in uks:
             u.stop()
         comms[1]._c.free(skew)
+
+
+def _mp_uk_worker(rank, n, uid, q):
+    import torch
+
+    from uccl_b200 import Communicator
+    from uccl_b200 import ukernel as uk
+
+    c = Communicator.init(uid, rank, n, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20, timeout_ms=20000)
+    if rank == 1:
+        c._c.alloc(4096, 256)  # asymmetric heaps across processes
+    pg = uk.ProcessGroup(c, nlanes=2, tile_bytes=8192, staging_bytes=128 << 10)
+    x = torch.arange(30000, dtype=torch.float32) + rank
+    pg.all_reduce(x, "sum", )
+    z = torch.zeros(n * 100, dtype=torch.int64)
+    pg.all_to_all_single(z, torch.arange(n * 100, dtype=torch.int64) + 1000 * rank)
+    pg.barrier()
+    pg.shutdown()
+    exp = sum(torch.arange(30000, dtype=torch.float32) + r for r in range(n))
+    exp_z = torch.cat([torch.arange(rank * 100, (rank + 1) * 100, dtype=torch.int64) + 1000 * s for s in range(n)])
+    q.put((rank, bool(torch.equal(x, exp)), bool(torch.equal(z, exp_z))))
+
+
+def test_ukcomm_two_processes_over_shared_memory():
+    """The FIFO workers of two real processes signal each other through the shm-backed symmetric heap."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    uid = Communicator.create_unique_id()
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_mp_uk_worker, args=(r, 2, uid, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(30) for p in ps]
+    assert got == [(0, True, True), (1, True, True)]
