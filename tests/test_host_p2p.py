@@ -1,0 +1,131 @@
+"""P2P engine in host mode (``Endpoint(-1)``): the TCP control plane, send/recv matching with advertised
+receives, one-sided vector write/read against exchanged descriptors, async handles + polling, notifications
+and error paths run exactly the production code; only the copy itself is a memcpy.  Mirrors the
+reference's p2p/tests/test_engine_{send,read,write,metadata}.py without needing a GPU."""
+import threading
+import time
+
+import pytest
+import torch
+
+from uccl_b200.p2p import Endpoint
+
+
+def _pair():
+    a, b = Endpoint(-1), Endpoint(-1)
+    ok, conn = a.connect(remote_metadata=b.get_metadata())
+    assert ok
+    ok2, ip, gpu, conn_b = b.accept(5000)
+    assert ok2 and gpu == -1
+    return a, b, conn, conn_b
+
+
+def test_host_metadata_and_connect():
+    a, b, conn, conn_b = _pair()
+    ip, port, gpu = Endpoint.parse_metadata(b.get_metadata())
+    assert gpu == -1 and port > 0 and ip
+    assert conn != 0 and conn_b != 0
+
+
+@pytest.mark.parametrize("nbytes", [1, 4096, (3 << 20) + 5])
+def test_host_send_recv(nbytes):
+    a, b, conn, conn_b = _pair()
+    src = torch.randint(0, 255, (nbytes,), dtype=torch.uint8)
+    dst = torch.zeros(nbytes, dtype=torch.uint8)
+    ok, rt = b.recv_async(conn_b, 0, dst.data_ptr(), nbytes)  # receiver advertises first ...
+    assert ok
+    assert a.send(conn, 0, src.data_ptr(), nbytes)              # ... the sender's engine matches and copies
+    assert b.wait(rt, 10000)
+    assert torch.equal(dst, src)
+    # the other order: send posted before the receive exists
+    dst2 = torch.zeros(nbytes, dtype=torch.uint8)
+    ok, st = a.send_async(conn, 0, src.data_ptr(), nbytes)
+    assert ok
+    time.sleep(0.05)
+    assert b.recv(conn_b, 0, dst2.data_ptr(), nbytes)
+    assert a.wait(st, 10000)
+    assert torch.equal(dst2, src)
+    assert a.stats()["bytes_sent"] == 2 * nbytes and b.stats()["bytes_received"] == 2 * nbytes
+
+
+def test_host_onesided_vector_ops_and_polling():
+    a, b, conn, conn_b = _pair()
+    sizes = [1000, 33, 1 << 18, 7]
+    srcs = [torch.full((s,), i + 1, dtype=torch.uint8) for i, s in enumerate(sizes)]
+    dsts = [torch.zeros(s, dtype=torch.uint8) for s in sizes]
+    remote = a.deserialize_descs(b.get_serialized_descs(b.register_memory(dsts)))
+    local = a.register_memory(srcs)
+    ok, tid = a.transfer(conn, "write", local, remote)
+    assert ok and a.wait(tid, 10000)
+    for i, d in enumerate(dsts):
+        assert bool((d == i + 1).all())
+    back = [torch.zeros(s, dtype=torch.uint8) for s in sizes]
+    ok, tid = a.transfer(conn, "read", a.register_memory(back), remote)
+    assert ok
+    done = False
+    for _ in range(100000):
+        ok, done = a.poll_async(tid)
+        assert ok
+        if done:
+            break
+    assert done
+    for i, d in enumerate(back):
+        assert bool((d == i + 1).all())
+    ok, _ = a.poll_async(tid)  # handles are released once reported done
+    assert not ok
+    # a raw write larger than the advertised window is refused (transfer() itself clips to the window)
+    big = torch.zeros(sizes[1] + 1, dtype=torch.uint8)
+    ok, _ = a.write_async(conn, 0, big.data_ptr(), big.numel(), remote[1])
+    assert not ok
+    assert a.stats()["bytes_written"] == sum(sizes) and a.stats()["bytes_read"] == sum(sizes)
+
+
+def test_host_notifications_and_wait_timeout():
+    a, b, conn, conn_b = _pair()
+    assert a.send_notif(conn, b"kv-ready:42")
+    got = []
+    t0 = time.time()
+    while not got and time.time() - t0 < 5:
+        got = b.get_notifs()
+        time.sleep(0.005)
+    assert got and got[0][1] == b"kv-ready:42"
+    # a receive nobody sends to: wait() returns False after the timeout, the handle stays valid
+    dst = torch.zeros(16, dtype=torch.uint8)
+    ok, rt = b.recv_async(conn_b, 0, dst.data_ptr(), 16)
+    assert ok
+    t0 = time.time()
+    assert not b.wait(rt, 150)
+    assert 0.1 < time.time() - t0 < 2.0
+    src = torch.ones(16, dtype=torch.uint8)
+    assert a.send(conn, 0, src.data_ptr(), 16) and b.wait(rt, 5000) and bool((dst == 1).all())
+    assert not b.wait(12345678, 10)  # unknown transfer id
+
+
+def test_host_concurrent_streams_of_messages():
+    """Several in-flight sends and receives on one connection complete in order of their sequence numbers."""
+    a, b, conn, conn_b = _pair()
+    n = 32
+    srcs = [torch.full((1000 + i,), i, dtype=torch.uint8) for i in range(n)]
+    dsts = [torch.zeros(1000 + i, dtype=torch.uint8) for i in range(n)]
+    rts = []
+
+    def receiver():
+        for d in dsts:
+            ok, rt = b.recv_async(conn_b, 0, d.data_ptr(), d.numel())
+            assert ok
+            rts.append(rt)
+
+    th = threading.Thread(target=receiver)
+    th.start()
+    sts = []
+    for s in srcs:
+        ok, st = a.send_async(conn, 0, s.data_ptr(), s.numel())
+        assert ok
+        sts.append(st)
+    th.join()
+    for st in sts:
+        assert a.wait(st, 10000)
+    for rt in rts:
+        assert b.wait(rt, 10000)
+    for i, d in enumerate(dsts):
+        assert bool((d == i).all())

@@ -90,13 +90,18 @@ struct Endpoint::Transfer {
   cudaEvent_t ev = nullptr;
 };
 
+// local_gpu_idx < 0 selects the host mode: buffers are ordinary host memory of this process, copies are
+// memcpy and complete immediately.  Everything else (TCP control plane, send/recv matching, transfer
+// tables, notifications, polling) is the production code, which is what the GPU-less CI exercises.
 Endpoint::Endpoint(int local_gpu_idx, int num_streams) : gpu_(local_gpu_idx) {
-  UB_CUDA(cudaSetDevice(gpu_));
-  UB_CUDA(cudaFree(0));
-  for (int i = 0; i < std::max(1, num_streams); ++i) {
-    cudaStream_t s;
-    UB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    streams_.push_back(s);
+  if (gpu_ >= 0) {
+    UB_CUDA(cudaSetDevice(gpu_));
+    UB_CUDA(cudaFree(0));
+    for (int i = 0; i < std::max(1, num_streams); ++i) {
+      cudaStream_t s;
+      UB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      streams_.push_back(s);
+    }
   }
   ip_ = param_load_str("P2P_IP", "127.0.0.1");
   listen_fd_ = ::socket(AF_INET, SOCK_STREAM, 0);
@@ -130,6 +135,7 @@ Endpoint::~Endpoint() {
   }
   if (listen_fd_ >= 0) ::close(listen_fd_);
   if (wake_fd_ >= 0) ::close(wake_fd_);
+  if (gpu_ < 0) return;
   cudaSetDevice(gpu_);
   for (auto& kv : ipc_open_) cudaIpcCloseMemHandle(kv.second);
   for (auto s : streams_) cudaStreamDestroy(s);
@@ -298,6 +304,11 @@ bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
   out->size = size;
   out->pid = (int32_t)getpid();
   out->dev = gpu_;
+  if (gpu_ < 0) {  // host mode: plain memory of this process
+    out->kind = 1;
+    out->base = (uint64_t)ptr;
+    return true;
+  }
   cudaPointerAttributes attr;
   memset(&attr, 0, sizeof(attr));
   cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
@@ -357,6 +368,11 @@ bool Endpoint::advertise(uint64_t conn, const void* ptr, size_t size, XferDesc* 
 }
 
 void* Endpoint::map_remote(const XferDesc& d) {
+  if (gpu_ < 0) {
+    if (d.pid == (int32_t)getpid()) return (void*)d.addr;
+    UB_WARN("p2p(host mode): descriptors of another process cannot be mapped");
+    return nullptr;
+  }
   if (d.pid == (int32_t)getpid()) {
     // same-process short-circuit (reference: direct_addr); a pointer of another device needs
     // peer access from ours (cudaMalloc memory is not peer-mapped by default)
@@ -405,6 +421,12 @@ void* Endpoint::map_remote(const XferDesc& d) {
 // ------------------------------------------------------------------ data path
 bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
                            const std::vector<size_t>& sizes, cudaEvent_t ev) {
+  if (gpu_ < 0) {
+    for (size_t i = 0; i < src.size(); ++i) memmove(dst[i], src[i], sizes[i]);
+    std::lock_guard<std::mutex> g(mu_);
+    stats_.memcpy_fallbacks += src.size();
+    return true;  // complete: transfers carry no event in host mode
+  }
   cudaStream_t st;
   {
     std::lock_guard<std::mutex> g(mu_);
@@ -521,7 +543,7 @@ bool Endpoint::write_async(uint64_t conn, const std::vector<const void*>& src, c
                            const std::vector<XferDesc>& remote, uint64_t* tid) {
   auto c = find_conn(conn);
   if (!c || src.size() != sizes.size() || src.size() != remote.size() || src.empty()) return false;
-  cudaSetDevice(gpu_);
+  if (gpu_ >= 0) cudaSetDevice(gpu_);
   std::vector<const char*> s;
   std::vector<char*> d;
   for (size_t i = 0; i < src.size(); ++i) {
@@ -534,7 +556,7 @@ bool Endpoint::write_async(uint64_t conn, const std::vector<const void*>& src, c
   auto t = std::make_shared<Transfer>();
   t->conn = c;
   t->state = Transfer::COPYING;
-  t->ev = new_event();
+  t->ev = gpu_ >= 0 ? new_event() : nullptr;
   if (!launch_copy(s, d, sizes, t->ev)) return false;
   std::lock_guard<std::mutex> g(mu_);
   t->id = next_tid_++;
@@ -549,7 +571,7 @@ bool Endpoint::read_async(uint64_t conn, const std::vector<void*>& dst, const st
                           const std::vector<XferDesc>& remote, uint64_t* tid) {
   auto c = find_conn(conn);
   if (!c || dst.size() != sizes.size() || dst.size() != remote.size() || dst.empty()) return false;
-  cudaSetDevice(gpu_);
+  if (gpu_ >= 0) cudaSetDevice(gpu_);
   std::vector<const char*> s;
   std::vector<char*> d;
   for (size_t i = 0; i < dst.size(); ++i) {
@@ -562,7 +584,7 @@ bool Endpoint::read_async(uint64_t conn, const std::vector<void*>& dst, const st
   auto t = std::make_shared<Transfer>();
   t->conn = c;
   t->state = Transfer::COPYING;
-  t->ev = new_event();
+  t->ev = gpu_ >= 0 ? new_event() : nullptr;
   if (!launch_copy(s, d, sizes, t->ev)) return false;
   std::lock_guard<std::mutex> g(mu_);
   t->id = next_tid_++;
@@ -583,7 +605,7 @@ bool Endpoint::poll_async(uint64_t tid, bool* done) {
   }
   if (t->state == Transfer::COPYING && !t->notify_done) {
     // one-sided ops are driven by the caller: no engine-thread latency on the hot path
-    cudaError_t q = cudaEventQuery(t->ev);
+    cudaError_t q = t->ev ? cudaEventQuery(t->ev) : cudaSuccess;
     if (q == cudaSuccess) t->state = Transfer::DONE;
     else if (q != cudaErrorNotReady) t->state = Transfer::FAILED;
     (void)cudaGetLastError();
@@ -679,7 +701,7 @@ void Endpoint::progress_locked() {
           if (!r) ok = false;
           dst.push_back((char*)r);
         }
-        cudaEvent_t ev = ok ? new_event() : nullptr;
+        cudaEvent_t ev = (ok && gpu_ >= 0) ? new_event() : nullptr;
         if (ok) ok = launch_copy(t->src, dst, t->sizes, ev);
         mu_.lock();
         t->ev = ev;
@@ -688,7 +710,7 @@ void Endpoint::progress_locked() {
       }
       case Transfer::COPYING: {
         if (!t->notify_done) break;  // caller-driven
-        cudaError_t q = cudaEventQuery(t->ev);
+        cudaError_t q = t->ev ? cudaEventQuery(t->ev) : cudaSuccess;
         if (q == cudaSuccess) {
           mu_.unlock();
           bool ok = send_msg(c, MSG_DONE, t->seq, nullptr, 0);
@@ -717,7 +739,7 @@ void Endpoint::progress_locked() {
 }
 
 void Endpoint::engine_loop() {
-  cudaSetDevice(gpu_);
+  if (gpu_ >= 0) cudaSetDevice(gpu_);
   while (!stop_) {
     std::vector<pollfd> fds;
     std::vector<std::shared_ptr<Conn>> cs;

@@ -53,8 +53,11 @@ class Endpoint:
 
         C = _native.C()
         if local_gpu_idx is None:
-            local_gpu_idx = torch.cuda.current_device()
-        torch.cuda.init()
+            local_gpu_idx = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        if int(local_gpu_idx) >= 0:
+            torch.cuda.init()
+        # local_gpu_idx < 0: host mode (buffers are host memory of this process, copies are memcpy) --
+        # the control plane, matching and transfer bookkeeping are the production code (GPU-less CI)
         self._e = C.P2PEndpoint(int(local_gpu_idx), max(1, int(num_cpus)))
         self.local_gpu_idx = int(local_gpu_idx)
         self._mrs = {}
