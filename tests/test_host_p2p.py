@@ -129,3 +129,22 @@ def test_host_concurrent_streams_of_messages():
         assert b.wait(rt, 10000)
     for i, d in enumerate(dsts):
         assert bool((d == i).all())
+
+
+def test_uccl_engine_c_api_host_mode(tmp_path):
+    """The NIXL-plugin C surface (`uccl_engine_*`) driven from C++ against two host-mode engines."""
+    import os
+    import subprocess
+
+    from uccl_b200 import _build
+
+    _build.build()
+    lib = _build.nccl_shim_path()  # carries the whole native core incl. the engine C API
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "uccl_engine_test"
+    cmd = ["g++", "-std=c++17", "-O1", os.path.join(root, "tests/cpp/uccl_engine_test.cc"),
+           "-I" + os.path.join(root, "uccl_b200/csrc/p2p"), "-L" + str(lib.parent), "-luccl_b200_nccl",
+           "-Wl,-rpath," + str(lib.parent), "-lpthread", "-o", str(exe)]
+    subprocess.run(cmd, check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "uccl_engine_test: OK" in r.stdout, r.stdout + r.stderr
