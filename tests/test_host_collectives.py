@@ -132,3 +132,16 @@ def test_multiprocess_bootstrap_world2():
     got = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(30) for p in ps]
     assert got == [(0, True), (1, True)]
+
+
+def test_lost_peer_is_a_diagnosable_timeout():
+    """Failure detection (reference: spin timeouts that name the site instead of hanging): a rank
+    whose peer never shows up gets an error that names the missing rank -- not a hang."""
+    import time
+
+    comms = Communicator.local_world(2, host=True, heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=300)
+    t0 = time.time()
+    with pytest.raises(RuntimeError) as ei:
+        comms[0].all_reduce(torch.ones(8), "sum")  # rank 1 never calls
+    assert 0.2 < time.time() - t0 < 5.0
+    assert "timeout" in str(ei.value) and "rank 1" in str(ei.value)

@@ -325,3 +325,14 @@ def test_ukcomm_two_processes_over_shared_memory():
     got = sorted(q.get(timeout=120) for _ in range(2))
     [p.join(30) for p in ps]
     assert got == [(0, True, True), (1, True, True)]
+
+
+def test_host_worker_wait_timeout_sets_error_word():
+    """A WAIT task whose signal never arrives ends with an error word the producer sees, not a hang."""
+    w = uk.Worker(device=-1, nlanes=1, timeout_ms=200)
+    flag = torch.zeros(1, dtype=torch.int64)
+    t = w.wait_value(0, flag.data_ptr(), 1)
+    with pytest.raises(RuntimeError) as ei:
+        w.wait(0, t, timeout_s=5.0)
+    assert "error" in str(ei.value)
+    assert w.error != 0

@@ -270,6 +270,8 @@ void UkWorker::wait(int lane, uint64_t ticket, double timeout_s) const {
       if ((spins & 0xffff) == 0) const_cast<UkWorker*>(this)->kick();
     }
   }
+  // a lane that gave up on a WAIT publishes "done" to unblock its waiters: completion alone is not success
+  UB_CHECK(error() == 0, "ukernel: worker reported error 0x%x", error());
 }
 
 void UkWorker::wait_all(double timeout_s) const {
