@@ -22,6 +22,9 @@ namespace ub {
 UB_PARAM(P2PCtas, "P2P_CTAS", 32)
 UB_PARAM(P2PChunkKB, "P2P_CHUNK_KB", 32)
 UB_PARAM(P2PUseKernel, "P2P_USE_KERNEL", 1)
+// engine status line every N seconds at INFO level (reference: per-engine stats thread every 2 s unless
+// UCCL_ENGINE_QUIET, collective/rdma/transport.cc:1797-1825); 0 = off
+UB_PARAM(P2PStatsSec, "ENGINE_STATS_SEC", 0)
 
 cudaError_t launch_p2p_copy(const P2PCopyBatch& b, int grid, cudaStream_t st);
 
@@ -740,7 +743,20 @@ void Endpoint::progress_locked() {
 
 void Endpoint::engine_loop() {
   if (gpu_ >= 0) cudaSetDevice(gpu_);
+  const int64_t stats_sec = ubParamP2PStatsSec();
+  auto last_stats = std::chrono::steady_clock::now();
   while (!stop_) {
+    if (stats_sec > 0 && std::chrono::steady_clock::now() - last_stats >= std::chrono::seconds(stats_sec)) {
+      last_stats = std::chrono::steady_clock::now();
+      std::lock_guard<std::mutex> g(mu_);
+      UB_INFO(SUB_P2P,
+              "p2p engine gpu %d: %zu conns, %zu transfers in flight, %llu done, sent %llu B, recv %llu B, written "
+              "%llu B, read %llu B, %llu kernel launches, %llu memcpy fallbacks",
+              gpu_, conns_.size(), transfers_.size(), (unsigned long long)stats_.transfers,
+              (unsigned long long)stats_.bytes_sent, (unsigned long long)stats_.bytes_received,
+              (unsigned long long)stats_.bytes_written, (unsigned long long)stats_.bytes_read,
+              (unsigned long long)stats_.kernel_launches, (unsigned long long)stats_.memcpy_fallbacks);
+    }
     std::vector<pollfd> fds;
     std::vector<std::shared_ptr<Conn>> cs;
     bool active = false;
