@@ -336,3 +336,46 @@ def test_host_worker_wait_timeout_sets_error_word():
         w.wait(0, t, timeout_s=5.0)
     assert "error" in str(ei.value)
     assert w.error != 0
+
+
+def test_reduce_scatter_and_broadcast_plans():
+    for n in (1, 2, 3, 8):
+        for lanes in (1, 3):
+            assert uk.validate("reduce_scatter", 5008, n, lanes, 1024, 4) == ""
+            for root in (0, n - 1):
+                assert uk.validate("broadcast", 5000, n, lanes, 1024, root=root) == ""
+    n, per = 4, 3000
+    ins = [torch.randn(n * per, generator=torch.Generator().manual_seed(r)) for r in range(n)]
+    outs = [torch.zeros(per) for _ in range(n)]
+    assert uk.simulate("reduce_scatter", ins, outs, "sum", nlanes=2, tile_bytes=2048) == ""  # several tiles per lane
+    ref = torch.stack(ins).sum(0).view(n, per)
+    for r in range(n):
+        assert torch.allclose(outs[r], ref[r], atol=1e-5)
+    bins = [torch.full((4097,), float(r)) for r in range(n)]
+    bouts = [torch.zeros(4097) for _ in range(n)]
+    assert uk.simulate("broadcast", bins, bouts, nlanes=3, tile_bytes=1024, root=2) == ""
+    for o in bouts:
+        assert torch.equal(o, bins[2])
+
+
+def test_host_ukcomm_reduce_scatter_broadcast():
+    n = 4
+    comms = Communicator.local_world(n, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20)
+
+    def fn(c):
+        pg = uk.ProcessGroup(c, nlanes=2, tile_bytes=4096, staging_bytes=64 << 10)
+        x = (torch.arange(n * 7001, dtype=torch.float32) % 13) + c.rank   # 7001 per rank: odd size, several segments
+        out = torch.zeros(7001)
+        pg.reduce_scatter_tensor(out, x, "sum")
+        avg = torch.zeros(16)
+        pg.reduce_scatter_tensor(avg, torch.full((n * 16,), float(c.rank)), "avg")
+        b = torch.full((70001,), float(c.rank), dtype=torch.bfloat16)
+        pg.broadcast(b, src=3)
+        pg.shutdown()
+        return out, avg, b
+
+    for r, (out, avg, b) in enumerate(_run_threads(comms, fn)):
+        exp = sum((torch.arange(n * 7001, dtype=torch.float32) % 13) + s for s in range(n)).view(n, 7001)[r]
+        assert torch.equal(out, exp)
+        assert torch.allclose(avg, torch.full((16,), (n - 1) / 2))
+        assert bool((b == 3).all())

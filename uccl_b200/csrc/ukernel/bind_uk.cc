@@ -29,13 +29,16 @@ py::list plan_ops(const UkPlan& p) {
   }
   return out;
 }
-UkPlan make(int coll, uint64_t bytes, int nranks, int rank, int nlanes, uint64_t tile, uint64_t elem, int algo) {
+UkPlan make(int coll, uint64_t bytes, int nranks, int rank, int nlanes, uint64_t tile, uint64_t elem, int algo,
+            int root = 0) {
   UkPlanParams p;
   p.nranks = nranks, p.rank = rank, p.nlanes = nlanes, p.tile_bytes = tile, p.elem_size = elem, p.algo = (UkAlgo)algo;
   switch ((UkColl)coll) {
     case UkColl::AllReduce: return uk_plan_allreduce(bytes, p);
     case UkColl::AllToAll: return uk_plan_alltoall(bytes, p);
     case UkColl::AllGather: return uk_plan_allgather(bytes, p);
+    case UkColl::ReduceScatter: return uk_plan_reduce_scatter(bytes, p);
+    case UkColl::Broadcast: return uk_plan_broadcast(bytes, root, p);
     default: return uk_plan_barrier(p);
   }
 }
@@ -47,6 +50,8 @@ void bind_uk(py::module_& m) {
   uk.attr("ALLTOALL") = (int)UkColl::AllToAll;
   uk.attr("ALLGATHER") = (int)UkColl::AllGather;
   uk.attr("BARRIER") = (int)UkColl::Barrier;
+  uk.attr("REDUCE_SCATTER") = (int)UkColl::ReduceScatter;
+  uk.attr("BROADCAST") = (int)UkColl::Broadcast;
   uk.attr("ALGO_AUTO") = (int)UkAlgo::Auto;
   uk.attr("ALGO_RING") = (int)UkAlgo::Ring;
   uk.attr("ALGO_FULLMESH") = (int)UkAlgo::FullMesh;
@@ -62,29 +67,29 @@ void bind_uk(py::module_& m) {
   });
   // plan for one rank: (description, [op dicts])
   uk.def("plan",
-         [](int coll, uint64_t bytes, int nranks, int rank, int nlanes, uint64_t tile, uint64_t elem, int algo) {
-           UkPlan p = make(coll, bytes, nranks, rank, nlanes, tile, elem, algo);
+         [](int coll, uint64_t bytes, int nranks, int rank, int nlanes, uint64_t tile, uint64_t elem, int algo, int root) {
+           UkPlan p = make(coll, bytes, nranks, rank, nlanes, tile, elem, algo, root);
            return py::make_tuple(p.describe(), plan_ops(p));
          },
          py::arg("coll"), py::arg("bytes"), py::arg("nranks"), py::arg("rank"), py::arg("nlanes") = 1,
-         py::arg("tile_bytes") = 1 << 20, py::arg("elem_size") = 1, py::arg("algo") = 0);
+         py::arg("tile_bytes") = 1 << 20, py::arg("elem_size") = 1, py::arg("algo") = 0, py::arg("root") = 0);
   // plans of all ranks: structural validation, "" when consistent
   uk.def("validate",
-         [](int coll, uint64_t bytes, int nranks, int nlanes, uint64_t tile, uint64_t elem, int algo) {
+         [](int coll, uint64_t bytes, int nranks, int nlanes, uint64_t tile, uint64_t elem, int algo, int root) {
            std::vector<UkPlan> plans;
-           for (int r = 0; r < nranks; ++r) plans.push_back(make(coll, bytes, nranks, r, nlanes, tile, elem, algo));
+           for (int r = 0; r < nranks; ++r) plans.push_back(make(coll, bytes, nranks, r, nlanes, tile, elem, algo, root));
            return uk_validate(plans);
          },
          py::arg("coll"), py::arg("bytes"), py::arg("nranks"), py::arg("nlanes") = 1, py::arg("tile_bytes") = 1 << 20,
-         py::arg("elem_size") = 1, py::arg("algo") = 0);
+         py::arg("elem_size") = 1, py::arg("algo") = 0, py::arg("root") = 0);
   // run the plans of all ranks over host buffers (in_ptrs / out_ptrs: one per rank); "" on success
   uk.def("simulate",
          [](int coll, uint64_t bytes, int nranks, int nlanes, uint64_t tile, int dtype, int op, int algo,
-            std::vector<uintptr_t> in_ptrs, std::vector<uintptr_t> out_ptrs) {
+            std::vector<uintptr_t> in_ptrs, std::vector<uintptr_t> out_ptrs, int root) {
            UB_CHECK((int)in_ptrs.size() == nranks && (int)out_ptrs.size() == nranks, "simulate: one buffer per rank");
            std::vector<UkPlan> plans;
            for (int r = 0; r < nranks; ++r)
-             plans.push_back(make(coll, bytes, nranks, r, nlanes, tile, dtype_size(dtype), algo));
+             plans.push_back(make(coll, bytes, nranks, r, nlanes, tile, dtype_size(dtype), algo, root));
            std::string err = uk_validate(plans);
            if (!err.empty()) return err;
            std::vector<std::vector<char>> scratch(nranks);
@@ -97,7 +102,9 @@ void bind_uk(py::module_& m) {
            }
            py::gil_scoped_release rel;
            return uk_simulate(plans, b, dtype, op);
-         });
+         },
+         py::arg("coll"), py::arg("bytes"), py::arg("nranks"), py::arg("nlanes"), py::arg("tile_bytes"), py::arg("dtype"),
+         py::arg("op"), py::arg("algo"), py::arg("in_ptrs"), py::arg("out_ptrs"), py::arg("root") = 0);
 
   py::class_<UkWorker, std::shared_ptr<UkWorker>>(uk, "Worker")
       .def(py::init<int, int, uint64_t, int64_t>(), py::arg("device"), py::arg("nlanes"), py::arg("timeout_ms") = 20000,
@@ -172,6 +179,18 @@ void bind_uk(py::module_& m) {
            },
            py::arg("inp"), py::arg("out"), py::arg("count_per_rank"), py::arg("dtype"), py::arg("stream") = 0,
            py::arg("symmetric") = false)
+      .def("reduce_scatter",
+           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             return u.reduce_scatter((const void*)in, (void*)out, count, dtype, op, (cudaStream_t)stream);
+           },
+           py::arg("inp"), py::arg("out"), py::arg("recv_count"), py::arg("dtype"), py::arg("op"), py::arg("stream") = 0)
+      .def("broadcast",
+           [](UkComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int root, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             return u.broadcast((const void*)in, (void*)out, count, dtype, root, (cudaStream_t)stream);
+           },
+           py::arg("inp"), py::arg("out"), py::arg("count"), py::arg("dtype"), py::arg("root"), py::arg("stream") = 0)
       .def("barrier",
            [](UkComm& u, uintptr_t stream) {
              py::gil_scoped_release rel;

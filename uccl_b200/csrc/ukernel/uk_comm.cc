@@ -403,6 +403,57 @@ uint64_t UkComm::all_gather(const void* in, void* out, size_t count_per_rank, in
   return end_op(stream);
 }
 
+uint64_t UkComm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel reduce_scatter: bad dtype %d", dtype);
+  UB_CHECK(op == kSum || op == kProd || op == kMax || op == kMin, "ukernel reduce_scatter: op %d unsupported", op);
+  const int n = comm_->nranks();
+  const uint64_t es = dtype_size(dtype), block = recv_count * es;
+  begin_op(stream);
+  UkPlanParams p;
+  p.nranks = n, p.rank = comm_->rank(), p.nlanes = cfg_.nlanes, p.tile_bytes = cfg_.tile_bytes, p.elem_size = es;
+  // n pieces must fit the input staging buffer; pieces stay multiples of 16 bytes (and of the element size)
+  const uint64_t seg_max = cfg_.staging_bytes / n / 16 * 16;
+  for (uint64_t off = 0; off < block; off += seg_max) {
+    const uint64_t seg = std::min<uint64_t>(seg_max, block - off);
+    const uint64_t pitch = round_up(seg, 16);
+    ++stats_.segments;
+    for (int q = 0; q < n; ++q) {
+      UkTask t;
+      memset(&t, 0, sizeof(t));
+      t.op = UK_COPY;
+      t.dst = (uint64_t)(stage_in_ + (uint64_t)q * pitch);
+      t.src = (uint64_t)((const char*)in + (uint64_t)q * block + off);
+      t.bytes = seg;
+      push(q % cfg_.nlanes, t);
+    }
+    lane_barrier();
+    // the plan reduces `pitch` bytes per piece; the (< 16 byte) padding holds stale data that is never copied out
+    run_plan(uk_plan_reduce_scatter(pitch, p), Bufs{stage_in_, stage_out_}, dtype, op);
+    lane_barrier();
+    copy_sliced((char*)out + off, stage_out_, seg);
+  }
+  return end_op(stream);
+}
+
+uint64_t UkComm::broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel broadcast: bad dtype %d", dtype);
+  UB_CHECK(root >= 0 && root < comm_->nranks(), "ukernel broadcast: bad root %d", root);
+  const uint64_t bytes = count * dtype_size(dtype);
+  begin_op(stream);
+  UkPlanParams p;
+  p.nranks = comm_->nranks(), p.rank = comm_->rank(), p.nlanes = cfg_.nlanes, p.tile_bytes = cfg_.tile_bytes;
+  for (uint64_t off = 0; off < bytes; off += cfg_.staging_bytes) {
+    const uint64_t seg = std::min<uint64_t>(cfg_.staging_bytes, bytes - off);
+    ++stats_.segments;
+    if (comm_->rank() == root) copy_sliced(stage_in_, (const char*)in + off, seg);
+    lane_barrier();
+    run_plan(uk_plan_broadcast(seg, root, p), Bufs{stage_in_, stage_out_}, dtype, kSum);
+    lane_barrier();
+    copy_sliced((char*)out + off, stage_out_, seg);
+  }
+  return end_op(stream);
+}
+
 uint64_t UkComm::barrier(cudaStream_t stream) {
   begin_op(stream);
   UkPlanParams p;

@@ -42,6 +42,8 @@ class UkComm {
                       bool symmetric = false);
   uint64_t all_gather(const void* in, void* out, size_t count_per_rank, int dtype, cudaStream_t stream,
                       bool symmetric = false);
+  uint64_t reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream);
+  uint64_t broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream);
   uint64_t barrier(cudaStream_t stream);
   bool test(uint64_t ticket);
   void wait(uint64_t ticket, double timeout_s = 60.0);

@@ -88,7 +88,9 @@ UkPlan make_plan(UkColl coll, UkAlgo algo, uint64_t bytes, const UkPlanParams& p
   pl.coll = coll, pl.algo = algo;
   pl.nranks = p.nranks, pl.rank = p.rank, pl.nlanes = p.nlanes;
   pl.bytes = bytes, pl.tile_bytes = p.tile_bytes;
-  pl.scratch_bytes = coll == UkColl::AllReduce ? uk_scratch_bytes(algo, p.nranks, p.nlanes, p.tile_bytes) : 0;
+  pl.scratch_bytes = (coll == UkColl::AllReduce || coll == UkColl::ReduceScatter)
+                         ? uk_scratch_bytes(algo, p.nranks, p.nlanes, p.tile_bytes)
+                         : 0;
   return pl;
 }
 
@@ -225,6 +227,74 @@ UkPlan uk_plan_allgather(uint64_t block, const UkPlanParams& p) {
   return pl;
 }
 
+UkPlan uk_plan_reduce_scatter(uint64_t block, const UkPlanParams& p) {
+  check_params(p);
+  UB_CHECK(block % p.elem_size == 0, "ukernel plan: %lu bytes is not a whole number of elements", (unsigned long)block);
+  UkPlan pl = make_plan(UkColl::ReduceScatter, UkAlgo::FullMesh, block, p);
+  Emitter e(pl);
+  const int n = p.nranks, r = p.rank, L = p.nlanes;
+  const int T = (int)std::max<uint64_t>(1, ceil_div(block, p.tile_bytes));
+  auto slot = [&](int lane, int src) { return ((uint64_t)lane * n + src) * p.tile_bytes; };
+  // unlike AllReduce there is no all-gather phase whose receipt proves that the peers are done with their
+  // scratch, so every lane starts with the "I have entered" handshake
+  for (int lane = 0; lane < std::min(L, T); ++lane)
+    if (n > 1) handshake(e, lane, n, r);
+  for (int t = 0; t < T; ++t) {
+    const int lane = t % L;
+    const uint64_t lo = (uint64_t)t * p.tile_bytes;
+    const uint64_t len = lo >= block ? 0 : std::min(p.tile_bytes, block - lo);
+    if (!len) continue;
+    for (int k = 1; k < n; ++k) {
+      const int q = (r + k) % n;
+      e.send(lane, t, 1, q, UkBuf::Scratch, slot(lane, r), UkBuf::In, (uint64_t)q * block + lo, len);
+    }
+    bool first = true;
+    for (int k = 1; k < n; ++k) {
+      const int q = (r + k) % n;
+      e.recv(lane, t, 1, q, len);
+      e.reduce(lane, t, 1, UkBuf::Out, lo, first ? UkBuf::In : UkBuf::Out, first ? (uint64_t)r * block + lo : lo,
+               UkBuf::Scratch, slot(lane, q), len);
+      first = false;
+    }
+    if (n == 1) e.copy(lane, t, 1, UkBuf::Out, lo, UkBuf::In, lo, len);
+    // the next tile of this lane reuses the slots: peers must have consumed this tile's data first
+    if (n > 1 && t + L < T) handshake(e, lane, n, r);
+  }
+  return pl;
+}
+
+UkPlan uk_plan_broadcast(uint64_t bytes, int root, const UkPlanParams& p) {
+  check_params(p);
+  UB_CHECK(root >= 0 && root < p.nranks, "ukernel plan: bad root %d", root);
+  UkPlan pl = make_plan(UkColl::Broadcast, UkAlgo::FullMesh, bytes, p);
+  pl.root = root;
+  Emitter e(pl);
+  const int n = p.nranks, r = p.rank, L = p.nlanes;
+  const int T = (int)std::max<uint64_t>(1, ceil_div(bytes, p.tile_bytes));
+  for (int lane = 0; lane < std::min(L, T); ++lane) {
+    if (n == 1) break;
+    // the root may only write once a peer has entered the operation: peers signal the root, the root waits
+    if (r == root) {
+      for (int k = 1; k < n; ++k) e.recv(lane, -1, 0, (r + k) % n, 0);
+    } else {
+      e.send(lane, -1, 0, root, UkBuf::Out, 0, UkBuf::In, 0, 0);
+    }
+  }
+  for (int t = 0; t < T; ++t) {
+    const int lane = t % L;
+    const uint64_t lo = (uint64_t)t * p.tile_bytes;
+    const uint64_t len = lo >= bytes ? 0 : std::min(p.tile_bytes, bytes - lo);
+    if (!len) continue;
+    if (r == root) {
+      for (int k = 1; k < n; ++k) e.send(lane, t, 1, (r + k) % n, UkBuf::Out, lo, UkBuf::In, lo, len);
+      e.copy(lane, t, 1, UkBuf::Out, lo, UkBuf::In, lo, len);
+    } else {
+      e.recv(lane, t, 1, root, len);
+    }
+  }
+  return pl;
+}
+
 UkPlan uk_plan_barrier(const UkPlanParams& p) {
   check_params(p);
   UkPlan pl = make_plan(UkColl::Barrier, UkAlgo::FullMesh, 0, p);
@@ -234,7 +304,7 @@ UkPlan uk_plan_barrier(const UkPlanParams& p) {
 }
 
 std::string UkPlan::describe() const {
-  static const char* coll_names[] = {"allreduce", "alltoall", "allgather", "barrier"};
+  static const char* coll_names[] = {"allreduce", "alltoall", "allgather", "barrier", "reduce_scatter", "broadcast"};
   static const char* algo_names[] = {"auto", "ring", "fullmesh"};
   static const char* kind_names[] = {"copy", "reduce", "send", "recv"};
   static const char* buf_names[] = {"in", "out", "scratch"};

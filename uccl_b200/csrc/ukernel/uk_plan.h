@@ -16,7 +16,7 @@
 
 namespace ub {
 
-enum class UkColl : int { AllReduce = 0, AllToAll = 1, AllGather = 2, Barrier = 3 };
+enum class UkColl : int { AllReduce = 0, AllToAll = 1, AllGather = 2, Barrier = 3, ReduceScatter = 4, Broadcast = 5 };
 enum class UkAlgo : int { Auto = 0, Ring = 1, FullMesh = 2 };
 enum class UkBuf : int { In = 0, Out = 1, Scratch = 2 };
 
@@ -41,7 +41,8 @@ struct UkPlan {
   UkColl coll = UkColl::AllReduce;
   UkAlgo algo = UkAlgo::FullMesh;
   int nranks = 1, rank = 0, nlanes = 1;
-  uint64_t bytes = 0;          // AllReduce: message bytes; AllToAll/AllGather: bytes per peer block
+  uint64_t bytes = 0;          // AllReduce/Broadcast: message bytes; AllToAll/AllGather/ReduceScatter: bytes per peer block
+  int root = 0;                // Broadcast
   uint64_t tile_bytes = 0;
   uint64_t scratch_bytes = 0;  // scratch this plan addresses
   std::vector<UkPlanOp> ops;   // emission order == per-lane program order
@@ -62,6 +63,10 @@ UkPlan uk_plan_allreduce(uint64_t bytes, const UkPlanParams& p);
 UkPlan uk_plan_alltoall(uint64_t bytes_per_peer, const UkPlanParams& p);
 UkPlan uk_plan_allgather(uint64_t bytes_per_rank, const UkPlanParams& p);
 UkPlan uk_plan_barrier(const UkPlanParams& p);
+// In holds nranks pieces of `bytes_per_rank`; Out receives the reduction of piece `rank`
+UkPlan uk_plan_reduce_scatter(uint64_t bytes_per_rank, const UkPlanParams& p);
+// `bytes` of the root's In end up in every rank's Out
+UkPlan uk_plan_broadcast(uint64_t bytes, int root, const UkPlanParams& p);
 
 // Structural checks: deps acyclic and backwards, every Send of rank a to rank b on lane l is matched by
 // a Recv of b from a on lane l with the same ordinal and size.  `plans` holds one plan per rank.

@@ -23,7 +23,7 @@ import torch
 from .. import _native
 from ..parallel.comm import Communicator, dtype_code, op_code
 
-COLLS = {"allreduce": 0, "alltoall": 1, "allgather": 2, "barrier": 3}
+COLLS = {"allreduce": 0, "alltoall": 1, "allgather": 2, "barrier": 3, "reduce_scatter": 4, "broadcast": 5}
 ALGOS = {"auto": 0, "ring": 1, "fullmesh": 2}
 
 
@@ -32,19 +32,19 @@ def _uk():
 
 
 def plan(coll: str, nbytes: int, nranks: int, rank: int, nlanes: int = 1, tile_bytes: int = 1 << 20,
-         elem_size: int = 1, algo: str = "auto"):
+         elem_size: int = 1, algo: str = "auto", root: int = 0):
     """Plan of one rank: ``(text, [op dict, ...])``."""
-    return _uk().plan(COLLS[coll], int(nbytes), nranks, rank, nlanes, int(tile_bytes), elem_size, ALGOS[algo])
+    return _uk().plan(COLLS[coll], int(nbytes), nranks, rank, nlanes, int(tile_bytes), elem_size, ALGOS[algo], root)
 
 
 def validate(coll: str, nbytes: int, nranks: int, nlanes: int = 1, tile_bytes: int = 1 << 20, elem_size: int = 1,
-             algo: str = "auto") -> str:
+             algo: str = "auto", root: int = 0) -> str:
     """Cross-rank structural validation of the plans of all ranks; '' when consistent."""
-    return _uk().validate(COLLS[coll], int(nbytes), nranks, nlanes, int(tile_bytes), elem_size, ALGOS[algo])
+    return _uk().validate(COLLS[coll], int(nbytes), nranks, nlanes, int(tile_bytes), elem_size, ALGOS[algo], root)
 
 
 def simulate(coll: str, ins: Sequence[torch.Tensor], outs: Sequence[torch.Tensor], op="sum", nlanes: int = 1,
-             tile_bytes: int = 1 << 20, algo: str = "auto") -> str:
+             tile_bytes: int = 1 << 20, algo: str = "auto", root: int = 0) -> str:
     """Execute the plans of all ranks over CPU tensors with the reference scheduler (greedy: a rank
     runs ahead as far as its dependencies allow).  Returns '' on success, else the failure."""
     n = len(ins)
@@ -52,12 +52,12 @@ def simulate(coll: str, ins: Sequence[torch.Tensor], outs: Sequence[torch.Tensor
     dt = ins[0].dtype
     if coll == "allreduce":
         nbytes = ins[0].numel() * ins[0].element_size()
-    elif coll == "alltoall":
+    elif coll in ("alltoall", "reduce_scatter"):
         nbytes = ins[0].numel() * ins[0].element_size() // n
     else:
         nbytes = ins[0].numel() * ins[0].element_size()
     return _uk().simulate(COLLS[coll], nbytes, n, nlanes, int(tile_bytes), dtype_code(dt), op_code(op), ALGOS[algo],
-                          [t.data_ptr() for t in ins], [t.data_ptr() for t in outs])
+                          [t.data_ptr() for t in ins], [t.data_ptr() for t in outs], root)
 
 
 class Worker:
@@ -185,6 +185,26 @@ class UkCommunicator:
                                bool(symmetric))
         return UkWork(self._u, t, out)
 
+    def reduce_scatter_tensor(self, out: torch.Tensor, inp: torch.Tensor, op="sum", stream=None) -> UkWork:
+        self._check(inp), self._check(out)
+        if inp.numel() != out.numel() * self.world_size:
+            raise ValueError("uccl_b200.ukernel: reduce_scatter input must hold world_size * out.numel() elements")
+        code = op_code(op)
+        avg = code == 4
+        t = self._u.reduce_scatter(inp.data_ptr(), out.data_ptr(), out.numel(), dtype_code(inp.dtype), 0 if avg else code,
+                                   self._stream(stream))
+        if avg:
+            if self.comm.is_host:
+                self._u.wait(t, 60.0)
+            out.div_(self.world_size)
+        return UkWork(self._u, t, out)
+
+    def broadcast(self, tensor: torch.Tensor, root: int = 0, stream=None) -> UkWork:
+        self._check(tensor)
+        t = self._u.broadcast(tensor.data_ptr(), tensor.data_ptr(), tensor.numel(), dtype_code(tensor.dtype), int(root),
+                              self._stream(stream))
+        return UkWork(self._u, t, tensor)
+
     def barrier(self, stream=None) -> UkWork:
         return UkWork(self._u, self._u.barrier(self._stream(stream)))
 
@@ -217,6 +237,12 @@ class ProcessGroup:
 
     def all_gather_into_tensor(self, output, input, async_op: bool = False):
         return self._finish(self._uk.all_gather_into_tensor(output, input), async_op)
+
+    def reduce_scatter_tensor(self, output, input, op="sum", async_op: bool = False):
+        return self._finish(self._uk.reduce_scatter_tensor(output, input, op), async_op)
+
+    def broadcast(self, tensor, src: int = 0, async_op: bool = False):
+        return self._finish(self._uk.broadcast(tensor, src), async_op)
 
     def barrier(self, async_op: bool = False):
         return self._finish(self._uk.barrier(), async_op)
