@@ -251,3 +251,40 @@ def test_moe_layer_backward_matches_dense_autograd():
         assert close(gx, xr[r].grad, 6e-2)
         assert close(gw1, w1[r].grad, 6e-2) and close(gw2, w2[r].grad, 6e-2)
         assert close(grw, rw[r].grad, 8e-2)
+
+
+def _moe_train_worker(rank, world, port, q):
+    import os
+    import sys
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import moe_train
+
+    losses = moe_train.run(rank, world, cpu=True, steps=6, tokens=64, hidden=128, ffn=128, verbose=False, lr=1.0,
+                           fixed_batch=True)
+    q.put((rank, losses))
+    dist.destroy_process_group()
+
+
+def test_moe_training_example_two_processes():
+    """examples/moe_train.py on the CPU backend: two processes, shm symmetric heaps, EP forward + backward,
+    router gradient all-reduce; the loss goes down and both ranks agree on it."""
+    import multiprocessing as mp
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_moe_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = dict(q.get(timeout=240) for _ in range(2))
+    [p.join(60) for p in ps]
+    assert got[0] == pytest.approx(got[1])
+    assert all(b < a for a, b in zip(got[0], got[0][1:])), got[0]  # fixed batch: monotonically decreasing
