@@ -148,3 +148,135 @@ def test_uccl_engine_c_api_host_mode(tmp_path):
     subprocess.run(cmd, check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "uccl_engine_test: OK" in r.stdout, r.stdout + r.stderr
+
+
+def _tcp_server(q_md, q_res, nbytes):
+    import time
+
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    e = Endpoint(-1)
+    q_md.put(e.get_metadata())
+    ok, ip, gpu, conn = e.accept(60000)
+    buf = torch.zeros(nbytes, dtype=torch.uint8)
+    win = torch.full((nbytes,), 7, dtype=torch.uint8)
+    inbox = torch.zeros(nbytes, dtype=torch.uint8)
+    okr = e.recv(conn, 0, buf.data_ptr(), nbytes)                 # two-sided receive (payload arrives over TCP)
+    descs = e.register_memory([win, inbox])
+    e.send_notif(conn, e.get_serialized_descs(descs))              # windows for the client's read and write
+    back = torch.arange(1000, dtype=torch.int32)
+    oks = e.send(conn, 0, back.data_ptr(), 4000)                  # and a message in the other direction
+    t0 = time.time()
+    fin = False
+    while time.time() - t0 < 60 and not fin:
+        for _, m in e.get_notifs():
+            fin = fin or m == b"done"
+        time.sleep(0.002)
+    q_res.put((bool(ok), bool(okr), int(buf.sum().item()), bool(oks), int(inbox.to(torch.int64).sum().item()), fin))
+
+
+def _tcp_client(q_md, q_res, nbytes):
+    import time
+
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    e = Endpoint(-1)
+    ok, conn = e.connect(remote_metadata=q_md.get(timeout=60))
+    src = torch.ones(nbytes, dtype=torch.uint8)
+    oks = e.send(conn, 0, src.data_ptr(), nbytes)
+    blob = None
+    t0 = time.time()
+    while blob is None and time.time() - t0 < 60:
+        for _, m in e.get_notifs():
+            blob = m
+        time.sleep(0.002)
+    remote = e.deserialize_descs(blob)
+    dst = torch.zeros(nbytes, dtype=torch.uint8)
+    okr = e.read(conn, 0, dst.data_ptr(), nbytes, remote[0])       # one-sided read of the server's window
+    three = torch.full((nbytes,), 3, dtype=torch.uint8)
+    okw = e.write(conn, 0, three.data_ptr(), nbytes, remote[1])    # one-sided write, acknowledged by a flush
+    got = torch.zeros(1000, dtype=torch.int32)
+    okb = e.recv(conn, 0, got.data_ptr(), 4000)
+    e.send_notif(conn, b"done")
+    q_res.put((bool(ok), bool(oks), bool(okr), int(dst.to(torch.int64).sum().item()), bool(okw), bool(okb),
+               bool(torch.equal(got, torch.arange(1000, dtype=torch.int32)))))
+    time.sleep(0.3)
+
+
+def test_host_mode_between_processes_uses_the_tcp_data_path():
+    """Two processes without any shared memory: payloads of send/recv, one-sided write (+flush/ack) and
+    one-sided read (request/response) travel on the control connection (the reference's TCP backend role)."""
+    import multiprocessing as mp
+
+    nbytes = (3 << 20) + 17
+    ctx = mp.get_context("spawn")
+    q_md, q_s, q_c = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_tcp_server, args=(q_md, q_s, nbytes)), ctx.Process(target=_tcp_client, args=(q_md, q_c, nbytes))]
+    [p.start() for p in ps]
+    rs = q_s.get(timeout=180)
+    rc = q_c.get(timeout=180)
+    [p.join(30) for p in ps]
+    assert rs == (True, True, nbytes, True, 3 * nbytes, True)
+    assert rc == (True, True, True, 7 * nbytes, True, True, True)
+
+
+def _coll_worker(rank, world, port, q):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uccl_b200 import collective as C
+
+    ctx = C.init_collective(local_gpu_idx=-1, heap_bytes=128 << 20)
+    peer = 1 - rank
+    x = torch.full((5000,), float(rank + 1))
+    y = torch.zeros(5000)
+    if rank == 0:
+        C.send(x, peer)
+        C.recv(y, peer)
+    else:
+        C.recv(y, peer)
+        C.send(x, peer)
+    ok_sr = bool((y == peer + 1).all())
+    # non-blocking + batch (ring step) + registration bookkeeping
+    C.register_tensor(x)
+    z = torch.zeros(5000)
+    hs = C.batch_isend_irecv([ctx.P2POp("irecv", z, peer), ctx.P2POp("isend", x, peer)])
+    C.wait_all(hs)
+    ok_batch = bool((z == peer + 1).all()) and ctx.check_tensor_registered(x) is not None
+    g = torch.zeros(2 * 5000)
+    C.allgather(x, g)
+    ok_ag = bool((g.view(2, -1)[0] == 1).all() and (g.view(2, -1)[1] == 2).all())
+    a = torch.full((64,), float(rank))
+    C.all_reduce(a, "sum")
+    ok_ar = bool((a == 1.0).all())
+    C.barrier()
+    C.finalize_collective()
+    q.put((rank, ok_sr, ok_batch, ok_ag, ok_ar))
+    dist.destroy_process_group()
+
+
+def test_collective_context_on_cpu_two_processes():
+    """`uccl_b200.collective` (the `uccl.collective` surface: send/recv, isend/irecv, batch, allgather, native
+    collectives) with host-mode endpoints and the host communicator, two processes rendezvousing over gloo."""
+    import multiprocessing as mp
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_coll_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=240) for _ in range(2))
+    [p.join(60) for p in ps]
+    assert got == [(0, True, True, True, True), (1, True, True, True, True)]

@@ -45,7 +45,10 @@ class CollectiveContext:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
-        self.local_gpu_idx = local_gpu_idx if local_gpu_idx is not None else torch.cuda.current_device()
+        if local_gpu_idx is None:
+            local_gpu_idx = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        self.local_gpu_idx = local_gpu_idx
+        self.host = local_gpu_idx < 0  # CPU reference mode: host-mode endpoint (TCP data path) + host communicator
         self.use_nccl_p2p = use_nccl_p2p
         self.num_cpus = num_cpus
         self.ep: Optional[Endpoint] = None
@@ -61,7 +64,8 @@ class CollectiveContext:
     def init(self):
         if self.initialized:
             return
-        torch.cuda.set_device(self.local_gpu_idx)
+        if not self.host:
+            torch.cuda.set_device(self.local_gpu_idx)
         self.ep = Endpoint(self.local_gpu_idx, self.num_cpus)
         md = self.ep.get_metadata()
         all_md: List[Optional[bytes]] = [None] * self.world_size
@@ -93,8 +97,12 @@ class CollectiveContext:
             assert time.time() - t0 < 60, "peer identification timed out"
             time.sleep(0.001)
         if self._with_native:
-            self.comm = Communicator.from_torch_dist(self.group, device=self.local_gpu_idx,
-                                                     heap_bytes=self._heap_bytes)
+            if self.host:
+                self.comm = Communicator.from_torch_dist(self.group, host=True, heap_bytes=min(self._heap_bytes, 256 << 20),
+                                                         stage_bytes=4 << 20)
+            else:
+                self.comm = Communicator.from_torch_dist(self.group, device=self.local_gpu_idx,
+                                                         heap_bytes=self._heap_bytes)
         dist.barrier(group=self.group)
         self.initialized = True
 
@@ -124,7 +132,8 @@ class CollectiveContext:
     def isend(self, tensor: torch.Tensor, dst: int) -> Union[int, "dist.Work"]:
         if self.use_nccl_p2p:
             return dist.isend(tensor, dst, group=self.group)
-        torch.cuda.current_stream().synchronize()  # payload must be materialised before the side-stream copy
+        if not self.host:
+            torch.cuda.current_stream().synchronize()  # payload must be materialised before the side-stream copy
         ptr, n = self._buf(tensor)
         ok, tid = self.ep.send_async(self.send_connections[dst], 0, ptr, n)
         assert ok
@@ -182,6 +191,8 @@ class CollectiveContext:
         assert recv_tensor.numel() == send_tensor.numel() * self.world_size
         if self.comm is not None:
             self.comm.all_gather(recv_tensor, send_tensor)
+            if self.host:
+                return []  # the host communicator is synchronous
             ev = torch.cuda.Event()
             ev.record()
             return [ev]

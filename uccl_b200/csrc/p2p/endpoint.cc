@@ -29,7 +29,15 @@ UB_PARAM(P2PStatsSec, "ENGINE_STATS_SEC", 0)
 cudaError_t launch_p2p_copy(const P2PCopyBatch& b, int grid, cudaStream_t st);
 
 namespace {
-enum MsgType : uint32_t { MSG_HELLO = 1, MSG_ADV = 2, MSG_DONE = 3, MSG_NOTIF = 4, MSG_BYE = 5 };
+enum MsgType : uint32_t {
+  MSG_HELLO = 1, MSG_ADV = 2, MSG_DONE = 3, MSG_NOTIF = 4, MSG_BYE = 5,
+  // host mode between processes: the payload itself travels on the connection (TCP data path)
+  MSG_WRITE = 6,      // {u64 dst_addr, u64 bytes, data}: the target's engine copies data to dst_addr
+  MSG_FLUSH = 7,      // seq = initiator transfer id; answered by MSG_FLUSH_ACK once every earlier WRITE is applied
+  MSG_FLUSH_ACK = 8,
+  MSG_READ_REQ = 9,   // seq = initiator transfer id; payload = {u64 src_addr, u64 bytes} per buffer
+  MSG_READ_RESP = 10  // seq = same id; payload = the concatenated data
+};
 struct MsgHdr {
   uint32_t type;
   uint32_t len;
@@ -77,18 +85,20 @@ struct Endpoint::Conn {
   std::mutex send_mu;
   std::map<uint64_t, std::vector<XferDesc>> advs;  // seq -> advertised windows (from the peer's recv)
   std::map<uint64_t, bool> dones;                  // seq -> DONE received
+  std::map<uint64_t, bool> acks;                   // transfer id -> FLUSH_ACK received (TCP data path)
   uint64_t next_send_seq = 0, next_recv_seq = 0;
   bool alive = true;
 };
 
 struct Endpoint::Transfer {
-  enum State { SEND_WAIT_ADV, COPYING, RECV_WAIT_DONE, DONE, FAILED };
+  enum State { SEND_WAIT_ADV, COPYING, RECV_WAIT_DONE, DONE, FAILED, WAIT_ACK, WAIT_RESP, TCP_SENDING };
   uint64_t id = 0;
   State state = DONE;
   std::shared_ptr<Conn> conn;
   uint64_t seq = 0;
   bool notify_done = false;  // send DONE{seq} to the peer when the copy finishes
   std::vector<const char*> src;
+  std::vector<char*> dst;  // read over the TCP data path: where the response is scattered to
   std::vector<size_t> sizes;
   cudaEvent_t ev = nullptr;
 };
@@ -130,6 +140,17 @@ Endpoint::~Endpoint() {
   stop_ = true;
   wake();
   if (engine_.joinable()) engine_.join();
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto& kv : conns_)
+      if (kv.second->fd >= 0) ::shutdown(kv.second->fd, SHUT_RDWR);  // unblock helper threads stuck in send()
+  }
+  {
+    std::lock_guard<std::mutex> g(helpers_mu_);
+    for (auto& t : helpers_)
+      if (t.joinable()) t.join();
+    helpers_.clear();
+  }
   {
     std::lock_guard<std::mutex> g(mu_);
     for (auto& kv : conns_)
@@ -282,6 +303,39 @@ bool Endpoint::send_msg(Conn& c, uint32_t type, uint64_t seq, const void* payloa
   if (!write_full(c.fd, &h, sizeof(h))) return false;
   if (len && !write_full(c.fd, payload, len)) return false;
   return true;
+}
+
+// header + two payload parts as one frame (the connection is shared by several threads)
+bool Endpoint::send_msg2(Conn& c, uint32_t type, uint64_t seq, const void* p1, uint32_t len1, const void* p2,
+                         uint32_t len2) {
+  std::lock_guard<std::mutex> g(c.send_mu);
+  if (c.fd < 0) return false;
+  MsgHdr h{type, len1 + len2, seq};
+  if (!write_full(c.fd, &h, sizeof(h))) return false;
+  if (len1 && !write_full(c.fd, p1, len1)) return false;
+  if (len2 && !write_full(c.fd, p2, len2)) return false;
+  return true;
+}
+
+// TCP data path (host mode, peer in another process): one MSG_WRITE frame per buffer, cut into pieces
+// that fit the 32-bit frame length.
+bool Endpoint::tcp_write_buffers(Conn& c, const std::vector<const char*>& src, const std::vector<uint64_t>& dst_addr,
+                                 const std::vector<size_t>& sizes) {
+  constexpr size_t kPiece = 64u << 20;
+  for (size_t i = 0; i < src.size(); ++i)
+    for (size_t off = 0; off < sizes[i]; off += kPiece) {
+      const uint64_t n = std::min(kPiece, sizes[i] - off);
+      const uint64_t pre[2] = {dst_addr[i] + off, n};
+      if (!send_msg2(c, MSG_WRITE, 0, pre, sizeof(pre), src[i] + off, (uint32_t)n)) return false;
+    }
+  return true;
+}
+
+bool Endpoint::remote_is_other_process(const XferDesc& d) const { return gpu_ < 0 && d.pid != (int32_t)getpid(); }
+
+void Endpoint::run_helper(std::function<void()> fn) {
+  std::lock_guard<std::mutex> g(helpers_mu_);
+  helpers_.emplace_back(std::move(fn));
 }
 
 // ------------------------------------------------------------------ registration
@@ -546,6 +600,33 @@ bool Endpoint::write_async(uint64_t conn, const std::vector<const void*>& src, c
                            const std::vector<XferDesc>& remote, uint64_t* tid) {
   auto c = find_conn(conn);
   if (!c || src.size() != sizes.size() || src.size() != remote.size() || src.empty()) return false;
+  if (remote_is_other_process(remote[0])) {
+    // TCP data path: the caller's thread streams the payload, then asks for an acknowledgement
+    std::vector<const char*> sp;
+    std::vector<uint64_t> da;
+    for (size_t i = 0; i < src.size(); ++i) {
+      if (sizes[i] > remote[i].size) return false;
+      sp.push_back((const char*)src[i]);
+      da.push_back(remote[i].addr);
+    }
+    auto t = std::make_shared<Transfer>();
+    t->conn = c;
+    t->state = Transfer::WAIT_ACK;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      t->id = next_tid_++;
+      transfers_[t->id] = t;
+      stats_.transfers++;
+      for (size_t b : sizes) stats_.bytes_written += b;
+    }
+    if (!tcp_write_buffers(*c, sp, da, sizes) || !send_msg(*c, MSG_FLUSH, t->id, nullptr, 0)) {
+      std::lock_guard<std::mutex> g(mu_);
+      transfers_.erase(t->id);
+      return false;
+    }
+    if (tid) *tid = t->id;
+    return true;
+  }
   if (gpu_ >= 0) cudaSetDevice(gpu_);
   std::vector<const char*> s;
   std::vector<char*> d;
@@ -574,6 +655,33 @@ bool Endpoint::read_async(uint64_t conn, const std::vector<void*>& dst, const st
                           const std::vector<XferDesc>& remote, uint64_t* tid) {
   auto c = find_conn(conn);
   if (!c || dst.size() != sizes.size() || dst.size() != remote.size() || dst.empty()) return false;
+  if (remote_is_other_process(remote[0])) {
+    std::vector<uint64_t> req;
+    auto t = std::make_shared<Transfer>();
+    for (size_t i = 0; i < dst.size(); ++i) {
+      if (sizes[i] > remote[i].size) return false;
+      req.push_back(remote[i].addr);
+      req.push_back(sizes[i]);
+      t->dst.push_back((char*)dst[i]);
+    }
+    t->conn = c;
+    t->sizes = sizes;
+    t->state = Transfer::WAIT_RESP;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      t->id = next_tid_++;
+      transfers_[t->id] = t;
+      stats_.transfers++;
+      for (size_t b : sizes) stats_.bytes_read += b;
+    }
+    if (!send_msg(*c, MSG_READ_REQ, t->id, req.data(), (uint32_t)(req.size() * sizeof(uint64_t)))) {
+      std::lock_guard<std::mutex> g(mu_);
+      transfers_.erase(t->id);
+      return false;
+    }
+    if (tid) *tid = t->id;
+    return true;
+  }
   if (gpu_ >= 0) cudaSetDevice(gpu_);
   std::vector<const char*> s;
   std::vector<char*> d;
@@ -605,6 +713,16 @@ bool Endpoint::poll_async(uint64_t tid, bool* done) {
     auto it = transfers_.find(tid);
     if (it == transfers_.end()) return false;
     t = it->second;
+  }
+  if (t->state == Transfer::WAIT_ACK) {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = t->conn->acks.find(tid);
+    if (it != t->conn->acks.end()) {
+      t->conn->acks.erase(it);
+      t->state = Transfer::DONE;
+    } else if (!t->conn->alive) {
+      t->state = Transfer::FAILED;
+    }
   }
   if (t->state == Transfer::COPYING && !t->notify_done) {
     // one-sided ops are driven by the caller: no engine-thread latency on the hot path
@@ -670,6 +788,52 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
       break;
     }
     case MSG_DONE: c.dones[seq] = true; break;
+    case MSG_WRITE: {
+      if (gpu_ >= 0 || payload.size() < 16) break;  // only the host mode exposes its memory to the wire
+      uint64_t pre[2];
+      memcpy(pre, payload.data(), 16);
+      if (pre[1] == payload.size() - 16) memcpy((void*)pre[0], payload.data() + 16, pre[1]);
+      break;
+    }
+    case MSG_FLUSH: {
+      // frames are processed in order, so every WRITE sent before this FLUSH has been applied
+      MsgHdr h{MSG_FLUSH_ACK, 0, seq};
+      std::lock_guard<std::mutex> sg(c.send_mu);
+      if (c.fd >= 0) write_full(c.fd, &h, sizeof(h));
+      break;
+    }
+    case MSG_FLUSH_ACK: c.acks[seq] = true; break;
+    case MSG_READ_REQ: {
+      if (gpu_ >= 0) break;
+      const size_t nb = payload.size() / 16;
+      auto data = std::make_shared<std::vector<char>>();
+      for (size_t i = 0; i < nb; ++i) {
+        uint64_t e[2];
+        memcpy(e, payload.data() + i * 16, 16);
+        const size_t at = data->size();
+        data->resize(at + e[1]);
+        memcpy(data->data() + at, (const void*)e[0], e[1]);
+      }
+      std::shared_ptr<Conn> conn;
+      for (auto& kv : conns_)
+        if (kv.second.get() == &c) conn = kv.second;
+      if (conn) run_helper([this, conn, data, seq] { send_msg(*conn, MSG_READ_RESP, seq, data->data(), (uint32_t)data->size()); });
+      break;
+    }
+    case MSG_READ_RESP: {
+      auto it = transfers_.find(seq);
+      if (it == transfers_.end() || it->second->state != Transfer::WAIT_RESP) break;
+      auto& t = it->second;
+      size_t at = 0;
+      bool ok = true;
+      for (size_t i = 0; i < t->dst.size() && ok; ++i) {
+        if (at + t->sizes[i] > payload.size()) ok = false;
+        else memcpy(t->dst[i], payload.data() + at, t->sizes[i]);
+        at += t->sizes[i];
+      }
+      t->state = ok ? Transfer::DONE : Transfer::FAILED;
+      break;
+    }
     case MSG_NOTIF: notifs_.emplace_back(c.id, std::string(payload.begin(), payload.end())); break;
     case MSG_BYE: c.alive = false; break;
     default: break;
@@ -693,6 +857,26 @@ void Endpoint::progress_locked() {
         if (descs.size() != t->src.size()) {
           UB_WARN("p2p send: receiver posted %zu buffers, sender has %zu", descs.size(), t->src.size());
           t->state = Transfer::FAILED;
+          break;
+        }
+        if (remote_is_other_process(descs[0])) {
+          // TCP data path: a helper thread streams the payload (the engine thread must keep reading),
+          // then tells the receiver that the message is complete
+          for (size_t i = 0; i < descs.size(); ++i)
+            if (descs[i].size < t->sizes[i]) {
+              t->state = Transfer::FAILED;
+              break;
+            }
+          if (t->state == Transfer::FAILED) break;
+          t->state = Transfer::TCP_SENDING;
+          std::vector<uint64_t> da;
+          for (auto& d : descs) da.push_back(d.addr);
+          auto conn = t->conn;
+          run_helper([this, t, conn, da] {
+            bool ok = tcp_write_buffers(*conn, t->src, da, t->sizes) && send_msg(*conn, MSG_DONE, t->seq, nullptr, 0);
+            std::lock_guard<std::mutex> g(mu_);
+            t->state = ok ? Transfer::DONE : Transfer::FAILED;
+          });
           break;
         }
         std::vector<char*> dst;

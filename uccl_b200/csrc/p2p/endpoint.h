@@ -14,6 +14,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -82,6 +83,11 @@ class Endpoint {
   void engine_loop();
   void handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<char>& payload);
   bool send_msg(Conn& c, uint32_t type, uint64_t seq, const void* payload, uint32_t len);
+  bool send_msg2(Conn& c, uint32_t type, uint64_t seq, const void* p1, uint32_t len1, const void* p2, uint32_t len2);
+  bool tcp_write_buffers(Conn& c, const std::vector<const char*>& src, const std::vector<uint64_t>& dst_addr,
+                         const std::vector<size_t>& sizes);
+  bool remote_is_other_process(const XferDesc& d) const;
+  void run_helper(std::function<void()> fn);
   void progress_locked();
   bool launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
                    const std::vector<size_t>& sizes, cudaEvent_t ev);
@@ -115,6 +121,8 @@ class Endpoint {
   std::vector<cudaEvent_t> event_pool_;
   P2PStats stats_;
   uint32_t peer_enabled_mask_ = 0;
+  std::mutex helpers_mu_;
+  std::vector<std::thread> helpers_;  // blocking TCP payload sends never run on the engine thread
 };
 
 }  // namespace ub
