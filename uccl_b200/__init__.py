@@ -5,6 +5,11 @@ with the capabilities of uccl-project/uccl:
   symmetric heap) + torch ProcessGroup glue + DDP hooks
 * ``uccl_b200.ep``          DeepEP-compatible expert-parallel dispatch / combine
 * ``uccl_b200.p2p``         NIXL-style initiator/target transfer engine (KV-cache moves)
+* ``uccl_b200.ukernel``     launch-free collectives: persistent worker kernel + CCL planner
+* ``uccl_b200.models``      ResNet (DDP example), expert-parallel MoE layer (inference + training)
+
+Everything also runs on a CPU-only machine through reference backends (host communicators,
+``ep.Buffer(comm=<host comm>)``, ``p2p.Endpoint(-1)``, ``ukernel.Worker(device=-1)``).
 
 Reference entry points mirrored: ``uccl/__init__.py:12-54`` (version + library path helpers).
 """
