@@ -79,6 +79,24 @@ static int run(int rank, int n, ncclUniqueId id) {
     EXPECT(ncclAllReduce(pin.data(), pout.data(), 9, ncclFloat, premul, comm, nullptr) == ncclInvalidArgument);
   }
 
+  // grouped send/recv (ring step) and a lone send / recv pair
+  {
+    const int next = (rank + 1) % n, prev = (rank + n - 1) % n;
+    std::vector<int> sbuf(5000, 1000 + rank), rbuf(5000, -1);
+    CHECK(ncclGroupStart());
+    CHECK(ncclSend(sbuf.data(), sbuf.size(), ncclInt32, next, comm, nullptr));
+    CHECK(ncclRecv(rbuf.data(), rbuf.size(), ncclInt32, prev, comm, nullptr));
+    CHECK(ncclGroupEnd());
+    for (auto v : rbuf) EXPECT(v == 1000 + prev);
+    float token = (float)rank, got = -1.f;
+    if (rank == 0) {
+      CHECK(ncclSend(&token, 1, ncclFloat, 1, comm, nullptr));
+    } else if (rank == 1) {
+      CHECK(ncclRecv(&got, 1, ncclFloat, 0, comm, nullptr));
+      EXPECT(got == 0.f);
+    }
+  }
+
   // error paths
   EXPECT(ncclAllReduce(x.data(), y.data(), 4, (ncclDataType_t)99, ncclSum, comm, nullptr) == ncclInvalidArgument);
   EXPECT(ncclBroadcast(b.data(), b.data(), 1, ncclInt64, 7, comm, nullptr) == ncclInvalidArgument);

@@ -96,6 +96,34 @@ def test_host_alltoallv_multi_round(world4):
         assert torch.equal(o, exp)
 
 
+def test_host_grouped_send_recv(world4):
+    """Grouped point-to-point on the host backend: a ring step with a message larger than a mailbox chunk,
+    then an all-to-all pattern incl. self, twice (sequence numbers persist across groups)."""
+    n = len(world4)
+
+    def fn(c):
+        r = c.rank
+        big = torch.arange(3_000_000, dtype=torch.float32) + r          # 12 MB > the 4 MiB mailbox
+        got = torch.zeros(3_000_000)
+        c.batch_send_recv([("recv", got, (r - 1) % n), ("send", big, (r + 1) % n)])
+        outs = []
+        for rep in range(2):
+            src = torch.stack([torch.full((1000,), float(100 * r + p + rep)) for p in range(n)])
+            dst = torch.zeros(n, 1000)
+            ops = []
+            for p in range(n):
+                ops += [("send", src[p], p), ("recv", dst[p], p)]
+            c.batch_send_recv(ops)
+            outs.append(dst)
+        return got, outs
+
+    for r, (got, outs) in enumerate(run_host_ranks(world4, fn)):
+        assert torch.equal(got, torch.arange(3_000_000, dtype=torch.float32) + (r - 1) % n)
+        for rep, dst in enumerate(outs):
+            for p in range(n):
+                assert bool((dst[p] == 100 * p + r + rep).all())
+
+
 def test_symmetric_heap_alloc(world4):
     c = world4[0]
     free0 = c.native.heap_free_bytes

@@ -38,8 +38,33 @@ def _worker(rank, world, path, q):
     gsum = model.weight.grad.clone()
     exp = torch.full((4, 8), sum(2.0 * (r + 1) for r in range(world)) / world)
     ok6 = torch.allclose(gsum, exp)
+    # point-to-point + all_to_all (equal and unequal splits) + reduce
+    peer = 1 - rank
+    t = torch.full((7,), float(rank))
+    if rank == 0:
+        dist.send(t, peer)
+        dist.recv(t, peer)
+    else:
+        r_ = torch.empty(7)
+        dist.recv(r_, peer)
+        dist.send(t, peer)
+        t = r_
+    ok7 = bool((t == peer).all()) if rank == 0 else bool((t == 0).all())
+    a_out = torch.empty(world * 3)
+    dist.all_to_all_single(a_out, torch.arange(world * 3, dtype=torch.float32) + 10 * rank)
+    ok8 = a_out.tolist() == [float(10 * s + 3 * rank + i) for s in range(world) for i in range(3)]
+    splits_in = [1, 3] if rank == 0 else [2, 1]
+    splits_out = [1, 2] if rank == 0 else [3, 1]
+    v_in = torch.arange(sum(splits_in), dtype=torch.float32) + 100 * rank
+    v_out = torch.empty(sum(splits_out))
+    dist.all_to_all_single(v_out, v_in, output_split_sizes=splits_out, input_split_sizes=splits_in)
+    exp_v = [0.0, 100.0, 101.0] if rank == 0 else [1.0, 2.0, 3.0, 102.0]
+    ok9 = v_out.tolist() == exp_v
+    red = torch.full((4,), float(rank + 1))
+    dist.reduce(red, dst=1, op=dist.ReduceOp.SUM)
+    ok10 = rank != 1 or bool((red == 3.0).all())
     dist.barrier()
-    q.put((rank, ok1, ok2, ok3, ok4, ok5, ok6))
+    q.put((rank, ok1, ok2, ok3, ok4, ok5, ok6 and ok7 and ok8 and ok9 and ok10))
     dist.destroy_process_group()
 
 

@@ -160,6 +160,15 @@ PYBIND11_MODULE(_C, m) {
              int algo = c.select_allreduce(bytes, symmetric, dtype, op, &ctas);
              return py::make_tuple(algo, ctas);
            })
+      // grouped point-to-point: ops = [(is_send, ptr, bytes, peer), ...] (ncclGroupStart/Send/Recv/End)
+      .def("group_p2p",
+           [](Comm& c, const std::vector<std::tuple<bool, uintptr_t, size_t, int>>& ops, uintptr_t stream) {
+             std::vector<Comm::P2pOp> v;
+             for (auto& o : ops) v.push_back(Comm::P2pOp{std::get<0>(o), P(std::get<1>(o)), std::get<2>(o), std::get<3>(o)});
+             py::gil_scoped_release rel;
+             c.group_p2p(v, S(stream));
+           },
+           py::arg("ops"), py::arg("stream") = 0)
       .def("set_tuning", &Comm::set_tuning)
       .def("set_xchg_ll_max", &Comm::set_xchg_ll_max)
       .def("set_rs_push", &Comm::set_rs_push)

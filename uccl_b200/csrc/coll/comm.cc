@@ -725,7 +725,10 @@ void Comm::alltoallv(const void* in, const size_t* send_counts, const size_t* se
 
 void Comm::group_p2p(const std::vector<P2pOp>& ops, cudaStream_t stream) {
   if (ops.empty()) return;
-  UB_CHECK(!is_host(), "send/recv: host backend does not implement point-to-point");
+  if (is_host()) {
+    host_group_p2p(ops);
+    return;
+  }
   const int n = nranks();
   std::vector<std::vector<const P2pOp*>> sends(n), recvs(n);
   for (const auto& o : ops) {

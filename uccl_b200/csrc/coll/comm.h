@@ -136,6 +136,7 @@ class Comm {
   void host_broadcast(const void* in, void* out, size_t bytes, int root);
   void host_reduce(const void* in, void* out, size_t count, int dtype, int op, int root);
   void host_alltoall(const void* in, void* out, size_t bytes);
+  void host_group_p2p(const std::vector<P2pOp>& ops);
   void host_alltoallv(const void* in, const size_t* send_bytes, const size_t* send_off, void* out,
                       const size_t* recv_bytes, const size_t* recv_off);
 
@@ -149,6 +150,7 @@ class Comm {
   uint32_t* err_host_ = nullptr;
   uint64_t launches_ = 0;
   uint32_t host_epoch_ = 0;
+  std::vector<uint64_t> host_send_seq_, host_recv_seq_;  // host send/recv mailboxes: chunks sent to / received from each peer
   unsigned long long* trace_dev_ = nullptr;
   size_t trace_cap_ = 0;
   std::vector<TuneEntry> tune_sym_, tune_unsym_;

@@ -298,4 +298,106 @@ void Comm::host_alltoallv(const void* in, const size_t* send_bytes, const size_t
   }
 }
 
+// Grouped point-to-point on the host backend.  Every ordered pair (src -> dst) owns a mailbox in the
+// *destination's* heap (inside the send/recv staging area): {ready seq, acked seq, chunk}.  The sender
+// fills the chunk when the previous one has been acknowledged and publishes its sequence number; the
+// receiver copies the chunk out and acknowledges.  One rank usually has sends and receives in the same
+// group (ring step, all-to-all pattern), so all of its operations are progressed round-robin -- nothing
+// blocks on a single peer.  Only the two ranks of a pair synchronise (no global barrier), like the
+// send/recv kernel of the CUDA backend.
+void Comm::host_group_p2p(const std::vector<P2pOp>& ops) {
+  const int n = nranks(), me = rank();
+  const uint64_t box_bytes = kSrStageBytes / kMaxRanks;  // data area per source rank
+  const uint64_t chunk = box_bytes;
+  struct Prog {
+    const P2pOp* op;
+    size_t done = 0;
+  };
+  // operations towards one peer complete in posting order
+  std::vector<std::vector<Prog>> sends(n), recvs(n);
+  for (const auto& o : ops) {
+    UB_CHECK(o.peer >= 0 && o.peer < n, "send/recv: bad peer %d", o.peer);
+    (o.is_send ? sends : recvs)[o.peer].push_back(Prog{&o, 0});
+  }
+  if (host_send_seq_.empty()) {
+    host_send_seq_.assign(n, 0);
+    host_recv_seq_.assign(n, 0);
+  }
+  auto box = [&](int dst, int src) { return fabric_->heap(dst) + layout_.sr_stage_off + (uint64_t)src * box_bytes; };
+  // {ready, acked} of the pair live in the flag area, which is part of the zero-initialised control region
+  auto flags = [&](int dst, int src) {
+    return reinterpret_cast<uint64_t*>(fabric_->heap(dst) + layout_.sr_flag_off) + (uint64_t)src * 2;
+  };
+  std::vector<size_t> si(n, 0), ri(n, 0);  // index of the operation in progress per peer
+  auto t0 = std::chrono::steady_clock::now();
+  uint32_t idle = 0;
+  while (true) {
+    bool pending = false, progressed = false;
+    for (int p = 0; p < n; ++p) {
+      // skip zero-byte operations
+      while (si[p] < sends[p].size() && sends[p][si[p]].op->bytes == 0) ++si[p];
+      while (ri[p] < recvs[p].size() && recvs[p][ri[p]].op->bytes == 0) ++ri[p];
+      if (si[p] < sends[p].size()) {
+        pending = true;
+        Prog& s = sends[p][si[p]];
+        char* b = box(p, me);
+        uint64_t* ready = flags(p, me);
+        uint64_t* acked = flags(p, me) + 1;
+        if (__atomic_load_n(acked, __ATOMIC_ACQUIRE) == host_send_seq_[p]) {  // mailbox free
+          const size_t c = std::min<size_t>(chunk, s.op->bytes - s.done);
+          memcpy(b, (const char*)s.op->buf + s.done, c);
+          __atomic_store_n(ready, ++host_send_seq_[p], __ATOMIC_RELEASE);
+          s.done += c;
+          if (s.done == s.op->bytes) ++si[p];
+          progressed = true;
+        }
+      }
+      if (ri[p] < recvs[p].size()) {
+        pending = true;
+        Prog& r = recvs[p][ri[p]];
+        char* b = box(me, p);
+        uint64_t* ready = flags(me, p);
+        uint64_t* acked = flags(me, p) + 1;
+        if (__atomic_load_n(ready, __ATOMIC_ACQUIRE) == host_recv_seq_[p] + 1) {
+          const size_t c = std::min<size_t>(chunk, r.op->bytes - r.done);
+          memcpy((char*)r.op->buf + r.done, b, c);
+          __atomic_store_n(acked, ++host_recv_seq_[p], __ATOMIC_RELEASE);
+          r.done += c;
+          if (r.done == r.op->bytes) ++ri[p];
+          progressed = true;
+        }
+      }
+    }
+    if (!pending) break;
+    if (progressed) {
+      idle = 0;
+      continue;
+    }
+    if ((++idle & 0xff) == 0) {
+      sched_yield();
+      if (dev_.timeout_ns) {
+        auto dt = std::chrono::steady_clock::now() - t0;
+        if ((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(dt).count() > dev_.timeout_ns)
+          UB_THROW("host send/recv timeout on rank %d (a peer did not post the matching operation)", me);
+      }
+    }
+  }
+  // my last chunks must be consumed before the buffers may be reused: wait for the acknowledgements
+  for (int p = 0; p < n; ++p) {
+    if (sends[p].empty()) continue;
+    uint64_t* acked = flags(p, me) + 1;
+    uint32_t spins = 0;
+    while (__atomic_load_n(acked, __ATOMIC_ACQUIRE) != host_send_seq_[p]) {
+      if ((++spins & 0xff) == 0) {
+        sched_yield();
+        if (dev_.timeout_ns) {
+          auto dt = std::chrono::steady_clock::now() - t0;
+          if ((uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(dt).count() > dev_.timeout_ns)
+            UB_THROW("host send/recv timeout on rank %d waiting for rank %d to drain", me, p);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace ub

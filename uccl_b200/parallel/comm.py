@@ -293,6 +293,24 @@ class Communicator:
     def barrier(self, stream=None) -> None:
         self._c.barrier(self._stream(stream))
 
+    # ---------------------------------------------------------------- point-to-point
+    def batch_send_recv(self, ops, stream=None) -> None:
+        """Grouped point-to-point (``ncclGroupStart .. ncclSend/ncclRecv .. ncclGroupEnd``):
+        ``ops = [("send", tensor, peer) | ("recv", tensor, peer), ...]``.  Operations towards one peer
+        match the peer's operations in posting order; a rank may send to and receive from the same peer
+        in one group (ring steps, all-to-all patterns)."""
+        raw = []
+        for kind, t, peer in ops:
+            self._check(t, kind)
+            raw.append((kind == "send", t.data_ptr(), t.numel() * t.element_size(), int(peer)))
+        self._c.group_p2p(raw, self._stream(stream))
+
+    def send(self, tensor: torch.Tensor, dst: int, stream=None) -> None:
+        self.batch_send_recv([("send", tensor, dst)], stream)
+
+    def recv(self, tensor: torch.Tensor, src: int, stream=None) -> None:
+        self.batch_send_recv([("recv", tensor, src)], stream)
+
     # ---------------------------------------------------------------------- tracing
     _TRACE_CODES = {1: "kernel_begin", 2: "kernel_end", 3: "barrier_enter", 4: "barrier_exit", 5: "phase"}
 

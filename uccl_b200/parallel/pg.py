@@ -180,12 +180,16 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(None)
 
     def send(self, tensors, dst_rank, tag=0):
-        raise NotImplementedError("uccl_b200 process group: use the NCCL group (or uccl_b200.collective) for "
-                                  "pipeline send/recv -- the north-star keeps PP p2p on NCCL")
+        # native staged send/recv kernel (CUDA) / mailbox protocol (host); tags are not used, operations
+        # towards one peer match in posting order like NCCL's
+        for t in tensors:
+            self.comm.send(self._prep(t), dst_rank)
+        return _Work(tensors)
 
     def recv(self, tensors, src_rank, tag=0):
-        raise NotImplementedError("uccl_b200 process group: use the NCCL group (or uccl_b200.collective) for "
-                                  "pipeline send/recv")
+        for t in tensors:
+            self.comm.recv(self._prep(t), src_rank)
+        return _Work(tensors)
 
 
 def _create(store, rank, world_size, timeout=None):
