@@ -15,3 +15,7 @@ $R benchmarks/ep_sweep.py --ll --out "$OUT/ep$N.json"
 $R benchmarks/ep_baseline.py --out "$OUT/ep_baseline$N.json" || true
 python benchmarks/p2p_bench.py --out "$OUT/p2p.json" || true
 python benchmarks/d2h_fifo_bench.py --out "$OUT/d2h.json" || true
+$R benchmarks/uk_bench.py --out "$OUT/uk$N.json" || true
+python benchmarks/compress_bench.py --out "$OUT/compress.json" || true
+$R benchmarks/p2p_traffic.py --pattern permutation --out "$OUT/perm$N.json" || true
+$R benchmarks/p2p_traffic.py --pattern incast --out "$OUT/incast$N.json" || true
