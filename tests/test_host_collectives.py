@@ -74,6 +74,32 @@ def test_host_other_collectives(world4):
         assert torch.equal(a2a, exp_a2a)
 
 
+def test_host_allreduce_fused_scale_and_cast(world4):
+    """fp32 gradients reduced with a fused scale and rounded once to bf16 / fp16 (and the reverse widening):
+    the host backend follows the CUDA epilogue's arithmetic -- fp32 accumulate, one rounding."""
+    n = len(world4)
+    g = torch.Generator().manual_seed(1)
+    ins = [torch.randn(3001, generator=g) for _ in range(n)]
+    ref = torch.stack(ins).sum(0) * 0.5
+
+    def fn(c):
+        outs = {}
+        for dt in (torch.bfloat16, torch.float16):
+            o = torch.zeros(3001, dtype=dt)
+            c.all_reduce(ins[c.rank].clone(), "sum", out=o, scale=0.5)
+            outs[dt] = o
+        w = torch.zeros(3001)
+        c.all_reduce(ins[c.rank].to(torch.bfloat16), "avg", out=w)  # bf16 in, fp32 out
+        return outs, w
+
+    res = run_host_ranks(world4, fn)
+    wide_ref = torch.stack([x.to(torch.bfloat16).float() for x in ins]).sum(0) / n
+    for outs, w in res:
+        assert torch.equal(outs[torch.bfloat16], ref.to(torch.bfloat16))
+        assert torch.equal(outs[torch.float16], ref.to(torch.float16))
+        assert torch.allclose(w, wide_ref, rtol=1e-6, atol=1e-6)
+
+
 def test_host_alltoallv_multi_round(world4):
     """Variable-size all-to-all incl. empty pairs and messages larger than the per-destination stage
     slice (several rounds, ranks finishing in different rounds)."""

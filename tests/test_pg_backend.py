@@ -78,3 +78,56 @@ def test_pg_backend_world2_cpu():
         got = sorted(q.get(timeout=180) for _ in range(2))
         [p.join(30) for p in ps]
     assert got == [(0, True, True, True, True, True, True), (1, True, True, True, True, True, True)]
+
+
+def _hook_worker(rank, world, port, q):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uccl_b200 import Communicator
+    from uccl_b200.parallel.ddp import wrap_ddp
+
+    comm = Communicator.from_torch_dist(None, host=True, heap_bytes=128 << 20, stage_bytes=2 << 20)
+    res = []
+    for compress in (False, True):
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8))
+        ddp = wrap_ddp(model, comm, compress=compress)
+        x = torch.full((4, 16), float(rank + 1))
+        ddp(x).sum().backward()
+        res.append([p.grad.clone() for p in model.parameters()])
+    # reference: average of the per-rank local gradients
+    torch.manual_seed(0)
+    ref_model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8))
+    grads = []
+    for r in range(world):
+        ref_model.zero_grad()
+        ref_model(torch.full((4, 16), float(r + 1))).sum().backward()
+        grads.append([p.grad.clone() for p in ref_model.parameters()])
+    exp = [sum(g[i] for g in grads) / world for i in range(len(grads[0]))]
+    ok_plain = all(torch.allclose(a, b, rtol=1e-5, atol=1e-6) for a, b in zip(res[0], exp))
+    ok_bf16 = all(torch.allclose(a, b, rtol=2e-2, atol=2e-2) for a, b in zip(res[1], exp))
+    q.put((rank, ok_plain, ok_bf16))
+    dist.destroy_process_group()
+
+
+def test_ddp_comm_hooks_world2_cpu():
+    """DDP over gloo with the gradient reduction swapped for our all-reduce (fused averaging) and for the
+    bf16-on-the-wire variant whose widening cast is fused into the reduction."""
+    import socket
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_hook_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=180) for _ in range(2))
+    [p.join(30) for p in ps]
+    assert got == [(0, True, True), (1, True, True)]

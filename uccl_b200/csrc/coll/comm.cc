@@ -356,8 +356,7 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
     else idiv = n;
   }
   if (is_host()) {
-    UB_CHECK(out_dtype == dtype, "host backend: fused cast unsupported");
-    host_allreduce(in, out, count, dtype, op, is_float_dtype(dtype) ? scale : 1.0f);
+    host_allreduce(in, out, count, dtype, op, is_float_dtype(dtype) ? scale : 1.0f, out_dtype);
     return;
   }
   DeviceGuard g(device());

@@ -130,7 +130,7 @@ class Comm {
   void check_buf(const void* p, const char* what) const;
   // host fake implementations (host_coll.cc)
   void host_barrier();
-  void host_allreduce(const void* in, void* out, size_t count, int dtype, int op, float scale);
+  void host_allreduce(const void* in, void* out, size_t count, int dtype, int op, float scale, int out_dtype);
   void host_allgather(const void* in, void* out, size_t bytes);
   void host_reduce_scatter(const void* in, void* out, size_t count, int dtype, int op);
   void host_broadcast(const void* in, void* out, size_t bytes, int root);

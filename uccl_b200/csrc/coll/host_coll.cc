@@ -128,6 +128,29 @@ void reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype
 #undef UB_PLAIN
 }
 
+// float family with a different output type: accumulate in fp32 over the ranks, round once
+// (same arithmetic as the fused-cast epilogue of the CUDA kernels)
+void reduce_n_cast(void* dst, const void* const* srcs, int n, size_t count, int in_dtype, int out_dtype, int op,
+                   float scale) {
+  auto load = [&](const void* p, size_t i) -> float {
+    switch (in_dtype) {
+      case kF32: return ((const float*)p)[i];
+      case kBF16: return bf16_to_f32(((const uint16_t*)p)[i]);
+      default: return f16_to_f32(((const uint16_t*)p)[i]);
+    }
+  };
+  for (size_t i = 0; i < count; ++i) {
+    float acc = load(srcs[0], i);
+    for (int r = 1; r < n; ++r) acc = apply<float>(op, acc, load(srcs[r], i));
+    if (scale != 1.0f) acc *= scale;
+    switch (out_dtype) {
+      case kF32: ((float*)dst)[i] = acc; break;
+      case kBF16: ((uint16_t*)dst)[i] = f32_to_bf16(acc); break;
+      default: ((uint16_t*)dst)[i] = f32_to_f16(acc); break;
+    }
+  }
+}
+
 }  // namespace
 
 void host_reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale) {
@@ -163,10 +186,16 @@ void Comm::host_barrier() {
 }
 
 // All host collectives: copy my input into my stage (chunked), barrier, read peers' stages.
-void Comm::host_allreduce(const void* in, void* out, size_t count, int dtype, int op, float scale) {
+void Comm::host_allreduce(const void* in, void* out, size_t count, int dtype, int op, float scale, int out_dtype) {
   const int n = nranks(), me = rank();
   const size_t es = dtype_size(dtype);
-  const size_t chunk_elems = layout_.stage_bytes / es;
+  const size_t eo = dtype_size(out_dtype);
+  const bool cast = out_dtype != dtype;
+  if (cast) {
+    auto fl = [](int d) { return d == kF32 || d == kBF16 || d == kF16; };
+    UB_CHECK(fl(dtype) && fl(out_dtype), "host backend: fused cast only between fp32 / bf16 / fp16");
+  }
+  const size_t chunk_elems = layout_.stage_bytes / std::max(es, eo);
   for (size_t base = 0; base < count; base += chunk_elems) {
     const size_t c = std::min(chunk_elems, count - base);
     memcpy(fabric_->local() + layout_.stage_in_off, (const char*)in + base * es, c * es);
@@ -176,12 +205,13 @@ void Comm::host_allreduce(const void* in, void* out, size_t count, int dtype, in
     split_range(c, n, me, lo, hi);
     const void* srcs[kMaxRanks];
     for (int r = 0; r < n; ++r) srcs[r] = fabric_->heap(r) + layout_.stage_in_off + lo * es;
-    reduce_n(fabric_->local() + layout_.stage_out_off + lo * es, srcs, n, hi - lo, dtype, op, scale);
+    if (cast) reduce_n_cast(fabric_->local() + layout_.stage_out_off + lo * eo, srcs, n, hi - lo, dtype, out_dtype, op, scale);
+    else reduce_n(fabric_->local() + layout_.stage_out_off + lo * es, srcs, n, hi - lo, dtype, op, scale);
     host_barrier();
     for (int r = 0; r < n; ++r) {
       uint64_t l2, h2;
       split_range(c, n, r, l2, h2);
-      memcpy((char*)out + (base + l2) * es, fabric_->heap(r) + layout_.stage_out_off + l2 * es, (h2 - l2) * es);
+      memcpy((char*)out + (base + l2) * eo, fabric_->heap(r) + layout_.stage_out_off + l2 * eo, (h2 - l2) * eo);
     }
     host_barrier();
   }
