@@ -18,18 +18,24 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 
-def main():
+def main(argv=None):
     p = argparse.ArgumentParser()
     p.add_argument("--backend", default="uccl_b200", choices=["uccl_b200", "nccl", "hook"])
     p.add_argument("--model", default="resnet18", choices=["resnet18", "resnet50"])
     p.add_argument("--batch", type=int, default=128)
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
-    args = p.parse_args()
+    p.add_argument("--cpu", action="store_true", help="CPU reference backend (host fabric); for smoke-testing the flow")
+    args = p.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    if args.cpu:
+        dev = torch.device("cpu")
+        assert args.backend == "uccl_b200", "--cpu runs the uccl_b200 torch backend over the host fabric"
+    else:
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+    sync = (lambda: None) if args.cpu else torch.cuda.synchronize
     if args.backend == "uccl_b200":
         import uccl_b200.parallel.pg  # noqa: F401
 
@@ -54,20 +60,21 @@ def main():
     t0 = None
     for step in range(args.warmup + args.steps):
         if step == args.warmup:
-            torch.cuda.synchronize()
+            sync()
             dist.barrier()
             t0 = time.perf_counter()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
+        with torch.autocast("cpu" if args.cpu else "cuda", dtype=torch.bfloat16, enabled=not args.cpu):
             loss = F.cross_entropy(ddp(x), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
-    torch.cuda.synchronize()
+    sync()
     dt = time.perf_counter() - t0
     if rank == 0:
         print(f"[{args.backend}] {args.model} x{world}: {args.steps * args.batch * world / dt:.0f} img/s, "
               f"{dt / args.steps * 1e3:.2f} ms/step, final loss {loss.item():.4f}")
     dist.destroy_process_group()
+    return float(loss.item())
 
 
 if __name__ == "__main__":

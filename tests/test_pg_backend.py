@@ -131,3 +131,40 @@ def test_ddp_comm_hooks_world2_cpu():
     got = sorted(q.get(timeout=180) for _ in range(2))
     [p.join(30) for p in ps]
     assert got == [(0, True, True), (1, True, True)]
+
+
+def _resnet_worker(rank, world, path, q):
+    import sys
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    torch.set_num_threads(2)
+    import torch.distributed as dist
+
+    import uccl_b200.parallel.pg  # noqa: F401
+
+    # the example calls init_process_group("uccl_b200") itself: give it a file store through the env-free API
+    orig = dist.init_process_group
+
+    def init(backend, **kw):
+        return orig(backend, rank=rank, world_size=world, store=dist.FileStore(path, world))
+
+    dist.init_process_group = init
+    import ddp_train
+
+    loss = ddp_train.main(["--cpu", "--steps", "2", "--warmup", "1", "--batch", "4"])
+    q.put((rank, loss))
+
+
+def test_resnet_ddp_example_on_cpu():
+    """examples/ddp_train.py (ResNet-18, synthetic CIFAR shapes) for a few steps over the torch backend on the
+    host fabric: the BASELINE 'DDP through the drop-in' flow, runnable without a GPU."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "store")
+        ps = [ctx.Process(target=_resnet_worker, args=(r, 2, path, q)) for r in range(2)]
+        [p.start() for p in ps]
+        got = dict(q.get(timeout=300) for _ in range(2))
+        [p.join(60) for p in ps]
+    assert all(v == v and v < 20 for v in got.values()), got  # finite, sane cross-entropy
