@@ -250,3 +250,26 @@ def test_tuning_table_from_sweep_and_env(tmp_path, monkeypatch):
     shipped = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "tuning_8xB200.json")
     d = json.load(open(shipped))
     assert {"symmetric", "plain"} <= set(d["tables"])
+
+
+def test_prometheus_exporter_renders_runtime_counters():
+    import torch
+
+    from uccl_b200 import Communicator
+    from uccl_b200.p2p import Endpoint
+    from uccl_b200.utils.metrics import MetricsExporter
+
+    c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
+    a, b = Endpoint(-1), Endpoint(-1)
+    ok, conn = a.connect(remote_metadata=b.get_metadata())
+    b.accept(5000)
+    src, dst = torch.ones(256, dtype=torch.uint8), torch.zeros(256, dtype=torch.uint8)
+    ok, rt = b.recv_async(1, 0, dst.data_ptr(), 256)
+    assert a.send(conn, 0, src.data_ptr(), 256) and b.wait(rt, 5000)
+    exp = MetricsExporter(rank=3)
+    exp.watch_communicator(c)
+    exp.watch_endpoint(a)
+    exp.watch("custom", lambda: {"answer": 42})
+    text = exp.render()
+    assert 'uccl_b200_p2p_bytes_sent{rank="3"} 256.0' in text
+    assert 'uccl_b200_comm_heap_free_bytes{rank="3"}' in text and 'uccl_b200_custom_answer{rank="3"} 42.0' in text
