@@ -273,3 +273,25 @@ def test_prometheus_exporter_renders_runtime_counters():
     text = exp.render()
     assert 'uccl_b200_p2p_bytes_sent{rank="3"} 256.0' in text
     assert 'uccl_b200_comm_heap_free_bytes{rank="3"}' in text and 'uccl_b200_custom_answer{rank="3"} 42.0' in text
+
+
+def test_ep_harness_helpers():
+    import torch
+
+    from uccl_b200.ep import utils as U
+
+    a = torch.arange(1000, dtype=torch.float32)
+    b = a.clone()
+    b[17] = -1
+    assert U.hash_tensor(a) == U.hash_tensor(a.clone()) != U.hash_tensor(b)
+    assert U.hash_tensor(torch.ones(3, dtype=torch.uint8)) == 0x010101  # sizes that are not multiples of 8
+    s = torch.rand(6, 8)
+    g = U.create_grouped_scores(s, torch.tensor([[1, 3]] * 6), 4).view(6, 4, 2)
+    assert bool((g[:, 0] == 0).all() and (g[:, 2] == 0).all() and (g[:, 1] == s.view(6, 4, 2)[:, 1]).all())
+    x = torch.tensor([[3, 3, -1, 5], [0, 0, 0, -1]])
+    U.inplace_unique(x, 8)
+    assert sorted(v for v in x[0].tolist() if v >= 0) == [3, 5] and [v for v in x[1].tolist() if v >= 0] == [0]
+    assert U.detect_group_topology() == (1, 1, 0, True) and U.initialize_uccl() == ([], None)
+    with U.suppress_stdout_stderr():
+        print("not shown")
+    assert abs(U.calc_diff(a, a)) < 1e-9

@@ -121,3 +121,159 @@ def unpack_ue8m0(packed: torch.Tensor) -> torch.Tensor:
     assert packed.dtype == torch.int32
     exp = packed.contiguous().view(torch.uint8).to(torch.int32)
     return (exp << 23).view(torch.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Harness helpers with the reference's names (ep/bench/utils.py) so that its test / benchmark scripts port over.
+def hash_tensor(t: torch.Tensor) -> int:
+    """Order-independent 64-bit checksum of a tensor's bytes (determinism checks across variants)."""
+    b = t.contiguous().view(torch.uint8).to(torch.int64)
+    pad = (-b.numel()) % 8
+    if pad:
+        b = torch.cat([b.reshape(-1), torch.zeros(pad, dtype=torch.int64, device=b.device)])
+    w = b.reshape(-1, 8)
+    shifts = torch.arange(8, device=b.device, dtype=torch.int64) * 8
+    return int((w << shifts).sum().item() & 0xFFFFFFFFFFFFFFFF)
+
+
+def create_grouped_scores(scores: torch.Tensor, group_idx: torch.Tensor, num_groups: int) -> torch.Tensor:
+    """Keep only the scores of the selected expert groups (group-limited routing, DeepSeek-V3 style)."""
+    num_tokens, num_experts = scores.shape
+    s = scores.view(num_tokens, num_groups, -1)
+    mask = torch.zeros((num_tokens, num_groups), dtype=torch.bool, device=scores.device)
+    mask = mask.scatter_(1, group_idx, True).unsqueeze(-1).expand_as(s)
+    return (s * mask).view(num_tokens, num_experts)
+
+
+def init_dist(local_rank: int, num_local_ranks: int, backend: Optional[str] = None):
+    """``(rank, world_size, group)`` from the usual MASTER_ADDR / MASTER_PORT / WORLD_SIZE / RANK variables
+    (WORLD_SIZE = number of nodes and RANK = node index, as in the reference's launcher convention)."""
+    import os
+
+    import torch.distributed as dist
+
+    ip = os.getenv("MASTER_ADDR", "127.0.0.1")
+    port = int(os.getenv("MASTER_PORT", "8361"))
+    num_nodes = int(os.getenv("WORLD_SIZE", 1))
+    node_rank = int(os.getenv("RANK", 0))
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend=backend or ("cpu:gloo,cuda:nccl" if cuda else "gloo"),
+                            init_method=f"tcp://{ip}:{port}", world_size=num_nodes * num_local_ranks,
+                            rank=node_rank * num_local_ranks + local_rank)
+    return dist.get_rank(), dist.get_world_size(), dist.new_group(list(range(num_local_ranks * num_nodes)))
+
+
+def init_dist_under_torchrun(local_rank: Optional[int] = None, num_local_ranks: Optional[int] = None):
+    import os
+
+    import torch.distributed as dist
+
+    cuda = torch.cuda.is_available()
+    if cuda:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", local_rank or 0)))
+    dist.init_process_group("cpu:gloo,cuda:nccl" if cuda else "gloo")
+    return dist.get_rank(), dist.get_world_size(), dist.new_group(list(range(dist.get_world_size())))
+
+
+def detect_group_topology(group=None) -> Tuple[int, int, int, bool]:
+    """``(num_nodes, ranks_per_node, node_index, is_intranode)``: one NVLink domain is one "node" here."""
+    import torch.distributed as dist
+
+    n = dist.get_world_size(group) if dist.is_initialized() else 1
+    return 1, n, 0, True
+
+
+def check_nvlink_connections(group=None) -> bool:
+    """True when every pair of visible GPUs can reach each other over P2P (NVLink / NVSwitch)."""
+    if not torch.cuda.is_available():
+        return False
+    n = torch.cuda.device_count()
+    return all(torch.cuda.can_device_access_peer(a, b) for a in range(n) for b in range(n) if a != b)
+
+
+def initialize_uccl(scratch=None, scratch_nbytes: int = 0, rank: int = 0, num_ranks: int = 1, group=None, **kw):
+    """The reference spawns CPU proxy threads and exchanges their metadata here; kernels address peers directly in
+    this library, so there is nothing to start.  Kept for script compatibility: returns ``([], None)``."""
+    return [], None
+
+
+def destroy_uccl(proxies=None, workers=None) -> None:
+    return None
+
+
+class suppress_stdout_stderr:
+    """Silence both C-level and Python-level stdout / stderr inside the block (profiler chatter)."""
+
+    def __enter__(self):
+        import os
+        import sys
+
+        sys.stdout.flush()
+        sys.stderr.flush()
+        self._null = [os.open(os.devnull, os.O_RDWR) for _ in range(2)]
+        self._saved = [os.dup(1), os.dup(2)]
+        os.dup2(self._null[0], 1)
+        os.dup2(self._null[1], 2)
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        import sys
+
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os.dup2(self._saved[0], 1)
+        os.dup2(self._saved[1], 2)
+        for fd in self._null + self._saved:
+            os.close(fd)
+        return False
+
+
+class empty_suppress:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def bench_kineto(fn, kernel_names, num_tests: int = 30, suppress_kineto_output: bool = False,
+                 trace_path: Optional[str] = None, barrier_comm_profiling: bool = False, num_kernels_per_period: int = 1):
+    """Average device time (seconds) of the kernels whose names contain ``kernel_names`` over ``num_tests`` calls of
+    ``fn``, measured with the torch profiler (splits dispatch from combine inside one call, like the reference's
+    ep/bench/utils.py:408-544).  A tuple of names returns a tuple of times."""
+    names = (kernel_names,) if isinstance(kernel_names, str) else tuple(kernel_names)
+    ctx = suppress_stdout_stderr if suppress_kineto_output else empty_suppress
+    with ctx():
+        sched = torch.profiler.schedule(wait=0, warmup=1, active=1, repeat=1)
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA], schedule=sched) as prof:
+            for _ in range(2):
+                if barrier_comm_profiling:
+                    import torch.distributed as dist
+
+                    dev = torch.cuda.current_device()
+                    lhs = torch.randn((4096, 4096), device=f"cuda:{dev}")
+                    lhs @ lhs  # soak up launch skew before the measured region
+                    if dist.is_initialized():
+                        dist.all_reduce(torch.ones(1, device=f"cuda:{dev}"))
+                for _ in range(num_tests):
+                    fn()
+                torch.cuda.synchronize()
+                prof.step()
+    if trace_path is not None:
+        prof.export_chrome_trace(trace_path)
+    events = prof.key_averages()
+    out = []
+    for name in names:
+        tot, cnt = 0.0, 0
+        for ev in events:
+            if name in ev.key:
+                t = getattr(ev, "device_time_total", None)
+                if t is None:
+                    t = getattr(ev, "cuda_time_total", 0.0)
+                tot += float(t)
+                cnt += int(ev.count)
+        out.append(tot / max(cnt, 1) * 1e-6 * num_kernels_per_period)
+    return out[0] if isinstance(kernel_names, str) else tuple(out)
