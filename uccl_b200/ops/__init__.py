@@ -60,5 +60,17 @@ def all_to_all_v(out, tensor, send_counts, recv_counts, send_displs=None, recv_d
     return default().all_to_all_v(out, tensor, send_counts, recv_counts, send_displs, recv_displs)
 
 
+def send(tensor, dst):
+    return default().send(tensor, dst)
+
+
+def recv(tensor, src):
+    return default().recv(tensor, src)
+
+
+def batch_send_recv(ops):
+    return default().batch_send_recv(ops)
+
+
 def barrier():
     return default().barrier()
