@@ -1,0 +1,258 @@
+"""The scale-out path on a CPU-only box: multipath reliable datagram transport (csrc/net), its NCCL net
+plugin, the rank-group collectives on top, and the hierarchical multi-node communicator -- all over
+loopback UDP, with injected packet loss (the reference tests its transports with two hosts; the protocol
+logic is the same on one).  SURVEY N1 / N2 / N4 / N6 / N7."""
+import os
+import subprocess
+import sys
+import threading
+
+import pytest
+import torch
+
+from helpers import run_host_ranks
+from uccl_b200 import Communicator, net
+from uccl_b200.parallel import MultiNodeCommunicator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.timeout(300)
+
+
+@pytest.fixture(scope="module")
+def engine_test_exe(tmp_path_factory):
+    exe = tmp_path_factory.mktemp("net") / "net_engine_test"
+    csrc = os.path.join(ROOT, "uccl_b200", "csrc")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + csrc, os.path.join(ROOT, "tests/cpp/net_engine_test.cc"),
+                    os.path.join(csrc, "net/net_engine.cc"), "-lpthread", "-o", str(exe)], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("drop,cc", [(0, "swift"), (5, "swift"), (3, "none"), (2, "timely"), (2, "eqds")])
+def test_engine_loopback_with_loss(engine_test_exe, drop, cc):
+    """C++ level: handshake, eager/unexpected + rendezvous messages, bidirectional 24 MB transfers, 64
+    pipelined messages, spraying over every path, retransmissions under loss, dead-peer abort."""
+    r = subprocess.run([str(engine_test_exe), str(drop), cc, "8"], capture_output=True, text=True, timeout=240)
+    sys.stdout.write(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASS" in r.stdout
+
+
+def test_nccl_net_plugin_vtable(tmp_path):
+    """dlopen the plugin and drive the ncclNet v8 vtable like NCCL's proxy thread."""
+    from uccl_b200 import _build
+
+    _build.build()
+    plugin = _build.nccl_net_plugin_path()
+    assert plugin.exists()
+    syms = subprocess.run(["nm", "-D", str(plugin)], capture_output=True, text=True).stdout
+    assert "ncclNetPlugin_v8" in syms
+    assert " U cuda" not in syms and " U cu" not in syms  # host-only object: loads into any NCCL process
+    exe = tmp_path / "net_plugin_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests/cpp/net_plugin_test.cc"), "-ldl", "-lpthread",
+                    "-o", str(exe)], check=True)
+    env = dict(os.environ, UCCL_B200_NET_IFNAME="lo")
+    r = subprocess.run([str(exe), str(plugin)], capture_output=True, text=True, timeout=200, env=env)
+    sys.stdout.write(r.stdout + r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout
+    assert "dev0 lo" in r.stdout
+
+
+def test_python_engine_tensors_and_stats():
+    a = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.03)
+    b = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.03)
+    lid = b.listen()
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("fb", b.accept(lid)))
+    t.start()
+    fa = a.connect("127.0.0.1", b.port, lid)
+    t.join()
+    fb = box["fb"]
+    x = torch.randn(3_000_000)
+    y = torch.zeros_like(x)
+    small = torch.arange(100, dtype=torch.int32)
+    got_small = torch.zeros(100, dtype=torch.int32)
+    w1 = b.irecv(fb, y)
+    w2 = a.isend(fa, x)
+    a.send(fa, small)  # eager, queued behind the large message
+    assert w1.wait(60000) == x.numel() * 4 and w2.wait(60000) == x.numel() * 4
+    assert b.recv(fb, got_small, 60000) == 400
+    assert torch.equal(x, y) and torch.equal(small, got_small)
+    # a receive that is too small fails loudly instead of truncating
+    big = torch.ones(5000)
+    tiny = torch.zeros(10)
+    wr = b.irecv(fb, tiny)
+    a.send(fa, big, 60000)
+    with pytest.raises(RuntimeError, match="larger than the posted receive"):
+        wr.wait(60000)
+    st = a.flow_stats(fa)
+    assert st["state"] == 2  # FL_ESTABLISHED
+    assert all(p > 0 for p in st["path_tx"]) and len(st["path_tx"]) == 4
+    assert st["fast_rexmit"] + st["rto_rexmit"] > 0 and st["srtt_us"] > 0
+    assert a.stats()["dropped_tx"] > 0
+    with pytest.raises(ValueError):
+        a.isend(fa, torch.zeros(4, 4).t())
+    a.close(fa)
+
+
+class _Exchange:
+    """In-process all-gather of python objects between rank threads (stands in for a TCPStore)."""
+
+    def __init__(self, n):
+        self.slots, self.bar = [None] * n, threading.Barrier(n)
+
+    def for_rank(self, r):
+        def ex(obj):
+            self.slots[r] = obj
+            self.bar.wait()
+            out = list(self.slots)
+            self.bar.wait()
+            return out
+
+        return ex
+
+
+def _run_threads(n, fn):
+    out, errs = [None] * n, []
+
+    def body(r):
+        try:
+            out[r] = fn(r)
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_net_communicator_collectives(n):
+    ex = _Exchange(n)
+    g = torch.Generator().manual_seed(n)
+    ins = [torch.randint(-50, 50, (10007,), generator=g).float() for _ in range(n)]
+
+    def fn(r):
+        c = net.NetCommunicator(r, n, ex.for_rank(r), engine=net.Engine(bind_ip="127.0.0.1", paths=3, drop_prob=0.01))
+        res = {}
+        x = ins[r].clone()
+        c.all_reduce(x)
+        res["sum"] = x
+        res["max"] = c.all_reduce(ins[r].clone(), "max")
+        res["avg"] = c.all_reduce(ins[r].clone(), "avg")
+        res["tiny"] = c.all_reduce(torch.tensor([float(r + 1)]))  # fewer elements than ranks
+        ag = torch.zeros(n * 33)
+        c.all_gather(ag, torch.full((33,), float(r)))
+        res["ag"] = ag
+        rs = torch.zeros(50)
+        c.reduce_scatter(rs, torch.arange(n * 50, dtype=torch.float32) * (r + 1))
+        res["rs"] = rs
+        b = torch.full((1000,), float(r))
+        c.broadcast(b, root=n - 1)
+        res["b"] = b
+        a2a = torch.zeros(n * 4, dtype=torch.int64)
+        c.all_to_all(a2a, torch.arange(n * 4, dtype=torch.int64) + 100 * r)
+        res["a2a"] = a2a
+        c.barrier()
+        res["stats"] = c.stats()
+        c.close()
+        return res
+
+    outs = _run_threads(n, fn)
+    ref = torch.stack(ins)
+    for r, o in enumerate(outs):
+        assert torch.equal(o["sum"], ref.sum(0)) and torch.equal(o["max"], ref.max(0).values)
+        assert torch.allclose(o["avg"], ref.sum(0) / n)
+        assert o["tiny"].item() == n * (n + 1) / 2
+        assert torch.equal(o["ag"].view(n, 33)[:, 0], torch.arange(n, dtype=torch.float32))
+        assert torch.equal(o["rs"], torch.arange(n * 50, dtype=torch.float32).view(n, 50)[r] * (n * (n + 1) / 2))
+        assert torch.equal(o["b"], torch.full((1000,), float(n - 1)))
+        assert torch.equal(o["a2a"], torch.cat([torch.arange(4) + 4 * r + 100 * s for s in range(n)]))
+        assert o["stats"]["engine"]["tx_pkts"] > 0
+
+
+def test_multinode_communicator_two_nodes_of_two():
+    """2 'nodes' x 2 local ranks in one process: host symmetric heaps inside a node, datagram transport
+    between nodes.  Every hierarchical collective must equal the flat 4-rank reference."""
+    N, L = 2, 2
+    W = N * L
+    nodes = [Communicator.local_world(L, host=True, heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=30000)
+             for _ in range(N)]
+    rails = [_Exchange(N) for _ in range(L)]
+    g = torch.Generator().manual_seed(9)
+    ins = [torch.randint(-9, 9, (4099,), generator=g).float() for _ in range(W)]
+
+    def fn(gr):
+        k, l = divmod(gr, L)
+        nc = net.NetCommunicator(k, N, rails[l].for_rank(k), engine=net.Engine(bind_ip="127.0.0.1", paths=2, drop_prob=0.01))
+        m = MultiNodeCommunicator(nodes[k][l], nc)
+        assert (m.rank, m.world_size, m.node_rank, m.local_rank) == (gr, W, k, l)
+        res = {}
+        res["sum"] = m.all_reduce(ins[gr].clone())             # 4099 is not a multiple of L: padded path
+        res["avg"] = m.all_reduce(ins[gr].clone(), "avg")
+        res["max"] = m.all_reduce(ins[gr][:4096].clone(), "max")
+        ag = torch.zeros(W * 17)
+        m.all_gather(ag, torch.full((17,), float(gr)))
+        res["ag"] = ag
+        rs = torch.zeros(25)
+        m.reduce_scatter(rs, torch.arange(W * 25, dtype=torch.float32) * (gr + 1))
+        res["rs"] = rs
+        for root in (0, 3):
+            b = torch.full((1001,), float(gr))
+            m.broadcast(b, root=root)
+            res[f"b{root}"] = b
+        a2a = torch.zeros(W * 3)
+        m.all_to_all(a2a, torch.arange(W * 3, dtype=torch.float32) + 100 * gr)
+        res["a2a"] = a2a
+        m.barrier()
+        m.close()
+        return res
+
+    outs = _run_threads(W, fn)
+    ref = torch.stack(ins)
+    for gr, o in enumerate(outs):
+        assert torch.equal(o["sum"], ref.sum(0))
+        assert torch.allclose(o["avg"], ref.sum(0) / W)
+        assert torch.equal(o["max"], ref[:, :4096].max(0).values)
+        assert torch.equal(o["ag"].view(W, 17)[:, 0], torch.arange(W, dtype=torch.float32))
+        assert torch.equal(o["rs"], torch.arange(W * 25, dtype=torch.float32).view(W, 25)[gr] * (W * (W + 1) / 2))
+        assert torch.equal(o["b0"], torch.zeros(1001)) and torch.equal(o["b3"], torch.full((1001,), 3.0))
+        assert torch.equal(o["a2a"], torch.cat([torch.arange(3, dtype=torch.float32) + 3 * gr + 100 * s for s in range(W)]))
+
+
+_MP_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["UB_ROOT"])
+from uccl_b200 import net
+from uccl_b200.parallel import MultiNodeCommunicator
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+m = MultiNodeCommunicator.from_torch_dist(local_size=2, engine=net.Engine(bind_ip="127.0.0.1", paths=2), host=True,
+                                         heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=60000)
+x = torch.arange(100000, dtype=torch.float32) + rank
+m.all_reduce(x)
+exp = torch.arange(100000, dtype=torch.float32) * world + sum(range(world))
+ok = bool(torch.equal(x, exp))
+m.barrier()
+print(f"rank {rank} node {m.node_rank} local {m.local_rank} ok={ok}", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_multinode_from_torch_dist_four_processes(tmp_path):
+    """The documented bootstrap: torchrun world (gloo) -> node groups (shared-memory heaps) + rail groups
+    (datagram flows) -> hierarchical all-reduce, 4 real processes."""
+    script = tmp_path / "mn.py"
+    script.write_text(_MP_SCRIPT)
+    env = dict(os.environ, UB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    sys.stdout.write(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok=True") == 4

@@ -38,6 +38,11 @@ def nccl_shim_path() -> Path:
     return ROOT / "lib" / "libuccl_b200_nccl.so"
 
 
+def nccl_net_plugin_path() -> Path:
+    """NCCL network plugin (inter-node transport): ``NCCL_NET_PLUGIN=uccl_b200`` resolves to this name."""
+    return ROOT / "lib" / "libnccl-net-uccl_b200.so"
+
+
 def _sources():
     cu = sorted(CSRC.glob("kernels/*.cu")) + sorted(CSRC.glob("ep/*.cu")) + sorted(CSRC.glob("p2p/*.cu"))
     cu += sorted(CSRC.glob("ukernel/*.cu"))
@@ -48,6 +53,7 @@ def _sources():
         + sorted(CSRC.glob("p2p/*.cc"))
         + sorted(CSRC.glob("common/*.cc"))
         + sorted(CSRC.glob("ukernel/*.cc"))
+        + sorted(CSRC.glob("net/*.cc"))
     )
     bind = sorted(CSRC.glob("bind/*.cc"))
     return cu, cc, bind
@@ -120,8 +126,9 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
             list(ex.map(lambda so: _compile_one(so[0], so[1], verbose), todo))
     out = module_path()
     shim_objs = [o for o in objs if o.name == "coll_nccl_shim.o"]
+    plugin_objs = [o for o in objs if o.name == "net_nccl_net_plugin.o"]
     bind_objs = [o for o in objs if o.name.startswith("bind_") or "_bind_" in o.name]
-    core_objs = [o for o in objs if o not in shim_objs and o not in bind_objs]
+    core_objs = [o for o in objs if o not in shim_objs and o not in bind_objs and o not in plugin_objs]
 
     def link(target: Path, these):
         target.parent.mkdir(parents=True, exist_ok=True)
@@ -137,6 +144,15 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
     if shim_objs and (todo or not shim.exists()):
         # NCCL-API drop-in: same kernels/runtime, nccl.h symbols, no python
         link(shim, core_objs + shim_objs)
+    plugin = nccl_net_plugin_path()
+    if plugin_objs and (todo or not plugin.exists()):
+        # NCCL net plugin: host-only code (sockets), no CUDA runtime dependency
+        net_core = [o for o in core_objs if o.name == "net_net_engine.o"]
+        cmd = ["g++", "-shared", "-o", str(plugin)] + [str(o) for o in plugin_objs + net_core] + ["-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError(f"link failed: {plugin}")
     return out
 
 

@@ -17,6 +17,7 @@ void bind_ep(py::module_& m);
 void bind_p2p(py::module_& m);
 void bind_util(py::module_& m);
 void bind_uk(py::module_& m);
+void bind_net(py::module_& m);
 
 static inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline void* P(uintptr_t p) { return reinterpret_cast<void*>(p); }
@@ -210,4 +211,5 @@ PYBIND11_MODULE(_C, m) {
   bind_ep(m);
   bind_p2p(m);
   bind_uk(m);
+  bind_net(m);
 }

@@ -26,6 +26,7 @@ enum LogSubsys : uint32_t {
   SUB_UTIL = 1u << 5,
   SUB_NCCL = 1u << 6,
   SUB_CC = 1u << 7,
+  SUB_NET = 1u << 8,
   SUB_ALL = 0xffffffffu
 };
 
@@ -69,6 +70,7 @@ inline LogState& log_state() {
         else if (!strcasecmp(tok.c_str(), "UTIL")) mask |= SUB_UTIL;
         else if (!strcasecmp(tok.c_str(), "NCCL")) mask |= SUB_NCCL;
         else if (!strcasecmp(tok.c_str(), "CC")) mask |= SUB_CC;
+        else if (!strcasecmp(tok.c_str(), "NET")) mask |= SUB_NET;
         else if (!strcasecmp(tok.c_str(), "ALL")) mask |= SUB_ALL;
         pos = e + 1;
       }

@@ -1,0 +1,1204 @@
+// Engine thread of the inter-node datagram transport; see net_engine.h for the design.
+#include "net_engine.h"
+
+#include <arpa/inet.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <ifaddrs.h>
+#include <net/if.h>
+#include <string.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+
+#include "../common/log.h"
+#include "../common/param.h"
+#include "../common/timers.h"
+
+namespace ub {
+namespace net {
+
+namespace {
+constexpr int kRxBatch = 32;
+constexpr size_t kRxSlot = 65536 + 256;
+constexpr uint64_t kLingerNs = 2000000000ull;
+
+inline int32_t seq_diff(uint32_t a, uint32_t b) { return (int32_t)(a - b); }
+
+// shift a kSackWords*64 bit little-endian bitmap right by t (0 < t <= kSackBits)
+inline void shr_bits(uint64_t* w, int t) {
+  const int ws = t / 64, bs = t % 64;
+  for (int i = 0; i < kSackWords; ++i) {
+    const int s = i + ws;
+    uint64_t lo = s < kSackWords ? w[s] : 0, hi = s + 1 < kSackWords ? w[s + 1] : 0;
+    w[i] = bs ? (lo >> bs) | (hi << (64 - bs)) : lo;
+  }
+}
+inline int trailing_ones(const uint64_t* w) {
+  int n = 0;
+  for (int i = 0; i < kSackWords; ++i) {
+    if (~w[i] == 0) {
+      n += 64;
+      continue;
+    }
+    return n + __builtin_ctzll(~w[i]);
+  }
+  return n;
+}
+}  // namespace
+
+EngineConfig EngineConfig::from_env() {
+  EngineConfig c;
+  c.bind_ip = param_load_str("NET_BIND_IP", c.bind_ip.c_str());
+  c.paths = (int)param_load("NET_PATHS", c.paths);
+  c.payload = (int)param_load("NET_PAYLOAD", c.payload);
+  c.max_inflight = (int)param_load("NET_MAX_INFLIGHT", c.max_inflight);
+  c.eager_max = (size_t)param_load("NET_EAGER_MAX", (int64_t)c.eager_max);
+  c.rto_min_us = (int)param_load("NET_RTO_MIN_US", c.rto_min_us);
+  c.rto_abort = (int)param_load("NET_RTO_ABORT", c.rto_abort);
+  c.link_gbps = (double)param_load("NET_LINK_GBPS", (int64_t)c.link_gbps);
+  c.swift_target_us = (double)param_load("NET_SWIFT_TARGET_US", (int64_t)c.swift_target_us);
+  c.busy_poll = param_load("NET_BUSY_POLL", 0) != 0;
+  c.drop_prob = (double)param_load("NET_DROP_PPM", 0) * 1e-6;
+  const std::string cc = param_load_str("NET_CC", "swift");
+  if (cc == "none") c.cc = CC_NONE;
+  else if (cc == "timely") c.cc = CC_TIMELY;
+  else if (cc == "eqds") c.cc = CC_EQDS;
+  else c.cc = CC_SWIFT;
+  return c;
+}
+
+std::vector<std::pair<std::string, std::string>> list_interfaces() {
+  std::vector<std::pair<std::string, std::string>> out, lo;
+  ifaddrs* ifa = nullptr;
+  if (getifaddrs(&ifa) != 0) return out;
+  const std::string want = param_load_str("NET_IFNAME", "");
+  for (ifaddrs* p = ifa; p; p = p->ifa_next) {
+    if (!p->ifa_addr || p->ifa_addr->sa_family != AF_INET || !(p->ifa_flags & IFF_UP)) continue;
+    char ip[INET_ADDRSTRLEN];
+    inet_ntop(AF_INET, &reinterpret_cast<sockaddr_in*>(p->ifa_addr)->sin_addr, ip, sizeof(ip));
+    const std::string name = p->ifa_name;
+    if (!want.empty()) {
+      // comma separated prefixes, like NCCL_SOCKET_IFNAME
+      bool ok = false;
+      size_t pos = 0;
+      while (pos <= want.size()) {
+        size_t e = want.find(',', pos);
+        if (e == std::string::npos) e = want.size();
+        const std::string tok = want.substr(pos, e - pos);
+        if (!tok.empty() && name.compare(0, tok.size(), tok) == 0) ok = true;
+        pos = e + 1;
+      }
+      if (!ok) continue;
+      out.emplace_back(name, ip);
+    } else if (p->ifa_flags & IFF_LOOPBACK) {
+      lo.emplace_back(name, ip);
+    } else if (name.compare(0, 6, "docker") != 0) {
+      out.emplace_back(name, ip);
+    }
+  }
+  freeifaddrs(ifa);
+  if (out.empty()) out = lo;  // a box without a NIC still gets a (loopback) device
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------- setup
+Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), rng_(std::random_device{}()) {
+  cfg_.paths = std::max(1, std::min(cfg_.paths, kMaxPaths));
+  cfg_.payload = std::max(256, std::min(cfg_.payload, 60000));
+  cfg_.max_inflight = std::max(4, std::min(cfg_.max_inflight, kSackBits - 8));
+  drop_prob_.store(cfg_.drop_prob);
+  cc::EqdsConfig ec;
+  ec.link_gbps = cfg_.link_gbps;
+  ec.credit_bytes = (uint32_t)cfg_.payload * 8;
+  ec.max_backlog_credits = 8;
+  pacer_ = cc::EqdsPacer(ec);
+  for (int i = 0; i < kMaxPaths; ++i) socks_[i] = -1, ports_[i] = 0;
+  epfd_ = epoll_create1(EPOLL_CLOEXEC);
+  evfd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+  UB_CHECK(epfd_ >= 0 && evfd_ >= 0, "net: epoll/eventfd: %s", strerror(errno));
+  epoll_event ev{};
+  ev.events = EPOLLIN;
+  ev.data.u32 = 0xffffffffu;
+  epoll_ctl(epfd_, EPOLL_CTL_ADD, evfd_, &ev);
+  for (int i = 0; i < cfg_.paths; ++i) {
+    int s = socket(AF_INET, SOCK_DGRAM | SOCK_NONBLOCK | SOCK_CLOEXEC, 0);
+    UB_CHECK(s >= 0, "net: socket: %s", strerror(errno));
+    int sz = cfg_.sockbuf_bytes;
+    setsockopt(s, SOL_SOCKET, SO_RCVBUF, &sz, sizeof(sz));
+    setsockopt(s, SOL_SOCKET, SO_SNDBUF, &sz, sizeof(sz));
+    sockaddr_in a{};
+    a.sin_family = AF_INET;
+    a.sin_port = 0;
+    UB_CHECK(inet_pton(AF_INET, cfg_.bind_ip.c_str(), &a.sin_addr) == 1, "net: bad bind ip '%s'", cfg_.bind_ip.c_str());
+    UB_CHECK(bind(s, reinterpret_cast<sockaddr*>(&a), sizeof(a)) == 0, "net: bind %s: %s", cfg_.bind_ip.c_str(),
+             strerror(errno));
+    socklen_t al = sizeof(a);
+    getsockname(s, reinterpret_cast<sockaddr*>(&a), &al);
+    socks_[i] = s;
+    ports_[i] = ntohs(a.sin_port);
+    ev.data.u32 = (uint32_t)i;
+    epoll_ctl(epfd_, EPOLL_CTL_ADD, s, &ev);
+  }
+  rx_buf_.resize((size_t)kRxBatch * kRxSlot);
+  UB_INFO(SUB_NET, "net engine up: %s paths=%d port0=%u payload=%d cc=%d", cfg_.bind_ip.c_str(), cfg_.paths, ports_[0],
+          cfg_.payload, cfg_.cc);
+  thr_ = std::thread([this] { run(); });
+}
+
+void Engine::shutdown(int linger_ms) {
+  if (linger_ms < 0) linger_ms = (int)param_load("NET_LINGER_MS", 2000);
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (shut_) return;
+    shut_ = true;
+    for (auto& kv : flows_) {
+      const int st = kv.second->state.load();
+      if (st == FL_ESTABLISHED || st == FL_SYN_SENT) {
+        Cmd c;
+        c.op = 4;
+        c.flow = kv.first;
+        cmds_.push_back(c);
+      }
+    }
+  }
+  wake();
+  const uint64_t deadline = now_ns() + (uint64_t)linger_ms * 1000000ull;
+  for (;;) {
+    bool all_done = true;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& kv : flows_) {
+        const int st = kv.second->state.load();
+        if (st == FL_ERROR) continue;
+        if (st != FL_CLOSED || !kv.second->peer_fin.load()) all_done = false;
+      }
+    }
+    const uint64_t now = now_ns();
+    // quiet period: the peer may still retransmit its FIN if our last ACK was lost
+    if (all_done && now - last_rx_ns_.load() > 3ull * (uint64_t)cfg_.rto_min_us * 1000ull) break;
+    if (now > deadline) break;
+    std::this_thread::sleep_for(std::chrono::microseconds(200));
+  }
+}
+
+Engine::~Engine() {
+  shutdown(-1);
+  stop_.store(true);
+  wake();
+  if (thr_.joinable()) thr_.join();
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& kv : flows_) {
+      Flow& f = *kv.second;
+      if (f.state.load() != FL_ERROR) fail_flow(f, nullptr);
+    }
+    for (auto& c : cmds_)
+      if (c.req) complete(c.req, 0, 1);
+    cmds_.clear();
+  }
+  for (int i = 0; i < cfg_.paths; ++i)
+    if (socks_[i] >= 0) close(socks_[i]);
+  if (epfd_ >= 0) close(epfd_);
+  if (evfd_ >= 0) close(evfd_);
+}
+
+void Engine::wake() {
+  uint64_t one = 1;
+  ssize_t r = write(evfd_, &one, sizeof(one));
+  (void)r;
+}
+
+std::shared_ptr<Engine::Flow> Engine::find(uint32_t id) const {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = flows_.find(id);
+  return it == flows_.end() ? nullptr : it->second;
+}
+
+// ----------------------------------------------------------------------------------- app-side API
+uint32_t Engine::listen() {
+  std::lock_guard<std::mutex> lk(mu_);
+  const uint32_t id = next_listen_++;
+  listeners_[id];
+  return id;
+}
+
+void Engine::close_listen(uint32_t listen_id) {
+  std::lock_guard<std::mutex> lk(mu_);
+  listeners_.erase(listen_id);
+}
+
+uint32_t Engine::connect_async(const std::string& ip, uint16_t port, uint32_t listen_id) {
+  auto f = std::make_shared<Flow>();
+  f->id = next_flow_++;
+  f->listen_id = listen_id;
+  UB_CHECK(inet_pton(AF_INET, ip.c_str(), &f->peer_ip) == 1, "net: bad peer ip '%s'", ip.c_str());
+  f->syn_port = port;
+  const uint64_t now = now_ns();
+  f->syn_next_ns = now;
+  f->syn_deadline_ns = now + (uint64_t)cfg_.connect_timeout_ms * 1000000ull;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    f->nonce = (((uint64_t)std::random_device{}() << 32) ^ now) | 1;  // rng_ belongs to the engine thread
+    f->state.store(FL_SYN_SENT);
+    flows_[f->id] = f;
+    active_dirty_ = true;
+  }
+  wake();
+  return f->id;
+}
+
+int Engine::flow_state(uint32_t flow) const {
+  auto f = find(flow);
+  return f ? f->state.load(std::memory_order_acquire) : 0;
+}
+
+bool Engine::accept_nb(uint32_t listen_id, uint32_t* flow) {
+  std::lock_guard<std::mutex> lk(mu_);
+  auto it = listeners_.find(listen_id);
+  if (it == listeners_.end() || it->second.ready.empty()) return false;
+  *flow = it->second.ready.front();
+  it->second.ready.pop_front();
+  return true;
+}
+
+uint32_t Engine::connect(const std::string& ip, uint16_t port, uint32_t listen_id, int timeout_ms) {
+  const uint32_t id = connect_async(ip, port, listen_id);
+  const uint64_t t0 = now_ns();
+  for (;;) {
+    const int st = flow_state(id);
+    if (st == FL_ESTABLISHED) return id;
+    UB_CHECK(st == FL_SYN_SENT, "net: connect to %s:%u failed (state %d)", ip.c_str(), port, st);
+    UB_CHECK(timeout_ms < 0 || now_ns() - t0 < (uint64_t)timeout_ms * 1000000ull, "net: connect to %s:%u timed out",
+             ip.c_str(), port);
+    std::this_thread::sleep_for(std::chrono::microseconds(100));
+  }
+}
+
+uint32_t Engine::accept(uint32_t listen_id, int timeout_ms) {
+  const uint64_t t0 = now_ns();
+  uint32_t id = 0;
+  while (!accept_nb(listen_id, &id)) {
+    UB_CHECK(timeout_ms < 0 || now_ns() - t0 < (uint64_t)timeout_ms * 1000000ull, "net: accept timed out");
+    std::this_thread::sleep_for(std::chrono::microseconds(100));
+  }
+  return id;
+}
+
+void Engine::close_flow(uint32_t flow) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    Cmd c;
+    c.op = 4;
+    c.flow = flow;
+    cmds_.push_back(c);
+  }
+  wake();
+}
+
+Request* Engine::send_async(uint32_t flow, const void* data, size_t bytes) {
+  Request* r = new Request();
+  r->flow = flow;
+  r->is_send = true;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    Cmd c;
+    c.op = 2;
+    c.flow = flow;
+    c.req = r;
+    c.ptr = const_cast<void*>(data);
+    c.len = bytes;
+    cmds_.push_back(c);
+  }
+  wake();
+  return r;
+}
+
+Request* Engine::recv_async(uint32_t flow, void* data, size_t capacity) {
+  Request* r = new Request();
+  r->flow = flow;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    Cmd c;
+    c.op = 3;
+    c.flow = flow;
+    c.req = r;
+    c.ptr = data;
+    c.len = capacity;
+    cmds_.push_back(c);
+  }
+  wake();
+  return r;
+}
+
+bool Engine::test(Request* r, size_t* bytes, int* err) {
+  if (!r->done.load(std::memory_order_acquire)) return false;
+  if (bytes) *bytes = r->bytes;
+  if (err) *err = r->err.load(std::memory_order_relaxed);
+  delete r;
+  return true;
+}
+
+bool Engine::wait(Request* r, size_t* bytes, int timeout_ms) {
+  const uint64_t t0 = now_ns();
+  int err = 0;
+  uint32_t spins = 0;
+  while (!test(r, bytes, &err)) {
+    if (timeout_ms >= 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull) return false;  // request stays live
+    if (++spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(20));
+    else std::this_thread::yield();
+  }
+  return err == 0;
+}
+
+EngineStats Engine::stats() const {
+  std::lock_guard<std::mutex> lk(st_mu_);
+  return est_;
+}
+
+bool Engine::flow_stats(uint32_t flow, FlowStats* out) const {
+  auto f = find(flow);
+  if (!f) return false;
+  std::lock_guard<std::mutex> lk(st_mu_);
+  *out = f->st;
+  out->state = f->state.load();
+  return true;
+}
+
+void Engine::complete(Request* r, size_t bytes, int err) {
+  if (!r) return;
+  r->bytes = bytes;
+  r->err.store(err, std::memory_order_relaxed);
+  r->done.store(1, std::memory_order_release);
+}
+
+// ------------------------------------------------------------------------------------ engine loop
+void Engine::run() {
+  std::unordered_map<uint32_t, Flow*> index;
+  uint64_t last_stats = 0;
+  while (!stop_.load(std::memory_order_relaxed)) {
+    bool busy = false;
+    // commands + working set
+    {
+      std::vector<Cmd> cmds;
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        cmds.swap(cmds_);
+        if (active_dirty_) {
+          active_.clear();
+          for (auto& kv : flows_) active_.push_back(kv.second);
+          active_dirty_ = false;
+        }
+      }
+      for (auto& c : cmds) {
+        busy = true;
+        std::shared_ptr<Flow> f = find(c.flow);
+        if (!f) {
+          if (c.req) complete(c.req, 0, 1);
+          continue;
+        }
+        if (c.op == 2) post_send(*f, c.req, c.ptr, c.len);
+        else if (c.op == 3) post_recv(*f, c.req, c.ptr, c.len);
+        else if (c.op == 4) {
+          const int st = f->state.load();
+          if (st == FL_ESTABLISHED) {
+            f->fin_pending = true;
+            f->state.store(FL_CLOSING);
+            f->last_progress_ns = now_ns();
+          } else if (st == FL_SYN_SENT) {
+            fail_flow(*f, nullptr);
+          }
+        }
+      }
+    }
+    busy |= rx_poll();
+    const uint64_t now = now_ns();
+    timers(now);
+    if (cfg_.cc == CC_EQDS) eqds_tick(now);
+    bool pending = false;
+    for (auto& sp : active_) {
+      Flow& f = *sp;
+      const int st = f.state.load(std::memory_order_relaxed);
+      if (st == FL_ESTABLISHED || st == FL_CLOSING) {
+        busy |= tx_pump(f, now);
+        if (f.need_ack || f.credit_dirty) send_ack(f);
+        if (f.snd_una != f.snd_nxt || f.tx_cursor < f.txq.size()) pending = true;
+      } else if (st == FL_SYN_SENT) {
+        pending = true;
+      } else if (st == FL_CLOSED && f.need_ack) {
+        send_ack(f);  // linger: late retransmissions of the peer still get their ACK
+      }
+    }
+    ++est_.loops;
+    if (now - last_stats > 1000000ull) {
+      last_stats = now;
+      std::lock_guard<std::mutex> lk(st_mu_);
+      // counters are single-writer (this thread) aligned words; readers tolerate slightly stale values
+      for (auto& sp : active_) {
+        Flow& f = *sp;
+        f.st.srtt_us = f.srtt_us;
+        f.st.min_rtt_us = f.min_rtt_us;
+        f.st.cwnd = f.swift.cwnd();
+        f.st.rate_gbps = f.timely.rate_gbps();
+      }
+      est_.flows = (int)active_.size();
+    }
+    if (!busy && !cfg_.busy_poll) {
+      const bool eq = cfg_.cc == CC_EQDS && pacer_.active_senders() > 0;
+      const int to = pending ? 1 : 50;
+      // the credit pacer and the rate pacer need a fine-grained clock while there is work: spin
+      if (eq || (cfg_.cc == CC_TIMELY && pending)) continue;
+      ++est_.sleeps;
+      epoll_event evs[8];
+      const int n = epoll_wait(epfd_, evs, 8, to);
+      for (int i = 0; i < n; ++i)
+        if (evs[i].data.u32 == 0xffffffffu) {
+          uint64_t v;
+          ssize_t r = read(evfd_, &v, sizeof(v));
+          (void)r;
+        }
+    }
+  }
+}
+
+bool Engine::rx_poll() {
+  bool any = false;
+  mmsghdr msgs[kRxBatch];
+  iovec iov[kRxBatch];
+  sockaddr_in from[kRxBatch];
+  for (int s = 0; s < cfg_.paths; ++s) {
+    for (int round = 0; round < 4; ++round) {
+      for (int i = 0; i < kRxBatch; ++i) {
+        iov[i].iov_base = rx_buf_.data() + (size_t)i * kRxSlot;
+        iov[i].iov_len = kRxSlot;
+        memset(&msgs[i], 0, sizeof(msgs[i]));
+        msgs[i].msg_hdr.msg_iov = &iov[i];
+        msgs[i].msg_hdr.msg_iovlen = 1;
+        msgs[i].msg_hdr.msg_name = &from[i];
+        msgs[i].msg_hdr.msg_namelen = sizeof(sockaddr_in);
+      }
+      const int n = recvmmsg(socks_[s], msgs, kRxBatch, MSG_DONTWAIT, nullptr);
+      if (n <= 0) break;
+      any = true;
+      for (int i = 0; i < n; ++i) on_packet(s, from[i], static_cast<uint8_t*>(iov[i].iov_base), msgs[i].msg_len);
+      if (n < kRxBatch) break;
+    }
+  }
+  return any;
+}
+
+void Engine::on_packet(int sock_idx, const sockaddr_in& from, uint8_t* buf, size_t n) {
+  last_rx_ns_.store(now_ns(), std::memory_order_relaxed);
+  ++est_.rx_pkts;
+  est_.rx_bytes += n;
+  if (n < sizeof(PktHdr)) {
+    ++est_.bad_pkts;
+    return;
+  }
+  PktHdr h;
+  memcpy(&h, buf, sizeof(h));
+  if (h.magic != kMagic || sizeof(PktHdr) + h.len > n) {
+    ++est_.bad_pkts;
+    return;
+  }
+  const uint8_t* body = buf + sizeof(PktHdr);
+  if (h.type == PKT_SYN || h.type == PKT_SYNACK) {
+    if (h.len < sizeof(SynBody)) {
+      ++est_.bad_pkts;
+      return;
+    }
+    SynBody b;
+    memcpy(&b, body, sizeof(b));
+    if (h.type == PKT_SYN) on_syn(sock_idx, from, h, b);
+    else on_synack(from, h, b);
+    return;
+  }
+  Flow* f = nullptr;
+  for (auto& sp : active_)  // small working sets; the lock-protected map is the slow path
+    if (sp->id == h.dst_flow) {
+      f = sp.get();
+      break;
+    }
+  std::shared_ptr<Flow> hold;
+  if (!f) {
+    hold = find(h.dst_flow);
+    f = hold.get();
+  }
+  if (!f || f->peer_ip.s_addr != from.sin_addr.s_addr) {
+    if (h.type == PKT_DATA) send_rst(sock_idx, from, 0);
+    return;
+  }
+  const int st = f->state.load(std::memory_order_relaxed);
+  if (h.type == PKT_RST) {
+    if (st == FL_ESTABLISHED || st == FL_SYN_SENT || st == FL_CLOSING) fail_flow(*f, "reset by peer");
+    return;
+  }
+  if (st == FL_SYN_SENT) return;  // SYNACK not seen yet: the peer will retransmit
+  if (st == FL_ERROR) {
+    if (h.type == PKT_DATA) send_rst(sock_idx, from, f->peer_flow);
+    return;
+  }
+  if (h.type == PKT_DATA) {
+    on_data(*f, h, body);
+  } else if (h.type == PKT_ACK) {
+    if (h.len < sizeof(AckBody)) return;
+    AckBody b;
+    memcpy(&b, body, sizeof(b));
+    on_ack(*f, h, b);
+  }
+}
+
+// ------------------------------------------------------------------------------------- handshake
+void Engine::fill_syn_body(SynBody* b, const Flow& f) const {
+  memset(b, 0, sizeof(*b));
+  b->nonce = f.nonce;
+  b->src_flow = f.id;
+  b->listen_id = f.listen_id;
+  b->npaths = (uint16_t)cfg_.paths;
+  for (int i = 0; i < cfg_.paths; ++i) b->ports[i] = htons(ports_[i]);
+}
+
+void Engine::send_syn(Flow& f, bool synack, int sock_idx, const sockaddr_in* to) {
+  PktHdr h{};
+  h.magic = kMagic;
+  h.type = synack ? PKT_SYNACK : PKT_SYN;
+  h.dst_flow = synack ? f.peer_flow : 0;
+  h.len = sizeof(SynBody);
+  h.ts_ns = now_ns();
+  SynBody b;
+  fill_syn_body(&b, f);
+  sockaddr_in a{};
+  if (to) {
+    a = *to;
+  } else {
+    a.sin_family = AF_INET;
+    a.sin_addr = f.peer_ip;
+    a.sin_port = htons(f.syn_port);
+  }
+  raw_send(sock_idx, a, &h, sizeof(h), &b, sizeof(b));
+}
+
+void Engine::on_syn(int sock_idx, const sockaddr_in& from, const PktHdr& h, const SynBody& b) {
+  (void)h;
+  std::shared_ptr<Flow> f;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto lit = listeners_.find(b.listen_id);
+    if (lit == listeners_.end()) {
+      f = nullptr;
+    } else {
+      const std::pair<uint64_t, uint64_t> key(((uint64_t)from.sin_addr.s_addr << 32) | b.src_flow, b.nonce);
+      auto it = syn_index_.find(key);
+      if (it != syn_index_.end()) {
+        auto fit = flows_.find(it->second);
+        if (fit != flows_.end()) f = fit->second;
+      } else {
+        f = std::make_shared<Flow>();
+        f->id = next_flow_++;
+        f->peer_flow = b.src_flow;
+        f->nonce = b.nonce;
+        f->listen_id = b.listen_id;
+        f->peer_ip = from.sin_addr;
+        f->npaths = std::max(1, std::min<int>(cfg_.paths, b.npaths));
+        for (int i = 0; i < f->npaths; ++i) {
+          f->peer_addr[i] = sockaddr_in{};
+          f->peer_addr[i].sin_family = AF_INET;
+          f->peer_addr[i].sin_addr = from.sin_addr;
+          f->peer_addr[i].sin_port = b.ports[i];
+        }
+        f->rto_ns = (uint64_t)cfg_.rto_min_us * 1000ull;
+        cc::SwiftConfig sc;
+        sc.base_target_us = cfg_.swift_target_us;
+        sc.max_cwnd = cfg_.max_inflight;
+        f->swift = cc::Swift(sc);
+        cc::TimelyConfig tc;
+        tc.min_rtt_us = 50, tc.t_low_us = 200, tc.t_high_us = 2000, tc.link_gbps = cfg_.link_gbps;
+        tc.add_step_gbps = cfg_.link_gbps / 40, tc.min_rate_gbps = cfg_.link_gbps / 1000;
+        f->timely = cc::Timely(tc);
+        f->state.store(FL_ESTABLISHED, std::memory_order_release);
+        flows_[f->id] = f;
+        syn_index_[key] = f->id;
+        lit->second.ready.push_back(f->id);
+        active_.push_back(f);
+      }
+    }
+  }
+  if (!f) {
+    send_rst(sock_idx, from, b.src_flow);
+    return;
+  }
+  send_syn(*f, true, 0, &from);
+}
+
+void Engine::on_synack(const sockaddr_in& from, const PktHdr& h, const SynBody& b) {
+  std::shared_ptr<Flow> f = find(h.dst_flow);
+  if (!f || f->state.load() != FL_SYN_SENT || b.nonce != f->nonce || from.sin_addr.s_addr != f->peer_ip.s_addr) return;
+  f->peer_flow = b.src_flow;
+  f->npaths = std::max(1, std::min<int>(cfg_.paths, b.npaths));
+  for (int i = 0; i < f->npaths; ++i) {
+    f->peer_addr[i] = sockaddr_in{};
+    f->peer_addr[i].sin_family = AF_INET;
+    f->peer_addr[i].sin_addr = f->peer_ip;
+    f->peer_addr[i].sin_port = b.ports[i];
+  }
+  f->rto_ns = (uint64_t)cfg_.rto_min_us * 1000ull;
+  cc::SwiftConfig sc;
+  sc.base_target_us = cfg_.swift_target_us;
+  sc.max_cwnd = cfg_.max_inflight;
+  f->swift = cc::Swift(sc);
+  cc::TimelyConfig tc;
+  tc.min_rtt_us = 50, tc.t_low_us = 200, tc.t_high_us = 2000, tc.link_gbps = cfg_.link_gbps;
+  tc.add_step_gbps = cfg_.link_gbps / 40, tc.min_rate_gbps = cfg_.link_gbps / 1000;
+  f->timely = cc::Timely(tc);
+  f->state.store(FL_ESTABLISHED, std::memory_order_release);
+}
+
+void Engine::send_rst(int sock_idx, const sockaddr_in& to, uint32_t dst_flow) {
+  if (dst_flow == 0) return;  // we do not know the peer's flow id: stay silent, its RTO will give up
+  PktHdr h{};
+  h.magic = kMagic;
+  h.type = PKT_RST;
+  h.dst_flow = dst_flow;
+  raw_send(sock_idx, to, &h, sizeof(h), nullptr, 0);
+}
+
+// ------------------------------------------------------------------------------------- raw output
+void Engine::raw_send(int path, const sockaddr_in& to, const void* hdr, size_t hlen, const void* body, size_t blen) {
+  const double dp = drop_prob_.load(std::memory_order_relaxed);
+  if (dp > 0.0 && std::uniform_real_distribution<double>(0.0, 1.0)(rng_) < dp) {
+    ++est_.dropped_tx;
+    return;
+  }
+  iovec iov[2];
+  iov[0].iov_base = const_cast<void*>(hdr);
+  iov[0].iov_len = hlen;
+  iov[1].iov_base = const_cast<void*>(body);
+  iov[1].iov_len = blen;
+  msghdr m{};
+  m.msg_name = const_cast<sockaddr_in*>(&to);
+  m.msg_namelen = sizeof(to);
+  m.msg_iov = iov;
+  m.msg_iovlen = blen ? 2 : 1;
+  const ssize_t r = sendmsg(socks_[path], &m, MSG_DONTWAIT);
+  if (r < 0) {
+    ++est_.dropped_tx;  // full socket buffer == a drop; the reliability layer repairs it
+    return;
+  }
+  ++est_.tx_pkts;
+  est_.tx_bytes += (uint64_t)r;
+}
+
+// ------------------------------------------------------------------------------- message posting
+void Engine::post_send(Flow& f, Request* r, const void* ptr, size_t len) {
+  const int st = f.state.load();
+  if (st != FL_ESTABLISHED && st != FL_SYN_SENT) {
+    complete(r, 0, 1);
+    return;
+  }
+  TxMsg* m = new TxMsg();
+  m->req = r;
+  m->ptr = static_cast<const uint8_t*>(ptr);
+  m->len = len;
+  m->id = f.next_tx_msg++;
+  f.txq.push_back(m);
+}
+
+void Engine::post_recv(Flow& f, Request* r, void* ptr, size_t cap) {
+  const int st = f.state.load();
+  if (st != FL_ESTABLISHED && st != FL_SYN_SENT) {
+    complete(r, 0, 1);
+    return;
+  }
+  const uint32_t id = f.rx_posted++;
+  RxMsg m;
+  m.req = r;
+  m.ptr = static_cast<uint8_t*>(ptr);
+  m.cap = cap;
+  auto it = f.unexpected.find(id);
+  if (it != f.unexpected.end()) {
+    Unexpected& u = it->second;
+    m.total = u.total;
+    m.have_total = true;
+    m.got = u.got;
+    if (u.total > cap) m.overflow = true;
+    else if (u.total) memcpy(m.ptr, u.buf.data(), u.total);
+    f.unexpected.erase(it);
+  }
+  if (m.have_total && m.got >= m.total) {
+    complete(r, m.total, m.overflow ? 2 : 0);
+    m.req = nullptr;
+  }
+  f.rxq.push_back(m);
+  while (!f.rxq.empty() && f.rxq.front().req == nullptr) {
+    f.rxq.pop_front();
+    ++f.rx_base;
+  }
+  if (f.peer_fin.load(std::memory_order_relaxed) && !f.rxq.empty()) {
+    for (auto& q : f.rxq)
+      if (q.req) complete(q.req, 0, 3), q.req = nullptr;
+    while (!f.rxq.empty()) f.rxq.pop_front(), ++f.rx_base;
+  }
+  f.rtr_pending = true;
+}
+
+// ------------------------------------------------------------------------------------ receive side
+void Engine::on_data(Flow& f, const PktHdr& h, const uint8_t* payload) {
+  ++f.st.rx_pkts;
+  f.need_ack = true;
+  f.echo_ts = h.ts_ns;
+  f.echo_path = h.path;
+  if (cfg_.cc == CC_EQDS && h.aux > f.demand_seen) {
+    pacer_.add_demand(f.id, h.aux - f.demand_seen);
+    f.demand_seen = h.aux;
+  }
+  const int32_t d = seq_diff(h.seq, f.rcv_nxt);
+  if (d < 0) {
+    ++f.st.rx_dup;
+    return;
+  }
+  if (d >= kSackBits) return;  // beyond the window: the sender never does this unless state is stale
+  uint64_t& w = f.rx_bits[d / 64];
+  const uint64_t bit = 1ull << (d % 64);
+  if (w & bit) {
+    ++f.st.rx_dup;
+    return;
+  }
+  w |= bit;
+  deliver_frame(f, h, payload);
+  const int t = trailing_ones(f.rx_bits);
+  if (t > 0) {
+    shr_bits(f.rx_bits, t);
+    f.rcv_nxt += (uint32_t)t;
+  }
+  if (f.have_fin && !f.peer_fin.load(std::memory_order_relaxed) && seq_diff(f.rcv_nxt, f.fin_seq) > 0) apply_peer_fin(f);
+}
+
+void Engine::apply_peer_fin(Flow& f) {
+  f.peer_fin.store(true);
+  for (auto& q : f.rxq)
+    if (q.req) complete(q.req, 0, 3), q.req = nullptr;
+  while (!f.rxq.empty()) f.rxq.pop_front(), ++f.rx_base;
+}
+
+void Engine::deliver_frame(Flow& f, const PktHdr& h, const uint8_t* payload) {
+  if (h.kind == FR_RTR) {
+    if (seq_diff(h.msg_id, f.peer_posted) > 0) f.peer_posted = h.msg_id;
+    return;
+  }
+  if (h.kind == FR_FIN) {
+    // frames are delivered out of order: the FIN only takes effect once everything before it has arrived
+    f.have_fin = true;
+    f.fin_seq = h.seq;
+    return;
+  }
+  if (h.kind != FR_MSG) return;
+  f.st.rx_bytes += h.len;
+  if (cfg_.cc == CC_EQDS) pacer_.on_data(f.id, h.len);
+  const int32_t idx = seq_diff(h.msg_id, f.rx_base);
+  if (idx < 0) return;
+  if ((size_t)idx < f.rxq.size()) {
+    RxMsg& m = f.rxq[(size_t)idx];
+    if (!m.req) return;
+    if (!m.have_total) {
+      m.total = h.msg_len;
+      m.have_total = true;
+      if (m.total > m.cap) m.overflow = true;
+    }
+    if (!m.overflow && h.len && h.offset + h.len <= m.total) memcpy(m.ptr + h.offset, payload, h.len);
+    m.got += h.len;
+    if (m.got >= m.total) {
+      complete(m.req, m.total, m.overflow ? 2 : 0);
+      m.req = nullptr;
+      while (!f.rxq.empty() && f.rxq.front().req == nullptr) {
+        f.rxq.pop_front();
+        ++f.rx_base;
+      }
+    }
+    return;
+  }
+  // receive not posted yet: only eager messages get here
+  if (h.msg_len > (64ull << 20)) {
+    fail_flow(f, "unexpected message larger than 64 MiB (protocol violation)");
+    return;
+  }
+  auto it = f.unexpected.find(h.msg_id);
+  if (it == f.unexpected.end()) {
+    Unexpected u;
+    u.total = h.msg_len;
+    u.buf.resize(h.msg_len);
+    it = f.unexpected.emplace(h.msg_id, std::move(u)).first;
+    ++f.st.unexpected_msgs;
+  }
+  Unexpected& u = it->second;
+  if (h.len && h.offset + h.len <= u.total) memcpy(u.buf.data() + h.offset, payload, h.len);
+  u.got += h.len;
+}
+
+void Engine::send_ack(Flow& f) {
+  PktHdr h{};
+  h.magic = kMagic;
+  h.type = PKT_ACK;
+  const int path = f.npaths > 0 ? f.echo_path % f.npaths : 0;
+  h.path = (uint16_t)path;
+  h.dst_flow = f.peer_flow;
+  h.seq = f.rcv_nxt;
+  h.ts_ns = f.echo_ts;
+  h.msg_id = f.rx_posted;
+  h.len = sizeof(AckBody);
+  h.aux = f.grant_cum;
+  AckBody b{};
+  for (int i = 0; i < kSackWords; ++i) b.sack[i] = f.rx_bits[i];
+  b.echo_path = f.echo_path;
+  raw_send(path, f.peer_addr[path], &h, sizeof(h), &b, sizeof(b));
+  ++f.st.acks_tx;
+  f.need_ack = false;
+  f.credit_dirty = false;
+  f.echo_ts = 0;
+}
+
+void Engine::eqds_tick(uint64_t now) {
+  auto grants = pacer_.tick((double)now * 1e-3);
+  for (auto& g : grants)
+    for (auto& sp : active_)
+      if (sp->id == g.first) {
+        sp->grant_cum += g.second;
+        sp->credit_dirty = true;
+        break;
+      }
+}
+
+// --------------------------------------------------------------------------------------- send side
+void Engine::mark_acked(Flow& f, TxPkt& p, uint64_t now) {
+  (void)now;
+  p.acked = true;
+  if (!p.lost) {
+    if (f.inflight) --f.inflight;
+    if (f.path[p.path].inflight) --f.path[p.path].inflight;
+  }
+  p.lost = false;
+  if (p.ts_send > f.newest_acked_send_ts) f.newest_acked_send_ts = p.ts_send;
+  TxMsg* m = p.msg;
+  p.msg = nullptr;
+  if (m) {
+    m->acked += p.len;
+    ++m->pkts_acked;
+    if (m->all_queued && m->pkts_acked == m->pkts_out) {
+      complete(m->req, m->len, 0);
+      m->req = nullptr;
+      while (!f.txq.empty() && f.txq.front()->req == nullptr && f.txq.front()->all_queued &&
+             f.txq.front()->pkts_acked == f.txq.front()->pkts_out) {
+        delete f.txq.front();
+        f.txq.pop_front();
+        if (f.tx_cursor) --f.tx_cursor;
+      }
+    }
+  }
+}
+
+void Engine::on_ack(Flow& f, const PktHdr& h, const AckBody& b) {
+  ++f.st.acks_rx;
+  const uint64_t now = now_ns();
+  if (seq_diff(h.msg_id, f.peer_posted) > 0) f.peer_posted = h.msg_id;
+  if (h.aux > f.credit_cum) f.credit_cum = h.aux;
+  const uint32_t cum = h.seq;
+  const int32_t adv = seq_diff(cum, f.snd_una);
+  if (adv < 0 || seq_diff(cum, f.snd_nxt) > 0) return;  // stale or nonsensical
+  int newly = 0;
+  for (int32_t i = 0; i < adv; ++i) {
+    TxPkt& p = f.ring[(f.snd_una + (uint32_t)i) % kTxRing];
+    if (p.in_use) {
+      if (!p.acked) mark_acked(f, p, now), ++newly;
+      p.in_use = false;
+    }
+  }
+  f.snd_una = cum;
+  for (int i = 1; i < kSackBits; ++i) {
+    if (!(b.sack[i / 64] >> (i % 64) & 1)) continue;
+    const uint32_t s = cum + (uint32_t)i;
+    if (seq_diff(s, f.snd_nxt) >= 0) break;
+    TxPkt& p = f.ring[s % kTxRing];
+    if (p.in_use && p.seq == s && !p.acked) mark_acked(f, p, now), ++newly;
+  }
+  if (h.ts_ns != 0 && now > h.ts_ns) {
+    const double rtt = (double)(now - h.ts_ns) * 1e-3;
+    if (f.srtt_us == 0) {
+      f.srtt_us = rtt;
+      f.rttvar_us = rtt / 2;
+      f.min_rtt_us = rtt;
+    } else {
+      f.rttvar_us = 0.75 * f.rttvar_us + 0.25 * std::abs(rtt - f.srtt_us);
+      f.srtt_us = 0.875 * f.srtt_us + 0.125 * rtt;
+      f.min_rtt_us = std::min(f.min_rtt_us, rtt);
+    }
+    PathState& ps = f.path[b.echo_path % kMaxPaths];
+    ps.srtt_us = ps.srtt_us == 0 ? rtt : 0.875 * ps.srtt_us + 0.125 * rtt;
+    if (newly) {
+      if (cfg_.cc == CC_SWIFT) f.swift.on_ack(rtt, newly, (double)now * 1e-3, f.srtt_us);
+      else if (cfg_.cc == CC_TIMELY) f.timely.on_rtt(rtt);
+    }
+  }
+  if (newly) {
+    f.rto_count = 0;
+    const double rto_us = std::max<double>(cfg_.rto_min_us, f.srtt_us + 4 * f.rttvar_us);
+    f.rto_ns = (uint64_t)(std::min<double>(rto_us, cfg_.rto_max_us) * 1e3);
+    f.last_progress_ns = now;
+  }
+  detect_loss(f, now);
+}
+
+void Engine::detect_loss(Flow& f, uint64_t now) {
+  (void)now;
+  if (f.newest_acked_send_ts == 0) return;
+  // RACK: a packet is lost once a packet sent sufficiently LATER has been acknowledged.  Time based, so
+  // reordering between paths (which is the normal case here) does not trigger spurious retransmissions.
+  const uint64_t reo_ns = (uint64_t)(std::max(f.srtt_us / 4, 50.0) * 1e3);
+  const uint32_t n = f.snd_nxt - f.snd_una;
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t s = f.snd_una + i;
+    TxPkt& p = f.ring[s % kTxRing];
+    if (!p.in_use || p.acked || p.lost || p.seq != s) continue;
+    if (p.ts_send + reo_ns < f.newest_acked_send_ts) {
+      p.lost = true;
+      if (f.inflight) --f.inflight;
+      if (f.path[p.path].inflight) --f.path[p.path].inflight;
+      f.rexmit_q.push_back(s);
+      ++f.st.fast_rexmit;
+      ++est_.fast_rexmit;
+    }
+  }
+}
+
+int Engine::pick_path(Flow& f, int avoid) {
+  const int n = f.npaths;
+  if (n <= 1) return 0;
+  // power-of-two choices on (packets in flight, smoothed RTT) -- reference: select_qpidx_pot
+  int a = (int)(rng_() % (uint64_t)n), b = (int)(rng_() % (uint64_t)n);
+  if (a == avoid) a = (a + 1) % n;
+  if (b == avoid) b = (b + 1) % n;
+  const PathState &pa = f.path[a], &pb = f.path[b];
+  if (pa.inflight != pb.inflight) return pa.inflight < pb.inflight ? a : b;
+  return pa.srtt_us <= pb.srtt_us ? a : b;
+}
+
+void Engine::emit_data(Flow& f, TxPkt& p, uint64_t now, bool is_rexmit) {
+  const int path = pick_path(f, is_rexmit ? (int)p.path : -1);
+  p.path = (uint16_t)path;
+  p.ts_send = now;
+  p.lost = false;
+  if (is_rexmit) ++p.rexmits;
+  PktHdr h{};
+  h.magic = kMagic;
+  h.type = PKT_DATA;
+  h.kind = p.kind;
+  h.path = p.path;
+  h.dst_flow = f.peer_flow;
+  h.seq = p.seq;
+  h.ts_ns = now;
+  h.msg_id = p.msg_id;
+  h.len = p.len;
+  h.offset = p.offset;
+  h.msg_len = p.msg_len;
+  if (cfg_.cc == CC_EQDS) {  // cumulative demand: everything sent so far + everything still queued
+    uint64_t backlog = 0;
+    for (size_t i = f.tx_cursor; i < f.txq.size(); ++i) backlog += f.txq[i]->len - f.txq[i]->next_off;
+    h.aux = f.sent_payload_cum + backlog;
+  } else {
+    h.aux = 0;
+  }
+  ++f.inflight;
+  ++f.path[path].inflight;
+  ++f.path[path].tx;
+  ++f.st.tx_pkts;
+  ++f.st.path_tx[path];
+  f.st.tx_bytes += p.len;
+  raw_send(path, f.peer_addr[path], &h, sizeof(h), p.payload, p.len);
+  if (cfg_.cc == CC_TIMELY) {
+    const double gap_ns = (double)(p.len + sizeof(PktHdr) + 28) * 8.0 / f.timely.rate_gbps();
+    const uint64_t floor = now > 100000 ? now - 100000 : 0;  // allow a 100 us burst
+    f.pace_next_ns = std::max(f.pace_next_ns, floor) + (uint64_t)gap_ns;
+  }
+}
+
+bool Engine::can_send_new(Flow& f, uint64_t now) {
+  if ((uint32_t)(f.snd_nxt - f.snd_una) >= (uint32_t)(kSackBits - 1)) return false;
+  uint32_t wnd = (uint32_t)cfg_.max_inflight;
+  if (cfg_.cc == CC_SWIFT) wnd = std::min<uint32_t>(wnd, (uint32_t)std::max(1.0, f.swift.cwnd()));
+  if (f.inflight >= wnd) return false;
+  if (cfg_.cc == CC_TIMELY && now < f.pace_next_ns) return false;
+  return true;
+}
+
+bool Engine::tx_pump(Flow& f, uint64_t now) {
+  bool sent = false;
+  // 1. retransmissions first (they do not wait for window space: the lost packet already left the window)
+  while (!f.rexmit_q.empty()) {
+    const uint32_t s = f.rexmit_q.front();
+    TxPkt& p = f.ring[s % kTxRing];
+    if (!(p.in_use && p.seq == s && !p.acked && p.lost)) {
+      f.rexmit_q.pop_front();
+      continue;
+    }
+    if (cfg_.cc == CC_TIMELY && now < f.pace_next_ns) break;
+    f.rexmit_q.pop_front();
+    emit_data(f, p, now, true);
+    sent = true;
+  }
+  auto new_pkt = [&](uint8_t kind) -> TxPkt& {
+    const uint32_t s = f.snd_nxt++;
+    TxPkt& p = f.ring[s % kTxRing];
+    p = TxPkt();
+    p.seq = s;
+    p.kind = kind;
+    p.in_use = true;
+    return p;
+  };
+  // 2. control frames.  A sender that is parked behind the receiver's RTR with nothing in flight probes the
+  // peer once a second (an RTR frame of its own is a harmless reliable packet): a dead peer then surfaces
+  // through the retransmission limit instead of an unbounded wait.
+  if (f.tx_cursor < f.txq.size() && f.snd_una == f.snd_nxt && now - f.last_progress_ns > 1000000000ull) {
+    f.rtr_pending = true;
+    f.last_progress_ns = now;
+  }
+  if (f.rtr_pending && can_send_new(f, now)) {
+    TxPkt& p = new_pkt(FR_RTR);
+    p.msg_id = f.rx_posted;
+    f.rtr_pending = false;
+    emit_data(f, p, now, false);
+    sent = true;
+  }
+  // 3. message data, strictly in message order
+  while (f.tx_cursor < f.txq.size() && can_send_new(f, now)) {
+    TxMsg* m = f.txq[f.tx_cursor];
+    const int32_t ahead = seq_diff(m->id, f.peer_posted);  // < 0: the receive is already posted
+    const bool eager = m->len <= cfg_.eager_max && ahead < cfg_.eager_ahead;
+    if (ahead >= 0 && !eager) break;
+    const size_t chunk = std::min<size_t>((size_t)cfg_.payload, m->len - m->next_off);
+    if (cfg_.cc == CC_EQDS) {
+      const uint64_t spec = (uint64_t)cfg_.payload * 16;  // speculative first window, then credits
+      if (f.sent_payload_cum + chunk > f.credit_cum + spec) {
+        // starved of credit: keep the receiver's pacer informed with a zero-length demand update
+        break;
+      }
+    }
+    TxPkt& p = new_pkt(FR_MSG);
+    p.msg_id = m->id;
+    p.offset = m->next_off;
+    p.len = (uint32_t)chunk;
+    p.msg_len = m->len;
+    p.payload = m->ptr + m->next_off;
+    p.msg = m;
+    m->next_off += chunk;
+    ++m->pkts_out;
+    if (m->next_off >= m->len) {
+      m->all_queued = true;
+      ++f.tx_cursor;
+    }
+    f.sent_payload_cum += chunk;
+    emit_data(f, p, now, false);
+    sent = true;
+  }
+  if (f.fin_pending && !f.fin_sent && f.tx_cursor >= f.txq.size() && can_send_new(f, now)) {
+    TxPkt& p = new_pkt(FR_FIN);
+    f.fin_sent = true;
+    emit_data(f, p, now, false);
+    sent = true;
+  }
+  return sent;
+}
+
+// ------------------------------------------------------------------------------------------ timers
+void Engine::timers(uint64_t now) {
+  bool erased = false;
+  for (auto& sp : active_) {
+    Flow& f = *sp;
+    const int st = f.state.load(std::memory_order_relaxed);
+    if (st == FL_SYN_SENT) {
+      if (now > f.syn_deadline_ns) {
+        fail_flow(f, "connect timed out");
+      } else if (now >= f.syn_next_ns) {
+        send_syn(f, false, 0, nullptr);
+        f.syn_next_ns = now + (uint64_t)cfg_.syn_retry_ms * 1000000ull;
+      }
+      continue;
+    }
+    if (st == FL_CLOSED) {
+      if (now - f.last_progress_ns > kLingerNs) erased = true;
+      continue;
+    }
+    if (st != FL_ESTABLISHED && st != FL_CLOSING) continue;
+    if (f.snd_una != f.snd_nxt) {
+      TxPkt& p = f.ring[f.snd_una % kTxRing];
+      const uint64_t rto = f.rto_ns << std::min(f.rto_count, 6);
+      const uint64_t eff = std::min<uint64_t>(rto, (uint64_t)cfg_.rto_max_us * 1000ull);
+      if (p.in_use && !p.acked && now > p.ts_send + eff) {
+        ++f.rto_count;
+        ++f.st.rto_rexmit;
+        ++est_.rto_rexmit;
+        if (f.rto_count >= cfg_.rto_abort) {
+          fail_flow(f, "peer unreachable (retransmission limit)");
+          continue;
+        }
+        if (!p.lost) {
+          p.lost = true;
+          if (f.inflight) --f.inflight;
+          if (f.path[p.path].inflight) --f.path[p.path].inflight;
+        }
+        p.ts_send = now;  // re-arm; the retransmission below stamps it again
+        f.rexmit_q.push_front(f.snd_una);
+        if (f.rto_count >= 3 && cfg_.cc == CC_SWIFT) f.swift.on_retransmit_timeout();
+      }
+    }
+    if (st == FL_CLOSING) {
+      const bool drained = f.fin_sent && f.snd_una == f.snd_nxt && f.txq.empty();
+      if (drained || now - f.last_progress_ns > kLingerNs) {
+        for (auto& q : f.rxq)
+          if (q.req) complete(q.req, 0, 3), q.req = nullptr;
+        f.rxq.clear();
+        f.state.store(FL_CLOSED);
+        f.last_progress_ns = now;
+      }
+    }
+  }
+  if (erased) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto it = flows_.begin(); it != flows_.end();) {
+      Flow& f = *it->second;
+      if (f.state.load() == FL_CLOSED && now - f.last_progress_ns > kLingerNs) {
+        for (auto s = syn_index_.begin(); s != syn_index_.end();)
+          s = (s->second == f.id) ? syn_index_.erase(s) : std::next(s);
+        for (TxMsg* m : f.txq) delete m;
+        f.txq.clear();
+        it = flows_.erase(it);
+      } else {
+        ++it;
+      }
+    }
+    active_dirty_ = true;
+  }
+}
+
+void Engine::fail_flow(Flow& f, const char* why) {
+  if (why) UB_WARN("net: flow %u failed: %s", f.id, why);
+  const int prev = f.state.exchange(FL_ERROR);
+  if (prev == FL_ERROR) return;
+  for (TxMsg* m : f.txq) {
+    if (m->req) complete(m->req, 0, 1);
+    delete m;
+  }
+  f.txq.clear();
+  f.tx_cursor = 0;
+  for (auto& q : f.rxq)
+    if (q.req) complete(q.req, 0, 1);
+  f.rxq.clear();
+  for (auto& p : f.ring) p = TxPkt();
+  f.rexmit_q.clear();
+  f.snd_una = f.snd_nxt;
+  if (why && f.peer_flow && f.npaths > 0 && !stop_.load()) send_rst(0, f.peer_addr[0], f.peer_flow);
+}
+
+}  // namespace net
+}  // namespace ub

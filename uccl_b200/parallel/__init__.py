@@ -1,1 +1,9 @@
 from .comm import ALGOS, Communicator, dtype_code, op_code  # noqa: F401
+
+
+def __getattr__(name):  # lazy: the network stack is only needed for multi-node jobs
+    if name == "MultiNodeCommunicator":
+        from .multinode import MultiNodeCommunicator
+
+        return MultiNodeCommunicator
+    raise AttributeError(name)

@@ -1,0 +1,222 @@
+"""Collectives across several B200 boxes: NVLink inside a box, the datagram transport between boxes.
+
+The reference scales out by plugging its transport under NCCL's rings.  With a full-bandwidth NVSwitch
+inside every box the better shape is hierarchical and *rail aligned*: local rank ``l`` of every node owns
+NIC ``l``; a collective is (1) an NVLink kernel inside the box that leaves each local rank with 1/L of the
+node's data, (2) L independent inter-node collectives, one per rail, running concurrently on L NICs through
+:class:`uccl_b200.net.NetCommunicator`, (3) an NVLink kernel that re-assembles.  Every byte crosses the
+network exactly once per remote node and all NICs of a box are busy.
+
+``local`` is a :class:`uccl_b200.Communicator` (GPU symmetric heap, or the host backend on a CPU-only
+machine -- that is how ``tests/test_net_transport.py`` runs 2 "nodes" x 2 ranks on one box).  GPU data is
+staged through pinned host buffers (the transport is socket based; a GPUDirect verbs backend would slot in
+under the same ``NetCommunicator`` API).
+
+Reference: NCCL's net transport + collective/rdma (inter-node rings); thirdparty NCCL proxy staging.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from ..net import NetCommunicator
+from .comm import Communicator
+
+
+class MultiNodeCommunicator:
+    def __init__(self, local: Communicator, net: NetCommunicator):
+        self.local, self.net = local, net
+        self.local_rank, self.local_size = local.rank, local.world_size
+        self.node_rank, self.num_nodes = net.rank, net.world_size
+        self.rank = self.node_rank * self.local_size + self.local_rank
+        self.world_size = self.num_nodes * self.local_size
+        self.device = local.device
+        self._pinned: Dict[Tuple[int, torch.dtype, int], torch.Tensor] = {}
+
+    @classmethod
+    def from_torch_dist(cls, local_size: int, device: Optional[int] = None, engine=None, **comm_kw) -> "MultiNodeCommunicator":
+        """Build from an initialised ``torch.distributed`` world (any backend; only used for bootstrap):
+        ranks ``[k*local_size, (k+1)*local_size)`` form node ``k``."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(), dist.get_rank()
+        assert world % local_size == 0
+        nodes = world // local_size
+        node_groups = [dist.new_group(list(range(k * local_size, (k + 1) * local_size))) for k in range(nodes)]
+        rail_groups = [dist.new_group(list(range(l, world, local_size))) for l in range(local_size)]
+        local = Communicator.from_torch_dist(group=node_groups[rank // local_size], device=device, **comm_kw)
+        net = NetCommunicator.from_process_group(rail_groups[rank % local_size], engine=engine)
+        return cls(local, net)
+
+    # ------------------------------------------------------------------ staging
+    def _host(self, like: torch.Tensor, numel: int, slot: int = 0) -> torch.Tensor:
+        key = (slot, like.dtype, numel)
+        buf = self._pinned.get(key)
+        if buf is None:
+            pin = like.is_cuda
+            buf = torch.empty(numel, dtype=like.dtype, pin_memory=pin)
+            if len(self._pinned) > 16:
+                self._pinned.clear()
+            self._pinned[key] = buf
+        return buf
+
+    def _down(self, dev: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """device -> host staging (identity for host tensors)."""
+        if not dev.is_cuda:
+            return dev
+        h = self._host(dev, dev.numel(), slot)
+        h.copy_(dev.view(-1), non_blocking=True)
+        torch.cuda.current_stream(dev.device).synchronize()
+        return h
+
+    def _up(self, dev: torch.Tensor, host: torch.Tensor) -> None:
+        if dev.is_cuda:
+            dev.view(-1).copy_(host, non_blocking=True)
+        elif dev.data_ptr() != host.data_ptr():
+            dev.view(-1).copy_(host)
+
+    def _sync_local(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # -------------------------------------------------------------- collectives
+    def barrier(self) -> None:
+        self.local.barrier()
+        self._sync_local()
+        self.net.barrier()
+        self.local.barrier()
+        self._sync_local()
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        """In place.  reduce-scatter over NVLink -> per-rail all-reduce over the network -> all-gather over NVLink."""
+        L, N = self.local_size, self.num_nodes
+        if N == 1:
+            self.local.all_reduce(t, op)
+            return t
+        inner = "sum" if op == "avg" else op
+        flat = t.view(-1)
+        n = flat.numel()
+        per = (n + L - 1) // L
+        if per * L != n:  # pad to a multiple of the node size
+            work = torch.zeros(per * L, dtype=t.dtype, device=t.device)
+            work[:n].copy_(flat)
+        else:
+            work = flat
+        if L > 1:
+            shard = torch.empty(per, dtype=t.dtype, device=t.device)
+            self.local.reduce_scatter(shard, work, inner)
+        else:
+            shard = work
+        h = self._down(shard)
+        self.net.all_reduce(h, inner)
+        if op == "avg":
+            h.div_(self.world_size) if t.is_floating_point() else h.copy_(torch.div(h, self.world_size, rounding_mode="trunc"))
+        self._up(shard, h)
+        if L > 1:
+            self.local.all_gather(work, shard)
+        if work.data_ptr() != flat.data_ptr():
+            flat.copy_(work[:n])
+        return t
+
+    def all_gather(self, out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """out[g] = t of global rank g (node major).  Rail all-gather first (each NIC carries only its own
+        rank's rows), then one NVLink all-gather and a local transpose."""
+        L, N = self.local_size, self.num_nodes
+        c = t.numel()
+        rail = torch.empty(N * c, dtype=t.dtype, device=t.device)
+        if N > 1:
+            h_in = self._down(t.contiguous().view(-1), slot=0)
+            h_out = self._host(t, N * c, slot=1)
+            self.net.all_gather(h_out, h_in)
+            self._up(rail, h_out)
+        else:
+            rail.copy_(t.view(-1))
+        if L > 1:
+            g = torch.empty(L * N * c, dtype=t.dtype, device=t.device)
+            self.local.all_gather(g, rail)
+            out.view(N, L, c).copy_(g.view(L, N, c).transpose(0, 1))
+        else:
+            out.view(-1).copy_(rail)
+        return out
+
+    def reduce_scatter(self, out: torch.Tensor, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
+        """out = reduction over all ranks of segment ``rank`` of t ([world_size * out.numel()])."""
+        L, N = self.local_size, self.num_nodes
+        c = out.numel()
+        inner = "sum" if op == "avg" else op
+        if L > 1:
+            # bring the N segments that belong to local rank l of every node together, then reduce over NVLink
+            src = t.view(N, L, c).transpose(0, 1).contiguous().view(-1)
+            part = torch.empty(N * c, dtype=t.dtype, device=t.device)
+            self.local.reduce_scatter(part, src, inner)
+        else:
+            part = t.contiguous().view(-1)
+        if N > 1:
+            h_in = self._down(part, slot=0)
+            h_out = self._host(t, c, slot=1)
+            self.net.reduce_scatter(h_out, h_in, inner)
+            res = h_out
+        else:
+            res = part
+        if op == "avg":
+            res = res / self.world_size if t.is_floating_point() else torch.div(res, self.world_size, rounding_mode="trunc")
+        self._up(out, res)
+        return out
+
+    def broadcast(self, t: torch.Tensor, root: int = 0) -> torch.Tensor:
+        """Root's node fans out over NVLink; every rail then carries 1/L of the tensor to the other nodes,
+        which re-assemble with an NVLink all-gather."""
+        L, N = self.local_size, self.num_nodes
+        root_node, root_local = divmod(root, L)
+        if self.node_rank == root_node and L > 1:
+            self.local.broadcast(t, root_local)
+        if N == 1:
+            return t
+        flat = t.view(-1)
+        n = flat.numel()
+        per = (n + L - 1) // L
+        lo = min(self.local_rank * per, n)
+        hi = min(lo + per, n)
+        piece = torch.zeros(per, dtype=t.dtype, device=t.device)
+        if self.node_rank == root_node:
+            piece[: hi - lo].copy_(flat[lo:hi])
+        h = self._down(piece)
+        self.net.broadcast(h, root_node)
+        if self.node_rank != root_node:
+            self._up(piece, h)
+            if L > 1:
+                full = torch.empty(per * L, dtype=t.dtype, device=t.device)
+                self.local.all_gather(full, piece)
+                flat.copy_(full[:n])
+            else:
+                flat.copy_(piece[:n])
+        elif L > 1:
+            # keep the node's ranks in step with the other nodes' all-gather (same number of local collectives)
+            full = torch.empty(per * L, dtype=t.dtype, device=t.device)
+            self.local.all_gather(full, piece)
+        return t
+
+    def all_to_all(self, out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """Equal-split all-to-all in two hops (the shape of DeepEP's internode dispatch): NVLink moves every
+        chunk to the local rank that owns the destination's rail, then one all-to-all per rail."""
+        L, N = self.local_size, self.num_nodes
+        c = t.numel() // self.world_size
+        if L > 1:
+            hop1_in = t.view(N, L, c).transpose(0, 1).contiguous().view(-1)  # [dst local][dst node][c]
+            hop1 = torch.empty_like(hop1_in)
+            self.local.all_to_all(hop1, hop1_in)  # [src local][dst node][c]
+            rail_in = hop1.view(L, N, c).transpose(0, 1).contiguous().view(-1)  # [dst node][src local][c]
+        else:
+            rail_in = t.contiguous().view(-1)
+        if N > 1:
+            h_in = self._down(rail_in, slot=0)
+            h_out = self._host(t, rail_in.numel(), slot=1)
+            self.net.all_to_all(h_out, h_in)  # [src node][src local][c] == global source order
+            self._up(out, h_out)
+        else:
+            out.view(-1).copy_(rail_in)
+        return out
+
+    def close(self) -> None:
+        self.net.close()
