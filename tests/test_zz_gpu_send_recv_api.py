@@ -148,3 +148,50 @@ def test_ep_buffer_optional_arguments(n):
         assert o["wx"].size(0) == n * T and o["wpe"] == []
         assert torch.equal(o["wx"][:o["num_recv"]], exp_rows)
         assert bool((o["wi"][o["num_recv"]:] == -1).all())
+
+
+_NCCL_PLUGIN_SCRIPT = r"""
+import os, torch, torch.distributed as dist
+dist.init_process_group("nccl")
+rank = dist.get_rank()
+torch.cuda.set_device(rank)
+x = torch.full((1 << 20,), float(rank + 1), device="cuda")
+dist.all_reduce(x)
+torch.cuda.synchronize()
+w = dist.get_world_size()
+assert bool((x == w * (w + 1) / 2).all())
+y = [torch.empty(1000, device="cuda") for _ in range(w)]
+dist.all_gather(y, torch.full((1000,), float(rank), device="cuda"))
+assert all(bool((y[r] == r).all()) for r in range(w))
+print(f"rank {rank} ok", flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_nccl_runs_over_the_net_plugin(tmp_path):
+    """Stock NCCL (torch's) with NVLink P2P and SHM disabled is forced onto its network transport, and
+    NCCL_NET_PLUGIN points it at libnccl-net-uccl_b200.so: the all-reduce then crosses our multipath
+    datagram transport (host staged).  Needs 2 GPUs; this is the single-box stand-in for two boxes."""
+    import os
+    import subprocess
+    import sys
+
+    from uccl_b200 import _build
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _build.build()
+    plugin = _build.nccl_net_plugin_path()
+    script = tmp_path / "nccl_net.py"
+    script.write_text(_NCCL_PLUGIN_SCRIPT)
+    env = dict(os.environ, NCCL_NET_PLUGIN=str(plugin), NCCL_P2P_DISABLE="1", NCCL_SHM_DISABLE="1", NCCL_DEBUG="INFO",
+               NCCL_DEBUG_SUBSYS="INIT,NET", UCCL_B200_NET_IFNAME="lo", NCCL_IB_DISABLE="1",
+               LD_LIBRARY_PATH=str(plugin.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29741", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    out = r.stdout + r.stderr
+    sys.stdout.write(out[-3000:])
+    assert r.returncode == 0
+    assert out.count(" ok") >= 2
+    assert "uccl_b200" in out  # NCCL logged the plugin it selected

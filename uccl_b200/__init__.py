@@ -6,6 +6,8 @@ with the capabilities of uccl-project/uccl:
 * ``uccl_b200.ep``          DeepEP-compatible expert-parallel dispatch / combine
 * ``uccl_b200.p2p``         NIXL-style initiator/target transfer engine (KV-cache moves)
 * ``uccl_b200.ukernel``     launch-free collectives: persistent worker kernel + CCL planner
+* ``uccl_b200.net``         scale-out: multipath reliable datagram transport between boxes, NCCL net
+  plugin, ``parallel.MultiNodeCommunicator`` (NVLink inside a box, one rail per NIC between boxes)
 * ``uccl_b200.models``      ResNet (DDP example), expert-parallel MoE layer (inference + training)
 
 Everything also runs on a CPU-only machine through reference backends (host communicators,
@@ -29,13 +31,15 @@ def lib_dir() -> str:
 def nccl_shim_path() -> str:
     """Absolute path of the NCCL-API drop-in (``libuccl_b200_nccl.so``).
 
-    The reference exposes ``uccl.nccl_plugin_path()`` for ``NCCL_NET_PLUGIN``; on one NVSwitch
-    node no byte ever reaches a net plugin, so the drop-in here is the NCCL *API* itself."""
+    On one NVSwitch node no byte ever reaches a net plugin, so the intra-node drop-in is the NCCL *API*
+    itself (``LD_PRELOAD``); the net plugin for traffic between nodes is :func:`nccl_plugin_path`."""
     return os.path.join(lib_dir(), "libuccl_b200_nccl.so")
 
 
-def nccl_plugin_path() -> str:  # reference-compatible alias
-    return nccl_shim_path()
+def nccl_plugin_path() -> str:
+    """Absolute path of the NCCL *network* plugin (``libnccl-net-uccl_b200.so``, ``ncclNet_v8``): what
+    ``NCCL_NET_PLUGIN`` should point at for inter-node traffic (reference: ``uccl.nccl_plugin_path()``)."""
+    return os.path.join(lib_dir(), "libnccl-net-uccl_b200.so")
 
 
 def build(force: bool = False):

@@ -145,6 +145,7 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), r
     epoll_ctl(epfd_, EPOLL_CTL_ADD, s, &ev);
   }
   rx_buf_.resize((size_t)kRxBatch * kRxSlot);
+  txb_.resize((size_t)cfg_.paths);
   UB_INFO(SUB_NET, "net engine up: %s paths=%d port0=%u payload=%d cc=%d", cfg_.bind_ip.c_str(), cfg_.paths, ports_[0],
           cfg_.payload, cfg_.cc);
   thr_ = std::thread([this] { run(); });
@@ -433,6 +434,7 @@ void Engine::run() {
         send_ack(f);  // linger: late retransmissions of the peer still get their ACK
       }
     }
+    flush_all();
     ++est_.loops;
     if (now - last_stats > 1000000ull) {
       last_stats = now;
@@ -673,23 +675,52 @@ void Engine::raw_send(int path, const sockaddr_in& to, const void* hdr, size_t h
     ++est_.dropped_tx;
     return;
   }
-  iovec iov[2];
-  iov[0].iov_base = const_cast<void*>(hdr);
-  iov[0].iov_len = hlen;
-  iov[1].iov_base = const_cast<void*>(body);
-  iov[1].iov_len = blen;
-  msghdr m{};
-  m.msg_name = const_cast<sockaddr_in*>(&to);
-  m.msg_namelen = sizeof(to);
-  m.msg_iov = iov;
-  m.msg_iovlen = blen ? 2 : 1;
-  const ssize_t r = sendmsg(socks_[path], &m, MSG_DONTWAIT);
-  if (r < 0) {
-    ++est_.dropped_tx;  // full socket buffer == a drop; the reliability layer repairs it
-    return;
+  (void)hlen;
+  TxBatch& b = txb_[path];
+  if (b.n == kTxBatch) flush_path(path);
+  TxSlot& s = b.slot[b.n++];
+  memcpy(&s.hdr, hdr, sizeof(PktHdr));
+  s.to = to;
+  s.blen = (uint32_t)blen;
+  if (s.hdr.type == PKT_DATA) {
+    s.payload = body;  // user buffer: stays valid until the packet is acknowledged
+  } else {
+    if (blen) memcpy(s.body, body, std::min(blen, sizeof(s.body)));
+    s.payload = s.body;
   }
-  ++est_.tx_pkts;
-  est_.tx_bytes += (uint64_t)r;
+}
+
+void Engine::flush_path(int path) {
+  TxBatch& b = txb_[path];
+  if (b.n == 0) return;
+  mmsghdr msgs[kTxBatch];
+  iovec iov[kTxBatch][2];
+  for (int i = 0; i < b.n; ++i) {
+    TxSlot& s = b.slot[i];
+    iov[i][0].iov_base = &s.hdr;
+    iov[i][0].iov_len = sizeof(PktHdr);
+    iov[i][1].iov_base = const_cast<void*>(s.payload);
+    iov[i][1].iov_len = s.blen;
+    memset(&msgs[i], 0, sizeof(msgs[i]));
+    msgs[i].msg_hdr.msg_name = &s.to;
+    msgs[i].msg_hdr.msg_namelen = sizeof(s.to);
+    msgs[i].msg_hdr.msg_iov = iov[i];
+    msgs[i].msg_hdr.msg_iovlen = s.blen ? 2 : 1;
+  }
+  int sent = 0;
+  while (sent < b.n) {
+    const int r = sendmmsg(socks_[path], msgs + sent, (unsigned)(b.n - sent), MSG_DONTWAIT);
+    if (r <= 0) break;  // full socket buffer: the rest counts as dropped; the reliability layer repairs it
+    sent += r;
+  }
+  for (int i = 0; i < sent; ++i) est_.tx_bytes += sizeof(PktHdr) + b.slot[i].blen;
+  est_.tx_pkts += (uint64_t)sent;
+  est_.dropped_tx += (uint64_t)(b.n - sent);
+  b.n = 0;
+}
+
+void Engine::flush_all() {
+  for (int p = 0; p < cfg_.paths; ++p) flush_path(p);
 }
 
 // ------------------------------------------------------------------------------- message posting

@@ -274,6 +274,22 @@ class Engine {
   mutable std::mutex st_mu_;
   // rx scratch
   std::vector<uint8_t> rx_buf_;
+  // tx batching: datagrams queued per path during one loop iteration leave in one sendmmsg
+  static constexpr int kTxBatch = 32;
+  struct TxSlot {
+    PktHdr hdr;
+    uint8_t body[96];  // AckBody / SynBody (payload of DATA packets is referenced in place)
+    sockaddr_in to;
+    const void* payload;
+    uint32_t blen;
+  };
+  struct TxBatch {
+    TxSlot slot[kTxBatch];
+    int n = 0;
+  };
+  std::vector<TxBatch> txb_;
+  void flush_path(int path);
+  void flush_all();
 };
 
 std::vector<std::pair<std::string, std::string>> list_interfaces();  // (name, ipv4) of usable NICs
