@@ -195,6 +195,10 @@ def test_multinode_communicator_two_nodes_of_two():
         res["sum"] = m.all_reduce(ins[gr].clone())             # 4099 is not a multiple of L: padded path
         res["avg"] = m.all_reduce(ins[gr].clone(), "avg")
         res["max"] = m.all_reduce(ins[gr][:4096].clone(), "max")
+        m.pipeline_bytes = 1024                                  # 4099 floats -> 2050 per shard -> 9 chunks in flight
+        res["pipe_sum"] = m.all_reduce(ins[gr].clone())
+        res["pipe_avg"] = m.all_reduce(ins[gr].clone(), "avg")
+        m.pipeline_bytes = 8 << 20
         ag = torch.zeros(W * 17)
         m.all_gather(ag, torch.full((17,), float(gr)))
         res["ag"] = ag
@@ -218,6 +222,7 @@ def test_multinode_communicator_two_nodes_of_two():
         assert torch.equal(o["sum"], ref.sum(0))
         assert torch.allclose(o["avg"], ref.sum(0) / W)
         assert torch.equal(o["max"], ref[:, :4096].max(0).values)
+        assert torch.equal(o["pipe_sum"], ref.sum(0)) and torch.allclose(o["pipe_avg"], ref.sum(0) / W)
         assert torch.equal(o["ag"].view(W, 17)[:, 0], torch.arange(W, dtype=torch.float32))
         assert torch.equal(o["rs"], torch.arange(W * 25, dtype=torch.float32).view(W, 25)[gr] * (W * (W + 1) / 2))
         assert torch.equal(o["b0"], torch.zeros(1001)) and torch.equal(o["b3"], torch.full((1001,), 3.0))
@@ -256,3 +261,79 @@ def test_multinode_from_torch_dist_four_processes(tmp_path):
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ok=True") == 4
+
+
+def _pg_worker(rank, world, path, q):
+    import torch.distributed as dist
+
+    os.environ["UCCL_B200_LOCAL_SIZE"] = "2"       # 4 ranks = 2 "boxes" of 2
+    os.environ["UCCL_B200_NET_BIND_IP"] = "127.0.0.1"
+    os.environ["UCCL_B200_NET_PATHS"] = "2"
+    import uccl_b200.parallel.pg  # noqa: F401  (registers the backend)
+    from uccl_b200.parallel import MultiNodeCommunicator
+
+    torch.set_num_threads(1)
+    dist.init_process_group("uccl_b200", rank=rank, world_size=world, store=dist.FileStore(path, world))
+    ok = []
+    x = torch.arange(5001, dtype=torch.float32) + rank
+    dist.all_reduce(x)
+    ok.append(torch.equal(x, torch.arange(5001, dtype=torch.float32) * world + sum(range(world))))
+    g = torch.empty(world * 4, dtype=torch.int64)
+    dist.all_gather_into_tensor(g, torch.full((4,), rank, dtype=torch.int64))
+    ok.append(g.view(world, 4)[:, 0].tolist() == list(range(world)))
+    b = torch.full((9,), float(rank))
+    dist.broadcast(b, src=2)
+    ok.append(bool((b == 2.0).all()))
+    rs = torch.empty(10)
+    dist.reduce_scatter_tensor(rs, torch.arange(world * 10, dtype=torch.float32) * (rank + 1))
+    ok.append(torch.equal(rs, torch.arange(world * 10, dtype=torch.float32).view(world, 10)[rank] * sum(range(1, world + 1))))
+    red = torch.full((6,), float(rank + 1))
+    dist.reduce(red, dst=1)
+    ok.append(bool((red == (10.0 if rank == 1 else rank + 1)).all()))
+    a_out = torch.empty(world * 3)
+    dist.all_to_all_single(a_out, torch.arange(world * 3, dtype=torch.float32) + 10 * rank)
+    ok.append(a_out.tolist() == [float(10 * s + 3 * rank + i) for s in range(world) for i in range(3)])
+    # unequal splits: rank s sends (s + d) % 3 + 1 elements to rank d
+    sc = [(rank + d) % 3 + 1 for d in range(world)]
+    rc = [(s + rank) % 3 + 1 for s in range(world)]
+    v_in = torch.cat([torch.full((sc[d],), float(100 * rank + d)) for d in range(world)])
+    v_out = torch.empty(sum(rc))
+    dist.all_to_all_single(v_out, v_in, output_split_sizes=rc, input_split_sizes=sc)
+    ok.append(torch.equal(v_out, torch.cat([torch.full((rc[s],), float(100 * s + rank)) for s in range(world)])))
+    # DDP across the two boxes
+    torch.manual_seed(0)
+    model = torch.nn.Linear(8, 4)
+    ddp = torch.nn.parallel.DistributedDataParallel(model)
+    ddp(torch.full((2, 8), float(rank + 1))).sum().backward()
+    ok.append(torch.allclose(model.weight.grad, torch.full((4, 8), sum(2.0 * (r + 1) for r in range(world)) / world)))
+    # point to point: inside the box and along the rail
+    for peer in (rank ^ 1, (rank + 2) % world):
+        s, r_ = torch.full((5,), float(rank)), torch.empty(5)
+        if rank < peer:
+            dist.send(s, peer)
+            dist.recv(r_, peer)
+        else:
+            dist.recv(r_, peer)
+            dist.send(s, peer)
+        ok.append(bool((r_ == peer).all()))
+    dist.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_torch_backend_spans_two_boxes():
+    """dist.init_process_group("uccl_b200") with LOCAL size 2 and world size 4: the backend builds a
+    MultiNodeCommunicator (shm heap per box + datagram rails) and every c10d collective + DDP works."""
+    import multiprocessing as mp
+    import tempfile
+
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as d:
+        ps = [ctx.Process(target=_pg_worker, args=(r, world, os.path.join(d, "store"), q)) for r in range(world)]
+        [p.start() for p in ps]
+        got = sorted(q.get(timeout=200) for _ in range(world))
+        [p.join(60) for p in ps]
+    for rank, ok in got:
+        assert all(ok), (rank, ok)

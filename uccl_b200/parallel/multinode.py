@@ -16,6 +16,9 @@ Reference: NCCL's net transport + collective/rdma (inter-node rings); thirdparty
 """
 from __future__ import annotations
 
+import os
+import queue
+import threading
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -33,6 +36,8 @@ class MultiNodeCommunicator:
         self.world_size = self.num_nodes * self.local_size
         self.device = local.device
         self._pinned: Dict[Tuple[int, torch.dtype, int], torch.Tensor] = {}
+        # all_reduce of more than this many bytes per rank-shard runs as a 3-stage pipeline over chunks
+        self.pipeline_bytes = int(os.environ.get("UCCL_B200_MN_PIPELINE_BYTES", str(8 << 20)))
 
     @classmethod
     def from_torch_dist(cls, local_size: int, device: Optional[int] = None, engine=None, **comm_kw) -> "MultiNodeCommunicator":
@@ -48,6 +53,25 @@ class MultiNodeCommunicator:
         local = Communicator.from_torch_dist(group=node_groups[rank // local_size], device=device, **comm_kw)
         net = NetCommunicator.from_process_group(rail_groups[rank % local_size], engine=engine)
         return cls(local, net)
+
+    @classmethod
+    def from_store(cls, store, rank: int, world_size: int, local_size: int, prefix: str = "uccl_b200/mn",
+                   engine=None, **comm_kw) -> "MultiNodeCommunicator":
+        """Bootstrap through a c10d-style store (``set`` / ``get``): one unique id per node, one address
+        exchange per rail.  This is what the ``"uccl_b200"`` torch backend uses for multi-node groups."""
+        assert world_size % local_size == 0
+        node, lrank = divmod(rank, local_size)
+        key = f"{prefix}/uid/{node}"
+        if lrank == 0:
+            store.set(key, Communicator.create_unique_id())
+        uid = bytes(store.get(key))
+        local = Communicator.init(uid, lrank, local_size, **comm_kw)
+        net = NetCommunicator.from_store(store, node, world_size // local_size, prefix=f"{prefix}/rail{lrank}", engine=engine)
+        return cls(local, net)
+
+    @property
+    def is_host(self) -> bool:
+        return self.local.is_host
 
     # ------------------------------------------------------------------ staging
     def _host(self, like: torch.Tensor, numel: int, slot: int = 0) -> torch.Tensor:
@@ -103,6 +127,11 @@ class MultiNodeCommunicator:
             work[:n].copy_(flat)
         else:
             work = flat
+        if L > 1 and per * t.element_size() > self.pipeline_bytes:
+            self._all_reduce_pipelined(work, per, inner, op)
+            if work.data_ptr() != flat.data_ptr():
+                flat.copy_(work[:n])
+            return t
         if L > 1:
             shard = torch.empty(per, dtype=t.dtype, device=t.device)
             self.local.reduce_scatter(shard, work, inner)
@@ -118,6 +147,82 @@ class MultiNodeCommunicator:
         if work.data_ptr() != flat.data_ptr():
             flat.copy_(work[:n])
         return t
+
+    def _all_reduce_pipelined(self, work: torch.Tensor, per: int, inner: str, op: str) -> None:
+        """Chunked 3-stage pipeline: while chunk k is on the network (helper thread, one rail per local rank),
+        the NVLink reduce-scatter of chunk k+1 and the NVLink all-gather of chunk k-1 run on this thread.
+
+        A chunk is a column block: ``work`` viewed as [L, per], chunk c = columns [lo, hi) of every row, so the
+        local reduce-scatter of the block leaves this rank with its own row's columns -- the same bytes the
+        unchunked algorithm would send over this rank's rail."""
+        L = self.local_size
+        es = work.element_size()
+        cols = max(1, self.pipeline_bytes // es)
+        bounds = [(lo, min(lo + cols, per)) for lo in range(0, per, cols)]
+        rows = work.view(L, per)
+        cuda = work.is_cuda
+        todo: "queue.Queue" = queue.Queue()
+        done: "queue.Queue" = queue.Queue()
+
+        def network():
+            while True:
+                item = todo.get()
+                if item is None:
+                    return
+                k, h, ev = item
+                try:
+                    if ev is not None:
+                        ev.synchronize()
+                    self.net.all_reduce(h, inner)
+                    if op == "avg":
+                        h.div_(self.world_size) if h.is_floating_point() else h.copy_(
+                            torch.div(h, self.world_size, rounding_mode="trunc"))
+                    done.put((k, None))
+                except Exception as e:  # surface in the caller
+                    done.put((k, e))
+
+        th = threading.Thread(target=network, daemon=True)
+        th.start()
+        state = {}
+
+        def stage_a(k):
+            lo, hi = bounds[k]
+            blk = rows[:, lo:hi].contiguous().view(-1)          # [L * w]
+            shard = torch.empty(hi - lo, dtype=work.dtype, device=work.device)
+            self.local.reduce_scatter(shard, blk, inner)
+            if cuda:
+                h = self._host(shard, cols, slot=10 + k % 3)[: hi - lo]
+                h.copy_(shard, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(work.device))
+            else:
+                h, ev = shard, None
+            state[k] = (shard, h)
+            todo.put((k, h, ev))
+
+        def stage_c(k):
+            lo, hi = bounds[k]
+            shard, h = state.pop(k)
+            self._up(shard, h)
+            full = torch.empty(L * (hi - lo), dtype=work.dtype, device=work.device)
+            self.local.all_gather(full, shard)
+            rows[:, lo:hi].copy_(full.view(L, hi - lo))
+
+        depth = 2
+        try:
+            for k in range(min(depth, len(bounds))):
+                stage_a(k)
+            for k in range(len(bounds)):
+                kk, err = done.get()
+                if err is not None:
+                    raise err
+                assert kk == k
+                stage_c(k)
+                if k + depth < len(bounds):
+                    stage_a(k + depth)
+        finally:
+            todo.put(None)
+            th.join()
 
     def all_gather(self, out: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """out[g] = t of global rank g (node major).  Rail all-gather first (each NIC carries only its own
@@ -217,6 +322,62 @@ class MultiNodeCommunicator:
         else:
             out.view(-1).copy_(rail_in)
         return out
+
+    def reduce(self, t: torch.Tensor, root: int = 0, op: str = "sum") -> torch.Tensor:
+        """Result only at ``root`` (the other ranks keep their input, like NCCL)."""
+        tmp = t.clone()
+        self.all_reduce(tmp, op)
+        if self.rank == root:
+            t.copy_(tmp)
+        return t
+
+    def all_to_all_v(self, out: torch.Tensor, t: torch.Tensor, send_counts, recv_counts) -> torch.Tensor:
+        """Variable all-to-all through the equal-split two-hop path: chunks are padded to the global maximum
+        (one scalar max-all-reduce), exchanged, and unpadded.  Correct for any split; bandwidth-optimal only
+        for balanced ones (the EP case)."""
+        W = self.world_size
+        mx = torch.tensor([max(list(send_counts) + [0])], dtype=torch.int64, device=t.device)
+        self.all_reduce(mx, "max")
+        m = int(mx.item())
+        flat = t.reshape(-1)
+        pad_in = torch.zeros(W * m, dtype=t.dtype, device=t.device)
+        off = 0
+        for d, c in enumerate(send_counts):
+            pad_in[d * m: d * m + c].copy_(flat[off: off + c])
+            off += c
+        pad_out = torch.empty_like(pad_in)
+        self.all_to_all(pad_out, pad_in)
+        oflat = out.reshape(-1)
+        off = 0
+        for s_, c in enumerate(recv_counts):
+            oflat[off: off + c].copy_(pad_out[s_ * m: s_ * m + c])
+            off += c
+        return out
+
+    def _route(self, peer: int):
+        node, lrank = divmod(peer, self.local_size)
+        if node == self.node_rank:
+            return "local", lrank
+        if lrank == self.local_rank:
+            return "rail", node
+        raise NotImplementedError("uccl_b200: point-to-point between different rails of different nodes is not routed; "
+                                  "send to the peer's rail-mate on your node first")
+
+    def send(self, t: torch.Tensor, dst: int) -> None:
+        kind, r = self._route(dst)
+        if kind == "local":
+            self.local.send(t, r)
+        else:
+            self.net.send(self._down(t.contiguous().view(-1)), r)
+
+    def recv(self, t: torch.Tensor, src: int) -> None:
+        kind, r = self._route(src)
+        if kind == "local":
+            self.local.recv(t, r)
+        else:
+            h = t.view(-1) if not t.is_cuda else self._host(t, t.numel(), slot=2)
+            self.net.recv(h, r)
+            self._up(t, h)
 
     def close(self) -> None:
         self.net.close()

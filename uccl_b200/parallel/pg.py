@@ -79,7 +79,17 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         host = not torch.cuda.is_available()
         heap = heap_bytes or int(os.environ.get("UCCL_B200_PG_HEAP_MB", "128" if host else "2048")) << 20
         stage = (8 << 20) if host else (128 << 20)
-        self.comm = Communicator.init(uid, rank, world_size, heap_bytes=heap, stage_bytes=stage, host=host)
+        # ranks per NVLink domain: torchrun's LOCAL_WORLD_SIZE, or UCCL_B200_LOCAL_SIZE to override
+        local = int(os.environ.get("UCCL_B200_LOCAL_SIZE", os.environ.get("LOCAL_WORLD_SIZE", str(world_size))))
+        if 0 < local < world_size and world_size % local == 0:
+            # the group spans several boxes: NVLink kernels inside a box, datagram rails between boxes
+            from .multinode import MultiNodeCommunicator
+
+            seq = os.environ.get("UCCL_B200_PG_SEQ", "0")
+            self.comm = MultiNodeCommunicator.from_store(store, rank, world_size, local, prefix=f"uccl_b200/mn{seq}",
+                                                         heap_bytes=heap, stage_bytes=stage, host=host)
+        else:
+            self.comm = Communicator.init(uid, rank, world_size, heap_bytes=heap, stage_bytes=stage, host=host)
 
     # ---- required plumbing
     def getBackendName(self):
