@@ -337,3 +337,46 @@ def test_torch_backend_spans_two_boxes():
         [p.join(60) for p in ps]
     for rank, ok in got:
         assert all(ok), (rank, ok)
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_p2p_net_channel_kv_blocks(staged):
+    """Cross-box P2P: a list of KV blocks through NetChannel, in place for host tensors and through the
+    chunked pinned-staging pipeline (the path GPU tensors take), with loss on the wire."""
+    from uccl_b200.p2p import NetChannel
+
+    ea = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.01)
+    eb = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.01)
+    srv = NetChannel.listen(eb, chunk_bytes=100_000, force_staging=staged)
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("ch", srv.accept()))
+    t.start()
+    cli = NetChannel.connect(ea, ("127.0.0.1", eb.port, srv.address[2]), chunk_bytes=100_000, force_staging=staged)
+    t.join()
+    g = torch.Generator().manual_seed(3)
+    blocks = [torch.randn(n, generator=g).to(dt) for n, dt in ((250_001, torch.float32), (7, torch.bfloat16), (131072, torch.float16), (1, torch.int64))]
+    outs = [torch.zeros_like(b) for b in blocks]
+    rt = threading.Thread(target=lambda: box.setdefault("n", srv.recv_tensors(outs)))
+    rt.start()
+    sent = cli.send_tensors(blocks)
+    rt.join()
+    assert box["n"] == sent == sum(b.numel() * b.element_size() for b in blocks)
+    for a, b in zip(blocks, outs):
+        assert torch.equal(a, b)
+    # a receiver that expects a different layout is told so instead of getting garbage
+    et = threading.Thread(target=lambda: box.setdefault("err", _catch(lambda: srv.recv_tensors(outs[:2]))))
+    et.start()
+    with pytest.raises(RuntimeError, match="rejected"):
+        cli.send_tensors(blocks[:1] + blocks[2:3])
+    et.join()
+    assert isinstance(box["err"], RuntimeError) and "announced" in str(box["err"])
+    cli.close()
+    srv.close()
+
+
+def _catch(fn):
+    try:
+        fn()
+    except Exception as e:  # noqa: BLE001
+        return e
+    return None

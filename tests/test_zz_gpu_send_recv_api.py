@@ -195,3 +195,35 @@ def test_nccl_runs_over_the_net_plugin(tmp_path):
     assert r.returncode == 0
     assert out.count(" ok") >= 2
     assert "uccl_b200" in out  # NCCL logged the plugin it selected
+
+
+def test_p2p_net_channel_gpu_tensors():
+    """Cross-box P2P path with CUDA tensors on both ends (pinned staging pipelines), over loopback."""
+    import threading
+
+    from uccl_b200 import net
+    from uccl_b200.p2p import NetChannel
+
+    dev = torch.device("cuda", 0)
+    ea, eb = net.Engine(bind_ip="127.0.0.1", paths=4), net.Engine(bind_ip="127.0.0.1", paths=4)
+    srv = NetChannel.listen(eb, chunk_bytes=1 << 20)
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("ch", srv.accept()))
+    t.start()
+    cli = NetChannel.connect(ea, ("127.0.0.1", eb.port, srv.address[2]), chunk_bytes=1 << 20)
+    t.join()
+    blocks = [torch.randn(3_000_001, device=dev), torch.randn(1000, device=dev).to(torch.bfloat16)]
+    outs = [torch.zeros_like(b) for b in blocks]
+
+    def rx():
+        torch.cuda.set_device(0)
+        box["n"] = srv.recv_tensors(outs)
+
+    rt = threading.Thread(target=rx)
+    rt.start()
+    sent = cli.send_tensors(blocks)
+    rt.join()
+    torch.cuda.synchronize()
+    assert box["n"] == sent
+    for a, b in zip(blocks, outs):
+        assert torch.equal(a, b)

@@ -327,3 +327,11 @@ class Endpoint:
 
     def stats(self) -> dict:
         return dict(self._e.stats())
+
+
+def __getattr__(name):  # inter-node channel: pulls in the network stack only when used
+    if name == "NetChannel":
+        from .internode import NetChannel
+
+        return NetChannel
+    raise AttributeError(name)
