@@ -380,3 +380,44 @@ def _catch(fn):
     except Exception as e:  # noqa: BLE001
         return e
     return None
+
+
+def test_expert_parallel_buffer_across_boxes():
+    """DeepEP Buffer over a group that spans 2 boxes x 2 ranks: the token exchange is the hierarchical two-hop
+    all-to-all (shared-memory heap inside a box, datagram rails between boxes).  Same oracle as the intranode
+    tests: received rows in source-rank-major order, combine == x * fan-out; plus the low-latency pair."""
+    from test_host_ep import _inputs
+    from uccl_b200.ep import Buffer
+
+    N, L = 2, 2
+    W = N * L
+    nodes = [Communicator.local_world(L, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20, timeout_ms=30000)
+             for _ in range(N)]
+    rails = [_Exchange(N) for _ in range(L)]
+    T, H, K, E, M = 37, 256, 3, 8, 48
+    e_per = E // W
+    xs, idxs, ws = _inputs(W, T, H, K, E, seed=5)
+
+    def fn(gr):
+        k, l = divmod(gr, L)
+        nc = net.NetCommunicator(k, N, rails[l].for_rank(k), engine=net.Engine(bind_ip="127.0.0.1", paths=2, drop_prob=0.005))
+        m = MultiNodeCommunicator(nodes[k][l], nc)
+        b = Buffer(comm=m, num_nvl_bytes=1 << 20, num_rdma_bytes=1 << 20, low_latency_mode=True)
+        assert (b.rank, b.group_size, b.get_num_rdma_ranks()) == (gr, W, N)
+        tpr, _, tpe, inr, _ = b.get_dispatch_layout(idxs[gr], E)
+        rx, ri, rw, pe, h, _ = b.internode_dispatch(xs[gr], None, tpr, None, inr, tpe, idxs[gr], ws[gr])
+        comb, _, _ = b.internode_combine(rx, h, topk_weights=rw)
+        lx, cnt, lh, _, _ = b.low_latency_dispatch(xs[gr], idxs[gr], M, E, use_fp8=False)
+        lout, _, _ = b.low_latency_combine(lx, idxs[gr], ws[gr], lh)
+        m.close()
+        return dict(rx=rx, inr=inr, comb=comb, pe=pe, cnt=cnt, lout=lout)
+
+    outs = _run_threads(W, fn)
+    for r, o in enumerate(outs):
+        exp = torch.cat([xs[s][outs[s]["inr"][:, r].nonzero().flatten()] for s in range(W)])
+        assert torch.equal(o["rx"], exp)
+        assert torch.allclose(o["comb"].float(), xs[r].float() * o["inr"].sum(1).float()[:, None], rtol=2e-2, atol=1e-1)
+        counts = [int(sum((idxs[s] == r * e_per + e).sum() for s in range(W))) for e in range(e_per)]
+        assert o["pe"] == counts and o["cnt"].tolist() == counts
+        wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(o["lout"].float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)

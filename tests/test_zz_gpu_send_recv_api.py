@@ -227,3 +227,62 @@ def test_p2p_net_channel_gpu_tensors():
     assert box["n"] == sent
     for a, b in zip(blocks, outs):
         assert torch.equal(a, b)
+
+
+def test_ep_buffer_across_boxes_with_gpu_tensors():
+    """Two 'boxes' of one GPU rank each (same physical GPU), datagram rail between them: the portable
+    multi-box EP path accepts CUDA tensors and returns CUDA results."""
+    import threading
+
+    from uccl_b200 import Communicator, net
+    from uccl_b200.ep import Buffer
+    from uccl_b200.parallel import MultiNodeCommunicator
+
+    dev = torch.device("cuda", 0)
+    W, T, H, K, E = 2, 64, 256, 2, 4
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(T, H, generator=g).to(torch.bfloat16) for _ in range(W)]
+    idxs = [torch.rand(T, E, generator=g).topk(K, dim=1).indices.contiguous() for _ in range(W)]
+    ws = [torch.rand(T, K, generator=g) for _ in range(W)]
+    locals_ = [Communicator.local_world(1, devices=[0], heap_bytes=256 << 20, stage_bytes=8 << 20, timeout_ms=5000)[0] for _ in range(W)]
+    slots, bar = [None] * W, threading.Barrier(W)
+
+    def exchange_for(r):
+        def ex(obj):
+            slots[r] = obj
+            bar.wait()
+            out = list(slots)
+            bar.wait()
+            return out
+        return ex
+
+    outs, errs = [None] * W, []
+
+    def fn(r):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                m = MultiNodeCommunicator(locals_[r], net.NetCommunicator(r, W, exchange_for(r), engine=net.Engine(bind_ip="127.0.0.1", paths=2)))
+                b = Buffer(comm=m, num_nvl_bytes=1 << 20)
+                x, idx, w = xs[r].to(dev), idxs[r].to(dev), ws[r].to(dev)
+                tpr, _, tpe, inr, _ = b.get_dispatch_layout(idx, E)
+                rx, ri, rw, pe, h, _ = b.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=inr, num_tokens_per_expert=tpe,
+                                                  topk_idx=idx, topk_weights=w)
+                comb, _, _ = b.combine(rx, h, topk_weights=rw)
+                assert rx.is_cuda and comb.is_cuda
+                outs[r] = (rx.cpu(), inr.cpu(), comb.cpu())
+                m.close()
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=fn, args=(r,)) for r in range(W)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    for r, (rx, inr, comb) in enumerate(outs):
+        exp = torch.cat([xs[s][outs[s][1][:, r].nonzero().flatten()] for s in range(W)])
+        assert torch.equal(rx, exp)
+        assert torch.allclose(comb.float(), xs[r].float() * inr.sum(1).float()[:, None], rtol=2e-2, atol=1e-1)

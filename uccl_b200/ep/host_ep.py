@@ -29,13 +29,79 @@ def _a2av(comm: Communicator, send: torch.Tensor, send_rows: List[int], recv_row
     return out.view(send.dtype).reshape((sum(recv_rows),) + tuple(send.shape[1:]))
 
 
+class _DeviceCommAdapter:
+    """Lets the CPU reference algorithm run over a communicator whose collectives want device tensors
+    (a :class:`MultiNodeCommunicator` built on GPU communicators): operands hop to the device for the call."""
+
+    def __init__(self, comm):
+        self._c, self.rank, self.world_size, self._dev = comm, comm.rank, comm.world_size, comm.device
+
+    def _call(self, fn, out, t, *a):
+        o, d = out.to(self._dev), t.to(self._dev)
+        fn(o, d, *a)
+        torch.cuda.current_stream(self._dev).synchronize()
+        out.copy_(o)
+        return out
+
+    def all_gather(self, out, t):
+        return self._call(self._c.all_gather, out, t)
+
+    def all_to_all_v(self, out, t, send_counts, recv_counts):
+        return self._call(self._c.all_to_all_v, out, t, send_counts, recv_counts)
+
+
+def _portable(fn):
+    """Public-method wrapper: tensors (also inside tuples / handles) are brought to the CPU for the reference
+    algorithm and results go back to the caller's device.  A no-op for host tensors."""
+    import functools
+
+    def to_cpu(v, seen):
+        if isinstance(v, torch.Tensor):
+            if v.is_cuda:
+                seen.append(v.device)
+                return v.cpu()
+            return v
+        if isinstance(v, tuple):
+            return tuple(to_cpu(e, seen) for e in v)
+        if isinstance(v, list):
+            return [to_cpu(e, seen) for e in v]
+        return v
+
+    def to_dev(v, dev):
+        if isinstance(v, torch.Tensor):
+            return v.to(dev)
+        if isinstance(v, tuple):
+            return tuple(to_dev(e, dev) for e in v)
+        return v
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        seen = []
+        stats = kw.get("cumulative_local_expert_recv_stats")
+        a = [to_cpu(v, seen) for v in args]
+        k = {n: to_cpu(v, seen) for n, v in kw.items()}
+        res = fn(self, *a, **k)
+        if not seen:
+            return res
+        if isinstance(stats, torch.Tensor) and stats.is_cuda:  # in-place output argument
+            stats.copy_(k["cumulative_local_expert_recv_stats"])
+        return to_dev(res, seen[0])
+
+    return wrapper
+
+
 class HostBuffer:
+    """DeepEP ``Buffer`` API on the CPU -- and the *portable* path for groups that span boxes: with a
+    :class:`uccl_b200.parallel.MultiNodeCommunicator` the token exchange rides its two-hop all-to-all (NVLink
+    inside a box, one datagram rail per NIC between boxes), which is the shape of the reference's internode
+    dispatch; GPU tensors are accepted (the permutation itself then runs on the host -- functional, not fast)."""
+
     num_sms: int = 24
 
     def __init__(self, comm: Communicator, num_nvl_bytes: int = 0, num_rdma_bytes: int = 0,
                  low_latency_mode: bool = False, **_):
-        assert comm.is_host
-        self.comm = comm
+        self._raw_comm = comm
+        self.comm = comm if comm.is_host else _DeviceCommAdapter(comm)
         self.group = getattr(comm, "group", None)
         self.rank = comm.rank
         self.group_size = comm.world_size
@@ -61,9 +127,10 @@ class HostBuffer:
         return EventOverlap()
 
     def get_num_rdma_ranks(self) -> int:
-        return 1
+        return int(getattr(self._raw_comm, "num_nodes", 1))  # boxes the group spans
 
     # ------------------------------------------------------------------ layout
+    @_portable
     def get_dispatch_layout(self, topk_idx: torch.Tensor, num_experts: int, previous_event=None, async_finish=False,
                             allocate_on_comm_stream=False):
         assert topk_idx.dtype == torch.int64 and topk_idx.dim() == 2
@@ -88,6 +155,7 @@ class HostBuffer:
         self.comm.all_gather(mat, send_counts.to(torch.int64).contiguous())
         return mat.view(R, R)
 
+    @_portable
     def dispatch(self, x: Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]], handle: Optional[Tuple] = None,
                  num_tokens_per_rank=None, num_tokens_per_rdma_rank=None, is_token_in_rank=None,
                  num_tokens_per_expert=None, topk_idx=None, topk_weights=None, expert_alignment: int = 1,
@@ -167,6 +235,7 @@ class HostBuffer:
     def get_combine_buffer(self, num_tokens: int, hidden: int, num_topk: int = 0) -> torch.Tensor:
         return torch.empty(num_tokens, hidden, dtype=torch.bfloat16)
 
+    @_portable
     def combine(self, x: torch.Tensor, handle: Tuple, topk_weights: Optional[torch.Tensor] = None, bias=None,
                 config=None, previous_event=None, async_finish: bool = False, allocate_on_comm_stream: bool = False):
         R, me = self.group_size, self.rank
@@ -203,6 +272,7 @@ class HostBuffer:
     def clean_low_latency_buffer(self, *a, **kw):
         pass
 
+    @_portable
     def low_latency_dispatch(self, x: torch.Tensor, topk_idx: torch.Tensor, num_max_dispatch_tokens_per_rank: int,
                              num_experts: int, cumulative_local_expert_recv_stats=None,
                              dispatch_wait_recv_cost_stats=None, use_fp8: bool = True, round_scale: bool = False,
@@ -287,6 +357,7 @@ class HostBuffer:
         src_info, layout_range, M, H, E = handle[:5]
         return torch.zeros(E // self.group_size, self.group_size * M, H, dtype=torch.bfloat16)
 
+    @_portable
     def low_latency_combine(self, x: torch.Tensor, topk_idx: torch.Tensor, topk_weights: torch.Tensor, handle,
                             use_logfmt: bool = False, zero_copy: bool = False, async_finish: bool = False,
                             return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
