@@ -421,3 +421,29 @@ def test_expert_parallel_buffer_across_boxes():
         assert o["pe"] == counts and o["cnt"].tolist() == counts
         wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
         assert torch.allclose(o["lout"].float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)
+
+
+def test_black_holed_path_is_quarantined():
+    """One of four paths silently drops everything (a dead ECMP route): transfers keep completing, the loss
+    streak quarantines the path, and it carries only a sliver of the traffic."""
+    a = net.Engine(bind_ip="127.0.0.1", paths=4)
+    b = net.Engine(bind_ip="127.0.0.1", paths=4)
+    lid = b.listen()
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("fb", b.accept(lid)))
+    t.start()
+    fa = a.connect("127.0.0.1", b.port, lid)
+    t.join()
+    a.set_path_drop(1, 1.0)
+    x = torch.randn(4_000_000)
+    y = torch.zeros_like(x)
+    for _ in range(2):
+        w = b.irecv(box["fb"], y)
+        a.send(fa, x, 120000)
+        w.wait(120000)
+        assert torch.equal(x, y)
+    st = a.flow_stats(fa)
+    assert st["path_bans"] >= 1
+    healthy = [st["path_tx"][i] for i in (0, 2, 3)]
+    assert st["path_tx"][1] < 0.25 * min(healthy), st["path_tx"]
+    a.set_path_drop(-1, 0.0)

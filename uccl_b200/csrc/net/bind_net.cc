@@ -116,6 +116,7 @@ void bind_net(py::module_& root) {
           },
           py::arg("request"), py::arg("timeout_ms") = -1)
       .def("set_drop_prob", &Engine::set_drop_prob)
+      .def("set_path_drop", &Engine::set_path_drop, py::arg("path"), py::arg("prob") = 1.0)
       .def("stats",
            [](Engine& e) {
              const EngineStats s = e.stats();
@@ -134,6 +135,7 @@ void bind_net(py::module_& root) {
         d["acks_tx"] = s.acks_tx, d["acks_rx"] = s.acks_rx, d["unexpected_msgs"] = s.unexpected_msgs;
         d["srtt_us"] = s.srtt_us, d["min_rtt_us"] = s.min_rtt_us, d["cwnd"] = s.cwnd, d["rate_gbps"] = s.rate_gbps;
         d["state"] = s.state;
+        d["path_bans"] = s.path_bans;
         std::vector<uint64_t> paths(s.path_tx, s.path_tx + e.paths());
         d["path_tx"] = paths;
         return d;

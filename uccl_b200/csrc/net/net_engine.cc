@@ -676,6 +676,13 @@ void Engine::raw_send(int path, const sockaddr_in& to, const void* hdr, size_t h
     return;
   }
   (void)hlen;
+  if (path == path_drop_idx_.load(std::memory_order_relaxed)) {
+    const double pp = path_drop_prob_.load(std::memory_order_relaxed);
+    if (pp > 0.0 && std::uniform_real_distribution<double>(0.0, 1.0)(rng_) < pp) {
+      ++est_.dropped_tx;
+      return;
+    }
+  }
   TxBatch& b = txb_[path];
   if (b.n == kTxBatch) flush_path(path);
   TxSlot& s = b.slot[b.n++];
@@ -911,6 +918,7 @@ void Engine::mark_acked(Flow& f, TxPkt& p, uint64_t now) {
     if (f.path[p.path].inflight) --f.path[p.path].inflight;
   }
   p.lost = false;
+  f.path[p.path].loss_streak = 0;
   if (p.ts_send > f.newest_acked_send_ts) f.newest_acked_send_ts = p.ts_send;
   TxMsg* m = p.msg;
   p.msg = nullptr;
@@ -981,8 +989,19 @@ void Engine::on_ack(Flow& f, const PktHdr& h, const AckBody& b) {
   detect_loss(f, now);
 }
 
+void Engine::note_path_loss(Flow& f, int path, uint64_t now) {
+  PathState& ps = f.path[path];
+  if (++ps.loss_streak < 8 || now < ps.banned_until_ns) return;
+  // eight losses in a row with no ACK in between: treat the path as black-holed and quarantine it
+  // (100 ms, doubling up to 3.2 s); when the quarantine ends a few packets probe it again
+  ps.loss_streak = 0;
+  ps.banned_until_ns = now + (100000000ull << std::min<uint32_t>(ps.bans, 5));
+  ++ps.bans;
+  ++f.st.path_bans;
+  UB_INFO(SUB_NET, "net: flow %u path %d quarantined (%u)", f.id, path, ps.bans);
+}
+
 void Engine::detect_loss(Flow& f, uint64_t now) {
-  (void)now;
   if (f.newest_acked_send_ts == 0) return;
   // RACK: a packet is lost once a packet sent sufficiently LATER has been acknowledged.  Time based, so
   // reordering between paths (which is the normal case here) does not trigger spurious retransmissions.
@@ -999,6 +1018,7 @@ void Engine::detect_loss(Flow& f, uint64_t now) {
       f.rexmit_q.push_back(s);
       ++f.st.fast_rexmit;
       ++est_.fast_rexmit;
+      note_path_loss(f, p.path, now);
     }
   }
 }
@@ -1010,6 +1030,9 @@ int Engine::pick_path(Flow& f, int avoid) {
   int a = (int)(rng_() % (uint64_t)n), b = (int)(rng_() % (uint64_t)n);
   if (a == avoid) a = (a + 1) % n;
   if (b == avoid) b = (b + 1) % n;
+  const uint64_t now = now_ns();
+  for (int tries = 0; tries < n && f.path[a].banned_until_ns > now; ++tries) a = (a + 1) % n;
+  for (int tries = 0; tries < n && f.path[b].banned_until_ns > now; ++tries) b = (b + 1) % n;
   const PathState &pa = f.path[a], &pb = f.path[b];
   if (pa.inflight != pb.inflight) return pa.inflight < pb.inflight ? a : b;
   return pa.srtt_us <= pb.srtt_us ? a : b;
@@ -1177,6 +1200,7 @@ void Engine::timers(uint64_t now) {
           p.lost = true;
           if (f.inflight) --f.inflight;
           if (f.path[p.path].inflight) --f.path[p.path].inflight;
+          note_path_loss(f, p.path, now);
         }
         p.ts_send = now;  // re-arm; the retransmission below stamps it again
         f.rexmit_q.push_front(f.snd_una);

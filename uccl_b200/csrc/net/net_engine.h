@@ -76,6 +76,7 @@ struct FlowStats {
   uint64_t tx_pkts = 0, tx_bytes = 0, rx_pkts = 0, rx_bytes = 0, rx_dup = 0;
   uint64_t fast_rexmit = 0, rto_rexmit = 0, acks_tx = 0, acks_rx = 0, unexpected_msgs = 0;
   uint64_t path_tx[kMaxPaths] = {0};
+  uint64_t path_bans = 0;
   double srtt_us = 0, min_rtt_us = 0, cwnd = 0, rate_gbps = 0;
   int state = 0;
 };
@@ -121,6 +122,11 @@ class Engine {
   bool wait(Request* r, size_t* bytes, int timeout_ms = -1);  // false on timeout / error (request freed)
 
   void set_drop_prob(double p) { drop_prob_.store(p); }
+  // fault injection on ONE local path (models a black-holed ECMP route); path < 0 clears
+  void set_path_drop(int path, double p) {
+    path_drop_idx_.store(path);
+    path_drop_prob_.store(p);
+  }
   EngineStats stats() const;
   bool flow_stats(uint32_t flow, FlowStats* out) const;
 
@@ -157,6 +163,9 @@ class Engine {
     double srtt_us = 0;
     uint32_t inflight = 0;
     uint64_t tx = 0;
+    uint32_t loss_streak = 0;      // consecutive packets declared lost on this path (reset by any ACK from it)
+    uint32_t bans = 0;             // how often it was quarantined (quarantine time backs off)
+    uint64_t banned_until_ns = 0;  // path quarantine: a black-holed ECMP path stops getting new packets
   };
   struct Flow {
     uint32_t id = 0, peer_flow = 0, listen_id = 0;
@@ -255,7 +264,9 @@ class Engine {
   int epfd_ = -1, evfd_ = -1;
   std::thread thr_;
   std::atomic<bool> stop_{false};
-  std::atomic<double> drop_prob_{0.0};
+  std::atomic<double> drop_prob_{0.0}, path_drop_prob_{0.0};
+  std::atomic<int> path_drop_idx_{-1};
+  void note_path_loss(Flow& f, int path, uint64_t now);
   std::atomic<uint32_t> next_flow_{1}, next_listen_{1};
   std::atomic<uint64_t> last_rx_ns_{0};
   bool shut_ = false;

@@ -139,6 +139,10 @@ class Engine:
     def set_drop_prob(self, p: float) -> None:
         self._native.set_drop_prob(p)
 
+    def set_path_drop(self, path: int, prob: float = 1.0) -> None:
+        """Fault injection: black-hole one local path (``path < 0`` clears)."""
+        self._native.set_path_drop(path, prob)
+
     def stats(self) -> Dict:
         return self._native.stats()
 
