@@ -380,7 +380,8 @@ void Engine::complete(Request* r, size_t bytes, int err) {
 // ------------------------------------------------------------------------------------ engine loop
 void Engine::run() {
   std::unordered_map<uint32_t, Flow*> index;
-  uint64_t last_stats = 0;
+  uint64_t last_stats = 0, last_busy_ns = 0;
+  const uint64_t spin_ns = (uint64_t)param_load("NET_SPIN_US", 0) * 1000ull;
   while (!stop_.load(std::memory_order_relaxed)) {
     bool busy = false;
     // commands + working set
@@ -449,7 +450,11 @@ void Engine::run() {
       }
       est_.flows = (int)active_.size();
     }
+    if (busy) last_busy_ns = now;
     if (!busy && !cfg_.busy_poll) {
+      // hybrid polling: keep spinning for a short while after the last activity -- request/response
+      // patterns (ring steps, rendezvous RTR -> data) then never pay an epoll wake-up per hop
+      if (now - last_busy_ns < spin_ns) continue;
       const bool eq = cfg_.cc == CC_EQDS && pacer_.active_senders() > 0;
       const int to = pending ? 1 : 50;
       // the credit pacer and the rate pacer need a fine-grained clock while there is work: spin
