@@ -270,7 +270,12 @@ def test_prometheus_exporter_renders_runtime_counters():
     exp.watch_communicator(c)
     exp.watch_endpoint(a)
     exp.watch("custom", lambda: {"answer": 42})
+    from uccl_b200 import net
+
+    eng = net.Engine(bind_ip="127.0.0.1", paths=2)
+    exp.watch_net_engine(eng)
     text = exp.render()
+    assert 'uccl_b200_net_tx_pkts{rank="3"}' in text and 'uccl_b200_net_rto_rexmit{rank="3"}' in text
     assert 'uccl_b200_p2p_bytes_sent{rank="3"} 256.0' in text
     assert 'uccl_b200_comm_heap_free_bytes{rank="3"}' in text and 'uccl_b200_custom_answer{rank="3"} 42.0' in text
 

@@ -6,7 +6,7 @@ deployment wants the same numbers scrapeable::
 
     from uccl_b200.utils.metrics import MetricsExporter
     exp = MetricsExporter(rank=comm.rank)
-    exp.watch_communicator(comm); exp.watch_endpoint(ep); exp.watch_ukernel(uk_comm)
+    exp.watch_communicator(comm); exp.watch_endpoint(ep); exp.watch_ukernel(uk_comm); exp.watch_net_engine(engine)
     exp.start_http_server(9400 + comm.rank)      # or: text = exp.render()
 """
 from __future__ import annotations
@@ -52,6 +52,23 @@ class MetricsExporter:
 
     def watch_proxy(self, proxy, name: str = "proxy"):
         self._sources.append((name, lambda: {k: v for k, v in proxy.stats().items()}))
+
+    def watch_net_engine(self, engine, name: str = "net"):
+        """Inter-node transport: datagrams, retransmissions, drops, engine-loop activity (``uccl_b200.net.Engine``)."""
+        self._sources.append((name, lambda: {k: v for k, v in engine.stats().items()}))
+
+    def watch_net_communicator(self, nc, name: str = "net_flow"):
+        """Per-peer flow health of a ``NetCommunicator``: srtt, cwnd, retransmissions, quarantined paths."""
+
+        def fn():
+            out = {}
+            for peer, f in nc.flows.items():
+                st = nc.engine.flow_stats(f) or {}
+                for k in ("srtt_us", "cwnd", "fast_rexmit", "rto_rexmit", "path_bans", "tx_bytes", "rx_bytes"):
+                    out[f"peer{peer}_{k}"] = st.get(k, 0)
+            return out
+
+        self._sources.append((name, fn))
 
     def watch(self, name: str, fn: Callable[[], Dict[str, float]]):
         self._sources.append((name, fn))
