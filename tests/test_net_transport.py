@@ -27,11 +27,16 @@ def engine_test_exe(tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("drop,cc", [(0, "swift"), (5, "swift"), (3, "none"), (2, "timely"), (2, "eqds")])
-def test_engine_loopback_with_loss(engine_test_exe, drop, cc):
-    """C++ level: handshake, eager/unexpected + rendezvous messages, bidirectional 24 MB transfers, 64
-    pipelined messages, spraying over every path, retransmissions under loss, dead-peer abort."""
-    r = subprocess.run([str(engine_test_exe), str(drop), cc, "8"], capture_output=True, text=True, timeout=240)
+@pytest.mark.parametrize("drop,cc,isn", [(0, "swift", None), (5, "swift", None), (3, "none", None), (2, "timely", None),
+                                         (2, "eqds", None), (3, "swift", 4294967000)])
+def test_engine_loopback_with_loss(engine_test_exe, drop, cc, isn):
+    """C++ level: handshake, eager/unexpected + rendezvous messages, bidirectional transfers, 64 pipelined
+    messages, spraying over every path, retransmissions under loss, dead-peer abort; the last case pins the
+    initial sequence numbers just below 2^32 so that every window computation crosses the wrap."""
+    env = dict(os.environ)
+    if isn is not None:
+        env["UCCL_B200_NET_ISN"] = str(isn)
+    r = subprocess.run([str(engine_test_exe), str(drop), cc, "8"], capture_output=True, text=True, timeout=240, env=env)
     sys.stdout.write(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASS" in r.stdout

@@ -245,6 +245,9 @@ uint32_t Engine::connect_async(const std::string& ip, uint16_t port, uint32_t li
   {
     std::lock_guard<std::mutex> lk(mu_);
     f->nonce = (((uint64_t)std::random_device{}() << 32) ^ now) | 1;  // rng_ belongs to the engine thread
+    const int64_t pin = param_load("NET_ISN", -1);  // tests pin it just below the 32-bit wrap
+    f->isn = pin >= 0 ? (uint32_t)pin : (uint32_t)std::random_device{}();
+    f->snd_nxt = f->snd_una = f->isn;
     f->state.store(FL_SYN_SENT);
     flows_[f->id] = f;
     active_dirty_ = true;
@@ -576,6 +579,7 @@ void Engine::send_syn(Flow& f, bool synack, int sock_idx, const sockaddr_in* to)
   h.dst_flow = synack ? f.peer_flow : 0;
   h.len = sizeof(SynBody);
   h.ts_ns = now_ns();
+  h.seq = f.isn;  // our direction starts here; random so that stale datagrams of an earlier flow never match
   SynBody b;
   fill_syn_body(&b, f);
   sockaddr_in a{};
@@ -590,7 +594,6 @@ void Engine::send_syn(Flow& f, bool synack, int sock_idx, const sockaddr_in* to)
 }
 
 void Engine::on_syn(int sock_idx, const sockaddr_in& from, const PktHdr& h, const SynBody& b) {
-  (void)h;
   std::shared_ptr<Flow> f;
   {
     std::lock_guard<std::mutex> lk(mu_);
@@ -616,6 +619,12 @@ void Engine::on_syn(int sock_idx, const sockaddr_in& from, const PktHdr& h, cons
           f->peer_addr[i].sin_family = AF_INET;
           f->peer_addr[i].sin_addr = from.sin_addr;
           f->peer_addr[i].sin_port = b.ports[i];
+        }
+        f->rcv_nxt = h.seq;  // the client's initial sequence number
+        {
+          const int64_t pin = param_load("NET_ISN", -1);
+          f->isn = pin >= 0 ? (uint32_t)pin : (uint32_t)rng_();
+          f->snd_nxt = f->snd_una = f->isn;
         }
         f->rto_ns = (uint64_t)cfg_.rto_min_us * 1000ull;
         cc::SwiftConfig sc;
@@ -645,6 +654,7 @@ void Engine::on_synack(const sockaddr_in& from, const PktHdr& h, const SynBody& 
   std::shared_ptr<Flow> f = find(h.dst_flow);
   if (!f || f->state.load() != FL_SYN_SENT || b.nonce != f->nonce || from.sin_addr.s_addr != f->peer_ip.s_addr) return;
   f->peer_flow = b.src_flow;
+  f->rcv_nxt = h.seq;  // the server's initial sequence number
   f->npaths = std::max(1, std::min<int>(cfg_.paths, b.npaths));
   for (int i = 0; i < f->npaths; ++i) {
     f->peer_addr[i] = sockaddr_in{};

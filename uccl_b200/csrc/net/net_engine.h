@@ -178,7 +178,7 @@ class Engine {
     uint64_t syn_next_ns = 0, syn_deadline_ns = 0;
     uint16_t syn_port = 0;
     // tx reliability
-    uint32_t snd_nxt = 0, snd_una = 0;
+    uint32_t snd_nxt = 0, snd_una = 0, isn = 0;  // isn: initial sequence number of OUR direction (random)
     TxPkt ring[kTxRing];
     uint32_t inflight = 0;  // sent, not acked, not marked lost
     std::deque<uint32_t> rexmit_q;
