@@ -118,6 +118,7 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), r
   ec.max_backlog_credits = 8;
   pacer_ = cc::EqdsPacer(ec);
   for (int i = 0; i < kMaxPaths; ++i) socks_[i] = -1, ports_[i] = 0;
+  gro_ok_ = param_load("NET_GRO", 1) != 0;
   epfd_ = epoll_create1(EPOLL_CLOEXEC);
   evfd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
   UB_CHECK(epfd_ >= 0 && evfd_ >= 0, "net: epoll/eventfd: %s", strerror(errno));
@@ -139,6 +140,10 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), r
              strerror(errno));
     socklen_t al = sizeof(a);
     getsockname(s, reinterpret_cast<sockaddr*>(&a), &al);
+    if (gro_ok_) {
+      int one = 1;
+      if (setsockopt(s, IPPROTO_UDP, 104 /* UDP_GRO */, &one, sizeof(one)) != 0) gro_ok_ = false;
+    }
     socks_[i] = s;
     ports_[i] = ntohs(a.sin_port);
     ev.data.u32 = (uint32_t)i;
@@ -146,6 +151,7 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), r
   }
   rx_buf_.resize((size_t)kRxBatch * kRxSlot);
   txb_.resize((size_t)cfg_.paths);
+  gso_ok_ = param_load("NET_GSO", 1) != 0;
   UB_INFO(SUB_NET, "net engine up: %s paths=%d port0=%u payload=%d cc=%d", cfg_.bind_ip.c_str(), cfg_.paths, ports_[0],
           cfg_.payload, cfg_.cc);
   thr_ = std::thread([this] { run(); });
@@ -480,6 +486,7 @@ bool Engine::rx_poll() {
   mmsghdr msgs[kRxBatch];
   iovec iov[kRxBatch];
   sockaddr_in from[kRxBatch];
+  alignas(cmsghdr) char ctrl[kRxBatch][CMSG_SPACE(sizeof(int))];
   for (int s = 0; s < cfg_.paths; ++s) {
     for (int round = 0; round < 4; ++round) {
       for (int i = 0; i < kRxBatch; ++i) {
@@ -490,11 +497,33 @@ bool Engine::rx_poll() {
         msgs[i].msg_hdr.msg_iovlen = 1;
         msgs[i].msg_hdr.msg_name = &from[i];
         msgs[i].msg_hdr.msg_namelen = sizeof(sockaddr_in);
+        if (gro_ok_) {
+          msgs[i].msg_hdr.msg_control = ctrl[i];
+          msgs[i].msg_hdr.msg_controllen = sizeof(ctrl[i]);
+        }
       }
       const int n = recvmmsg(socks_[s], msgs, kRxBatch, MSG_DONTWAIT, nullptr);
       if (n <= 0) break;
       any = true;
-      for (int i = 0; i < n; ++i) on_packet(s, from[i], static_cast<uint8_t*>(iov[i].iov_base), msgs[i].msg_len);
+      for (int i = 0; i < n; ++i) {
+        uint8_t* buf = static_cast<uint8_t*>(iov[i].iov_base);
+        size_t len = msgs[i].msg_len;
+        // UDP GRO: the kernel hands over a train of equal-sized datagrams of one sender as one buffer and
+        // reports the segment size in a control message; every segment starts with its own PktHdr
+        size_t seg = 0;
+        if (gro_ok_)
+          for (cmsghdr* cm = CMSG_FIRSTHDR(&msgs[i].msg_hdr); cm; cm = CMSG_NXTHDR(&msgs[i].msg_hdr, cm))
+            if (cm->cmsg_level == IPPROTO_UDP && cm->cmsg_type == 104 /* UDP_GRO */) {
+              int v = 0;
+              memcpy(&v, CMSG_DATA(cm), sizeof(v));
+              seg = v > 0 ? (size_t)v : 0;
+            }
+        if (seg == 0 || seg >= len) {
+          on_packet(s, from[i], buf, len);
+        } else {
+          for (size_t off = 0; off < len; off += seg) on_packet(s, from[i], buf + off, std::min(seg, len - off));
+        }
+      }
       if (n < kRxBatch) break;
     }
   }
@@ -715,27 +744,81 @@ void Engine::raw_send(int path, const sockaddr_in& to, const void* hdr, size_t h
 void Engine::flush_path(int path) {
   TxBatch& b = txb_[path];
   if (b.n == 0) return;
+  // Build the messages of one sendmmsg.  With UDP GSO (UDP_SEGMENT) a run of equal-sized DATA packets to
+  // the same destination leaves as ONE super-datagram whose iovec is hdr0,payload0,hdr1,payload1,...: the
+  // kernel cuts it every gso_size bytes, so the stack is traversed once per run instead of once per packet.
   mmsghdr msgs[kTxBatch];
-  iovec iov[kTxBatch][2];
-  for (int i = 0; i < b.n; ++i) {
-    TxSlot& s = b.slot[i];
-    iov[i][0].iov_base = &s.hdr;
-    iov[i][0].iov_len = sizeof(PktHdr);
-    iov[i][1].iov_base = const_cast<void*>(s.payload);
-    iov[i][1].iov_len = s.blen;
-    memset(&msgs[i], 0, sizeof(msgs[i]));
-    msgs[i].msg_hdr.msg_name = &s.to;
-    msgs[i].msg_hdr.msg_namelen = sizeof(s.to);
-    msgs[i].msg_hdr.msg_iov = iov[i];
-    msgs[i].msg_hdr.msg_iovlen = s.blen ? 2 : 1;
+  iovec iov[kTxBatch * 2];
+  alignas(cmsghdr) char ctrl[kTxBatch][CMSG_SPACE(sizeof(uint16_t))];
+  int run_len[kTxBatch];
+  int nm = 0, i = 0;
+  while (i < b.n) {
+    TxSlot& s0 = b.slot[i];
+    int jn = i + 1;
+    const size_t seg = sizeof(PktHdr) + s0.blen;
+    if (gso_ok_ && s0.hdr.type == PKT_DATA && s0.blen > 0) {
+      size_t total = seg;
+      while (jn < b.n && jn - i < 64) {
+        TxSlot& sj = b.slot[jn];
+        if (sj.hdr.type != PKT_DATA || sj.to.sin_port != s0.to.sin_port || sj.to.sin_addr.s_addr != s0.to.sin_addr.s_addr) break;
+        if (sj.blen > s0.blen || sj.blen == 0 || total + sizeof(PktHdr) + sj.blen > 65000) break;
+        total += sizeof(PktHdr) + sj.blen;
+        ++jn;
+        if (sj.blen < s0.blen) break;  // a shorter segment may only be the last one
+      }
+    }
+    iovec* v = &iov[2 * i];
+    for (int k = i; k < jn; ++k) {
+      TxSlot& s = b.slot[k];
+      v[2 * (k - i)].iov_base = &s.hdr;
+      v[2 * (k - i)].iov_len = sizeof(PktHdr);
+      v[2 * (k - i) + 1].iov_base = const_cast<void*>(s.payload);
+      v[2 * (k - i) + 1].iov_len = s.blen;
+    }
+    memset(&msgs[nm], 0, sizeof(msgs[nm]));
+    msgs[nm].msg_hdr.msg_name = &s0.to;
+    msgs[nm].msg_hdr.msg_namelen = sizeof(s0.to);
+    msgs[nm].msg_hdr.msg_iov = v;
+    msgs[nm].msg_hdr.msg_iovlen = (jn - i == 1 && s0.blen == 0) ? 1 : (size_t)(2 * (jn - i));
+    if (jn - i > 1) {
+      msgs[nm].msg_hdr.msg_control = ctrl[nm];
+      msgs[nm].msg_hdr.msg_controllen = sizeof(ctrl[nm]);
+      cmsghdr* cm = CMSG_FIRSTHDR(&msgs[nm].msg_hdr);
+      cm->cmsg_level = IPPROTO_UDP;  // == SOL_UDP
+      cm->cmsg_type = 103;  // UDP_SEGMENT
+      cm->cmsg_len = CMSG_LEN(sizeof(uint16_t));
+      const uint16_t gs = (uint16_t)seg;
+      memcpy(CMSG_DATA(cm), &gs, sizeof(gs));
+    }
+    run_len[nm] = jn - i;
+    ++nm;
+    i = jn;
+  }
+  int sent_msgs = 0;
+  while (sent_msgs < nm) {
+    const int r = sendmmsg(socks_[path], msgs + sent_msgs, (unsigned)(nm - sent_msgs), MSG_DONTWAIT);
+    if (r <= 0) {
+      if (gso_ok_ && r < 0 && run_len[sent_msgs] > 1 && (errno == EINVAL || errno == EIO || errno == EOPNOTSUPP || errno == ENOPROTOOPT)) {
+        // no UDP GSO on this kernel / device: fall back to one datagram per packet for good
+        gso_ok_ = false;
+        UB_INFO(SUB_NET, "net: UDP_SEGMENT unavailable (%s): GSO off", strerror(errno));
+        int done = 0;
+        for (int m = 0; m < sent_msgs; ++m) done += run_len[m];
+        memmove(&b.slot[0], &b.slot[done], sizeof(TxSlot) * (size_t)(b.n - done));
+        b.n -= done;
+        for (int k = 0; k < b.n; ++k)  // control packets reference their own slot's body: re-point after the move
+          if (b.slot[k].hdr.type != PKT_DATA) b.slot[k].payload = b.slot[k].body;
+        est_.tx_pkts += (uint64_t)done;
+        flush_path(path);
+        return;
+      }
+      break;  // full socket buffer: the rest counts as dropped; the reliability layer repairs it
+    }
+    sent_msgs += r;
   }
   int sent = 0;
-  while (sent < b.n) {
-    const int r = sendmmsg(socks_[path], msgs + sent, (unsigned)(b.n - sent), MSG_DONTWAIT);
-    if (r <= 0) break;  // full socket buffer: the rest counts as dropped; the reliability layer repairs it
-    sent += r;
-  }
-  for (int i = 0; i < sent; ++i) est_.tx_bytes += sizeof(PktHdr) + b.slot[i].blen;
+  for (int m = 0; m < sent_msgs; ++m) sent += run_len[m];
+  for (int k = 0; k < sent; ++k) est_.tx_bytes += sizeof(PktHdr) + b.slot[k].blen;
   est_.tx_pkts += (uint64_t)sent;
   est_.dropped_tx += (uint64_t)(b.n - sent);
   b.n = 0;

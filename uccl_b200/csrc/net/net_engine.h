@@ -299,6 +299,8 @@ class Engine {
     int n = 0;
   };
   std::vector<TxBatch> txb_;
+  bool gro_ok_ = true;  // UDP_GRO on the receive sockets (coalesced trains are split in rx_poll)
+  bool gso_ok_ = true;  // UDP_SEGMENT super-datagrams (cleared at the first EINVAL/EIO from the kernel)
   void flush_path(int path);
   void flush_all();
 };
