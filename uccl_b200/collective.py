@@ -15,6 +15,8 @@ send/recv on NCCL p2p as the north-star allows.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Union
 
 import torch
@@ -38,6 +40,20 @@ class P2POp:
         return f"P2POp({self.op}, peer={self.peer}, numel={self.tensor.numel()})"
 
 
+class _NetHandle:
+    """Completion handle of an inter-box send / recv (runs on the peer's ordered worker thread)."""
+
+    def __init__(self, fut):
+        self._f = fut
+
+    def is_completed(self) -> bool:
+        return self._f.done()
+
+    def wait(self):
+        self._f.result()
+        return True
+
+
 class CollectiveContext:
     def __init__(self, num_cpus: int = 4, local_gpu_idx: Optional[int] = None, group=None,
                  use_nccl_p2p: bool = False, with_native_collectives: bool = True, heap_bytes: int = 1 << 30):
@@ -59,6 +75,11 @@ class CollectiveContext:
         self._heap_bytes = heap_bytes
         self._registered: Dict[int, int] = {}
         self.initialized = False
+        # peers on other boxes: tensors ride the datagram transport (p2p.internode.NetChannel)
+        self.remote_peers: Dict[int, "object"] = {}   # rank -> NetChannel
+        self._net_tx: Dict[int, "object"] = {}        # rank -> single-thread executor (keeps per-peer order)
+        self._net_rx: Dict[int, "object"] = {}
+        self.net_engine = None
 
     # ------------------------------------------------------------------------- init
     def init(self):
@@ -70,10 +91,11 @@ class CollectiveContext:
         md = self.ep.get_metadata()
         all_md: List[Optional[bytes]] = [None] * self.world_size
         dist.all_gather_object(all_md, md, group=self.group)
+        remote = self._setup_remote_peers()
         # unidirectional connections like the reference: i -> j for every ordered pair.
         # Lower rank connects first to every higher rank, then accepts from lower ranks.
         for peer in range(self.world_size):
-            if peer == self.rank:
+            if peer == self.rank or peer in remote:
                 continue
             ok, conn = self.ep.connect(remote_metadata=all_md[peer])
             assert ok, f"connect to rank {peer} failed"
@@ -81,7 +103,7 @@ class CollectiveContext:
         # identify inbound connections by a hello notification carrying the sender's rank
         for peer, conn in self.send_connections.items():
             self.ep.send_notif(conn, b"rank:%d" % self.rank)
-        pending = self.world_size - 1
+        pending = self.world_size - 1 - len(remote)
         accepted = []
         while len(accepted) < pending:
             ok, ip, gpu, conn = self.ep.accept(60000)
@@ -96,7 +118,15 @@ class CollectiveContext:
                     self.recv_connections[int(msg[5:])] = conn
             assert time.time() - t0 < 60, "peer identification timed out"
             time.sleep(0.001)
-        if self._with_native:
+        if self._with_native and remote:
+            # the group spans boxes: NVLink kernels inside a box, one datagram rail per local rank between boxes
+            from .parallel.multinode import MultiNodeCommunicator
+
+            kw = dict(host=True, heap_bytes=min(self._heap_bytes, 256 << 20), stage_bytes=4 << 20) if self.host else dict(
+                device=self.local_gpu_idx, heap_bytes=self._heap_bytes)
+            assert self.group is None, "multi-box native collectives need the default process group"
+            self.comm = MultiNodeCommunicator.from_torch_dist(self._local_size, **kw)
+        elif self._with_native:
             if self.host:
                 self.comm = Communicator.from_torch_dist(self.group, host=True, heap_bytes=min(self._heap_bytes, 256 << 20),
                                                          stage_bytes=4 << 20)
@@ -105,6 +135,46 @@ class CollectiveContext:
                                                          heap_bytes=self._heap_bytes)
         dist.barrier(group=self.group)
         self.initialized = True
+
+    def _setup_remote_peers(self):
+        """Find the ranks that live on another box and open one NetChannel (one flow) to each of them.
+        Boxes are told apart by hostname + boot id; ``UCCL_B200_LOCAL_SIZE`` overrides (ranks
+        ``[k*L, (k+1)*L)`` = box k), which is also how one machine stands in for several in the tests."""
+        import socket
+        from concurrent.futures import ThreadPoolExecutor
+
+        forced = int(os.environ.get("UCCL_B200_LOCAL_SIZE", "0"))
+        if forced > 0:
+            box = self.rank // forced
+        else:
+            try:
+                boot = open("/proc/sys/kernel/random/boot_id").read().strip()
+            except OSError:
+                boot = ""
+            box = socket.gethostname() + "/" + boot
+        boxes: List[object] = [None] * self.world_size
+        dist.all_gather_object(boxes, box, group=self.group)
+        remote = {p for p in range(self.world_size) if boxes[p] != box}
+        self._local_size = forced if forced > 0 else sum(1 for b in boxes if b == box)
+        if not remote:
+            return remote
+        from . import net
+        from .p2p.internode import NetChannel
+
+        self.net_engine = net.Engine()
+        lower = [p for p in sorted(remote) if p > self.rank]          # they connect to me
+        listeners = {p: NetChannel.listen(self.net_engine) for p in lower}
+        addrs: List[object] = [None] * self.world_size
+        dist.all_gather_object(addrs, {p: ch.address for p, ch in listeners.items()}, group=self.group)
+        for p in sorted(remote):
+            if p < self.rank:
+                self.remote_peers[p] = NetChannel.connect(self.net_engine, addrs[p][self.rank])
+        for p, ch in listeners.items():
+            self.remote_peers[p] = ch.accept()
+        for p in remote:
+            self._net_tx[p] = ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"uccl-net-tx{p}")
+            self._net_rx[p] = ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"uccl-net-rx{p}")
+        return remote
 
     # ----------------------------------------------------------------- registration
     def register_tensor(self, tensor: torch.Tensor) -> int:
@@ -134,6 +204,8 @@ class CollectiveContext:
             return dist.isend(tensor, dst, group=self.group)
         if not self.host:
             torch.cuda.current_stream().synchronize()  # payload must be materialised before the side-stream copy
+        if dst in self.remote_peers:
+            return _NetHandle(self._net_tx[dst].submit(self._net_job, self.remote_peers[dst].send_tensor, tensor))
         ptr, n = self._buf(tensor)
         ok, tid = self.ep.send_async(self.send_connections[dst], 0, ptr, n)
         assert ok
@@ -142,10 +214,17 @@ class CollectiveContext:
     def irecv(self, tensor: torch.Tensor, src: int) -> Union[int, "dist.Work"]:
         if self.use_nccl_p2p:
             return dist.irecv(tensor, src, group=self.group)
+        if src in self.remote_peers:
+            return _NetHandle(self._net_rx[src].submit(self._net_job, self.remote_peers[src].recv_tensor, tensor))
         ptr, n = self._buf(tensor)
         ok, tid = self.ep.recv_async(self.recv_connections[src], 0, ptr, n)
         assert ok
         return tid
+
+    def _net_job(self, fn, tensor):
+        if tensor.is_cuda:
+            torch.cuda.set_device(tensor.device)
+        return fn(tensor)
 
     def send(self, tensor: torch.Tensor, dst: int):
         self.wait(self.isend(tensor, dst))
@@ -214,6 +293,14 @@ class CollectiveContext:
                 self.wait(h)
 
     def finalize(self):
+        for ex in list(self._net_tx.values()) + list(self._net_rx.values()):
+            ex.shutdown(wait=True)
+        for ch in self.remote_peers.values():
+            ch.close()
+        self.remote_peers.clear()
+        self._net_tx.clear()
+        self._net_rx.clear()
+        self.net_engine = None
         if self.ep is not None:
             for conn in list(self.send_connections.values()):
                 self.ep.remove_remote_endpoint(conn)
