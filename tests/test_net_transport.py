@@ -510,3 +510,39 @@ def test_collective_module_across_boxes():
     [p.join(60) for p in ps]
     for rank, ok in got:
         assert all(ok), (rank, ok)
+
+
+def test_many_flows_share_one_engine():
+    """48 flows between two engines (NCCL opens several comms per peer and channel): interleaved transfers on
+    all of them complete and stay separated."""
+    a = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.005)
+    b = net.Engine(bind_ip="127.0.0.1", paths=4, drop_prob=0.005)
+    lid = b.listen()
+    nflows = 48
+    fa = [a._native.connect_async("127.0.0.1", b.port, lid) for _ in range(nflows)]
+    fb = [b.accept(lid) for _ in range(nflows)]
+    import time
+
+    t0 = time.time()
+    while any(a.flow_state(f) != 2 for f in fa):
+        assert time.time() - t0 < 30
+        time.sleep(0.001)
+    # accept order is not connect order: every flow introduces itself
+    tags = [torch.tensor([i], dtype=torch.int64) for i in range(nflows)]
+    ws = [a.isend(f, t) for f, t in zip(fa, tags)]
+    ident = {}
+    for f in fb:
+        who = torch.zeros(1, dtype=torch.int64)
+        b.recv(f, who, 30000)
+        ident[int(who)] = f
+    [w.wait(30000) for w in ws]
+    assert sorted(ident) == list(range(nflows))
+    xs = [torch.full((25_000,), float(i)) for i in range(nflows)]
+    ys = [torch.zeros(25_000) for _ in range(nflows)]
+    rws = [b.irecv(ident[i], ys[i]) for i in range(nflows)]
+    sws = [a.isend(fa[i], xs[i]) for i in range(nflows)]
+    for w in rws + sws:
+        w.wait(60000)
+    for i in range(nflows):
+        assert bool((ys[i] == i).all())
+    assert a.stats()["flows"] >= nflows

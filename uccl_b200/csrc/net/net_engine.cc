@@ -388,7 +388,6 @@ void Engine::complete(Request* r, size_t bytes, int err) {
 
 // ------------------------------------------------------------------------------------ engine loop
 void Engine::run() {
-  std::unordered_map<uint32_t, Flow*> index;
   uint64_t last_stats = 0, last_busy_ns = 0;
   const uint64_t spin_ns = (uint64_t)param_load("NET_SPIN_US", 0) * 1000ull;
   while (!stop_.load(std::memory_order_relaxed)) {
@@ -401,7 +400,11 @@ void Engine::run() {
         cmds.swap(cmds_);
         if (active_dirty_) {
           active_.clear();
-          for (auto& kv : flows_) active_.push_back(kv.second);
+          index_.clear();
+          for (auto& kv : flows_) {
+            active_.push_back(kv.second);
+            index_[kv.first] = kv.second.get();
+          }
           active_dirty_ = false;
         }
       }
@@ -557,11 +560,10 @@ void Engine::on_packet(int sock_idx, const sockaddr_in& from, uint8_t* buf, size
     return;
   }
   Flow* f = nullptr;
-  for (auto& sp : active_)  // small working sets; the lock-protected map is the slow path
-    if (sp->id == h.dst_flow) {
-      f = sp.get();
-      break;
-    }
+  {
+    auto it = index_.find(h.dst_flow);  // engine-thread index of active_; the lock-protected map is the slow path
+    if (it != index_.end()) f = it->second;
+  }
   std::shared_ptr<Flow> hold;
   if (!f) {
     hold = find(h.dst_flow);
@@ -669,6 +671,7 @@ void Engine::on_syn(int sock_idx, const sockaddr_in& from, const PktHdr& h, cons
         syn_index_[key] = f->id;
         lit->second.ready.push_back(f->id);
         active_.push_back(f);
+        index_[f->id] = f.get();
       }
     }
   }

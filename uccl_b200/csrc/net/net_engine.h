@@ -277,6 +277,7 @@ class Engine {
   std::map<std::pair<uint64_t, uint64_t>, uint32_t> syn_index_;  // (peer addr, nonce) -> flow
   std::vector<Cmd> cmds_;
   std::vector<std::shared_ptr<Flow>> active_;  // engine thread's working set
+  std::unordered_map<uint32_t, Flow*> index_;  // id -> flow of active_ (engine thread only)
   bool active_dirty_ = true;
 
   cc::EqdsPacer pacer_;

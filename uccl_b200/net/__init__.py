@@ -63,6 +63,12 @@ class Work:
             req, self._req = self._req, None
             try:
                 self.bytes = self._e._native.wait(req, timeout_ms)
+            except RuntimeError as e:
+                if "timed out" in str(e):
+                    # the engine still owns the request and may yet read / write the buffer: keep both alive
+                    # for the lifetime of the engine instead of letting the tensor be freed under it
+                    self._e._zombies.append((req, self._t))
+                raise
             finally:
                 self._t = None
         return self.bytes
@@ -76,6 +82,7 @@ class Engine:
                  link_gbps: float = 0.0, busy_poll: bool = False):
         self._native = C().net.Engine(bind_ip, paths, payload, max_inflight, eager_max, CC[cc] if cc else -1, drop_prob,
                                       rto_min_us, rto_abort, link_gbps, busy_poll)
+        self._zombies: List = []  # (request, tensor) pairs whose wait timed out; see Work.wait
 
     # ---- addressing / connections
     @property
