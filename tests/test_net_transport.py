@@ -546,3 +546,24 @@ def test_many_flows_share_one_engine():
     for i in range(nflows):
         assert bool((ys[i] == i).all())
     assert a.stats()["flows"] >= nflows
+
+
+def test_gpu_nic_matching_is_rail_aligned():
+    """HGX-like tree: two root complexes, two PCIe switches each, one NIC next to each GPU pair."""
+    from uccl_b200.net.topology import nic_for_gpu, pci_distance
+
+    def dev(root, sw, leaf):
+        return f"/sys/devices/pci0000:{root}/0000:{root}:01.0/0000:{sw}:00.0/0000:{leaf}:00.0"
+
+    gpus = {0: dev("17", "18", "1a"), 1: dev("17", "18", "1b"), 2: dev("17", "28", "2a"), 3: dev("17", "28", "2b"),
+            4: dev("97", "98", "9a"), 5: dev("97", "98", "9b"), 6: dev("97", "a8", "aa"), 7: dev("97", "a8", "ab")}
+    nics = {"mlx0": dev("17", "18", "1c"), "mlx1": dev("17", "28", "2c"), "mlx2": dev("97", "98", "9c"),
+            "mlx3": dev("97", "a8", "ac"), "eno1": "/sys/devices/pci0000:00/0000:00:1f.6"}
+    ifs = [(n, f"10.0.0.{i}") for i, n in enumerate(nics)]
+    assert pci_distance(gpus[0], nics["mlx0"]) < pci_distance(gpus[0], nics["mlx1"]) < pci_distance(gpus[0], nics["mlx2"])
+    picks = [nic_for_gpu(g, local_rank=g, interfaces=ifs, nic_path=nics.get, gpu_path=gpus.get)[0] for g in range(8)]
+    assert picks == ["mlx0", "mlx0", "mlx1", "mlx1", "mlx2", "mlx2", "mlx3", "mlx3"]
+    # no PCI information (VMs, this container): NICs are shared round robin by local rank
+    rr = [nic_for_gpu(None, local_rank=l, interfaces=ifs[:4], nic_path=lambda n: None)[0] for l in range(6)]
+    assert rr == ["mlx0", "mlx1", "mlx2", "mlx3", "mlx0", "mlx1"]
+    assert nic_for_gpu(None, interfaces=[])[1] == "127.0.0.1"

@@ -39,6 +39,19 @@ class MultiNodeCommunicator:
         # all_reduce of more than this many bytes per rank-shard runs as a 3-stage pipeline over chunks
         self.pipeline_bytes = int(os.environ.get("UCCL_B200_MN_PIPELINE_BYTES", str(8 << 20)))
 
+    @staticmethod
+    def _rail_engine(local_rank: int, device: Optional[int]):
+        """Engine bound to the NIC closest to this rank's GPU (round robin by local rank without PCI data);
+        ``UCCL_B200_NET_BIND_IP`` overrides."""
+        from ..net import Engine
+        from ..net.topology import nic_for_gpu
+
+        if os.environ.get("UCCL_B200_NET_BIND_IP"):
+            return Engine()
+        gpu = device if (device is not None and device >= 0) else (torch.cuda.current_device() if torch.cuda.is_available() else None)
+        _, ip = nic_for_gpu(gpu, local_rank)
+        return Engine(bind_ip=ip)
+
     @classmethod
     def from_torch_dist(cls, local_size: int, device: Optional[int] = None, engine=None, **comm_kw) -> "MultiNodeCommunicator":
         """Build from an initialised ``torch.distributed`` world (any backend; only used for bootstrap):
@@ -51,6 +64,7 @@ class MultiNodeCommunicator:
         node_groups = [dist.new_group(list(range(k * local_size, (k + 1) * local_size))) for k in range(nodes)]
         rail_groups = [dist.new_group(list(range(l, world, local_size))) for l in range(local_size)]
         local = Communicator.from_torch_dist(group=node_groups[rank // local_size], device=device, **comm_kw)
+        engine = engine or cls._rail_engine(rank % local_size, device)
         net = NetCommunicator.from_process_group(rail_groups[rank % local_size], engine=engine)
         return cls(local, net)
 
@@ -66,6 +80,7 @@ class MultiNodeCommunicator:
             store.set(key, Communicator.create_unique_id())
         uid = bytes(store.get(key))
         local = Communicator.init(uid, lrank, local_size, **comm_kw)
+        engine = engine or cls._rail_engine(lrank, comm_kw.get("device"))
         net = NetCommunicator.from_store(store, node, world_size // local_size, prefix=f"{prefix}/rail{lrank}", engine=engine)
         return cls(local, net)
 
