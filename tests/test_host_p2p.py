@@ -165,7 +165,8 @@ def _tcp_server(q_md, q_res, nbytes):
     inbox = torch.zeros(nbytes, dtype=torch.uint8)
     okr = e.recv(conn, 0, buf.data_ptr(), nbytes)                 # two-sided receive (payload arrives over TCP)
     descs = e.register_memory([win, inbox])
-    e.send_notif(conn, e.get_serialized_descs(descs))              # windows for the client's read and write
+    secret = torch.full((4096,), 9, dtype=torch.uint8)             # never registered / advertised
+    e.send_notif(conn, e.get_serialized_descs(descs) + secret.data_ptr().to_bytes(8, "little"))
     back = torch.arange(1000, dtype=torch.int32)
     oks = e.send(conn, 0, back.data_ptr(), 4000)                  # and a message in the other direction
     t0 = time.time()
@@ -174,7 +175,8 @@ def _tcp_server(q_md, q_res, nbytes):
         for _, m in e.get_notifs():
             fin = fin or m == b"done"
         time.sleep(0.002)
-    q_res.put((bool(ok), bool(okr), int(buf.sum().item()), bool(oks), int(inbox.to(torch.int64).sum().item()), fin))
+    q_res.put((bool(ok), bool(okr), int(buf.sum().item()), bool(oks), int(inbox.to(torch.int64).sum().item()), fin,
+               int(secret.to(torch.int64).sum().item())))
 
 
 def _tcp_client(q_md, q_res, nbytes):
@@ -194,16 +196,28 @@ def _tcp_client(q_md, q_res, nbytes):
         for _, m in e.get_notifs():
             blob = m
         time.sleep(0.002)
-    remote = e.deserialize_descs(blob)
+    secret_addr = int.from_bytes(blob[-8:], "little")
+    remote = e.deserialize_descs(blob[:-8])
     dst = torch.zeros(nbytes, dtype=torch.uint8)
     okr = e.read(conn, 0, dst.data_ptr(), nbytes, remote[0])       # one-sided read of the server's window
     three = torch.full((nbytes,), 3, dtype=torch.uint8)
     okw = e.write(conn, 0, three.data_ptr(), nbytes, remote[1])    # one-sided write, acknowledged by a flush
     got = torch.zeros(1000, dtype=torch.int32)
     okb = e.recv(conn, 0, got.data_ptr(), 4000)
+    # a forged descriptor that points at memory the server never exposed: the write is dropped, the read refused
+    from uccl_b200.p2p import XferDesc
+
+    forged = bytearray(remote[1].raw)
+    forged[72:80] = secret_addr.to_bytes(8, "little")
+    forged[80:88] = (4096).to_bytes(8, "little")
+    forged = XferDesc(bytes(forged))
+    evil = torch.full((4096,), 1, dtype=torch.uint8)
+    e.write(conn, 0, evil.data_ptr(), 4096, forged)
+    leak = torch.zeros(4096, dtype=torch.uint8)
+    ok_leak = e.read(conn, 0, leak.data_ptr(), 4096, forged)
     e.send_notif(conn, b"done")
     q_res.put((bool(ok), bool(oks), bool(okr), int(dst.to(torch.int64).sum().item()), bool(okw), bool(okb),
-               bool(torch.equal(got, torch.arange(1000, dtype=torch.int32)))))
+               bool(torch.equal(got, torch.arange(1000, dtype=torch.int32))), bool(ok_leak), int(leak.sum().item())))
     time.sleep(0.3)
 
 
@@ -220,8 +234,8 @@ def test_host_mode_between_processes_uses_the_tcp_data_path():
     rs = q_s.get(timeout=180)
     rc = q_c.get(timeout=180)
     [p.join(30) for p in ps]
-    assert rs == (True, True, nbytes, True, 3 * nbytes, True)
-    assert rc == (True, True, True, 7 * nbytes, True, True, True)
+    assert rs == (True, True, nbytes, True, 3 * nbytes, True, 9 * 4096)     # the unexposed buffer is untouched
+    assert rc == (True, True, True, 7 * nbytes, True, True, True, False, 0)  # and could not be read either
 
 
 def _coll_worker(rank, world, port, q):

@@ -355,6 +355,24 @@ bool Endpoint::dereg(uint64_t mr_id) {
   return mrs_.erase(mr_id) > 0;
 }
 
+void Endpoint::expose(uint64_t addr, uint64_t size) {
+  std::lock_guard<std::mutex> g(exp_mu_);
+  for (auto& r : exposed_)
+    if (r.first == addr) {
+      if (size > r.second) r.second = size;
+      return;
+    }
+  if (exposed_.size() >= 65536) exposed_.erase(exposed_.begin(), exposed_.begin() + 32768);  // bounded; oldest go
+  exposed_.emplace_back(addr, size);
+}
+
+bool Endpoint::is_exposed(uint64_t addr, uint64_t n) {
+  std::lock_guard<std::mutex> g(exp_mu_);
+  for (auto& r : exposed_)
+    if (addr >= r.first && addr + n <= r.first + r.second && addr + n >= addr) return true;
+  return false;
+}
+
 bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
   memset(out, 0, sizeof(*out));
   out->addr = (uint64_t)ptr;
@@ -364,6 +382,7 @@ bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
   if (gpu_ < 0) {  // host mode: plain memory of this process
     out->kind = 1;
     out->base = (uint64_t)ptr;
+    expose((uint64_t)ptr, size);
     return true;
   }
   cudaPointerAttributes attr;
@@ -792,7 +811,13 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
       if (gpu_ >= 0 || payload.size() < 16) break;  // only the host mode exposes its memory to the wire
       uint64_t pre[2];
       memcpy(pre, payload.data(), 16);
-      if (pre[1] == payload.size() - 16) memcpy((void*)pre[0], payload.data() + 16, pre[1]);
+      if (pre[1] != payload.size() - 16) break;
+      if (!is_exposed(pre[0], pre[1])) {
+        UB_LOG_FIRST_N(5, LOG_WARN, SUB_P2P, "p2p: peer tried to write %llu bytes outside every exposed window: ignored",
+                       (unsigned long long)pre[1]);
+        break;
+      }
+      memcpy((void*)pre[0], payload.data() + 16, pre[1]);
       break;
     }
     case MSG_FLUSH: {
@@ -810,6 +835,11 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
       for (size_t i = 0; i < nb; ++i) {
         uint64_t e[2];
         memcpy(e, payload.data() + i * 16, 16);
+        if (!is_exposed(e[0], e[1])) {  // the short response makes the requester's transfer fail
+          UB_LOG_FIRST_N(5, LOG_WARN, SUB_P2P, "p2p: peer tried to read outside every exposed window: refused");
+          data->clear();
+          break;
+        }
         const size_t at = data->size();
         data->resize(at + e[1]);
         memcpy(data->data() + at, (const void*)e[0], e[1]);

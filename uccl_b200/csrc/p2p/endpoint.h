@@ -102,6 +102,13 @@ class Endpoint {
   int wake_fd_ = -1;
   std::atomic<bool> stop_{false};
   std::thread engine_;
+  // host mode: the windows this process has handed to peers (registered / advertised / posted receives).
+  // The TCP data path only touches memory inside one of them -- a peer cannot aim MSG_WRITE / READ_REQ at
+  // an arbitrary address of this process.
+  std::mutex exp_mu_;
+  std::vector<std::pair<uint64_t, uint64_t>> exposed_;
+  void expose(uint64_t addr, uint64_t size);
+  bool is_exposed(uint64_t addr, uint64_t n);
   mutable std::mutex mu_;  // guards every table below
   std::condition_variable accept_cv_;
   std::map<uint64_t, std::shared_ptr<Conn>> conns_;
