@@ -2,6 +2,7 @@
 of SURVEY Appendix C checked without a GPU -- receive order, local-expert remapping, cached handles,
 fp8 payloads, expert_alignment, num_worst_tokens, unweighted combine, low-latency dispatch/combine."""
 import threading
+import warnings
 
 import pytest
 import torch
@@ -114,7 +115,9 @@ def test_host_ep_low_latency():
                                                            return_recv_hook=True)
         hook()
         bx, cntb, hb, _, _ = b.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=False)
-        out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb, use_logfmt=True)  # accepted: bf16 payload kept
         return dict(qx=qx, qs=qs, cnt=cnt, stats=stats, bx=bx, cntb=cntb, out=out, hb=hb)
 
     res = _run(comms, fn)

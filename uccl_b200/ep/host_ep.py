@@ -19,6 +19,21 @@ from ..parallel.comm import Communicator
 from .utils import EventOverlap, per_token_cast_to_fp8
 
 
+_LOGFMT_WARNED = False
+
+
+def _warn_logfmt_once() -> None:
+    """``use_logfmt=True`` is accepted for DeepEP API compatibility: the combine payload stays bf16 (a superset of
+    LogFMT-10 in precision); over NVLink the 10-bit encoding would cost more SM time than the bytes it saves."""
+    global _LOGFMT_WARNED
+    if not _LOGFMT_WARNED:
+        _LOGFMT_WARNED = True
+        import warnings
+
+        warnings.warn("uccl_b200.ep: use_logfmt=True is a no-op (payload stays bf16)", stacklevel=3)
+
+
+
 def _a2av(comm: Communicator, send: torch.Tensor, send_rows: List[int], recv_rows: List[int]) -> torch.Tensor:
     """all_to_all_v of whole rows of a 2-D (or 1-D) tensor; rows are ordered by destination rank."""
     width = torch.Size(send.shape[1:]).numel()  # 1 for 1-D tensors
@@ -362,7 +377,8 @@ class HostBuffer:
                             use_logfmt: bool = False, zero_copy: bool = False, async_finish: bool = False,
                             return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                             combine_wait_recv_cost_stats=None):
-        assert not use_logfmt
+        if use_logfmt:
+            _warn_logfmt_once()
         R, me = self.group_size, self.rank
         src_info, layout_range, M, H, E, _, send_pos, allc = handle
         e_per = E // R

@@ -18,6 +18,21 @@ import torch
 from .utils import EventHandle, EventOverlap
 
 
+_LOGFMT_WARNED = False
+
+
+def _warn_logfmt_once() -> None:
+    """``use_logfmt=True`` is accepted for DeepEP API compatibility: the combine payload stays bf16 (a superset of
+    LogFMT-10 in precision); over NVLink the 10-bit encoding would cost more SM time than the bytes it saves."""
+    global _LOGFMT_WARNED
+    if not _LOGFMT_WARNED:
+        _LOGFMT_WARNED = True
+        import warnings
+
+        warnings.warn("uccl_b200.ep: use_logfmt=True is a no-op (payload stays bf16)", stacklevel=3)
+
+
+
 def ll_size_hint(num_max_dispatch_tokens_per_rank: int, hidden: int, num_ranks: int, num_experts: int) -> int:
     from .. import _native
 
@@ -105,7 +120,8 @@ class LowLatencyRuntime:
                 use_logfmt: bool = False, zero_copy: bool = False, async_finish: bool = False,
                 return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                 combine_wait_recv_cost_stats: Optional[torch.Tensor] = None):
-        assert not use_logfmt, "LogFMT compression is not implemented (NVLink bandwidth makes it a net loss here)"
+        if use_logfmt:
+            _warn_logfmt_once()
         src_info, layout_range, M, H, E, idx, send_pos = handle
         b = self.buf
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[-1] == H
