@@ -183,6 +183,7 @@ class NetCommunicator:
         self.engine = engine or Engine()
         self.timeout_ms = timeout_ms
         self.chunk_bytes = chunk_bytes
+        self.small_bytes = int(os.environ.get("UCCL_B200_NET_AR_SMALL_BYTES", str(32 << 10)))  # recursive doubling below
         self.flows: Dict[int, int] = {}
         lid = self.engine.listen()
         addrs = exchange((self.engine.address, self.engine.port, lid))
@@ -270,6 +271,17 @@ class NetCommunicator:
         avg = op == "avg"
         red = _REDUCE["sum" if avg else op]
         flat = t.view(-1)
+        if n & (n - 1) == 0 and flat.numel() * t.element_size() <= self.small_bytes:
+            # latency bound: recursive doubling, log2(n) exchanges of the whole (small) vector
+            tmp = torch.empty_like(flat)
+            d = 1
+            while d < n:
+                self._sendrecv(flat, r ^ d, tmp, r ^ d)
+                red(flat, tmp)
+                d <<= 1
+            if avg:
+                flat.div_(n) if t.is_floating_point() else flat.copy_(torch.div(flat, n, rounding_mode="trunc"))
+            return t
         seg = self._segments(flat.numel())
         nxt, prv = (r + 1) % n, (r - 1) % n
         tmp = torch.empty(max(s.stop - s.start for s in seg), dtype=t.dtype)
