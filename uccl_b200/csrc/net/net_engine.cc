@@ -410,7 +410,11 @@ void Engine::run() {
       }
       for (auto& c : cmds) {
         busy = true;
-        std::shared_ptr<Flow> f = find(c.flow);
+        Flow* f = nullptr;
+        {
+          auto it = index_.find(c.flow);  // rebuilt above whenever the flow table changed
+          if (it != index_.end()) f = it->second;
+        }
         if (!f) {
           if (c.req) complete(c.req, 0, 1);
           continue;
@@ -947,7 +951,7 @@ void Engine::deliver_frame(Flow& f, const PktHdr& h, const uint8_t* payload) {
       m.have_total = true;
       if (m.total > m.cap) m.overflow = true;
     }
-    if (!m.overflow && h.len && h.offset + h.len <= m.total) memcpy(m.ptr + h.offset, payload, h.len);
+    if (!m.overflow && h.len && h.offset <= m.total && h.len <= m.total - h.offset) memcpy(m.ptr + h.offset, payload, h.len);
     m.got += h.len;
     if (m.got >= m.total) {
       complete(m.req, m.total, m.overflow ? 2 : 0);
@@ -960,8 +964,8 @@ void Engine::deliver_frame(Flow& f, const PktHdr& h, const uint8_t* payload) {
     return;
   }
   // receive not posted yet: only eager messages get here
-  if (h.msg_len > (64ull << 20)) {
-    fail_flow(f, "unexpected message larger than 64 MiB (protocol violation)");
+  if (h.msg_len > (64ull << 20) || f.unexpected.size() > (size_t)(8 * cfg_.eager_ahead + 64)) {
+    fail_flow(f, "unexpected-message buffer limits exceeded (protocol violation)");
     return;
   }
   auto it = f.unexpected.find(h.msg_id);
@@ -973,7 +977,7 @@ void Engine::deliver_frame(Flow& f, const PktHdr& h, const uint8_t* payload) {
     ++f.st.unexpected_msgs;
   }
   Unexpected& u = it->second;
-  if (h.len && h.offset + h.len <= u.total) memcpy(u.buf.data() + h.offset, payload, h.len);
+  if (h.len && h.offset <= u.total && h.len <= u.total - h.offset) memcpy(u.buf.data() + h.offset, payload, h.len);
   u.got += h.len;
 }
 
@@ -1284,6 +1288,10 @@ void Engine::timers(uint64_t now) {
       if (now - f.last_progress_ns > kLingerNs) erased = true;
       continue;
     }
+    if (st == FL_ERROR) {  // kept for a while so that the owner can still read the state, then reclaimed
+      if (now - f.last_progress_ns > 15 * kLingerNs) erased = true;
+      continue;
+    }
     if (st != FL_ESTABLISHED && st != FL_CLOSING) continue;
     if (f.snd_una != f.snd_nxt) {
       TxPkt& p = f.ring[f.snd_una % kTxRing];
@@ -1323,7 +1331,9 @@ void Engine::timers(uint64_t now) {
     std::lock_guard<std::mutex> lk(mu_);
     for (auto it = flows_.begin(); it != flows_.end();) {
       Flow& f = *it->second;
-      if (f.state.load() == FL_CLOSED && now - f.last_progress_ns > kLingerNs) {
+      const int fst = f.state.load();
+      if ((fst == FL_CLOSED && now - f.last_progress_ns > kLingerNs) ||
+          (fst == FL_ERROR && now - f.last_progress_ns > 15 * kLingerNs)) {
         for (auto s = syn_index_.begin(); s != syn_index_.end();)
           s = (s->second == f.id) ? syn_index_.erase(s) : std::next(s);
         for (TxMsg* m : f.txq) delete m;
@@ -1341,6 +1351,7 @@ void Engine::fail_flow(Flow& f, const char* why) {
   if (why) UB_WARN("net: flow %u failed: %s", f.id, why);
   const int prev = f.state.exchange(FL_ERROR);
   if (prev == FL_ERROR) return;
+  f.last_progress_ns = now_ns();
   for (TxMsg* m : f.txq) {
     if (m->req) complete(m->req, 0, 1);
     delete m;
