@@ -567,3 +567,31 @@ def test_gpu_nic_matching_is_rail_aligned():
     rr = [nic_for_gpu(None, local_rank=l, interfaces=ifs[:4], nic_path=lambda n: None)[0] for l in range(6)]
     assert rr == ["mlx0", "mlx1", "mlx2", "mlx3", "mlx0", "mlx1"]
     assert nic_for_gpu(None, interfaces=[])[1] == "127.0.0.1"
+
+
+def test_net_communicator_stripes_large_messages_over_engines():
+    """Two engine threads per rank: messages above the stripe threshold are cut in two and both engines carry
+    traffic; small messages stay on the primary engine; results are unchanged."""
+    n = 2
+    ex = _Exchange(n)
+    ins = [torch.arange(600_000, dtype=torch.float32) * (r + 1) for r in range(n)]
+
+    def fn(r):
+        mk = lambda: net.Engine(bind_ip="127.0.0.1", paths=2)  # noqa: E731
+        c = net.NetCommunicator(r, n, ex.for_rank(r), engine=mk(), extra_engines=[mk()], stripe_min_bytes=256 << 10)
+        assert len(c.engines) == 2
+        x = ins[r].clone()
+        c.all_reduce(x)                      # 1.2 MB segments: striped
+        small = c.all_reduce(torch.full((10,), float(r)))
+        g = torch.zeros(n * 300_000)
+        c.all_gather(g, torch.full((300_000,), float(r)))
+        c.barrier()
+        st = c.stats()
+        c.close()
+        return x, small, g, [e["tx_bytes"] for e in st["engines"]]
+
+    outs = _run_threads(n, fn)
+    for r, (x, small, g, txb) in enumerate(outs):
+        assert torch.equal(x, ins[0] + ins[1]) and bool((small == 1.0).all())
+        assert torch.equal(g.view(n, -1)[:, 0], torch.arange(n, dtype=torch.float32))
+        assert min(txb) > 1_000_000, txb     # both engines moved megabytes

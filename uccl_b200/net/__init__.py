@@ -74,6 +74,21 @@ class Work:
         return self.bytes
 
 
+class _MultiWork:
+    """Completion of a message that was striped over several engines."""
+
+    def __init__(self, parts: List[Work]):
+        self._parts = parts
+        self.bytes: Optional[int] = None
+
+    def done(self) -> bool:
+        return all(p.done() for p in self._parts)
+
+    def wait(self, timeout_ms: int = -1) -> int:
+        self.bytes = sum(p.wait(timeout_ms) for p in self._parts)
+        return self.bytes
+
+
 class Engine:
     """One transport engine (= one NIC, one engine thread, ``paths`` UDP source ports)."""
 
@@ -178,29 +193,46 @@ class NetCommunicator:
     """
 
     def __init__(self, rank: int, world_size: int, exchange: Callable[[object], List[object]],
-                 engine: Optional[Engine] = None, timeout_ms: int = 60000, chunk_bytes: int = 4 << 20):
+                 engine: Optional[Engine] = None, timeout_ms: int = 60000, chunk_bytes: int = 4 << 20,
+                 extra_engines: Sequence[Engine] = (), stripe_min_bytes: int = 1 << 20):
+        """``extra_engines``: more engine threads (each with its own sockets / paths) for the same rank; messages
+        of at least ``stripe_min_bytes`` are cut into one contiguous slice per engine, so one rank can drive a
+        NIC that a single engine thread cannot fill (the reference runs several engines per NIC for the same
+        reason: collective/rdma NUM_ENGINES)."""
         self.rank, self.world_size = rank, world_size
         self.engine = engine or Engine()
+        self.engines: List[Engine] = [self.engine] + list(extra_engines)
         self.timeout_ms = timeout_ms
         self.chunk_bytes = chunk_bytes
+        self.stripe_min_bytes = stripe_min_bytes
         self.small_bytes = int(os.environ.get("UCCL_B200_NET_AR_SMALL_BYTES", str(32 << 10)))  # recursive doubling below
-        self.flows: Dict[int, int] = {}
-        lid = self.engine.listen()
-        addrs = exchange((self.engine.address, self.engine.port, lid))
-        # pair (i < j): j connects to i and introduces itself with its rank
+        self.flows: Dict[int, int] = {}                 # peer -> flow on the primary engine
+        self.stripe_flows: Dict[int, List[int]] = {}    # peer -> one flow per engine (index 0 == self.flows[peer])
+        lids = [e.listen() for e in self.engines]
+        addrs = exchange([(e.address, e.port, lid) for e, lid in zip(self.engines, lids)])
+        ne = min(len(a) for a in addrs)                 # engines every member has
+        self.engines = self.engines[:ne]
+        # pair (i < j): j connects to i and introduces itself with its rank, once per engine
         hello = torch.tensor([rank], dtype=torch.int64)
-        for peer in range(rank):
-            ip, port, plid = addrs[peer]
-            f = self.engine.connect(ip, port, plid, timeout_ms)
-            self.engine.send(f, hello, timeout_ms)
-            self.flows[peer] = f
-        for _ in range(rank + 1, world_size):
-            f = self.engine.accept(lid, timeout_ms)
-            who = torch.zeros(1, dtype=torch.int64)
-            self.engine.recv(f, who, timeout_ms)
-            self.flows[int(who.item())] = f
-        self.engine.close_listen(lid)
-        assert sorted(self.flows) == [p for p in range(world_size) if p != rank]
+        per_engine: List[Dict[int, int]] = []
+        for k, e in enumerate(self.engines):
+            fl: Dict[int, int] = {}
+            for peer in range(rank):
+                ip, port, plid = addrs[peer][k]
+                f = e.connect(ip, port, plid, timeout_ms)
+                e.send(f, hello, timeout_ms)
+                fl[peer] = f
+            for _ in range(rank + 1, world_size):
+                f = e.accept(lids[k], timeout_ms)
+                who = torch.zeros(1, dtype=torch.int64)
+                e.recv(f, who, timeout_ms)
+                fl[int(who.item())] = f
+            assert sorted(fl) == [p for p in range(world_size) if p != rank]
+            per_engine.append(fl)
+        for e, lid in zip([self.engine] + list(extra_engines), lids):
+            e.close_listen(lid)
+        self.flows = per_engine[0]
+        self.stripe_flows = {p: [fl[p] for fl in per_engine] for p in self.flows}
 
     # ---- constructors
     @classmethod
@@ -227,11 +259,23 @@ class NetCommunicator:
         return cls(rank, world, exchange, **kw)
 
     # ---- point to point
+    def _striped(self, t: torch.Tensor, peer: int, post) -> "Work":
+        ne = len(self.engines)
+        nbytes = t.numel() * t.element_size()
+        if ne == 1 or nbytes < self.stripe_min_bytes or not t.is_contiguous():
+            return post(self.engine, self.flows[peer], t)
+        b = t.view(-1).view(torch.uint8)
+        step = -(-nbytes // ne)
+        step += (-step) % 64  # slice boundaries on 64-byte lines
+        parts = [post(self.engines[k], self.stripe_flows[peer][k], b[k * step: min((k + 1) * step, nbytes)])
+                 for k in range(ne) if k * step < nbytes]
+        return _MultiWork(parts)
+
     def isend(self, t: torch.Tensor, dst: int) -> Work:
-        return self.engine.isend(self.flows[dst], t)
+        return self._striped(t, dst, lambda e, f, x: e.isend(f, x))
 
     def irecv(self, t: torch.Tensor, src: int) -> Work:
-        return self.engine.irecv(self.flows[src], t)
+        return self._striped(t, src, lambda e, f, x: e.irecv(f, x))
 
     def send(self, t: torch.Tensor, dst: int) -> None:
         self.isend(t, dst).wait(self.timeout_ms)
@@ -351,12 +395,15 @@ class NetCommunicator:
         return out
 
     def stats(self) -> Dict:
-        return {"engine": self.engine.stats(), "flows": {p: self.engine.flow_stats(f) for p, f in self.flows.items()}}
+        return {"engine": self.engine.stats(), "flows": {p: self.engine.flow_stats(f) for p, f in self.flows.items()},
+                "engines": [e.stats() for e in self.engines]}
 
     def close(self) -> None:
-        for f in self.flows.values():
-            self.engine.close(f)
+        for fl in self.stripe_flows.values():
+            for e, f in zip(self.engines, fl):
+                e.close(f)
         self.flows.clear()
+        self.stripe_flows.clear()
 
 
 __all__ = ["Engine", "NetCommunicator", "Work", "list_interfaces", "nccl_net_plugin_path", "CC"]

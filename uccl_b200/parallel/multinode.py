@@ -53,6 +53,12 @@ class MultiNodeCommunicator:
         return Engine(bind_ip=ip)
 
     @classmethod
+    def _extra_engines(cls, local_rank: int, device: Optional[int]):
+        """``UCCL_B200_NET_ENGINES`` engine threads per rail (default 1): large messages are striped over them."""
+        n = int(os.environ.get("UCCL_B200_NET_ENGINES", "1"))
+        return [cls._rail_engine(local_rank, device) for _ in range(max(0, n - 1))]
+
+    @classmethod
     def from_torch_dist(cls, local_size: int, device: Optional[int] = None, engine=None, **comm_kw) -> "MultiNodeCommunicator":
         """Build from an initialised ``torch.distributed`` world (any backend; only used for bootstrap):
         ranks ``[k*local_size, (k+1)*local_size)`` form node ``k``."""
@@ -65,7 +71,8 @@ class MultiNodeCommunicator:
         rail_groups = [dist.new_group(list(range(l, world, local_size))) for l in range(local_size)]
         local = Communicator.from_torch_dist(group=node_groups[rank // local_size], device=device, **comm_kw)
         engine = engine or cls._rail_engine(rank % local_size, device)
-        net = NetCommunicator.from_process_group(rail_groups[rank % local_size], engine=engine)
+        net = NetCommunicator.from_process_group(rail_groups[rank % local_size], engine=engine,
+                                                 extra_engines=cls._extra_engines(rank % local_size, device))
         return cls(local, net)
 
     @classmethod
@@ -81,7 +88,8 @@ class MultiNodeCommunicator:
         uid = bytes(store.get(key))
         local = Communicator.init(uid, lrank, local_size, **comm_kw)
         engine = engine or cls._rail_engine(lrank, comm_kw.get("device"))
-        net = NetCommunicator.from_store(store, node, world_size // local_size, prefix=f"{prefix}/rail{lrank}", engine=engine)
+        net = NetCommunicator.from_store(store, node, world_size // local_size, prefix=f"{prefix}/rail{lrank}", engine=engine,
+                                         extra_engines=cls._extra_engines(lrank, comm_kw.get("device")))
         return cls(local, net)
 
     @property
