@@ -330,11 +330,27 @@ class NetCommunicator:
         nxt, prv = (r + 1) % n, (r - 1) % n
         tmp = torch.empty(max(s.stop - s.start for s in seg), dtype=t.dtype)
         # reduce-scatter: after n-1 steps rank r owns the full reduction of segment (r+1) % n
+        es = t.element_size()
         for step in range(n - 1):
             s_idx, r_idx = (r - step) % n, (r - step - 1) % n
-            rbuf = tmp[: seg[r_idx].stop - seg[r_idx].start]
-            self._sendrecv(flat[seg[s_idx]], nxt, rbuf, prv)
-            red(flat[seg[r_idx]], rbuf)
+            s_seg, r_seg = flat[seg[s_idx]], flat[seg[r_idx]]
+            rbuf = tmp[: r_seg.numel()]
+            # channels: the segment travels as K slices posted back to back; slice k is reduced while slices
+            # > k are still on the wire, so only 1/K of the reduction time is exposed per step
+            K = max(1, min(8, (r_seg.numel() * es) // self.chunk_bytes))
+            if K == 1:
+                self._sendrecv(s_seg, nxt, rbuf, prv)
+                red(r_seg, rbuf)
+                continue
+            rb = [(k * r_seg.numel() // K, (k + 1) * r_seg.numel() // K) for k in range(K)]
+            sb = [(k * s_seg.numel() // K, (k + 1) * s_seg.numel() // K) for k in range(K)]
+            rws = [self.irecv(rbuf[lo:hi], prv) for lo, hi in rb]
+            sws = [self.isend(s_seg[lo:hi], nxt) for lo, hi in sb]
+            for (lo, hi), w in zip(rb, rws):
+                w.wait(self.timeout_ms)
+                red(r_seg[lo:hi], rbuf[lo:hi])
+            for w in sws:
+                w.wait(self.timeout_ms)
         if avg:
             own = flat[seg[(r + 1) % n]]
             own.div_(n) if t.is_floating_point() else own.copy_(torch.div(own, n, rounding_mode="trunc"))
