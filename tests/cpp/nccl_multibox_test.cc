@@ -1,0 +1,149 @@
+// NCCL API over a group that spans boxes: 4 processes = 2 "boxes" x 2 ranks (UCCL_B200_LOCAL_SIZE=2) on the
+// host backend.  Inside a box the native communicator (shared-memory heap), between boxes the datagram
+// rails; every collective is checked against its closed form.
+#include <nccl.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CHECK(x)                                                                                                       \
+  do {                                                                                                                 \
+    ncclResult_t _r = (x);                                                                                             \
+    if (_r != ncclSuccess) {                                                                                           \
+      fprintf(stderr, "rank %d: %s failed: %s (%s)\n", g_rank, #x, ncclGetErrorString(_r), ncclGetLastError(nullptr)); \
+      exit(2);                                                                                                         \
+    }                                                                                                                  \
+  } while (0)
+#define EXPECT(c)                                                                           \
+  do {                                                                                      \
+    if (!(c)) {                                                                             \
+      fprintf(stderr, "rank %d: expectation failed: %s (line %d)\n", g_rank, #c, __LINE__); \
+      exit(3);                                                                              \
+    }                                                                                       \
+  } while (0)
+
+static int g_rank = -1;
+// exported by the drop-in (and by newer NCCL), not declared in nccl.h 2.27
+extern "C" ncclResult_t ncclAllToAll(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+
+static int run(int rank, int n, ncclUniqueId id) {
+  g_rank = rank;
+  ncclComm_t comm;
+  CHECK(ncclCommInitRank(&comm, n, id, rank));
+  int cnt = 0, ur = -1;
+  CHECK(ncclCommCount(comm, &cnt));
+  CHECK(ncclCommUserRank(comm, &ur));
+  EXPECT(cnt == n && ur == rank);
+  const float tri = (float)(n * (n - 1) / 2);
+
+  // all-reduce: a count that is not a multiple of the box size, in and out of place, sum / avg / max
+  const size_t N = 200003;
+  std::vector<float> x(N), y(N, 0.f);
+  for (size_t i = 0; i < N; ++i) x[i] = (float)(i % 89) + rank;
+  CHECK(ncclAllReduce(x.data(), y.data(), N, ncclFloat, ncclSum, comm, nullptr));
+  for (size_t i = 0; i < N; ++i) EXPECT(y[i] == (float)n * (i % 89) + tri);
+  CHECK(ncclAllReduce(x.data(), x.data(), N, ncclFloat, ncclAvg, comm, nullptr));
+  for (size_t i = 0; i < N; ++i) EXPECT(std::fabs(x[i] - ((i % 89) + tri / n)) < 1e-4f);
+  std::vector<int> mi(777, rank * 10), mo(777, -1);
+  CHECK(ncclAllReduce(mi.data(), mo.data(), 777, ncclInt32, ncclMax, comm, nullptr));
+  for (auto v : mo) EXPECT(v == (n - 1) * 10);
+  {
+    float scalar = 0.5f;
+    ncclRedOp_t premul;
+    CHECK(ncclRedOpCreatePreMulSum(&premul, &scalar, ncclFloat, ncclScalarHostImmediate, comm));
+    std::vector<float> pin(11, (float)(rank + 1)), pout(11, 0.f);
+    CHECK(ncclAllReduce(pin.data(), pout.data(), 11, ncclFloat, premul, comm, nullptr));
+    for (auto v : pout) EXPECT(v == 0.5f * (tri + n));
+    CHECK(ncclRedOpDestroy(premul, comm));
+  }
+
+  std::vector<int> g(n * 1000), mine(1000, rank + 1);
+  CHECK(ncclAllGather(mine.data(), g.data(), 1000, ncclInt32, comm, nullptr));
+  for (int r = 0; r < n; ++r)
+    for (int i = 0; i < 1000; ++i) EXPECT(g[r * 1000 + i] == r + 1);
+
+  std::vector<double> rs_in(n * 513), rs_out(513);
+  for (size_t i = 0; i < rs_in.size(); ++i) rs_in[i] = (double)i * (rank + 1);
+  CHECK(ncclReduceScatter(rs_in.data(), rs_out.data(), 513, ncclDouble, ncclSum, comm, nullptr));
+  for (int i = 0; i < 513; ++i) EXPECT(rs_out[i] == (double)(rank * 513 + i) * (tri + n));
+
+  for (int root : {3, 0, 1}) {
+    std::vector<long long> b(100001, rank == root ? 4242 + root : -1);
+    CHECK(ncclBroadcast(b.data(), b.data(), b.size(), ncclInt64, root, comm, nullptr));
+    for (auto v : b) EXPECT(v == 4242 + root);
+  }
+
+  std::vector<float> red(50, (float)(rank + 1)), red_out(50, 0.f);
+  CHECK(ncclReduce(red.data(), red_out.data(), 50, ncclFloat, ncclProd, 2, comm, nullptr));
+  if (rank == 2)
+    for (auto v : red_out) EXPECT(v == 24.f);
+
+  std::vector<int> a_in(n * 300), a_out(n * 300, -1);
+  for (int d = 0; d < n; ++d)
+    for (int i = 0; i < 300; ++i) a_in[d * 300 + i] = 1000 * rank + 10 * d + (i % 7);
+  CHECK(ncclAllToAll(a_in.data(), a_out.data(), 300, ncclInt32, comm, nullptr));
+  for (int s = 0; s < n; ++s)
+    for (int i = 0; i < 300; ++i) EXPECT(a_out[s * 300 + i] == 1000 * s + 10 * rank + (i % 7));
+
+  // grouped send/recv: the box-mate (native kernel path) and the rail-mate (datagram path) in one group
+  {
+    const int mate = rank ^ 1, rail = (rank + 2) % n;
+    std::vector<int> s1(70000, 100 + rank), r1(70000, -1), s2(70000, 200 + rank), r2(70000, -1);
+    CHECK(ncclGroupStart());
+    CHECK(ncclSend(s1.data(), s1.size(), ncclInt32, mate, comm, nullptr));
+    CHECK(ncclRecv(r1.data(), r1.size(), ncclInt32, mate, comm, nullptr));
+    CHECK(ncclSend(s2.data(), s2.size(), ncclInt32, rail, comm, nullptr));
+    CHECK(ncclRecv(r2.data(), r2.size(), ncclInt32, rail, comm, nullptr));
+    CHECK(ncclGroupEnd());
+    for (auto v : r1) EXPECT(v == 100 + mate);
+    for (auto v : r2) EXPECT(v == 200 + rail);
+    // a peer on another rail of another box is refused with a clear error, not a hang
+    const int diag = (rank + 2) % n ^ 1;
+    EXPECT(ncclSend(s1.data(), 1, ncclInt32, diag, comm, nullptr) != ncclSuccess);
+    EXPECT(strstr(ncclGetLastError(comm), "not routed") != nullptr);
+  }
+  ncclComm_t sub = nullptr;
+  EXPECT(ncclCommSplit(comm, 0, rank, &sub, nullptr) == ncclInvalidUsage);
+  CHECK(ncclCommDestroy(comm));
+  return 0;
+}
+
+int main() {
+  setenv("UCCL_B200_HOST_FAKE", "1", 1);
+  setenv("UCCL_B200_LOCAL_SIZE", "2", 1);
+  setenv("UCCL_B200_NET_BIND_IP", "127.0.0.1", 1);
+  setenv("UCCL_B200_NET_PATHS", "2", 0);
+  setenv("UCCL_B200_TIMEOUT_MS", "30000", 0);
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) {
+    fprintf(stderr, "ncclGetUniqueId failed\n");
+    return 1;
+  }
+  const int n = 4;
+  pid_t pids[4] = {0};
+  for (int r = 1; r < n; ++r) {
+    pids[r] = fork();
+    if (pids[r] == 0) _exit(run(r, n, id));
+  }
+  int rc = run(0, n, id);
+  bool ok = rc == 0;
+  for (int r = 1; r < n; ++r) {
+    int st = 0;
+    waitpid(pids[r], &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) {
+      fprintf(stderr, "rank %d exited with status %d\n", r, st);
+      ok = false;
+    }
+  }
+  if (!ok) {
+    fprintf(stderr, "FAILED\n");
+    return 1;
+  }
+  printf("nccl_multibox_test: OK\n");
+  return 0;
+}

@@ -32,6 +32,24 @@ def test_nccl_api_world2_cpu(tmp_path):
     assert "nccl_api_test: OK" in r.stdout
 
 
+@pytest.mark.timeout(300)
+def test_nccl_api_spans_boxes_cpu(tmp_path):
+    """ncclCommInitRank with 4 ranks and a box size of 2: the drop-in builds a MultiComm (native communicator per
+    box + datagram rails) and every NCCL collective, PreMulSum and grouped send/recv work across the boxes."""
+    from uccl_b200 import _build
+
+    _build.build()
+    shim = _build.nccl_shim_path()
+    exe = tmp_path / "nccl_multibox_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests/cpp/nccl_multibox_test.cc"), "-I/usr/include",
+                    "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl",
+                    "-Wl,-rpath," + str(shim.parent), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=240)
+    sys.stdout.write(r.stdout)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "nccl_multibox_test: OK" in r.stdout
+
+
 def test_exported_symbols():
     from uccl_b200 import _build
 

@@ -286,3 +286,24 @@ def test_ep_buffer_across_boxes_with_gpu_tensors():
         exp = torch.cat([xs[s][outs[s][1][:, r].nonzero().flatten()] for s in range(W)])
         assert torch.equal(rx, exp)
         assert torch.allclose(comb.float(), xs[r].float() * inr.sum(1).float()[:, None], rtol=2e-2, atol=1e-1)
+
+
+def test_nccl_api_across_boxes_with_device_buffers(tmp_path):
+    """The NCCL drop-in with more ranks than the configured box size (2 processes x 1 GPU rank on device 0):
+    MultiComm's pinned staging + rail ring with cudaMalloc'd buffers."""
+    import os
+    import subprocess
+    import sys
+
+    from uccl_b200 import _build
+
+    _build.build()
+    shim = _build.nccl_shim_path()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "nccl_multibox_gpu_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "tests/cpp/nccl_multibox_gpu_test.cc"), "-I/usr/include",
+                    "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl", "-Wl,-rpath," + str(shim.parent),
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=240)
+    sys.stdout.write(r.stdout + r.stderr[-2000:])
+    assert r.returncode == 0 and "nccl_multibox_gpu_test: OK" in r.stdout

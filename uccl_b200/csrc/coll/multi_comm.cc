@@ -1,0 +1,482 @@
+// Hierarchical (NVLink inside a box, datagram rails between boxes) collectives in C++; see multi_comm.h.
+#include "multi_comm.h"
+
+#include <arpa/inet.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../common/log.h"
+#include "../common/param.h"
+#include "../fabric/cu_api.h"
+
+namespace ub {
+
+namespace {
+bool float_dtype(int dt) { return dt == kF16 || dt == kF32 || dt == kF64 || dt == kBF16 || dt == kF8E4M3 || dt == kF8E5M2; }
+struct RailAddr {
+  uint32_t ip_be;
+  uint16_t port;
+  uint16_t pad;
+  uint32_t listen_id;
+};
+inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+}  // namespace
+
+std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int nranks, int local_size, int device,
+                                             const CommConfig& cfg) {
+  UB_CHECK(local_size >= 1 && local_size <= kMaxRanks && nranks % local_size == 0,
+           "multi-box communicator: %d ranks are not a multiple of the box size %d", nranks, local_size);
+  auto m = std::shared_ptr<MultiComm>(new MultiComm());
+  m->rank_ = rank;
+  m->nranks_ = nranks;
+  m->L_ = local_size;
+  m->N_ = nranks / local_size;
+  m->node_ = rank / local_size;
+  m->lrank_ = rank % local_size;
+  m->timeout_ms_ = (int)param_load("MN_TIMEOUT_MS", 120000);
+  Bootstrap g(id, rank, nranks);
+  // one rendezvous per box for its NVLink communicator (the relay lives on the box: loopback)
+  UniqueId mine;
+  memset(&mine, 0, sizeof(mine));
+  if (m->lrank_ == 0) mine = Bootstrap::create_id("127.0.0.1");
+  std::vector<UniqueId> ids((size_t)nranks);
+  g.allgather(&mine, ids.data(), sizeof(UniqueId));
+  m->local_ = Comm::create(ids[(size_t)m->node_ * local_size], m->lrank_, local_size, device, cfg);
+  // one rail per local rank
+  net::EngineConfig ec = net::EngineConfig::from_env();
+  m->engine_.reset(new net::Engine(ec));
+  std::string ip = ec.bind_ip;
+  if (ip == "0.0.0.0") {
+    auto ifs = net::list_interfaces();
+    ip = ifs.empty() ? "127.0.0.1" : ifs[(size_t)m->lrank_ % ifs.size()].second;
+  }
+  RailAddr me{};
+  inet_pton(AF_INET, ip.c_str(), &me.ip_be);
+  me.port = m->engine_->port();
+  me.listen_id = m->engine_->listen();
+  std::vector<RailAddr> addrs((size_t)nranks);
+  g.allgather(&me, addrs.data(), sizeof(RailAddr));
+  m->rail_.assign((size_t)m->N_, 0);
+  for (int k = 0; k < m->node_; ++k) {  // higher node connects to lower node of the same rail
+    const RailAddr& a = addrs[(size_t)k * local_size + m->lrank_];
+    char ipb[INET_ADDRSTRLEN];
+    inet_ntop(AF_INET, &a.ip_be, ipb, sizeof(ipb));
+    const uint32_t f = m->engine_->connect(ipb, a.port, a.listen_id, m->timeout_ms_);
+    uint32_t who = (uint32_t)m->node_;
+    m->wait_req(m->engine_->send_async(f, &who, sizeof(who)), "rail hello");
+    m->rail_[(size_t)k] = f;
+  }
+  for (int i = m->node_ + 1; i < m->N_; ++i) {
+    const uint32_t f = m->engine_->accept(me.listen_id, m->timeout_ms_);
+    uint32_t who = 0;
+    m->wait_req(m->engine_->recv_async(f, &who, sizeof(who)), "rail hello");
+    UB_CHECK(who < (uint32_t)m->N_ && (int)who != m->node_, "rail hello from unknown node %u", who);
+    m->rail_[who] = f;
+  }
+  m->engine_->close_listen(me.listen_id);
+  g.barrier();
+  UB_INFO(SUB_INIT, "multi-box communicator: rank %d/%d = box %d/%d local %d/%d, rail via %s", rank, nranks, m->node_,
+          m->N_, m->lrank_, m->L_, ip.c_str());
+  return m;
+}
+
+MultiComm::~MultiComm() {
+  for (auto& d : dbuf_)
+    if (d.p && local_) local_->free(d.p);
+  engine_.reset();  // graceful: FIN exchange + linger
+  for (auto& h : hbuf_) {
+    if (!h.p) continue;
+    if (h.pinned) cudaFreeHost(h.p);
+    else ::free(h.p);
+  }
+}
+
+std::string MultiComm::describe() const {
+  char b[256];
+  snprintf(b, sizeof(b), "MultiComm rank %d/%d box %d/%d local %d/%d | ", rank_, nranks_, node_, N_, lrank_, L_);
+  return std::string(b) + local_->describe();
+}
+
+// ------------------------------------------------------------------------------------------ staging
+char* MultiComm::host_stage(size_t bytes, int slot) {
+  HostBuf& h = hbuf_[slot];
+  if (h.cap >= bytes && h.p) return h.p;
+  if (h.p) {
+    if (h.pinned) cudaFreeHost(h.p);
+    else ::free(h.p);
+  }
+  const size_t cap = std::max<size_t>(bytes, 1 << 16) * 5 / 4;
+  h.pinned = !is_host();
+  if (h.pinned) UB_CUDA(cudaHostAlloc((void**)&h.p, cap, cudaHostAllocDefault));
+  else h.p = (char*)::malloc(cap);
+  UB_CHECK(h.p, "host staging allocation of %zu bytes failed", cap);
+  h.cap = cap;
+  return h.p;
+}
+
+void* MultiComm::scratch(size_t bytes, int slot) {
+  DevBuf& d = dbuf_[slot];
+  if (d.cap >= bytes && d.p) return d.p;
+  if (d.p) local_->free(d.p);
+  const size_t cap = std::max<size_t>(bytes, 1 << 16) * 5 / 4;  // same growth on every local rank: collective alloc
+  d.p = local_->alloc(cap);
+  d.cap = cap;
+  return d.p;
+}
+
+void MultiComm::to_host(void* host, const void* dev, size_t bytes, cudaStream_t s) {
+  if (!bytes || host == dev) return;
+  if (is_host()) memcpy(host, dev, bytes);
+  else UB_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s));
+}
+void MultiComm::to_dev(void* dev, const void* host, size_t bytes, cudaStream_t s) {
+  if (!bytes || host == dev) return;
+  if (is_host()) memcpy(dev, host, bytes);
+  else UB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s));
+}
+void MultiComm::copy_dd(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (!bytes || dst == src) return;
+  if (is_host()) memmove(dst, src, bytes);
+  else UB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+}
+void MultiComm::zero(void* p, size_t bytes, cudaStream_t s) {
+  if (!bytes) return;
+  if (is_host()) memset(p, 0, bytes);
+  else UB_CUDA(cudaMemsetAsync(p, 0, bytes, s));
+}
+void MultiComm::sync(cudaStream_t s) {
+  if (!is_host()) UB_CUDA(cudaStreamSynchronize(s));
+}
+
+// ------------------------------------------------------------------------------------ rail primitives
+void MultiComm::wait_req(net::Request* r, const char* what) {
+  size_t n = 0;
+  UB_CHECK(engine_->wait(r, &n, timeout_ms_), "multi-box %s failed or timed out after %d ms (box %d, rail %d)", what,
+           timeout_ms_, node_, lrank_);
+}
+
+void MultiComm::rail_sendrecv(const void* sbuf, size_t sbytes, int to_node, void* rbuf, size_t rbytes, int from_node) {
+  net::Request* rr = engine_->recv_async(rail_[(size_t)from_node], rbuf, rbytes);
+  net::Request* sr = engine_->send_async(rail_[(size_t)to_node], sbuf, sbytes);
+  wait_req(rr, "rail receive");
+  wait_req(sr, "rail send");
+}
+
+void MultiComm::rail_allreduce(void* buf, size_t count, int dtype, int op) {
+  const int n = N_, r = node_;
+  if (n == 1 || count == 0) return;
+  const size_t es = (size_t)dtype_size(dtype);
+  auto lo = [&](int k) { return (size_t)k * count / (size_t)n; };
+  size_t mx = 0;
+  for (int k = 0; k < n; ++k) mx = std::max(mx, lo(k + 1) - lo(k));
+  char* tmp = host_stage(mx * es, 3);
+  char* b = static_cast<char*>(buf);
+  const int nxt = (r + 1) % n, prv = (r - 1 + n) % n;
+  for (int step = 0; step < n - 1; ++step) {  // reduce-scatter: box r ends up owning segment (r+1) % n
+    const int si = (r - step + n) % n, ri = (r - step - 1 + 2 * n) % n;
+    const size_t sc = lo(si + 1) - lo(si), rc = lo(ri + 1) - lo(ri);
+    rail_sendrecv(b + lo(si) * es, sc * es, nxt, tmp, rc * es, prv);
+    const void* srcs[2] = {b + lo(ri) * es, tmp};
+    host_reduce_n(b + lo(ri) * es, srcs, 2, rc, dtype, op, 1.0f);
+  }
+  for (int step = 0; step < n - 1; ++step) {  // all-gather of the reduced segments
+    const int si = (r + 1 - step + 2 * n) % n, ri = (r - step + 2 * n) % n;
+    rail_sendrecv(b + lo(si) * es, (lo(si + 1) - lo(si)) * es, nxt, b + lo(ri) * es, (lo(ri + 1) - lo(ri)) * es, prv);
+  }
+}
+
+void MultiComm::rail_allgather(void* buf, size_t bytes) {
+  const int n = N_, r = node_;
+  char* b = static_cast<char*>(buf);
+  const int nxt = (r + 1) % n, prv = (r - 1 + n) % n;
+  for (int step = 0; step < n - 1; ++step) {
+    const int si = (r - step + 2 * n) % n, ri = (r - step - 1 + 2 * n) % n;
+    rail_sendrecv(b + (size_t)si * bytes, bytes, nxt, b + (size_t)ri * bytes, bytes, prv);
+  }
+}
+
+void MultiComm::rail_reduce_scatter(void* buf, size_t count, int dtype, int op, void* out) {
+  const int n = N_, r = node_;
+  const size_t es = (size_t)dtype_size(dtype), bytes = count * es;
+  char* b = static_cast<char*>(buf);
+  char* tmp = host_stage(bytes, 3);
+  const int nxt = (r + 1) % n, prv = (r - 1 + n) % n;
+  for (int step = 0; step < n - 1; ++step) {  // ring shifted so that the block finished at box r is block r
+    const int si = (r - step - 1 + 2 * n) % n, ri = (r - step - 2 + 2 * n) % n;
+    rail_sendrecv(b + (size_t)si * bytes, bytes, nxt, tmp, bytes, prv);
+    const void* srcs[2] = {b + (size_t)ri * bytes, tmp};
+    host_reduce_n(b + (size_t)ri * bytes, srcs, 2, count, dtype, op, 1.0f);
+  }
+  memcpy(out, b + (size_t)r * bytes, bytes);
+}
+
+void MultiComm::rail_broadcast(void* buf, size_t bytes, int root_node) {
+  const int n = N_;
+  const int vr = (node_ - root_node + n) % n;  // binomial tree relative to the root box
+  int mask = 1;
+  while (mask < n) {
+    if (vr & mask) {
+      wait_req(engine_->recv_async(rail_[(size_t)((vr - mask + root_node) % n)], buf, bytes), "rail broadcast receive");
+      break;
+    }
+    mask <<= 1;
+  }
+  mask >>= 1;
+  while (mask > 0) {
+    if (vr + mask < n) wait_req(engine_->send_async(rail_[(size_t)((vr + mask + root_node) % n)], buf, bytes), "rail broadcast send");
+    mask >>= 1;
+  }
+}
+
+void MultiComm::rail_alltoall(const void* in, void* out, size_t bytes) {
+  const int n = N_, r = node_;
+  const char* i = static_cast<const char*>(in);
+  char* o = static_cast<char*>(out);
+  memcpy(o + (size_t)r * bytes, i + (size_t)r * bytes, bytes);
+  for (int d = 1; d < n; ++d) {
+    const int to = (r + d) % n, from = (r - d + n) % n;
+    rail_sendrecv(i + (size_t)to * bytes, bytes, to, o + (size_t)from * bytes, bytes, from);
+  }
+}
+
+void MultiComm::rail_barrier() {
+  const int n = N_, r = node_;
+  char tok = 1, got = 0;
+  for (int d = 1; d < n; d <<= 1) rail_sendrecv(&tok, 1, (r + d) % n, &got, 1, (r - d % n + n) % n);
+}
+
+// ---------------------------------------------------------------------------------------- collectives
+void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t st, float scale) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes && op >= 0 && op < kNumOps, "allreduce: bad dtype/op");
+  if (count == 0) return;
+  UB_CHECK((op != kAvg && scale == 1.0f) || float_dtype(dtype), "allreduce across boxes: avg / scale need a floating-point dtype");
+  if (N_ == 1) {
+    ArOpts o;
+    o.scale = scale;
+    local_->allreduce(in, out, count, dtype, op, st, o);
+    return;
+  }
+  const int inner = op == kAvg ? kSum : op;
+  const float sc = scale * (op == kAvg ? 1.0f / (float)nranks_ : 1.0f);
+  const size_t es = (size_t)dtype_size(dtype), per = ceil_div(count, (size_t)L_);
+  char* W = static_cast<char*>(scratch(per * L_ * es, 0));
+  char* S = static_cast<char*>(scratch(per * es, 1));
+  copy_dd(W, in, count * es, st);
+  zero(W + count * es, (per * L_ - count) * es, st);
+  if (L_ > 1) local_->reduce_scatter(W, S, per, dtype, inner, st, 1.0f);
+  else copy_dd(S, W, per * es, st);
+  char* H = is_host() ? S : host_stage(per * es, 0);
+  to_host(H, S, per * es, st);
+  sync(st);
+  rail_allreduce(H, per, dtype, inner);
+  if (sc != 1.0f) {
+    const void* one[1] = {H};
+    host_reduce_n(H, one, 1, per, dtype, kSum, sc);
+  }
+  to_dev(S, H, per * es, st);
+  if (L_ > 1) local_->allgather(S, W, per, dtype, st);
+  else copy_dd(W, S, per * es, st);
+  copy_dd(out, W, count * es, st);
+}
+
+void MultiComm::allgather(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {
+  if (count == 0) return;
+  if (N_ == 1) {
+    local_->allgather(in, out, count, dtype, st);
+    return;
+  }
+  const size_t c = count * (size_t)dtype_size(dtype);
+  char* H = host_stage((size_t)N_ * c, 0);
+  to_host(H + (size_t)node_ * c, in, c, st);
+  sync(st);
+  rail_allgather(H, c);
+  char* R = static_cast<char*>(scratch((size_t)N_ * c, 0));
+  to_dev(R, H, (size_t)N_ * c, st);
+  char* o = static_cast<char*>(out);
+  if (L_ > 1) {
+    char* G = static_cast<char*>(scratch((size_t)L_ * N_ * c, 1));
+    local_->allgather(R, G, (size_t)N_ * count, dtype, st);
+    for (int k = 0; k < N_; ++k)  // G is [local rank][box], the result is [box][local rank]
+      for (int l = 0; l < L_; ++l) copy_dd(o + ((size_t)k * L_ + l) * c, G + ((size_t)l * N_ + k) * c, c, st);
+  } else {
+    copy_dd(o, R, (size_t)N_ * c, st);
+  }
+  if (!is_host()) sync(st);  // the pinned buffer is reused by the next call
+}
+
+void MultiComm::reduce_scatter(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t st) {
+  if (count == 0) return;
+  UB_CHECK(op != kAvg || float_dtype(dtype), "reduce_scatter across boxes: avg needs a floating-point dtype");
+  if (N_ == 1) {
+    local_->reduce_scatter(in, out, count, dtype, op, st);
+    return;
+  }
+  const int inner = op == kAvg ? kSum : op;
+  const float sc = op == kAvg ? 1.0f / (float)nranks_ : 1.0f;
+  const size_t c = count * (size_t)dtype_size(dtype);
+  const char* i = static_cast<const char*>(in);
+  char* part = static_cast<char*>(scratch((size_t)N_ * c, 1));
+  if (L_ > 1) {
+    char* P = static_cast<char*>(scratch((size_t)L_ * N_ * c, 0));  // [dst local rank][box] <- in [box][local rank]
+    for (int k = 0; k < N_; ++k)
+      for (int l = 0; l < L_; ++l) copy_dd(P + ((size_t)l * N_ + k) * c, i + ((size_t)k * L_ + l) * c, c, st);
+    local_->reduce_scatter(P, part, (size_t)N_ * count, dtype, inner, st, 1.0f);
+  } else {
+    copy_dd(part, i, (size_t)N_ * c, st);
+  }
+  char* H = is_host() ? part : host_stage((size_t)N_ * c, 0);
+  to_host(H, part, (size_t)N_ * c, st);
+  sync(st);
+  char* O = host_stage(c, 1);
+  rail_reduce_scatter(H, count, dtype, inner, O);
+  if (sc != 1.0f) {
+    const void* one[1] = {O};
+    host_reduce_n(O, one, 1, count, dtype, kSum, sc);
+  }
+  to_dev(out, O, c, st);
+  if (!is_host()) sync(st);
+}
+
+void MultiComm::broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t st) {
+  UB_CHECK(root >= 0 && root < nranks_, "broadcast: bad root %d", root);
+  if (count == 0) return;
+  if (N_ == 1) {
+    local_->broadcast(in, out, count, dtype, root, st);
+    return;
+  }
+  const size_t b = count * (size_t)dtype_size(dtype);
+  const int root_node = root / L_, root_l = root % L_;
+  char* o = static_cast<char*>(out);
+  if (node_ == root_node) {
+    if (L_ > 1) local_->broadcast(in, out, count, dtype, root_l, st);
+    else copy_dd(out, in, b, st);
+  }
+  // rail l carries bytes [l*per, (l+1)*per) to the other boxes, which re-assemble over NVLink
+  const size_t per = (ceil_div(b, (size_t)L_) + 15) / 16 * 16;
+  const size_t lo = std::min((size_t)lrank_ * per, b), hi = std::min(lo + per, b);
+  char* H = host_stage(per, 0);
+  if (node_ == root_node) {
+    to_host(H, o + lo, hi - lo, st);
+    sync(st);
+  }
+  rail_broadcast(H, per, root_node);
+  if (node_ != root_node) {
+    char* P = static_cast<char*>(scratch(per, 0));
+    to_dev(P, H, per, st);
+    if (L_ > 1) {
+      char* F = static_cast<char*>(scratch(per * L_, 1));
+      local_->allgather(P, F, per, kU8, st);
+      copy_dd(o, F, b, st);
+    } else {
+      copy_dd(o, P, b, st);
+    }
+    if (!is_host()) sync(st);
+  }
+}
+
+void MultiComm::reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t st) {
+  UB_CHECK(root >= 0 && root < nranks_, "reduce: bad root %d", root);
+  if (count == 0) return;
+  const size_t b = count * (size_t)dtype_size(dtype);
+  void* T = scratch(b, 2);
+  allreduce(in, T, count, dtype, op, st);
+  if (rank_ == root) copy_dd(out, T, b, st);
+}
+
+void MultiComm::alltoall(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {
+  if (count == 0) return;
+  if (N_ == 1) {
+    local_->alltoall(in, out, count, dtype, st);
+    return;
+  }
+  const size_t c = count * (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  const char* i = static_cast<const char*>(in);
+  char* C = static_cast<char*>(scratch(W * c, 0));
+  if (L_ > 1) {
+    char* A = C;                                             // [dst local][dst box]
+    char* B = static_cast<char*>(scratch(W * c, 1));         // [src local][dst box] after the NVLink hop
+    for (int k = 0; k < N_; ++k)
+      for (int l = 0; l < L_; ++l) copy_dd(A + ((size_t)l * N_ + k) * c, i + ((size_t)k * L_ + l) * c, c, st);
+    local_->alltoall(A, B, (size_t)N_ * count, dtype, st);
+    char* C2 = static_cast<char*>(scratch(W * c, 2));        // [dst box][src local]: what the rail exchanges
+    for (int l = 0; l < L_; ++l)
+      for (int k = 0; k < N_; ++k) copy_dd(C2 + ((size_t)k * L_ + l) * c, B + ((size_t)l * N_ + k) * c, c, st);
+    C = C2;
+  } else {
+    copy_dd(C, i, W * c, st);
+  }
+  char* H = host_stage(W * c, 0);
+  to_host(H, C, W * c, st);
+  sync(st);
+  char* O = host_stage(W * c, 1);
+  rail_alltoall(H, O, (size_t)L_ * c);  // result is [src box][src local] = global source order
+  to_dev(out, O, W * c, st);
+  if (!is_host()) sync(st);
+}
+
+void MultiComm::barrier(cudaStream_t st) {
+  local_->barrier(st);
+  sync(st);
+  rail_barrier();
+  local_->barrier(st);
+  sync(st);
+}
+
+void MultiComm::group_p2p(const std::vector<Comm::P2pOp>& ops, cudaStream_t st) {
+  std::vector<Comm::P2pOp> local_ops;
+  struct NetOp {
+    Comm::P2pOp op;
+    int node;
+    std::vector<char> stage;
+    net::Request* req = nullptr;
+  };
+  std::vector<NetOp> net_ops;
+  for (const auto& o : ops) {
+    UB_CHECK(o.peer >= 0 && o.peer < nranks_, "send/recv: bad peer %d", o.peer);
+    const int pn = o.peer / L_, pl = o.peer % L_;
+    if (pn == node_) {
+      Comm::P2pOp lo = o;
+      lo.peer = pl;
+      local_ops.push_back(lo);
+    } else {
+      UB_CHECK(pl == lrank_, "send/recv between different rails of different boxes is not routed (rank %d -> %d): go through "
+               "the peer's rail-mate on this box", rank_, o.peer);
+      NetOp n;
+      n.op = o;
+      n.node = pn;
+      net_ops.push_back(std::move(n));
+    }
+  }
+  // receives first so that data lands in place, then sends; the NVLink part runs concurrently on the stream
+  for (auto& n : net_ops)
+    if (!n.op.is_send) {
+      void* dst = n.op.buf;
+      if (!is_host()) {
+        n.stage.resize(n.op.bytes);
+        dst = n.stage.data();
+      }
+      n.req = engine_->recv_async(rail_[(size_t)n.node], dst, n.op.bytes);
+    }
+  bool staged = false;
+  for (auto& n : net_ops)
+    if (n.op.is_send && !is_host()) {
+      n.stage.resize(n.op.bytes);
+      to_host(n.stage.data(), n.op.buf, n.op.bytes, st);
+      staged = true;
+    }
+  if (staged) sync(st);
+  for (auto& n : net_ops)
+    if (n.op.is_send) n.req = engine_->send_async(rail_[(size_t)n.node], is_host() ? n.op.buf : (void*)n.stage.data(), n.op.bytes);
+  if (!local_ops.empty()) local_->group_p2p(local_ops, st);
+  for (auto& n : net_ops) wait_req(n.req, n.op.is_send ? "send" : "recv");
+  bool up = false;
+  for (auto& n : net_ops)
+    if (!n.op.is_send && !is_host()) {
+      to_dev(n.op.buf, n.stage.data(), n.op.bytes, st);
+      up = true;
+    }
+  if (up) sync(st);  // pageable staging vectors die with this call
+}
+
+}  // namespace ub

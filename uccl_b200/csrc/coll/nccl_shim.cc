@@ -23,6 +23,7 @@
 #include "../common/log.h"
 #include "../common/param.h"
 #include "comm.h"
+#include "multi_comm.h"
 #include "../fabric/cu_api.h"
 #include <algorithm>
 
@@ -33,7 +34,8 @@ UB_PARAM(ShimStageMB, "NCCL_STAGE_MB", 128)
 UB_PARAM(ShimHostFake, "HOST_FAKE", 0)
 
 struct ncclComm {
-  std::shared_ptr<Comm> comm;
+  std::shared_ptr<Comm> comm;        // one NVLink domain ...
+  std::shared_ptr<MultiComm> multi;  // ... or a group that spans boxes (then `comm` is null)
   std::map<int, float> premul;  // user-created PreMulSum ops: op id -> scalar
   int next_op = (int)ncclNumOps;
   std::string last_error;
@@ -81,7 +83,25 @@ ncclResult_t guarded(ncclComm* c, F&& f) {
   }
 }
 
-bool valid(ncclComm_t c) { return c != nullptr && c->comm != nullptr; }
+bool valid(ncclComm_t c) { return c != nullptr && (c->comm != nullptr || c->multi != nullptr); }
+// the NVLink-domain communicator behind a handle (for device / heap / error-word queries)
+Comm* local_of(ncclComm_t c) { return c->multi ? c->multi->local().get() : c->comm.get(); }
+int nranks_of(ncclComm_t c) { return c->multi ? c->multi->nranks() : c->comm->nranks(); }
+
+// Ranks per NVLink domain when the job spans boxes: UCCL_B200_LOCAL_SIZE, else the launcher's hint.
+int box_size_hint(int nranks) {
+  int64_t v = param_load("LOCAL_SIZE", 0);
+  if (v <= 0)
+    for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "SLURM_NTASKS_PER_NODE", "MPI_LOCALNRANKS"}) {
+      const char* e = getenv(name);
+      if (e && atoi(e) > 0) {
+        v = atoi(e);
+        break;
+      }
+    }
+  if (v <= 0 && nranks > kMaxRanks) v = kMaxRanks;
+  return (int)v;
+}
 
 ncclResult_t flush_group() {
   // launch queued send/recv per (comm, stream)
@@ -92,7 +112,10 @@ ncclResult_t flush_group() {
   for (auto& p : pend) by[{p.comm, p.stream}].push_back(p.op);
   for (auto& kv : by) {
     ncclComm* c = kv.first.first;
-    ncclResult_t r = guarded(c, [&] { c->comm->group_p2p(kv.second, kv.first.second); });
+    ncclResult_t r = guarded(c, [&] {
+      if (c->multi) c->multi->group_p2p(kv.second, kv.first.second);
+      else c->comm->group_p2p(kv.second, kv.first.second);
+    });
     if (r != ncclSuccess) res = r;
   }
   return res;
@@ -123,8 +146,10 @@ UB_EXPORT ncclResult_t ncclGetUniqueId(ncclUniqueId* uniqueId) {
 UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank,
                                               ncclConfig_t* /*config*/) {
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return ncclInvalidArgument;
-  if (nranks > kMaxRanks) {
-    g_last_error = "uccl_b200: communicators are limited to one NVSwitch node (<= 8 ranks)";
+  const int box = box_size_hint(nranks);
+  const bool spans_boxes = box > 0 && box < nranks;
+  if (spans_boxes && (nranks % box != 0 || box > kMaxRanks)) {
+    g_last_error = "uccl_b200: " + std::to_string(nranks) + " ranks are not a multiple of the box size " + std::to_string(box);
     return ncclInvalidUsage;
   }
   *comm = nullptr;
@@ -136,7 +161,9 @@ UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, nccl
     if (!cfg.host_fake) UB_CHECK(cudaGetDevice(&dev) == cudaSuccess, "cudaGetDevice failed");
     auto c = new ncclComm();
     try {
-      c->comm = Comm::create(id, rank, nranks, dev, cfg);
+      // more ranks than one NVLink domain: NVLink kernels inside each box + datagram rails between boxes
+      if (spans_boxes) c->multi = MultiComm::create(id, rank, nranks, box, dev, cfg);
+      else c->comm = Comm::create(id, rank, nranks, dev, cfg);
     } catch (...) {
       delete c;
       throw;
@@ -186,10 +213,10 @@ UB_EXPORT ncclResult_t ncclCommDestroy(ncclComm_t comm) {
     std::lock_guard<std::mutex> g(g_mu);
     g_comms.erase(comm);
   }
-  if (comm->comm && !comm->comm->is_host()) {
+  if (valid(comm) && !local_of(comm)->is_host()) {
     int prev = -1;
     cudaGetDevice(&prev);
-    cudaSetDevice(comm->comm->device());
+    cudaSetDevice(local_of(comm)->device());
     cudaDeviceSynchronize();
     if (prev >= 0) cudaSetDevice(prev);
   }
@@ -202,6 +229,10 @@ UB_EXPORT ncclResult_t ncclCommAbort(ncclComm_t comm) { return ncclCommDestroy(c
 UB_EXPORT ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, ncclConfig_t* config) {
   if (!valid(comm) || !newcomm) return ncclInvalidArgument;
   *newcomm = nullptr;
+  if (comm->multi) {
+    g_last_error = comm->last_error = "uccl_b200: ncclCommSplit of a communicator that spans boxes is not supported";
+    return ncclInvalidUsage;
+  }
   Comm& c = *comm->comm;
   const int n = c.nranks(), me = c.rank();
   struct Rec {
@@ -271,25 +302,25 @@ UB_EXPORT const char* ncclGetLastError(ncclComm_t comm) {
 
 UB_EXPORT ncclResult_t ncclCommGetAsyncError(ncclComm_t comm, ncclResult_t* asyncError) {
   if (!valid(comm) || !asyncError) return ncclInvalidArgument;
-  *asyncError = comm->comm->error_word() ? ncclInternalError : ncclSuccess;
+  *asyncError = local_of(comm)->error_word() ? ncclInternalError : ncclSuccess;
   return ncclSuccess;
 }
 
 UB_EXPORT ncclResult_t ncclCommCount(const ncclComm_t comm, int* count) {
   if (!valid(comm) || !count) return ncclInvalidArgument;
-  *count = comm->comm->nranks();
+  *count = nranks_of(comm);
   return ncclSuccess;
 }
 
 UB_EXPORT ncclResult_t ncclCommCuDevice(const ncclComm_t comm, int* device) {
   if (!valid(comm) || !device) return ncclInvalidArgument;
-  *device = comm->comm->device();
+  *device = local_of(comm)->device();
   return ncclSuccess;
 }
 
 UB_EXPORT ncclResult_t ncclCommUserRank(const ncclComm_t comm, int* rank) {
   if (!valid(comm) || !rank) return ncclInvalidArgument;
-  *rank = comm->comm->rank();
+  *rank = comm->multi ? comm->multi->rank() : comm->comm->rank();
   return ncclSuccess;
 }
 
@@ -318,13 +349,13 @@ UB_EXPORT ncclResult_t ncclMemAlloc(void** ptr, size_t size) {
     {
       std::lock_guard<std::mutex> g(g_mu);
       for (auto* c : g_comms)
-        if (c->comm && !c->comm->is_host() && c->comm->device() == dev) {
+        if (valid(c) && !local_of(c)->is_host() && local_of(c)->device() == dev) {
           owner = c;
           break;
         }
     }
     if (owner) {
-      *ptr = owner->comm->alloc(size);
+      *ptr = local_of(owner)->alloc(size);
     } else {
       UB_CUDA(cudaMalloc(ptr, size));
     }
@@ -336,8 +367,8 @@ UB_EXPORT ncclResult_t ncclMemFree(void* ptr) {
   return guarded(nullptr, [&] {
     std::lock_guard<std::mutex> g(g_mu);
     for (auto* c : g_comms)
-      if (c->comm && c->comm->in_heap(ptr, 1)) {
-        c->comm->free(ptr);
+      if (valid(c) && local_of(c)->in_heap(ptr, 1)) {
+        local_of(c)->free(ptr);
         return;
       }
     UB_CUDA(cudaFree(ptr));
@@ -354,7 +385,7 @@ UB_EXPORT ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, n
   return guarded(comm, [&] {
     unsigned char raw[8] = {0};
     const size_t es = dtype_size((int)datatype);
-    if (residence == ncclScalarDevice && !comm->comm->is_host()) {
+    if (residence == ncclScalarDevice && !local_of(comm)->is_host()) {
       UB_CUDA(cudaMemcpy(raw, scalar, es, cudaMemcpyDeviceToHost));
     } else {
       memcpy(raw, scalar, es);
@@ -425,7 +456,10 @@ UB_EXPORT ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_
   int rop;
   ArOpts o;
   if (!resolve_op(comm, op, &rop, &o.scale)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->allreduce(sendbuff, recvbuff, count, (int)datatype, rop, stream, o); });
+  return guarded(comm, [&] {
+    if (comm->multi) comm->multi->allreduce(sendbuff, recvbuff, count, (int)datatype, rop, stream, o.scale);
+    else comm->comm->allreduce(sendbuff, recvbuff, count, (int)datatype, rop, stream, o);
+  });
 }
 
 UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
@@ -434,13 +468,23 @@ UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t c
   int rop;
   float scale;
   if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->reduce(sendbuff, recvbuff, count, (int)datatype, rop, root, stream, scale); });
+  return guarded(comm, [&] {
+    if (comm->multi) {
+      UB_CHECK(scale == 1.0f, "PreMulSum reduce across boxes is not supported");
+      comm->multi->reduce(sendbuff, recvbuff, count, (int)datatype, rop, root, stream);
+    } else {
+      comm->comm->reduce(sendbuff, recvbuff, count, (int)datatype, rop, root, stream, scale);
+    }
+  });
 }
 
 UB_EXPORT ncclResult_t ncclBroadcast(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                      int root, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream); });
+  return guarded(comm, [&] {
+    if (comm->multi) comm->multi->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream);
+    else comm->comm->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream);
+  });
 }
 
 UB_EXPORT ncclResult_t ncclBcast(void* buff, size_t count, ncclDataType_t datatype, int root, ncclComm_t comm,
@@ -455,21 +499,33 @@ UB_EXPORT ncclResult_t ncclReduceScatter(const void* sendbuff, void* recvbuff, s
   int rop;
   float scale;
   if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
-  return guarded(comm,
-                 [&] { comm->comm->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, rop, stream, scale); });
+  return guarded(comm, [&] {
+    if (comm->multi) {
+      UB_CHECK(scale == 1.0f, "PreMulSum reduce_scatter across boxes is not supported");
+      comm->multi->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, rop, stream);
+    } else {
+      comm->comm->reduce_scatter(sendbuff, recvbuff, recvcount, (int)datatype, rop, stream, scale);
+    }
+  });
 }
 
 UB_EXPORT ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype,
                                      ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream); });
+  return guarded(comm, [&] {
+    if (comm->multi) comm->multi->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream);
+    else comm->comm->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream);
+  });
 }
 
 // Not part of nccl.h 2.27 but exported by newer NCCL / the reference's shim (as stubs there).
 UB_EXPORT ncclResult_t ncclAllToAll(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                     ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  return guarded(comm, [&] { comm->comm->alltoall(sendbuff, recvbuff, count, (int)datatype, stream); });
+  return guarded(comm, [&] {
+    if (comm->multi) comm->multi->alltoall(sendbuff, recvbuff, count, (int)datatype, stream);
+    else comm->comm->alltoall(sendbuff, recvbuff, count, (int)datatype, stream);
+  });
 }
 
 UB_EXPORT ncclResult_t ncclAllToAllv(const void* sendbuff, const size_t sendcounts[], const size_t sdispls[],
@@ -477,6 +533,7 @@ UB_EXPORT ncclResult_t ncclAllToAllv(const void* sendbuff, const size_t sendcoun
                                      ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
   return guarded(comm, [&] {
+    UB_CHECK(!comm->multi, "ncclAllToAllv across boxes is not supported (use ncclAllToAll or grouped send/recv)");
     comm->comm->alltoallv(sendbuff, sendcounts, sdispls, recvbuff, recvcounts, rdispls, (int)datatype, stream);
   });
 }
@@ -500,7 +557,7 @@ UB_EXPORT ncclResult_t ncclGroupSimulateEnd(ncclSimInfo_t* simInfo) {
 static ncclResult_t post_p2p(bool is_send, void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t comm,
                              cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
-  if ((int)dt < 0 || (int)dt >= kNumDTypes || peer < 0 || peer >= comm->comm->nranks()) return ncclInvalidArgument;
+  if ((int)dt < 0 || (int)dt >= kNumDTypes || peer < 0 || peer >= nranks_of(comm)) return ncclInvalidArgument;
   PendingP2p p;
   p.comm = comm;
   p.op.is_send = is_send;

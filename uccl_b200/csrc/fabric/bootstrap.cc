@@ -142,14 +142,14 @@ void fill_uds_addr(sockaddr_un& a, socklen_t& len, const std::string& name) {
 
 }  // namespace
 
-UniqueId Bootstrap::create_id() {
+UniqueId Bootstrap::create_id(const char* ip_override) {
   UniqueId id;
   memset(&id, 0, sizeof(id));
   int lfd = ::socket(AF_INET, SOCK_STREAM, 0);
   UB_CHECK(lfd >= 0, "socket() failed: %s", strerror(errno));
   int one = 1;
   setsockopt(lfd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-  std::string ip = param_load_str("BOOTSTRAP_IP", "127.0.0.1");
+  std::string ip = ip_override ? std::string(ip_override) : param_load_str("BOOTSTRAP_IP", "127.0.0.1");
   sockaddr_in addr;
   memset(&addr, 0, sizeof(addr));
   addr.sin_family = AF_INET;

@@ -21,7 +21,8 @@ struct UniqueId {
 class Bootstrap {
  public:
   // Creates a rendezvous root (listening socket + relay thread) in this process.
-  static UniqueId create_id();
+  // `ip`: address the relay listens on (default: UCCL_B200_BOOTSTRAP_IP, else 127.0.0.1)
+  static UniqueId create_id(const char* ip = nullptr);
   Bootstrap(const UniqueId& id, int rank, int nranks);
   ~Bootstrap();
   Bootstrap(const Bootstrap&) = delete;
