@@ -30,6 +30,8 @@
 static int g_rank = -1;
 // exported by the drop-in (and by newer NCCL), not declared in nccl.h 2.27
 extern "C" ncclResult_t ncclAllToAll(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+extern "C" ncclResult_t ncclAllToAllv(const void*, const size_t*, const size_t*, void*, const size_t*, const size_t*,
+                                      ncclDataType_t, ncclComm_t, cudaStream_t);
 
 static int run(int rank, int n, ncclUniqueId id) {
   g_rank = rank;
@@ -89,6 +91,21 @@ static int run(int rank, int n, ncclUniqueId id) {
   CHECK(ncclAllToAll(a_in.data(), a_out.data(), 300, ncclInt32, comm, nullptr));
   for (int s = 0; s < n; ++s)
     for (int i = 0; i < 300; ++i) EXPECT(a_out[s * 300 + i] == 1000 * s + 10 * rank + (i % 7));
+
+  {  // variable splits: rank s sends (s + 2 d) % 5 + 1 values to rank d
+    std::vector<size_t> sc(n), sd(n), rc(n), rd(n);
+    size_t st = 0, rt = 0;
+    for (int d = 0; d < n; ++d) {
+      sc[d] = (size_t)((rank + 2 * d) % 5 + 1) * 100, sd[d] = st, st += sc[d];
+      rc[d] = (size_t)((d + 2 * rank) % 5 + 1) * 100, rd[d] = rt, rt += rc[d];
+    }
+    std::vector<float> vin(st), vout(rt, -1.f);
+    for (int d = 0; d < n; ++d)
+      for (size_t i = 0; i < sc[d]; ++i) vin[sd[d] + i] = (float)(100 * rank + d);
+    CHECK(ncclAllToAllv(vin.data(), sc.data(), sd.data(), vout.data(), rc.data(), rd.data(), ncclFloat, comm, nullptr));
+    for (int s = 0; s < n; ++s)
+      for (size_t i = 0; i < rc[s]; ++i) EXPECT(vout[rd[s] + i] == (float)(100 * s + rank));
+  }
 
   // grouped send/recv: the box-mate (native kernel path) and the rail-mate (datagram path) in one group
   {

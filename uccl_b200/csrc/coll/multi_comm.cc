@@ -415,6 +415,34 @@ void MultiComm::alltoall(const void* in, void* out, size_t count, int dtype, cud
   if (!is_host()) sync(st);
 }
 
+void MultiComm::alltoallv(const void* in, const size_t* sc, const size_t* sd, void* out, const size_t* rc, const size_t* rd,
+                          int dtype, cudaStream_t st) {
+  if (N_ == 1) {
+    local_->alltoallv(in, sc, sd, out, rc, rd, dtype, st);
+    return;
+  }
+  const size_t es = (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  // global maximum chunk (one scalar max-all-reduce), then the padded equal-split exchange
+  long long mx = 0;
+  for (size_t d = 0; d < W; ++d) mx = std::max<long long>(mx, (long long)sc[d]);
+  long long* dm = static_cast<long long*>(scratch(64, 3));
+  to_dev(dm, &mx, sizeof(mx), st);
+  sync(st);  // `mx` is a stack variable
+  allreduce(dm, dm, 1, kI64, kMax, st);
+  to_host(&mx, dm, sizeof(mx), st);
+  sync(st);
+  if (mx == 0) return;
+  const size_t m = (size_t)mx;
+  char* pin = static_cast<char*>(scratch(W * m * es, 4));
+  char* pout = static_cast<char*>(scratch(W * m * es, 5));
+  const char* i = static_cast<const char*>(in);
+  char* o = static_cast<char*>(out);
+  for (size_t d = 0; d < W; ++d) copy_dd(pin + d * m * es, i + sd[d] * es, sc[d] * es, st);
+  alltoall(pin, pout, m, dtype, st);
+  for (size_t s = 0; s < W; ++s) copy_dd(o + rd[s] * es, pout + s * m * es, rc[s] * es, st);
+  if (!is_host()) sync(st);
+}
+
 void MultiComm::barrier(cudaStream_t st) {
   local_->barrier(st);
   sync(st);

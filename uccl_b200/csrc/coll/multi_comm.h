@@ -44,6 +44,9 @@ class MultiComm {
   void broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream);
   void reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t stream);
   void alltoall(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream);
+  // variable splits through the equal-split two-hop path: chunks are padded to the global maximum
+  void alltoallv(const void* in, const size_t* send_counts, const size_t* send_displs, void* out, const size_t* recv_counts,
+                 const size_t* recv_displs, int dtype, cudaStream_t stream);
   void barrier(cudaStream_t stream);
   // grouped point-to-point: peers inside the box go to the native kernel, rail peers to the transport;
   // peers on another rail of another box are not routed (error)
@@ -84,7 +87,7 @@ class MultiComm {
     void* p = nullptr;
     size_t cap = 0;
   };
-  DevBuf dbuf_[4];
+  DevBuf dbuf_[8];
 };
 
 }  // namespace ub

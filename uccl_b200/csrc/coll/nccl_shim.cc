@@ -533,8 +533,8 @@ UB_EXPORT ncclResult_t ncclAllToAllv(const void* sendbuff, const size_t sendcoun
                                      ncclDataType_t datatype, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
   return guarded(comm, [&] {
-    UB_CHECK(!comm->multi, "ncclAllToAllv across boxes is not supported (use ncclAllToAll or grouped send/recv)");
-    comm->comm->alltoallv(sendbuff, sendcounts, sdispls, recvbuff, recvcounts, rdispls, (int)datatype, stream);
+    if (comm->multi) comm->multi->alltoallv(sendbuff, sendcounts, sdispls, recvbuff, recvcounts, rdispls, (int)datatype, stream);
+    else comm->comm->alltoallv(sendbuff, sendcounts, sdispls, recvbuff, recvcounts, rdispls, (int)datatype, stream);
   });
 }
 
