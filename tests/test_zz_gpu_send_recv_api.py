@@ -11,7 +11,7 @@ import torch
 
 from helpers import get_world, run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(150),
               pytest.mark.xfail(strict=False, reason="added after the GPU budget was spent; first hardware run pending")]
 
 
@@ -189,7 +189,7 @@ def test_nccl_runs_over_the_net_plugin(tmp_path):
                LD_LIBRARY_PATH=str(plugin.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", "29741", str(script)],
-                       capture_output=True, text=True, timeout=240, env=env)
+                       capture_output=True, text=True, timeout=120, env=env)
     out = r.stdout + r.stderr
     sys.stdout.write(out[-3000:])
     assert r.returncode == 0
@@ -304,6 +304,6 @@ def test_nccl_api_across_boxes_with_device_buffers(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "tests/cpp/nccl_multibox_gpu_test.cc"), "-I/usr/include",
                     "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl", "-Wl,-rpath," + str(shim.parent),
                     "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread", "-o", str(exe)], check=True)
-    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=240)
+    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=120)
     sys.stdout.write(r.stdout + r.stderr[-2000:])
     assert r.returncode == 0 and "nccl_multibox_gpu_test: OK" in r.stdout
