@@ -135,6 +135,7 @@ int main() {
   setenv("UCCL_B200_LOCAL_SIZE", "2", 1);
   setenv("UCCL_B200_NET_BIND_IP", "127.0.0.1", 1);
   setenv("UCCL_B200_NET_PATHS", "2", 0);
+  setenv("UCCL_B200_MN_PIPELINE_BYTES", "65536", 0);  // the 200003-float all-reduce runs as a 7-block pipeline
   setenv("UCCL_B200_TIMEOUT_MS", "30000", 0);
   ncclUniqueId id;
   if (ncclGetUniqueId(&id) != ncclSuccess) {

@@ -5,6 +5,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <thread>
 
 #include "../common/log.h"
 #include "../common/param.h"
@@ -35,6 +37,7 @@ std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int n
   m->node_ = rank / local_size;
   m->lrank_ = rank % local_size;
   m->timeout_ms_ = (int)param_load("MN_TIMEOUT_MS", 120000);
+  m->pipeline_bytes_ = (size_t)param_load("MN_PIPELINE_BYTES", 8 << 20);
   Bootstrap g(id, rank, nranks);
   // one rendezvous per box for its NVLink communicator (the relay lives on the box: loopback)
   UniqueId mine;
@@ -264,6 +267,11 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
   char* S = static_cast<char*>(scratch(per * es, 1));
   copy_dd(W, in, count * es, st);
   zero(W + count * es, (per * L_ - count) * es, st);
+  if (per * es > pipeline_bytes_) {
+    allreduce_pipelined(W, per, dtype, inner, sc, st);
+    copy_dd(out, W, count * es, st);
+    return;
+  }
   if (L_ > 1) local_->reduce_scatter(W, S, per, dtype, inner, st, 1.0f);
   else copy_dd(S, W, per * es, st);
   char* H = is_host() ? S : host_stage(per * es, 0);
@@ -278,6 +286,79 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
   if (L_ > 1) local_->allgather(S, W, per, dtype, st);
   else copy_dd(W, S, per * es, st);
   copy_dd(out, W, count * es, st);
+}
+
+// Block b = columns [lo, hi) of every row of work[L][per].  While block b is on the rail (helper thread), this
+// thread runs the NVLink reduce-scatter of block b+1 and the NVLink all-gather of block b-1.
+void MultiComm::allreduce_pipelined(char* work, size_t per, int dtype, int op, float sc, cudaStream_t st) {
+  const size_t es = (size_t)dtype_size(dtype);
+  const size_t cols = std::max<size_t>(1, pipeline_bytes_ / es);
+  const size_t nblk = ceil_div(per, cols);
+  char* B[2] = {static_cast<char*>(scratch((size_t)L_ * cols * es, 6)), static_cast<char*>(scratch((size_t)L_ * cols * es, 7))};
+  char* S[2] = {static_cast<char*>(scratch(cols * es, 8)), static_cast<char*>(scratch(cols * es, 9))};
+  char* H[2] = {is_host() ? S[0] : host_stage(cols * es, 4), is_host() ? S[1] : host_stage(cols * es, 5)};
+  (void)host_stage(ceil_div(cols, (size_t)N_) * es + 64, 3);  // the rail's receive buffer: allocate before threads run
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  if (!is_host())
+    for (auto& e : ev) UB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  auto width = [&](size_t b) { return std::min(cols, per - b * cols); };
+  auto stage_a = [&](size_t b) {  // gather the block, reduce inside the box, start the download
+    const size_t w = width(b), lo = b * cols;
+    const int k = (int)(b & 1);
+    for (int l = 0; l < L_; ++l) copy_dd(B[k] + (size_t)l * w * es, work + ((size_t)l * per + lo) * es, w * es, st);
+    if (L_ > 1) local_->reduce_scatter(B[k], S[k], w, dtype, op, st, 1.0f);
+    else copy_dd(S[k], B[k], w * es, st);
+    to_host(H[k], S[k], w * es, st);
+    if (!is_host()) UB_CUDA(cudaEventRecord(ev[k], st));
+  };
+  auto stage_c = [&](size_t b) {  // upload, re-assemble inside the box, scatter the block back
+    const size_t w = width(b), lo = b * cols;
+    const int k = (int)(b & 1);
+    to_dev(S[k], H[k], w * es, st);
+    if (L_ > 1) local_->allgather(S[k], B[k], w, dtype, st);
+    else copy_dd(B[k], S[k], w * es, st);
+    for (int l = 0; l < L_; ++l) copy_dd(work + ((size_t)l * per + lo) * es, B[k] + (size_t)l * w * es, w * es, st);
+  };
+  std::exception_ptr net_err;
+  std::thread net;
+  auto start_net = [&](size_t b) {
+    net = std::thread([this, b, &ev, &H, &net_err, width, dtype, op, sc] {
+      try {
+        const int k = (int)(b & 1);
+        if (!is_host()) UB_CUDA(cudaEventSynchronize(ev[k]));
+        rail_allreduce(H[k], width(b), dtype, op);
+        if (sc != 1.0f) {
+          const void* one[1] = {H[k]};
+          host_reduce_n(H[k], one, 1, width(b), dtype, kSum, sc);
+        }
+      } catch (...) {
+        net_err = std::current_exception();
+      }
+    });
+  };
+  auto join_net = [&] {
+    if (net.joinable()) net.join();
+    if (net_err) {
+      if (!is_host())
+        for (auto& e : ev) cudaEventDestroy(e);
+      std::rethrow_exception(net_err);
+    }
+  };
+  stage_a(0);
+  start_net(0);
+  for (size_t b = 1; b < nblk; ++b) {
+    // block b reuses the buffers of block b-2, whose upload (stage_c) was issued on this stream before: ordered
+    stage_a(b);
+    join_net();      // block b-1 is off the rail
+    start_net(b);
+    stage_c(b - 1);  // overlaps block b's network time
+  }
+  join_net();
+  stage_c(nblk - 1);
+  if (!is_host()) {
+    sync(st);  // pinned buffers and events are reused / destroyed
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
 }
 
 void MultiComm::allgather(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {

@@ -70,6 +70,8 @@ class MultiComm {
   void rail_broadcast(void* buf, size_t bytes, int root_node);
   void rail_alltoall(const void* in, void* out, size_t bytes_per_node);
   void rail_barrier();
+  // all-reduce of `work` ([L][per] elements, already padded) as a 3-stage pipeline over column blocks
+  void allreduce_pipelined(char* work, size_t per, int dtype, int op, float scale, cudaStream_t st);
   void wait_req(net::Request* r, const char* what);
 
   int rank_ = 0, nranks_ = 1, L_ = 1, N_ = 1, node_ = 0, lrank_ = 0;
@@ -77,17 +79,18 @@ class MultiComm {
   std::unique_ptr<net::Engine> engine_;
   std::vector<uint32_t> rail_;  // flow to the same local rank of node k (own entry unused)
   int timeout_ms_ = 120000;
+  size_t pipeline_bytes_ = 8u << 20;  // shard bytes above which all-reduce is pipelined (UCCL_B200_MN_PIPELINE_BYTES)
   struct HostBuf {
     char* p = nullptr;
     size_t cap = 0;
     bool pinned = false;
   };
-  HostBuf hbuf_[4];
+  HostBuf hbuf_[6];
   struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
   };
-  DevBuf dbuf_[8];
+  DevBuf dbuf_[12];
 };
 
 }  // namespace ub
