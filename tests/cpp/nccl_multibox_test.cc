@@ -124,8 +124,28 @@ static int run(int rank, int n, ncclUniqueId id) {
     EXPECT(ncclSend(s1.data(), 1, ncclInt32, diag, comm, nullptr) != ncclSuccess);
     EXPECT(strstr(ncclGetLastError(comm), "not routed") != nullptr);
   }
-  ncclComm_t sub = nullptr;
-  EXPECT(ncclCommSplit(comm, 0, rank, &sub, nullptr) == ncclInvalidUsage);
+  {  // split into rails (one member per box -> still spans boxes) and into boxes (plain NVLink communicators)
+    ncclComm_t rail_comm = nullptr, box_comm = nullptr;
+    CHECK(ncclCommSplit(comm, rank % 2, rank, &rail_comm, nullptr));
+    CHECK(ncclCommSplit(comm, rank / 2, rank, &box_comm, nullptr));
+    int c1 = 0, c2 = 0, r1 = -1, r2 = -1;
+    CHECK(ncclCommCount(rail_comm, &c1));
+    CHECK(ncclCommCount(box_comm, &c2));
+    CHECK(ncclCommUserRank(rail_comm, &r1));
+    CHECK(ncclCommUserRank(box_comm, &r2));
+    EXPECT(c1 == 2 && c2 == 2 && r1 == rank / 2 && r2 == rank % 2);
+    std::vector<float> v(3000, (float)rank), o(3000, -1.f);
+    CHECK(ncclAllReduce(v.data(), o.data(), v.size(), ncclFloat, ncclSum, rail_comm, nullptr));
+    for (auto e : o) EXPECT(e == (float)(rank % 2) * 2 + 2);          // ranks {l, l+2}
+    CHECK(ncclAllReduce(v.data(), o.data(), v.size(), ncclFloat, ncclSum, box_comm, nullptr));
+    for (auto e : o) EXPECT(e == (float)(rank / 2) * 4 + 1);          // ranks {2k, 2k+1}
+    CHECK(ncclCommDestroy(rail_comm));
+    CHECK(ncclCommDestroy(box_comm));
+    // members per box must be equal: {0,1,2} vs {3} is refused
+    ncclComm_t bad = nullptr;
+    EXPECT(ncclCommSplit(comm, rank == 3 ? 1 : 0, rank, &bad, nullptr) == (rank == 3 ? ncclSuccess : ncclInvalidUsage));
+    if (bad) CHECK(ncclCommDestroy(bad));
+  }
   CHECK(ncclCommDestroy(comm));
   return 0;
 }

@@ -143,10 +143,10 @@ UB_EXPORT ncclResult_t ncclGetUniqueId(ncclUniqueId* uniqueId) {
   });
 }
 
-UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank,
-                                              ncclConfig_t* /*config*/) {
+// box_override: > 0 = ranks per box are known (ncclCommSplit derives them from the parent), 0 = use the hints
+static ncclResult_t init_rank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank, int box_override) {
   if (!comm || nranks < 1 || rank < 0 || rank >= nranks) return ncclInvalidArgument;
-  const int box = box_size_hint(nranks);
+  const int box = box_override > 0 ? box_override : box_size_hint(nranks);
   const bool spans_boxes = box > 0 && box < nranks;
   if (spans_boxes && (nranks % box != 0 || box > kMaxRanks)) {
     g_last_error = "uccl_b200: " + std::to_string(nranks) + " ranks are not a multiple of the box size " + std::to_string(box);
@@ -172,6 +172,11 @@ UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, nccl
     g_comms.insert(c);
     *comm = c;
   });
+}
+
+UB_EXPORT ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank,
+                                              ncclConfig_t* /*config*/) {
+  return init_rank(comm, nranks, commId, rank, 0);
 }
 
 UB_EXPORT ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId commId, int rank) {
@@ -229,12 +234,13 @@ UB_EXPORT ncclResult_t ncclCommAbort(ncclComm_t comm) { return ncclCommDestroy(c
 UB_EXPORT ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, ncclConfig_t* config) {
   if (!valid(comm) || !newcomm) return ncclInvalidArgument;
   *newcomm = nullptr;
-  if (comm->multi) {
-    g_last_error = comm->last_error = "uccl_b200: ncclCommSplit of a communicator that spans boxes is not supported";
-    return ncclInvalidUsage;
-  }
-  Comm& c = *comm->comm;
-  const int n = c.nranks(), me = c.rank();
+  const bool multi = comm->multi != nullptr;
+  Comm& c = *local_of(comm);
+  const int n = nranks_of(comm), me = multi ? comm->multi->rank() : c.rank();
+  auto gather = [&](const void* in, void* out, size_t bytes) {
+    if (multi) comm->multi->allgather(in, out, bytes, kU8, nullptr);
+    else c.allgather(in, out, bytes, kU8, nullptr);
+  };
   struct Rec {
     int color, key, rank, pad;
     char uid[128];
@@ -249,13 +255,13 @@ UB_EXPORT ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclCo
     UniqueId id = Bootstrap::create_id();  // every rank offers one; the group leader's is used
     memcpy(mine.uid, id.data, sizeof(id.data));
     if (c.is_host()) {
-      c.allgather(&mine, all.data(), sizeof(Rec), kU8, nullptr);
+      gather(&mine, all.data(), sizeof(Rec));
     } else {
       Rec *d_in = nullptr, *d_out = nullptr;
       UB_CUDA(cudaMalloc((void**)&d_in, sizeof(Rec)));
       UB_CUDA(cudaMalloc((void**)&d_out, sizeof(Rec) * n));
       UB_CUDA(cudaMemcpy(d_in, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
-      c.allgather(d_in, d_out, sizeof(Rec), kU8, nullptr);
+      gather(d_in, d_out, sizeof(Rec));
       UB_CUDA(cudaMemcpy(all.data(), d_out, sizeof(Rec) * n, cudaMemcpyDeviceToHost));
       cudaFree(d_in);
       cudaFree(d_out);
@@ -273,7 +279,34 @@ UB_EXPORT ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclCo
   ncclUniqueId uid;
   memset(&uid, 0, sizeof(uid));
   memcpy(uid.internal, grp[0].uid, 128);
-  return ncclCommInitRankConfig(newcomm, (int)grp.size(), uid, newrank, config);
+  (void)config;
+  int box_override = (int)grp.size();  // a single-box parent: the group cannot span boxes
+  if (multi) {
+    // which boxes do the members live in?  The new communicator needs its ranks box-major with the same
+    // number of members per box (that is what rails are built on); one box = a plain NVLink communicator.
+    const int L = comm->multi->local_size();
+    std::vector<int> per_box;
+    int last_box = -1;
+    bool ordered = true;
+    for (auto& x : grp) {
+      const int b = x.rank / L;
+      if (b != last_box) {
+        if (b < last_box) ordered = false;
+        per_box.push_back(0);
+        last_box = b;
+      }
+      ++per_box.back();
+    }
+    for (int cnt : per_box)
+      if (cnt != per_box[0]) ordered = false;
+    if (!ordered) {
+      g_last_error = comm->last_error =
+          "uccl_b200: ncclCommSplit across boxes needs the group's ranks ordered box by box with equally many members per box";
+      return ncclInvalidUsage;
+    }
+    box_override = per_box[0];
+  }
+  return init_rank(newcomm, (int)grp.size(), uid, newrank, box_override);
 }
 
 UB_EXPORT ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t*, ncclConfig_t*, int) {
