@@ -10,6 +10,10 @@ python -c "import sys; sys.path.insert(0, '$root'); from uccl_b200 import _build
 g++ -std=c++17 -O2 "$here/nccl_perf.cc" -I/usr/include -I/usr/local/cuda/include \
     -L"$root/uccl_b200/lib" -luccl_b200_nccl -Wl,-rpath,"$root/uccl_b200/lib" \
     -L/usr/local/cuda/lib64 -lcudart -lpthread -o "$out/nccl_perf_uccl_b200"
+# one process per rank (ncclCommInitRank): also the way to exercise the multi-box path (UCCL_B200_LOCAL_SIZE)
+g++ -std=c++17 -O2 "$here/nccl_perf_mp.cc" -I/usr/include -I/usr/local/cuda/include \
+    -L"$root/uccl_b200/lib" -luccl_b200_nccl -Wl,-rpath,"$root/uccl_b200/lib" \
+    -L/usr/local/cuda/lib64 -lcudart -lpthread -o "$out/nccl_perf_mp_uccl_b200"
 nccl_lib=$(python - <<'PY'
 import glob, os, sys
 cands = glob.glob(os.path.join(sys.prefix, "lib/python*/site-packages/nvidia/nccl/lib/libnccl.so.2")) + glob.glob("/usr/lib/x86_64-linux-gnu/libnccl.so.2")

@@ -153,7 +153,58 @@ void reduce_n_cast(void* dst, const void* const* srcs, int n, size_t count, int 
 
 }  // namespace
 
+namespace {
+// Two-source, unscaled reductions are the inner loop of every inter-box ring step (MultiComm::rail_*): the
+// operator is a template parameter so that the compiler vectorises the loop (the generic reduce_n switches on
+// `op` per element).  dst may alias a.
+template <typename T, int OP>
+void reduce2_plain(T* __restrict__ dst, const T* a, const T* __restrict__ b, size_t n) {
+#pragma GCC ivdep
+  for (size_t i = 0; i < n; ++i) {
+    const T x = a[i], y = b[i];
+    dst[i] = OP == kSum ? (T)(x + y) : OP == kProd ? (T)(x * y) : OP == kMax ? (x > y ? x : y) : (x < y ? x : y);
+  }
+}
+template <int OP>
+void reduce2_bf16(uint16_t* __restrict__ dst, const uint16_t* a, const uint16_t* __restrict__ b, size_t n) {
+#pragma GCC ivdep
+  for (size_t i = 0; i < n; ++i) {
+    const float x = bf16_to_f32(a[i]), y = bf16_to_f32(b[i]);
+    dst[i] = f32_to_bf16(OP == kSum ? x + y : OP == kProd ? x * y : OP == kMax ? (x > y ? x : y) : (x < y ? x : y));
+  }
+}
+template <typename T>
+bool reduce2_dispatch(T* dst, const T* a, const T* b, size_t n, int op) {
+  switch (op) {
+    case kSum: reduce2_plain<T, kSum>(dst, a, b, n); return true;
+    case kProd: reduce2_plain<T, kProd>(dst, a, b, n); return true;
+    case kMax: reduce2_plain<T, kMax>(dst, a, b, n); return true;
+    case kMin: reduce2_plain<T, kMin>(dst, a, b, n); return true;
+    default: return false;
+  }
+}
+bool reduce2_fast(void* dst, const void* a, const void* b, size_t n, int dtype, int op) {
+  switch (dtype) {
+    case kF32: return reduce2_dispatch((float*)dst, (const float*)a, (const float*)b, n, op);
+    case kF64: return reduce2_dispatch((double*)dst, (const double*)a, (const double*)b, n, op);
+    case kI32: return reduce2_dispatch((int32_t*)dst, (const int32_t*)a, (const int32_t*)b, n, op);
+    case kU32: return reduce2_dispatch((uint32_t*)dst, (const uint32_t*)a, (const uint32_t*)b, n, op);
+    case kI64: return reduce2_dispatch((int64_t*)dst, (const int64_t*)a, (const int64_t*)b, n, op);
+    case kU64: return reduce2_dispatch((uint64_t*)dst, (const uint64_t*)a, (const uint64_t*)b, n, op);
+    case kBF16:
+      switch (op) {
+        case kSum: reduce2_bf16<kSum>((uint16_t*)dst, (const uint16_t*)a, (const uint16_t*)b, n); return true;
+        case kMax: reduce2_bf16<kMax>((uint16_t*)dst, (const uint16_t*)a, (const uint16_t*)b, n); return true;
+        case kMin: reduce2_bf16<kMin>((uint16_t*)dst, (const uint16_t*)a, (const uint16_t*)b, n); return true;
+        default: return false;
+      }
+    default: return false;
+  }
+}
+}  // namespace
+
 void host_reduce_n(void* dst, const void* const* srcs, int n, size_t count, int dtype, int op, float scale) {
+  if (n == 2 && scale == 1.0f && reduce2_fast(dst, srcs[0], srcs[1], count, dtype, op)) return;
   reduce_n(dst, srcs, n, count, dtype, op, scale);
 }
 

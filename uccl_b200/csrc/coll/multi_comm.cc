@@ -263,15 +263,14 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
   const int inner = op == kAvg ? kSum : op;
   const float sc = scale * (op == kAvg ? 1.0f / (float)nranks_ : 1.0f);
   const size_t es = (size_t)dtype_size(dtype), per = ceil_div(count, (size_t)L_);
+  if (per * es > pipeline_bytes_) {  // large: block pipeline straight from `in` to `out` (scratch = a few blocks)
+    allreduce_pipelined(static_cast<const char*>(in), static_cast<char*>(out), count, per, dtype, inner, sc, st);
+    return;
+  }
   char* W = static_cast<char*>(scratch(per * L_ * es, 0));
   char* S = static_cast<char*>(scratch(per * es, 1));
   copy_dd(W, in, count * es, st);
   zero(W + count * es, (per * L_ - count) * es, st);
-  if (per * es > pipeline_bytes_) {
-    allreduce_pipelined(W, per, dtype, inner, sc, st);
-    copy_dd(out, W, count * es, st);
-    return;
-  }
   if (L_ > 1) local_->reduce_scatter(W, S, per, dtype, inner, st, 1.0f);
   else copy_dd(S, W, per * es, st);
   char* H = is_host() ? S : host_stage(per * es, 0);
@@ -290,7 +289,8 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
 
 // Block b = columns [lo, hi) of every row of work[L][per].  While block b is on the rail (helper thread), this
 // thread runs the NVLink reduce-scatter of block b+1 and the NVLink all-gather of block b-1.
-void MultiComm::allreduce_pipelined(char* work, size_t per, int dtype, int op, float sc, cudaStream_t st) {
+void MultiComm::allreduce_pipelined(const char* in, char* out, size_t count, size_t per, int dtype, int op, float sc,
+                                    cudaStream_t st) {
   const size_t es = (size_t)dtype_size(dtype);
   const size_t cols = std::max<size_t>(1, pipeline_bytes_ / es);
   const size_t nblk = ceil_div(per, cols);
@@ -305,7 +305,12 @@ void MultiComm::allreduce_pipelined(char* work, size_t per, int dtype, int op, f
   auto stage_a = [&](size_t b) {  // gather the block, reduce inside the box, start the download
     const size_t w = width(b), lo = b * cols;
     const int k = (int)(b & 1);
-    for (int l = 0; l < L_; ++l) copy_dd(B[k] + (size_t)l * w * es, work + ((size_t)l * per + lo) * es, w * es, st);
+    for (int l = 0; l < L_; ++l) {  // row l of the (virtually padded) [L][per] view of `in`
+      const size_t g0 = (size_t)l * per + lo;
+      const size_t valid = g0 >= count ? 0 : std::min(w, count - g0);
+      copy_dd(B[k] + (size_t)l * w * es, in + g0 * es, valid * es, st);
+      zero(B[k] + ((size_t)l * w + valid) * es, (w - valid) * es, st);
+    }
     if (L_ > 1) local_->reduce_scatter(B[k], S[k], w, dtype, op, st, 1.0f);
     else copy_dd(S[k], B[k], w * es, st);
     to_host(H[k], S[k], w * es, st);
@@ -317,7 +322,11 @@ void MultiComm::allreduce_pipelined(char* work, size_t per, int dtype, int op, f
     to_dev(S[k], H[k], w * es, st);
     if (L_ > 1) local_->allgather(S[k], B[k], w, dtype, st);
     else copy_dd(B[k], S[k], w * es, st);
-    for (int l = 0; l < L_; ++l) copy_dd(work + ((size_t)l * per + lo) * es, B[k] + (size_t)l * w * es, w * es, st);
+    for (int l = 0; l < L_; ++l) {
+      const size_t g0 = (size_t)l * per + lo;
+      const size_t valid = g0 >= count ? 0 : std::min(w, count - g0);
+      copy_dd(out + g0 * es, B[k] + (size_t)l * w * es, valid * es, st);
+    }
   };
   std::exception_ptr net_err;
   std::thread net;

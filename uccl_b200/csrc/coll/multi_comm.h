@@ -70,8 +70,8 @@ class MultiComm {
   void rail_broadcast(void* buf, size_t bytes, int root_node);
   void rail_alltoall(const void* in, void* out, size_t bytes_per_node);
   void rail_barrier();
-  // all-reduce of `work` ([L][per] elements, already padded) as a 3-stage pipeline over column blocks
-  void allreduce_pipelined(char* work, size_t per, int dtype, int op, float scale, cudaStream_t st);
+  // all-reduce of `count` elements viewed as [L][per] (zero padded) as a 3-stage pipeline over column blocks
+  void allreduce_pipelined(const char* in, char* out, size_t count, size_t per, int dtype, int op, float scale, cudaStream_t st);
   void wait_req(net::Request* r, const char* what);
 
   int rank_ = 0, nranks_ = 1, L_ = 1, N_ = 1, node_ = 0, lrank_ = 0;
