@@ -6,6 +6,7 @@
 #include <unistd.h>
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,14 @@ static int run(int rank, int n, ncclUniqueId id) {
   std::vector<int> mi(777, rank * 10), mo(777, -1);
   CHECK(ncclAllReduce(mi.data(), mo.data(), 777, ncclInt32, ncclMax, comm, nullptr));
   for (auto v : mo) EXPECT(v == (n - 1) * 10);
+  {  // bf16: 1, 2, 3, 4 -> 10 (0x4120) and max -> 4 (0x4080); exercises the vectorised rail reduction
+    const uint16_t enc[4] = {0x3F80, 0x4000, 0x4040, 0x4080};
+    std::vector<uint16_t> bi(4099, enc[rank]), bo(4099, 0);
+    CHECK(ncclAllReduce(bi.data(), bo.data(), bi.size(), ncclBfloat16, ncclSum, comm, nullptr));
+    for (auto v : bo) EXPECT(v == 0x4120);
+    CHECK(ncclAllReduce(bi.data(), bo.data(), bi.size(), ncclBfloat16, ncclMax, comm, nullptr));
+    for (auto v : bo) EXPECT(v == 0x4080);
+  }
   {
     float scalar = 0.5f;
     ncclRedOp_t premul;
