@@ -595,3 +595,43 @@ def test_net_communicator_stripes_large_messages_over_engines():
         assert torch.equal(x, ins[0] + ins[1]) and bool((small == 1.0).all())
         assert torch.equal(g.view(n, -1)[:, 0], torch.arange(n, dtype=torch.float32))
         assert min(txb) > 1_000_000, txb     # both engines moved megabytes
+
+
+def test_engine_edge_cases():
+    """Mismatched path counts negotiate the minimum; connecting to nobody times out with an error; requests
+    that are still pending when the peer goes away fail instead of hanging."""
+    a = net.Engine(bind_ip="127.0.0.1", paths=8, rto_min_us=2000, rto_abort=6)
+    b = net.Engine(bind_ip="127.0.0.1", paths=3)
+    lid = b.listen()
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("fb", b.accept(lid)))
+    t.start()
+    fa = a.connect("127.0.0.1", b.port, lid)
+    t.join()
+    x, y = torch.randn(500_000), torch.zeros(500_000)
+    w = b.irecv(box["fb"], y)
+    a.send(fa, x, 60000)
+    w.wait(60000)
+    assert torch.equal(x, y)
+    used = [p for p in a.flow_stats(fa)["path_tx"] if p > 0]
+    assert len(used) == 3                                   # only the paths both sides have
+    # nobody listens on this port: the SYN is never answered
+    s = __import__("socket").socket(__import__("socket").AF_INET, __import__("socket").SOCK_DGRAM)
+    s.bind(("127.0.0.1", 0))
+    dead_port = s.getsockname()[1]
+    with pytest.raises(RuntimeError, match="timed out"):
+        a.connect("127.0.0.1", dead_port, 1, timeout_ms=400)
+    s.close()
+    # the peer disappears while a rendezvous send is parked and a receive is posted
+    big = torch.ones(1_000_000)
+    ws = a.isend(fa, big)                                   # waits for b's RTR, which never comes
+    wr = a.irecv(fa, torch.zeros(10))
+    del b, w                                                # b's engine shuts down: FIN reaches a
+    import gc
+
+    gc.collect()
+    with pytest.raises(RuntimeError, match="peer closed"):
+        wr.wait(30000)
+    with pytest.raises(RuntimeError):                       # keep-alive probe -> retransmission limit -> flow error
+        ws.wait(60000)
+    assert a.flow_state(fa) == 5
