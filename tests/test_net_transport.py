@@ -635,3 +635,48 @@ def test_engine_edge_cases():
     with pytest.raises(RuntimeError):                       # keep-alive probe -> retransmission limit -> flow error
         ws.wait(60000)
     assert a.flow_state(fa) == 5
+
+
+@pytest.mark.parametrize("n,algo", [(2, "auto"), (3, "ring"), (4, "fullmesh"), (4, "ring")])
+def test_ukernel_plans_over_the_datagram_transport(n, algo):
+    """The ukernel planner's tile DAGs executed by the message-transport adapter (Send = header + payload message,
+    placement on arrival, Recv = arrival counter), with loss on the wire; several tiles and lanes per collective."""
+    from uccl_b200 import ukernel
+
+    ex = _Exchange(n)
+    g = torch.Generator().manual_seed(7 * n)
+    ins = [torch.randint(-20, 20, (50_003,), generator=g).float() for _ in range(n)]
+
+    def fn(r):
+        u = ukernel.UkNetCommunicator(r, n, ex.for_rank(r), engine=net.Engine(bind_ip="127.0.0.1", paths=2, drop_prob=0.005),
+                                      nlanes=2, tile_bytes=16 << 10)
+        res = {}
+        res["sum"] = u.all_reduce(ins[r].clone(), algo=algo)
+        o = torch.zeros_like(ins[r])
+        u.all_reduce(ins[r], "max", out=o, algo=algo)            # out of place
+        res["max"] = o
+        a2a = torch.zeros(n * 3000, dtype=torch.int64)
+        u.all_to_all_single(a2a, torch.arange(n * 3000, dtype=torch.int64) + 100_000 * r)
+        res["a2a"] = a2a
+        ag = torch.zeros(n * 5000)
+        u.all_gather_into_tensor(ag, torch.full((5000,), float(r)))
+        res["ag"] = ag
+        rs = torch.zeros(4000)
+        u.reduce_scatter_tensor(rs, torch.arange(n * 4000, dtype=torch.float32) * (r + 1))
+        res["rs"] = rs
+        b = torch.full((30_000,), float(r))
+        u.broadcast(b, root=n - 1)
+        res["b"] = b
+        u.barrier()
+        res["stats"] = u.stats()
+        return res
+
+    outs = _run_threads(n, fn)
+    ref = torch.stack(ins)
+    for r, o in enumerate(outs):
+        assert torch.equal(o["sum"], ref.sum(0)) and torch.equal(o["max"], ref.max(0).values)
+        assert torch.equal(o["a2a"], torch.cat([torch.arange(3000) + 3000 * r + 100_000 * s for s in range(n)]))
+        assert torch.equal(o["ag"].view(n, -1)[:, 0], torch.arange(n, dtype=torch.float32))
+        assert torch.equal(o["rs"], torch.arange(n * 4000, dtype=torch.float32).view(n, 4000)[r] * (n * (n + 1) / 2))
+        assert bool((o["b"] == n - 1).all())
+        assert o["stats"]["sends"] > 0 and o["stats"]["recvs"] > 0

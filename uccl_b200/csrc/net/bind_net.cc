@@ -45,8 +45,14 @@ void bind_net(py::module_& root) {
              c.busy_poll = c.busy_poll || busy_poll;
              // the destructor lingers for the FIN exchange: never do that while holding the GIL
              return std::shared_ptr<Engine>(new Engine(c), [](Engine* e) {
-               py::gil_scoped_release rel;
-               delete e;
+               // the last reference may be dropped by Python (GIL held) or by a native owner that already
+               // released it (e.g. a ukernel communicator being destroyed)
+               if (PyGILState_Check()) {
+                 py::gil_scoped_release rel;
+                 delete e;
+               } else {
+                 delete e;
+               }
              });
            }),
            py::arg("bind_ip") = "", py::arg("paths") = 0, py::arg("payload") = 0, py::arg("max_inflight") = 0,

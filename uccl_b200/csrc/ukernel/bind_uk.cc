@@ -4,6 +4,7 @@
 
 #include "../common/log.h"
 #include "uk_comm.h"
+#include "uk_net.h"
 
 namespace py = pybind11;
 using namespace ub;
@@ -206,6 +207,59 @@ void bind_uk(py::module_& m) {
         py::dict d;
         d["ops"] = s.ops, d["segments"] = s.segments, d["tasks"] = s.tasks, d["zero_copy_ops"] = s.zero_copy_ops;
         d["stream_ordered_ops"] = s.stream_ordered_ops;
+        return d;
+      });
+  // plans over the message transport (ranks on other boxes)
+  py::class_<UkNetComm, std::shared_ptr<UkNetComm>>(uk, "UkNetComm")
+      .def(py::init([](int rank, int nranks, std::shared_ptr<net::Engine> engine, std::vector<uint32_t> flows, int nlanes,
+                       uint64_t tile_bytes, int timeout_ms) {
+             UkNetConfig c;
+             c.nlanes = nlanes, c.tile_bytes = tile_bytes, c.timeout_ms = timeout_ms;
+             return std::shared_ptr<UkNetComm>(new UkNetComm(rank, nranks, std::move(engine), std::move(flows), c),
+                                               [](UkNetComm* u) {
+                                                 if (PyGILState_Check()) {
+                                                   py::gil_scoped_release rel;
+                                                   delete u;
+                                                 } else {
+                                                   delete u;
+                                                 }
+                                               });
+           }),
+           py::arg("rank"), py::arg("nranks"), py::arg("engine"), py::arg("flows"), py::arg("nlanes") = 2,
+           py::arg("tile_bytes") = 1 << 20, py::arg("timeout_ms") = 60000)
+      .def_property_readonly("rank", &UkNetComm::rank)
+      .def_property_readonly("nranks", &UkNetComm::nranks)
+      .def("all_reduce",
+           [](UkNetComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int algo) {
+             py::gil_scoped_release rel;
+             u.all_reduce((const void*)in, (void*)out, count, dtype, op, (UkAlgo)algo);
+           },
+           py::arg("inp"), py::arg("out"), py::arg("count"), py::arg("dtype"), py::arg("op"), py::arg("algo") = 0)
+      .def("all_to_all",
+           [](UkNetComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype) {
+             py::gil_scoped_release rel;
+             u.all_to_all((const void*)in, (void*)out, count, dtype);
+           })
+      .def("all_gather",
+           [](UkNetComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype) {
+             py::gil_scoped_release rel;
+             u.all_gather((const void*)in, (void*)out, count, dtype);
+           })
+      .def("reduce_scatter",
+           [](UkNetComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int op) {
+             py::gil_scoped_release rel;
+             u.reduce_scatter((const void*)in, (void*)out, count, dtype, op);
+           })
+      .def("broadcast",
+           [](UkNetComm& u, uintptr_t in, uintptr_t out, size_t count, int dtype, int root) {
+             py::gil_scoped_release rel;
+             u.broadcast((const void*)in, (void*)out, count, dtype, root);
+           })
+      .def("barrier", &UkNetComm::barrier, py::call_guard<py::gil_scoped_release>())
+      .def("stats", [](UkNetComm& u) {
+        auto s = u.stats();
+        py::dict d;
+        d["ops"] = s.ops, d["sends"] = s.sends, d["recvs"] = s.recvs, d["bytes_sent"] = s.bytes_sent;
         return d;
       });
 }

@@ -249,3 +249,60 @@ class ProcessGroup:
 
     def shutdown(self):
         self._uk.stop()
+
+
+class UkNetCommunicator:
+    """ukernel collectives for ranks on *different boxes*: the same planner (ring / full-mesh tile DAGs), executed
+    over the multipath datagram transport instead of load/store -- the role of the reference's TCP / UCCL
+    transport adapters (experimental/ukernel/src/transport/adapter).  Tensors are host (or pinned) memory.
+
+    ``exchange`` is an all-gather of small python objects between the members (as for ``net.NetCommunicator``);
+    the communicator opens its own flows on ``engine``.
+    """
+
+    def __init__(self, rank: int, world_size: int, exchange, engine=None, nlanes: int = 2, tile_bytes: int = 1 << 20,
+                 timeout_ms: int = 60000):
+        from .. import net
+
+        self._boot = net.NetCommunicator(rank, world_size, exchange, engine=engine or net.Engine(), timeout_ms=timeout_ms)
+        flows = [self._boot.flows.get(p, 0) for p in range(world_size)]
+        self.rank, self.world_size = rank, world_size
+        self._u = _uk().UkNetComm(rank, world_size, self._boot.engine._native, flows, nlanes, int(tile_bytes), timeout_ms)
+
+    @staticmethod
+    def _host(t: torch.Tensor, name: str) -> torch.Tensor:
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"ukernel net: {name} must be a contiguous host tensor")
+        return t
+
+    def all_reduce(self, tensor: torch.Tensor, op: str = "sum", out: Optional[torch.Tensor] = None, algo: str = "auto"):
+        out = tensor if out is None else out
+        self._u.all_reduce(self._host(tensor, "tensor").data_ptr(), self._host(out, "out").data_ptr(), tensor.numel(),
+                           dtype_code(tensor.dtype), op_code(op), ALGOS[algo])
+        return out
+
+    def all_to_all_single(self, out: torch.Tensor, inp: torch.Tensor):
+        self._u.all_to_all(self._host(inp, "inp").data_ptr(), self._host(out, "out").data_ptr(),
+                           inp.numel() // self.world_size, dtype_code(inp.dtype))
+        return out
+
+    def all_gather_into_tensor(self, out: torch.Tensor, inp: torch.Tensor):
+        self._u.all_gather(self._host(inp, "inp").data_ptr(), self._host(out, "out").data_ptr(), inp.numel(),
+                           dtype_code(inp.dtype))
+        return out
+
+    def reduce_scatter_tensor(self, out: torch.Tensor, inp: torch.Tensor, op: str = "sum"):
+        self._u.reduce_scatter(self._host(inp, "inp").data_ptr(), self._host(out, "out").data_ptr(), out.numel(),
+                               dtype_code(inp.dtype), op_code(op))
+        return out
+
+    def broadcast(self, tensor: torch.Tensor, root: int = 0):
+        self._u.broadcast(self._host(tensor, "tensor").data_ptr(), tensor.data_ptr(), tensor.numel(),
+                          dtype_code(tensor.dtype), root)
+        return tensor
+
+    def barrier(self):
+        self._u.barrier()
+
+    def stats(self):
+        return self._u.stats()
