@@ -680,3 +680,56 @@ def test_ukernel_plans_over_the_datagram_transport(n, algo):
         assert torch.equal(o["rs"], torch.arange(n * 4000, dtype=torch.float32).view(n, 4000)[r] * (n * (n + 1) / 2))
         assert bool((o["b"] == n - 1).all())
         assert o["stats"]["sends"] > 0 and o["stats"]["recvs"] > 0
+
+
+def test_proxy_link_put_with_signal_across_boxes():
+    """The network half of the EP CPU proxy: box s writes a pattern into the heap of (box d, local rank l) and then
+    bumps a counter there; whenever the counter shows k completed puts, the k blocks are already in place
+    (ordering of put-then-add on one flow), with loss on the wire."""
+    from uccl_b200.ep.proxy import ProxyLink
+
+    nb, L, HB = 3, 2, 2 << 20
+    ex = _Exchange(nb)
+    heaps = [[torch.zeros(HB, dtype=torch.uint8) for _ in range(L)] for _ in range(nb)]
+    blocks, BS = 24, 20_000
+    barrier = threading.Barrier(nb)
+
+    def fn(b):
+        rail = net.NetCommunicator(b, nb, ex.for_rank(b), engine=net.Engine(bind_ip="127.0.0.1", paths=2, drop_prob=0.01))
+        link = ProxyLink(rail, heaps[b])
+        ok = True
+        for d in range(nb):
+            if d == b:
+                continue
+            for k in range(blocks):
+                l = k % L
+                # block k of sender b lands at a per-sender region of local rank l on box d
+                off = 4096 + (b * blocks + k) * BS
+                link.put(d, l, off, torch.full((BS,), (17 * b + k) % 251 + 1, dtype=torch.uint8))
+                link.add(d, l, 8 * b, 1)                      # counter of sender b at offset 8*b of that heap
+        # consumer side: poll my counters; every time one advances, the announced blocks must be complete
+        import time
+
+        t0 = time.time()
+        seen = {(s, l): 0 for s in range(nb) if s != b for l in range(L)}
+        while any(v < blocks // L for v in seen.values()):
+            assert time.time() - t0 < 60, seen
+            for (s, l), have in list(seen.items()):
+                cnt = int(heaps[b][l][8 * s: 8 * s + 8].view(torch.int64).item())
+                for j in range(have, cnt):
+                    k = j * L + l                                # the j-th block sender s aimed at local rank l
+                    off = 4096 + (s * blocks + k) * BS
+                    ok &= bool((heaps[b][l][off: off + BS] == (17 * s + k) % 251 + 1).all())
+                seen[(s, l)] = cnt
+            time.sleep(0.0005)
+        link.flush()
+        barrier.wait()
+        st = link.stats()
+        rail.close()
+        return ok, st
+
+    outs = _run_threads(nb, fn)
+    for ok, st in outs:
+        assert ok
+        assert st["puts"] == (nb - 1) * blocks and st["applied_writes"] == (nb - 1) * blocks
+        assert st["applied_adds"] == (nb - 1) * blocks and st["bytes_in"] == (nb - 1) * blocks * BS

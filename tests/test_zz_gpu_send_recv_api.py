@@ -307,3 +307,63 @@ def test_nccl_api_across_boxes_with_device_buffers(tmp_path):
     r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=120)
     sys.stdout.write(r.stdout + r.stderr[-2000:])
     assert r.returncode == 0 and "nccl_multibox_gpu_test: OK" in r.stdout
+
+
+def test_proxy_forwards_device_commands_to_another_box():
+    """GPU kernel -> D2H command queue -> CPU proxy -> datagram transport -> remote proxy -> remote GPU heap +
+    signal: two 'boxes' of one GPU rank each (same device), destinations addressed by global rank."""
+    import threading
+    import time
+
+    from uccl_b200 import Communicator, net
+    from uccl_b200.ep.proxy import Proxy
+
+    W = 2
+    comms = [Communicator.local_world(1, devices=[0], heap_bytes=256 << 20, stage_bytes=8 << 20, timeout_ms=5000)[0] for _ in range(W)]
+    slots, bar = [None] * W, threading.Barrier(W)
+
+    def exchange_for(r):
+        def ex(obj):
+            slots[r] = obj
+            bar.wait()
+            out = list(slots)
+            bar.wait()
+            return out
+        return ex
+
+    res, errs = [None] * W, []
+
+    def fn(b):
+        try:
+            torch.cuda.set_device(0)
+            with torch.cuda.stream(torch.cuda.Stream(device=0)):
+                c = comms[b]
+                rail = net.NetCommunicator(b, W, exchange_for(b), engine=net.Engine(bind_ip="127.0.0.1", paths=2))
+                inbox = c.zeros(1 << 16, dtype=torch.uint8)
+                counter = c.zeros(1, dtype=torch.int64)
+                src = c.empty(1 << 16, dtype=torch.uint8)
+                src.fill_(b + 7)
+                torch.cuda.current_stream().synchronize()
+                p = Proxy(c, rail=rail)
+                bar.wait()
+                other = 1 - b
+                p.device_write(other, src, c.native.heap_offset(inbox.data_ptr()),
+                               signal_offset=c.native.heap_offset(counter.data_ptr()), signal_value=5)
+                t0 = time.time()
+                while int(counter.item()) != 5:
+                    assert time.time() - t0 < 20
+                    time.sleep(0.001)
+                res[b] = bool((inbox == other + 7).all())
+                bar.wait()
+                p.stop()
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=fn, args=(b,)) for b in range(W)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    assert not errs, errs
+    assert res == [True, True]

@@ -81,7 +81,42 @@ void bind_ep(py::module_& m) {
   m.attr("D2H_WRITE") = (int)D2H_WRITE;
   m.attr("D2H_ATOMIC") = (int)D2H_ATOMIC;
   m.attr("D2H_NOTIFY") = (int)D2H_NOTIFY;
+  // network half of the proxy on its own (host heaps): what tests and CPU-only runs use
+  py::class_<ProxyLink, std::shared_ptr<ProxyLink>>(m, "EpProxyLink")
+      .def(py::init([](int box, int nboxes, std::shared_ptr<net::Engine> engine, std::vector<uint32_t> flows,
+                       std::vector<uintptr_t> heaps, uint64_t heap_bytes) {
+             std::vector<char*> hs;
+             for (auto h : heaps) hs.push_back((char*)h);
+             return std::shared_ptr<ProxyLink>(
+                 new ProxyLink(box, nboxes, std::move(engine), std::move(flows), ProxyLink::host_write(hs, heap_bytes),
+                               ProxyLink::host_add(hs, heap_bytes)),
+                 [](ProxyLink* l) {
+                   if (PyGILState_Check()) {
+                     py::gil_scoped_release rel;
+                     delete l;
+                   } else {
+                     delete l;
+                   }
+                 });
+           }),
+           py::arg("box"), py::arg("nboxes"), py::arg("engine"), py::arg("flows"), py::arg("heaps"), py::arg("heap_bytes"))
+      .def("put", [](ProxyLink& l, int dst_box, int dst_local, uint64_t off, uintptr_t src, uint32_t bytes) {
+        l.put(dst_box, dst_local, off, (const void*)src, bytes);
+      })
+      .def("add", &ProxyLink::add)
+      .def("notify", &ProxyLink::notify)
+      .def("flush", &ProxyLink::flush, py::arg("timeout_ms") = 30000, py::call_guard<py::gil_scoped_release>())
+      .def("stats", [](ProxyLink& l) {
+        auto s = l.stats();
+        py::dict d;
+        d["puts"] = s.puts, d["adds"] = s.adds, d["notifies"] = s.notifies, d["bytes_out"] = s.bytes_out;
+        d["applied_writes"] = s.applied_writes, d["applied_adds"] = s.applied_adds, d["bytes_in"] = s.bytes_in;
+        d["applied_notifies"] = s.applied_notifies;
+        return d;
+      });
   py::class_<Proxy, std::shared_ptr<Proxy>>(m, "EpProxy")
+      .def("attach_link", &Proxy::attach_link, py::arg("engine"), py::arg("flows"), py::arg("box"), py::arg("nboxes"),
+           py::arg("local_size"))
       .def(py::init([](std::shared_ptr<Comm> c, uint32_t cap) {
              py::gil_scoped_release rel;
              return std::make_shared<Proxy>(c, cap);

@@ -59,7 +59,13 @@ Proxy::~Proxy() {
     stop();
   } catch (...) {
   }
+  link_.reset();  // stops the link's receiver before its stream goes away
   DevGuard g(comm_->device());
+  if (link_stream_) {
+    cudaStreamSynchronize(link_stream_);
+    cudaStreamDestroy(link_stream_);
+  }
+  if (bounce_) cudaFreeHost(bounce_);
   if (stream_) cudaStreamDestroy(stream_);
   if (dev_.head) cudaFree(dev_.head);
   if (ring_) cudaFreeHost(ring_);
@@ -115,8 +121,70 @@ void Proxy::loop() {
   }
 }
 
+void Proxy::attach_link(std::shared_ptr<net::Engine> engine, std::vector<uint32_t> flows, int box, int nboxes,
+                        int local_size) {
+  UB_CHECK(!running_, "proxy: attach_link before start()");
+  UB_CHECK(local_size == comm_->nranks(), "proxy: local_size (%d) must equal the box communicator's size (%d)", local_size,
+           comm_->nranks());
+  box_ = box;
+  local_size_ = local_size;
+  DevGuard g(comm_->device());
+  UB_CUDA(cudaStreamCreateWithFlags(&link_stream_, cudaStreamNonBlocking));
+  const int dev = comm_->device();
+  auto check = [this](int l, uint64_t off, uint64_t bytes) {
+    UB_CHECK(l >= 0 && l < comm_->nranks() && off + bytes <= comm_->fabric().heap_bytes(), "proxy link: access outside the heap");
+  };
+  // inbound: applied on one stream, so an ATOMIC lands after every WRITE that preceded it on the wire
+  ProxyLink::WriteFn w = [this, dev, check](int l, uint64_t off, const void* data, uint32_t bytes) {
+    check(l, off, bytes);
+    cudaSetDevice(dev);
+    // pageable source: cudaMemcpyAsync returns once the data is staged, the link may reuse its buffer
+    UB_CUDA(cudaMemcpyAsync(comm_->fabric().heap(l) + off, data, bytes, cudaMemcpyHostToDevice, link_stream_));
+  };
+  ProxyLink::AddFn a = [this, dev, check](int l, uint64_t off, uint64_t value) {
+    check(l, off, 8);
+    cudaSetDevice(dev);
+    cudaError_t e = launch_u64_add((uint64_t*)(comm_->fabric().heap(l) + off), value, link_stream_);
+    UB_CHECK(e == cudaSuccess, "proxy link: atomic launch failed: %s", cudaGetErrorString(e));
+  };
+  ProxyLink::NotifyFn nf = [this](int src_box, uint32_t a_, uint32_t b_) {
+    std::lock_guard<std::mutex> lk(mu_);
+    notifs_.emplace_back(a_ | ((uint32_t)src_box << 24), b_);
+  };
+  link_.reset(new ProxyLink(box, nboxes, std::move(engine), std::move(flows), std::move(w), std::move(a), std::move(nf)));
+}
+
 void Proxy::handle(const D2HCmd& c) {
-  const uint32_t type = c.type_dst_aux & 0xffu, dst = (c.type_dst_aux >> 8) & 0xffu, aux = c.type_dst_aux >> 16;
+  const uint32_t type = c.type_dst_aux & 0xffu, aux = c.type_dst_aux >> 16;
+  uint32_t dst = (c.type_dst_aux >> 8) & 0xffu;
+  if (link_) {  // destinations are global ranks (box major): split into (box, local rank)
+    const int dbox = (int)dst / local_size_;
+    const int dl = (int)dst % local_size_;
+    if (dbox != box_ && (type == D2H_WRITE || type == D2H_ATOMIC)) {
+      UB_CHECK(dbox < link_->nboxes(), "proxy: bad destination rank %u", dst);
+      if (type == D2H_WRITE) {
+        const Fabric& f = comm_->fabric();
+        UB_CHECK(c.src_off + c.bytes <= f.heap_bytes(), "proxy: WRITE source outside the heap");
+        if (bounce_cap_ < c.bytes) {
+          if (bounce_) cudaFreeHost(bounce_);
+          bounce_cap_ = std::max<size_t>(c.bytes, 1 << 20);
+          UB_CUDA(cudaHostAlloc((void**)&bounce_, bounce_cap_, cudaHostAllocDefault));
+        }
+        UB_CUDA(cudaMemcpyAsync(bounce_, f.heap(comm_->rank()) + c.src_off, c.bytes, cudaMemcpyDeviceToHost, stream_));
+        UB_CUDA(cudaStreamSynchronize(stream_));
+        link_->put(dbox, dl, c.dst_off, bounce_, c.bytes);  // copies the bounce buffer
+        std::lock_guard<std::mutex> g(mu_);
+        ++stats_.writes;
+        stats_.bytes += c.bytes;
+      } else {
+        link_->add(dbox, dl, c.dst_off, c.value);  // same flow as the puts: ordered after them
+        std::lock_guard<std::mutex> g(mu_);
+        ++stats_.atomics;
+      }
+      return;
+    }
+    dst = (uint32_t)dl;
+  }
   switch (type) {
     case D2H_NOP: {
       __atomic_fetch_add(ack_, 1, __ATOMIC_RELEASE);

@@ -14,6 +14,7 @@
 #include "../coll/comm.h"
 #include "../common/latency.h"
 #include "d2h_queue.h"
+#include "proxy_link.h"
 
 namespace ub {
 
@@ -37,6 +38,12 @@ class Proxy {
   uint64_t consumed() const { return __atomic_load_n(tail_, __ATOMIC_ACQUIRE); }
   std::vector<std::pair<uint32_t, uint32_t>> poll_notifications();
   ProxyStats stats() const;
+
+  // Groups that span boxes: commands whose destination rank (a GLOBAL rank, box-major) lives on another box are
+  // forwarded over the datagram transport to the rail-mate proxy there, which applies them to the heap of the
+  // final local rank over NVLink -- the reference's "proxy posts RDMA" half.  flows[k] = flow to box k's rail-mate.
+  void attach_link(std::shared_ptr<net::Engine> engine, std::vector<uint32_t> flows, int box, int nboxes, int local_size);
+  ProxyLink* link() const { return link_.get(); }
 
   // microbenchmarks (ep/src/bench_kernel.cu role): returns {commands/s} resp. {mean round trip in us}
   double bench_throughput(int blocks, int threads, int per_thread, cudaStream_t st);
@@ -62,6 +69,11 @@ class Proxy {
   std::deque<std::pair<uint32_t, uint32_t>> notifs_;
   ProxyStats stats_;
   double handle_us_sum_ = 0;
+  std::unique_ptr<ProxyLink> link_;
+  int box_ = 0, local_size_ = 0;
+  char* bounce_ = nullptr;  // pinned staging for outbound remote WRITEs
+  size_t bounce_cap_ = 0;
+  cudaStream_t link_stream_ = nullptr;  // inbound remote WRITE / ATOMIC are applied on this stream (in order)
 };
 
 cudaError_t launch_d2h_bench(const D2HQueueDev& q, int blocks, int threads, int per_thread, cudaStream_t st);

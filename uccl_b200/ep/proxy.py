@@ -17,9 +17,17 @@ from ..parallel.comm import Communicator
 
 
 class Proxy:
-    def __init__(self, comm: Communicator, capacity: int = 4096, start: bool = True):
+    def __init__(self, comm: Communicator, capacity: int = 4096, start: bool = True, rail=None):
+        """``rail``: a dedicated :class:`uccl_b200.net.NetCommunicator` of this rank's rail-mates (the same local rank
+        of every box).  With it, destination ranks are GLOBAL (box-major) ranks: commands for another box travel
+        over the datagram transport to the rail-mate proxy, which applies them over NVLink -- the reference's
+        "CPU proxy posts RDMA" path (ep/src/proxy.cpp)."""
         self.comm = comm
         self._p = _native.C().EpProxy(comm._c, int(capacity))
+        self._rail = rail
+        if rail is not None:
+            flows = [rail.flows.get(k, 0) for k in range(rail.world_size)]
+            self._p.attach_link(rail.engine._native, flows, rail.rank, rail.world_size, comm.world_size)
         if start:
             self._p.start()
 
@@ -66,6 +74,36 @@ class Proxy:
 
     def stop(self):
         self._p.stop()
+
+
+class ProxyLink:
+    """The network half of the proxy on host memory: ``put`` / ``add`` / ``notify`` towards the rail-mate proxy of
+    another box, applied there in issue order (put-with-signal).  ``heaps[l]`` is the flat uint8 "symmetric heap"
+    of local rank ``l`` of THIS box that remote writes may target.  GPU proxies get the same object through
+    ``Proxy(comm, rail=...)``; this class is the CPU-only stand-in and the unit-test surface."""
+
+    def __init__(self, rail, heaps: List[torch.Tensor]):
+        assert all(h.dtype == torch.uint8 and h.is_contiguous() and not h.is_cuda for h in heaps)
+        self._rail, self._heaps = rail, heaps
+        flows = [rail.flows.get(k, 0) for k in range(rail.world_size)]
+        self._l = _native.C().EpProxyLink(rail.rank, rail.world_size, rail.engine._native, flows,
+                                          [h.data_ptr() for h in heaps], min(h.numel() for h in heaps))
+
+    def put(self, dst_box: int, dst_local: int, dst_offset: int, src: torch.Tensor) -> None:
+        assert src.is_contiguous() and not src.is_cuda
+        self._l.put(dst_box, dst_local, int(dst_offset), src.data_ptr(), src.numel() * src.element_size())
+
+    def add(self, dst_box: int, dst_local: int, dst_offset: int, value: int = 1) -> None:
+        self._l.add(dst_box, dst_local, int(dst_offset), int(value))
+
+    def notify(self, dst_box: int, a: int, b: int) -> None:
+        self._l.notify(dst_box, int(a), int(b))
+
+    def flush(self, timeout_ms: int = 30000) -> None:
+        self._l.flush(timeout_ms)
+
+    def stats(self) -> dict:
+        return self._l.stats()
 
 
 FifoProxy = Proxy
