@@ -8,6 +8,7 @@
 #include <net/if.h>
 #include <string.h>
 #include <sys/epoll.h>
+#include <sys/ioctl.h>
 #include <sys/eventfd.h>
 #include <sys/socket.h>
 #include <unistd.h>
@@ -106,10 +107,45 @@ std::vector<std::pair<std::string, std::string>> list_interfaces() {
   return out;
 }
 
+namespace {
+// MTU of the interface that owns `ip` (0 if unknown, e.g. 0.0.0.0)
+int mtu_of_ip(const std::string& ip) {
+  in_addr want{};
+  if (inet_pton(AF_INET, ip.c_str(), &want) != 1 || want.s_addr == 0) return 0;
+  ifaddrs* ifa = nullptr;
+  if (getifaddrs(&ifa) != 0) return 0;
+  int mtu = 0;
+  for (ifaddrs* p = ifa; p; p = p->ifa_next) {
+    if (!p->ifa_addr || p->ifa_addr->sa_family != AF_INET) continue;
+    if (reinterpret_cast<sockaddr_in*>(p->ifa_addr)->sin_addr.s_addr != want.s_addr) continue;
+    ifreq r{};
+    snprintf(r.ifr_name, sizeof(r.ifr_name), "%s", p->ifa_name);
+    int fd = socket(AF_INET, SOCK_DGRAM, 0);
+    if (fd >= 0) {
+      if (ioctl(fd, SIOCGIFMTU, &r) == 0) mtu = r.ifr_mtu;
+      close(fd);
+    }
+    break;
+  }
+  freeifaddrs(ifa);
+  return mtu;
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------- setup
 Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), rng_(std::random_device{}()) {
   cfg_.paths = std::max(1, std::min(cfg_.paths, kMaxPaths));
   cfg_.payload = std::max(256, std::min(cfg_.payload, 60000));
+  if (param_load("NET_PAYLOAD_CLAMP", 1) != 0) {
+    // keep every datagram inside the NIC's MTU: no IP fragmentation (one lost fragment loses the whole datagram)
+    // and UDP GSO stays usable (its segments may not be fragmented)
+    const int mtu = mtu_of_ip(cfg_.bind_ip);
+    const int room = mtu - 28 - (int)sizeof(PktHdr);
+    if (mtu > 0 && room >= 256 && cfg_.payload > room) {
+      UB_INFO(SUB_NET, "net: payload %d -> %d to fit the %d-byte MTU of %s", cfg_.payload, room / 64 * 64, mtu, cfg_.bind_ip.c_str());
+      cfg_.payload = room / 64 * 64;
+    }
+  }
   cfg_.max_inflight = std::max(4, std::min(cfg_.max_inflight, kSackBits - 8));
   drop_prob_.store(cfg_.drop_prob);
   cc::EqdsConfig ec;
