@@ -39,41 +39,41 @@ typedef void (*ncclDebugLogger_t)(ncclDebugLogLevel level, unsigned long flags, 
 typedef enum { NCCL_NET_DEVICE_HOST = 0, NCCL_NET_DEVICE_UNPACK = 1 } ncclNetDeviceType;
 typedef struct ncclNetDeviceHandle_v8 ncclNetDeviceHandle_v8_t;
 
-typedef struct {
-  char* name;
-  char* pciPath;
-  uint64_t guid;
-  int ptrSupport;
-  int regIsGlobal;
-  int speed;
-  int port;
-  float latency;
-  int maxComms;
-  int maxRecvs;
-  ncclNetDeviceType netDeviceType;
-  int netDeviceVersion;
+typedef struct {       // layout of ncclNetProperties_v8_t (field names are ours; only the layout is ABI)
+  char* dev_name;
+  char* pci_path;
+  uint64_t chip_guid;
+  int ptr_kinds;         // NCCL_PTR_* bit mask
+  int mr_is_global;
+  int speed_mbps;
+  int port_num;
+  float latency_us;
+  int max_comms;
+  int max_grouped_recvs;
+  ncclNetDeviceType offload_type;
+  int offload_version;
 } ncclNetProperties_v8_t;
 
-typedef struct {
-  const char* name;
-  ncclResult_t (*init)(ncclDebugLogger_t logFunction);
-  ncclResult_t (*devices)(int* ndev);
-  ncclResult_t (*getProperties)(int dev, ncclNetProperties_v8_t* props);
-  ncclResult_t (*listen)(int dev, void* handle, void** listenComm);
-  ncclResult_t (*connect)(int dev, void* handle, void** sendComm, ncclNetDeviceHandle_v8_t** sendDevComm);
-  ncclResult_t (*accept)(void* listenComm, void** recvComm, ncclNetDeviceHandle_v8_t** recvDevComm);
-  ncclResult_t (*regMr)(void* comm, void* data, size_t size, int type, void** mhandle);
-  ncclResult_t (*regMrDmaBuf)(void* comm, void* data, size_t size, int type, uint64_t offset, int fd, void** mhandle);
-  ncclResult_t (*deregMr)(void* comm, void* mhandle);
-  ncclResult_t (*isend)(void* sendComm, void* data, int size, int tag, void* mhandle, void** request);
-  ncclResult_t (*irecv)(void* recvComm, int n, void** data, int* sizes, int* tags, void** mhandles, void** request);
-  ncclResult_t (*iflush)(void* recvComm, int n, void** data, int* sizes, void** mhandles, void** request);
-  ncclResult_t (*test)(void* request, int* done, int* sizes);
-  ncclResult_t (*closeSend)(void* sendComm);
-  ncclResult_t (*closeRecv)(void* recvComm);
-  ncclResult_t (*closeListen)(void* listenComm);
-  ncclResult_t (*getDeviceMr)(void* comm, void* mhandle, void** dptr_mhandle);
-  ncclResult_t (*irecvConsumed)(void* recvComm, int n, void* request);
+typedef struct {       // ncclNet_v8_t: 19 entries in this order
+  const char* plugin_name;
+  ncclResult_t (*fn_init)(ncclDebugLogger_t);
+  ncclResult_t (*fn_devices)(int*);
+  ncclResult_t (*fn_properties)(int, ncclNetProperties_v8_t*);
+  ncclResult_t (*fn_listen)(int, void*, void**);
+  ncclResult_t (*fn_connect)(int, void*, void**, ncclNetDeviceHandle_v8_t**);
+  ncclResult_t (*fn_accept)(void*, void**, ncclNetDeviceHandle_v8_t**);
+  ncclResult_t (*fn_reg_mr)(void*, void*, size_t, int, void**);
+  ncclResult_t (*fn_reg_mr_dmabuf)(void*, void*, size_t, int, uint64_t, int, void**);
+  ncclResult_t (*fn_dereg_mr)(void*, void*);
+  ncclResult_t (*fn_isend)(void*, void*, int, int, void*, void**);
+  ncclResult_t (*fn_irecv)(void*, int, void**, int*, int*, void**, void**);
+  ncclResult_t (*fn_iflush)(void*, int, void**, int*, void**, void**);
+  ncclResult_t (*fn_test)(void*, int*, int*);
+  ncclResult_t (*fn_close_send)(void*);
+  ncclResult_t (*fn_close_recv)(void*);
+  ncclResult_t (*fn_close_listen)(void*);
+  ncclResult_t (*fn_device_mr)(void*, void*, void**);
+  ncclResult_t (*fn_recv_consumed)(void*, int, void*);
 } ncclNet_v8_t;
 }
 
@@ -169,18 +169,18 @@ ncclResult_t p_props(int dev, ncclNetProperties_v8_t* p) {
   if (dev < 0 || dev >= (int)g_devs.size()) return ncclInvalidArgument;
   Device& d = g_devs[dev];
   memset(p, 0, sizeof(*p));
-  p->name = const_cast<char*>(d.name.c_str());
-  p->pciPath = d.pci.empty() ? nullptr : const_cast<char*>(d.pci.c_str());
-  p->guid = (uint64_t)dev;
-  p->ptrSupport = NCCL_PTR_HOST;
-  p->regIsGlobal = 0;
-  p->speed = d.speed_mbps;
-  p->port = 0;
-  p->latency = 0;
-  p->maxComms = 65536;
-  p->maxRecvs = 1;
-  p->netDeviceType = NCCL_NET_DEVICE_HOST;
-  p->netDeviceVersion = 0;
+  p->dev_name = const_cast<char*>(d.name.c_str());
+  p->pci_path = d.pci.empty() ? nullptr : const_cast<char*>(d.pci.c_str());
+  p->chip_guid = (uint64_t)dev;
+  p->ptr_kinds = NCCL_PTR_HOST;
+  p->mr_is_global = 0;
+  p->speed_mbps = d.speed_mbps;
+  p->port_num = 0;
+  p->latency_us = 0;
+  p->max_comms = 65536;
+  p->max_grouped_recvs = 1;
+  p->offload_type = NCCL_NET_DEVICE_HOST;
+  p->offload_version = 0;
   return ncclSuccess;
 }
 
