@@ -137,7 +137,7 @@ void bind_net(py::module_& root) {
         if (!e.flow_stats(flow, &s)) return py::none();
         py::dict d;
         d["tx_pkts"] = s.tx_pkts, d["tx_bytes"] = s.tx_bytes, d["rx_pkts"] = s.rx_pkts, d["rx_bytes"] = s.rx_bytes;
-        d["rx_dup"] = s.rx_dup, d["fast_rexmit"] = s.fast_rexmit, d["rto_rexmit"] = s.rto_rexmit;
+        d["rx_dup"] = s.rx_dup, d["fast_rexmit"] = s.fast_rexmit, d["rto_rexmit"] = s.rto_rexmit, d["tlp"] = s.tlp;
         d["acks_tx"] = s.acks_tx, d["acks_rx"] = s.acks_rx, d["unexpected_msgs"] = s.unexpected_msgs;
         d["srtt_us"] = s.srtt_us, d["min_rtt_us"] = s.min_rtt_us, d["cwnd"] = s.cwnd, d["rate_gbps"] = s.rate_gbps;
         d["state"] = s.state;

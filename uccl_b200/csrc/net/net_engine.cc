@@ -426,6 +426,7 @@ void Engine::complete(Request* r, size_t bytes, int err) {
 void Engine::run() {
   uint64_t last_stats = 0, last_busy_ns = 0;
   const uint64_t spin_ns = (uint64_t)param_load("NET_SPIN_US", 0) * 1000ull;
+  const int pace_nap_us = (int)param_load("NET_PACE_NAP_US", 20);
   while (!stop_.load(std::memory_order_relaxed)) {
     bool busy = false;
     // commands + working set
@@ -509,8 +510,13 @@ void Engine::run() {
       if (now - last_busy_ns < spin_ns) continue;
       const bool eq = cfg_.cc == CC_EQDS && pacer_.active_senders() > 0;
       const int to = pending ? 1 : 50;
-      // the credit pacer and the rate pacer need a fine-grained clock while there is work: spin
-      if (eq || (cfg_.cc == CC_TIMELY && pending)) continue;
+      // the credit pacer and the rate pacer need a fine-grained clock while there is work: nap instead of
+      // sleeping in epoll.  (A hard spin is faster on an idle core but gets the thread throttled in 4 ms
+      // quanta under a CPU quota; UCCL_B200_NET_BUSY_POLL=1 selects the spin.)
+      if (eq || (cfg_.cc == CC_TIMELY && pending)) {
+        std::this_thread::sleep_for(std::chrono::microseconds(pace_nap_us));
+        continue;
+      }
       ++est_.sleeps;
       epoll_event evs[8];
       const int n = epoll_wait(epfd_, evs, 8, to);
@@ -1123,6 +1129,7 @@ void Engine::on_ack(Flow& f, const PktHdr& h, const AckBody& b) {
     }
   }
   if (newly) {
+    f.tlp_fired = false;
     f.rto_count = 0;
     const double rto_us = std::max<double>(cfg_.rto_min_us, f.srtt_us + 4 * f.rttvar_us);
     f.rto_ns = (uint64_t)(std::min<double>(rto_us, cfg_.rto_max_us) * 1e3);
@@ -1184,6 +1191,7 @@ void Engine::emit_data(Flow& f, TxPkt& p, uint64_t now, bool is_rexmit) {
   const int path = pick_path(f, is_rexmit ? (int)p.path : -1);
   p.path = (uint16_t)path;
   p.ts_send = now;
+  f.last_tx_ns = now;
   p.lost = false;
   if (is_rexmit) ++p.rexmits;
   PktHdr h{};
@@ -1351,6 +1359,26 @@ void Engine::timers(uint64_t now) {
         p.ts_send = now;  // re-arm; the retransmission below stamps it again
         f.rexmit_q.push_front(f.snd_una);
         if (f.rto_count >= 3 && cfg_.cc == CC_SWIFT) f.swift.on_retransmit_timeout();
+      } else if (!f.tlp_fired && f.rexmit_q.empty() && f.srtt_us > 0 &&
+                 now > std::max(f.last_tx_ns, f.last_progress_ns) + (uint64_t)(std::max(2.0 * f.srtt_us, 300.0) * 1e3)) {
+        // Tail-loss probe: the flight has been silent for two RTTs.  If the LAST packets of a burst were lost no
+        // later packet will ever be acknowledged, so RACK cannot see the hole and only the (much longer) RTO
+        // would; re-sending the newest unacknowledged packet draws an ACK whose SACK exposes the loss.
+        for (uint32_t s = f.snd_nxt - 1; seq_diff(s, f.snd_una) >= 0; --s) {
+          TxPkt& q = f.ring[s % kTxRing];
+          if (q.in_use && q.seq == s && !q.acked) {
+            if (!q.lost) {
+              q.lost = true;
+              if (f.inflight) --f.inflight;
+              if (f.path[q.path].inflight) --f.path[q.path].inflight;
+            }
+            f.rexmit_q.push_back(s);
+            ++f.st.tlp;
+            break;
+          }
+          if (s == f.snd_una) break;
+        }
+        f.tlp_fired = true;
       }
     }
     if (st == FL_CLOSING) {

@@ -74,7 +74,7 @@ struct Request {
 
 struct FlowStats {
   uint64_t tx_pkts = 0, tx_bytes = 0, rx_pkts = 0, rx_bytes = 0, rx_dup = 0;
-  uint64_t fast_rexmit = 0, rto_rexmit = 0, acks_tx = 0, acks_rx = 0, unexpected_msgs = 0;
+  uint64_t fast_rexmit = 0, rto_rexmit = 0, tlp = 0, acks_tx = 0, acks_rx = 0, unexpected_msgs = 0;
   uint64_t path_tx[kMaxPaths] = {0};
   uint64_t path_bans = 0;
   double srtt_us = 0, min_rtt_us = 0, cwnd = 0, rate_gbps = 0;
@@ -187,6 +187,8 @@ class Engine {
     uint64_t rto_ns = 0;
     int rto_count = 0;
     uint64_t last_progress_ns = 0;
+    uint64_t last_tx_ns = 0;   // last (re)transmission of a DATA packet
+    bool tlp_fired = false;    // one tail-loss probe per quiet period
     PathState path[kMaxPaths];
     // congestion control
     cc::Swift swift;
