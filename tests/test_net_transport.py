@@ -200,6 +200,9 @@ def test_multinode_communicator_two_nodes_of_two():
         res["sum"] = m.all_reduce(ins[gr].clone())             # 4099 is not a multiple of L: padded path
         res["avg"] = m.all_reduce(ins[gr].clone(), "avg")
         res["max"] = m.all_reduce(ins[gr][:4096].clone(), "max")
+        o16 = torch.zeros(4099, dtype=torch.bfloat16)
+        m.all_reduce(ins[gr].clone(), "sum", out=o16, scale=0.5)  # the DDP compress-hook contract
+        res["scaled"] = o16
         m.pipeline_bytes = 1024                                  # 4099 floats -> 2050 per shard -> 9 chunks in flight
         res["pipe_sum"] = m.all_reduce(ins[gr].clone())
         res["pipe_avg"] = m.all_reduce(ins[gr].clone(), "avg")
@@ -227,6 +230,7 @@ def test_multinode_communicator_two_nodes_of_two():
         assert torch.equal(o["sum"], ref.sum(0))
         assert torch.allclose(o["avg"], ref.sum(0) / W)
         assert torch.equal(o["max"], ref[:, :4096].max(0).values)
+        assert torch.equal(o["scaled"], (ref.sum(0) * 0.5).to(torch.bfloat16))
         assert torch.equal(o["pipe_sum"], ref.sum(0)) and torch.allclose(o["pipe_avg"], ref.sum(0) / W)
         assert torch.equal(o["ag"].view(W, 17)[:, 0], torch.arange(W, dtype=torch.float32))
         assert torch.equal(o["rs"], torch.arange(W * 25, dtype=torch.float32).view(W, 25)[gr] * (W * (W + 1) / 2))

@@ -135,8 +135,22 @@ class MultiNodeCommunicator:
         self.local.barrier()
         self._sync_local()
 
-    def all_reduce(self, t: torch.Tensor, op: str = "sum") -> torch.Tensor:
-        """In place.  reduce-scatter over NVLink -> per-rail all-reduce over the network -> all-gather over NVLink."""
+    def all_reduce(self, t: torch.Tensor, op: str = "sum", out: Optional[torch.Tensor] = None, scale: float = 1.0,
+                   **_ignored) -> torch.Tensor:
+        """reduce-scatter over NVLink -> per-rail all-reduce over the network -> all-gather over NVLink.
+        In place unless ``out`` is given (which may have another float dtype: the cast happens once, at the end);
+        ``scale`` multiplies the result (same contract as :meth:`Communicator.all_reduce`)."""
+        if out is not None and out is not t:
+            tmp = t.clone()
+            self.all_reduce(tmp, op, scale=scale)
+            out.view(-1).copy_(tmp.view(-1))
+            return out
+        if scale != 1.0:
+            if not t.is_floating_point():
+                raise ValueError("uccl_b200: all_reduce scale needs a floating-point tensor")
+            self.all_reduce(t, op)
+            t.mul_(scale)
+            return t
         L, N = self.local_size, self.num_nodes
         if N == 1:
             self.local.all_reduce(t, op)
