@@ -220,6 +220,11 @@ def test_multinode_communicator_two_nodes_of_two():
         a2a = torch.zeros(W * 3)
         m.all_to_all(a2a, torch.arange(W * 3, dtype=torch.float32) + 100 * gr)
         res["a2a"] = a2a
+        mate, rail = gr ^ 1, (gr + L) % W                      # box-mate and rail-mate in one group
+        r1, r2 = torch.zeros(3000), torch.zeros(3000)
+        m.batch_send_recv([("recv", r1, mate), ("recv", r2, rail), ("send", torch.full((3000,), 10.0 + gr), mate),
+                           ("send", torch.full((3000,), 20.0 + gr), rail)])
+        res["p2p"] = (bool((r1 == 10.0 + mate).all()), bool((r2 == 20.0 + rail).all()))
         m.barrier()
         m.close()
         return res
@@ -236,6 +241,7 @@ def test_multinode_communicator_two_nodes_of_two():
         assert torch.equal(o["rs"], torch.arange(W * 25, dtype=torch.float32).view(W, 25)[gr] * (W * (W + 1) / 2))
         assert torch.equal(o["b0"], torch.zeros(1001)) and torch.equal(o["b3"], torch.full((1001,), 3.0))
         assert torch.equal(o["a2a"], torch.cat([torch.arange(3, dtype=torch.float32) + 3 * gr + 100 * s for s in range(W)]))
+        assert o["p2p"] == (True, True)
 
 
 _MP_SCRIPT = r"""

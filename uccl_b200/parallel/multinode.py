@@ -400,6 +400,32 @@ class MultiNodeCommunicator:
         raise NotImplementedError("uccl_b200: point-to-point between different rails of different nodes is not routed; "
                                   "send to the peer's rail-mate on your node first")
 
+    def batch_send_recv(self, ops) -> None:
+        """Grouped point-to-point like :meth:`Communicator.batch_send_recv` with GLOBAL peer ranks: box-mates go to
+        the native grouped kernel, rail-mates to the datagram transport (receives are posted first), all concurrently."""
+        local_ops, works, staged = [], [], []
+        for kind, t, peer in ops:
+            route, r = self._route(peer)
+            if route == "local":
+                local_ops.append((kind, t, r))
+            elif kind == "recv":
+                h = t.view(-1) if not t.is_cuda else torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+                works.append(self.net.irecv(h, r))
+                if t.is_cuda:
+                    staged.append((t, h))
+        for kind, t, peer in ops:
+            route, r = self._route(peer)
+            if route == "rail" and kind == "send":
+                h = t.contiguous().view(-1) if not t.is_cuda else t.contiguous().view(-1).to("cpu", non_blocking=False)
+                works.append(self.net.isend(h, r))
+        if local_ops:
+            self.local.batch_send_recv(local_ops)
+        for w in works:
+            w.wait(self.net.timeout_ms)
+        for t, h in staged:
+            t.view(-1).copy_(h, non_blocking=True)
+        self._sync_local()
+
     def send(self, t: torch.Tensor, dst: int) -> None:
         kind, r = self._route(dst)
         if kind == "local":
