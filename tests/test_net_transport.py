@@ -271,7 +271,7 @@ def test_multinode_from_torch_dist_four_processes(tmp_path):
     script.write_text(_MP_SCRIPT)
     env = dict(os.environ, UB_ROOT=ROOT, OMP_NUM_THREADS="1")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
@@ -743,3 +743,11 @@ def test_proxy_link_put_with_signal_across_boxes():
         assert ok
         assert st["puts"] == (nb - 1) * blocks and st["applied_writes"] == (nb - 1) * blocks
         assert st["applied_adds"] == (nb - 1) * blocks and st["bytes_in"] == (nb - 1) * blocks * BS
+
+
+def _free_port() -> int:
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]

@@ -188,7 +188,7 @@ def test_nccl_runs_over_the_net_plugin(tmp_path):
                NCCL_DEBUG_SUBSYS="INIT,NET", UCCL_B200_NET_IFNAME="lo", NCCL_IB_DISABLE="1",
                LD_LIBRARY_PATH=str(plugin.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29741", str(script)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
                        capture_output=True, text=True, timeout=120, env=env)
     out = r.stdout + r.stderr
     sys.stdout.write(out[-3000:])
@@ -367,3 +367,11 @@ def test_proxy_forwards_device_commands_to_another_box():
     [t.join() for t in ths]
     assert not errs, errs
     assert res == [True, True]
+
+
+def _free_port() -> int:
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
