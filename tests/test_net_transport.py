@@ -751,3 +751,63 @@ def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _native_mn_worker(rank, world, uid, q):
+    os.environ.update(UCCL_B200_NET_BIND_IP="127.0.0.1", UCCL_B200_NET_PATHS="2", UCCL_B200_MN_PIPELINE_BYTES="32768")
+    torch.set_num_threads(1)
+    from uccl_b200.parallel import NativeMultiNodeCommunicator
+
+    m = NativeMultiNodeCommunicator.init(uid, rank, world, local_size=2, host=True, heap_bytes=192 << 20, stage_bytes=1 << 20,
+                                         timeout_ms=30000)
+    ok = [(m.rank, m.world_size, m.node_rank, m.local_rank, m.num_nodes) == (rank, world, rank // 2, rank % 2, 2)]
+    g = torch.Generator().manual_seed(1234)
+    ins = [torch.randn(70_001, generator=g) for _ in range(world)]          # same on every rank
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 3e-2), (torch.float16, 2e-3), (torch.float64, 1e-12)):
+        x = ins[rank].clone().to(dt)
+        m.all_reduce(x)                                                        # pipelined path (70001 elements)
+        ref = torch.stack([t.to(dt).double() for t in ins]).sum(0)
+        ok.append(torch.allclose(x.double(), ref, rtol=tol, atol=tol * 8))
+    xi = torch.arange(5000, dtype=torch.int32) * (rank + 1)
+    m.all_reduce(xi, "max")
+    ok.append(torch.equal(xi, torch.arange(5000, dtype=torch.int32) * world))
+    avg = ins[rank].clone()
+    m.all_reduce(avg, "avg")
+    ok.append(torch.allclose(avg, torch.stack(ins).mean(0), rtol=1e-5, atol=1e-6))
+    out16 = torch.zeros(70_001, dtype=torch.bfloat16)
+    m.all_reduce(ins[rank].clone(), "sum", out=out16, scale=0.25)
+    ok.append(torch.allclose(out16.float(), torch.stack(ins).sum(0) * 0.25, rtol=2e-2, atol=2e-2))
+    ag = torch.zeros(world * 333)
+    m.all_gather(ag, torch.full((333,), float(rank)))
+    ok.append(ag.view(world, 333)[:, 0].tolist() == [float(r) for r in range(world)])
+    rs = torch.zeros(100)
+    m.reduce_scatter(rs, torch.arange(world * 100, dtype=torch.float32) * (rank + 1), "sum")
+    ok.append(torch.equal(rs, torch.arange(world * 100, dtype=torch.float32).view(world, 100)[rank] * 10))
+    b = torch.full((12345,), float(rank))
+    m.broadcast(b, root=3)
+    ok.append(bool((b == 3).all()))
+    a2a = torch.zeros(world * 7)
+    m.all_to_all(a2a, torch.arange(world * 7, dtype=torch.float32) + 100 * rank)
+    ok.append(a2a.tolist() == [float(100 * s + 7 * rank + i) for s in range(world) for i in range(7)])
+    r1 = torch.zeros(2000)
+    m.batch_send_recv([("recv", r1, (rank + 2) % world), ("send", torch.full((2000,), float(rank)), (rank + 2) % world)])
+    ok.append(bool((r1 == (rank + 2) % world).all()))
+    m.barrier()
+    q.put((rank, ok))
+
+
+def test_native_multinode_communicator_four_processes():
+    """The C++ MultiComm through its Python wrapper: 2 boxes x 2 processes on the host backend, all dtypes of the
+    rail reduction against torch references, pipelined all-reduce, fused scale + cast, every collective."""
+    import multiprocessing as mp
+
+    world = 4
+    ctx = mp.get_context("spawn")
+    uid = Communicator.create_unique_id()
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_native_mn_worker, args=(r, world, uid, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    [p.join(60) for p in ps]
+    for rank, ok in got:
+        assert all(ok), (rank, ok)

@@ -6,6 +6,7 @@
 #include <pybind11/stl.h>
 
 #include "../coll/comm.h"
+#include "../coll/multi_comm.h"
 #include "../common/log.h"
 #include "../common/param.h"
 #include "../kernels/launch.h"
@@ -210,6 +211,83 @@ PYBIND11_MODULE(_C, m) {
   bind_util(m);
   bind_ep(m);
   bind_p2p(m);
+  // hierarchical communicator across boxes in C++ (what the NCCL drop-in uses); same calling convention as Comm
+  py::class_<MultiComm, std::shared_ptr<MultiComm>>(m, "MultiComm")
+      .def_static(
+          "create",
+          [](py::bytes uid, int rank, int nranks, int local_size, int device, size_t heap_bytes, size_t stage_bytes,
+             bool host_fake, int timeout_ms) {
+            std::string s = uid;
+            UB_CHECK(s.size() == sizeof(UniqueId), "unique id must be %zu bytes", sizeof(UniqueId));
+            UniqueId id;
+            memcpy(id.data, s.data(), sizeof(id.data));
+            CommConfig cfg;
+            cfg.heap_bytes = heap_bytes;
+            cfg.stage_bytes = stage_bytes;
+            cfg.host_fake = host_fake;
+            cfg.timeout_ms = timeout_ms;
+            py::gil_scoped_release rel;
+            return MultiComm::create(id, rank, nranks, local_size, device, cfg);
+          },
+          py::arg("uid"), py::arg("rank"), py::arg("nranks"), py::arg("local_size"), py::arg("device"),
+          py::arg("heap_bytes"), py::arg("stage_bytes") = (size_t)(64ull << 20), py::arg("host_fake") = false,
+          py::arg("timeout_ms") = -1)
+      .def_property_readonly("rank", &MultiComm::rank)
+      .def_property_readonly("nranks", &MultiComm::nranks)
+      .def_property_readonly("local_rank", &MultiComm::local_rank)
+      .def_property_readonly("local_size", &MultiComm::local_size)
+      .def_property_readonly("node", &MultiComm::node)
+      .def_property_readonly("nnodes", &MultiComm::nnodes)
+      .def_property_readonly("is_host", &MultiComm::is_host)
+      .def_property_readonly("device", &MultiComm::device)
+      .def_property_readonly("local", [](MultiComm& c) { return c.local(); })
+      .def("describe", &MultiComm::describe)
+      .def("allreduce",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, uintptr_t stream, float scale) {
+             py::gil_scoped_release rel;
+             c.allreduce(P(in), P(out), count, dtype, op, S(stream), scale);
+           },
+           py::arg("inp"), py::arg("out"), py::arg("count"), py::arg("dtype"), py::arg("op"), py::arg("stream") = 0,
+           py::arg("scale") = 1.0f)
+      .def("allgather",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.allgather(P(in), P(out), count, dtype, S(stream));
+           })
+      .def("reduce_scatter",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.reduce_scatter(P(in), P(out), count, dtype, op, S(stream));
+           })
+      .def("broadcast",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int root, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.broadcast(P(in), P(out), count, dtype, root, S(stream));
+           })
+      .def("reduce",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int root, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.reduce(P(in), P(out), count, dtype, op, root, S(stream));
+           })
+      .def("alltoall",
+           [](MultiComm& c, uintptr_t in, uintptr_t out, size_t count, int dtype, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.alltoall(P(in), P(out), count, dtype, S(stream));
+           })
+      .def("barrier",
+           [](MultiComm& c, uintptr_t stream) {
+             py::gil_scoped_release rel;
+             c.barrier(S(stream));
+           },
+           py::arg("stream") = 0)
+      .def("group_p2p",
+           [](MultiComm& c, std::vector<std::tuple<bool, uintptr_t, size_t, int>> ops, uintptr_t stream) {
+             std::vector<Comm::P2pOp> v;
+             for (auto& o : ops) v.push_back(Comm::P2pOp{std::get<0>(o), P(std::get<1>(o)), std::get<2>(o), std::get<3>(o)});
+             py::gil_scoped_release rel;
+             c.group_p2p(v, S(stream));
+           },
+           py::arg("ops"), py::arg("stream") = 0);
   bind_uk(m);
   bind_net(m);
 }

@@ -2,8 +2,8 @@ from .comm import ALGOS, Communicator, dtype_code, op_code  # noqa: F401
 
 
 def __getattr__(name):  # lazy: the network stack is only needed for multi-node jobs
-    if name == "MultiNodeCommunicator":
-        from .multinode import MultiNodeCommunicator
+    if name in ("MultiNodeCommunicator", "NativeMultiNodeCommunicator"):
+        from . import multinode
 
-        return MultiNodeCommunicator
+        return getattr(multinode, name)
     raise AttributeError(name)

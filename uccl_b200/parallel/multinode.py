@@ -444,3 +444,111 @@ class MultiNodeCommunicator:
 
     def close(self) -> None:
         self.net.close()
+
+
+class NativeMultiNodeCommunicator:
+    """The same hierarchy executed entirely in C++ (`csrc/coll/multi_comm.cc`, the object behind the NCCL drop-in):
+    one call per collective, block pipeline on a helper thread, pinned staging owned by the runtime.  Bootstraps
+    from a 128-byte unique id like :class:`Communicator` (rank 0 creates it, everybody gets it out of band);
+    ranks ``[k*local_size, (k+1)*local_size)`` form box ``k``.  Set ``UCCL_B200_BOOTSTRAP_IP`` on rank 0 to an
+    address the other boxes can reach before creating the id."""
+
+    def __init__(self, native):
+        from .comm import dtype_code, op_code
+
+        self._m = native
+        self._dt, self._op = dtype_code, op_code
+        self.rank, self.world_size = native.rank, native.nranks
+        self.local_rank, self.local_size = native.local_rank, native.local_size
+        self.node_rank, self.num_nodes = native.node, native.nnodes
+        self.is_host = native.is_host
+        self.device = torch.device("cpu") if native.is_host else torch.device("cuda", native.device)
+
+    @classmethod
+    def init(cls, uid: bytes, rank: int, world_size: int, local_size: int, device: Optional[int] = None,
+             heap_bytes: int = 1 << 30, stage_bytes: int = 64 << 20, host: Optional[bool] = None,
+             timeout_ms: int = -1) -> "NativeMultiNodeCommunicator":
+        from .. import _native
+
+        if host is None:
+            host = not torch.cuda.is_available()
+        if device is None:
+            device = -1 if host else torch.cuda.current_device()
+        if not host:
+            torch.cuda.set_device(device)
+            torch.cuda.init()
+        return cls(_native.C().MultiComm.create(uid, rank, world_size, local_size, device, heap_bytes, stage_bytes, host,
+                                                timeout_ms))
+
+    @classmethod
+    def from_torch_dist(cls, local_size: int, group=None, **kw) -> "NativeMultiNodeCommunicator":
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [Communicator.create_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls.init(box[0], rank, world, local_size, **kw)
+
+    def _stream(self, stream=None) -> int:
+        if self.is_host:
+            return 0
+        s = stream or torch.cuda.current_stream(self.device)
+        return s.cuda_stream
+
+    @staticmethod
+    def _c(t: torch.Tensor) -> torch.Tensor:
+        if not t.is_contiguous():
+            raise ValueError("uccl_b200: tensors must be contiguous")
+        return t
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum", out: Optional[torch.Tensor] = None, scale: float = 1.0, stream=None):
+        out = t if out is None else out
+        if out.dtype != t.dtype:
+            tmp = torch.empty_like(t)
+            self.all_reduce(t, op, out=tmp, scale=scale, stream=stream)
+            out.copy_(tmp)
+            return out
+        self._m.allreduce(self._c(t).data_ptr(), self._c(out).data_ptr(), t.numel(), self._dt(t.dtype), self._op(op),
+                          self._stream(stream), float(scale))
+        return out
+
+    def all_gather(self, out: torch.Tensor, t: torch.Tensor, stream=None):
+        self._m.allgather(self._c(t).data_ptr(), self._c(out).data_ptr(), t.numel(), self._dt(t.dtype), self._stream(stream))
+        return out
+
+    def reduce_scatter(self, out: torch.Tensor, t: torch.Tensor, op: str = "sum", stream=None):
+        self._m.reduce_scatter(self._c(t).data_ptr(), self._c(out).data_ptr(), out.numel(), self._dt(t.dtype), self._op(op),
+                               self._stream(stream))
+        return out
+
+    def broadcast(self, t: torch.Tensor, root: int = 0, out: Optional[torch.Tensor] = None, stream=None):
+        out = t if out is None else out
+        self._m.broadcast(self._c(t).data_ptr(), self._c(out).data_ptr(), t.numel(), self._dt(t.dtype), root, self._stream(stream))
+        return out
+
+    def reduce(self, t: torch.Tensor, root: int = 0, op: str = "sum", out: Optional[torch.Tensor] = None, stream=None):
+        out = t if out is None else out
+        self._m.reduce(self._c(t).data_ptr(), self._c(out).data_ptr(), t.numel(), self._dt(t.dtype), self._op(op), root,
+                       self._stream(stream))
+        return out
+
+    def all_to_all(self, out: torch.Tensor, t: torch.Tensor, stream=None):
+        self._m.alltoall(self._c(t).data_ptr(), self._c(out).data_ptr(), t.numel() // self.world_size, self._dt(t.dtype),
+                         self._stream(stream))
+        return out
+
+    def batch_send_recv(self, ops, stream=None) -> None:
+        self._m.group_p2p([(kind == "send", self._c(t).data_ptr(), t.numel() * t.element_size(), int(peer))
+                           for kind, t, peer in ops], self._stream(stream))
+
+    def send(self, t: torch.Tensor, dst: int, stream=None) -> None:
+        self.batch_send_recv([("send", t, dst)], stream)
+
+    def recv(self, t: torch.Tensor, src: int, stream=None) -> None:
+        self.batch_send_recv([("recv", t, src)], stream)
+
+    def barrier(self, stream=None) -> None:
+        self._m.barrier(self._stream(stream))
+
+    def describe(self) -> str:
+        return self._m.describe()
