@@ -34,8 +34,16 @@ typedef enum {
   ncclRemoteError = 6,
   ncclInProgress = 7
 } ncclResult_t;
-typedef enum { NCCL_LOG_NONE = 0, NCCL_LOG_VERSION = 1, NCCL_LOG_WARN = 2, NCCL_LOG_INFO = 3, NCCL_LOG_ABORT = 4, NCCL_LOG_TRACE = 5 } ncclDebugLogLevel;
-typedef void (*ncclDebugLogger_t)(ncclDebugLogLevel level, unsigned long flags, const char* file, int line, const char* fmt, ...);
+typedef enum {
+  NCCL_LOG_NONE = 0,
+  NCCL_LOG_VERSION = 1,
+  NCCL_LOG_WARN = 2,
+  NCCL_LOG_INFO = 3,
+  NCCL_LOG_ABORT = 4,
+  NCCL_LOG_TRACE = 5
+} ncclDebugLogLevel;
+typedef void (*ncclDebugLogger_t)(ncclDebugLogLevel level, unsigned long flags, const char* file, int line,
+                                  const char* fmt, ...);
 typedef enum { NCCL_NET_DEVICE_HOST = 0, NCCL_NET_DEVICE_UNPACK = 1 } ncclNetDeviceType;
 typedef struct ncclNetDeviceHandle_v8 ncclNetDeviceHandle_v8_t;
 
@@ -275,7 +283,8 @@ ncclResult_t p_test(void* request, int* done, int* sizes) {
   if (sizes) sizes[0] = (int)bytes;
   delete q;
   if (err) {
-    PLOG(NCCL_LOG_WARN, "NET/uccl_b200: request failed (%s)", err == 2 ? "message larger than the receive" : err == 3 ? "peer closed" : "flow error");
+    const char* why = err == 2 ? "message larger than the receive" : err == 3 ? "peer closed" : "flow error";
+    PLOG(NCCL_LOG_WARN, "NET/uccl_b200: request failed (%s)", why);
     return ncclRemoteError;
   }
   return ncclSuccess;

@@ -847,7 +847,9 @@ void Engine::flush_path(int path) {
   while (sent_msgs < nm) {
     const int r = sendmmsg(socks_[path], msgs + sent_msgs, (unsigned)(nm - sent_msgs), MSG_DONTWAIT);
     if (r <= 0) {
-      if (gso_ok_ && r < 0 && run_len[sent_msgs] > 1 && (errno == EINVAL || errno == EIO || errno == EOPNOTSUPP || errno == ENOPROTOOPT || errno == EMSGSIZE)) {
+      const bool gso_refused = errno == EINVAL || errno == EIO || errno == EOPNOTSUPP || errno == ENOPROTOOPT ||
+                               errno == EMSGSIZE;
+      if (gso_ok_ && r < 0 && run_len[sent_msgs] > 1 && gso_refused) {
         // no UDP GSO on this kernel / device, or segments larger than the path MTU (EMSGSIZE: GSO segments may not
         // be IP-fragmented): fall back to one datagram per packet for good
         gso_ok_ = false;
