@@ -6,6 +6,8 @@
 #include <fcntl.h>
 #include <ifaddrs.h>
 #include <net/if.h>
+#include <pthread.h>
+#include <sched.h>
 #include <string.h>
 #include <sys/epoll.h>
 #include <sys/ioctl.h>
@@ -132,6 +134,59 @@ int mtu_of_ip(const std::string& ip) {
 }
 }  // namespace
 
+namespace {
+// "0-3,8,10-11" -> cpu set
+bool parse_cpulist(const std::string& txt, cpu_set_t* set) {
+  CPU_ZERO(set);
+  bool any = false;
+  size_t pos = 0;
+  while (pos < txt.size()) {
+    size_t e = txt.find(',', pos);
+    if (e == std::string::npos) e = txt.size();
+    const std::string tok = txt.substr(pos, e - pos);
+    int a = -1, b = -1;
+    if (sscanf(tok.c_str(), "%d-%d", &a, &b) == 2 && a >= 0 && b >= a) {
+      for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, set), any = true;
+    } else if (sscanf(tok.c_str(), "%d", &a) == 1 && a >= 0 && a < CPU_SETSIZE) {
+      CPU_SET(a, set), any = true;
+    }
+    pos = e + 1;
+  }
+  return any;
+}
+
+// Engine threads belong on the cores next to their NIC (the reference pins its engine threads per NIC as well):
+// UCCL_B200_NET_CPUS="8-15" wins; otherwise the NIC's own local_cpulist from sysfs; otherwise no pinning.
+void pin_engine_thread(std::thread& t, const std::string& bind_ip) {
+  std::string list = param_load_str("NET_CPUS", "");
+  if (list.empty()) {
+    in_addr want{};
+    if (inet_pton(AF_INET, bind_ip.c_str(), &want) == 1 && want.s_addr != 0) {
+      ifaddrs* ifa = nullptr;
+      if (getifaddrs(&ifa) == 0) {
+        for (ifaddrs* p = ifa; p; p = p->ifa_next) {
+          if (!p->ifa_addr || p->ifa_addr->sa_family != AF_INET) continue;
+          if (reinterpret_cast<sockaddr_in*>(p->ifa_addr)->sin_addr.s_addr != want.s_addr) continue;
+          char path[256];
+          snprintf(path, sizeof(path), "/sys/class/net/%s/device/local_cpulist", p->ifa_name);
+          if (FILE* f = fopen(path, "r")) {
+            char buf[512] = {0};
+            if (fgets(buf, sizeof(buf), f)) list = buf;
+            fclose(f);
+          }
+          break;
+        }
+        freeifaddrs(ifa);
+      }
+    }
+  }
+  cpu_set_t set;
+  if (list.empty() || !parse_cpulist(list, &set)) return;
+  if (pthread_setaffinity_np(t.native_handle(), sizeof(set), &set) == 0)
+    UB_INFO(SUB_NET, "net: engine thread of %s pinned to cpus %s", bind_ip.c_str(), list.c_str());
+}
+}  // namespace
+
 // ------------------------------------------------------------------------------------------- setup
 Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), rng_(std::random_device{}()) {
   cfg_.paths = std::max(1, std::min(cfg_.paths, kMaxPaths));
@@ -191,6 +246,7 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg), pacer_(cc::EqdsConfig()), r
   UB_INFO(SUB_NET, "net engine up: %s paths=%d port0=%u payload=%d cc=%d", cfg_.bind_ip.c_str(), cfg_.paths, ports_[0],
           cfg_.payload, cfg_.cc);
   thr_ = std::thread([this] { run(); });
+  pin_engine_thread(thr_, cfg_.bind_ip);
 }
 
 void Engine::shutdown(int linger_ms) {
