@@ -285,6 +285,7 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
   if (L_ > 1) local_->allgather(S, W, per, dtype, st);
   else copy_dd(W, S, per * es, st);
   copy_dd(out, W, count * es, st);
+  if (!is_host()) sync(st);  // the pinned staging buffer and the scratch are reused by the next call (maybe on another stream)
 }
 
 // Block b = columns [lo, hi) of every row of work[L][per].  While block b is on the rail (helper thread), this
