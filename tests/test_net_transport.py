@@ -811,3 +811,38 @@ def test_native_multinode_communicator_four_processes():
     [p.join(60) for p in ps]
     for rank, ok in got:
         assert all(ok), (rank, ok)
+
+
+def test_multinode_error_paths():
+    """Things that must fail loudly: point-to-point across rails of different boxes, scale on integer tensors,
+    CUDA tensors handed to the raw engine, non-contiguous tensors."""
+    N, L = 2, 2
+    W = N * L
+    nodes = [Communicator.local_world(L, host=True, heap_bytes=96 << 20, stage_bytes=1 << 20, timeout_ms=30000)
+             for _ in range(N)]
+    rails = [_Exchange(N) for _ in range(L)]
+
+    def fn(gr):
+        k, l = divmod(gr, L)
+        nc = net.NetCommunicator(k, N, rails[l].for_rank(k), engine=net.Engine(bind_ip="127.0.0.1", paths=2))
+        m = MultiNodeCommunicator(nodes[k][l], nc)
+        diag = ((k + 1) % N) * L + (l + 1) % L               # other box, other rail
+        seen = []
+        try:
+            m.send(torch.zeros(4), diag)
+        except NotImplementedError as e:
+            seen.append("not routed" in str(e))
+        try:
+            m.all_reduce(torch.ones(4, dtype=torch.int32), "sum", scale=0.5)
+        except ValueError:
+            seen.append(True)
+        try:
+            nc.engine.isend(nc.flows[(k + 1) % N], torch.zeros(4, 4).t())
+        except ValueError:
+            seen.append(True)
+        m.barrier()
+        m.close()
+        return seen
+
+    for seen in _run_threads(W, fn):
+        assert seen == [True, True, True]
