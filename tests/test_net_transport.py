@@ -846,3 +846,59 @@ def test_multinode_error_paths():
 
     for seen in _run_threads(W, fn):
         assert seen == [True, True, True]
+
+
+def _async_ddp_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), UCCL_B200_NET_BIND_IP="127.0.0.1", UCCL_B200_NET_PATHS="2")
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from uccl_b200.parallel import AsyncMultiNode, MultiNodeCommunicator
+
+    m = MultiNodeCommunicator.from_torch_dist(2, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20, timeout_ms=60000)
+    am = AsyncMultiNode(m)
+    # several collectives in flight, completed in submission order
+    xs = [torch.full((20_000,), float(rank + i)) for i in range(4)]
+    ws = [am.all_reduce_async(x) for x in xs]
+    ok = [all(bool((w.wait(60) == sum(r + i for r in range(world))).all()) for i, w in enumerate(ws))]
+    # DDP with the asynchronous multi-box hook (small buckets -> several hook calls per backward)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8))
+    ddp = torch.nn.parallel.DistributedDataParallel(model, bucket_cap_mb=0.005)
+    ddp.register_comm_hook(None, am.ddp_hook("avg"))
+    torch.manual_seed(100 + rank)
+    x = torch.randn(16, 64)
+    ddp(x).pow(2).sum().backward()
+    # reference: average of the per-rank gradients computed without DDP
+    torch.manual_seed(0)
+    ref = torch.nn.Sequential(torch.nn.Linear(64, 64), torch.nn.ReLU(), torch.nn.Linear(64, 8))
+    grads = []
+    for r in range(world):
+        ref.zero_grad()
+        torch.manual_seed(100 + r)
+        ref(torch.randn(16, 64)).pow(2).sum().backward()
+        grads.append([p.grad.clone() for p in ref.parameters()])
+    for i, p in enumerate(model.parameters()):
+        ok.append(torch.allclose(p.grad, sum(g[i] for g in grads) / world, rtol=1e-4, atol=1e-5))
+    am.close()
+    m.barrier()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_async_multibox_allreduce_and_ddp_hook():
+    """Collectives queued on the helper thread complete in order, and DDP's bucketed gradient averaging across
+    2 boxes x 2 ranks through the asynchronous hook equals the average of the single-rank gradients."""
+    import multiprocessing as mp
+
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_async_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    [p.join(60) for p in ps]
+    for rank, ok in got:
+        assert all(ok), (rank, ok)

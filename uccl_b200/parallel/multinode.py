@@ -552,3 +552,100 @@ class NativeMultiNodeCommunicator:
 
     def describe(self) -> str:
         return self._m.describe()
+
+
+class MultiNodeWork:
+    """Handle of a collective queued with :meth:`AsyncMultiNode.all_reduce_async` (c10d ``Work``-like)."""
+
+    def __init__(self):
+        self._done = threading.Event()
+        self._err: Optional[BaseException] = None
+        self._ev_out = None
+        self.result: Optional[torch.Tensor] = None
+
+    def is_completed(self) -> bool:
+        return self._done.is_set()
+
+    def wait(self, timeout: Optional[float] = None) -> torch.Tensor:
+        if not self._done.wait(timeout):
+            raise TimeoutError("uccl_b200: multi-box collective did not finish in time")
+        if self._err is not None:
+            raise self._err
+        if self._ev_out is not None:  # order the caller's stream after the side stream's last device op
+            torch.cuda.current_stream().wait_event(self._ev_out)
+        return self.result
+
+
+class AsyncMultiNode:
+    """Runs a communicator's collectives on a helper thread (and, on GPUs, a side stream), in submission order, so
+    that the network phase of gradient bucket k overlaps the backward pass that produces bucket k+1 -- what NCCL's
+    proxy thread gives DDP for free.  Works with :class:`MultiNodeCommunicator` and
+    :class:`NativeMultiNodeCommunicator`; every rank must submit the same sequence of operations."""
+
+    def __init__(self, comm):
+        self.comm = comm
+        self._q: "queue.Queue" = queue.Queue()
+        self._cuda = comm.device.type == "cuda"
+        self._side = torch.cuda.Stream(device=comm.device) if self._cuda else None
+        self._th = threading.Thread(target=self._loop, daemon=True, name="uccl-mn-async")
+        self._th.start()
+
+    def _loop(self):
+        if self._cuda:
+            torch.cuda.set_device(self.comm.device)
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            fn, work, ev_in = item
+            try:
+                if self._cuda:
+                    with torch.cuda.stream(self._side):
+                        self._side.wait_event(ev_in)
+                        work.result = fn()
+                        work._ev_out = torch.cuda.Event()
+                        work._ev_out.record(self._side)
+                else:
+                    work.result = fn()
+            except BaseException as e:  # noqa: BLE001 - surfaced by wait()
+                work._err = e
+            work._done.set()
+
+    def submit(self, fn) -> MultiNodeWork:
+        w = MultiNodeWork()
+        ev = None
+        if self._cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.comm.device))
+        self._q.put((fn, w, ev))
+        return w
+
+    def all_reduce_async(self, t: torch.Tensor, op: str = "sum", **kw) -> MultiNodeWork:
+        return self.submit(lambda: self.comm.all_reduce(t, op, **kw))
+
+    def ddp_hook(self, op: str = "avg"):
+        """``model.register_comm_hook(None, async_mn.ddp_hook())``: bucketed gradient all-reduce across boxes that
+        overlaps the rest of the backward pass."""
+
+        def hook(state, bucket):
+            buf = bucket.buffer()
+            fut: torch.futures.Future = torch.futures.Future()
+            w = self.all_reduce_async(buf, op)
+
+            def finish():
+                try:
+                    w.wait()
+                    if w._ev_out is not None:
+                        w._ev_out.synchronize()
+                    fut.set_result(buf)
+                except BaseException as e:  # noqa: BLE001
+                    fut.set_exception(e)
+
+            threading.Thread(target=finish, daemon=True).start()
+            return fut
+
+        return hook
+
+    def close(self) -> None:
+        self._q.put(None)
+        self._th.join(timeout=30)
