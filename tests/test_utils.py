@@ -300,3 +300,28 @@ def test_ep_harness_helpers():
     with U.suppress_stdout_stderr():
         print("not shown")
     assert abs(U.calc_diff(a, a)) < 1e-9
+
+
+def test_timing_wheel_never_fires_early_and_keeps_far_deadlines():
+    """2000 random deadlines up to 8x the wheel's horizon, clock advanced in random steps: nothing fires before its
+    deadline, nothing is lost, lateness is bounded by the step plus one slot."""
+    import random
+
+    from uccl_b200._native import C
+
+    w = C().util.TimingWheel(1000, 64, 0)  # 1 us slots, 64 us horizon
+    assert w.horizon_ns == 64_000
+    rnd = random.Random(1)
+    items = {i: rnd.randrange(0, 500_000) for i in range(2000)}
+    for i, d in items.items():
+        w.insert(d, i)
+    fired, now = {}, 0
+    while len(w):
+        step = rnd.randrange(1, 5000)
+        now += step
+        for i in w.advance(now):
+            assert i not in fired
+            fired[i] = now
+    assert set(fired) == set(items)
+    assert min(fired[i] - items[i] for i in items) >= 0
+    assert max(fired[i] - items[i] for i in items) <= 5000 + 1000

@@ -13,6 +13,7 @@
 #include "pool.h"
 #include "ring.h"
 #include "timers.h"
+#include "timing_wheel.h"
 
 namespace py = pybind11;
 using namespace ub;
@@ -112,6 +113,17 @@ void bind_util(py::module_& m) {
     return SeqNo<32>(a) < SeqNo<32>(b);
   });
 
+  py::class_<TimingWheel<uint64_t>>(u, "TimingWheel")
+      .def(py::init<uint64_t, size_t, uint64_t>(), py::arg("granularity_ns"), py::arg("slots"), py::arg("now_ns") = 0)
+      .def("insert", &TimingWheel<uint64_t>::insert)
+      .def("advance",
+           [](TimingWheel<uint64_t>& w, uint64_t now) {
+             std::vector<uint64_t> out;
+             w.advance(now, &out);
+             return out;
+           })
+      .def("__len__", &TimingWheel<uint64_t>::size)
+      .def_property_readonly("horizon_ns", &TimingWheel<uint64_t>::horizon_ns);
   py::class_<cc::Timely>(u, "Timely")
       .def(py::init<>())
       .def("on_rtt", &cc::Timely::on_rtt)
