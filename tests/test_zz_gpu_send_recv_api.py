@@ -375,3 +375,80 @@ def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _xhost_server(q_md, q_res, nbytes):
+    import os
+    import time
+
+    os.environ["UCCL_B200_P2P_HOST_ID"] = "1001"    # pretend to be another machine than the client
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    torch.cuda.set_device(0)
+    e = Endpoint(0)
+    q_md.put(e.get_metadata())
+    ok, ip, gpu, conn = e.accept(60000)
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    win = torch.full((nbytes,), 7, dtype=torch.uint8, device="cuda")
+    inbox = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    okr = e.recv(conn, 0, buf.data_ptr(), nbytes)
+    descs = e.register_memory([win, inbox])
+    e.send_notif(conn, e.get_serialized_descs(descs))
+    t0, fin = time.time(), False
+    while time.time() - t0 < 60 and not fin:
+        for _, m in e.get_notifs():
+            fin = fin or m == b"done"
+        time.sleep(0.002)
+    torch.cuda.synchronize()
+    q_res.put((bool(ok), bool(okr), int(buf.sum().item()), int(inbox.to(torch.int64).sum().item()), fin))
+
+
+def _xhost_client(q_md, q_res, nbytes):
+    import os
+    import time
+
+    os.environ["UCCL_B200_P2P_HOST_ID"] = "1002"
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    torch.cuda.set_device(0)
+    e = Endpoint(0)
+    ok, conn = e.connect(remote_metadata=q_md.get(timeout=60))
+    src = torch.ones(nbytes, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    oks = e.send(conn, 0, src.data_ptr(), nbytes)
+    blob, t0 = None, time.time()
+    while blob is None and time.time() - t0 < 60:
+        for _, m in e.get_notifs():
+            blob = m
+        time.sleep(0.002)
+    remote = e.deserialize_descs(blob)
+    dst = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    okr = e.read(conn, 0, dst.data_ptr(), nbytes, remote[0])
+    three = torch.full((nbytes,), 3, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    okw = e.write(conn, 0, three.data_ptr(), nbytes, remote[1])
+    e.send_notif(conn, b"done")
+    torch.cuda.synchronize()
+    q_res.put((bool(ok), bool(oks), bool(okr), int(dst.to(torch.int64).sum().item()), bool(okw)))
+    time.sleep(0.3)
+
+
+def test_p2p_endpoint_between_hosts_stages_gpu_memory():
+    """Two GPU endpoints that believe they sit on different machines (UCCL_B200_P2P_HOST_ID): send/recv, one-sided
+    read and write of device memory travel over the connection, staged through host bounce buffers on both ends."""
+    import multiprocessing as mp
+
+    nbytes = (5 << 20) + 3
+    ctx = mp.get_context("spawn")
+    q_md, q_s, q_c = ctx.Queue(), ctx.Queue(), ctx.Queue()
+    ps = [ctx.Process(target=_xhost_server, args=(q_md, q_s, nbytes)), ctx.Process(target=_xhost_client, args=(q_md, q_c, nbytes))]
+    [p.start() for p in ps]
+    rs = q_s.get(timeout=120)
+    rc = q_c.get(timeout=120)
+    [p.join(30) for p in ps]
+    assert rs == (True, True, nbytes, 3 * nbytes, True)
+    assert rc == (True, True, True, 7 * nbytes, True)

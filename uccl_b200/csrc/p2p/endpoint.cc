@@ -321,17 +321,65 @@ bool Endpoint::send_msg2(Conn& c, uint32_t type, uint64_t seq, const void* p1, u
 // that fit the 32-bit frame length.
 bool Endpoint::tcp_write_buffers(Conn& c, const std::vector<const char*>& src, const std::vector<uint64_t>& dst_addr,
                                  const std::vector<size_t>& sizes) {
-  constexpr size_t kPiece = 64u << 20;
+  const size_t kPiece = gpu_ >= 0 ? (4u << 20) : (64u << 20);
+  std::vector<char> bounce;  // GPU endpoints: the socket cannot read device memory
+  if (gpu_ >= 0) bounce.resize(kPiece);
   for (size_t i = 0; i < src.size(); ++i)
     for (size_t off = 0; off < sizes[i]; off += kPiece) {
       const uint64_t n = std::min(kPiece, sizes[i] - off);
       const uint64_t pre[2] = {dst_addr[i] + off, n};
-      if (!send_msg2(c, MSG_WRITE, 0, pre, sizeof(pre), src[i] + off, (uint32_t)n)) return false;
+      const char* from = src[i] + off;
+      if (gpu_ >= 0) {
+        copy_any(bounce.data(), from, n);
+        from = bounce.data();
+      }
+      if (!send_msg2(c, MSG_WRITE, 0, pre, sizeof(pre), from, (uint32_t)n)) return false;
     }
   return true;
 }
 
-bool Endpoint::remote_is_other_process(const XferDesc& d) const { return gpu_ < 0 && d.pid != (int32_t)getpid(); }
+namespace {
+// Identity of this machine (hostname + boot id); UCCL_B200_P2P_HOST_ID overrides (tests emulate two hosts with it).
+uint64_t local_host_id() {
+  static const uint64_t id = [] {
+    const int64_t forced = param_load("P2P_HOST_ID", 0);
+    if (forced > 0) return (uint64_t)forced;
+    char buf[320] = {0};
+    gethostname(buf, 255);
+    if (FILE* f = fopen("/proc/sys/kernel/random/boot_id", "r")) {
+      const size_t at = strlen(buf);
+      if (fgets(buf + at, (int)(sizeof(buf) - at), f) == nullptr) buf[at] = 0;
+      fclose(f);
+    }
+    uint64_t h = 1469598103934665603ull;  // FNV-1a
+    for (const char* p = buf; *p; ++p) h = (h ^ (unsigned char)*p) * 1099511628211ull;
+    return h ? h : 1;
+  }();
+  return id;
+}
+}  // namespace
+
+// Same host: GPU endpoints map each other's memory (CUDA IPC) and host endpoints of one process share an address
+// space.  Everything else -- a host-mode peer in another process, any peer on another machine -- gets its payload
+// over the (TCP) connection; GPU memory is staged through host bounce buffers on both sides.
+bool Endpoint::remote_is_other_process(const XferDesc& d) const {
+  if (d.host_id != 0 && d.host_id != local_host_id()) return true;
+  return gpu_ < 0 && d.pid != (int32_t)getpid();
+}
+
+void Endpoint::copy_any(void* dst, const void* src, size_t n) {
+  if (!n) return;
+  if (gpu_ < 0) {
+    memcpy(dst, src, n);
+    return;
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != gpu_) cudaSetDevice(gpu_);
+  cudaError_t e = cudaMemcpy(dst, src, n, cudaMemcpyDefault);  // either side may be device or host memory
+  if (e != cudaSuccess) UB_WARN("p2p: staged copy of %zu bytes failed: %s", n, cudaGetErrorString(e));
+  if (prev >= 0 && prev != gpu_) cudaSetDevice(prev);
+}
 
 void Endpoint::run_helper(std::function<void()> fn) {
   std::lock_guard<std::mutex> g(helpers_mu_);
@@ -379,6 +427,7 @@ bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
   out->size = size;
   out->pid = (int32_t)getpid();
   out->dev = gpu_;
+  out->host_id = local_host_id();
   if (gpu_ < 0) {  // host mode: plain memory of this process
     out->kind = 1;
     out->base = (uint64_t)ptr;
@@ -392,6 +441,7 @@ bool Endpoint::describe(const void* ptr, size_t size, XferDesc* out) {
     (void)cudaGetLastError();
     return false;
   }
+  expose((uint64_t)ptr, size);  // a peer on another host may address this window through the wire
   if (attr.type == cudaMemoryTypeHost) {
     out->kind = 1;
     out->base = (uint64_t)ptr;
@@ -808,7 +858,7 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
     }
     case MSG_DONE: c.dones[seq] = true; break;
     case MSG_WRITE: {
-      if (gpu_ >= 0 || payload.size() < 16) break;  // only the host mode exposes its memory to the wire
+      if (payload.size() < 16) break;
       uint64_t pre[2];
       memcpy(pre, payload.data(), 16);
       if (pre[1] != payload.size() - 16) break;
@@ -817,7 +867,7 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
                        (unsigned long long)pre[1]);
         break;
       }
-      memcpy((void*)pre[0], payload.data() + 16, pre[1]);
+      copy_any((void*)pre[0], payload.data() + 16, pre[1]);
       break;
     }
     case MSG_FLUSH: {
@@ -829,7 +879,6 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
     }
     case MSG_FLUSH_ACK: c.acks[seq] = true; break;
     case MSG_READ_REQ: {
-      if (gpu_ >= 0) break;
       const size_t nb = payload.size() / 16;
       auto data = std::make_shared<std::vector<char>>();
       for (size_t i = 0; i < nb; ++i) {
@@ -842,7 +891,7 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
         }
         const size_t at = data->size();
         data->resize(at + e[1]);
-        memcpy(data->data() + at, (const void*)e[0], e[1]);
+        copy_any(data->data() + at, (const void*)e[0], e[1]);
       }
       std::shared_ptr<Conn> conn;
       for (auto& kv : conns_)
@@ -858,7 +907,7 @@ void Endpoint::handle_message(Conn& c, uint32_t type, uint64_t seq, std::vector<
       bool ok = true;
       for (size_t i = 0; i < t->dst.size() && ok; ++i) {
         if (at + t->sizes[i] > payload.size()) ok = false;
-        else memcpy(t->dst[i], payload.data() + at, t->sizes[i]);
+        else copy_any(t->dst[i], payload.data() + at, t->sizes[i]);
         at += t->sizes[i];
       }
       t->state = ok ? Transfer::DONE : Transfer::FAILED;

@@ -86,7 +86,8 @@ class Endpoint {
   bool send_msg2(Conn& c, uint32_t type, uint64_t seq, const void* p1, uint32_t len1, const void* p2, uint32_t len2);
   bool tcp_write_buffers(Conn& c, const std::vector<const char*>& src, const std::vector<uint64_t>& dst_addr,
                          const std::vector<size_t>& sizes);
-  bool remote_is_other_process(const XferDesc& d) const;
+  bool remote_is_other_process(const XferDesc& d) const;  // not load/store reachable: payload goes over the connection
+  void copy_any(void* dst, const void* src, size_t n);    // memcpy in host mode, cudaMemcpy(Default) with a GPU
   void run_helper(std::function<void()> fn);
   void progress_locked();
   bool launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,

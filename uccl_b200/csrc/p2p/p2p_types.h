@@ -32,7 +32,8 @@ struct XferDesc {
   int32_t dev;                   // owner CUDA device
   uint32_t kind;                 // 0 = CUDA IPC, 1 = pinned host (same process only), 2 = same-process device ptr
   uint32_t mr_id;
-  unsigned char pad[24];
+  uint64_t host_id;              // which machine owns the window (0 = unknown / legacy): other hosts use the wire
+  unsigned char pad[16];
 };
 static_assert(sizeof(XferDesc) == 128, "XferDesc must be 128 bytes");
 
