@@ -38,6 +38,7 @@ std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int n
   m->lrank_ = rank % local_size;
   m->timeout_ms_ = (int)param_load("MN_TIMEOUT_MS", 120000);
   m->pipeline_bytes_ = (size_t)param_load("MN_PIPELINE_BYTES", 8 << 20);
+  m->small_bytes_ = (size_t)param_load("MN_SMALL_BYTES", 16 << 10);
   Bootstrap g(id, rank, nranks);
   // one rendezvous per box for its NVLink communicator (the relay lives on the box: loopback)
   UniqueId mine;
@@ -170,6 +171,15 @@ void MultiComm::rail_allreduce(void* buf, size_t count, int dtype, int op) {
   const int n = N_, r = node_;
   if (n == 1 || count == 0) return;
   const size_t es = (size_t)dtype_size(dtype);
+  if ((n & (n - 1)) == 0 && count * es <= small_bytes_) {  // log2(n) exchanges of the whole vector
+    char* tmp = host_stage(count * es, 3);
+    for (int d = 1; d < n; d <<= 1) {
+      rail_sendrecv(buf, count * es, r ^ d, tmp, count * es, r ^ d);
+      const void* srcs[2] = {buf, tmp};
+      host_reduce_n(buf, srcs, 2, count, dtype, op, 1.0f);
+    }
+    return;
+  }
   auto lo = [&](int k) { return (size_t)k * count / (size_t)n; };
   size_t mx = 0;
   for (int k = 0; k < n; ++k) mx = std::max(mx, lo(k + 1) - lo(k));
@@ -263,6 +273,28 @@ void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, in
   const int inner = op == kAvg ? kSum : op;
   const float sc = scale * (op == kAvg ? 1.0f / (float)nranks_ : 1.0f);
   const size_t es = (size_t)dtype_size(dtype), per = ceil_div(count, (size_t)L_);
+  if (count * es <= small_bytes_) {
+    // latency bound: two phases instead of three -- one NVLink all-reduce, then EVERY local rank all-reduces the
+    // whole (tiny) vector along its rail (L x the bytes on the network, one kernel and one staging hop less)
+    char* T = static_cast<char*>(scratch(count * es, 1));
+    if (L_ > 1) {
+      ArOpts o;
+      local_->allreduce(in, T, count, dtype, inner, st, o);
+    } else {
+      copy_dd(T, in, count * es, st);
+    }
+    char* H = is_host() ? T : host_stage(count * es, 0);
+    to_host(H, T, count * es, st);
+    sync(st);
+    rail_allreduce(H, count, dtype, inner);
+    if (sc != 1.0f) {
+      const void* one[1] = {H};
+      host_reduce_n(H, one, 1, count, dtype, kSum, sc);
+    }
+    to_dev(out, H, count * es, st);
+    if (!is_host()) sync(st);
+    return;
+  }
   if (per * es > pipeline_bytes_) {  // large: block pipeline straight from `in` to `out` (scratch = a few blocks)
     allreduce_pipelined(static_cast<const char*>(in), static_cast<char*>(out), count, per, dtype, inner, sc, st);
     return;

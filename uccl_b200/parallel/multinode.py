@@ -38,6 +38,7 @@ class MultiNodeCommunicator:
         self._pinned: Dict[Tuple[int, torch.dtype, int], torch.Tensor] = {}
         # all_reduce of more than this many bytes per rank-shard runs as a 3-stage pipeline over chunks
         self.pipeline_bytes = int(os.environ.get("UCCL_B200_MN_PIPELINE_BYTES", str(8 << 20)))
+        self.small_bytes = int(os.environ.get("UCCL_B200_MN_SMALL_BYTES", str(16 << 10)))
 
     @staticmethod
     def _rail_engine(local_rank: int, device: Optional[int]):
@@ -158,6 +159,17 @@ class MultiNodeCommunicator:
         inner = "sum" if op == "avg" else op
         flat = t.view(-1)
         n = flat.numel()
+        if n * t.element_size() <= self.small_bytes:
+            # latency bound: one NVLink all-reduce, then every local rank all-reduces the whole (tiny) vector along
+            # its rail -- two phases instead of three
+            if L > 1:
+                self.local.all_reduce(flat, inner)
+            h = self._down(flat)
+            self.net.all_reduce(h, inner)
+            if op == "avg":
+                h.div_(self.world_size) if t.is_floating_point() else h.copy_(torch.div(h, self.world_size, rounding_mode="trunc"))
+            self._up(flat, h)
+            return t
         per = (n + L - 1) // L
         if per * L != n:  # pad to a multiple of the node size
             work = torch.zeros(per * L, dtype=t.dtype, device=t.device)
