@@ -68,6 +68,41 @@ class _Work(dist._Work if hasattr(dist, "_Work") else dist.Work):
         return self._result
 
 
+class _AsyncWork(_Work):
+    """Work of a collective that runs on the multi-box helper thread: `wait()` blocks until it is done and orders the
+    caller's stream after it; the future completes from the helper thread, which is what lets DDP overlap the
+    gradient all-reduce of one bucket with the backward pass of the next."""
+
+    def __init__(self, mn_work, result):
+        import threading
+
+        dist.Work.__init__(self) if not hasattr(dist, "_Work") else dist._Work.__init__(self)
+        self._w = mn_work
+        self._result = result
+        self._fut = torch.futures.Future()
+
+        def finish():
+            try:
+                mn_work.wait()
+                if mn_work._ev_out is not None:
+                    mn_work._ev_out.synchronize()
+                self._fut.set_result(result)
+            except BaseException as e:  # noqa: BLE001
+                self._fut.set_exception(e)
+
+        threading.Thread(target=finish, daemon=True).start()
+
+    def wait(self, timeout=None):
+        self._w.wait()
+        return True
+
+    def is_completed(self):
+        return self._w.is_completed()
+
+    def is_success(self):
+        return self._w.is_completed() and self._w._err is None
+
+
 class ProcessGroupUCCL(dist.ProcessGroup):
     def __init__(self, store, rank: int, world_size: int, timeout=None, heap_bytes: Optional[int] = None):
         super().__init__(rank, world_size)
@@ -88,6 +123,10 @@ class ProcessGroupUCCL(dist.ProcessGroup):
             seq = os.environ.get("UCCL_B200_PG_SEQ", "0")
             self.comm = MultiNodeCommunicator.from_store(store, rank, world_size, local, prefix=f"uccl_b200/mn{seq}",
                                                          heap_bytes=heap, stage_bytes=stage, host=host)
+            if os.environ.get("UCCL_B200_PG_ASYNC", "1") != "0":
+                from .multinode import AsyncMultiNode
+
+                self._async = AsyncMultiNode(self.comm)  # all-reduce returns a live Work: DDP overlaps buckets
         else:
             self.comm = Communicator.init(uid, rank, world_size, heap_bytes=heap, stage_bytes=stage, host=host)
 
@@ -107,8 +146,24 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return t
 
     # ---- collectives (signatures of c10d::ProcessGroup)
+    _async = None
+
+    def _drain_async(self):
+        """Collectives that do not go through the helper thread must not overtake the ones that did."""
+        if self._async is not None:
+            self._async.submit(lambda: None).wait()
+
     def allreduce(self, tensors: List[torch.Tensor], opts=None):
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
+        if self._async is not None:
+            ts = [self._prep(t) for t in tensors]
+
+            def run():
+                for t in ts:
+                    self.comm.all_reduce(t, op)
+                return ts
+
+            return _AsyncWork(self._async.submit(run), tensors)
         for t in tensors:
             self.comm.all_reduce(self._prep(t), op)
         return _Work(tensors)
@@ -117,12 +172,14 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return self.allreduce(tensors, opts)
 
     def broadcast(self, tensors: List[torch.Tensor], opts=None):
+        self._drain_async()
         root = opts.rootRank if opts is not None else 0
         for t in tensors:
             self.comm.broadcast(self._prep(t), root=root)
         return _Work(tensors)
 
     def allgather(self, output_tensors: List[List[torch.Tensor]], input_tensors: List[torch.Tensor], opts=None):
+        self._drain_async()
         for outs, inp in zip(output_tensors, input_tensors):
             flat = torch.empty((self._world,) + tuple(inp.shape), dtype=inp.dtype, device=inp.device)
             self.comm.all_gather(flat, self._prep(inp))
@@ -131,15 +188,18 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(output_tensors)
 
     def _allgather_base(self, output: torch.Tensor, input: torch.Tensor, opts=None):
+        self._drain_async()
         self.comm.all_gather(self._prep(output), self._prep(input))
         return _Work(output)
 
     def allgather_into_tensor_coalesced(self, outputs, inputs, opts=None):
+        self._drain_async()
         for o, i in zip(outputs, inputs):
             self.comm.all_gather(self._prep(o), self._prep(i))
         return _Work(outputs)
 
     def reduce_scatter(self, output_tensors: List[torch.Tensor], input_tensors: List[List[torch.Tensor]], opts=None):
+        self._drain_async()
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
         for out, ins in zip(output_tensors, input_tensors):
             flat = torch.stack([self._prep(t) for t in ins]).contiguous()
@@ -147,17 +207,20 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(output_tensors)
 
     def _reduce_scatter_base(self, output: torch.Tensor, input: torch.Tensor, opts=None):
+        self._drain_async()
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
         self.comm.reduce_scatter(self._prep(output), self._prep(input), op)
         return _Work(output)
 
     def reduce_scatter_tensor_coalesced(self, outputs, inputs, opts=None):
+        self._drain_async()
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
         for o, i in zip(outputs, inputs):
             self.comm.reduce_scatter(self._prep(o), self._prep(i), op)
         return _Work(outputs)
 
     def reduce(self, tensors: List[torch.Tensor], opts=None):
+        self._drain_async()
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
         root = opts.rootRank if opts is not None else 0
         for t in tensors:
@@ -166,6 +229,7 @@ class ProcessGroupUCCL(dist.ProcessGroup):
 
     def alltoall_base(self, output: torch.Tensor, input: torch.Tensor, output_split_sizes, input_split_sizes,
                       opts=None):
+        self._drain_async()
         if not output_split_sizes and not input_split_sizes:
             self.comm.all_to_all(self._prep(output), self._prep(input))
         else:
@@ -176,6 +240,7 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(output)
 
     def alltoall(self, output_tensors, input_tensors, opts=None):
+        self._drain_async()
         inp = torch.stack([self._prep(t) for t in input_tensors]).contiguous()
         out = torch.empty_like(inp)
         self.comm.all_to_all(out, inp)
@@ -184,12 +249,14 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(output_tensors)
 
     def barrier(self, opts=None):
+        self._drain_async()
         self.comm.barrier()
         if not self.comm.is_host:
             torch.cuda.current_stream().synchronize()
         return _Work(None)
 
     def send(self, tensors, dst_rank, tag=0):
+        self._drain_async()
         # native staged send/recv kernel (CUDA) / mailbox protocol (host); tags are not used, operations
         # towards one peer match in posting order like NCCL's
         for t in tensors:
@@ -197,6 +264,7 @@ class ProcessGroupUCCL(dist.ProcessGroup):
         return _Work(tensors)
 
     def recv(self, tensors, src_rank, tag=0):
+        self._drain_async()
         for t in tensors:
             self.comm.recv(self._prep(t), src_rank)
         return _Work(tensors)
