@@ -39,6 +39,7 @@ std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int n
   m->timeout_ms_ = (int)param_load("MN_TIMEOUT_MS", 120000);
   m->pipeline_bytes_ = (size_t)param_load("MN_PIPELINE_BYTES", 8 << 20);
   m->small_bytes_ = (size_t)param_load("MN_SMALL_BYTES", 16 << 10);
+  m->scratch_cap_ = (size_t)param_load("MN_SCRATCH_MB", 32) << 20;
   Bootstrap g(id, rank, nranks);
   // one rendezvous per box for its NVLink communicator (the relay lives on the box: loopback)
   UniqueId mine;
@@ -403,29 +404,38 @@ void MultiComm::allreduce_pipelined(const char* in, char* out, size_t count, siz
   }
 }
 
+// all_gather / reduce_scatter / all_to_all work on [world][count] layouts.  They run in column chunks of at most
+// scratch_cap_ bytes per buffer, so the symmetric-heap scratch stays small however large the message is: chunk
+// [off, off+m) of every rank block is gathered into dense scratch, exchanged, and scattered back.
 void MultiComm::allgather(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {
   if (count == 0) return;
   if (N_ == 1) {
     local_->allgather(in, out, count, dtype, st);
     return;
   }
-  const size_t c = count * (size_t)dtype_size(dtype);
-  char* H = host_stage((size_t)N_ * c, 0);
-  to_host(H + (size_t)node_ * c, in, c, st);
-  sync(st);
-  rail_allgather(H, c);
-  char* R = static_cast<char*>(scratch((size_t)N_ * c, 0));
-  to_dev(R, H, (size_t)N_ * c, st);
+  const size_t es = (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  const size_t step = std::max<size_t>(1, scratch_cap_ / (W * es));
+  const char* i = static_cast<const char*>(in);
   char* o = static_cast<char*>(out);
-  if (L_ > 1) {
-    char* G = static_cast<char*>(scratch((size_t)L_ * N_ * c, 1));
-    local_->allgather(R, G, (size_t)N_ * count, dtype, st);
-    for (int k = 0; k < N_; ++k)  // G is [local rank][box], the result is [box][local rank]
-      for (int l = 0; l < L_; ++l) copy_dd(o + ((size_t)k * L_ + l) * c, G + ((size_t)l * N_ + k) * c, c, st);
-  } else {
-    copy_dd(o, R, (size_t)N_ * c, st);
+  for (size_t off = 0; off < count; off += step) {
+    const size_t m = std::min(step, count - off), mb = m * es;
+    char* H = host_stage((size_t)N_ * mb, 0);
+    to_host(H + (size_t)node_ * mb, i + off * es, mb, st);
+    sync(st);
+    rail_allgather(H, mb);
+    char* R = static_cast<char*>(scratch((size_t)N_ * mb, 0));
+    to_dev(R, H, (size_t)N_ * mb, st);
+    if (L_ > 1) {
+      char* G = static_cast<char*>(scratch((size_t)L_ * N_ * mb, 1));
+      local_->allgather(R, G, (size_t)N_ * m, dtype, st);
+      for (int k = 0; k < N_; ++k)  // G is [local rank][box], the result is [box][local rank]
+        for (int l = 0; l < L_; ++l)
+          copy_dd(o + (((size_t)k * L_ + l) * count + off) * es, G + ((size_t)l * N_ + k) * mb, mb, st);
+    } else {
+      for (int k = 0; k < N_; ++k) copy_dd(o + ((size_t)k * count + off) * es, R + (size_t)k * mb, mb, st);
+    }
+    if (!is_host()) sync(st);  // the pinned buffer is reused by the next chunk / call
   }
-  if (!is_host()) sync(st);  // the pinned buffer is reused by the next call
 }
 
 void MultiComm::reduce_scatter(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t st) {
@@ -437,28 +447,34 @@ void MultiComm::reduce_scatter(const void* in, void* out, size_t count, int dtyp
   }
   const int inner = op == kAvg ? kSum : op;
   const float sc = op == kAvg ? 1.0f / (float)nranks_ : 1.0f;
-  const size_t c = count * (size_t)dtype_size(dtype);
+  const size_t es = (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  const size_t step = std::max<size_t>(1, scratch_cap_ / (W * es));
   const char* i = static_cast<const char*>(in);
-  char* part = static_cast<char*>(scratch((size_t)N_ * c, 1));
-  if (L_ > 1) {
-    char* P = static_cast<char*>(scratch((size_t)L_ * N_ * c, 0));  // [dst local rank][box] <- in [box][local rank]
-    for (int k = 0; k < N_; ++k)
-      for (int l = 0; l < L_; ++l) copy_dd(P + ((size_t)l * N_ + k) * c, i + ((size_t)k * L_ + l) * c, c, st);
-    local_->reduce_scatter(P, part, (size_t)N_ * count, dtype, inner, st, 1.0f);
-  } else {
-    copy_dd(part, i, (size_t)N_ * c, st);
+  char* o = static_cast<char*>(out);
+  for (size_t off = 0; off < count; off += step) {
+    const size_t m = std::min(step, count - off), mb = m * es;
+    char* part = static_cast<char*>(scratch((size_t)N_ * mb, 1));
+    if (L_ > 1) {
+      char* P = static_cast<char*>(scratch((size_t)L_ * N_ * mb, 0));  // [dst local rank][box] <- in [box][local rank]
+      for (int k = 0; k < N_; ++k)
+        for (int l = 0; l < L_; ++l)
+          copy_dd(P + ((size_t)l * N_ + k) * mb, i + (((size_t)k * L_ + l) * count + off) * es, mb, st);
+      local_->reduce_scatter(P, part, (size_t)N_ * m, dtype, inner, st, 1.0f);
+    } else {
+      for (int k = 0; k < N_; ++k) copy_dd(part + (size_t)k * mb, i + ((size_t)k * count + off) * es, mb, st);
+    }
+    char* H = is_host() ? part : host_stage((size_t)N_ * mb, 0);
+    to_host(H, part, (size_t)N_ * mb, st);
+    sync(st);
+    char* O = host_stage(mb, 1);
+    rail_reduce_scatter(H, m, dtype, inner, O);
+    if (sc != 1.0f) {
+      const void* one[1] = {O};
+      host_reduce_n(O, one, 1, m, dtype, kSum, sc);
+    }
+    to_dev(o + off * es, O, mb, st);
+    if (!is_host()) sync(st);
   }
-  char* H = is_host() ? part : host_stage((size_t)N_ * c, 0);
-  to_host(H, part, (size_t)N_ * c, st);
-  sync(st);
-  char* O = host_stage(c, 1);
-  rail_reduce_scatter(H, count, dtype, inner, O);
-  if (sc != 1.0f) {
-    const void* one[1] = {O};
-    host_reduce_n(O, one, 1, count, dtype, kSum, sc);
-  }
-  to_dev(out, O, c, st);
-  if (!is_host()) sync(st);
 }
 
 void MultiComm::broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t st) {
@@ -513,29 +529,33 @@ void MultiComm::alltoall(const void* in, void* out, size_t count, int dtype, cud
     local_->alltoall(in, out, count, dtype, st);
     return;
   }
-  const size_t c = count * (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  const size_t es = (size_t)dtype_size(dtype), W = (size_t)nranks_;
+  const size_t step = std::max<size_t>(1, scratch_cap_ / (W * es));
   const char* i = static_cast<const char*>(in);
-  char* C = static_cast<char*>(scratch(W * c, 0));
-  if (L_ > 1) {
-    char* A = C;                                             // [dst local][dst box]
-    char* B = static_cast<char*>(scratch(W * c, 1));         // [src local][dst box] after the NVLink hop
-    for (int k = 0; k < N_; ++k)
-      for (int l = 0; l < L_; ++l) copy_dd(A + ((size_t)l * N_ + k) * c, i + ((size_t)k * L_ + l) * c, c, st);
-    local_->alltoall(A, B, (size_t)N_ * count, dtype, st);
-    char* C2 = static_cast<char*>(scratch(W * c, 2));        // [dst box][src local]: what the rail exchanges
-    for (int l = 0; l < L_; ++l)
-      for (int k = 0; k < N_; ++k) copy_dd(C2 + ((size_t)k * L_ + l) * c, B + ((size_t)l * N_ + k) * c, c, st);
-    C = C2;
-  } else {
-    copy_dd(C, i, W * c, st);
+  char* o = static_cast<char*>(out);
+  for (size_t off = 0; off < count; off += step) {
+    const size_t m = std::min(step, count - off), mb = m * es;
+    char* C = static_cast<char*>(scratch(W * mb, 2));  // [dst box][src local]: what the rail exchanges
+    if (L_ > 1) {
+      char* A = static_cast<char*>(scratch(W * mb, 0));  // [dst local][dst box]
+      char* B = static_cast<char*>(scratch(W * mb, 1));  // [src local][dst box] after the NVLink hop
+      for (int k = 0; k < N_; ++k)
+        for (int l = 0; l < L_; ++l)
+          copy_dd(A + ((size_t)l * N_ + k) * mb, i + (((size_t)k * L_ + l) * count + off) * es, mb, st);
+      local_->alltoall(A, B, (size_t)N_ * m, dtype, st);
+      for (int l = 0; l < L_; ++l)
+        for (int k = 0; k < N_; ++k) copy_dd(C + ((size_t)k * L_ + l) * mb, B + ((size_t)l * N_ + k) * mb, mb, st);
+    } else {
+      for (int k = 0; k < N_; ++k) copy_dd(C + (size_t)k * mb, i + ((size_t)k * count + off) * es, mb, st);
+    }
+    char* H = host_stage(W * mb, 0);
+    to_host(H, C, W * mb, st);
+    sync(st);
+    char* O = host_stage(W * mb, 1);
+    rail_alltoall(H, O, (size_t)L_ * mb);  // result is [src box][src local] = global source order
+    for (size_t s_ = 0; s_ < W; ++s_) to_dev(o + (s_ * count + off) * es, O + s_ * mb, mb, st);
+    if (!is_host()) sync(st);
   }
-  char* H = host_stage(W * c, 0);
-  to_host(H, C, W * c, st);
-  sync(st);
-  char* O = host_stage(W * c, 1);
-  rail_alltoall(H, O, (size_t)L_ * c);  // result is [src box][src local] = global source order
-  to_dev(out, O, W * c, st);
-  if (!is_host()) sync(st);
 }
 
 void MultiComm::alltoallv(const void* in, const size_t* sc, const size_t* sd, void* out, const size_t* rc, const size_t* rd,

@@ -80,6 +80,7 @@ class MultiComm {
   std::vector<uint32_t> rail_;  // flow to the same local rank of node k (own entry unused)
   int timeout_ms_ = 120000;
   size_t small_bytes_ = 16u << 10;     // messages up to this size take the two-phase latency path (UCCL_B200_MN_SMALL_BYTES)
+  size_t scratch_cap_ = 32u << 20;     // upper size of one scratch buffer: large all_gather / reduce_scatter / all_to_all run in chunks
   size_t pipeline_bytes_ = 8u << 20;  // shard bytes above which all-reduce is pipelined (UCCL_B200_MN_PIPELINE_BYTES)
   struct HostBuf {
     char* p = nullptr;
