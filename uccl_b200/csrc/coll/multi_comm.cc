@@ -491,26 +491,29 @@ void MultiComm::broadcast(const void* in, void* out, size_t count, int dtype, in
     if (L_ > 1) local_->broadcast(in, out, count, dtype, root_l, st);
     else copy_dd(out, in, b, st);
   }
-  // rail l carries bytes [l*per, (l+1)*per) to the other boxes, which re-assemble over NVLink
-  const size_t per = (ceil_div(b, (size_t)L_) + 15) / 16 * 16;
-  const size_t lo = std::min((size_t)lrank_ * per, b), hi = std::min(lo + per, b);
-  char* H = host_stage(per, 0);
-  if (node_ == root_node) {
-    to_host(H, o + lo, hi - lo, st);
-    sync(st);
-  }
-  rail_broadcast(H, per, root_node);
-  if (node_ != root_node) {
-    char* P = static_cast<char*>(scratch(per, 0));
-    to_dev(P, H, per, st);
-    if (L_ > 1) {
-      char* F = static_cast<char*>(scratch(per * L_, 1));
-      local_->allgather(P, F, per, kU8, st);
-      copy_dd(o, F, b, st);
-    } else {
-      copy_dd(o, P, b, st);
+  // rail l carries bytes [l*per, (l+1)*per) of every chunk to the other boxes, which re-assemble over NVLink
+  for (size_t base = 0; base < b; base += scratch_cap_ ? scratch_cap_ : b) {
+    const size_t nb = std::min(scratch_cap_ ? scratch_cap_ : b, b - base);
+    const size_t per = (ceil_div(nb, (size_t)L_) + 15) / 16 * 16;
+    const size_t lo = std::min((size_t)lrank_ * per, nb), hi = std::min(lo + per, nb);
+    char* H = host_stage(per, 0);
+    if (node_ == root_node) {
+      to_host(H, o + base + lo, hi - lo, st);
+      sync(st);
     }
-    if (!is_host()) sync(st);
+    rail_broadcast(H, per, root_node);
+    if (node_ != root_node) {
+      char* P = static_cast<char*>(scratch(per, 0));
+      to_dev(P, H, per, st);
+      if (L_ > 1) {
+        char* F = static_cast<char*>(scratch(per * L_, 1));
+        local_->allgather(P, F, per, kU8, st);
+        copy_dd(o + base, F, nb, st);
+      } else {
+        copy_dd(o + base, P, nb, st);
+      }
+      if (!is_host()) sync(st);
+    }
   }
 }
 
