@@ -789,6 +789,11 @@ def _native_mn_worker(rank, world, uid, q):
     a2a = torch.zeros(world * 7)
     m.all_to_all(a2a, torch.arange(world * 7, dtype=torch.float32) + 100 * rank)
     ok.append(a2a.tolist() == [float(100 * s + 7 * rank + i) for s in range(world) for i in range(7)])
+    sc = [(rank + 2 * d) % 4 + 1 for d in range(world)]
+    rc = [(s_ + 2 * rank) % 4 + 1 for s_ in range(world)]
+    vout = torch.zeros(sum(rc))
+    m.all_to_all_v(vout, torch.cat([torch.full((sc[d],), float(100 * rank + d)) for d in range(world)]), sc, rc)
+    ok.append(torch.equal(vout, torch.cat([torch.full((rc[s_],), float(100 * s_ + rank)) for s_ in range(world)])))
     r1 = torch.zeros(2000)
     m.batch_send_recv([("recv", r1, (rank + 2) % world), ("send", torch.full((2000,), float(rank)), (rank + 2) % world)])
     ok.append(bool((r1 == (rank + 2) % world).all()))

@@ -274,6 +274,15 @@ PYBIND11_MODULE(_C, m) {
              py::gil_scoped_release rel;
              c.alltoall(P(in), P(out), count, dtype, S(stream));
            })
+      .def("alltoallv",
+           [](MultiComm& c, uintptr_t in, std::vector<size_t> sc, std::vector<size_t> sd, uintptr_t out, std::vector<size_t> rc,
+              std::vector<size_t> rd, int dtype, uintptr_t stream) {
+             UB_CHECK((int)sc.size() == c.nranks() && (int)sd.size() == c.nranks() && (int)rc.size() == c.nranks() &&
+                          (int)rd.size() == c.nranks(),
+                      "alltoallv: count / displacement lists must have one entry per rank");
+             py::gil_scoped_release rel;
+             c.alltoallv(P(in), sc.data(), sd.data(), P(out), rc.data(), rd.data(), dtype, S(stream));
+           })
       .def("barrier",
            [](MultiComm& c, uintptr_t stream) {
              py::gil_scoped_release rel;

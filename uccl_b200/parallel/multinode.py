@@ -549,6 +549,13 @@ class NativeMultiNodeCommunicator:
                          self._stream(stream))
         return out
 
+    def all_to_all_v(self, out: torch.Tensor, t: torch.Tensor, send_counts, recv_counts, stream=None):
+        sc, rc = [int(c) for c in send_counts], [int(c) for c in recv_counts]
+        sd = [sum(sc[:i]) for i in range(len(sc))]
+        rd = [sum(rc[:i]) for i in range(len(rc))]
+        self._m.alltoallv(self._c(t).data_ptr(), sc, sd, self._c(out).data_ptr(), rc, rd, self._dt(t.dtype), self._stream(stream))
+        return out
+
     def batch_send_recv(self, ops, stream=None) -> None:
         self._m.group_p2p([(kind == "send", self._c(t).data_ptr(), t.numel() * t.element_size(), int(peer))
                            for kind, t, peer in ops], self._stream(stream))
