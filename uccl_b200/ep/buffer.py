@@ -48,7 +48,7 @@ class Buffer:
     num_sms: int = 24
 
     def __new__(cls, group=None, *args, comm: Optional[Communicator] = None, **kwargs):
-        if comm is not None and (comm.is_host or type(comm).__name__ == "MultiNodeCommunicator"):
+        if comm is not None and (comm.is_host or type(comm).__name__ in ("MultiNodeCommunicator", "NativeMultiNodeCommunicator")):
             # CPU reference backend with the same API (GPU-less CI) -- also the portable path for groups that span
             # boxes (MultiNodeCommunicator: two-hop all-to-all, NVLink + datagram rails): see host_ep.HostBuffer
             from .host_ep import HostBuffer
