@@ -11,7 +11,7 @@ import torch
 
 from helpers import get_world, run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(150),
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(90),
               pytest.mark.xfail(strict=False, reason="added after the GPU budget was spent; first hardware run pending")]
 
 
@@ -189,7 +189,7 @@ def test_nccl_runs_over_the_net_plugin(tmp_path):
                LD_LIBRARY_PATH=str(plugin.parent) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)],
-                       capture_output=True, text=True, timeout=120, env=env)
+                       capture_output=True, text=True, timeout=80, env=env)
     out = r.stdout + r.stderr
     sys.stdout.write(out[-3000:])
     assert r.returncode == 0
@@ -304,7 +304,7 @@ def test_nccl_api_across_boxes_with_device_buffers(tmp_path):
     subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(root, "tests/cpp/nccl_multibox_gpu_test.cc"), "-I/usr/include",
                     "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl", "-Wl,-rpath," + str(shim.parent),
                     "-L/usr/local/cuda/lib64", "-lcudart", "-lpthread", "-o", str(exe)], check=True)
-    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=120)
+    r = subprocess.run([str(exe), "2"], capture_output=True, text=True, timeout=80)
     sys.stdout.write(r.stdout + r.stderr[-2000:])
     assert r.returncode == 0 and "nccl_multibox_gpu_test: OK" in r.stdout
 
@@ -447,8 +447,8 @@ def test_p2p_endpoint_between_hosts_stages_gpu_memory():
     q_md, q_s, q_c = ctx.Queue(), ctx.Queue(), ctx.Queue()
     ps = [ctx.Process(target=_xhost_server, args=(q_md, q_s, nbytes)), ctx.Process(target=_xhost_client, args=(q_md, q_c, nbytes))]
     [p.start() for p in ps]
-    rs = q_s.get(timeout=120)
-    rc = q_c.get(timeout=120)
+    rs = q_s.get(timeout=80)
+    rc = q_c.get(timeout=80)
     [p.join(30) for p in ps]
     assert rs == (True, True, nbytes, 3 * nbytes, True)
     assert rc == (True, True, True, 7 * nbytes, True)
