@@ -122,6 +122,7 @@ void bind_net(py::module_& root) {
           },
           py::arg("request"), py::arg("timeout_ms") = -1)
       .def("set_drop_prob", &Engine::set_drop_prob)
+      .def("set_reorder", &Engine::set_reorder, py::arg("prob"), py::arg("delay_us") = 300)
       .def("set_path_drop", &Engine::set_path_drop, py::arg("path"), py::arg("prob") = 1.0)
       .def("stats",
            [](Engine& e) {

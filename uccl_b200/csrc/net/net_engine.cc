@@ -545,6 +545,10 @@ void Engine::run() {
       }
     }
     flush_all();
+    if (!held_.empty()) {
+      release_held(now_ns());
+      busy = true;  // keep the loop turning until the held datagrams have left
+    }
     ++est_.loops;
     if (now - last_stats > 1000000ull) {
       last_stats = now;
@@ -832,6 +836,18 @@ void Engine::raw_send(int path, const sockaddr_in& to, const void* hdr, size_t h
       return;
     }
   }
+  const double rp = reorder_prob_.load(std::memory_order_relaxed);
+  if (rp > 0.0 && std::uniform_real_distribution<double>(0.0, 1.0)(rng_) < rp) {
+    Held h;
+    h.release_ns = now_ns() + (uint64_t)reorder_delay_us_.load(std::memory_order_relaxed) * 1000ull;
+    h.path = path;
+    h.to = to;
+    h.bytes.resize(sizeof(PktHdr) + blen);
+    memcpy(h.bytes.data(), hdr, sizeof(PktHdr));
+    if (blen) memcpy(h.bytes.data() + sizeof(PktHdr), body, blen);
+    held_.push_back(std::move(h));
+    return;
+  }
   TxBatch& b = txb_[path];
   if (b.n == kTxBatch) flush_path(path);
   TxSlot& s = b.slot[b.n++];
@@ -930,6 +946,15 @@ void Engine::flush_path(int path) {
   est_.tx_pkts += (uint64_t)sent;
   est_.dropped_tx += (uint64_t)(b.n - sent);
   b.n = 0;
+}
+
+void Engine::release_held(uint64_t now) {
+  while (!held_.empty() && held_.front().release_ns <= now) {
+    Held& h = held_.front();
+    (void)::sendto(socks_[h.path], h.bytes.data(), h.bytes.size(), MSG_DONTWAIT, reinterpret_cast<sockaddr*>(&h.to), sizeof(h.to));
+    ++est_.tx_pkts;
+    held_.pop_front();
+  }
 }
 
 void Engine::flush_all() {
@@ -1097,6 +1122,7 @@ void Engine::send_ack(Flow& f) {
   AckBody b{};
   for (int i = 0; i < kSackWords; ++i) b.sack[i] = f.rx_bits[i];
   b.echo_path = f.echo_path;
+  b.dup_cum = (uint32_t)f.st.rx_dup;
   raw_send(path, f.peer_addr[path], &h, sizeof(h), &b, sizeof(b));
   ++f.st.acks_tx;
   f.need_ack = false;
@@ -1149,6 +1175,16 @@ void Engine::on_ack(Flow& f, const PktHdr& h, const AckBody& b) {
   const uint64_t now = now_ns();
   if (seq_diff(h.msg_id, f.peer_posted) > 0) f.peer_posted = h.msg_id;
   if (h.aux > f.credit_cum) f.credit_cum = h.aux;
+  if ((int32_t)(b.dup_cum - f.peer_dup_seen) > 0) {
+    // the receiver got packets twice: some of our retransmissions were not needed, i.e. the network reorders by
+    // more than the current window -- widen it (RACK's DSACK adaptation); it decays again after a quiet while
+    f.peer_dup_seen = b.dup_cum;
+    if (f.reo_mult < 16) ++f.reo_mult;
+    f.reo_decay_ns = now + 16ull * (uint64_t)(std::max(f.srtt_us, 100.0) * 1e3);
+  } else if (f.reo_mult > 1 && now > f.reo_decay_ns) {
+    --f.reo_mult;
+    f.reo_decay_ns = now + 16ull * (uint64_t)(std::max(f.srtt_us, 100.0) * 1e3);
+  }
   const uint32_t cum = h.seq;
   const int32_t adv = seq_diff(cum, f.snd_una);
   if (adv < 0 || seq_diff(cum, f.snd_nxt) > 0) return;  // stale or nonsensical
@@ -1212,7 +1248,7 @@ void Engine::detect_loss(Flow& f, uint64_t now) {
   if (f.newest_acked_send_ts == 0) return;
   // RACK: a packet is lost once a packet sent sufficiently LATER has been acknowledged.  Time based, so
   // reordering between paths (which is the normal case here) does not trigger spurious retransmissions.
-  const uint64_t reo_ns = (uint64_t)(std::max(f.srtt_us / 4, 50.0) * 1e3);
+  const uint64_t reo_ns = (uint64_t)(std::min(std::max(f.srtt_us / 4 * f.reo_mult, 50.0), std::max(4 * f.srtt_us, 50.0)) * 1e3);
   const uint32_t n = f.snd_nxt - f.snd_una;
   for (uint32_t i = 0; i < n; ++i) {
     const uint32_t s = f.snd_una + i;

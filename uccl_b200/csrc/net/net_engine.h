@@ -122,6 +122,11 @@ class Engine {
   bool wait(Request* r, size_t* bytes, int timeout_ms = -1);  // false on timeout / error (request freed)
 
   void set_drop_prob(double p) { drop_prob_.store(p); }
+  // fault injection: hold back a fraction of the outgoing datagrams for `delay_us` (reordering inside and across paths)
+  void set_reorder(double prob, int delay_us) {
+    reorder_delay_us_.store(delay_us);
+    reorder_prob_.store(prob);
+  }
   // fault injection on ONE local path (models a black-holed ECMP route); path < 0 clears
   void set_path_drop(int path, double p) {
     path_drop_idx_.store(path);
@@ -189,6 +194,9 @@ class Engine {
     uint64_t last_progress_ns = 0;
     uint64_t last_tx_ns = 0;   // last (re)transmission of a DATA packet
     bool tlp_fired = false;    // one tail-loss probe per quiet period
+    uint32_t peer_dup_seen = 0;   // last AckBody.dup_cum
+    uint32_t reo_mult = 1;        // RACK reordering window = reo_mult * srtt/4 (adapts to observed spurious retransmissions)
+    uint64_t reo_decay_ns = 0;
     PathState path[kMaxPaths];
     // congestion control
     cc::Swift swift;
@@ -268,6 +276,16 @@ class Engine {
   std::atomic<bool> stop_{false};
   std::atomic<double> drop_prob_{0.0}, path_drop_prob_{0.0};
   std::atomic<int> path_drop_idx_{-1};
+  std::atomic<double> reorder_prob_{0.0};
+  std::atomic<int> reorder_delay_us_{300};
+  struct Held {
+    uint64_t release_ns;
+    int path;
+    sockaddr_in to;
+    std::vector<char> bytes;  // header + payload, copied: the user buffer may be gone when the datagram finally leaves
+  };
+  std::deque<Held> held_;
+  void release_held(uint64_t now);
   void note_path_loss(Flow& f, int path, uint64_t now);
   std::atomic<uint32_t> next_flow_{1}, next_listen_{1};
   std::atomic<uint64_t> last_rx_ns_{0};

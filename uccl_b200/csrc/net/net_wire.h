@@ -53,7 +53,8 @@ static_assert(sizeof(PktHdr) == 56, "PktHdr layout");
 struct AckBody {
   uint64_t sack[kSackWords];  // bit i <=> packet (ack + i) has been received (bit 0 is always 0)
   uint16_t echo_path;         // path of the DATA packet whose timestamp is echoed
-  uint16_t reserved[3];
+  uint16_t reserved;
+  uint32_t dup_cum;           // duplicates this receiver has seen so far (low 32 bits): the sender's spurious-rexmit signal
 };
 
 struct SynBody {

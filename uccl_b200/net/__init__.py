@@ -161,6 +161,10 @@ class Engine:
     def set_drop_prob(self, p: float) -> None:
         self._native.set_drop_prob(p)
 
+    def set_reorder(self, prob: float, delay_us: int = 300) -> None:
+        """Fault injection: hold back this fraction of the outgoing datagrams for ``delay_us`` (reordering)."""
+        self._native.set_reorder(prob, delay_us)
+
     def set_path_drop(self, path: int, prob: float = 1.0) -> None:
         """Fault injection: black-hole one local path (``path < 0`` clears)."""
         self._native.set_path_drop(path, prob)
