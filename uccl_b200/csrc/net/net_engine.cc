@@ -1357,10 +1357,16 @@ bool Engine::tx_pump(Flow& f, uint64_t now) {
   // 2. control frames.  A sender that is parked behind the receiver's RTR with nothing in flight probes the
   // peer once a second (an RTR frame of its own is a harmless reliable packet): a dead peer then surfaces
   // through the retransmission limit instead of an unbounded wait.
-  if (f.tx_cursor < f.txq.size() && f.snd_una == f.snd_nxt && now - f.last_progress_ns > 1000000000ull) {
+  // (With EQDS a lost credit ACK parks the sender the same way; there the probe goes out after a few RTTs -- its
+  // ACK carries the receiver's current grant.)
+  const uint64_t probe_after = (cfg_.cc == CC_EQDS && f.credit_starved)
+                                   ? (uint64_t)(std::max(4 * f.srtt_us, 1000.0) * 1e3)
+                                   : 1000000000ull;
+  if (f.tx_cursor < f.txq.size() && f.snd_una == f.snd_nxt && now - std::max(f.last_progress_ns, f.last_tx_ns) > probe_after) {
     f.rtr_pending = true;
     f.last_progress_ns = now;
   }
+  f.credit_starved = false;
   if (f.rtr_pending && can_send_new(f, now)) {
     TxPkt& p = new_pkt(FR_RTR);
     p.msg_id = f.rx_posted;
@@ -1378,7 +1384,7 @@ bool Engine::tx_pump(Flow& f, uint64_t now) {
     if (cfg_.cc == CC_EQDS) {
       const uint64_t spec = (uint64_t)cfg_.payload * 16;  // speculative first window, then credits
       if (f.sent_payload_cum + chunk > f.credit_cum + spec) {
-        // starved of credit: keep the receiver's pacer informed with a zero-length demand update
+        f.credit_starved = true;  // see the probe above
         break;
       }
     }

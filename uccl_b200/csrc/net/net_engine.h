@@ -205,6 +205,7 @@ class Engine {
     uint64_t credit_cum = 0, sent_payload_cum = 0;  // EQDS (sender side)
     uint64_t grant_cum = 0, demand_seen = 0;        // EQDS (receiver side)
     bool credit_dirty = false;
+    bool credit_starved = false;  // sender: blocked on EQDS credit in the last pump
     // tx messages
     std::deque<TxMsg*> txq;       // not yet fully acked, in id order
     size_t tx_cursor = 0;         // index into txq of the message being cut into packets
