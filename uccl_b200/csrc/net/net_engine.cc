@@ -1487,6 +1487,9 @@ void Engine::timers(uint64_t now) {
         for (auto& q : f.rxq)
           if (q.req) complete(q.req, 0, 3), q.req = nullptr;
         f.rxq.clear();
+        if (!drained)  // gave up waiting for the peer: whatever was still queued will never be delivered
+          for (TxMsg* m : f.txq)
+            if (m->req) complete(m->req, 0, 1), m->req = nullptr;
         f.state.store(FL_CLOSED);
         f.last_progress_ns = now;
       }
