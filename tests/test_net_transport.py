@@ -937,3 +937,45 @@ def test_reordering_and_loss_together():
     assert st["tx_pkts"] > 200
     # duplicates at the receiver = retransmissions that were not needed; they must stay a small fraction
     assert sb["rx_dup"] < 0.25 * sb["rx_pkts"], (sb["rx_dup"], sb["rx_pkts"])
+
+
+def _deepep_mb_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), UCCL_B200_LOCAL_SIZE="2", UCCL_B200_NET_BIND_IP="127.0.0.1",
+                      UCCL_B200_NET_PATHS="2")
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import deep_ep
+
+    buf = deep_ep.Buffer(dist.group.WORLD, num_nvl_bytes=1 << 20, num_rdma_bytes=1 << 20)   # how vLLM / SGLang build it
+    T, H, K, E = 33, 128, 2, 8
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randn(T, H, generator=g).to(torch.bfloat16)
+    idx = torch.rand(T, E, generator=g).topk(K, dim=1).indices.contiguous()
+    w = torch.rand(T, K, generator=g)
+    tpr, _, tpe, inr, _ = buf.get_dispatch_layout(idx, E)
+    rx, ri, rw, pe, h, _ = buf.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=inr, num_tokens_per_expert=tpe, topk_idx=idx,
+                                        topk_weights=w)
+    comb, _, _ = buf.combine(rx, h, topk_weights=rw)
+    ok = [type(buf).__name__ == "HostBuffer", buf.group_size == world, buf.get_num_rdma_ranks() == 2,
+          torch.allclose(comb.float(), x.float() * inr.sum(1).float()[:, None], rtol=2e-2, atol=1e-1),
+          sum(pe) == int(rx.size(0) and (ri >= 0).sum())]
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_deep_ep_buffer_from_a_process_group_that_spans_boxes():
+    """`deep_ep.Buffer(group, ...)` exactly as the serving frameworks call it, with 4 ranks and 2 ranks per box."""
+    import multiprocessing as mp
+
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_deepep_mb_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    [p.join(60) for p in ps]
+    for rank, ok in got:
+        assert all(ok), (rank, ok)

@@ -47,7 +47,35 @@ class Config:
 class Buffer:
     num_sms: int = 24
 
+    @staticmethod
+    def _spans_boxes(group) -> int:
+        """Ranks per box if ``group`` (the default process group) has more members than one box holds, else 0."""
+        try:
+            import os
+
+            import torch.distributed as dist
+
+            if not dist.is_initialized() or (group is not None and group is not dist.group.WORLD):
+                return 0
+            world = dist.get_world_size()
+            local = int(os.environ.get("UCCL_B200_LOCAL_SIZE", os.environ.get("LOCAL_WORLD_SIZE", str(world))))
+            return local if 0 < local < world and world % local == 0 else 0
+        except Exception:  # noqa: BLE001
+            return 0
+
     def __new__(cls, group=None, *args, comm: Optional[Communicator] = None, **kwargs):
+        if comm is None and group is not None:
+            local = cls._spans_boxes(group)
+            if local:
+                # DeepEP-style construction from a process group that spans boxes (more ranks than LOCAL_WORLD_SIZE):
+                # build the hierarchical communicator and take the portable path (docs/multinode.md)
+                import torch
+
+                from ..parallel.multinode import MultiNodeCommunicator
+
+                host = not torch.cuda.is_available()
+                kw = dict(host=True, heap_bytes=256 << 20, stage_bytes=4 << 20) if host else dict(heap_bytes=1 << 30, stage_bytes=64 << 20)
+                comm = MultiNodeCommunicator.from_torch_dist(local, **kw)
         if comm is not None and (comm.is_host or type(comm).__name__ in ("MultiNodeCommunicator", "NativeMultiNodeCommunicator")):
             # CPU reference backend with the same API (GPU-less CI) -- also the portable path for groups that span
             # boxes (MultiNodeCommunicator: two-hop all-to-all, NVLink + datagram rails): see host_ep.HostBuffer
