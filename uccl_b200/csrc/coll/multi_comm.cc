@@ -23,6 +23,23 @@ struct RailAddr {
   uint32_t listen_id;
 };
 inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }
+// The staging copies and pinned allocations below are issued directly (not through Comm, which guards itself):
+// make the communicator's GPU current for the duration of a call, whatever device the calling thread had selected.
+struct DevScope {
+  int prev = -1;
+  bool active = false;
+  explicit DevScope(const MultiComm& m) {
+    if (m.is_host()) return;
+    cudaGetDevice(&prev);
+    if (prev != m.device()) {
+      cudaSetDevice(m.device());
+      active = true;
+    }
+  }
+  ~DevScope() {
+    if (active) cudaSetDevice(prev);
+  }
+};
 }  // namespace
 
 std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int nranks, int local_size, int device,
@@ -262,6 +279,7 @@ void MultiComm::rail_barrier() {
 
 // ---------------------------------------------------------------------------------------- collectives
 void MultiComm::allreduce(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t st, float scale) {
+  DevScope dev_scope(*this);
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes && op >= 0 && op < kNumOps, "allreduce: bad dtype/op");
   if (count == 0) return;
   UB_CHECK((op != kAvg && scale == 1.0f) || float_dtype(dtype), "allreduce across boxes: avg / scale need a floating-point dtype");
@@ -408,6 +426,7 @@ void MultiComm::allreduce_pipelined(const char* in, char* out, size_t count, siz
 // scratch_cap_ bytes per buffer, so the symmetric-heap scratch stays small however large the message is: chunk
 // [off, off+m) of every rank block is gathered into dense scratch, exchanged, and scattered back.
 void MultiComm::allgather(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {
+  DevScope dev_scope(*this);
   if (count == 0) return;
   if (N_ == 1) {
     local_->allgather(in, out, count, dtype, st);
@@ -439,6 +458,7 @@ void MultiComm::allgather(const void* in, void* out, size_t count, int dtype, cu
 }
 
 void MultiComm::reduce_scatter(const void* in, void* out, size_t count, int dtype, int op, cudaStream_t st) {
+  DevScope dev_scope(*this);
   if (count == 0) return;
   UB_CHECK(op != kAvg || float_dtype(dtype), "reduce_scatter across boxes: avg needs a floating-point dtype");
   if (N_ == 1) {
@@ -478,6 +498,7 @@ void MultiComm::reduce_scatter(const void* in, void* out, size_t count, int dtyp
 }
 
 void MultiComm::broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t st) {
+  DevScope dev_scope(*this);
   UB_CHECK(root >= 0 && root < nranks_, "broadcast: bad root %d", root);
   if (count == 0) return;
   if (N_ == 1) {
@@ -518,6 +539,7 @@ void MultiComm::broadcast(const void* in, void* out, size_t count, int dtype, in
 }
 
 void MultiComm::reduce(const void* in, void* out, size_t count, int dtype, int op, int root, cudaStream_t st) {
+  DevScope dev_scope(*this);
   UB_CHECK(root >= 0 && root < nranks_, "reduce: bad root %d", root);
   if (count == 0) return;
   const size_t b = count * (size_t)dtype_size(dtype);
@@ -527,6 +549,7 @@ void MultiComm::reduce(const void* in, void* out, size_t count, int dtype, int o
 }
 
 void MultiComm::alltoall(const void* in, void* out, size_t count, int dtype, cudaStream_t st) {
+  DevScope dev_scope(*this);
   if (count == 0) return;
   if (N_ == 1) {
     local_->alltoall(in, out, count, dtype, st);
@@ -563,6 +586,7 @@ void MultiComm::alltoall(const void* in, void* out, size_t count, int dtype, cud
 
 void MultiComm::alltoallv(const void* in, const size_t* sc, const size_t* sd, void* out, const size_t* rc, const size_t* rd,
                           int dtype, cudaStream_t st) {
+  DevScope dev_scope(*this);
   if (N_ == 1) {
     local_->alltoallv(in, sc, sd, out, rc, rd, dtype, st);
     return;
@@ -590,6 +614,7 @@ void MultiComm::alltoallv(const void* in, const size_t* sc, const size_t* sd, vo
 }
 
 void MultiComm::barrier(cudaStream_t st) {
+  DevScope dev_scope(*this);
   local_->barrier(st);
   sync(st);
   rail_barrier();
@@ -598,6 +623,7 @@ void MultiComm::barrier(cudaStream_t st) {
 }
 
 void MultiComm::group_p2p(const std::vector<Comm::P2pOp>& ops, cudaStream_t st) {
+  DevScope dev_scope(*this);
   std::vector<Comm::P2pOp> local_ops;
   struct NetOp {
     Comm::P2pOp op;
