@@ -979,3 +979,24 @@ def test_deep_ep_buffer_from_a_process_group_that_spans_boxes():
     [p.join(60) for p in ps]
     for rank, ok in got:
         assert all(ok), (rank, ok)
+
+
+@pytest.mark.parametrize("payload,inflight,cc", [(256, 8, "swift"), (60000, 240, "none"), (1400, 16, "eqds"), (1400, 248, "timely")])
+def test_engine_configuration_corners(payload, inflight, cc):
+    """Tiny and maximal datagrams, a window of 8 and of 248 packets, every congestion controller, unequal path counts,
+    2 % loss: message sizes around the datagram boundary arrive intact in both directions at once."""
+    a = net.Engine(bind_ip="127.0.0.1", paths=3, payload=payload, max_inflight=inflight, cc=cc, drop_prob=0.02)
+    b = net.Engine(bind_ip="127.0.0.1", paths=5, payload=payload, max_inflight=inflight, cc=cc, drop_prob=0.02)
+    lid = b.listen()
+    box = {}
+    t = threading.Thread(target=lambda: box.setdefault("f", b.accept(lid)))
+    t.start()
+    fa = a.connect("127.0.0.1", b.port, lid)
+    t.join()
+    for n in (0, 1, payload - 1, payload, payload + 1, 70_001, 600_000):
+        x = torch.randint(0, 255, (n,), dtype=torch.uint8)
+        y, z = torch.zeros_like(x), torch.zeros_like(x)
+        ws = [b.irecv(box["f"], y), a.irecv(fa, z), a.isend(fa, x), b.isend(box["f"], x)]
+        for w in ws:
+            w.wait(120000)
+        assert torch.equal(x, y) and torch.equal(x, z), n
