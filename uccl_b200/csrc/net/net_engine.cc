@@ -274,12 +274,14 @@ void Engine::shutdown(int linger_ms) {
       for (auto& kv : flows_) {
         const int st = kv.second->state.load();
         if (st == FL_ERROR) continue;
-        if (st != FL_CLOSED || !kv.second->peer_fin.load()) all_done = false;
+        if (st != FL_CLOSED) all_done = false;  // CLOSED = our FIN is acknowledged (or we gave up on the peer)
       }
     }
     const uint64_t now = now_ns();
-    // quiet period: the peer may still retransmit its FIN if our last ACK was lost
-    if (all_done && now - last_rx_ns_.load() > 3ull * (uint64_t)cfg_.rto_min_us * 1000ull) break;
+    // quiet period: a peer whose last data (or FIN) we received may not have our ACK yet -- it retransmits within its
+    // RTO, and every such packet restarts this timer.  We do not wait for the peer to close its side: whatever it
+    // sends after our close would not be delivered to anybody anyway.
+    if (all_done && now - last_rx_ns_.load() > std::max<uint64_t>(3ull * (uint64_t)cfg_.rto_min_us * 1000ull, 20000000ull)) break;
     if (now > deadline) break;
     std::this_thread::sleep_for(std::chrono::microseconds(200));
   }
@@ -1483,7 +1485,9 @@ void Engine::timers(uint64_t now) {
     }
     if (st == FL_CLOSING) {
       const bool drained = f.fin_sent && f.snd_una == f.snd_nxt && f.txq.empty();
-      if (drained || now - f.last_progress_ns > kLingerNs) {
+      // a peer that has already closed its side may be gone by now: do not wait long for it to acknowledge our FIN
+      const uint64_t give_up = f.peer_fin.load(std::memory_order_relaxed) ? 100000000ull : kLingerNs;
+      if (drained || now - f.last_progress_ns > give_up) {
         for (auto& q : f.rxq)
           if (q.req) complete(q.req, 0, 3), q.req = nullptr;
         f.rxq.clear();
