@@ -110,8 +110,9 @@ class Engine {
   uint32_t accept(uint32_t listen_id, int timeout_ms = -1);                                         // blocking
   void close_flow(uint32_t flow);
   // Graceful stop (also run by the destructor): close every flow, then linger -- like TCP's TIME_WAIT -- until
-  // both FINs are exchanged and the wire is quiet, so that a peer whose last packets or whose ACKs were lost
-  // still gets its retransmissions answered.  Bounded by linger_ms (UCCL_B200_NET_LINGER_MS, default 2000).
+  // our FINs are acknowledged and the wire has been quiet for a few RTOs, so that a peer whose last packets or
+  // whose ACKs were lost still gets its retransmissions answered.  Bounded by linger_ms
+  // (UCCL_B200_NET_LINGER_MS, default 2000).
   void shutdown(int linger_ms = -1);
 
   // ---- data path: the i-th send of a flow matches the i-th recv of its peer
