@@ -25,6 +25,9 @@ def main():
     p.add_argument("--experts", type=int, default=256)
     p.add_argument("--sms", default="16,24,32,48,64,96,128,148")
     p.add_argument("--iters", type=int, default=20)
+    p.add_argument("--impls", default="reg,tma", help="kernel implementations to sweep: reg (register path), tma (TMA pipelines)")
+    p.add_argument("--modes", default="fp8_fused,bf16")
+    p.add_argument("--stages", default="0", help="TMA pipeline depths to try (0 = fill shared memory), e.g. 0,4,6")
     p.add_argument("--ll", action="store_true", help="also time the low-latency path (128 tokens)")
     p.add_argument("--out", default=None)
     args = p.parse_args()
@@ -74,16 +77,27 @@ def main():
         return mx(sum(v) / len(v)) * 1e3, mx(v[0]) * 1e3
 
     rows = []
-    for sms in [int(s) for s in args.sms.split(",")]:
+    C = buf._C
+    impl_ids = {"reg": C.EP_IMPL_REG, "tma": C.EP_IMPL_TMA, "auto": C.EP_IMPL_AUTO}
+    mode_kw = {"fp8_fused": dict(use_fp8=True), "bf16": dict()}
+    combos = []
+    for impl in args.impls.split(","):
+        for stg in ([int(s) for s in args.stages.split(",")] if impl == "tma" else [0]):
+            for sms in [int(s) for s in args.sms.split(",")]:
+                combos.append((impl, stg, sms))
+    for impl, stg, sms in combos:
         cfg = Config(sms)
+        buf.runtime.impl = impl_ids[impl]
+        buf.runtime.set_stages(stg, stg, stg)
         tpr, _, tpe, in_rank, _ = buf.get_dispatch_layout(idx, E)
-        for mode, kw in (("fp8_fused", dict(use_fp8=True)), ("bf16", dict())):
+        for mode in args.modes.split(","):
+            kw = mode_kw[mode]
             rx, ri, rw, pe, handle, _ = buf.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank,
                                                      num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w,
                                                      config=cfg, **kw)
             nrecv = handle[4]
             d_avg, d_min = timed(lambda: buf.dispatch(x, handle=handle, config=cfg, **kw))
-            row = {"sms": sms, "mode": mode, "num_recv": nrecv, "dispatch_us": d_avg, "dispatch_min_us": d_min,
+            row = {"impl": impl, "stages": stg, "sms": sms, "mode": mode, "num_recv": nrecv, "dispatch_us": d_avg, "dispatch_min_us": d_min,
                    "dispatch_GBps": nrecv * (H if mode != "bf16" else 2 * H) / (d_avg * 1e-6) / 1e9}
             if mode == "bf16":
                 cin = buf.get_combine_buffer(nrecv, H, K)

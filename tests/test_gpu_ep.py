@@ -74,13 +74,21 @@ def ref_layout(idx, n, E):
     return in_rank.sum(0).to(torch.int32), per_expert, in_rank
 
 
+def set_impl(bufs, impl):
+    """Force the register-path (1) or the TMA-pipelined (2) dispatch/combine kernels; 0 = auto."""
+    for b in bufs:
+        b.runtime.impl = impl
+
+
 @pytest.mark.parametrize("n", [2, 4, 8])
 @pytest.mark.parametrize("mode", ["bf16", "fp8_fused", "fp8_pre"])
-def test_dispatch_combine(n, mode):
+@pytest.mark.parametrize("impl", ["reg", "tma"])
+def test_dispatch_combine(n, mode, impl):
     T, H, K = 257, 1024, 4
     E = n * 4
     E_local = E // n
     bufs = get_buffers(n)
+    set_impl(bufs, 1 if impl == "reg" else 2)
     xs, idxs, ws = make_inputs(n, T, H, K, E, seed=n)
     layouts = [ref_layout(idxs[r], n, E) for r in range(n)]
 
@@ -121,6 +129,9 @@ def test_dispatch_combine(n, mode):
                     src=handle[2].cpu(), comb=comb.cpu(), comb_w=comb_w.cpu(), raw=recv_x)
 
     outs = run_threads(bufs, fn)
+    want = 1 if impl == "reg" else 2
+    assert all(b.runtime.last_dispatch_impl == want and b.runtime.last_combine_impl == want for b in bufs)
+    set_impl(bufs, 0)
     for r in range(n):
         o = outs[r]
         # expected receive order: source rank major, token order minor
@@ -160,6 +171,106 @@ def test_dispatch_combine(n, mode):
         assert badc.float().mean().item() < (0 if mode == "bf16" else 5e-3) + 1e-9, badc.float().mean().item()
         exp_cw = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r]))
         assert torch.allclose(o["comb_w"], exp_cw, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,H", [(1, 7168), (2, 7168), (2, 4096), (4, 2560), (8, 512)])
+def test_tma_pipeline_matches_register_path(n, H):
+    """The TMA-pipelined kernels (ep_tma_kernels.cu) must reproduce the register path bit for bit: same
+    quantiser, same fixed summation order, incl. bias, routed weights, cached handles and the
+    num_worst_tokens (CUDA-graph) mode, on row sizes that span one / several / partial pipeline slices."""
+    T, K = 301, 8
+    E = n * 4
+    bufs = get_buffers(n)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=100 + n)
+    g = torch.Generator().manual_seed(5)
+    biases = [((torch.randn(T, H, generator=g)).to(torch.bfloat16), (torch.randn(T, H, generator=g)).to(torch.bfloat16))
+              for _ in range(n)]
+
+    def run(impl):
+        set_impl(bufs, impl)
+
+        def fn(b):
+            dev = b.device
+            x, idx, w = xs[b.rank].to(dev), idxs[b.rank].to(dev), ws[b.rank].to(dev)
+            b0, b1 = (t.to(dev) for t in biases[b.rank])
+            res = {}
+            tpr, _, tpe, in_rank, _ = b.get_dispatch_layout(idx, E)
+            for mode in ("bf16", "fp8_fused", "fp8_pre"):
+                xin = per_token_cast_to_fp8(x) if mode == "fp8_pre" else x
+                kw = dict(use_fp8=True) if mode == "fp8_fused" else {}
+                rx, ridx, rw, pe, handle, _ = b.dispatch(xin, num_tokens_per_rank=tpr, is_token_in_rank=in_rank,
+                                                         num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w, **kw)
+                torch.cuda.current_stream().synchronize()
+                parts = list(rx) if isinstance(rx, tuple) else [rx]
+                res[mode] = [p.clone().view(torch.uint8).cpu() for p in parts] + [ridx.cpu(), rw.cpu(), handle[2].cpu(), pe]
+                rx2, *_ = b.dispatch(xin, handle=handle, **kw)
+                torch.cuda.current_stream().synchronize()
+                parts2 = list(rx2) if isinstance(rx2, tuple) else [rx2]
+                res[mode + "_cached"] = [p.clone().view(torch.uint8).cpu() for p in parts2]
+                if mode == "bf16":
+                    cb = b.get_combine_buffer(rx.size(0), H, K)
+                    cb.copy_(rx)
+                    out, out_w, _ = b.combine(cb, handle, topk_weights=rw)
+                    outb, _, _ = b.combine(cb, handle, bias=(b0, b1))
+                    torch.cuda.current_stream().synchronize()
+                    res["combine"] = [out.cpu(), out_w.cpu(), outb.cpu()]
+            # CUDA-graph friendly mode: no CPU sync, padded tail
+            worst = n * T
+            rx, ridx, rw, pe, handle, _ = b.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank,
+                                                     num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w,
+                                                     num_worst_tokens=worst)
+            torch.cuda.current_stream().synchronize()
+            res["worst"] = [ridx.cpu()]
+            return res
+
+        return run_threads(bufs, fn)
+
+    ref = run(1)
+    got = run(2)
+    assert all(b.runtime.last_dispatch_impl == 2 for b in bufs)
+    set_impl(bufs, 0)
+    for r in range(n):
+        assert ref[r].keys() == got[r].keys()
+        for k in ref[r]:
+            for a, b_ in zip(ref[r][k], got[r][k]):
+                if isinstance(a, torch.Tensor):
+                    assert a.shape == b_.shape and torch.equal(a, b_), (r, k)
+                else:
+                    assert a == b_, (r, k)
+    # and the register path itself is right: combine(identity experts) = x * fan-out (+ biases)
+    for r in range(n):
+        in_rank = ref_layout(idxs[r], n, E)[2]
+        fan = in_rank.sum(1).float()[:, None]
+        exp = xs[r].float() * fan
+        assert torch.allclose(got[r]["combine"][0].float(), exp, rtol=2e-2, atol=2e-1)
+        expb = exp + biases[r][0].float() + biases[r][1].float()
+        assert torch.allclose(got[r]["combine"][2].float(), expb, rtol=2e-2, atol=3e-1)
+
+
+@pytest.mark.parametrize("T", [0, 1, 127, 128, 129, 4096, 9001])
+def test_layout_multi_cta(T):
+    """Multi-CTA layout (chained per-CTA counts) against a torch reference, incl. the stable positions."""
+    n, K = 4, 8
+    E = n * 8
+    bufs = get_buffers(n)
+    b = bufs[0]
+    g = torch.Generator().manual_seed(T)
+    idx = torch.rand(max(T, 1), E, generator=g).topk(K, dim=1).indices.to(torch.int64)[:T]
+    idx = idx.masked_fill(torch.rand(T, K, generator=g) < 0.1, -1).contiguous()
+    exp_tpr, exp_tpe, exp_in = ref_layout(idx, n, E) if T else (torch.zeros(n, dtype=torch.int32),
+                                                                  torch.zeros(E, dtype=torch.int32),
+                                                                  torch.zeros(0, n, dtype=torch.bool))
+    with torch.cuda.device(b.device):
+        for _ in range(2):  # twice: the device-side call epoch must advance
+            tpr, _, tpe, in_rank, _ = b.get_dispatch_layout(idx.to(b.device), E)
+            pos = b._layout_cache[2]
+            torch.cuda.synchronize()
+            assert torch.equal(tpr.cpu(), exp_tpr)
+            assert torch.equal(tpe.cpu(), exp_tpe)
+            assert torch.equal(in_rank.cpu(), exp_in)
+            exp_pos = torch.where(exp_in, exp_in.to(torch.int32).cumsum(0).to(torch.int32) - 1,
+                                  torch.full((T, n), -1, dtype=torch.int32))
+            assert torch.equal(pos.cpu(), exp_pos)
 
 
 def test_internode_api_runs_on_the_fabric():

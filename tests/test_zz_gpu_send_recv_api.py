@@ -2,17 +2,14 @@
 patterns as the C++ NCCL-API test (ring step with a multi-chunk message, all-to-all incl. self), through
 the pybind path; plus the EP Buffer's optional arguments and the MoE training step on the CUDA kernels.
 
-Everything in this module was written after the round's GPU budget was spent: the same assertions pass
-against the CPU reference backends (tests/test_host_ep.py, test_host_collectives.py) but have not yet run on
-hardware, so the module is collected last and marked non-strict xfail -- an XPASS is the expected outcome,
-an XFAIL is a to-do for the next round, and neither hides a regression of the verified suite."""
+The same assertions also run against the CPU reference backends (tests/test_host_ep.py,
+test_host_collectives.py)."""
 import pytest
 import torch
 
 from helpers import get_world, run_ranks
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(90),
-              pytest.mark.xfail(strict=False, reason="added after the GPU budget was spent; first hardware run pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(90)]
 
 
 @pytest.mark.parametrize("n", [2, 4])

@@ -20,6 +20,8 @@ UB_PARAM(ArForceAlgo, "AR_ALGO", 0)
 UB_PARAM(XchgLLMaxBytes, "XCHG_LL_MAX_BYTES", 0)
 UB_PARAM(RsPush, "RS_PUSH", 1)  // staged ReduceScatter: 1 = push into the peers' stages (default), 0 = copy-in + pull
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
+// 1: a one-rank communicator launches the real kernels instead of a cudaMemcpy (profiling / smoke tests on one GPU)
+UB_PARAM(ForceKernels, "FORCE_KERNELS", 0)
 
 const char* algo_name(int algo) {
   switch (algo) {
@@ -360,7 +362,7 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
     return;
   }
   DeviceGuard g(device());
-  if (n == 1 && out_dtype == dtype && scale == 1.0f && idiv == 1) {
+  if (!ubParamForceKernels() && n == 1 && out_dtype == dtype && scale == 1.0f && idiv == 1) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -453,7 +455,7 @@ void Comm::allgather(const void* in, void* out, size_t count_per_rank, int dtype
     return;
   }
   DeviceGuard g(device());
-  if (n == 1) {
+  if (!ubParamForceKernels() && n == 1) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -512,7 +514,7 @@ void Comm::reduce_scatter(const void* in, void* out, size_t recv_count, int dtyp
     if (is_float_dtype(dtype)) a.ep.scale *= 1.0f / (float)n;
     else a.ep.idiv = n;
   }
-  if (n == 1 && op != kAvg && scale == 1.0f) {
+  if (!ubParamForceKernels() && n == 1 && op != kAvg && scale == 1.0f) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -559,7 +561,7 @@ void Comm::broadcast(const void* in, void* out, size_t count, int dtype, int roo
     return;
   }
   DeviceGuard g(device());
-  if (nranks() == 1) {
+  if (!ubParamForceKernels() && nranks() == 1) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -605,7 +607,7 @@ void Comm::reduce(const void* in, void* out, size_t count, int dtype, int op, in
     if (is_float_dtype(dtype)) a.ep.scale *= 1.0f / (float)n;
     else a.ep.idiv = n;
   }
-  if (n == 1 && op != kAvg && scale == 1.0f) {
+  if (!ubParamForceKernels() && n == 1 && op != kAvg && scale == 1.0f) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -638,7 +640,7 @@ void Comm::alltoall(const void* in, void* out, size_t count_per_peer, int dtype,
     return;
   }
   DeviceGuard g(device());
-  if (n == 1) {
+  if (!ubParamForceKernels() && n == 1) {
     if (in != out) UB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
     return;
   }
@@ -683,7 +685,7 @@ void Comm::alltoallv(const void* in, const size_t* send_counts, const size_t* se
   DeviceGuard g(device());
   size_t in_total = 0;
   for (int p = 0; p < n; ++p) in_total = std::max(in_total, (send_displs[p] + send_counts[p]) * es);
-  if (n == 1) {
+  if (!ubParamForceKernels() && n == 1) {
     size_t b = std::min(send_counts[0], recv_counts[0]) * es;
     if (b) UB_CUDA(cudaMemcpyAsync((char*)out + recv_displs[0] * es, (const char*)in + send_displs[0] * es, b,
                                    cudaMemcpyDeviceToDevice, stream));

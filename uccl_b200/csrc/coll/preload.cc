@@ -77,6 +77,11 @@ cudaError_t preload_all_kernels() {
   EpLayoutArgs la;
   memset(&la, 0, sizeof(la));
   ok(launch_ep_layout(la, 0));
+  {
+    uint32_t dummy_scratch = 0;
+    la.scratch = &dummy_scratch;  // multi-CTA variant
+    ok(launch_ep_layout(la, 0));
+  }
   EpDispatchArgs da;
   memset(&da, 0, sizeof(da));
   EpCombineArgs ca;
@@ -93,6 +98,19 @@ cudaError_t preload_all_kernels() {
     ok(launch_ep_combine(cn, ca, 1, 0));
     ca.bias0 = &dummy_bias;
     ok(launch_ep_combine(cn, ca, 1, 0));
+  }
+  {
+    DevComm cn = c;
+    cn.nranks = 8;
+    da.H = ca.H = 1024;
+    for (int m = 0; m < 3; ++m) {
+      da.mode = m;
+      ok(launch_ep_dispatch_tma(cn, da, 1, 0));
+    }
+    ca.bias0 = nullptr;
+    ok(launch_ep_combine_tma(cn, ca, 1, 0));
+    ca.bias0 = &dummy_bias;
+    ok(launch_ep_combine_tma(cn, ca, 1, 0));
   }
   {
     EpLLDispatchArgs ld;

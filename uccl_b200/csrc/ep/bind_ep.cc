@@ -13,6 +13,9 @@ void bind_ep(py::module_& m) {
   m.attr("EP_X_FP8_SCALED") = (int)EP_X_FP8_SCALED;
   m.attr("EP_X_FUSED_FP8") = (int)EP_X_FUSED_FP8;
   m.attr("EP_MAX_TOPK") = kEpMaxTopk;
+  m.attr("EP_IMPL_AUTO") = (int)EP_IMPL_AUTO;
+  m.attr("EP_IMPL_REG") = (int)EP_IMPL_REG;
+  m.attr("EP_IMPL_TMA") = (int)EP_IMPL_TMA;
   py::class_<EpDispatchOut>(m, "EpDispatchOut")
       .def_readonly("recv_x", &EpDispatchOut::recv_x)
       .def_readonly("recv_scales", &EpDispatchOut::recv_scales)
@@ -30,6 +33,11 @@ void bind_ep(py::module_& m) {
       .def_property_readonly("num_slots", &EpBuffer::num_slots)
       .def_property_readonly("launches", &EpBuffer::launches)
       .def_property_readonly("dev_counts_ptr", &EpBuffer::dev_counts_ptr)
+      .def_property("impl", &EpBuffer::impl, &EpBuffer::set_impl)
+      .def("set_stages", &EpBuffer::set_stages, py::arg("dispatch_in") = 0, py::arg("dispatch_out") = 0,
+           py::arg("combine") = 0)
+      .def_property_readonly("last_dispatch_impl", &EpBuffer::last_dispatch_impl)
+      .def_property_readonly("last_combine_impl", &EpBuffer::last_combine_impl)
       .def("capacity_for", &EpBuffer::capacity_for)
       .def("combine_capacity_for", &EpBuffer::combine_capacity_for)
       .def("layout",

@@ -13,6 +13,8 @@
 namespace ub {
 
 UB_PARAM(EpCpuTimeoutSecs, "EP_CPU_TIMEOUT_SECS", 100)  // reference: UCCL_EP_CPU_TIMEOUT_SECS (ep/include/common.hpp:153-176)
+UB_PARAM(EpImpl, "EP_IMPL", 0)                 // 0 auto, 1 register path, 2 TMA pipelines
+UB_PARAM(EpLayoutMultiCta, "EP_LAYOUT_MC", 1)  // 0: single-CTA layout scan
 
 namespace {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -56,6 +58,11 @@ EpBuffer::EpBuffer(std::shared_ptr<Comm> comm, size_t num_nvl_bytes, int num_slo
   host_counts_dev_ = (int32_t*)d;
   UB_CUDA(cudaMalloc((void**)&dev_counts_, sizeof(int32_t) * (1 + kEpMaxLocalExperts)));
   UB_CUDA(cudaMemset(dev_counts_, 0, sizeof(int32_t) * (1 + kEpMaxLocalExperts)));
+  if (ubParamEpLayoutMultiCta()) {
+    UB_CUDA(cudaMalloc((void**)&layout_scratch_, sizeof(uint32_t) * kEpLayoutScratchWords));
+    UB_CUDA(cudaMemset(layout_scratch_, 0, sizeof(uint32_t) * kEpLayoutScratchWords));
+  }
+  set_impl((int)ubParamEpImpl());
   UB_CUDA(cudaDeviceSynchronize());
   UB_INFO(SUB_EP, "EpBuffer rank %d: %zu MiB, %d dispatch arenas + 1 combine arena of %zu MiB", comm->rank(),
           bytes_ >> 20, num_slots_, arena_bytes_ >> 20);
@@ -69,10 +76,26 @@ EpBuffer::~EpBuffer() {
   }
   if (host_counts_) cudaFreeHost(host_counts_);
   if (dev_counts_) cudaFree(dev_counts_);
+  if (layout_scratch_) cudaFree(layout_scratch_);
   try {
     if (base_) comm_->free(base_);
   } catch (...) {
   }
+}
+
+void EpBuffer::set_impl(int impl) {
+  UB_CHECK(impl >= EP_IMPL_AUTO && impl <= EP_IMPL_TMA, "EP impl must be 0 (auto), 1 (register path) or 2 (TMA)");
+  impl_ = impl;
+}
+
+// The TMA pipelines keep a fixed number of bytes in flight per CTA, so they win whenever few CTAs
+// must saturate NVLink (the DeepEP budget of 20-24 SMs); with most of the GPU available the
+// register path has as many rows in flight and a shorter per-token critical path
+// (profiles/ep_sweep_*.json).
+int EpBuffer::pick_impl(int grid) const {
+  if (impl_ != EP_IMPL_AUTO) return impl_;
+  if (nranks() == 1) return EP_IMPL_REG;
+  return grid <= 64 ? EP_IMPL_TMA : EP_IMPL_REG;
 }
 
 int EpBuffer::capacity_for(int hidden, int mode, int topk) const {
@@ -123,6 +146,8 @@ void EpBuffer::layout(uintptr_t topk_idx, int T, int K, int E, uintptr_t tokens_
   a.tokens_per_expert = (int32_t*)tokens_per_expert;
   a.is_token_in_rank = (uint8_t*)is_token_in_rank;
   a.token_pos = (int32_t*)token_pos;
+  a.scratch = layout_scratch_;
+  a.tokens_per_block = 0;
   cudaError_t e = launch_ep_layout(a, st);
   UB_CHECK(e == cudaSuccess, "ep layout launch failed: %s", cudaGetErrorString(e));
   ++launches_;
@@ -187,7 +212,11 @@ EpDispatchOut EpBuffer::dispatch(uintptr_t x, uintptr_t x_scales, uintptr_t topk
     __atomic_thread_fence(__ATOMIC_SEQ_CST);
   }
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
-  cudaError_t e = launch_ep_dispatch(comm_->dev(), a, grid, st);
+  a.in_stages = st_in_;
+  a.out_stages = st_out_;
+  const bool tma = pick_impl(grid) == EP_IMPL_TMA && ep_dispatch_tma_supported(a);
+  last_disp_impl_ = tma ? EP_IMPL_TMA : EP_IMPL_REG;
+  cudaError_t e = tma ? launch_ep_dispatch_tma(comm_->dev(), a, grid, st) : launch_ep_dispatch(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep dispatch launch failed: %s", cudaGetErrorString(e));
   ++launches_;
   last_stream_ = st;
@@ -278,7 +307,10 @@ void EpBuffer::combine(uintptr_t x, int num_recv, uintptr_t topk_w, uintptr_t se
   a.H = H;
   a.K = K;
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
-  cudaError_t e = launch_ep_combine(comm_->dev(), a, grid, st);
+  a.stages = st_comb_;
+  const bool tma = pick_impl(grid) == EP_IMPL_TMA && ep_combine_tma_supported(a);
+  last_comb_impl_ = tma ? EP_IMPL_TMA : EP_IMPL_REG;
+  cudaError_t e = tma ? launch_ep_combine_tma(comm_->dev(), a, grid, st) : launch_ep_combine(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep combine launch failed: %s", cudaGetErrorString(e));
   ++launches_;
 }

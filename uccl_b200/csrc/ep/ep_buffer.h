@@ -33,6 +33,13 @@ class EpBuffer {
   int combine_capacity_for(int hidden, int topk) const;
   uint64_t launches() const { return launches_; }
   uint64_t base_offset() const { return base_off_; }  // heap offset of the EP block (must match on every rank)
+  // kernel implementation of dispatch / combine: EP_IMPL_AUTO (default, UCCL_B200_EP_IMPL), _REG or _TMA
+  int impl() const { return impl_; }
+  void set_impl(int impl);
+  // TMA pipeline depths (0 = fill shared memory): dispatch in/out stages, combine stages
+  void set_stages(int disp_in, int disp_out, int comb) { st_in_ = disp_in, st_out_ = disp_out, st_comb_ = comb; }
+  int last_dispatch_impl() const { return last_disp_impl_; }
+  int last_combine_impl() const { return last_comb_impl_; }
 
   // topk_idx != 0: full layout (counts + membership + positions); topk_idx == 0: positions only
   void layout(uintptr_t topk_idx, int T, int K, int E, uintptr_t tokens_per_rank, uintptr_t tokens_per_expert,
@@ -80,6 +87,11 @@ class EpBuffer {
   int32_t* dev_counts_ = nullptr;
   uint64_t launches_ = 0;
   cudaStream_t last_stream_ = nullptr;
+  uint32_t* layout_scratch_ = nullptr;  // multi-CTA layout: epoch, flags, per-CTA counts
+  int impl_ = EP_IMPL_AUTO;
+  int st_in_ = 0, st_out_ = 0, st_comb_ = 0;
+  int last_disp_impl_ = 0, last_comb_impl_ = 0;
+  int pick_impl(int grid) const;
   // low latency
   struct LLLayout {
     uint64_t cnt_tab_off, recv_x_off, recv_scales_off, recv_src_off, comb_x_off;
@@ -95,6 +107,11 @@ class EpBuffer {
 cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st);
 cudaError_t launch_ep_dispatch(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_combine(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st);
+// TMA-pipelined implementations (ep_tma_kernels.cu)
+bool ep_dispatch_tma_supported(const EpDispatchArgs& a);
+bool ep_combine_tma_supported(const EpCombineArgs& a);
+cudaError_t launch_ep_dispatch_tma(const DevComm& c, const EpDispatchArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ep_combine_tma(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_combine(const DevComm& c, const EpLLCombineArgs& a, int grid, cudaStream_t st);
 constexpr int kEpLLMaxBlocks = 64;

@@ -33,6 +33,20 @@ struct EpLayoutArgs {
   int32_t* tokens_per_expert;  // [E]
   uint8_t* is_token_in_rank;   // [T, R] (torch.bool)
   int32_t* token_pos;          // [T, R] exclusive position among my tokens going to rank r, -1 if none
+  // multi-CTA layout (ep_layout_mc_kernel): device scratch of kEpLayoutScratchWords u32
+  //   [0] call epoch, [16 + b] flag of block b, [16 + kEpLayoutMaxBlocks + b * kMaxRanks + r] tokens of block b for rank r
+  uint32_t* scratch;
+  int tokens_per_block;        // contiguous tokens owned by one CTA (multiple of the block size)
+};
+constexpr int kEpLayoutMaxBlocks = 64;
+constexpr int kEpLayoutThreads = 128;
+constexpr int kEpLayoutScratchWords = 16 + kEpLayoutMaxBlocks + kEpLayoutMaxBlocks * kMaxRanks;
+
+// Kernel implementation of the high-throughput dispatch / combine.
+enum EpImpl : int {
+  EP_IMPL_AUTO = 0,  // pick per (ranks, CTAs): see EpBuffer::pick_impl
+  EP_IMPL_REG = 1,   // register path: every warp loads a row with LDG.128 and stores it with STG.128 (ep_kernels.cu)
+  EP_IMPL_TMA = 2    // warp-specialised cp.async.bulk pipelines through shared memory (ep_tma_kernels.cu)
 };
 
 struct EpDispatchArgs {
@@ -56,6 +70,7 @@ struct EpDispatchArgs {
   int expert_alignment;
   int num_worst_tokens;
   int round_scale;  // power-of-two scales (UE8M0-compatible), like DeepEP's round_scale
+  int in_stages, out_stages;  // TMA pipeline depth (ep_tma_kernels.cu); 0 = launcher default
 };
 
 struct EpCombineArgs {
@@ -67,6 +82,7 @@ struct EpCombineArgs {
   void* out;                 // [T, H] bf16
   float* out_topk_w;         // [T, K] or null
   int T, H, K;
+  int stages;                // TMA pipeline depth (ep_tma_kernels.cu); 0 = launcher default
 };
 
 // ---- low-latency (decode) mode -------------------------------------------------------
