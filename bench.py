@@ -43,8 +43,9 @@ def parse_args():
     p.add_argument("--topk", type=int, default=8)
     p.add_argument("--experts", type=int, default=256)
     p.add_argument("--num-sms", type=int, default=int(os.environ.get("UCCL_B200_EP_SMS", "0")),
-                   help="CTAs per EP kernel (0: 148 at 1 GPU, 96 otherwise)")
+                   help="CTAs per EP kernel of the headline (0: 148 at 1 GPU, else 24 = the reference's budget)")
     p.add_argument("--no-allreduce-sweep", action="store_true")
+    p.add_argument("--no-sm-sweep", action="store_true", help="only time the headline SM budget")
     p.add_argument("--out", default=None, help="also write the JSON line to this file")
     return p.parse_args()
 
@@ -125,14 +126,57 @@ def run_reference(args):
             sys.path.insert(0, ref)
             try:
                 import uccl  # noqa: F401
-                from uccl import ep  # noqa: F401
+                from uccl import ep as ref_ep  # noqa: F401
             except Exception as e:  # ImportError: native ep module absent
                 why = ("reference installs offline only as a pure-python stub: uccl.ep native module missing "
                        f"(needs nanobind/libibverbs to build): {type(e).__name__}: {e}")
         if why is None:
-            why = "uccl.ep imported but no offline-buildable DeepEP runtime is wired"
+            # the native module imported: run the reference's own DeepEP-style Buffer (ep/bench/buffer.py)
+            try:
+                return run_reference_ep(args, ref)
+            except Exception as e:  # noqa: BLE001
+                why = f"uccl.ep imported but its intranode bench failed: {type(e).__name__}: {e}"
+        out = {"impl": "reference", "unavailable": why[:300]}
+        # labelled DIAGNOSTIC (not the reference arm): the upstream DeepEP kernels the reference vendors and
+        # re-hosts as its intranode path, built from baseline/_ref/deepep, same config, num_sms = 24
+        diag = None
+        if args.gpus >= 2:
+            # watchdog: a diagnostic must never hang the reference arm (the JSON line above is what the driver needs)
+            import signal
+
+            def _give_up(signum, frame):
+                if rank == 0:
+                    out["diagnostic"] = {"vendored_upstream_deepep_intranode": {"unavailable": "timed out after 300 s"}}
+                    emit(out)
+                os._exit(0)
+
+            signal.signal(signal.SIGALRM, _give_up)
+            signal.alarm(300)
+            try:
+                sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "benchmarks"))
+                import deepep_baseline
+
+                if deepep_baseline.available() is None:
+                    import torch
+                    import torch.distributed as dist
+
+                    local = int(os.environ.get("LOCAL_RANK", "0"))
+                    torch.cuda.set_device(local)
+                    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+                    diag = deepep_baseline.run(args.tokens, args.hidden, args.topk, args.experts, 24,
+                                               iters=max(5, min(args.steps, 20)), quiet=True)
+                    dist.barrier()
+                    dist.destroy_process_group()
+                else:
+                    diag = {"unavailable": deepep_baseline.available()}
+            except Exception as e:  # noqa: BLE001
+                diag = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if args.gpus >= 2:
+            signal.alarm(0)
+        if diag is not None:
+            out["diagnostic"] = {"vendored_upstream_deepep_intranode": diag}
         if rank == 0:
-            emit({"impl": "reference", "unavailable": why[:300]})
+            emit(out)
         return 0
     # allreduce: the reference's collective product is stock NCCL + its net plugin
     # (README.md:109-119); on one NVSwitch node no byte reaches the plugin, so this arm is NCCL
@@ -176,6 +220,66 @@ def run_reference(args):
         emit({"impl": "reference", "metric": "allreduce_busbw_1GiB_bf16", "value": busbw, "unit": "GB/s",
               "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(),
               "higher_is_better": True, "dtype": "bf16", "data": "synthetic"})
+    dist.destroy_process_group()
+    return 0
+
+
+def run_reference_ep(args, ref):
+    """The reference's own EP path (only reachable where `uccl.ep` builds: nanobind + libibverbs): its
+    DeepEP-compatible Buffer from ep/bench/buffer.py, cached-handle fp8 dispatch + bf16 combine at its
+    default SM budget, timed like our arm."""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ref, "uccl", "ep_bench"))
+    sys.path.insert(0, os.path.join("/root/reference", "ep", "bench"))
+    from buffer import Buffer as RefBuffer  # type: ignore
+    from utils import per_token_cast_to_fp8 as ref_cast  # type: ignore
+
+    n = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    T, H, K, E = args.tokens, args.hidden, args.topk, args.experts
+    buf = RefBuffer(dist.group.WORLD, int(2e9), 0)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    x = torch.randn(T, H, generator=g).to(torch.bfloat16).to(dev)
+    scores = torch.randn(T, E, generator=g).abs() + 1
+    idx = scores.topk(K, dim=-1, largest=True, sorted=False).indices.to(torch.int64).contiguous().to(dev)
+    w = torch.rand(T, K, generator=g).float().to(dev)
+    tpr, _, tpe, in_rank, _ = buf.get_dispatch_layout(idx, E)
+    x8 = ref_cast(x)
+    rx, _, _, _, handle, _ = buf.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank,
+                                          num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        buf.dispatch(x8, handle=handle)
+        buf.combine(rx, handle)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step()
+        e0.record()
+        evs.append((s0, e0))
+    torch.cuda.synchronize()
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / len(evs)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        emit({"impl": "reference", "metric": "ep_dispatch_combine_tokens_per_s", "value": n * T / (ms.item() * 1e-3),
+              "unit": "tokens/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+              "ms_per_step": ms.item(), "higher_is_better": True, "scaling": "weak", "dtype": "bf16",
+              "data": "synthetic"})
+    dist.barrier()
     dist.destroy_process_group()
     return 0
 
@@ -240,8 +344,14 @@ def main():
     else:
         comm = Communicator.local_world(1, devices=[dev.index], heap_bytes=heap, stage_bytes=64 << 20)[0]
     buf = Buffer(comm=comm, num_nvl_bytes=nvl_bytes)
-    cfg = Buffer.get_dispatch_config(n)
-    cfg.num_sms = args.num_sms if args.num_sms > 0 else (148 if n == 1 else 96)
+    from uccl_b200.ep import Config
+
+    # SM budget of the headline: the reference publishes its numbers at 24 SMs (ep/bench/test_intranode.py:571)
+    # so that expert GEMMs can run beside the communication kernels -- the same budget is the default here for
+    # N > 1 (like for like); other budgets are measured too and reported under "sm_sweep" / "best".  At N = 1
+    # nothing crosses NVLink (a pure HBM permutation) and the whole GPU is used.
+    head_sms = args.num_sms if args.num_sms > 0 else (148 if n == 1 else 24)
+    cfg = Config(head_sms)
 
     def barrier():
         torch.cuda.synchronize()
@@ -277,91 +387,118 @@ def main():
     barrier()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step_cached():
-        buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
-        out, _, _ = buf.combine(comb_in, handle, config=cfg)
-        return out
+    impl_name = {1: "register", 2: "tma"}
 
     def launches():
         return int(buf.runtime.launches) + int(comm.native.launches)
 
-    for _ in range(max(args.warmup, 3)):
-        step_cached()
-    barrier()
+    def measure(num_sms: int, steps: int, warm: int, sample_clocks: bool = False):
+        """Times `steps` (dispatch + combine) steps at one SM budget: CUDA events around every step on the
+        launching stream, 256 MiB L2 flush write between steps (untimed), max over ranks."""
+        c = Config(num_sms)
 
-    # ---- the step is launch-bound at small N (two short kernels per step, ~0.5 ms of Python per call):
-    # capture dispatch and combine into CUDA graphs so the timed region measures the GPU, not the
-    # interpreter (the kernels keep their cross-rank epochs on the device, so replays are safe).
-    graphs = None
-    per_step_launches = 2
-    if not args.no_graph:
-        try:
-            l_before = launches()
-            g_d, g_c = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_d):
-                buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
-            with torch.cuda.graph(g_c):
-                buf.combine(comb_in, handle, config=cfg)
-            per_step_launches = launches() - l_before
-            graphs = (g_d, g_c)
-        except Exception as exc:  # pragma: no cover - fall back to eager launches
-            if rank == 0:
-                print(f"[bench] CUDA graph capture unavailable ({type(exc).__name__}: {exc}); eager launches",
-                      file=sys.stderr)
-            graphs = None
-            torch.cuda.synchronize()
-    use_graph = torch.tensor([1 if graphs is not None else 0], device=dev)
-    if dist is not None:
-        dist.all_reduce(use_graph, op=dist.ReduceOp.MIN)  # every rank must take the same path
-    if int(use_graph.item()) == 0:
+        def step_cached():
+            buf.dispatch(x, handle=handle, use_fp8=True, config=c)
+            buf.combine(comb_in, handle, config=c)
+
+        for _ in range(warm):
+            step_cached()
+        barrier()
+        # ---- the step is launch-bound at small N (two short kernels per step, ~0.5 ms of Python per call):
+        # capture dispatch and combine into CUDA graphs so the timed region measures the GPU, not the
+        # interpreter (the kernels keep their cross-rank epochs on the device, so replays are safe).
         graphs = None
-    if graphs is not None:
-        for _ in range(3):
-            graphs[0].replay()
-            graphs[1].replay()
-    barrier()
-
-    # ---- timed region: exactly K steps, device-timed per step, L2 flushed between steps
-    sampler = ClockSampler(dev.index)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    # The host-side barrier above releases the ranks up to ~1 ms apart; without re-aligning the GPUs the
-    # first timed dispatch would absorb that skew in its cross-rank entry barrier.  A device-side
-    # barrier kernel (untimed) lines the GPUs up to within microseconds.
-    comm.barrier()
-    l0 = launches()
-    sampler.start()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
+        per_step_launches = 2
+        if not args.no_graph:
+            try:
+                l_before = launches()
+                g_d, g_c = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_d):
+                    buf.dispatch(x, handle=handle, use_fp8=True, config=c)
+                with torch.cuda.graph(g_c):
+                    buf.combine(comb_in, handle, config=c)
+                per_step_launches = launches() - l_before
+                graphs = (g_d, g_c)
+            except Exception as exc:  # pragma: no cover - fall back to eager launches
+                if rank == 0:
+                    print(f"[bench] CUDA graph capture unavailable ({type(exc).__name__}: {exc}); eager launches",
+                          file=sys.stderr)
+                graphs = None
+                torch.cuda.synchronize()
+        use_graph = torch.tensor([1 if graphs is not None else 0], device=dev)
+        if dist is not None:
+            dist.all_reduce(use_graph, op=dist.ReduceOp.MIN)  # every rank must take the same path
+        if int(use_graph.item()) == 0:
+            graphs = None
         if graphs is not None:
-            graphs[0].replay()
-            mids[i].record()
-            graphs[1].replay()
-        else:
-            buf.dispatch(x, handle=handle, use_fp8=True, config=cfg)
-            mids[i].record()
-            buf.combine(comb_in, handle, config=cfg)
-        ends[i].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
-    gpu_launches = (launches() - l0) if graphs is None else per_step_launches * args.steps
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    ms_per_step = max_over_ranks(sum(step_ms) / len(step_ms))
-    tokens_per_s = n * T / (ms_per_step * 1e-3)
-    # split of the same timed steps (dispatch = start..mid, combine = mid..end)
-    disp_ms = max_over_ranks(sum(s.elapsed_time(m) for s, m in zip(starts, mids)) / args.steps)
-    comb_ms = max_over_ranks(sum(m.elapsed_time(e) for m, e in zip(mids, ends)) / args.steps)
+            for _ in range(3):
+                graphs[0].replay()
+                graphs[1].replay()
+        barrier()
+        sampler = ClockSampler(dev.index) if sample_clocks else None
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        mids = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        # The host-side barrier above releases the ranks up to ~1 ms apart; without re-aligning the GPUs the
+        # first timed dispatch would absorb that skew in its cross-rank entry barrier.  A device-side
+        # barrier kernel (untimed) lines the GPUs up to within microseconds.
+        comm.barrier()
+        l0 = launches()
+        if sampler:
+            sampler.start()
+        wall0 = time.perf_counter()
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            if graphs is not None:
+                graphs[0].replay()
+                mids[i].record()
+                graphs[1].replay()
+            else:
+                buf.dispatch(x, handle=handle, use_fp8=True, config=c)
+                mids[i].record()
+                buf.combine(comb_in, handle, config=c)
+            ends[i].record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        clocks = sampler.stop() if sampler else None
+        step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+        r = {
+            "num_sms": num_sms,
+            "ms_per_step": max_over_ranks(sum(step_ms) / len(step_ms)),
+            # split of the same timed steps (dispatch = start..mid, combine = mid..end)
+            "dispatch_us": max_over_ranks(sum(s.elapsed_time(m) for s, m in zip(starts, mids)) / steps) * 1e3,
+            "combine_us": max_over_ranks(sum(m.elapsed_time(e) for m, e in zip(mids, ends)) / steps) * 1e3,
+            "kernels": {"dispatch": impl_name.get(int(buf.runtime.last_dispatch_impl), "?"),
+                        "combine": impl_name.get(int(buf.runtime.last_combine_impl), "?")},
+            "steps": steps,
+            "launch": "cuda_graph_replay" if graphs is not None else "eager",
+            "gpu_launches": (launches() - l0) if graphs is None else per_step_launches * steps,
+            "step_us_min_med_max": [min(step_ms) * 1e3, statistics.median(step_ms) * 1e3, max(step_ms) * 1e3],
+            "wall_s": wall, "clocks": clocks,
+        }
+        r["tokens_per_s"] = n * T / (r["ms_per_step"] * 1e-3)
+        return r
+
+    # ---- timed region of the headline: exactly K steps after W warm-up steps
+    head = measure(head_sms, args.steps, max(args.warmup, 3), sample_clocks=True)
+    ms_per_step, disp_ms, comb_ms = head["ms_per_step"], head["dispatch_us"] * 1e-3, head["combine_us"] * 1e-3
+    tokens_per_s = head["tokens_per_s"]
+    clocks, gpu_launches, wall, step_ms_stats = head["clocks"], head["gpu_launches"], head["wall_s"], head["step_us_min_med_max"]
+    graphs_used = head["launch"]
+    # other SM budgets (shorter runs): the reference's 24 and the budgets between it and most of the GPU
+    sweep_rows = [head]
+    if not args.no_sm_sweep:
+        for sms in ([24, 48, 96] if n > 1 else [24, 64]):
+            if sms != head_sms:
+                sweep_rows.append(measure(sms, max(5, min(args.steps, 10)), 3))
+    best = max(sweep_rows, key=lambda r: r["tokens_per_s"])
+
     disp_bytes = num_recv * (H + H // 128 * 4)   # fp8 payload + scales received per rank
     comb_bytes = num_recv * H * 2                # bf16 rows pulled per rank
     remote_frac = (n - 1) / n
-    nvlink_gbs = 770.0  # measured one-direction peer-copy bandwidth (B200_PROFILING.md); with both
-    # directions loaded (every EP kernel sends and receives at once) ~600 GB/s/dir is what NCCL,
-    # cudaMemcpyPeer pairs and these kernels all top out at on this box (profiles/RESULTS.md)
+    nvlink_gbs = 770.0   # measured one-direction peer-copy bandwidth on this pool (B200_PROFILING.md)
+    nvlink_nominal = 900.0
 
     # ---- end-to-end through the public API, inputs from pinned host memory every step
     # Inputs of step i+1 are copied on a side stream while step i runs (every step still copies its
@@ -386,7 +523,11 @@ def main():
         a, _, b, c, _ = buf.get_dispatch_layout(idd, E)
         rx, ri, rw, pe, h, _ = buf.dispatch(xd, num_tokens_per_rank=a, is_token_in_rank=c, num_tokens_per_expert=b,
                                             topk_idx=idd, topk_weights=wd, use_fp8=True, config=cfg)
+        # stand-in for the expert MLP: dequantise the received (e4m3, scale) rows into the combine arena
+        # (a real pass over every received token; the expert GEMMs themselves are not part of this metric)
         cin = buf.get_combine_buffer(h[4], H, K)
+        torch.mul(rx[0].view(h[4], H // 128, 128).to(torch.bfloat16), rx[1].to(torch.bfloat16).unsqueeze(2),
+                  out=cin.view(h[4], H // 128, 128))
         out, _, _ = buf.combine(cin, h, config=cfg)
         return out[:, :8].float().sum(dim=1).cpu()  # D2H read of a per-token checksum
 
@@ -430,32 +571,41 @@ def main():
             "model": "DeepEP intranode dispatch+combine (DeepSeek-V3 MoE shape)",
             "global_batch": n * T, "seq_len": T, "tokens_per_rank": T, "hidden": H, "num_topk": K,
             "num_experts": E, "parallelism": f"ep{n}", "dispatch": "bf16 -> fused e4m3 + per-128 scales",
-            "combine": "bf16", "num_sms": cfg.num_sms, "handle": "cached (as the reference times it)",
-            "launch": "cuda_graph_replay" if graphs is not None else "eager",
+            "combine": "bf16", "num_sms": head_sms, "kernels": head["kernels"],
+            "handle": "cached (as the reference times it)", "launch": graphs_used,
             "l2": "256 MiB flush write between timed steps (untimed); per-step working set > 126 MB L2",
         },
         "dispatch_us": disp_ms * 1e3,
         "combine_us": comb_ms * 1e3,
         "dispatch_recv_GBps": disp_bytes / (disp_ms * 1e-3) / 1e9,
         "combine_recv_GBps": comb_bytes / (comb_ms * 1e-3) / 1e9,
+        # roofline: bytes that must cross NVLink / link bandwidth (measured 770 GB/s/dir peer copy; 900 nominal)
         "roofline": {
-            "nvlink_GBps_measured": nvlink_gbs,
-            "nvlink_GBps_bidirectional_observed": 600.0,
-            "dispatch_frac_of_bidir_floor": (disp_bytes * remote_frac / 600e9) / (disp_ms * 1e-3) if n > 1 else None,
-            "combine_frac_of_bidir_floor": (comb_bytes * remote_frac / 600e9) / (comb_ms * 1e-3) if n > 1 else None,
+            "nvlink_GBps_measured": nvlink_gbs, "nvlink_GBps_nominal": nvlink_nominal,
+            "dispatch_nvlink_GBps": disp_bytes * remote_frac / (disp_ms * 1e-3) / 1e9 if n > 1 else None,
+            "combine_nvlink_GBps": comb_bytes * remote_frac / (comb_ms * 1e-3) / 1e9 if n > 1 else None,
             "dispatch_floor_us": disp_bytes * remote_frac / (nvlink_gbs * 1e9) * 1e6 if n > 1 else None,
             "combine_floor_us": comb_bytes * remote_frac / (nvlink_gbs * 1e9) * 1e6 if n > 1 else None,
-            "dispatch_frac_of_floor": (disp_bytes * remote_frac / (nvlink_gbs * 1e9)) / (disp_ms * 1e-3) if n > 1 else None,
-            "combine_frac_of_floor": (comb_bytes * remote_frac / (nvlink_gbs * 1e9)) / (comb_ms * 1e-3) if n > 1 else None,
+            "dispatch_frac_of_measured": (disp_bytes * remote_frac / (nvlink_gbs * 1e9)) / (disp_ms * 1e-3) if n > 1 else None,
+            "combine_frac_of_measured": (comb_bytes * remote_frac / (nvlink_gbs * 1e9)) / (comb_ms * 1e-3) if n > 1 else None,
+            "dispatch_frac_of_nominal": (disp_bytes * remote_frac / (nvlink_nominal * 1e9)) / (disp_ms * 1e-3) if n > 1 else None,
+            "combine_frac_of_nominal": (comb_bytes * remote_frac / (nvlink_nominal * 1e9)) / (comb_ms * 1e-3) if n > 1 else None,
+            "hbm_GBps_single_gpu": ((T * H * 2 + disp_bytes) / (disp_ms * 1e-3) / 1e9) if n == 1 else None,
         },
+        # the same step at other SM budgets (shorter runs); "best" = highest tokens/s of the sweep
+        "sm_sweep": [{k: r[k] for k in ("num_sms", "ms_per_step", "dispatch_us", "combine_us", "tokens_per_s", "kernels", "steps")}
+                     for r in sweep_rows],
+        "best": {k: best[k] for k in ("num_sms", "ms_per_step", "dispatch_us", "combine_us", "tokens_per_s", "kernels")},
         "baseline_us": {"dispatch": BASELINE_DISPATCH_US, "combine": BASELINE_COMBINE_US, "n_gpus": 8},
         "num_recv_tokens": num_recv,
         "clocks": clocks,
         "e2e": {"value": n * T / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "note": "pinned-host inputs of step i+1 are copied on a side stream during step i"},
+                "note": "per step: H2D of x/topk_idx/topk_weights from pinned memory (step i+1 prefetched on a side stream), "
+                        "get_dispatch_layout, non-cached fp8 dispatch incl. count exchange + CPU sync, dequantise into the "
+                        "combine arena (expert stand-in), combine, D2H checksum"},
         "gpu_launches": gpu_launches,
-        "step_us_min_med_max": [min(step_ms) * 1e3, statistics.median(step_ms) * 1e3, max(step_ms) * 1e3],
+        "step_us_min_med_max": step_ms_stats,
         "wall_s_timed_region": wall,
         "nvls": bool(comm.has_multicast),
     }

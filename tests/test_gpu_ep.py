@@ -179,7 +179,7 @@ def test_tma_pipeline_matches_register_path(n, H):
     quantiser, same fixed summation order, incl. bias, routed weights, cached handles and the
     num_worst_tokens (CUDA-graph) mode, on row sizes that span one / several / partial pipeline slices."""
     T, K = 301, 8
-    E = n * 4
+    E = n * 8
     bufs = get_buffers(n)
     xs, idxs, ws = make_inputs(n, T, H, K, E, seed=100 + n)
     g = torch.Generator().manual_seed(5)
@@ -359,7 +359,9 @@ def test_low_latency_dispatch_combine(n, use_fp8):
         x, idx, w = xs[r].to(dev), idxs[r].to(dev), ws[r].to(dev)
         recv_x, recv_count, handle, _, _ = b.low_latency_dispatch(x, idx, M, E, use_fp8=use_fp8)
         torch.cuda.current_stream().synchronize()
-        rx = per_token_cast_back(recv_x[0].view(-1, H), recv_x[1].view(-1, H // 128)).view(E_local, n * M, H) if use_fp8 else recv_x
+        if use_fp8:
+            assert recv_x[1].shape == (E_local, n * M, H // 128) and recv_x[1].stride(1) == 1  # DeepEP's column-major view
+        rx = per_token_cast_back(recv_x[0].view(-1, H), recv_x[1].reshape(-1, H // 128)).view(E_local, n * M, H) if use_fp8 else recv_x
         # "expert" = multiply by (global expert id + 1), written into the zero-copy combine buffer
         cb = b.get_next_low_latency_combine_buffer(handle)
         for el in range(E_local):
@@ -397,3 +399,141 @@ def test_low_latency_dispatch_combine(n, use_fp8):
         exp_out = base * coef[:, None]
         bad = ~torch.isclose(o["out"].float(), exp_out, rtol=3e-2, atol=3e-1)
         assert bad.float().mean().item() < 5e-3, bad.float().mean().item()
+
+
+def _ll_setup(n, M, H):
+    from uccl_b200.ep.low_latency import LowLatencyRuntime, ll_size_hint
+
+    bufs = get_buffers(n)
+    for b in bufs:
+        if b._ll is None:
+            with torch.cuda.device(b.device):
+                b._ll = LowLatencyRuntime(b, ll_size_hint(64, 1024, n, 16))
+    torch.cuda.synchronize()
+    return bufs
+
+
+def _unpack_ue8m0(words, H):
+    """[.., rows, H/512] int32 (4 exponent bytes per word) -> [.., rows, H/128] float32 power-of-two scales."""
+    w = words.contiguous().to(torch.int64) & 0xffffffff
+    ex = torch.stack([(w >> (8 * b)) & 0xff for b in range(4)], dim=-1).reshape(*words.shape[:-1], H // 128)
+    return torch.pow(2.0, ex.float() - 127.0)
+
+
+@pytest.mark.parametrize("n", [2, 4])
+@pytest.mark.parametrize("variant", ["col_major", "row_major", "ue8m0"])
+def test_low_latency_scale_layouts_hooks_and_stats(n, variant):
+    """The fp8 scale layouts the kernel emits (DeepEP's column-major view, plain row-major, packed UE8M0), the
+    SEND/RECV hook split (results must be bit-identical to the single-kernel path), a combine input that does not
+    live in the symmetric buffer (occupied rows are packed in) and the wait-cost / receive-count statistics."""
+    T, H, K, M = 40, 1024, 4, 64
+    E = n * 2
+    E_local = E // n
+    bufs = _ll_setup(n, M, H)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=300 + n)
+    kw = dict(use_fp8=True)
+    if variant == "row_major":
+        kw["scales_row_major"] = True
+    if variant == "ue8m0":
+        kw.update(round_scale=True, use_ue8m0=True)
+
+    def run(use_hook):
+        def fn(b):
+            r, dev = b.rank, b.device
+            x, idx, w = xs[r].to(dev), idxs[r].to(dev), ws[r].to(dev)
+            cum = torch.zeros(E_local, dtype=torch.int32, device=dev)
+            dstat = torch.zeros(n, dtype=torch.int64, device=dev)
+            cstat = torch.zeros(n, dtype=torch.int64, device=dev)
+            (q, sc), cnt, handle, _, hook = b.low_latency_dispatch(
+                x, idx, M, E, cumulative_local_expert_recv_stats=cum, dispatch_wait_recv_cost_stats=dstat,
+                return_recv_hook=use_hook, **kw)
+            assert (hook is not None) == use_hook
+            if use_hook:
+                hook()
+            torch.cuda.current_stream().synchronize()
+            if variant == "ue8m0":
+                assert sc.dtype == torch.int32 and sc.shape == (E_local, n * M, H // 512) and sc.stride(1) == 1
+                scf = _unpack_ue8m0(sc, H)
+            else:
+                assert sc.dtype == torch.float32 and sc.shape == (E_local, n * M, H // 128)
+                assert sc.stride(1) == (H // 128 if variant == "row_major" else 1)
+                scf = sc
+            rx = per_token_cast_back(q.view(-1, H), scf.reshape(-1, H // 128).contiguous()).view(E_local, n * M, H)
+            # expert outputs in an ORDINARY tensor (not the symmetric combine buffer): combine packs the occupied rows in
+            eo = torch.zeros(E_local, n * M, H, dtype=torch.bfloat16, device=dev)
+            for el in range(E_local):
+                c = int(cnt[el])
+                eo[el, :c] = (rx[el, :c].float() * (r * E_local + el + 1)).to(torch.bfloat16)
+            out, _, chook = b.low_latency_combine(eo, idx, w, handle, return_recv_hook=use_hook,
+                                                  combine_wait_recv_cost_stats=cstat)
+            if use_hook:
+                chook()
+            torch.cuda.current_stream().synchronize()
+            return dict(q=q.view(torch.uint8).cpu().clone(), sc=sc.cpu().clone(), cnt=cnt.cpu(), cum=cum.cpu(), out=out.cpu(),
+                        src=handle[0].cpu().clone(), lr=handle[1].cpu(), dstat=dstat.cpu(), cstat=cstat.cpu())
+
+        return run_threads(bufs, fn)
+
+    plain = run(False)
+    hooked = run(True)
+    for r in range(n):
+        a, h = plain[r], hooked[r]
+        assert torch.equal(a["cnt"], h["cnt"]) and torch.equal(a["cum"], a["cnt"]) and torch.equal(a["lr"], h["lr"])
+        assert (a["dstat"] >= 0).all() and (a["cstat"] >= 0).all() and int(a["dstat"][r]) == 0
+        # combine: sum_k w[t,k] * (e_k + 1) * dequant(x[t])
+        if variant == "ue8m0":
+            base = xs[r].float()  # power-of-two scales: compare against the original with the e4m3 tolerance
+        else:
+            base = per_token_cast_back(*per_token_cast_to_fp8(xs[r])).float()
+        coef = (torch.where(idxs[r] >= 0, ws[r] * (idxs[r] + 1).float(), torch.zeros_like(ws[r]))).sum(1)
+        exp_out = base * coef[:, None]
+        for o in (a, h):
+            bad = ~torch.isclose(o["out"].float(), exp_out, rtol=8e-2 if variant == "ue8m0" else 3e-2, atol=3e-1)
+            assert bad.float().mean().item() < 1e-2, bad.float().mean().item()
+        # hash determinism across the hook / non-hook variants: identical rows per (expert, source rank) block as a
+        # multiset (slot order inside a block is claimed atomically), identical combine output bit for bit
+        assert torch.equal(a["out"], h["out"])
+        for el in range(E_local):
+            for s_ in range(n):
+                beg, c = int(a["lr"][el, s_] >> 32), int(a["lr"][el, s_] & 0xffffffff)
+                ka = sorted(zip(a["src"][el, beg:beg + c].tolist(), [hash(bytes(v.tolist())) for v in a["q"].view(E_local, n * M, H)[el, beg:beg + c]]))
+                kh = sorted(zip(h["src"][el, beg:beg + c].tolist(), [hash(bytes(v.tolist())) for v in h["q"].view(E_local, n * M, H)[el, beg:beg + c]]))
+                assert ka == kh
+
+
+def test_low_latency_pressure_loop():
+    """Back-to-back decode steps alternating hook / non-hook calls and both LL buffers (reference: the pressure
+    mode of ep/bench/test_low_latency.py:619-622): epochs, parities and the pending-hook bookkeeping must hold."""
+    n, T, H, K, M = 4, 32, 1024, 4, 64
+    E = n * 2
+    bufs = _ll_setup(n, M, H)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=900)
+
+    def fn(b):
+        r, dev = b.rank, b.device
+        x, idx, w = xs[r].to(dev), idxs[r].to(dev), ws[r].to(dev)
+        first, prev = None, None
+        for it in range(24):
+            use_hook = it % 3 != 0
+            rx, cnt, handle, _, hook = b.low_latency_dispatch(x, idx, M, E, use_fp8=False, return_recv_hook=use_hook)
+            if prev is not None:  # a combine hook left pending was run by the dispatch call above
+                if first is None:
+                    first = prev.clone()
+                assert torch.equal(prev, first), it
+            if hook is not None:
+                hook()
+            cb = b.get_next_low_latency_combine_buffer(handle)
+            cb.copy_(rx)
+            out, _, chook = b.low_latency_combine(cb, idx, w, handle, return_recv_hook=use_hook)
+            if chook is not None and it % 2 == 0:
+                chook()
+            prev = out
+        b._ll._finish_pending()
+        assert torch.equal(prev, first)
+        torch.cuda.current_stream().synchronize()
+        return first.cpu()
+
+    outs = run_threads(bufs, fn)
+    for r in range(n):
+        coef = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(outs[r].float(), xs[r].float() * coef[:, None], rtol=3e-2, atol=3e-1)

@@ -115,9 +115,9 @@ def test_host_ep_low_latency():
                                                            return_recv_hook=True)
         hook()
         bx, cntb, hb, _, _ = b.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=False)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb, use_logfmt=True)  # accepted: bf16 payload kept
+        with pytest.raises(NotImplementedError):  # not silently ignored: the combine payload is bf16 only
+            b.low_latency_combine(bx, idxs[r], ws[r], hb, use_logfmt=True)
+        out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb)
         return dict(qx=qx, qs=qs, cnt=cnt, stats=stats, bx=bx, cntb=cntb, out=out, hb=hb)
 
     res = _run(comms, fn)

@@ -66,13 +66,17 @@ std::shared_ptr<MultiComm> MultiComm::create(const UniqueId& id, int rank, int n
   g.allgather(&mine, ids.data(), sizeof(UniqueId));
   m->local_ = Comm::create(ids[(size_t)m->node_ * local_size], m->lrank_, local_size, device, cfg);
   // one rail per local rank
+  // pick the rail's NIC FIRST and bind the engine to it: an engine on 0.0.0.0 would leave through the routing
+  // table's default interface with a source address other than the advertised one (peers drop such packets),
+  // and would skip the MTU clamp / NIC-local CPU pinning.  UCCL_B200_NET_BIND_IP still overrides.
   net::EngineConfig ec = net::EngineConfig::from_env();
-  m->engine_.reset(new net::Engine(ec));
   std::string ip = ec.bind_ip;
-  if (ip == "0.0.0.0") {
+  if (ip.empty() || ip == "0.0.0.0") {
     auto ifs = net::list_interfaces();
     ip = ifs.empty() ? "127.0.0.1" : ifs[(size_t)m->lrank_ % ifs.size()].second;
+    ec.bind_ip = ip;
   }
+  m->engine_.reset(new net::Engine(ec));
   RailAddr me{};
   inet_pton(AF_INET, ip.c_str(), &me.ip_be);
   me.port = m->engine_->port();

@@ -121,6 +121,9 @@ cudaError_t preload_all_kernels() {
     EpLLCombineArgs lc;
     memset(&lc, 0, sizeof(lc));
     ok(launch_ep_ll_combine(c, lc, 1, 0));
+    EpLLPackArgs lp;
+    memset(&lp, 0, sizeof(lp));
+    ok(launch_ep_ll_pack(lp, 0));
   }
   ok(preload_p2p_kernels());
   ok(cmp_compress_async(nullptr, 0, kBF16, nullptr, 0));

@@ -32,6 +32,12 @@ class EqdsPacer {
       s.queued = true;
     }
   }
+  // the sender's flow is gone (closed or failed): forget its demand so it neither blocks the grant loop nor
+  // keeps the engine thread in its pacing nap
+  void remove(uint32_t sender) {
+    if (senders_.erase(sender) == 0) return;
+    for (auto it = active_.begin(); it != active_.end();) it = (*it == sender) ? active_.erase(it) : std::next(it);
+  }
   // sender consumed previously granted credit
   void on_data(uint32_t sender, uint64_t bytes) {
     auto it = senders_.find(sender);

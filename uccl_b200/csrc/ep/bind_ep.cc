@@ -16,6 +16,12 @@ void bind_ep(py::module_& m) {
   m.attr("EP_IMPL_AUTO") = (int)EP_IMPL_AUTO;
   m.attr("EP_IMPL_REG") = (int)EP_IMPL_REG;
   m.attr("EP_IMPL_TMA") = (int)EP_IMPL_TMA;
+  m.attr("EP_LL_FULL") = (int)EP_LL_FULL;
+  m.attr("EP_LL_SEND") = (int)EP_LL_SEND;
+  m.attr("EP_LL_RECV") = (int)EP_LL_RECV;
+  m.attr("EP_LL_SCALES_ROW_MAJOR") = (int)EP_LL_SCALES_ROW_MAJOR;
+  m.attr("EP_LL_SCALES_COL_MAJOR") = (int)EP_LL_SCALES_COL_MAJOR;
+  m.attr("EP_LL_SCALES_COL_UE8M0") = (int)EP_LL_SCALES_COL_UE8M0;
   py::class_<EpDispatchOut>(m, "EpDispatchOut")
       .def_readonly("recv_x", &EpDispatchOut::recv_x)
       .def_readonly("recv_scales", &EpDispatchOut::recv_scales)
@@ -67,17 +73,28 @@ void bind_ep(py::module_& m) {
       .def_static("ll_size_hint", &EpBuffer::ll_size_hint)
       .def("ll_dispatch",
            [](EpBuffer& b, uintptr_t x, uintptr_t ti, int T, int H, int K, int E, int M, bool use_fp8, bool round_scale,
-              uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, uintptr_t st) {
+              uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, uintptr_t st, int phase,
+              int scale_layout, uintptr_t wait_stats) {
              auto o = b.ll_dispatch(x, ti, T, H, K, E, M, use_fp8, round_scale, recv_count, layout_range, send_pos,
-                                    num_sms, (cudaStream_t)st);
+                                    num_sms, (cudaStream_t)st, phase, scale_layout, wait_stats);
              return py::make_tuple(o.recv_x, o.recv_scales, o.recv_src_info, o.combine_x, o.buffer_idx);
-           })
+           },
+           py::arg("x"), py::arg("topk_idx"), py::arg("T"), py::arg("H"), py::arg("K"), py::arg("E"), py::arg("M"),
+           py::arg("use_fp8"), py::arg("round_scale"), py::arg("recv_count"), py::arg("layout_range"),
+           py::arg("send_pos"), py::arg("num_sms"), py::arg("stream"), py::arg("phase") = (int)EP_LL_FULL,
+           py::arg("scale_layout") = (int)EP_LL_SCALES_ROW_MAJOR, py::arg("wait_stats") = 0)
+      .def("ll_dispatch_recv",
+           [](EpBuffer& b, int num_sms, uintptr_t wait_stats, uintptr_t st) { b.ll_dispatch_recv(num_sms, wait_stats, (cudaStream_t)st); },
+           py::arg("num_sms"), py::arg("wait_stats"), py::arg("stream"))
       .def("ll_combine_buffer", &EpBuffer::ll_combine_buffer)
       .def("ll_combine",
            [](EpBuffer& b, uintptr_t x, int idx, uintptr_t tw, uintptr_t sp, uintptr_t out, int T, int H, int K, int E,
-              int M, int num_sms, uintptr_t st) {
-             b.ll_combine(x, idx, tw, sp, out, T, H, K, E, M, num_sms, (cudaStream_t)st);
-           })
+              int M, int num_sms, uintptr_t st, int phase, uintptr_t layout_range, uintptr_t wait_stats) {
+             b.ll_combine(x, idx, tw, sp, out, T, H, K, E, M, num_sms, (cudaStream_t)st, phase, layout_range, wait_stats);
+           },
+           py::arg("x"), py::arg("buffer_idx"), py::arg("topk_weights"), py::arg("send_pos"), py::arg("out"),
+           py::arg("T"), py::arg("H"), py::arg("K"), py::arg("E"), py::arg("M"), py::arg("num_sms"), py::arg("stream"),
+           py::arg("phase") = (int)EP_LL_FULL, py::arg("layout_range") = 0, py::arg("wait_stats") = 0)
       .def("combine_input_ptr", &EpBuffer::combine_input_ptr)
       .def("combine", [](EpBuffer& b, uintptr_t x, int num_recv, uintptr_t tw, uintptr_t ss, uintptr_t b0,
                          uintptr_t b1, uintptr_t out, uintptr_t otw, int T, int H, int K, int num_sms, uintptr_t st) {

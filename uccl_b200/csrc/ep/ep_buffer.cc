@@ -366,8 +366,14 @@ EpBuffer::LLLayout EpBuffer::ll_layout(int buffer_idx, int H, int E, int M) cons
 
 EpBuffer::LLOut EpBuffer::ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, int H, int K, int E, int M, bool use_fp8,
                                       bool round_scale, uintptr_t recv_count, uintptr_t layout_range,
-                                      uintptr_t send_pos, int num_sms, cudaStream_t st) {
+                                      uintptr_t send_pos, int num_sms, cudaStream_t st, int phase, int scale_layout,
+                                      uintptr_t wait_stats) {
   const int R = nranks();
+  UB_CHECK(phase == EP_LL_FULL || phase == EP_LL_SEND, "ll_dispatch: phase must be FULL or SEND");
+  UB_CHECK(ll_pending_grid_ == 0, "ll_dispatch: the receive hook of the previous dispatch has not been called");
+  UB_CHECK(scale_layout >= EP_LL_SCALES_ROW_MAJOR && scale_layout <= EP_LL_SCALES_COL_UE8M0, "ll_dispatch: bad scale layout");
+  if (scale_layout == EP_LL_SCALES_COL_UE8M0)
+    UB_CHECK(use_fp8 && round_scale && H % 512 == 0, "ll_dispatch: UE8M0 scales need fp8, round_scale and hidden %% 512 == 0");
   UB_CHECK(E > 0 && E % R == 0 && E <= kMaxRanks * kEpMaxLocalExperts, "ll_dispatch: bad num_experts %d", E);
   UB_CHECK(H % 128 == 0 && H <= 8192, "ll_dispatch: hidden must be a multiple of 128 and <= 8192 (got %d)", H);
   UB_CHECK(K > 0 && K <= 32, "ll_dispatch: bad num_topk %d", K);
@@ -398,10 +404,14 @@ EpBuffer::LLOut EpBuffer::ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, in
   a.send_pos = (int64_t*)send_pos;
   a.recv_count = (int32_t*)recv_count;
   a.layout_range = (int64_t*)layout_range;
+  a.phase = phase;
+  a.scale_layout = use_fp8 ? scale_layout : EP_LL_SCALES_ROW_MAJOR;
+  a.wait_stats = (long long*)wait_stats;
   int grid = std::max(1, std::min(num_sms, kEpLLMaxBlocks));
   cudaError_t e = launch_ep_ll_dispatch(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep ll_dispatch launch failed: %s", cudaGetErrorString(e));
   ++launches_;
+  if (phase == EP_LL_SEND) ll_pending_grid_ = grid;
   char* heap = comm_->fabric().local();
   LLOut o;
   o.recv_x = (uintptr_t)(heap + l.recv_x_off);
@@ -412,19 +422,55 @@ EpBuffer::LLOut EpBuffer::ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, in
   return o;
 }
 
+void EpBuffer::ll_dispatch_recv(int num_sms, uintptr_t wait_stats, cudaStream_t st) {
+  UB_CHECK(ll_pending_grid_ > 0, "ll_dispatch_recv: no send-phase dispatch is pending");
+  DevGuard g(comm_->device());
+  EpLLDispatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.phase = EP_LL_RECV;
+  a.H = 128;
+  a.E = nranks();
+  a.wait_stats = (long long*)wait_stats;
+  const int grid = ll_pending_grid_;  // the same block indices that signalled
+  (void)num_sms;
+  cudaError_t e = launch_ep_ll_dispatch(comm_->dev(), a, grid, st);
+  UB_CHECK(e == cudaSuccess, "ep ll_dispatch (receive half) launch failed: %s", cudaGetErrorString(e));
+  ++launches_;
+  ll_pending_grid_ = 0;
+}
+
 uintptr_t EpBuffer::ll_combine_buffer(int buffer_idx, int H, int E, int M) const {
   LLLayout l = ll_layout(buffer_idx, H, E, M);
   return (uintptr_t)(comm_->fabric().local() + l.comb_x_off);
 }
 
 void EpBuffer::ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T,
-                          int H, int K, int E, int M, int num_sms, cudaStream_t st) {
+                          int H, int K, int E, int M, int num_sms, cudaStream_t st, int phase, uintptr_t layout_range,
+                          uintptr_t wait_stats) {
   const int R = nranks();
+  UB_CHECK(phase >= EP_LL_FULL && phase <= EP_LL_RECV, "ll_combine: bad phase %d", phase);
   DevGuard g(comm_->device());
   LLLayout l = ll_layout(buffer_idx, H, E, M);
   char* arena = comm_->fabric().local() + l.comb_x_off;
-  const size_t bytes = (size_t)(E / R) * R * M * H * 2;
-  if (x != (uintptr_t)arena) UB_CUDA(cudaMemcpyAsync(arena, (void*)x, bytes, cudaMemcpyDeviceToDevice, st));
+  if (x != (uintptr_t)arena && phase != EP_LL_RECV) {
+    // expert outputs that do not live in the symmetric buffer: bring them in, occupied rows only
+    if (layout_range) {
+      EpLLPackArgs pa;
+      pa.src = (const void*)x;
+      pa.dst = arena;
+      pa.layout_range = (const int64_t*)layout_range;
+      pa.E_local = E / R;
+      pa.R = R;
+      pa.M = M;
+      pa.H = H;
+      cudaError_t pe = launch_ep_ll_pack(pa, st);
+      UB_CHECK(pe == cudaSuccess, "ep ll pack launch failed: %s", cudaGetErrorString(pe));
+      ++launches_;
+    } else {
+      const size_t bytes = (size_t)(E / R) * R * M * H * 2;
+      UB_CUDA(cudaMemcpyAsync(arena, (void*)x, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+  }
   EpLLCombineArgs a;
   memset(&a, 0, sizeof(a));
   a.x_off = l.comb_x_off;
@@ -434,6 +480,8 @@ void EpBuffer::ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr
   a.T = T;
   a.H = H;
   a.K = K;
+  a.phase = phase;
+  a.wait_stats = (long long*)wait_stats;
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
   cudaError_t e = launch_ep_ll_combine(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep ll_combine launch failed: %s", cudaGetErrorString(e));

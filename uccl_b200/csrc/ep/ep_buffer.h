@@ -61,11 +61,16 @@ class EpBuffer {
     int buffer_idx;
   };
   static size_t ll_size_hint(int M, int H, int R, int E);
+  // phase: EP_LL_FULL, or EP_LL_SEND followed later by ll_dispatch_recv() (return_recv_hook)
   LLOut ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, int H, int K, int E, int M, bool use_fp8, bool round_scale,
-                    uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, cudaStream_t st);
+                    uintptr_t recv_count, uintptr_t layout_range, uintptr_t send_pos, int num_sms, cudaStream_t st,
+                    int phase = EP_LL_FULL, int scale_layout = EP_LL_SCALES_ROW_MAJOR, uintptr_t wait_stats = 0);
+  void ll_dispatch_recv(int num_sms, uintptr_t wait_stats, cudaStream_t st);  // receive half of the last SEND-phase dispatch
   uintptr_t ll_combine_buffer(int buffer_idx, int H, int E, int M) const;
+  // layout_range != 0: a non-arena `x` is packed (occupied rows only) instead of copied whole
   void ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T, int H, int K,
-                  int E, int M, int num_sms, cudaStream_t st);
+                  int E, int M, int num_sms, cudaStream_t st, int phase = EP_LL_FULL, uintptr_t layout_range = 0,
+                  uintptr_t wait_stats = 0);
 
   // zero-copy combine input: a [num_tokens, hidden] bf16 view of the combine arena
   uintptr_t combine_input_ptr(int num_tokens, int hidden, int topk);
@@ -102,6 +107,7 @@ class EpBuffer {
   int ll_next_ = 0;
   int32_t* ll_send_cnt_ = nullptr;
   int ll_parity_ = 0;
+  int ll_pending_grid_ = 0;  // grid of a SEND-phase dispatch whose receive half has not run yet
 };
 
 cudaError_t launch_ep_layout(const EpLayoutArgs& a, cudaStream_t st);
@@ -114,6 +120,7 @@ cudaError_t launch_ep_dispatch_tma(const DevComm& c, const EpDispatchArgs& a, in
 cudaError_t launch_ep_combine_tma(const DevComm& c, const EpCombineArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_combine(const DevComm& c, const EpLLCombineArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ep_ll_pack(const EpLLPackArgs& a, cudaStream_t st);
 constexpr int kEpLLMaxBlocks = 64;
 
 }  // namespace ub

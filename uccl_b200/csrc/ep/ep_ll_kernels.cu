@@ -16,26 +16,12 @@
 //     buffers and does the top-k weighted sum in fp32 -- no [token][topk] staging, no recv phase.
 #include "../kernels/launch.h"
 #include "../kernels/prims.cuh"
+#include "ep_common.cuh"
 #include "ep_types.h"
 
 namespace ub {
 
 constexpr int kLLWarps = 8;  // 256 threads: one staged token per warp (<= 14.6 KB each at H = 7168 bf16)
-
-__device__ __forceinline__ void ll_bf16x8_to_float(const uint4& v, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float2 p = __bfloat1622float2(h[i]);
-    f[2 * i] = p.x;
-    f[2 * i + 1] = p.y;
-  }
-}
-__device__ __forceinline__ uint32_t ll_pack4_e4m3(float a, float b, float c, float d) {
-  __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
-  __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
-  return (uint32_t)lo | ((uint32_t)hi << 16);
-}
 
 __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const __grid_constant__ DevComm c,
                                                                           const __grid_constant__ EpLLDispatchArgs a) {
@@ -52,6 +38,13 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
   unsigned char* s_stage = ll_smem + (((size_t)2 * E * 4 + 127) / 128 * 128) + (size_t)warp * stage_stride;
 
   BlockSync s = sync_begin(c, kDomEpLL, blockIdx.x);
+  if (a.phase == EP_LL_RECV) {
+    // receive half of a hook-split dispatch: the send half has published its epoch; wait until every
+    // peer's rows (and counts) have landed here
+    sync_wait(c, s, blockIdx.x == 0 ? a.wait_stats : nullptr);
+    sync_end(s);
+    return;
+  }
   // ---- phase A: histogram + all-gather of the [R][E] count matrix
   for (int e = tid; e < E; e += blockDim.x) s_cnt[e] = 0;
   if (blockIdx.x == 0)
@@ -62,12 +55,22 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
     if (e >= 0 && e < E) atomicAdd(&s_cnt[(int)e], 1);
   }
   __syncthreads();
-  for (int i = tid; i < R * E; i += blockDim.x) {
-    const int dst = i / E, e = i % E;
-    int* p = reinterpret_cast<int*>(c.heap[dst] + a.cnt_tab_off) + ((size_t)blockIdx.x * kMaxRanks + me) * E + e;
-    *p = s_cnt[e];
+  if ((E & 3) == 0) {  // 16-byte stores: E / 4 per peer
+    const int E4 = E >> 2;
+    for (int i = tid; i < R * E4; i += blockDim.x) {
+      const int dst = i / E4, q = i % E4;
+      int* p = reinterpret_cast<int*>(c.heap[dst] + a.cnt_tab_off) + ((size_t)blockIdx.x * kMaxRanks + me) * E + q * 4;
+      st_v4(p, *reinterpret_cast<const uint4*>(s_cnt + q * 4));
+    }
+  } else {
+    for (int i = tid; i < R * E; i += blockDim.x) {
+      const int dst = i / E, e = i % E;
+      int* p = reinterpret_cast<int*>(c.heap[dst] + a.cnt_tab_off) + ((size_t)blockIdx.x * kMaxRanks + me) * E + e;
+      *p = s_cnt[e];
+    }
   }
-  sync_barrier(c, s);
+  sync_signal(c, s);
+  sync_wait(c, s, blockIdx.x == 0 ? a.wait_stats : nullptr);
   const int* tab = reinterpret_cast<const int*>(c.heap[me] + a.cnt_tab_off) + (size_t)blockIdx.x * kMaxRanks * E;
   for (int e = tid; e < E; e += blockDim.x) {
     int b = 0;
@@ -104,32 +107,22 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
           v1 = ld_nc_v4(src + (size_t)u * 32 + 16);
         }
         float f[16];
-        ll_bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
-        ll_bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
+        bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
+        bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
         float amax = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-        amax = fmaxf(amax, 1e-4f);
         float scale, scale_inv;
-        if (a.round_scale) {
-          const float raw = amax * (1.0f / 448.0f);
-          int ex = ((__float_as_int(raw) >> 23) & 0xff) - 127;
-          if ((__float_as_int(raw) & 0x7fffff) != 0) ex += 1;
-          scale_inv = __int_as_float((ex + 127) << 23);
-          scale = __int_as_float((127 - ex) << 23);
-        } else {
-          scale = 448.0f / amax;
-          scale_inv = __fdiv_rn(amax, 448.0f);  // bit-identical to torch's amax / 448
-        }
+        fp8_group_scale(amax, a.round_scale, scale, scale_inv);
         if (valid) {
           uint4 o;
-          o.x = ll_pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
-          o.y = ll_pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
-          o.z = ll_pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
-          o.w = ll_pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
+          o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+          o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+          o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
+          o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
           *reinterpret_cast<uint4*>(s_stage + (size_t)u * 16) = o;
           if ((lane & 7) == 0) sc[u >> 3] = scale_inv;
         }
@@ -154,6 +147,8 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
       a.send_pos[(size_t)t * a.K + lane] = pos;
     }
     const bool bulk_ok = (row_bytes % 16 == 0) && (scale_bytes % 16 == 0);
+    const size_t rows_per_expert = (size_t)R * a.M;
+    const float* sc_stage = reinterpret_cast<const float*>(s_stage + row_bytes);
     for (int k = 0; k < a.K; ++k) {
       const long long ek = __shfl_sync(0xffffffffu, e, k);
       const int sk = __shfl_sync(0xffffffffu, slot, k);
@@ -162,7 +157,25 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
       const size_t row = (size_t)el * R * a.M + sk;
       char* dx = c.heap[r] + a.recv_x_off + row * row_bytes;
       char* ds = c.heap[r] + a.recv_scales_off + row * scale_bytes;
-      if (bulk_ok) {
+      if (scale_bytes && a.scale_layout != EP_LL_SCALES_ROW_MAJOR) {
+        // column-major forms: element (row, j) of expert el lives at [el][j][row] -- strided 4-byte stores
+        if (a.scale_layout == EP_LL_SCALES_COL_MAJOR) {
+          float* base = reinterpret_cast<float*>(c.heap[r] + a.recv_scales_off) + (size_t)el * n_scales * rows_per_expert + sk;
+          for (int jx = lane; jx < n_scales; jx += 32) base[(size_t)jx * rows_per_expert] = sc_stage[jx];
+        } else {
+          const int n_words = n_scales / 4;  // H % 512 == 0 (checked on the host)
+          uint32_t* base = reinterpret_cast<uint32_t*>(c.heap[r] + a.recv_scales_off) + (size_t)el * n_words * rows_per_expert + sk;
+          for (int jx = lane; jx < n_words; jx += 32) {
+            uint32_t wv = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) wv |= ((__float_as_uint(sc_stage[jx * 4 + b]) >> 23) & 0xffu) << (8 * b);
+            base[(size_t)jx * rows_per_expert] = wv;
+          }
+        }
+        if (bulk_ok && lane == 0) tma_store_1d(dx, s_stage, (uint32_t)row_bytes);
+        if (!bulk_ok)
+          for (size_t i = lane * 4; i < row_bytes; i += 128) *reinterpret_cast<uint32_t*>(dx + i) = *reinterpret_cast<const uint32_t*>(s_stage + i);
+      } else if (bulk_ok) {
         if (lane == 0) {
           tma_store_1d(dx, s_stage, (uint32_t)row_bytes);
           if (scale_bytes) tma_store_1d(ds, s_stage + row_bytes, (uint32_t)scale_bytes);
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
     __syncwarp();
   }
   if (lane == 0) tma_store_wait<0>();  // all bulk stores of this thread are globally visible before the barrier
-  sync_barrier(c, s);
+  sync_signal(c, s);  // "everything I send has been written"
+  if (a.phase == EP_LL_FULL) sync_wait(c, s, blockIdx.x == 0 ? a.wait_stats : nullptr);  // else: the hook's kernel waits
   sync_end(s);
 }
 
@@ -191,7 +205,14 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
                                                                const __grid_constant__ EpLLCombineArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   BlockSync s = sync_begin(c, kDomEpLL, blockIdx.x);
-  sync_barrier(c, s);
+  // pull design: the "send" of a combine is just announcing that my expert outputs are in place; the
+  // receive half waits for every peer's announcement, pulls the rows and reduces
+  if (a.phase != EP_LL_RECV) sync_signal(c, s);
+  if (a.phase == EP_LL_SEND) {
+    sync_end(s);
+    return;
+  }
+  sync_wait(c, s, blockIdx.x == 0 ? a.wait_stats : nullptr);
   const size_t row_bytes = (size_t)a.H * 2;
   const int chunks = (int)(row_bytes / 16);
   // One CTA per token, its warps split the row: the K source rows of a token live in K different
@@ -231,7 +252,7 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
       for (int k = 0; k < 9; ++k) {
         if (rowp[k] && valid) {
           float f[8];
-          ll_bf16x8_to_float(v[k], f);
+          bf16x8_to_float(v[k], f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] += wk[k] * f[q];
         }
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
         const float wkk = __shfl_sync(0xffffffffu, w, k);
         if (pk >= 0 && valid) {
           float f[8];
-          ll_bf16x8_to_float(ld_nc_v4(c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes + (size_t)i * 16), f);
+          bf16x8_to_float(ld_nc_v4(c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes + (size_t)i * 16), f);
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] += wkk * f[q];
         }
@@ -255,6 +276,26 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
   }
   sync_barrier_relaxed(c, s);
   sync_end(s);
+}
+
+// Copies only the occupied rows of every local expert (contiguous: rows [0, recv_count[e]) of expert e).
+__global__ void __launch_bounds__(256) ep_ll_pack_kernel(const EpLLPackArgs a) {
+  const size_t row16 = (size_t)a.H * 2 / 16;
+  for (int e = blockIdx.y; e < a.E_local; e += gridDim.y) {
+    int rows = 0;
+    for (int q = 0; q < a.R; ++q) rows += (int)(a.layout_range[(size_t)e * a.R + q] & 0xffffffffll);
+    const size_t n16 = (size_t)rows * row16;
+    const uint4* src = reinterpret_cast<const uint4*>(a.src) + (size_t)e * a.R * a.M * row16;
+    uint4* dst = reinterpret_cast<uint4*>(a.dst) + (size_t)e * a.R * a.M * row16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = ld_nc_v4(src + i);
+  }
+}
+
+cudaError_t launch_ep_ll_pack(const EpLLPackArgs& a, cudaStream_t st) {
+  dim3 grid(16, (unsigned)(a.E_local < 1 ? 1 : (a.E_local > 64 ? 64 : a.E_local)));
+  UB_LAUNCH((ep_ll_pack_kernel), grid, 256, 0, st, a);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ launchers

@@ -113,33 +113,45 @@ __global__ void __launch_bounds__(kDispThreads, 1) ep_dispatch_tma_kernel(const 
   if (!sh.abort_flag) {
     if (warp == 0) {
       // ------------------------------------------------------------------ loader
+      // Slots are fetched for kGroup tokens at once (lane = token-in-group * kMaxRanks + rank) and one group
+      // ahead, so the L2 latency of that lookup never sits between two bulk loads.
       uint32_t j = 0;
-      for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
-        int my = -1;
-        if (lane < R) {
-          if (a.cached) {
-            my = a.send_slot[(size_t)t * R + lane];
-          } else {
-            const int p = a.token_pos[(size_t)t * R + lane];
-            my = p >= 0 ? sh.base[lane] + p : -1;
-            a.send_slot[(size_t)t * R + lane] = my;
+      constexpr int kGroup = 32 / kMaxRanks;
+      const int gq = lane / kMaxRanks, gr = lane % kMaxRanks;
+      auto fetch = [&](int t0) -> int {  // slot of token t0 + gq * grid at rank gr (-1: none / out of range)
+        const long long t = (long long)t0 + (long long)gq * gridDim.x;
+        if (t >= a.T || gr >= R) return -1;
+        if (a.cached) return a.send_slot[(size_t)t * R + gr];
+        const int p = a.token_pos[(size_t)t * R + gr];
+        const int v = p >= 0 ? sh.base[gr] + p : -1;
+        a.send_slot[(size_t)t * R + gr] = v;
+        return v;
+      };
+      int nxt = fetch(blockIdx.x);
+      for (int t0 = blockIdx.x; t0 < a.T; t0 += kGroup * gridDim.x) {
+        const int cur = nxt;
+        nxt = fetch(t0 + kGroup * (int)gridDim.x);
+#pragma unroll
+        for (int q = 0; q < kGroup; ++q) {
+          const int t = t0 + q * (int)gridDim.x;
+          if (t >= a.T) break;  // warp-uniform
+          const int my = __shfl_sync(0xffffffffu, cur, q * kMaxRanks + (lane % kMaxRanks));
+          if (__ballot_sync(0xffffffffu, my >= 0) == 0) continue;
+          const int st = j % IN_ST;
+          mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1);
+          EpItemMeta& m = sh.meta[j % kMetaRing];
+          if (lane < kMaxRanks) m.slot[lane] = my;
+          if (lane == 0) m.t = t;
+          __syncwarp();
+          if (lane == 0) {
+            unsigned char* dst = in_base + (size_t)st * in_stage_bytes;
+            mbar_expect_tx(&sh.in_full[st], in_row + ((MODE == EP_X_FP8_SCALED) ? sc_bytes : 0u));
+            tma_load_1d(dst, reinterpret_cast<const char*>(a.x) + (size_t)t * in_row, in_row, &sh.in_full[st]);
+            if constexpr (MODE == EP_X_FP8_SCALED)
+              tma_load_1d(dst + in_row, a.x_scales + (size_t)t * n_scales, sc_bytes, &sh.in_full[st]);
           }
+          ++j;
         }
-        if (__ballot_sync(0xffffffffu, my >= 0) == 0) continue;
-        const int st = j % IN_ST;
-        mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1);
-        EpItemMeta& m = sh.meta[j % kMetaRing];
-        if (lane < kMaxRanks) m.slot[lane] = my;
-        if (lane == 0) m.t = t;
-        __syncwarp();
-        if (lane == 0) {
-          unsigned char* dst = in_base + (size_t)st * in_stage_bytes;
-          mbar_expect_tx(&sh.in_full[st], in_row + ((MODE == EP_X_FP8_SCALED) ? sc_bytes : 0u));
-          tma_load_1d(dst, reinterpret_cast<const char*>(a.x) + (size_t)t * in_row, in_row, &sh.in_full[st]);
-          if constexpr (MODE == EP_X_FP8_SCALED)
-            tma_load_1d(dst + in_row, a.x_scales + (size_t)t * n_scales, sc_bytes, &sh.in_full[st]);
-        }
-        ++j;
       }
       const int st = j % IN_ST;
       mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1);
@@ -320,24 +332,40 @@ __global__ void __launch_bounds__(kCombThreads, 1) ep_combine_tma_kernel(const _
     // -------------------------------------------------------------------- loader
     fence_proxy_async_all();
     uint32_t j = 0;
-    for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
-      const int my = lane < R ? a.send_slot[(size_t)t * R + lane] : -1;
-      const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
-      const char* src = my >= 0 ? c.heap[lane] + a.x_off + (size_t)my * row_bytes : nullptr;
-      for (int sl = 0; sl < n_slices; ++sl, ++j) {
-        const int st = j % ST;
-        mbar_wait(&empty[st], ((j / ST) & 1) ^ 1);
-        const uint32_t bytes = min(SB, row_bytes - (uint32_t)sl * SB);
-        if (lane == 0) {
-          EpItemMeta& m = sh.meta[j % kMetaRing];
-          m.t = t;
-          m.aux = sl;
-          m.mask = mask;
-          mbar_expect_tx(&full[st], (uint32_t)__popc(mask) * bytes);
+    // slots of kGroup tokens per lookup, one group ahead (see the dispatch loader)
+    constexpr int kGroup = 32 / kMaxRanks;
+    const int gq = lane / kMaxRanks, gr = lane % kMaxRanks;
+    auto fetch = [&](int t0) -> int {
+      const long long t = (long long)t0 + (long long)gq * gridDim.x;
+      return (t < a.T && gr < R) ? a.send_slot[(size_t)t * R + gr] : -1;
+    };
+    int nxt = fetch(blockIdx.x);
+    for (int t0 = blockIdx.x; t0 < a.T; t0 += kGroup * gridDim.x) {
+      const int cur = nxt;
+      nxt = fetch(t0 + kGroup * (int)gridDim.x);
+#pragma unroll
+      for (int q = 0; q < kGroup; ++q) {
+        const int t = t0 + q * (int)gridDim.x;
+        if (t >= a.T) break;  // warp-uniform
+        int my = __shfl_sync(0xffffffffu, cur, q * kMaxRanks + (lane % kMaxRanks));
+        if (lane >= kMaxRanks) my = -1;
+        const unsigned mask = __ballot_sync(0xffffffffu, my >= 0);
+        const char* src = my >= 0 ? c.heap[lane] + a.x_off + (size_t)my * row_bytes : nullptr;
+        for (int sl = 0; sl < n_slices; ++sl, ++j) {
+          const int st = j % ST;
+          mbar_wait(&empty[st], ((j / ST) & 1) ^ 1);
+          const uint32_t bytes = min(SB, row_bytes - (uint32_t)sl * SB);
+          if (lane == 0) {
+            EpItemMeta& m = sh.meta[j % kMetaRing];
+            m.t = t;
+            m.aux = sl;
+            m.mask = mask;
+            mbar_expect_tx(&full[st], (uint32_t)__popc(mask) * bytes);
+          }
+          __syncwarp();
+          if (my >= 0)
+            tma_load_1d(stages + (size_t)st * stage_bytes + (size_t)lane * src_stride, src + (size_t)sl * SB, bytes, &full[st]);
         }
-        __syncwarp();
-        if (my >= 0)
-          tma_load_1d(stages + (size_t)st * stage_bytes + (size_t)lane * src_stride, src + (size_t)sl * SB, bytes, &full[st]);
       }
     }
     const int st = j % ST;

@@ -100,7 +100,18 @@ struct EpLLDispatchArgs {
   int64_t* send_pos;         // local [T, K]: (dst rank << 32) | row index at the destination, -1 if unused
   int32_t* recv_count;       // local [E_local]
   int64_t* layout_range;     // local [E_local, R]: (begin << 32) | count
+  int phase;                 // EpLLPhase: full kernel, send half, or receive half (return_recv_hook)
+  int scale_layout;          // EpLLScaleLayout of recv_scales
+  long long* wait_stats;     // optional [R] int64: cycles spent waiting for each source rank (DeepEP dispatch_wait_recv_cost_stats)
 };
+
+// Hook split of the low-latency kernels (reference: LOW_LATENCY_SEND_PHASE / _RECV_PHASE, ep/src/internode_ll.cu:115,458-464)
+enum EpLLPhase : int { EP_LL_FULL = 0, EP_LL_SEND = 1, EP_LL_RECV = 2 };
+// recv_scales formats.  DeepEP hands out the column-major ("transposed", TMA-friendly for the grouped GEMM) forms:
+//   ROW_MAJOR  float  [E_local][R*M][H/128]
+//   COL_MAJOR  float  [E_local][H/128][R*M]            (viewed as [E_local][R*M][H/128] with strides (.., 1, R*M))
+//   COL_UE8M0  int32  [E_local][H/512][R*M], each word packs the exponent bytes of 4 consecutive 128-channel groups
+enum EpLLScaleLayout : int { EP_LL_SCALES_ROW_MAJOR = 0, EP_LL_SCALES_COL_MAJOR = 1, EP_LL_SCALES_COL_UE8M0 = 2 };
 
 struct EpLLCombineArgs {
   uint64_t x_off;             // symmetric [E_local][R*M][H] bf16 expert outputs
@@ -108,6 +119,17 @@ struct EpLLCombineArgs {
   const float* topk_weights;  // [T, K]
   void* out;                  // [T, H] bf16
   int T, H, K;
+  int phase;                  // EpLLPhase
+  long long* wait_stats;      // optional [R] int64 (DeepEP combine_wait_recv_cost_stats)
+};
+
+// Packs a user tensor of expert outputs into the symmetric combine buffer: only the rows that hold tokens
+// (layout_range) are copied, not the worst-case [E_local][R*M] block.
+struct EpLLPackArgs {
+  const void* src;              // [E_local][R*M][H] bf16, any device memory
+  void* dst;                    // same shape inside the symmetric heap
+  const int64_t* layout_range;  // [E_local, R]
+  int E_local, R, M, H;
 };
 
 }  // namespace ub

@@ -293,6 +293,36 @@ __device__ __forceinline__ void sync_barrier(const DevComm& c, BlockSync& s) {
   __syncthreads();
   trace_event(c, TR_BARRIER_EXIT, s.e - 1);
 }
+// Split barrier for kernels that are cut into a SEND and a RECV launch (EP low-latency hooks):
+// sync_signal publishes "my writes up to here are done" to every peer without waiting, sync_wait (same
+// block index, possibly a later kernel) blocks until every peer has published the same epoch.
+// sync_signal does NOT advance the epoch: the kernel that signals stores epoch e-1 in sync_end, the
+// kernel that waits re-reads it, waits for e and stores e.
+__device__ __forceinline__ void sync_signal(const DevComm& c, BlockSync& s) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < c.nranks && t != c.rank) {
+    uint32_t* peer_slot = reinterpret_cast<uint32_t*>(c.heap[t] + s.sig_block_off) + c.rank;
+    st_release_sys(peer_slot, s.e);
+  }
+}
+// wait_cycles (optional, [nranks] int64): clock cycles thread t spent waiting for rank t are added to it
+__device__ __forceinline__ void sync_wait(const DevComm& c, BlockSync& s, long long* wait_cycles = nullptr) {
+  const int t = threadIdx.x;
+  trace_event(c, TR_BARRIER_ENTER, s.e);
+  if (t < c.nranks && t != c.rank) {
+    const long long t0 = clock64();
+    SpinGuard g(c.timeout_ns);
+    while ((int32_t)(ld_acquire_sys(s.my_sig + t) - s.e) < 0) {
+      if (g.expired()) comm_abort(c, 3, t, (int)s.e);
+    }
+    if (wait_cycles) atomicAdd(reinterpret_cast<unsigned long long*>(wait_cycles + t), (unsigned long long)(clock64() - t0));
+  }
+  s.e += 1;
+  __syncthreads();
+  trace_event(c, TR_BARRIER_EXIT, s.e - 1);
+}
+
 // Barrier that also all-gathers two 64-bit words per rank (e.g. the heap offsets of this
 // rank's input / output buffers) between same-index blocks.  `sh` is shared memory for
 // 2 * kMaxRanks words: sh[r] = word0 of rank r, sh[kMaxRanks + r] = word1 of rank r.

@@ -447,16 +447,42 @@ bool Engine::test(Request* r, size_t* bytes, int* err) {
   return true;
 }
 
-bool Engine::wait(Request* r, size_t* bytes, int timeout_ms) {
+Engine::WaitResult Engine::wait3(Request* r, size_t* bytes, int timeout_ms) {
   const uint64_t t0 = now_ns();
   int err = 0;
   uint32_t spins = 0;
   while (!test(r, bytes, &err)) {
-    if (timeout_ms >= 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull) return false;  // request stays live
+    if (timeout_ms >= 0 && now_ns() - t0 > (uint64_t)timeout_ms * 1000000ull) return WAIT_TIMEOUT;  // request stays live
     if (++spins > 2000) std::this_thread::sleep_for(std::chrono::microseconds(20));
     else std::this_thread::yield();
   }
-  return err == 0;
+  return err == 0 ? WAIT_OK : WAIT_ERROR;
+}
+
+void Engine::abort_flow(uint32_t flow) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    Cmd c;
+    c.op = 5;
+    c.flow = flow;
+    cmds_.push_back(c);
+  }
+  wake();
+}
+
+bool Engine::cancel(Request* r, int grace_ms) {
+  abort_flow(r->flow);  // fail_flow() completes every request of the flow, `r` included
+  size_t bytes = 0;
+  return wait3(r, &bytes, grace_ms) != WAIT_TIMEOUT;
+}
+
+bool Engine::wait(Request* r, size_t* bytes, int timeout_ms) {
+  const WaitResult w = wait3(r, bytes, timeout_ms);
+  if (w == WAIT_TIMEOUT) {
+    if (!cancel(r)) UB_WARN("net: engine thread did not release a timed-out request (leaked, buffer must stay valid)");
+    return false;
+  }
+  return w == WAIT_OK;
 }
 
 EngineStats Engine::stats() const {
@@ -522,9 +548,12 @@ void Engine::run() {
             f->fin_pending = true;
             f->state.store(FL_CLOSING);
             f->last_progress_ns = now_ns();
+            f->close_start_ns = f->last_progress_ns;
           } else if (st == FL_SYN_SENT) {
             fail_flow(*f, nullptr);
           }
+        } else if (c.op == 5) {
+          if (f->state.load() != FL_ERROR) fail_flow(*f, "aborted by the application (request timed out)");
         }
       }
     }
@@ -1366,7 +1395,9 @@ bool Engine::tx_pump(Flow& f, uint64_t now) {
                                    : 1000000000ull;
   if (f.tx_cursor < f.txq.size() && f.snd_una == f.snd_nxt && now - std::max(f.last_progress_ns, f.last_tx_ns) > probe_after) {
     f.rtr_pending = true;
-    f.last_progress_ns = now;
+    // a closing flow must not look alive because of its own probes (and their ACKs): its give-up timer keeps running
+    if (f.state.load(std::memory_order_relaxed) != FL_CLOSING) f.last_progress_ns = now;
+    else f.last_tx_ns = now;
   }
   f.credit_starved = false;
   if (f.rtr_pending && can_send_new(f, now)) {
@@ -1487,7 +1518,9 @@ void Engine::timers(uint64_t now) {
       const bool drained = f.fin_sent && f.snd_una == f.snd_nxt && f.txq.empty();
       // a peer that has already closed its side may be gone by now: do not wait long for it to acknowledge our FIN
       const uint64_t give_up = f.peer_fin.load(std::memory_order_relaxed) ? 100000000ull : kLingerNs;
-      if (drained || now - f.last_progress_ns > give_up) {
+      // hard bound: probes parked behind the peer's RTR are acknowledged and would refresh last_progress_ns forever
+      const bool overdue = f.close_start_ns && now - f.close_start_ns > 4 * kLingerNs;
+      if (drained || overdue || now - f.last_progress_ns > give_up) {
         for (auto& q : f.rxq)
           if (q.req) complete(q.req, 0, 3), q.req = nullptr;
         f.rxq.clear();
@@ -1496,6 +1529,7 @@ void Engine::timers(uint64_t now) {
             if (m->req) complete(m->req, 0, 1), m->req = nullptr;
         f.state.store(FL_CLOSED);
         f.last_progress_ns = now;
+        if (cfg_.cc == CC_EQDS) pacer_.remove(f.id);
       }
     }
   }
@@ -1536,6 +1570,7 @@ void Engine::fail_flow(Flow& f, const char* why) {
   for (auto& p : f.ring) p = TxPkt();
   f.rexmit_q.clear();
   f.snd_una = f.snd_nxt;
+  if (cfg_.cc == CC_EQDS) pacer_.remove(f.id);
   if (why && f.peer_flow && f.npaths > 0 && !stop_.load()) send_rst(0, f.peer_addr[0], f.peer_flow);
 }
 

@@ -120,7 +120,18 @@ class Engine {
   Request* recv_async(uint32_t flow, void* data, size_t capacity);
   // true when complete (the request is freed); *bytes = message size; *err != 0 on failure
   bool test(Request* r, size_t* bytes, int* err);
-  bool wait(Request* r, size_t* bytes, int timeout_ms = -1);  // false on timeout / error (request freed)
+  // Blocking completion.  Returns WAIT_OK / WAIT_ERROR (request freed in both cases) or WAIT_TIMEOUT: the
+  // request is then still owned by the engine, which may yet read / write the caller's buffer -- call
+  // cancel() before that buffer goes away (or keep waiting).
+  enum WaitResult : int { WAIT_OK = 0, WAIT_ERROR = 1, WAIT_TIMEOUT = 2 };
+  WaitResult wait3(Request* r, size_t* bytes, int timeout_ms = -1);
+  // Fails the request's flow (every request queued on it completes with an error, the peer gets a reset) and
+  // waits until the engine has dropped `r`; afterwards neither the request nor its buffer is referenced.
+  // Returns false if the engine thread did not react within grace_ms (the request is then leaked, not freed).
+  bool cancel(Request* r, int grace_ms = 5000);
+  void abort_flow(uint32_t flow);  // application-initiated failure of one flow
+  // wait3 + cancel on timeout: true only on success; the request is always released and the buffer is free again
+  bool wait(Request* r, size_t* bytes, int timeout_ms = -1);
 
   void set_drop_prob(double p) { drop_prob_.store(p); }
   // fault injection: hold back a fraction of the outgoing datagrams for `delay_us` (reordering inside and across paths)
@@ -193,6 +204,7 @@ class Engine {
     uint64_t rto_ns = 0;
     int rto_count = 0;
     uint64_t last_progress_ns = 0;
+    uint64_t close_start_ns = 0;  // when the flow entered FL_CLOSING: hard bound of the close handshake
     uint64_t last_tx_ns = 0;   // last (re)transmission of a DATA packet
     bool tlp_fired = false;    // one tail-loss probe per quiet period
     uint32_t peer_dup_seen = 0;   // last AckBody.dup_cum

@@ -399,8 +399,24 @@ bool Endpoint::reg(const void* ptr, size_t size, uint64_t* mr_id) {
 }
 
 bool Endpoint::dereg(uint64_t mr_id) {
-  std::lock_guard<std::mutex> g(mu_);
-  return mrs_.erase(mr_id) > 0;
+  MR gone;
+  bool still_covered = false;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = mrs_.find(mr_id);
+    if (it == mrs_.end()) return false;
+    gone = it->second;
+    mrs_.erase(it);
+    for (auto& kv : mrs_)  // another registration of the same window keeps it reachable
+      if (kv.second.ptr == gone.ptr && kv.second.size >= gone.size) still_covered = true;
+  }
+  if (!still_covered) {
+    // revoke the window: a peer on another host must not write into memory that was deregistered (and maybe freed)
+    std::lock_guard<std::mutex> g(exp_mu_);
+    for (auto it = exposed_.begin(); it != exposed_.end();)
+      it = (it->first == (uint64_t)gone.ptr && it->second <= gone.size) ? exposed_.erase(it) : std::next(it);
+  }
+  return true;
 }
 
 void Endpoint::expose(uint64_t addr, uint64_t size) {

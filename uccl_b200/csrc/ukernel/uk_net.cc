@@ -75,6 +75,11 @@ void UkNetComm::receiver() {
         progress = true;
         if (s->hdr.bytes == 0) {
           arrived_[(size_t)p * cfg_.nlanes + s->hdr.lane].fetch_add(1, std::memory_order_release);
+        } else if (s->hdr.off + s->hdr.bytes > ext_[(int)s->hdr.buf] || s->hdr.off + s->hdr.bytes < s->hdr.off) {
+          // a count mismatch between ranks or a corrupt header must not overwrite memory outside this op's buffers
+          rx_error_.store(102);
+          s->parked = true;
+          s->hdr.op_seq = 0xffffffffu;
         } else {
           s->pay_req = eng_->recv_async(s->flow, base((int)s->hdr.buf) + s->hdr.off, s->hdr.bytes);
         }
@@ -105,6 +110,16 @@ void UkNetComm::run(const UkPlan& plan, char* in, char* out, int dtype, int op) 
   bases_[0] = in;
   bases_[1] = out;
   bases_[2] = scratch_.data();
+  ext_[0] = ext_[1] = ext_[2] = 0;
+  // plans are symmetric across ranks: whatever a peer may send me lies inside the ranges my own plan touches
+  for (const UkPlanOp& o : plan.ops) {
+    if (o.kind == UkPlanOp::Recv) continue;
+    for (const UkRef* r : {&o.dst, &o.src, &o.src2}) {
+      if (o.kind != UkPlanOp::Reduce && r == &o.src2) continue;
+      const int b = (int)r->buf;
+      if (b >= 0 && b <= 2) ext_[b] = std::max<uint64_t>(ext_[b], r->off + o.bytes);
+    }
+  }
   const uint32_t seq = cur_seq_.load(std::memory_order_relaxed) + 1;
   cur_seq_.store(seq, std::memory_order_release);  // parked headers of this op may now be served
   ++stats_.ops;
@@ -127,6 +142,18 @@ void UkNetComm::run(const UkPlan& plan, char* in, char* out, int dtype, int op) 
   size_t done = 0;
   const uint64_t t0 = now_ns();
   uint32_t idle = 0;
+  // the engine holds pointers into `outs` (headers) and the user buffers until a send completes: if this call
+  // unwinds, fail those flows and wait until the engine has let go before the vector is destroyed
+  struct Reaper {
+    net::Engine* eng;
+    std::vector<Out>& outs;
+    ~Reaper() {
+      for (Out& s : outs) {
+        if (s.h) eng->cancel(s.h);
+        if (s.p) eng->cancel(s.p);
+      }
+    }
+  } reaper{eng_.get(), outs};
   while (done < nops) {
     bool progress = false;
     for (size_t i = 0; i < nops; ++i) {

@@ -71,6 +71,7 @@ class UkNetComm {
   std::atomic<bool> stop_{false};
   std::atomic<uint32_t> cur_seq_{0};
   std::atomic<int> rx_error_{0};
+  uint64_t ext_[3] = {0, 0, 0};  // bytes of each buffer that a Recv of the op in flight may write (header bounds check)
   char* bases_[3] = {nullptr, nullptr, nullptr};  // In / Out / Scratch of the op in flight (valid while cur_seq_ names it)
   std::vector<char> scratch_;
   std::vector<std::atomic<uint64_t>> arrived_;  // [peer * nlanes + lane]

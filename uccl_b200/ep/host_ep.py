@@ -19,21 +19,6 @@ from ..parallel.comm import Communicator
 from .utils import EventOverlap, per_token_cast_to_fp8
 
 
-_LOGFMT_WARNED = False
-
-
-def _warn_logfmt_once() -> None:
-    """``use_logfmt=True`` is accepted for DeepEP API compatibility: the combine payload stays bf16 (a superset of
-    LogFMT-10 in precision); over NVLink the 10-bit encoding would cost more SM time than the bytes it saves."""
-    global _LOGFMT_WARNED
-    if not _LOGFMT_WARNED:
-        _LOGFMT_WARNED = True
-        import warnings
-
-        warnings.warn("uccl_b200.ep: use_logfmt=True is a no-op (payload stays bf16)", stacklevel=3)
-
-
-
 def _a2av(comm: Communicator, send: torch.Tensor, send_rows: List[int], recv_rows: List[int]) -> torch.Tensor:
     """all_to_all_v of whole rows of a 2-D (or 1-D) tensor; rows are ordered by destination rank."""
     width = torch.Size(send.shape[1:]).numel()  # 1 for 1-D tensors
@@ -291,7 +276,8 @@ class HostBuffer:
     def low_latency_dispatch(self, x: torch.Tensor, topk_idx: torch.Tensor, num_max_dispatch_tokens_per_rank: int,
                              num_experts: int, cumulative_local_expert_recv_stats=None,
                              dispatch_wait_recv_cost_stats=None, use_fp8: bool = True, round_scale: bool = False,
-                             use_ue8m0: bool = False, async_finish: bool = False, return_recv_hook: bool = False):
+                             use_ue8m0: bool = False, async_finish: bool = False, return_recv_hook: bool = False,
+                             scales_row_major: bool = False):
         R, me = self.group_size, self.rank
         T, H = x.shape
         K = topk_idx.size(1)
@@ -351,6 +337,9 @@ class HostBuffer:
 
                 assert round_scale and H % 512 == 0
                 scales = pack_ue8m0(torch.where(scales > 0, scales, torch.ones_like(scales)))
+            elif not scales_row_major:
+                # same strides as the CUDA path / DeepEP: column-major in the last two dims
+                scales = scales.transpose(1, 2).contiguous().transpose(1, 2)
             out_x = (recv_x.view(torch.float8_e4m3fn), scales)
         else:
             out_x = recv_x
@@ -378,7 +367,7 @@ class HostBuffer:
                             return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                             combine_wait_recv_cost_stats=None):
         if use_logfmt:
-            _warn_logfmt_once()
+            raise NotImplementedError("uccl_b200.ep: use_logfmt=True is not supported (the combine payload is bf16)")
         R, me = self.group_size, self.rank
         src_info, layout_range, M, H, E, _, send_pos, allc = handle
         e_per = E // R

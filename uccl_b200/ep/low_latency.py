@@ -4,9 +4,15 @@ Reference: ep/bench/buffer.py:263-566 (python), ep/src/internode_ll.cu (kernels)
 Return conventions follow DeepEP:
   dispatch -> (recv_x | (recv_x_fp8, scales), recv_count, handle, event, hook)
      recv_x  [E_local, R*M, H]; tokens of expert e are rows [0, recv_count[e]) (packed)
-     scales  [E_local, R*M, H/128] float32 (row-major here; DeepEP hands out a transposed view)
+     scales  [E_local, R*M, H/128] float32, column-major in the last two dims like DeepEP's transposed view
+             (ep/src/internode_ll.cu:608-636); ``use_ue8m0`` -> [E_local, R*M, H/512] int32 (4 exponent bytes
+             per word), packed by the kernel; ``scales_row_major=True`` keeps plain row-major fp32
      handle  (src_info, layout_range, M, H, E, buffer_idx, send_pos)
   combine  -> (combined_x [T, H] bf16, event, hook)
+``return_recv_hook=True`` splits each call into a SEND kernel (launched now; it returns as soon as everything is
+on the wire) and a RECV kernel launched by ``hook()`` -- between the two no SM is held, which is what lets two
+micro-batches overlap (ep/src/uccl_ep.cc:1269-1283).  Outputs are valid after ``hook()``.
+Kernels run on the CURRENT stream (as in DeepEP's low-latency path): no stream hop on the decode critical path.
 Only two LL buffers exist (as in DeepEP): at most two dispatch results may be alive.
 """
 from __future__ import annotations
@@ -16,21 +22,6 @@ from typing import Optional
 import torch
 
 from .utils import EventHandle, EventOverlap
-
-
-_LOGFMT_WARNED = False
-
-
-def _warn_logfmt_once() -> None:
-    """``use_logfmt=True`` is accepted for DeepEP API compatibility: the combine payload stays bf16 (a superset of
-    LogFMT-10 in precision); over NVLink the 10-bit encoding would cost more SM time than the bytes it saves."""
-    global _LOGFMT_WARNED
-    if not _LOGFMT_WARNED:
-        _LOGFMT_WARNED = True
-        import warnings
-
-        warnings.warn("uccl_b200.ep: use_logfmt=True is a no-op (payload stays bf16)", stacklevel=3)
-
 
 
 def ll_size_hint(num_max_dispatch_tokens_per_rank: int, hidden: int, num_ranks: int, num_experts: int) -> int:
@@ -47,6 +38,7 @@ class LowLatencyRuntime:
         if self.num_bytes > 0:
             self.rt.ll_init(self.num_bytes)
         self._state = {}
+        self._pending = None  # receive hook of a SEND-phase call that has not run yet
 
     def _ensure(self, M, H, E):
         need = ll_size_hint(M, H, self.buf.group_size, E)
@@ -65,17 +57,26 @@ class LowLatencyRuntime:
         # dispatch: one warp per token (8 warps / CTA); combine: one CTA per token
         return self.buf._sms(Config(128 if combine else min(self.buf.num_sms * 2, 64)))
 
+    def _finish_pending(self):
+        """A hook that was never called would leave the next kernel waiting on a stale epoch: run it now."""
+        h, self._pending = getattr(self, "_pending", None), None
+        if h is not None:
+            h()
+
     def dispatch(self, x: torch.Tensor, topk_idx: torch.Tensor, num_max_dispatch_tokens_per_rank: int,
                  num_experts: int, cumulative_local_expert_recv_stats: Optional[torch.Tensor] = None,
                  dispatch_wait_recv_cost_stats: Optional[torch.Tensor] = None, use_fp8: bool = True,
                  round_scale: bool = False, use_ue8m0: bool = False, async_finish: bool = False,
-                 return_recv_hook: bool = False):
+                 return_recv_hook: bool = False, scales_row_major: bool = False):
         if use_ue8m0:
             assert use_fp8 and round_scale, "use_ue8m0 needs use_fp8=True and round_scale=True (power-of-two scales)"
             assert x.size(1) % 512 == 0, "use_ue8m0 packs four per-128-channel scales per word: hidden % 512 == 0"
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
         assert topk_idx.dtype == torch.int64 and topk_idx.is_contiguous()
+        assert not (async_finish and return_recv_hook), "async_finish and return_recv_hook are mutually exclusive"
+        self._finish_pending()
         b = self.buf
+        C = b._C
         R = b.group_size
         T, H = x.shape
         K = topk_idx.size(1)
@@ -83,31 +84,56 @@ class LowLatencyRuntime:
         E_local = E // R
         self._ensure(M, H, E)
         dev = b.device
-        compute = b._enter(None, False)
-        with torch.cuda.stream(b.comm_stream):
-            recv_count = torch.empty(E_local, dtype=torch.int32, device=dev)
-            layout_range = torch.empty((E_local, R), dtype=torch.int64, device=dev)
-            send_pos = torch.empty((T, K), dtype=torch.int64, device=dev)
-            rx, rs, rsrc, cx, idx = self.rt.ll_dispatch(x.data_ptr(), topk_idx.data_ptr(), T, H, K, E, M, use_fp8,
-                                                        round_scale, recv_count.data_ptr(), layout_range.data_ptr(),
-                                                        send_pos.data_ptr(), self._sms(), b.comm_stream.cuda_stream)
-            if cumulative_local_expert_recv_stats is not None:
-                cumulative_local_expert_recv_stats.add_(recv_count)
+        st = torch.cuda.current_stream(dev)
+        if dispatch_wait_recv_cost_stats is not None:
+            assert dispatch_wait_recv_cost_stats.dtype == torch.int64 and dispatch_wait_recv_cost_stats.numel() >= R
+        stats_ptr = dispatch_wait_recv_cost_stats.data_ptr() if dispatch_wait_recv_cost_stats is not None else 0
+        layout = C.EP_LL_SCALES_ROW_MAJOR
+        if use_fp8 and not scales_row_major:
+            layout = C.EP_LL_SCALES_COL_UE8M0 if use_ue8m0 else C.EP_LL_SCALES_COL_MAJOR
+        recv_count = torch.empty(E_local, dtype=torch.int32, device=dev)
+        layout_range = torch.empty((E_local, R), dtype=torch.int64, device=dev)
+        send_pos = torch.empty((T, K), dtype=torch.int64, device=dev)
+        sms = self._sms()
+        rx, rs, rsrc, cx, idx = self.rt.ll_dispatch(
+            x.data_ptr(), topk_idx.data_ptr(), T, H, K, E, M, use_fp8, round_scale, recv_count.data_ptr(),
+            layout_range.data_ptr(), send_pos.data_ptr(), sms, st.cuda_stream,
+            phase=C.EP_LL_SEND if return_recv_hook else C.EP_LL_FULL, scale_layout=layout, wait_stats=stats_ptr)
         rows = R * M
         if use_fp8:
-            scales = b._view(rs, (E_local, rows, H // 128), torch.float32)
-            if use_ue8m0:
-                from .utils import pack_ue8m0
+            if layout == C.EP_LL_SCALES_ROW_MAJOR:
+                scales = b._view(rs, (E_local, rows, H // 128), torch.float32)
+                if use_ue8m0:
+                    from .utils import pack_ue8m0
 
-                with torch.cuda.stream(b.comm_stream):
-                    scales = pack_ue8m0(scales)  # [E_local, rows, H // 512] int32, column-major last two dims
+                    scales = pack_ue8m0(scales)  # torch post-pass (row-major request only)
+            elif layout == C.EP_LL_SCALES_COL_MAJOR:
+                scales = b._view(rs, (E_local, H // 128, rows), torch.float32).transpose(1, 2)
+            else:
+                scales = b._view(rs, (E_local, H // 512, rows), torch.int32).transpose(1, 2)
             recv_x = (b._view(rx, (E_local, rows, H), torch.float8_e4m3fn), scales)
         else:
             recv_x = b._view(rx, (E_local, rows, H), torch.bfloat16)
         src_info = b._view(rsrc, (E_local, rows), torch.int32)
         handle = (src_info, layout_range, M, H, E, idx, send_pos)
-        ev = b._exit(compute, async_finish, (x, topk_idx, recv_count, layout_range, send_pos))
-        hook = (lambda: None) if return_recv_hook else None
+
+        def finish():
+            if cumulative_local_expert_recv_stats is not None:
+                cumulative_local_expert_recv_stats.add_(recv_count)
+
+        hook = None
+        if return_recv_hook:
+            def hook():
+                if self._pending is hook:
+                    self._pending = None
+                    with torch.cuda.device(dev):
+                        self.rt.ll_dispatch_recv(sms, stats_ptr, torch.cuda.current_stream(dev).cuda_stream)
+                        finish()
+
+            self._pending = hook
+        else:
+            finish()
+        ev = EventOverlap(EventHandle(st)) if async_finish else EventOverlap()
         return recv_x, recv_count, handle, ev, hook
 
     def next_combine_buffer(self, handle):
@@ -121,18 +147,44 @@ class LowLatencyRuntime:
                 return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                 combine_wait_recv_cost_stats: Optional[torch.Tensor] = None):
         if use_logfmt:
-            _warn_logfmt_once()
+            # DeepEP's LogFMT-10 shrinks the combine payload on RDMA links (ep/src/internode_ll.cu:735-1204); this
+            # path pulls bf16 rows over NVLink and has no encoded form -- fail loudly instead of silently ignoring it
+            raise NotImplementedError("uccl_b200.ep: use_logfmt=True is not supported (the NVLink combine moves bf16)")
+        assert not (async_finish and return_recv_hook), "async_finish and return_recv_hook are mutually exclusive"
+        self._finish_pending()
         src_info, layout_range, M, H, E, idx, send_pos = handle
         b = self.buf
+        C = b._C
+        R = b.group_size
+        dev = b.device
         assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[-1] == H
         assert topk_weights.dtype == torch.float32 and topk_weights.is_contiguous()
         T, K = topk_weights.shape
-        compute = b._enter(None, False)
-        with torch.cuda.stream(b.comm_stream):
-            if out is None:
-                out = torch.empty((T, H), dtype=torch.bfloat16, device=b.device)
-            self.rt.ll_combine(x.data_ptr(), idx, topk_weights.data_ptr(), send_pos.data_ptr(), out.data_ptr(), T, H,
-                               K, E, M, self._sms(combine=True), b.comm_stream.cuda_stream)
-        ev = b._exit(compute, async_finish, (x, topk_weights, send_pos, out))
-        hook = (lambda: None) if return_recv_hook else None
+        st = torch.cuda.current_stream(dev)
+        if out is None:
+            out = torch.empty((T, H), dtype=torch.bfloat16, device=dev)
+        if combine_wait_recv_cost_stats is not None:
+            assert combine_wait_recv_cost_stats.dtype == torch.int64 and combine_wait_recv_cost_stats.numel() >= R
+        stats_ptr = combine_wait_recv_cost_stats.data_ptr() if combine_wait_recv_cost_stats is not None else 0
+        sms = self._sms(combine=True)
+        args = (x.data_ptr(), idx, topk_weights.data_ptr(), send_pos.data_ptr(), out.data_ptr(), T, H, K, E, M, sms)
+        hook = None
+        if return_recv_hook:
+            # SEND half: (pack the expert outputs into the symmetric buffer and) announce that they are in place
+            self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_SEND, layout_range=layout_range.data_ptr(),
+                               wait_stats=stats_ptr)
+
+            def hook():
+                if self._pending is hook:
+                    self._pending = None
+                    with torch.cuda.device(dev):
+                        self.rt.ll_combine(*args, torch.cuda.current_stream(dev).cuda_stream, phase=C.EP_LL_RECV,
+                                           layout_range=layout_range.data_ptr(), wait_stats=stats_ptr)
+
+            hook._keep = (x, topk_weights, send_pos, out, layout_range)  # alive until the receive half has run
+            self._pending = hook
+        else:
+            self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_FULL, layout_range=layout_range.data_ptr(),
+                               wait_stats=stats_ptr)
+        ev = EventOverlap(EventHandle(st)) if async_finish else EventOverlap()
         return out, ev, hook

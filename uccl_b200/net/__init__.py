@@ -284,13 +284,21 @@ class NetCommunicator:
     def send(self, t: torch.Tensor, dst: int) -> None:
         self.isend(t, dst).wait(self.timeout_ms)
 
+    def _wait_recv(self, w, t: torch.Tensor) -> None:
+        """A receive of a collective must fill its buffer exactly: a short message means the two ends disagree
+        on the message size, and silently continuing would reduce stale bytes."""
+        got = w.wait(self.timeout_ms)
+        want = t.numel() * t.element_size()
+        if got != want:
+            raise RuntimeError(f"net: received {got} bytes into a {want}-byte receive (size mismatch between ranks)")
+
     def recv(self, t: torch.Tensor, src: int) -> None:
-        self.irecv(t, src).wait(self.timeout_ms)
+        self._wait_recv(self.irecv(t, src), t)
 
     def _sendrecv(self, s: torch.Tensor, dst: int, r: torch.Tensor, src: int) -> None:
         wr = self.irecv(r, src)
         ws = self.isend(s, dst)
-        wr.wait(self.timeout_ms)
+        self._wait_recv(wr, r)
         ws.wait(self.timeout_ms)
 
     # ---- collectives (in place on contiguous host tensors)
@@ -341,7 +349,9 @@ class NetCommunicator:
             rbuf = tmp[: r_seg.numel()]
             # channels: the segment travels as K slices posted back to back; slice k is reduced while slices
             # > k are still on the wire, so only 1/K of the reduction time is exposed per step
-            K = max(1, min(8, (r_seg.numel() * es) // self.chunk_bytes))
+            # K must be the same on both ends of every step: derive it from numel // n, not from the local
+            # segment (segments differ by one element when numel % n != 0 and could straddle a chunk multiple)
+            K = max(1, min(8, ((flat.numel() // n) * es) // self.chunk_bytes))
             if K == 1:
                 self._sendrecv(s_seg, nxt, rbuf, prv)
                 red(r_seg, rbuf)
@@ -351,7 +361,7 @@ class NetCommunicator:
             rws = [self.irecv(rbuf[lo:hi], prv) for lo, hi in rb]
             sws = [self.isend(s_seg[lo:hi], nxt) for lo, hi in sb]
             for (lo, hi), w in zip(rb, rws):
-                w.wait(self.timeout_ms)
+                self._wait_recv(w, rbuf[lo:hi])
                 red(r_seg[lo:hi], rbuf[lo:hi])
             for w in sws:
                 w.wait(self.timeout_ms)
