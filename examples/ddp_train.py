@@ -26,6 +26,10 @@ def main(argv=None):
     p.add_argument("--steps", type=int, default=30)
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--cpu", action="store_true", help="CPU reference backend (host fabric); for smoke-testing the flow")
+    p.add_argument("--sym-buckets", action="store_true",
+                   help="uccl_b200 / hook: allocate DDP's gradient buckets in the symmetric heap (zero-copy NVLS "
+                        "all-reduce instead of the staged kernels) -- the torch-side analogue of ncclMemAlloc")
+    p.add_argument("--json", default=None, help="append the result as one JSON line to this file (rank 0)")
     args = p.parse_args(argv)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -46,12 +50,22 @@ def main(argv=None):
 
     small = args.model == "resnet18"
     model = (resnet18(10, True) if small else resnet50(1000, False)).to(dev).to(memory_format=torch.channels_last)
-    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local] if args.backend != "uccl_b200" else None)
+    import contextlib
+
+    comm = None
     if args.backend == "hook":
         from uccl_b200 import Communicator
-        from uccl_b200.parallel.ddp import allreduce_hook
 
         comm = Communicator.from_torch_dist(heap_bytes=2 << 30)
+    elif args.backend == "uccl_b200" and not args.cpu:
+        comm = uccl_b200.parallel.pg.default_communicator()
+    pool_ctx = comm.use_mem_pool() if (args.sym_buckets and comm is not None) else contextlib.nullcontext()
+    with pool_ctx:  # DDP allocates its flat gradient buckets in the constructor
+        ddp = torch.nn.parallel.DistributedDataParallel(
+            model, device_ids=[local] if args.backend != "uccl_b200" else None, gradient_as_bucket_view=True)
+    if args.backend == "hook":
+        from uccl_b200.parallel.ddp import allreduce_hook
+
         ddp.register_comm_hook(None, allreduce_hook(comm))
     opt = torch.optim.SGD(ddp.parameters(), lr=0.05, momentum=0.9)
     res = 32 if small else 224
@@ -71,8 +85,16 @@ def main(argv=None):
     sync()
     dt = time.perf_counter() - t0
     if rank == 0:
-        print(f"[{args.backend}] {args.model} x{world}: {args.steps * args.batch * world / dt:.0f} img/s, "
+        tag = args.backend + ("+sym" if args.sym_buckets else "")
+        print(f"[{tag}] {args.model} x{world}: {args.steps * args.batch * world / dt:.0f} img/s, "
               f"{dt / args.steps * 1e3:.2f} ms/step, final loss {loss.item():.4f}")
+        if args.json:
+            import json
+
+            with open(args.json, "a") as f:
+                f.write(json.dumps({"backend": tag, "model": args.model, "gpus": world, "batch_per_gpu": args.batch,
+                                    "img_per_s": args.steps * args.batch * world / dt,
+                                    "ms_per_step": dt / args.steps * 1e3, "loss": float(loss.item())}) + "\n")
     dist.destroy_process_group()
     return float(loss.item())
 

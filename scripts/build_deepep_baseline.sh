@@ -27,7 +27,7 @@ EOF
 # Its setup.py compiles with -rdc=true but only adds the device-link step on the NVSHMEM branch, so the
 # module it links has an unresolved __cudaRegisterLinkedBinary_*; do the device link here (objects untouched).
 T="$(echo build/temp.*/csrc)"
-nvcc -dlink -Xcompiler -fPIC -gencode=arch=compute_100,code=sm_100 "$T"/kernels/intranode.o "$T"/kernels/layout.o \
+nvcc -dlink -Xcompiler -fPIC -Xnvlink -ignore-host-info -gencode=arch=compute_100,code=sm_100 "$T"/kernels/intranode.o "$T"/kernels/layout.o \
   "$T"/kernels/runtime.o -o "$T"/dlink.o
 TORCH_LIB="$(python -c 'import torch, os; print(os.path.join(os.path.dirname(torch.__file__), "lib"))')"
 g++ -shared "$T"/deep_ep.o "$T"/kernels/intranode.o "$T"/kernels/layout.o "$T"/kernels/runtime.o "$T"/dlink.o \

@@ -407,7 +407,7 @@ EpBuffer::LLOut EpBuffer::ll_dispatch(uintptr_t x, uintptr_t topk_idx, int T, in
   a.phase = phase;
   a.scale_layout = use_fp8 ? scale_layout : EP_LL_SCALES_ROW_MAJOR;
   a.wait_stats = (long long*)wait_stats;
-  int grid = std::max(1, std::min(num_sms, kEpLLMaxBlocks));
+  int grid = std::max(1, std::min(std::min(num_sms, kEpLLMaxBlocks), std::max(T, 1)));  // one CTA per token
   cudaError_t e = launch_ep_ll_dispatch(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep ll_dispatch launch failed: %s", cudaGetErrorString(e));
   ++launches_;

@@ -121,6 +121,6 @@ cudaError_t launch_ep_combine_tma(const DevComm& c, const EpCombineArgs& a, int 
 cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_combine(const DevComm& c, const EpLLCombineArgs& a, int grid, cudaStream_t st);
 cudaError_t launch_ep_ll_pack(const EpLLPackArgs& a, cudaStream_t st);
-constexpr int kEpLLMaxBlocks = 64;
+constexpr int kEpLLMaxBlocks = 128;  // one CTA per token of a decode batch
 
 }  // namespace ub

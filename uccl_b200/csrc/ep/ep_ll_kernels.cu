@@ -21,7 +21,7 @@
 
 namespace ub {
 
-constexpr int kLLWarps = 8;  // 256 threads: one staged token per warp (<= 14.6 KB each at H = 7168 bf16)
+constexpr int kLLWarps = 8;  // 256 threads cooperate on one token (one staged row per CTA)
 
 __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const __grid_constant__ DevComm c,
                                                                           const __grid_constant__ EpLLDispatchArgs a) {
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
   const size_t stage_stride = (row_bytes + scale_bytes + 127) / 128 * 128;
   int* s_cnt = reinterpret_cast<int*>(ll_smem);         // [E] my histogram, then reused
   int* s_begin = s_cnt + E;                             // [E] packed offset of my tokens at each expert
-  unsigned char* s_stage = ll_smem + (((size_t)2 * E * 4 + 127) / 128 * 128) + (size_t)warp * stage_stride;
+  (void)stage_stride;
 
   BlockSync s = sync_begin(c, kDomEpLL, blockIdx.x);
   if (a.phase == EP_LL_RECV) {
@@ -90,70 +90,97 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
   }
   __syncthreads();
 
-  // ---- phase B: one warp per token
-  const int warps_total = gridDim.x * kLLWarps;
-  for (int t = blockIdx.x * kLLWarps + warp; t < a.T; t += warps_total) {
+  // ---- phase B: one CTA per token.  A decode batch has about as many tokens as the GPU has SMs, so the
+  // latency of ONE token is what matters: all 256 threads load the row at once (every 16-byte load of the
+  // row is in flight together), the slot claims (global atomics) overlap those loads, and the K copies are
+  // issued by K different warps.
+  int* s_slot = s_begin + E;             // [kEpMaxTopk] claimed slot per top-k entry
+  int* s_exp = s_slot + kEpMaxTopk;      // [kEpMaxTopk] expert id per top-k entry (-1: none)
+  unsigned char* stage = ll_smem + ((((size_t)2 * E + 2 * kEpMaxTopk) * 4 + 127) / 128 * 128);
+  const bool bulk_ok = (row_bytes % 16 == 0) && (scale_bytes % 16 == 0);
+  const size_t rows_per_expert = (size_t)R * a.M;
+  const float* sc_stage = reinterpret_cast<const float*>(stage + row_bytes);
+  bool pending = false;  // this lane has bulk stores in flight that still read the stage
+  for (int t = blockIdx.x; t < a.T; t += gridDim.x) {
     const char* src = reinterpret_cast<const char*>(a.x) + (size_t)t * a.H * 2;
-    // stage the row (cast or copy) + scales in shared memory
+    // slot claim first: its latency hides behind the row loads
+    if (tid < a.K) {
+      const long long e = a.topk_idx[(size_t)t * a.K + tid];
+      int slot = -1;
+      if (e >= 0 && e < E) slot = s_begin[(int)e] + atomicAdd(&a.send_cnt[a.parity * E + (int)e], 1);
+      s_exp[tid] = (e >= 0 && e < E) ? (int)e : -1;
+      s_slot[tid] = slot;
+      int64_t pos = -1;
+      if (slot >= 0) pos = ((int64_t)((int)e / E_local) << 32) | (int64_t)((size_t)((int)e % E_local) * R * a.M + slot);
+      a.send_pos[(size_t)t * a.K + tid] = pos;
+    }
     if (a.use_fp8) {
-      const int units = a.H / 16;
-      float* sc = reinterpret_cast<float*>(s_stage + row_bytes);
-      for (int u0 = 0; u0 < units; u0 += 32) {
-        const int u = u0 + lane;
-        const bool valid = u < units;
-        uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
-        if (valid) {
-          v0 = ld_nc_v4(src + (size_t)u * 32);
-          v1 = ld_nc_v4(src + (size_t)u * 32 + 16);
-        }
-        float f[16];
-        bf16x8_to_float(v0, *reinterpret_cast<float(*)[8]>(&f[0]));
-        bf16x8_to_float(v1, *reinterpret_cast<float(*)[8]>(&f[8]));
-        float amax = 0.f;
+      const int units = a.H / 16;  // 16 channels per unit; 8 consecutive lanes share a 128-channel scale
+      float* sc = reinterpret_cast<float*>(stage + row_bytes);
+      constexpr int U = 2;  // units per thread per pass: 512 units (H = 8192) in one pass
+      for (int ub = 0; ub < units; ub += U * kLLWarps * 32) {
+        uint4 v0[U], v1[U];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
-        float scale, scale_inv;
-        fp8_group_scale(amax, a.round_scale, scale, scale_inv);
-        if (valid) {
-          uint4 o;
-          o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
-          o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
-          o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
-          o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
-          *reinterpret_cast<uint4*>(s_stage + (size_t)u * 16) = o;
-          if ((lane & 7) == 0) sc[u >> 3] = scale_inv;
+        for (int j = 0; j < U; ++j) {
+          const int u = ub + j * kLLWarps * 32 + tid;
+          v0[j] = make_uint4(0, 0, 0, 0);
+          v1[j] = v0[j];
+          if (u < units) {
+            v0[j] = ld_nc_v4(src + (size_t)u * 32);
+            v1[j] = ld_nc_v4(src + (size_t)u * 32 + 16);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int u = ub + j * kLLWarps * 32 + tid;
+          if (ub + j * kLLWarps * 32 + (tid & ~31) >= units) break;  // warp-uniform
+          const bool valid = u < units;
+          float f[16];
+          bf16x8_to_float(v0[j], *reinterpret_cast<float(*)[8]>(&f[0]));
+          bf16x8_to_float(v1[j], *reinterpret_cast<float(*)[8]>(&f[8]));
+          float amax = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(f[i]));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+          float scale, scale_inv;
+          fp8_group_scale(amax, a.round_scale, scale, scale_inv);
+          if (valid) {
+            uint4 o;
+            o.x = pack4_e4m3(f[0] * scale, f[1] * scale, f[2] * scale, f[3] * scale);
+            o.y = pack4_e4m3(f[4] * scale, f[5] * scale, f[6] * scale, f[7] * scale);
+            o.z = pack4_e4m3(f[8] * scale, f[9] * scale, f[10] * scale, f[11] * scale);
+            o.w = pack4_e4m3(f[12] * scale, f[13] * scale, f[14] * scale, f[15] * scale);
+            *reinterpret_cast<uint4*>(stage + (size_t)u * 16) = o;
+            if ((lane & 7) == 0) sc[u >> 3] = scale_inv;
+          }
         }
       }
     } else {
       const int chunks = (int)(row_bytes / 16);
-      for (int i = lane; i < chunks; i += 32) *reinterpret_cast<uint4*>(s_stage + (size_t)i * 16) = ld_nc_v4(src + (size_t)i * 16);
+      constexpr int U = 4;
+      for (int cb = 0; cb < chunks; cb += U * kLLWarps * 32) {
+        uint4 v[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int i = cb + j * kLLWarps * 32 + tid;
+          if (i < chunks) v[j] = ld_nc_v4(src + (size_t)i * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const int i = cb + j * kLLWarps * 32 + tid;
+          if (i < chunks) *reinterpret_cast<uint4*>(stage + (size_t)i * 16) = v[j];
+        }
+      }
     }
     fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy (async) proxy
-    __syncwarp();
-    // claim slots + issue the stores, one top-k entry per lane for the bookkeeping
-    long long e = -1;
-    if (lane < a.K) e = a.topk_idx[(size_t)t * a.K + lane];
-    int slot = -1;
-    if (e >= 0 && e < E) slot = s_begin[(int)e] + atomicAdd(&a.send_cnt[a.parity * E + (int)e], 1);
-    if (lane < a.K) {
-      int64_t pos = -1;
-      if (slot >= 0) {
-        const int r = (int)e / E_local, el = (int)e % E_local;
-        pos = ((int64_t)r << 32) | (int64_t)((size_t)el * R * a.M + slot);
-      }
-      a.send_pos[(size_t)t * a.K + lane] = pos;
-    }
-    const bool bulk_ok = (row_bytes % 16 == 0) && (scale_bytes % 16 == 0);
-    const size_t rows_per_expert = (size_t)R * a.M;
-    const float* sc_stage = reinterpret_cast<const float*>(s_stage + row_bytes);
-    for (int k = 0; k < a.K; ++k) {
-      const long long ek = __shfl_sync(0xffffffffu, e, k);
-      const int sk = __shfl_sync(0xffffffffu, slot, k);
+    __syncthreads();
+    // one top-k entry per warp (round robin): bulk-store the staged row (+ scales) to its packed position
+    for (int k = warp; k < a.K; k += kLLWarps) {
+      const int ek = s_exp[k], sk = s_slot[k];
       if (ek < 0 || sk < 0) continue;
-      const int r = (int)ek / E_local, el = (int)ek % E_local;
+      const int r = ek / E_local, el = ek % E_local;
       const size_t row = (size_t)el * R * a.M + sk;
       char* dx = c.heap[r] + a.recv_x_off + row * row_bytes;
       char* ds = c.heap[r] + a.recv_scales_off + row * scale_bytes;
@@ -172,28 +199,31 @@ __global__ void __launch_bounds__(kLLWarps * 32, 1) ep_ll_dispatch_kernel(const 
             base[(size_t)jx * rows_per_expert] = wv;
           }
         }
-        if (bulk_ok && lane == 0) tma_store_1d(dx, s_stage, (uint32_t)row_bytes);
+        if (bulk_ok && lane == 0) tma_store_1d(dx, stage, (uint32_t)row_bytes);
         if (!bulk_ok)
-          for (size_t i = lane * 4; i < row_bytes; i += 128) *reinterpret_cast<uint32_t*>(dx + i) = *reinterpret_cast<const uint32_t*>(s_stage + i);
+          for (size_t i = lane * 4; i < row_bytes; i += 128) *reinterpret_cast<uint32_t*>(dx + i) = *reinterpret_cast<const uint32_t*>(stage + i);
       } else if (bulk_ok) {
         if (lane == 0) {
-          tma_store_1d(dx, s_stage, (uint32_t)row_bytes);
-          if (scale_bytes) tma_store_1d(ds, s_stage + row_bytes, (uint32_t)scale_bytes);
+          tma_store_1d(dx, stage, (uint32_t)row_bytes);
+          if (scale_bytes) tma_store_1d(ds, stage + row_bytes, (uint32_t)scale_bytes);
         }
       } else {
         for (size_t i = lane * 4; i < row_bytes + scale_bytes; i += 128) {
-          const uint32_t w = *reinterpret_cast<const uint32_t*>(s_stage + i);
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + i);
           if (i < row_bytes) *reinterpret_cast<uint32_t*>(dx + i) = w;
           else *reinterpret_cast<uint32_t*>(ds + (i - row_bytes)) = w;
         }
       }
-      if (lane == 0) reinterpret_cast<int*>(c.heap[r] + a.recv_src_off)[row] = t;
+      if (lane == 0) {
+        reinterpret_cast<int*>(c.heap[r] + a.recv_src_off)[row] = t;
+        pending = true;
+      }
     }
-    if (lane == 0) {
+    if (lane == 0 && pending) {
       tma_store_commit();
-      tma_store_wait_read<0>();  // the staging row may be overwritten by the next token
+      if (t + (int)gridDim.x < a.T) tma_store_wait_read<0>();  // the stage is overwritten by the next token
     }
-    __syncwarp();
+    __syncthreads();
   }
   if (lane == 0) tma_store_wait<0>();  // all bulk stores of this thread are globally visible before the barrier
   sync_signal(c, s);  // "everything I send has been written"
@@ -238,40 +268,51 @@ __global__ void __launch_bounds__(512, 1) ep_ll_combine_kernel(const __grid_cons
         rowp[k] = c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes;
     }
     char* out = reinterpret_cast<char*>(a.out) + (size_t)t * row_bytes;
-    for (int i0 = warp * 32; i0 < chunks; i0 += nwarps * 32) {  // warp-uniform trip count
-      const int i = i0 + lane;
-      const bool valid = i < chunks;
-      uint4 v[9];
+    // two 16-byte chunks per thread per pass: with 512 threads a 14 KB row is covered by ONE pass, so all
+    // K x 2 loads of a thread are in flight together (one NVLink round trip per token instead of two)
+    constexpr int PF = 2;
+    for (int i0 = warp * 32; i0 < chunks; i0 += PF * nwarps * 32) {  // warp-uniform trip count
+      uint4 v[PF][9];
+      bool valid[PF];
 #pragma unroll
-      for (int k = 0; k < 9; ++k)
-        if (rowp[k] && valid) v[k] = ld_nc_v4(rowp[k] + (size_t)i * 16);
-      float acc[8];
+      for (int j = 0; j < PF; ++j) {
+        const int i = i0 + j * nwarps * 32 + lane;
+        valid[j] = i < chunks;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        if (rowp[k] && valid) {
-          float f[8];
-          bf16x8_to_float(v[k], f);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += wk[k] * f[q];
-        }
+        for (int k = 0; k < 9; ++k)
+          if (rowp[k] && valid[j]) v[j][k] = ld_nc_v4(rowp[k] + (size_t)i * 16);
       }
-      for (int k = 9; k < a.K; ++k) {  // DeepEP's LL limit is 9; keep larger top-k correct
-        const long long pk = __shfl_sync(0xffffffffu, pos, k);
-        const float wkk = __shfl_sync(0xffffffffu, w, k);
-        if (pk >= 0 && valid) {
-          float f[8];
-          bf16x8_to_float(ld_nc_v4(c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes + (size_t)i * 16), f);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[q] += wkk * f[q];
+      for (int j = 0; j < PF; ++j) {
+        const int i = i0 + j * nwarps * 32 + lane;
+        float acc[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          if (rowp[k] && valid[j]) {
+            float f[8];
+            bf16x8_to_float(v[j][k], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] += wk[k] * f[q];
+          }
         }
-      }
-      uint4 o;
-      __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+        for (int k = 9; k < a.K; ++k) {  // DeepEP's LL limit is 9; keep larger top-k correct
+          const long long pk = __shfl_sync(0xffffffffu, pos, k);
+          const float wkk = __shfl_sync(0xffffffffu, w, k);
+          if (pk >= 0 && valid[j]) {
+            float f[8];
+            bf16x8_to_float(ld_nc_v4(c.heap[(int)(pk >> 32)] + a.x_off + (size_t)(pk & 0xffffffffll) * row_bytes + (size_t)i * 16), f);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
-      if (valid) st_v4(out + (size_t)i * 16, o);
+            for (int q = 0; q < 8; ++q) acc[q] += wkk * f[q];
+          }
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) oh[q] = __floats2bfloat162_rn(acc[2 * q], acc[2 * q + 1]);
+        if (valid[j]) st_v4(out + (size_t)i * 16, o);
+      }
     }
   }
   sync_barrier_relaxed(c, s);
@@ -303,7 +344,7 @@ cudaError_t launch_ep_ll_dispatch(const DevComm& c, const EpLLDispatchArgs& a, i
   const size_t row_bytes = a.use_fp8 ? (size_t)a.H : (size_t)a.H * 2;
   const size_t scale_bytes = a.use_fp8 ? (size_t)(a.H / 128) * 4 : 0;
   const size_t stage_stride = (row_bytes + scale_bytes + 127) / 128 * 128;
-  const size_t smem = (((size_t)2 * a.E * 4 + 127) / 128 * 128) + (size_t)kLLWarps * stage_stride;
+  const size_t smem = ((((size_t)2 * a.E + 2 * kEpMaxTopk) * 4 + 127) / 128 * 128) + stage_stride;  // one staged row per CTA
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);

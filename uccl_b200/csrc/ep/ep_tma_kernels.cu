@@ -34,6 +34,7 @@ constexpr int kTmaMaxStages = 12;
 constexpr int kMetaRing = 32;    // > in_stages + out_stages + kStoreLag + 2
 constexpr int kStoreLag = 2;     // bulk-store groups a storer lane leaves in flight before recycling a stage
 constexpr int kWorkWarps = 14;   // cast warps (dispatch) / reduce warps (combine): 448 threads = 7168 B of 16-byte chunks
+constexpr int kCastGroupWarps = kWorkWarps / 2;  // dispatch: two cast groups work on alternate tokens
 constexpr int kDispThreads = (kWorkWarps + 3) * 32;  // loader | cast x14 | storer | metadata
 constexpr int kCombThreads = (kWorkWarps + 2) * 32;  // loader | reduce x14 | weights
 constexpr uint32_t kSliceBytes = kWorkWarps * 32 * 16;  // combine: bytes of one row slice handled per pipeline item
@@ -70,6 +71,12 @@ __device__ __forceinline__ void sts128(void* p, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
 }
+// One lane polls the mbarrier, the warp then reconverges: 32x fewer try_wait operations on the shared-memory
+// pipe that the TMA engine and the cast / reduce warps are using at the same time.
+__device__ __forceinline__ void warp_mbar_wait(uint64_t* bar, uint32_t phase, int lane) {
+  if (lane == 0) mbar_wait(bar, phase);
+  __syncwarp();
+}
 // orders earlier generic-proxy accesses of this thread with later async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -100,10 +107,10 @@ __global__ void __launch_bounds__(kDispThreads, 1) ep_dispatch_tma_kernel(const 
     sh.recv_total = 0;
     for (int i = 0; i < IN_ST; ++i) {
       mbar_init(&sh.in_full[i], 1);
-      mbar_init(&sh.in_empty[i], MODE == EP_X_FUSED_FP8 ? kWorkWarps : 1);
+      mbar_init(&sh.in_empty[i], MODE == EP_X_FUSED_FP8 ? kCastGroupWarps : 1);
     }
     for (int i = 0; i < OUT_ST; ++i) {
-      mbar_init(&sh.out_full[i], kWorkWarps);
+      mbar_init(&sh.out_full[i], kCastGroupWarps);
       mbar_init(&sh.out_empty[i], 1);
     }
     mbar_fence_init();
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) ep_dispatch_tma_kernel(const 
           const int my = __shfl_sync(0xffffffffu, cur, q * kMaxRanks + (lane % kMaxRanks));
           if (__ballot_sync(0xffffffffu, my >= 0) == 0) continue;
           const int st = j % IN_ST;
-          mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1);
+          warp_mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1, lane);
           EpItemMeta& m = sh.meta[j % kMetaRing];
           if (lane < kMaxRanks) m.slot[lane] = my;
           if (lane == 0) m.t = t;
@@ -153,29 +160,38 @@ __global__ void __launch_bounds__(kDispThreads, 1) ep_dispatch_tma_kernel(const 
           ++j;
         }
       }
-      const int st = j % IN_ST;
-      mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1);
-      if (lane == 0) {
-        sh.meta[j % kMetaRing].t = -1;  // end of stream
-        mbar_arrive(&sh.in_full[st]);
+      // end of stream: one sentinel per consumer chain (fused mode: one for each of the two cast groups; the
+      // first one, aux = 0, is forwarded to the storer)
+      for (int sidx = 0; sidx < (MODE == EP_X_FUSED_FP8 ? 2 : 1); ++sidx, ++j) {
+        const int st = j % IN_ST;
+        warp_mbar_wait(&sh.in_empty[st], ((j / IN_ST) & 1) ^ 1, lane);
+        if (lane == 0) {
+          sh.meta[j % kMetaRing].t = -1;
+          sh.meta[j % kMetaRing].aux = sidx;
+          mbar_arrive(&sh.in_full[st]);
+        }
       }
     } else if (warp <= kWorkWarps) {
       // ------------------------------------------------------------- cast warps (fused fp8 only)
       if constexpr (MODE == EP_X_FUSED_FP8) {
-        const int ctid = tid - 32;
+        // two groups of 7 warps take alternate tokens: while one group waits for its row / its output stage
+        // or runs the amax -> scale -> cast dependency chain, the other one is converting the next token
+        const int grp = (warp - 1) / kCastGroupWarps;
+        const int gtid = tid - 32 - grp * kCastGroupWarps * 32;
         const int units = a.H / 16;  // 16 channels (32 B in, 16 B out) per thread-iteration
-        for (uint32_t j = 0;; ++j) {
+        for (uint32_t j = grp;; j += 2) {
           const int st = j % IN_ST;
-          mbar_wait(&sh.in_full[st], (j / IN_ST) & 1);
+          warp_mbar_wait(&sh.in_full[st], (j / IN_ST) & 1, lane);
           const int t = sh.meta[j % kMetaRing].t;
+          if (t < 0 && sh.meta[j % kMetaRing].aux != 0) break;  // the other group forwards the end of stream
           const int o = j % OUT_ST;
-          mbar_wait(&sh.out_empty[o], ((j / OUT_ST) & 1) ^ 1);
+          warp_mbar_wait(&sh.out_empty[o], ((j / OUT_ST) & 1) ^ 1, lane);
           if (t >= 0) {
             const unsigned char* src = in_base + (size_t)st * in_stage_bytes;
             unsigned char* dst = out_base + (size_t)o * out_stage_bytes;
             float* dsc = reinterpret_cast<float*>(dst + out_row);
-            for (int ub = 0; ub < units; ub += kWorkWarps * 32) {
-              const int u = ub + ctid;
+            for (int ub = 0; ub < units; ub += kCastGroupWarps * 32) {
+              const int u = ub + gtid;
               const bool valid = u < units;
               uint4 v0 = make_uint4(0, 0, 0, 0), v1 = v0;
               if (valid) {
@@ -225,7 +241,7 @@ __global__ void __launch_bounds__(kDispThreads, 1) ep_dispatch_tma_kernel(const 
       char* my_heap = lane < R ? c.heap[lane] : nullptr;
       for (uint32_t j = 0;; ++j) {
         const int st = j % NST;
-        mbar_wait(&full[st], (j / NST) & 1);
+        warp_mbar_wait(&full[st], (j / NST) & 1, lane);
         const EpItemMeta& m = sh.meta[j % kMetaRing];
         if (m.t < 0) break;
         const int my = lane < kMaxRanks ? m.slot[lane] : -1;
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(kCombThreads, 1) ep_combine_tma_kernel(const _
         const char* src = my >= 0 ? c.heap[lane] + a.x_off + (size_t)my * row_bytes : nullptr;
         for (int sl = 0; sl < n_slices; ++sl, ++j) {
           const int st = j % ST;
-          mbar_wait(&empty[st], ((j / ST) & 1) ^ 1);
+          warp_mbar_wait(&empty[st], ((j / ST) & 1) ^ 1, lane);
           const uint32_t bytes = min(SB, row_bytes - (uint32_t)sl * SB);
           if (lane == 0) {
             EpItemMeta& m = sh.meta[j % kMetaRing];
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(kCombThreads, 1) ep_combine_tma_kernel(const _
       }
     }
     const int st = j % ST;
-    mbar_wait(&empty[st], ((j / ST) & 1) ^ 1);
+    warp_mbar_wait(&empty[st], ((j / ST) & 1) ^ 1, lane);
     if (lane == 0) {
       sh.meta[j % kMetaRing].t = -1;
       mbar_arrive(&full[st]);
@@ -379,7 +395,7 @@ __global__ void __launch_bounds__(kCombThreads, 1) ep_combine_tma_kernel(const _
     const uint32_t off = (uint32_t)(tid - 32) * 16u;
     for (uint32_t j = 0;; ++j) {
       const int st = j % ST;
-      mbar_wait(&full[st], (j / ST) & 1);
+      warp_mbar_wait(&full[st], (j / ST) & 1, lane);
       const EpItemMeta& m = sh.meta[j % kMetaRing];
       const int t = m.t;
       if (t < 0) break;

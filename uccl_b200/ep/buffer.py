@@ -218,6 +218,15 @@ class Buffer:
         R = self.group_size
         dev = self.device
         compute = self._enter(previous_event, allocate_on_comm_stream)
+        if T == 0:  # a rank without tokens in this step: nothing to scan
+            with torch.cuda.stream(self.comm_stream):
+                num_tokens_per_rank = torch.zeros(R, dtype=torch.int32, device=dev)
+                num_tokens_per_expert = torch.zeros(num_experts, dtype=torch.int32, device=dev)
+                is_token_in_rank = torch.zeros((1, R), dtype=torch.bool, device=dev)[:0]
+                token_pos = torch.zeros((1, R), dtype=torch.int32, device=dev)[:0]
+            self._layout_cache = (is_token_in_rank.data_ptr(), 0, token_pos)
+            ev = self._exit(compute, async_finish, (num_tokens_per_rank, num_tokens_per_expert))
+            return num_tokens_per_rank, None, num_tokens_per_expert, is_token_in_rank, ev
         with torch.cuda.stream(self.comm_stream):
             num_tokens_per_rank = torch.empty(R, dtype=torch.int32, device=dev)
             num_tokens_per_expert = torch.empty(num_experts, dtype=torch.int32, device=dev)
@@ -287,10 +296,11 @@ class Buffer:
             if cache is not None and cache[0] == is_token_in_rank.data_ptr() and cache[1] == T:
                 token_pos = cache[2]
             else:
-                token_pos = torch.empty((T, R), dtype=torch.int32, device=dev)
-                self.runtime.layout(0, T, 0, 0, 0, 0, is_token_in_rank.data_ptr(), token_pos.data_ptr(),
-                                    self.comm_stream.cuda_stream)
-            send_slot = torch.empty((T, R), dtype=torch.int32, device=dev)
+                token_pos = torch.empty((max(T, 1), R), dtype=torch.int32, device=dev)[:T]
+                if T > 0:
+                    self.runtime.layout(0, T, 0, 0, 0, 0, is_token_in_rank.data_ptr(), token_pos.data_ptr(),
+                                        self.comm_stream.cuda_stream)
+            send_slot = torch.empty((max(T, 1), R), dtype=torch.int32, device=dev)[:T]  # non-null even for T == 0
             rank_prefix = torch.empty((R, R), dtype=torch.int32, device=dev)
             o = self.runtime.dispatch(
                 x_data.data_ptr(), x_scales.data_ptr() if x_scales is not None else 0,

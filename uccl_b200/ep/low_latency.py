@@ -54,14 +54,14 @@ class LowLatencyRuntime:
     def _sms(self, combine: bool = False):
         from .buffer import Config
 
-        # dispatch: one warp per token (8 warps / CTA); combine: one CTA per token
-        return self.buf._sms(Config(128 if combine else min(self.buf.num_sms * 2, 64)))
+        # one CTA per token in both directions (a decode batch has about as many tokens as the GPU has SMs)
+        return self.buf._sms(Config(128))
 
     def _finish_pending(self):
         """A hook that was never called would leave the next kernel waiting on a stale epoch: run it now."""
-        h, self._pending = getattr(self, "_pending", None), None
+        h = self._pending
         if h is not None:
-            h()
+            h()  # clears self._pending itself
 
     def dispatch(self, x: torch.Tensor, topk_idx: torch.Tensor, num_max_dispatch_tokens_per_rank: int,
                  num_experts: int, cumulative_local_expert_recv_stats: Optional[torch.Tensor] = None,

@@ -11,15 +11,38 @@ import torch
 from .comm import Communicator
 
 
+def _comm_stream(comm: Communicator):
+    cs = getattr(comm, "_ddp_stream", None)
+    if cs is None and not comm.is_host:
+        cs = comm._ddp_stream = torch.cuda.Stream(device=comm.device, priority=-1)
+    return cs
+
+
+def _run_async(comm: Communicator, buf: torch.Tensor, fn):
+    """Runs `fn()` on the communicator's high-priority side stream (ordered after the current stream) and
+    returns a CUDA-aware future: DDP chains its bucket callbacks on it, so the reduction of one bucket
+    overlaps the backward pass that fills the next."""
+    cs = _comm_stream(comm)
+    if cs is None:  # host backend: synchronous
+        fn()
+        fut = torch.futures.Future()
+        fut.set_result(buf)
+        return fut
+    cs.wait_stream(torch.cuda.current_stream(comm.device))
+    fut = torch.futures.Future(devices=[comm.device])
+    with torch.cuda.stream(cs):
+        fn()
+        buf.record_stream(cs)
+        fut.set_result(buf)
+    return fut
+
+
 def allreduce_hook(comm: Communicator):
     """``model.register_comm_hook(None, allreduce_hook(comm))``"""
 
     def hook(state, bucket):
         buf = bucket.buffer()
-        comm.all_reduce(buf, "avg")
-        fut = torch.futures.Future()
-        fut.set_result(buf)
-        return fut
+        return _run_async(comm, buf, lambda: comm.all_reduce(buf, "avg"))
 
     return hook
 
@@ -30,14 +53,15 @@ def bf16_compress_hook(comm: Communicator):
 
     def hook(state, bucket):
         buf = bucket.buffer()
-        if buf.dtype != torch.float32 or (buf.numel() * 2) % 16 != 0:
-            comm.all_reduce(buf, "avg")
-        else:
-            low = buf.to(torch.bfloat16)
-            comm.all_reduce(low, "avg", out=buf)
-        fut = torch.futures.Future()
-        fut.set_result(buf)
-        return fut
+
+        def run():
+            if buf.dtype != torch.float32 or (buf.numel() * 2) % 16 != 0:
+                comm.all_reduce(buf, "avg")
+            else:
+                low = buf.to(torch.bfloat16)
+                comm.all_reduce(low, "avg", out=buf)
+
+        return _run_async(comm, buf, run)
 
     return hook
 

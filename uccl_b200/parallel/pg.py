@@ -68,6 +68,32 @@ class _Work(dist._Work if hasattr(dist, "_Work") else dist.Work):
         return self._result
 
 
+class _StreamWork(_Work):
+    """Work of a collective enqueued on the backend's communication stream (the way ProcessGroupNCCL does it):
+    the call returned immediately, `wait()` orders the CALLER's current stream after the collective, and the
+    CUDA-aware future lets DDP chain its bucket callbacks -- so the all-reduce of one gradient bucket runs
+    while the backward pass of the next is still computing."""
+
+    def __init__(self, done_event, result, fut):
+        dist.Work.__init__(self) if not hasattr(dist, "_Work") else dist._Work.__init__(self)
+        self._ev = done_event
+        self._result = result
+        self._fut = fut
+
+    def wait(self, timeout=None):
+        torch.cuda.current_stream().wait_event(self._ev)
+        return True
+
+    def is_completed(self):
+        return self._ev.query()
+
+    def is_success(self):
+        return True
+
+    def synchronize(self):
+        self.wait()
+
+
 class _AsyncWork(_Work):
     """Work of a collective that runs on the multi-box helper thread: `wait()` blocks until it is done and orders the
     caller's stream after it; the future completes from the helper thread, which is what lets DDP overlap the
@@ -103,9 +129,19 @@ class _AsyncWork(_Work):
         return self._w.is_completed() and self._w._err is None
 
 
+_GROUPS: List["ProcessGroupUCCL"] = []
+
+
+def default_communicator():
+    """The Communicator of the most recently created ``uccl_b200`` process group (e.g. to allocate DDP's
+    gradient buckets in its symmetric heap: ``with default_communicator().use_mem_pool(): ddp = DDP(model)``)."""
+    return _GROUPS[-1].comm if _GROUPS else None
+
+
 class ProcessGroupUCCL(dist.ProcessGroup):
     def __init__(self, store, rank: int, world_size: int, timeout=None, heap_bytes: Optional[int] = None):
         super().__init__(rank, world_size)
+        _GROUPS.append(self)
         self._rank, self._world = rank, world_size
         key = "uccl_b200/uid/%d" % int(os.environ.get("UCCL_B200_PG_SEQ", "0"))
         if rank == 0:
@@ -129,6 +165,10 @@ class ProcessGroupUCCL(dist.ProcessGroup):
                 self._async = AsyncMultiNode(self.comm)  # all-reduce returns a live Work: DDP overlaps buckets
         else:
             self.comm = Communicator.init(uid, rank, world_size, heap_bytes=heap, stage_bytes=stage, host=host)
+            # CUDA: collectives run on a high-priority communication stream and return a live Work
+            # (UCCL_B200_PG_ASYNC=0 enqueues them on the caller's stream instead)
+            if not host and os.environ.get("UCCL_B200_PG_ASYNC", "1") != "0":
+                self._comm_stream = torch.cuda.Stream(device=self.comm.device, priority=-1)
 
     # ---- required plumbing
     def getBackendName(self):
@@ -147,11 +187,32 @@ class ProcessGroupUCCL(dist.ProcessGroup):
 
     # ---- collectives (signatures of c10d::ProcessGroup)
     _async = None
+    _comm_stream = None
+
+    def _on_comm_stream(self, tensors, fn, result):
+        """Run `fn()` (which enqueues kernels) on the communication stream, ordered after the caller's stream."""
+        cs = self._comm_stream
+        dev = self.comm.device
+        cur = torch.cuda.current_stream(dev)
+        cs.wait_stream(cur)
+        fut = torch.futures.Future(devices=[dev])
+        with torch.cuda.stream(cs):
+            fn()
+            for t in tensors:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(cs)
+            done = torch.cuda.Event()
+            done.record(cs)
+            fut.set_result(result)  # CUDA-aware future: records the completion on the communication stream
+        return _StreamWork(done, result, fut)
 
     def _drain_async(self):
-        """Collectives that do not go through the helper thread must not overtake the ones that did."""
+        """Collectives that do not go through the helper thread / communication stream must not overtake the ones
+        that did (every rank issues them in the same order; the kernels match by launch order)."""
         if self._async is not None:
             self._async.submit(lambda: None).wait()
+        if self._comm_stream is not None:
+            torch.cuda.current_stream(self.comm.device).wait_stream(self._comm_stream)
 
     def allreduce(self, tensors: List[torch.Tensor], opts=None):
         op = _op_name(opts.reduceOp) if opts is not None else "sum"
@@ -164,6 +225,9 @@ class ProcessGroupUCCL(dist.ProcessGroup):
                 return ts
 
             return _AsyncWork(self._async.submit(run), tensors)
+        if self._comm_stream is not None and all(t.is_cuda for t in tensors):
+            ts = [self._prep(t) for t in tensors]
+            return self._on_comm_stream(ts, lambda: [self.comm.all_reduce(t, op) for t in ts], tensors)
         for t in tensors:
             self.comm.all_reduce(self._prep(t), op)
         return _Work(tensors)
