@@ -284,7 +284,9 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
     // defaults measured on B200 (benchmarks/allreduce_perf.py, profiles/): the packet path wins
     // until its N-fold traffic outweighs the two barriers of the two-shot kernels
     uint64_t ll_max = (uint64_t)ubParamArLLMaxBytes();
-    if (ll_max == 0) ll_max = n <= 2 ? (512u << 10) : (n <= 4 ? (256u << 10) : (128u << 10));
+    // n = 2: the two barriers of the two-shot kernels cost ~20 us when both GPUs are driven by one host thread
+    // (nccl-tests -g 2: 35 us at 1 MiB vs 15 us for the packet path), so packets carry up to the 1 MiB cap there
+    if (ll_max == 0) ll_max = n <= 2 ? (1u << 20) : (n <= 4 ? (256u << 10) : (128u << 10));
     ll_max = std::min<uint64_t>(ll_max, kLLMaxData);
     // with 2 ranks the switch cannot reduce traffic (both paths move `size` per direction) and the
     // plain P2P kernel sustains more bytes in flight per SM than multimem.ld_reduce
@@ -750,9 +752,12 @@ void Comm::group_p2p(const std::vector<P2pOp>& ops, cudaStream_t stream) {
       const P2pOp* s = r < sends[p].size() ? sends[p][r] : nullptr;
       const P2pOp* v = r < recvs[p].size() ? recvs[p][r] : nullptr;
       if ((!s || s->bytes == 0) && (!v || v->bytes == 0)) continue;
+      a.s_off[p] = kNoOff;
       if (s) {
         a.sbuf[p] = (const char*)s->buf;
         a.sbytes[p] = s->bytes;
+        // a source inside the symmetric heap is pulled by the receiver straight from where it is (no staging)
+        if (s->bytes && in_heap(s->buf, s->bytes)) a.s_off[p] = heap_offset(s->buf);
       }
       if (v) {
         a.rbuf[p] = (char*)v->buf;

@@ -486,25 +486,38 @@ static __global__ void __launch_bounds__(512, 1) a2av_kernel(const __grid_consta
 
 namespace ub {
 // ------------------------------------------------------------------ Send / Recv
-// ncclSend/ncclRecv for arbitrary (non-symmetric) user buffers: the sender stages chunks in its
-// own heap and publishes a sequence number in the receiver's heap; the receiver pulls the chunk
-// over NVLink and acks.  Grid = npeers * kSrBlocks CTAs; in each CTA warps 0-7 run the send
-// flow and warps 8-15 the receive flow of one (peer, sub-block) so both directions always make
-// progress (no deadlock for symmetric exchanges).  Sequence counters are persistent and
-// monotonic per (peer, sub-block): no reset, graph-replay safe.
-// (reference: lite's host-staged ncclSend/Recv, experimental/lite/nccl/nccl.cu:1145-1350,2033-2067)
+// ncclSend/ncclRecv.  Grid = npeers * kSrBlocks CTAs; in each CTA warps 0-7 run the send flow and
+// warps 8-15 the receive flow of one (peer, sub-block), so both directions always make progress (no
+// deadlock for symmetric exchanges).  Two data paths, chosen per message by the SENDER and announced in
+// a header word that travels with the first "ready" signal:
+//   * zero-copy: the source lives in the symmetric heap -> the receiver pulls its slice straight from
+//     the sender's buffer with a TMA pipeline (cp.async.bulk peer -> smem -> local) and acks; the sender
+//     only waits for that ack (its buffer may be reused when the kernel returns, NCCL semantics);
+//   * staged: arbitrary user buffers -> the sender stages chunks in its own heap and publishes a
+//     sequence number in the receiver's heap; the receiver pulls the chunk over NVLink and acks.
+// Sequence counters are persistent and monotonic per (peer, sub-block): no reset, graph-replay safe.
+// (reference: lite's host-staged ncclSend/Recv, experimental/lite/nccl/nccl.cu:1145-1350,2033-2067;
+//  the first version of this kernel moved 512 KB slots with one 16-byte load in flight per thread and
+//  reached 9 GB/s in nccl-tests' alltoall_perf)
 __device__ __forceinline__ void half_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+
+constexpr int kSrTmaStages = 10;
+constexpr uint32_t kSrTmaChunk = 16u << 10;
 
 static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_constant__ DevComm c,
                                                                 const __grid_constant__ SendRecvArgs a) {
+  extern __shared__ __align__(128) unsigned char sr_smem[];  // receive half: kSrTmaStages x kSrTmaChunk
+  __shared__ __align__(8) uint64_t sr_full[kSrTmaStages];
+  __shared__ uint64_t s_hdr;
   const int me = c.rank;
   const int pi = blockIdx.x / kSrBlocks, j = blockIdx.x % kSrBlocks;
   const int peer = a.peers[pi];
   const bool is_send = threadIdx.x < 256;
   const int t = threadIdx.x & 255;
-  // flag words (u32) inside every heap: ready[src][j], ack[dst][j], sseq[dst][j], rseq[src][j]
+  // flag words (u32) inside every heap: ready[src][j], ack[dst][j], sseq[dst][j], rseq[src][j], then u64 hdr[src][j]
   auto flags = [&](int rank) { return reinterpret_cast<uint32_t*>(c.heap[rank] + a.sr_flag_off); };
   const int W = kMaxRanks * kSrBlocks;
+  auto hdrs = [&](int rank) { return reinterpret_cast<uint64_t*>(flags(rank) + 4 * W); };
   uint32_t* my_flags = flags(me);
   if (peer == me) {
     // self send/recv: plain local copy by the whole CTA slice
@@ -522,8 +535,33 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
     uint32_t seq = my_flags[2 * W + peer * kSrBlocks + j];
     uint32_t* my_ack = my_flags + 1 * W + peer * kSrBlocks + j;
     uint32_t* peer_ready = flags(peer) + 0 * W + me * kSrBlocks + j;
+    uint64_t* peer_hdr = hdrs(peer) + me * kSrBlocks + j;
+    const bool direct = a.s_off[peer] != kNoOff && (bytes % 16) == 0;
+    if (direct) {
+      // announce where the data is and wait until the receiver has pulled my slice
+      if (t == 0) {
+        ++seq;
+        *reinterpret_cast<volatile uint64_t*>(peer_hdr) = a.s_off[peer];
+        st_release_sys(peer_ready, seq);  // also orders the (earlier) writes of the source buffer
+        SpinGuard g(c.timeout_ns);
+        while ((int32_t)(ld_acquire_sys(my_ack) - seq) < 0) {
+          if (g.expired()) comm_abort(c, 22, peer, (int)seq);
+        }
+        my_flags[2 * W + peer * kSrBlocks + j] = seq;
+      }
+      return;
+    }
     char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
+    if (lo >= hi) {  // an empty slice still announces the mode once (the receiver waits for one header)
+      if (t == 0) {
+        ++seq;
+        *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
+        st_release_sys(peer_ready, seq);
+        my_flags[2 * W + peer * kSrBlocks + j] = seq;
+      }
+      return;
+    }
     for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
       const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;
       ++seq;
@@ -535,12 +573,25 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       }
       half_sync(1);
       char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
-      for (uint64_t u = u0 + t; u < u1; u += 256) {
-        uint4 v = load16_partial(a.sbuf[peer], u * 16, bytes);
-        st_v4(slot + (u - u0) * 16, v);
+      constexpr int B = 8;  // loads in flight per thread
+      for (uint64_t ub = u0; ub < u1; ub += (uint64_t)B * 256) {
+        uint4 v[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const uint64_t u = ub + (uint64_t)q * 256 + t;
+          if (u < u1) v[q] = load16_partial(a.sbuf[peer], u * 16, bytes);
+        }
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const uint64_t u = ub + (uint64_t)q * 256 + t;
+          if (u < u1) st_v4(slot + (u - u0) * 16, v[q]);
+        }
       }
       half_sync(1);
-      if (t == 0) st_release_sys(peer_ready, seq);
+      if (t == 0) {
+        if (u0 == lo) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;  // staged mode
+        st_release_sys(peer_ready, seq);
+      }
     }
     if (t == 0) my_flags[2 * W + peer * kSrBlocks + j] = seq;
   } else {
@@ -551,22 +602,90 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
     uint32_t seq = my_flags[3 * W + peer * kSrBlocks + j];
     uint32_t* my_ready = my_flags + 0 * W + peer * kSrBlocks + j;
     uint32_t* peer_ack = flags(peer) + 1 * W + me * kSrBlocks + j;
+    const uint64_t* my_hdr = hdrs(me) + peer * kSrBlocks + j;
+    // first signal of the message: learn the mode
+    ++seq;
+    if (t == 0) {
+      SpinGuard g(c.timeout_ns);
+      while ((int32_t)(ld_acquire_sys(my_ready) - seq) < 0) {
+        if (g.expired()) comm_abort(c, 21, peer, (int)seq);
+      }
+      s_hdr = *reinterpret_cast<const volatile uint64_t*>(my_hdr);
+      for (int st = 0; st < kSrTmaStages; ++st) mbar_init(&sr_full[st], 1);
+      mbar_fence_init();
+    }
+    half_sync(2);
+    const uint64_t hdr = s_hdr;
+    if (hdr != kNoOff) {
+      // ---- zero-copy: pull my slice [lo, hi) of the peer's buffer; one elected thread runs the pipeline
+      if (t == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        const char* src = c.heap[peer] + hdr;
+        char* dst = a.rbuf[peer];
+        const uint64_t b0 = lo * 16, b1 = hi * 16 < bytes ? hi * 16 : bytes;
+        const uint64_t total = b1 > b0 ? (b1 - b0 + kSrTmaChunk - 1) / kSrTmaChunk : 0;
+        uint64_t issued = 0, stored = 0;
+        uint32_t phase_bits = 0;
+        while (stored < total) {
+          while (issued < total && issued < stored + kSrTmaStages) {
+            const int st = (int)(issued % kSrTmaStages);
+            if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<kSrTmaStages - 1>();
+            const uint64_t off = b0 + issued * kSrTmaChunk;
+            const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+            mbar_expect_tx(&sr_full[st], nb);
+            tma_load_1d(sr_smem + (size_t)st * kSrTmaChunk, src + off, nb, &sr_full[st]);
+            ++issued;
+          }
+          const int st = (int)(stored % kSrTmaStages);
+          mbar_wait(&sr_full[st], (phase_bits >> st) & 1u);
+          phase_bits ^= 1u << st;
+          const uint64_t off = b0 + stored * kSrTmaChunk;
+          const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+          tma_store_1d(dst + off, sr_smem + (size_t)st * kSrTmaChunk, nb);
+          tma_store_commit();
+          ++stored;
+        }
+        tma_store_wait<0>();
+        st_release_sys(peer_ack, seq);
+        my_flags[3 * W + peer * kSrBlocks + j] = seq;
+      }
+      return;
+    }
+    // ---- staged
     const char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
+    if (lo >= hi) {
+      if (t == 0) my_flags[3 * W + peer * kSrBlocks + j] = seq;
+      return;
+    }
+    bool first = true;
     for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
       const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;
-      ++seq;
-      if (t == 0) {
-        SpinGuard g(c.timeout_ns);
-        while ((int32_t)(ld_acquire_sys(my_ready) - seq) < 0) {
-          if (g.expired()) comm_abort(c, 21, peer, (int)seq);
+      if (!first) {
+        ++seq;
+        if (t == 0) {
+          SpinGuard g(c.timeout_ns);
+          while ((int32_t)(ld_acquire_sys(my_ready) - seq) < 0) {
+            if (g.expired()) comm_abort(c, 21, peer, (int)seq);
+          }
         }
+        half_sync(2);
       }
-      half_sync(2);
+      first = false;
       const char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
-      for (uint64_t u = u0 + t; u < u1; u += 256) {
-        uint4 v = ld_v4(slot + (u - u0) * 16);
-        store16_partial(a.rbuf[peer], u * 16, bytes, v);
+      constexpr int B = 8;
+      for (uint64_t ub = u0; ub < u1; ub += (uint64_t)B * 256) {
+        uint4 v[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const uint64_t u = ub + (uint64_t)q * 256 + t;
+          if (u < u1) v[q] = ld_v4(slot + (u - u0) * 16);
+        }
+#pragma unroll
+        for (int q = 0; q < B; ++q) {
+          const uint64_t u = ub + (uint64_t)q * 256 + t;
+          if (u < u1) store16_partial(a.rbuf[peer], u * 16, bytes, v[q]);
+        }
       }
       half_sync(2);
       if (t == 0) st_release_sys(peer_ack, seq);

@@ -41,7 +41,16 @@ cudaError_t launch_alltoallv(const DevComm& c, const CollArgs& a, const A2AvArgs
 
 namespace ub {
 cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st) {
-  UB_LAUNCH((sendrecv_kernel), (a.npeers > 0 ? a.npeers : 1) * kSrBlocks, 512, 0, st, c, a);
+  const size_t smem = (size_t)kSrTmaStages * kSrTmaChunk;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(sendrecv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done[dev & 63] = true;
+  }
+  UB_LAUNCH((sendrecv_kernel), (a.npeers > 0 ? a.npeers : 1) * kSrBlocks, 512, smem, st, c, a);
   return cudaGetLastError();
 }
 __global__ void barrier_kernel(const __grid_constant__ DevComm c, int domain) {

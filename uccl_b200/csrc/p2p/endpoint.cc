@@ -19,8 +19,8 @@
 
 namespace ub {
 
-UB_PARAM(P2PCtas, "P2P_CTAS", 32)
-UB_PARAM(P2PChunkKB, "P2P_CHUNK_KB", 32)
+UB_PARAM(P2PCtas, "P2P_CTAS", 0)       // 0: by transfer size (8 / 32 / 64 CTAs)
+UB_PARAM(P2PChunkKB, "P2P_CHUNK_KB", 16)  // bytes per bulk copy; 4 pipelines x 3 stages of it per CTA
 UB_PARAM(P2PUseKernel, "P2P_USE_KERNEL", 1)
 // engine status line every N seconds at INFO level (reference: per-engine stats thread every 2 s unless
 // UCCL_ENGINE_QUIET, collective/rdma/transport.cc:1797-1825); 0 = off
@@ -162,8 +162,15 @@ Endpoint::~Endpoint() {
   if (gpu_ < 0) return;
   cudaSetDevice(gpu_);
   for (auto& kv : ipc_open_) cudaIpcCloseMemHandle(kv.second);
-  for (auto s : streams_) cudaStreamDestroy(s);
+  for (auto s : streams_) {
+    cudaStreamSynchronize(s);  // descriptor-table callbacks reference this object
+    cudaStreamDestroy(s);
+  }
   for (auto e : event_pool_) cudaEventDestroy(e);
+  for (auto* t : tables_all_) {
+    cudaFreeHost(t->host);
+    delete t;
+  }
 }
 
 void Endpoint::wake() {
@@ -593,36 +600,90 @@ bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vecto
     std::lock_guard<std::mutex> g(mu_);
     stats_.memcpy_fallbacks += n;
   } else {
-    const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(48, ubParamP2PChunkKB())) * 1024;
-    for (size_t i0 = 0; i0 < n; i0 += kP2PMaxEntries) {
+    const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(16, ubParamP2PChunkKB())) * 1024;
+    const size_t per_launch = n > (size_t)kP2PMaxEntries ? (size_t)kP2PTableEntries : (size_t)kP2PMaxEntries;
+    for (size_t i0 = 0; i0 < n; i0 += per_launch) {
       P2PCopyBatch b;
       memset(&b, 0, sizeof(b));
       b.chunk_bytes = chunk;
-      const size_t m = std::min<size_t>(kP2PMaxEntries, n - i0);
-      uint32_t total = 0;
+      const size_t m = std::min<size_t>(per_launch, n - i0);
+      DescTable* tab = nullptr;
+      P2PCopyEntry* ents = b.e;
+      uint32_t* pfx = b.chunk_prefix;
+      if (m > (size_t)kP2PMaxEntries) {
+        tab = acquire_table();
+        if (!tab) return false;
+        ents = (P2PCopyEntry*)tab->host;
+        pfx = (uint32_t*)((char*)tab->host + sizeof(P2PCopyEntry) * kP2PTableEntries);
+        b.table = (const P2PCopyEntry*)tab->dev;
+        b.table_prefix = (const uint32_t*)((char*)tab->dev + sizeof(P2PCopyEntry) * kP2PTableEntries);
+      }
+      uint64_t total = 0, bytes_total = 0;
       for (size_t j = 0; j < m; ++j) {
-        auto& e = b.e[j];
+        auto& e = ents[j];
         e.src = src[i0 + j];
         e.dst = dst[i0 + j];
         e.bytes = sizes[i0 + j];
         const bool al = ((((uintptr_t)e.src) | ((uintptr_t)e.dst)) & 15) == 0;
         e.bulk_bytes = al ? (e.bytes / 16 * 16) : 0;
-        b.chunk_prefix[j] = total;
-        total += (uint32_t)((e.bulk_bytes + chunk - 1) / chunk);
+        pfx[j] = (uint32_t)total;
+        total += (e.bulk_bytes + chunk - 1) / chunk;
+        bytes_total += e.bytes;
       }
-      b.chunk_prefix[m] = total;
+      pfx[m] = (uint32_t)total;
       b.n = (int)m;
-      int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ubParamP2PCtas(), std::max<uint32_t>(total, 1)));
+      // enough CTAs for the bytes in flight the link needs (4 pipelines x 3 stages x chunk each); small
+      // transfers keep the launch small so they do not take SMs from a co-running kernel
+      int64_t want = ubParamP2PCtas();
+      if (want <= 0) want = bytes_total >= (8u << 20) ? 64 : (bytes_total >= (1u << 20) ? 32 : 8);
+      int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)((total + kP2PWarps - 1) / kP2PWarps)));
       cudaError_t e = launch_p2p_copy(b, grid, st);
       if (e != cudaSuccess) {
         UB_WARN("p2p copy kernel launch failed: %s", cudaGetErrorString(e));
+        if (tab) release_table_cb(tab);
         return false;
+      }
+      if (tab && cudaLaunchHostFunc(st, release_table_cb, tab) != cudaSuccess) {
+        (void)cudaGetLastError();  // could not enqueue the callback: drain the stream and recycle by hand
+        cudaStreamSynchronize(st);
+        release_table_cb(tab);
       }
       std::lock_guard<std::mutex> g(mu_);
       stats_.kernel_launches++;
     }
   }
   return cudaEventRecord(ev, st) == cudaSuccess;
+}
+
+Endpoint::DescTable* Endpoint::acquire_table() {
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!table_pool_.empty()) {
+      DescTable* t = table_pool_.back();
+      table_pool_.pop_back();
+      return t;
+    }
+  }
+  auto* t = new DescTable();
+  t->owner = this;
+  const size_t bytes = sizeof(P2PCopyEntry) * kP2PTableEntries + sizeof(uint32_t) * (kP2PTableEntries + 1);
+  if (cudaHostAlloc(&t->host, bytes, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(&t->dev, t->host, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (t->host) cudaFreeHost(t->host);
+    delete t;
+    UB_WARN("p2p: could not allocate a pinned descriptor table");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> g(mu_);
+  tables_all_.push_back(t);
+  return t;
+}
+
+void Endpoint::release_table_cb(void* p) {
+  auto* t = (DescTable*)p;
+  std::lock_guard<std::mutex> g(t->owner->mu_);
+  t->owner->table_pool_.push_back(t);
 }
 
 static cudaEvent_t new_event() {

@@ -127,6 +127,17 @@ class Endpoint {
   std::vector<cudaStream_t> streams_;
   size_t next_stream_ = 0;
   std::vector<cudaEvent_t> event_pool_;
+  // pinned, device-mapped descriptor tables for batches of more than kP2PMaxEntries blocks; a table goes back
+  // to the pool from a stream callback once its kernel has finished
+  struct DescTable {
+    void* host = nullptr;  // [kP2PTableEntries] P2PCopyEntry, then [kP2PTableEntries + 1] u32 chunk prefix
+    void* dev = nullptr;
+    Endpoint* owner = nullptr;
+  };
+  std::vector<DescTable*> table_pool_;
+  std::vector<DescTable*> tables_all_;
+  DescTable* acquire_table();
+  static void release_table_cb(void* p);
   P2PStats stats_;
   uint32_t peer_enabled_mask_ = 0;
   std::mutex helpers_mu_;

@@ -4,8 +4,10 @@
 
 namespace ub {
 
-constexpr int kP2PStages = 4;
-constexpr int kP2PMaxEntries = 64;
+constexpr int kP2PStages = 3;        // bulk loads in flight per warp pipeline
+constexpr int kP2PWarps = 4;         // independent TMA pipelines per CTA (one elected lane each)
+constexpr int kP2PMaxEntries = 64;   // entries that travel in the kernel parameters
+constexpr int kP2PTableEntries = 8192;  // entries of one pinned descriptor table (larger batches: several launches)
 
 struct P2PCopyEntry {
   const char* src;
@@ -19,6 +21,10 @@ struct P2PCopyBatch {
   uint32_t chunk_prefix[kP2PMaxEntries + 1];  // exclusive prefix of per-entry bulk chunk counts
   int n;
   uint32_t chunk_bytes;
+  // n > kP2PMaxEntries: the descriptors live in pinned, device-mapped host memory instead (one launch moves
+  // thousands of KV blocks); `table_prefix` has n + 1 words
+  const P2PCopyEntry* table;
+  const uint32_t* table_prefix;
 };
 
 // A registered/advertised memory window, shipped between endpoints (128 bytes on the wire).

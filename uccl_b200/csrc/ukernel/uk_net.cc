@@ -111,11 +111,18 @@ void UkNetComm::run(const UkPlan& plan, char* in, char* out, int dtype, int op) 
   bases_[1] = out;
   bases_[2] = scratch_.data();
   ext_[0] = ext_[1] = ext_[2] = 0;
-  // plans are symmetric across ranks: whatever a peer may send me lies inside the ranges my own plan touches
+  // what a peer may legally write: the scratch area the plan addresses and the collective's In / Out size
+  // (`bytes` is the whole message for AllReduce / Broadcast and the per-peer block for the others); the ranges
+  // my own ops touch are folded in as a lower bound
+  const uint64_t whole = (plan.coll == UkColl::AllReduce || plan.coll == UkColl::Broadcast) ? plan.bytes
+                                                                                              : plan.bytes * (uint64_t)plan.nranks;
+  ext_[0] = ext_[1] = whole;
+  ext_[2] = plan.scratch_bytes;
   for (const UkPlanOp& o : plan.ops) {
     if (o.kind == UkPlanOp::Recv) continue;
     for (const UkRef* r : {&o.dst, &o.src, &o.src2}) {
       if (o.kind != UkPlanOp::Reduce && r == &o.src2) continue;
+      if (o.kind == UkPlanOp::Send && r == &o.dst) continue;  // lives in the peer's buffers
       const int b = (int)r->buf;
       if (b >= 0 && b <= 2) ext_[b] = std::max<uint64_t>(ext_[b], r->off + o.bytes);
     }
