@@ -22,6 +22,8 @@ UB_PARAM(RsPush, "RS_PUSH", 1)  // staged ReduceScatter: 1 = push into the peers
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 // 1: a one-rank communicator launches the real kernels instead of a cudaMemcpy (profiling / smoke tests on one GPU)
 UB_PARAM(ForceKernels, "FORCE_KERNELS", 0)
+// plain (non-symmetric) buffers of at least this size take the block-pipelined staged kernel (needs NVLS, > 2 ranks)
+UB_PARAM(ArPipeMinBytes, "AR_PIPE_MIN_BYTES", 96 << 20)
 
 const char* algo_name(int algo) {
   switch (algo) {
@@ -32,6 +34,7 @@ const char* algo_name(int algo) {
     case ALGO_TWOSHOT_NVLS: return "twoshot_nvls";
     case ALGO_STAGED_P2P: return "staged_p2p";
     case ALGO_STAGED_NVLS: return "staged_nvls";
+    case ALGO_STAGED_PIPE: return "staged_pipe";
     default: return "?";
   }
 }
@@ -294,12 +297,16 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
     if (p2p_min < 0) p2p_min = n <= 2 ? (8 << 20) : INT64_MAX;
     if (bytes <= ll_max || n == 1) algo = mc ? ALGO_ONESHOT_MC : ALGO_ONESHOT_LL;
     else if (symmetric) algo = (nvls_ok && (int64_t)bytes < p2p_min) ? ALGO_TWOSHOT_NVLS : ALGO_TWOSHOT_P2P;
-    else algo = (nvls_ok && n > 2) ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
+    else if (nvls_ok && n > 2)
+      algo = ((int64_t)bytes >= ubParamArPipeMinBytes() && max_ctas_ >= 48 && layout_.stage_bytes >= (32u << 20))
+                 ? ALGO_STAGED_PIPE : ALGO_STAGED_NVLS;
+    else algo = ALGO_STAGED_P2P;
     if (n == 1 && bytes > kLLMaxData) algo = ALGO_STAGED_P2P;
   }
   // degrade gracefully when a tuned/forced choice is impossible here
   if ((algo == ALGO_ONESHOT_MC) && !mc) algo = ALGO_ONESHOT_LL;
   if ((algo == ALGO_TWOSHOT_NVLS) && !nvls_ok) algo = ALGO_TWOSHOT_P2P;
+  if (algo == ALGO_STAGED_PIPE && (!nvls_ok || bytes % 16 != 0 || max_ctas_ < 12)) algo = ALGO_STAGED_NVLS;
   if ((algo == ALGO_STAGED_NVLS) && !nvls_ok) algo = ALGO_STAGED_P2P;
   if ((algo == ALGO_TWOSHOT_P2P || algo == ALGO_TWOSHOT_NVLS) && !symmetric)
     algo = (algo == ALGO_TWOSHOT_NVLS) ? ALGO_STAGED_NVLS : ALGO_STAGED_P2P;
@@ -310,6 +317,7 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
       case ALGO_ONESHOT_LL:
       case ALGO_ONESHOT_MC: c = ctas_for(bytes, std::min(max_ctas_, 64), 8192); break;  // 512 thr x 16 B
       case ALGO_TWOSHOT_NVLS: c = ctas_for(bytes, nvls_ctas(), 64 << 10); break;
+      case ALGO_STAGED_PIPE: c = std::min(max_ctas_, 80); break;  // split into the three groups at launch
       case ALGO_STAGED_NVLS:
       case ALGO_STAGED_P2P: c = ctas_for(bytes, max_ctas_, 64 << 10); break;
       default: c = ctas_for(bytes, max_ctas_, 128 << 10); break;
@@ -377,9 +385,12 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
   } else {
     (void)select_allreduce(bytes, sym, dtype, op, &ctas);
     // validate a forced choice
-    if (algo == ALGO_ONESHOT_MC || algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
+    if (algo == ALGO_ONESHOT_MC || algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS || algo == ALGO_STAGED_PIPE)
       UB_CHECK(has_multicast(), "allreduce: algo %s needs NVLS multicast", algo_name(algo));
-    if (algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS)
+    if (algo == ALGO_STAGED_PIPE)
+      UB_CHECK(bytes % 16 == 0 && out_dtype == dtype && max_ctas_ >= 12,
+               "allreduce: staged_pipe needs 16-byte multiples, no fused cast and >= 12 CTAs");
+    if (algo == ALGO_TWOSHOT_NVLS || algo == ALGO_STAGED_NVLS || algo == ALGO_STAGED_PIPE)
       UB_CHECK(nvls_reduce_supported(dtype, op), "allreduce: NVLS cannot reduce dtype %d op %d", dtype, op);
     if (algo == ALGO_TWOSHOT_P2P || algo == ALGO_TWOSHOT_NVLS)
       UB_CHECK(sym, "allreduce: algo %s needs buffers from the symmetric heap", algo_name(algo));
@@ -387,10 +398,12 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       UB_CHECK(bytes <= kLLMaxData, "allreduce: one-shot limited to %lu bytes", (unsigned long)kLLMaxData);
     if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) ctas = ctas_for(bytes, std::min(max_ctas_, 64), 8192);
     else if (algo == ALGO_TWOSHOT_NVLS) ctas = ctas_for(bytes, nvls_ctas(), 64 << 10);
+    else if (algo == ALGO_STAGED_PIPE) ctas = std::min(max_ctas_, 80);
     else if (algo == ALGO_STAGED_NVLS || algo == ALGO_STAGED_P2P) ctas = ctas_for(bytes, max_ctas_, 64 << 10);
     else ctas = ctas_for(bytes, max_ctas_, 128 << 10);
   }
   if (opts.max_ctas > 0) ctas = std::min(ctas, opts.max_ctas);
+  if (algo == ALGO_STAGED_PIPE && (out_dtype != dtype || ctas < 12)) algo = ALGO_STAGED_NVLS;
   if (out_dtype != dtype) {
     if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC)
       algo = sym ? ALGO_TWOSHOT_P2P : ALGO_STAGED_P2P;  // cast is fused only in the two-shot/staged kernels
@@ -412,6 +425,12 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
     if (sym) {
       a.in_off = heap_offset(in);
       a.out_off = heap_offset(out);
+    }
+    if (algo == ALGO_STAGED_PIPE) {
+      // 40 % of the CTAs reduce through the switch, 30 % each copy in / out (HBM passes are the cheaper phases)
+      const int nB = std::max(4, ctas * 2 / 5), nA = std::max(4, (ctas - nB) / 2), nC = std::max(4, ctas - nB - nA);
+      a.variant = nB | (nA << 8) | (nC << 16);
+      ctas = nA + nB + nC;
     }
     cudaError_t e = launch_ar_any(algo, dtype, op, out_dtype, dev_, a, ctas, block, stream);
     if (e != cudaSuccess) {

@@ -34,7 +34,8 @@ enum ArAlgoId : int {
   ALGO_TWOSHOT_P2P = 3,
   ALGO_TWOSHOT_NVLS = 4,
   ALGO_STAGED_P2P = 5,
-  ALGO_STAGED_NVLS = 6
+  ALGO_STAGED_NVLS = 6,
+  ALGO_STAGED_PIPE = 7  // staged + NVLS with copy-in / reduce / copy-out running concurrently on three CTA groups
 };
 
 struct ArOpts {

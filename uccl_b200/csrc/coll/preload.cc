@@ -38,7 +38,7 @@ cudaError_t preload_all_kernels() {
     if (e == cudaSuccess) ++loaded;
     else (void)cudaGetLastError();  // unsupported combination: nothing to load
   };
-  for (int algo = 1; algo <= 6; ++algo)
+  for (int algo = 1; algo <= 7; ++algo)
     for (int op = 0; op < 4; ++op) {
       for (int dt : {(int)kF32, (int)kBF16, (int)kF16}) ok(launch_allreduce_f(algo, dt, op, dt, c, a, 1, 512, 0));
       for (int dt : {(int)kI8, (int)kU8, (int)kI32, (int)kU32, (int)kI64, (int)kU64})

@@ -319,6 +319,130 @@ __global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevC
   sync_end(s);
 }
 
+// ------------------------------------------------------- staged, block-pipelined (NVLS)
+// Large ordinary (cudaMalloc / torch) buffers.  ar_staged runs copy-in -> in-switch reduce -> copy-out
+// strictly one after the other per chunk, so the two HBM passes (2 x S read + 2 x S written) are added to
+// the NVLink time and the kernel loses to NCCL from 256 MiB up.  Here the three phases run CONCURRENTLY on
+// three groups of CTAs, two chunks deep:
+//     group A (copy-in)   user input  -> stage_in[k & 1]                       local HBM
+//     group B (reduce)    multimem.ld_reduce my shard of stage_in[k & 1] over all ranks, multimem.st the result
+//                         into every rank's stage_out[k & 1]                    NVLink / NVSwitch
+//     group C (copy-out)  stage_out[k & 1] -> user output                       local HBM
+// Inside a rank the groups hand chunks to each other through three monotonic device counters (zeroed by the last
+// CTA to leave); across ranks only the B CTAs of equal index synchronise (two barriers per chunk, as before).
+//   A(k) needs red >= (k-1) nB   (all ranks finished reading stage_in slot k&1 for chunk k-2)
+//   B(k) needs in  >= (k+1) nA   and out >= (k-1) nC, then barrier -> every rank's slot is filled / drained
+//   C(k) needs red >= (k+1) nB   (every shard of chunk k has been written into my stage_out)
+// a.variant = nB | nA << 8 | nC << 16; grid = nA + nB + nC (<= SM count: the groups wait for each other).
+template <typename T, int OP>
+__global__ void __launch_bounds__(512, 1) ar_staged_pipe(const __grid_constant__ DevComm c,
+                                                         const __grid_constant__ CollArgs a) {
+  constexpr int N = Vec16<T, OP>::N;
+  const int n = c.nranks, rank = c.rank;
+  const int nB = a.variant & 0xff, nA = (a.variant >> 8) & 0xff, nC = (a.variant >> 16) & 0xff;
+  const int bid = blockIdx.x;
+  const int role = bid < nB ? 1 : (bid < nB + nA ? 0 : 2);  // 0 copy-in, 1 reduce, 2 copy-out
+  const int idx = role == 1 ? bid : (role == 0 ? bid - nB : bid - nB - nA);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(c.heap[rank] + a.misc_off);
+  uint32_t* in_cnt = misc + kPipeIn;
+  uint32_t* red_cnt = misc + kPipeRed;
+  uint32_t* out_cnt = misc + kPipeOut;
+
+  const uint64_t nvec_total = a.bytes / 16;
+  const uint64_t slot_vec = (a.stage_bytes / 2) / 16;
+  // chunk: about a sixth of the message (pipeline depth vs. barrier count), 512 KiB granules, at most one slot
+  uint64_t chunk_vec = (nvec_total + 5) / 6;
+  const uint64_t gran = (512u << 10) / 16;
+  chunk_vec = (chunk_vec + gran - 1) / gran * gran;
+  if (chunk_vec < (8u << 20) / 16) chunk_vec = (8u << 20) / 16;
+  if (chunk_vec > slot_vec) chunk_vec = slot_vec / gran * gran;
+  const uint64_t nchunks = (nvec_total + chunk_vec - 1) / chunk_vec;
+  const char* in = reinterpret_cast<const char*>(a.in);
+  char* out = reinterpret_cast<char*>(a.out);
+
+  auto wait_ge = [&](uint32_t* p, uint64_t target) {
+    if (threadIdx.x == 0) {
+      SpinGuard g(c.timeout_ns);
+      while ((uint64_t)ld_acquire_gpu(p) < target) {
+        if (g.expired()) comm_abort(c, 30 + role, (int)target, (int)ld_acquire_gpu(p));
+      }
+    }
+    __syncthreads();
+  };
+  auto bump = [&](uint32_t* p) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(p, 1u);
+  };
+
+  BlockSync s;
+  if (role == 1) s = sync_begin(c, kDomColl, idx);
+  for (uint64_t k = 0; k < nchunks; ++k) {
+    const uint64_t base = k * chunk_vec;
+    const uint64_t cvec = (nvec_total - base) < chunk_vec ? (nvec_total - base) : chunk_vec;
+    const uint64_t slot_off = (k & 1) * slot_vec * 16;
+    if (role == 0) {
+      if (k >= 2) wait_ge(red_cnt, (k - 1) * (uint64_t)nB);
+      uint64_t lo, hi;
+      split_range(cvec, nA, idx, lo, hi);
+      copy_units16(c.heap[rank] + a.stage_in_off + slot_off, in + base * 16, lo, hi);
+      bump(in_cnt);
+    } else if (role == 1) {
+      wait_ge(in_cnt, (k + 1) * (uint64_t)nA);
+      if (k >= 2) wait_ge(out_cnt, (k - 1) * (uint64_t)nC);
+      sync_barrier(c, s);  // every rank: stage_in slot filled, stage_out slot drained
+      uint64_t blo, bhi, lo, hi;
+      split_range(cvec, nB, idx, blo, bhi);
+      split_range(bhi - blo, n, rank, lo, hi);
+      lo += blo;
+      hi += blo;
+      const char* in_mc = c.mc + a.stage_in_off + slot_off;
+      T* out_mc = reinterpret_cast<T*>(c.mc + a.stage_out_off + slot_off);
+      constexpr int U = 8;  // 8 multimem.ld_reduce in flight per thread
+      for (uint64_t v0 = lo + threadIdx.x; v0 < hi; v0 += (uint64_t)U * blockDim.x) {
+        uint4 r[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + v * 16);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          const uint64_t v = v0 + (uint64_t)j * blockDim.x;
+          if (v < hi) {
+            Vec16<T, OP> acc;
+            acc.init(r[j]);
+            acc.epilogue(a.ep);
+            store_out<T, OP, T, true>(out_mc, v * N, acc);
+          }
+        }
+      }
+      sync_barrier(c, s);  // every rank's shard of my slice has landed in my stage_out; peers are done with my stage_in
+      bump(red_cnt);
+    } else {
+      wait_ge(red_cnt, (k + 1) * (uint64_t)nB);
+      uint64_t lo, hi;
+      split_range(cvec, nC, idx, lo, hi);
+      copy_units16(out + base * 16, c.heap[rank] + a.stage_out_off + slot_off, lo, hi);
+      bump(out_cnt);
+    }
+  }
+  if (role == 1) sync_end(s);
+  // the last CTA to leave zeroes the hand-off counters for the next launch (graph-replay safe: no host state)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t old = atomicAdd(misc + kPipeExit, 1u);
+    if (old == gridDim.x - 1) {
+      *reinterpret_cast<volatile uint32_t*>(in_cnt) = 0;
+      *reinterpret_cast<volatile uint32_t*>(red_cnt) = 0;
+      *reinterpret_cast<volatile uint32_t*>(out_cnt) = 0;
+      *reinterpret_cast<volatile uint32_t*>(misc + kPipeExit) = 0;
+      __threadfence();
+    }
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 enum ArAlgo : int {
   AR_AUTO = 0,
@@ -328,7 +452,8 @@ enum ArAlgo : int {
   AR_TWOSHOT_NVLS = 4,
   AR_STAGED_P2P = 5,
   AR_STAGED_NVLS = 6,
-  AR_NUM_ALGOS = 7
+  AR_STAGED_PIPE = 7,
+  AR_NUM_ALGOS = 8
 };
 
 template <typename T, int OP, typename TO>
@@ -348,6 +473,9 @@ cudaError_t launch_ar_typed(int algo, const DevComm& c, const CollArgs& a, int g
       return cudaErrorInvalidValue;
     case AR_STAGED_NVLS:
       if constexpr (MmLdRed<T, OP>::ok) { UB_LAUNCH((ar_staged<T, OP, TO, true>), grid, block, 0, st, c, a); break; }
+      return cudaErrorInvalidValue;
+    case AR_STAGED_PIPE:
+      if constexpr (MmLdRed<T, OP>::ok && same) { UB_LAUNCH((ar_staged_pipe<T, OP>), grid, block, 0, st, c, a); break; }
       return cudaErrorInvalidValue;
     default: return cudaErrorInvalidValue;
   }

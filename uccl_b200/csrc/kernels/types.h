@@ -96,7 +96,7 @@ constexpr uint64_t kLLSlotBytes = 2 * kLLMaxData;     // 8 data bytes per 16-byt
 constexpr uint64_t kLLBytes = 2 * kMaxRanks * kLLSlotBytes;  // 2 parities x src ranks
 
 // misc words
-enum MiscWord : int { kLLEpoch = 0, kLLDone = 1, kMiscWords = 64 };
+enum MiscWord : int { kLLEpoch = 0, kLLDone = 1, kPipeIn = 8, kPipeRed = 9, kPipeOut = 10, kPipeExit = 11, kMiscWords = 64 };
 
 struct HeapLayout {
   uint64_t sig_off, epoch_off, xchg_off, misc_off, a2av_tab_off, sr_flag_off, ll_off, sr_stage_off, stage_in_off, stage_out_off, user_off;

@@ -50,6 +50,7 @@ ALGOS = {
     "twoshot_nvls": 4,
     "staged_p2p": 5,
     "staged_nvls": 6,
+    "staged_pipe": 7,
 }
 
 
