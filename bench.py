@@ -381,7 +381,7 @@ def main():
     recv_x, recv_idx, recv_w, per_expert, handle, _ = buf.dispatch(
         x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe, topk_idx=topk_idx,
         topk_weights=topk_w, use_fp8=True, config=cfg)
-    num_recv = handle[4]
+    num_recv = handle.num_recv
     comb_in = buf.get_combine_buffer(num_recv, H, K)
     comb_in.normal_()  # stand-in for the expert MLP output (bf16), lives in the symmetric arena
     barrier()
@@ -525,9 +525,9 @@ def main():
                                             topk_idx=idd, topk_weights=wd, use_fp8=True, config=cfg)
         # stand-in for the expert MLP: dequantise the received (e4m3, scale) rows into the combine arena
         # (a real pass over every received token; the expert GEMMs themselves are not part of this metric)
-        cin = buf.get_combine_buffer(h[4], H, K)
-        torch.mul(rx[0].view(h[4], H // 128, 128).to(torch.bfloat16), rx[1].to(torch.bfloat16).unsqueeze(2),
-                  out=cin.view(h[4], H // 128, 128))
+        cin = buf.get_combine_buffer(h.num_recv, H, K)
+        torch.mul(rx[0].view(h.num_recv, H // 128, 128).to(torch.bfloat16), rx[1].to(torch.bfloat16).unsqueeze(2),
+                  out=cin.view(h.num_recv, H // 128, 128))
         out, _, _ = buf.combine(cin, h, config=cfg)
         return out[:, :8].float().sum(dim=1).cpu()  # D2H read of a per-token checksum
 

@@ -95,7 +95,7 @@ def main():
             rx, ri, rw, pe, handle, _ = buf.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank,
                                                      num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w,
                                                      config=cfg, **kw)
-            nrecv = handle[4]
+            nrecv = handle.num_recv
             d_avg, d_min = timed(lambda: buf.dispatch(x, handle=handle, config=cfg, **kw))
             row = {"impl": impl, "stages": stg, "sms": sms, "mode": mode, "num_recv": nrecv, "dispatch_us": d_avg, "dispatch_min_us": d_min,
                    "dispatch_GBps": nrecv * (H if mode != "bf16" else 2 * H) / (d_avg * 1e-6) / 1e9}

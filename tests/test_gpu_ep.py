@@ -126,7 +126,7 @@ def test_dispatch_combine(n, mode, impl):
         torch.cuda.current_stream().synchronize()
         rx2 = per_token_cast_back(*recv_x2) if isinstance(recv_x2, tuple) else recv_x2
         return dict(rx=rx.cpu(), rx2=rx2.cpu(), idx=recv_idx.cpu(), w=recv_w.cpu(), per_expert=per_expert,
-                    src=handle[2].cpu(), comb=comb.cpu(), comb_w=comb_w.cpu(), raw=recv_x)
+                    src=handle.recv_src_idx.cpu(), comb=comb.cpu(), comb_w=comb_w.cpu(), raw=recv_x)
 
     outs = run_threads(bufs, fn)
     want = 1 if impl == "reg" else 2
@@ -202,7 +202,7 @@ def test_tma_pipeline_matches_register_path(n, H):
                                                          num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w, **kw)
                 torch.cuda.current_stream().synchronize()
                 parts = list(rx) if isinstance(rx, tuple) else [rx]
-                res[mode] = [p.clone().view(torch.uint8).cpu() for p in parts] + [ridx.cpu(), rw.cpu(), handle[2].cpu(), pe]
+                res[mode] = [p.clone().view(torch.uint8).cpu() for p in parts] + [ridx.cpu(), rw.cpu(), handle.recv_src_idx.cpu(), pe]
                 rx2, *_ = b.dispatch(xin, handle=handle, **kw)
                 torch.cuda.current_stream().synchronize()
                 parts2 = list(rx2) if isinstance(rx2, tuple) else [rx2]
@@ -271,6 +271,36 @@ def test_layout_multi_cta(T):
             exp_pos = torch.where(exp_in, exp_in.to(torch.int32).cumsum(0).to(torch.int32) - 1,
                                   torch.full((T, n), -1, dtype=torch.int32))
             assert torch.equal(pos.cpu(), exp_pos)
+
+
+def test_owned_results_survive_later_dispatches():
+    """`copy_out=True` / `Buffer(owned_results=True)` (what the `deep_ep` compatibility package uses) returns
+    tensors the caller owns, like the reference (ep/bench/buffer.py:1068-1106): they must survive more
+    dispatches than the arena ring has slots, while the default zero-copy views are recycled."""
+    n, T, H, K = 2, 130, 512, 4
+    E = n * 4
+    bufs = get_buffers(n)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=55)
+
+    def fn(b):
+        dev = b.device
+        x, idx, w = xs[b.rank].to(dev), idxs[b.rank].to(dev), ws[b.rank].to(dev)
+        tpr, _, tpe, in_rank, _ = b.get_dispatch_layout(idx, E)
+        kw = dict(num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe, topk_idx=idx, topk_weights=w)
+        own_x, own_idx, own_w, _, h, _ = b.dispatch(x, copy_out=True, **kw)
+        view_x, *_ = b.dispatch(x, **kw)
+        torch.cuda.current_stream().synchronize()
+        assert len(h) == 7 and h[3] == own_x.size(0) and h[6].shape == (T, n)
+        assert torch.equal(own_x, view_x)
+        ref = own_x.clone()
+        for i in range(b.runtime.num_slots + 1):  # recycle every arena with different payloads
+            b.dispatch(x * (i + 2), **kw)
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(own_x, ref), "owned result was overwritten"
+        assert not torch.equal(view_x, ref), "the zero-copy view is expected to be recycled"
+        return True
+
+    assert run_threads(bufs, fn) == [True] * n
 
 
 def test_internode_api_runs_on_the_fabric():

@@ -83,7 +83,9 @@ def test_host_ep_dispatch_combine(n):
         exp_rows = torch.cat(rows)
         assert torch.equal(o["rx"], exp_rows) and torch.equal(o["rxc"], exp_rows)
         assert torch.equal(o["ri"], torch.cat(eidx)) and torch.equal(o["rw"], torch.cat(ew))
-        assert torch.equal(o["h"][2], torch.cat(src)) and o["h"][4] == exp_rows.size(0)
+        # handle fields sit where the reference puts them (ep/bench/buffer.py:1147-1158)
+        assert torch.equal(o["h"][4], torch.cat(src)) and o["h"][3] == exp_rows.size(0) and len(o["h"]) == 7
+        assert torch.equal(o["h"].recv_src_idx, o["h"][4]) and o["h"][6].shape == (T, n) and o["h"][0].shape == (n, n)
         assert torch.equal(o["tpr"], o["inr"].sum(0).to(torch.int32))
         assert torch.equal(o["tpe"], torch.bincount(idxs[r][idxs[r] >= 0], minlength=E).to(torch.int32))
         counts = [int(sum((idxs[s_] == r * e_per + e).sum() for s_ in range(n))) for e in range(e_per)]

@@ -501,13 +501,17 @@ namespace ub {
 //  reached 9 GB/s in nccl-tests' alltoall_perf)
 __device__ __forceinline__ void half_sync(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 
-constexpr int kSrTmaStages = 10;
+constexpr int kSrTmaStages = 8;      // receive half: bulk loads in flight (zero-copy pull and staged copy-out)
+constexpr int kSrSendStages = 4;     // send half (staged push)
 constexpr uint32_t kSrTmaChunk = 16u << 10;
+constexpr int kSrPiecesPerSlot = (int)(kSrChunkBytes / kSrTmaChunk);
 
 static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_constant__ DevComm c,
                                                                 const __grid_constant__ SendRecvArgs a) {
-  extern __shared__ __align__(128) unsigned char sr_smem[];  // receive half: kSrTmaStages x kSrTmaChunk
+  extern __shared__ __align__(128) unsigned char sr_smem[];  // [recv: kSrTmaStages | send: kSrSendStages] x kSrTmaChunk
   __shared__ __align__(8) uint64_t sr_full[kSrTmaStages];
+  __shared__ __align__(8) uint64_t sr_sfull[kSrSendStages];
+  unsigned char* send_smem = sr_smem + (size_t)kSrTmaStages * kSrTmaChunk;
   __shared__ uint64_t s_hdr;
   const int me = c.rank;
   const int pi = blockIdx.x / kSrBlocks, j = blockIdx.x % kSrBlocks;
@@ -551,7 +555,9 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       }
       return;
     }
-    char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    // staged: the chunks go straight into the RECEIVER's staging slots (push: remote stores are posted, a pull
+    // would pay the NVLink round trip per slot), the receiver copies them out locally
+    char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
     if (lo >= hi) {  // an empty slice still announces the mode once (the receiver waits for one header)
       if (t == 0) {
@@ -562,38 +568,63 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       }
       return;
     }
-    for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
-      const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;
-      ++seq;
-      if (t == 0) {
-        SpinGuard g(c.timeout_ns);
-        while ((int32_t)(ld_acquire_sys(my_ack) - (seq - kSrSlots)) < 0 && seq > (uint32_t)kSrSlots) {
-          if (g.expired()) comm_abort(c, 20, peer, (int)seq);
+    if ((bytes % 16) == 0) {
+      // ---- one elected thread: sbuf -> smem -> peer slot with bulk copies, kSrSendStages pieces in flight;
+      //      slot c is announced one slot later, once its stores have completed (no stall on the newest stores)
+      if (t != 0) return;
+      for (int st = 0; st < kSrSendStages; ++st) mbar_init(&sr_sfull[st], 1);
+      mbar_fence_init();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      const uint32_t seq0 = seq;
+      const uint64_t b0 = lo * 16, b1 = hi * 16;
+      const uint64_t npieces = (b1 - b0 + kSrTmaChunk - 1) / kSrTmaChunk;
+      const uint64_t nslots = (npieces + kSrPiecesPerSlot - 1) / kSrPiecesPerSlot;
+      uint64_t issued = 0, stored = 0, announced = 0;
+      uint32_t phase_bits = 0;
+      auto announce = [&](uint64_t upto) {  // slots [announced, upto) are complete at the receiver
+        for (; announced < upto; ++announced) {
+          if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
+          st_release_sys(peer_ready, seq0 + 1 + (uint32_t)announced);
+        }
+      };
+      while (stored < npieces) {
+        while (issued < npieces && issued < stored + kSrSendStages) {
+          const int st = (int)(issued % kSrSendStages);
+          if (issued >= (uint64_t)kSrSendStages) tma_store_wait_read<kSrSendStages - 1>();
+          const uint64_t off = b0 + issued * kSrTmaChunk;
+          const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+          mbar_expect_tx(&sr_sfull[st], nb);
+          tma_load_1d(send_smem + (size_t)st * kSrTmaChunk, a.sbuf[peer] + off, nb, &sr_sfull[st]);
+          ++issued;
+        }
+        const uint64_t slot_i = stored / kSrPiecesPerSlot, piece = stored % kSrPiecesPerSlot;
+        const uint32_t sseq = seq0 + 1 + (uint32_t)slot_i;
+        if (piece == 0 && slot_i >= (uint64_t)kSrSlots) {  // the slot must have been drained by the receiver
+          SpinGuard g(c.timeout_ns);
+          while ((int32_t)(ld_acquire_sys(my_ack) - (sseq - kSrSlots)) < 0) {
+            if (g.expired()) comm_abort(c, 20, peer, (int)sseq);
+          }
+        }
+        const int st = (int)(stored % kSrSendStages);
+        mbar_wait(&sr_sfull[st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+        const uint64_t off = b0 + stored * kSrTmaChunk;
+        const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+        char* dst = stage + (uint64_t)(sseq % kSrSlots) * kSrChunkBytes + piece * kSrTmaChunk;
+        tma_store_1d(dst, send_smem + (size_t)st * kSrTmaChunk, nb);
+        tma_store_commit();
+        ++stored;
+        if (piece == kSrPiecesPerSlot - 1 && slot_i >= 1) {
+          tma_store_wait<kSrPiecesPerSlot>();  // everything but the newest slot's pieces has landed
+          announce(slot_i);
         }
       }
-      half_sync(1);
-      char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
-      constexpr int B = 8;  // loads in flight per thread
-      for (uint64_t ub = u0; ub < u1; ub += (uint64_t)B * 256) {
-        uint4 v[B];
-#pragma unroll
-        for (int q = 0; q < B; ++q) {
-          const uint64_t u = ub + (uint64_t)q * 256 + t;
-          if (u < u1) v[q] = load16_partial(a.sbuf[peer], u * 16, bytes);
-        }
-#pragma unroll
-        for (int q = 0; q < B; ++q) {
-          const uint64_t u = ub + (uint64_t)q * 256 + t;
-          if (u < u1) st_v4(slot + (u - u0) * 16, v[q]);
-        }
-      }
-      half_sync(1);
-      if (t == 0) {
-        if (u0 == lo) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;  // staged mode
-        st_release_sys(peer_ready, seq);
-      }
+      tma_store_wait<0>();
+      announce(nslots);
+      my_flags[2 * W + peer * kSrBlocks + j] = seq0 + (uint32_t)nslots;
+      return;
     }
-    if (t == 0) my_flags[2 * W + peer * kSrBlocks + j] = seq;
+    // ---- odd sizes: register path (partial last vector)
   } else {
     const uint64_t bytes = a.rbytes[peer];
     if (bytes == 0) return;
@@ -651,13 +682,62 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       }
       return;
     }
-    // ---- staged
-    const char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    // ---- staged: the sender pushed the chunks into MY slots
+    const char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
     if (lo >= hi) {
       if (t == 0) my_flags[3 * W + peer * kSrBlocks + j] = seq;
       return;
     }
+    if ((bytes % 16) == 0) {
+      // ---- one elected thread: my slot -> smem -> rbuf; a slot is acked as soon as its pieces sit in smem
+      if (t != 0) return;
+      asm volatile("fence.proxy.async;" ::: "memory");
+      const uint32_t seq0 = seq - 1;  // seq already names the first slot (its ready flag has been seen)
+      const uint64_t b0 = lo * 16, b1 = hi * 16;
+      const uint64_t npieces = (b1 - b0 + kSrTmaChunk - 1) / kSrTmaChunk;
+      const uint64_t nslots = (npieces + kSrPiecesPerSlot - 1) / kSrPiecesPerSlot;
+      uint64_t issued = 0, stored = 0, ready_slots = 1;
+      uint32_t phase_bits = 0;
+      char* dst = a.rbuf[peer];
+      while (stored < npieces) {
+        while (issued < npieces && issued < stored + kSrTmaStages) {
+          const uint64_t slot_i = issued / kSrPiecesPerSlot, piece = issued % kSrPiecesPerSlot;
+          if (slot_i >= ready_slots) {
+            if (issued > stored) break;  // drain what is in flight before blocking on the sender
+            SpinGuard g(c.timeout_ns);
+            while ((int32_t)(ld_acquire_sys(my_ready) - (seq0 + 1 + (uint32_t)slot_i)) < 0) {
+              if (g.expired()) comm_abort(c, 21, peer, (int)(seq0 + 1 + slot_i));
+            }
+            ready_slots = slot_i + 1;
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          const int st = (int)(issued % kSrTmaStages);
+          if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<kSrTmaStages - 1>();
+          const uint64_t off = b0 + issued * kSrTmaChunk;
+          const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+          const char* src = stage + (uint64_t)((seq0 + 1 + (uint32_t)slot_i) % kSrSlots) * kSrChunkBytes + piece * kSrTmaChunk;
+          mbar_expect_tx(&sr_full[st], nb);
+          tma_load_1d(sr_smem + (size_t)st * kSrTmaChunk, src, nb, &sr_full[st]);
+          ++issued;
+        }
+        const int st = (int)(stored % kSrTmaStages);
+        mbar_wait(&sr_full[st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+        const uint64_t off = b0 + stored * kSrTmaChunk;
+        const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
+        tma_store_1d(dst + off, sr_smem + (size_t)st * kSrTmaChunk, nb);
+        tma_store_commit();
+        const uint64_t slot_i = stored / kSrPiecesPerSlot;
+        ++stored;
+        // last piece of a slot has left the slot (it is in shared memory): hand the slot back
+        if (stored % kSrPiecesPerSlot == 0 || stored == npieces) st_release_sys(peer_ack, seq0 + 1 + (uint32_t)slot_i);
+      }
+      tma_store_wait<0>();
+      my_flags[3 * W + peer * kSrBlocks + j] = seq0 + (uint32_t)nslots;
+      return;
+    }
+    // ---- odd sizes: register path
     bool first = true;
     for (uint64_t u0 = lo; u0 < hi; u0 += cu) {
       const uint64_t u1 = (u0 + cu < hi) ? u0 + cu : hi;

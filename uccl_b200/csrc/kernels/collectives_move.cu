@@ -41,7 +41,7 @@ cudaError_t launch_alltoallv(const DevComm& c, const CollArgs& a, const A2AvArgs
 
 namespace ub {
 cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st) {
-  const size_t smem = (size_t)kSrTmaStages * kSrTmaChunk;
+  const size_t smem = (size_t)(kSrTmaStages + kSrSendStages) * kSrTmaChunk;
   static bool attr_done[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);

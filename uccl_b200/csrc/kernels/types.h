@@ -87,8 +87,8 @@ constexpr uint64_t kMiscBytes = 4096;
 constexpr uint64_t kXchgBytes = (uint64_t)kNumSyncDomains * kMaxSyncBlocks * kMaxRanks * 16;
 constexpr uint64_t kA2AvTabBytes = (uint64_t)kMaxSyncBlocks * kMaxRanks * 2 * sizeof(uint64_t);
 constexpr int kSrBlocks = 16;                        // CTAs per send/recv peer pair
-constexpr int kSrSlots = 2;                          // staging slots per (peer, block)
-constexpr uint64_t kSrChunkBytes = 128u << 10;       // bytes per staging slot
+constexpr int kSrSlots = 4;                          // staging slots per (peer, block)
+constexpr uint64_t kSrChunkBytes = 64u << 10;        // bytes per staging slot
 constexpr uint64_t kSrStageBytes = (uint64_t)kMaxRanks * kSrBlocks * kSrSlots * kSrChunkBytes;
 constexpr uint64_t kSrFlagBytes = 4096;              // ready/ack/sseq/rseq words
 constexpr uint64_t kLLMaxData = 1u << 20;           // max payload of the one-shot LL path

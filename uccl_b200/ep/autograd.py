@@ -33,12 +33,12 @@ class _Dispatch(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_x, _g_idx, g_w):
         buf, handle = ctx.buf, ctx.handle
-        num_recv = handle[4]
+        num_recv = handle.num_recv
         gx = g_x.contiguous() if g_x is not None else None
         if gx is None:
             return None, None, None, None, None, None, None
         gw = g_w.contiguous().float() if g_w is not None else None
-        cin = buf.get_combine_buffer(num_recv, gx.size(1), handle[6])
+        cin = buf.get_combine_buffer(num_recv, gx.size(1), handle.num_topk)
         cin[:num_recv].copy_(gx[:num_recv])
         grad_x, grad_w, _ = buf.combine(cin, handle, topk_weights=gw)
         return grad_x, grad_w, None, None, None, None, None
@@ -48,8 +48,8 @@ class _Combine(torch.autograd.Function):
     @staticmethod
     def forward(ctx, expert_out, buf, handle):
         ctx.buf, ctx.handle = buf, handle
-        num_recv = handle[4]
-        cin = buf.get_combine_buffer(num_recv, expert_out.size(1), handle[6])
+        num_recv = handle.num_recv
+        cin = buf.get_combine_buffer(num_recv, expert_out.size(1), handle.num_topk)
         cin[:num_recv].copy_(expert_out[:num_recv])
         y, _, _ = buf.combine(cin, handle)
         return y

@@ -4,8 +4,11 @@ API surface follows the reference's ``ep/bench/buffer.py`` (ctor :58-69, get_dis
 :736, dispatch :837, combine :1190, low_latency_* :263-566, configs :680-733) so code written
 against ``deep_ep.Buffer`` / ``uccl.ep`` switches over unchanged.  Differences that matter:
 
-* results (``recv_x`` ...) are zero-copy *views* of a ring of receive arenas inside the
-  symmetric heap -- valid until ``num_slots`` further dispatches (default 2);
+* results (``recv_x`` ...) are by default zero-copy *views* of a ring of receive arenas inside the
+  symmetric heap -- valid until ``num_slots`` further dispatches (default 2).  ``Buffer(owned_results=True)``
+  (or ``dispatch(..., copy_out=True)``, or the ``deep_ep`` compatibility package) returns freshly allocated
+  tensors like the reference does (ep/bench/buffer.py:1068-1106) at the price of one extra pass;
+* handles are :class:`EpHandle` tuples in the reference's field order (ep/bench/buffer.py:1147-1158);
 * ``dispatch(..., use_fp8=True)`` fuses the per-128-channel amax/scale/e4m3 cast into the
   send (the reference casts with separate torch kernels beforehand, ep/bench/utils.py:666-675);
 * ``get_combine_buffer`` hands out the symmetric arena the expert MLP should write into so
@@ -19,7 +22,7 @@ import torch
 
 from .. import _native
 from ..parallel.comm import Communicator
-from .utils import EventHandle, EventOverlap
+from .utils import EpHandle, EventHandle, EventOverlap
 
 
 class Config:
@@ -88,11 +91,16 @@ class Buffer:
     def __init__(self, group=None, num_nvl_bytes: int = 0, num_rdma_bytes: int = 0, low_latency_mode: bool = False,
                  num_qps_per_rank: int = 24, allow_nvlink_for_low_latency_mode: bool = True,
                  allow_mnnvl: bool = False, explicitly_destroy: bool = False, is_intranode: Optional[bool] = None,
-                 comm: Optional[Communicator] = None, num_slots: int = 2):
+                 comm: Optional[Communicator] = None, num_slots: int = 2, owned_results: Optional[bool] = None):
         """Either pass a ``torch.distributed`` group (one process per GPU; a private
         Communicator sized for ``num_nvl_bytes + num_rdma_bytes`` is created) or an existing
         ``comm`` (e.g. one rank of ``Communicator.local_world``)."""
         self.group = group
+        if owned_results is None:
+            import os
+
+            owned_results = os.environ.get("UCCL_B200_EP_OWNED_RESULTS", "0") == "1"
+        self.owned_results = bool(owned_results)
         self.low_latency_mode = low_latency_mode
         self.explicitly_destroy = explicitly_destroy
         self.num_nvl_bytes = int(num_nvl_bytes)
@@ -250,8 +258,9 @@ class Buffer:
                  topk_weights: Optional[torch.Tensor] = None, expert_alignment: int = 1, num_worst_tokens: int = 0,
                  config: Optional[Config] = None, previous_event: Optional[EventOverlap] = None,
                  async_finish: bool = False, allocate_on_comm_stream: bool = False, use_fp8: bool = False,
-                 round_scale: bool = False):
+                 round_scale: bool = False, copy_out: Optional[bool] = None):
         C = self._C
+        copy_out = self.owned_results if copy_out is None else bool(copy_out)
         config = config or self.get_dispatch_config(self.group_size)
         R = self.group_size
         dev = self.device
@@ -272,13 +281,19 @@ class Buffer:
 
         if handle is not None:
             # cached mode: only the payload moves (reference: buffer.py:1013-1023)
-            (rank_prefix, send_slot, recv_src_idx, h_is_in_rank, num_recv, slot, h_K) = handle
+            rank_prefix, num_recv, recv_src_idx, h_is_in_rank, send_slot = (handle.rank_prefix, handle.num_recv,
+                                                                            handle.recv_src_idx, handle.is_token_in_rank,
+                                                                            handle.send_slot)
+            h_K = handle.num_topk
             assert send_slot.shape == (T, R)
             with torch.cuda.stream(self.comm_stream):
                 o = self.runtime.dispatch(x_data.data_ptr(), x_scales.data_ptr() if x_scales is not None else 0, 0, 0,
                                           0, send_slot.data_ptr(), 0, 0, T, H, h_K, 0, mode, True, -1, 0, 1, 0,
                                           round_scale, self._sms(config), self.comm_stream.cuda_stream)
             recv_x = self._view_x(o, num_recv, H, out_fp8)
+            if copy_out:
+                with torch.cuda.stream(self.comm_stream):
+                    recv_x = tuple(t.clone() for t in recv_x) if isinstance(recv_x, tuple) else recv_x.clone()
             ev = self._exit(compute, async_finish, (x_data, x_scales, send_slot))
             return recv_x, None, None, None, None, ev
 
@@ -321,7 +336,13 @@ class Buffer:
             if topk_weights is not None:
                 recv_topk_weights = self._view(o.recv_topk_w, (num_recv, K), torch.float32)
         recv_src_idx = self._view(o.recv_src_idx, (num_recv,), torch.int32)
-        handle = (rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, o.slot, K)
+        if copy_out:  # owned tensors (DeepEP semantics): survive any number of later dispatches
+            with torch.cuda.stream(self.comm_stream):
+                recv_x = tuple(t.clone() for t in recv_x) if isinstance(recv_x, tuple) else recv_x.clone()
+                recv_topk_idx = recv_topk_idx.clone() if recv_topk_idx is not None else None
+                recv_topk_weights = recv_topk_weights.clone() if recv_topk_weights is not None else None
+                recv_src_idx = recv_src_idx.clone()
+        handle = EpHandle(rank_prefix, num_recv, recv_src_idx, is_token_in_rank, send_slot, slot=o.slot, num_topk=K)
         ev = self._exit(compute, async_finish, (x_data, x_scales, topk_idx, topk_weights, send_slot, rank_prefix,
                                                 token_pos, num_tokens_per_rank, num_tokens_per_expert))
         return recv_x, recv_topk_idx, recv_topk_weights, per_expert, handle, ev
@@ -355,7 +376,7 @@ class Buffer:
                 config: Optional[Config] = None, previous_event: Optional[EventOverlap] = None,
                 async_finish: bool = False, allocate_on_comm_stream: bool = False):
         config = config or self.get_combine_config(self.group_size)
-        (rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, slot, K) = handle
+        send_slot, num_recv = handle.send_slot, handle.num_recv
         assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous()
         assert x.size(0) >= num_recv or x.size(0) == num_recv
         H = x.size(1)

@@ -16,7 +16,7 @@ from typing import List, Optional, Tuple, Union
 import torch
 
 from ..parallel.comm import Communicator
-from .utils import EventOverlap, per_token_cast_to_fp8
+from .utils import EpHandle, EventOverlap, per_token_cast_to_fp8
 
 
 def _a2av(comm: Communicator, send: torch.Tensor, send_rows: List[int], recv_rows: List[int]) -> torch.Tensor:
@@ -61,6 +61,9 @@ def _portable(fn):
                 seen.append(v.device)
                 return v.cpu()
             return v
+        if isinstance(v, EpHandle):
+            return EpHandle(to_cpu(v.rank_prefix, seen), v.num_recv, to_cpu(v.recv_src_idx, seen),
+                            to_cpu(v.is_token_in_rank, seen), to_cpu(v.send_slot, seen), slot=v.slot, num_topk=v.num_topk)
         if isinstance(v, tuple):
             return tuple(to_cpu(e, seen) for e in v)
         if isinstance(v, list):
@@ -70,6 +73,9 @@ def _portable(fn):
     def to_dev(v, dev):
         if isinstance(v, torch.Tensor):
             return v.to(dev)
+        if isinstance(v, EpHandle):
+            return EpHandle(to_dev(v.rank_prefix, dev), v.num_recv, to_dev(v.recv_src_idx, dev),
+                            to_dev(v.is_token_in_rank, dev), to_dev(v.send_slot, dev), slot=v.slot, num_topk=v.num_topk)
         if isinstance(v, tuple):
             return tuple(to_dev(e, dev) for e in v)
         return v
@@ -172,7 +178,8 @@ class HostBuffer:
         T, H = x_data.shape
         cached = handle is not None
         if cached:
-            rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, _, K = handle
+            rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, K = (
+                handle.rank_prefix, handle.send_slot, handle.recv_src_idx, handle.is_token_in_rank, handle.num_recv, handle.num_topk)
         else:
             assert is_token_in_rank is not None and num_tokens_per_expert is not None
             rank_prefix = self._exchange_counts(is_token_in_rank.sum(0))
@@ -228,7 +235,7 @@ class HostBuffer:
             cnt = torch.bincount(recv_idx[recv_idx >= 0], minlength=e_per) if recv_idx is not None else torch.zeros(e_per, dtype=torch.int64)
             per_expert = [int((int(c) + expert_alignment - 1) // expert_alignment * expert_alignment) for c in cnt]
             num_recv = total
-        handle = (rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, 0, K)
+        handle = EpHandle(rank_prefix, num_recv, recv_src_idx, is_token_in_rank, send_slot, slot=0, num_topk=K)
         return recv_x, recv_idx, recv_w, per_expert, handle, EventOverlap()
 
     # ------------------------------------------------------------------ combine
@@ -239,7 +246,8 @@ class HostBuffer:
     def combine(self, x: torch.Tensor, handle: Tuple, topk_weights: Optional[torch.Tensor] = None, bias=None,
                 config=None, previous_event=None, async_finish: bool = False, allocate_on_comm_stream: bool = False):
         R, me = self.group_size, self.rank
-        rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, _, K = handle
+        rank_prefix, send_slot, recv_src_idx, is_token_in_rank, num_recv, K = (
+            handle.rank_prefix, handle.send_slot, handle.recv_src_idx, handle.is_token_in_rank, handle.num_recv, handle.num_topk)
         T = send_slot.size(0)
         H = x.size(1)
         back_send = [int(v) for v in rank_prefix[:, me]]   # what I received, grouped by source, goes back

@@ -18,6 +18,35 @@ class EventHandle:
         torch.cuda.current_stream().wait_event(self.event)
 
 
+class EpHandle(tuple):
+    """Handle of an intranode dispatch, in the reference's field order (ep/bench/buffer.py:1147-1158):
+
+        (rank_prefix_matrix, channel_prefix_matrix, recv_channel_prefix_matrix, num_recv_tokens,
+         recv_src_idx, is_token_in_rank, send_head)
+
+    so code that unpacks or indexes a DeepEP / uccl.ep handle keeps working.  This library has no channels
+    (tokens are placed directly), so the two channel matrices are [R, 1] placeholders, and ``send_head``
+    -- [num_tokens, num_ranks] int32 like DeepEP's -- holds the destination slot of every token at every
+    rank (-1: not routed there).  ``slot`` (receive arena of the dispatch) and ``num_topk`` ride along as
+    attributes."""
+
+    def __new__(cls, rank_prefix, num_recv, recv_src_idx, is_token_in_rank, send_slot, slot=0, num_topk=0):
+        R = rank_prefix.size(0) if hasattr(rank_prefix, "size") else 1
+        import torch as _t
+
+        dummy = _t.zeros((R, 1), dtype=_t.int32, device=getattr(rank_prefix, "device", None))
+        self = super().__new__(cls, (rank_prefix, dummy, dummy, int(num_recv), recv_src_idx, is_token_in_rank, send_slot))
+        self.slot = int(slot)
+        self.num_topk = int(num_topk)
+        return self
+
+    rank_prefix = property(lambda self: self[0])
+    num_recv = property(lambda self: self[3])
+    recv_src_idx = property(lambda self: self[4])
+    is_token_in_rank = property(lambda self: self[5])
+    send_slot = property(lambda self: self[6])
+
+
 class EventOverlap:
     """Returned by every Buffer call; lets the caller overlap communication with compute.
 
