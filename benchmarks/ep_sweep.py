@@ -115,8 +115,26 @@ def main():
             d_avg, d_min = timed(lambda: buf.low_latency_dispatch(xl, il, M, E, use_fp8=use_fp8))
             cb = buf.get_next_low_latency_combine_buffer(handle)
             c_avg, c_min = timed(lambda: buf.low_latency_combine(cb, il, wl, handle))
+            # back-to-back pairs without the L2 flush and without host gaps between the ranks (how the reference times
+            # its low-latency kernels: kineto kernel time over many iterations, ep/bench/test_low_latency.py)
+            def pair():
+                _, _, h2, _, _ = buf.low_latency_dispatch(xl, il, M, E, use_fp8=use_fp8)
+                buf.low_latency_combine(buf.get_next_low_latency_combine_buffer(h2), il, wl, h2)
+
+            for _ in range(5):
+                pair()
+            torch.cuda.synchronize()
+            if n > 1:
+                dist.barrier()
+            s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(50):
+                pair()
+            e0.record()
+            torch.cuda.synchronize()
+            pair_us = mx(s0.elapsed_time(e0) / 50) * 1e3
             row = {"ll": True, "use_fp8": use_fp8, "tokens": M, "dispatch_us": d_avg, "dispatch_min_us": d_min,
-                   "combine_us": c_avg, "combine_min_us": c_min}
+                   "combine_us": c_avg, "combine_min_us": c_min, "pair_back_to_back_us": pair_us}
             rows.append(row)
             if rank == 0:
                 print(json.dumps(row), flush=True)

@@ -23,7 +23,7 @@ UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 // 1: a one-rank communicator launches the real kernels instead of a cudaMemcpy (profiling / smoke tests on one GPU)
 UB_PARAM(ForceKernels, "FORCE_KERNELS", 0)
 // plain (non-symmetric) buffers of at least this size take the block-pipelined staged kernel (needs NVLS, > 2 ranks)
-UB_PARAM(ArPipeMinBytes, "AR_PIPE_MIN_BYTES", 96 << 20)
+UB_PARAM(ArPipeMinBytes, "AR_PIPE_MIN_BYTES", 192 << 20)
 
 const char* algo_name(int algo) {
   switch (algo) {
@@ -317,7 +317,7 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
       case ALGO_ONESHOT_LL:
       case ALGO_ONESHOT_MC: c = ctas_for(bytes, std::min(max_ctas_, 64), 8192); break;  // 512 thr x 16 B
       case ALGO_TWOSHOT_NVLS: c = ctas_for(bytes, nvls_ctas(), 64 << 10); break;
-      case ALGO_STAGED_PIPE: c = std::min(max_ctas_, 80); break;  // split into the three groups at launch
+      case ALGO_STAGED_PIPE: c = std::min(max_ctas_, 112); break;  // split into the three groups at launch
       case ALGO_STAGED_NVLS:
       case ALGO_STAGED_P2P: c = ctas_for(bytes, max_ctas_, 64 << 10); break;
       default: c = ctas_for(bytes, max_ctas_, 128 << 10); break;
@@ -398,7 +398,7 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       UB_CHECK(bytes <= kLLMaxData, "allreduce: one-shot limited to %lu bytes", (unsigned long)kLLMaxData);
     if (algo == ALGO_ONESHOT_LL || algo == ALGO_ONESHOT_MC) ctas = ctas_for(bytes, std::min(max_ctas_, 64), 8192);
     else if (algo == ALGO_TWOSHOT_NVLS) ctas = ctas_for(bytes, nvls_ctas(), 64 << 10);
-    else if (algo == ALGO_STAGED_PIPE) ctas = std::min(max_ctas_, 80);
+    else if (algo == ALGO_STAGED_PIPE) ctas = std::min(max_ctas_, 112);
     else if (algo == ALGO_STAGED_NVLS || algo == ALGO_STAGED_P2P) ctas = ctas_for(bytes, max_ctas_, 64 << 10);
     else ctas = ctas_for(bytes, max_ctas_, 128 << 10);
   }
@@ -427,8 +427,8 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       a.out_off = heap_offset(out);
     }
     if (algo == ALGO_STAGED_PIPE) {
-      // 40 % of the CTAs reduce through the switch, 30 % each copy in / out (HBM passes are the cheaper phases)
-      const int nB = std::max(4, ctas * 2 / 5), nA = std::max(4, (ctas - nB) / 2), nC = std::max(4, ctas - nB - nA);
+      // the in-switch reduce saturates with ~32 CTAs; the copy groups get the rest (they bound the fill / drain time)
+      const int nB = std::max(4, std::min(32, ctas * 2 / 5)), nA = std::max(4, (ctas - nB) / 2), nC = std::max(4, ctas - nB - nA);
       a.variant = nB | (nA << 8) | (nC << 16);
       ctas = nA + nB + nC;
     }

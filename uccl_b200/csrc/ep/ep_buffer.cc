@@ -88,14 +88,14 @@ void EpBuffer::set_impl(int impl) {
   impl_ = impl;
 }
 
-// The TMA pipelines keep a fixed number of bytes in flight per CTA, so they win whenever few CTAs
-// must saturate NVLink (the DeepEP budget of 20-24 SMs); with most of the GPU available the
-// register path has as many rows in flight and a shorter per-token critical path
-// (profiles/ep_sweep_*.json).
+// Measured (profiles/ep_sweep_{2,8}xB200.json): across NVLink the TMA pipelines match the register path on
+// dispatch at every SM budget and win the combine by 5-10 % (458 vs 511 us at 24 SMs, 436 vs 461 us at 96 on
+// 8 GPUs); on ONE GPU (HBM-only permutation, nothing to hide) the register path's shorter per-token critical
+// path is faster (29 vs 37 us combine at 148 CTAs).
 int EpBuffer::pick_impl(int grid) const {
+  (void)grid;
   if (impl_ != EP_IMPL_AUTO) return impl_;
-  if (nranks() == 1) return EP_IMPL_REG;
-  return grid <= 64 ? EP_IMPL_TMA : EP_IMPL_REG;
+  return nranks() == 1 ? EP_IMPL_REG : EP_IMPL_TMA;
 }
 
 int EpBuffer::capacity_for(int hidden, int mode, int topk) const {

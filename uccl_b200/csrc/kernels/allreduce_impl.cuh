@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(512, 1) ar_staged(const __grid_constant__ DevC
 // Inside a rank the groups hand chunks to each other through three monotonic device counters (zeroed by the last
 // CTA to leave); across ranks only the B CTAs of equal index synchronise (two barriers per chunk, as before).
 //   A(k) needs red >= (k-1) nB   (all ranks finished reading stage_in slot k&1 for chunk k-2)
-//   B(k) needs in  >= (k+1) nA   and out >= (k-1) nC, then barrier -> every rank's slot is filled / drained
+//   B(k) reduces, then needs in >= (k+2) nA and out >= k nC before the barrier that ends chunk k and opens k+1
 //   C(k) needs red >= (k+1) nB   (every shard of chunk k has been written into my stage_out)
 // a.variant = nB | nA << 8 | nC << 16; grid = nA + nB + nC (<= SM count: the groups wait for each other).
 template <typename T, int OP>
@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(512, 1) ar_staged_pipe(const __grid_constant__
 
   const uint64_t nvec_total = a.bytes / 16;
   const uint64_t slot_vec = (a.stage_bytes / 2) / 16;
-  // chunk: about a sixth of the message (pipeline depth vs. barrier count), 512 KiB granules, at most one slot
-  uint64_t chunk_vec = (nvec_total + 5) / 6;
+  // chunk: about a tenth of the message (fill / drain of the pipeline vs. one barrier per chunk), 512 KiB granules,
+  // at most one slot
+  uint64_t chunk_vec = (nvec_total + 9) / 10;
   const uint64_t gran = (512u << 10) / 16;
   chunk_vec = (chunk_vec + gran - 1) / gran * gran;
   if (chunk_vec < (8u << 20) / 16) chunk_vec = (8u << 20) / 16;
@@ -376,7 +377,11 @@ __global__ void __launch_bounds__(512, 1) ar_staged_pipe(const __grid_constant__
   };
 
   BlockSync s;
-  if (role == 1) s = sync_begin(c, kDomColl, idx);
+  if (role == 1) {
+    s = sync_begin(c, kDomColl, idx);
+    wait_ge(in_cnt, (uint64_t)nA);
+    sync_barrier(c, s);  // every rank has staged chunk 0
+  }
   for (uint64_t k = 0; k < nchunks; ++k) {
     const uint64_t base = k * chunk_vec;
     const uint64_t cvec = (nvec_total - base) < chunk_vec ? (nvec_total - base) : chunk_vec;
@@ -388,9 +393,6 @@ __global__ void __launch_bounds__(512, 1) ar_staged_pipe(const __grid_constant__
       copy_units16(c.heap[rank] + a.stage_in_off + slot_off, in + base * 16, lo, hi);
       bump(in_cnt);
     } else if (role == 1) {
-      wait_ge(in_cnt, (k + 1) * (uint64_t)nA);
-      if (k >= 2) wait_ge(out_cnt, (k - 1) * (uint64_t)nC);
-      sync_barrier(c, s);  // every rank: stage_in slot filled, stage_out slot drained
       uint64_t blo, bhi, lo, hi;
       split_range(cvec, nB, idx, blo, bhi);
       split_range(bhi - blo, n, rank, lo, hi);
@@ -417,7 +419,14 @@ __global__ void __launch_bounds__(512, 1) ar_staged_pipe(const __grid_constant__
           }
         }
       }
-      sync_barrier(c, s);  // every rank's shard of my slice has landed in my stage_out; peers are done with my stage_in
+      // ONE barrier per chunk: it says "my shard of chunk k is written everywhere" and, because the local
+      // conditions of chunk k + 1 are checked first, also "my stage_in holds chunk k + 1 and my stage_out slot of
+      // chunk k + 1 has been drained"
+      if (k + 1 < nchunks) {
+        wait_ge(in_cnt, (k + 2) * (uint64_t)nA);
+        if (k >= 1) wait_ge(out_cnt, k * (uint64_t)nC);
+      }
+      sync_barrier(c, s);
       bump(red_cnt);
     } else {
       wait_ge(red_cnt, (k + 1) * (uint64_t)nB);
