@@ -5,6 +5,7 @@ reference's p2p/benchmarks/benchmark_uccl.py --write-ipc / --read-ipc [--num-kvb
 
 Modes per (total bytes, num_kvblocks):
   write / read      one transfer() of the whole block vector, then wait()          (ONE kernel launch)
+  prepared_write    prepare_transfer() once, then post_transfer() + wait() per iteration (NIXL prepXfer/postXfer)
   async             `--inflight` transfers issued back to back on the engine's side streams, then all waited
   dual              both endpoints write to each other at the same time (bidirectional NVLink load)
   memcpy            the copy-engine baseline the reference's engine uses: one cudaMemcpyAsync per block
@@ -89,6 +90,17 @@ def main():
                 dt = timed(lambda: one(op), iters, sync)
                 res[op] = {"us": dt * 1e6, "GBps": total / dt / 1e9}
 
+            # prepared: descriptor lists resolved once, every post is one bare kernel launch
+            prep = a.prepare_transfer(conn_ab, "write", la, ra)
+
+            def posted():
+                ok_, tid = a.post_transfer(prep)
+                a.wait(tid)
+
+            dt = timed(posted, iters, sync)
+            res["prepared_write"] = {"us": dt * 1e6, "GBps": total / dt / 1e9}
+            a.release_transfer(prep)
+
             def many():
                 tids = [a.transfer(conn_ab, "write", la, ra)[1] for _ in range(args.inflight)]
                 for t_ in tids:
@@ -120,7 +132,9 @@ def main():
             res["speedup_write_vs_memcpy"] = res["memcpy_per_block"]["us"] / res["write"]["us"]
             assert bool((dst1 == 1).all()), "payload mismatch"
             rows.append(res)
+            res["speedup_prepared_vs_memcpy"] = res["memcpy_per_block"]["us"] / res["prepared_write"]["us"]
             print(f"{total:>11d} B in {nb:4d} blocks: write {res['write']['GBps']:7.1f} GB/s ({res['write']['us']:8.1f} us) | "
+                  f"prepared {res['prepared_write']['GBps']:7.1f} ({res['prepared_write']['us']:8.1f} us) | "
                   f"read {res['read']['GBps']:7.1f} | async {res['async']['GBps']:7.1f} | dual {res['dual']['GBps_per_direction']:7.1f}/dir | "
                   f"memcpy/block {res['memcpy_per_block']['GBps']:7.1f} GB/s ({res['memcpy_per_block']['us']:8.1f} us) "
                   f"-> x{res['speedup_write_vs_memcpy']:.2f}", flush=True)

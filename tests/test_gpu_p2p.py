@@ -190,3 +190,43 @@ def test_two_processes_cuda_ipc():
     [p.join(30) for p in ps]
     assert rs == (True, True, nbytes, True)
     assert rc == (True, True, True, 7 * nbytes)
+
+
+def test_prepared_transfer_moves_thousands_of_blocks_in_one_launch():
+    """prepare_transfer / post_transfer (NIXL prepXfer / postXfer): 2000 KV blocks -- more than fit in the kernel
+    parameters, so they travel in a pinned descriptor table -- move with ONE launch per post, in both directions,
+    repeatedly, incl. blocks whose size is not a multiple of 16 bytes."""
+    import torch
+
+    from uccl_b200.p2p import Endpoint
+
+    d0, d1 = 0, (1 if torch.cuda.device_count() > 1 else 0)
+    a, b = Endpoint(d0), Endpoint(d1)
+    ok, conn = a.connect(remote_metadata=b.get_metadata())
+    assert ok
+    b.accept(5000)
+    nb, blk = 2000, 4096 + 8
+    g = torch.Generator().manual_seed(1)
+    src = torch.randint(0, 255, (nb, blk), dtype=torch.uint8, generator=g).to(f"cuda:{d0}")
+    dst = torch.zeros(nb, blk, dtype=torch.uint8, device=f"cuda:{d1}")
+    back = torch.zeros(nb, blk, dtype=torch.uint8, device=f"cuda:{d0}")
+    perm = torch.randperm(nb, generator=g).tolist()  # scatter: block i lands in row perm[i]
+    la = a.register_memory([src[i] for i in range(nb)])
+    ra = a.deserialize_descs(b.get_serialized_descs(b.register_memory([dst[perm[i]] for i in range(nb)])))
+    lback = a.register_memory([back[i] for i in range(nb)])
+    torch.cuda.synchronize(d0)
+    torch.cuda.synchronize(d1)
+    k0 = a.stats()["kernel_launches"]
+    wr = a.prepare_transfer(conn, "write", la, ra)
+    rd = a.prepare_transfer(conn, "read", lback, ra)
+    for it in range(3):
+        ok, tid = a.post_transfer(wr)
+        assert ok and a.wait(tid)
+        ok, tid = a.post_transfer(rd)
+        assert ok and a.wait(tid)
+    assert a.stats()["kernel_launches"] - k0 == 6  # one launch per post
+    torch.cuda.synchronize(d0)
+    torch.cuda.synchronize(d1)
+    assert torch.equal(dst[perm].cpu(), src.cpu())
+    assert torch.equal(back.cpu(), src.cpu())
+    assert a.release_transfer(wr) and a.release_transfer(rd) and not a.release_transfer(wr)

@@ -22,6 +22,7 @@ UB_PARAM(RsPush, "RS_PUSH", 1)  // staged ReduceScatter: 1 = push into the peers
 UB_PARAM(NvlsCtas, "NVLS_CTAS", 0)  // 0: 256 / nranks
 // 1: a one-rank communicator launches the real kernels instead of a cudaMemcpy (profiling / smoke tests on one GPU)
 UB_PARAM(ForceKernels, "FORCE_KERNELS", 0)
+UB_PARAM(NvlsUnroll, "NVLS_UNROLL", 4)  // multimem.ld_reduce in flight per thread of twoshot_nvls (4 or 8)
 // plain (non-symmetric) buffers of at least this size take the block-pipelined staged kernel (needs NVLS, > 2 ranks)
 UB_PARAM(ArPipeMinBytes, "AR_PIPE_MIN_BYTES", 192 << 20)
 
@@ -426,6 +427,7 @@ void Comm::allreduce(const void* in, void* out, size_t count, int dtype, int op,
       a.in_off = heap_offset(in);
       a.out_off = heap_offset(out);
     }
+    if (algo == ALGO_TWOSHOT_NVLS) a.variant = ubParamNvlsUnroll() >= 8 ? 8 : 4;
     if (algo == ALGO_STAGED_PIPE) {
       // the in-switch reduce saturates with ~32 CTAs; the copy groups get the rest (they bound the fill / drain time)
       const int nB = std::max(4, std::min(32, ctas * 2 / 5)), nA = std::max(4, (ctas - nB) / 2), nC = std::max(4, ctas - nB - nA);

@@ -19,6 +19,8 @@
 // Fused epilogue everywhere: post-scale (avg / user scale) and output dtype cast happen in
 // registers before the result is stored -- the reference has no such fusion.
 #pragma once
+#include <type_traits>
+
 #include "launch.h"
 #include "coll_common.cuh"
 
@@ -183,25 +185,30 @@ __global__ void __launch_bounds__(512, 1) ar_twoshot(const __grid_constant__ Dev
     if constexpr (NVLS) {
       const char* in_mc = c.mc + a.in_off;
       TO* out_mc = reinterpret_cast<TO*>(c.mc + a.out_off);
-      constexpr int U = 4;
-      for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
-        uint4 r[U];
+      // in-switch reductions in flight per thread: a.variant = 8 doubles the default of 4 (UCCL_B200_NVLS_UNROLL)
+      auto body = [&](auto uc) {
+        constexpr int U = decltype(uc)::value;
+        for (uint64_t v = lo + threadIdx.x; v < hi; v += (uint64_t)blockDim.x * U) {
+          uint4 r[U];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          uint64_t vv = v + (uint64_t)j * blockDim.x;
-          if (vv < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + vv * 16);
-        }
+          for (int j = 0; j < U; ++j) {
+            uint64_t vv = v + (uint64_t)j * blockDim.x;
+            if (vv < hi) r[j] = MmLdRed<T, OP>::ld(in_mc + vv * 16);
+          }
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          uint64_t vv = v + (uint64_t)j * blockDim.x;
-          if (vv < hi) {
-            Vec16<T, OP> acc;
-            acc.init(r[j]);
-            acc.epilogue(a.ep);
-            store_out<T, OP, TO, true>(out_mc, vv * N, acc);
+          for (int j = 0; j < U; ++j) {
+            uint64_t vv = v + (uint64_t)j * blockDim.x;
+            if (vv < hi) {
+              Vec16<T, OP> acc;
+              acc.init(r[j]);
+              acc.epilogue(a.ep);
+              store_out<T, OP, TO, true>(out_mc, vv * N, acc);
+            }
           }
         }
-      }
+      };
+      if (a.variant == 8) body(std::integral_constant<int, 8>{});
+      else body(std::integral_constant<int, 4>{});
     }
   } else {
     twoshot_p2p_body<T, OP, TO>(c, a, s_off, lo, hi);

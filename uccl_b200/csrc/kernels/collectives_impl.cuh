@@ -514,6 +514,12 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
   unsigned char* send_smem = sr_smem + (size_t)kSrTmaStages * kSrTmaChunk;
   __shared__ uint64_t s_hdr;
   const int me = c.rank;
+  // the staging area is sized for kMaxRanks peers x kSrBlocks x kSrSlots slots: with fewer ranks every (peer, sub-block)
+  // pair gets a proportionally deeper window (2 ranks: 16 slots = 1 MiB in flight per pair), which is what hides the
+  // NVLink round trip of the ready / ack handshake when ONE peer must take the whole link bandwidth
+  int npow2 = 1;
+  while (npow2 < c.nranks) npow2 <<= 1;
+  const int nslots_pair = kSrSlots * (kMaxRanks / npow2);
   const int pi = blockIdx.x / kSrBlocks, j = blockIdx.x % kSrBlocks;
   const int peer = a.peers[pi];
   const bool is_send = threadIdx.x < 256;
@@ -557,7 +563,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
     }
     // staged: the chunks go straight into the RECEIVER's staging slots (push: remote stores are posted, a pull
     // would pay the NVLink round trip per slot), the receiver copies them out locally
-    char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    char* stage = c.heap[peer] + a.sr_stage_off + ((uint64_t)(me * kSrBlocks + j) * nslots_pair) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
     if (lo >= hi) {  // an empty slice still announces the mode once (the receiver waits for one header)
       if (t == 0) {
@@ -583,8 +589,14 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       uint32_t phase_bits = 0;
       auto announce = [&](uint64_t upto) {  // slots [announced, upto) are complete at the receiver
         for (; announced < upto; ++announced) {
-          if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
-          st_release_sys(peer_ready, seq0 + 1 + (uint32_t)announced);
+          if (announced == 0) {
+            *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
+            st_release_sys(peer_ready, seq0 + 1);  // orders the header word before the flag
+          } else {
+            // the slot's bulk stores have COMPLETED at the receiver (cp.async.bulk.wait_group above), so a relaxed flag
+            // store cannot overtake them; a release here would add a system-scope fence (~3 us) per 64 KiB slot
+            st_relaxed_sys(peer_ready, seq0 + 1 + (uint32_t)announced);
+          }
         }
       };
       while (stored < npieces) {
@@ -599,9 +611,11 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         }
         const uint64_t slot_i = stored / kSrPiecesPerSlot, piece = stored % kSrPiecesPerSlot;
         const uint32_t sseq = seq0 + 1 + (uint32_t)slot_i;
-        if (piece == 0 && slot_i >= (uint64_t)kSrSlots) {  // the slot must have been drained by the receiver
+        // the slot must have been drained by the receiver -- also by its kernel of the PREVIOUS message on this
+        // (peer, sub-block) pair, which may still be copying out while this launch already runs: sequence numbers are global
+        if (piece == 0 && sseq > (uint32_t)nslots_pair) {
           SpinGuard g(c.timeout_ns);
-          while ((int32_t)(ld_acquire_sys(my_ack) - (sseq - kSrSlots)) < 0) {
+          while ((int32_t)(ld_acquire_sys(my_ack) - (sseq - (uint32_t)nslots_pair)) < 0) {
             if (g.expired()) comm_abort(c, 20, peer, (int)sseq);
           }
         }
@@ -610,7 +624,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         phase_bits ^= 1u << st;
         const uint64_t off = b0 + stored * kSrTmaChunk;
         const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
-        char* dst = stage + (uint64_t)(sseq % kSrSlots) * kSrChunkBytes + piece * kSrTmaChunk;
+        char* dst = stage + (uint64_t)(sseq % (uint32_t)nslots_pair) * kSrChunkBytes + piece * kSrTmaChunk;
         tma_store_1d(dst, send_smem + (size_t)st * kSrTmaChunk, nb);
         tma_store_commit();
         ++stored;
@@ -683,7 +697,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       return;
     }
     // ---- staged: the sender pushed the chunks into MY slots
-    const char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * kSrSlots) * kSrChunkBytes;
+    const char* stage = c.heap[me] + a.sr_stage_off + ((uint64_t)(peer * kSrBlocks + j) * nslots_pair) * kSrChunkBytes;
     const uint64_t cu = kSrChunkBytes / 16;
     if (lo >= hi) {
       if (t == 0) my_flags[3 * W + peer * kSrBlocks + j] = seq;
@@ -716,7 +730,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
           if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<kSrTmaStages - 1>();
           const uint64_t off = b0 + issued * kSrTmaChunk;
           const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
-          const char* src = stage + (uint64_t)((seq0 + 1 + (uint32_t)slot_i) % kSrSlots) * kSrChunkBytes + piece * kSrTmaChunk;
+          const char* src = stage + (uint64_t)((seq0 + 1 + (uint32_t)slot_i) % (uint32_t)nslots_pair) * kSrChunkBytes + piece * kSrTmaChunk;
           mbar_expect_tx(&sr_full[st], nb);
           tma_load_1d(sr_smem + (size_t)st * kSrTmaChunk, src, nb, &sr_full[st]);
           ++issued;
@@ -731,7 +745,8 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         const uint64_t slot_i = stored / kSrPiecesPerSlot;
         ++stored;
         // last piece of a slot has left the slot (it is in shared memory): hand the slot back
-        if (stored % kSrPiecesPerSlot == 0 || stored == npieces) st_release_sys(peer_ack, seq0 + 1 + (uint32_t)slot_i);
+        // (relaxed: the slot's bytes already sit in shared memory -- the mbarrier waits above -- nothing to order)
+        if (stored % kSrPiecesPerSlot == 0 || stored == npieces) st_relaxed_sys(peer_ack, seq0 + 1 + (uint32_t)slot_i);
       }
       tma_store_wait<0>();
       my_flags[3 * W + peer * kSrBlocks + j] = seq0 + (uint32_t)nslots;
@@ -752,7 +767,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         half_sync(2);
       }
       first = false;
-      const char* slot = stage + (uint64_t)(seq % kSrSlots) * kSrChunkBytes;
+      const char* slot = stage + (uint64_t)(seq % (uint32_t)nslots_pair) * kSrChunkBytes;
       constexpr int B = 8;
       for (uint64_t ub = u0; ub < u1; ub += (uint64_t)B * 256) {
         uint4 v[B];

@@ -110,6 +110,28 @@ void bind_p2p(py::module_& m) {
              bool ok = e.recv_async(conn, to_ptrs<void*>(ptrs), sizes, &tid);
              return py::make_tuple(ok, tid);
            })
+      .def("prepare",
+           [](Endpoint& e, uint64_t conn, bool is_write, std::vector<uintptr_t> ptrs, std::vector<size_t> sizes,
+              std::vector<py::bytes> blobs) {
+             std::vector<const void*> lp;
+             for (auto p : ptrs) lp.push_back((const void*)p);
+             std::vector<XferDesc> rd(blobs.size());
+             for (size_t i = 0; i < blobs.size(); ++i) {
+               std::string b = blobs[i];
+               UB_CHECK(b.size() == sizeof(XferDesc), "prepare: descriptor must be %zu bytes", sizeof(XferDesc));
+               memcpy(&rd[i], b.data(), sizeof(XferDesc));
+             }
+             uint64_t id = 0;
+             bool ok = e.prepare(conn, is_write, lp, sizes, rd, &id);
+             return py::make_tuple(ok, id);
+           })
+      .def("post",
+           [](Endpoint& e, uint64_t prep) {
+             uint64_t tid = 0;
+             bool ok = e.post(prep, &tid);
+             return py::make_tuple(ok, tid);
+           })
+      .def("release", &Endpoint::release)
       .def("write_async",
            [](Endpoint& e, uint64_t conn, std::vector<uintptr_t> src, std::vector<size_t> sizes,
               std::vector<std::string> remote) {

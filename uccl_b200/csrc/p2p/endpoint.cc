@@ -22,6 +22,9 @@ namespace ub {
 UB_PARAM(P2PCtas, "P2P_CTAS", 0)       // 0: by transfer size (8 / 32 / 64 CTAs)
 UB_PARAM(P2PChunkKB, "P2P_CHUNK_KB", 16)  // bytes per bulk copy; 4 pipelines x 3 stages of it per CTA
 UB_PARAM(P2PUseKernel, "P2P_USE_KERNEL", 1)
+// a handful of very large blocks is what the copy engines are best at (754 vs 700 GB/s at 512 MiB on 2 B200): up to 8
+// blocks of at least this many MiB each go through cudaMemcpyAsync, everything else through the TMA copy kernel
+UB_PARAM(P2PMemcpyMinMB, "P2P_MEMCPY_MIN_MB", 32)
 // engine status line every N seconds at INFO level (reference: per-engine stats thread every 2 s unless
 // UCCL_ENGINE_QUIET, collective/rdma/transport.cc:1797-1825); 0 = off
 UB_PARAM(P2PStatsSec, "ENGINE_STATS_SEC", 0)
@@ -568,6 +571,155 @@ void* Endpoint::map_remote(const XferDesc& d) {
 }
 
 // ------------------------------------------------------------------ data path
+static cudaEvent_t new_event();
+
+bool Endpoint::is_device_ptr(const void* p) {
+  const uint64_t key = (uint64_t)(uintptr_t)p >> 21;  // allocations are at least 2 MiB-granular in the VA space
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = ptr_is_device_.find(key);
+    if (it != ptr_is_device_.end()) return it->second;
+  }
+  cudaPointerAttributes a;
+  memset(&a, 0, sizeof(a));
+  bool dev = cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice;
+  (void)cudaGetLastError();
+  if (dev) {  // only positive answers are cached: host memory can be remapped, device VA ranges are not reused as host
+    std::lock_guard<std::mutex> g(mu_);
+    if (ptr_is_device_.size() > (1u << 16)) ptr_is_device_.clear();
+    ptr_is_device_[key] = true;
+  }
+  return dev;
+}
+
+// Cuts a block vector into launches of the copy kernel: up to kP2PMaxEntries blocks ride in the kernel parameters,
+// larger batches in pinned descriptor tables of kP2PTableEntries entries each.
+bool Endpoint::build_launches(const std::vector<const char*>& src, const std::vector<char*>& dst,
+                              const std::vector<size_t>& sizes, std::vector<CopyLaunch>* out) {
+  const size_t n = src.size();
+  const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(16, ubParamP2PChunkKB())) * 1024;
+  const size_t per_launch = n > (size_t)kP2PMaxEntries ? (size_t)kP2PTableEntries : (size_t)kP2PMaxEntries;
+  for (size_t i0 = 0; i0 < n; i0 += per_launch) {
+    out->emplace_back();
+    CopyLaunch& l = out->back();
+    P2PCopyBatch& b = l.b;
+    memset(&b, 0, sizeof(b));
+    b.chunk_bytes = chunk;
+    const size_t m = std::min<size_t>(per_launch, n - i0);
+    P2PCopyEntry* ents = b.e;
+    uint32_t* pfx = b.chunk_prefix;
+    if (m > (size_t)kP2PMaxEntries) {
+      l.tab = acquire_table();
+      if (!l.tab) {
+        for (auto& r : *out)
+          if (r.tab) release_table_cb(r.tab);
+        out->clear();
+        return false;
+      }
+      ents = (P2PCopyEntry*)l.tab->host;
+      pfx = (uint32_t*)((char*)l.tab->host + sizeof(P2PCopyEntry) * kP2PTableEntries);
+      b.table = (const P2PCopyEntry*)l.tab->dev;
+      b.table_prefix = (const uint32_t*)((char*)l.tab->dev + sizeof(P2PCopyEntry) * kP2PTableEntries);
+    }
+    uint64_t total = 0, bytes_total = 0;
+    for (size_t j = 0; j < m; ++j) {
+      auto& e = ents[j];
+      e.src = src[i0 + j];
+      e.dst = dst[i0 + j];
+      e.bytes = sizes[i0 + j];
+      const bool al = ((((uintptr_t)e.src) | ((uintptr_t)e.dst)) & 15) == 0;
+      e.bulk_bytes = al ? (e.bytes / 16 * 16) : 0;
+      pfx[j] = (uint32_t)total;
+      total += (e.bulk_bytes + chunk - 1) / chunk;
+      bytes_total += e.bytes;
+    }
+    pfx[m] = (uint32_t)total;
+    b.n = (int)m;
+    // enough CTAs for the bytes in flight the link needs (4 pipelines x 3 stages x chunk each); small
+    // transfers keep the launch small so they do not take SMs from a co-running kernel
+    int64_t want = ubParamP2PCtas();
+    if (want <= 0) want = bytes_total >= (8u << 20) ? 64 : (bytes_total >= (1u << 20) ? 32 : 8);
+    l.grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)((total + kP2PWarps - 1) / kP2PWarps)));
+  }
+  return true;
+}
+
+bool Endpoint::prepare(uint64_t conn, bool is_write, const std::vector<const void*>& local,
+                       const std::vector<size_t>& sizes, const std::vector<XferDesc>& remote, uint64_t* prep_id) {
+  auto c = find_conn(conn);
+  if (!c || gpu_ < 0 || local.size() != sizes.size() || local.size() != remote.size() || local.empty()) return false;
+  if (remote_is_other_process(remote[0])) return false;  // not load/store reachable: use write_async / read_async
+  cudaSetDevice(gpu_);
+  std::vector<const char*> s;
+  std::vector<char*> d;
+  auto p = std::make_shared<Prepared>();
+  for (size_t i = 0; i < local.size(); ++i) {
+    if (sizes[i] > remote[i].size) return false;
+    void* r = map_remote(remote[i]);
+    if (!r || !is_device_ptr(r) || !is_device_ptr(local[i])) return false;
+    s.push_back(is_write ? (const char*)local[i] : (const char*)r);
+    d.push_back(is_write ? (char*)r : (char*)local[i]);
+    p->bytes += sizes[i];
+  }
+  if (!build_launches(s, d, sizes, &p->launches)) return false;
+  p->conn = c;
+  p->is_write = is_write;
+  std::lock_guard<std::mutex> g(mu_);
+  const uint64_t id = next_prep_++;
+  prepared_[id] = p;
+  if (prep_id) *prep_id = id;
+  return true;
+}
+
+bool Endpoint::post(uint64_t prep_id, uint64_t* tid) {
+  std::shared_ptr<Prepared> p;
+  cudaStream_t st;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = prepared_.find(prep_id);
+    if (it == prepared_.end()) return false;
+    p = it->second;
+    st = streams_[next_stream_++ % streams_.size()];
+  }
+  cudaSetDevice(gpu_);
+  for (auto& l : p->launches) {
+    cudaError_t e = launch_p2p_copy(l.b, l.grid, st);
+    if (e != cudaSuccess) {
+      UB_WARN("p2p copy kernel launch failed: %s", cudaGetErrorString(e));
+      return false;
+    }
+  }
+  auto t = std::make_shared<Transfer>();
+  t->conn = p->conn;
+  t->state = Transfer::COPYING;
+  t->ev = new_event();
+  if (cudaEventRecord(t->ev, st) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> g(mu_);
+  t->id = next_tid_++;
+  transfers_[t->id] = t;
+  stats_.transfers++;
+  stats_.kernel_launches += p->launches.size();
+  (p->is_write ? stats_.bytes_written : stats_.bytes_read) += p->bytes;
+  if (tid) *tid = t->id;
+  return true;
+}
+
+bool Endpoint::release(uint64_t prep_id) {
+  std::shared_ptr<Prepared> p;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    auto it = prepared_.find(prep_id);
+    if (it == prepared_.end()) return false;
+    p = it->second;
+    prepared_.erase(it);
+  }
+  // launches that still read the tables must finish before the tables are reused
+  for (auto st : streams_) cudaStreamSynchronize(st);
+  for (auto& l : p->launches)
+    if (l.tab) release_table_cb(l.tab);
+  return true;
+}
+
 bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
                            const std::vector<size_t>& sizes, cudaEvent_t ev) {
   if (gpu_ < 0) {
@@ -583,71 +735,31 @@ bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vecto
   }
   const size_t n = src.size();
   bool any_host = false;
-  for (size_t i = 0; i < n; ++i) {
-    cudaPointerAttributes a;
-    memset(&a, 0, sizeof(a));
-    if (cudaPointerGetAttributes(&a, src[i]) != cudaSuccess || a.type == cudaMemoryTypeHost ||
-        a.type == cudaMemoryTypeUnregistered)
-      any_host = true;
-    if (cudaPointerGetAttributes(&a, dst[i]) != cudaSuccess || a.type == cudaMemoryTypeHost ||
-        a.type == cudaMemoryTypeUnregistered)
-      any_host = true;
-    (void)cudaGetLastError();
-  }
-  if (any_host || !ubParamP2PUseKernel()) {
+  for (size_t i = 0; i < n && !any_host; ++i) any_host = !is_device_ptr(src[i]) || !is_device_ptr(dst[i]);
+  bool few_large = n <= 8 && ubParamP2PMemcpyMinMB() > 0;
+  for (size_t i = 0; i < n && few_large; ++i) few_large = sizes[i] >= ((size_t)ubParamP2PMemcpyMinMB() << 20);
+  if (any_host || few_large || !ubParamP2PUseKernel()) {
     for (size_t i = 0; i < n; ++i)
       if (cudaMemcpyAsync(dst[i], src[i], sizes[i], cudaMemcpyDefault, st) != cudaSuccess) return false;
     std::lock_guard<std::mutex> g(mu_);
     stats_.memcpy_fallbacks += n;
   } else {
-    const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(16, ubParamP2PChunkKB())) * 1024;
-    const size_t per_launch = n > (size_t)kP2PMaxEntries ? (size_t)kP2PTableEntries : (size_t)kP2PMaxEntries;
-    for (size_t i0 = 0; i0 < n; i0 += per_launch) {
-      P2PCopyBatch b;
-      memset(&b, 0, sizeof(b));
-      b.chunk_bytes = chunk;
-      const size_t m = std::min<size_t>(per_launch, n - i0);
-      DescTable* tab = nullptr;
-      P2PCopyEntry* ents = b.e;
-      uint32_t* pfx = b.chunk_prefix;
-      if (m > (size_t)kP2PMaxEntries) {
-        tab = acquire_table();
-        if (!tab) return false;
-        ents = (P2PCopyEntry*)tab->host;
-        pfx = (uint32_t*)((char*)tab->host + sizeof(P2PCopyEntry) * kP2PTableEntries);
-        b.table = (const P2PCopyEntry*)tab->dev;
-        b.table_prefix = (const uint32_t*)((char*)tab->dev + sizeof(P2PCopyEntry) * kP2PTableEntries);
-      }
-      uint64_t total = 0, bytes_total = 0;
-      for (size_t j = 0; j < m; ++j) {
-        auto& e = ents[j];
-        e.src = src[i0 + j];
-        e.dst = dst[i0 + j];
-        e.bytes = sizes[i0 + j];
-        const bool al = ((((uintptr_t)e.src) | ((uintptr_t)e.dst)) & 15) == 0;
-        e.bulk_bytes = al ? (e.bytes / 16 * 16) : 0;
-        pfx[j] = (uint32_t)total;
-        total += (e.bulk_bytes + chunk - 1) / chunk;
-        bytes_total += e.bytes;
-      }
-      pfx[m] = (uint32_t)total;
-      b.n = (int)m;
-      // enough CTAs for the bytes in flight the link needs (4 pipelines x 3 stages x chunk each); small
-      // transfers keep the launch small so they do not take SMs from a co-running kernel
-      int64_t want = ubParamP2PCtas();
-      if (want <= 0) want = bytes_total >= (8u << 20) ? 64 : (bytes_total >= (1u << 20) ? 32 : 8);
-      int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)((total + kP2PWarps - 1) / kP2PWarps)));
-      cudaError_t e = launch_p2p_copy(b, grid, st);
+    std::vector<CopyLaunch> ls;
+    if (!build_launches(src, dst, sizes, &ls)) return false;
+    for (auto& l : ls) {
+      cudaError_t e = launch_p2p_copy(l.b, l.grid, st);
       if (e != cudaSuccess) {
         UB_WARN("p2p copy kernel launch failed: %s", cudaGetErrorString(e));
-        if (tab) release_table_cb(tab);
+        for (auto& r : ls)
+          if (r.tab) release_table_cb(r.tab);
         return false;
       }
-      if (tab && cudaLaunchHostFunc(st, release_table_cb, tab) != cudaSuccess) {
+      if (l.tab && cudaLaunchHostFunc(st, release_table_cb, l.tab) != cudaSuccess) {
         (void)cudaGetLastError();  // could not enqueue the callback: drain the stream and recycle by hand
         cudaStreamSynchronize(st);
-        release_table_cb(tab);
+        release_table_cb(l.tab);
       }
+      l.tab = nullptr;
       std::lock_guard<std::mutex> g(mu_);
       stats_.kernel_launches++;
     }

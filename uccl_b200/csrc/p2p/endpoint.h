@@ -66,6 +66,13 @@ class Endpoint {
   bool read_async(uint64_t conn, const std::vector<void*>& dst, const std::vector<size_t>& sizes,
                   const std::vector<XferDesc>& remote, uint64_t* tid);
   bool advertise(uint64_t conn, const void* ptr, size_t size, XferDesc* out);
+  // ---- prepared transfers (NIXL's prepXfer / postXfer): descriptors are resolved, peers mapped and the copy kernel's
+  //      descriptor tables built ONCE; every post() is then a bare kernel launch + event, however many blocks it moves
+  //      (a KV-cache mover re-sends the same page lists).  Load/store reachable peers only (returns false otherwise).
+  bool prepare(uint64_t conn, bool is_write, const std::vector<const void*>& local, const std::vector<size_t>& sizes,
+               const std::vector<XferDesc>& remote, uint64_t* prep_id);
+  bool post(uint64_t prep_id, uint64_t* tid);
+  bool release(uint64_t prep_id);
 
   // poll once: *done = finished (the handle is released when done, like the reference's poll_async)
   bool poll_async(uint64_t tid, bool* done);
@@ -92,6 +99,24 @@ class Endpoint {
   void progress_locked();
   bool launch_copy(const std::vector<const char*>& src, const std::vector<char*>& dst,
                    const std::vector<size_t>& sizes, cudaEvent_t ev);
+  struct DescTable;
+  struct CopyLaunch {  // one launch of the copy kernel
+    P2PCopyBatch b;
+    int grid = 1;
+    DescTable* tab = nullptr;
+  };
+  bool is_device_ptr(const void* p);  // cached cudaPointerGetAttributes (2 MiB granules)
+  bool build_launches(const std::vector<const char*>& src, const std::vector<char*>& dst, const std::vector<size_t>& sizes,
+                      std::vector<CopyLaunch>* out);
+  struct Prepared {
+    std::shared_ptr<Conn> conn;
+    bool is_write = true;
+    uint64_t bytes = 0;
+    std::vector<CopyLaunch> launches;
+  };
+  std::map<uint64_t, std::shared_ptr<Prepared>> prepared_;
+  uint64_t next_prep_ = 1;
+  std::unordered_map<uint64_t, bool> ptr_is_device_;
   void* map_remote(const XferDesc& d);
   std::shared_ptr<Conn> find_conn(uint64_t id);
   void wake();

@@ -312,6 +312,27 @@ class Endpoint:
         fn = self._e.write_async if op == "write" else self._e.read_async
         return fn(conn_id, ptrs, sizes, blobs)
 
+    # ---- prepared transfers (NIXL prepXfer / postXfer)
+    def prepare_transfer(self, conn_id: int, op: str, local_descs: Sequence[XferDesc], remote_descs: Sequence[XferDesc]):
+        """Resolve the descriptor lists once (peer mapping, kernel descriptor tables in pinned memory).  Returns a
+        handle for :meth:`post_transfer`; every post is then a bare kernel launch, however many blocks it moves --
+        the shape of a KV-cache mover that re-sends the same page lists.  Raises if the peer is not load/store
+        reachable (another host): use :meth:`transfer` there."""
+        assert op in ("read", "write") and len(local_descs) == len(remote_descs)
+        ptrs = [d.addr for d in local_descs]
+        sizes = [min(l.size, r.size) for l, r in zip(local_descs, remote_descs)]
+        ok, prep = self._e.prepare(conn_id, op == "write", ptrs, sizes, [r.raw for r in remote_descs])
+        if not ok:
+            raise RuntimeError("uccl_b200.p2p: prepare_transfer needs a load/store reachable peer and device memory")
+        return prep
+
+    def post_transfer(self, prep: int):
+        """Launch a prepared transfer: ``(ok, transfer_id)`` like :meth:`transfer`."""
+        return self._e.post(prep)
+
+    def release_transfer(self, prep: int) -> bool:
+        return self._e.release(prep)
+
     def poll_async(self, transfer_id: int):
         return self._e.poll_async(transfer_id)
 
