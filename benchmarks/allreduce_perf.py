@@ -83,6 +83,8 @@ def main():
                 variants += [("oneshot_ll", True)] + ([("oneshot_mc", True)] if comm.has_multicast else [])
             variants += [("twoshot_p2p", True)] + ([("twoshot_nvls", True)] if comm.has_multicast else [])
             variants += [("staged_p2p", False)] + ([("staged_nvls", False)] if comm.has_multicast else [])
+            if comm.has_multicast and n > 2 and size >= (32 << 20) and size % 16 == 0:
+                variants += [("staged_pipe", False)]
             for algo, sym in variants:
                 for ctas in cta_list:
                     src = big_in if sym else plain_in

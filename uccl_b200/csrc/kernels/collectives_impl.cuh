@@ -522,6 +522,12 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
   const int nslots_pair = kSrSlots * (kMaxRanks / npow2);
   const int pi = blockIdx.x / kSrBlocks, j = blockIdx.x % kSrBlocks;
   const int peer = a.peers[pi];
+  // sub-blocks that take part in a message: one per 64 KiB, so a small message costs one handshake, not sixteen
+  // (both ends derive the count from the byte count they were given, which NCCL semantics require to match)
+  auto active_blocks = [](uint64_t bytes) -> int {
+    const uint64_t nb = (bytes + (64u << 10) - 1) / (64u << 10);
+    return nb < 1 ? 1 : (nb > (uint64_t)kSrBlocks ? kSrBlocks : (int)nb);
+  };
   const bool is_send = threadIdx.x < 256;
   const int t = threadIdx.x & 255;
   // flag words (u32) inside every heap: ready[src][j], ack[dst][j], sseq[dst][j], rseq[src][j], then u64 hdr[src][j]
@@ -540,8 +546,10 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
   if (is_send) {
     const uint64_t bytes = a.sbytes[peer];
     if (bytes == 0) return;
+    const int nb = active_blocks(bytes);
+    if (j >= nb) return;
     uint64_t lo, hi;
-    split_range((bytes + 15) / 16, kSrBlocks, j, lo, hi);
+    split_range((bytes + 15) / 16, nb, j, lo, hi);
     uint32_t seq = my_flags[2 * W + peer * kSrBlocks + j];
     uint32_t* my_ack = my_flags + 1 * W + peer * kSrBlocks + j;
     uint32_t* peer_ready = flags(peer) + 0 * W + me * kSrBlocks + j;
@@ -642,8 +650,10 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
   } else {
     const uint64_t bytes = a.rbytes[peer];
     if (bytes == 0) return;
+    const int nb = active_blocks(bytes);
+    if (j >= nb) return;
     uint64_t lo, hi;
-    split_range((bytes + 15) / 16, kSrBlocks, j, lo, hi);
+    split_range((bytes + 15) / 16, nb, j, lo, hi);
     uint32_t seq = my_flags[3 * W + peer * kSrBlocks + j];
     uint32_t* my_ready = my_flags + 0 * W + peer * kSrBlocks + j;
     uint32_t* peer_ack = flags(peer) + 1 * W + me * kSrBlocks + j;

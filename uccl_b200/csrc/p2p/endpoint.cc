@@ -172,6 +172,7 @@ Endpoint::~Endpoint() {
   for (auto e : event_pool_) cudaEventDestroy(e);
   for (auto* t : tables_all_) {
     cudaFreeHost(t->host);
+    cudaFree(t->dev);
     delete t;
   }
 }
@@ -595,7 +596,7 @@ bool Endpoint::is_device_ptr(const void* p) {
 // Cuts a block vector into launches of the copy kernel: up to kP2PMaxEntries blocks ride in the kernel parameters,
 // larger batches in pinned descriptor tables of kP2PTableEntries entries each.
 bool Endpoint::build_launches(const std::vector<const char*>& src, const std::vector<char*>& dst,
-                              const std::vector<size_t>& sizes, std::vector<CopyLaunch>* out) {
+                              const std::vector<size_t>& sizes, std::vector<CopyLaunch>* out, cudaStream_t st) {
   const size_t n = src.size();
   const uint32_t chunk = (uint32_t)std::max<int64_t>(4, std::min<int64_t>(16, ubParamP2PChunkKB())) * 1024;
   const size_t per_launch = n > (size_t)kP2PMaxEntries ? (size_t)kP2PTableEntries : (size_t)kP2PMaxEntries;
@@ -632,9 +633,22 @@ bool Endpoint::build_launches(const std::vector<const char*>& src, const std::ve
       pfx[j] = (uint32_t)total;
       total += (e.bulk_bytes + chunk - 1) / chunk;
       bytes_total += e.bytes;
+      if (e.bulk_bytes != e.bytes) b.any_tail = 1;
     }
     pfx[m] = (uint32_t)total;
     b.n = (int)m;
+    if (l.tab) {  // upload the part of the table that is in use
+      const size_t eb = sizeof(P2PCopyEntry) * m, pb = sizeof(uint32_t) * (m + 1);
+      const size_t poff = sizeof(P2PCopyEntry) * kP2PTableEntries;
+      if (cudaMemcpyAsync(l.tab->dev, l.tab->host, eb, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+          cudaMemcpyAsync((char*)l.tab->dev + poff, (char*)l.tab->host + poff, pb, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        (void)cudaGetLastError();
+        for (auto& r : *out)
+          if (r.tab) release_table_cb(r.tab);
+        out->clear();
+        return false;
+      }
+    }
     // enough CTAs for the bytes in flight the link needs (4 pipelines x 3 stages x chunk each); small
     // transfers keep the launch small so they do not take SMs from a co-running kernel
     int64_t want = ubParamP2PCtas();
@@ -661,7 +675,9 @@ bool Endpoint::prepare(uint64_t conn, bool is_write, const std::vector<const voi
     d.push_back(is_write ? (char*)r : (char*)local[i]);
     p->bytes += sizes[i];
   }
-  if (!build_launches(s, d, sizes, &p->launches)) return false;
+  cudaStream_t up = streams_[0];
+  if (!build_launches(s, d, sizes, &p->launches, up)) return false;
+  cudaStreamSynchronize(up);  // the tables are resident before the first post (which may use another stream)
   p->conn = c;
   p->is_write = is_write;
   std::lock_guard<std::mutex> g(mu_);
@@ -745,7 +761,7 @@ bool Endpoint::launch_copy(const std::vector<const char*>& src, const std::vecto
     stats_.memcpy_fallbacks += n;
   } else {
     std::vector<CopyLaunch> ls;
-    if (!build_launches(src, dst, sizes, &ls)) return false;
+    if (!build_launches(src, dst, sizes, &ls, st)) return false;
     for (auto& l : ls) {
       cudaError_t e = launch_p2p_copy(l.b, l.grid, st);
       if (e != cudaSuccess) {
@@ -779,8 +795,7 @@ Endpoint::DescTable* Endpoint::acquire_table() {
   auto* t = new DescTable();
   t->owner = this;
   const size_t bytes = sizeof(P2PCopyEntry) * kP2PTableEntries + sizeof(uint32_t) * (kP2PTableEntries + 1);
-  if (cudaHostAlloc(&t->host, bytes, cudaHostAllocMapped) != cudaSuccess ||
-      cudaHostGetDevicePointer(&t->dev, t->host, 0) != cudaSuccess) {
+  if (cudaHostAlloc(&t->host, bytes, cudaHostAllocDefault) != cudaSuccess || cudaMalloc(&t->dev, bytes) != cudaSuccess) {
     (void)cudaGetLastError();
     if (t->host) cudaFreeHost(t->host);
     delete t;

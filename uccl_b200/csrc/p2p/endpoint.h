@@ -106,8 +106,9 @@ class Endpoint {
     DescTable* tab = nullptr;
   };
   bool is_device_ptr(const void* p);  // cached cudaPointerGetAttributes (2 MiB granules)
+  // tables are uploaded on `st` (stream-ordered before the launches that read them)
   bool build_launches(const std::vector<const char*>& src, const std::vector<char*>& dst, const std::vector<size_t>& sizes,
-                      std::vector<CopyLaunch>* out);
+                      std::vector<CopyLaunch>* out, cudaStream_t st);
   struct Prepared {
     std::shared_ptr<Conn> conn;
     bool is_write = true;
@@ -155,8 +156,8 @@ class Endpoint {
   // pinned, device-mapped descriptor tables for batches of more than kP2PMaxEntries blocks; a table goes back
   // to the pool from a stream callback once its kernel has finished
   struct DescTable {
-    void* host = nullptr;  // [kP2PTableEntries] P2PCopyEntry, then [kP2PTableEntries + 1] u32 chunk prefix
-    void* dev = nullptr;
+    void* host = nullptr;  // pinned staging: [kP2PTableEntries] P2PCopyEntry, then [kP2PTableEntries + 1] u32 chunk prefix
+    void* dev = nullptr;   // the device copy the kernel reads
     Endpoint* owner = nullptr;
   };
   std::vector<DescTable*> table_pool_;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(kCopyThreads) p2p_copy_kernel(const __grid_con
       ++stored;
     }
     tma_store_wait<0>();
-  } else {
+  } else if (b.any_tail) {
     // ---- the other lanes: unaligned entries and < 16-byte tails with plain loads/stores
     const int t = warp * 31 + (lane - 1), nt = kP2PWarps * 31;
     for (int e = 0; e < b.n; ++e) {

@@ -21,10 +21,12 @@ struct P2PCopyBatch {
   uint32_t chunk_prefix[kP2PMaxEntries + 1];  // exclusive prefix of per-entry bulk chunk counts
   int n;
   uint32_t chunk_bytes;
-  // n > kP2PMaxEntries: the descriptors live in pinned, device-mapped host memory instead (one launch moves
-  // thousands of KV blocks); `table_prefix` has n + 1 words
+  // n > kP2PMaxEntries: the descriptors live in a DEVICE table instead (filled through a pinned staging copy; a
+  // first version let the kernel read the pinned table itself and spent 1.8 ms on PCIe round trips for 1024
+  // blocks); one launch moves thousands of KV blocks.  `table_prefix` has n + 1 words
   const P2PCopyEntry* table;
   const uint32_t* table_prefix;
+  int any_tail;  // some entry is not a 16-byte multiple / aligned: the non-issuing lanes copy those bytes
 };
 
 // A registered/advertised memory window, shipped between endpoints (128 bytes on the wire).

@@ -102,10 +102,15 @@ class Communicator:
         self.device_index: int = c.device
         self.is_host: bool = c.is_host
         self.device = torch.device("cpu") if self.is_host else torch.device("cuda", c.device)
-        if os.environ.get("UCCL_B200_TUNE_FILE"):  # measured (algorithm, CTAs) per size: utils/tuner.py
-            from ..utils.tuner import load_tuning_from_env
+        # measured (algorithm, CTAs) per size: UCCL_B200_TUNE_FILE, else the table shipped for this world size
+        from ..utils.tuner import load_tuning_from_env
 
+        try:
             load_tuning_from_env(self)
+        except Exception as e:  # noqa: BLE001 - a bad table must not prevent communication
+            import warnings
+
+            warnings.warn(f"uccl_b200: tuning table ignored ({e})")
 
     # ------------------------------------------------------------------ construction
     @staticmethod

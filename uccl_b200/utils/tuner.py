@@ -107,7 +107,7 @@ def tuning_from_sweep(sweep: dict) -> Dict[str, List[Tuple[int, str, int, float]
     the device-timed latency of every algorithm, optionally ``algo@ctas`` columns): the fastest symmetric
     algorithm and the fastest plain-buffer algorithm per size.  CTA count -1 keeps the built-in choice."""
     sym_algos = ("oneshot_ll", "oneshot_mc", "twoshot_p2p", "twoshot_nvls")
-    plain_algos = ("oneshot_ll", "oneshot_mc", "staged_p2p", "staged_nvls")
+    plain_algos = ("oneshot_ll", "oneshot_mc", "staged_p2p", "staged_nvls", "staged_pipe")
     out: Dict[str, List[Tuple[int, str, int, float]]] = {"symmetric": [], "plain": []}
     for row in sweep["rows"]:
         for key, cands in (("symmetric", sym_algos), ("plain", plain_algos)):
@@ -125,12 +125,25 @@ def tuning_from_sweep(sweep: dict) -> Dict[str, List[Tuple[int, str, int, float]
     return out
 
 
+def packaged_tuning_path(world_size: int) -> str:
+    """Measured table shipped with the package for an N x B200 NVSwitch box (uccl_b200/tuning/)."""
+    import os
+
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tuning", f"tuning_{world_size}xB200.json")
+
+
 def load_tuning_from_env(comm) -> bool:
-    """Install the table named by ``UCCL_B200_TUNE_FILE`` (written by :func:`save_tuning`), if any."""
+    """Install the table named by ``UCCL_B200_TUNE_FILE`` (written by :func:`save_tuning`); without the variable the
+    table measured on this box type for this world size (uccl_b200/tuning/tuning_<N>xB200.json) is used if it is
+    shipped.  ``UCCL_B200_TUNE_FILE=none`` keeps the built-in thresholds of ``Comm::select_allreduce``."""
     import os
 
     path = os.environ.get("UCCL_B200_TUNE_FILE", "")
-    if not path:
+    if path.lower() in ("none", "off", "0"):
         return False
+    if not path:
+        path = packaged_tuning_path(comm.world_size)
+        if comm.is_host or not os.path.exists(path):
+            return False
     load_tuning(comm, path)
     return True
