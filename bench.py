@@ -382,6 +382,24 @@ def main():
         x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe, topk_idx=topk_idx,
         topk_weights=topk_w, use_fp8=True, config=cfg)
     num_recv = handle.num_recv
+    # ---- correctness on THIS world before anything is timed: identity experts through the same kernels must give
+    #      back every token multiplied by the number of ranks it was routed to (bf16 round trip is exact for x, the sum of
+    #      f identical bf16 values is exact for f <= 8); fp8 round trip within e4m3 tolerance
+    vx, _, _, _, vh, _ = buf.dispatch(x, num_tokens_per_rank=tpr, is_token_in_rank=in_rank, num_tokens_per_expert=tpe,
+                                      topk_idx=topk_idx, topk_weights=topk_w, config=cfg)
+    vin = buf.get_combine_buffer(vh.num_recv, H, K)
+    vin.copy_(vx)
+    vout, _, _ = buf.combine(vin, vh, config=cfg)
+    fan = in_rank.sum(dim=1, keepdim=True).to(torch.float32)
+    ok_bf16 = bool(torch.equal(vout.float(), x.float() * fan))
+    q8, sc8 = recv_x
+    deq = (q8[: min(num_recv, 2048)].float().view(-1, H // 128, 128) * sc8[: min(num_recv, 2048)].unsqueeze(2)).view(-1, H)
+    src_rows = vx[: deq.size(0)].float()  # same arena order: bf16 dispatch of the same routing
+    ok_fp8 = bool(torch.allclose(deq, src_rows, rtol=0.07, atol=0.05))
+    verified = torch.tensor([1 if (ok_bf16 and ok_fp8) else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(verified, op=dist.ReduceOp.MIN)
+    assert int(verified.item()) == 1, f"EP dispatch/combine verification failed on rank {rank}: bf16 {ok_bf16}, fp8 {ok_fp8}"
     comb_in = buf.get_combine_buffer(num_recv, H, K)
     comb_in.normal_()  # stand-in for the expert MLP output (bf16), lives in the symmetric arena
     barrier()
@@ -598,6 +616,7 @@ def main():
         "best": {k: best[k] for k in ("num_sms", "ms_per_step", "dispatch_us", "combine_us", "tokens_per_s", "kernels")},
         "baseline_us": {"dispatch": BASELINE_DISPATCH_US, "combine": BASELINE_COMBINE_US, "n_gpus": 8},
         "num_recv_tokens": num_recv,
+        "verified": "identity-expert round trip exact in bf16, fused fp8 dispatch within e4m3 tolerance, on every rank",
         "clocks": clocks,
         "e2e": {"value": n * T / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

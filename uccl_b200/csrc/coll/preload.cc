@@ -52,7 +52,7 @@ cudaError_t preload_all_kernels() {
     ok(launch_allreduce_f(algo, kF16, kSum, kF32, c, a, 1, 512, 0));
   }
   for (int m = 0; m < 5; ++m) ok(launch_allgather(m, c, a, 1, 512, 0));
-  for (int m = 0; m < 3; ++m) ok(launch_broadcast(m, c, a, 1, 512, 0));
+  for (int m = 0; m < 4; ++m) ok(launch_broadcast(m, c, a, 1, 512, 0));
   for (int m = 0; m < 3; ++m) ok(launch_alltoall(m, c, a, 1, 512, 0));
   ok(launch_alltoallv(c, a, v, 1, 512, 0));
   ok(launch_barrier(c, 0, 0));

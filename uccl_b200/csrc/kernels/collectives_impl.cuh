@@ -308,6 +308,39 @@ __global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ D
       }
     }
     sync_barrier(c, s);
+  } else if constexpr (MODE == 3) {
+    // ordinary output buffers + NVLS: the root stores every 16-byte word ONCE into the multicast address of the
+    // staging area (the switch replicates it to all ranks), everybody copies its stage to the user buffer.  A pull from
+    // the root's stage would be bound by the root's egress (N - 1 copies of the message over one GPU's links:
+    // 111 GB/s on 8 GPUs vs 650 for NCCL).  Stage halves alternate, so one barrier per chunk suffices: the root
+    // rewrites half k & 1 only after the barrier of chunk k - 1, which every peer enters after copying chunk k - 2 out.
+    const uint64_t half = (a.stage_bytes / 2) / 16 * 16;
+    uint64_t k = 0;
+    for (uint64_t base = 0; base < a.bytes; base += half, ++k) {
+      const uint64_t cb = (a.bytes - base) < half ? (a.bytes - base) : half;
+      const uint64_t hoff = a.stage_out_off + (k & 1) * half;
+      uint64_t blo, bhi;
+      chunk_slice(a.bytes, half, cb, blo, bhi);
+      if (rank == root) {
+        constexpr int B = 4;
+        for (uint64_t u0 = blo + threadIdx.x; u0 < bhi; u0 += (uint64_t)B * blockDim.x) {
+          uint4 v[B];
+#pragma unroll
+          for (int q = 0; q < B; ++q) {
+            const uint64_t u = u0 + (uint64_t)q * blockDim.x;
+            if (u < bhi) v[q] = load16_partial(in + base, u * 16, cb);
+          }
+#pragma unroll
+          for (int q = 0; q < B; ++q) {
+            const uint64_t u = u0 + (uint64_t)q * blockDim.x;
+            if (u < bhi) multimem_st_v4(c.mc + hoff + u * 16, v[q]);
+          }
+        }
+      }
+      sync_barrier(c, s);
+      if (rank != root || out != in) copy_bytes16(out + base, c.heap[rank] + hoff, blo, bhi, cb, cb);
+    }
+    sync_barrier_relaxed(c, s);  // the next collective may reuse the stage
   } else {
     const uint64_t chunk_bytes = a.stage_bytes / 16 * 16;
     for (uint64_t base = 0; base < a.bytes; base += chunk_bytes) {
@@ -595,17 +628,17 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       const uint64_t nslots = (npieces + kSrPiecesPerSlot - 1) / kSrPiecesPerSlot;
       uint64_t issued = 0, stored = 0, announced = 0;
       uint32_t phase_bits = 0;
-      auto announce = [&](uint64_t upto) {  // slots [announced, upto) are complete at the receiver
-        for (; announced < upto; ++announced) {
-          if (announced == 0) {
-            *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
-            st_release_sys(peer_ready, seq0 + 1);  // orders the header word before the flag
-          } else {
-            // the slot's bulk stores have COMPLETED at the receiver (cp.async.bulk.wait_group above), so a relaxed flag
-            // store cannot overtake them; a release here would add a system-scope fence (~3 us) per 64 KiB slot
-            st_relaxed_sys(peer_ready, seq0 + 1 + (uint32_t)announced);
-          }
-        }
+      // Slots [announced, upto) have been stored: publish them with ONE release (a system-scope fence, ~3 us).  The
+      // fence is required -- cp.async.bulk.wait_group only says the bulk stores left this SM; NVLink spreads addresses
+      // over 18 links, so an unfenced flag can overtake the data (seen as 93k wrong elements in nccl-tests'
+      // alltoall_perf at 1 GiB on 8 GPUs) -- so it is amortised: with a deep window (few ranks) slots are announced
+      // in batches of a quarter window.
+      const uint64_t batch = (uint64_t)(nslots_pair >= 8 ? nslots_pair / 4 : 1);
+      auto announce = [&](uint64_t upto) {
+        if (upto <= announced) return;
+        if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
+        announced = upto;
+        st_release_sys(peer_ready, seq0 + (uint32_t)upto);
       };
       while (stored < npieces) {
         while (issued < npieces && issued < stored + kSrSendStages) {
@@ -636,8 +669,8 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         tma_store_1d(dst, send_smem + (size_t)st * kSrTmaChunk, nb);
         tma_store_commit();
         ++stored;
-        if (piece == kSrPiecesPerSlot - 1 && slot_i >= 1) {
-          tma_store_wait<kSrPiecesPerSlot>();  // everything but the newest slot's pieces has landed
+        if (piece == kSrPiecesPerSlot - 1 && slot_i >= 1 && (slot_i % batch) == 0) {
+          tma_store_wait<kSrPiecesPerSlot>();  // everything but the newest slot's pieces has been issued to the fabric
           announce(slot_i);
         }
       }

@@ -19,6 +19,7 @@ cudaError_t launch_broadcast(int mode, const DevComm& c, const CollArgs& a, int 
     case 0: UB_LAUNCH((bcast_kernel<0>), grid, block, 0, st, c, a); break;
     case 1: UB_LAUNCH((bcast_kernel<1>), grid, block, 0, st, c, a); break;
     case 2: UB_LAUNCH((bcast_kernel<2>), grid, block, 0, st, c, a); break;
+    case 3: UB_LAUNCH((bcast_kernel<3>), grid, block, 0, st, c, a); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
