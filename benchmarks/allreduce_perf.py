@@ -22,8 +22,9 @@ from uccl_b200 import Communicator
 def main():
     p = argparse.ArgumentParser()
     p.add_argument("--coll", default="allreduce", choices=["allreduce", "allgather", "reduce_scatter", "alltoall", "broadcast"])
-    p.add_argument("--min", type=int, default=1 << 10)
-    p.add_argument("--max", type=int, default=1 << 30)
+    # (--min-bytes / --max-bytes: torchrun's own parser swallows an unambiguous-prefix-less "--max" as --max-restarts)
+    p.add_argument("--min", "--min-bytes", dest="min", type=int, default=1 << 10)
+    p.add_argument("--max", "--max-bytes", dest="max", type=int, default=1 << 30)
     p.add_argument("--factor", type=int, default=4)
     p.add_argument("--dtype", default="bf16")
     p.add_argument("--iters", type=int, default=20)

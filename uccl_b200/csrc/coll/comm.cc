@@ -290,7 +290,9 @@ int Comm::select_allreduce(size_t bytes, bool symmetric, int dtype, int op, int*
     uint64_t ll_max = (uint64_t)ubParamArLLMaxBytes();
     // n = 2: the two barriers of the two-shot kernels cost ~20 us when both GPUs are driven by one host thread
     // (nccl-tests -g 2: 35 us at 1 MiB vs 15 us for the packet path), so packets carry up to the 1 MiB cap there
-    if (ll_max == 0) ll_max = n <= 2 ? (1u << 20) : (n <= 4 ? (256u << 10) : (128u << 10));
+    // n = 4 (nccl-tests + bench on 4xB200): ordinary buffers at 512 KiB - 1 MiB take 26-30 us through the staged kernels
+    // vs 20-22 us for NCCL; the packet path has no barrier
+    if (ll_max == 0) ll_max = n <= 4 ? (1u << 20) : (128u << 10);
     ll_max = std::min<uint64_t>(ll_max, kLLMaxData);
     // with 2 ranks the switch cannot reduce traffic (both paths move `size` per direction) and the
     // plain P2P kernel sustains more bytes in flight per SM than multimem.ld_reduce
@@ -345,7 +347,7 @@ static cudaError_t launch_ar_any(int algo, int dtype, int op, int out_dtype, con
 // per-rank piece size up to which the barrier-free LL exchange kernels are used
 static uint64_t xchg_ll_limit(int64_t v, int n, bool symmetric_push) {
   if (v < 0) return 0;
-  uint64_t m = v > 0 ? (uint64_t)v : (n <= 2 ? (256u << 10) : (128u << 10));
+  uint64_t m = v > 0 ? (uint64_t)v : (n <= 4 ? (256u << 10) : (128u << 10));  // 4 ranks: reduce_scatter of 1 MiB was 30 vs 20 us (NCCL) staged
   if (v == 0 && symmetric_push) m = 32u << 10;  // the push kernels only pay one barrier
   return std::min<uint64_t>(m, kLLMaxData);
 }

@@ -631,9 +631,8 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       // Slots [announced, upto) have been stored: publish them with ONE release (a system-scope fence, ~3 us).  The
       // fence is required -- cp.async.bulk.wait_group only says the bulk stores left this SM; NVLink spreads addresses
       // over 18 links, so an unfenced flag can overtake the data (seen as 93k wrong elements in nccl-tests'
-      // alltoall_perf at 1 GiB on 8 GPUs) -- so it is amortised: with a deep window (few ranks) slots are announced
-      // in batches of a quarter window.
-      const uint64_t batch = (uint64_t)(nslots_pair >= 8 ? nslots_pair / 4 : 1);
+      // alltoall_perf at 1 GiB on 8 GPUs) -- so it is amortised: slots are announced in batches of half a window.
+      const uint64_t batch = (uint64_t)(nslots_pair / 2);  // half a window per fence: 128 KiB (8 ranks) ... 512 KiB (2 ranks)
       auto announce = [&](uint64_t upto) {
         if (upto <= announced) return;
         if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;

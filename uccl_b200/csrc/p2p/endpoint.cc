@@ -675,9 +675,18 @@ bool Endpoint::prepare(uint64_t conn, bool is_write, const std::vector<const voi
     d.push_back(is_write ? (char*)r : (char*)local[i]);
     p->bytes += sizes[i];
   }
-  cudaStream_t up = streams_[0];
-  if (!build_launches(s, d, sizes, &p->launches, up)) return false;
-  cudaStreamSynchronize(up);  // the tables are resident before the first post (which may use another stream)
+  bool few_large = local.size() <= 8 && ubParamP2PMemcpyMinMB() > 0;
+  for (size_t i = 0; i < sizes.size() && few_large; ++i) few_large = sizes[i] >= ((size_t)ubParamP2PMemcpyMinMB() << 20);
+  if (few_large || !ubParamP2PUseKernel()) {
+    p->use_memcpy = true;
+    p->src = s;
+    p->dst = d;
+    p->sizes = sizes;
+  } else {
+    cudaStream_t up = streams_[0];
+    if (!build_launches(s, d, sizes, &p->launches, up)) return false;
+    cudaStreamSynchronize(up);  // the tables are resident before the first post (which may use another stream)
+  }
   p->conn = c;
   p->is_write = is_write;
   std::lock_guard<std::mutex> g(mu_);
@@ -698,6 +707,9 @@ bool Endpoint::post(uint64_t prep_id, uint64_t* tid) {
     st = streams_[next_stream_++ % streams_.size()];
   }
   cudaSetDevice(gpu_);
+  if (p->use_memcpy)
+    for (size_t i = 0; i < p->src.size(); ++i)
+      if (cudaMemcpyAsync(p->dst[i], p->src[i], p->sizes[i], cudaMemcpyDefault, st) != cudaSuccess) return false;
   for (auto& l : p->launches) {
     cudaError_t e = launch_p2p_copy(l.b, l.grid, st);
     if (e != cudaSuccess) {

@@ -114,6 +114,11 @@ class Endpoint {
     bool is_write = true;
     uint64_t bytes = 0;
     std::vector<CopyLaunch> launches;
+    // a few very large blocks: the copy engines move them (same policy as launch_copy)
+    bool use_memcpy = false;
+    std::vector<const char*> src;
+    std::vector<char*> dst;
+    std::vector<size_t> sizes;
   };
   std::map<uint64_t, std::shared_ptr<Prepared>> prepared_;
   uint64_t next_prep_ = 1;
