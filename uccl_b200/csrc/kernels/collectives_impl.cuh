@@ -544,7 +544,10 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
   extern __shared__ __align__(128) unsigned char sr_smem[];  // [recv: kSrTmaStages | send: kSrSendStages] x kSrTmaChunk
   __shared__ __align__(8) uint64_t sr_full[kSrTmaStages];
   __shared__ __align__(8) uint64_t sr_sfull[kSrSendStages];
+  __shared__ uint32_t s_send_done;  // staged push: slots whose bulk stores have completed (pump thread -> announcer thread)
   unsigned char* send_smem = sr_smem + (size_t)kSrTmaStages * kSrTmaChunk;
+  if (threadIdx.x == 0) s_send_done = 0;
+  __syncthreads();
   __shared__ uint64_t s_hdr;
   const int me = c.rank;
   // the staging area is sized for kMaxRanks peers x kSrBlocks x kSrSlots slots: with fewer ranks every (peer, sub-block)
@@ -616,28 +619,39 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       return;
     }
     if ((bytes % 16) == 0) {
-      // ---- one elected thread: sbuf -> smem -> peer slot with bulk copies, kSrSendStages pieces in flight;
-      //      slot c is announced one slot later, once its stores have completed (no stall on the newest stores)
-      if (t != 0) return;
-      for (int st = 0; st < kSrSendStages; ++st) mbar_init(&sr_sfull[st], 1);
-      mbar_fence_init();
-      asm volatile("fence.proxy.async;" ::: "memory");
+      // ---- two elected threads.  The PUMP (t == 0) moves sbuf -> smem -> peer slot with bulk copies, kSrSendStages
+      //      pieces in flight, and publishes in shared memory how many slots have completed.  The ANNOUNCER (t == 32)
+      //      turns that into ready flags for the receiver: each announcement needs a system-scope release fence
+      //      (~3 us; without it the flag can overtake the data on another NVLink), and on its own thread the fence
+      //      overlaps the next slots' copies and batches itself: while it is fencing, more slots complete.
       const uint32_t seq0 = seq;
       const uint64_t b0 = lo * 16, b1 = hi * 16;
       const uint64_t npieces = (b1 - b0 + kSrTmaChunk - 1) / kSrTmaChunk;
       const uint64_t nslots = (npieces + kSrPiecesPerSlot - 1) / kSrPiecesPerSlot;
-      uint64_t issued = 0, stored = 0, announced = 0;
+      if (t == 32) {
+        uint32_t announced = 0;
+        SpinGuard g(c.timeout_ns);
+        while (announced < (uint32_t)nslots) {
+          uint32_t d;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(d) : "r"(smem_u32(&s_send_done)) : "memory");
+          if (d > announced) {
+            if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
+            st_release_sys(peer_ready, seq0 + d);
+            announced = d;
+          } else if (g.expired()) {
+            comm_abort(c, 23, peer, (int)announced);
+          }
+        }
+        return;
+      }
+      if (t != 0) return;
+      for (int st = 0; st < kSrSendStages; ++st) mbar_init(&sr_sfull[st], 1);
+      mbar_fence_init();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      uint64_t issued = 0, stored = 0;
       uint32_t phase_bits = 0;
-      // Slots [announced, upto) have been stored: publish them with ONE release (a system-scope fence, ~3 us).  The
-      // fence is required -- cp.async.bulk.wait_group only says the bulk stores left this SM; NVLink spreads addresses
-      // over 18 links, so an unfenced flag can overtake the data (seen as 93k wrong elements in nccl-tests'
-      // alltoall_perf at 1 GiB on 8 GPUs) -- so it is amortised: slots are announced in batches of half a window.
-      const uint64_t batch = (uint64_t)(nslots_pair / 2);  // half a window per fence: 128 KiB (8 ranks) ... 512 KiB (2 ranks)
-      auto announce = [&](uint64_t upto) {
-        if (upto <= announced) return;
-        if (announced == 0) *reinterpret_cast<volatile uint64_t*>(peer_hdr) = kNoOff;
-        announced = upto;
-        st_release_sys(peer_ready, seq0 + (uint32_t)upto);
+      auto publish = [&](uint64_t upto) {  // slots [0, upto) have completed at the receiver's memory system
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_send_done)), "r"((uint32_t)upto) : "memory");
       };
       while (stored < npieces) {
         while (issued < npieces && issued < stored + kSrSendStages) {
@@ -668,13 +682,13 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         tma_store_1d(dst, send_smem + (size_t)st * kSrTmaChunk, nb);
         tma_store_commit();
         ++stored;
-        if (piece == kSrPiecesPerSlot - 1 && slot_i >= 1 && (slot_i % batch) == 0) {
-          tma_store_wait<kSrPiecesPerSlot>();  // everything but the newest slot's pieces has been issued to the fabric
-          announce(slot_i);
+        if (piece == kSrPiecesPerSlot - 1 && slot_i >= 1) {
+          tma_store_wait<kSrPiecesPerSlot>();  // everything but the newest slot's pieces has completed
+          publish(slot_i);
         }
       }
       tma_store_wait<0>();
-      announce(nslots);
+      publish(nslots);
       my_flags[2 * W + peer * kSrBlocks + j] = seq0 + (uint32_t)nslots;
       return;
     }
