@@ -325,3 +325,40 @@ def test_timing_wheel_never_fires_early_and_keeps_far_deadlines():
     assert set(fired) == set(items)
     assert min(fired[i] - items[i] for i in items) >= 0
     assert max(fired[i] - items[i] for i in items) <= 5000 + 1000
+
+
+def test_ep_handle_has_the_reference_field_order():
+    """Handles are 7-tuples in the reference's order (ep/bench/buffer.py:1147-1158) with the extras as attributes."""
+    import torch
+
+    from uccl_b200.ep.utils import EpHandle
+
+    rp = torch.zeros(4, 4, dtype=torch.int32)
+    src = torch.arange(5, dtype=torch.int32)
+    inr = torch.zeros(7, 4, dtype=torch.bool)
+    slot = torch.full((7, 4), -1, dtype=torch.int32)
+    h = EpHandle(rp, 5, src, inr, slot, slot=1, num_topk=8)
+    assert isinstance(h, tuple) and len(h) == 7
+    rank_prefix, ch, rch, num_recv, recv_src_idx, is_in, send_head = h  # unpacks like the reference's handle
+    assert rank_prefix is rp and num_recv == 5 and recv_src_idx is src and is_in is inr and send_head is slot
+    assert ch.shape == (4, 1) and rch.shape == (4, 1)
+    assert (h.slot, h.num_topk, h.num_recv) == (1, 8, 5) and h.send_slot is slot
+
+
+def test_packaged_tuning_is_optional_and_env_can_disable_it(monkeypatch):
+    from uccl_b200.utils import tuner
+
+    assert tuner.packaged_tuning_path(8).endswith("tuning/tuning_8xB200.json")
+
+    class FakeComm:
+        world_size, is_host = 3, False  # no table is shipped for 3 ranks
+        calls = []
+
+        def set_tuning(self, sym, rows):
+            self.calls.append((sym, rows))
+
+    c = FakeComm()
+    monkeypatch.delenv("UCCL_B200_TUNE_FILE", raising=False)
+    assert tuner.load_tuning_from_env(c) is False and not c.calls
+    monkeypatch.setenv("UCCL_B200_TUNE_FILE", "none")
+    assert tuner.load_tuning_from_env(c) is False
