@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(512, 1) ep_dispatch_kernel(const __grid_consta
 
       if constexpr (MODE == EP_X_FUSED_FP8) {
         const int units = a.H / 16;  // 16 output bytes (16 channels) per lane-iteration
-        constexpr int PF = 7;        // iterations whose loads are in flight together (14 x 16 B per lane: a 7168-channel row in two rounds)
+        constexpr int PF = 4;        // iterations whose loads are in flight together (8 x 16 B per lane; 7 was not faster at 148 CTAs and spills)
         for (int ub = 0; ub < units; ub += 32 * PF) {
           uint4 v0[PF], v1[PF];
 #pragma unroll
