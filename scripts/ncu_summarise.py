@@ -22,7 +22,10 @@ KEEP = [
 
 
 def raw_rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):  # already exported on the GPU box (scripts/ncu_capture.sh)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rd = list(csv.reader(io.StringIO(out)))
     if len(rd) < 3:
         return [], []
@@ -31,7 +34,7 @@ def raw_rows(rep):
 
 def main():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    reps = sys.argv[1:] or [os.path.join(root, "gpurun_out", f) for f in ("ncu_ep.ncu-rep", "ncu_coll.ncu-rep")]
+    reps = sys.argv[1:] or [os.path.join(root, "gpurun_out", f) for f in ("ncu_ep_raw.csv", "ncu_coll_raw.csv")]
     os.makedirs(os.path.join(root, "profiles"), exist_ok=True)
     table = []
     for rep in reps:
