@@ -79,22 +79,9 @@ def _includes():
     ]
 
 
-def _defines():
-    d = []
-    if list(CSRC.glob("ep/*.cc")):
-        d.append("-DUB_HAVE_EP")
-    if list(CSRC.glob("p2p/*.cc")):
-        d.append("-DUB_HAVE_P2P")
-    if list(CSRC.glob("common/bind_util.cc")):
-        d.append("-DUB_HAVE_UTIL")
-    if list(CSRC.glob("ukernel/bind_uk.cc")):
-        d.append("-DUB_HAVE_UK")
-    return d
-
-
 def _compile_one(src: Path, obj: Path, verbose: bool) -> None:
     common = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function"]
-    cmd = [NVCC] + ARCH_FLAGS + common + _includes() + _defines()
+    cmd = [NVCC] + ARCH_FLAGS + common + _includes()
     if src.suffix == ".cu":
         cmd += ["-Xptxas", "-v"] if verbose else []
     cmd += ["-c", str(src), "-o", str(obj)]

@@ -654,9 +654,11 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(&s_send_done)), "r"((uint32_t)upto) : "memory");
       };
       while (stored < npieces) {
-        while (issued < npieces && issued < stored + kSrSendStages) {
+        // a stage is refilled one iteration after its store was committed: wait_group.read 1 then covers that store
+        // (everything but the newest group has left shared memory) without ever blocking on the store just issued
+        while (issued < npieces && issued < stored + kSrSendStages - 1) {
           const int st = (int)(issued % kSrSendStages);
-          if (issued >= (uint64_t)kSrSendStages) tma_store_wait_read<kSrSendStages - 1>();
+          if (issued >= (uint64_t)kSrSendStages) tma_store_wait_read<1>();
           const uint64_t off = b0 + issued * kSrTmaChunk;
           const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
           mbar_expect_tx(&sr_sfull[st], nb);
@@ -728,9 +730,9 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
         uint64_t issued = 0, stored = 0;
         uint32_t phase_bits = 0;
         while (stored < total) {
-          while (issued < total && issued < stored + kSrTmaStages) {
+          while (issued < total && issued < stored + kSrTmaStages - 1) {  // refill lags the store by one iteration (see the send pump)
             const int st = (int)(issued % kSrTmaStages);
-            if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<kSrTmaStages - 1>();
+            if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<1>();
             const uint64_t off = b0 + issued * kSrTmaChunk;
             const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
             mbar_expect_tx(&sr_full[st], nb);
@@ -771,7 +773,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
       uint32_t phase_bits = 0;
       char* dst = a.rbuf[peer];
       while (stored < npieces) {
-        while (issued < npieces && issued < stored + kSrTmaStages) {
+        while (issued < npieces && issued < stored + kSrTmaStages - 1) {  // refill lags the store by one iteration
           const uint64_t slot_i = issued / kSrPiecesPerSlot, piece = issued % kSrPiecesPerSlot;
           if (slot_i >= ready_slots) {
             if (issued > stored) break;  // drain what is in flight before blocking on the sender
@@ -783,7 +785,7 @@ static __global__ void __launch_bounds__(512, 1) sendrecv_kernel(const __grid_co
             asm volatile("fence.proxy.async;" ::: "memory");
           }
           const int st = (int)(issued % kSrTmaStages);
-          if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<kSrTmaStages - 1>();
+          if (issued >= (uint64_t)kSrTmaStages) tma_store_wait_read<1>();
           const uint64_t off = b0 + issued * kSrTmaChunk;
           const uint32_t nb = (uint32_t)((b1 - off) < kSrTmaChunk ? (b1 - off) : kSrTmaChunk);
           const char* src = stage + (uint64_t)((seq0 + 1 + (uint32_t)slot_i) % (uint32_t)nslots_pair) * kSrChunkBytes + piece * kSrTmaChunk;

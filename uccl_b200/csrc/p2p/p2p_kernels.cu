@@ -62,9 +62,11 @@ __global__ void __launch_bounds__(kCopyThreads) p2p_copy_kernel(const __grid_con
     };
     uint32_t issued = 0, stored = 0, phase_bits = 0;
     while (stored < mine) {
-      while (issued < mine && issued < stored + kP2PStages) {
+      // a stage is refilled one iteration after its store was committed, so wait_group.read 1 (everything but the newest
+      // store has left shared memory) covers it without blocking on the store that was just issued
+      while (issued < mine && issued < stored + kP2PStages - 1) {
         const int s = issued % kP2PStages;
-        if (issued >= kP2PStages) tma_store_wait_read<kP2PStages - 1>();  // the stage's previous store has left smem
+        if (issued >= kP2PStages) tma_store_wait_read<1>();
         const char* src;
         char* dst;
         uint32_t bytes;
