@@ -333,12 +333,17 @@ __global__ void __launch_bounds__(512, 1) bcast_kernel(const __grid_constant__ D
 #pragma unroll
           for (int q = 0; q < B; ++q) {
             const uint64_t u = u0 + (uint64_t)q * blockDim.x;
-            if (u < bhi) multimem_st_v4(c.mc + hoff + u * 16, v[q]);
+            if (u < bhi) {
+              multimem_st_v4(c.mc + hoff + u * 16, v[q]);
+              // the root's own output comes straight from the registers: no second pass over its stage, so after the
+              // barrier it starts on chunk k + 1 while the peers are still copying chunk k out
+              if (out != in) store16_partial(out + base, u * 16, cb, v[q]);
+            }
           }
         }
       }
       sync_barrier(c, s);
-      if (rank != root || out != in) copy_bytes16(out + base, c.heap[rank] + hoff, blo, bhi, cb, cb);
+      if (rank != root) copy_bytes16(out + base, c.heap[rank] + hoff, blo, bhi, cb, cb);
     }
     sync_barrier_relaxed(c, s);  // the next collective may reuse the stage
   } else {
