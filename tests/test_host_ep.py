@@ -117,10 +117,12 @@ def test_host_ep_low_latency():
                                                            return_recv_hook=True)
         hook()
         bx, cntb, hb, _, _ = b.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=False)
-        with pytest.raises(NotImplementedError):  # not silently ignored: the combine payload is bf16 only
-            b.low_latency_combine(bx, idxs[r], ws[r], hb, use_logfmt=True)
+        with pytest.raises(ValueError):  # as in the reference: the in-place buffer cannot be re-encoded
+            b.low_latency_combine(bx, idxs[r], ws[r], hb, use_logfmt=True, zero_copy=True)
+        small = (bx.float() * 0.125).to(torch.bfloat16)  # |x| <= 1 almost everywhere: the LogFMT grid applies
+        out_l, _, _ = b.low_latency_combine(small, idxs[r], ws[r], hb, use_logfmt=True)
         out, _, _ = b.low_latency_combine(bx, idxs[r], ws[r], hb)
-        return dict(qx=qx, qs=qs, cnt=cnt, stats=stats, bx=bx, cntb=cntb, out=out, hb=hb)
+        return dict(qx=qx, qs=qs, cnt=cnt, stats=stats, bx=bx, cntb=cntb, out=out, hb=hb, out_l=out_l)
 
     res = _run(comms, fn)
     for r, o in enumerate(res):
@@ -142,6 +144,12 @@ def test_host_ep_low_latency():
             assert torch.equal(src_info[e, :counts[e]], torch.cat(exp_src))
         wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
         assert torch.allclose(o["out"].float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)
+        # use_logfmt: every routed copy of token t is the simulated cast of the same row
+        from uccl_b200.ep.utils import logfmt10_simulate
+
+        q = logfmt10_simulate((xs[r].float() * 0.125).to(torch.bfloat16)).float()
+        assert torch.allclose(o["out_l"].float(), q * wsum[:, None], rtol=3e-2, atol=2e-2)
+        assert not torch.equal(q, xs[r].float() * 0.125)  # the grid really changed the values
 
 
 def test_deep_ep_package_uses_the_same_buffer():

@@ -362,3 +362,32 @@ def test_packaged_tuning_is_optional_and_env_can_disable_it(monkeypatch):
     assert tuner.load_tuning_from_env(c) is False and not c.calls
     monkeypatch.setenv("UCCL_B200_TUNE_FILE", "none")
     assert tuner.load_tuning_from_env(c) is False
+
+
+def test_logfmt10_simulated_cast_properties():
+    """Definition check of the LogFMT-10 simulated cast (reference: ep/src/internode_ll.cu:934-995)."""
+    import torch
+
+    from uccl_b200.ep.utils import logfmt10_simulate
+
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(64, 512, generator=g) * 0.2).to(torch.bfloat16)
+    x[0, :128] *= 40          # a group with |max| > 1 passes through untouched
+    x[1, 128:256] = 0         # all-zero group
+    x[2, 5] = 0               # a zero inside a live group stays zero
+    x[3, 256:384] = 0.25      # a single magnitude: nothing to quantise
+    q = logfmt10_simulate(x)
+    assert q.dtype == torch.bfloat16 and q.shape == x.shape
+    assert torch.equal(q[0, :128], x[0, :128]) and torch.equal(q[1, 128:256], x[1, 128:256])
+    assert q[2, 5] == 0 and torch.equal(q[3, 256:384], x[3, 256:384])
+    xf, qf = x.float(), q.float()
+    assert torch.equal(torch.signbit(qf), torch.signbit(xf))
+    live = (xf.reshape(64, 4, 128).abs().amax(-1, keepdim=True) <= 1).expand(64, 4, 128).reshape(64, 512) & (xf != 0)
+    # one grid step is at most 32 / 510 octaves -> < 4.5 % relative error (plus bf16 rounding), except where the
+    # magnitude falls below the clipped range (2^-32 of the group maximum), which random data never reaches
+    rel = ((qf - xf).abs() / xf.abs())[live]
+    assert float(rel.max()) < 0.05 and float(rel.mean()) > 1e-4
+    # at most 2^9 - 1 magnitudes per group
+    for grp in qf.reshape(-1, 128)[:16]:
+        assert grp.abs().unique().numel() <= 511
+    assert torch.equal(logfmt10_simulate(q), logfmt10_simulate(logfmt10_simulate(q)))  # stable under re-application

@@ -124,6 +124,9 @@ cudaError_t preload_all_kernels() {
     EpLLPackArgs lp;
     memset(&lp, 0, sizeof(lp));
     ok(launch_ep_ll_pack(lp, 0));
+    lp.logfmt = 1;
+    lp.H = 128;
+    ok(launch_ep_ll_pack(lp, 0));
   }
   ok(preload_p2p_kernels());
   ok(cmp_compress_async(nullptr, 0, kBF16, nullptr, 0));

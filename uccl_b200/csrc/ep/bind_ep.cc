@@ -89,12 +89,14 @@ void bind_ep(py::module_& m) {
       .def("ll_combine_buffer", &EpBuffer::ll_combine_buffer)
       .def("ll_combine",
            [](EpBuffer& b, uintptr_t x, int idx, uintptr_t tw, uintptr_t sp, uintptr_t out, int T, int H, int K, int E,
-              int M, int num_sms, uintptr_t st, int phase, uintptr_t layout_range, uintptr_t wait_stats) {
-             b.ll_combine(x, idx, tw, sp, out, T, H, K, E, M, num_sms, (cudaStream_t)st, phase, layout_range, wait_stats);
+              int M, int num_sms, uintptr_t st, int phase, uintptr_t layout_range, uintptr_t wait_stats, bool use_logfmt) {
+             b.ll_combine(x, idx, tw, sp, out, T, H, K, E, M, num_sms, (cudaStream_t)st, phase, layout_range, wait_stats,
+                          use_logfmt);
            },
            py::arg("x"), py::arg("buffer_idx"), py::arg("topk_weights"), py::arg("send_pos"), py::arg("out"),
            py::arg("T"), py::arg("H"), py::arg("K"), py::arg("E"), py::arg("M"), py::arg("num_sms"), py::arg("stream"),
-           py::arg("phase") = (int)EP_LL_FULL, py::arg("layout_range") = 0, py::arg("wait_stats") = 0)
+           py::arg("phase") = (int)EP_LL_FULL, py::arg("layout_range") = 0, py::arg("wait_stats") = 0,
+           py::arg("use_logfmt") = false)
       .def("combine_input_ptr", &EpBuffer::combine_input_ptr)
       .def("combine", [](EpBuffer& b, uintptr_t x, int num_recv, uintptr_t tw, uintptr_t ss, uintptr_t b0,
                          uintptr_t b1, uintptr_t out, uintptr_t otw, int T, int H, int K, int num_sms, uintptr_t st) {

@@ -446,14 +446,17 @@ uintptr_t EpBuffer::ll_combine_buffer(int buffer_idx, int H, int E, int M) const
 
 void EpBuffer::ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T,
                           int H, int K, int E, int M, int num_sms, cudaStream_t st, int phase, uintptr_t layout_range,
-                          uintptr_t wait_stats) {
+                          uintptr_t wait_stats, bool use_logfmt) {
   const int R = nranks();
   UB_CHECK(phase >= EP_LL_FULL && phase <= EP_LL_RECV, "ll_combine: bad phase %d", phase);
   DevGuard g(comm_->device());
   LLLayout l = ll_layout(buffer_idx, H, E, M);
   char* arena = comm_->fabric().local() + l.comb_x_off;
-  if (x != (uintptr_t)arena && phase != EP_LL_RECV) {
-    // expert outputs that do not live in the symmetric buffer: bring them in, occupied rows only
+  if (use_logfmt && phase != EP_LL_RECV)
+    UB_CHECK(layout_range != 0 && H % 128 == 0, "ll_combine: use_logfmt needs layout_range and hidden %% 128 == 0 (H = %d)", H);
+  if ((x != (uintptr_t)arena || use_logfmt) && phase != EP_LL_RECV) {
+    // expert outputs that do not live in the symmetric buffer: bring them in, occupied rows only; with use_logfmt
+    // the same pass applies the reference's simulated LogFMT-10 cast (in place when x already is the buffer)
     if (layout_range) {
       EpLLPackArgs pa;
       pa.src = (const void*)x;
@@ -463,6 +466,7 @@ void EpBuffer::ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr
       pa.R = R;
       pa.M = M;
       pa.H = H;
+      pa.logfmt = use_logfmt ? 1 : 0;
       cudaError_t pe = launch_ep_ll_pack(pa, st);
       UB_CHECK(pe == cudaSuccess, "ep ll pack launch failed: %s", cudaGetErrorString(pe));
       ++launches_;

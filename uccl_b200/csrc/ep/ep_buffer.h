@@ -70,7 +70,7 @@ class EpBuffer {
   // layout_range != 0: a non-arena `x` is packed (occupied rows only) instead of copied whole
   void ll_combine(uintptr_t x, int buffer_idx, uintptr_t topk_w, uintptr_t send_pos, uintptr_t out, int T, int H, int K,
                   int E, int M, int num_sms, cudaStream_t st, int phase = EP_LL_FULL, uintptr_t layout_range = 0,
-                  uintptr_t wait_stats = 0);
+                  uintptr_t wait_stats = 0, bool use_logfmt = false);
 
   // zero-copy combine input: a [num_tokens, hidden] bf16 view of the combine arena
   uintptr_t combine_input_ptr(int num_tokens, int hidden, int topk);

@@ -333,9 +333,76 @@ __global__ void __launch_bounds__(256) ep_ll_pack_kernel(const EpLLPackArgs a) {
   }
 }
 
+// LogFMT-10 "simulated cast" of the reference's low-latency combine (ep/src/internode_ll.cu:934-995): every group of
+// 128 channels whose |max| <= 1 is snapped to a 9-bit logarithmic grid between its smallest and largest magnitude
+// (range clipped to 2^-32 of the maximum) and stays bf16 on the wire -- use_logfmt only changes the numerics, which
+// is what a consumer that was tuned with it expects.  Sixteen consecutive lanes hold one group (8 channels each):
+// all 32 lanes of the warp must call this.
+__device__ __forceinline__ void logfmt10_simulate(uint4& v) {
+  float f[8], la[8];
+  bf16x8_to_float(v, f);
+  float amax = 0.f, lmax = -INFINITY, lmin = INFINITY;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float av = fabsf(f[q]);
+    la[q] = log2f(av);  // -inf for 0
+    amax = fmaxf(amax, av);
+    lmax = fmaxf(lmax, la[q]);
+    if (av != 0.f) lmin = fminf(lmin, la[q]);
+  }
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+  }
+  lmin = fmaxf(lmin, lmax - 32.f);
+  if (!(amax <= 1.f && lmin < lmax)) return;  // uniform over the 16 lanes of the group
+  const float step = (lmax - lmin) / 510.f;   // 2^9 - 2 intervals
+  const float step_inv = 1.f / step;
+  const float rounding = 2.f - log2f((1.f + exp2f(step)) * 0.5f) * step_inv;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float enc = floorf((la[q] - lmin) * step_inv + rounding);
+    const float dec = exp2f((enc - 1.f) * step + lmin);
+    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(dec));
+    const int sh = (q & 1) * 16;
+    const uint32_t sign = (w[q >> 1] >> sh) & 0x8000u;
+    w[q >> 1] = (w[q >> 1] & ~(0xffffu << sh)) | ((sign | bits) << sh);
+  }
+}
+
+// pack + simulated LogFMT cast of the occupied rows (src may equal dst: every thread rewrites only what it read)
+__global__ void __launch_bounds__(256) ep_ll_pack_logfmt_kernel(const EpLLPackArgs a) {
+  const size_t row16 = (size_t)a.H * 2 / 16;  // H % 128 == 0 (host check): 16-lane groups never straddle rows
+  const int lane = threadIdx.x & 31;
+  for (int e = blockIdx.y; e < a.E_local; e += gridDim.y) {
+    int rows = 0;
+    for (int q = 0; q < a.R; ++q) rows += (int)(a.layout_range[(size_t)e * a.R + q] & 0xffffffffll);
+    const size_t n16 = (size_t)rows * row16;
+    const uint4* src = reinterpret_cast<const uint4*>(a.src) + (size_t)e * a.R * a.M * row16;
+    uint4* dst = reinterpret_cast<uint4*>(a.dst) + (size_t)e * a.R * a.M * row16;
+    // warp-uniform trip count: the shuffles inside need all 32 lanes
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); i0 < n16; i0 += (size_t)gridDim.x * blockDim.x) {
+      const size_t i = i0 + lane;
+      const bool valid = i < n16;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (valid) v = ld_v4(reinterpret_cast<const char*>(src + i));
+      logfmt10_simulate(v);
+      if (valid) st_v4(reinterpret_cast<char*>(dst + i), v);
+    }
+  }
+}
+
 cudaError_t launch_ep_ll_pack(const EpLLPackArgs& a, cudaStream_t st) {
   dim3 grid(16, (unsigned)(a.E_local < 1 ? 1 : (a.E_local > 64 ? 64 : a.E_local)));
-  UB_LAUNCH((ep_ll_pack_kernel), grid, 256, 0, st, a);
+  if (a.logfmt) {
+    if (a.H % 128 != 0) return cudaErrorInvalidValue;
+    UB_LAUNCH((ep_ll_pack_logfmt_kernel), grid, 256, 0, st, a);
+  } else {
+    UB_LAUNCH((ep_ll_pack_kernel), grid, 256, 0, st, a);
+  }
   return cudaGetLastError();
 }
 

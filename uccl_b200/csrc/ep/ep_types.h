@@ -130,6 +130,7 @@ struct EpLLPackArgs {
   void* dst;                    // same shape inside the symmetric heap
   const int64_t* layout_range;  // [E_local, R]
   int E_local, R, M, H;
+  int logfmt;                   // 1: apply DeepEP's simulated LogFMT-10 cast to the rows on the way (src may equal dst)
 };
 
 }  // namespace ub

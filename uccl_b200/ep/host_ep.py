@@ -375,7 +375,11 @@ class HostBuffer:
                             return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                             combine_wait_recv_cost_stats=None):
         if use_logfmt:
-            raise NotImplementedError("uccl_b200.ep: use_logfmt=True is not supported (the combine payload is bf16)")
+            if zero_copy:
+                raise ValueError("uccl_b200.ep: zero_copy and use_logfmt are mutually exclusive (as in the reference)")
+            from .utils import logfmt10_simulate
+
+            x = logfmt10_simulate(x)  # the reference's simulated cast: payload stays bf16, numerics change
         R, me = self.group_size, self.rank
         src_info, layout_range, M, H, E, _, send_pos, allc = handle
         e_per = E // R

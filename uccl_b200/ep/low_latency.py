@@ -147,9 +147,13 @@ class LowLatencyRuntime:
                 return_recv_hook: bool = False, out: Optional[torch.Tensor] = None,
                 combine_wait_recv_cost_stats: Optional[torch.Tensor] = None):
         if use_logfmt:
-            # DeepEP's LogFMT-10 shrinks the combine payload on RDMA links (ep/src/internode_ll.cu:735-1204); this
-            # path pulls bf16 rows over NVLink and has no encoded form -- fail loudly instead of silently ignoring it
-            raise NotImplementedError("uccl_b200.ep: use_logfmt=True is not supported (the NVLink combine moves bf16)")
+            # the reference's LogFMT-10 is a *simulated* cast (ep/src/internode_ll.cu:934-995): rows are snapped to the
+            # logarithmic grid and still travel as bf16.  Here the pass that brings the expert outputs into the
+            # symmetric buffer applies it (in place when x already is that buffer).
+            if zero_copy:
+                raise ValueError("uccl_b200.ep: zero_copy and use_logfmt are mutually exclusive (as in the reference)")
+            if x.shape[-1] % 128 != 0:
+                raise ValueError("uccl_b200.ep: use_logfmt needs hidden % 128 == 0")
         assert not (async_finish and return_recv_hook), "async_finish and return_recv_hook are mutually exclusive"
         self._finish_pending()
         src_info, layout_range, M, H, E, idx, send_pos = handle
@@ -172,7 +176,7 @@ class LowLatencyRuntime:
         if return_recv_hook:
             # SEND half: (pack the expert outputs into the symmetric buffer and) announce that they are in place
             self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_SEND, layout_range=layout_range.data_ptr(),
-                               wait_stats=stats_ptr)
+                               wait_stats=stats_ptr, use_logfmt=bool(use_logfmt))
 
             def hook():
                 if self._pending is hook:
@@ -185,6 +189,6 @@ class LowLatencyRuntime:
             self._pending = hook
         else:
             self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_FULL, layout_range=layout_range.data_ptr(),
-                               wait_stats=stats_ptr)
+                               wait_stats=stats_ptr, use_logfmt=bool(use_logfmt))
         ev = EventOverlap(EventHandle(st)) if async_finish else EventOverlap()
         return out, ev, hook

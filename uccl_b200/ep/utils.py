@@ -92,6 +92,32 @@ def per_token_cast_back(x_fp8: torch.Tensor, scales: torch.Tensor) -> torch.Tens
     return (xv * scales.float().view(m, -1, 1)).view(m, n).to(torch.bfloat16)
 
 
+def logfmt10_simulate(x: torch.Tensor) -> torch.Tensor:
+    """The reference's LogFMT-10 "simulated cast" of the low-latency combine payload (ep/src/internode_ll.cu:934-995):
+    per group of 128 channels with ``|max| <= 1`` every value is snapped to a 9-bit logarithmic grid between the
+    group's smallest and largest magnitude (range clipped to ``2**-32`` of the maximum), the sign is kept and the
+    result is bf16 again -- the wire format does not change, only the numerics.  Groups with ``|max| > 1`` (or a single
+    magnitude) pass through.  This is the fp32 definition the CUDA kernel (``ep_ll_pack_logfmt_kernel``) is tested
+    against; the host backend uses it directly."""
+    assert x.dtype == torch.bfloat16 and x.shape[-1] % 128 == 0
+    xf = x.float().reshape(*x.shape[:-1], x.shape[-1] // 128, 128)
+    a = xf.abs()
+    la = torch.log2(a)  # -inf at 0
+    amax = a.amax(-1, keepdim=True)
+    lmax = la.amax(-1, keepdim=True)
+    inf = torch.full_like(la, float("inf"))
+    lmin = torch.where(a > 0, la, inf).amin(-1, keepdim=True)
+    lmin = torch.maximum(lmin, lmax - 32.0)
+    step = (lmax - lmin) / 510.0
+    step_inv = 1.0 / step
+    rounding = 2.0 - torch.log2((1.0 + torch.exp2(step)) * 0.5) * step_inv
+    enc = torch.floor((la - lmin) * step_inv + rounding)
+    dec = torch.exp2((enc - 1.0) * step + lmin).to(torch.bfloat16).float()
+    use = (amax <= 1.0) & (lmin < lmax)
+    out = torch.where(use, torch.copysign(dec, xf), xf)
+    return out.reshape(x.shape).to(torch.bfloat16)
+
+
 def calc_diff(x: torch.Tensor, y: torch.Tensor) -> float:
     x, y = x.double() + 1, y.double() + 1
     denom = (x * x + y * y).sum()
