@@ -30,6 +30,51 @@ py::list plan_ops(const UkPlan& p) {
   }
   return out;
 }
+// inverse of plan_ops(): a user-authored plan (uccl_b200.ukernel.dsl) -> UkPlan
+UkRef ref_from(const py::handle& h) {
+  py::tuple t = py::reinterpret_borrow<py::tuple>(h);
+  UB_CHECK(t.size() == 2, "ukernel plan: a buffer reference is (name, offset)");
+  const std::string name = t[0].cast<std::string>();
+  UkRef r;
+  r.buf = name == "in" ? UkBuf::In : (name == "out" ? UkBuf::Out : UkBuf::Scratch);
+  UB_CHECK(name == "in" || name == "out" || name == "scratch", "ukernel plan: unknown buffer '%s'", name.c_str());
+  r.off = t[1].cast<uint64_t>();
+  return r;
+}
+UkPlan plan_from(int nranks, int rank, int nlanes, uint64_t scratch_bytes, const py::list& ops) {
+  UkPlan p;
+  p.coll = UkColl::AllReduce;  // informational only for custom programs
+  p.algo = UkAlgo::Auto;
+  p.nranks = nranks, p.rank = rank, p.nlanes = nlanes, p.scratch_bytes = scratch_bytes;
+  static const char* kinds[] = {"copy", "reduce", "send", "recv"};
+  for (auto h : ops) {
+    py::dict d = py::reinterpret_borrow<py::dict>(h);
+    UkPlanOp o;
+    const std::string k = d["kind"].cast<std::string>();
+    o.kind = -1;
+    for (int i = 0; i < 4; ++i)
+      if (k == kinds[i]) o.kind = i;
+    UB_CHECK(o.kind >= 0, "ukernel plan: unknown op kind '%s'", k.c_str());
+    o.lane = d.contains("lane") ? d["lane"].cast<int>() : 0;
+    o.tile = d.contains("tile") ? d["tile"].cast<int>() : 0;
+    o.step = d.contains("step") ? d["step"].cast<int>() : 0;
+    o.peer = d.contains("peer") ? d["peer"].cast<int>() : -1;
+    o.bytes = d.contains("bytes") ? d["bytes"].cast<uint64_t>() : 0;
+    if (d.contains("dst")) o.dst = ref_from(d["dst"]);
+    if (d.contains("src")) o.src = ref_from(d["src"]);
+    if (d.contains("src2")) o.src2 = ref_from(d["src2"]);
+    if (d.contains("deps")) o.deps = d["deps"].cast<std::vector<int>>();
+    p.ops.push_back(o);
+  }
+  return p;
+}
+std::vector<UkPlan> plans_from(int nlanes, const std::vector<uint64_t>& scratch, const py::list& per_rank) {
+  const int n = (int)per_rank.size();
+  UB_CHECK((int)scratch.size() == n, "ukernel plans: one scratch size per rank");
+  std::vector<UkPlan> plans;
+  for (int r = 0; r < n; ++r) plans.push_back(plan_from(n, r, nlanes, scratch[r], py::reinterpret_borrow<py::list>(per_rank[r])));
+  return plans;
+}
 UkPlan make(int coll, uint64_t bytes, int nranks, int rank, int nlanes, uint64_t tile, uint64_t elem, int algo,
             int root = 0) {
   UkPlanParams p;
@@ -106,6 +151,45 @@ void bind_uk(py::module_& m) {
          },
          py::arg("coll"), py::arg("bytes"), py::arg("nranks"), py::arg("nlanes"), py::arg("tile_bytes"), py::arg("dtype"),
          py::arg("op"), py::arg("algo"), py::arg("in_ptrs"), py::arg("out_ptrs"), py::arg("root") = 0);
+
+  // ---- user-authored programs (uccl_b200.ukernel.dsl): per-rank op lists in the format uk.plan() returns
+  uk.def("validate_ops",
+         [](int nlanes, std::vector<uint64_t> scratch, py::list per_rank, uint64_t in_bytes, uint64_t out_bytes,
+            uint64_t elem_size) {
+           std::vector<UkPlan> plans = plans_from(nlanes, scratch, per_rank);
+           for (auto& p : plans) {
+             std::string e = uk_check_bounds(p, in_bytes, out_bytes, p.scratch_bytes, nlanes, elem_size);
+             if (!e.empty()) return e;
+           }
+           return uk_validate(plans);
+         },
+         py::arg("nlanes"), py::arg("scratch_bytes"), py::arg("ops"), py::arg("in_bytes"), py::arg("out_bytes"),
+         py::arg("elem_size") = 1);
+  uk.def("simulate_ops",
+         [](int nlanes, std::vector<uint64_t> scratch, py::list per_rank, uint64_t in_bytes, uint64_t out_bytes, int dtype,
+            int op, std::vector<uintptr_t> in_ptrs, std::vector<uintptr_t> out_ptrs) {
+           std::vector<UkPlan> plans = plans_from(nlanes, scratch, per_rank);
+           const int n = (int)plans.size();
+           UB_CHECK((int)in_ptrs.size() == n && (int)out_ptrs.size() == n, "simulate_ops: one buffer per rank");
+           for (auto& p : plans) {
+             std::string e = uk_check_bounds(p, in_bytes, out_bytes, p.scratch_bytes, nlanes, dtype_size(dtype));
+             if (!e.empty()) return e;
+           }
+           std::string err = uk_validate(plans);
+           if (!err.empty()) return err;
+           std::vector<std::vector<char>> sc(n);
+           UkSimBuffers b;
+           for (int r = 0; r < n; ++r) {
+             sc[r].assign(plans[r].scratch_bytes + 16, 0x5a);
+             b.in.push_back((char*)in_ptrs[r]);
+             b.out.push_back((char*)out_ptrs[r]);
+             b.scratch.push_back(sc[r].data());
+           }
+           py::gil_scoped_release rel;
+           return uk_simulate(plans, b, dtype, op);
+         },
+         py::arg("nlanes"), py::arg("scratch_bytes"), py::arg("ops"), py::arg("in_bytes"), py::arg("out_bytes"),
+         py::arg("dtype"), py::arg("op"), py::arg("in_ptrs"), py::arg("out_ptrs"));
 
   py::class_<UkWorker, std::shared_ptr<UkWorker>>(uk, "Worker")
       .def(py::init<int, int, uint64_t, int64_t>(), py::arg("device"), py::arg("nlanes"), py::arg("timeout_ms") = 20000,
@@ -198,6 +282,17 @@ void bind_uk(py::module_& m) {
              return u.barrier((cudaStream_t)stream);
            },
            py::arg("stream") = 0)
+      .def("run_custom",
+           [](UkComm& u, int nlanes, uint64_t scratch_bytes, py::list ops, uintptr_t in, uint64_t in_bytes, uintptr_t out,
+              uint64_t out_bytes, int dtype, int op, uintptr_t stream, bool symmetric) {
+             UkPlan p = plan_from(u.nranks(), u.rank(), nlanes, scratch_bytes, ops);
+             py::gil_scoped_release rel;
+             return u.run_custom(p, (const void*)in, in_bytes, (void*)out, out_bytes, dtype, op, (cudaStream_t)stream, symmetric);
+           },
+           py::arg("nlanes"), py::arg("scratch_bytes"), py::arg("ops"), py::arg("in_ptr"), py::arg("in_bytes"),
+           py::arg("out_ptr"), py::arg("out_bytes"), py::arg("dtype"), py::arg("op"), py::arg("stream") = 0,
+           py::arg("symmetric") = false)
+      .def("scratch_capacity", &UkComm::scratch_capacity)
       .def("test", &UkComm::test)
       .def("wait", &UkComm::wait, py::arg("ticket"), py::arg("timeout_s") = 60.0, py::call_guard<py::gil_scoped_release>())
       .def("stop", &UkComm::stop, py::call_guard<py::gil_scoped_release>())

@@ -317,6 +317,50 @@ uint64_t UkComm::all_reduce(const void* in, void* out, size_t count, int dtype, 
   return end_op(stream);
 }
 
+uint64_t UkComm::run_custom(const UkPlan& plan, const void* in, uint64_t in_bytes, void* out, uint64_t out_bytes,
+                            int dtype, int op, cudaStream_t stream, bool symmetric) {
+  UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel run_custom: bad dtype %d", dtype);
+  UB_CHECK(op == kSum || op == kProd || op == kMax || op == kMin, "ukernel run_custom: op %d unsupported", op);
+  UB_CHECK(plan.nranks == comm_->nranks() && plan.rank == comm_->rank(), "ukernel run_custom: plan of rank %d/%d on rank %d/%d",
+           plan.rank, plan.nranks, comm_->rank(), comm_->nranks());
+  const std::string why = uk_check_bounds(plan, in_bytes, out_bytes, scratch_capacity(), cfg_.nlanes, dtype_size(dtype));
+  UB_CHECK(why.empty(), "ukernel run_custom: %s", why.c_str());
+  begin_op(stream);
+  const bool zero_copy = symmetric && comm_->in_heap(in, std::max<uint64_t>(in_bytes, 1)) &&
+                         comm_->in_heap(out, std::max<uint64_t>(out_bytes, 1)) && (((uintptr_t)in | (uintptr_t)out) & 15) == 0;
+  UkPlanParams bp;
+  bp.nranks = comm_->nranks(), bp.rank = comm_->rank(), bp.nlanes = cfg_.nlanes, bp.tile_bytes = cfg_.tile_bytes;
+  // A user program may Send into ANY buffer of a peer, so -- unlike the built-in plans, whose structure guarantees
+  // it -- nothing says the peer is done staging / still reading that buffer: fence the program with a rank barrier
+  // on both sides (all lanes join through lane_barrier).
+  auto rank_barrier = [&]() {
+    lane_barrier();
+    run_plan(uk_plan_barrier(bp), Bufs{stage_in_, stage_out_}, kU8, kSum);
+    lane_barrier();
+  };
+  ++stats_.segments;
+  if (zero_copy) {
+    ++stats_.zero_copy_ops;
+    rank_barrier();
+    run_plan(plan, Bufs{(char*)in, (char*)out}, dtype, op);
+    rank_barrier();
+  } else {
+    UB_CHECK(in_bytes <= cfg_.staging_bytes && out_bytes <= cfg_.staging_bytes,
+             "ukernel run_custom: %lu / %lu bytes do not fit the staging buffers (%lu); use symmetric tensors",
+             (unsigned long)in_bytes, (unsigned long)out_bytes, (unsigned long)cfg_.staging_bytes);
+    const bool in_place = (const void*)out == in;  // one staged buffer serves both names
+    // the program may read Out before writing it (in-place algorithms): stage both in
+    const uint64_t stage_in_bytes = in_place ? std::max(in_bytes, out_bytes) : in_bytes;
+    if (stage_in_bytes) copy_sliced(stage_in_, (const char*)in, stage_in_bytes);
+    if (out_bytes && !in_place) copy_sliced(stage_out_, (const char*)out, out_bytes);
+    rank_barrier();
+    run_plan(plan, Bufs{stage_in_, in_place ? stage_in_ : stage_out_}, dtype, op);
+    rank_barrier();
+    if (out_bytes) copy_sliced((char*)out, in_place ? stage_in_ : stage_out_, out_bytes);
+  }
+  return end_op(stream);
+}
+
 uint64_t UkComm::all_to_all(const void* in, void* out, size_t count_per_peer, int dtype, cudaStream_t stream,
                             bool symmetric) {
   UB_CHECK(dtype >= 0 && dtype < kNumDTypes, "ukernel all_to_all: bad dtype %d", dtype);

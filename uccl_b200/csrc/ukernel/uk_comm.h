@@ -45,6 +45,12 @@ class UkComm {
   uint64_t reduce_scatter(const void* in, void* out, size_t recv_count, int dtype, int op, cudaStream_t stream);
   uint64_t broadcast(const void* in, void* out, size_t count, int dtype, int root, cudaStream_t stream);
   uint64_t barrier(cudaStream_t stream);
+  // Executes a user-authored plan of THIS rank (uk_check_bounds must accept it; every rank calls with its own plan
+  // of the same program).  In / Out that are symmetric heap tensors are used in place, anything else is staged
+  // through the heap (then both must fit the staging buffers).
+  uint64_t run_custom(const UkPlan& plan, const void* in, uint64_t in_bytes, void* out, uint64_t out_bytes, int dtype,
+                      int op, cudaStream_t stream, bool symmetric = false);
+  uint64_t scratch_capacity() const { return region_bytes_[1]; }
   bool test(uint64_t ticket);
   void wait(uint64_t ticket, double timeout_s = 60.0);
   void stop();

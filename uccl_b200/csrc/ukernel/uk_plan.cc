@@ -387,6 +387,52 @@ std::string uk_validate(const std::vector<UkPlan>& plans) {
   return "";
 }
 
+std::string uk_check_bounds(const UkPlan& plan, uint64_t in_bytes, uint64_t out_bytes, uint64_t scratch_cap,
+                            int max_lanes, uint64_t elem_size) {
+  std::ostringstream err;
+  if (plan.nlanes < 1 || plan.nlanes > max_lanes) {
+    err << "plan uses " << plan.nlanes << " lanes, the communicator has " << max_lanes;
+    return err.str();
+  }
+  if (plan.scratch_bytes > scratch_cap) {
+    err << "plan needs " << plan.scratch_bytes << " scratch bytes, the communicator has " << scratch_cap;
+    return err.str();
+  }
+  auto cap = [&](const UkRef& r) -> uint64_t {
+    switch (r.buf) {
+      case UkBuf::In: return in_bytes;
+      case UkBuf::Out: return out_bytes;
+      default: return plan.scratch_bytes;
+    }
+  };
+  auto bad = [&](const UkRef& r, uint64_t bytes) {
+    return (int)r.buf < 0 || (int)r.buf > 2 || (r.off & 15) != 0 || r.off > cap(r) || bytes > cap(r) - r.off;
+  };
+  for (size_t i = 0; i < plan.ops.size(); ++i) {
+    const UkPlanOp& o = plan.ops[i];
+    bool wrong = false;
+    switch (o.kind) {
+      case UkPlanOp::Copy: wrong = bad(o.dst, o.bytes) || bad(o.src, o.bytes); break;
+      case UkPlanOp::Reduce:
+        wrong = bad(o.dst, o.bytes) || bad(o.src, o.bytes) || bad(o.src2, o.bytes) || elem_size == 0 ||
+                o.bytes % elem_size != 0;
+        break;
+      case UkPlanOp::Send: wrong = o.bytes != 0 && (bad(o.dst, o.bytes) || bad(o.src, o.bytes)); break;
+      case UkPlanOp::Recv: break;
+      default: wrong = true;
+    }
+    if (o.lane < 0 || o.lane >= plan.nlanes) wrong = true;
+    if ((o.kind == UkPlanOp::Send || o.kind == UkPlanOp::Recv) && (o.peer < 0 || o.peer >= plan.nranks || o.peer == plan.rank))
+      wrong = true;
+    if (wrong) {
+      err << "rank " << plan.rank << " op " << i << " (kind " << o.kind << ", lane " << o.lane << ", peer " << o.peer << ", "
+          << o.bytes << " bytes): outside its buffers, misaligned (16 bytes) or malformed";
+      return err.str();
+    }
+  }
+  return "";
+}
+
 std::string uk_simulate(const std::vector<UkPlan>& plans, const UkSimBuffers& b, int dtype, int redop) {
   const int n = (int)plans.size();
   auto ptr = [&](int rank, const UkRef& ref) -> char* {

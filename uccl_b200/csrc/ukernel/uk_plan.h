@@ -73,6 +73,14 @@ UkPlan uk_plan_broadcast(uint64_t bytes, int root, const UkPlanParams& p);
 // Returns "" if valid, otherwise a description of the first violation.
 std::string uk_validate(const std::vector<UkPlan>& plans);
 
+// User-authored plans (uccl_b200.ukernel.dsl -- the role of the reference's MSCCL++-DSL JSON plans and their
+// interpreter, experimental/lite/collective/execution_kernel.hpp:898): checks one rank's plan against the buffers it
+// is going to run on.  Every reference must stay inside its buffer (In / Out sizes are the same on every rank,
+// Scratch is bounded by `scratch_cap`), offsets must be 16-byte aligned (the worker's copy units), Reduce sizes a
+// multiple of the element size, lanes < max_lanes.  Returns "" if the plan may be executed.
+std::string uk_check_bounds(const UkPlan& plan, uint64_t in_bytes, uint64_t out_bytes, uint64_t scratch_cap,
+                            int max_lanes, uint64_t elem_size);
+
 // Reference executor over plain host memory (all ranks in one address space): runs the plans of
 // all ranks to completion with a round-robin scheduler that only fires an op when its deps and its
 // matching Send have fired.  Detects deadlock.  Used by the unit tests as the "ring-allreduce

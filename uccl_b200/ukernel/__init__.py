@@ -10,6 +10,9 @@ Three layers (all native, see ``csrc/ukernel``):
 * :class:`UkCommunicator` / :class:`ProcessGroup` -- collectives over a
   :class:`uccl_b200.Communicator`'s symmetric heap, ordered against torch streams with stream
   memory operations instead of kernel launches.
+* :mod:`uccl_b200.ukernel.dsl` -- write your own collective (``Program``: copy / reduce / send on
+  In / Out / Scratch), validate and simulate it on the CPU, ship it as JSON, run it on the same executor
+  (the role of the reference's MSCCL++-DSL plans and their interpreter kernel).
 
 Reference parity: ``experimental/ukernel`` (persistent kernel, CCL planner/executor, torch
 ProcessGroup with ``all_reduce / all_to_all_single / barrier``: ``ukernel_ccl/__init__.py:171-290``).
