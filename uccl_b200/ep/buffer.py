@@ -420,6 +420,10 @@ class Buffer:
                            expert_alignment: int = 1, num_worst_tokens: int = 0, config: Optional[Config] = None,
                            previous_event: Optional[EventOverlap] = None, async_finish: bool = False,
                            allocate_on_comm_stream: bool = False, **kw):
+        if num_tokens_per_rdma_rank is not None and num_tokens_per_rdma_rank.numel() != self.get_num_rdma_ranks():
+            # a layout computed for several RDMA groups does not describe this (single NVLink domain) group
+            raise ValueError(f"internode_dispatch: num_tokens_per_rdma_rank has {num_tokens_per_rdma_rank.numel()} entries, "
+                             f"this group is {self.get_num_rdma_ranks()} NVLink domain")
         return self.dispatch(x, handle=handle, num_tokens_per_rank=num_tokens_per_rank,
                              num_tokens_per_rdma_rank=None, is_token_in_rank=is_token_in_rank,
                              num_tokens_per_expert=num_tokens_per_expert, topk_idx=topk_idx,
