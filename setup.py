@@ -4,8 +4,15 @@ entry point `__graft_entry__.build()` uses."""
 import importlib.util
 import pathlib
 
-from setuptools import setup
+import sys
+
+from setuptools import Distribution, setup
 from setuptools.command.build_py import build_py
+
+try:
+    from setuptools.command.bdist_wheel import bdist_wheel
+except ImportError:  # older setuptools: the command lives in the wheel package
+    from wheel.bdist_wheel import bdist_wheel
 
 ROOT = pathlib.Path(__file__).parent
 
@@ -23,4 +30,23 @@ class BuildWithNative(build_py):
         super().run()
 
 
-setup(cmdclass={"build_py": BuildWithNative})
+class PlatformWheel(bdist_wheel):
+    """The package data holds a pybind11 module for THIS interpreter and platform: tag the wheel accordingly
+    (the reference forces the tag with an empty C extension, uccl/_platform_tag_stub.c + setup.py:42-47)."""
+
+    def finalize_options(self):
+        super().finalize_options()
+        self.root_is_pure = False
+
+    def get_tag(self):
+        _, _, plat = super().get_tag()
+        py = f"cp{sys.version_info.major}{sys.version_info.minor}"
+        return py, py, plat
+
+
+class BinaryDistribution(Distribution):
+    def has_ext_modules(self):
+        return True
+
+
+setup(cmdclass={"build_py": BuildWithNative, "bdist_wheel": PlatformWheel}, distclass=BinaryDistribution)
