@@ -301,3 +301,24 @@ def test_moe_training_example_two_processes():
     [p.join(60) for p in ps]
     assert got[0] == pytest.approx(got[1])
     assert all(b < a for a, b in zip(got[0], got[0][1:])), got[0]  # fixed batch: monotonically decreasing
+
+
+def test_host_buffer_raw_views_and_resets():
+    """DeepEP surface that frameworks poke at: get_local_buffer_tensor (slices, dtypes), reset_rdma_buffer,
+    connect_atomic_buffer (reference: ep/bench/buffer.py:213-221,606-647)."""
+    c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
+    b = Buffer(comm=c, num_nvl_bytes=1 << 16, num_rdma_bytes=1 << 12, low_latency_mode=True)
+    t = b.get_local_buffer_tensor(torch.float32)
+    assert t.dtype == torch.float32 and t.numel() == (1 << 16) // 4
+    t[5] = 3.0
+    v = b.get_local_buffer_tensor(torch.float32, torch.Size([2, 3]), offset=4)
+    assert v.shape == (2, 3) and float(v[0, 1]) == 3.0  # same memory
+    r = b.get_local_buffer_tensor(torch.int32, use_rdma_buffer=True)
+    assert r.numel() == (1 << 12) // 4
+    r.fill_(7)
+    b.reset_rdma_buffer()
+    assert int(b.get_local_buffer_tensor(torch.int32, use_rdma_buffer=True).abs().sum()) == 0
+    with pytest.raises(ValueError):
+        b.get_local_buffer_tensor(torch.float32, torch.Size([1 << 20]))
+    with pytest.raises(TypeError):
+        b.connect_atomic_buffer(None)

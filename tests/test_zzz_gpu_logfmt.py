@@ -57,3 +57,56 @@ def test_low_latency_combine_logfmt(n, in_place):
         assert bool((err <= 0.06 * exp_l.abs() + 1e-3).all())
         assert float((err <= 2e-2 * exp_l.abs() + 1e-3).float().mean()) > 0.995
         assert not torch.allclose(res[r]["out_l"], exp, rtol=1e-3, atol=1e-4)  # the grid was applied
+
+
+def test_raw_buffer_views_and_reset():
+    """get_local_buffer_tensor / reset_rdma_buffer / connect_atomic_buffer of the CUDA Buffer (reference:
+    ep/bench/buffer.py:213-221,606-647); low-latency traffic still works after a reset."""
+    n, T, H, K, M = 2, 16, 1024, 2, 64
+    E = n * 2
+    bufs = _ll_setup(n, M, H)
+    xs, idxs, ws = make_inputs(n, T, H, K, E, seed=77)
+
+    def fn(b):
+        dev = b.device
+        t = b.get_local_buffer_tensor(torch.bfloat16)
+        assert t.is_cuda and t.numel() * 2 == int(b.runtime.arena_area_bytes)
+        v = b.get_local_buffer_tensor(torch.float32, torch.Size([4, 8]), offset=t.numel() // 2 - 64)
+        v.fill_(1.5)
+        again = b.get_local_buffer_tensor(torch.float32, torch.Size([32]), offset=t.numel() // 2 - 64)
+        assert bool((again == 1.5).all())
+        x, idx, w = xs[b.rank].to(dev), idxs[b.rank].to(dev), ws[b.rank].to(dev)
+        rx, cnt, handle, _, _ = b.low_latency_dispatch(x, idx, M, E, use_fp8=False)
+        torch.cuda.current_stream().synchronize()
+        r = b.get_local_buffer_tensor(torch.uint8, use_rdma_buffer=True)
+        assert r.numel() == int(b.runtime.ll_nbytes) and r.numel() > 0
+        with pytest.raises(TypeError):
+            b.connect_atomic_buffer(None)
+        return int(cnt.sum())
+
+    first = run_threads(bufs, fn)
+
+    def after_reset(b):
+        b.reset_rdma_buffer()
+        torch.cuda.current_stream().synchronize()
+        return 0
+
+    run_threads(bufs, after_reset)
+
+    def roundtrip(b):
+        dev = b.device
+        x, idx, w = xs[b.rank].to(dev), idxs[b.rank].to(dev), ws[b.rank].to(dev)
+        rx, cnt, handle, _, _ = b.low_latency_dispatch(x, idx, M, E, use_fp8=False)
+        eo = b.get_next_low_latency_combine_buffer(handle)
+        for el in range(E // n):
+            c = int(cnt[el])
+            eo[el, :c] = rx[el, :c]
+        out, _, _ = b.low_latency_combine(eo, idx, w, handle)
+        torch.cuda.current_stream().synchronize()
+        return out.float().cpu(), int(cnt.sum())
+
+    res = run_threads(bufs, roundtrip)
+    for r in range(n):
+        wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(res[r][0], xs[r].float() * wsum[:, None], rtol=2e-2, atol=2e-2)
+        assert res[r][1] == first[r]

@@ -58,6 +58,10 @@ void bind_ep(py::module_& m) {
                                expert_alignment, num_worst_tokens, round_scale, num_sms, (cudaStream_t)st);
            })
       .def_property_readonly("base_offset", &EpBuffer::base_offset)
+      .def_property_readonly("arena_area_ptr", &EpBuffer::arena_area_ptr)
+      .def_property_readonly("arena_area_bytes", &EpBuffer::arena_area_bytes)
+      .def_property_readonly("ll_ptr", &EpBuffer::ll_ptr)
+      .def_property_readonly("ll_nbytes", &EpBuffer::ll_nbytes)
       .def("wait_counts",
            [](EpBuffer& b, int E_local, double timeout_s) {
              std::vector<int> pe;

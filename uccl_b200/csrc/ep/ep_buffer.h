@@ -33,6 +33,12 @@ class EpBuffer {
   int combine_capacity_for(int hidden, int topk) const;
   uint64_t launches() const { return launches_; }
   uint64_t base_offset() const { return base_off_; }  // heap offset of the EP block (must match on every rank)
+  // raw views for DeepEP's get_local_buffer_tensor: the arena area of the EP block (control words excluded) and
+  // the low-latency block (0 / 0 before ll_init)
+  uintptr_t arena_area_ptr() const { return (uintptr_t)(base_ + ctrl_bytes_); }
+  size_t arena_area_bytes() const { return bytes_ - ctrl_bytes_; }
+  uintptr_t ll_ptr() const { return (uintptr_t)ll_base_; }
+  size_t ll_nbytes() const { return ll_bytes_; }
   // kernel implementation of dispatch / combine: EP_IMPL_AUTO (default, UCCL_B200_EP_IMPL), _REG or _TMA
   int impl() const { return impl_; }
   void set_impl(int impl);

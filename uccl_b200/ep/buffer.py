@@ -438,6 +438,51 @@ class Buffer:
                             previous_event=previous_event, async_finish=async_finish,
                             allocate_on_comm_stream=allocate_on_comm_stream)
 
+    def get_local_buffer_tensor(self, dtype: torch.dtype, size: Optional[torch.Size] = None, offset: int = 0,
+                                use_rdma_buffer: bool = False) -> torch.Tensor:
+        """Raw view (slice supported) of this rank's communication memory as a tensor, like the reference's
+        (ep/bench/buffer.py:606-647): the NVLink arenas of the EP block, or with ``use_rdma_buffer=True`` the
+        low-latency block.  `offset` and `size` count elements of `dtype`.  The control words (barrier flags,
+        count tables) are not part of the view."""
+        if use_rdma_buffer:
+            self._need_ll()
+            ptr, nbytes = int(self.runtime.ll_ptr), int(self.runtime.ll_nbytes)
+            if nbytes == 0:
+                raise RuntimeError("uccl_b200.ep: the low-latency block is allocated by the first low_latency_dispatch")
+        else:
+            ptr, nbytes = int(self.runtime.arena_area_ptr), int(self.runtime.arena_area_bytes)
+        es = torch.empty((), dtype=dtype).element_size()
+        total = nbytes // es
+        if not 0 <= offset <= total:
+            raise ValueError(f"get_local_buffer_tensor: offset {offset} outside the buffer ({total} elements)")
+        t = self._view(ptr + offset * es, (total - offset,), dtype)
+        if size is None:
+            return t
+        n = 1
+        for d in size:
+            n *= int(d)
+        if n > t.numel():
+            raise ValueError(f"get_local_buffer_tensor: {n} elements requested, {t.numel()} available")
+        return t[:n].view(size)
+
+    def reset_rdma_buffer(self) -> None:
+        """Reference: zeroes the RDMA buffer for a fresh run (ep/bench/buffer.py:213-218).  Signalling here is epoch
+        based, so nothing NEEDS zeroing; the call completes a pending receive hook and clears the low-latency block
+        on the current stream so that stale rows cannot be mistaken for results."""
+        ll = self._need_ll()
+        ll._finish_pending()
+        if int(self.runtime.ll_nbytes) > 0:
+            self.get_local_buffer_tensor(torch.uint8, use_rdma_buffer=True).zero_()
+
+    def connect_atomic_buffer(self, proxy) -> None:
+        """Reference: hands the proxy the buffer its emulated RDMA atomics land in (ep/bench/buffer.py:220-221).
+        A :class:`uccl_b200.ep.Proxy` addresses any location of any peer's heap directly (ordered release-add on the
+        copy stream), so there is nothing to connect; the call only checks the argument."""
+        from .proxy import Proxy
+
+        if not isinstance(proxy, Proxy):
+            raise TypeError("connect_atomic_buffer expects a uccl_b200.ep.Proxy")
+
     def get_num_rdma_ranks(self) -> int:
         """Number of RDMA (inter-node) hops groups: always 1 -- the whole group is one NVLink domain."""
         return 1

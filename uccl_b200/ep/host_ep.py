@@ -135,6 +135,37 @@ class HostBuffer:
     def get_num_rdma_ranks(self) -> int:
         return int(getattr(self._raw_comm, "num_nodes", 1))  # boxes the group spans
 
+    def get_local_buffer_tensor(self, dtype: torch.dtype, size=None, offset: int = 0, use_rdma_buffer: bool = False):
+        """Same contract as the CUDA Buffer: a raw view of this rank's communication memory -- here a host scratch
+        block of `num_nvl_bytes` / `num_rdma_bytes` that exists for API compatibility (the host path exchanges
+        tensors through the communicator, not through these blocks)."""
+        key = "_scratch_rdma" if use_rdma_buffer else "_scratch_nvl"
+        nbytes = self.num_rdma_bytes if use_rdma_buffer else self.num_nvl_bytes
+        buf = getattr(self, key, None)
+        if buf is None:
+            buf = torch.zeros(max(nbytes, 8) // 8 * 8, dtype=torch.uint8)
+            setattr(self, key, buf)
+        t = buf.view(dtype)
+        if not 0 <= offset <= t.numel():
+            raise ValueError(f"get_local_buffer_tensor: offset {offset} outside the buffer ({t.numel()} elements)")
+        t = t[offset:]
+        if size is None:
+            return t
+        n = 1
+        for d in size:
+            n *= int(d)
+        if n > t.numel():
+            raise ValueError(f"get_local_buffer_tensor: {n} elements requested, {t.numel()} available")
+        return t[:n].view(size)
+
+    def reset_rdma_buffer(self) -> None:
+        if getattr(self, "_scratch_rdma", None) is not None:
+            self._scratch_rdma.zero_()
+
+    def connect_atomic_buffer(self, proxy) -> None:
+        if proxy is None:
+            raise TypeError("connect_atomic_buffer expects a proxy")
+
     # ------------------------------------------------------------------ layout
     @_portable
     def get_dispatch_layout(self, topk_idx: torch.Tensor, num_experts: int, previous_event=None, async_finish=False,
