@@ -294,3 +294,25 @@ def test_collective_context_on_cpu_two_processes():
     got = sorted(q.get(timeout=240) for _ in range(2))
     [p.join(60) for p in ps]
     assert got == [(0, True, True, True, True), (1, True, True, True, True)]
+
+
+def test_registration_type_tags_and_handles():
+    """FloatType tags travel with registrations (reference: p2p/engine_api.cc:171-177,279-293), XferHandle / repr."""
+    import torch
+
+    from uccl_b200.p2p import Endpoint, FloatType, XferHandle
+
+    e = Endpoint(-1)
+    t = torch.zeros(64, dtype=torch.bfloat16)
+    ok, mr = e.reg(t.data_ptr(), t.numel() * 2, FloatType.kBFloat16)
+    assert ok and e.float_type(mr) == FloatType.kBFloat16
+    ok2, mr2 = e.reg(t.data_ptr(), 16)
+    assert ok2 and e.float_type(mr2) == FloatType.kUndefined
+    d = e.register_memory([torch.zeros(8, dtype=torch.float32), torch.zeros(8, dtype=torch.int32)])
+    assert e.float_type(d[0].mr_id) == FloatType.kFloat32 and e.float_type(d[1].mr_id) == FloatType.kUndefined
+    e.dereg(mr)
+    assert e.float_type(mr) == FloatType.kUndefined
+    assert FloatType.from_tensor(torch.zeros(1, dtype=torch.float8_e4m3fn)) == FloatType.kFloat8E4M3FN
+    h = XferHandle(3, "write", 17)
+    assert h.conn_id == 3 and h.op_name == "write" and h.transfer_id == 17
+    assert "host mode" in repr(e)

@@ -181,10 +181,17 @@ class CollectiveContext:
         ptr = tensor.data_ptr()
         if ptr in self._registered:
             return self._registered[ptr]
-        ok, mr = self.ep.reg(ptr, tensor.numel() * tensor.element_size())
+        ok, mr = self.ep.reg(ptr, tensor.numel() * tensor.element_size(), self.float_type_from_tensor(tensor))
         assert ok
         self._registered[ptr] = mr
         return mr
+
+    @staticmethod
+    def float_type_from_tensor(t: torch.Tensor):
+        """Element type tag of a registration (reference: p2p/collective.py:321-333)."""
+        from .p2p import FloatType
+
+        return FloatType.from_tensor(t)
 
     def check_tensor_registered(self, tensor: torch.Tensor) -> Optional[int]:
         return self._registered.get(tensor.data_ptr())

@@ -7,10 +7,11 @@ by an in-kernel TMA (cp.async.bulk) copy pipeline on side streams, vectorised pe
 """
 from __future__ import annotations
 
+import enum
 import os
 import socket
 import struct
-from typing import List, Optional, Sequence, Tuple
+from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 from .. import _native
 
@@ -39,6 +40,34 @@ class XferDesc:
         return f"XferDesc(addr=0x{self.addr:x}, size={self.size})"
 
 
+class FloatType(enum.IntEnum):
+    """Element type a registration may carry (reference: uccl::FloatType, p2p/engine_api.cc:171-177); the lossless
+    compression hook (`uccl_b200.p2p.compress`) uses it to pick the exponent / mantissa split."""
+
+    kUndefined = 0
+    kFloat16 = 1
+    kBFloat16 = 2
+    kFloat32 = 3
+    kFloat8E4M3FN = 4
+    kFloat8E5M2 = 5
+
+    @staticmethod
+    def from_tensor(t) -> "FloatType":
+        import torch
+
+        return {torch.float16: FloatType.kFloat16, torch.bfloat16: FloatType.kBFloat16, torch.float32: FloatType.kFloat32,
+                torch.float8_e4m3fn: FloatType.kFloat8E4M3FN, torch.float8_e5m2: FloatType.kFloat8E5M2}.get(
+                    t.dtype, FloatType.kUndefined)
+
+
+class XferHandle(NamedTuple):
+    """Identifies a started transfer (reference: XferHandle, p2p/engine_api.cc:24,147-150)."""
+
+    conn_id: int
+    op_name: str
+    transfer_id: int
+
+
 def get_oob_ip() -> str:
     return os.environ.get("UCCL_B200_P2P_IP", "127.0.0.1")
 
@@ -61,6 +90,7 @@ class Endpoint:
         self._e = C.P2PEndpoint(int(local_gpu_idx), max(1, int(num_cpus)))
         self.local_gpu_idx = int(local_gpu_idx)
         self._mrs = {}
+        self._mr_types = {}
         self._ipc_pending = {}
         # local rendezvous file for connect_local (reference: shm inbox keyed by GPU BDF)
         try:
@@ -107,11 +137,20 @@ class Endpoint:
         return ok, gpu, conn
 
     # -------------------------------------------------------------- registration
-    def reg(self, ptr: int, size: int):
+    def reg(self, ptr: int, size: int, floatType: FloatType = FloatType.kUndefined):
         ok, mr = self._e.reg(int(ptr), int(size))
         if ok:
             self._mrs[mr] = (int(ptr), int(size))
+            self._mr_types[mr] = FloatType(int(floatType))
         return ok, mr
+
+    def float_type(self, mr_id: int) -> FloatType:
+        """Element type recorded at registration (kUndefined if none was given)."""
+        return self._mr_types.get(mr_id, FloatType.kUndefined)
+
+    def __repr__(self):
+        mode = f"gpu {self.local_gpu_idx}" if self.local_gpu_idx >= 0 else "host mode"
+        return f"<uccl_b200 P2P Endpoint ({mode}, {len(self._mrs)} registrations)>"
 
     def regv(self, ptrs: Sequence[int], sizes: Sequence[int]):
         ids = []
@@ -124,13 +163,14 @@ class Endpoint:
 
     def dereg(self, mr_id: int) -> bool:
         self._mrs.pop(mr_id, None)
+        self._mr_types.pop(mr_id, None)
         return self._e.dereg(mr_id)
 
     def register_memory(self, tensors) -> List[XferDesc]:
         descs = []
         for t in tensors:
             ptr, size = t.data_ptr(), t.numel() * t.element_size()
-            ok, mr = self.reg(ptr, size)
+            ok, mr = self.reg(ptr, size, FloatType.from_tensor(t))
             if not ok:
                 raise RuntimeError("uccl_b200.p2p: register_memory failed")
             descs.append(XferDesc(bytes(self._e.describe(ptr, size)), mr))
