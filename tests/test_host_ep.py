@@ -322,3 +322,26 @@ def test_host_buffer_raw_views_and_resets():
         b.get_local_buffer_tensor(torch.float32, torch.Size([1 << 20]))
     with pytest.raises(TypeError):
         b.connect_atomic_buffer(None)
+
+
+def test_uccl_ep_module_level_functions():
+    """Functions scripts call on the reference's native `uccl.ep` module (ep/src/uccl_ep.cc:1676-1760,2187)."""
+    import uccl_b200.ep as ep
+
+    assert ep.get_low_latency_rdma_size_hint(128, 7168, 8, 288) == Buffer.get_low_latency_rdma_size_hint(128, 7168, 8, 288) > 0
+    assert ep.get_num_proxy_threads() == 1 and isinstance(ep.get_oob_ip(), str) and isinstance(ep.is_sm90_compiled(), bool)
+    assert ep.can_register_rdma_gpu_buffer(0, 1 << 20) and not ep.rdma_buffer_should_use_host_alloc(0)
+    t, host = ep.get_rdma_buffer(4096, -1)
+    assert t.numel() == 4096 and host is False
+
+    class P:
+        stopped = 0
+
+        def stop(self):
+            P.stopped += 1
+
+    ep.register_proxies(0, [P(), P()])
+    ep.register_proxies(1, [P()])
+    ep.stop_all_registered_proxies()
+    ep.stop_all_registered_proxies()
+    assert P.stopped == 3
