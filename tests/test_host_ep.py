@@ -345,3 +345,13 @@ def test_uccl_ep_module_level_functions():
     ep.stop_all_registered_proxies()
     ep.stop_all_registered_proxies()
     assert P.stopped == 3
+
+
+def test_ep_bootstrap_helpers():
+    import uccl_b200.ep as ep
+
+    hca = ep.detect_ib_hca()
+    assert hca is None or isinstance(hca, str)
+    assert ep.get_peer_ip(0, 1) == ""
+    meta = ep.get_cpu_proxies_meta([object(), object()], 0, 4096, 64, 1)
+    assert meta[0]["ptr"] == 4096 and meta[0]["nbytes"] == 64 and meta[0]["listen_ports"] == [0, 0]

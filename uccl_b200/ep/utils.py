@@ -332,3 +332,55 @@ def bench_kineto(fn, kernel_names, num_tests: int = 30, suppress_kineto_output: 
                 cnt += int(ev.count)
         out.append(tot / max(cnt, 1) * 1e-6 * num_kernels_per_period)
     return out[0] if isinstance(kernel_names, str) else tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bootstrap helpers of the reference's ep/bench/utils.py that launch scripts import (detect_ib_hca :293-320,
+# get_peer_ip :139-148, get_cpu_proxies_meta :151-180).  Inside one NVSwitch box nothing of this is needed to build a
+# Buffer; they exist so that those scripts run unchanged and for groups that span boxes.
+def detect_ib_hca() -> Optional[str]:
+    """Name of the first RDMA device of the host (Mellanox `mlx5_*` first, then Intel `irdma*`, then anything else),
+    or None.  The scale-out transport of this library binds rails by network interface instead
+    (`uccl_b200.net.topology.nic_for_gpu`), so this is informational."""
+    import glob
+    import os
+
+    try:
+        names = sorted(os.path.basename(p) for p in glob.glob("/sys/class/infiniband/*"))
+    except OSError:
+        return None
+    for prefix in ("mlx5", "irdma", ""):
+        for n in names:
+            if n.startswith(prefix):
+                return n
+    return None
+
+
+def _gather_objects(obj, num_ranks: int, group):
+    if num_ranks <= 1:
+        return [obj]
+    import torch.distributed as dist
+
+    out = [None] * num_ranks
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def get_peer_ip(rank: int, num_ranks: int, group=None) -> str:
+    """Out-of-band address of the next rank of the ring ("" for a single rank)."""
+    if num_ranks <= 1:
+        return ""
+    from ..p2p import get_oob_ip
+
+    ips = _gather_objects(get_oob_ip(), num_ranks, group)
+    return ips[(rank + 1) % num_ranks] or ""
+
+
+def get_cpu_proxies_meta(proxies, rank: int, scratch_ptr: int, scratch_bytes: int, num_ranks: int, group=None) -> dict:
+    """``{rank: {rank, ptr, nbytes, ip, listen_ports}}`` of every rank -- what the reference exchanges before it wires
+    its proxies to each other (a :class:`uccl_b200.ep.Proxy` has no listen port: 0 is reported)."""
+    from ..p2p import get_oob_ip
+
+    meta = dict(rank=int(rank), ptr=int(scratch_ptr), nbytes=int(scratch_bytes), ip=get_oob_ip(),
+                listen_ports=[int(getattr(p, "get_listen_port", lambda: 0)()) for p in (proxies or [])])
+    return {m["rank"]: m for m in _gather_objects(meta, num_ranks, group)}
