@@ -92,10 +92,14 @@ void EpBuffer::set_impl(int impl) {
 // dispatch at every SM budget and win the combine by 5-10 % (458 vs 511 us at 24 SMs, 436 vs 461 us at 96 on
 // 8 GPUs); on ONE GPU (HBM-only permutation, nothing to hide) the register path's shorter per-token critical
 // path is faster (29 vs 37 us combine at 148 CTAs).
-int EpBuffer::pick_impl(int grid) const {
-  (void)grid;
+int EpBuffer::pick_impl(int grid, bool combine) const {
   if (impl_ != EP_IMPL_AUTO) return impl_;
-  return nranks() == 1 ? EP_IMPL_REG : EP_IMPL_TMA;
+  if (nranks() == 1) return EP_IMPL_REG;
+  // 2 GPUs, few CTAs: a token has two copies and one of them is local, so combine is bound by a CTA's own critical
+  // path, not by bytes in flight -- the register path wins there (24 CTAs: 166 vs 201 us; 48 CTAs: 118 vs 113 us,
+  // profiles/ep_sweep_2xB200.json); dispatch favours the pipelines at every CTA count (119 vs 136 us at 24)
+  if (combine && nranks() == 2 && grid <= 32) return EP_IMPL_REG;
+  return EP_IMPL_TMA;
 }
 
 int EpBuffer::capacity_for(int hidden, int mode, int topk) const {
@@ -214,7 +218,7 @@ EpDispatchOut EpBuffer::dispatch(uintptr_t x, uintptr_t x_scales, uintptr_t topk
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
   a.in_stages = st_in_;
   a.out_stages = st_out_;
-  const bool tma = pick_impl(grid) == EP_IMPL_TMA && ep_dispatch_tma_supported(a);
+  const bool tma = pick_impl(grid, false) == EP_IMPL_TMA && ep_dispatch_tma_supported(a);
   last_disp_impl_ = tma ? EP_IMPL_TMA : EP_IMPL_REG;
   cudaError_t e = tma ? launch_ep_dispatch_tma(comm_->dev(), a, grid, st) : launch_ep_dispatch(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep dispatch launch failed: %s", cudaGetErrorString(e));
@@ -308,7 +312,7 @@ void EpBuffer::combine(uintptr_t x, int num_recv, uintptr_t topk_w, uintptr_t se
   a.K = K;
   int grid = std::max(1, std::min(num_sms, kEpMaxBlocks));
   a.stages = st_comb_;
-  const bool tma = pick_impl(grid) == EP_IMPL_TMA && ep_combine_tma_supported(a);
+  const bool tma = pick_impl(grid, true) == EP_IMPL_TMA && ep_combine_tma_supported(a);
   last_comb_impl_ = tma ? EP_IMPL_TMA : EP_IMPL_REG;
   cudaError_t e = tma ? launch_ep_combine_tma(comm_->dev(), a, grid, st) : launch_ep_combine(comm_->dev(), a, grid, st);
   UB_CHECK(e == cudaSuccess, "ep combine launch failed: %s", cudaGetErrorString(e));

@@ -102,7 +102,7 @@ class EpBuffer {
   int impl_ = EP_IMPL_AUTO;
   int st_in_ = 0, st_out_ = 0, st_comb_ = 0;
   int last_disp_impl_ = 0, last_comb_impl_ = 0;
-  int pick_impl(int grid) const;
+  int pick_impl(int grid, bool combine) const;
   // low latency
   struct LLLayout {
     uint64_t cnt_tab_off, recv_x_off, recv_scales_off, recv_src_off, comb_x_off;
