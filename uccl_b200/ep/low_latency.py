@@ -123,13 +123,21 @@ class LowLatencyRuntime:
 
         hook = None
         if return_recv_hook:
+            sent = torch.cuda.Event()
+            sent.record(st)
+
             def hook():
                 if self._pending is hook:
                     self._pending = None
                     with torch.cuda.device(dev):
-                        self.rt.ll_dispatch_recv(sms, stats_ptr, torch.cuda.current_stream(dev).cuda_stream)
+                        cur = torch.cuda.current_stream(dev)
+                        cur.wait_event(sent)  # the receive half reads the epoch the send half stored: order them even
+                        self.rt.ll_dispatch_recv(sms, stats_ptr, cur.cuda_stream)  # when the hook runs on another stream
                         finish()
 
+            # everything the receive half touches stays alive until it has run
+            hook._keep = (x, topk_idx, recv_count, layout_range, send_pos, dispatch_wait_recv_cost_stats,
+                          cumulative_local_expert_recv_stats)
             self._pending = hook
         else:
             finish()
@@ -178,14 +186,20 @@ class LowLatencyRuntime:
             self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_SEND, layout_range=layout_range.data_ptr(),
                                wait_stats=stats_ptr, use_logfmt=bool(use_logfmt))
 
+            sent = torch.cuda.Event()
+            sent.record(st)
+
             def hook():
                 if self._pending is hook:
                     self._pending = None
                     with torch.cuda.device(dev):
-                        self.rt.ll_combine(*args, torch.cuda.current_stream(dev).cuda_stream, phase=C.EP_LL_RECV,
+                        cur = torch.cuda.current_stream(dev)
+                        cur.wait_event(sent)  # see dispatch: epoch hand-over between the two halves
+                        self.rt.ll_combine(*args, cur.cuda_stream, phase=C.EP_LL_RECV,
                                            layout_range=layout_range.data_ptr(), wait_stats=stats_ptr)
 
-            hook._keep = (x, topk_weights, send_pos, out, layout_range)  # alive until the receive half has run
+            # alive until the receive half has run
+            hook._keep = (x, topk_weights, send_pos, out, layout_range, combine_wait_recv_cost_stats)
             self._pending = hook
         else:
             self.rt.ll_combine(*args, st.cuda_stream, phase=C.EP_LL_FULL, layout_range=layout_range.data_ptr(),
