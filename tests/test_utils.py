@@ -391,3 +391,75 @@ def test_logfmt10_simulated_cast_properties():
     for grp in qf.reshape(-1, 128)[:16]:
         assert grp.abs().unique().numel() <= 511
     assert torch.equal(logfmt10_simulate(q), logfmt10_simulate(logfmt10_simulate(q)))  # stable under re-application
+
+
+def test_region_index_matches_brute_force():
+    """Containment lookup of registered regions (reference: interval tree in p2p/utils.py:114-206 and its
+    test_util_interval_tree.py): randomized against a linear scan, with nested / overlapping / adjacent regions."""
+    import random
+
+    from uccl_b200.utils.regions import RegionIndex
+
+    rng = random.Random(7)
+    idx = RegionIndex()
+    live = {}
+    for step in range(3000):
+        op = rng.random()
+        if op < 0.45 or not live:
+            start, size = rng.randrange(0, 5000), rng.randrange(1, 400)
+            if (start, size) in live:
+                continue
+            live[(start, size)] = step
+            idx.add(start, size, step)
+        elif op < 0.6:
+            (start, size), v = rng.choice(list(live.items()))
+            assert idx.remove(start, size) == v
+            del live[(start, size)]
+        else:
+            q, n = rng.randrange(0, 5400), rng.randrange(1, 64)
+            cands = [(sz, s, v) for (s, sz), v in live.items() if s <= q and q + n <= s + sz]
+            got = idx.find(q, n)
+            if not cands:
+                assert got is None
+            else:
+                assert got is not None and got[1] == min(c[0] for c in cands)
+                assert (got[0], got[1]) in live and live[(got[0], got[1])] == got[2]
+        assert len(idx) == len(live)
+    assert idx.remove(10 ** 9) is None and idx.exact(10 ** 9) is None
+    with pytest.raises(ValueError):
+        idx.add(0, 0, 1)
+
+
+def test_collective_registration_covers_views():
+    """A view into a registered buffer resolves to the covering registration instead of registering again."""
+    import torch
+
+    from uccl_b200.collective import CollectiveContext
+
+    class FakeEndpoint:
+        def __init__(self):
+            self.regs, self.deregs = [], []
+
+        def reg(self, ptr, size, ftype=None):
+            self.regs.append((ptr, size))
+            return True, len(self.regs)
+
+        def dereg(self, mr):
+            self.deregs.append(mr)
+            return True
+
+    ctx = CollectiveContext.__new__(CollectiveContext)
+    from uccl_b200.utils.regions import RegionIndex
+
+    ctx._registered, ctx.ep = RegionIndex(), FakeEndpoint()
+    big = torch.zeros(4096, dtype=torch.float32)
+    mr = ctx.register_tensor(big)
+    view = big[1024:2048]
+    assert ctx.register_tensor(view) == mr and ctx.check_tensor_registered(view) == mr and len(ctx.ep.regs) == 1
+    other = torch.zeros(16)
+    assert ctx.check_tensor_registered(other) is None
+    mr2 = ctx.register_tensor(other)
+    assert mr2 != mr and len(ctx.ep.regs) == 2
+    assert not ctx.deregister_tensor(view)          # a view does not own the registration
+    assert ctx.deregister_tensor(big) and ctx.ep.deregs == [mr]
+    assert ctx.check_tensor_registered(view) is None

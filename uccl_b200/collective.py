@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from .p2p import Endpoint
 from .parallel.comm import Communicator
+from .utils.regions import RegionIndex
 
 
 class P2POp:
@@ -73,7 +74,7 @@ class CollectiveContext:
         self.comm: Optional[Communicator] = None
         self._with_native = with_native_collectives
         self._heap_bytes = heap_bytes
-        self._registered: Dict[int, int] = {}
+        self._registered = RegionIndex()  # (ptr, bytes) -> mr id, containment lookup (views into registered buffers)
         self.initialized = False
         # peers on other boxes: tensors ride the datagram transport (p2p.internode.NetChannel)
         self.remote_peers: Dict[int, "object"] = {}   # rank -> NetChannel
@@ -178,12 +179,15 @@ class CollectiveContext:
 
     # ----------------------------------------------------------------- registration
     def register_tensor(self, tensor: torch.Tensor) -> int:
-        ptr = tensor.data_ptr()
-        if ptr in self._registered:
-            return self._registered[ptr]
-        ok, mr = self.ep.reg(ptr, tensor.numel() * tensor.element_size(), self.float_type_from_tensor(tensor))
+        """Registers the tensor's memory unless a registration already covers it (e.g. it is a view into a buffer
+        that was registered as a whole): returns the covering registration's id."""
+        ptr, nbytes = tensor.data_ptr(), max(tensor.numel() * tensor.element_size(), 1)
+        hit = self._registered.find(ptr, nbytes)
+        if hit is not None:
+            return hit[2]
+        ok, mr = self.ep.reg(ptr, nbytes, self.float_type_from_tensor(tensor))
         assert ok
-        self._registered[ptr] = mr
+        self._registered.add(ptr, nbytes, mr)
         return mr
 
     @staticmethod
@@ -194,10 +198,12 @@ class CollectiveContext:
         return FloatType.from_tensor(t)
 
     def check_tensor_registered(self, tensor: torch.Tensor) -> Optional[int]:
-        return self._registered.get(tensor.data_ptr())
+        hit = self._registered.find(tensor.data_ptr(), max(tensor.numel() * tensor.element_size(), 1))
+        return hit[2] if hit is not None else None
 
     def deregister_tensor(self, tensor: torch.Tensor) -> bool:
-        mr = self._registered.pop(tensor.data_ptr(), None)
+        """Drops the registration that STARTS at this tensor (a view inside a larger registration leaves it alone)."""
+        mr = self._registered.remove(tensor.data_ptr())
         return bool(mr is not None and self.ep.dereg(mr))
 
     # -------------------------------------------------------------------- send/recv
