@@ -463,3 +463,15 @@ def test_collective_registration_covers_views():
     assert not ctx.deregister_tensor(view)          # a view does not own the registration
     assert ctx.deregister_tensor(big) and ctx.ep.deregs == [mr]
     assert ctx.check_tensor_registered(view) is None
+
+
+def test_info_cli_reports_the_installation():
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, "-m", "uccl_b200", "--json"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout)
+    assert d["module_built"] and d["nccl_shim_built"] and d["native"]["max_ranks"] == 8
+    assert "sm_100a" in d["arch_flags"] and isinstance(d["gpus"], list)
