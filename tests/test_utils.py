@@ -470,7 +470,10 @@ def test_info_cli_reports_the_installation():
     import subprocess
     import sys
 
-    r = subprocess.run([sys.executable, "-m", "uccl_b200", "--json"], capture_output=True, text=True, timeout=300)
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "uccl_b200", "--json"], capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode == 0, r.stderr
     d = json.loads(r.stdout)
     assert d["module_built"] and d["nccl_shim_built"] and d["native"]["max_ranks"] == 8
