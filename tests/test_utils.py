@@ -478,3 +478,26 @@ def test_info_cli_reports_the_installation():
     d = json.loads(r.stdout)
     assert d["module_built"] and d["nccl_shim_built"] and d["native"]["max_ranks"] == 8
     assert "sm_100a" in d["arch_flags"] and isinstance(d["gpus"], list)
+
+
+def test_perf_gate_flags_regressions(tmp_path):
+    """scripts/perf_gate.py: the committed 8-GPU bench line passes against itself, a 20 % slower dispatch fails."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = os.path.join(root, "profiles", "bench8.json")
+    gate = os.path.join(root, "scripts", "perf_gate.py")
+    ok = subprocess.run([sys.executable, gate, base], capture_output=True, text=True)
+    assert ok.returncode == 0 and "passed" in ok.stdout, ok.stdout + ok.stderr
+    d = json.loads(open(base).read().strip().splitlines()[-1])
+    d["dispatch_us"] *= 1.2
+    worse = tmp_path / "worse.json"
+    worse.write_text(json.dumps(d))
+    bad = subprocess.run([sys.executable, gate, str(worse)], capture_output=True, text=True)
+    assert bad.returncode == 1 and "REGRESSION" in bad.stdout
+    d["dispatch_us"] /= 1.2 * 1.1  # faster than the baseline is fine
+    worse.write_text(json.dumps(d))
+    assert subprocess.run([sys.executable, gate, str(worse)], capture_output=True, text=True).returncode == 0
