@@ -35,7 +35,8 @@ def collect() -> dict:
             p = torch.cuda.get_device_properties(i)
             gpus.append({"index": i, "name": p.name, "cc": f"{p.major}.{p.minor}", "sms": p.multi_processor_count,
                          "memory_GiB": round(p.total_memory / 2 ** 30, 1)})
-        info["peer_access"] = [[bool(i == j or torch.cuda.can_device_access_peer(i, j)) for j in range(n)] for i in range(n)]
+        info["peer_access"] = [[bool(i == j or torch.cuda.can_device_access_peer(i, j)) for j in range(n)]
+                               for i in range(n)]
         try:
             from cuda import cuda as drv  # cuda-python, optional
 
@@ -67,7 +68,8 @@ def main(argv=None) -> int:
     print(f"uccl_b200 {info['version']}  (python {info['python']}, torch {info['torch']}, CUDA {info['torch_cuda']})")
     print(f"  build: {info['arch_flags']}  nvcc={info['nvcc']}")
     for k in ("module", "nccl_shim", "nccl_net_plugin"):
-        print(f"  {k:16s} {info[k]}  [{'built' if info[k + '_built'] else 'MISSING: python -c \"import uccl_b200; uccl_b200.build()\"'}]")
+        state = "built" if info[k + "_built"] else 'MISSING: python -c "import uccl_b200; uccl_b200.build()"'
+        print(f"  {k:16s} {info[k]}  [{state}]")
     print(f"  native: {info['native']}")
     if info["gpus"]:
         for g in info["gpus"]:

@@ -136,7 +136,8 @@ class Program:
 
         out = inp if out is None else out
         if uk_comm.world_size != self.nranks:
-            raise ValueError(f"Program {self.name} is written for {self.nranks} ranks, the communicator has {uk_comm.world_size}")
+            raise ValueError(f"Program {self.name} is written for {self.nranks} ranks, "
+                             f"the communicator has {uk_comm.world_size}")
         uk_comm._check(inp), uk_comm._check(out)
         ib, ob = inp.numel() * inp.element_size(), out.numel() * out.element_size()
         if ib < self.in_bytes or ob < self.out_bytes:
@@ -158,7 +159,8 @@ class Program:
     def from_dict(cls, d: Dict) -> "Program":
         if d.get("format") != cls.FORMAT:
             raise ValueError(f"not a {cls.FORMAT} document")
-        p = cls(d["name"], d["nranks"], d["nlanes"], d["in_bytes"], d["out_bytes"], d["scratch_bytes"], d.get("elem_size", 1))
+        p = cls(d["name"], d["nranks"], d["nlanes"], d["in_bytes"], d["out_bytes"], d["scratch_bytes"],
+                d.get("elem_size", 1))
         if len(d["ranks"]) != p.nranks:
             raise ValueError("program document: one op list per rank expected")
         for r, ops in enumerate(d["ranks"]):
