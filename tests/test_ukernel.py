@@ -512,3 +512,24 @@ def test_custom_collective_example_cpu():
                         "--numel", "5000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "pair_reduce_doubling_4" in r.stdout and "executed on the host backend: ok" in r.stdout
+
+
+def test_planner_cpp_unit_under_sanitizers(tmp_path):
+    """tests/cpp/uk_plan_test.cc: planner + validator + bounds checker + simulator as a plain C++ program under
+    ASan + UBSan (no Python, no CUDA) -- the reference's C++ unit layer for the ukernel CCL."""
+    import os
+    import shutil
+    import subprocess
+
+    if shutil.which("g++") is None:
+        pytest.skip("no host compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "uccl_b200", "csrc")
+    exe = str(tmp_path / "uk_plan_test")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-I" + csrc, "-I/usr/local/cuda/include",
+           os.path.join(root, "tests/cpp/uk_plan_test.cc"), os.path.join(csrc, "ukernel/uk_plan.cc"),
+           os.path.join(csrc, "coll/host_coll.cc"), "-o", exe, "-lpthread"]
+    b = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert b.returncode == 0, b.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
