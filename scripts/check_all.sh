@@ -12,6 +12,8 @@ for san in address,undefined thread; do
   ASAN_OPTIONS=detect_leaks=0 /tmp/net_san_$$ 3 swift 8 | tail -1
   rm -f /tmp/net_san_$$
 done
+# (the P2P engine stress and the ukernel planner run under TSan / ASan+UBSan from inside the pytest suite:
+#  tests/test_host_p2p.py::test_engine_concurrency_stress_under_sanitizers, tests/test_ukernel.py::test_planner_cpp_unit_under_sanitizers)
 python -m pytest tests -m gpu --collect-only -q | tail -1
 if [ "${1:-}" = "--profiles" ]; then ./scripts/run_scaleout_cpu.sh; fi
 echo "check_all: ok"

@@ -1,5 +1,7 @@
 #include "endpoint.h"
 
+#include <atomic>
+
 #include <arpa/inet.h>
 #include <errno.h>
 #include <netinet/in.h>
@@ -90,13 +92,15 @@ struct Endpoint::Conn {
   std::map<uint64_t, bool> dones;                  // seq -> DONE received
   std::map<uint64_t, bool> acks;                   // transfer id -> FLUSH_ACK received (TCP data path)
   uint64_t next_send_seq = 0, next_recv_seq = 0;
-  bool alive = true;
+  // written by the engine thread (EOF / BYE) and by remove_remote_endpoint(); read everywhere
+  std::atomic<bool> alive{true};
 };
 
 struct Endpoint::Transfer {
   enum State { SEND_WAIT_ADV, COPYING, RECV_WAIT_DONE, DONE, FAILED, WAIT_ACK, WAIT_RESP, TCP_SENDING };
   uint64_t id = 0;
-  State state = DONE;
+  // written by the engine thread under mu_ and by the polling caller; read without the lock on the poll path
+  std::atomic<State> state{DONE};
   std::shared_ptr<Conn> conn;
   uint64_t seq = 0;
   bool notify_done = false;  // send DONE{seq} to the peer when the copy finishes
@@ -156,6 +160,7 @@ Endpoint::~Endpoint() {
   }
   {
     std::lock_guard<std::mutex> g(mu_);
+    retire_closed_locked();
     for (auto& kv : conns_)
       if (kv.second->fd >= 0) ::close(kv.second->fd);
     conns_.clear();
@@ -300,11 +305,25 @@ bool Endpoint::remove_remote_endpoint(uint64_t conn_id) {
   }
   send_msg(*c, MSG_BYE, 0, nullptr, 0);
   c->alive = false;
+  // The engine thread may be inside read() on this descriptor: shut the socket down (that wakes it with EOF) but
+  // leave close() to the engine thread, which retires the connection at the top of its next iteration -- closing
+  // here could hand the descriptor number to a new socket while the old read is still in flight.
   ::shutdown(c->fd, SHUT_RDWR);
-  ::close(c->fd);
-  c->fd = -1;
+  {
+    std::lock_guard<std::mutex> g(mu_);
+    closing_.push_back(c);
+  }
   wake();
   return true;
+}
+
+void Endpoint::retire_closed_locked() {
+  for (auto& c : closing_) {
+    std::lock_guard<std::mutex> sg(c->send_mu);  // no sender is between its fd check and its write
+    if (c->fd >= 0) ::close(c->fd);
+    c->fd = -1;
+  }
+  closing_.clear();
 }
 
 bool Endpoint::send_msg(Conn& c, uint32_t type, uint64_t seq, const void* payload, uint32_t len) {
@@ -1241,6 +1260,7 @@ void Endpoint::engine_loop() {
     bool active = false;
     {
       std::lock_guard<std::mutex> g(mu_);
+      retire_closed_locked();  // nothing of this thread is reading those descriptors now
       for (auto& kv : conns_)
         if (kv.second->fd >= 0 && kv.second->alive) {
           fds.push_back({kv.second->fd, POLLIN, 0});

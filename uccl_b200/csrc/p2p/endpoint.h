@@ -144,6 +144,8 @@ class Endpoint {
   mutable std::mutex mu_;  // guards every table below
   std::condition_variable accept_cv_;
   std::map<uint64_t, std::shared_ptr<Conn>> conns_;
+  std::vector<std::shared_ptr<Conn>> closing_;  // removed connections whose descriptor the engine thread still has to close
+  void retire_closed_locked();
   std::deque<uint64_t> accepted_;
   std::map<uint64_t, std::shared_ptr<Transfer>> transfers_;
   std::deque<std::pair<uint64_t, std::string>> notifs_;
