@@ -14,6 +14,7 @@ for san in address,undefined thread; do
 done
 # (the P2P engine stress and the ukernel planner run under TSan / ASan+UBSan from inside the pytest suite:
 #  tests/test_host_p2p.py::test_engine_concurrency_stress_under_sanitizers, tests/test_ukernel.py::test_planner_cpp_unit_under_sanitizers)
+for san in thread address; do bash scripts/sanitize_host.sh $san | tail -1; done
 python -m pytest tests -m gpu --collect-only -q | tail -1
 if [ "${1:-}" = "--profiles" ]; then ./scripts/run_scaleout_cpu.sh; fi
 echo "check_all: ok"
