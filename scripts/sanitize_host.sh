@@ -35,10 +35,11 @@ run() {  # name, args...: prints the sanitizer findings (if any) and the test's 
 }
 LINK=(-I/usr/include -Iuccl_b200/csrc -I/usr/local/cuda/include -L"$OUT" -luccl_b200_nccl_$SAN -Wl,-rpath,"$PWD/$OUT"
       -Wl,-rpath,/usr/local/cuda/lib64 -lpthread)
-for t in nccl_api_test nccl_multibox_test host_world_stress; do
+for t in nccl_api_test nccl_multibox_test host_world_stress uk_net_stress; do
   g++ -std=c++17 -O1 -g -fsanitize=$FLAG tests/cpp/$t.cc "${LINK[@]}" -o "$OUT/$t"
 done
 run nccl_api_test          # 2 processes, every NCCL entry point on the host backend
 run nccl_multibox_test     # 2 boxes x 2 ranks: MultiComm over the datagram transport
 run host_world_stress 40   # 4 ranks as threads: native collectives + ukernel worker threads
+run uk_net_stress 30       # 3 ranks as threads: ukernel plans over the datagram transport (receiver threads)
 [ $RC = 0 ] && echo "sanitize_host($SAN): clean" || { echo "sanitize_host($SAN): FINDINGS (logs in $OUT)"; exit 1; }
