@@ -118,15 +118,26 @@ static int run(int rank, int n, ncclUniqueId id) {
 int main() {
   setenv("UCCL_B200_HOST_FAKE", "1", 1);
   setenv("UCCL_B200_TIMEOUT_MS", "30000", 0);
+  // fork FIRST, then create the id in the parent and hand it over a pipe: ncclGetUniqueId starts the rendezvous relay
+  // thread, and a child forked from a multi-threaded parent inherits whatever locks that thread held at the moment
+  // of the fork (allocator, logger) -- under ASan the child's own relay then hung about one run in ten.
+  int fds[2];
+  if (pipe(fds) != 0) return 1;
+  pid_t pid = fork();
+  if (pid == 0) {
+    close(fds[1]);
+    ncclUniqueId cid;
+    if (read(fds[0], &cid, sizeof(cid)) != (ssize_t)sizeof(cid)) _exit(3);
+    close(fds[0]);
+    _exit(run(1, 2, cid));
+  }
+  close(fds[0]);
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) {
+  if (ncclGetUniqueId(&id) != ncclSuccess || write(fds[1], &id, sizeof(id)) != (ssize_t)sizeof(id)) {
     fprintf(stderr, "ncclGetUniqueId failed\n");
     return 1;
   }
-  pid_t pid = fork();
-  if (pid == 0) {
-    _exit(run(1, 2, id));
-  }
+  close(fds[1]);
   int rc = run(0, 2, id);
   int st = 0;
   waitpid(pid, &st, 0);

@@ -75,19 +75,45 @@ static int run(int rank, int n, ncclUniqueId id) {
   return 0;
 }
 
+// fork the ranks FIRST and hand them the id over pipes: ncclGetUniqueId starts the rendezvous relay thread, and a child
+// forked from a multi-threaded parent inherits whatever locks that thread held at the fork (allocator, logger)
+static ncclUniqueId fork_ranks_then_make_id(int n, pid_t* pids, int (*body)(int, int, ncclUniqueId)) {
+  std::vector<int> wr(n, -1);
+  for (int r = 1; r < n; ++r) {
+    int fds[2];
+    if (pipe(fds) != 0) _exit(4);
+    pids[r] = fork();
+    if (pids[r] == 0) {
+      for (int q = 1; q < r; ++q) close(wr[q]);
+      close(fds[1]);
+      ncclUniqueId cid;
+      if (read(fds[0], &cid, sizeof(cid)) != (ssize_t)sizeof(cid)) _exit(3);
+      close(fds[0]);
+      _exit(body(r, n, cid));
+    }
+    close(fds[0]);
+    wr[r] = fds[1];
+  }
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) {
+    fprintf(stderr, "ncclGetUniqueId failed\n");
+    exit(1);
+  }
+  for (int r = 1; r < n; ++r) {
+    if (write(wr[r], &id, sizeof(id)) != (ssize_t)sizeof(id)) exit(1);
+    close(wr[r]);
+  }
+  return id;
+}
+
 int main(int argc, char** argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 2;
   setenv("UCCL_B200_LOCAL_SIZE", "1", 1);
   setenv("UCCL_B200_NET_BIND_IP", "127.0.0.1", 1);
   setenv("UCCL_B200_NCCL_HEAP_MB", "512", 0);
   setenv("UCCL_B200_NCCL_STAGE_MB", "16", 0);
-  ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return 1;
   std::vector<pid_t> pids(n, 0);
-  for (int r = 1; r < n; ++r) {  // fork before any CUDA call in this process
-    pids[r] = fork();
-    if (pids[r] == 0) _exit(run(r, n, id));
-  }
+  ncclUniqueId id = fork_ranks_then_make_id(n, pids.data(), run);  // also: fork before any CUDA call in this process
   bool ok = run(0, n, id) == 0;
   for (int r = 1; r < n; ++r) {
     int s = 0;

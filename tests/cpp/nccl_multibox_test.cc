@@ -159,6 +159,37 @@ static int run(int rank, int n, ncclUniqueId id) {
   return 0;
 }
 
+// fork the ranks FIRST and hand them the id over pipes: ncclGetUniqueId starts the rendezvous relay thread, and a child
+// forked from a multi-threaded parent inherits whatever locks that thread held at the fork (allocator, logger)
+static ncclUniqueId fork_ranks_then_make_id(int n, pid_t* pids, int (*body)(int, int, ncclUniqueId)) {
+  std::vector<int> wr(n, -1);
+  for (int r = 1; r < n; ++r) {
+    int fds[2];
+    if (pipe(fds) != 0) _exit(4);
+    pids[r] = fork();
+    if (pids[r] == 0) {
+      for (int q = 1; q < r; ++q) close(wr[q]);
+      close(fds[1]);
+      ncclUniqueId cid;
+      if (read(fds[0], &cid, sizeof(cid)) != (ssize_t)sizeof(cid)) _exit(3);
+      close(fds[0]);
+      _exit(body(r, n, cid));
+    }
+    close(fds[0]);
+    wr[r] = fds[1];
+  }
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) {
+    fprintf(stderr, "ncclGetUniqueId failed\n");
+    exit(1);
+  }
+  for (int r = 1; r < n; ++r) {
+    if (write(wr[r], &id, sizeof(id)) != (ssize_t)sizeof(id)) exit(1);
+    close(wr[r]);
+  }
+  return id;
+}
+
 int main() {
   setenv("UCCL_B200_HOST_FAKE", "1", 1);
   setenv("UCCL_B200_LOCAL_SIZE", "2", 1);
@@ -166,17 +197,9 @@ int main() {
   setenv("UCCL_B200_NET_PATHS", "2", 0);
   setenv("UCCL_B200_MN_PIPELINE_BYTES", "65536", 0);  // the 200003-float all-reduce runs as a 7-block pipeline
   setenv("UCCL_B200_TIMEOUT_MS", "30000", 0);
-  ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) {
-    fprintf(stderr, "ncclGetUniqueId failed\n");
-    return 1;
-  }
   const int n = 4;
   pid_t pids[4] = {0};
-  for (int r = 1; r < n; ++r) {
-    pids[r] = fork();
-    if (pids[r] == 0) _exit(run(r, n, id));
-  }
+  ncclUniqueId id = fork_ranks_then_make_id(n, pids, run);
   int rc = run(0, n, id);
   bool ok = rc == 0;
   for (int r = 1; r < n; ++r) {

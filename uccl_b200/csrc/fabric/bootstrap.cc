@@ -54,7 +54,10 @@ bool read_full(int fd, void* p, size_t n) {
       if (errno == EINTR) continue;
       return false;
     }
-    if (r == 0) return false;
+    if (r == 0) {
+      errno = ECONNRESET;  // orderly close by the peer: report it as such, not with a stale errno
+      return false;
+    }
     c += r;
     n -= (size_t)r;
   }
@@ -75,6 +78,7 @@ void relay_main(int lfd) {
     setsockopt(c, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
     uint32_t hello[2];
     if (!read_full(c, hello, sizeof(hello))) {
+      UB_WARN("bootstrap relay: a connection closed before its hello (%s)", strerror(errno));
       ::close(c);
       continue;
     }
@@ -91,7 +95,12 @@ void relay_main(int lfd) {
     ++accepted;
   }
   ::close(lfd);
-  if (accepted != nranks) return;
+  if (accepted != nranks) {
+    UB_WARN("bootstrap relay: accept failed after %d of %d ranks (%s)", accepted, nranks, strerror(errno));
+    for (int c : conns)
+      if (c >= 0) ::close(c);
+    return;
+  }
   // rounds: gather one blob per rank, send the concatenation back to everyone
   std::vector<char> buf;
   bool alive = true;
@@ -100,6 +109,10 @@ void relay_main(int lfd) {
     for (int r = 0; r < nranks && alive; ++r) {
       uint64_t b;
       if (!read_full(conns[r], &b, sizeof(b))) {
+        // rank 0 hanging up between rounds is the normal end of a communicator; anything else is a rank that died
+        // (or left) in the middle of an exchange: its peers will see their connection close
+        if (r != 0) UB_WARN("bootstrap relay: rank %d of %d left in the middle of a round (%s)", r, nranks, strerror(errno));
+        else UB_INFO(SUB_INIT, "bootstrap relay: rank 0 of %d hung up (%s): group ends", nranks, strerror(errno));
         alive = false;
         break;
       }
@@ -224,7 +237,11 @@ void Bootstrap::send_all(const void* p, size_t n) {
   UB_CHECK(write_full(sock_, p, n), "bootstrap send failed: %s", strerror(errno));
 }
 void Bootstrap::recv_all(void* p, size_t n) {
-  UB_CHECK(read_full(sock_, p, n), "bootstrap recv failed (peer died or timeout): %s", strerror(errno));
+  if (read_full(sock_, p, n)) return;
+  const int e = errno;
+  UB_CHECK(false, "bootstrap recv failed (group %016lx, rank %d/%d): %s", (unsigned long)nonce_, rank_, nranks_,
+           e == EAGAIN || e == EWOULDBLOCK ? "timed out waiting for the other ranks (UCCL_B200_BOOTSTRAP_TIMEOUT_SECS)"
+                                            : (e == ECONNRESET ? "a peer left the rendezvous" : strerror(e)));
 }
 
 void Bootstrap::allgather(const void* in, void* out, size_t bytes) {
