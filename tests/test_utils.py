@@ -521,3 +521,34 @@ def test_lockfree_rings_and_pool_under_tsan(tmp_path):
     r = subprocess.run([exe, "100000"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1 exitcode=66"))
     assert r.returncode == 0 and "ring_pool_stress: OK" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_logfmt10_kernel_arithmetic_matches_definition():
+    """csrc/ep/ep_logfmt.h -- the lines `ep_ll_pack_logfmt_kernel` compiles (grid parameters, quantiser, bf16 rounding, sign
+    packing) -- run on the host through `_C.ep_logfmt10_host` and compared with the PyTorch definition: bit-identical
+    up to a handful of values that sit on a grid boundary (libm vs torch log2 / exp2)."""
+    import torch
+
+    from uccl_b200.ep.utils import logfmt10_simulate
+
+    C = _native.C()
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(256, 1024, generator=g) * 0.2).to(torch.bfloat16)
+    x[0, :128] *= 40
+    x[1, 128:256] = 0
+    x[2, 5] = 0
+    x[3, 256:384] = 0.25
+    x[4, :128] = -x[4, :128].abs()
+    x[5, :128] *= 1e-6          # tiny magnitudes: the 2^-32 range clip is not reached, the grid still applies
+    x[6, 0] = 1.0               # a group whose maximum is exactly the threshold
+    ref = logfmt10_simulate(x)
+    y = x.clone()
+    C.ep_logfmt10_host(y.data_ptr(), y.size(0), y.size(1))
+    same = y.view(torch.int16) == ref.view(torch.int16)
+    assert float(same.float().mean()) > 0.9999
+    if not bool(same.all()):
+        rel = ((y.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-30))[~same]
+        assert float(rel.max()) < 0.05  # one grid step
+    assert torch.equal(y[0, :128], x[0, :128]) and torch.equal(torch.signbit(y.float()), torch.signbit(x.float()))
+    with pytest.raises(RuntimeError):
+        C.ep_logfmt10_host(y.data_ptr(), 1, 100)

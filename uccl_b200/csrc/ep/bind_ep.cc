@@ -2,7 +2,9 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "../common/log.h"
 #include "ep_buffer.h"
+#include "ep_logfmt.h"
 #include "proxy.h"
 
 namespace py = pybind11;
@@ -106,6 +108,14 @@ void bind_ep(py::module_& m) {
                          uintptr_t b1, uintptr_t out, uintptr_t otw, int T, int H, int K, int num_sms, uintptr_t st) {
         b.combine(x, num_recv, tw, ss, b0, b1, out, otw, T, H, K, num_sms, (cudaStream_t)st);
       });
+
+  // host reference of the LogFMT-10 simulated cast: the same arithmetic the CUDA pass compiles (ep_logfmt.h), in place
+  // on [rows, H] bf16 host memory
+  m.def("ep_logfmt10_host", [](uintptr_t ptr, size_t rows, size_t H) {
+    UB_CHECK(H % 128 == 0, "ep_logfmt10_host: hidden %% 128 != 0");
+    py::gil_scoped_release rel;
+    logfmt10_host((uint16_t*)ptr, rows, H);
+  });
 
   // ---- GPU -> CPU command queue + proxy
   m.attr("D2H_NOP") = (int)D2H_NOP;

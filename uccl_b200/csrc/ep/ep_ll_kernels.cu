@@ -17,6 +17,7 @@
 #include "../kernels/launch.h"
 #include "../kernels/prims.cuh"
 #include "ep_common.cuh"
+#include "ep_logfmt.h"
 #include "ep_types.h"
 
 namespace ub {
@@ -339,12 +340,12 @@ __global__ void __launch_bounds__(256) ep_ll_pack_kernel(const EpLLPackArgs a) {
 // is what a consumer that was tuned with it expects.  Sixteen consecutive lanes hold one group (8 channels each):
 // all 32 lanes of the warp must call this.
 __device__ __forceinline__ void logfmt10_simulate(uint4& v) {
-  float f[8], la[8];
-  bf16x8_to_float(v, f);
+  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  float la[8];
   float amax = 0.f, lmax = -INFINITY, lmin = INFINITY;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float av = fabsf(f[q]);
+    const float av = fabsf(bf16_bits_to_f32((uint16_t)(w[q >> 1] >> ((q & 1) * 16))));
     la[q] = log2f(av);  // -inf for 0
     amax = fmaxf(amax, av);
     lmax = fmaxf(lmax, la[q]);
@@ -356,20 +357,13 @@ __device__ __forceinline__ void logfmt10_simulate(uint4& v) {
     lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     lmin = fminf(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
   }
-  lmin = fmaxf(lmin, lmax - 32.f);
-  if (!(amax <= 1.f && lmin < lmax)) return;  // uniform over the 16 lanes of the group
-  const float step = (lmax - lmin) / 510.f;   // 2^9 - 2 intervals
-  const float step_inv = 1.f / step;
-  const float rounding = 2.f - log2f((1.f + exp2f(step)) * 0.5f) * step_inv;
-  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+  const LogFmtParams p = logfmt10_params(amax, lmax, lmin);  // identical on the 16 lanes of the group
+  if (!p.use) return;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const float enc = floorf((la[q] - lmin) * step_inv + rounding);
-    const float dec = exp2f((enc - 1.f) * step + lmin);
-    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(dec));
     const int sh = (q & 1) * 16;
-    const uint32_t sign = (w[q >> 1] >> sh) & 0x8000u;
-    w[q >> 1] = (w[q >> 1] & ~(0xffffu << sh)) | ((sign | bits) << sh);
+    const uint32_t nb = logfmt10_quantize_bits((uint16_t)(w[q >> 1] >> sh), la[q], p);
+    w[q >> 1] = (w[q >> 1] & ~(0xffffu << sh)) | (nb << sh);
   }
 }
 
