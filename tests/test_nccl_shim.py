@@ -86,3 +86,23 @@ def test_nccl_api_gpu(tmp_path, n):
     sys.stderr.write(r.stderr)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "nccl_gpu_test: OK" in r.stdout
+
+
+@pytest.mark.timeout(300)
+def test_nccl_fallback_forwarding_cpu(tmp_path):
+    """UCCL_B200_NCCL_FALLBACK_{LIB,OPS,MIN_BYTES}: listed operations go to a dlopen'd libnccl (here the stand-in
+    tests/cpp/fake_nccl.cc), everything else stays native; rank 0's id reaches every rank; a misspelt operation
+    fails communicator creation (reference: lite's dlopen fallback + force list, nccl.cu:707-860,1866-1872)."""
+    from uccl_b200 import _build
+
+    _build.build()
+    shim = _build.nccl_shim_path()
+    fake = tmp_path / "libfake_nccl.so"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", os.path.join(ROOT, "tests/cpp/fake_nccl.cc"),
+                    "-I/usr/include", "-I/usr/local/cuda/include", "-o", str(fake)], check=True)
+    exe = tmp_path / "nccl_fallback_test"
+    subprocess.run(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests/cpp/nccl_fallback_test.cc"), "-I/usr/include",
+                    "-I/usr/local/cuda/include", "-L" + str(shim.parent), "-luccl_b200_nccl",
+                    "-Wl,-rpath," + str(shim.parent), "-ldl", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), str(fake)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "nccl_fallback_test: OK" in r.stdout, r.stdout + r.stderr[-3000:]

@@ -24,6 +24,7 @@
 #include "../common/param.h"
 #include "comm.h"
 #include "multi_comm.h"
+#include "nccl_fallback.h"
 #include "../fabric/cu_api.h"
 #include <algorithm>
 
@@ -41,6 +42,7 @@ struct ncclComm {
   std::string last_error;
   ncclResult_t async_error = ncclSuccess;
   bool finalized = false;
+  std::unique_ptr<NcclFallback> fallback;  // optional dlopen'd libnccl for the operations named in UCCL_B200_NCCL_FALLBACK_OPS
 };
 
 namespace {
@@ -52,6 +54,8 @@ struct PendingP2p {
   ncclComm* comm;
   Comm::P2pOp op;
   cudaStream_t stream;
+  size_t count = 0;          // as given by the caller (forwarded verbatim when the communicator sends p2p to libnccl)
+  ncclDataType_t dt = ncclChar;
 };
 thread_local std::vector<PendingP2p> g_pending;
 thread_local std::string g_last_error;
@@ -103,13 +107,53 @@ int box_size_hint(int nranks) {
   return (int)v;
 }
 
+// 128 bytes from rank 0 to everybody through the native communicator (device staging unless it is the host backend)
+void share_from_rank0(Comm& c, void* buf128) {
+  const int n = c.nranks();
+  std::vector<char> all((size_t)n * 128);
+  if (c.is_host()) {
+    c.allgather(buf128, all.data(), 128, kU8, nullptr);
+  } else {
+    char *d_in = nullptr, *d_out = nullptr;
+    UB_CUDA(cudaMalloc((void**)&d_in, 128));
+    UB_CUDA(cudaMalloc((void**)&d_out, (size_t)n * 128));
+    UB_CUDA(cudaMemcpy(d_in, buf128, 128, cudaMemcpyHostToDevice));
+    c.allgather(d_in, d_out, 128, kU8, nullptr);
+    UB_CUDA(cudaMemcpy(all.data(), d_out, (size_t)n * 128, cudaMemcpyDeviceToHost));
+    cudaFree(d_in);
+    cudaFree(d_out);
+  }
+  memcpy(buf128, all.data(), 128);
+}
+
+std::unique_ptr<NcclFallback> make_fallback(Comm& c) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  return NcclFallback::create(c.rank(), c.nranks(), [&](void* id) { share_from_rank0(c, id); });
+}
+
 ncclResult_t flush_group() {
   // launch queued send/recv per (comm, stream)
   std::vector<PendingP2p> pend;
   pend.swap(g_pending);
   ncclResult_t res = ncclSuccess;
   std::map<std::pair<ncclComm*, cudaStream_t>, std::vector<Comm::P2pOp>> by;
-  for (auto& p : pend) by[{p.comm, p.stream}].push_back(p.op);
+  std::map<ncclComm*, std::vector<PendingP2p*>> fwd;  // communicators whose send/recv go to the fallback library
+  for (auto& p : pend) {
+    if (p.comm->fallback && p.comm->fallback->takes(NcclFallback::kSendRecv, p.op.bytes)) fwd[p.comm].push_back(&p);
+    else by[{p.comm, p.stream}].push_back(p.op);
+  }
+  for (auto& kv : fwd) {
+    NcclFallback& fb = *kv.first->fallback;
+    ncclResult_t r = fb.group_start();
+    for (PendingP2p* p : kv.second) {
+      if (r != ncclSuccess) break;
+      r = p->op.is_send ? fb.send(p->op.buf, p->count, p->dt, p->op.peer, p->stream)
+                        : fb.recv(p->op.buf, p->count, p->dt, p->op.peer, p->stream);
+    }
+    const ncclResult_t e = fb.group_end();
+    if (r == ncclSuccess) r = e;
+    if (r != ncclSuccess) res = r;
+  }
   for (auto& kv : by) {
     ncclComm* c = kv.first.first;
     ncclResult_t r = guarded(c, [&] {
@@ -119,6 +163,14 @@ ncclResult_t flush_group() {
     if (r != ncclSuccess) res = r;
   }
   return res;
+}
+
+// Does the communicator hand this collective to the fallback library?  `count` elements of `dt` is the message size
+// NCCL's own tuning uses (all-gather / reduce-scatter: the whole buffer).  User-created PreMulSum operators only
+// exist in this library, so they always stay native.
+bool forwards(ncclComm_t c, NcclFallback::Op what, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+  if (!c->fallback || (int)dt < 0 || (int)dt >= kNumDTypes || (int)op >= (int)ncclNumOps) return false;
+  return c->fallback->takes(what, count * (size_t)dtype_size((int)dt));
 }
 
 }  // namespace
@@ -167,6 +219,14 @@ static ncclResult_t init_rank(ncclComm_t* comm, int nranks, ncclUniqueId commId,
     } catch (...) {
       delete c;
       throw;
+    }
+    if (c->comm) {
+      try {
+        c->fallback = make_fallback(*c->comm);
+      } catch (...) {
+        delete c;
+        throw;
+      }
     }
     std::lock_guard<std::mutex> g(g_mu);
     g_comms.insert(c);
@@ -486,6 +546,8 @@ bool resolve_op(ncclComm* c, ncclRedOp_t op, int* out_op, float* scale) {
 UB_EXPORT ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                      ncclRedOp_t op, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
+  if (forwards(comm, NcclFallback::kAllReduce, count, datatype, op))
+    return comm->fallback->all_reduce(sendbuff, recvbuff, count, datatype, op, stream);
   int rop;
   ArOpts o;
   if (!resolve_op(comm, op, &rop, &o.scale)) return ncclInvalidArgument;
@@ -498,6 +560,8 @@ UB_EXPORT ncclResult_t ncclAllReduce(const void* sendbuff, void* recvbuff, size_
 UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                   ncclRedOp_t op, int root, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
+  if (forwards(comm, NcclFallback::kReduce, count, datatype, op))
+    return comm->fallback->reduce(sendbuff, recvbuff, count, datatype, op, root, stream);
   int rop;
   float scale;
   if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
@@ -514,6 +578,8 @@ UB_EXPORT ncclResult_t ncclReduce(const void* sendbuff, void* recvbuff, size_t c
 UB_EXPORT ncclResult_t ncclBroadcast(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
                                      int root, ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
+  if (forwards(comm, NcclFallback::kBroadcast, count, datatype, ncclSum))
+    return comm->fallback->broadcast(sendbuff, recvbuff, count, datatype, root, stream);
   return guarded(comm, [&] {
     if (comm->multi) comm->multi->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream);
     else comm->comm->broadcast(sendbuff, recvbuff, count, (int)datatype, root, stream);
@@ -529,6 +595,8 @@ UB_EXPORT ncclResult_t ncclReduceScatter(const void* sendbuff, void* recvbuff, s
                                          ncclDataType_t datatype, ncclRedOp_t op, ncclComm_t comm,
                                          cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
+  if (forwards(comm, NcclFallback::kReduceScatter, recvcount * (size_t)nranks_of(comm), datatype, op))
+    return comm->fallback->reduce_scatter(sendbuff, recvbuff, recvcount, datatype, op, stream);
   int rop;
   float scale;
   if (!resolve_op(comm, op, &rop, &scale)) return ncclInvalidArgument;
@@ -545,6 +613,8 @@ UB_EXPORT ncclResult_t ncclReduceScatter(const void* sendbuff, void* recvbuff, s
 UB_EXPORT ncclResult_t ncclAllGather(const void* sendbuff, void* recvbuff, size_t sendcount, ncclDataType_t datatype,
                                      ncclComm_t comm, cudaStream_t stream) {
   if (!valid(comm)) return ncclInvalidArgument;
+  if (forwards(comm, NcclFallback::kAllGather, sendcount * (size_t)nranks_of(comm), datatype, ncclSum))
+    return comm->fallback->all_gather(sendbuff, recvbuff, sendcount, datatype, stream);
   return guarded(comm, [&] {
     if (comm->multi) comm->multi->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream);
     else comm->comm->allgather(sendbuff, recvbuff, sendcount, (int)datatype, stream);
@@ -598,6 +668,8 @@ static ncclResult_t post_p2p(bool is_send, void* buf, size_t count, ncclDataType
   p.op.bytes = count * (size_t)dtype_size((int)dt);
   p.op.peer = peer;
   p.stream = stream;
+  p.count = count;
+  p.dt = dt;
   g_pending.push_back(p);
   if (g_group_depth == 0) return flush_group();
   return ncclSuccess;
