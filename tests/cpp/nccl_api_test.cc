@@ -27,6 +27,14 @@
     }                                                                     \
   } while (0)
 
+// NCCL 2.28 entry points the drop-in exports; the system header of this image is 2.27
+extern "C" {
+ncclResult_t ncclAlltoAll(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+ncclResult_t ncclGather(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+ncclResult_t ncclScatter(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+ncclResult_t ncclCommRevoke(ncclComm_t, int);
+}
+
 static int g_rank = -1;
 
 static int run(int rank, int n, ncclUniqueId id) {
@@ -95,6 +103,29 @@ static int run(int rank, int n, ncclUniqueId id) {
       CHECK(ncclRecv(&got, 1, ncclFloat, 0, comm, nullptr));
       EXPECT(got == 0.f);
     }
+  }
+
+  // NCCL 2.28 additions: ncclAlltoAll (spelling), ncclGather / ncclScatter (rooted), ncclCommRevoke
+  {
+    std::vector<int> ain(n * 7), aout(n * 7, -1);
+    for (int j = 0; j < n; ++j)
+      for (int k = 0; k < 7; ++k) ain[j * 7 + k] = rank * 100 + j;
+    CHECK(ncclAlltoAll(ain.data(), aout.data(), 7, ncclInt32, comm, nullptr));
+    for (int i = 0; i < n; ++i) EXPECT(aout[i * 7] == i * 100 + rank && aout[i * 7 + 6] == i * 100 + rank);
+    std::vector<double> gin(11, 10.0 + rank), gout(n * 11, -1.0);
+    CHECK(ncclGather(gin.data(), gout.data(), 11, ncclFloat64, 1, comm, nullptr));
+    if (rank == 1)
+      for (int i = 0; i < n; ++i) EXPECT(gout[i * 11] == 10.0 + i && gout[i * 11 + 10] == 10.0 + i);
+    std::vector<short> sin(n * 13), sout(13, -1);
+    for (int j = 0; j < n; ++j)
+      for (int k = 0; k < 13; ++k) sin[j * 13 + k] = (short)(500 + j);
+    CHECK(ncclScatter(sin.data(), sout.data(), 13, ncclHalf, 0, comm, nullptr));  // 2-byte elements, moved as bytes
+    for (auto v : sout) EXPECT(v == (short)(500 + rank));
+    // in place on the root: recvbuff == sendbuff + root * count
+    CHECK(ncclScatter(sin.data(), rank == 0 ? sin.data() : sout.data(), 13, ncclHalf, 0, comm, nullptr));
+    EXPECT(ncclGather(gin.data(), gout.data(), 11, ncclFloat64, 9, comm, nullptr) == ncclInvalidArgument);
+    EXPECT(ncclCommRevoke(comm, 1) == ncclInvalidArgument);
+    CHECK(ncclCommRevoke(comm, 0));
   }
 
   // error paths

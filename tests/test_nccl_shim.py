@@ -106,3 +106,33 @@ def test_nccl_fallback_forwarding_cpu(tmp_path):
                     "-Wl,-rpath," + str(shim.parent), "-ldl", "-o", str(exe)], check=True)
     r = subprocess.run([str(exe), str(fake)], capture_output=True, text=True, timeout=240)
     assert r.returncode == 0 and "nccl_fallback_test: OK" in r.stdout, r.stdout + r.stderr[-3000:]
+
+
+def test_drop_in_covers_what_torch_and_the_newest_header_need():
+    """Symbol audit (role of the reference's lite/nccl/audit_nccl.cc): every nccl* symbol torch's CUDA library imports,
+    and every entry point of the newest nccl.h found on this machine, must be exported by the drop-in -- a preloaded
+    drop-in that lacks one would let that call fall through to another libnccl with a foreign communicator handle."""
+    import glob
+    import re
+
+    import torch
+
+    from uccl_b200 import _build
+
+    _build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_build.nccl_shim_path())], capture_output=True, text=True).stdout
+    ours = set(re.findall(r"\bp?nccl[A-Za-z0-9_]+", out))
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib", "libtorch_cuda.so")
+    if os.path.exists(tlib):
+        und = subprocess.run(["nm", "-D", "--undefined-only", tlib], capture_output=True, text=True).stdout
+        need = set(re.findall(r"\bnccl[A-Za-z0-9_]+", und))
+        assert need, "torch imports no nccl symbols?"
+        assert not (need - ours), f"torch needs {sorted(need - ours)}"
+    headers = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "include", "nccl.h"))
+    headers.append("/usr/include/nccl.h")
+    for h in headers:
+        if not os.path.exists(h):
+            continue
+        api = set(re.findall(r"^(?:ncclResult_t|const char\*)\s+(nccl[A-Za-z0-9_]+)\s*\(", open(h).read(), flags=re.M))
+        assert len(api) > 30
+        assert not (api - ours), f"{h}: not exported: {sorted(api - ours)}"

@@ -641,6 +641,81 @@ UB_EXPORT ncclResult_t ncclAllToAllv(const void* sendbuff, const size_t sendcoun
   });
 }
 
+// NCCL 2.28 spelling of the same operation
+UB_EXPORT ncclResult_t ncclAlltoAll(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype,
+                                    ncclComm_t comm, cudaStream_t stream) {
+  return ncclAllToAll(sendbuff, recvbuff, count, datatype, comm, stream);
+}
+
+namespace {
+// rooted fan-in / fan-out (NCCL 2.28 ncclGather / ncclScatter) as one grouped send/recv launch plus the root's local copy
+ncclResult_t rooted_p2p(bool gather, const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t dt, int root,
+                        ncclComm_t comm, cudaStream_t stream) {
+  if (!valid(comm)) return ncclInvalidArgument;
+  const int n = nranks_of(comm);
+  if ((int)dt < 0 || (int)dt >= kNumDTypes || root < 0 || root >= n) return ncclInvalidArgument;
+  Comm* lc = local_of(comm);
+  const int me = comm->multi ? comm->multi->rank() : lc->rank();
+  const size_t bytes = count * (size_t)dtype_size((int)dt);
+  return guarded(comm, [&] {
+    std::vector<Comm::P2pOp> ops;
+    if (me == root) {
+      char* mine_dst = gather ? (char*)recvbuff + (size_t)root * bytes : (char*)recvbuff;
+      const char* mine_src = gather ? (const char*)sendbuff : (const char*)sendbuff + (size_t)root * bytes;
+      if (bytes && mine_dst != mine_src) {
+        if (lc->is_host()) memcpy(mine_dst, mine_src, bytes);
+        else UB_CUDA(cudaMemcpyAsync(mine_dst, mine_src, bytes, cudaMemcpyDeviceToDevice, stream));
+      }
+      for (int r = 0; r < n; ++r) {
+        if (r == root) continue;
+        if (gather) ops.push_back({false, (char*)recvbuff + (size_t)r * bytes, bytes, r});
+        else ops.push_back({true, const_cast<char*>((const char*)sendbuff) + (size_t)r * bytes, bytes, r});
+      }
+    } else {
+      if (gather) ops.push_back({true, const_cast<void*>(sendbuff), bytes, root});
+      else ops.push_back({false, recvbuff, bytes, root});
+    }
+    if (ops.empty() || bytes == 0) return;
+    if (comm->multi) comm->multi->group_p2p(ops, stream);
+    else comm->comm->group_p2p(ops, stream);
+  });
+}
+}  // namespace
+
+UB_EXPORT ncclResult_t ncclGather(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype, int root,
+                                  ncclComm_t comm, cudaStream_t stream) {
+  return rooted_p2p(true, sendbuff, recvbuff, count, datatype, root, comm, stream);
+}
+
+UB_EXPORT ncclResult_t ncclScatter(const void* sendbuff, void* recvbuff, size_t count, ncclDataType_t datatype, int root,
+                                   ncclComm_t comm, cudaStream_t stream) {
+  return rooted_p2p(false, sendbuff, recvbuff, count, datatype, root, comm, stream);
+}
+
+// NCCL 2.28: stop what is in flight and leave the communicator ready for destroy / split.  Every operation of this
+// library is a kernel with a bounded spin, so quiescing is a device synchronisation.
+UB_EXPORT ncclResult_t ncclCommRevoke(ncclComm_t comm, int revokeFlags) {
+  if (!valid(comm) || revokeFlags != 0) return ncclInvalidArgument;
+  Comm* lc = local_of(comm);
+  if (!lc->is_host()) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(lc->device());
+    cudaDeviceSynchronize();
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  return ncclSuccess;
+}
+
+// NCCL 2.28 device-side communicators (nccl_device/core.h) belong to NCCL's own device API: kernels written against it
+// cannot run on this library's communicators.  Exported so that a preloaded drop-in answers -- with an error -- instead
+// of letting the call fall through to another libnccl with a foreign communicator handle.
+UB_EXPORT ncclResult_t ncclDevCommCreate(ncclComm_t, const void*, void*) {
+  g_last_error = "uccl_b200: NCCL device communicators (ncclDevCommCreate) are not provided by the drop-in";
+  return ncclInvalidUsage;
+}
+UB_EXPORT ncclResult_t ncclDevCommDestroy(ncclComm_t, const void*) { return ncclInvalidUsage; }
+
 UB_EXPORT ncclResult_t ncclGroupStart() {
   ++g_group_depth;
   return ncclSuccess;
@@ -712,5 +787,12 @@ UB_ALIAS(ncclResult_t, ncclSend, (const void* s, size_t n, ncclDataType_t d, int
          (s, n, d, p, c, st))
 UB_ALIAS(ncclResult_t, ncclRecv, (void* r, size_t n, ncclDataType_t d, int p, ncclComm_t c, cudaStream_t st),
          (r, n, d, p, c, st))
+UB_ALIAS(ncclResult_t, ncclAlltoAll, (const void* s, void* r, size_t n, ncclDataType_t d, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, c, st))
+UB_ALIAS(ncclResult_t, ncclGather, (const void* s, void* r, size_t n, ncclDataType_t d, int root, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, root, c, st))
+UB_ALIAS(ncclResult_t, ncclScatter, (const void* s, void* r, size_t n, ncclDataType_t d, int root, ncclComm_t c, cudaStream_t st),
+         (s, r, n, d, root, c, st))
+UB_ALIAS(ncclResult_t, ncclCommRevoke, (ncclComm_t c, int f), (c, f))
 
 }  // extern "C"
