@@ -355,3 +355,37 @@ def test_ep_bootstrap_helpers():
     assert ep.get_peer_ip(0, 1) == ""
     meta = ep.get_cpu_proxies_meta([object(), object()], 0, 4096, 64, 1)
     assert meta[0]["ptr"] == 4096 and meta[0]["nbytes"] == 64 and meta[0]["listen_ports"] == [0, 0]
+
+
+def test_buffer_signature_audit_against_the_reference_and_upstream_deepep():
+    """Every public method of the reference's `Buffer` (ep/bench/buffer.py) and of the upstream DeepEP it vendors
+    (thirdparty/DeepEP/deep_ep/buffer.py) exists here with the same parameter names (frameworks call them by keyword).
+    Skipped where the reference tree is not mounted."""
+    import ast
+    import inspect
+    import os
+
+    import deep_ep
+    from uccl_b200.ep.buffer import Buffer as Native
+    from uccl_b200.ep.low_latency import LowLatencyRuntime
+
+    files = ["/root/reference/ep/bench/buffer.py", "/root/reference/thirdparty/DeepEP/deep_ep/buffer.py"]
+    files = [f for f in files if os.path.exists(f)]
+    if not files:
+        pytest.skip("reference tree not available")
+    ll = {"low_latency_dispatch": LowLatencyRuntime.dispatch, "low_latency_combine": LowLatencyRuntime.combine}
+    internal = {"connect_atomic_buffer"}  # takes the reference's own proxy type; checked by name only
+    for path in files:
+        tree = ast.parse(open(path).read())
+        cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "Buffer")
+        for f in cls.body:
+            if not isinstance(f, ast.FunctionDef) or (f.name.startswith("_") and f.name != "__init__"):
+                continue
+            assert hasattr(deep_ep.Buffer, f.name) and hasattr(Native, f.name), f"{path}: Buffer.{f.name} missing"
+            if f.name in internal:
+                continue
+            want = [a.arg for a in f.args.posonlyargs + f.args.args + f.args.kwonlyargs if a.arg != "self"]
+            target = ll.get(f.name, getattr(Native, f.name))
+            have = set(inspect.signature(target).parameters)
+            missing = [w for w in want if w not in have]
+            assert not missing, f"{path}: Buffer.{f.name} lacks parameters {missing}"
