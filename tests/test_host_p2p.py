@@ -343,3 +343,41 @@ def test_engine_concurrency_stress_under_sanitizers(tmp_path, san):
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", TSAN_OPTIONS="halt_on_error=1 exitcode=66")
     r = subprocess.run([exe, "80"], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "p2p_engine_stress: OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_endpoint_signature_audit_against_the_reference_binding():
+    """Every method of the reference's nanobind `Endpoint` (p2p/engine_api.cc) exists with the same keyword names
+    (`nb::arg(...)`) in the same order.  Skipped where the reference tree is not mounted."""
+    import inspect
+    import os
+    import re
+
+    from uccl_b200 import p2p
+    from uccl_b200.p2p import Endpoint
+
+    path = "/root/reference/p2p/engine_api.cc"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    src = open(path).read()
+    src = src[src.index('nb::class_<Endpoint>'):] if 'nb::class_<Endpoint>' in src else src
+    checked = 0
+    for d in re.split(r'\.def\(\s*"', src)[1:]:
+        name = d.split('"', 1)[0]
+        if name.startswith("__"):
+            continue
+        assert hasattr(Endpoint, name), f"Endpoint.{name} missing"
+        want = re.findall(r'nb::arg\("([a-zA-Z_0-9]+)"\)', d.split(".def(", 1)[0])
+        if name == "get_metadata":
+            continue  # the reference fills a caller-provided vector; here the bytes are returned
+        have = [p for p in inspect.signature(getattr(Endpoint, name)).parameters if p != "self"]
+        pos = [h for h in have]
+        for i, w in enumerate(want):
+            assert w in have, f"Endpoint.{name}: no parameter {w!r} (has {have})"
+            if w not in ("remote_gpu_bdf",):  # an alias keyword placed after this library's own name for it
+                assert pos.index(w) == i, f"Endpoint.{name}: {w!r} is argument {pos.index(w)}, the reference has it at {i}"
+        checked += 1
+    assert checked > 40 and hasattr(p2p, "get_oob_ip")
+    e = Endpoint(-1)
+    assert e.conn_id_of_rank(3) == 2 ** 64 - 1
+    e.set_rank_conn(3, 17)
+    assert e.conn_id_of_rank(3) == 17

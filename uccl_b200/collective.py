@@ -101,6 +101,7 @@ class CollectiveContext:
             ok, conn = self.ep.connect(remote_metadata=all_md[peer])
             assert ok, f"connect to rank {peer} failed"
             self.send_connections[peer] = conn
+            self.ep.set_rank_conn(peer, conn)
         # identify inbound connections by a hello notification carrying the sender's rank
         for peer, conn in self.send_connections.items():
             self.ep.send_notif(conn, b"rank:%d" % self.rank)

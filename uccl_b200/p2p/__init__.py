@@ -91,6 +91,7 @@ class Endpoint:
         self.local_gpu_idx = int(local_gpu_idx)
         self._mrs = {}
         self._mr_types = {}
+        self._rank2conn = {}
         self._ipc_pending = {}
         # local rendezvous file for connect_local (reference: shm inbox keyed by GPU BDF)
         try:
@@ -108,12 +109,27 @@ class Endpoint:
         return _native.C().P2PEndpoint.parse_metadata(bytes(metadata))
 
     # --------------------------------------------------------------- connections
-    def connect(self, ip_addr=None, remote_gpu_idx: int = 0, remote_port: int = 0, remote_metadata=None):
-        if remote_metadata is None and isinstance(ip_addr, (bytes, bytearray)):
-            remote_metadata = ip_addr
+    def connect(self, remote_ip_addr=None, remote_gpu_idx: int = 0, remote_port: int = 0, remote_metadata=None,
+                remote_gpu_bdf=None, ip_addr=None):
+        """``connect(ip, gpu, port)`` like the reference (whose second argument is the peer GPU's PCI BDF; here the GPU
+        index -- `remote_gpu_bdf` is accepted as its keyword), or ``connect(remote_metadata=md)``."""
+        if remote_ip_addr is None:
+            remote_ip_addr = ip_addr
+        if remote_gpu_bdf is not None:
+            remote_gpu_idx = int(remote_gpu_bdf)
+        if remote_metadata is None and isinstance(remote_ip_addr, (bytes, bytearray)):
+            remote_metadata = remote_ip_addr
         if remote_metadata is not None:
             return self._e.add_remote_endpoint(bytes(remote_metadata))
-        return self._e.connect(str(ip_addr), int(remote_gpu_idx), int(remote_port))
+        return self._e.connect(str(remote_ip_addr), int(remote_gpu_idx), int(remote_port))
+
+    def set_rank_conn(self, rank: int, conn_id: int) -> None:
+        """Remember which connection leads to a peer rank (filled by `uccl_b200.collective`)."""
+        self._rank2conn[int(rank)] = int(conn_id)
+
+    def conn_id_of_rank(self, rank: int) -> int:
+        """Connection id of a peer rank, 2**64 - 1 if none (reference: Endpoint::conn_id_of_rank, p2p/engine.h:456)."""
+        return self._rank2conn.get(int(rank), 0xFFFFFFFFFFFFFFFF)
 
     def accept(self, timeout_ms: int = -1):
         return self._e.accept(timeout_ms)
@@ -121,13 +137,15 @@ class Endpoint:
     def start_passive_accept(self) -> bool:
         return self._e.start_passive_accept()
 
-    def add_remote_endpoint(self, metadata: bytes):
-        return self._e.add_remote_endpoint(bytes(metadata))
+    def add_remote_endpoint(self, metadata_bytes: bytes):
+        return self._e.add_remote_endpoint(bytes(metadata_bytes))
 
     def remove_remote_endpoint(self, conn_id: int) -> bool:
         return self._e.remove_remote_endpoint(conn_id)
 
-    def connect_local(self, remote_gpu_idx: int):
+    def connect_local(self, remote_gpu_idx: Optional[int] = None, remote_gpu_bdf=None):
+        if remote_gpu_idx is None:
+            remote_gpu_idx = remote_gpu_bdf
         with open(_registry_path(int(remote_gpu_idx)), "rb") as f:
             md = f.read()
         return self._e.add_remote_endpoint(md)
@@ -166,9 +184,9 @@ class Endpoint:
         self._mr_types.pop(mr_id, None)
         return self._e.dereg(mr_id)
 
-    def register_memory(self, tensors) -> List[XferDesc]:
+    def register_memory(self, tensor_list) -> List[XferDesc]:
         descs = []
-        for t in tensors:
+        for t in tensor_list:
             ptr, size = t.data_ptr(), t.numel() * t.element_size()
             ok, mr = self.reg(ptr, size, FloatType.from_tensor(t))
             if not ok:
@@ -176,19 +194,19 @@ class Endpoint:
             descs.append(XferDesc(bytes(self._e.describe(ptr, size)), mr))
         return descs
 
-    def deregister_memory(self, descs: Sequence[XferDesc]) -> None:
-        for d in descs:
+    def deregister_memory(self, desc_list: Sequence[XferDesc]) -> None:
+        for d in desc_list:
             if d.mr_id:
                 self.dereg(d.mr_id)
 
     @staticmethod
-    def get_serialized_descs(descs: Sequence[XferDesc]) -> bytes:
-        return struct.pack("<I", len(descs)) + b"".join(d.raw for d in descs)
+    def get_serialized_descs(desc_list: Sequence[XferDesc]) -> bytes:
+        return struct.pack("<I", len(desc_list)) + b"".join(d.raw for d in desc_list)
 
     @staticmethod
-    def deserialize_descs(blob: bytes) -> List[XferDesc]:
-        (n,) = struct.unpack_from("<I", blob, 0)
-        return [XferDesc(blob[4 + i * XFER_DESC_BYTES: 4 + (i + 1) * XFER_DESC_BYTES]) for i in range(n)]
+    def deserialize_descs(serialized_bytes: bytes) -> List[XferDesc]:
+        (n,) = struct.unpack_from("<I", serialized_bytes, 0)
+        return [XferDesc(serialized_bytes[4 + i * XFER_DESC_BYTES: 4 + (i + 1) * XFER_DESC_BYTES]) for i in range(n)]
 
     # ------------------------------------------------------------------ two-sided
     def send_async(self, conn_id, mr_id, ptr, size):
@@ -197,11 +215,11 @@ class Endpoint:
     def recv_async(self, conn_id, mr_id, ptr, size):
         return self._e.recv_async(conn_id, [int(ptr)], [int(size)])
 
-    def sendv_async(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
-        return self._e.send_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes])
+    def sendv_async(self, conn_id, mr_id_v, data_ptr_v, size_v, num_iovs=None):
+        return self._e.send_async(conn_id, [int(p) for p in data_ptr_v], [int(s) for s in size_v])
 
-    def recvv_async(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
-        return self._e.recv_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes])
+    def recvv_async(self, conn_id, mr_id_v, data_ptr_v, size_v, num_iovs=None):
+        return self._e.recv_async(conn_id, [int(p) for p in data_ptr_v], [int(s) for s in size_v])
 
     def _block(self, res) -> bool:
         ok, tid = res
@@ -256,48 +274,48 @@ class Endpoint:
         torch.cuda.current_stream(out.device).synchronize()
         return True
 
-    def sendv(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None) -> bool:
-        return self._block(self.sendv_async(conn_id, mr_ids, ptrs, sizes))
+    def sendv(self, conn_id, mr_id_v, data_ptr_v, size_v, num_iovs=None) -> bool:
+        return self._block(self.sendv_async(conn_id, mr_id_v, data_ptr_v, size_v))
 
-    def recvv(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None) -> bool:
-        return self._block(self.recvv_async(conn_id, mr_ids, ptrs, sizes))
+    def recvv(self, conn_id, mr_id_v, data_ptr_v, size_v, num_iovs=None) -> bool:
+        return self._block(self.recvv_async(conn_id, mr_id_v, data_ptr_v, size_v))
 
     # ------------------------------------------------------------------ one-sided
     def advertise(self, conn_id, mr_id, ptr, size):
         return True, bytes(self._e.describe(int(ptr), int(size)))
 
-    def advertisev(self, conn_id, mr_ids, ptrs, sizes, num_iovs=None):
-        return True, [bytes(self._e.describe(int(p), int(s))) for p, s in zip(ptrs, sizes)]
+    def advertisev(self, conn_id, mr_id_v, ptr_v, size_v, num_iovs=None):
+        return True, [bytes(self._e.describe(int(p), int(s))) for p, s in zip(ptr_v, size_v)]
 
     @staticmethod
     def _raw(d):
         return d.raw if isinstance(d, XferDesc) else bytes(d)
 
-    def write_async(self, conn_id, mr_id, ptr, size, fifo_blob):
-        return self._e.write_async(conn_id, [int(ptr)], [int(size)], [self._raw(fifo_blob)])
+    def write_async(self, conn_id, mr_id, ptr, size, meta):
+        return self._e.write_async(conn_id, [int(ptr)], [int(size)], [self._raw(meta)])
 
-    def read_async(self, conn_id, mr_id, ptr, size, fifo_blob):
-        return self._e.read_async(conn_id, [int(ptr)], [int(size)], [self._raw(fifo_blob)])
+    def read_async(self, conn_id, mr_id, ptr, size, meta):
+        return self._e.read_async(conn_id, [int(ptr)], [int(size)], [self._raw(meta)])
 
-    def writev_async(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None):
-        return self._e.write_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes],
-                                   [self._raw(b) for b in fifo_blobs])
+    def writev_async(self, conn_id, mr_id_v, ptr_v, size_v, meta_blob_v, num_iovs=None):
+        return self._e.write_async(conn_id, [int(p) for p in ptr_v], [int(s) for s in size_v],
+                                   [self._raw(b) for b in meta_blob_v])
 
-    def readv_async(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None):
-        return self._e.read_async(conn_id, [int(p) for p in ptrs], [int(s) for s in sizes],
-                                  [self._raw(b) for b in fifo_blobs])
+    def readv_async(self, conn_id, mr_id_v, ptr_v, size_v, meta_blob_v, num_iovs=None):
+        return self._e.read_async(conn_id, [int(p) for p in ptr_v], [int(s) for s in size_v],
+                                  [self._raw(b) for b in meta_blob_v])
 
-    def write(self, conn_id, mr_id, ptr, size, fifo_blob) -> bool:
-        return self._block(self.write_async(conn_id, mr_id, ptr, size, fifo_blob))
+    def write(self, conn_id, mr_id, ptr, size, meta) -> bool:
+        return self._block(self.write_async(conn_id, mr_id, ptr, size, meta))
 
-    def read(self, conn_id, mr_id, ptr, size, fifo_blob) -> bool:
-        return self._block(self.read_async(conn_id, mr_id, ptr, size, fifo_blob))
+    def read(self, conn_id, mr_id, ptr, size, meta) -> bool:
+        return self._block(self.read_async(conn_id, mr_id, ptr, size, meta))
 
-    def writev(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None) -> bool:
-        return self._block(self.writev_async(conn_id, mr_ids, ptrs, sizes, fifo_blobs))
+    def writev(self, conn_id, mr_id_v, ptr_v, size_v, meta_blob_v, num_iovs=None) -> bool:
+        return self._block(self.writev_async(conn_id, mr_id_v, ptr_v, size_v, meta_blob_v))
 
-    def readv(self, conn_id, mr_ids, ptrs, sizes, fifo_blobs, num_iovs=None) -> bool:
-        return self._block(self.readv_async(conn_id, mr_ids, ptrs, sizes, fifo_blobs))
+    def readv(self, conn_id, mr_id_v, ptr_v, size_v, meta_blob_v, num_iovs=None) -> bool:
+        return self._block(self.readv_async(conn_id, mr_id_v, ptr_v, size_v, meta_blob_v))
 
     # ------------------------------------------ IPC-named variants (same engine here)
     def send_ipc(self, conn_id, ptr, size) -> bool:
@@ -315,53 +333,56 @@ class Endpoint:
     def advertise_ipc(self, conn_id, ptr, size):
         return self.advertise(conn_id, 0, ptr, size)
 
-    def advertisev_ipc(self, conn_id, ptrs, sizes, num_iovs=None):
-        return self.advertisev(conn_id, None, ptrs, sizes)
+    def advertisev_ipc(self, conn_id, ptr_v, size_v, num_iovs=None):
+        return self.advertisev(conn_id, None, ptr_v, size_v)
 
-    def write_ipc(self, conn_id, ptr, size, info_blob) -> bool:
-        return self.write(conn_id, 0, ptr, size, info_blob)
+    def write_ipc(self, conn_id, ptr, size, info) -> bool:
+        return self.write(conn_id, 0, ptr, size, info)
 
-    def read_ipc(self, conn_id, ptr, size, info_blob) -> bool:
-        return self.read(conn_id, 0, ptr, size, info_blob)
+    def read_ipc(self, conn_id, ptr, size, info) -> bool:
+        return self.read(conn_id, 0, ptr, size, info)
 
-    def write_ipc_async(self, conn_id, ptr, size, info_blob):
-        return self.write_async(conn_id, 0, ptr, size, info_blob)
+    def write_ipc_async(self, conn_id, ptr, size, info):
+        return self.write_async(conn_id, 0, ptr, size, info)
 
-    def read_ipc_async(self, conn_id, ptr, size, info_blob):
-        return self.read_async(conn_id, 0, ptr, size, info_blob)
+    def read_ipc_async(self, conn_id, ptr, size, info):
+        return self.read_async(conn_id, 0, ptr, size, info)
 
-    def writev_ipc(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None) -> bool:
-        return self.writev(conn_id, None, ptrs, sizes, info_blobs)
+    def writev_ipc(self, conn_id, ptr_v, size_v, info_v, num_iovs=None) -> bool:
+        return self.writev(conn_id, None, ptr_v, size_v, info_v)
 
-    def readv_ipc(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None) -> bool:
-        return self.readv(conn_id, None, ptrs, sizes, info_blobs)
+    def readv_ipc(self, conn_id, ptr_v, size_v, info_v, num_iovs=None) -> bool:
+        return self.readv(conn_id, None, ptr_v, size_v, info_v)
 
-    def writev_ipc_async(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None):
-        return self.writev_async(conn_id, None, ptrs, sizes, info_blobs)
+    def writev_ipc_async(self, conn_id, ptr_v, size_v, info_v, num_iovs=None):
+        return self.writev_async(conn_id, None, ptr_v, size_v, info_v)
 
-    def readv_ipc_async(self, conn_id, ptrs, sizes, info_blobs, num_iovs=None):
-        return self.readv_async(conn_id, None, ptrs, sizes, info_blobs)
+    def readv_ipc_async(self, conn_id, ptr_v, size_v, info_v, num_iovs=None):
+        return self.readv_async(conn_id, None, ptr_v, size_v, info_v)
 
     # ---------------------------------------------------------------- descriptor API
-    def transfer(self, conn_id: int, op: str, local_descs: Sequence[XferDesc], remote_descs: Sequence[XferDesc]):
-        """NIXL-style: move every (local, remote) window pair with ONE kernel launch."""
-        assert op in ("read", "write") and len(local_descs) == len(remote_descs)
-        ptrs = [d.addr for d in local_descs]
-        sizes = [min(l.size, r.size) for l, r in zip(local_descs, remote_descs)]
-        blobs = [r.raw for r in remote_descs]
-        fn = self._e.write_async if op == "write" else self._e.read_async
+    def transfer(self, conn_id: int, op_name: str, local_desc_list: Sequence[XferDesc],
+                 remote_desc_list: Sequence[XferDesc]):
+        """NIXL-style: move every (local, remote) window pair with ONE kernel launch.  Parameter names as in the
+        reference's binding (p2p/engine_api.cc:447-663)."""
+        assert op_name in ("read", "write") and len(local_desc_list) == len(remote_desc_list)
+        ptrs = [d.addr for d in local_desc_list]
+        sizes = [min(l.size, r.size) for l, r in zip(local_desc_list, remote_desc_list)]
+        blobs = [r.raw for r in remote_desc_list]
+        fn = self._e.write_async if op_name == "write" else self._e.read_async
         return fn(conn_id, ptrs, sizes, blobs)
 
     # ---- prepared transfers (NIXL prepXfer / postXfer)
-    def prepare_transfer(self, conn_id: int, op: str, local_descs: Sequence[XferDesc], remote_descs: Sequence[XferDesc]):
+    def prepare_transfer(self, conn_id: int, op_name: str, local_desc_list: Sequence[XferDesc],
+                         remote_desc_list: Sequence[XferDesc]):
         """Resolve the descriptor lists once (peer mapping, kernel descriptor tables in pinned memory).  Returns a
         handle for :meth:`post_transfer`; every post is then a bare kernel launch, however many blocks it moves --
         the shape of a KV-cache mover that re-sends the same page lists.  Raises if the peer is not load/store
         reachable (another host): use :meth:`transfer` there."""
-        assert op in ("read", "write") and len(local_descs) == len(remote_descs)
-        ptrs = [d.addr for d in local_descs]
-        sizes = [min(l.size, r.size) for l, r in zip(local_descs, remote_descs)]
-        ok, prep = self._e.prepare(conn_id, op == "write", ptrs, sizes, [r.raw for r in remote_descs])
+        assert op_name in ("read", "write") and len(local_desc_list) == len(remote_desc_list)
+        ptrs = [d.addr for d in local_desc_list]
+        sizes = [min(l.size, r.size) for l, r in zip(local_desc_list, remote_desc_list)]
+        ok, prep = self._e.prepare(conn_id, op_name == "write", ptrs, sizes, [r.raw for r in remote_desc_list])
         if not ok:
             raise RuntimeError("uccl_b200.p2p: prepare_transfer needs a load/store reachable peer and device memory")
         return prep
