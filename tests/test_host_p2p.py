@@ -381,3 +381,35 @@ def test_endpoint_signature_audit_against_the_reference_binding():
     assert e.conn_id_of_rank(3) == 2 ** 64 - 1
     e.set_rank_conn(3, 17)
     assert e.conn_id_of_rank(3) == 17
+
+
+def test_collective_signature_audit_against_the_reference():
+    """Module functions and `CollectiveContext` methods of the reference's `uccl.collective` (p2p/collective.py) exist
+    here with the same parameter names."""
+    import ast
+    import inspect
+    import os
+
+    import uccl_b200.collective as c
+
+    path = "/root/reference/p2p/collective.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not available")
+
+    def params(f):
+        a = f.args
+        return [x.arg for x in a.posonlyargs + a.args + a.kwonlyargs if x.arg != "self"]
+
+    n = 0
+    for node in ast.parse(open(path).read()).body:
+        if isinstance(node, ast.FunctionDef) and not node.name.startswith("_"):
+            have = list(inspect.signature(getattr(c, node.name)).parameters)
+            assert not [p for p in params(node) if p not in have], (node.name, params(node), have)
+            n += 1
+        if isinstance(node, ast.ClassDef) and node.name == "CollectiveContext":
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and (not f.name.startswith("_") or f.name == "__init__"):
+                    have = list(inspect.signature(getattr(c.CollectiveContext, f.name)).parameters)
+                    assert not [p for p in params(f) if p not in have], (f.name, params(f), have)
+                    n += 1
+    assert n > 25

@@ -56,9 +56,15 @@ class _NetHandle:
 
 
 class CollectiveContext:
-    def __init__(self, num_cpus: int = 4, local_gpu_idx: Optional[int] = None, group=None,
-                 use_nccl_p2p: bool = False, with_native_collectives: bool = True, heap_bytes: int = 1 << 30):
+    def __init__(self, num_cpus: int = 4, local_gpu_idx: Optional[int] = None,
+                 use_copy_engine_for_intra: Optional[bool] = None, group=None, use_nccl_p2p: bool = False,
+                 with_native_collectives: bool = True, heap_bytes: int = 1 << 30):
+        """Argument order of the reference (p2p/collective.py:43-70).  `use_copy_engine_for_intra` chooses there between
+        torch's NCCL (default) and cudaMemcpy over IPC for peers on the same node; here the P2P engine's copy kernel
+        serves them in both cases, so the flag is accepted and has no effect -- `use_nccl_p2p=True` is the switch that
+        routes send / recv through torch's NCCL group instead."""
         assert dist.is_initialized(), "torch.distributed must be initialised first"
+        self.use_copy_engine_for_intra = use_copy_engine_for_intra
         self.group = group
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
@@ -246,7 +252,8 @@ class CollectiveContext:
     def recv(self, tensor: torch.Tensor, src: int):
         self.wait(self.irecv(tensor, src))
 
-    def test(self, handle) -> bool:
+    def test(self, transfer_handle) -> bool:
+        handle = transfer_handle
         if not isinstance(handle, int):
             return handle.is_completed()
         ok, done = self.ep.poll_async(handle)
@@ -254,15 +261,16 @@ class CollectiveContext:
             raise RuntimeError("uccl_b200.collective: transfer failed")
         return bool(done)
 
-    def wait(self, handle):
+    def wait(self, transfer_handle):
+        handle = transfer_handle
         if not isinstance(handle, int):
             handle.wait()
             return
         if not self.ep.wait(handle, -1):
             raise RuntimeError("uccl_b200.collective: transfer failed")
 
-    def wait_all(self, handles):
-        for h in handles:
+    def wait_all(self, transfer_handles):
+        for h in transfer_handles:
             self.wait(h)
 
     def P2POp(self, op, tensor: torch.Tensor, peer: int) -> P2POp:
@@ -326,9 +334,10 @@ class CollectiveContext:
 _ctx: Optional[CollectiveContext] = None
 
 
-def init_collective(num_cpus: int = 4, local_gpu_idx: Optional[int] = None, **kw) -> CollectiveContext:
+def init_collective(num_cpus: int = 4, local_gpu_idx: Optional[int] = None,
+                    use_copy_engine_for_intra: Optional[bool] = None, **kw) -> CollectiveContext:
     global _ctx
-    _ctx = CollectiveContext(num_cpus, local_gpu_idx, **kw)
+    _ctx = CollectiveContext(num_cpus, local_gpu_idx, use_copy_engine_for_intra, **kw)
     _ctx.init()
     return _ctx
 
@@ -363,16 +372,16 @@ def irecv(tensor, src):
     return get_collective().irecv(tensor, src)
 
 
-def test(handle):
-    return get_collective().test(handle)
+def test(transfer_handle):
+    return get_collective().test(transfer_handle)
 
 
-def wait(handle):
-    return get_collective().wait(handle)
+def wait(transfer_handle):
+    return get_collective().wait(transfer_handle)
 
 
-def wait_all(handles):
-    return get_collective().wait_all(handles)
+def wait_all(transfer_handles):
+    return get_collective().wait_all(transfer_handles)
 
 
 def batch_isend_irecv(ops):
