@@ -83,6 +83,39 @@ int main() {
                                   {std::string(f2, sizeof(f2)), std::string(f3, sizeof(f3))}, 2, &tid) == 0 &&
          wait_done(ca, tid));
   EXPECT(memcmp(d2.data(), src.data(), 64) == 0 && memcmp(d3.data(), src.data() + 64, 32) == 0);
+  // the reference header's spellings (FifoItem by value / by reference, FIFO_SIZE buffers, string GPU identity)
+  {
+    char fbuf[FIFO_SIZE];
+    EXPECT(uccl_engine_prepare_fifo(b, mrb, dst.data(), dst.size(), fbuf) == 0);
+    FifoItem item;
+    deserialize_fifo_item(fbuf, &item);
+    memset(dst.data(), 0, dst.size());
+    EXPECT(uccl_engine_update_fifo(item, (uint64_t)(uintptr_t)(dst.data() + 64), 128) == 0);
+    EXPECT(uccl_engine_write(ca, mra, src.data(), 128, item, &tid) == 0 && wait_done(ca, tid));
+    EXPECT(dst[63] == 0 && dst[64] == src[0] && dst[191] == src[127] && dst[192] == 0);
+    std::vector<unsigned char> rb(128, 0);
+    EXPECT(uccl_engine_read(ca, mra, rb.data(), 128, item, &tid) == 0 && wait_done(ca, tid));
+    EXPECT(memcmp(rb.data(), src.data(), 128) == 0);
+    FifoItem i2, i3;
+    deserialize_fifo_item(f2, &i2);
+    deserialize_fifo_item(f3, &i3);
+    memset(d2.data(), 0, d2.size());
+    memset(d3.data(), 0, d3.size());
+    EXPECT(uccl_engine_write_vector(ca, {mra, mra}, {src.data() + 1, src.data() + 100}, {64, 32}, std::vector<FifoItem>{i2, i3}, 2,
+                                    &tid) == 0 && wait_done(ca, tid));
+    EXPECT(memcmp(d2.data(), src.data() + 1, 64) == 0 && memcmp(d3.data(), src.data() + 100, 32) == 0);
+    char sbuf[FIFO_SIZE];
+    serialize_fifo_item(i2, sbuf);
+    EXPECT(memcmp(sbuf, f2, FIFO_SIZE) == 0);
+    uccl_conn_t* c2 = uccl_engine_connect(a, ip.c_str(), "0", port);  // GPU identity as a string
+    EXPECT(c2 != nullptr);
+    char ipbuf2[64];
+    int g2 = 0;
+    uccl_conn_t* cb2 = uccl_engine_accept(b, ipbuf2, sizeof(ipbuf2), &g2);
+    EXPECT(cb2 != nullptr);
+    uccl_engine_conn_destroy(c2);
+    uccl_engine_conn_destroy(cb2);
+  }
   // two-sided
   std::vector<unsigned char> r(4096, 0);
   std::thread rx([&] { EXPECT(uccl_engine_recv(cb, mrb, r.data(), r.size()) == 0); });
