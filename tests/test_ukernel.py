@@ -533,3 +533,68 @@ def test_planner_cpp_unit_under_sanitizers(tmp_path):
     assert b.returncode == 0, b.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_process_group_surface_of_the_reference(n):
+    """ReduceOp / Work / properties / uneven all_to_all_single / functional API of the reference's ukernel_ccl
+    (experimental/ukernel/py/ukernel_ccl/__init__.py:19-25,171-430) on the host backend."""
+    comms = Communicator.local_world(n, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20)
+
+    def fn(c):
+        pg = uk.ProcessGroup(c, nlanes=2, tile_bytes=4096, staging_bytes=64 << 10)
+        r = c.rank
+        assert (pg.rank, pg.world_size, pg.gpu_id, pg.backend) == (r, n, -1, "ukernel")
+        assert pg.same_host((r + 1) % n) and pg.peer_transport(r) == "self" and pg.peer_transport((r + 1) % n) == "host-shm"
+        x = torch.full((300,), float(r + 1))
+        assert pg.all_reduce(x, uk.ReduceOp.MAX, tile_bytes=64 << 10, num_flows=2) is None
+        w = pg.all_reduce(torch.ones(8), op=uk.ReduceOp.SUM, async_op=True)
+        assert isinstance(w, uk.Work)
+        w.wait()
+        assert w.is_completed()
+        with pytest.raises(ValueError):
+            pg.all_reduce(x, uk.ReduceOp.BAND)
+        # uneven splits: rank r sends (d + 1) rows of 3 values to rank d
+        isp = [d + 1 for d in range(n)]
+        osp = [r + 1] * n
+        inp = torch.cat([torch.full((d + 1, 3), float(10 * r + d)) for d in range(n)])
+        out = torch.zeros(sum(osp), 3)
+        pg.all_to_all_single(out, inp, output_split_sizes=osp, input_split_sizes=isp)
+        y = torch.arange(n * 4, dtype=torch.float32) + 100 * r
+        z = torch.zeros(n * 4)
+        pg.all_to_all_single(z, y, output_split_sizes=[4] * n, input_split_sizes=[4] * n)  # explicit but even
+        with pytest.raises(ValueError):
+            pg.all_to_all_single(out, inp, output_split_sizes=osp, input_split_sizes=[1] * n)
+        pg.barrier()
+        pg.shutdown()
+        return x, out, z
+
+    for r, (x, out, z) in enumerate(_run_threads(comms, fn)):
+        assert bool((x == float(n)).all())
+        exp = torch.cat([torch.full((r + 1, 3), float(10 * s + r)) for s in range(n)])
+        assert torch.equal(out, exp)
+        assert torch.equal(z, torch.cat([torch.arange(r * 4, r * 4 + 4, dtype=torch.float32) + 100 * s for s in range(n)]))
+
+
+def test_functional_api_on_a_default_group():
+    c = Communicator.local_world(1, host=True, heap_bytes=160 << 20, stage_bytes=1 << 20)[0]
+    assert not uk.is_initialized()
+    with pytest.raises(RuntimeError):
+        uk.get_rank()
+    pg = uk.init_process_group("ukernel", comm=c, nlanes=1, tile_bytes=4096, staging_bytes=64 << 10)
+    try:
+        assert uk.is_initialized() and uk.get_rank() == 0 and uk.get_world_size() == 1 and uk.get_rank(pg) == 0
+        t = torch.full((10,), 2.0)
+        uk.all_reduce(t, uk.ReduceOp.SUM)
+        o = torch.zeros(6)
+        uk.all_to_all_single(o, torch.arange(6, dtype=torch.float32))
+        uk.barrier()
+        assert bool((t == 2.0).all()) and torch.equal(o, torch.arange(6, dtype=torch.float32))
+        with pytest.raises(RuntimeError):
+            uk.init_process_group("ukernel", comm=c)
+        with pytest.raises(ValueError):
+            uk.destroy_process_group()
+            uk.init_process_group("nccl", comm=c)
+    finally:
+        uk.destroy_process_group()
+    assert not uk.is_initialized()

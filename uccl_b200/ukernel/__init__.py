@@ -19,6 +19,7 @@ ProcessGroup with ``all_reduce / all_to_all_single / barrier``: ``ukernel_ccl/__
 """
 from __future__ import annotations
 
+import enum
 from typing import List, Optional, Sequence
 
 import torch
@@ -218,31 +219,126 @@ class UkCommunicator:
         self._u.stop()
 
 
+class ReduceOp(enum.IntEnum):
+    """Operator names / values of the reference's ``ukernel_ccl.ReduceOp`` (ukernel_ccl/__init__.py:19-25)."""
+
+    SUM = 1
+    PRODUCT = 2
+    MAX = 3
+    MIN = 4
+    BAND = 5
+
+
+_REDUCE_NAMES = {ReduceOp.SUM: "sum", ReduceOp.PRODUCT: "prod", ReduceOp.MAX: "max", ReduceOp.MIN: "min"}
+
+
+def _op_name(op) -> str:
+    if isinstance(op, str):
+        return {"product": "prod"}.get(op.lower(), op.lower())
+    try:
+        return _REDUCE_NAMES[ReduceOp(int(op))]
+    except (KeyError, ValueError):
+        raise ValueError(f"uccl_b200.ukernel: reduce op {op!r} is not supported (sum / prod / max / min)") from None
+
+
+class Work:
+    """Completion handle with the reference's two methods (``wait``, ``is_completed``)."""
+
+    def __init__(self, inner):
+        self._inner = inner
+
+    def wait(self):
+        return self._inner.wait()
+
+    def is_completed(self) -> bool:
+        return self._inner.is_completed()
+
+
+class _DoneWork:
+    def wait(self):
+        return True
+
+    def is_completed(self) -> bool:
+        return True
+
+
 class ProcessGroup:
-    """The reference's ``ukernel_ccl.ProcessGroup`` surface: ``all_reduce``, ``all_to_all_single``,
-    ``barrier`` (synchronous by default, ``async_op=True`` returns the work handle)."""
+    """The reference's ``ukernel_ccl.ProcessGroup`` surface (ukernel_ccl/__init__.py:171-290): ``all_reduce``,
+    ``all_to_all_single`` (equal or explicit split sizes), ``barrier``, ``rank`` / ``world_size`` / ``gpu_id`` /
+    ``backend``, ``same_host`` / ``peer_transport`` -- synchronous by default, ``async_op=True`` returns a ``Work`` --
+    plus ``all_gather_into_tensor`` / ``reduce_scatter_tensor`` / ``broadcast``.  Built over an existing
+    :class:`uccl_b200.Communicator` (the reference builds its own transport from rank / world size / exchanger
+    address: :func:`init_process_group` does that from ``torch.distributed`` or the environment)."""
 
     def __init__(self, comm: Communicator, **kw):
         self._uk = UkCommunicator(comm, **kw)
-        self.rank, self.world_size = comm.rank, comm.world_size
+        self._comm = comm
 
-    def _finish(self, w: UkWork, async_op: bool):
+    @property
+    def rank(self) -> int:
+        return self._comm.rank
+
+    @property
+    def world_size(self) -> int:
+        return self._comm.world_size
+
+    @property
+    def gpu_id(self) -> int:
+        d = self._comm.device
+        return -1 if self._comm.is_host else int(d.index or 0)
+
+    @property
+    def backend(self) -> str:
+        return "ukernel"
+
+    def same_host(self, peer_rank: int) -> bool:
+        if not 0 <= int(peer_rank) < self.world_size:
+            raise ValueError(f"peer rank {peer_rank} out of range")
+        return True  # one communicator = one NVLink domain (boxes are joined by UkNetCommunicator)
+
+    def peer_transport(self, peer_rank: int) -> str:
+        self.same_host(peer_rank)
+        if int(peer_rank) == self.rank:
+            return "self"
+        return "host-shm" if self._comm.is_host else "nvlink"
+
+    def _finish(self, w, async_op: bool):
         if async_op:
-            return w
+            return Work(w)
         w.wait()
         return None
 
-    def all_reduce(self, tensor, op="sum", async_op: bool = False):
-        return self._finish(self._uk.all_reduce(tensor, op), async_op)
+    def all_reduce(self, tensor, op=ReduceOp.SUM, async_op: bool = False, tile_bytes: Optional[int] = None,
+                   num_flows: Optional[int] = None):
+        """`tile_bytes` / `num_flows` are per-call knobs of the reference; here the tile size and the lane count are
+        fixed when the group is built (``ProcessGroup(comm, tile_bytes=..., nlanes=...)``) and the arguments are
+        accepted for source compatibility."""
+        return self._finish(self._uk.all_reduce(tensor, _op_name(op)), async_op)
 
-    def all_to_all_single(self, output, input, async_op: bool = False):
-        return self._finish(self._uk.all_to_all_single(output, input), async_op)
+    def all_to_all_single(self, output, input, output_split_sizes=None, input_split_sizes=None, async_op: bool = False,
+                          tile_bytes: Optional[int] = None, num_flows: Optional[int] = None):
+        n = self.world_size
+        isp = list(input_split_sizes) if input_split_sizes is not None else None
+        osp = list(output_split_sizes) if output_split_sizes is not None else None
+        even = lambda sp, t: sp is None or (len(sp) == n and len(set(sp)) == 1 and sp[0] * n == t.size(0))  # noqa: E731
+        if even(isp, input) and even(osp, output):
+            return self._finish(self._uk.all_to_all_single(output, input), async_op)
+        # explicit (uneven) splits along dim 0: the native all-to-all-v kernel moves them (the worker's plans are
+        # equal-split); ordered after the worker's queue by a barrier on the same stream
+        if isp is None or osp is None or len(isp) != n or len(osp) != n:
+            raise ValueError("all_to_all_single: give both split lists with one entry per rank")
+        if sum(isp) != input.size(0) or sum(osp) != output.size(0):
+            raise ValueError("all_to_all_single: split sizes do not add up to the tensors' first dimension")
+        row = input[0].numel() if input.dim() > 1 and input.size(0) else 1
+        self._uk.barrier().wait()
+        self._comm.all_to_all_v(output.view(-1), input.reshape(-1), [s * row for s in isp], [s * row for s in osp])
+        return Work(_DoneWork()) if async_op else None
 
     def all_gather_into_tensor(self, output, input, async_op: bool = False):
         return self._finish(self._uk.all_gather_into_tensor(output, input), async_op)
 
-    def reduce_scatter_tensor(self, output, input, op="sum", async_op: bool = False):
-        return self._finish(self._uk.reduce_scatter_tensor(output, input, op), async_op)
+    def reduce_scatter_tensor(self, output, input, op=ReduceOp.SUM, async_op: bool = False):
+        return self._finish(self._uk.reduce_scatter_tensor(output, input, _op_name(op)), async_op)
 
     def broadcast(self, tensor, src: int = 0, async_op: bool = False):
         return self._finish(self._uk.broadcast(tensor, src), async_op)
@@ -252,6 +348,66 @@ class ProcessGroup:
 
     def shutdown(self):
         self._uk.stop()
+
+
+# ---- functional API on a default group (reference: ukernel_ccl/__init__.py:346-430)
+_DEFAULT_GROUP: Optional[ProcessGroup] = None
+
+
+def init_process_group(backend: str = "ukernel", comm: Optional[Communicator] = None, **kw) -> ProcessGroup:
+    """Creates the default group.  `comm`: an existing Communicator; otherwise one is built from the initialised
+    ``torch.distributed`` world (``Communicator.from_torch_dist``).  Keyword arguments go to :class:`ProcessGroup`
+    (``nlanes``, ``tile_bytes``, ``staging_bytes``)."""
+    global _DEFAULT_GROUP
+    if backend != "ukernel":
+        raise ValueError(f"unsupported backend {backend!r}")
+    if _DEFAULT_GROUP is not None:
+        raise RuntimeError("default ukernel process group already initialised")
+    if comm is None:
+        comm = Communicator.from_torch_dist()
+    _DEFAULT_GROUP = ProcessGroup(comm, **kw)
+    return _DEFAULT_GROUP
+
+
+def _group(group: Optional[ProcessGroup]) -> ProcessGroup:
+    pg = _DEFAULT_GROUP if group is None else group
+    if pg is None:
+        raise RuntimeError("ukernel process group is not initialised")
+    return pg
+
+
+def destroy_process_group(group: Optional[ProcessGroup] = None) -> None:
+    global _DEFAULT_GROUP
+    pg = _DEFAULT_GROUP if group is None else group
+    if pg is not None:
+        pg.shutdown()
+    if group is None or group is _DEFAULT_GROUP:
+        _DEFAULT_GROUP = None
+
+
+def is_initialized() -> bool:
+    return _DEFAULT_GROUP is not None
+
+
+def get_rank(group: Optional[ProcessGroup] = None) -> int:
+    return _group(group).rank
+
+
+def get_world_size(group: Optional[ProcessGroup] = None) -> int:
+    return _group(group).world_size
+
+
+def barrier(group: Optional[ProcessGroup] = None, async_op: bool = False):
+    return _group(group).barrier(async_op=async_op)
+
+
+def all_reduce(tensor, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False):
+    return _group(group).all_reduce(tensor, op=op, async_op=async_op)
+
+
+def all_to_all_single(output, input, output_split_sizes=None, input_split_sizes=None,
+                      group: Optional[ProcessGroup] = None, async_op: bool = False):
+    return _group(group).all_to_all_single(output, input, output_split_sizes, input_split_sizes, async_op=async_op)
 
 
 class UkNetCommunicator:
