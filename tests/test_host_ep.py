@@ -389,3 +389,13 @@ def test_buffer_signature_audit_against_the_reference_and_upstream_deepep():
             have = set(inspect.signature(target).parameters)
             missing = [w for w in want if w not in have]
             assert not missing, f"{path}: Buffer.{f.name} lacks parameters {missing}"
+
+
+def test_upstream_sizing_snippet_runs():
+    """The buffer-sizing loop every DeepEP consumer copies from upstream's README works unchanged."""
+    hidden_bytes = 7168 * 2
+    num_nvl_bytes = num_rdma_bytes = 0
+    for config in (Buffer.get_dispatch_config(8), Buffer.get_combine_config(8)):
+        num_nvl_bytes = max(config.get_nvl_buffer_size_hint(hidden_bytes, 8), num_nvl_bytes)
+        num_rdma_bytes = max(config.get_rdma_buffer_size_hint(hidden_bytes, 8), num_rdma_bytes)
+    assert num_nvl_bytes > (1 << 20) and num_rdma_bytes == 0

@@ -46,6 +46,13 @@ class Config:
         per_tok = hidden_bytes + (hidden_bytes // 128) * 4 + num_topk * 12 + 4
         return int((num_slots + 1) * (cap * per_tok + 8 * 256) + (1 << 20))
 
+    def get_rdma_buffer_size_hint(self, hidden_bytes: int, num_ranks: int) -> int:
+        """Bytes of RDMA buffer the normal (high-throughput) kernels need -- the second half of upstream's sizing
+        snippet (``max(config.get_rdma_buffer_size_hint(hidden_bytes, group.size()), num_rdma_bytes)``).  Like the
+        reference (ep/include/ep_config.hpp:94-97) this is 0 inside one NVLink domain; a group that spans boxes runs
+        the host two-hop path, which stages through the communicator and needs no buffer of its own either."""
+        return 0
+
 
 class Buffer:
     num_sms: int = 24
