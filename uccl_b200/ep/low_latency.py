@@ -67,7 +67,13 @@ class LowLatencyRuntime:
                  num_experts: int, cumulative_local_expert_recv_stats: Optional[torch.Tensor] = None,
                  dispatch_wait_recv_cost_stats: Optional[torch.Tensor] = None, use_fp8: bool = True,
                  round_scale: bool = False, use_ue8m0: bool = False, async_finish: bool = False,
-                 return_recv_hook: bool = False, scales_row_major: bool = False):
+                 return_recv_hook: bool = False, scales_row_major: bool = False, use_nvfp4: bool = False,
+                 x_global_scale: Optional[torch.Tensor] = None):
+        if use_nvfp4 or x_global_scale is not None:
+            # newer DeepEP builds can dispatch NVFP4 (e2m1 + a global scale): vLLM passes these only for NVFP4-quantised
+            # models.  Not provided here -- fail with a message instead of a TypeError on an unknown keyword.
+            raise NotImplementedError("uccl_b200.ep: NVFP4 low-latency dispatch (use_nvfp4 / x_global_scale) is not "
+                                      "supported; use use_fp8=True (e4m3 + per-128 scales) or bf16")
         if use_ue8m0:
             assert use_fp8 and round_scale, "use_ue8m0 needs use_fp8=True and round_scale=True (power-of-two scales)"
             assert x.size(1) % 512 == 0, "use_ue8m0 packs four per-128-channel scales per word: hidden % 512 == 0"
