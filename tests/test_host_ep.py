@@ -399,3 +399,52 @@ def test_upstream_sizing_snippet_runs():
         num_nvl_bytes = max(config.get_nvl_buffer_size_hint(hidden_bytes, 8), num_nvl_bytes)
         num_rdma_bytes = max(config.get_rdma_buffer_size_hint(hidden_bytes, 8), num_rdma_bytes)
     assert num_nvl_bytes > (1 << 20) and num_rdma_bytes == 0
+
+
+def test_vllm_call_shapes_on_the_host_backend():
+    """The exact keyword calls vLLM's DeepEP integration makes (vllm/model_executor/layers/fused_moe/prepare_finalize/
+    deepep_ht.py:114-170,362-376 and deepep_ll.py:298-314,399-408 in vLLM 0.22) run against the Buffer API."""
+    n, T, H, K, E, M = 2, 24, 512, 4, 8, 32
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    xs, idxs, ws = _inputs(n, T, H, K, E, seed=21)
+
+    def fn(c):
+        buffer = Buffer(comm=c, num_nvl_bytes=1 << 20, num_rdma_bytes=1 << 20, low_latency_mode=True,
+                        num_qps_per_rank=E // n, allow_nvlink_for_low_latency_mode=True, allow_mnnvl=False,
+                        explicitly_destroy=True)
+        r = c.rank
+        previous_event = None
+        (num_tokens_per_rank, num_tokens_per_rdma_rank, dispatch_expert_num_tokens, is_token_in_rank, event) = \
+            buffer.get_dispatch_layout(topk_idx=idxs[r], num_experts=E, previous_event=previous_event, async_finish=False,
+                                       allocate_on_comm_stream=False)
+        (token_data, expert_topk_ids, expert_topk_weights, expert_num_tokens_per_expert_list, handle, event) = buffer.dispatch(
+            x=xs[r], handle=None, num_tokens_per_rank=num_tokens_per_rank, num_tokens_per_rdma_rank=num_tokens_per_rdma_rank,
+            is_token_in_rank=is_token_in_rank, num_tokens_per_expert=dispatch_expert_num_tokens, topk_idx=idxs[r],
+            topk_weights=ws[r], expert_alignment=1, config=Buffer.get_dispatch_config(n), previous_event=previous_event,
+            async_finish=False, allocate_on_comm_stream=False)
+        assert isinstance(expert_num_tokens_per_expert_list, list) and len(expert_num_tokens_per_expert_list) == E // n
+        if event.event is not None:
+            event.current_stream_wait()
+        combined_x, _, event = buffer.combine(x=token_data, handle=handle, topk_weights=None,
+                                              config=Buffer.get_combine_config(n), previous_event=previous_event,
+                                              async_finish=False, allocate_on_comm_stream=False)
+        # low latency, as deepep_ll.py calls it
+        expert_x, expert_num_tokens, ll_handle, _, hook = buffer.low_latency_dispatch(
+            xs[r], idxs[r], M, E, use_fp8=False, round_scale=False, use_ue8m0=False, async_finish=False,
+            return_recv_hook=True)
+        hook()
+        output = torch.empty(T, H, dtype=torch.bfloat16)
+        _, _, recv_hook = buffer.low_latency_combine(expert_x, idxs[r], ws[r], ll_handle, async_finish=False,
+                                                    zero_copy=False, return_recv_hook=True, out=output)
+        recv_hook()
+        with pytest.raises(NotImplementedError):
+            buffer.low_latency_dispatch(xs[r], idxs[r], M, E, use_fp8=True, use_nvfp4=True)
+        type(buffer).set_num_sms(20)
+        buffer.destroy()
+        return combined_x, output
+
+    for r, (comb, out) in enumerate(_run(comms, fn)):
+        in_rank = torch.stack([((idxs[r] >= d * (E // n)) & (idxs[r] < (d + 1) * (E // n))).any(1) for d in range(n)], 1)
+        assert torch.allclose(comb.float(), xs[r].float() * in_rank.sum(1, keepdim=True), rtol=2e-2, atol=1e-2)
+        wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(out.float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)

@@ -316,7 +316,10 @@ class HostBuffer:
                              num_experts: int, cumulative_local_expert_recv_stats=None,
                              dispatch_wait_recv_cost_stats=None, use_fp8: bool = True, round_scale: bool = False,
                              use_ue8m0: bool = False, async_finish: bool = False, return_recv_hook: bool = False,
-                             scales_row_major: bool = False):
+                             scales_row_major: bool = False, use_nvfp4: bool = False, x_global_scale=None):
+        if use_nvfp4 or x_global_scale is not None:
+            raise NotImplementedError("uccl_b200.ep: NVFP4 low-latency dispatch (use_nvfp4 / x_global_scale) is not "
+                                      "supported; use use_fp8=True (e4m3 + per-128 scales) or bf16")
         R, me = self.group_size, self.rank
         T, H = x.shape
         K = topk_idx.size(1)
