@@ -136,3 +136,25 @@ def test_drop_in_covers_what_torch_and_the_newest_header_need():
         api = set(re.findall(r"^(?:ncclResult_t|const char\*)\s+(nccl[A-Za-z0-9_]+)\s*\(", open(h).read(), flags=re.M))
         assert len(api) > 30
         assert not (api - ours), f"{h}: not exported: {sorted(api - ours)}"
+
+
+def test_drop_in_covers_vllm_pynccl_bindings():
+    """vLLM loads libnccl with ctypes (VLLM_NCCL_SO_PATH selects the file): every function its wrapper binds must be
+    an export of the drop-in.  Skipped when vLLM is not installed."""
+    import importlib.util
+    import re
+
+    from uccl_b200 import _build
+
+    spec = importlib.util.find_spec("vllm")
+    if spec is None or not spec.submodule_search_locations:
+        pytest.skip("vLLM not installed")
+    path = os.path.join(list(spec.submodule_search_locations)[0], "distributed", "device_communicators", "pynccl_wrapper.py")
+    if not os.path.exists(path):
+        pytest.skip("this vLLM has no pynccl_wrapper.py")
+    bound = set(re.findall(r'Function\(\s*"(nccl[A-Za-z0-9_]+)"', open(path).read()))
+    assert len(bound) >= 10, bound
+    _build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_build.nccl_shim_path())], capture_output=True, text=True).stdout
+    ours = set(re.findall(r"\bnccl[A-Za-z0-9_]+", out))
+    assert not (bound - ours), f"vLLM binds {sorted(bound - ours)}"
