@@ -154,6 +154,12 @@ def test_host_ep_low_latency():
 
 def test_deep_ep_package_uses_the_same_buffer():
     import deep_ep
+    import deep_ep.buffer
+    import deep_ep.utils
+    import deep_ep_cpp
+
+    assert deep_ep.buffer.Buffer is deep_ep.Buffer and deep_ep.utils.EventOverlap is deep_ep.EventOverlap
+    assert deep_ep_cpp.Config is deep_ep.Config and callable(deep_ep.utils.check_nvlink_connections)
 
     c = Communicator.local_world(1, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)[0]
     b = deep_ep.Buffer(comm=c)
