@@ -552,3 +552,30 @@ def test_logfmt10_kernel_arithmetic_matches_definition():
     assert torch.equal(y[0, :128], x[0, :128]) and torch.equal(torch.signbit(y.float()), torch.signbit(x.float()))
     with pytest.raises(RuntimeError):
         C.ep_logfmt10_host(y.data_ptr(), 1, 100)
+
+
+def test_uccl_alias_package():
+    """`uccl_b200.compat.install()`: code written against the reference's package names imports unchanged."""
+    import importlib
+    import sys
+
+    import uccl_b200
+    import uccl_b200.compat as compat
+
+    assert "uccl" not in sys.modules or getattr(sys.modules["uccl"], "__uccl_b200_alias__", False)
+    compat.install()
+    try:
+        import uccl
+        from uccl import collective, p2p
+        from uccl.ep import Buffer
+        from uccl.p2p import Endpoint
+
+        assert p2p is uccl_b200.p2p and collective is uccl_b200.collective and Buffer is uccl_b200.ep.Buffer
+        assert Endpoint is uccl_b200.p2p.Endpoint and uccl.nccl_plugin_path() == uccl_b200.nccl_plugin_path()
+        assert importlib.import_module("uccl.ep") is uccl_b200.ep
+        with pytest.raises(NotImplementedError):
+            uccl.rccl_plugin_path()
+        assert compat.install() is uccl  # idempotent
+    finally:
+        compat.uninstall()
+    assert "uccl" not in sys.modules and "uccl.p2p" not in sys.modules
