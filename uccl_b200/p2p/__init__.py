@@ -36,8 +36,18 @@ class XferDesc:
     def size(self) -> int:
         return struct.unpack_from("<Q", self.raw, 80)[0]
 
+    @property
+    def lkeys(self) -> list:
+        """NIC keys of the reference's descriptor (p2p/engine_api.cc:163-164).  Always empty: nothing is registered with
+        a NIC, the window is reached by load/store (the reference calls this "IPC-only metadata")."""
+        return []
+
+    @property
+    def rkeys(self) -> list:
+        return []
+
     def __repr__(self):
-        return f"XferDesc(addr=0x{self.addr:x}, size={self.size})"
+        return f"XferDesc(addr=0x{self.addr:x}, size={self.size}, mr_id={self.mr_id})"
 
 
 class FloatType(enum.IntEnum):
@@ -83,6 +93,9 @@ class Endpoint:
         C = _native.C()
         if local_gpu_idx is None:
             local_gpu_idx = torch.cuda.current_device() if torch.cuda.is_available() else -1
+        if int(local_gpu_idx) >= 0 and not torch.cuda.is_available() and os.environ.get("UCCL_B200_P2P_HOST_FALLBACK") == "1":
+            # GPU-less CI running scripts that name a GPU: same engine in host mode (buffers must then be host memory)
+            local_gpu_idx = -1
         if int(local_gpu_idx) >= 0:
             torch.cuda.init()
         # local_gpu_idx < 0: host mode (buffers are host memory of this process, copies are memcpy) --
