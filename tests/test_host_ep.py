@@ -397,6 +397,46 @@ def test_buffer_signature_audit_against_the_reference_and_upstream_deepep():
             assert not missing, f"{path}: Buffer.{f.name} lacks parameters {missing}"
 
 
+def test_utils_signature_audit_against_the_reference_helpers():
+    """Every public helper of the reference's ep/bench/utils.py (what its tests and benchmarks import) and of
+    upstream DeepEP's utils exists under `uccl_b200.ep` with the same parameter names."""
+    import ast
+    import inspect
+    import os
+
+    import uccl_b200.ep as E
+    import uccl_b200.ep.utils as U
+
+    files = ["/root/reference/ep/bench/utils.py", "/root/reference/thirdparty/DeepEP/deep_ep/utils.py",
+             "/root/reference/thirdparty/DeepEP/tests/utils.py"]
+    files = [f for f in files if os.path.exists(f)]
+    if not files:
+        pytest.skip("reference tree not available")
+    for path in files:
+        for f in ast.parse(open(path).read()).body:
+            if not isinstance(f, ast.FunctionDef) or f.name.startswith("_"):
+                continue
+            target = getattr(U, f.name, None) or getattr(E, f.name, None)
+            assert target is not None, f"{path}: {f.name} missing"
+            want = [a.arg for a in f.args.posonlyargs + f.args.args + f.args.kwonlyargs]
+            have = set(inspect.signature(target).parameters)
+            missing = [w for w in want if w not in have]
+            assert not missing, f"{path}: {f.name} lacks parameters {missing}"
+
+
+def test_per_token_cast_back_accepts_both_spellings():
+    from uccl_b200.ep.utils import per_token_cast_back, per_token_cast_to_fp8
+
+    if not hasattr(torch, "float8_e4m3fn"):
+        pytest.skip("no fp8 dtype")
+    x = torch.randn(4, 256, dtype=torch.bfloat16)
+    q, s = per_token_cast_to_fp8(x)
+    a = per_token_cast_back(q, s)
+    assert torch.equal(a, per_token_cast_back(x_fp8=q, x_scales=s)) and torch.equal(a, per_token_cast_back(q, scales=s))
+    with pytest.raises(TypeError):
+        per_token_cast_back(q)
+
+
 def test_upstream_sizing_snippet_runs():
     """The buffer-sizing loop every DeepEP consumer copies from upstream's README works unchanged."""
     hidden_bytes = 7168 * 2

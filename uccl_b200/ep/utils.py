@@ -86,10 +86,16 @@ def per_token_cast_to_fp8(x: torch.Tensor, round_scale: bool = False):
     return q, scale_inv
 
 
-def per_token_cast_back(x_fp8: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+def per_token_cast_back(x_fp8: torch.Tensor, x_scales: torch.Tensor = None, *, scales: torch.Tensor = None) -> torch.Tensor:
+    """Inverse of ``per_token_cast_to_fp8`` (reference ep/bench/utils.py:per_token_cast_back); ``scales`` is the
+    older spelling of ``x_scales``."""
+    if x_scales is None:
+        x_scales = scales
+    if x_scales is None:
+        raise TypeError("per_token_cast_back needs x_scales")
     m, n = x_fp8.shape
     xv = x_fp8.float().view(m, -1, 128)
-    return (xv * scales.float().view(m, -1, 1)).view(m, n).to(torch.bfloat16)
+    return (xv * x_scales.float().view(m, -1, 1)).view(m, n).to(torch.bfloat16)
 
 
 def logfmt10_simulate(x: torch.Tensor) -> torch.Tensor:
@@ -139,8 +145,9 @@ def inplace_unique(x: torch.Tensor, num_slots: int) -> None:
     x[:, :valid] = sorted_idx[:, :valid]
 
 
-def bench(fn, num_warmups: int = 5, num_tests: int = 20, flush_l2: bool = True):
-    """Device-timed (CUDA events) avg/min/max seconds with an L2 flush between iterations."""
+def bench(fn, num_warmups: int = 5, num_tests: int = 20, post_fn=None, flush_l2: bool = True):
+    """Device-timed (CUDA events) avg/min/max seconds with an L2 flush between iterations; ``post_fn`` runs after
+    each timed call, outside its event pair (reference ep/bench/utils.py:bench)."""
     torch.cuda.synchronize()
     cache = torch.empty(int(256e6 // 4), dtype=torch.int, device="cuda") if flush_l2 else None
     for _ in range(num_warmups):
@@ -153,6 +160,8 @@ def bench(fn, num_warmups: int = 5, num_tests: int = 20, flush_l2: bool = True):
         starts[i].record()
         fn()
         ends[i].record()
+        if post_fn is not None:
+            post_fn()
     torch.cuda.synchronize()
     ts = [s.elapsed_time(e) / 1e3 for s, e in zip(starts, ends)]
     return sum(ts) / len(ts), min(ts), max(ts)
@@ -248,7 +257,9 @@ def check_nvlink_connections(group=None) -> bool:
     return all(torch.cuda.can_device_access_peer(a, b) for a in range(n) for b in range(n) if a != b)
 
 
-def initialize_uccl(scratch=None, scratch_nbytes: int = 0, rank: int = 0, num_ranks: int = 1, group=None, **kw):
+def initialize_uccl(scratch_ptr=None, scratch_nbytes: int = 0, rank: int = 0, num_ranks: int = 1, group=None,
+                    num_experts: int = 0, is_intranode=None, use_normal_mode: bool = False,
+                    rdma_buffer_is_host_allocated: bool = False, **kw):
     """The reference spawns CPU proxy threads and exchanges their metadata here; kernels address peers directly in
     this library, so there is nothing to start.  Kept for script compatibility: returns ``([], None)``."""
     return [], None
