@@ -1,5 +1,5 @@
 """Ad-hoc GPU diagnostics (not part of the test-suite)."""
-import os, sys, threading
+import os, sys
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -34,7 +34,7 @@ def a2a_debug():
 def ep_debug():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
     import test_gpu_ep as T
-    from uccl_b200.ep import per_token_cast_to_fp8, per_token_cast_back
+    from uccl_b200.ep import per_token_cast_to_fp8
     n = 2
     Tn, H, K = 257, 1024, 4
     E = n * 4

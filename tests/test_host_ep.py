@@ -2,7 +2,6 @@
 of SURVEY Appendix C checked without a GPU -- receive order, local-expert remapping, cached handles,
 fp8 payloads, expert_alignment, num_worst_tokens, unweighted combine, low-latency dispatch/combine."""
 import threading
-import warnings
 
 import pytest
 import torch
@@ -132,14 +131,14 @@ def test_host_ep_low_latency():
         assert o["qs"].dtype == torch.int32 and o["qs"].shape == (e_per, n * M, H // 512)
         src_info, layout_range = o["hb"][0], o["hb"][1]
         for e in range(e_per):
-            # rows of expert e: source-rank major, token order minor; layout_range packs (count << 32 | begin)
+            # rows of expert e: source-rank major, token order minor; layout_range packs (begin << 32 | count) like the reference
             exp_rows, exp_src = [], []
             for s_ in range(n):
                 toks = (idxs[s_] == r * e_per + e).any(1).nonzero().flatten()
                 exp_rows.append(xs[s_][toks])
                 exp_src.append(toks.to(torch.int32))
                 lr = int(layout_range[e, s_])
-                assert lr >> 32 == toks.numel() and (lr & 0xFFFFFFFF) == sum(x.size(0) for x in exp_rows[:-1])
+                assert (lr & 0xFFFFFFFF) == toks.numel() and lr >> 32 == sum(x.size(0) for x in exp_rows[:-1])
             assert torch.equal(o["bx"][e, :counts[e]], torch.cat(exp_rows))
             assert torch.equal(src_info[e, :counts[e]], torch.cat(exp_src))
         wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)

@@ -10,7 +10,6 @@ import threading
 import pytest
 import torch
 
-from helpers import run_host_ranks
 from uccl_b200 import Communicator, net
 from uccl_b200.parallel import MultiNodeCommunicator
 

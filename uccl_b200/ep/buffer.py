@@ -475,7 +475,8 @@ class Buffer:
     def reset_rdma_buffer(self) -> None:
         """Reference: zeroes the RDMA buffer for a fresh run (ep/bench/buffer.py:213-218).  Signalling here is epoch
         based, so nothing NEEDS zeroing; the call completes a pending receive hook and clears the low-latency block
-        on the current stream so that stale rows cannot be mistaken for results."""
+        on the current stream so that stale rows cannot be mistaken for results.  Like the reference's it is a LOCAL
+        memset: peers write into this block, so call it with the group quiescent (a barrier on both sides)."""
         ll = self._need_ll()
         ll._finish_pending()
         if int(self.runtime.ll_nbytes) > 0:

@@ -361,7 +361,7 @@ class HostBuffer:
             for e in range(e_per):
                 c = int(mine[s, e])
                 b = int(begin[s, e])
-                layout_range[e, s] = (c << 32) | b
+                layout_range[e, s] = (b << 32) | c  # begin in the high word, count in the low one (internode_ll.cu:573)
                 if c:
                     seg = slice(pos, pos + c)
                     recv_x[e, b:b + c] = rq[seg].view(torch.uint8) if use_fp8 else rq[seg]

@@ -4,7 +4,6 @@ Router -> get_dispatch_layout -> dispatch (optionally fused fp8) -> grouped expe
 zero-copy combine."""
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -18,7 +18,6 @@ from it are zero-copy for every collective (peer-mapped and multicast-bound).
 from __future__ import annotations
 
 import ctypes
-import os
 from typing import Iterable, List, Optional, Sequence
 
 import torch
