@@ -579,3 +579,17 @@ def test_uccl_alias_package():
     finally:
         compat.uninstall()
     assert "uccl" not in sys.modules and "uccl.p2p" not in sys.modules
+
+
+def test_sm_partition_reports_unavailable_without_a_gpu():
+    """SM partitions (green contexts) need a device: on a CPU box the probe says why and split raises."""
+    import torch
+
+    from uccl_b200.utils import SmPartition
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU box: covered by tests/test_zzzz_gpu_sm_partition.py")
+    ok, why = SmPartition.supported()
+    assert not ok and why
+    with pytest.raises(RuntimeError, match="unavailable"):
+        SmPartition.split(24)

@@ -129,6 +129,7 @@ cudaError_t preload_all_kernels() {
     ok(launch_ep_ll_pack(lp, 0));
   }
   ok(preload_p2p_kernels());
+  ok(launch_smid_probe(nullptr, 1, 0, 0));
   ok(cmp_compress_async(nullptr, 0, kBF16, nullptr, 0));
   ok(cmp_compress_async(nullptr, 0, kF32, nullptr, 0));
   ok(cmp_decompress_async(nullptr, nullptr, 0, kBF16, 0));

@@ -12,6 +12,8 @@
 #include "param.h"
 #include "pool.h"
 #include "ring.h"
+#include "sm_partition.h"
+#include "../kernels/launch.h"
 #include "timers.h"
 #include "timing_wheel.h"
 
@@ -23,6 +25,35 @@ void bind_util(py::module_& m) {
   u.def("now_ns", &now_ns);
   u.def("tsc_ghz", &tsc_ghz);
   u.def("log", [](int level, const std::string& msg) { log_emit(level, SUB_UTIL, "python", 0, "%s", msg.c_str()); });
+  // SM partitions (CUDA green contexts): see sm_partition.h
+  py::class_<SmPartition, std::shared_ptr<SmPartition>>(u, "SmPartition")
+      .def_static("supported",
+                  [](int device) {
+                    std::string why;
+                    const bool ok = SmPartition::supported(device, &why);
+                    return py::make_tuple(ok, why);
+                  })
+      .def_static("device_sm_count", &SmPartition::device_sm_count)
+      .def_static(
+          "split",
+          [](int device, int sm_count, bool fine_grained) {
+            SmPartition::Pair p = SmPartition::split(device, sm_count, fine_grained);
+            return py::make_tuple(p.part, p.rest);
+          },
+          py::arg("device"), py::arg("sm_count"), py::arg("fine_grained") = false)
+      .def_property_readonly("device", &SmPartition::device)
+      .def_property_readonly("sm_count", &SmPartition::sm_count)
+      .def("stream", [](SmPartition& p, int priority) { return (uintptr_t)p.stream(priority); }, py::arg("priority") = 0);
+
+  u.def(
+      "smid_probe",
+      [](uintptr_t out, int blocks, uint64_t hold_ns, uintptr_t stream) {
+        cudaError_t e = launch_smid_probe(reinterpret_cast<int*>(out), blocks, hold_ns, reinterpret_cast<cudaStream_t>(stream));
+        UB_CHECK(e == cudaSuccess, "smid probe launch failed: %s", cudaGetErrorString(e));
+      },
+      py::arg("out"), py::arg("blocks"), py::arg("hold_ns") = 20000, py::arg("stream") = 0,
+      "out[b] (int32, device) = id of the SM CTA b ran on");
+
   u.def("param_str", [](const std::string& k, const std::string& d) { return param_load_str(k.c_str(), d.c_str()); });
 
   py::class_<SpscRing<uint64_t>>(u, "SpscRing")

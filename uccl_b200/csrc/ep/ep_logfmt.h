@@ -7,9 +7,9 @@
 #include <string.h>
 
 #if defined(__CUDACC__)
-#define UB_HD __host__ __device__ __forceinline__
+#define UB_LF_HD __host__ __device__ __forceinline__
 #else
-#define UB_HD inline
+#define UB_LF_HD inline
 #endif
 
 namespace ub {
@@ -21,7 +21,7 @@ struct LogFmtParams {
 
 // amax: largest magnitude of the 128-channel group; lmax / lmin: log2 of the largest / smallest NON-ZERO magnitude
 // (lmin = +inf when the group is all zero)
-UB_HD LogFmtParams logfmt10_params(float amax, float lmax, float lmin) {
+UB_LF_HD LogFmtParams logfmt10_params(float amax, float lmax, float lmin) {
   LogFmtParams p;
   p.lmin = fmaxf(lmin, lmax - 32.f);  // range clipped to 2^-32 of the maximum
   p.use = amax <= 1.f && p.lmin < lmax;
@@ -31,7 +31,7 @@ UB_HD LogFmtParams logfmt10_params(float amax, float lmax, float lmin) {
   return p;
 }
 
-UB_HD uint16_t f32_to_bf16_rn_bits(float f) {
+UB_LF_HD uint16_t f32_to_bf16_rn_bits(float f) {
   uint32_t u;
   memcpy(&u, &f, 4);
   if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN stays NaN
@@ -39,7 +39,7 @@ UB_HD uint16_t f32_to_bf16_rn_bits(float f) {
   return (uint16_t)(u >> 16);
 }
 
-UB_HD float bf16_bits_to_f32(uint16_t b) {
+UB_LF_HD float bf16_bits_to_f32(uint16_t b) {
   const uint32_t u = (uint32_t)b << 16;
   float f;
   memcpy(&f, &u, 4);
@@ -47,7 +47,7 @@ UB_HD float bf16_bits_to_f32(uint16_t b) {
 }
 
 // la = log2(|value|) (-inf for 0); returns the bf16 bits of the value snapped to the group's grid, sign kept
-UB_HD uint16_t logfmt10_quantize_bits(uint16_t bits, float la, const LogFmtParams& p) {
+UB_LF_HD uint16_t logfmt10_quantize_bits(uint16_t bits, float la, const LogFmtParams& p) {
   const float enc = floorf((la - p.lmin) * p.step_inv + p.rounding);
   const float dec = exp2f((enc - 1.f) * p.step + p.lmin);
   return (uint16_t)((bits & 0x8000u) | f32_to_bf16_rn_bits(dec));

@@ -40,7 +40,20 @@ struct CuApi {
   CUresult (*MulticastUnbind)(CUmemGenericAllocationHandle, CUdevice, size_t, size_t) = nullptr;
   CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*,
                                       CUmulticastGranularity_flags) = nullptr;
+  // green contexts (SM partitions, common/sm_partition.cc): optional, driver >= 12.4
+  CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*,
+                                        unsigned int, unsigned int) = nullptr;
+  CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+  CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+  CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+  CUresult (*GreenCtxGetDevResource)(CUgreenCtx, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
   bool ok = false;
+  bool green() const {
+    return DeviceGetDevResource && DevSmResourceSplitByCount && DevResourceGenerateDesc && GreenCtxCreate &&
+           GreenCtxDestroy && GreenCtxGetDevResource && GreenCtxStreamCreate;
+  }
 };
 
 inline const CuApi& cu() {
@@ -83,6 +96,13 @@ inline const CuApi& cu() {
     get("cuMulticastBindMem", (void**)&a->MulticastBindMem);
     get("cuMulticastUnbind", (void**)&a->MulticastUnbind);
     get("cuMulticastGetGranularity", (void**)&a->MulticastGetGranularity);
+    get("cuDeviceGetDevResource", (void**)&a->DeviceGetDevResource);
+    get("cuDevSmResourceSplitByCount", (void**)&a->DevSmResourceSplitByCount);
+    get("cuDevResourceGenerateDesc", (void**)&a->DevResourceGenerateDesc);
+    get("cuGreenCtxCreate", (void**)&a->GreenCtxCreate);
+    get("cuGreenCtxDestroy", (void**)&a->GreenCtxDestroy);
+    get("cuGreenCtxGetDevResource", (void**)&a->GreenCtxGetDevResource);
+    get("cuGreenCtxStreamCreate", (void**)&a->GreenCtxStreamCreate);
 #undef UB_GET
     return a;
   }();

@@ -50,4 +50,6 @@ cudaError_t launch_rs_ll_i(int dtype, int op, const DevComm& c, const CollArgs& 
                            cudaStream_t st);
 cudaError_t launch_sendrecv(const DevComm& c, const SendRecvArgs& a, cudaStream_t st);
 cudaError_t launch_barrier(const DevComm& c, int domain, cudaStream_t st);
+// out[b] = SM id CTA b ran on; every CTA holds its SM for hold_ns (probe.cu)
+cudaError_t launch_smid_probe(int* out, int blocks, unsigned long long hold_ns, cudaStream_t st);
 }  // namespace ub

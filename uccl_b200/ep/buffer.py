@@ -133,8 +133,32 @@ class Buffer:
             self._ll = LowLatencyRuntime(self, self.num_rdma_bytes)
         with torch.cuda.device(self.device):
             self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._sm_partition = None
         self._layout_cache = None
         self._destroyed = False
+
+    def use_sm_partition(self, partition) -> None:
+        """Run this buffer's dispatch / combine kernels on the SMs of `partition`
+        (:class:`uccl_b200.utils.SmPartition`, a CUDA green context) instead of wherever the scheduler finds room: the
+        communication stream becomes the partition's stream and the SM budget of every launch is capped at the
+        partition's size (the kernels synchronise their CTAs with each other, so all of them must be resident).  Give
+        the rest of the device to the compute streams (``with rest: ...``) to keep GEMMs off these SMs.  ``None``
+        restores an ordinary stream.  The low-latency kernels run on the caller's current stream (DeepEP's contract):
+        enter the partition (``with partition:``) around those calls instead."""
+        if partition is None:
+            with torch.cuda.device(self.device):
+                self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._sm_partition = None
+            return
+        if int(partition.device) != int(self.device.index):
+            raise ValueError(f"uccl_b200.ep.Buffer: the partition lives on GPU {partition.device}, the buffer on {self.device}")
+        if self.comm.native.single_process and self.group_size > 1:
+            raise ValueError("uccl_b200.ep.Buffer: a single-process world shares one GPU between its ranks; "
+                             "SM partitions are for one process per GPU")
+        torch.cuda.current_stream(self.device).synchronize()
+        self.comm_stream.synchronize()
+        self.comm_stream = partition.stream()
+        self._sm_partition = partition
 
     def _check_symmetric_placement(self):
         """The kernels address a peer's arenas as `peer_heap + my_offset`, so the EP block must sit at the
@@ -202,6 +226,8 @@ class Buffer:
             # conservative: assume every rank of the single-process world sits on this GPU
             share = torch.cuda.get_device_properties(self.device).multi_processor_count
             n = max(1, min(n, share // self.group_size))
+        if self._sm_partition is not None:
+            n = max(1, min(n, int(self._sm_partition.sm_count)))
         return n
 
     # ------------------------------------------------------------------ stream choreography
