@@ -11,5 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import uccl_b200.compat  # noqa: E402
 
 uccl_b200.compat.install()
+if os.environ.get("UCCL_B200_ALIAS_TOPLEVEL_UTILS") == "1":
+    # p2p/tests/test_util_interval_tree.py imports the sibling file p2p/utils.py as a top-level module
+    sys.modules["utils"] = sys.modules["uccl.utils"]
 sys.argv = sys.argv[1:]
 runpy.run_path(sys.argv[0], run_name="__main__")

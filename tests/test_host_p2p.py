@@ -413,3 +413,68 @@ def test_collective_signature_audit_against_the_reference():
                     assert not [p for p in params(f) if p not in have], (f.name, params(f), have)
                     n += 1
     assert n > 25
+
+
+def test_p2p_utils_helpers():
+    """uccl_b200.p2p.utils: the helpers the reference ships next to its engine (p2p/utils.py)."""
+    import random
+    import socket
+    import threading
+
+    from uccl_b200.p2p.utils import (ClosedIntervalTree, create_socket_and_connect, recv_obj, send_obj,
+                                     set_files_limit)
+
+    soft, hard = set_files_limit(verbose=False)
+    assert soft == hard or soft == -1
+    # framed pickles over a real TCP connection made by the retrying connect (listener comes up late)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    port = srv.getsockname()[1]
+    got = {}
+
+    def serve():
+        import time
+
+        time.sleep(0.3)
+        srv.listen(1)
+        c, _ = srv.accept()
+        got["obj"] = recv_obj(c)
+        got["none"] = recv_obj(c)
+        send_obj(c, {"ok": True, "blob": b"x" * 100000})
+        c.close()
+
+    t = threading.Thread(target=serve)
+    t.start()
+    s = create_socket_and_connect("127.0.0.1", port, max_retries=20, initial_delay=0.05, backoff=1.5, max_delay=0.2)
+    send_obj(s, ("meta", [1, 2, 3]))
+    s.sendall(b"\x00" * 8)  # zero-length frame
+    back = recv_obj(s)
+    t.join()
+    s.close()
+    srv.close()
+    assert got["obj"] == ("meta", [1, 2, 3]) and got["none"] is None and back["ok"] and len(back["blob"]) == 100000
+    with pytest.raises(OSError):
+        create_socket_and_connect("127.0.0.1", port, max_retries=1, initial_delay=0.01)
+    # closed-interval index against brute force
+    rng = random.Random(3)
+    for _ in range(50):
+        tree, ref = ClosedIntervalTree(), []
+        for _ in range(rng.randint(1, 25)):
+            a = rng.randint(0, 40)
+            b = a + rng.randint(0, 15)
+            d = rng.randint(0, 2)
+            tree.add(a, b, d)
+            ref.append((a, b, d))
+        a, b, d = rng.choice(ref)
+        n = tree.remove(a, b, d)
+        assert n == sum(1 for r in ref if r == (a, b, d))
+        ref = [r for r in ref if r != (a, b, d)]
+        for _ in range(10):
+            qa = rng.randint(0, 45)
+            qb = qa + rng.randint(0, 10)
+            assert sorted(tree.query_containing(qa, qb)) == sorted(r for r in ref if r[0] <= qa and r[1] >= qb)
+            assert sorted(tree.query_overlap(qa, qb)) == sorted(r for r in ref if r[0] <= qb and r[1] >= qa)
+            assert sorted(tree.query_exact_match(qa, qb)) == sorted(r for r in ref if r[:2] == (qa, qb))
+        assert sorted(tree) == sorted(ref) and len(tree) == len(ref)
+    with pytest.raises(ValueError):
+        ClosedIntervalTree().add(5, 4, None)

@@ -17,6 +17,7 @@ SCRIPTS = [
     ("test_remove_remote_endpoint.py", "0 failed"),
     ("test_gpu_index_mapping.py", "5/5 passed"),
     ("test_register_memory_cache.py", None),
+    ("test_util_interval_tree.py", "Exact matches: 2 intervals"),
 ]
 
 
@@ -25,7 +26,7 @@ def test_reference_p2p_script(script, marker):
     path = os.path.join(REF, script)
     if not os.path.exists(path):
         pytest.skip("reference tree not available")
-    env = dict(os.environ, UCCL_B200_P2P_HOST_FALLBACK="1")
+    env = dict(os.environ, UCCL_B200_P2P_HOST_FALLBACK="1", UCCL_B200_ALIAS_TOPLEVEL_UTILS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_script.py"), path], capture_output=True,
                        text=True, timeout=300, env=env, cwd=ROOT)
     out = r.stdout + r.stderr

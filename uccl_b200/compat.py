@@ -4,7 +4,8 @@
     from uccl import p2p, collective                         # -> uccl_b200.p2p / uccl_b200.collective
     from uccl.ep import Buffer                               # -> uccl_b200.ep
 
-``install()`` registers module aliases in ``sys.modules`` (``uccl``, ``uccl.p2p``, ``uccl.collective``, ``uccl.ep``)
+``install()`` registers module aliases in ``sys.modules`` (``uccl``, ``uccl.p2p``, ``uccl.collective``, ``uccl.utils``,
+``uccl.ep``)
 and refuses to shadow a real ``uccl`` distribution that is already imported.  The reference's package root offers
 ``nccl_plugin_path`` / ``rccl_plugin_path`` / ``efa_plugin_path`` / ``efa_nccl_path`` (uccl/__init__.py:12-54): the first
 exists here, the other three name libraries of other hardware and raise.
@@ -20,6 +21,7 @@ def install(name: str = "uccl") -> types.ModuleType:
     import uccl_b200.collective
     import uccl_b200.ep
     import uccl_b200.p2p
+    import uccl_b200.p2p.utils
 
     cur = sys.modules.get(name)
     if cur is not None and getattr(cur, "__uccl_b200_alias__", False):
@@ -31,6 +33,9 @@ def install(name: str = "uccl") -> types.ModuleType:
     m.__version__ = uccl_b200.__version__
     m.__path__ = []  # a package: `import uccl.p2p` consults sys.modules first
     m.p2p, m.collective, m.ep = uccl_b200.p2p, uccl_b200.collective, uccl_b200.ep
+    m.utils = uccl_b200.p2p.utils  # the reference ships p2p/utils.py as uccl/utils.py (build_inner.sh:183)
+    m.has_efa = lambda: False  # uccl/__init__.py:12-20: an NVLink box has no EFA devices to prefer
+    m.is_efa = False
     m.nccl_plugin_path = uccl_b200.nccl_plugin_path
     m.nccl_shim_path = uccl_b200.nccl_shim_path
 
@@ -44,7 +49,7 @@ def install(name: str = "uccl") -> types.ModuleType:
     m.efa_plugin_path = _other_hardware("EFA plugin")
     m.efa_nccl_path = _other_hardware("EFA build of NCCL")
     sys.modules[name] = m
-    for sub in ("p2p", "collective", "ep"):
+    for sub in ("p2p", "collective", "ep", "utils"):
         sys.modules[f"{name}.{sub}"] = getattr(m, sub)
     return m
 
@@ -52,5 +57,5 @@ def install(name: str = "uccl") -> types.ModuleType:
 def uninstall(name: str = "uccl") -> None:
     cur = sys.modules.get(name)
     if cur is not None and getattr(cur, "__uccl_b200_alias__", False):
-        for k in [name] + [f"{name}.{s}" for s in ("p2p", "collective", "ep")]:
+        for k in [name] + [f"{name}.{s}" for s in ("p2p", "collective", "ep", "utils")]:
             sys.modules.pop(k, None)

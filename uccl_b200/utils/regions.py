@@ -65,6 +65,66 @@ class RegionIndex(Generic[V]):
             i -= 1
         return best
 
+    def containing(self, start: int, size: int = 1) -> List[Tuple[int, int, V]]:
+        """Every region that contains [start, start + size), in (start, end) order."""
+        end = start + max(size, 1)
+        i = bisect.bisect_right(self._starts, start) - 1
+        out = []
+        while i >= 0 and self._max_end[i] >= end:
+            s, e, v = self._items[i]
+            if e >= end:
+                out.append((s, e - s, v))
+            i -= 1
+        out.reverse()
+        return out
+
+    def overlapping(self, start: int, size: int = 1) -> List[Tuple[int, int, V]]:
+        """Every region that shares at least one byte with [start, start + size)."""
+        end = start + max(size, 1)
+        hi = bisect.bisect_left(self._starts, end)  # regions starting at or after `end` cannot overlap
+        out = []
+        i = hi - 1
+        while i >= 0 and self._max_end[i] > start:
+            s, e, v = self._items[i]
+            if e > start:
+                out.append((s, e - s, v))
+            i -= 1
+        out.reverse()
+        return out
+
+    def matching(self, start: int, size: int) -> List[Tuple[int, int, V]]:
+        """Every region with exactly these bounds (several registrations may share them)."""
+        i = bisect.bisect_left(self._starts, start)
+        out = []
+        while i < len(self._items) and self._items[i][0] == start:
+            if self._items[i][1] == start + size:
+                out.append((start, size, self._items[i][2]))
+            i += 1
+        return out
+
+    def remove_matching(self, start: int, size: int, value=None, any_value: bool = True) -> int:
+        """Removes every region with exactly these bounds (and this value unless `any_value`); returns how many."""
+        i = bisect.bisect_left(self._starts, start)
+        first, n = i, 0
+        while i < len(self._items) and self._items[i][0] == start:
+            if self._items[i][1] == start + size and (any_value or self._items[i][2] == value):
+                self._items.pop(i)
+                self._starts.pop(i)
+                n += 1
+            else:
+                i += 1
+        if n:
+            self._rebuild(first)
+        return n
+
+    def clear(self) -> None:
+        self._starts.clear()
+        self._items.clear()
+        self._max_end.clear()
+
+    def __iter__(self):
+        return iter([(s, e - s, v) for s, e, v in self._items])
+
     def exact(self, start: int) -> Optional[V]:
         i = bisect.bisect_left(self._starts, start)
         return self._items[i][2] if i < len(self._items) and self._items[i][0] == start else None
