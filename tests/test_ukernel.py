@@ -598,3 +598,85 @@ def test_functional_api_on_a_default_group():
     finally:
         uk.destroy_process_group()
     assert not uk.is_initialized()
+
+
+def test_rank_addressed_p2p_communicator():
+    """`uccl_b200.ukernel.p2p.Communicator` -- the reference's ukernel_p2p surface (experimental/ukernel/py/
+    ukernel_p2p.cpp:407-444): connect / accept by rank through the exchanger, published buffer ids, isend / irecv with
+    byte offsets, request polling, named barriers.  Three ranks in one process, host memory."""
+    import socket
+    import threading
+
+    from uccl_b200 import compat
+    from uccl_b200.ukernel.p2p import Communicator
+
+    compat.install_ukernel()
+    import ukernel_p2p
+
+    assert ukernel_p2p.Communicator is Communicator
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    W = 3
+    res, comms, errs = {}, {}, []
+
+    def body(r):
+        c = ukernel_p2p.Communicator(gpu_id=-1, rank=r, world_size=W, exchanger_ip="127.0.0.1", exchanger_port=port,
+                                     transport="auto")
+        comms[r] = c
+        assert c.rank == r and c.world_size == W
+        for p in range(W):
+            if p != r:
+                assert c.accept_peer(p) if r < p else c.connect_peer(p)
+        nxt, prv = (r + 1) % W, (r - 1) % W
+        assert c.same_host(nxt) and c.peer_transport(nxt) == "tcp"
+        buf = torch.zeros(64, dtype=torch.float32)
+        with pytest.raises(ValueError):
+            c.reg_rdma(0, buf)
+        assert c.reg_rdma(100 + r, buf, publish=True)
+        assert c.wait_mr(nxt, 100 + nxt) and not c.wait_mr(nxt, 999, timeout_ms=50)
+        src = torch.arange(64, dtype=torch.float32) + 1000 * r
+        rq = c.irecv(prv, buf, offset=64, len=128)
+        sq = c.isend(nxt, src, offset=32, len=128, remote_buffer_id=100 + nxt, remote_offset=64)
+        assert rq and sq and c.wait_finish_multi([sq, rq]) and c.poll(sq)
+        with pytest.raises(ValueError):
+            c.isend(nxt, src, offset=200, len=128)
+        with pytest.raises(RuntimeError):
+            c.isend(nxt, src, remote_buffer_id=4242)
+        res[r] = buf.clone()
+        assert c.barrier() and c.barrier("phase2", 5000)
+        done, got = torch.full((1,), float(r)), torch.zeros(1)
+        if r % 2 == 0:
+            c.send(nxt, done)
+            c.recv(prv, got)
+        else:
+            c.recv(prv, got)
+            c.send(nxt, done)
+        assert float(got) == float(prv)
+        assert c.unreg_rdma(100 + r) and not c.unreg_rdma(100 + r)
+        assert c.barrier("end")
+
+    def run(r):
+        try:
+            body(r)
+        except Exception as e:  # pragma: no cover
+            import traceback
+
+            traceback.print_exc()
+            errs.append(e)
+
+    ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+    [t.start() for t in ths]
+    [t.join(120) for t in ths]
+    assert not errs, errs
+    for r in range(W):
+        prv = (r - 1) % W
+        exp = torch.zeros(64)
+        exp[16:48] = torch.arange(8, 40, dtype=torch.float32) + 1000 * prv
+        assert torch.equal(res[r], exp)
+    for r in sorted(comms, reverse=True):
+        comms[r].close()
+    compat.uninstall()
+    with pytest.raises(ValueError):
+        Communicator(gpu_id=-1, rank=0, world_size=1, exchanger_port=port, transport="carrier-pigeon")

@@ -54,7 +54,24 @@ def install(name: str = "uccl") -> types.ModuleType:
     return m
 
 
+def install_ukernel() -> None:
+    """Aliases for the reference's experimental ukernel packages: ``ukernel_ccl`` (ProcessGroup + functional API,
+    experimental/ukernel/py/ukernel_ccl) -> ``uccl_b200.ukernel`` and ``ukernel_p2p`` (rank-addressed Communicator,
+    experimental/ukernel/py/ukernel_p2p) -> ``uccl_b200.ukernel.p2p``."""
+    import uccl_b200.ukernel
+    import uccl_b200.ukernel.p2p
+
+    for name, mod in (("ukernel_ccl", uccl_b200.ukernel), ("ukernel_p2p", uccl_b200.ukernel.p2p)):
+        cur = sys.modules.get(name)
+        if cur is not None and cur is not mod:
+            raise RuntimeError(f"a different '{name}' module is already imported ({getattr(cur, '__file__', '?')})")
+        sys.modules[name] = mod
+
+
 def uninstall(name: str = "uccl") -> None:
+    for extra, target in (("ukernel_ccl", "uccl_b200.ukernel"), ("ukernel_p2p", "uccl_b200.ukernel.p2p")):
+        if sys.modules.get(extra) is sys.modules.get(target) and extra in sys.modules:
+            sys.modules.pop(extra)
     cur = sys.modules.get(name)
     if cur is not None and getattr(cur, "__uccl_b200_alias__", False):
         for k in [name] + [f"{name}.{s}" for s in ("p2p", "collective", "ep", "utils")]:
