@@ -34,6 +34,10 @@ def test_split_is_physical_and_usable():
     torch.cuda.synchronize()
     assert torch.allclose(z, ref, rtol=1e-4, atol=1e-2) and torch.allclose(z2, ref, rtol=1e-4, atol=1e-2)
     assert "SmPartition" in repr(part)
+    # tensors that were allocated while a partition stream was current go first, then the partitions
+    del z, z2
+    torch.cuda.synchronize()
+    del part, rest
 
 
 def test_ep_buffer_on_a_partition():
@@ -77,3 +81,5 @@ def test_ep_buffer_on_a_partition():
         assert torch.equal(a, b)
     for a, b in zip(base, again):
         assert torch.equal(a, b)
+    torch.cuda.synchronize()
+    del part, rest

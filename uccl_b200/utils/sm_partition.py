@@ -13,6 +13,9 @@ communication SMs.  Native side: ``csrc/common/sm_partition.{h,cc}``; the refere
     with comm_sms:                                           # ... the all-to-all to its own SMs
         recv, *_ = buffer.dispatch(...)
 
+Lifetime: a partition owns its streams.  Release tensors that were allocated while one of them was the current stream
+(and synchronise) before dropping the partition, as with any stream that outlives its users.
+
 Kernels of this library synchronise their CTAs with each other and with the same CTA on peer GPUs: never launch them
 on a partition with fewer SMs than their budget.
 """
