@@ -680,3 +680,34 @@ def test_rank_addressed_p2p_communicator():
     compat.uninstall()
     with pytest.raises(ValueError):
         Communicator(gpu_id=-1, rank=0, world_size=1, exchanger_port=port, transport="carrier-pigeon")
+
+
+def test_functional_api_standalone_world():
+    """`ukernel_ccl.init_process_group(rank=, world_size=, gpu_id=, exchanger_ip=, exchanger_port=, transport=)` as in
+    the reference's test_collective.py: no torch.distributed, the world is rendezvoused through the exchanger that
+    rank 0 serves.  Two processes, host memory (tests/uk_ccl_worker.py)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", EXCHANGER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(root, "tests", "uk_ccl_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            o, _ = p.communicate()
+        outs.append(o)
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in o, o[-3000:]

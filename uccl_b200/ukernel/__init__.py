@@ -354,17 +354,69 @@ class ProcessGroup:
 _DEFAULT_GROUP: Optional[ProcessGroup] = None
 
 
-def init_process_group(backend: str = "ukernel", comm: Optional[Communicator] = None, **kw) -> ProcessGroup:
-    """Creates the default group.  `comm`: an existing Communicator; otherwise one is built from the initialised
-    ``torch.distributed`` world (``Communicator.from_torch_dist``).  Keyword arguments go to :class:`ProcessGroup`
-    (``nlanes``, ``tile_bytes``, ``staging_bytes``)."""
+def _comm_from_exchanger(rank: int, world_size: int, gpu_id: int, exchanger_ip: str, exchanger_port: int,
+                         heap_bytes: int, stage_bytes: int):
+    """A Communicator for a world that has no torch.distributed: rank 0 serves a key/value exchanger
+    (`ukernel.p2p.Exchanger`, the reference's socket OOB) and publishes the 128-byte unique id through it."""
+    from .p2p import Exchanger, _ExchangerClient
+
+    server = Exchanger(exchanger_ip, exchanger_port) if rank == 0 else None
+    x = _ExchangerClient(exchanger_ip, exchanger_port)
+    try:
+        if rank == 0:
+            x.put("ukernel_ccl/uid", Communicator.create_unique_id())
+        ok, uid = x.get("ukernel_ccl/uid", 120000)
+        if not ok:
+            raise RuntimeError("ukernel: rank 0 never published the communicator id")
+        host = not torch.cuda.is_available() or gpu_id is None or int(gpu_id) < 0
+        comm = Communicator.init(uid, rank, world_size, device=None if host else int(gpu_id), host=host,
+                                 heap_bytes=heap_bytes, stage_bytes=stage_bytes)
+        # nobody may tear the exchanger down while a peer is still fetching the id
+        x.put(f"ukernel_ccl/up/{rank}", True)
+        x.count("ukernel_ccl/up/", world_size, 120000)
+    finally:
+        x.close()
+    comm._exchanger = server  # rank 0 keeps it alive as long as the communicator
+    return comm
+
+
+def init_process_group(backend: str = "ukernel", comm: Optional[Communicator] = None, *, rank: Optional[int] = None,
+                       world_size: Optional[int] = None, gpu_id: Optional[int] = None,
+                       exchanger_ip: Optional[str] = None, exchanger_port: Optional[int] = None,
+                       transport: str = "auto", heap_bytes: int = 1 << 30, stage_bytes: int = 64 << 20,
+                       **kw) -> ProcessGroup:
+    """Creates the default group.  Three ways to say which world it spans:
+
+    * `comm`: an existing Communicator;
+    * nothing, with ``torch.distributed`` initialised: ``Communicator.from_torch_dist()``;
+    * the reference's keywords (ukernel_ccl/__init__.py:350-393) -- ``rank / world_size / gpu_id / exchanger_ip /
+      exchanger_port`` with its defaults from ``RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT``: a
+      stand-alone world rendezvoused through an exchanger that rank 0 serves.  `transport` is accepted ("auto";
+      inside a box the transport is load/store over NVLink) and the reference's worker sizing knobs
+      (``device_task_capacity, max_device_fifos, threads_per_block, fifo_capacity, smem_size``) are ignored.
+
+    Other keyword arguments go to :class:`ProcessGroup` (``nlanes``, ``tile_bytes``, ``staging_bytes``)."""
     global _DEFAULT_GROUP
-    if backend != "ukernel":
+    if backend not in ("ukernel", "ucc", "ccl"):
         raise ValueError(f"unsupported backend {backend!r}")
     if _DEFAULT_GROUP is not None:
         raise RuntimeError("default ukernel process group already initialised")
+    for knob in ("device_task_capacity", "max_device_fifos", "threads_per_block", "fifo_capacity", "smem_size"):
+        kw.pop(knob, None)
     if comm is None:
-        comm = Communicator.from_torch_dist()
+        import os
+        import torch.distributed as dist
+
+        explicit = rank is not None or world_size is not None or exchanger_port is not None or exchanger_ip is not None
+        if explicit or not (dist.is_available() and dist.is_initialized()):
+            rank = int(os.environ.get("RANK", 0)) if rank is None else int(rank)
+            world_size = int(os.environ.get("WORLD_SIZE", 1)) if world_size is None else int(world_size)
+            gpu_id = int(os.environ.get("LOCAL_RANK", rank)) if gpu_id is None else int(gpu_id)
+            exchanger_ip = os.environ.get("MASTER_ADDR", "127.0.0.1") if exchanger_ip is None else exchanger_ip
+            exchanger_port = int(os.environ.get("MASTER_PORT", 29500)) if exchanger_port is None else int(exchanger_port)
+            comm = _comm_from_exchanger(rank, world_size, gpu_id, exchanger_ip, exchanger_port, heap_bytes, stage_bytes)
+        else:
+            comm = Communicator.from_torch_dist(heap_bytes=heap_bytes, stage_bytes=stage_bytes)
     _DEFAULT_GROUP = ProcessGroup(comm, **kw)
     return _DEFAULT_GROUP
 
@@ -401,13 +453,16 @@ def barrier(group: Optional[ProcessGroup] = None, async_op: bool = False):
     return _group(group).barrier(async_op=async_op)
 
 
-def all_reduce(tensor, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False):
-    return _group(group).all_reduce(tensor, op=op, async_op=async_op)
+def all_reduce(tensor, op=ReduceOp.SUM, group: Optional[ProcessGroup] = None, async_op: bool = False, *,
+               tile_bytes: Optional[int] = None, num_flows: Optional[int] = None):
+    return _group(group).all_reduce(tensor, op=op, async_op=async_op, tile_bytes=tile_bytes, num_flows=num_flows)
 
 
 def all_to_all_single(output, input, output_split_sizes=None, input_split_sizes=None,
-                      group: Optional[ProcessGroup] = None, async_op: bool = False):
-    return _group(group).all_to_all_single(output, input, output_split_sizes, input_split_sizes, async_op=async_op)
+                      group: Optional[ProcessGroup] = None, async_op: bool = False, *,
+                      tile_bytes: Optional[int] = None, num_flows: Optional[int] = None):
+    return _group(group).all_to_all_single(output, input, output_split_sizes, input_split_sizes, async_op=async_op,
+                                           tile_bytes=tile_bytes, num_flows=num_flows)
 
 
 class UkNetCommunicator:
