@@ -150,9 +150,10 @@ def main():
     _, out["gemm_alone_us"] = timed(s1, s2, False, True)
     out["plain_streams_ep_us"], out["plain_streams_gemm_us"] = timed(s1, s2, True, True)
     buf.use_sm_partition(part)  # the buffer's communication stream is now the partition's stream
-    out["ep_on_partition_alone_us"], _ = timed(part.stream(), rest.stream(), True, False)
-    _, out["gemm_on_rest_alone_us"] = timed(part.stream(), rest.stream(), False, True)
-    out["partitioned_ep_us"], out["partitioned_gemm_us"] = timed(part.stream(), rest.stream(), True, True)
+    ps, rs = buf.get_comm_stream(), rest.stream()
+    out["ep_on_partition_alone_us"], _ = timed(ps, rs, True, False)
+    _, out["gemm_on_rest_alone_us"] = timed(ps, rs, False, True)
+    out["partitioned_ep_us"], out["partitioned_gemm_us"] = timed(ps, rs, True, True)
     out["partition_sms"], out["rest_sms"], out["ep_num_sms"] = part.sm_count, rest.sm_count, cfg.num_sms
     res["ep_vs_gemm"] = out
     buf.use_sm_partition(None)

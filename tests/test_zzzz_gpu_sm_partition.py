@@ -72,7 +72,7 @@ def test_ep_buffer_on_a_partition():
     base = roundtrip()
     part, rest = SmPartition.split(24)
     buf.use_sm_partition(part)
-    assert buf._sms(Config(64)) <= part.sm_count and buf.get_comm_stream().cuda_stream == part.stream().cuda_stream
+    assert buf._sms(Config(64)) <= part.sm_count and buf.get_comm_stream().cuda_stream == part.stream(-1).cuda_stream
     with rest:
         got = roundtrip()
     buf.use_sm_partition(None)

@@ -157,7 +157,7 @@ class Buffer:
                              "SM partitions are for one process per GPU")
         torch.cuda.current_stream(self.device).synchronize()
         self.comm_stream.synchronize()
-        self.comm_stream = partition.stream()
+        self.comm_stream = partition.stream(-1)  # high priority, like the ordinary communication stream
         self._sm_partition = partition
 
     def _check_symmetric_placement(self):
