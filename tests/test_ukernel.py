@@ -666,10 +666,11 @@ def test_rank_addressed_p2p_communicator():
             traceback.print_exc()
             errs.append(e)
 
-    ths = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+    ths = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(W)]
     [t.start() for t in ths]
     [t.join(120) for t in ths]
     assert not errs, errs
+    assert not any(t.is_alive() for t in ths), "a rank is stuck"
     for r in range(W):
         prv = (r - 1) % W
         exp = torch.zeros(64)

@@ -49,7 +49,7 @@ def test_ep_buffer_on_a_partition():
     from uccl_b200.ep import Buffer, Config
 
     T, H, K, E = 256, 1024, 4, 8
-    comm = Communicator.local_world(1, devices=[0], heap_bytes=512 << 20)[0]
+    comm = Communicator.local_world(1, devices=[0], heap_bytes=512 << 20, timeout_ms=20000)[0]
     buf = Buffer(comm=comm, num_nvl_bytes=64 << 20)
     g = torch.Generator().manual_seed(5)
     x = torch.randn(T, H, generator=g).to(torch.bfloat16).cuda()

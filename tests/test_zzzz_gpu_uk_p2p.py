@@ -48,10 +48,11 @@ def test_two_ranks_device_tensors():
             traceback.print_exc()
             errs.append(e)
 
-    ths = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    ths = [threading.Thread(target=run, args=(r,), daemon=True) for r in range(2)]
     [t.start() for t in ths]
-    [t.join(200) for t in ths]
+    [t.join(120) for t in ths]
     assert not errs, errs
+    assert not any(t.is_alive() for t in ths), "a rank is stuck"
     for r in range(2):
         exp = torch.zeros(n)
         exp[1024:1024 + n // 2] = torch.arange(256, 256 + n // 2, dtype=torch.float32) + 7 * (2 - r)
