@@ -51,6 +51,13 @@ def collect() -> dict:
             info["topology"] = r.stdout.strip().splitlines()[: n + 2]
     info["gpus"] = gpus
     try:
+        from uccl_b200.utils import SmPartition
+
+        ok, why = SmPartition.supported(0 if gpus else None)
+        info["sm_partitions"] = "supported" if ok else f"unavailable ({why})"
+    except Exception as e:  # noqa: BLE001
+        info["sm_partitions"] = f"unavailable ({type(e).__name__}: {e})"
+    try:
         from uccl_b200.net import topology
 
         info["nics"] = [str(x) for x in topology.list_nics()] if hasattr(topology, "list_nics") else None
@@ -76,6 +83,7 @@ def main(argv=None) -> int:
             print(f"  GPU {g['index']}: {g['name']} cc {g['cc']}, {g['sms']} SMs, {g['memory_GiB']} GiB")
         full = all(all(r) for r in info["peer_access"])
         print(f"  peer access: {'full mesh' if full else info['peer_access']}; NVLS multicast: {info['multicast_supported']}")
+        print(f"  SM partitions (green contexts): {info['sm_partitions']}")
         for line in info.get("topology", []):
             print("   ", line)
     else:
