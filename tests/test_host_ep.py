@@ -493,3 +493,54 @@ def test_vllm_call_shapes_on_the_host_backend():
         assert torch.allclose(comb.float(), xs[r].float() * in_rank.sum(1, keepdim=True), rtol=2e-2, atol=1e-2)
         wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
         assert torch.allclose(out.float(), xs[r].float() * wsum[:, None], rtol=3e-2, atol=1e-1)
+
+
+def test_megatron_call_shapes_on_the_host_backend():
+    """The keyword calls of Megatron-LM's flex dispatcher (megatron/core/transformer/moe/fused_a2a.py: FusedDispatch /
+    FusedCombine, forward and backward) against the Buffer API: sizing through the Config hints, dispatch with
+    probabilities, combine of the expert outputs, then the backward pair -- combine of the dispatched gradient with
+    `topk_weights=` the probability gradient, dispatch of the combined gradient through the cached handle."""
+    n, T, H, K, E = 2, 32, 256, 2, 4
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    xs, idxs, ws = _inputs(n, T, H, K, E, seed=33)
+
+    def fn(c):
+        r = c.rank
+        x, token_indices, token_probs = xs[r], idxs[r], ws[r]
+        hidden_bytes = x.size(1) * max(x.element_size(), 2)
+        num_nvl_bytes, num_rdma_bytes = 0, 0
+        for config in (Buffer.get_dispatch_config(n), Buffer.get_combine_config(n)):
+            num_nvl_bytes = max(config.get_nvl_buffer_size_hint(hidden_bytes, n), num_nvl_bytes)
+            num_rdma_bytes = max(config.get_rdma_buffer_size_hint(hidden_bytes, n), num_rdma_bytes)
+        buffer = Buffer(comm=c, num_nvl_bytes=num_nvl_bytes, num_rdma_bytes=num_rdma_bytes)
+        # FusedDispatch.forward
+        (num_tokens_per_rank, num_tokens_per_rdma_rank, num_tokens_per_expert, is_token_in_rank, previous_event) = \
+            buffer.get_dispatch_layout(token_indices, E, previous_event=None, async_finish=False,
+                                       allocate_on_comm_stream=False)
+        (recv_x, recv_token_indices, recv_token_probs, num_recv_tokens_per_expert_list, handle, event) = buffer.dispatch(
+            x, topk_idx=token_indices, topk_weights=token_probs.float(), num_tokens_per_rank=num_tokens_per_rank,
+            num_tokens_per_rdma_rank=num_tokens_per_rdma_rank, is_token_in_rank=is_token_in_rank,
+            num_tokens_per_expert=num_tokens_per_expert, previous_event=None, async_finish=False,
+            allocate_on_comm_stream=False)
+        tokens_per_expert = torch.tensor(num_recv_tokens_per_expert_list)
+        assert int(tokens_per_expert.sum()) == int((recv_token_indices >= 0).sum())
+        # FusedCombine.forward (experts = identity)
+        combined_x, _, event = buffer.combine(recv_x, handle=handle, async_finish=False, previous_event=None,
+                                              allocate_on_comm_stream=False)
+        # FusedCombine.backward: the gradient of the combined activations is dispatched through the cached handle
+        grad_out = torch.ones_like(combined_x)
+        grad_x, _, _, _, _, event = buffer.dispatch(grad_out.contiguous(), handle=handle, previous_event=None,
+                                                    async_finish=False, allocate_on_comm_stream=False)
+        assert grad_x.shape == recv_x.shape
+        # FusedDispatch.backward: gradients of the received rows and of their probabilities travel back together
+        grad_probs = torch.where(recv_token_indices >= 0, torch.ones_like(recv_token_probs), torch.zeros_like(recv_token_probs))
+        gx, gprobs, event = buffer.combine(grad_x.contiguous(), handle, topk_weights=grad_probs.float(),
+                                           previous_event=None, async_finish=False, allocate_on_comm_stream=False)
+        return combined_x, gx, gprobs
+
+    for r, (comb, gx, gprobs) in enumerate(_run(comms, fn)):
+        in_rank = torch.stack([((idxs[r] >= d * (E // n)) & (idxs[r] < (d + 1) * (E // n))).any(1) for d in range(n)], 1)
+        fan = in_rank.sum(1, keepdim=True).float()
+        assert torch.allclose(comb.float(), xs[r].float() * fan, rtol=2e-2, atol=1e-2)
+        assert torch.allclose(gx.float(), torch.ones(T, H) * fan, rtol=2e-2, atol=1e-2)
+        assert torch.equal(gprobs, (idxs[r] >= 0).float())
