@@ -544,3 +544,55 @@ def test_megatron_call_shapes_on_the_host_backend():
         assert torch.allclose(comb.float(), xs[r].float() * fan, rtol=2e-2, atol=1e-2)
         assert torch.allclose(gx.float(), torch.ones(T, H) * fan, rtol=2e-2, atol=1e-2)
         assert torch.equal(gprobs, (idxs[r] >= 0).float())
+
+
+def test_sglang_call_shapes_on_the_host_backend():
+    """SGLang's DeepEP dispatcher (sglang/srt/layers/moe/token_dispatcher/deepep.py): normal mode with a captured
+    previous event, async_finish and a pre-cast fp8 input; low-latency mode with async_finish (no hook) followed by
+    clean_low_latency_buffer; Config built from explicit numbers."""
+    from uccl_b200.ep import Config
+
+    n, T, H, K, E, M = 2, 16, 512, 2, 4, 16
+    comms = Communicator.local_world(n, host=True, heap_bytes=128 << 20, stage_bytes=1 << 20)
+    xs, idxs, ws = _inputs(n, T, H, K, E, seed=44)
+
+    def fn(c):
+        r = c.rank
+        buffer = Buffer(comm=c, num_nvl_bytes=1 << 20,
+                        num_rdma_bytes=Buffer.get_low_latency_rdma_size_hint(M, H, n, E), low_latency_mode=True,
+                        num_qps_per_rank=max(E // n, Buffer.num_sms // 2), allow_mnnvl=True)
+        cfg = Config(Buffer.num_sms, 6, 256, 6, 128)
+        previous_event = Buffer.capture()
+        (num_tokens_per_rank, num_tokens_per_rdma_rank, num_tokens_per_expert, is_token_in_rank, previous_event) = \
+            buffer.get_dispatch_layout(idxs[r], E, previous_event=previous_event, async_finish=True,
+                                       allocate_on_comm_stream=previous_event is not None)
+        x8 = per_token_cast_to_fp8(xs[r])
+        (recv_x, recv_topk_idx, recv_topk_weights, num_recv_tokens_per_expert_list, handle, event) = buffer.dispatch(
+            x8, topk_idx=idxs[r], topk_weights=ws[r], num_tokens_per_rank=num_tokens_per_rank,
+            num_tokens_per_rdma_rank=num_tokens_per_rdma_rank, is_token_in_rank=is_token_in_rank,
+            num_tokens_per_expert=num_tokens_per_expert, previous_event=previous_event, async_finish=True,
+            allocate_on_comm_stream=True, expert_alignment=128, config=cfg)
+        event.current_stream_wait()
+        assert isinstance(recv_x, tuple) and all(v % 128 == 0 for v in num_recv_tokens_per_expert_list)
+        y = per_token_cast_back(*recv_x)
+        combined, _, event = buffer.combine(y, handle, async_finish=True, previous_event=Buffer.capture(),
+                                            allocate_on_comm_stream=True, config=cfg)
+        event.current_stream_wait()
+        packed, counts, ll_handle, event, hook = buffer.low_latency_dispatch(
+            xs[r], idxs[r], M, E, use_fp8=True, async_finish=True, return_recv_hook=False, round_scale=False,
+            use_ue8m0=False)
+        assert hook is None
+        event.current_stream_wait()
+        q, s = packed
+        deq = per_token_cast_back(q.view(-1, H), s.reshape(-1, H // 128).contiguous()).view(E // n, n * M, H)
+        out, event, hook = buffer.low_latency_combine(deq, idxs[r], ws[r], ll_handle, async_finish=True,
+                                                      return_recv_hook=False)
+        event.current_stream_wait()
+        buffer.clean_low_latency_buffer(M, H, E)
+        return combined, out
+
+    for r, (comb, out) in enumerate(_run(comms, fn)):
+        in_rank = torch.stack([((idxs[r] >= d * (E // n)) & (idxs[r] < (d + 1) * (E // n))).any(1) for d in range(n)], 1)
+        assert torch.allclose(comb.float(), xs[r].float() * in_rank.sum(1, keepdim=True), rtol=0.08, atol=0.3)
+        wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
+        assert torch.allclose(out.float(), xs[r].float() * wsum[:, None], rtol=0.08, atol=0.3)

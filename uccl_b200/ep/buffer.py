@@ -198,6 +198,10 @@ class Buffer:
 
     @staticmethod
     def capture() -> EventOverlap:
+        """An event on the current stream (DeepEP: `Buffer.capture`); an empty overlap object on a machine without
+        CUDA, where the host backend has nothing to order."""
+        if not torch.cuda.is_available():
+            return EventOverlap()
         return EventOverlap(EventHandle())
 
     def get_comm_stream(self) -> torch.cuda.Stream:
