@@ -6,7 +6,7 @@ layers in flight), so the ``Buffer`` exported here hands out OWNED tensors like 
 (``owned_results=True``); ``uccl_b200.ep.Buffer`` itself defaults to zero-copy views of its receive arenas."""
 from uccl_b200.ep import Buffer as _Buffer
 from uccl_b200.ep import Config, EventOverlap  # noqa: F401
-from uccl_b200.ep.utils import EventHandle  # noqa: F401
+from uccl_b200.ep.utils import EventHandle, check_nvlink_connections, destroy_uccl, initialize_uccl  # noqa: F401
 
 
 class Buffer(_Buffer):
@@ -15,4 +15,5 @@ class Buffer(_Buffer):
         super().__init__(*args, **kwargs)
 
 
-__all__ = ["Buffer", "Config", "EventOverlap", "EventHandle"]
+# the reference's wrapper also exports its set-up helpers from the package root (ep/deep_ep_wrapper/deep_ep/__init__.py)
+__all__ = ["Buffer", "Config", "EventOverlap", "EventHandle", "check_nvlink_connections", "initialize_uccl", "destroy_uccl"]

@@ -596,3 +596,20 @@ def test_sglang_call_shapes_on_the_host_backend():
         assert torch.allclose(comb.float(), xs[r].float() * in_rank.sum(1, keepdim=True), rtol=0.08, atol=0.3)
         wsum = torch.where(idxs[r] >= 0, ws[r], torch.zeros_like(ws[r])).sum(1)
         assert torch.allclose(out.float(), xs[r].float() * wsum[:, None], rtol=0.08, atol=0.3)
+
+
+def test_deep_ep_package_exports_what_the_reference_wrapper_exports():
+    import ast
+    import os
+
+    import deep_ep
+
+    path = "/root/reference/ep/deep_ep_wrapper/deep_ep/__init__.py"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not available")
+    for n in ast.walk(ast.parse(open(path).read())):
+        if isinstance(n, ast.Assign) and any(getattr(t, "id", "") == "__all__" for t in n.targets):
+            missing = [x for x in ast.literal_eval(n.value) if not hasattr(deep_ep, x)]
+            assert not missing, missing
+            return
+    raise AssertionError("no __all__ in the reference wrapper")
