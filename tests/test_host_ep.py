@@ -374,7 +374,8 @@ def test_buffer_signature_audit_against_the_reference_and_upstream_deepep():
     from uccl_b200.ep.buffer import Buffer as Native
     from uccl_b200.ep.low_latency import LowLatencyRuntime
 
-    files = ["/root/reference/ep/bench/buffer.py", "/root/reference/thirdparty/DeepEP/deep_ep/buffer.py"]
+    files = ["/root/reference/ep/bench/buffer.py", "/root/reference/thirdparty/DeepEP/deep_ep/buffer.py",
+             "/root/reference/ep/deep_ep_wrapper/deep_ep/buffer.py"]
     files = [f for f in files if os.path.exists(f)]
     if not files:
         pytest.skip("reference tree not available")
@@ -407,7 +408,7 @@ def test_utils_signature_audit_against_the_reference_helpers():
     import uccl_b200.ep.utils as U
 
     files = ["/root/reference/ep/bench/utils.py", "/root/reference/thirdparty/DeepEP/deep_ep/utils.py",
-             "/root/reference/thirdparty/DeepEP/tests/utils.py"]
+             "/root/reference/thirdparty/DeepEP/tests/utils.py", "/root/reference/ep/deep_ep_wrapper/deep_ep/utils.py"]
     files = [f for f in files if os.path.exists(f)]
     if not files:
         pytest.skip("reference tree not available")
