@@ -19,3 +19,5 @@ $R benchmarks/uk_bench.py --out "$OUT/uk$N.json" || true
 python benchmarks/compress_bench.py --out "$OUT/compress.json" || true
 $R benchmarks/p2p_traffic.py --pattern permutation --out "$OUT/perm$N.json" || true
 $R benchmarks/p2p_traffic.py --pattern incast --out "$OUT/incast$N.json" || true
+python benchmarks/hostlink_bench.py --out "$OUT/hostlink.json" || true
+$R benchmarks/sm_partition_bench.py --out "$OUT/sm_partition$N.json" || true
