@@ -144,7 +144,8 @@ class Buffer:
         partition's size (the kernels synchronise their CTAs with each other, so all of them must be resident).  Give
         the rest of the device to the compute streams (``with rest: ...``) to keep GEMMs off these SMs.  ``None``
         restores an ordinary stream.  The low-latency kernels run on the caller's current stream (DeepEP's contract):
-        enter the partition (``with partition:``) around those calls instead."""
+        enter the partition (``with partition:``) around those calls instead; while a partition is set they, too, bring at
+        most its SM count of CTAs, so that doing so can never leave part of a launch waiting for an SM."""
         if partition is None:
             with torch.cuda.device(self.device):
                 self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
