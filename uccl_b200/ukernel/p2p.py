@@ -30,7 +30,8 @@ _TRANSPORTS = ("auto", "ipc", "uccl", "tcp")
 
 class Exchanger:
     """Key/value rendezvous.  ``put`` stores, ``get`` blocks until the key exists (or the timeout passes),
-    ``count`` blocks until `n` keys with a prefix exist.  One thread per client connection; values are pickles."""
+    ``count`` blocks until `n` keys with a prefix exist.  One thread per client connection; values are pickles, so --
+    like torch.distributed's object collectives -- bind it to an address only trusted peers can reach."""
 
     def __init__(self, ip: str, port: int):
         self._kv: Dict[str, Any] = {}
