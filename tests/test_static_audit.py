@@ -100,3 +100,49 @@ def test_documentation_snippets_import_existing_names():
                             except ImportError:
                                 problems.append(f"{os.path.relpath(f, ROOT)}: {n.module}.{a.name} does not exist")
     assert checked > 5 and not problems, "\n".join(problems)
+
+
+def test_every_environment_knob_is_documented():
+    """Each UCCL_B200_* variable the sources read appears in docs/config.md (families may be abbreviated there as
+    `UCCL_B200_X_A` / `_B`)."""
+
+    names = set()
+    for pat in ("*.py", "*.cc", "*.h", "*.cu", "*.cuh"):
+        for f in glob.glob(os.path.join(ROOT, "uccl_b200", "**", pat), recursive=True) + [os.path.join(ROOT, "bench.py")]:
+            try:
+                names.update(re.findall(r"UCCL_B200_[A-Z0-9_]+", open(f, errors="ignore").read()))
+            except OSError:
+                pass
+    doc = open(os.path.join(ROOT, "docs", "config.md")).read()
+    assert len(names) > 25
+    missing = []
+    for n in sorted(names):
+        if n in doc or n.endswith("_"):
+            continue
+        parts = n.split("_")
+        # abbreviated family member: some suffix "_X_Y" of the name appears in backticks or after a slash
+        if any(("`_" + "_".join(parts[i:]) + "`") in doc or ("/ `_" + "_".join(parts[i:])) in doc or ("_" + "_".join(parts[i:]) + "`") in doc
+               for i in range(2, len(parts))):
+            continue
+        missing.append(n)
+    assert not missing, missing
+
+
+def test_every_prefixed_native_parameter_is_documented():
+    """Parameters the native code reads through UB_PARAM / param_load (the UCCL_B200_ prefix is added at run time)."""
+    names = set()
+    for f in glob.glob(os.path.join(ROOT, "uccl_b200", "csrc", "**", "*.*"), recursive=True):
+        if f.endswith((".cc", ".h", ".cu", ".cuh")):
+            src = open(f, errors="ignore").read()
+            names.update(re.findall(r'UB_PARAM\([A-Za-z0-9_]+,\s*"([A-Z0-9_]+)"', src))
+            names.update(re.findall(r'param_load(?:_str)?\("([A-Z0-9_]+)"', src))
+    names.discard("ENV_SUFFIX")
+    doc = open(os.path.join(ROOT, "docs", "config.md")).read()
+    assert len(names) > 30
+    missing = []
+    for n in sorted(names):
+        parts = n.split("_")
+        if n in doc or any(("_" + "_".join(parts[i:]) + "`") in doc for i in range(1, len(parts))):
+            continue
+        missing.append(n)
+    assert not missing, missing
